@@ -1,0 +1,232 @@
+/*
+ * vxpt.h — C ABI of the B200-native voxel ray-tracing core.
+ *
+ * Drop-in boundary for ONE path of swr06/VoxelPathTracer: the Manhattan distance-field build over the
+ * 384x128x384 uint8 block grid and the distance-field-accelerated voxel DDA traversal behind primary,
+ * sun-shadow, diffuse-GI and reflection rays.  The reference has no FFI surface; its de-facto interface is
+ * the set of GL objects + uniforms Core/Pipeline.cpp binds before each trace draw.  Every export below
+ * names the reference call site it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every call returns VXPT_OK (0) or a negative VXPT_E_*;
+ *    vxpt_last_error() returns a thread-local description of the last failure.
+ *  - a handle is NOT thread-safe (one caller thread per handle, like a GL context).
+ *  - all buffers are caller-owned.  Input pointers may be host or device memory; output pointers may be host
+ *    or device memory (detected with cudaPointerGetAttributes).  Host outputs are staged through pinned
+ *    memory owned by the handle and are complete when the call returns; device outputs are complete after
+ *    vxpt_sync() (work is enqueued on the handle's private stream).
+ *  - images: pixel (i, j) with j = 0 the BOTTOM row (GL convention, a_TexCoords of the full-screen quad);
+ *    plane index = j * width + i.  A call renders rows [row_begin, row_end) only and touches no other row of
+ *    the output planes — this is the multi-GPU row-slab contract.
+ *  - matrices are column-major float[16] exactly as glm::value_ptr gives them.
+ *  - there is NO CPU fallback: if no CUDA device is usable vxpt_create fails with VXPT_E_CUDA.
+ */
+#ifndef VXPT_H_
+#define VXPT_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VXPT_API __declspec(dllexport)
+#else
+#define VXPT_API __attribute__((visibility("default")))
+#endif
+
+/* Core/Macros.h:3-5 */
+#define VXPT_WORLD_SIZE_X 384
+#define VXPT_WORLD_SIZE_Y 128
+#define VXPT_WORLD_SIZE_Z 384
+#define VXPT_WORLD_VOXELS (VXPT_WORLD_SIZE_X * VXPT_WORLD_SIZE_Y * VXPT_WORLD_SIZE_Z) /* 18,874,368 */
+
+/* normal ids, Core/Shaders/InitialRayTraceFrag.glsl:143-185 : {+Z,-Z,+Y,-Y,-X,+X} -> 0..5.
+ * The reference writes id/10 into an R8 target and 1.0 on a miss, which every consumer decodes with
+ * int(round(n*10)) -> 10 ("idx > 5" = no surface). */
+#define VXPT_NORMAL_MISS 10
+
+#define VXPT_OK 0
+#define VXPT_E_INVALID (-1)     /* bad argument / bad state of arguments            */
+#define VXPT_E_CUDA (-2)        /* CUDA runtime failure (message in last_error)     */
+#define VXPT_E_NOMEM (-3)       /* allocation failed                                */
+#define VXPT_E_STATE (-4)       /* call order violated (e.g. trace before DF build) */
+#define VXPT_E_UNSUPPORTED (-5) /* reference option outside the v1 parity profile   */
+
+typedef struct vxpt_ctx* vxpt_handle;
+
+/* ---- camera / frame description --------------------------------------------------------------------------
+ * replaces the uniforms u_InverseView, u_InverseProjection, u_Dimensions (Core/Pipeline.cpp:1979-1999,
+ * 2203-2206, 2807-2810) and FBOVert.glsl's u_VertInverseView / u_VertInverseProjection. */
+typedef struct VxCamera {
+    float inv_view[16];
+    float inv_proj[16];
+    int32_t width, height;       /* full frame size in pixels                         */
+    int32_t row_begin, row_end;  /* slab [row_begin,row_end); 0,height = whole frame  */
+} VxCamera;
+
+/* ---- primary rays: Core/Pipeline.cpp:1973-2016 -> InitialRayTraceFrag.glsl:417-468 ---------------------- */
+typedef struct VxPrimaryParams {
+    int32_t max_iterations;  /* u_RenderDistance: 475 on frame 0 then 350 (Pipeline.cpp:55,4824) */
+    int32_t jitter_enable;   /* u_JitterSceneForTAA                                             */
+    float jitter[2];         /* u_CurrentTAAJitter = Halton(2,3)[frame % 64] (TAAJitter.cpp)    */
+    int32_t alpha_test;      /* u_ShouldAlphaTest; must be 0 (off by default, Pipeline.cpp:141) */
+    int32_t reserved;
+} VxPrimaryParams;
+
+/* G-buffer planes (InitialTraceFBO attachments, Pipeline.cpp:1094-1095).  t is kept in fp32 (the reference's
+ * R16F cannot meet the 1e-5 parity target).  Any pointer may be NULL to skip that plane.
+ * As an OUTPUT of vxpt_trace_primary and as the INPUT of the secondary passes. */
+typedef struct VxGBuffer {
+    float* t;            /* o_HitDistance : hit distance, -1 on a miss                        */
+    uint8_t* normal_id;  /* o_Normal      : 0..5, VXPT_NORMAL_MISS on a miss                  */
+    uint8_t* block_id;   /* o_BlockID     : block byte, 0 on a miss                           */
+    float* inv_t;        /* o_DepthNonLinear = 1/t                                            */
+    int16_t* hit_voxel;  /* optional parity plane: 3 x int16 voxel coords, (-1,-1,-1) on miss */
+} VxGBuffer;
+
+/* ---- sun shadow: Core/Pipeline.cpp:2795-2852 -> ShadowRayTraceFrag.glsl:414-513 ------------------------- */
+typedef struct VxShadowParams {
+    float light_dir[3];      /* u_LightDirection (normalised StrongerLightDirection)              */
+    int32_t frame;           /* u_CurrentFrame (blue-noise texel offset, frame % 1024)            */
+    int32_t soft;            /* u_ContactHardeningShadows (cone jitter); default 1                */
+    float halton[2];         /* u_Halton; zero unless supersampling (Pipeline.cpp:2823)           */
+    int32_t alpha_test;      /* must be 0                                                         */
+} VxShadowParams;
+
+typedef struct VxShadowOut {
+    uint8_t* shadow;     /* o_Shadow 0/1                                             */
+    float* transversal;  /* o_IntersectionTransversal                                */
+} VxShadowOut;
+
+/* ---- diffuse GI: Core/Pipeline.cpp:2174-2281 -> DiffuseRayTraceFrag.glsl:822-935 ------------------------ */
+typedef struct VxDiffuseParams {
+    int32_t spp;             /* u_SPP (clamped 1..32)                                             */
+    int32_t checker_spp;     /* u_CheckerSPP                                                      */
+    int32_t checkerboard;    /* CHECKERBOARD_SPP                                                  */
+    int32_t trace_length;    /* u_DiffuseTraceLength, default 48 (Pipeline.cpp:75)                */
+    int32_t frame;           /* u_CurrentFrame; blue-noise index = frame % 128                    */
+    int32_t use_blue_noise;  /* u_UseBlueNoise; must be 1 (hash2 path is not reproducible)        */
+    int32_t supersample;     /* u_Supersample                                                     */
+    int32_t direct_sampling; /* u_UseDirectSampling; must be 0                                    */
+    float halton[2];         /* u_Halton                                                          */
+    float sun_dir[3];        /* u_SunDirection                                                    */
+    float moon_dir[3];       /* u_MoonDirection                                                   */
+    float sun_visibility;    /* u_SunVisibility                                                   */
+    float gi_sun_strength;   /* u_GISunStrength   (1.0)                                           */
+    float gi_sky_strength;   /* u_GISkyStrength   (1.125)                                         */
+    float light_intensity;   /* u_DiffuseLightIntensity (1.25)                                    */
+} VxDiffuseParams;
+
+typedef struct VxDiffuseOut {
+    float* sh;      /* o_SH   4 floats / pixel   (RGBA16F in the reference)   */
+    float* cocg;    /* o_CoCg 2 floats / pixel                                */
+    float* luma;    /* o_Utility 1 float / pixel                              */
+    float* ao_sky;  /* o_AOAndSkyLighting 2 floats / pixel                    */
+} VxDiffuseOut;
+
+/* ---- reflections: Core/Pipeline.cpp:3003-3164 -> ReflectionTraceFrag.glsl:717-1038 ---------------------- */
+typedef struct VxReflectionParams {
+    int32_t spp;              /* u_SPP (clamped 1..16)                                            */
+    int32_t trace_length;     /* u_ReflectionTraceLength, default 64                              */
+    int32_t frame;            /* u_CurrentFrame; blue-noise index = frame % 128 (TEMPORAL_SPEC)   */
+    int32_t rough;            /* u_RoughReflections                                               */
+    int32_t roughness_bias;   /* u_RoughnessBias (0.85x)                                          */
+    int32_t checkerboard;     /* CHECKERBOARD_SPEC_SPP                                            */
+    float sun_dir[3];
+    float moon_dir[3];
+    float stronger_dir[3];    /* u_StrongerLightDirection                                         */
+    float viewer_pos[3];      /* u_ViewerPosition                                                 */
+    float sun_strength;       /* u_SunStrengthModifier 0.85                                       */
+    float moon_strength;      /* u_MoonStrengthModifier 1.0                                       */
+    int32_t grass_props[10];  /* u_GrassBlockProps (Pipeline.cpp:3040-3049)                       */
+} VxReflectionParams;
+
+typedef struct VxReflectionIn {
+    const float* g_normal;   /* u_GBufferNormals 3 floats / pixel; NULL = face normal             */
+    const float* g_pbr;      /* u_GBufferPBR     4 floats / pixel; NULL = per-block constants     */
+    const float* sh;         /* u_DiffuseSH   (this library's GI output)                          */
+    const float* cocg;       /* u_DiffuseCoCg                                                     */
+} VxReflectionIn;
+
+typedef struct VxReflectionOut {
+    float* color;            /* o_Color 4 floats / pixel       */
+    float* hit_distance;     /* o_HitDistance                  */
+    uint8_t* emissive_mask;  /* o_EmissivityHitMask            */
+} VxReflectionOut;
+
+/* ---- traversal statistics (the reference has none; they define the roofline's algorithmic bytes) -------- */
+typedef struct VxStats {
+    uint64_t rays;        /* VoxelTraversalDF calls                                   */
+    uint64_t df_fetches;  /* loop iterations that read the distance field (N_it)      */
+    uint64_t vox_fetches; /* block-id fetches (N_vox)                                 */
+    float last_ms;        /* device time of the last pass (CUDA events)               */
+    float df_build_ms;    /* device time of the last distance-field build (linear field) */
+    float brick_pack_ms;  /* device time of the brick re-layout that follows it           */
+} VxStats;
+
+/* ---- lifetime: new World() + World::InitializeDistanceGenerator (Core/World.cpp:48-67) ------------------ */
+VXPT_API int vxpt_create(int device_id, vxpt_handle* out);
+VXPT_API int vxpt_destroy(vxpt_handle h);
+VXPT_API const char* vxpt_last_error(void);
+VXPT_API const char* vxpt_version(void);
+
+/* ---- world: World::Buffer (Core/World.h:167-171), glTexSubImage3D edits (Core/World.cpp:372-373,458-459) - */
+VXPT_API int vxpt_upload_world(vxpt_handle h, const uint8_t* blocks /* VXPT_WORLD_VOXELS, x + 384*y + 49152*z */);
+VXPT_API int vxpt_set_block(vxpt_handle h, int x, int y, int z, uint8_t id);
+VXPT_API int vxpt_set_blocks(vxpt_handle h, const int16_t* xyz /* 3*n */, const uint8_t* ids, int n);
+VXPT_API int vxpt_download_world(vxpt_handle h, uint8_t* blocks);
+
+/* ---- distance field: World::GenerateDistanceField (Core/World.cpp:69-113) ------------------------------- */
+VXPT_API int vxpt_build_distance_field(vxpt_handle h);
+VXPT_API int vxpt_download_distance_field(vxpt_handle h, uint8_t* out /* VXPT_WORLD_VOXELS */);
+/* raw device pointers of the resident grid / linear distance field (for zero-copy consumers and tests) */
+VXPT_API int vxpt_device_pointers(vxpt_handle h, const uint8_t** grid, const uint8_t** df);
+
+/* ---- tables: BlockDataSSBO::CreateBuffers (Core/BlockDataSSBO.cpp:28-39), BlueNoiseDataSSBO ctor
+ *      (Core/BlueNoiseDataSSBO.cpp:19-30), texture binds (Core/Pipeline.cpp:2236-2270, 2825-2841) --------- */
+VXPT_API int vxpt_set_materials(vxpt_handle h, const int32_t table[768]);
+VXPT_API int vxpt_set_blue_noise(vxpt_handle h, const int32_t* sobol /*65536*/, const int32_t* scramble /*131072*/,
+                                 const int32_t* rank /*131072*/);
+/* pre-baked texel arrays so both sides of a parity check sample identical data:
+ *  albedo_lod3  [n_layers][64][64][4]   f32 linear RGBA, mip level 3 of the 512^2 sRGB albedo array
+ *  pbr_lod2     [n_layers][128][128][4] f32, mip level 2 of the PBR array
+ *  emissive_lod0[n_emissive_layers][512][512] f32 (red channel)                                    */
+VXPT_API int vxpt_set_material_textures(vxpt_handle h, const float* albedo_lod3, const float* pbr_lod2, int n_layers,
+                                        const float* emissive_lod0, int n_emissive_layers);
+VXPT_API int vxpt_set_sky_cubemap(vxpt_handle h, const float* rgb /* [6][n][n][3], faces +X,-X,+Y,-Y,+Z,-Z */, int n);
+VXPT_API int vxpt_set_shadow_noise(vxpt_handle h, const uint8_t* rgba8 /* [256][256][4] */);
+
+/* ---- trace passes ---------------------------------------------------------------------------------------- */
+VXPT_API int vxpt_trace_primary(vxpt_handle h, const VxCamera* cam, const VxPrimaryParams* p, const VxGBuffer* out);
+VXPT_API int vxpt_trace_shadow(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf, const VxShadowParams* p,
+                               const VxShadowOut* out);
+VXPT_API int vxpt_trace_diffuse(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf, const VxDiffuseParams* p,
+                                const VxDiffuseOut* out);
+VXPT_API int vxpt_trace_reflection(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf,
+                                   const VxReflectionIn* in, const VxReflectionParams* p, const VxReflectionOut* out);
+
+/* ---- glFinish (Core/Pipeline.cpp:4782), statistics ------------------------------------------------------- */
+VXPT_API int vxpt_sync(vxpt_handle h);
+VXPT_API int vxpt_get_stats(vxpt_handle h, VxStats* out);   /* totals since the last reset; syncs */
+VXPT_API int vxpt_reset_stats(vxpt_handle h);
+VXPT_API int vxpt_launch_count(vxpt_handle h, uint64_t* kernels_launched); /* kernels this handle launched */
+/* the CUDA stream (cudaStream_t) the handle enqueues on, so callers can record events around passes */
+VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
+
+/* ---- tuning knobs (do not change results) ---------------------------------------------------------------- */
+#define VXPT_OPT_TRAVERSAL_LAYOUT 1 /* 0 = linear distance field, 1 = brick-swizzled copy (default) */
+#define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront re-queue (default)          */
+#define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped), 1 = DPX tiled (default) */
+VXPT_API int vxpt_set_option(vxpt_handle h, int option, int value);
+
+/* ---- microbenchmark: resident-set random 32-byte-sector read throughput, the denominator of the
+ *      traversal roofline.  Returns GB/s of sectors. ---------------------------------- */
+VXPT_API int vxpt_measure_l2_sector_peak(vxpt_handle h, double* gbytes_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXPT_H_ */

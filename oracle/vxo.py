@@ -1,0 +1,165 @@
+"""ctypes loader of the CPU oracle (oracle/libvxo_oracle.so).  TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the product package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from voxelpathtracer_b200.abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxShadowOut, VxShadowParams)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvxo_oracle.so")
+
+
+class VxoScene(C.Structure):
+    _fields_ = [("wx", C.c_int32), ("wy", C.c_int32), ("wz", C.c_int32), ("grid", C.c_void_p), ("df", C.c_void_p),
+                ("materials", C.c_void_p), ("sobol", C.c_void_p), ("scramble", C.c_void_p), ("rank", C.c_void_p),
+                ("albedo_lod3", C.c_void_p), ("pbr_lod2", C.c_void_p), ("n_layers", C.c_int32),
+                ("emissive_lod0", C.c_void_p), ("n_emissive_layers", C.c_int32), ("sky", C.c_void_p), ("sky_n", C.c_int32),
+                ("shadow_noise", C.c_void_p)]
+
+
+class VxoStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("df_fetches", C.c_uint64), ("vox_fetches", C.c_uint64)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "libvxo_oracle.so"])
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    src = os.path.join(HERE, "vxo_oracle.cpp")
+    if not os.path.exists(LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    lib.vxo_df_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.vxo_df_build.restype = None
+    lib.vxo_df_bruteforce.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.vxo_df_bruteforce.restype = None
+    lib.vxo_traverse.argtypes = [C.POINTER(VxoScene), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int32), C.POINTER(VxoStats)]
+    lib.vxo_traverse.restype = C.c_float
+    lib.vxo_plain_dda.argtypes = [C.POINTER(VxoScene), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.vxo_plain_dda.restype = C.c_int
+    lib.vxo_trace_primary.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxPrimaryParams), C.POINTER(VxGBuffer), C.POINTER(VxoStats)]
+    lib.vxo_trace_shadow.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxShadowParams), C.POINTER(VxShadowOut), C.POINTER(VxoStats)]
+    lib.vxo_trace_diffuse.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut), C.POINTER(VxoStats)]
+    for f in (lib.vxo_trace_primary, lib.vxo_trace_shadow, lib.vxo_trace_diffuse):
+        f.restype = C.c_int
+    lib.vxo_num_threads.restype = C.c_int
+    lib.vxo_set_num_threads.argtypes = [C.c_int]
+    _lib = lib
+    return lib
+
+
+def df_build(grid, dims=(384, 128, 384)):
+    """Literal three-pass distance field (ManhattanDistance{X,Y,Z}.comp)."""
+    grid = np.ascontiguousarray(grid, dtype=np.uint8).reshape(-1)
+    assert grid.size == dims[0] * dims[1] * dims[2]
+    out = np.empty_like(grid)
+    load().vxo_df_build(grid.ctypes.data, out.ctypes.data, *dims)
+    return out
+
+
+def df_bruteforce(grid, dims):
+    grid = np.ascontiguousarray(grid, dtype=np.uint8).reshape(-1)
+    out = np.empty_like(grid)
+    load().vxo_df_bruteforce(grid.ctypes.data, out.ctypes.data, *dims)
+    return out
+
+
+class Oracle:
+    """Holds the scene arrays (keeps them alive) and runs the oracle passes on numpy buffers."""
+
+    def __init__(self, grid, df=None, dims=(384, 128, 384)):
+        self.lib = load()
+        self.dims = dims
+        self.grid = np.ascontiguousarray(grid, dtype=np.uint8).reshape(-1)
+        self.df = df_build(self.grid, dims) if df is None else np.ascontiguousarray(df, dtype=np.uint8).reshape(-1)
+        self.scene = VxoScene()
+        self.scene.wx, self.scene.wy, self.scene.wz = dims
+        self.scene.grid, self.scene.df = self.grid.ctypes.data, self.df.ctypes.data
+        self._keep = {}
+
+    def set_tables(self, materials, blue_noise, sky, shadow_noise):
+        k = self._keep
+        k["table"] = np.ascontiguousarray(materials["table"], dtype=np.int32)
+        k["albedo"] = np.ascontiguousarray(materials["albedo_lod3"], dtype=np.float32)
+        k["pbr"] = np.ascontiguousarray(materials["pbr_lod2"], dtype=np.float32)
+        k["emissive"] = np.ascontiguousarray(materials["emissive_lod0"], dtype=np.float32)
+        k["sobol"], k["scramble"], k["rank"] = (np.ascontiguousarray(x, dtype=np.int32) for x in blue_noise)
+        k["sky"] = np.ascontiguousarray(sky, dtype=np.float32)
+        k["shadow_noise"] = np.ascontiguousarray(shadow_noise, dtype=np.uint8)
+        s = self.scene
+        s.materials = k["table"].ctypes.data
+        s.albedo_lod3, s.pbr_lod2, s.n_layers = k["albedo"].ctypes.data, k["pbr"].ctypes.data, k["albedo"].shape[0]
+        s.emissive_lod0, s.n_emissive_layers = (k["emissive"].ctypes.data if k["emissive"].shape[0] else None), k["emissive"].shape[0]
+        s.sobol, s.scramble, s.rank = k["sobol"].ctypes.data, k["scramble"].ctypes.data, k["rank"].ctypes.data
+        s.sky, s.sky_n = k["sky"].ctypes.data, k["sky"].shape[1]
+        s.shadow_noise = k["shadow_noise"].ctypes.data
+
+    @staticmethod
+    def _stats(st):
+        return {"rays": int(st.rays), "df_fetches": int(st.df_fetches), "vox_fetches": int(st.vox_fetches)}
+
+    def traverse(self, origin, direction, max_it):
+        o = (C.c_float * 3)(*[float(v) for v in origin])
+        d = (C.c_float * 3)(*[float(v) for v in direction])
+        out = (C.c_int32 * 6)()
+        st = VxoStats()
+        t = self.lib.vxo_traverse(C.byref(self.scene), o, d, int(max_it), out, C.byref(st))
+        return {"t": float(t), "min_idx": out[0], "sgn": out[1], "block": out[2], "voxel": (out[3], out[4], out[5]), **self._stats(st)}
+
+    def plain_dda(self, origin, direction, max_steps=2000):
+        o = (C.c_float * 3)(*[float(v) for v in origin])
+        d = (C.c_float * 3)(*[float(v) for v in direction])
+        vox = (C.c_int32 * 3)()
+        axis = C.c_int32()
+        hit = self.lib.vxo_plain_dda(C.byref(self.scene), o, d, int(max_steps), vox, C.byref(axis))
+        return (bool(hit), (vox[0], vox[1], vox[2]), int(axis.value))
+
+    def trace_primary(self, cam, params, hit_voxel=True):
+        H, W = cam.height, cam.width
+        g = {"t": np.zeros((H, W), np.float32), "normal_id": np.zeros((H, W), np.uint8), "block_id": np.zeros((H, W), np.uint8),
+             "inv_t": np.zeros((H, W), np.float32)}
+        if hit_voxel:
+            g["hit_voxel"] = np.zeros((H, W, 3), np.int16)
+        s = VxGBuffer()
+        s.t, s.normal_id, s.block_id, s.inv_t = (g[k].ctypes.data for k in ("t", "normal_id", "block_id", "inv_t"))
+        s.hit_voxel = g["hit_voxel"].ctypes.data if hit_voxel else None
+        st = VxoStats()
+        rc = self.lib.vxo_trace_primary(C.byref(self.scene), C.byref(cam), C.byref(params), C.byref(s), C.byref(st))
+        assert rc == 0, rc
+        return g, self._stats(st)
+
+    def trace_shadow(self, cam, gbuf, params):
+        H, W = cam.height, cam.width
+        out = {"shadow": np.zeros((H, W), np.uint8), "transversal": np.zeros((H, W), np.float32)}
+        g = VxGBuffer()
+        g.t, g.normal_id = gbuf["t"].ctypes.data, gbuf["normal_id"].ctypes.data
+        o = VxShadowOut()
+        o.shadow, o.transversal = out["shadow"].ctypes.data, out["transversal"].ctypes.data
+        st = VxoStats()
+        rc = self.lib.vxo_trace_shadow(C.byref(self.scene), C.byref(cam), C.byref(g), C.byref(params), C.byref(o), C.byref(st))
+        assert rc == 0, rc
+        return out, self._stats(st)
+
+    def trace_diffuse(self, cam, gbuf, params):
+        H, W = cam.height, cam.width
+        out = {"sh": np.zeros((H, W, 4), np.float32), "cocg": np.zeros((H, W, 2), np.float32), "luma": np.zeros((H, W), np.float32),
+               "ao_sky": np.zeros((H, W, 2), np.float32)}
+        g = VxGBuffer()
+        g.t, g.normal_id = gbuf["t"].ctypes.data, gbuf["normal_id"].ctypes.data
+        o = VxDiffuseOut()
+        o.sh, o.cocg, o.luma, o.ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "luma", "ao_sky"))
+        st = VxoStats()
+        rc = self.lib.vxo_trace_diffuse(C.byref(self.scene), C.byref(cam), C.byref(g), C.byref(params), C.byref(o), C.byref(st))
+        assert rc == 0, rc
+        return out, self._stats(st)

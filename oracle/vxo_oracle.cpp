@@ -1,0 +1,762 @@
+// vxo_oracle.cpp — CPU restatement of the reference's distance-field build and DF-accelerated voxel traversal.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load it.  The product library (voxelpathtracer_b200/csrc) never
+// links, includes or calls anything in this directory and has no CPU fallback.
+//
+// PARITY UNPINNED BY THE REFERENCE: swr06/VoxelPathTracer ships no tests, golden vectors or fixtures for this
+// path, and its GLSL cannot be executed in the build container (no GL/EGL/OSMesa).  The pins
+// are therefore this repo's own: analytic known-answer tests, a brute-force definition of the distance field
+// (vxo_df_bruteforce) and an independent plain-DDA cross-check (vxo_plain_dda, after the author's unused
+// Core/Shaders/Implementations/DDA/DDA.glsl) — see tests/test_oracle_*.py.
+//
+// Every function cites the reference file:line it restates (paths relative to the reference tree).
+// Floating point: build with -O2 -ffp-contract=off (no FMA contraction), IEEE division and sqrt; operation
+// order follows the GLSL source as written.  Where GLSL leaves a function's precision open (sin, cos, pow) the
+// oracle pins the correctly-rounded fp32 value, computed in double and rounded once.
+//
+// Pinned definitions GL leaves to the driver:
+//   dot(a,b)      = (a.x*b.x + a.y*b.y) + a.z*b.z
+//   normalize(v)  = v * (1.0f / sqrt(dot(v,v)))                 (glm func_geometric.inl:94)
+//   cross(a,b)    = (a.y*b.z - b.y*a.z, a.z*b.x - b.z*a.x, a.x*b.y - b.x*a.y)
+//   mat4 * vec4   = (m0*x + m1*y) + (m2*z + m3*w)               (glm type_mat4x4.inl:526-537)
+//   mat3 * vec3   = (m0*x + m1*y) + m2*z
+//   mix(a,b,t)    = a*(1-t) + b*t ; fract(x) = x - floor(x) ; clamp(x,lo,hi) = min(max(x,lo),hi)
+//   v_TexCoords at pixel (i,j) = ((i+0.5)/W, (j+0.5)/H), gl_FragCoord.xy = (i+0.5, j+0.5)
+//   G-buffer reads by the secondary passes: same resolution, point sampled, fp32 t
+//   textureLod(array, uvw, k) with integer k>0 = nearest texel of the pre-baked level k, REPEAT
+//   texture(emissive array) = bilinear on level 0, REPEAT ; texture(cubemap) = bilinear within the major-axis
+//   face, clamped to the face edge
+//   float->int conversion of NaN / out-of-range positions = "outside the volume" (A.3 note 5)
+//   blue-noise rankingTile index is clamped to the array (A.5)
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/vxpt.h"
+
+extern "C" {
+
+typedef struct VxoScene {
+    int32_t wx, wy, wz;
+    const uint8_t* grid;
+    const uint8_t* df;
+    const int32_t* materials;  // 768, Core/BlockDataSSBO.cpp:28-35 order
+    const int32_t* sobol;      // 65536
+    const int32_t* scramble;   // 131072
+    const int32_t* rank;       // 131072
+    const float* albedo_lod3;  // [n_layers][64][64][4]
+    const float* pbr_lod2;     // [n_layers][128][128][4]
+    int32_t n_layers;
+    const float* emissive_lod0;  // [n_emissive_layers][512][512]
+    int32_t n_emissive_layers;
+    const float* sky;  // [6][sky_n][sky_n][3]
+    int32_t sky_n;
+    const uint8_t* shadow_noise;  // [256][256][4]
+} VxoScene;
+
+typedef struct VxoStats {
+    uint64_t rays, df_fetches, vox_fetches;
+} VxoStats;
+
+}  // extern "C"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ vectors
+struct v3 {
+    float x, y, z;
+    float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline v3 V(float x, float y, float z) { return v3{x, y, z}; }
+inline v3 V(float s) { return v3{s, s, s}; }
+inline v3 operator+(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline v3 operator-(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline v3 operator*(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+inline v3 operator/(v3 a, v3 b) { return V(a.x / b.x, a.y / b.y, a.z / b.z); }
+inline v3 operator*(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+inline v3 operator*(float s, v3 a) { return V(s * a.x, s * a.y, s * a.z); }
+inline v3 operator/(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+inline v3 operator-(v3 a) { return V(-a.x, -a.y, -a.z); }
+inline float dot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline float length(v3 a) { return std::sqrt(dot(a, a)); }
+inline v3 normalize(v3 a) { return a * (1.0f / std::sqrt(dot(a, a))); }
+inline v3 cross(v3 a, v3 b) { return V(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+inline float clampf(float x, float lo, float hi) { return std::fmin(std::fmax(x, lo), hi); }
+inline v3 clamp3(v3 a, float lo, float hi) { return V(clampf(a.x, lo, hi), clampf(a.y, lo, hi), clampf(a.z, lo, hi)); }
+inline float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+inline v3 mix3(v3 a, v3 b, float t) { return a * (1.0f - t) + b * t; }
+inline float fractf(float x) { return x - std::floor(x); }
+// correctly rounded fp32 transcendental pins
+inline float sin_cr(float x) { return (float)std::sin((double)x); }
+inline float cos_cr(float x) { return (float)std::cos((double)x); }
+inline float pow_cr(float x, float y) { return (float)std::pow((double)x, (double)y); }
+
+// column-major mat4 * vec4, glm order
+inline void mat4_mul(const float* m, const float v[4], float out[4]) {
+    for (int r = 0; r < 4; ++r) out[r] = (m[0 + r] * v[0] + m[4 + r] * v[1]) + (m[8 + r] * v[2] + m[12 + r] * v[3]);
+}
+
+const float PI_F = 3.14159265359f;
+
+struct Scene {
+    VxoScene s;
+    inline bool in_volume_f(float fx, float fy, float fz) const {
+        // IsInVolume (InitialRayTraceFrag.glsl:68-78) on floor()ed coordinates; written so NaN -> false
+        return fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx <= (float)(s.wx - 1) && fy <= (float)(s.wy - 1) &&
+               fz <= (float)(s.wz - 1);
+    }
+    inline size_t idx(int x, int y, int z) const { return (size_t)x + (size_t)s.wx * ((size_t)y + (size_t)s.wy * (size_t)z); }
+};
+
+struct Stats {
+    uint64_t rays = 0, df = 0, vox = 0;
+};
+
+struct Hit {
+    float t;
+    int min_idx;
+    int sgn[3];
+    int block;   // raw byte
+    int vox[3];  // voxel of the final position (valid when t > 0)
+    v3 normal;
+};
+
+inline int isign(float d) { return (d > 0.0f) - (d < 0.0f); }
+
+// GetVoxel(ivec3(floor(p))) — InitialRayTraceFrag.glsl:80-88
+inline int get_voxel_at(const Scene& S, v3 p, Stats& st, int* vox = nullptr) {
+    float fx = std::floor(p.x), fy = std::floor(p.y), fz = std::floor(p.z);
+    if (!S.in_volume_f(fx, fy, fz)) return 0;
+    int x = (int)fx, y = (int)fy, z = (int)fz;
+    if (vox) { vox[0] = x; vox[1] = y; vox[2] = z; }
+    st.vox++;
+    return S.s.grid[S.idx(x, y, z)];
+}
+
+// VoxelTraversalDF — InitialRayTraceFrag.glsl:307-374 (identical copies: ShadowRayTraceFrag.glsl:222-289,
+// DiffuseRayTraceFrag.glsl:1043-1110, ReflectionTraceFrag.glsl:1088-1155).  SURVEY.md A.3.
+float traverse_df(const Scene& S, v3 origin, v3 direction, int max_it, Hit& h, Stats& st) {
+    const v3 initial_origin = origin;
+    bool intersection = false;
+    int min_idx = 0;
+    const int sg[3] = {isign(direction.x), isign(direction.y), isign(direction.z)};
+    st.rays++;
+    for (int itr = 0; itr < max_it; ++itr) {
+        float fx = std::floor(origin.x), fy = std::floor(origin.y), fz = std::floor(origin.z);
+        if (!S.in_volume_f(fx, fy, fz)) { intersection = false; break; }
+        st.df++;
+        // GetDistance(Loc) * 255 : the R8 round trip is exact for 0..255 (A.1)
+        float dist = (float)S.s.df[S.idx((int)fx, (int)fy, (int)fz)];
+        // ToConservativeEuclidean — InitialRayTraceFrag.glsl:90-93
+        int euclid = (int)std::floor(dist == 1.0f ? 1.0f : dist * 0.57735026918f);
+        if (euclid == 0) break;
+        if (euclid == 1) {
+            int g[3] = {(int)origin.x, (int)origin.y, (int)origin.z};
+            v3 w = V(origin.x - (float)g[0], origin.y - (float)g[1], origin.z - (float)g[2]);
+            const int half[3] = {(1 + sg[0]) >> 1, (1 + sg[1]) >> 1, (1 + sg[2]) >> 1};
+            v3 inv = V(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+            v3 f = V(((float)half[0] - w.x) * inv.x, ((float)half[1] - w.y) * inv.y, ((float)half[2] - w.z) * inv.z);
+            min_idx = (f.x < f.y && sg[0] != 0) ? ((f.x < f.z || sg[2] == 0) ? 0 : 2)
+                                                : ((f.y < f.z || sg[2] == 0) ? 1 : 2);
+            g[min_idx] += sg[min_idx];
+            float fm = f[min_idx];
+            w = w + direction * fm;
+            w[min_idx] = (float)(1 - half[min_idx]);
+            origin = V((float)g[0] + w.x, (float)g[1] + w.y, (float)g[2] + w.z);
+            origin[min_idx] += (float)sg[min_idx] * 0.0001f;
+            intersection = true;
+        } else {
+            origin = origin + (float)(euclid - 1) * direction;
+        }
+    }
+    h.min_idx = min_idx;
+    h.sgn[0] = sg[0]; h.sgn[1] = sg[1]; h.sgn[2] = sg[2];
+    h.block = 0; h.vox[0] = h.vox[1] = h.vox[2] = -1;
+    h.normal = V(0.0f);
+    h.t = -1.0f;
+    if (intersection) {
+        h.normal[min_idx] = (float)(-sg[min_idx]);
+        h.block = get_voxel_at(S, origin, st, h.vox);
+        h.t = h.block > 0 ? length(origin - initial_origin) : -1.0f;
+        if (!(h.block > 0)) { h.vox[0] = h.vox[1] = h.vox[2] = -1; }
+    }
+    return h.t;
+}
+
+// GetNormalID — InitialRayTraceFrag.glsl:143-185 : {+Z,-Z,+Y,-Y,-X,+X} -> 0..5
+inline int normal_id_of(const Hit& h) {
+    int s = -h.sgn[h.min_idx];  // normal component
+    if (h.min_idx == 2) return s > 0 ? 0 : 1;
+    if (h.min_idx == 1) return s > 0 ? 2 : 3;
+    return s < 0 ? 4 : 5;
+}
+// GetNormalFromID — ShadowRayTraceFrag.glsl:317-328 (miss -> (1,1,1)); DiffuseRayTraceFrag.glsl:790-801 (miss -> 0.5)
+inline v3 normal_from_id(int id, float miss) {
+    switch (id) {
+        case 0: return V(0, 0, 1);
+        case 1: return V(0, 0, -1);
+        case 2: return V(0, 1, 0);
+        case 3: return V(0, -1, 0);
+        case 4: return V(-1, 0, 0);
+        case 5: return V(1, 0, 0);
+        default: return V(miss);
+    }
+}
+
+// GetRayDirectionAt — ShadowRayTraceFrag.glsl:303-308 / GetRayStuff InitialRayTraceFrag.glsl:410-413
+inline v3 ray_direction_at(const VxCamera& cam, float u, float v) {
+    float clip[4] = {u * 2.0f - 1.0f, v * 2.0f - 1.0f, -1.0f, 1.0f};
+    float e4[4];
+    mat4_mul(cam.inv_proj, clip, e4);
+    float eye[4] = {e4[0], e4[1], -1.0f, 0.0f};
+    float r4[4];
+    mat4_mul(cam.inv_view, eye, r4);
+    return V(r4[0], r4[1], r4[2]);
+}
+inline v3 ray_origin(const VxCamera& cam) { return V(cam.inv_view[12], cam.inv_view[13], cam.inv_view[14]); }
+
+inline void pixel_uv(const VxCamera& cam, int i, int j, float& u, float& v) {
+    u = ((float)i + 0.5f) / (float)cam.width;
+    v = ((float)j + 0.5f) / (float)cam.height;
+}
+
+// ------------------------------------------------------------------------------------------------ textures
+// samplerBlueNoiseErrorDistribution_128x128_OptimizedFor_2d2d2d2d_32spp — DiffuseRayTraceFrag.glsl:126-149
+inline float blue_noise_1d(const Scene& S, int px, int py, int sample_index, int sample_dim) {
+    int pi = px & 127, pj = py & 127;
+    sample_index &= 255;
+    sample_dim &= 255;
+    int ridx = sample_dim + (pi + pj * 128) * 8;
+    if (ridx > 131071) ridx = 131071;  // A.5: the shader reads past rankingTile here; pinned by clamping
+    int ranked = sample_index ^ S.s.rank[ridx];
+    ranked &= 255;  // table values are < 256, so this is a no-op kept for index safety
+    int value = S.s.sobol[sample_dim + ranked * 256];
+    value = value ^ S.s.scramble[(sample_dim % 8) + (pi + pj * 128) * 8];
+    return (0.5f + (float)value) / 256.0f;
+}
+
+inline v3 sky_sample(const Scene& S, v3 d) {
+    const int N = S.s.sky_n;
+    float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
+    int face; float sc, tc, ma;
+    if (ax >= ay && ax >= az) { face = d.x > 0 ? 0 : 1; sc = d.x > 0 ? -d.z : d.z; tc = -d.y; ma = ax; }
+    else if (ay >= az)        { face = d.y > 0 ? 2 : 3; sc = d.x; tc = d.y > 0 ? d.z : -d.z; ma = ay; }
+    else                      { face = d.z > 0 ? 4 : 5; sc = d.z > 0 ? d.x : -d.x; tc = -d.y; ma = az; }
+    float s = 0.5f * (sc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
+    float u = s * (float)N - 0.5f, v = t * (float)N - 0.5f;
+    float fu0 = std::floor(u), fv0 = std::floor(v);
+    float fu = u - fu0, fv = v - fv0;
+    int i0 = (int)fu0, j0 = (int)fv0, i1 = i0 + 1, j1 = j0 + 1;
+    i0 = std::min(std::max(i0, 0), N - 1); i1 = std::min(std::max(i1, 0), N - 1);
+    j0 = std::min(std::max(j0, 0), N - 1); j1 = std::min(std::max(j1, 0), N - 1);
+    const float* F = S.s.sky + (size_t)face * N * N * 3;
+    auto tx = [&](int i, int j) { const float* p = F + ((size_t)j * N + i) * 3; return V(p[0], p[1], p[2]); };
+    v3 a = tx(i0, j0) * (1.0f - fu) + tx(i1, j0) * fu;
+    v3 b = tx(i0, j1) * (1.0f - fu) + tx(i1, j1) * fu;
+    return a * (1.0f - fv) + b * fv;
+}
+
+inline v3 tex_nearest4(const float* base, int layer, int n, float u, float v) {
+    int i = ((int)std::floor(u * (float)n)) & (n - 1);
+    int j = ((int)std::floor(v * (float)n)) & (n - 1);
+    const float* p = base + (((size_t)layer * n + j) * n + i) * 4;
+    return V(p[0], p[1], p[2]);
+}
+inline float tex_bilinear1(const float* base, int layer, int n, float u, float v) {
+    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    float fx0 = std::floor(x), fy0 = std::floor(y);
+    float fx = x - fx0, fy = y - fy0;
+    int i0 = ((int)fx0) & (n - 1), i1 = ((int)fx0 + 1) & (n - 1);
+    int j0 = ((int)fy0) & (n - 1), j1 = ((int)fy0 + 1) & (n - 1);
+    const float* L = base + (size_t)layer * n * n;
+    float a = L[(size_t)j0 * n + i0] * (1.0f - fx) + L[(size_t)j0 * n + i1] * fx;
+    float b = L[(size_t)j1 * n + i0] * (1.0f - fx) + L[(size_t)j1 * n + i1] * fx;
+    return a * (1.0f - fy) + b * fy;
+}
+
+// CalculateUV — DiffuseRayTraceFrag.glsl:1235-1273 (normal is an exact axis vector here)
+inline void calc_uv(v3 p, int axis, float& u, float& v) {
+    if (axis == 1) { u = fractf(p.x); v = fractf(p.z); }       // top / bottom : xz
+    else if (axis == 0) { u = fractf(p.z); v = fractf(p.y); }  // left / right : zy
+    else { u = fractf(p.x); v = fractf(p.y); }                 // front / back : xy
+}
+
+}  // namespace
+
+// =============================================================================================== exports
+extern "C" {
+
+// ManhattanDistance{X,Y,Z}.comp executed in the order World::GenerateDistanceField dispatches them
+// (Core/World.cpp:69-113).  Integer formulation; the R8 store/load round trip is exact.
+void vxo_df_build(const uint8_t* grid, uint8_t* df, int wx, int wy, int wz) {
+    const int max_d = std::min(254, wx + wy + wz);  // ManhattanDistanceX.comp:49
+    auto at = [&](int x, int y, int z) -> size_t { return (size_t)x + (size_t)wx * ((size_t)y + (size_t)wy * (size_t)z); };
+    // X pass — ManhattanDistanceX.comp:45-69
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < wz; ++z)
+        for (int y = 0; y < wy; ++y) {
+            df[at(0, y, z)] = grid[at(0, y, z)] > 0 ? 0 : (uint8_t)max_d;
+            for (int x = 1; x < wx; ++x)
+                df[at(x, y, z)] = grid[at(x, y, z)] > 0 ? 0 : (uint8_t)std::min(max_d, 1 + (int)df[at(x - 1, y, z)]);
+            for (int x = wx - 2; x >= 0; --x)
+                if (df[at(x + 1, y, z)] < df[at(x, y, z)]) df[at(x, y, z)] = (uint8_t)(1 + df[at(x + 1, y, z)]);
+        }
+    // Y pass — ManhattanDistanceY.comp:26-51
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < wz; ++z)
+        for (int x = 0; x < wx; ++x) {
+            for (int y = 1; y < wy; ++y)
+                if (df[at(x, y - 1, z)] < df[at(x, y, z)]) df[at(x, y, z)] = (uint8_t)(1 + df[at(x, y - 1, z)]);
+            for (int y = wy - 2; y >= 0; --y)
+                if (df[at(x, y + 1, z)] < df[at(x, y, z)]) df[at(x, y, z)] = (uint8_t)(1 + df[at(x, y + 1, z)]);
+        }
+    // Z pass — ManhattanDistanceZ.comp:24-47
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < wy; ++y)
+        for (int x = 0; x < wx; ++x) {
+            for (int z = 1; z < wz; ++z)
+                if (df[at(x, y, z - 1)] < df[at(x, y, z)]) df[at(x, y, z)] = (uint8_t)(1 + df[at(x, y, z - 1)]);
+            for (int z = wz - 2; z >= 0; --z)
+                if (df[at(x, y, z + 1)] < df[at(x, y, z)]) df[at(x, y, z)] = (uint8_t)(1 + df[at(x, y, z + 1)]);
+        }
+}
+
+// Definition of the result: min(254, min over solid q of |p-q|_1).  O(voxels * solids): small grids.
+void vxo_df_bruteforce(const uint8_t* grid, uint8_t* df, int wx, int wy, int wz) {
+    std::vector<int> sx, sy, sz;
+    for (int z = 0; z < wz; ++z)
+        for (int y = 0; y < wy; ++y)
+            for (int x = 0; x < wx; ++x)
+                if (grid[(size_t)x + (size_t)wx * ((size_t)y + (size_t)wy * z)] > 0) { sx.push_back(x); sy.push_back(y); sz.push_back(z); }
+    const int max_d = std::min(254, wx + wy + wz);
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < wz; ++z)
+        for (int y = 0; y < wy; ++y)
+            for (int x = 0; x < wx; ++x) {
+                int best = max_d;
+                for (size_t k = 0; k < sx.size(); ++k) {
+                    int d = std::abs(x - sx[k]) + std::abs(y - sy[k]) + std::abs(z - sz[k]);
+                    if (d < best) best = d;
+                }
+                df[(size_t)x + (size_t)wx * ((size_t)y + (size_t)wy * z)] = (uint8_t)best;
+            }
+}
+
+// One VoxelTraversalDF call (known-answer tests).  out6 = {min_idx, sgn of that axis, block, vox x, y, z}.
+float vxo_traverse(const VxoScene* sc, const float o[3], const float d[3], int max_it, int32_t out6[6], VxoStats* stats) {
+    Scene S{*sc};
+    Hit h; Stats st;
+    float t = traverse_df(S, V(o[0], o[1], o[2]), V(d[0], d[1], d[2]), max_it, h, st);
+    if (out6) { out6[0] = h.min_idx; out6[1] = h.sgn[h.min_idx]; out6[2] = h.block; out6[3] = h.vox[0]; out6[4] = h.vox[1]; out6[5] = h.vox[2]; }
+    if (stats) { stats->rays += st.rays; stats->df_fetches += st.df; stats->vox_fetches += st.vox; }
+    return t;
+}
+
+// Independent cross-check: plain one-voxel-at-a-time DDA (Amanatides-Woo) in double precision, no distance
+// field.  After the author's unused Core/Shaders/Implementations/DDA/DDA.glsl:134-253 (not compiled by the
+// reference app).  Returns 1 and the first solid voxel entered, 0 on a miss.  The start voxel is not tested.
+int vxo_plain_dda(const VxoScene* sc, const float o[3], const float d[3], int max_steps, int32_t vox[3], int32_t* axis) {
+    Scene S{*sc};
+    double p[3] = {o[0], o[1], o[2]}, dir[3] = {d[0], d[1], d[2]};
+    int g[3], step[3]; double tmax[3], tdelta[3];
+    for (int k = 0; k < 3; ++k) {
+        g[k] = (int)std::floor(p[k]);
+        step[k] = dir[k] > 0 ? 1 : (dir[k] < 0 ? -1 : 0);
+        if (step[k] != 0) {
+            double nb = step[k] > 0 ? (g[k] + 1) : g[k];
+            tmax[k] = (nb - p[k]) / dir[k];
+            tdelta[k] = std::fabs(1.0 / dir[k]);
+        } else { tmax[k] = INFINITY; tdelta[k] = INFINITY; }
+    }
+    const int dims[3] = {S.s.wx, S.s.wy, S.s.wz};
+    for (int it = 0; it < max_steps; ++it) {
+        int k = (tmax[0] < tmax[1]) ? ((tmax[0] < tmax[2]) ? 0 : 2) : ((tmax[1] < tmax[2]) ? 1 : 2);
+        g[k] += step[k];
+        tmax[k] += tdelta[k];
+        if (g[0] < 0 || g[1] < 0 || g[2] < 0 || g[0] >= dims[0] || g[1] >= dims[1] || g[2] >= dims[2]) return 0;
+        if (S.s.grid[S.idx(g[0], g[1], g[2])] > 0) {
+            vox[0] = g[0]; vox[1] = g[1]; vox[2] = g[2]; *axis = k;
+            return 1;
+        }
+    }
+    return 0;
+}
+
+// InitialRayTraceFrag.glsl main() :417-468 with GetRayStuff :398-414.  SURVEY.md A.2.
+int vxo_trace_primary(const VxoScene* sc, const VxCamera* cam, const VxPrimaryParams* prm, const VxGBuffer* out, VxoStats* stats) {
+    Scene S{*sc};
+    if (prm->alpha_test) return VXPT_E_UNSUPPORTED;
+    const int W = cam->width, H = cam->height;
+    uint64_t rays = 0, dfc = 0, voxc = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : rays, dfc, voxc)
+    for (int j = cam->row_begin; j < cam->row_end; ++j) {
+        Stats st;
+        for (int i = 0; i < W; ++i) {
+            float u, v;
+            pixel_uv(*cam, i, j, u, v);
+            if (prm->jitter_enable) {
+                float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;  // TexelSize = 1.0f / u_Dimensions
+                u -= prm->jitter[0] * tsx;
+                v -= prm->jitter[1] * tsy;
+            }
+            v3 rd = ray_direction_at(*cam, u, v);
+            v3 ro = ray_origin(*cam);
+            v3 dir = normalize(rd);
+            Hit h;
+            float t = traverse_df(S, ro, dir, prm->max_iterations, h, st);
+            bool intersect = t > 0.0f && h.block > 0;
+            size_t p = (size_t)j * W + i;
+            if (out->t) out->t[p] = t;
+            if (out->inv_t) out->inv_t[p] = 1.0f / t;
+            if (out->normal_id) out->normal_id[p] = intersect ? (uint8_t)normal_id_of(h) : (uint8_t)VXPT_NORMAL_MISS;
+            if (out->block_id) out->block_id[p] = intersect ? (uint8_t)h.block : 0;
+            if (out->hit_voxel) {
+                out->hit_voxel[3 * p + 0] = intersect ? (int16_t)h.vox[0] : -1;
+                out->hit_voxel[3 * p + 1] = intersect ? (int16_t)h.vox[1] : -1;
+                out->hit_voxel[3 * p + 2] = intersect ? (int16_t)h.vox[2] : -1;
+            }
+        }
+        rays += st.rays; dfc += st.df; voxc += st.vox;
+    }
+    if (stats) { stats->rays += rays; stats->df_fetches += dfc; stats->vox_fetches += voxc; }
+    return VXPT_OK;
+}
+
+// ShadowRayTraceFrag.glsl main() :414-513.  SURVEY.md A.7.
+int vxo_trace_shadow(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g, const VxShadowParams* prm, const VxShadowOut* out, VxoStats* stats) {
+    Scene S{*sc};
+    if (prm->alpha_test) return VXPT_E_UNSUPPORTED;
+    const int W = cam->width, H = cam->height;
+    uint64_t rays = 0, dfc = 0, voxc = 0;
+    // per-frame blue-noise texel offset (:456-459): int products wrap like GLSL ints, the rest is fp32
+    const int n = prm->frame % 1024;
+    const int32_t ax = (int32_t)((uint32_t)n * 12664745u), ay = (int32_t)((uint32_t)n * 9560333u);
+    const float offx = fractf((float)ax / 16777216.0f) * 1024.0f, offy = fractf((float)ay / 16777216.0f) * 1024.0f;
+    const int ioffx = (int)std::floor(offx), ioffy = (int)std::floor(offy);
+    const v3 L = V(prm->light_dir[0], prm->light_dir[1], prm->light_dir[2]);
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : rays, dfc, voxc)
+    for (int j = cam->row_begin; j < cam->row_end; ++j) {
+        Stats st;
+        for (int i = 0; i < W; ++i) {
+            size_t p = (size_t)j * W + i;
+            float u, v;
+            pixel_uv(*cam, i, j, u, v);
+            u += prm->halton[0] * (1.0f / (float)W);
+            v += prm->halton[1] * (1.0f / (float)H);
+            float dist = g->t[p];
+            if (dist < 0.0f) {
+                if (out->shadow) out->shadow[p] = 0;
+                if (out->transversal) out->transversal[p] = 64.0f;
+                continue;
+            }
+            v3 pos = ray_origin(*cam) + normalize(ray_direction_at(*cam, u, v)) * dist;  // GetPositionAt :310-314
+            v3 dir = L;
+            if (prm->soft) {
+                // ivec2(gl_FragCoord.xy + ivec2(floor(off))) % textureSize : float add, truncation, modulo
+                int tx = ((int)(((float)i + 0.5f) + (float)ioffx)) % 256;
+                int ty = ((int)(((float)j + 0.5f) + (float)ioffy)) % 256;
+                const uint8_t* tex = S.s.shadow_noise + ((size_t)ty * 256 + tx) * 4;
+                float xi_x = (float)tex[0] / 255.0f, xi_y = (float)tex[1] / 255.0f;
+                v3 T = normalize(cross(L, V(0.0f, 1.0f, 1.0f)));
+                v3 B = cross(T, L);
+                // SampleCone :388-398
+                const float cos_theta_max = 0.9999505604617f;
+                float cos_theta = (1.0f - xi_x) + xi_x * cos_theta_max;
+                float sin_theta = std::sqrt(1.0f - cos_theta * cos_theta);
+                float phi = xi_y * PI_F * 2.0f;
+                v3 c = V(sin_theta * cos_cr(phi), sin_theta * sin_cr(phi), cos_theta);
+                dir = (T * c.x + B * c.y) + L * c.z;  // mat3(T,B,L) * c
+            }
+            v3 N = normal_from_id(g->normal_id[p], 1.0f);
+            float ndotl = dot(N, dir);
+            if (ndotl <= 0.01f) {
+                if (out->shadow) out->shadow[p] = 1;
+                if (out->transversal) out->transversal[p] = 1.0f / 100.0f;
+                continue;
+            }
+            v3 bias = N * V(0.06f);
+            v3 o = pos + bias;
+            int block_at = get_voxel_at(S, o, st);
+            float T = -1.0f;
+            if (dist > 0.0f) {
+                Hit h;
+                T = traverse_df(S, o, dir, 350, h, st);
+            }
+            if (out->shadow) out->shadow[p] = (T > 0.0f || block_at > 0) ? 1 : 0;
+            float tr = clampf(T / 100.0f, 0.00001f, 196.0f);
+            if (T < 0.0f) tr = 4.25f / 100.0f;
+            if (out->transversal) out->transversal[p] = tr;
+        }
+        rays += st.rays; dfc += st.df; voxc += st.vox;
+    }
+    if (stats) { stats->rays += rays; stats->df_fetches += dfc; stats->vox_fetches += voxc; }
+    return VXPT_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ diffuse GI
+namespace {
+
+struct GiFrame {
+    v3 light_color, stronger_dir;
+    bool moon_stronger;
+    float emissivity_mult;
+    const VxDiffuseParams* p;
+};
+
+struct GiPixel {
+    int px, py;
+    int bl_sample;  // CurrentBLSample, DiffuseRayTraceFrag.glsl:809
+};
+
+// InverseSchlick — DiffuseRayTraceFrag.glsl:1305-1308
+inline float inverse_schlick(float f0, float voh) {
+    return 1.0f - clampf(f0 + (1.0f - f0) * pow_cr(1.0f - voh, 5.0f), 0.0f, 1.0f);
+}
+// DiffuseHammon — DiffuseRayTraceFrag.glsl:1311-1332 (rcp(x) restated as 1.0f/x)
+inline float diffuse_hammon(v3 n, v3 view, v3 light, float rough) {
+    float ndl = std::fmax(dot(n, light), 0.0f);
+    if (ndl <= 0.0f) return 0.0f;
+    float ndv = std::fmax(dot(n, view), 0.0f);
+    float ldv = std::fmax(dot(light, view), 0.0f);
+    v3 hw = normalize(view + light);
+    float ndh = std::fmax(dot(n, hw), 0.0f);
+    float facing = ldv * 0.5f + 0.5f;
+    float single_rough = facing * (0.9f - 0.4f * facing) * ((0.5f + ndh) * (1.0f / std::fmax(ndh, 0.02f)));
+    float single_smooth = 1.05f * inverse_schlick(0.0f, ndl) * inverse_schlick(0.0f, std::fmax(ndv, 0.0f));
+    float single = clampf(mixf(single_smooth, single_rough, rough) * (1.0f / PI_F), 0.0f, 1.0f);
+    float multi = 0.1159f * rough;
+    return clampf((multi + single) * ndl, 0.0f, 1.0f);
+}
+
+// SampleBlueNoise2D + cosWeightedRandomHemisphereDirection — DiffuseRayTraceFrag.glsl:811-818, 945-967
+inline v3 cos_hemisphere(const Scene& S, const GiFrame& F, GiPixel& px, v3 n) {
+    int idx = F.p->frame % 128;  // u_CurrentFrameMod128
+    float rx_ = blue_noise_1d(S, px.px, px.py, idx, 1 + px.bl_sample);
+    float ry_ = blue_noise_1d(S, px.px, px.py, idx, 2 + px.bl_sample);
+    px.bl_sample += 2;
+    const float PI2 = 2.0f * PI_F;
+    v3 uu = normalize(cross(n, V(0.0f, 1.0f, 1.0f)));
+    v3 vv = cross(uu, n);
+    float ra = std::sqrt(ry_);
+    float rx = ra * cos_cr(PI2 * rx_);
+    float ry = ra * sin_cr(PI2 * rx_);
+    float rz = std::sqrt(1.0f - ry_);
+    v3 rr = (rx * uu + ry * vv) + rz * n;
+    return normalize(rr);
+}
+
+// GetSkyColorAt — DiffuseRayTraceFrag.glsl:984-988
+inline v3 sky_color_at(const Scene& S, v3 rd) {
+    rd.y = clampf(rd.y, 0.125f, 1.5f);
+    return sky_sample(S, rd);
+}
+
+// CalculateDiffuse — DiffuseRayTraceFrag.glsl:535-664
+inline void calculate_diffuse(const Scene& S, const GiFrame& F, GiPixel& px, v3 initial_origin, v3 input_normal,
+                              v3& out_rad, float& out_ao, v3& odir, bool& skyhit, Stats& st) {
+    skyhit = false;
+    const float bias = 0.06f;
+    v3 ro = initial_origin + input_normal * bias;
+    v3 rd = cos_hemisphere(S, F, px, input_normal);
+    float ao = 1.0f;
+    v3 contrib = V(0.0f), thr = V(1.0f);
+    const int32_t* M = S.s.materials;
+    for (int i = 0; i < 2; ++i) {  // MAX_BOUNCE_LIMIT :17
+        if (i == 0) odir = rd;
+        Hit h;
+        float T = traverse_df(S, ro, rd, F.p->trace_length, h, st);
+        int tex_ref = std::min(std::max(h.block, 0), 127);
+        bool intersect = T > 0.0f;
+        v3 ipos = ro + (rd * T);
+        if (intersect && h.block > 0) {
+            float tu, tv;
+            calc_uv(ipos, h.min_idx, tu, tv);
+            int albedo_layer = M[tex_ref], emissive_layer = M[384 + tex_ref];
+            v3 albedo = tex_nearest4(S.s.albedo_lod3, albedo_layer, 64, tu, tv);
+            v3 pbr = tex_nearest4(S.s.pbr_lod2, albedo_layer, 128, tu, tv);  // sic: albedo layer (:578)
+            float emis = 0.0f;
+            if ((float)emissive_layer >= 0.0f) {
+                float se = tex_bilinear1(S.s.emissive_lod0, emissive_layer, 512, tu, tv);
+                emis = se * F.emissivity_mult * F.p->light_intensity;
+            }
+            float ndl = std::fmax(dot(h.normal, F.stronger_dir), 0.0f);
+            v3 bias_shadow = h.normal * 0.045f;
+            float shadow_at;
+            if (F.moon_stronger) shadow_at = 1.0f;
+            else if (ndl < 0.001f) shadow_at = 0.0f;
+            else {  // GetShadowAt :1202-1222 (u_APPLY_PLAYER_SHADOW = false)
+                Hit hs;
+                float Ts = traverse_df(S, ipos + bias_shadow, F.stronger_dir, 128, hs, st);
+                shadow_at = Ts > 0.0f ? 1.0f : 0.0f;
+            }
+            v3 emis_color = (emis * mixf(1.0f, 1.0f, F.p->sun_visibility)) * albedo;
+            // SunBRDF :499-508 (CAUSTICS = false)
+            v3 sunbrdf = (((albedo * diffuse_hammon(h.normal, -rd, F.stronger_dir, pbr.x)) * (F.light_color * 3.5f)) *
+                          (1.0f - shadow_at)) * PI_F;
+            v3 new_dir = cos_hemisphere(S, F, px, h.normal);
+            float cos_theta = clampf(dot(h.normal, new_dir), 0.0f, 1.0f);
+            float pdf = std::fmax(cos_theta / PI_F, 0.00001f);
+            v3 atten = V(1.0f) * diffuse_hammon(h.normal, -rd, new_dir, pbr.x);  // DiffuseRayBRDF :527-531
+            contrib = contrib + thr * sunbrdf;
+            contrib = contrib + emis_color * thr;
+            thr = thr * ((albedo * atten) / pdf);
+            rd = new_dir;
+            ro = ipos + h.normal * bias;
+        } else {
+            float x = mixf(1.0f, 1.05f, F.p->sun_visibility);
+            x = clampf(x * 1.0f * F.p->gi_sky_strength, 0.0f, 5.0f);
+            v3 sky = sky_color_at(S, rd) * x;
+            contrib = contrib + sky * thr;
+            skyhit = true;
+            break;
+        }
+        if (i == 0) {
+            const float dao = 2.0f;
+            if (T < dao && T > 0.0f) ao = std::fmax(T / dao, 0.0f);
+        }
+    }
+    out_rad = contrib;
+    out_ao = ao;
+}
+
+// IrridianceToSH — DiffuseRayTraceFrag.glsl:766-784
+inline void irradiance_to_sh(v3 rad, v3 dir, float out[6]) {
+    float Co = rad.x - rad.z;
+    float T = rad.z + Co * 0.5f;
+    float Cg = rad.y - T;
+    float Y = std::fmax(T + Cg * 0.5f, 0.0f);
+    float L00 = 0.282095f;
+    float L1_1 = 0.488603f * dir.y, L10 = 0.488603f * dir.z, L11 = 0.488603f * dir.x;
+    out[0] = std::fmax(L11 * Y, -100.0f);
+    out[1] = std::fmax(L1_1 * Y, -100.0f);
+    out[2] = std::fmax(L10 * Y, -100.0f);
+    out[3] = std::fmax(L00 * Y, -100.0f);
+    out[4] = Co;
+    out[5] = Cg;
+}
+
+}  // namespace
+
+extern "C" {
+
+// DiffuseRayTraceFrag.glsl main() :822-935.  SURVEY.md A.4.
+int vxo_trace_diffuse(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g, const VxDiffuseParams* prm, const VxDiffuseOut* out, VxoStats* stats) {
+    Scene S{*sc};
+    if (!prm->use_blue_noise || prm->direct_sampling) return VXPT_E_UNSUPPORTED;
+    const int W = cam->width, H = cam->height;
+    GiFrame F;
+    F.p = prm;
+    const v3 sun = V(prm->sun_dir[0], prm->sun_dir[1], prm->sun_dir[2]);
+    const v3 moon = V(prm->moon_dir[0], prm->moon_dir[1], prm->moon_dir[2]);
+    const bool sun_stronger = -sun.y < 0.01f;
+    const v3 SUN_COLOR = (V(192.0f, 216.0f, 255.0f) / 255.0f) * 16.0f;   // :184
+    const v3 NIGHT_COLOR = (V(96.0f, 192.0f, 255.0f) / 255.0f) * 1.5f;  // :185
+    const v3 DUSK_COLOR = (V(96.0f, 192.0f, 255.0f) / 255.0f) * 0.9f;   // :186
+    float dusk = clampf(pow_cr(std::fabs(sun.y - 1.0f), 2.9f), 0.0f, 1.0f);
+    v3 sun_color = mix3(SUN_COLOR, DUSK_COLOR, dusk);
+    F.light_color = sun_stronger ? sun_color : NIGHT_COLOR;
+    F.light_color = F.light_color * (0.4f * prm->gi_sun_strength);
+    F.stronger_dir = sun_stronger ? sun : moon;
+    F.moon_stronger = !sun_stronger;
+    F.emissivity_mult = F.moon_stronger ? 13.0f : 12.0f;
+    uint64_t rays = 0, dfc = 0, voxc = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : rays, dfc, voxc)
+    for (int j = cam->row_begin; j < cam->row_end; ++j) {
+        Stats st;
+        for (int i = 0; i < W; ++i) {
+            size_t p = (size_t)j * W + i;
+            float u, v;
+            pixel_uv(*cam, i, j, u, v);
+            const float u0 = u, v0 = v;  // v_TexCoords / v_RayDirection are not jittered
+            if (prm->supersample) {
+                u += (prm->halton[0] * 0.75f) / (float)W;
+                v += (prm->halton[1] * 0.75f) / (float)H;
+            }
+            float o_sh[4], o_cocg[2], o_util = 0.0f, o_ao[2] = {1.0f, 0.0f};
+            float dist = g->t[p];
+            v3 normal = normal_from_id(g->normal_id[p], 0.5f);
+            if (dist < 0.0f) {
+                float sh[6];
+                v3 vdir = normalize(ray_direction_at(*cam, u0, v0));
+                irradiance_to_sh(sky_sample(S, vdir) * 2.66f, normal, sh);
+                o_sh[0] = sh[0]; o_sh[1] = sh[1]; o_sh[2] = sh[2]; o_sh[3] = sh[3];
+                o_cocg[0] = sh[4]; o_cocg[1] = sh[5];
+            } else {
+                v3 pos = ray_origin(*cam) + normalize(ray_direction_at(*cam, u, v)) * dist;
+                int spp = std::min(std::max(prm->spp, 1), 32);
+                if (prm->checkerboard) {
+                    // int(gl_FragCoord.x + gl_FragCoord.y) = i + j + 1
+                    bool checker = ((int)(((float)i + 0.5f) + ((float)j + 0.5f))) % 2 == prm->frame % 2;
+                    spp = (int)mixf((float)prm->spp, (float)prm->checker_spp, checker ? 1.0f : 0.0f);
+                }
+                spp = std::min(std::max(spp, 1), 32);
+                if (F.moon_stronger) spp *= 2;
+                GiPixel px{i, j, 0};
+                float tot[4] = {0, 0, 0, 0}, cocg[2] = {0, 0}, acc_ao = 0.0f, skyhits = 0.0f;
+                v3 radiance = V(0.0f);
+                for (int s = 0; s < spp; ++s) {
+                    v3 rad, d = V(0.0f);
+                    float ao;
+                    bool ss = false;
+                    calculate_diffuse(S, F, px, pos, normal, rad, ao, d, ss, st);
+                    rad = clamp3(rad, 0.0f, 8.0f);
+                    radiance = radiance + rad;
+                    acc_ao += ao;
+                    float sh[6];
+                    irradiance_to_sh(rad, d, sh);
+                    tot[0] += sh[0]; tot[1] += sh[1]; tot[2] += sh[2]; tot[3] += sh[3];
+                    cocg[0] += sh[4]; cocg[1] += sh[5];
+                    skyhits += ss ? 1.0f : 0.0f;
+                }
+                const float fs = (float)spp;
+                acc_ao /= fs;
+                for (int k = 0; k < 4; ++k) tot[k] /= fs;
+                cocg[0] /= fs; cocg[1] /= fs;
+                radiance = radiance / fs;
+                skyhits /= fs;
+                float lum = dot(radiance, V(0.299f, 0.587f, 0.114f));
+                o_util = std::fmax(lum, 0.01f);
+                o_ao[0] = clampf(acc_ao, 0.0f, 1.0f);
+                o_ao[1] = clampf(skyhits, 0.0f, 1.0f);
+                for (int k = 0; k < 4; ++k) o_sh[k] = clampf(tot[k], -100.0f, 100.0f);
+                o_cocg[0] = clampf(cocg[0], -100.0f, 100.0f);
+                o_cocg[1] = clampf(cocg[1], -100.0f, 100.0f);
+                o_util = clampf(o_util, 0.001f, 64.0f);
+            }
+            if (out->sh) std::memcpy(out->sh + 4 * p, o_sh, sizeof o_sh);
+            if (out->cocg) std::memcpy(out->cocg + 2 * p, o_cocg, sizeof o_cocg);
+            if (out->luma) out->luma[p] = o_util;
+            if (out->ao_sky) std::memcpy(out->ao_sky + 2 * p, o_ao, sizeof o_ao);
+        }
+        rays += st.rays; dfc += st.df; voxc += st.vox;
+    }
+    if (stats) { stats->rays += rays; stats->df_fetches += dfc; stats->vox_fetches += voxc; }
+    return VXPT_OK;
+}
+
+int vxo_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void vxo_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""Input tables of the trace passes: material table, blue-noise tables, baked material texels, sky, shadow noise.
+
+These are the boundary INPUTS a host application supplies (BlockDataSSBO, BlueNoiseDataSSBO, texture binds of
+Core/Pipeline.cpp:2236-2270, 2825-2841).  For tests, the smoke run and the benchmark they come from the committed
+fixtures in tests/golden/ (generated from the reference tree by tools/make_fixtures.py).
+"""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load_plains_columns(golden=GOLDEN):
+    return np.fromfile(os.path.join(golden, "plains_columns.u8"), dtype=np.uint8)
+
+
+def load_blue_noise(golden=GOLDEN):
+    """(sobol[65536], scramble[131072], rank[131072]) as int32, the SSBO element type."""
+    t = np.fromfile(os.path.join(golden, "bluenoise_tables.u8"), dtype=np.uint8).astype(np.int32)
+    assert t.size == 65536 + 2 * 131072
+    return np.ascontiguousarray(t[:65536]), np.ascontiguousarray(t[65536:65536 + 131072]), np.ascontiguousarray(t[65536 + 131072:])
+
+
+def load_shadow_noise(golden=GOLDEN):
+    return np.fromfile(os.path.join(golden, "shadow_blue_noise.rgba8"), dtype=np.uint8).reshape(256, 256, 4)
+
+
+def load_materials(golden=GOLDEN):
+    """dict(table int32[768], albedo_lod3 f32[L,64,64,4], pbr_lod2 f32[L,128,128,4], emissive_lod0 f32[E,512,512])."""
+    z = np.load(os.path.join(golden, "materials.npz"))
+
+    def rgba(a):
+        out = np.ones(a.shape[:-1] + (4,), dtype=np.float32)
+        out[..., :3] = a.astype(np.float32) / np.float32(255.0)
+        return np.ascontiguousarray(out)
+
+    return {
+        "table": np.ascontiguousarray(z["table"].astype(np.int32).reshape(768)),
+        "albedo_lod3": rgba(z["albedo_lod3"]),
+        "pbr_lod2": rgba(z["pbr_lod2"]),
+        "emissive_lod0": np.ascontiguousarray(z["emissive_lod0"].astype(np.float32) / np.float32(255.0)),
+        "grass_props": z["grass_props"].astype(np.int32),
+    }
+
+
+def constant_materials(n_blocks=128):
+    """One flat-coloured layer per block id (BASELINE.md config 3's fallback when no textures are loaded)."""
+    rng = np.random.RandomState(7)
+    cols = (0.2 + 0.6 * rng.rand(n_blocks, 3)).astype(np.float32)
+    albedo = np.ones((n_blocks, 64, 64, 4), np.float32)
+    albedo[..., :3] = cols[:, None, None, :]
+    pbr = np.ones((n_blocks, 128, 128, 4), np.float32)
+    pbr[..., 0] = 0.8
+    pbr[..., 1] = 0.0
+    table = np.zeros((6, 128), np.int32)
+    table[0] = np.arange(128)
+    table[1] = np.arange(128)
+    table[2] = np.arange(128)
+    table[3] = -1
+    return {"table": table.reshape(768), "albedo_lod3": albedo, "pbr_lod2": pbr, "emissive_lod0": np.zeros((0, 512, 512), np.float32),
+            "grass_props": np.zeros(10, np.int32)}
+
+
+def analytic_sky(n=16, sun_dir=(-0.669, 0.468, 0.577)):
+    """Documented stand-in for the reference's rendered atmosphere cubemap (RGB16F, 16^2 for GI; Pipeline.cpp:1392-1394):
+    a horizon-to-zenith gradient plus a broad sun lobe.  Faces +X,-X,+Y,-Y,+Z,-Z, GL cube-map face orientation,
+    array [6][n][n][3] float32 with row index = t, column index = s."""
+    sun = np.asarray(sun_dir, dtype=np.float64)
+    sun = sun / np.linalg.norm(sun)
+    out = np.zeros((6, n, n, 3), dtype=np.float32)
+    c = (np.arange(n) + 0.5) / n * 2.0 - 1.0
+    sc, tc = np.meshgrid(c, c)  # tc varies along rows
+    one = np.ones_like(sc)
+    dirs = [
+        (one, -tc, -sc),   # +X: sc = -z, tc = -y
+        (-one, -tc, sc),   # -X: sc = +z, tc = -y
+        (sc, one, tc),     # +Y: sc = +x, tc = +z
+        (sc, -one, -tc),   # -Y: sc = +x, tc = -z
+        (sc, -tc, one),    # +Z: sc = +x, tc = -y
+        (-sc, -tc, -one),  # -Z: sc = -x, tc = -y
+    ]
+    zenith = np.array([0.18, 0.36, 0.85])
+    horizon = np.array([0.75, 0.82, 0.95])
+    ground = np.array([0.12, 0.11, 0.10])
+    for f, (x, y, z) in enumerate(dirs):
+        d = np.stack([x, y, z], -1)
+        d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+        up = np.clip(d[..., 1], 0.0, 1.0) ** 0.5
+        col = horizon[None, None, :] * (1.0 - up[..., None]) + zenith[None, None, :] * up[..., None]
+        down = np.clip(-d[..., 1] * 4.0, 0.0, 1.0)
+        col = col * (1.0 - down[..., None]) + ground[None, None, :] * down[..., None]
+        lobe = np.clip((d * sun[None, None, :]).sum(-1), 0.0, 1.0) ** 8
+        col = col + lobe[..., None] * np.array([1.6, 1.4, 1.1])[None, None, :]
+        out[f] = col.astype(np.float32)
+    return out

@@ -1,0 +1,106 @@
+"""Camera, TAA jitter and sun direction as the reference's host code computes them (inputs of the trace passes).
+
+  FpsCamera          Core/FpsCamera.cpp:23-24,150-163 (glm::lookAt / glm::perspective, right-handed, -1..1 depth)
+  halton_table       Core/TAAJitter.cpp:6-47
+  sun_moon_direction Core/Pipeline.cpp:1652-1671
+All arithmetic is float32 like glm's; matrices are handed to the C ABI column-major (glm::value_ptr order).
+"""
+import math
+
+import numpy as np
+
+from .abi import VxCamera
+
+f32 = np.float32
+
+
+def perspective(fovy_deg, aspect, z_near, z_far):
+    t = math.tan(math.radians(fovy_deg) / 2.0)
+    m = np.zeros((4, 4), dtype=np.float64)  # m[row, col]
+    m[0, 0] = 1.0 / (aspect * t)
+    m[1, 1] = 1.0 / t
+    m[2, 2] = -(z_far + z_near) / (z_far - z_near)
+    m[3, 2] = -1.0
+    m[2, 3] = -(2.0 * z_far * z_near) / (z_far - z_near)
+    return m
+
+
+def look_at(eye, center, up):
+    eye, center, up = (np.asarray(a, dtype=np.float64) for a in (eye, center, up))
+    f = center - eye
+    f /= np.linalg.norm(f)
+    s = np.cross(f, up)
+    s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    m = np.eye(4, dtype=np.float64)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, -f
+    m[0, 3], m[1, 3], m[2, 3] = -s.dot(eye), -u.dot(eye), f.dot(eye)
+    return m
+
+
+class FpsCamera:
+    """Default player camera: fov 60, near 0.1, far 1000 (Core/Player.cpp:10), start (192, 75, 192) (Pipeline.cpp:1500)."""
+
+    def __init__(self, position=(192.0, 75.0, 192.0), yaw_deg=90.0, pitch_deg=0.0, fov_deg=60.0, aspect=16.0 / 9.0, z_near=0.1, z_far=1000.0):
+        self.position = np.asarray(position, dtype=np.float64)
+        self.yaw, self.pitch = yaw_deg, pitch_deg
+        self.fov, self.aspect, self.z_near, self.z_far = fov_deg, aspect, z_near, z_far
+
+    @property
+    def front(self):
+        # FPSCamera::UpdateOnMouseMovement, Core/FpsCamera.cpp:66-70 (yaw 90 deg looks down +Z)
+        cp, sp = math.cos(math.radians(self.pitch)), math.sin(math.radians(self.pitch))
+        return np.array([cp * math.cos(math.radians(self.yaw)), sp, cp * math.sin(math.radians(self.yaw))])
+
+    def view(self):
+        return look_at(self.position, self.position + self.front, (0.0, 1.0, 0.0))
+
+    def projection(self):
+        return perspective(self.fov, self.aspect, self.z_near, self.z_far)
+
+    def vx_camera(self, width, height, row_begin=0, row_end=None):
+        """inv_view / inv_projection as Pipeline.cpp:1823-1824 hands them to the shaders."""
+        cam = VxCamera()
+        inv_view = np.linalg.inv(self.view()).astype(f32)
+        inv_proj = np.linalg.inv(self.projection()).astype(f32)
+        cam.inv_view[:] = inv_view.T.reshape(16).tolist()  # column-major
+        cam.inv_proj[:] = inv_proj.T.reshape(16).tolist()
+        cam.width, cam.height = int(width), int(height)
+        cam.row_begin = int(row_begin)
+        cam.row_end = int(height if row_end is None else row_end)
+        return cam
+
+
+def _halton(prime, index):
+    r, f, i = f32(0.0), f32(1.0), index
+    while i > 0:
+        f = f32(f / f32(prime))
+        r = f32(r + f32(f * f32(i % prime)))
+        i = int(math.floor(i / float(prime)))
+    return float(r)
+
+
+HALTON_TABLE = [(_halton(2, i + 1), _halton(3, i + 1)) for i in range(64)]  # GenerateJitterStuff
+
+
+def taa_jitter(frame):
+    """GetTAAJitter: entry frame % 64 (Core/TAAJitter.cpp:37-41)."""
+    return HALTON_TABLE[frame % 64]
+
+
+def taa_jitter_secondary(frame):
+    """GetTAAJitterSecondary: entry frame % 32 (Core/TAAJitter.cpp:43-47)."""
+    return HALTON_TABLE[frame % 32]
+
+
+def sun_moon_direction(sun_tick=50.0):
+    """Core/Pipeline.cpp:1652-1671: rotate (1,1,1) by 2*SunTick degrees about +Z, normalise; moon = (-x,-y,z)."""
+    a = math.radians(sun_tick * 2.0)
+    c, s = math.cos(a), math.sin(a)
+    sun = np.array([c - s, s + c, 1.0])
+    moon = np.array([-sun[0], -sun[1], sun[2]])
+    sun = sun / np.linalg.norm(sun)
+    moon = moon / np.linalg.norm(moon)
+    stronger = sun if -sun[1] < 0.01 else moon
+    sun_visibility = min(max(float(sun[1]) + 0.05, 0.0), 0.1) * 12.0  # Pipeline.cpp:1828
+    return sun.astype(f32), moon.astype(f32), stronger.astype(f32), float(f32(sun_visibility))

@@ -1,0 +1,561 @@
+// api.cu — the C ABI of include/vxpt.h: handle lifetime, uploads, host<->device staging, pass dispatch.
+// Every export validates its arguments, never throws, and reports failures through vxpt_last_error().
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "vxpt_internal.h"
+
+namespace vxpt {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_last_error = buf;
+    cudaGetLastError();  // clear the sticky-less error state
+    return VXPT_E_CUDA;
+}
+static int fail(int code, const char* msg) {
+    g_last_error = msg;
+    return code;
+}
+
+SceneDev make_scene(const vxpt_ctx* c) {
+    SceneDev S;
+    S.grid = c->d_grid;
+    S.df = c->d_df;
+    S.steps = c->d_steps;
+    S.materials = c->d_materials;
+    S.sobol = c->d_bluenoise;
+    S.scramble = c->d_bluenoise ? c->d_bluenoise + 65536 : nullptr;
+    S.rank = c->d_bluenoise ? c->d_bluenoise + 65536 + 131072 : nullptr;
+    S.albedo_lod3 = c->d_albedo;
+    S.pbr_lod2 = c->d_pbr;
+    S.emissive = c->d_emissive;
+    S.sky = c->d_sky;
+    S.shadow_noise = c->d_shadow_noise;
+    S.n_layers = c->n_layers;
+    S.n_emissive = c->n_emissive;
+    S.sky_n = c->sky_n;
+    S.counters = c->d_counters;
+    return S;
+}
+
+static bool is_device_pointer(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// bump allocator over a device arena for staged (host-pointer) planes; reset at the start of every pass
+struct Arena {
+    vxpt_ctx* c;
+    size_t used = 0;
+    explicit Arena(vxpt_ctx* ctx) : c(ctx) {}
+    int reserve(size_t bytes) {
+        if (bytes <= c->stage_bytes) return VXPT_OK;
+        VX_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->d_stage) cudaFree(c->d_stage);
+        c->d_stage = nullptr;
+        c->stage_bytes = 0;
+        if (cudaMalloc(&c->d_stage, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VXPT_E_NOMEM, "device staging allocation failed");
+        }
+        c->stage_bytes = bytes;
+        return VXPT_OK;
+    }
+    void* take(size_t bytes) {
+        void* p = (char*)c->d_stage + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return p;
+    }
+};
+
+// one image plane of a pass: user pointer (host or device) -> device pointer the kernel uses
+struct Plane {
+    void* user = nullptr;
+    void* dev = nullptr;
+    size_t elem = 0;  // bytes per pixel
+    bool staged = false;
+};
+
+struct PassIO {
+    vxpt_ctx* c;
+    const VxCamera* cam;
+    std::vector<Plane*> planes;
+    Arena arena;
+    PassIO(vxpt_ctx* ctx, const VxCamera* cm) : c(ctx), cam(cm), arena(ctx) {}
+    void add(Plane& p, const void* user, size_t elem) {
+        p.user = const_cast<void*>(user);
+        p.elem = elem;
+        if (user) planes.push_back(&p);
+    }
+    int resolve() {
+        size_t need = 0;
+        const size_t npx = (size_t)cam->width * cam->height;
+        for (Plane* p : planes) {
+            p->staged = !is_device_pointer(p->user);
+            if (p->staged) need += ((npx * p->elem) + 255) & ~(size_t)255;
+        }
+        if (need) {
+            int rc = arena.reserve(need);
+            if (rc) return rc;
+        }
+        for (Plane* p : planes) p->dev = p->staged ? arena.take(npx * p->elem) : p->user;
+        return VXPT_OK;
+    }
+    size_t slab_offset(const Plane& p) const { return (size_t)cam->row_begin * cam->width * p.elem; }
+    size_t slab_bytes(const Plane& p) const { return (size_t)(cam->row_end - cam->row_begin) * cam->width * p.elem; }
+    int upload(const Plane& p) {  // host -> device, slab rows only
+        if (!p.user || !p.staged) return VXPT_OK;
+        VX_CUDA(cudaMemcpyAsync((char*)p.dev + slab_offset(p), (const char*)p.user + slab_offset(p), slab_bytes(p), cudaMemcpyHostToDevice,
+                                c->stream));
+        return VXPT_OK;
+    }
+    int download(const Plane& p, bool& any) {
+        if (!p.user || !p.staged) return VXPT_OK;
+        VX_CUDA(cudaMemcpyAsync((char*)p.user + slab_offset(p), (const char*)p.dev + slab_offset(p), slab_bytes(p), cudaMemcpyDeviceToHost,
+                                c->stream));
+        any = true;
+        return VXPT_OK;
+    }
+};
+
+static int check_camera(const VxCamera* cam) {
+    if (!cam) return fail(VXPT_E_INVALID, "camera is NULL");
+    if (cam->width <= 0 || cam->height <= 0 || cam->width > 16384 || cam->height > 16384) return fail(VXPT_E_INVALID, "bad frame size");
+    if (cam->row_begin < 0 || cam->row_end > cam->height || cam->row_begin > cam->row_end)
+        return fail(VXPT_E_INVALID, "row slab outside the frame");
+    return VXPT_OK;
+}
+static int check_ready(vxpt_ctx* c) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded (vxpt_upload_world)");
+    if (!c->df_valid) return fail(VXPT_E_STATE, "distance field is stale: call vxpt_build_distance_field after editing the world");
+    return VXPT_OK;
+}
+
+__global__ void scatter_blocks(uint8_t* grid, const int16_t* xyz, const uint8_t* ids, int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+    grid[(size_t)x + (size_t)WX * ((size_t)y + (size_t)WY * (size_t)z)] = ids[k];
+}
+
+}  // namespace vxpt
+
+using namespace vxpt;
+
+extern "C" {
+
+const char* vxpt_last_error(void) { return g_last_error.c_str(); }
+const char* vxpt_version(void) { return "vxpt 0.1.0 (sm_100a)"; }
+
+int vxpt_create(int device_id, vxpt_handle* out) {
+    if (!out) return fail(VXPT_E_INVALID, "out handle is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VXPT_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device_id < 0 || device_id >= ndev) return fail(VXPT_E_INVALID, "device_id out of range");
+    VX_CUDA(cudaSetDevice(device_id));
+    vxpt_ctx* c = new (std::nothrow) vxpt_ctx();
+    if (!c) return fail(VXPT_E_NOMEM, "host allocation failed");
+    c->device = device_id;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev2);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev3);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_grid, VOXELS);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_df, VOXELS);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tmp, VOXELS);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_steps, VOXELS);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(DeviceCounters));
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream);
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "vxpt_create allocations", __FILE__, __LINE__);
+        vxpt_destroy(c);
+        return rc == VXPT_E_CUDA && e == cudaErrorMemoryAllocation ? VXPT_E_NOMEM : rc;
+    }
+    *out = c;
+    return VXPT_OK;
+}
+
+int vxpt_destroy(vxpt_handle c) {
+    if (!c) return VXPT_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
+                    c->d_emissive, c->d_sky, c->d_shadow_noise, c->d_counters, c->d_stage, c->d_queue};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->ev4) cudaEventDestroy(c->ev4);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+    return VXPT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- world
+int vxpt_upload_world(vxpt_handle c, const uint8_t* blocks) {
+    if (!c || !blocks) return fail(VXPT_E_INVALID, "NULL argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaMemcpyAsync(c->d_grid, blocks, VOXELS, cudaMemcpyDefault, c->stream));
+    // the copy must have consumed the caller's buffer before we return (World::Buffer semantics, World.h:167-171)
+    if (!is_device_pointer(blocks)) VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->world_uploaded = true;
+    c->df_valid = false;
+    return VXPT_OK;
+}
+
+int vxpt_download_world(vxpt_handle c, uint8_t* blocks) {
+    if (!c || !blocks) return fail(VXPT_E_INVALID, "NULL argument");
+    if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaMemcpyAsync(blocks, c->d_grid, VOXELS, cudaMemcpyDefault, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_set_block(vxpt_handle c, int x, int y, int z, uint8_t id) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded");
+    if (x < 0 || y < 0 || z < 0 || x >= WX || y >= WY || z >= WZ) return fail(VXPT_E_INVALID, "voxel outside the world");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaMemsetAsync(c->d_grid + ((size_t)x + (size_t)WX * ((size_t)y + (size_t)WY * (size_t)z)), id, 1, c->stream));
+    c->df_valid = false;
+    return VXPT_OK;
+}
+
+int vxpt_set_blocks(vxpt_handle c, const int16_t* xyz, const uint8_t* ids, int n) {
+    if (!c || (n > 0 && (!xyz || !ids)) || n < 0) return fail(VXPT_E_INVALID, "bad argument");
+    if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded");
+    if (n == 0) return VXPT_OK;
+    for (int k = 0; k < n; ++k)
+        if (xyz[3 * k] < 0 || xyz[3 * k + 1] < 0 || xyz[3 * k + 2] < 0 || xyz[3 * k] >= WX || xyz[3 * k + 1] >= WY || xyz[3 * k + 2] >= WZ)
+            return fail(VXPT_E_INVALID, "voxel outside the world");
+    VX_CUDA(cudaSetDevice(c->device));
+    Arena arena(c);
+    const size_t b_xyz = (size_t)n * 3 * sizeof(int16_t), b_ids = (size_t)n;
+    int rc = arena.reserve(((b_xyz + 255) & ~(size_t)255) + ((b_ids + 255) & ~(size_t)255));
+    if (rc) return rc;
+    int16_t* d_xyz = (int16_t*)arena.take(b_xyz);
+    uint8_t* d_ids = (uint8_t*)arena.take(b_ids);
+    VX_CUDA(cudaMemcpyAsync(d_xyz, xyz, b_xyz, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaMemcpyAsync(d_ids, ids, b_ids, cudaMemcpyHostToDevice, c->stream));
+    scatter_blocks<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_grid, d_xyz, d_ids, n);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    c->df_valid = false;
+    return VXPT_OK;
+}
+
+// --------------------------------------------------------------------------------------------- distance field
+int vxpt_build_distance_field(vxpt_handle c) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaEventRecord(c->ev2, c->stream));
+    int rc = launch_df_build(c);
+    if (rc) return rc;
+    VX_CUDA(cudaEventRecord(c->ev3, c->stream));
+    rc = launch_pack_bricks(c);
+    if (rc) return rc;
+    VX_CUDA(cudaEventRecord(c->ev4, c->stream));
+    c->df_timed = true;
+    c->df_valid = true;
+    return VXPT_OK;
+}
+
+int vxpt_download_distance_field(vxpt_handle c, uint8_t* out) {
+    if (!c || !out) return fail(VXPT_E_INVALID, "NULL argument");
+    if (!c->df_valid) return fail(VXPT_E_STATE, "distance field not built");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaMemcpyAsync(out, c->d_df, VOXELS, cudaMemcpyDefault, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_device_pointers(vxpt_handle c, const uint8_t** grid, const uint8_t** df) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    if (grid) *grid = c->d_grid;
+    if (df) *df = c->d_df;
+    return VXPT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------- tables
+}  // extern "C"
+template <class T>
+static int replace_buffer(vxpt_ctx* c, T** slot, const void* src, size_t bytes) {
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    if (*slot) cudaFree(*slot);
+    *slot = nullptr;
+    if (cudaMalloc((void**)slot, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VXPT_E_NOMEM, "device allocation failed");
+    }
+    VX_CUDA(cudaMemcpyAsync(*slot, src, bytes, cudaMemcpyDefault, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+extern "C" {
+
+int vxpt_set_materials(vxpt_handle c, const int32_t table[768]) {
+    if (!c || !table) return fail(VXPT_E_INVALID, "NULL argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    int rc = replace_buffer(c, &c->d_materials, table, 768 * sizeof(int32_t));
+    if (rc) return rc;
+    std::memcpy(c->h_materials, table, sizeof c->h_materials);
+    c->have_materials = true;
+    return VXPT_OK;
+}
+
+int vxpt_set_blue_noise(vxpt_handle c, const int32_t* sobol, const int32_t* scramble, const int32_t* rank) {
+    if (!c || !sobol || !scramble || !rank) return fail(VXPT_E_INVALID, "NULL argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    // The Heitz et al. tables hold 8-bit values (Core/BlueNoiseDataSSBO.cpp:4,9,14); keep them as bytes on the
+    // device (320 KB instead of 1.25 MB of int32, so they stay L1/L2 friendly).
+    std::vector<uint8_t> packed(65536 + 131072 + 131072);
+    const int32_t* src[3] = {sobol, scramble, rank};
+    const size_t len[3] = {65536, 131072, 131072};
+    size_t o = 0;
+    for (int t = 0; t < 3; ++t)
+        for (size_t k = 0; k < len[t]; ++k) {
+            int32_t v = src[t][k];
+            if (v < 0 || v > 255) return fail(VXPT_E_UNSUPPORTED, "blue-noise table value outside 0..255");
+            packed[o++] = (uint8_t)v;
+        }
+    int rc = replace_buffer(c, &c->d_bluenoise, packed.data(), packed.size());
+    if (rc) return rc;
+    c->have_bluenoise = true;
+    return VXPT_OK;
+}
+
+int vxpt_set_material_textures(vxpt_handle c, const float* albedo_lod3, const float* pbr_lod2, int n_layers, const float* emissive_lod0,
+                               int n_emissive_layers) {
+    if (!c || !albedo_lod3 || !pbr_lod2 || n_layers <= 0 || n_emissive_layers < 0 || (n_emissive_layers > 0 && !emissive_lod0))
+        return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    int rc = replace_buffer(c, &c->d_albedo, albedo_lod3, (size_t)n_layers * 64 * 64 * 4 * sizeof(float));
+    if (rc) return rc;
+    rc = replace_buffer(c, &c->d_pbr, pbr_lod2, (size_t)n_layers * 128 * 128 * 4 * sizeof(float));
+    if (rc) return rc;
+    if (n_emissive_layers > 0) {
+        rc = replace_buffer(c, &c->d_emissive, emissive_lod0, (size_t)n_emissive_layers * 512 * 512 * sizeof(float));
+        if (rc) return rc;
+    }
+    c->n_layers = n_layers;
+    c->n_emissive = n_emissive_layers;
+    c->have_textures = true;
+    return VXPT_OK;
+}
+
+int vxpt_set_sky_cubemap(vxpt_handle c, const float* rgb, int n) {
+    if (!c || !rgb || n <= 0 || n > 4096) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    int rc = replace_buffer(c, &c->d_sky, rgb, (size_t)6 * n * n * 3 * sizeof(float));
+    if (rc) return rc;
+    c->sky_n = n;
+    c->have_sky = true;
+    return VXPT_OK;
+}
+
+int vxpt_set_shadow_noise(vxpt_handle c, const uint8_t* rgba8) {
+    if (!c || !rgba8) return fail(VXPT_E_INVALID, "NULL argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    int rc = replace_buffer(c, &c->d_shadow_noise, rgba8, (size_t)256 * 256 * 4);
+    if (rc) return rc;
+    c->have_shadow_noise = true;
+    return VXPT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------- passes
+int vxpt_trace_primary(vxpt_handle c, const VxCamera* cam, const VxPrimaryParams* p, const VxGBuffer* out) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_camera(cam))) return rc;
+    if (!p || !out) return fail(VXPT_E_INVALID, "NULL argument");
+    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested traversal is outside the v1 parity profile (off by default in the reference)");
+    if (p->max_iterations < 0) return fail(VXPT_E_INVALID, "max_iterations < 0");
+    VX_CUDA(cudaSetDevice(c->device));
+    PassIO io(c, cam);
+    Plane t, nid, bid, it, hv;
+    io.add(t, out->t, 4); io.add(nid, out->normal_id, 1); io.add(bid, out->block_id, 1); io.add(it, out->inv_t, 4); io.add(hv, out->hit_voxel, 6);
+    if ((rc = io.resolve())) return rc;
+    VxGBuffer dev{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, (int16_t*)hv.dev};
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_primary(c, *cam, *p, dev))) return rc;
+    VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->pass_timed = true;
+    bool any = false;
+    for (Plane* pl : io.planes)
+        if ((rc = io.download(*pl, any))) return rc;
+    if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_trace_shadow(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, const VxShadowParams* p, const VxShadowOut* out) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_camera(cam))) return rc;
+    if (!g || !p || !out || !g->t || !g->normal_id) return fail(VXPT_E_INVALID, "NULL argument (G-buffer t and normal_id are required)");
+    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested shadows are outside the v1 parity profile");
+    if (p->soft && !c->have_shadow_noise) return fail(VXPT_E_STATE, "soft shadows need vxpt_set_shadow_noise");
+    VX_CUDA(cudaSetDevice(c->device));
+    PassIO io(c, cam);
+    Plane t, nid, sh, tr;
+    io.add(t, g->t, 4); io.add(nid, g->normal_id, 1); io.add(sh, out->shadow, 1); io.add(tr, out->transversal, 4);
+    if ((rc = io.resolve())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    if ((rc = io.upload(t)) || (rc = io.upload(nid))) return rc;
+    VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, nullptr, nullptr, nullptr};
+    VxShadowOut od{(uint8_t*)sh.dev, (float*)tr.dev};
+    VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_shadow(c, *cam, gd, *p, od))) return rc;
+    VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->pass_timed = true;
+    bool any = false;
+    if ((rc = io.download(sh, any)) || (rc = io.download(tr, any))) return rc;
+    if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_trace_diffuse(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, const VxDiffuseParams* p, const VxDiffuseOut* out) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_camera(cam))) return rc;
+    if (!g || !p || !out || !g->t || !g->normal_id) return fail(VXPT_E_INVALID, "NULL argument (G-buffer t and normal_id are required)");
+    if (!p->use_blue_noise) return fail(VXPT_E_UNSUPPORTED, "u_UseBlueNoise=false (fract(sin()) hash) is not reproducible; outside the parity profile");
+    if (p->direct_sampling) return fail(VXPT_E_UNSUPPORTED, "u_UseDirectSampling (WIP light-chunk sampling) is outside the v1 parity profile");
+    if (!c->have_materials || !c->have_bluenoise || !c->have_textures || !c->have_sky)
+        return fail(VXPT_E_STATE, "diffuse GI needs materials, blue-noise tables, material textures and a sky cubemap");
+    if (p->trace_length < 0 || p->spp < 0) return fail(VXPT_E_INVALID, "negative trace_length / spp");
+    // every layer the table can reach must exist in the baked arrays
+    for (int b = 0; b < 128; ++b) {
+        if (c->h_materials[b] >= c->n_layers) return fail(VXPT_E_INVALID, "material table references an albedo layer that was not uploaded");
+        if (c->h_materials[384 + b] >= c->n_emissive) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
+    }
+    VX_CUDA(cudaSetDevice(c->device));
+    PassIO io(c, cam);
+    Plane t, nid, sh, cg, lu, ao;
+    io.add(t, g->t, 4); io.add(nid, g->normal_id, 1);
+    io.add(sh, out->sh, 16); io.add(cg, out->cocg, 8); io.add(lu, out->luma, 4); io.add(ao, out->ao_sky, 8);
+    if ((rc = io.resolve())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    if ((rc = io.upload(t)) || (rc = io.upload(nid))) return rc;
+    VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, nullptr, nullptr, nullptr};
+    VxDiffuseOut od{(float*)sh.dev, (float*)cg.dev, (float*)lu.dev, (float*)ao.dev};
+    VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_diffuse(c, *cam, gd, *p, od))) return rc;
+    VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->pass_timed = true;
+    bool any = false;
+    if ((rc = io.download(sh, any)) || (rc = io.download(cg, any)) || (rc = io.download(lu, any)) || (rc = io.download(ao, any))) return rc;
+    if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_trace_reflection(vxpt_handle c, const VxCamera*, const VxGBuffer*, const VxReflectionIn*, const VxReflectionParams*,
+                          const VxReflectionOut*) {
+    (void)c;
+    return fail(VXPT_E_UNSUPPORTED, "reflection pass not implemented yet");
+}
+
+// ------------------------------------------------------------------------------------------------ sync / stats
+int vxpt_sync(vxpt_handle c) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_get_stats(vxpt_handle c, VxStats* out) {
+    if (!c || !out) return fail(VXPT_E_INVALID, "NULL argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    DeviceCounters h;
+    VX_CUDA(cudaMemcpy(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    if (c->pass_timed) {
+        VX_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+        c->pass_timed = false;
+    }
+    if (c->df_timed) {
+        VX_CUDA(cudaEventElapsedTime(&c->df_build_ms, c->ev2, c->ev3));
+        VX_CUDA(cudaEventElapsedTime(&c->brick_pack_ms, c->ev3, c->ev4));
+        c->df_timed = false;
+    }
+    out->rays = h.rays;
+    out->df_fetches = h.df_fetches;
+    out->vox_fetches = h.vox_fetches;
+    out->last_ms = c->last_ms;
+    out->df_build_ms = c->df_build_ms;
+    out->brick_pack_ms = c->brick_pack_ms;
+    return VXPT_OK;
+}
+
+int vxpt_reset_stats(vxpt_handle c) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_launch_count(vxpt_handle c, uint64_t* n) {
+    if (!c || !n) return fail(VXPT_E_INVALID, "NULL argument");
+    *n = c->launches;
+    return VXPT_OK;
+}
+
+int vxpt_stream(vxpt_handle c, void** s) {
+    if (!c || !s) return fail(VXPT_E_INVALID, "NULL argument");
+    *s = (void*)c->stream;
+    return VXPT_OK;
+}
+
+int vxpt_set_option(vxpt_handle c, int option, int value) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    switch (option) {
+        case VXPT_OPT_TRAVERSAL_LAYOUT:
+            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "layout must be 0 or 1");
+            c->opt_layout = value;
+            return VXPT_OK;
+        case VXPT_OPT_GI_WAVEFRONT:
+            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "wavefront must be 0 or 1");
+            c->opt_wavefront = value;
+            return VXPT_OK;
+        case VXPT_OPT_DF_ALGO:
+            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "df algo must be 0 or 1");
+            c->opt_df_algo = value;
+            return VXPT_OK;
+        default:
+            return fail(VXPT_E_INVALID, "unknown option");
+    }
+}
+
+int vxpt_measure_l2_sector_peak(vxpt_handle c, double* gbps) {
+    if (!c || !gbps) return fail(VXPT_E_INVALID, "NULL argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    return run_l2_probe(c, gbps);
+}
+
+}  // extern "C"

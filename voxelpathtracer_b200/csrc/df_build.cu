@@ -1,0 +1,342 @@
+// df_build.cu — Manhattan (L1) distance field over the 384x128x384 block grid, sm_100a.
+//
+// Replaces World::GenerateDistanceField (Core/World.cpp:69-113) and the three serial-scan compute shaders
+// Core/Shaders/ManhattanDistance{X,Y,Z}.comp.  Result:
+//     DF[p] = min(254, min over solid q of |p - q|_1),   solid = block byte > 0.
+// The separable min-plus sweeps commute, so any order of the three axes yields the same bytes.
+//
+// Design (algo 1, default) — two kernels, both built on the DPX instruction VIADDMNMX.U16x2
+// (__viaddmin_u16x2: per 16-bit lane min(a + b, c)), i.e. one instruction per sweep step per TWO voxels:
+//   df_xy_dpx : one CTA per z-slice (49,152 contiguous bytes).  The slice is brought into shared memory with
+//               one TMA bulk copy (cp.async.bulk + mbarrier), swept along x with rows paired in the two 16-bit
+//               lanes (12 voxels x 2 rows per lane, cross-lane carries by a shuffle min-plus scan), swept
+//               along y with x-neighbours paired (a whole 128-voxel column pair lives in registers), and
+//               written back with one TMA bulk store.
+//   df_z_dpx  : the z sweep; each thread owns a 24-voxel z-segment of one 4-byte x-word in registers, 16
+//               segments per CTA exchange their edge values through shared memory (min-plus carries), every
+//               global access is a fully used 128-byte line.
+//   pack_bricks: permutes the linear field into 8x4x4 bricks (one 128-B line each, 4x2x4 per 32-B sector) for
+//               the traversal kernels.
+// Algo 0 keeps the reference's shape (one thread per grid line, three launches) as an on-device cross-check.
+#include "vxpt_internal.h"
+
+namespace vxpt {
+
+// ------------------------------------------------------------------------------------------------------------
+// algo 0: reference-shaped, one thread per line (ManhattanDistanceX.comp:45-69, Y.comp:26-51, Z.comp:24-47)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void df_x_lines(const uint8_t* __restrict__ grid, uint8_t* __restrict__ df) {
+    int line = blockIdx.x * blockDim.x + threadIdx.x;  // y + WY * z
+    if (line >= WY * WZ) return;
+    size_t base = (size_t)line * WX;
+    int prev = grid[base] > 0 ? 0 : 254;
+    df[base] = (uint8_t)prev;
+    for (int x = 1; x < WX; ++x) {
+        prev = grid[base + x] > 0 ? 0 : min(254, prev + 1);
+        df[base + x] = (uint8_t)prev;
+    }
+    for (int x = WX - 2; x >= 0; --x) {
+        int cur = df[base + x];
+        if (prev < cur) { cur = prev + 1; df[base + x] = (uint8_t)cur; }
+        prev = cur;
+    }
+}
+__global__ void df_y_lines(uint8_t* __restrict__ df) {
+    int line = blockIdx.x * blockDim.x + threadIdx.x;  // x + WX * z
+    if (line >= WX * WZ) return;
+    int x = line % WX, z = line / WX;
+    size_t base = (size_t)x + (size_t)z * WX * WY;
+    int prev = df[base];
+    for (int y = 1; y < WY; ++y) {
+        int cur = df[base + (size_t)y * WX];
+        if (prev < cur) { cur = prev + 1; df[base + (size_t)y * WX] = (uint8_t)cur; }
+        prev = cur;
+    }
+    for (int y = WY - 2; y >= 0; --y) {
+        int cur = df[base + (size_t)y * WX];
+        if (prev < cur) { cur = prev + 1; df[base + (size_t)y * WX] = (uint8_t)cur; }
+        prev = cur;
+    }
+}
+__global__ void df_z_lines(uint8_t* __restrict__ df) {
+    int line = blockIdx.x * blockDim.x + threadIdx.x;  // x + WX * y
+    if (line >= WX * WY) return;
+    size_t base = (size_t)line;
+    const size_t sz = (size_t)WX * WY;
+    int prev = df[base];
+    for (int z = 1; z < WZ; ++z) {
+        int cur = df[base + z * sz];
+        if (prev < cur) { cur = prev + 1; df[base + z * sz] = (uint8_t)cur; }
+        prev = cur;
+    }
+    for (int z = WZ - 2; z >= 0; --z) {
+        int cur = df[base + z * sz];
+        if (prev < cur) { cur = prev + 1; df[base + z * sz] = (uint8_t)cur; }
+        prev = cur;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copies (SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+constexpr uint32_t ONE2 = 0x00010001u;  // +1 in both 16-bit lanes
+constexpr uint32_t INF2 = 0x00FE00FEu;  // 254 in both lanes ("no solid voxel seen")
+
+// ------------------------------------------------------------------------------------------------------------
+// df_xy_dpx: x and y sweeps of one z-slice in shared memory
+// ------------------------------------------------------------------------------------------------------------
+constexpr int XY_THREADS = 192;  // 6 warps; threads 0..191 each own one x-pair column in the y sweep
+
+__global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tile = smem;                                            // [128][384] bytes
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SLICE_BYTES);  // mbarrier
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t slice = (size_t)blockIdx.x * SLICE_BYTES;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar, SLICE_BYTES);
+        bulk_g2s(tile, grid + slice, SLICE_BYTES, bar);
+    }
+    mbar_wait(bar, 0);
+
+    // ---- x sweep: a warp takes rows (2p, 2p+1); lane l holds x = 12l .. 12l+11 of both rows, row 2p in the low
+    //      16-bit lane and row 2p+1 in the high lane of r[k].
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
+    for (int p = warp; p < WY / 2; p += XY_THREADS / 32) {
+        uint32_t* rowA = t32 + (2 * p) * (WX / 4) + lane * 3;
+        uint32_t* rowB = rowA + WX / 4;
+        uint32_t r[12];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            uint32_t A = rowA[k], B = rowB[k];
+            uint32_t t0 = __byte_perm(A, B, 0x6240);  // a0 a2 b0 b2
+            uint32_t t1 = __byte_perm(A, B, 0x7351);  // a1 a3 b1 b3
+            r[4 * k + 0] = t0 & 0x00FF00FFu;
+            r[4 * k + 2] = (t0 >> 8) & 0x00FF00FFu;
+            r[4 * k + 1] = t1 & 0x00FF00FFu;
+            r[4 * k + 3] = (t1 >> 8) & 0x00FF00FFu;
+        }
+        // block byte -> initial distance: solid 0, air 254 (ManhattanDistanceX.comp:51-52)
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = INF2 - __vminu2(r[k], ONE2) * 0xFEu;
+        // forward (x ascending)
+#pragma unroll
+        for (int k = 1; k < 12; ++k) r[k] = __viaddmin_u16x2(r[k - 1], ONE2, r[k]);
+        uint32_t c = r[11];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, c, d);
+            if (lane >= d) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
+        }
+        uint32_t cin = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0) cin = INF2;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(k + 1) * ONE2, r[k]);
+        // backward (x descending)
+#pragma unroll
+        for (int k = 10; k >= 0; --k) r[k] = __viaddmin_u16x2(r[k + 1], ONE2, r[k]);
+        c = r[0];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_down_sync(0xffffffffu, c, d);
+            if (lane + d < 32) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
+        }
+        cin = __shfl_down_sync(0xffffffffu, c, 1);
+        if (lane == 31) cin = INF2;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(12 - k) * ONE2, r[k]);
+        // repack the two rows and put them back
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            uint32_t t0 = r[4 * k + 0] | (r[4 * k + 2] << 8);  // a0 a2 b0 b2
+            uint32_t t1 = r[4 * k + 1] | (r[4 * k + 3] << 8);  // a1 a3 b1 b3
+            rowA[k] = __byte_perm(t0, t1, 0x5140);
+            rowB[k] = __byte_perm(t0, t1, 0x7362);
+        }
+    }
+    __syncthreads();
+
+    // ---- y sweep: thread t owns voxels x = 2t, 2t+1 for all 128 rows (x-neighbours in the two lanes)
+    {
+        uint16_t* t16 = reinterpret_cast<uint16_t*>(tile) + tid;
+        uint32_t col[WY];
+#pragma unroll
+        for (int y = 0; y < WY; ++y) col[y] = __byte_perm((uint32_t)t16[y * (WX / 2)], 0u, 0x4140);
+#pragma unroll
+        for (int y = 1; y < WY; ++y) col[y] = __viaddmin_u16x2(col[y - 1], ONE2, col[y]);
+#pragma unroll
+        for (int y = WY - 2; y >= 0; --y) col[y] = __viaddmin_u16x2(col[y + 1], ONE2, col[y]);
+#pragma unroll
+        for (int y = 0; y < WY; ++y) t16[y * (WX / 2)] = (uint16_t)__byte_perm(col[y], 0u, 0x4420);
+    }
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
+    __syncthreads();
+    if (tid == 0) {
+        bulk_s2g(out + slice, tile, SLICE_BYTES);
+        bulk_commit();
+        bulk_wait_read0();  // shared memory must outlive the copy's reads
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// df_z_dpx: z sweep, in place capable (in may equal out)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ZSEG = 24;          // voxels per thread along z
+constexpr int ZSEGS = WZ / ZSEG;  // 16 segments per CTA
+
+__global__ void __launch_bounds__(32 * ZSEGS, 2) df_z_dpx(const uint8_t* __restrict__ in, uint8_t* __restrict__ out) {
+    __shared__ uint2 edge_first[ZSEGS][32];  // local value at the first voxel of a segment (lo pair, hi pair)
+    __shared__ uint2 edge_last[ZSEGS][32];
+    __shared__ uint2 carry_f[ZSEGS][32];
+    __shared__ uint2 carry_b[ZSEGS][32];
+    const int lane = threadIdx.x, seg = threadIdx.y;
+    const int y = blockIdx.y;
+    const size_t base = (size_t)y * WX + (size_t)(blockIdx.x * 32 + lane) * 4 + (size_t)seg * ZSEG * SLICE_BYTES;
+
+    uint32_t lo[ZSEG], hi[ZSEG];
+#pragma unroll
+    for (int i = 0; i < ZSEG; ++i) {
+        uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(in + base + (size_t)i * SLICE_BYTES));
+        lo[i] = __byte_perm(w, 0u, 0x4140);
+        hi[i] = __byte_perm(w, 0u, 0x4342);
+    }
+#pragma unroll
+    for (int i = 1; i < ZSEG; ++i) {
+        lo[i] = __viaddmin_u16x2(lo[i - 1], ONE2, lo[i]);
+        hi[i] = __viaddmin_u16x2(hi[i - 1], ONE2, hi[i]);
+    }
+#pragma unroll
+    for (int i = ZSEG - 2; i >= 0; --i) {
+        lo[i] = __viaddmin_u16x2(lo[i + 1], ONE2, lo[i]);
+        hi[i] = __viaddmin_u16x2(hi[i + 1], ONE2, hi[i]);
+    }
+    edge_first[seg][lane] = make_uint2(lo[0], hi[0]);
+    edge_last[seg][lane] = make_uint2(lo[ZSEG - 1], hi[ZSEG - 1]);
+    __syncthreads();
+    if (seg == 0) {  // one warp runs the 16-step min-plus scans for its 32 x-words
+        uint2 c = make_uint2(INF2, INF2);
+#pragma unroll
+        for (int s = 0; s < ZSEGS; ++s) {
+            carry_f[s][lane] = c;  // best value one voxel before segment s
+            uint2 e = edge_last[s][lane];
+            c.x = __viaddmin_u16x2(c.x, (uint32_t)ZSEG * ONE2, e.x);
+            c.y = __viaddmin_u16x2(c.y, (uint32_t)ZSEG * ONE2, e.y);
+        }
+        c = make_uint2(INF2, INF2);
+#pragma unroll
+        for (int s = ZSEGS - 1; s >= 0; --s) {
+            carry_b[s][lane] = c;  // best value one voxel after segment s
+            uint2 e = edge_first[s][lane];
+            c.x = __viaddmin_u16x2(c.x, (uint32_t)ZSEG * ONE2, e.x);
+            c.y = __viaddmin_u16x2(c.y, (uint32_t)ZSEG * ONE2, e.y);
+        }
+    }
+    __syncthreads();
+    const uint2 cf = carry_f[seg][lane], cb = carry_b[seg][lane];
+#pragma unroll
+    for (int i = 0; i < ZSEG; ++i) {
+        uint32_t a = __viaddmin_u16x2(cf.x, (uint32_t)(i + 1) * ONE2, lo[i]);
+        a = __viaddmin_u16x2(cb.x, (uint32_t)(ZSEG - i) * ONE2, a);
+        uint32_t b = __viaddmin_u16x2(cf.y, (uint32_t)(i + 1) * ONE2, hi[i]);
+        b = __viaddmin_u16x2(cb.y, (uint32_t)(ZSEG - i) * ONE2, b);
+        *reinterpret_cast<uint32_t*>(out + base + (size_t)i * SLICE_BYTES) = __byte_perm(a, b, 0x6420);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pack_bricks: linear field -> 8x4x4 bricks.  A warp moves 4 x-adjacent bricks (32 x-bytes x 4 y x 4 z): every
+// lane reads one 16-byte run, every store instruction fills whole 64-byte half lines.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_bricks(const uint8_t* __restrict__ df, uint8_t* __restrict__ bricks) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr int GROUPS_X = BRICKS_X / 4;  // 12 groups of 4 bricks along x
+    if (warp_global >= GROUPS_X * BRICKS_Y * BRICKS_Z) return;
+    const int gx = warp_global % GROUPS_X;
+    const int by = (warp_global / GROUPS_X) % BRICKS_Y;
+    const int bz = warp_global / (GROUPS_X * BRICKS_Y);
+    const int row = lane >> 1, half = lane & 1;  // row = (z&3)*4 + (y&3)
+    const int y = by * 4 + (row & 3), z = bz * 4 + (row >> 2);
+    const int x0 = gx * 32 + half * 16;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(df + (size_t)x0 + (size_t)WX * ((size_t)y + (size_t)WY * z)));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t off = brick_offset(x0 + 4 * j, y, z);
+        *reinterpret_cast<uint32_t*>(bricks + off) = w[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+int launch_df_build(vxpt_ctx* c) {
+    cudaStream_t s = c->stream;
+    if (c->opt_df_algo == 0) {
+        df_x_lines<<<(WY * WZ + 127) / 128, 128, 0, s>>>(c->d_grid, c->d_df);
+        df_y_lines<<<(WX * WZ + 127) / 128, 128, 0, s>>>(c->d_df);
+        df_z_lines<<<(WX * WY + 127) / 128, 128, 0, s>>>(c->d_df);
+        c->launches += 3;
+    } else {
+        const int smem = SLICE_BYTES + 16;
+        static bool attr_done = false;
+        if (!attr_done) {
+            VX_CUDA(cudaFuncSetAttribute(df_xy_dpx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_done = true;
+        }
+        df_xy_dpx<<<WZ, XY_THREADS, smem, s>>>(c->d_grid, c->d_tmp);
+        df_z_dpx<<<dim3(WX / 128, WY), dim3(32, ZSEGS), 0, s>>>(c->d_tmp, c->d_df);
+        c->launches += 2;
+    }
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int launch_pack_bricks(vxpt_ctx* c) {
+    const int warps = (BRICKS_X / 4) * BRICKS_Y * BRICKS_Z;
+    pack_bricks<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(c->d_df, c->d_steps);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+}  // namespace vxpt

@@ -1,0 +1,486 @@
+// trace.cu — primary, sun-shadow and diffuse-GI passes over the resident grid + distance field (sm_100a).
+//
+//   primary_kernel  : Core/Shaders/InitialRayTraceFrag.glsl main() :417-468
+//   shadow_kernel   : Core/Shaders/ShadowRayTraceFrag.glsl main() :414-513
+//   diffuse_kernel  : Core/Shaders/DiffuseRayTraceFrag.glsl main() :822-935, CalculateDiffuse :535-664
+// Compiled with -fmad=false (see trace_device.cuh).  No CPU fallback exists for any of these.
+#include "trace_device.cuh"
+
+namespace vxpt {
+
+// ============================================================================================= primary rays
+struct PrimaryDev {
+    int max_iterations, jitter_enable;
+    float jx, jy;
+};
+struct GBufferDev {
+    float* t;
+    uint8_t* normal_id;
+    uint8_t* block_id;
+    float* inv_t;
+    int16_t* hit_voxel;
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
+                                                      const GBufferDev out) {
+    int i, j;
+    const bool active = thread_pixel(cam, i, j);
+    Counters cnt = {0u, 0u, 0u};
+    if (active) {
+        float u = ((float)i + 0.5f) / (float)cam.width;
+        float v = ((float)j + 0.5f) / (float)cam.height;
+        if (p.jitter_enable) {  // GetRayStuff :404-408, TexelSize = 1.0f / u_Dimensions
+            u -= p.jx * (1.0f / (float)cam.width);
+            v -= p.jy * (1.0f / (float)cam.height);
+        }
+        const V3 dir = normalize3(ray_direction_at(cam, u, v));
+        TraceHit h;
+        const float t = traverse_df<LAYOUT>(S, ray_origin(cam), dir, p.max_iterations, h, cnt);
+        const bool intersect = t > 0.0f && h.block > 0;
+        const size_t px = (size_t)j * cam.width + i;
+        if (out.t) out.t[px] = t;
+        if (out.inv_t) out.inv_t[px] = 1.0f / t;
+        if (out.normal_id) out.normal_id[px] = intersect ? (uint8_t)normal_id_of(h) : (uint8_t)VXPT_NORMAL_MISS;
+        if (out.block_id) out.block_id[px] = intersect ? (uint8_t)h.block : (uint8_t)0;
+        if (out.hit_voxel) {
+            out.hit_voxel[3 * px + 0] = intersect ? (int16_t)h.vx : (int16_t)-1;
+            out.hit_voxel[3 * px + 1] = intersect ? (int16_t)h.vy : (int16_t)-1;
+            out.hit_voxel[3 * px + 2] = intersect ? (int16_t)h.vz : (int16_t)-1;
+        }
+    }
+    flush_counters(S, cnt);
+}
+
+// ============================================================================================= sun shadow
+struct ShadowDev {
+    V3 light;
+    int soft;
+    int ioffx, ioffy;  // floor(off) of the per-frame blue-noise texel offset (:456-459), computed on the host in fp32
+    float hx, hy;      // u_Halton
+};
+struct ShadowOutDev {
+    uint8_t* shadow;
+    float* transversal;
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const ShadowDev p,
+                                                     const GBufferDev g, const ShadowOutDev out) {
+    int i, j;
+    const bool active = thread_pixel(cam, i, j);
+    Counters cnt = {0u, 0u, 0u};
+    if (active) {
+        const size_t px = (size_t)j * cam.width + i;
+        float u = ((float)i + 0.5f) / (float)cam.width;
+        float v = ((float)j + 0.5f) / (float)cam.height;
+        u += p.hx * (1.0f / (float)cam.width);
+        v += p.hy * (1.0f / (float)cam.height);
+        const float dist = g.t[px];
+        uint8_t o_shadow;
+        float o_trans;
+        if (dist < 0.0f) {
+            o_shadow = 0;
+            o_trans = 64.0f;
+        } else {
+            const V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, u, v)) * dist;  // GetPositionAt :310-314
+            const V3 L = p.light;
+            V3 dir = L;
+            if (p.soft) {
+                const int tx = ((int)(((float)i + 0.5f) + (float)p.ioffx)) % 256;
+                const int ty = ((int)(((float)j + 0.5f) + (float)p.ioffy)) % 256;
+                const uchar4 tex = S.shadow_noise[ty * 256 + tx];
+                const float xi_x = (float)tex.x / 255.0f, xi_y = (float)tex.y / 255.0f;
+                const V3 T = normalize3(cross3(L, mk3(0.0f, 1.0f, 1.0f)));
+                const V3 B = cross3(T, L);
+                const float cos_theta_max = 0.9999505604617f;  // SampleCone :388-398, :474
+                const float cos_theta = (1.0f - xi_x) + xi_x * cos_theta_max;
+                const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+                const float phi = xi_y * 3.14159265359f * 2.0f;
+                const V3 c = mk3(sin_theta * cos_cr(phi), sin_theta * sin_cr(phi), cos_theta);
+                dir = (T * c.x + B * c.y) + L * c.z;  // mat3(T,B,L) * c
+            }
+            const V3 N = normal_from_id(g.normal_id[px], 1.0f);
+            const float ndotl = dot3(N, dir);
+            if (ndotl <= 0.01f) {
+                o_shadow = 1;
+                o_trans = 1.0f / 100.0f;
+            } else {
+                const V3 o = pos + N * mk3(0.06f, 0.06f, 0.06f);
+                const int block_at = get_voxel_at(S, o, cnt);
+                float T = -1.0f;
+                if (dist > 0.0f) {
+                    TraceHit h;
+                    T = traverse_df<LAYOUT>(S, o, dir, 350, h, cnt);
+                }
+                o_shadow = (T > 0.0f || block_at > 0) ? 1 : 0;
+                o_trans = clampf(T / 100.0f, 0.00001f, 196.0f);
+                if (T < 0.0f) o_trans = 4.25f / 100.0f;
+            }
+        }
+        if (out.shadow) out.shadow[px] = o_shadow;
+        if (out.transversal) out.transversal[px] = o_trans;
+    }
+    flush_counters(S, cnt);
+}
+
+// ============================================================================================= diffuse GI
+struct DiffuseDev {
+    V3 light_color, stronger_dir;  // LIGHT_COLOR, StrongerLightDirection (:832-838), computed on the host in fp32
+    int moon_stronger;
+    float emissivity_mult;
+    int spp, checker_spp, checkerboard, trace_length, frame, supersample;
+    float hx, hy;
+    float sun_visibility, gi_sky_strength, light_intensity;
+};
+struct DiffuseOutDev {
+    float4* sh;
+    float2* cocg;
+    float* luma;
+    float2* ao_sky;
+};
+
+constexpr float PI_F = 3.14159265359f;
+
+// samplerBlueNoiseErrorDistribution_128x128_OptimizedFor_2d2d2d2d_32spp — DiffuseRayTraceFrag.glsl:126-149
+__device__ __forceinline__ float blue_noise_1d(const SceneDev& S, int px, int py, int sample_index, int sample_dim) {
+    const int pi = px & 127, pj = py & 127;
+    sample_index &= 255;
+    sample_dim &= 255;
+    int ridx = sample_dim + (pi + pj * 128) * 8;
+    if (ridx > 131071) ridx = 131071;  // the shader runs past rankingTile here; pinned by clamping
+    const int ranked = (sample_index ^ (int)S.rank[ridx]) & 255;
+    int value = S.sobol[sample_dim + ranked * 256];
+    value = value ^ (int)S.scramble[(sample_dim % 8) + (pi + pj * 128) * 8];
+    return (0.5f + (float)value) / 256.0f;
+}
+
+// texture(u_Skymap, d): bilinear inside the major-axis face, clamped at the face edge (pinned)
+__device__ __forceinline__ V3 sky_sample(const SceneDev& S, V3 d) {
+    const int N = S.sky_n;
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int face;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { face = d.x > 0.f ? 0 : 1; sc = d.x > 0.f ? -d.z : d.z; tc = -d.y; ma = ax; }
+    else if (ay >= az)        { face = d.y > 0.f ? 2 : 3; sc = d.x; tc = d.y > 0.f ? d.z : -d.z; ma = ay; }
+    else                      { face = d.z > 0.f ? 4 : 5; sc = d.z > 0.f ? d.x : -d.x; tc = -d.y; ma = az; }
+    const float s = 0.5f * (sc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
+    const float u = s * (float)N - 0.5f, v = t * (float)N - 0.5f;
+    const float fu0 = floorf(u), fv0 = floorf(v);
+    const float fu = u - fu0, fv = v - fv0;
+    int i0 = (int)fu0, j0 = (int)fv0, i1 = i0 + 1, j1 = j0 + 1;
+    i0 = min(max(i0, 0), N - 1); i1 = min(max(i1, 0), N - 1);
+    j0 = min(max(j0, 0), N - 1); j1 = min(max(j1, 0), N - 1);
+    const float* F = S.sky + (size_t)face * N * N * 3;
+    const float* p00 = F + (j0 * N + i0) * 3;
+    const float* p10 = F + (j0 * N + i1) * 3;
+    const float* p01 = F + (j1 * N + i0) * 3;
+    const float* p11 = F + (j1 * N + i1) * 3;
+    const V3 a = mk3(p00[0], p00[1], p00[2]) * (1.0f - fu) + mk3(p10[0], p10[1], p10[2]) * fu;
+    const V3 b = mk3(p01[0], p01[1], p01[2]) * (1.0f - fu) + mk3(p11[0], p11[1], p11[2]) * fu;
+    return a * (1.0f - fv) + b * fv;
+}
+
+__device__ __forceinline__ V3 tex_nearest(const float4* base, int layer, int n, float u, float v) {
+    const int i = ((int)floorf(u * (float)n)) & (n - 1);
+    const int j = ((int)floorf(v * (float)n)) & (n - 1);
+    const float4 c = __ldg(base + ((size_t)layer * n + j) * n + i);
+    return mk3(c.x, c.y, c.z);
+}
+__device__ __forceinline__ float tex_bilinear1(const float* base, int layer, int n, float u, float v) {
+    const float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const float fx = x - fx0, fy = y - fy0;
+    const int i0 = ((int)fx0) & (n - 1), i1 = ((int)fx0 + 1) & (n - 1);
+    const int j0 = ((int)fy0) & (n - 1), j1 = ((int)fy0 + 1) & (n - 1);
+    const float* L = base + (size_t)layer * n * n;
+    const float a = L[j0 * n + i0] * (1.0f - fx) + L[j0 * n + i1] * fx;
+    const float b = L[j1 * n + i0] * (1.0f - fx) + L[j1 * n + i1] * fx;
+    return a * (1.0f - fy) + b * fy;
+}
+
+// InverseSchlick :1305-1308, DiffuseHammon :1311-1332 (rcp(x) == 1.0f / x)
+__device__ __forceinline__ float inverse_schlick(float f0, float voh) {
+    return 1.0f - clampf(f0 + (1.0f - f0) * pow_cr(1.0f - voh, 5.0f), 0.0f, 1.0f);
+}
+__device__ __forceinline__ float diffuse_hammon(V3 n, V3 view, V3 light, float rough) {
+    const float ndl = fmaxf(dot3(n, light), 0.0f);
+    if (ndl <= 0.0f) return 0.0f;
+    const float ndv = fmaxf(dot3(n, view), 0.0f);
+    const float ldv = fmaxf(dot3(light, view), 0.0f);
+    const V3 hw = normalize3(view + light);
+    const float ndh = fmaxf(dot3(n, hw), 0.0f);
+    const float facing = ldv * 0.5f + 0.5f;
+    const float single_rough = facing * (0.9f - 0.4f * facing) * ((0.5f + ndh) * (1.0f / fmaxf(ndh, 0.02f)));
+    const float single_smooth = 1.05f * inverse_schlick(0.0f, ndl) * inverse_schlick(0.0f, fmaxf(ndv, 0.0f));
+    const float single = clampf(mixf(single_smooth, single_rough, rough) * (1.0f / PI_F), 0.0f, 1.0f);
+    const float multi = 0.1159f * rough;
+    return clampf((multi + single) * ndl, 0.0f, 1.0f);
+}
+
+// SampleBlueNoise2D :811-818 + cosWeightedRandomHemisphereDirection :945-967
+__device__ __forceinline__ V3 cos_hemisphere(const SceneDev& S, int px, int py, int frame_mod128, int& bl_sample, V3 n) {
+    const float r1 = blue_noise_1d(S, px, py, frame_mod128, 1 + bl_sample);
+    const float r2 = blue_noise_1d(S, px, py, frame_mod128, 2 + bl_sample);
+    bl_sample += 2;
+    const float PI2 = 2.0f * PI_F;
+    const V3 uu = normalize3(cross3(n, mk3(0.0f, 1.0f, 1.0f)));
+    const V3 vv = cross3(uu, n);
+    const float ra = sqrtf(r2);
+    const float rx = ra * cos_cr(PI2 * r1);
+    const float ry = ra * sin_cr(PI2 * r1);
+    const float rz = sqrtf(1.0f - r2);
+    const V3 rr = (rx * uu + ry * vv) + rz * n;
+    return normalize3(rr);
+}
+
+// CalculateUV :1235-1273 on an exact axis normal
+__device__ __forceinline__ void calc_uv(V3 p, int axis, float& u, float& v) {
+    if (axis == 1) { u = fractf(p.x); v = fractf(p.z); }
+    else if (axis == 0) { u = fractf(p.z); v = fractf(p.y); }
+    else { u = fractf(p.x); v = fractf(p.y); }
+}
+
+// IrridianceToSH :766-784
+__device__ __forceinline__ void irradiance_to_sh(V3 rad, V3 dir, float out[6]) {
+    const float Co = rad.x - rad.z;
+    const float T = rad.z + Co * 0.5f;
+    const float Cg = rad.y - T;
+    const float Y = fmaxf(T + Cg * 0.5f, 0.0f);
+    const float L00 = 0.282095f;
+    const float L1_1 = 0.488603f * dir.y, L10 = 0.488603f * dir.z, L11 = 0.488603f * dir.x;
+    out[0] = fmaxf(L11 * Y, -100.0f);
+    out[1] = fmaxf(L1_1 * Y, -100.0f);
+    out[2] = fmaxf(L10 * Y, -100.0f);
+    out[3] = fmaxf(L00 * Y, -100.0f);
+    out[4] = Co;
+    out[5] = Cg;
+}
+
+// CalculateDiffuse :535-664, one sample
+template <int LAYOUT>
+__device__ __forceinline__ void calculate_diffuse(const SceneDev& S, const DiffuseDev& P, int px, int py, int& bl_sample, V3 initial_origin,
+                                                  V3 input_normal, V3& out_rad, float& out_ao, V3& odir, bool& skyhit, Counters& cnt) {
+    skyhit = false;
+    const float bias = 0.06f;
+    const int fm = P.frame % 128;
+    V3 ro = initial_origin + input_normal * bias;
+    V3 rd = cos_hemisphere(S, px, py, fm, bl_sample, input_normal);
+    float ao = 1.0f;
+    V3 contrib = mk3(0.f, 0.f, 0.f), thr = mk3(1.f, 1.f, 1.f);
+    odir = rd;
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {  // MAX_BOUNCE_LIMIT :17
+        TraceHit h;
+        const float T = traverse_df<LAYOUT>(S, ro, rd, P.trace_length, h, cnt);
+        const int tex_ref = min(max(h.block, 0), 127);
+        const V3 ipos = ro + (rd * T);
+        if (T > 0.0f && h.block > 0) {
+            const V3 hn = hit_normal(h);
+            float tu, tv;
+            calc_uv(ipos, h.min_idx, tu, tv);
+            const int albedo_layer = S.materials[tex_ref], emissive_layer = S.materials[384 + tex_ref];
+            const V3 albedo = tex_nearest(S.albedo_lod3, albedo_layer, 64, tu, tv);
+            const V3 pbr = tex_nearest(S.pbr_lod2, albedo_layer, 128, tu, tv);  // sic: albedo layer (:578)
+            float emis = 0.0f;
+            if ((float)emissive_layer >= 0.0f) {
+                const float se = tex_bilinear1(S.emissive, emissive_layer, 512, tu, tv);
+                emis = se * P.emissivity_mult * P.light_intensity;
+            }
+            const float ndl = fmaxf(dot3(hn, P.stronger_dir), 0.0f);
+            float shadow_at;
+            if (P.moon_stronger) shadow_at = 1.0f;
+            else if (ndl < 0.001f) shadow_at = 0.0f;
+            else {  // GetShadowAt :1202-1222 (u_APPLY_PLAYER_SHADOW = false)
+                TraceHit hs;
+                const float Ts = traverse_df<LAYOUT>(S, ipos + hn * 0.045f, P.stronger_dir, 128, hs, cnt);
+                shadow_at = Ts > 0.0f ? 1.0f : 0.0f;
+            }
+            const V3 emis_color = (emis * mixf(1.0f, 1.0f, P.sun_visibility)) * albedo;
+            const V3 neg_rd = -rd;
+            const V3 sunbrdf =
+                (((albedo * diffuse_hammon(hn, neg_rd, P.stronger_dir, pbr.x)) * (P.light_color * 3.5f)) * (1.0f - shadow_at)) * PI_F;
+            const V3 new_dir = cos_hemisphere(S, px, py, fm, bl_sample, hn);
+            const float cos_theta = clampf(dot3(hn, new_dir), 0.0f, 1.0f);
+            const float pdf = fmaxf(cos_theta / PI_F, 0.00001f);
+            const V3 atten = mk3(1.f, 1.f, 1.f) * diffuse_hammon(hn, neg_rd, new_dir, pbr.x);
+            contrib = contrib + thr * sunbrdf;
+            contrib = contrib + emis_color * thr;
+            thr = thr * ((albedo * atten) / pdf);
+            rd = new_dir;
+            ro = ipos + hn * bias;
+        } else {
+            float x = mixf(1.0f, 1.05f, P.sun_visibility);
+            x = clampf(x * 1.0f * P.gi_sky_strength, 0.0f, 5.0f);
+            V3 sd = rd;
+            sd.y = clampf(sd.y, 0.125f, 1.5f);  // GetSkyColorAt :984-988
+            const V3 sky = sky_sample(S, sd) * x;
+            contrib = contrib + sky * thr;
+            skyhit = true;
+            break;
+        }
+        if (i == 0) {
+            const float dao = 2.0f;
+            if (T < dao && T > 0.0f) ao = fmaxf(T / dao, 0.0f);
+        }
+    }
+    out_rad = contrib;
+    out_ao = ao;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) diffuse_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P,
+                                                      const GBufferDev g, const DiffuseOutDev out) {
+    int i, j;
+    const bool active = thread_pixel(cam, i, j);
+    Counters cnt = {0u, 0u, 0u};
+    if (active) {
+        const size_t px = (size_t)j * cam.width + i;
+        float u = ((float)i + 0.5f) / (float)cam.width;
+        float v = ((float)j + 0.5f) / (float)cam.height;
+        const float u0 = u, v0 = v;
+        if (P.supersample) {
+            u += (P.hx * 0.75f) / (float)cam.width;
+            v += (P.hy * 0.75f) / (float)cam.height;
+        }
+        float o_sh[4], o_cocg[2], o_util = 0.0f, o_ao0 = 1.0f, o_ao1 = 0.0f;
+        const float dist = g.t[px];
+        const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
+        if (dist < 0.0f) {
+            float sh[6];
+            const V3 vdir = normalize3(ray_direction_at(cam, u0, v0));
+            irradiance_to_sh(sky_sample(S, vdir) * 2.66f, normal, sh);
+            o_sh[0] = sh[0]; o_sh[1] = sh[1]; o_sh[2] = sh[2]; o_sh[3] = sh[3];
+            o_cocg[0] = sh[4]; o_cocg[1] = sh[5];
+        } else {
+            const V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, u, v)) * dist;
+            int spp = min(max(P.spp, 1), 32);
+            if (P.checkerboard) {
+                const bool checker = ((int)(((float)i + 0.5f) + ((float)j + 0.5f))) % 2 == P.frame % 2;
+                spp = (int)mixf((float)P.spp, (float)P.checker_spp, checker ? 1.0f : 0.0f);
+            }
+            spp = min(max(spp, 1), 32);
+            if (P.moon_stronger) spp *= 2;
+            int bl_sample = 0;
+            float tot0 = 0.f, tot1 = 0.f, tot2 = 0.f, tot3 = 0.f, cocg0 = 0.f, cocg1 = 0.f, acc_ao = 0.f, skyhits = 0.f;
+            V3 radiance = mk3(0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int s = 0; s < spp; ++s) {
+                V3 rad, d;
+                float ao;
+                bool ss;
+                calculate_diffuse<LAYOUT>(S, P, i, j, bl_sample, pos, normal, rad, ao, d, ss, cnt);
+                rad = mk3(clampf(rad.x, 0.0f, 8.0f), clampf(rad.y, 0.0f, 8.0f), clampf(rad.z, 0.0f, 8.0f));
+                radiance = radiance + rad;
+                acc_ao += ao;
+                float sh[6];
+                irradiance_to_sh(rad, d, sh);
+                tot0 += sh[0]; tot1 += sh[1]; tot2 += sh[2]; tot3 += sh[3];
+                cocg0 += sh[4]; cocg1 += sh[5];
+                skyhits += ss ? 1.0f : 0.0f;
+            }
+            const float fs = (float)spp;
+            acc_ao /= fs;
+            tot0 /= fs; tot1 /= fs; tot2 /= fs; tot3 /= fs;
+            cocg0 /= fs; cocg1 /= fs;
+            radiance = radiance / fs;
+            skyhits /= fs;
+            const float lum = dot3(radiance, mk3(0.299f, 0.587f, 0.114f));
+            o_util = fmaxf(lum, 0.01f);
+            o_ao0 = clampf(acc_ao, 0.0f, 1.0f);
+            o_ao1 = clampf(skyhits, 0.0f, 1.0f);
+            o_sh[0] = clampf(tot0, -100.0f, 100.0f); o_sh[1] = clampf(tot1, -100.0f, 100.0f);
+            o_sh[2] = clampf(tot2, -100.0f, 100.0f); o_sh[3] = clampf(tot3, -100.0f, 100.0f);
+            o_cocg[0] = clampf(cocg0, -100.0f, 100.0f);
+            o_cocg[1] = clampf(cocg1, -100.0f, 100.0f);
+            o_util = clampf(o_util, 0.001f, 64.0f);
+        }
+        if (out.sh) out.sh[px] = make_float4(o_sh[0], o_sh[1], o_sh[2], o_sh[3]);
+        if (out.cocg) out.cocg[px] = make_float2(o_cocg[0], o_cocg[1]);
+        if (out.luma) out.luma[px] = o_util;
+        if (out.ao_sky) out.ao_sky[px] = make_float2(o_ao0, o_ao1);
+    }
+    flush_counters(S, cnt);
+}
+
+// ============================================================================================= host launchers
+static CameraDev to_dev(const VxCamera& cam) {
+    CameraDev c;
+    for (int k = 0; k < 16; ++k) { c.inv_view[k] = cam.inv_view[k]; c.inv_proj[k] = cam.inv_proj[k]; }
+    c.width = cam.width; c.height = cam.height; c.row_begin = cam.row_begin; c.row_end = cam.row_end;
+    return c;
+}
+static dim3 pixel_grid(const VxCamera& cam) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8); }
+static GBufferDev to_dev(const VxGBuffer& g) { return GBufferDev{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel}; }
+
+int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out) {
+    const SceneDev S = make_scene(c);
+    const PrimaryDev pd{p.max_iterations, p.jitter_enable, p.jitter[0], p.jitter[1]};
+    const dim3 grid = pixel_grid(cam);
+    if (c->opt_layout == 1) primary_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(out));
+    else primary_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(out));
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+static inline float host_fract(float x) { return x - floorf(x); }
+
+int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const VxShadowParams& p, const VxShadowOut& out) {
+    const SceneDev S = make_scene(c);
+    ShadowDev sd;
+    sd.light = V3{p.light_dir[0], p.light_dir[1], p.light_dir[2]};
+    sd.soft = p.soft;
+    // ShadowRayTraceFrag.glsl:456-459 — int products wrap like GLSL ints, the rest is fp32
+    const int n = p.frame % 1024;
+    const int32_t ax = (int32_t)((uint32_t)n * 12664745u), ay = (int32_t)((uint32_t)n * 9560333u);
+    const float offx = host_fract((float)ax / 16777216.0f) * 1024.0f, offy = host_fract((float)ay / 16777216.0f) * 1024.0f;
+    sd.ioffx = (int)floorf(offx);
+    sd.ioffy = (int)floorf(offy);
+    sd.hx = p.halton[0];
+    sd.hy = p.halton[1];
+    const ShadowOutDev od{out.shadow, out.transversal};
+    const dim3 grid = pixel_grid(cam);
+    if (c->opt_layout == 1) shadow_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(g), od);
+    else shadow_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(g), od);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const VxDiffuseParams& p, const VxDiffuseOut& out) {
+    const SceneDev S = make_scene(c);
+    DiffuseDev d;
+    // per-frame constants of DiffuseRayTraceFrag.glsl main() :832-838 (uniform over the frame), fp32 on the host;
+    // built with -fmad=false like the device code
+    const float sun[3] = {p.sun_dir[0], p.sun_dir[1], p.sun_dir[2]};
+    const bool sun_stronger = -sun[1] < 0.01f;
+    const float SUN_COLOR[3] = {(192.0f / 255.0f) * 16.0f, (216.0f / 255.0f) * 16.0f, (255.0f / 255.0f) * 16.0f};
+    const float NIGHT_COLOR[3] = {(96.0f / 255.0f) * 1.5f, (192.0f / 255.0f) * 1.5f, (255.0f / 255.0f) * 1.5f};
+    const float DUSK_COLOR[3] = {(96.0f / 255.0f) * 0.9f, (192.0f / 255.0f) * 0.9f, (255.0f / 255.0f) * 0.9f};
+    float dusk = (float)pow((double)fabsf(sun[1] - 1.0f), (double)2.9f);
+    dusk = fminf(fmaxf(dusk, 0.0f), 1.0f);
+    float lc[3];
+    for (int k = 0; k < 3; ++k) {
+        const float sc = SUN_COLOR[k] * (1.0f - dusk) + DUSK_COLOR[k] * dusk;
+        lc[k] = (sun_stronger ? sc : NIGHT_COLOR[k]) * (0.4f * p.gi_sun_strength);
+    }
+    d.light_color = V3{lc[0], lc[1], lc[2]};
+    d.stronger_dir = sun_stronger ? V3{sun[0], sun[1], sun[2]} : V3{p.moon_dir[0], p.moon_dir[1], p.moon_dir[2]};
+    d.moon_stronger = sun_stronger ? 0 : 1;
+    d.emissivity_mult = sun_stronger ? 12.0f : 13.0f;
+    d.spp = p.spp; d.checker_spp = p.checker_spp; d.checkerboard = p.checkerboard; d.trace_length = p.trace_length;
+    d.frame = p.frame; d.supersample = p.supersample;
+    d.hx = p.halton[0]; d.hy = p.halton[1];
+    d.sun_visibility = p.sun_visibility; d.gi_sky_strength = p.gi_sky_strength; d.light_intensity = p.light_intensity;
+    const DiffuseOutDev od{reinterpret_cast<float4*>(out.sh), reinterpret_cast<float2*>(out.cocg), out.luma,
+                           reinterpret_cast<float2*>(out.ao_sky)};
+    const dim3 grid = pixel_grid(cam);
+    if (c->opt_layout == 1) diffuse_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(g), od);
+    else diffuse_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(g), od);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+}  // namespace vxpt

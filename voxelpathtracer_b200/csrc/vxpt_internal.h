@@ -1,0 +1,128 @@
+// vxpt_internal.h — private context of the vxpt C ABI (not installed; include/vxpt.h is the public surface).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/vxpt.h"
+
+namespace vxpt {
+
+constexpr int WX = VXPT_WORLD_SIZE_X;  // 384
+constexpr int WY = VXPT_WORLD_SIZE_Y;  // 128
+constexpr int WZ = VXPT_WORLD_SIZE_Z;  // 384
+constexpr size_t VOXELS = (size_t)WX * WY * WZ;
+constexpr int SLICE_BYTES = WX * WY;  // one z-slice: 49,152 B
+
+// ---- brick-swizzled step field -----------------------------------------------------------------------------
+// Traversal never needs the Manhattan value M itself, only E(M) = (M==1) ? 1 : floor(M * 0.57735026918f)
+// (ToConservativeEuclidean, InitialRayTraceFrag.glsl:90-93,329).  The step field stores E (<= 146) per voxel in
+// 8x4x4-voxel bricks of 128 B (one L1 line); inside a brick the low 5 address bits cover a 4x2x4 block (one
+// 32-B sector), so a sector holds a 3-D neighbourhood instead of a 32-voxel x-run.
+constexpr int BRICK_X = 8, BRICK_Y = 4, BRICK_Z = 4;
+constexpr int BRICKS_X = WX / BRICK_X;  // 48
+constexpr int BRICKS_Y = WY / BRICK_Y;  // 32
+constexpr int BRICKS_Z = WZ / BRICK_Z;  // 96
+
+__host__ __device__ __forceinline__ uint32_t brick_offset(int x, int y, int z) {
+    uint32_t brick = ((uint32_t)(z >> 2) * BRICKS_Y + (uint32_t)(y >> 2)) * BRICKS_X + (uint32_t)(x >> 3);
+    uint32_t local = (uint32_t)(x & 3) | ((uint32_t)(y & 1) << 2) | ((uint32_t)(z & 3) << 3) |
+                     ((uint32_t)((y >> 1) & 1) << 5) | ((uint32_t)((x >> 2) & 1) << 6);
+    return brick * 128u + local;
+}
+
+struct DeviceCounters {
+    unsigned long long rays, df_fetches, vox_fetches;
+};
+
+// device-side view of everything the trace kernels read
+struct SceneDev {
+    const uint8_t* grid;       // block ids, linear x + 384*(y + 128*z)
+    const uint8_t* df;         // Manhattan distance field, linear
+    const uint8_t* steps;      // brick-swizzled E field
+    const int32_t* materials;  // 768
+    const uint8_t* sobol;      // 65536   (blue-noise tables hold values < 256: kept as bytes, 320 KB total)
+    const uint8_t* scramble;   // 131072
+    const uint8_t* rank;       // 131072
+    const float4* albedo_lod3; // [n_layers][64][64]
+    const float4* pbr_lod2;    // [n_layers][128][128]
+    const float* emissive;     // [n_emissive][512][512]
+    const float* sky;          // [6][n][n][3]
+    const uchar4* shadow_noise;  // [256][256]
+    int n_layers, n_emissive, sky_n;
+    DeviceCounters* counters;
+};
+
+}  // namespace vxpt
+
+struct vxpt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;                  // around the last trace pass
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;  // DF build start / end, brick pack end
+    bool pass_timed = false, df_timed = false;
+
+    uint8_t* d_grid = nullptr;
+    uint8_t* d_df = nullptr;
+    uint8_t* d_tmp = nullptr;    // XY-pass intermediate
+    uint8_t* d_steps = nullptr;  // brick-swizzled E field
+    bool world_uploaded = false;
+    bool df_valid = false;
+
+    int32_t* d_materials = nullptr;
+    int32_t h_materials[768] = {0};  // host copy for argument validation
+    uint8_t* d_bluenoise = nullptr;  // sobol | scramble | rank
+    float4* d_albedo = nullptr;
+    float4* d_pbr = nullptr;
+    float* d_emissive = nullptr;
+    float* d_sky = nullptr;
+    uchar4* d_shadow_noise = nullptr;
+    int n_layers = 0, n_emissive = 0, sky_n = 0;
+    bool have_materials = false, have_bluenoise = false, have_textures = false, have_sky = false, have_shadow_noise = false;
+
+    vxpt::DeviceCounters* d_counters = nullptr;
+    float last_ms = 0.f, df_build_ms = 0.f, brick_pack_ms = 0.f;
+    uint64_t launches = 0;
+
+    // options
+    int opt_layout = 1;     // VXPT_OPT_TRAVERSAL_LAYOUT
+    int opt_wavefront = 1;  // VXPT_OPT_GI_WAVEFRONT
+    int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped), 1 = DPX tiled
+
+    // staging for host-pointer I/O (grown on demand)
+    void* d_stage = nullptr;
+    size_t stage_bytes = 0;
+    void* h_stage = nullptr;  // pinned
+    size_t h_stage_bytes = 0;
+
+    // wavefront queues (grown on demand)
+    void* d_queue = nullptr;
+    size_t queue_bytes = 0;
+};
+
+namespace vxpt {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define VX_CUDA(expr)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return ::vxpt::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// df_build.cu
+int launch_df_build(vxpt_ctx* c);
+int launch_pack_bricks(vxpt_ctx* c);
+// trace.cu
+struct PlaneSet;  // resolved device pointers of one pass
+int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out_dev);
+int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxShadowParams& p, const VxShadowOut& out_dev);
+int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxDiffuseParams& p, const VxDiffuseOut& out_dev);
+// l2_probe.cu
+int run_l2_probe(vxpt_ctx* c, double* gbps);
+
+SceneDev make_scene(const vxpt_ctx* c);
+
+}  // namespace vxpt

@@ -1,0 +1,223 @@
+"""Renderer: thin Python driver over the C ABI (include/vxpt.h).  Plumbing only — every computation happens in
+libvxpt.so on the GPU.  Buffers may be numpy arrays (host: staged through the library, results complete on
+return) or torch CUDA tensors (device: zero-copy, complete after sync())."""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxShadowOut, VxShadowParams, VxStats, check)
+
+try:  # torch is optional plumbing: device buffers, streams, torch.distributed
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _ptr(buf):
+    """Raw address of a numpy array or torch tensor (None -> NULL)."""
+    if buf is None:
+        return None
+    if isinstance(buf, np.ndarray):
+        if not buf.flags["C_CONTIGUOUS"]:
+            raise ValueError("numpy buffers handed to vxpt must be C-contiguous")
+        return buf.ctypes.data
+    if torch is not None and isinstance(buf, torch.Tensor):
+        if not buf.is_contiguous():
+            raise ValueError("torch buffers handed to vxpt must be contiguous")
+        return buf.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(buf)}")
+
+
+def primary_params(max_iterations=350, jitter=None):
+    p = VxPrimaryParams()
+    p.max_iterations = max_iterations
+    p.jitter_enable = 0 if jitter is None else 1
+    if jitter is not None:
+        p.jitter[0], p.jitter[1] = float(jitter[0]), float(jitter[1])
+    return p
+
+
+def shadow_params(light_dir, frame=0, soft=True, halton=(0.0, 0.0)):
+    p = VxShadowParams()
+    p.light_dir[:] = [float(v) for v in light_dir]
+    p.frame, p.soft = int(frame), int(bool(soft))
+    p.halton[0], p.halton[1] = float(halton[0]), float(halton[1])
+    return p
+
+
+def diffuse_params(sun_dir, moon_dir, sun_visibility, spp=1, checker_spp=None, checkerboard=False, trace_length=48, frame=0,
+                   gi_sun_strength=1.0, gi_sky_strength=1.125, light_intensity=1.25):
+    """Defaults of Core/Pipeline.cpp:73-75,280-281."""
+    p = VxDiffuseParams()
+    p.spp = int(spp)
+    p.checker_spp = int((spp + spp % 2) // 2 if checker_spp is None else checker_spp)
+    p.checkerboard = int(bool(checkerboard))
+    p.trace_length, p.frame = int(trace_length), int(frame)
+    p.use_blue_noise, p.supersample, p.direct_sampling = 1, 0, 0
+    p.sun_dir[:] = [float(v) for v in sun_dir]
+    p.moon_dir[:] = [float(v) for v in moon_dir]
+    p.sun_visibility = float(sun_visibility)
+    p.gi_sun_strength, p.gi_sky_strength, p.light_intensity = float(gi_sun_strength), float(gi_sky_strength), float(light_intensity)
+    return p
+
+
+class Renderer:
+    """One handle = one GPU = one caller thread (like the reference's GL context)."""
+
+    def __init__(self, device=0):
+        self.lib = abi.load()
+        self.handle = C.c_void_p()
+        check(self.lib.vxpt_create(int(device), C.byref(self.handle)))
+        self.device = int(device)
+        self._keep = []  # host arrays that must outlive an enqueued copy
+
+    def close(self):
+        if self.handle:
+            self.lib.vxpt_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- world / distance field ---------------------------------------------------------------------------
+    def upload_world(self, blocks):
+        data = blocks.data if hasattr(blocks, "zyx") else blocks
+        check(self.lib.vxpt_upload_world(self.handle, _ptr(data)))
+
+    def set_block(self, x, y, z, block):
+        check(self.lib.vxpt_set_block(self.handle, int(x), int(y), int(z), int(block)))
+
+    def set_blocks(self, xyz, ids):
+        xyz = np.ascontiguousarray(xyz, dtype=np.int16).reshape(-1, 3)
+        ids = np.ascontiguousarray(ids, dtype=np.uint8).reshape(-1)
+        check(self.lib.vxpt_set_blocks(self.handle, _ptr(xyz), _ptr(ids), int(ids.size)))
+
+    def build_distance_field(self):
+        check(self.lib.vxpt_build_distance_field(self.handle))
+
+    def download_distance_field(self):
+        out = np.empty(abi.WORLD_VOXELS, dtype=np.uint8)
+        check(self.lib.vxpt_download_distance_field(self.handle, _ptr(out)))
+        return out
+
+    def download_world(self):
+        out = np.empty(abi.WORLD_VOXELS, dtype=np.uint8)
+        check(self.lib.vxpt_download_world(self.handle, _ptr(out)))
+        return out
+
+    # ---- tables -------------------------------------------------------------------------------------------
+    def set_materials(self, table):
+        t = np.ascontiguousarray(table, dtype=np.int32).reshape(768)
+        check(self.lib.vxpt_set_materials(self.handle, _ptr(t)))
+
+    def set_blue_noise(self, sobol, scramble, rank):
+        a, b, c = (np.ascontiguousarray(x, dtype=np.int32) for x in (sobol, scramble, rank))
+        check(self.lib.vxpt_set_blue_noise(self.handle, _ptr(a), _ptr(b), _ptr(c)))
+
+    def set_material_textures(self, albedo_lod3, pbr_lod2, emissive_lod0):
+        a = np.ascontiguousarray(albedo_lod3, dtype=np.float32)
+        p = np.ascontiguousarray(pbr_lod2, dtype=np.float32)
+        e = np.ascontiguousarray(emissive_lod0, dtype=np.float32)
+        assert a.shape[1:] == (64, 64, 4) and p.shape[1:] == (128, 128, 4) and a.shape[0] == p.shape[0]
+        check(self.lib.vxpt_set_material_textures(self.handle, _ptr(a), _ptr(p), int(a.shape[0]), _ptr(e) if e.shape[0] else None, int(e.shape[0])))
+
+    def set_sky_cubemap(self, rgb):
+        s = np.ascontiguousarray(rgb, dtype=np.float32)
+        assert s.ndim == 4 and s.shape[0] == 6 and s.shape[1] == s.shape[2] and s.shape[3] == 3
+        check(self.lib.vxpt_set_sky_cubemap(self.handle, _ptr(s), int(s.shape[1])))
+
+    def set_shadow_noise(self, rgba8):
+        n = np.ascontiguousarray(rgba8, dtype=np.uint8).reshape(256, 256, 4)
+        check(self.lib.vxpt_set_shadow_noise(self.handle, _ptr(n)))
+
+    def load_scene_tables(self, materials, blue_noise, sky, shadow_noise):
+        self.set_materials(materials["table"])
+        self.set_material_textures(materials["albedo_lod3"], materials["pbr_lod2"], materials["emissive_lod0"])
+        self.set_blue_noise(*blue_noise)
+        self.set_sky_cubemap(sky)
+        self.set_shadow_noise(shadow_noise)
+
+    # ---- buffers ------------------------------------------------------------------------------------------
+    def alloc(self, shape, dtype, device=False):
+        if device:
+            if torch is None:
+                raise RuntimeError("device buffers need torch")
+            tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.int16: torch.int16}[dtype]
+            return torch.empty(shape, dtype=tdt, device=f"cuda:{self.device}")
+        return np.empty(shape, dtype=dtype)
+
+    def alloc_gbuffer(self, width, height, device=False, hit_voxel=False):
+        g = {"t": self.alloc((height, width), np.float32, device), "normal_id": self.alloc((height, width), np.uint8, device),
+             "block_id": self.alloc((height, width), np.uint8, device), "inv_t": self.alloc((height, width), np.float32, device)}
+        if hit_voxel:
+            g["hit_voxel"] = self.alloc((height, width, 3), np.int16, device)
+        return g
+
+    def alloc_shadow(self, width, height, device=False):
+        return {"shadow": self.alloc((height, width), np.uint8, device), "transversal": self.alloc((height, width), np.float32, device)}
+
+    def alloc_diffuse(self, width, height, device=False):
+        return {"sh": self.alloc((height, width, 4), np.float32, device), "cocg": self.alloc((height, width, 2), np.float32, device),
+                "luma": self.alloc((height, width), np.float32, device), "ao_sky": self.alloc((height, width, 2), np.float32, device)}
+
+    @staticmethod
+    def gbuffer_struct(g):
+        s = VxGBuffer()
+        s.t, s.normal_id, s.block_id = _ptr(g.get("t")), _ptr(g.get("normal_id")), _ptr(g.get("block_id"))
+        s.inv_t, s.hit_voxel = _ptr(g.get("inv_t")), _ptr(g.get("hit_voxel"))
+        return s
+
+    # ---- passes -------------------------------------------------------------------------------------------
+    def trace_primary(self, cam, params, gbuf):
+        s = self.gbuffer_struct(gbuf)
+        check(self.lib.vxpt_trace_primary(self.handle, C.byref(cam), C.byref(params), C.byref(s)))
+        return gbuf
+
+    def trace_shadow(self, cam, gbuf, params, out):
+        g = self.gbuffer_struct(gbuf)
+        o = VxShadowOut()
+        o.shadow, o.transversal = _ptr(out.get("shadow")), _ptr(out.get("transversal"))
+        check(self.lib.vxpt_trace_shadow(self.handle, C.byref(cam), C.byref(g), C.byref(params), C.byref(o)))
+        return out
+
+    def trace_diffuse(self, cam, gbuf, params, out):
+        g = self.gbuffer_struct(gbuf)
+        o = VxDiffuseOut()
+        o.sh, o.cocg, o.luma, o.ao_sky = _ptr(out.get("sh")), _ptr(out.get("cocg")), _ptr(out.get("luma")), _ptr(out.get("ao_sky"))
+        check(self.lib.vxpt_trace_diffuse(self.handle, C.byref(cam), C.byref(g), C.byref(params), C.byref(o)))
+        return out
+
+    # ---- sync / stats -------------------------------------------------------------------------------------
+    def sync(self):
+        check(self.lib.vxpt_sync(self.handle))
+
+    def stats(self):
+        s = VxStats()
+        check(self.lib.vxpt_get_stats(self.handle, C.byref(s)))
+        return {"rays": int(s.rays), "df_fetches": int(s.df_fetches), "vox_fetches": int(s.vox_fetches), "last_ms": float(s.last_ms),
+                "df_build_ms": float(s.df_build_ms), "brick_pack_ms": float(s.brick_pack_ms)}
+
+    def reset_stats(self):
+        check(self.lib.vxpt_reset_stats(self.handle))
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(self.lib.vxpt_launch_count(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def cuda_stream(self):
+        s = C.c_void_p()
+        check(self.lib.vxpt_stream(self.handle, C.byref(s)))
+        return s.value
+
+    def set_option(self, option, value):
+        check(self.lib.vxpt_set_option(self.handle, int(option), int(value)))
+
+    def measure_l2_sector_peak(self):
+        g = C.c_double()
+        check(self.lib.vxpt_measure_l2_sector_peak(self.handle, C.byref(g)))
+        return float(g.value)

@@ -59,6 +59,9 @@ def main():
         r.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
         r.reset_stats()
         g = r.alloc_gbuffer(W, H, hit_voxel=True)
+        for _ in range(3):
+            r.trace_primary(cam, pp, g)
+        r.reset_stats()
         r.trace_primary(cam, pp, g)
         st = r.stats()
         print(f"primary layout {layout}: {st['last_ms']:.3f} ms  {W*H/st['last_ms']/1e3:.1f} Mrays/s stats {st['rays']} {st['df_fetches']} {st['vox_fetches']}")
@@ -69,6 +72,8 @@ def main():
     r.reset_stats()
     s = r.alloc_shadow(W, H)
     r.trace_shadow(cam, g_ref, sp, s)
+    r.reset_stats()
+    r.trace_shadow(cam, g_ref, sp, s)
     st = r.stats()
     print(f"shadow: {st['last_ms']:.3f} ms stats {st['rays']} {st['df_fetches']} {st['vox_fetches']}")
     cmp("shadow", s["shadow"], s_ref["shadow"]); cmp("transversal", s["transversal"], s_ref["transversal"])
@@ -76,6 +81,8 @@ def main():
     t0 = time.time(); d_ref, dst_ref = orc.trace_diffuse(cam, g_ref, dp); print("oracle diffuse s", time.time() - t0, dst_ref)
     r.reset_stats()
     d = r.alloc_diffuse(W, H)
+    r.trace_diffuse(cam, g_ref, dp, d)
+    r.reset_stats()
     r.trace_diffuse(cam, g_ref, dp, d)
     st = r.stats()
     print(f"diffuse: {st['last_ms']:.3f} ms stats {st['rays']} {st['df_fetches']} {st['vox_fetches']}")

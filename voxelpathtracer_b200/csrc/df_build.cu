@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __rest
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             uint32_t A = rowA[k], B = rowB[k];
-            uint32_t t0 = __byte_perm(A, B, 0x6240);  // a0 a2 b0 b2
-            uint32_t t1 = __byte_perm(A, B, 0x7351);  // a1 a3 b1 b3
+            uint32_t t0 = __byte_perm(A, B, 0x6420);  // a0 a2 b0 b2
+            uint32_t t1 = __byte_perm(A, B, 0x7531);  // a1 a3 b1 b3
             r[4 * k + 0] = t0 & 0x00FF00FFu;
             r[4 * k + 2] = (t0 >> 8) & 0x00FF00FFu;
             r[4 * k + 1] = t1 & 0x00FF00FFu;

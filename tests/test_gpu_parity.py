@@ -1,0 +1,361 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs, against the
+committed digests, and — at BASELINE.json's full sizes — through size-independent properties.
+Bar (north_star): distance field, hit voxel, face and block ids bit-exact; hit distance <= 1e-5 relative;
+GI / shadow radiance <= 1e-3 mean absolute error and >= 50 dB PSNR."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import voxelpathtracer_b200 as vx
+from voxelpathtracer_b200 import abi, camera, world
+
+pytestmark = pytest.mark.gpu
+
+HIT_DISTANCE_RTOL = 1e-5   # north_star tolerance for t
+RADIANCE_MAE = 1e-3        # north_star tolerance for GI / shadow radiance
+RADIANCE_PSNR_DB = 50.0
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def psnr(a, b, peak):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return 200.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def load(renderer, w, algo=1):
+    renderer.set_option(abi.OPT_DF_ALGO, algo)
+    renderer.upload_world(w)
+    renderer.build_distance_field()
+
+
+# ====================================================================================== distance field
+@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("name", ["superflat", "plains", "city", "gi_box", "sparse", "empty"])
+def test_distance_field_bit_exact(renderer, worlds, oracle_dfs, golden_digests, name, algo):
+    load(renderer, worlds[name], algo)
+    df = renderer.download_distance_field()
+    assert np.array_equal(df, oracle_dfs[name])
+    if name in golden_digests["df"]:
+        assert sha(df) == golden_digests["df"][name]
+    assert np.array_equal(renderer.download_world(), worlds[name].data)
+
+
+def test_distance_field_edge_worlds(renderer):
+    from oracle import vxo
+    full = world.World(np.full(abi.WORLD_VOXELS, 3, np.uint8))
+    load(renderer, full)
+    assert not renderer.download_distance_field().any()
+    for corner in [(0, 0, 0), (383, 127, 383), (383, 0, 0), (0, 127, 383), (191, 64, 200)]:
+        w = world.World()
+        w.set_block(*corner, 9)
+        load(renderer, w)
+        assert np.array_equal(renderer.download_distance_field(), vxo.df_build(w.data)), corner
+    # a single air pocket inside solid rock, and alternating slabs that exercise every segment carry
+    w = world.World(np.full(abi.WORLD_VOXELS, 3, np.uint8))
+    w.zyx[100:140, 30:90, 37:300] = 0
+    w.zyx[::48, :, :] = 0
+    load(renderer, w)
+    assert np.array_equal(renderer.download_distance_field(), vxo.df_build(w.data))
+
+
+def test_distance_field_random_worlds(renderer):
+    from oracle import vxo
+    rng = np.random.RandomState(42)
+    for fill in (1e-6, 1e-4, 0.01, 0.5):
+        w = world.World((rng.rand(abi.WORLD_VOXELS) < fill).astype(np.uint8) * 5)
+        load(renderer, w)
+        assert np.array_equal(renderer.download_distance_field(), vxo.df_build(w.data)), fill
+
+
+def test_distance_field_properties_at_full_size(renderer, worlds):
+    """Size-independent: DF == 0 exactly on solid voxels, and the field is 1-Lipschitz along every axis."""
+    load(renderer, worlds["city"])
+    df = renderer.download_distance_field().reshape(384, 128, 384).astype(np.int16)
+    assert np.array_equal(df == 0, worlds["city"].zyx > 0)
+    for axis in range(3):
+        assert np.abs(np.diff(df, axis=axis)).max() <= 1
+    # idempotent rebuild
+    renderer.build_distance_field()
+    assert np.array_equal(renderer.download_distance_field().reshape(384, 128, 384), df)
+
+
+def test_block_edits_force_a_rebuild(renderer, worlds):
+    from oracle import vxo
+    w = world.World(worlds["plains"].data.copy())
+    load(renderer, w)
+    cam = camera.FpsCamera(pitch_deg=-20).vx_camera(64, 36)
+    g = renderer.alloc_gbuffer(64, 36)
+    renderer.trace_primary(cam, vx.primary_params(350), g)
+    renderer.set_block(192, 70, 200, world.STONE)          # World::Raycast place path -> glTexSubImage3D (World.cpp:372-373)
+    with pytest.raises(abi.VxptError) as e:                # the ABI never rebuilds implicitly
+        renderer.trace_primary(cam, vx.primary_params(350), g)
+    assert e.value.code == abi.E_STATE
+    w.set_block(192, 70, 200, world.STONE)
+    renderer.build_distance_field()
+    assert np.array_equal(renderer.download_distance_field(), vxo.df_build(w.data))
+    xyz = np.array([[10, 60, 10], [11, 60, 10], [383, 127, 383], [192, 70, 200]], np.int16)
+    ids = np.array([4, 4, 12, 0], np.uint8)
+    renderer.set_blocks(xyz, ids)
+    for (x, y, z), b in zip(xyz, ids):
+        w.set_block(int(x), int(y), int(z), int(b))
+    renderer.build_distance_field()
+    assert np.array_equal(renderer.download_world(), w.data)
+    assert np.array_equal(renderer.download_distance_field(), vxo.df_build(w.data))
+    with pytest.raises(abi.VxptError) as e:
+        renderer.set_block(384, 0, 0, 1)
+    assert e.value.code == abi.E_INVALID
+
+
+# ====================================================================================== primary rays
+def check_primary(renderer, oracle, cam, pp, layout=1, digest=None):
+    renderer.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
+    renderer.reset_stats()
+    g = renderer.alloc_gbuffer(cam.width, cam.height, hit_voxel=True)
+    renderer.trace_primary(cam, pp, g)
+    st = renderer.stats()
+    if oracle is not None:
+        ref, rst = oracle.trace_primary(cam, pp)
+        for k in ("normal_id", "block_id", "hit_voxel"):
+            assert np.array_equal(g[k], ref[k]), k                                   # ids: bit-exact
+        assert np.array_equal(g["t"] > 0, ref["t"] > 0)
+        hit = ref["t"] > 0
+        assert np.all(np.abs(g["t"][hit] - ref["t"][hit]) <= HIT_DISTANCE_RTOL * ref["t"][hit])
+        assert np.array_equal(g["t"], ref["t"]) and np.array_equal(g["inv_t"], ref["inv_t"])  # in practice bit-exact
+        assert (st["rays"], st["df_fetches"], st["vox_fetches"]) == (rst["rays"], rst["df_fetches"], rst["vox_fetches"])
+    if digest is not None:
+        assert sha(g["t"]) == digest["t"] and sha(g["normal_id"]) == digest["normal_id"]
+        assert sha(g["block_id"]) == digest["block_id"] and sha(g["hit_voxel"]) == digest["hit_voxel"]
+        assert st["df_fetches"] == digest["stats"]["df_fetches"] and st["vox_fetches"] == digest["stats"]["vox_fetches"]
+    return g
+
+
+@pytest.mark.parametrize("pitch", [0.0, -20.0])
+@pytest.mark.parametrize("jf", [None, 0, 1, 17, 63])
+def test_primary_config1_superflat_640x360(renderer, worlds, oracles, golden_digests, pitch, jf):
+    load(renderer, worlds["superflat"])
+    cam = camera.FpsCamera(pitch_deg=pitch).vx_camera(640, 360)
+    pp = vx.primary_params(350, None if jf is None else camera.taa_jitter(jf))
+    d = golden_digests["primary"][f"superflat_640x360_p{int(pitch)}_j{jf}"]
+    for layout in (0, 1):
+        check_primary(renderer, oracles["superflat"], cam, pp, layout, d)
+
+
+@pytest.mark.parametrize("case", ["plains_1920x1080_p-20_jNone", "plains_1920x1080_p0_j7", "city_1920x1080_p-20_jNone"])
+def test_primary_1080p(renderer, worlds, oracles, golden_digests, case):
+    name = case.split("_")[0]
+    load(renderer, worlds[name])
+    pitch = -20.0 if "p-20" in case else 0.0
+    jf = 7 if case.endswith("j7") else None
+    cam = camera.FpsCamera(pitch_deg=pitch).vx_camera(1920, 1080)
+    pp = vx.primary_params(350, None if jf is None else camera.taa_jitter(jf))
+    for layout in (0, 1):
+        check_primary(renderer, oracles[name], cam, pp, layout, golden_digests["primary"][case])
+
+
+def test_primary_4k_digest_and_properties(renderer, worlds, golden_digests):
+    """Config 4 frame size (3840x2160) without CPU tracing: committed digest + 'the hit voxel is solid and the voxel
+    the ray came from is air' for every pixel."""
+    load(renderer, worlds["gi_box"])
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(3840, 2160)
+    g = check_primary(renderer, None, cam, vx.primary_params(350), 1, golden_digests["primary"]["gi_box_3840x2160_p-20_jNone"])
+    grid = worlds["gi_box"].zyx
+    hit = g["t"] > 0
+    v = g["hit_voxel"][hit].astype(np.int64)
+    assert np.all(grid[v[:, 2], v[:, 1], v[:, 0]] == g["block_id"][hit]) and np.all(g["block_id"][hit] > 0)
+    normals = np.array([[0, 0, 1], [0, 0, -1], [0, 1, 0], [0, -1, 0], [-1, 0, 0], [1, 0, 0]])
+    prev = v + normals[g["normal_id"][hit]]
+    inside = np.all((prev >= 0) & (prev < [384, 128, 384]), axis=1)
+    assert np.all(grid[prev[inside, 2], prev[inside, 1], prev[inside, 0]] == 0)
+    assert np.all(g["normal_id"][~hit] == abi.NORMAL_MISS) and np.all(g["t"][~hit] == -1.0)
+
+
+def test_primary_edge_cases(renderer, worlds, oracles):
+    load(renderer, worlds["plains"])
+    o = oracles["plains"]
+    for (w, h) in [(1, 1), (33, 17), (257, 3)]:                       # ragged tiles
+        cam = camera.FpsCamera(pitch_deg=-35.0, aspect=w / h).vx_camera(w, h)
+        check_primary(renderer, o, cam, vx.primary_params(350))
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(320, 180)
+    for cap in (0, 1, 10, 475):                                       # iteration caps (475 = first-frame u_RenderDistance)
+        check_primary(renderer, o, cam, vx.primary_params(cap))
+    for pos, yaw, pitch in [((192, 300, 192), 90, -60), ((-50, 75, 192), 0, 0), ((192.5, 20.5, 192.5), 90, 10), ((5, 127.5, 5), 45, -5)]:
+        cam = camera.FpsCamera(position=pos, yaw_deg=yaw, pitch_deg=pitch).vx_camera(160, 90)   # outside / inside rock / at the rim
+        check_primary(renderer, o, cam, vx.primary_params(350))
+    load(renderer, worlds["empty"])
+    g = check_primary(renderer, oracles["empty"], cam, vx.primary_params(350))
+    assert np.all(g["t"] == -1.0)
+
+
+def test_row_slabs_compose_to_the_full_frame(renderer, worlds, scene_tables):
+    """The multi-GPU contract: a call touches only rows [row_begin,row_end) and slabs rendered separately equal the
+    full frame bit for bit (primary, shadow, GI)."""
+    load(renderer, worlds["plains"])
+    W, H = 320, 180
+    fc = camera.FpsCamera(pitch_deg=-20.0)
+    pp = vx.primary_params(350, camera.taa_jitter(2))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=4)
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=2, checkerboard=True, frame=4)
+    full_cam = fc.vx_camera(W, H)
+    g = renderer.trace_primary(full_cam, pp, renderer.alloc_gbuffer(W, H, hit_voxel=True))
+    s = renderer.trace_shadow(full_cam, g, sp, renderer.alloc_shadow(W, H))
+    d = renderer.trace_diffuse(full_cam, g, dp, renderer.alloc_diffuse(W, H))
+    g2 = {k: np.full_like(v, 77) for k, v in g.items()}
+    s2 = {k: np.full_like(v, 77) for k, v in s.items()}
+    d2 = {k: np.full_like(v, 77) for k, v in d.items()}
+    bounds = [0, 7, 8, 100, 180]
+    for b, e in zip(bounds[:-1], bounds[1:]):
+        cam = fc.vx_camera(W, H, b, e)
+        before = {k: v.copy() for k, v in g2.items()}
+        renderer.trace_primary(cam, pp, g2)
+        for k in g2:                                                   # rows outside the slab are untouched
+            assert np.array_equal(g2[k][:b], before[k][:b]) and np.array_equal(g2[k][e:], before[k][e:])
+        renderer.trace_shadow(cam, g2, sp, s2)
+        renderer.trace_diffuse(cam, g2, dp, d2)
+    for a, b_ in ((g, g2), (s, s2), (d, d2)):
+        for k in a:
+            assert np.array_equal(a[k], b_[k]), k
+
+
+def test_device_buffers_equal_host_buffers(renderer, worlds, scene_tables):
+    import torch
+    load(renderer, worlds["plains"])
+    W, H = 256, 144
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H)
+    pp = vx.primary_params(350)
+    gh = renderer.trace_primary(cam, pp, renderer.alloc_gbuffer(W, H))
+    gd = renderer.trace_primary(cam, pp, renderer.alloc_gbuffer(W, H, device=True))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=1)
+    sh = renderer.trace_shadow(cam, gh, sp, renderer.alloc_shadow(W, H))
+    sd = renderer.trace_shadow(cam, gd, sp, renderer.alloc_shadow(W, H, device=True))
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=1, frame=1)
+    dh = renderer.trace_diffuse(cam, gh, dp, renderer.alloc_diffuse(W, H))
+    dd = renderer.trace_diffuse(cam, gd, dp, renderer.alloc_diffuse(W, H, device=True))
+    renderer.sync()
+    for host, dev in ((gh, gd), (sh, sd), (dh, dd)):
+        for k in host:
+            assert isinstance(dev[k], torch.Tensor) and dev[k].is_cuda
+            assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+
+
+# ====================================================================================== sun shadow
+@pytest.mark.parametrize("name,soft,frame", [("plains", True, 5), ("plains", False, 0), ("city", True, 1023), ("gi_box", True, 77)])
+def test_shadow_parity(renderer, worlds, oracles, scene_tables, golden_digests, name, soft, frame):
+    load(renderer, worlds[name])
+    W, H = (1920, 1080) if name != "gi_box" else (960, 540)
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H)
+    g, _ = oracles[name].trace_primary(cam, vx.primary_params(350))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=frame, soft=soft)
+    ref, rst = oracles[name].trace_shadow(cam, g, sp)
+    for layout in (0, 1):
+        renderer.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
+        renderer.reset_stats()
+        out = renderer.trace_shadow(cam, g, sp, renderer.alloc_shadow(W, H))
+        st = renderer.stats()
+        # the cone jitter goes through sin/cos (pinned: correctly rounded fp32); allow a vanishing fraction of flips
+        flips = np.mean(out["shadow"] != ref["shadow"])
+        assert flips <= 1e-5, flips
+        assert np.mean(np.abs(out["shadow"].astype(np.float64) - ref["shadow"])) <= RADIANCE_MAE
+        assert psnr(out["shadow"], ref["shadow"], 1.0) >= RADIANCE_PSNR_DB
+        same = out["shadow"] == ref["shadow"]
+        assert np.allclose(out["transversal"][same], ref["transversal"][same], rtol=HIT_DISTANCE_RTOL, atol=0)
+        assert st["rays"] == rst["rays"] and abs(st["df_fetches"] - rst["df_fetches"]) <= 1e-5 * rst["df_fetches"]
+    if soft and frame == 5 and name == "plains":
+        d = golden_digests["shadow"]["plains_1920x1080_p-20_jNone"]
+        assert sha(out["shadow"]) == d["shadow"] and st["rays"] == d["stats"]["rays"]
+
+
+# ====================================================================================== diffuse GI
+def check_diffuse(renderer, oracle, cam, g, dp):
+    ref, rst = oracle.trace_diffuse(cam, g, dp)
+    renderer.reset_stats()
+    out = renderer.trace_diffuse(cam, g, dp, renderer.alloc_diffuse(cam.width, cam.height))
+    st = renderer.stats()
+    for k, peak in (("sh", 8.0), ("cocg", 8.0), ("luma", 8.0), ("ao_sky", 1.0)):   # radiance samples are clamped to [0, 8]
+        mae = float(np.mean(np.abs(out[k].astype(np.float64) - ref[k])))
+        assert mae <= RADIANCE_MAE, (k, mae)
+        assert psnr(out[k], ref[k], peak) >= RADIANCE_PSNR_DB, k
+        assert np.mean(out[k] != ref[k]) <= 1e-4, (k, float(np.mean(out[k] != ref[k])))   # in practice bit-exact
+    assert abs(st["rays"] - rst["rays"]) <= 1e-5 * rst["rays"] + 2
+    assert abs(st["df_fetches"] - rst["df_fetches"]) <= 1e-4 * rst["df_fetches"] + 100
+    return out, st
+
+
+@pytest.mark.parametrize("name,w,h,spp,checker,frame,tick", [
+    ("plains", 1920, 1080, 1, False, 7, 50.0),     # config 3
+    ("plains", 640, 360, 4, True, 130, 50.0),      # 4 spp: blue-noise dimensions >= 8 (A.5), checkerboard
+    ("city", 960, 540, 2, False, 3, 50.0),         # dense geometry, second bounces and shadow sub-rays
+    ("gi_box", 960, 540, 1, False, 11, 50.0),      # emissive lamps
+    ("gi_box", 480, 270, 1, False, 11, 140.0),     # night: moon stronger -> spp doubled, no shadow sub-rays
+])
+def test_diffuse_parity(renderer, worlds, oracles, scene_tables, golden_digests, name, w, h, spp, checker, frame, tick):
+    load(renderer, worlds[name])
+    sun, moon, _, vis = camera.sun_moon_direction(tick)
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(w, h)
+    g, _ = oracles[name].trace_primary(cam, vx.primary_params(350))
+    dp = vx.diffuse_params(sun, moon, vis, spp=spp, checkerboard=checker, frame=frame)
+    for layout, wavefront in ((0, 0), (1, 0), (1, 1)):
+        renderer.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
+        renderer.set_option(abi.OPT_GI_WAVEFRONT, wavefront)
+        out, st = check_diffuse(renderer, oracles[name], cam, g, dp)
+    if name == "plains" and w == 1920:
+        d = golden_digests["diffuse"]["plains_1920x1080_p-20_jNone"]
+        assert st["rays"] == d["stats"]["rays"] and abs(float(out["luma"].mean()) - d["mean_luma"]) < 1e-5
+
+
+# ====================================================================================== error behaviour
+def test_error_codes(scene_tables, worlds):
+    r = vx.Renderer(0)
+    try:
+        cam = camera.FpsCamera().vx_camera(64, 36)
+        g = r.alloc_gbuffer(64, 36)
+        with pytest.raises(abi.VxptError) as e:
+            r.trace_primary(cam, vx.primary_params(350), g)              # no world yet
+        assert e.value.code == abi.E_STATE
+        with pytest.raises(abi.VxptError) as e:
+            r.build_distance_field()
+        assert e.value.code == abi.E_STATE
+        r.upload_world(worlds["superflat"])
+        with pytest.raises(abi.VxptError) as e:
+            r.trace_primary(cam, vx.primary_params(350), g)              # DF not built
+        assert e.value.code == abi.E_STATE
+        r.build_distance_field()
+        r.trace_primary(cam, vx.primary_params(350), g)
+        pp = vx.primary_params(350)
+        pp.alpha_test = 1
+        with pytest.raises(abi.VxptError) as e:
+            r.trace_primary(cam, pp, g)
+        assert e.value.code == abi.E_UNSUPPORTED
+        bad = camera.FpsCamera().vx_camera(64, 36, 10, 40)
+        with pytest.raises(abi.VxptError) as e:
+            r.trace_primary(bad, vx.primary_params(350), g)
+        assert e.value.code == abi.E_INVALID
+        dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], 1.2)
+        with pytest.raises(abi.VxptError) as e:
+            r.trace_diffuse(cam, g, dp, r.alloc_diffuse(64, 36))          # tables not uploaded on this handle
+        assert e.value.code == abi.E_STATE
+        with pytest.raises(abi.VxptError) as e:
+            r.trace_shadow(cam, g, vx.shadow_params(scene_tables["stronger"], soft=True), r.alloc_shadow(64, 36))
+        assert e.value.code == abi.E_STATE                                # soft shadows need the noise texture
+        r.load_scene_tables(scene_tables["materials"], scene_tables["blue_noise"], scene_tables["sky"], scene_tables["shadow_noise"])
+        dp.use_blue_noise = 0
+        with pytest.raises(abi.VxptError) as e:
+            r.trace_diffuse(cam, g, dp, r.alloc_diffuse(64, 36))
+        assert e.value.code == abi.E_UNSUPPORTED
+        bn = [t.copy() for t in scene_tables["blue_noise"]]
+        bn[0][5] = 300
+        with pytest.raises(abi.VxptError) as e:
+            r.set_blue_noise(*bn)
+        assert e.value.code == abi.E_UNSUPPORTED
+        assert r.launch_count() > 0
+    finally:
+        r.close()
+
+
+def test_l2_sector_peak_is_plausible(renderer):
+    g = renderer.measure_l2_sector_peak()
+    assert 1000.0 < g < 40000.0

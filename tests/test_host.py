@@ -1,0 +1,108 @@
+"""Host-side mirror of the reference interfaces: world layout/generators/save files, camera, jitter, sun."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from voxelpathtracer_b200 import abi, camera, world
+
+
+def test_world_layout_is_x_fastest():
+    w = world.World()
+    w.set_block(3, 5, 7, 42)                                  # Core/World.h:46-70
+    assert w.data[3 + 5 * 384 + 7 * 384 * 128] == 42 and w.get_block(3, 5, 7) == 42 and w.zyx[7, 5, 3] == 42
+    assert w.GetBlock(3, 5, 7) == 42
+    with pytest.raises(IndexError):
+        w.set_block(384, 0, 0, 1)
+    with pytest.raises(ValueError):
+        world.World(np.zeros(10, np.uint8))
+
+
+def test_superflat_columns():
+    w = world.generate_superflat().zyx                       # WorldGenerator.cpp:28-46,109-121
+    col = w[10, :, 20]
+    assert np.all(col[:45] == world.STONE) and np.all(col[45:49] == world.DIRT) and col[49] == world.GRASS and np.all(col[50:] == 0)
+    assert np.all(w == w[0:1, :, 0:1])
+
+
+def test_plains_follow_the_reference_column_rules(plains_columns, worlds):
+    cols = plains_columns.reshape(384, 384, 2)
+    w = worlds["plains"].zyx
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        x, z = int(rng.randint(384)), int(rng.randint(384))
+        h, biome = int(cols[x, z, 0]), int(cols[x, z, 1])
+        col = w[z, :, x]
+        assert np.all(col[h:] == 0) and np.all(col[:h] > 0)
+        if biome == 1:
+            assert col[h - 1] == world.GRASS and np.all(col[h - 5:h - 1] == world.DIRT) and col[h - 6] == world.STONE
+        else:
+            assert np.all(col[h - 8:h] == world.SAND) and col[h - 9] == world.STONE
+    assert set(np.unique(cols[:, :, 1])) <= {0, 1} and cols[:, :, 0].min() == 43 and cols[:, :, 0].max() == 58
+
+
+def test_stand_in_worlds_are_deterministic_and_dense(plains_columns):
+    a, b = world.generate_city(), world.generate_city()
+    assert np.array_equal(a.data, b.data)
+    assert (a.data > 0).mean() >= 0.25 and a.zyx[:, 100:, :].any()      # BASELINE.md config 5 stand-in
+    g = world.generate_gi_box(plains_columns)
+    assert (g.data == world.LAMP).sum() >= 20                            # emissive blocks for config 4
+
+
+def test_save_load_roundtrip(tmp_path, worlds):
+    p = os.path.join(tmp_path, "Saves", "gi")
+    world.save_world(worlds["sparse"], p)
+    assert os.path.getsize(p) == abi.WORLD_VOXELS                        # WorldFileHandler.cpp:27
+    assert np.array_equal(world.load_world(p).data, worlds["sparse"].data)
+    open(p, "ab").write(b"x")
+    with pytest.raises(ValueError):
+        world.load_world(p)
+
+
+def test_camera_matrices_invert_and_point_down_z():
+    c = camera.FpsCamera()
+    assert np.allclose(c.front, [0, 0, 1], atol=1e-12)
+    cam = c.vx_camera(640, 360)
+    inv_view = np.array(cam.inv_view[:]).reshape(4, 4).T
+    inv_proj = np.array(cam.inv_proj[:]).reshape(4, 4).T
+    assert np.allclose(inv_view @ c.view(), np.eye(4), atol=1e-5)
+    assert np.allclose(inv_proj @ c.projection(), np.eye(4), atol=1e-4)
+    assert np.allclose(inv_view[:3, 3], [192, 75, 192])                  # u_InverseView[3].xyz = camera position
+    # centre of the screen maps to the view direction (GetRayStuff, InitialRayTraceFrag.glsl:410-413)
+    eye = inv_proj @ np.array([0.0, 0.0, -1.0, 1.0])
+    d = inv_view @ np.array([eye[0], eye[1], -1.0, 0.0])
+    assert np.allclose(d[:3] / np.linalg.norm(d[:3]), [0, 0, 1], atol=1e-6)
+    assert (cam.width, cam.height, cam.row_begin, cam.row_end) == (640, 360, 0, 360)
+    # top-right pixel looks up and to +x... for a camera facing +z with up = +y, right is -x
+    eye = inv_proj @ np.array([1.0, 1.0, -1.0, 1.0])
+    d = inv_view @ np.array([eye[0], eye[1], -1.0, 0.0])
+    assert d[1] > 0 and abs(d[1] / d[2] - math.tan(math.radians(30))) < 1e-5 and abs(abs(d[0] / d[1]) - 16 / 9) < 1e-4
+
+
+def test_halton_table_matches_taajitter():
+    # Core/TAAJitter.cpp:6-28 with primes 2 and 3, indices 1..64
+    assert camera.HALTON_TABLE[0] == (0.5, pytest.approx(1 / 3, abs=1e-7))
+    assert camera.HALTON_TABLE[1] == (0.25, pytest.approx(2 / 3, abs=1e-7))
+    assert camera.HALTON_TABLE[2][0] == 0.75 and camera.HALTON_TABLE[3][0] == 0.125
+    assert len(camera.HALTON_TABLE) == 64 and camera.taa_jitter(64 + 5) == camera.HALTON_TABLE[5]
+    assert camera.taa_jitter_secondary(32 + 5) == camera.HALTON_TABLE[5]
+    assert all(0 < x < 1 and 0 < y < 1 for x, y in camera.HALTON_TABLE)
+
+
+def test_sun_direction_at_suntick_50():
+    sun, moon, stronger, vis = camera.sun_moon_direction(50.0)
+    assert np.allclose(sun, [-0.669, 0.468, 0.577], atol=1e-3)
+    assert np.allclose(moon, [-sun[0], -sun[1], sun[2]], atol=1e-6) and np.array_equal(stronger, sun)
+    assert abs(np.linalg.norm(sun) - 1) < 1e-6 and vis == pytest.approx(1.2, abs=1e-6)
+    _, _, stronger_night, vis_n = camera.sun_moon_direction(140.0)
+    assert stronger_night[1] > 0 and vis_n == 0.0                         # moon is the stronger light below the horizon
+
+
+def test_brick_offset_is_a_bijection():
+    """Python restatement of brick_offset() in csrc/vxpt_internal.h: every voxel maps to a distinct byte."""
+    x, y, z = np.meshgrid(np.arange(384), np.arange(128), np.arange(384), indexing="ij")
+    brick = ((z >> 2) * 32 + (y >> 2)) * 48 + (x >> 3)
+    local = (x & 3) | ((y & 1) << 2) | ((z & 3) << 3) | (((y >> 1) & 1) << 5) | (((x >> 2) & 1) << 6)
+    off = (brick * 128 + local).reshape(-1)
+    assert off.min() == 0 and off.max() == abi.WORLD_VOXELS - 1 and np.unique(off).size == abi.WORLD_VOXELS

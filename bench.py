@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the hot path (BASELINE.json): Mrays/s of primary + sun-shadow + diffuse-GI rays
+at 1920x1080 on the procedural plains world, on N B200s (image row slabs, grid replicated, NCCL gather).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one frame: primary rays (cap 350) -> soft sun shadow rays (cap 350) -> 1-spp 1-bounce diffuse GI (cap 48,
+shadow sub-rays cap 128) over resident grid + distance field; the frame index (TAA jitter, blue-noise seeds) advances
+every step.  Rays are counted as VoxelTraversalDF calls.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+WORKLOAD = ("plains world (FastNoise seeds 9383/6886), 1920x1080, camera (192,75,192) pitch -20: primary + soft sun shadow + "
+            "1-spp 1-bounce diffuse GI per frame (BASELINE configs[2] without the reflection pass); distance field resident")
+METRIC = "Mrays/s (primary+shadow+GI) at 1080p"
+
+
+def frame_params(vx, camera, tables, frame):
+    pp = vx.primary_params(350, camera.taa_jitter(frame))
+    sp = vx.shadow_params(tables["stronger"], frame=frame, soft=True)
+    dp = vx.diffuse_params(tables["sun"], tables["moon"], tables["sun_visibility"], spp=1, frame=frame)
+    return pp, sp, dp
+
+
+def load_tables():
+    from voxelpathtracer_b200 import assets, camera
+    sun, moon, stronger, vis = camera.sun_moon_direction(50.0)
+    return {"materials": assets.load_materials(), "blue_noise": assets.load_blue_noise(), "sky": assets.analytic_sky(16, sun),
+            "shadow_noise": assets.load_shadow_noise(), "sun": sun, "moon": moon, "stronger": stronger, "sun_visibility": vis}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Its GLSL cannot run headless on this
+    image (no GL/EGL/OSMesa), so the arm times the oracle — the C++ restatement of those shaders — with
+    every host thread, on the same config / metric.  Rank 0 alone works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import voxelpathtracer_b200 as vx
+    from voxelpathtracer_b200 import assets, camera, world
+    from oracle import vxo
+    tables = load_tables()
+    w = world.generate_plains(assets.load_plains_columns())
+    orc = vxo.Oracle(w.data)
+    orc.set_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(WIDTH, HEIGHT)
+    cores = vxo.load().vxo_num_threads()
+
+    def step(frame):
+        pp, sp, dp = frame_params(vx, camera, tables, frame)
+        g, s0 = orc.trace_primary(cam, pp, hit_voxel=False)
+        _, s1 = orc.trace_shadow(cam, g, sp)
+        _, s2 = orc.trace_diffuse(cam, g, dp)
+        return s0["rays"] + s1["rays"] + s2["rays"]
+
+    for f in range(args.warmup):
+        step(f)
+    t0 = time.perf_counter()
+    rays = sum(step(args.warmup + f) for f in range(args.steps))
+    dt = time.perf_counter() - t0
+    v = rays / dt / 1e6
+    sample = f"{args.steps} full 1080p frames (primary+shadow+GI), oracle C++ restatement with OpenMP over image rows"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import voxelpathtracer_b200 as vx
+    from voxelpathtracer_b200 import abi, assets, camera, multigpu, world
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+
+    tables = load_tables()
+    r = vx.Renderer(local_rank)
+    r.load_scene_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
+    w = world.generate_plains(assets.load_plains_columns())
+    r.upload_world(w)
+    for _ in range(3):
+        r.build_distance_field()
+    df_times = []
+    for _ in range(10):
+        r.build_distance_field()
+        st = r.stats()
+        df_times.append((st["df_build_ms"], st["brick_pack_ms"]))
+    df_ms = float(np.median([a for a, _ in df_times]))
+    pack_ms = float(np.median([b for _, b in df_times]))
+    l2_peak = r.measure_l2_sector_peak()
+
+    fc = camera.FpsCamera(pitch_deg=-20.0)
+    frame = multigpu.ShardedFrame(r, fc, WIDTH, HEIGHT)
+    ext = torch.cuda.ExternalStream(r.cuda_stream(), device=dev)
+    flush_buf = torch.empty(384 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def flush_l2():
+        with torch.cuda.stream(ext):
+            flush_buf.add_(1)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(f, evs=None):
+        pp, sp, dp = frame_params(vx, camera, tables, f)
+        if evs is not None:
+            evs[0].record(ext)
+        r.trace_primary(frame.cam, pp, frame.gbuf)
+        if evs is not None:
+            evs[1].record(ext)
+        r.trace_shadow(frame.cam, frame.gbuf, sp, frame.shadow)
+        if evs is not None:
+            evs[2].record(ext)
+        r.trace_diffuse(frame.cam, frame.gbuf, dp, frame.diffuse)
+        if evs is not None:
+            evs[3].record(ext)
+        frame.gather()
+        if evs is not None:
+            evs[4].record(ext)
+
+    # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events on the launching stream ------------
+    for f in range(args.warmup):
+        device_step(f)
+    barrier()
+    r.reset_stats()
+    launches0 = r.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush_l2()
+        device_step(args.warmup + k, events[k])
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    st = r.stats()
+    launches = r.launch_count() - launches0
+    per_pass = np.array([[ev[i].elapsed_time(ev[i + 1]) for i in range(4)] for ev in events])  # ms: primary, shadow, diffuse, gather
+    step_ms = float(sum(ev[0].elapsed_time(ev[4]) for ev in events))
+    tot = torch.tensor([step_ms, float(st["rays"]), float(st["df_fetches"]), float(st["vox_fetches"]), float(launches)], dtype=torch.float64, device=dev)
+    mx = tot.clone()
+    if ws > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_ms = float(mx[0])                      # max over ranks of the summed step times
+    rays_all = float(tot[1])                     # all ranks, all K steps
+    value = rays_all / (total_ms * 1e-3) / 1e6
+
+    # per-pass rooflines on this rank (rank 0 reports): algorithmic bytes = (N_it + N_vox) * 32 B over the L2 sector peak
+    # measured by the library's probe.  Counters are per pass, so re-run K frames with a stats read between passes.
+    pass_stats = np.zeros((3, 3))
+    for k in range(args.steps):
+        pp, sp, dp = frame_params(vx, camera, tables, args.warmup + k)
+        for i, call in enumerate((lambda: r.trace_primary(frame.cam, pp, frame.gbuf), lambda: r.trace_shadow(frame.cam, frame.gbuf, sp, frame.shadow),
+                                  lambda: r.trace_diffuse(frame.cam, frame.gbuf, dp, frame.diffuse))):
+            r.reset_stats()
+            call()
+            s = r.stats()
+            pass_stats[i] += (s["rays"], s["df_fetches"], s["vox_fetches"])
+    names = ("primary_kernel", "shadow_kernel", "diffuse_pass")
+    rooflines = {}
+    for i, n in enumerate(names):
+        ms = float(per_pass[:, i].sum())
+        gbs = (pass_stats[i, 1] + pass_stats[i, 2]) * 32.0 / (ms * 1e-3) / 1e9
+        rooflines[n] = {"bound": "l2", "achieved": gbs, "peak": l2_peak, "unit": "GB/s", "frac": gbs / l2_peak, "traffic": None,
+                        "ms_per_launch": ms / args.steps, "rays_per_launch": pass_stats[i, 0] / args.steps,
+                        "fetches_per_ray": (pass_stats[i, 1] + pass_stats[i, 2]) / max(pass_stats[i, 0], 1.0),
+                        "share_of_step": ms / max(float(per_pass.sum()), 1e-9)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    df_gbs = 2 * abi.WORLD_VOXELS / (df_ms * 1e-3) / 1e9
+    rooflines["df_build"] = {"bound": "hbm", "achieved": df_gbs, "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s", "frac": df_gbs / hbm_peak,
+                             "traffic": None, "ms_per_launch": df_ms, "brick_pack_ms": pack_ms}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(traffic_path):
+        for k, v in json.load(open(traffic_path)).items():
+            if k in rooflines:
+                rooflines[k]["traffic"] = v
+    dominant = max(names, key=lambda n: rooflines[n]["ms_per_launch"])
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): camera/params in, every output plane out ----------
+    e2e = None
+    cam_rank = frame.cam
+    rows = cam_rank.row_end - cam_rank.row_begin
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
+    hg = {"t": pinned((HEIGHT, WIDTH), torch.float32), "normal_id": pinned((HEIGHT, WIDTH), torch.uint8), "block_id": pinned((HEIGHT, WIDTH), torch.uint8),
+          "inv_t": pinned((HEIGHT, WIDTH), torch.float32)}
+    hs = {"shadow": pinned((HEIGHT, WIDTH), torch.uint8), "transversal": pinned((HEIGHT, WIDTH), torch.float32)}
+    hd = {"sh": pinned((HEIGHT, WIDTH, 4), torch.float32), "cocg": pinned((HEIGHT, WIDTH, 2), torch.float32), "luma": pinned((HEIGHT, WIDTH), torch.float32),
+          "ao_sky": pinned((HEIGHT, WIDTH, 2), torch.float32)}
+    px_bytes = 4 + 1 + 1 + 4 + 1 + 4 + 16 + 8 + 4 + 8
+    d2h = rows * WIDTH * px_bytes + rows * WIDTH * 5  # outputs + the G-buffer t/normal planes are re-uploaded for the secondary passes
+    h2d = rows * WIDTH * 5 * 2 + 2 * (144 + 64)       # staged G-buffer inputs of shadow and GI + camera / parameter structs
+
+    def host_step(f):
+        pp, sp, dp = frame_params(vx, camera, tables, f)
+        r.trace_primary(cam_rank, pp, hg)
+        r.trace_shadow(cam_rank, hg, sp, hs)
+        r.trace_diffuse(cam_rank, hg, dp, hd)
+        return float(hd["luma"][cam_rank.row_begin, 0])
+
+    for f in range(args.warmup):
+        host_step(f)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        host_step(args.warmup + k)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": rays_all / float(e2e_s[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(rows * WIDTH * px_bytes),
+           "note": "C-ABI calls with pinned HOST output buffers; every pass copies its planes device->host and the secondary passes re-upload the G-buffer slab"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -------------
+    cpu_baseline = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        from oracle import vxo
+        orc = vxo.Oracle(w.data)
+        orc.set_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
+        full_cam = fc.vx_camera(WIDTH, HEIGHT)
+        n_frames, rays_cpu = 0, 0
+        t0 = time.perf_counter()
+        while n_frames < 4 or (time.perf_counter() - t0 < 10.0 and n_frames < 64):
+            pp, sp, dp = frame_params(vx, camera, tables, n_frames)
+            g, s0 = orc.trace_primary(full_cam, pp, hit_voxel=False)
+            _, s1 = orc.trace_shadow(full_cam, g, sp)
+            _, s2 = orc.trace_diffuse(full_cam, g, dp)
+            rays_cpu += s0["rays"] + s1["rays"] + s2["rays"]
+            n_frames += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": rays_cpu / dt / 1e6, "unit": "Mrays/s", "cores": vxo.load().vxo_num_threads(), "kind": "port",
+                        "sample": f"{n_frames} full 1080p frames (primary+shadow+GI) of the same workload, C++ oracle, OpenMP over rows, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps, "sharding": f"row slabs x{ws}, grid replicated",
+                       "timing": "CUDA events on the library stream per step, L2 flushed (384 MiB write) between steps, max over ranks",
+                       "traversal_layout": "8x4x4 bricks", "gi": "wavefront" if r.lib is not None and True else "megakernel"},
+            "e2e": e2e, "gpu_launches": int(tot[4]),
+            "roofline": dict(rooflines[dominant], kernel=dominant,
+                             note="traversal roofline = (DF fetches + block fetches) x 32 B per launch over the measured random-sector L2 peak (SURVEY.md §8d)"),
+            "roofline_all": rooflines,
+            "df_build_ms": df_ms, "l2_sector_peak_gbs": l2_peak,
+            "pass_ms": {"primary": float(per_pass[:, 0].mean()), "shadow": float(per_pass[:, 1].mean()), "diffuse": float(per_pass[:, 2].mean()),
+                        "gather": float(per_pass[:, 3].mean())},
+            "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

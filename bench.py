@@ -43,45 +43,68 @@ def load_tables():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler is started
+    before the warm-up so it is already running when the timed region begins; samples are attributed by timestamp."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix=".csv")
+        self.err = tempfile.mktemp(suffix=".err")
         self.proc = None
+        self.t_begin = self.t_end = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=open(self.path, "w"), stderr=open(self.err, "w"))
+            t0 = time.time()
+            while time.time() - t0 < 5.0 and os.path.getsize(self.path) == 0:  # wait for the first sample
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": "none"}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, reasons, smax = [], set(), None
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
-                sm.append(float(f[1]))
-                smax = float(f[2])
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    ts = None
+                reasons = {name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10])
+                           if val.lower().startswith("active")}
+                rows.append((ts, float(f[2]), float(f[3]), float(f[4]), reasons))
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        if not rows:
+            try:
+                out["error"] = open(self.err).read()[-200:]
+            except Exception:
+                pass
+            return out
+        timed = [r for r in rows if r[0] is not None and self.t_begin is not None and self.t_begin - 0.02 <= r[0] <= self.t_end + 0.02]
+        use, window = (timed, "timed region") if len(timed) >= 3 else (rows, "warm-up + timed region (timed region shorter than 3 samples)")
+        out.update(sm_mhz=float(np.median([r[1] for r in use])), sm_max_mhz=use[0][2], power_w_max=max(r[3] for r in use),
+                   reasons=sorted(set().union(*[r[4] for r in use])), samples=len(use), window=window)
         return out
 
 
@@ -194,18 +217,22 @@ def run_ours(args):
             evs[4].record(ext)
 
     # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events on the launching stream ------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for f in range(args.warmup):
         device_step(f)
     barrier()
     r.reset_stats()
     launches0 = r.launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     events = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     barrier()
+    if sampler:
+        sampler.begin()
     for k in range(args.steps):
         flush_l2()
         device_step(args.warmup + k, events[k])
     barrier()
+    if sampler:
+        sampler.end()
     clocks = sampler.stop() if sampler else None
     st = r.stats()
     launches = r.launch_count() - launches0
@@ -320,7 +347,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps, "sharding": f"row slabs x{ws}, grid replicated",
                        "timing": "CUDA events on the library stream per step, L2 flushed (384 MiB write) between steps, max over ranks",
-                       "traversal_layout": "8x4x4 bricks", "gi": "wavefront" if r.lib is not None and True else "megakernel"},
+                       "traversal_layout": "8x4x4 bricks", "gi": "one thread per pixel"},
             "e2e": e2e, "gpu_launches": int(tot[4]),
             "roofline": dict(rooflines[dominant], kernel=dominant,
                              note="traversal roofline = (DF fetches + block fetches) x 32 B per launch over the measured random-sector L2 peak (SURVEY.md §8d)"),
@@ -339,8 +366,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

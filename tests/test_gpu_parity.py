@@ -158,8 +158,9 @@ def test_primary_1080p(renderer, worlds, oracles, golden_digests, case):
 
 
 def test_primary_4k_digest_and_properties(renderer, worlds, golden_digests):
-    """Config 4 frame size (3840x2160) without CPU tracing: committed digest + 'the hit voxel is solid and the voxel
-    the ray came from is air' for every pixel."""
+    """Config 4 frame size (3840x2160) without CPU tracing: committed digest + 'the hit voxel is solid' for every pixel
+    and 'the voxel the ray came from (hit + face normal) is air' for all but grazing rays (the reference keeps a stale
+    face after a skip step, InitialRayTraceFrag.glsl:331-334: ~1e-5 of the hits on these worlds)."""
     load(renderer, worlds["gi_box"])
     cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(3840, 2160)
     g = check_primary(renderer, None, cam, vx.primary_params(350), 1, golden_digests["primary"]["gi_box_3840x2160_p-20_jNone"])
@@ -170,7 +171,7 @@ def test_primary_4k_digest_and_properties(renderer, worlds, golden_digests):
     normals = np.array([[0, 0, 1], [0, 0, -1], [0, 1, 0], [0, -1, 0], [-1, 0, 0], [1, 0, 0]])
     prev = v + normals[g["normal_id"][hit]]
     inside = np.all((prev >= 0) & (prev < [384, 128, 384]), axis=1)
-    assert np.all(grid[prev[inside, 2], prev[inside, 1], prev[inside, 0]] == 0)
+    assert np.mean(grid[prev[inside, 2], prev[inside, 1], prev[inside, 0]] != 0) < 1e-4
     assert np.all(g["normal_id"][~hit] == abi.NORMAL_MISS) and np.all(g["t"][~hit] == -1.0)
 
 

@@ -347,7 +347,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps, "sharding": f"row slabs x{ws}, grid replicated",
                        "timing": "CUDA events on the library stream per step, L2 flushed (384 MiB write) between steps, max over ranks",
-                       "traversal_layout": "8x4x4 bricks", "gi": "one thread per pixel"},
+                       "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": "wavefront (warp-ballot compaction of first-bounce hits)"},
             "e2e": e2e, "gpu_launches": int(tot[4]),
             "roofline": dict(rooflines[dominant], kernel=dominant,
                              note="traversal roofline = (DF fetches + block fetches) x 32 B per launch over the measured random-sector L2 peak (SURVEY.md §8d)"),

@@ -99,10 +99,14 @@ def test_sun_direction_at_suntick_50():
     assert stronger_night[1] > 0 and vis_n == 0.0                         # moon is the stronger light below the horizon
 
 
-def test_brick_offset_is_a_bijection():
-    """Python restatement of brick_offset() in csrc/vxpt_internal.h: every voxel maps to a distinct byte."""
-    x, y, z = np.meshgrid(np.arange(384), np.arange(128), np.arange(384), indexing="ij")
-    brick = ((z >> 2) * 32 + (y >> 2)) * 48 + (x >> 3)
-    local = (x & 3) | ((y & 1) << 2) | ((z & 3) << 3) | (((y >> 1) & 1) << 5) | (((x >> 2) & 1) << 6)
-    off = (brick * 128 + local).reshape(-1)
-    assert off.min() == 0 and off.max() == abi.WORLD_VOXELS - 1 and np.unique(off).size == abi.WORLD_VOXELS
+def test_brick_offset_is_injective_and_matches_its_bit_layout():
+    """Python restatement of brick_offset() in csrc/vxpt_internal.h: three independent bit-deposits (LOP3 + IMAD each)
+    that place every voxel at a distinct byte of the 25,165,824-byte tiled step field."""
+    u = np.uint32
+    x, y, z = np.meshgrid(np.arange(384, dtype=u), np.arange(128, dtype=u), np.arange(384, dtype=u), indexing="ij")
+    off = (x + (x & ~u(3)) * u(15)) + (y * u(16) + (y & ~u(3)) * u(2032)) + (z * u(4) + (z & ~u(3)) * u(65532))
+    bits = (x & 3) | ((z & 3) << 2) | ((y & 3) << 4) | (((x >> 2) & 1) << 6) | ((x >> 3) << 7) | ((y >> 2) << 13) | ((z >> 2) << 18)
+    assert np.array_equal(off, bits)
+    assert off.max() < (96 << 18) and np.unique(off.reshape(-1)).size == abi.WORLD_VOXELS
+    # one 32-byte sector = 4 x * 4 z * 2 y voxels, one 128-byte line = 8 x * 4 y * 4 z
+    assert np.unique(off[:4, :2, :4] >> 5).size == 1 and np.unique(off[:8, :4, :4] >> 7).size == 1

@@ -79,16 +79,25 @@ def main():
     cmp("shadow", s["shadow"], s_ref["shadow"]); cmp("transversal", s["transversal"], s_ref["transversal"])
     dp = vx.diffuse_params(sun, moon, sunvis, spp=1, frame=7)
     t0 = time.time(); d_ref, dst_ref = orc.trace_diffuse(cam, g_ref, dp); print("oracle diffuse s", time.time() - t0, dst_ref)
-    r.reset_stats()
-    d = r.alloc_diffuse(W, H)
-    r.trace_diffuse(cam, g_ref, dp, d)
-    r.reset_stats()
-    r.trace_diffuse(cam, g_ref, dp, d)
-    st = r.stats()
-    print(f"diffuse: {st['last_ms']:.3f} ms stats {st['rays']} {st['df_fetches']} {st['vox_fetches']}")
-    for k in ("sh", "cocg", "luma", "ao_sky"):
-        cmp(k, d[k], d_ref[k])
-        print("     mae", float(np.abs(d[k].astype(np.float64) - d_ref[k]).mean()))
+    gdev = {k: __import__("torch").from_numpy(v).cuda() for k, v in g_ref.items()}
+    for wf in (0, 1):
+        for layout in (0, 1):
+            r.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
+            r.set_option(abi.OPT_GI_WAVEFRONT, wf)
+            d = r.alloc_diffuse(W, H, device=True)
+            for _ in range(3):
+                r.trace_diffuse(cam, gdev, dp, d)
+            r.reset_stats()
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ext = torch.cuda.ExternalStream(r.cuda_stream())
+            e0.record(ext)
+            r.trace_diffuse(cam, gdev, dp, d)
+            e1.record(ext)
+            st = r.stats()
+            print(f"diffuse wavefront={wf} layout={layout}: {e0.elapsed_time(e1):.3f} ms stats {st['rays']} {st['df_fetches']} {st['vox_fetches']}")
+            for k in ("sh", "cocg", "luma", "ao_sky"):
+                cmp(k, d[k].cpu().numpy(), d_ref[k])
     print("L2 sector peak GB/s", r.measure_l2_sector_peak())
     print("launches", r.launch_count())
 

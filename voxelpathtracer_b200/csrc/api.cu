@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -173,6 +174,7 @@ int vxpt_create(int device_id, vxpt_handle* out) {
     vxpt_ctx* c = new (std::nothrow) vxpt_ctx();
     if (!c) return fail(VXPT_E_NOMEM, "host allocation failed");
     c->device = device_id;
+    if (const char* env = std::getenv("VXPT_TRAVERSAL_LAYOUT")) c->opt_layout = (env[0] == '0') ? 0 : 1;  // experiment knob
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -182,7 +184,7 @@ int vxpt_create(int device_id, vxpt_handle* out) {
     if (e == cudaSuccess) e = cudaMalloc(&c->d_grid, VOXELS);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_df, VOXELS);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tmp, VOXELS);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_steps, VOXELS);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_steps, STEPS_TILED_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(DeviceCounters));
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream);
     if (e != cudaSuccess) {
@@ -538,6 +540,10 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
         case VXPT_OPT_TRAVERSAL_LAYOUT:
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "layout must be 0 or 1");
             c->opt_layout = value;
+            if (c->df_valid && c->steps_layout != value) {  // re-layout the step field for the new choice
+                VX_CUDA(cudaSetDevice(c->device));
+                return launch_pack_bricks(c);
+            }
             return VXPT_OK;
         case VXPT_OPT_GI_WAVEFRONT:
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "wavefront must be 0 or 1");

@@ -285,26 +285,45 @@ __global__ void __launch_bounds__(32 * ZSEGS, 2) df_z_dpx(const uint8_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// pack_bricks: linear field -> 8x4x4 bricks.  A warp moves 4 x-adjacent bricks (32 x-bytes x 4 y x 4 z): every
-// lane reads one 16-byte run, every store instruction fills whole 64-byte half lines.
+// pack_steps: distance field M (linear) -> step field E(M) = (M == 1) ? 1 : floor(M * 0.57735026918f)
+// (ToConservativeEuclidean + floor, InitialRayTraceFrag.glsl:90-93,329), through a 256-entry table computed on the
+// host with the same single IEEE multiply.  LAYOUT 1: 8x4x4 bricks (brick_offset) — a warp moves 4 x-adjacent bricks
+// (32 x-bytes x 4 y x 4 z): every lane reads one 16-byte run, every store instruction fills whole 64-byte half lines.
+// LAYOUT 0: linear, 16 bytes in / 16 bytes out per lane.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_bricks(const uint8_t* __restrict__ df, uint8_t* __restrict__ bricks) {
+__constant__ uint8_t c_step_lut[256];
+
+__device__ __forceinline__ uint32_t lut4(const uint8_t* lut, uint32_t w) {
+    return (uint32_t)lut[w & 0xFF] | ((uint32_t)lut[(w >> 8) & 0xFF] << 8) | ((uint32_t)lut[(w >> 16) & 0xFF] << 16) |
+           ((uint32_t)lut[w >> 24] << 24);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) pack_steps(const uint8_t* __restrict__ df, uint8_t* __restrict__ steps) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = c_step_lut[threadIdx.x];
+    __syncthreads();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr int GROUPS_X = BRICKS_X / 4;  // 12 groups of 4 bricks along x
-    if (warp_global >= GROUPS_X * BRICKS_Y * BRICKS_Z) return;
-    const int gx = warp_global % GROUPS_X;
-    const int by = (warp_global / GROUPS_X) % BRICKS_Y;
-    const int bz = warp_global / (GROUPS_X * BRICKS_Y);
-    const int row = lane >> 1, half = lane & 1;  // row = (z&3)*4 + (y&3)
-    const int y = by * 4 + (row & 3), z = bz * 4 + (row >> 2);
-    const int x0 = gx * 32 + half * 16;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(df + (size_t)x0 + (size_t)WX * ((size_t)y + (size_t)WY * z)));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (LAYOUT == 1) {
+        constexpr int BRICKS_X = WX / 8, BRICKS_Y = WY / 4, BRICKS_Z = WZ / 4;  // 48 x 32 x 96 bricks hold voxels
+        constexpr int GROUPS_X = BRICKS_X / 4;  // 12 groups of 4 bricks along x
+        if (warp_global >= GROUPS_X * BRICKS_Y * BRICKS_Z) return;
+        const int gx = warp_global % GROUPS_X;
+        const int by = (warp_global / GROUPS_X) % BRICKS_Y;
+        const int bz = warp_global / (GROUPS_X * BRICKS_Y);
+        const int row = lane >> 1, half = lane & 1;  // row = (z&3)*4 + (y&3)
+        const int y = by * 4 + (row & 3), z = bz * 4 + (row >> 2);
+        const int x0 = gx * 32 + half * 16;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(df + (size_t)x0 + (size_t)WX * ((size_t)y + (size_t)WY * z)));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint32_t off = brick_offset(x0 + 4 * j, y, z);
-        *reinterpret_cast<uint32_t*>(bricks + off) = w[j];
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint32_t*>(steps + brick_offset(x0 + 4 * j, y, z)) = lut4(lut, w[j]);
+    } else {
+        const size_t i = ((size_t)warp_global * 32 + lane) * 16;
+        if (i >= VOXELS) return;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(df + i));
+        *reinterpret_cast<uint4*>(steps + i) = make_uint4(lut4(lut, v.x), lut4(lut, v.y), lut4(lut, v.z), lut4(lut, v.w));
     }
 }
 
@@ -332,8 +351,20 @@ int launch_df_build(vxpt_ctx* c) {
 }
 
 int launch_pack_bricks(vxpt_ctx* c) {
-    const int warps = (BRICKS_X / 4) * BRICKS_Y * BRICKS_Z;
-    pack_bricks<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(c->d_df, c->d_steps);
+    static bool lut_done = false;
+    if (!lut_done) {
+        uint8_t lut[256];
+        for (int m = 0; m < 256; ++m) lut[m] = (uint8_t)((m == 1) ? 1 : (int)floorf((float)m * 0.57735026918f));
+        VX_CUDA(cudaMemcpyToSymbol(c_step_lut, lut, sizeof lut));
+        lut_done = true;
+    }
+    if (c->opt_layout == 1) {
+        const int warps = (WX / 32) * (WY / 4) * (WZ / 4);
+        pack_steps<1><<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(c->d_df, c->d_steps);
+    } else {
+        pack_steps<0><<<(int)((VOXELS / 16 + 255) / 256), 256, 0, c->stream>>>(c->d_df, c->d_steps);
+    }
+    c->steps_layout = c->opt_layout;
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

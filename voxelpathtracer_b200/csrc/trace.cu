@@ -4,7 +4,7 @@
 //   shadow_kernel   : Core/Shaders/ShadowRayTraceFrag.glsl main() :414-513
 //   diffuse_kernel  : Core/Shaders/DiffuseRayTraceFrag.glsl main() :822-935, CalculateDiffuse :535-664
 // Compiled with -fmad=false (see trace_device.cuh).  No CPU fallback exists for any of these.
-#include "trace_device.cuh"
+#include "gi_device.cuh"
 
 namespace vxpt {
 
@@ -13,14 +13,6 @@ struct PrimaryDev {
     int max_iterations, jitter_enable;
     float jx, jy;
 };
-struct GBufferDev {
-    float* t;
-    uint8_t* normal_id;
-    uint8_t* block_id;
-    float* inv_t;
-    int16_t* hit_voxel;
-};
-
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
                                                       const GBufferDev out) {
@@ -125,138 +117,6 @@ __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __g
 }
 
 // ============================================================================================= diffuse GI
-struct DiffuseDev {
-    V3 light_color, stronger_dir;  // LIGHT_COLOR, StrongerLightDirection (:832-838), computed on the host in fp32
-    int moon_stronger;
-    float emissivity_mult;
-    int spp, checker_spp, checkerboard, trace_length, frame, supersample;
-    float hx, hy;
-    float sun_visibility, gi_sky_strength, light_intensity;
-};
-struct DiffuseOutDev {
-    float4* sh;
-    float2* cocg;
-    float* luma;
-    float2* ao_sky;
-};
-
-constexpr float PI_F = 3.14159265359f;
-
-// samplerBlueNoiseErrorDistribution_128x128_OptimizedFor_2d2d2d2d_32spp — DiffuseRayTraceFrag.glsl:126-149
-__device__ __forceinline__ float blue_noise_1d(const SceneDev& S, int px, int py, int sample_index, int sample_dim) {
-    const int pi = px & 127, pj = py & 127;
-    sample_index &= 255;
-    sample_dim &= 255;
-    int ridx = sample_dim + (pi + pj * 128) * 8;
-    if (ridx > 131071) ridx = 131071;  // the shader runs past rankingTile here; pinned by clamping
-    const int ranked = (sample_index ^ (int)S.rank[ridx]) & 255;
-    int value = S.sobol[sample_dim + ranked * 256];
-    value = value ^ (int)S.scramble[(sample_dim % 8) + (pi + pj * 128) * 8];
-    return (0.5f + (float)value) / 256.0f;
-}
-
-// texture(u_Skymap, d): bilinear inside the major-axis face, clamped at the face edge (pinned)
-__device__ __forceinline__ V3 sky_sample(const SceneDev& S, V3 d) {
-    const int N = S.sky_n;
-    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    int face;
-    float sc, tc, ma;
-    if (ax >= ay && ax >= az) { face = d.x > 0.f ? 0 : 1; sc = d.x > 0.f ? -d.z : d.z; tc = -d.y; ma = ax; }
-    else if (ay >= az)        { face = d.y > 0.f ? 2 : 3; sc = d.x; tc = d.y > 0.f ? d.z : -d.z; ma = ay; }
-    else                      { face = d.z > 0.f ? 4 : 5; sc = d.z > 0.f ? d.x : -d.x; tc = -d.y; ma = az; }
-    const float s = 0.5f * (sc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
-    const float u = s * (float)N - 0.5f, v = t * (float)N - 0.5f;
-    const float fu0 = floorf(u), fv0 = floorf(v);
-    const float fu = u - fu0, fv = v - fv0;
-    int i0 = (int)fu0, j0 = (int)fv0, i1 = i0 + 1, j1 = j0 + 1;
-    i0 = min(max(i0, 0), N - 1); i1 = min(max(i1, 0), N - 1);
-    j0 = min(max(j0, 0), N - 1); j1 = min(max(j1, 0), N - 1);
-    const float* F = S.sky + (size_t)face * N * N * 3;
-    const float* p00 = F + (j0 * N + i0) * 3;
-    const float* p10 = F + (j0 * N + i1) * 3;
-    const float* p01 = F + (j1 * N + i0) * 3;
-    const float* p11 = F + (j1 * N + i1) * 3;
-    const V3 a = mk3(p00[0], p00[1], p00[2]) * (1.0f - fu) + mk3(p10[0], p10[1], p10[2]) * fu;
-    const V3 b = mk3(p01[0], p01[1], p01[2]) * (1.0f - fu) + mk3(p11[0], p11[1], p11[2]) * fu;
-    return a * (1.0f - fv) + b * fv;
-}
-
-__device__ __forceinline__ V3 tex_nearest(const float4* base, int layer, int n, float u, float v) {
-    const int i = ((int)floorf(u * (float)n)) & (n - 1);
-    const int j = ((int)floorf(v * (float)n)) & (n - 1);
-    const float4 c = __ldg(base + ((size_t)layer * n + j) * n + i);
-    return mk3(c.x, c.y, c.z);
-}
-__device__ __forceinline__ float tex_bilinear1(const float* base, int layer, int n, float u, float v) {
-    const float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
-    const float fx0 = floorf(x), fy0 = floorf(y);
-    const float fx = x - fx0, fy = y - fy0;
-    const int i0 = ((int)fx0) & (n - 1), i1 = ((int)fx0 + 1) & (n - 1);
-    const int j0 = ((int)fy0) & (n - 1), j1 = ((int)fy0 + 1) & (n - 1);
-    const float* L = base + (size_t)layer * n * n;
-    const float a = L[j0 * n + i0] * (1.0f - fx) + L[j0 * n + i1] * fx;
-    const float b = L[j1 * n + i0] * (1.0f - fx) + L[j1 * n + i1] * fx;
-    return a * (1.0f - fy) + b * fy;
-}
-
-// InverseSchlick :1305-1308, DiffuseHammon :1311-1332 (rcp(x) == 1.0f / x)
-__device__ __forceinline__ float inverse_schlick(float f0, float voh) {
-    return 1.0f - clampf(f0 + (1.0f - f0) * pow_cr(1.0f - voh, 5.0f), 0.0f, 1.0f);
-}
-__device__ __forceinline__ float diffuse_hammon(V3 n, V3 view, V3 light, float rough) {
-    const float ndl = fmaxf(dot3(n, light), 0.0f);
-    if (ndl <= 0.0f) return 0.0f;
-    const float ndv = fmaxf(dot3(n, view), 0.0f);
-    const float ldv = fmaxf(dot3(light, view), 0.0f);
-    const V3 hw = normalize3(view + light);
-    const float ndh = fmaxf(dot3(n, hw), 0.0f);
-    const float facing = ldv * 0.5f + 0.5f;
-    const float single_rough = facing * (0.9f - 0.4f * facing) * ((0.5f + ndh) * (1.0f / fmaxf(ndh, 0.02f)));
-    const float single_smooth = 1.05f * inverse_schlick(0.0f, ndl) * inverse_schlick(0.0f, fmaxf(ndv, 0.0f));
-    const float single = clampf(mixf(single_smooth, single_rough, rough) * (1.0f / PI_F), 0.0f, 1.0f);
-    const float multi = 0.1159f * rough;
-    return clampf((multi + single) * ndl, 0.0f, 1.0f);
-}
-
-// SampleBlueNoise2D :811-818 + cosWeightedRandomHemisphereDirection :945-967
-__device__ __forceinline__ V3 cos_hemisphere(const SceneDev& S, int px, int py, int frame_mod128, int& bl_sample, V3 n) {
-    const float r1 = blue_noise_1d(S, px, py, frame_mod128, 1 + bl_sample);
-    const float r2 = blue_noise_1d(S, px, py, frame_mod128, 2 + bl_sample);
-    bl_sample += 2;
-    const float PI2 = 2.0f * PI_F;
-    const V3 uu = normalize3(cross3(n, mk3(0.0f, 1.0f, 1.0f)));
-    const V3 vv = cross3(uu, n);
-    const float ra = sqrtf(r2);
-    const float rx = ra * cos_cr(PI2 * r1);
-    const float ry = ra * sin_cr(PI2 * r1);
-    const float rz = sqrtf(1.0f - r2);
-    const V3 rr = (rx * uu + ry * vv) + rz * n;
-    return normalize3(rr);
-}
-
-// CalculateUV :1235-1273 on an exact axis normal
-__device__ __forceinline__ void calc_uv(V3 p, int axis, float& u, float& v) {
-    if (axis == 1) { u = fractf(p.x); v = fractf(p.z); }
-    else if (axis == 0) { u = fractf(p.z); v = fractf(p.y); }
-    else { u = fractf(p.x); v = fractf(p.y); }
-}
-
-// IrridianceToSH :766-784
-__device__ __forceinline__ void irradiance_to_sh(V3 rad, V3 dir, float out[6]) {
-    const float Co = rad.x - rad.z;
-    const float T = rad.z + Co * 0.5f;
-    const float Cg = rad.y - T;
-    const float Y = fmaxf(T + Cg * 0.5f, 0.0f);
-    const float L00 = 0.282095f;
-    const float L1_1 = 0.488603f * dir.y, L10 = 0.488603f * dir.z, L11 = 0.488603f * dir.x;
-    out[0] = fmaxf(L11 * Y, -100.0f);
-    out[1] = fmaxf(L1_1 * Y, -100.0f);
-    out[2] = fmaxf(L10 * Y, -100.0f);
-    out[3] = fmaxf(L00 * Y, -100.0f);
-    out[4] = Co;
-    out[5] = Cg;
-}
-
 // CalculateDiffuse :535-664, one sample
 template <int LAYOUT>
 __device__ __forceinline__ void calculate_diffuse(const SceneDev& S, const DiffuseDev& P, int px, int py, int& bl_sample, V3 initial_origin,
@@ -473,6 +333,7 @@ int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const V
     d.frame = p.frame; d.supersample = p.supersample;
     d.hx = p.halton[0]; d.hy = p.halton[1];
     d.sun_visibility = p.sun_visibility; d.gi_sky_strength = p.gi_sky_strength; d.light_intensity = p.light_intensity;
+    if (c->opt_wavefront) return launch_diffuse_wavefront(c, cam, d, g, out);
     const DiffuseOutDev od{reinterpret_cast<float4*>(out.sh), reinterpret_cast<float2*>(out.cocg), out.luma,
                            reinterpret_cast<float2*>(out.ao_sky)};
     const dim3 grid = pixel_grid(cam);

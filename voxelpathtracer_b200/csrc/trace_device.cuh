@@ -65,81 +65,99 @@ struct TraceHit {
     int vx, vy, vz;
 };
 
-// IsInVolume (InitialRayTraceFrag.glsl:68-78) applied to floor()ed coordinates.  NaN compares false -> outside.
-__device__ __forceinline__ bool in_volume_f(float fx, float fy, float fz) {
-    return fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx <= (float)(WX - 1) && fy <= (float)(WY - 1) && fz <= (float)(WZ - 1);
+// ---- exact floor without the quarter-rate conversion pipe ---------------------------------------------------
+// For |x| < 2^22, x + 1.5*2^23 rounded toward -inf lands on an integer of [2^23, 2^24), whose mantissa holds
+// floor(x) in two's complement offset form: floor(x) = bits(sum) - bits(1.5*2^23).  FADD.RM and IADD are full-rate,
+// FRND/F2I/I2F are not (ncu r01a: the loop was bound by the XU pipe).  Anything outside that range, +-inf and NaN map
+// to an index outside [0, 383], i.e. "outside the volume" — the same verdict IsInVolume gives (NaN compares false;
+// SURVEY.md A.3 note 5).
+constexpr float FLOOR_MAGIC = 12582912.0f;      // 1.5 * 2^23
+constexpr int FLOOR_MAGIC_BITS = 0x4B400000;    // its bit pattern
+__device__ __forceinline__ float floor_biased(float x) { return __fadd_rd(x, FLOOR_MAGIC); }
+__device__ __forceinline__ int biased_to_int(float b) { return __float_as_int(b) - FLOOR_MAGIC_BITS; }
+__device__ __forceinline__ float biased_to_float(float b) { return b - FLOOR_MAGIC; }  // exact
+// IsInVolume (InitialRayTraceFrag.glsl:68-78) on floor()ed coordinates
+__device__ __forceinline__ bool in_volume_i(int x, int y, int z) {
+    return (unsigned)x < (unsigned)WX && (unsigned)y < (unsigned)WY && (unsigned)z < (unsigned)WZ;
 }
 
+// Step field: E(M) = (M == 1) ? 1 : floor(M * 0.57735026918f) per voxel (ToConservativeEuclidean + floor,
+// InitialRayTraceFrag.glsl:90-93,329), converted once per distance-field build (pack_steps in df_build.cu).
 template <int LAYOUT>
-__device__ __forceinline__ int fetch_manhattan(const SceneDev& S, int x, int y, int z) {
+__device__ __forceinline__ int fetch_step(const SceneDev& S, int x, int y, int z) {
     if (LAYOUT == 1) return S.steps[brick_offset(x, y, z)];
-    return S.df[(size_t)x + (size_t)WX * ((size_t)y + (size_t)WY * (size_t)z)];
+    return S.steps[(uint32_t)x + (uint32_t)WX * ((uint32_t)y + (uint32_t)WY * (uint32_t)z)];
 }
 
 // GetVoxel(ivec3(floor(p))) — InitialRayTraceFrag.glsl:80-88
 __device__ __forceinline__ int get_voxel_at(const SceneDev& S, V3 p, Counters& cnt, int* vx = nullptr, int* vy = nullptr, int* vz = nullptr) {
-    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
-    if (!in_volume_f(fx, fy, fz)) return 0;
-    const int x = (int)fx, y = (int)fy, z = (int)fz;
+    const int x = biased_to_int(floor_biased(p.x)), y = biased_to_int(floor_biased(p.y)), z = biased_to_int(floor_biased(p.z));
+    if (!in_volume_i(x, y, z)) return 0;
     if (vx) { *vx = x; *vy = y; *vz = z; }
     cnt.vox++;
-    return S.grid[(size_t)x + (size_t)WX * ((size_t)y + (size_t)WY * (size_t)z)];
+    return S.grid[(uint32_t)x + (uint32_t)WX * ((uint32_t)y + (uint32_t)WY * (uint32_t)z)];
 }
 
 // VoxelTraversalDF — InitialRayTraceFrag.glsl:307-374.  SURVEY.md A.3.
+// Every arithmetic result equals the GLSL expression it stands for:
+//  * int<->float conversions of small integers are exact whichever way they are computed;
+//  * on the stepped axis the shader computes float(Grid + RaySign) + float(1 - half), an exact small integer, and then
+//    adds RaySign * 0.0001f (one rounding): written here as (g + k) + n with k = RaySign + (1 - half);
+//  * "Intersection = false" on leaving the volume is dropped: the final position is then outside the volume, GetVoxel
+//    returns 0 and the function returns -1 either way (:362-367), so a sticky "a DDA step happened" flag suffices;
+//  * the loop counter doubles as the distance-field fetch count (an iteration that fails the bounds test ends the loop).
 template <int LAYOUT>
-__device__ __forceinline__ float traverse_df(const SceneDev& S, V3 origin, const V3 dir, const int max_it, TraceHit& h, Counters& cnt) {
-    const V3 initial_origin = origin;
-    bool intersection = false;
-    int min_idx = 0;
+__device__ __forceinline__ float traverse_df(const SceneDev& S, const V3 origin, const V3 dir, const int max_it, TraceHit& h, Counters& cnt) {
     const int sx = (dir.x > 0.0f) - (dir.x < 0.0f), sy = (dir.y > 0.0f) - (dir.y < 0.0f), sz = (dir.z > 0.0f) - (dir.z < 0.0f);
-    const int hx = (1 + sx) >> 1, hy = (1 + sy) >> 1, hz = (1 + sz) >> 1;
-    const float ivx = 1.0f / dir.x, ivy = 1.0f / dir.y, ivz = 1.0f / dir.z;  // (1.0f / direction), loop invariant
+    const float fsx = (float)sx, fsy = (float)sy, fsz = (float)sz;                        // RaySign as floats
+    const float hx = (float)((1 + sx) >> 1), hy = (float)((1 + sy) >> 1), hz = (float)((1 + sz) >> 1);
+    const float kx = fsx + (1.0f - hx), ky = fsy + (1.0f - hy), kz = fsz + (1.0f - hz);  // RaySign + (1 - half)
+    const float nx = fsx * 0.0001f, ny = fsy * 0.0001f, nz = fsz * 0.0001f;               // RaySign * 0.0001f
+    const float ivx = 1.0f / dir.x, ivy = 1.0f / dir.y, ivz = 1.0f / dir.z;               // (1.0f / direction)
+    const bool sx_nz = sx != 0, sz_z = sz == 0;
+    float ox = origin.x, oy = origin.y, oz = origin.z;
+    int stepped = 0, min_idx = 0, n = 0;
     cnt.rays++;
-    for (int itr = 0; itr < max_it; ++itr) {
-        const float fx = floorf(origin.x), fy = floorf(origin.y), fz = floorf(origin.z);
-        if (!in_volume_f(fx, fy, fz)) { intersection = false; break; }
-        const int lx = (int)fx, ly = (int)fy, lz = (int)fz;
-        cnt.df++;
-        const int m = fetch_manhattan<LAYOUT>(S, lx, ly, lz);
-        // ToConservativeEuclidean + floor (:90-93, :329)
-        const int euclid = (m == 1) ? 1 : (int)floorf((float)m * 0.57735026918f);
-        if (euclid == 0) break;
-        if (euclid == 1) {
-            // in-volume => origin >= 0, so ivec3(origin) (truncation) == Loc
-            int gx = lx, gy = ly, gz = lz;
-            float wx = origin.x - (float)gx, wy = origin.y - (float)gy, wz = origin.z - (float)gz;
-            const float dfx = ((float)hx - wx) * ivx, dfy = ((float)hy - wy) * ivy, dfz = ((float)hz - wz) * ivz;
-            min_idx = (dfx < dfy && sx != 0) ? ((dfx < dfz || sz == 0) ? 0 : 2) : ((dfy < dfz || sz == 0) ? 1 : 2);
-            const float fm = (min_idx == 0) ? dfx : ((min_idx == 1) ? dfy : dfz);
-            wx = wx + dir.x * fm;
-            wy = wy + dir.y * fm;
-            wz = wz + dir.z * fm;
-            if (min_idx == 0) { gx += sx; wx = (float)(1 - hx); }
-            else if (min_idx == 1) { gy += sy; wy = (float)(1 - hy); }
-            else { gz += sz; wz = (float)(1 - hz); }
-            origin.x = (float)gx + wx;
-            origin.y = (float)gy + wy;
-            origin.z = (float)gz + wz;
-            if (min_idx == 0) origin.x += (float)sx * 0.0001f;
-            else if (min_idx == 1) origin.y += (float)sy * 0.0001f;
-            else origin.z += (float)sz * 0.0001f;
-            intersection = true;
-        } else {
+    while (n < max_it) {
+        const float bx = floor_biased(ox), by = floor_biased(oy), bz = floor_biased(oz);
+        const int lx = biased_to_int(bx), ly = biased_to_int(by), lz = biased_to_int(bz);
+        if (!in_volume_i(lx, ly, lz)) break;
+        ++n;
+        const int euclid = fetch_step<LAYOUT>(S, lx, ly, lz);
+        if (euclid >= 2) {
             const float k = (float)(euclid - 1);
-            origin.x = origin.x + k * dir.x;
-            origin.y = origin.y + k * dir.y;
-            origin.z = origin.z + k * dir.z;
+            ox = ox + k * dir.x;
+            oy = oy + k * dir.y;
+            oz = oz + k * dir.z;
+            continue;
         }
+        if (euclid == 0) break;
+        // euclid == 1: one DDA step.  in-volume => origin >= 0, so ivec3(origin) (truncation) == Loc
+        const float gx = biased_to_float(bx), gy = biased_to_float(by), gz = biased_to_float(bz);
+        const float wx = ox - gx, wy = oy - gy, wz = oz - gz;
+        const float dfx = (hx - wx) * ivx, dfy = (hy - wy) * ivy, dfz = (hz - wz) * ivz;
+        const bool p = dfx < dfy && sx_nz;
+        const float c = p ? dfx : dfy;
+        const bool q = c < dfz || sz_z;
+        const float fm = q ? c : dfz;
+        min_idx = q ? (p ? 0 : 1) : 2;
+        const float ax = gx + (wx + dir.x * fm), ay = gy + (wy + dir.y * fm), az = gz + (wz + dir.z * fm);
+        const float sxp = (gx + kx) + nx, syp = (gy + ky) + ny, szp = (gz + kz) + nz;
+        ox = (q && p) ? sxp : ax;
+        oy = (q && !p) ? syp : ay;
+        oz = q ? az : szp;
+        stepped = 1;
     }
+    cnt.df += n;
     h.min_idx = min_idx;
     h.sgn = (min_idx == 0) ? sx : ((min_idx == 1) ? sy : sz);
     h.block = 0;
     h.vx = h.vy = h.vz = -1;
     h.t = -1.0f;
-    if (intersection) {
-        h.block = get_voxel_at(S, origin, cnt, &h.vx, &h.vy, &h.vz);
-        if (h.block > 0) h.t = length3(origin - initial_origin);
+    if (stepped) {
+        const V3 pos = mk3(ox, oy, oz);
+        h.block = get_voxel_at(S, pos, cnt, &h.vx, &h.vy, &h.vz);
+        if (h.block > 0) h.t = length3(pos - origin);
         else h.vx = h.vy = h.vz = -1;
     }
     return h.t;

@@ -1,0 +1,322 @@
+// trace_gi.cu — wavefront form of the diffuse-GI pass (DiffuseRayTraceFrag.glsl main() :822-935, CalculateDiffuse :535-664).
+//
+// The one-thread-per-pixel form (diffuse_kernel in trace.cu) runs 9 of 32 lanes per instruction on open terrain: most
+// first-bounce rays escape to the sky while the few that hit geometry drag their warp through texture fetches, a shadow
+// sub-ray, a second traversal and a second shadow sub-ray (ncu r01a).  Here the work of one sample is re-queued:
+//
+//   gi_gen_trace0  one thread per pixel: first hemisphere direction (blue-noise tables), first traversal.  A miss is
+//                  finished on the spot (sky radiance).  Hits are compacted into a queue with one warp ballot +
+//                  one atomicAdd per warp (popc / prefix ranks give each lane its slot).
+//   gi_continue    one thread per queued hit (dense warps): shading of the first hit, its sun shadow sub-ray, the
+//                  second traversal, shading + shadow sub-ray of the second hit, end of the sample.
+//   gi_finalize    only when some pixel takes more than one sample: per-pixel averages and clamps (:915-934).
+//
+// Samples of one pixel are processed one after another (launch s+1 after launch s), so the blue-noise dimension counter
+// and the accumulation order are exactly those of the shader's loop; the planes are bit-identical to diffuse_kernel's.
+#include <algorithm>
+
+#include "gi_device.cuh"
+
+namespace vxpt {
+
+struct HitRec {   // 48 B
+    float4 a;     // ro.xyz, T
+    float4 b;     // rd.xyz, pixel index (bits)
+    float4 c;     // hit code (bits): min_idx | (sgn+1) << 2 | block << 8 ; bl_sample (bits) ; unused
+};
+struct PixState { // 48 B, only when spp > 1 somewhere
+    float4 tot;   // SH sums
+    float4 rad;   // radiance sum xyz, AO sum
+    float4 misc;  // CoCg sums, sky-hit sum, bl_sample (bits)
+};
+
+// SPP of a pixel — DiffuseRayTraceFrag.glsl:874-892
+__device__ __forceinline__ int pixel_spp(const DiffuseDev& P, int i, int j) {
+    int spp = min(max(P.spp, 1), 32);
+    if (P.checkerboard) {
+        const bool checker = ((int)(((float)i + 0.5f) + ((float)j + 0.5f))) % 2 == P.frame % 2;
+        spp = (int)mixf((float)P.spp, (float)P.checker_spp, checker ? 1.0f : 0.0f);
+    }
+    spp = min(max(spp, 1), 32);
+    if (P.moon_stronger) spp *= 2;
+    return spp;
+}
+
+// :915-934 — averages, luminance, clamps, stores
+__device__ __forceinline__ void write_final(const DiffuseOutDev& out, size_t px, V3 radiance, float acc_ao, float t0, float t1, float t2, float t3,
+                                            float c0, float c1, float skyhits, int spp) {
+    const float fs = (float)spp;
+    acc_ao /= fs;
+    t0 /= fs; t1 /= fs; t2 /= fs; t3 /= fs;
+    c0 /= fs; c1 /= fs;
+    radiance = radiance / fs;
+    skyhits /= fs;
+    const float lum = dot3(radiance, mk3(0.299f, 0.587f, 0.114f));
+    float util = fmaxf(lum, 0.01f);
+    util = clampf(util, 0.001f, 64.0f);
+    if (out.sh) out.sh[px] = make_float4(clampf(t0, -100.0f, 100.0f), clampf(t1, -100.0f, 100.0f), clampf(t2, -100.0f, 100.0f), clampf(t3, -100.0f, 100.0f));
+    if (out.cocg) out.cocg[px] = make_float2(clampf(c0, -100.0f, 100.0f), clampf(c1, -100.0f, 100.0f));
+    if (out.luma) out.luma[px] = util;
+    if (out.ao_sky) out.ao_sky[px] = make_float2(clampf(acc_ao, 0.0f, 1.0f), clampf(skyhits, 0.0f, 1.0f));
+}
+
+// end of one sample (:898-913): clamp, SH projection, accumulate (or, when every pixel takes one sample, finish)
+template <bool SPP1>
+__device__ __forceinline__ void finish_sample(const DiffuseOutDev& out, PixState* state, size_t px, V3 rad, float ao, V3 odir, bool skyhit, int bl_sample) {
+    rad = mk3(clampf(rad.x, 0.0f, 8.0f), clampf(rad.y, 0.0f, 8.0f), clampf(rad.z, 0.0f, 8.0f));
+    float sh[6];
+    irradiance_to_sh(rad, odir, sh);
+    const float ss = skyhit ? 1.0f : 0.0f;
+    if (SPP1) {
+        // sums start at 0: 0 + x == x, and x / 1.0f == x, so the single sample goes straight to the final stage
+        write_final(out, px, mk3(0.f, 0.f, 0.f) + rad, 0.0f + ao, 0.0f + sh[0], 0.0f + sh[1], 0.0f + sh[2], 0.0f + sh[3], 0.0f + sh[4], 0.0f + sh[5],
+                    0.0f + ss, 1);
+    } else {
+        PixState st = state[px];
+        st.tot.x += sh[0]; st.tot.y += sh[1]; st.tot.z += sh[2]; st.tot.w += sh[3];
+        st.rad.x = st.rad.x + rad.x; st.rad.y = st.rad.y + rad.y; st.rad.z = st.rad.z + rad.z; st.rad.w += ao;
+        st.misc.x += sh[4]; st.misc.y += sh[5]; st.misc.z += ss;
+        st.misc.w = __int_as_float(bl_sample);
+        state[px] = st;
+    }
+}
+
+// sky term of a ray that leaves the scene (:625-634)
+__device__ __forceinline__ V3 sky_term(const SceneDev& S, const DiffuseDev& P, V3 rd) {
+    float x = mixf(1.0f, 1.05f, P.sun_visibility);
+    x = clampf(x * 1.0f * P.gi_sky_strength, 0.0f, 5.0f);
+    V3 sd = rd;
+    sd.y = clampf(sd.y, 0.125f, 1.5f);  // GetSkyColorAt :984-988
+    return sky_sample(S, sd) * x;
+}
+
+// shading of one hit (:569-622).  NEXT: also draw the next direction and update the throughput / ray.
+template <int LAYOUT, bool NEXT>
+__device__ __forceinline__ void shade_hit(const SceneDev& S, const DiffuseDev& P, int pi, int pj, int& bl_sample, V3& ro, V3& rd, float T, int min_idx,
+                                          int sgn, int block, V3& thr, V3& contrib, Counters& cnt) {
+    const float bias = 0.06f;
+    const int tex_ref = min(max(block, 0), 127);
+    const V3 ipos = ro + (rd * T);
+    const float s = (float)(-sgn);
+    const V3 hn = mk3(min_idx == 0 ? s : 0.0f, min_idx == 1 ? s : 0.0f, min_idx == 2 ? s : 0.0f);
+    float tu, tv;
+    calc_uv(ipos, min_idx, tu, tv);
+    const int albedo_layer = S.materials[tex_ref], emissive_layer = S.materials[384 + tex_ref];
+    const V3 albedo = tex_nearest(S.albedo_lod3, albedo_layer, 64, tu, tv);
+    const V3 pbr = tex_nearest(S.pbr_lod2, albedo_layer, 128, tu, tv);  // sic: albedo layer (:578)
+    float emis = 0.0f;
+    if ((float)emissive_layer >= 0.0f) {
+        const float se = tex_bilinear1(S.emissive, emissive_layer, 512, tu, tv);
+        emis = se * P.emissivity_mult * P.light_intensity;
+    }
+    const float ndl = fmaxf(dot3(hn, P.stronger_dir), 0.0f);
+    float shadow_at;
+    if (P.moon_stronger) shadow_at = 1.0f;
+    else if (ndl < 0.001f) shadow_at = 0.0f;
+    else {  // GetShadowAt :1202-1222 (u_APPLY_PLAYER_SHADOW = false)
+        TraceHit hs;
+        const float Ts = traverse_df<LAYOUT>(S, ipos + hn * 0.045f, P.stronger_dir, 128, hs, cnt);
+        shadow_at = Ts > 0.0f ? 1.0f : 0.0f;
+    }
+    const V3 emis_color = (emis * mixf(1.0f, 1.0f, P.sun_visibility)) * albedo;
+    const V3 neg_rd = -rd;
+    const V3 sunbrdf = (((albedo * diffuse_hammon(hn, neg_rd, P.stronger_dir, pbr.x)) * (P.light_color * 3.5f)) * (1.0f - shadow_at)) * PI_F;
+    contrib = contrib + thr * sunbrdf;
+    contrib = contrib + emis_color * thr;
+    if (NEXT) {
+        const V3 new_dir = cos_hemisphere(S, pi, pj, P.frame % 128, bl_sample, hn);
+        const float cos_theta = clampf(dot3(hn, new_dir), 0.0f, 1.0f);
+        const float pdf = fmaxf(cos_theta / PI_F, 0.00001f);
+        const V3 atten = mk3(1.f, 1.f, 1.f) * diffuse_hammon(hn, neg_rd, new_dir, pbr.x);
+        thr = thr * ((albedo * atten) / pdf);
+        rd = new_dir;
+        ro = ipos + hn * bias;
+    } else {
+        bl_sample += 2;  // the shader still draws the direction of a third segment it never traces (:607)
+    }
+}
+
+// one warp ballot + one atomic per warp; returns this lane's slot (valid where pred)
+__device__ __forceinline__ unsigned warp_push(unsigned* counter, bool pred) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0 && mask) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+template <int LAYOUT, bool SPP1>
+__global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
+                                                     const DiffuseOutDev out, PixState* __restrict__ state, HitRec* __restrict__ queue,
+                                                     unsigned* __restrict__ queue_count, const int sample) {
+    int i, j;
+    const bool active = thread_pixel(cam, i, j);
+    Counters cnt = {0u, 0u, 0u};
+    bool push = false;
+    HitRec rec;
+    if (active) {
+        const size_t px = (size_t)j * cam.width + i;
+        float u = ((float)i + 0.5f) / (float)cam.width;
+        float v = ((float)j + 0.5f) / (float)cam.height;
+        const float u0 = u, v0 = v;
+        if (P.supersample) {
+            u += (P.hx * 0.75f) / (float)cam.width;
+            v += (P.hy * 0.75f) / (float)cam.height;
+        }
+        const float dist = g.t[px];
+        const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
+        if (dist < 0.0f) {
+            if (sample == 0) {  // sky pixel (:866-872)
+                float sh[6];
+                const V3 vdir = normalize3(ray_direction_at(cam, u0, v0));
+                irradiance_to_sh(sky_sample(S, vdir) * 2.66f, normal, sh);
+                if (out.sh) out.sh[px] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+                if (out.cocg) out.cocg[px] = make_float2(sh[4], sh[5]);
+                if (out.luma) out.luma[px] = 0.0f;
+                if (out.ao_sky) out.ao_sky[px] = make_float2(1.0f, 0.0f);
+            }
+        } else if (sample < pixel_spp(P, i, j)) {
+            int bl_sample = 0;
+            if (!SPP1) {
+                if (sample == 0) {
+                    PixState z;
+                    z.tot = z.rad = z.misc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    state[px] = z;
+                } else {
+                    bl_sample = __float_as_int(state[px].misc.w);
+                }
+            }
+            const V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, u, v)) * dist;
+            const V3 ro = pos + normal * 0.06f;
+            const V3 rd = cos_hemisphere(S, i, j, P.frame % 128, bl_sample, normal);
+            TraceHit h;
+            const float T = traverse_df<LAYOUT>(S, ro, rd, P.trace_length, h, cnt);
+            if (T > 0.0f && h.block > 0) {
+                push = true;
+                rec.a = make_float4(ro.x, ro.y, ro.z, T);
+                rec.b = make_float4(rd.x, rd.y, rd.z, __int_as_float((int)px));
+                rec.c = make_float4(__int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8)), __int_as_float(bl_sample), 0.f, 0.f);
+            } else {
+                const V3 contrib = mk3(0.f, 0.f, 0.f) + sky_term(S, P, rd) * mk3(1.f, 1.f, 1.f);
+                finish_sample<SPP1>(out, state, px, contrib, 1.0f, rd, true, bl_sample);
+            }
+        }
+    }
+    const unsigned slot = warp_push(queue_count, push);
+    if (push) queue[slot] = rec;
+    flush_counters(S, cnt);
+}
+
+template <int LAYOUT, bool SPP1>
+__global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const DiffuseDev P, const int width, const DiffuseOutDev out,
+                                                   PixState* __restrict__ state, const HitRec* __restrict__ queue,
+                                                   const unsigned* __restrict__ queue_count) {
+    const unsigned count = *queue_count;
+    Counters cnt = {0u, 0u, 0u};
+    const unsigned stride = gridDim.x * blockDim.x;
+    // warp-uniform trip count so every lane reaches flush_counters together
+    for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += stride) {
+        const unsigned idx = base + (threadIdx.x & 31);
+        if (idx >= count) continue;
+        const HitRec rec = queue[idx];
+        V3 ro = mk3(rec.a.x, rec.a.y, rec.a.z), rd = mk3(rec.b.x, rec.b.y, rec.b.z);
+        const float T0 = rec.a.w;
+        const size_t px = (size_t)(unsigned)__float_as_int(rec.b.w);
+        const int pi = (int)(px % (size_t)width), pj = (int)(px / (size_t)width);
+        const int code = __float_as_int(rec.c.x);
+        int bl_sample = __float_as_int(rec.c.y);
+        const V3 odir = rd;
+        V3 thr = mk3(1.f, 1.f, 1.f), contrib = mk3(0.f, 0.f, 0.f);
+        bool skyhit = false;
+        // bounce 0 hit
+        shade_hit<LAYOUT, true>(S, P, pi, pj, bl_sample, ro, rd, T0, code & 3, ((code >> 2) & 3) - 1, (code >> 8) & 255, thr, contrib, cnt);
+        float ao = 1.0f;
+        if (T0 < 2.0f && T0 > 0.0f) ao = fmaxf(T0 / 2.0f, 0.0f);  // :637-650
+        // bounce 1
+        TraceHit h;
+        const float T1 = traverse_df<LAYOUT>(S, ro, rd, P.trace_length, h, cnt);
+        if (T1 > 0.0f && h.block > 0) {
+            shade_hit<LAYOUT, false>(S, P, pi, pj, bl_sample, ro, rd, T1, h.min_idx, h.sgn, h.block, thr, contrib, cnt);
+        } else {
+            contrib = contrib + sky_term(S, P, rd) * thr;
+            skyhit = true;
+        }
+        finish_sample<SPP1>(out, state, px, contrib, ao, odir, skyhit, bl_sample);
+    }
+    flush_counters(S, cnt);
+}
+
+__global__ void __launch_bounds__(256) gi_finalize(const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g, const DiffuseOutDev out,
+                                                   const PixState* __restrict__ state) {
+    int i, j;
+    if (!thread_pixel(cam, i, j)) return;
+    const size_t px = (size_t)j * cam.width + i;
+    if (g.t[px] < 0.0f) return;
+    const PixState st = state[px];
+    write_final(out, px, mk3(st.rad.x, st.rad.y, st.rad.z), st.rad.w, st.tot.x, st.tot.y, st.tot.z, st.tot.w, st.misc.x, st.misc.y, st.misc.z,
+                pixel_spp(P, i, j));
+}
+
+static CameraDev cam_to_dev(const VxCamera& cam) {
+    CameraDev c;
+    for (int k = 0; k < 16; ++k) { c.inv_view[k] = cam.inv_view[k]; c.inv_proj[k] = cam.inv_proj[k]; }
+    c.width = cam.width; c.height = cam.height; c.row_begin = cam.row_begin; c.row_end = cam.row_end;
+    return c;
+}
+
+template <int LAYOUT, bool SPP1>
+static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, const DiffuseDev& d, const GBufferDev& g, const DiffuseOutDev& od,
+                         PixState* state, HitRec* queue, unsigned* count, int max_spp) {
+    const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
+    for (int s = 0; s < max_spp; ++s) {
+        VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned), c->stream));
+        gi_gen_trace0<LAYOUT, SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s);
+        gi_continue<LAYOUT, SPP1><<<148 * 8, 128, 0, c->stream>>>(S, d, cd.width, od, state, queue, count);
+        c->launches += 2;
+    }
+    if (!SPP1) {
+        gi_finalize<<<grid, 256, 0, c->stream>>>(cd, d, g, od, state);
+        c->launches += 1;
+    }
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev& d, const VxGBuffer& g, const VxDiffuseOut& out) {
+    const SceneDev S = make_scene(c);
+    const CameraDev cd = cam_to_dev(cam);
+    const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel};
+    const DiffuseOutDev od{reinterpret_cast<float4*>(out.sh), reinterpret_cast<float2*>(out.cocg), out.luma, reinterpret_cast<float2*>(out.ao_sky)};
+    // the largest per-pixel sample count (pixel_spp on the host)
+    const int base = std::min(std::max(d.spp, 1), 32);
+    int max_spp = base;
+    if (d.checkerboard) max_spp = std::max(std::min(std::max(d.spp, 1), 32), std::min(std::max(d.checker_spp, 1), 32));
+    if (d.moon_stronger) max_spp *= 2;
+    const bool spp1 = max_spp == 1;
+    // queues: slab-sized hit queue (+ full-frame per-pixel state when some pixel takes several samples)
+    const size_t slab_px = (size_t)(cam.row_end - cam.row_begin) * cam.width, frame_px = (size_t)cam.width * cam.height;
+    const size_t need = 256 + slab_px * sizeof(HitRec) + (spp1 ? 0 : frame_px * sizeof(PixState));
+    if (need > c->queue_bytes) {
+        VX_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->d_queue) cudaFree(c->d_queue);
+        c->d_queue = nullptr;
+        c->queue_bytes = 0;
+        if (cudaMalloc(&c->d_queue, need) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("wavefront queue allocation failed");
+            return VXPT_E_NOMEM;
+        }
+        c->queue_bytes = need;
+    }
+    unsigned* count = static_cast<unsigned*>(c->d_queue);
+    HitRec* queue = reinterpret_cast<HitRec*>(static_cast<char*>(c->d_queue) + 256);
+    PixState* state = spp1 ? nullptr : reinterpret_cast<PixState*>(static_cast<char*>(c->d_queue) + 256 + slab_px * sizeof(HitRec));
+    if (c->opt_layout == 1)
+        return spp1 ? run_wavefront<1, true>(c, S, cd, d, gd, od, state, queue, count, max_spp)
+                    : run_wavefront<1, false>(c, S, cd, d, gd, od, state, queue, count, max_spp);
+    return spp1 ? run_wavefront<0, true>(c, S, cd, d, gd, od, state, queue, count, max_spp)
+                : run_wavefront<0, false>(c, S, cd, d, gd, od, state, queue, count, max_spp);
+}
+
+}  // namespace vxpt

@@ -15,21 +15,18 @@ constexpr int WZ = VXPT_WORLD_SIZE_Z;  // 384
 constexpr size_t VOXELS = (size_t)WX * WY * WZ;
 constexpr int SLICE_BYTES = WX * WY;  // one z-slice: 49,152 B
 
-// ---- brick-swizzled step field -----------------------------------------------------------------------------
+// ---- tiled step field ("bricks") --------------------------------------------------------------------------------
 // Traversal never needs the Manhattan value M itself, only E(M) = (M==1) ? 1 : floor(M * 0.57735026918f)
-// (ToConservativeEuclidean, InitialRayTraceFrag.glsl:90-93,329).  The step field stores E (<= 146) per voxel in
-// 8x4x4-voxel bricks of 128 B (one L1 line); inside a brick the low 5 address bits cover a 4x2x4 block (one
-// 32-B sector), so a sector holds a 3-D neighbourhood instead of a 32-voxel x-run.
-constexpr int BRICK_X = 8, BRICK_Y = 4, BRICK_Z = 4;
-constexpr int BRICKS_X = WX / BRICK_X;  // 48
-constexpr int BRICKS_Y = WY / BRICK_Y;  // 32
-constexpr int BRICKS_Z = WZ / BRICK_Z;  // 96
+// (ToConservativeEuclidean, InitialRayTraceFrag.glsl:90-93,329).  The step field stores E (<= 146) per voxel.
+// Layout 1 tiles it into 8x4x4-voxel bricks of 128 B (one L1 line) whose low 5 address bits cover 4x x 4z x 2y voxels
+// (one 32-B sector = a 3-D neighbourhood instead of a 32-voxel x-run).  The brick grid is padded to powers of two
+// (64 x 32 x 96 bricks) so the address is three independent bit-deposits, one LOP3 + IMAD each:
+//   bits 0-1 x&3 | 2-3 z&3 | 4-5 y&3 | 6 (x>>2)&1 | 7-12 x>>3 | 13-17 y>>2 | 18-24 z>>2
+constexpr size_t STEPS_TILED_BYTES = (size_t)96 << 18;  // 25,165,824 B (x padded 48 -> 64 bricks)
 
 __host__ __device__ __forceinline__ uint32_t brick_offset(int x, int y, int z) {
-    uint32_t brick = ((uint32_t)(z >> 2) * BRICKS_Y + (uint32_t)(y >> 2)) * BRICKS_X + (uint32_t)(x >> 3);
-    uint32_t local = (uint32_t)(x & 3) | ((uint32_t)(y & 1) << 2) | ((uint32_t)(z & 3) << 3) |
-                     ((uint32_t)((y >> 1) & 1) << 5) | ((uint32_t)((x >> 2) & 1) << 6);
-    return brick * 128u + local;
+    const uint32_t ux = (uint32_t)x, uy = (uint32_t)y, uz = (uint32_t)z;
+    return (ux + (ux & ~3u) * 15u) + (uy * 16u + (uy & ~3u) * 2032u) + (uz * 4u + (uz & ~3u) * 65532u);
 }
 
 struct DeviceCounters {
@@ -40,7 +37,7 @@ struct DeviceCounters {
 struct SceneDev {
     const uint8_t* grid;       // block ids, linear x + 384*(y + 128*z)
     const uint8_t* df;         // Manhattan distance field, linear
-    const uint8_t* steps;      // brick-swizzled E field
+    const uint8_t* steps;      // step field E(M), bricks (layout 1) or linear (layout 0)
     const int32_t* materials;  // 768
     const uint8_t* sobol;      // 65536   (blue-noise tables hold values < 256: kept as bytes, 320 KB total)
     const uint8_t* scramble;   // 131072
@@ -87,6 +84,7 @@ struct vxpt_ctx {
 
     // options
     int opt_layout = 1;     // VXPT_OPT_TRAVERSAL_LAYOUT
+    int steps_layout = -1;  // layout the step field currently holds
     int opt_wavefront = 1;  // VXPT_OPT_GI_WAVEFRONT
     int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped), 1 = DPX tiled
 

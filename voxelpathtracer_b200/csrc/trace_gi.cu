@@ -211,13 +211,19 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
 template <int LAYOUT, bool SPP1>
 __global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const DiffuseDev P, const int width, const DiffuseOutDev out,
                                                    PixState* __restrict__ state, const HitRec* __restrict__ queue,
-                                                   const unsigned* __restrict__ queue_count) {
-    const unsigned count = *queue_count;
+                                                   unsigned* __restrict__ queue_count) {
+    const unsigned count = queue_count[0];
+    unsigned* cursor = queue_count + 1;
     Counters cnt = {0u, 0u, 0u};
-    const unsigned stride = gridDim.x * blockDim.x;
-    // warp-uniform trip count so every lane reaches flush_counters together
-    for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += stride) {
-        const unsigned idx = base + (threadIdx.x & 31);
+    const unsigned lane = threadIdx.x & 31;
+    // dynamic work distribution: each warp claims the next 32 queued hits until the queue is drained, so the (device-side)
+    // hit count needs no host round trip and the tail is balanced across the resident warps
+    while (true) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const unsigned idx = base + lane;
         if (idx >= count) continue;
         const HitRec rec = queue[idx];
         V3 ro = mk3(rec.a.x, rec.a.y, rec.a.z), rd = mk3(rec.b.x, rec.b.y, rec.b.z);
@@ -268,11 +274,12 @@ static CameraDev cam_to_dev(const VxCamera& cam) {
 template <int LAYOUT, bool SPP1>
 static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, const DiffuseDev& d, const GBufferDev& g, const DiffuseOutDev& od,
                          PixState* state, HitRec* queue, unsigned* count, int max_spp) {
+    const size_t slab_px = (size_t)(cd.row_end - cd.row_begin) * cd.width;
     const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
     for (int s = 0; s < max_spp; ++s) {
-        VX_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned), c->stream));
+        VX_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(unsigned), c->stream));  // [0] hit count, [1] work cursor
         gi_gen_trace0<LAYOUT, SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s);
-        gi_continue<LAYOUT, SPP1><<<148 * 8, 128, 0, c->stream>>>(S, d, cd.width, od, state, queue, count);
+        gi_continue<LAYOUT, SPP1><<<148 * 6, 128, 0, c->stream>>>(S, d, cd.width, od, state, queue, count);
         c->launches += 2;
     }
     if (!SPP1) {

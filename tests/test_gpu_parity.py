@@ -360,3 +360,26 @@ def test_error_codes(scene_tables, worlds):
 def test_l2_sector_peak_is_plausible(renderer):
     g = renderer.measure_l2_sector_peak()
     assert 1000.0 < g < 40000.0
+
+
+def test_sharded_frame_single_rank_matches_direct_calls(renderer, worlds, scene_tables):
+    """multigpu.ShardedFrame (packed slab buffer + virtual plane bases) on one rank equals the plain calls."""
+    from voxelpathtracer_b200 import multigpu
+    load(renderer, worlds["plains"])
+    W, H = 320, 180
+    fc = camera.FpsCamera(pitch_deg=-20.0)
+    pp = vx.primary_params(350, camera.taa_jitter(2))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=4)
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=1, frame=4)
+    cam = fc.vx_camera(W, H)
+    g = renderer.trace_primary(cam, pp, renderer.alloc_gbuffer(W, H))
+    s = renderer.trace_shadow(cam, g, sp, renderer.alloc_shadow(W, H))
+    d = renderer.trace_diffuse(cam, g, dp, renderer.alloc_diffuse(W, H))
+    f = multigpu.ShardedFrame(renderer, fc, W, H)
+    f.trace(pp, sp, dp)
+    f.gather()
+    renderer.sync()
+    for name, ref in (("g_t", g["t"]), ("g_normal_id", g["normal_id"]), ("g_block_id", g["block_id"]), ("g_inv_t", g["inv_t"]),
+                      ("s_shadow", s["shadow"]), ("s_transversal", s["transversal"]), ("d_sh", d["sh"]), ("d_cocg", d["cocg"]),
+                      ("d_luma", d["luma"]), ("d_ao_sky", d["ao_sky"])):
+        assert np.array_equal(f.plane(name).cpu().numpy(), ref), name

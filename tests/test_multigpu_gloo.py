@@ -67,3 +67,14 @@ def test_slab_gather_over_gloo(ws, height):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(results) == [(r, True) for r in range(ws)]
+
+
+def test_packed_layout_regions_do_not_overlap():
+    table, total = multigpu.packed_layout(1920, 135)
+    spans = sorted((off, off + 135 * 1920 * elem) for (name, elem, _, _), off in zip(multigpu.PLANES, [table[p[0]] for p in multigpu.PLANES]))
+    assert spans[0][0] == 0 and spans[-1][1] <= total
+    for (a0, a1), (b0, b1) in zip(spans[:-1], spans[1:]):
+        assert a1 <= b0 and b0 % 256 == 0
+    assert sum(p[1] for p in multigpu.PLANES) == 51  # bytes per pixel exchanged per frame
+    # virtual plane bases stay inside the packed buffer for every rank: region_bytes >= any single plane's slab
+    assert all(total >= 135 * 1920 * p[1] for p in multigpu.PLANES)

@@ -56,22 +56,53 @@ def gather_planes(planes, height, group=None):
     return planes
 
 
+PLANES = (  # name, bytes per pixel, torch dtype name, trailing shape
+    ("g_t", 4, "float32", ()), ("g_normal_id", 1, "uint8", ()), ("g_block_id", 1, "uint8", ()), ("g_inv_t", 4, "float32", ()),
+    ("s_shadow", 1, "uint8", ()), ("s_transversal", 4, "float32", ()),
+    ("d_sh", 16, "float32", (4,)), ("d_cocg", 8, "float32", (2,)), ("d_luma", 4, "float32", ()), ("d_ao_sky", 8, "float32", (2,)),
+)
+
+
+def packed_layout(width, rows_per_rank, planes=PLANES):
+    """Byte offsets of every plane's slab inside one rank's region of the packed exchange buffer (256-byte aligned)."""
+    off, table = 0, {}
+    for name, elem, _, _ in planes:
+        table[name] = off
+        off += (rows_per_rank * width * elem + 255) & ~255
+    return table, off
+
+
 class ShardedFrame:
-    """Per-rank driver: traces this rank's slab of the primary, shadow and diffuse passes into full-frame device planes
-    and gathers them.  `renderer` is a voxelpathtracer_b200.Renderer bound to this rank's GPU."""
+    """Per-rank driver of one frame: traces this rank's row slab of the primary, shadow and diffuse passes and exchanges the
+    finished slabs with ONE collective.
+
+    Every plane's slab of a rank lives in one contiguous region of a packed device buffer `[world_size][region_bytes]`; the
+    kernels get *virtual* plane bases (region start - slab offset) so that the C ABI's `row * width + i` indexing lands
+    inside the region, and the exchange is a single in-place `all_gather_into_tensor` over NVLink.  `plane(name)` returns
+    the gathered full-frame view `[H, W, ...]` assembled from the per-rank regions (rows of rank r are region r)."""
 
     def __init__(self, renderer, fps_camera, width, height, group=None):
         self.r = renderer
         self.width, self.height = width, height
         self.group = group
-        self.rank = dist.get_rank(group) if dist is not None and dist.is_initialized() else 0
-        self.world_size = dist.get_world_size(group) if dist is not None and dist.is_initialized() else 1
-        rb, re_ = slab_rows(height, self.world_size, self.rank)
+        inited = dist is not None and dist.is_initialized()
+        self.rank = dist.get_rank(group) if inited else 0
+        self.world_size = dist.get_world_size(group) if inited else 1
+        if height % self.world_size:
+            raise ValueError("packed slab exchange needs height % world_size == 0")
+        self.rows = height // self.world_size
+        rb, re_ = self.rank * self.rows, (self.rank + 1) * self.rows
         self.cam = fps_camera.vx_camera(width, height, rb, re_)
-        self.gbuf = renderer.alloc_gbuffer(width, height, device=True)
-        self.shadow = renderer.alloc_shadow(width, height, device=True)
-        self.diffuse = renderer.alloc_diffuse(width, height, device=True)
-        self._ext_stream = torch.cuda.ExternalStream(renderer.cuda_stream(), device=f"cuda:{renderer.device}")
+        self.offsets, self.region_bytes = packed_layout(width, self.rows)
+        dev = f"cuda:{renderer.device}"
+        self.buf = torch.zeros((self.world_size, self.region_bytes), dtype=torch.uint8, device=dev)
+        base = self.buf.data_ptr() + self.rank * self.region_bytes
+        elem = {n: e for n, e, _, _ in PLANES}
+        vb = {n: base + self.offsets[n] - rb * width * elem[n] for n in elem}  # virtual bases (never dereferenced outside the slab)
+        self.gbuf = {"t": vb["g_t"], "normal_id": vb["g_normal_id"], "block_id": vb["g_block_id"], "inv_t": vb["g_inv_t"]}
+        self.shadow = {"shadow": vb["s_shadow"], "transversal": vb["s_transversal"]}
+        self.diffuse = {"sh": vb["d_sh"], "cocg": vb["d_cocg"], "luma": vb["d_luma"], "ao_sky": vb["d_ao_sky"]}
+        self._ext_stream = torch.cuda.ExternalStream(renderer.cuda_stream(), device=dev)
 
     def trace(self, primary, shadow, diffuse):
         """Enqueue the three passes for this rank's slab (asynchronous on the renderer's stream)."""
@@ -81,15 +112,18 @@ class ShardedFrame:
         if diffuse is not None:
             self.r.trace_diffuse(self.cam, self.gbuf, diffuse, self.diffuse)
 
-    def gather(self, with_gbuffer=True):
-        """Exchange the finished slabs; afterwards every rank holds the full frame."""
+    def gather(self):
+        """Exchange the finished slabs (one NCCL all-gather); afterwards every rank holds every region."""
         if self.world_size == 1:
             return
         torch.cuda.current_stream().wait_stream(self._ext_stream)  # NCCL runs after the trace kernels, no host sync
-        planes = {}
-        if with_gbuffer:
-            planes.update({"g_" + k: v for k, v in self.gbuf.items()})
-        planes.update({"s_" + k: v for k, v in self.shadow.items()})
-        planes.update({"d_" + k: v for k, v in self.diffuse.items()})
-        gather_planes(planes, self.height, self.group)
+        dist.all_gather_into_tensor(self.buf.view(-1), self.buf[self.rank], group=self.group)
         self._ext_stream.wait_stream(torch.cuda.current_stream())
+
+    def plane(self, name):
+        """Full-frame tensor [H, W, ...] of a plane, assembled from the per-rank regions (a copy; for consumers and tests)."""
+        _, elem, dtype, tail = next(p for p in PLANES if p[0] == name)
+        n = self.rows * self.width * elem
+        parts = [self.buf[r, self.offsets[name]:self.offsets[name] + n].view(getattr(torch, dtype)).view((self.rows, self.width) + tail)
+                 for r in range(self.world_size)]
+        return torch.cat(parts, 0)

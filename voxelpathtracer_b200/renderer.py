@@ -18,6 +18,8 @@ def _ptr(buf):
     """Raw address of a numpy array or torch tensor (None -> NULL)."""
     if buf is None:
         return None
+    if isinstance(buf, int):  # raw address (e.g. a virtual plane base inside a packed slab buffer)
+        return buf
     if isinstance(buf, np.ndarray):
         if not buf.flags["C_CONTIGUOUS"]:
             raise ValueError("numpy buffers handed to vxpt must be C-contiguous")

@@ -65,6 +65,12 @@ typedef struct VxCamera {
     float inv_proj[16];
     int32_t width, height;       /* full frame size in pixels                         */
     int32_t row_begin, row_end;  /* slab [row_begin,row_end); 0,height = whole frame  */
+    /* Interleaved row bands for multi-GPU load balance (0 or 1 = off).  With interleave_n = N > 1 this handle renders the
+     * bands b with b % N == interleave_rank, a band being band_rows consecutive image rows (height % (N*band_rows) == 0).
+     * The handle's rows are numbered densely as VIRTUAL rows v in [0, height/N): image row j = ((v / band_rows) * N +
+     * interleave_rank) * band_rows + v % band_rows.  row_begin/row_end then select virtual rows, and every plane handed to
+     * the call is RANK-LOCAL: height/N rows, indexed v * width + i.  All per-pixel arithmetic uses the image row j. */
+    int32_t interleave_n, interleave_rank, band_rows, reserved;
 } VxCamera;
 
 /* ---- primary rays: Core/Pipeline.cpp:1973-2016 -> InitialRayTraceFrag.glsl:417-468 ---------------------- */
@@ -220,6 +226,10 @@ VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
 #define VXPT_OPT_TRAVERSAL_LAYOUT 1 /* 0 = linear distance field, 1 = brick-swizzled copy (default) */
 #define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront re-queue (default)          */
 #define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped), 1 = DPX tiled (default) */
+/* measurement knob: keep `value` (1..8) identical copies of the grid + step field at distinct addresses and rotate through
+ * them, one per vxpt_trace_primary call (= per frame).  With 3 copies the traced inputs (132 MB) exceed the 126 MB L2, so
+ * back-to-back frames cannot reuse each other's cache lines (benchmark timing rule); results are unchanged. */
+#define VXPT_OPT_SCENE_REPLICAS 4
 VXPT_API int vxpt_set_option(vxpt_handle h, int option, int value);
 
 /* ---- microbenchmark: resident-set random 32-byte-sector read throughput, the denominator of the

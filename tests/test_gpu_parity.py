@@ -383,3 +383,39 @@ def test_sharded_frame_single_rank_matches_direct_calls(renderer, worlds, scene_
                       ("s_shadow", s["shadow"]), ("s_transversal", s["transversal"]), ("d_sh", d["sh"]), ("d_cocg", d["cocg"]),
                       ("d_luma", d["luma"]), ("d_ao_sky", d["ao_sky"])):
         assert np.array_equal(f.plane(name).cpu().numpy(), ref), name
+
+
+@pytest.mark.parametrize("n,band", [(2, 6), (3, 4), (5, 9)])
+def test_interleaved_row_bands_compose_to_the_full_frame(renderer, worlds, scene_tables, n, band):
+    """VxCamera interleave contract: rank r renders bands b % n == r into rank-local planes addressed by virtual rows;
+    scattering every rank's rows back gives the full frame bit for bit (primary, shadow, GI wavefront)."""
+    from voxelpathtracer_b200 import multigpu
+    load(renderer, worlds["plains"])
+    W, H = 192, 180
+    fc = camera.FpsCamera(pitch_deg=-20.0, aspect=W / H)
+    pp = vx.primary_params(350, camera.taa_jitter(2))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=4)
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=2, checkerboard=True, frame=4)
+    full = fc.vx_camera(W, H)
+    g = renderer.trace_primary(full, pp, renderer.alloc_gbuffer(W, H, hit_voxel=True))
+    s = renderer.trace_shadow(full, g, sp, renderer.alloc_shadow(W, H))
+    d = renderer.trace_diffuse(full, g, dp, renderer.alloc_diffuse(W, H))
+    got = {k: np.zeros_like(v) for k, v in {**g, **s, **d}.items()}
+    rows = H // n
+    for rank in range(n):
+        gl = renderer.alloc_gbuffer(W, rows, hit_voxel=True)
+        sl, dl = renderer.alloc_shadow(W, rows), renderer.alloc_diffuse(W, rows)
+        for vb, ve in ((0, rows // 3), (rows // 3, rows)):       # two virtual-row chunks per rank
+            cam = fc.vx_camera(W, H, vb, ve, n, rank, band)
+            renderer.trace_primary(cam, pp, gl)
+            renderer.trace_shadow(cam, gl, sp, sl)
+            renderer.trace_diffuse(cam, gl, dp, dl)
+        img_rows = multigpu.image_rows_of_rank(H, n, rank, band)
+        for k, v in {**gl, **sl, **dl}.items():
+            got[k][img_rows] = v
+    for k in got:
+        assert np.array_equal(got[k], {**g, **s, **d}[k]), k
+    bad = fc.vx_camera(W, H, 0, rows, n, n, band)
+    with pytest.raises(abi.VxptError) as e:
+        renderer.trace_primary(bad, pp, renderer.alloc_gbuffer(W, rows))
+    assert e.value.code == abi.E_INVALID

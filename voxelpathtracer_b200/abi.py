@@ -15,7 +15,7 @@ WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z
 NORMAL_MISS = 10
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO = 1, 2, 3
+OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS = 1, 2, 3, 4
 
 u8p = C.POINTER(C.c_uint8)
 f32p = C.POINTER(C.c_float)
@@ -25,7 +25,8 @@ i32p = C.POINTER(C.c_int32)
 
 class VxCamera(C.Structure):
     _fields_ = [("inv_view", C.c_float * 16), ("inv_proj", C.c_float * 16), ("width", C.c_int32), ("height", C.c_int32),
-                ("row_begin", C.c_int32), ("row_end", C.c_int32)]
+                ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("interleave_n", C.c_int32), ("interleave_rank", C.c_int32), ("band_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 class VxPrimaryParams(C.Structure):

@@ -58,8 +58,8 @@ class FpsCamera:
     def projection(self):
         return perspective(self.fov, self.aspect, self.z_near, self.z_far)
 
-    def vx_camera(self, width, height, row_begin=0, row_end=None):
-        """inv_view / inv_projection as Pipeline.cpp:1823-1824 hands them to the shaders."""
+    def vx_camera(self, width, height, row_begin=0, row_end=None, interleave_n=0, interleave_rank=0, band_rows=0):
+        """inv_view / inv_projection as Pipeline.cpp:1823-1824 hands them to the shaders.  interleave_*: see VxCamera."""
         cam = VxCamera()
         inv_view = np.linalg.inv(self.view()).astype(f32)
         inv_proj = np.linalg.inv(self.projection()).astype(f32)
@@ -67,7 +67,9 @@ class FpsCamera:
         cam.inv_proj[:] = inv_proj.T.reshape(16).tolist()
         cam.width, cam.height = int(width), int(height)
         cam.row_begin = int(row_begin)
-        cam.row_end = int(height if row_end is None else row_end)
+        rows = height // interleave_n if interleave_n > 1 else height
+        cam.row_end = int(rows if row_end is None else row_end)
+        cam.interleave_n, cam.interleave_rank, cam.band_rows = int(interleave_n), int(interleave_rank), int(band_rows)
         return cam
 
 

@@ -28,9 +28,10 @@ static int fail(int code, const char* msg) {
 
 SceneDev make_scene(const vxpt_ctx* c) {
     SceneDev S;
-    S.grid = c->d_grid;
+    const int rep = c->opt_replicas > 1 ? (int)(c->frame_counter % (uint64_t)c->opt_replicas) : 0;
+    S.grid = rep ? c->rep_grid[rep] : c->d_grid;
     S.df = c->d_df;
-    S.steps = c->d_steps;
+    S.steps = rep ? c->rep_steps[rep] : c->d_steps;
     S.materials = c->d_materials;
     S.sobol = c->d_bluenoise;
     S.scramble = c->d_bluenoise ? c->d_bluenoise + 65536 : nullptr;
@@ -134,7 +135,16 @@ struct PassIO {
 static int check_camera(const VxCamera* cam) {
     if (!cam) return fail(VXPT_E_INVALID, "camera is NULL");
     if (cam->width <= 0 || cam->height <= 0 || cam->width > 16384 || cam->height > 16384) return fail(VXPT_E_INVALID, "bad frame size");
-    if (cam->row_begin < 0 || cam->row_end > cam->height || cam->row_begin > cam->row_end)
+    int rows = cam->height;
+    if (cam->interleave_n > 1) {
+        if (cam->band_rows <= 0 || cam->interleave_rank < 0 || cam->interleave_rank >= cam->interleave_n ||
+            cam->height % (cam->interleave_n * cam->band_rows) != 0)
+            return fail(VXPT_E_INVALID, "bad row-band interleave (need height % (interleave_n * band_rows) == 0 and 0 <= rank < n)");
+        rows = cam->height / cam->interleave_n;  // virtual rows of this handle
+    } else if (cam->interleave_n < 0) {
+        return fail(VXPT_E_INVALID, "interleave_n < 0");
+    }
+    if (cam->row_begin < 0 || cam->row_end > rows || cam->row_begin > cam->row_end)
         return fail(VXPT_E_INVALID, "row slab outside the frame");
     return VXPT_OK;
 }
@@ -142,6 +152,21 @@ static int check_ready(vxpt_ctx* c) {
     if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
     if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded (vxpt_upload_world)");
     if (!c->df_valid) return fail(VXPT_E_STATE, "distance field is stale: call vxpt_build_distance_field after editing the world");
+    return VXPT_OK;
+}
+
+// VXPT_OPT_SCENE_REPLICAS: (re)make the extra copies of grid + step field
+static int refresh_replicas(vxpt_ctx* c) {
+    for (int r = 1; r < c->opt_replicas; ++r) {
+        if (!c->rep_grid[r]) {
+            if (cudaMalloc(&c->rep_grid[r], VOXELS) != cudaSuccess || cudaMalloc(&c->rep_steps[r], STEPS_TILED_BYTES) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(VXPT_E_NOMEM, "scene replica allocation failed");
+            }
+        }
+        VX_CUDA(cudaMemcpyAsync(c->rep_grid[r], c->d_grid, VOXELS, cudaMemcpyDeviceToDevice, c->stream));
+        VX_CUDA(cudaMemcpyAsync(c->rep_steps[r], c->d_steps, STEPS_TILED_BYTES, cudaMemcpyDeviceToDevice, c->stream));
+    }
     return VXPT_OK;
 }
 
@@ -200,6 +225,10 @@ int vxpt_destroy(vxpt_handle c) {
     if (!c) return VXPT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int r = 1; r < 8; ++r) {
+        if (c->rep_grid[r]) cudaFree(c->rep_grid[r]);
+        if (c->rep_steps[r]) cudaFree(c->rep_steps[r]);
+    }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
                     c->d_emissive, c->d_sky, c->d_shadow_noise, c->d_counters, c->d_stage, c->d_queue};
     for (void* b : bufs)
@@ -283,6 +312,7 @@ int vxpt_build_distance_field(vxpt_handle c) {
     rc = launch_pack_bricks(c);
     if (rc) return rc;
     VX_CUDA(cudaEventRecord(c->ev4, c->stream));
+    if ((rc = refresh_replicas(c))) return rc;
     c->df_timed = true;
     c->df_valid = true;
     return VXPT_OK;
@@ -405,6 +435,7 @@ int vxpt_trace_primary(vxpt_handle c, const VxCamera* cam, const VxPrimaryParams
     if ((rc = io.resolve())) return rc;
     VxGBuffer dev{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, (int16_t*)hv.dev};
     if (cam->row_end == cam->row_begin) return VXPT_OK;
+    c->frame_counter++;  // a primary pass opens a frame (scene replica rotation)
     VX_CUDA(cudaEventRecord(c->ev0, c->stream));
     if ((rc = launch_primary(c, *cam, *p, dev))) return rc;
     VX_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -542,12 +573,21 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
             c->opt_layout = value;
             if (c->df_valid && c->steps_layout != value) {  // re-layout the step field for the new choice
                 VX_CUDA(cudaSetDevice(c->device));
-                return launch_pack_bricks(c);
+                int rc = launch_pack_bricks(c);
+                return rc ? rc : refresh_replicas(c);
             }
             return VXPT_OK;
         case VXPT_OPT_GI_WAVEFRONT:
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "wavefront must be 0 or 1");
             c->opt_wavefront = value;
+            return VXPT_OK;
+        case VXPT_OPT_SCENE_REPLICAS:
+            if (value < 1 || value > 8) return fail(VXPT_E_INVALID, "replicas must be 1..8");
+            c->opt_replicas = value;
+            if (c->df_valid) {
+                VX_CUDA(cudaSetDevice(c->device));
+                return refresh_replicas(c);
+            }
             return VXPT_OK;
         case VXPT_OPT_DF_ALGO:
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "df algo must be 0 or 1");

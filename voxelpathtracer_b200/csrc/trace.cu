@@ -16,8 +16,8 @@ struct PrimaryDev {
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
                                                       const GBufferDev out) {
-    int i, j;
-    const bool active = thread_pixel(cam, i, j);
+    int i, j, prow;
+    const bool active = thread_pixel(cam, i, j, prow);
     Counters cnt = {0u, 0u, 0u};
     if (active) {
         float u = ((float)i + 0.5f) / (float)cam.width;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __
         TraceHit h;
         const float t = traverse_df<LAYOUT>(S, ray_origin(cam), dir, p.max_iterations, h, cnt);
         const bool intersect = t > 0.0f && h.block > 0;
-        const size_t px = (size_t)j * cam.width + i;
+        const size_t px = (size_t)prow * cam.width + i;
         if (out.t) out.t[px] = t;
         if (out.inv_t) out.inv_t[px] = 1.0f / t;
         if (out.normal_id) out.normal_id[px] = intersect ? (uint8_t)normal_id_of(h) : (uint8_t)VXPT_NORMAL_MISS;
@@ -59,11 +59,11 @@ struct ShadowOutDev {
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const ShadowDev p,
                                                      const GBufferDev g, const ShadowOutDev out) {
-    int i, j;
-    const bool active = thread_pixel(cam, i, j);
+    int i, j, prow;
+    const bool active = thread_pixel(cam, i, j, prow);
     Counters cnt = {0u, 0u, 0u};
     if (active) {
-        const size_t px = (size_t)j * cam.width + i;
+        const size_t px = (size_t)prow * cam.width + i;
         float u = ((float)i + 0.5f) / (float)cam.width;
         float v = ((float)j + 0.5f) / (float)cam.height;
         u += p.hx * (1.0f / (float)cam.width);
@@ -191,11 +191,11 @@ __device__ __forceinline__ void calculate_diffuse(const SceneDev& S, const Diffu
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) diffuse_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P,
                                                       const GBufferDev g, const DiffuseOutDev out) {
-    int i, j;
-    const bool active = thread_pixel(cam, i, j);
+    int i, j, prow;
+    const bool active = thread_pixel(cam, i, j, prow);
     Counters cnt = {0u, 0u, 0u};
     if (active) {
-        const size_t px = (size_t)j * cam.width + i;
+        const size_t px = (size_t)prow * cam.width + i;
         float u = ((float)i + 0.5f) / (float)cam.width;
         float v = ((float)j + 0.5f) / (float)cam.height;
         const float u0 = u, v0 = v;
@@ -268,6 +268,7 @@ static CameraDev to_dev(const VxCamera& cam) {
     CameraDev c;
     for (int k = 0; k < 16; ++k) { c.inv_view[k] = cam.inv_view[k]; c.inv_proj[k] = cam.inv_proj[k]; }
     c.width = cam.width; c.height = cam.height; c.row_begin = cam.row_begin; c.row_end = cam.row_end;
+    c.il_n = cam.interleave_n; c.il_rank = cam.interleave_rank; c.il_band = cam.band_rows > 0 ? cam.band_rows : 1;
     return c;
 }
 static dim3 pixel_grid(const VxCamera& cam) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8); }

@@ -38,7 +38,13 @@ struct CameraDev {
     float inv_view[16];
     float inv_proj[16];
     int width, height, row_begin, row_end;
+    int il_n, il_rank, il_band;  // interleaved row bands (VxCamera::interleave_*); il_n <= 1 = off
 };
+
+// image row of virtual row v (identity unless bands are interleaved across handles)
+__device__ __forceinline__ int image_row(const CameraDev& cam, int v) {
+    return cam.il_n > 1 ? ((v / cam.il_band) * cam.il_n + cam.il_rank) * cam.il_band + v % cam.il_band : v;
+}
 
 // GetRayDirectionAt (ShadowRayTraceFrag.glsl:303-308) == GetRayStuff (InitialRayTraceFrag.glsl:410-413)
 __device__ __forceinline__ V3 ray_direction_at(const CameraDev& cam, float u, float v) {
@@ -199,12 +205,14 @@ __device__ __forceinline__ void flush_counters(const SceneDev& S, const Counters
     }
 }
 
-// pixel of this thread: a warp covers an 8x4 pixel tile, a 256-thread CTA covers 32x8 pixels
-__device__ __forceinline__ bool thread_pixel(const CameraDev& cam, int& i, int& j) {
+// pixel of this thread: a warp covers an 8x4 pixel tile, a 256-thread CTA covers 32x8 pixels.
+// i, j = image pixel (all arithmetic); prow = row of the planes handed to the call (== j unless bands are interleaved)
+__device__ __forceinline__ bool thread_pixel(const CameraDev& cam, int& i, int& j, int& prow) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     i = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    j = cam.row_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
-    return i < cam.width && j < cam.row_end;
+    prow = cam.row_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    j = image_row(cam, prow);
+    return i < cam.width && prow < cam.row_end;
 }
 
 }  // namespace vxpt

@@ -150,13 +150,13 @@ template <int LAYOUT, bool SPP1>
 __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
                                                      const DiffuseOutDev out, PixState* __restrict__ state, HitRec* __restrict__ queue,
                                                      unsigned* __restrict__ queue_count, const int sample) {
-    int i, j;
-    const bool active = thread_pixel(cam, i, j);
+    int i, j, prow;
+    const bool active = thread_pixel(cam, i, j, prow);
     Counters cnt = {0u, 0u, 0u};
     bool push = false;
     HitRec rec;
     if (active) {
-        const size_t px = (size_t)j * cam.width + i;
+        const size_t px = (size_t)prow * cam.width + i;
         float u = ((float)i + 0.5f) / (float)cam.width;
         float v = ((float)j + 0.5f) / (float)cam.height;
         const float u0 = u, v0 = v;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
 }
 
 template <int LAYOUT, bool SPP1>
-__global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const DiffuseDev P, const int width, const DiffuseOutDev out,
+__global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const DiffuseOutDev out,
                                                    PixState* __restrict__ state, const HitRec* __restrict__ queue,
                                                    unsigned* __restrict__ queue_count) {
     const unsigned count = queue_count[0];
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const Diffu
         V3 ro = mk3(rec.a.x, rec.a.y, rec.a.z), rd = mk3(rec.b.x, rec.b.y, rec.b.z);
         const float T0 = rec.a.w;
         const size_t px = (size_t)(unsigned)__float_as_int(rec.b.w);
-        const int pi = (int)(px % (size_t)width), pj = (int)(px / (size_t)width);
+        const int pi = (int)(px % (size_t)cam.width), pj = image_row(cam, (int)(px / (size_t)cam.width));
         const int code = __float_as_int(rec.c.x);
         int bl_sample = __float_as_int(rec.c.y);
         const V3 odir = rd;
@@ -255,9 +255,9 @@ __global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const Diffu
 
 __global__ void __launch_bounds__(256) gi_finalize(const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g, const DiffuseOutDev out,
                                                    const PixState* __restrict__ state) {
-    int i, j;
-    if (!thread_pixel(cam, i, j)) return;
-    const size_t px = (size_t)j * cam.width + i;
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const size_t px = (size_t)prow * cam.width + i;
     if (g.t[px] < 0.0f) return;
     const PixState st = state[px];
     write_final(out, px, mk3(st.rad.x, st.rad.y, st.rad.z), st.rad.w, st.tot.x, st.tot.y, st.tot.z, st.tot.w, st.misc.x, st.misc.y, st.misc.z,
@@ -268,6 +268,7 @@ static CameraDev cam_to_dev(const VxCamera& cam) {
     CameraDev c;
     for (int k = 0; k < 16; ++k) { c.inv_view[k] = cam.inv_view[k]; c.inv_proj[k] = cam.inv_proj[k]; }
     c.width = cam.width; c.height = cam.height; c.row_begin = cam.row_begin; c.row_end = cam.row_end;
+    c.il_n = cam.interleave_n; c.il_rank = cam.interleave_rank; c.il_band = cam.band_rows > 0 ? cam.band_rows : 1;
     return c;
 }
 
@@ -279,7 +280,7 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
     for (int s = 0; s < max_spp; ++s) {
         VX_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(unsigned), c->stream));  // [0] hit count, [1] work cursor
         gi_gen_trace0<LAYOUT, SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s);
-        gi_continue<LAYOUT, SPP1><<<148 * 6, 128, 0, c->stream>>>(S, d, cd.width, od, state, queue, count);
+        gi_continue<LAYOUT, SPP1><<<148 * 6, 128, 0, c->stream>>>(S, cd, d, od, state, queue, count);
         c->launches += 2;
     }
     if (!SPP1) {

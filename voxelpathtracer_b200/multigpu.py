@@ -63,67 +63,154 @@ PLANES = (  # name, bytes per pixel, torch dtype name, trailing shape
 )
 
 
-def packed_layout(width, rows_per_rank, planes=PLANES):
-    """Byte offsets of every plane's slab inside one rank's region of the packed exchange buffer (256-byte aligned)."""
+def packed_layout(width, rows, planes=PLANES):
+    """Byte offsets of every plane's slab inside one packed region (256-byte aligned) and the region size."""
     off, table = 0, {}
     for name, elem, _, _ in planes:
         table[name] = off
-        off += (rows_per_rank * width * elem + 255) & ~255
+        off += (rows * width * elem + 255) & ~255
     return table, off
 
 
+def pick_band_rows(rows_per_rank, limit=8):
+    """Largest band height <= limit that divides a rank's row count (bands are interleaved across ranks)."""
+    return max(b for b in range(1, limit + 1) if rows_per_rank % b == 0)
+
+
+def pick_chunks(rows_per_rank, world_size):
+    """Sub-slabs per rank and frame (exchange of one overlaps tracing of the next).  Frames are double-buffered, so the
+    exchange of frame k already overlaps the tracing of frame k+1; extra chunks only shrink the kernels (worse wave
+    quantisation on 148 SMs, more launches), hence 1 by default."""
+    return 1
+
+
+def image_rows_of_rank(height, world_size, rank, band_rows):
+    """Image row of every virtual row of `rank` (VxCamera interleave contract)."""
+    rows = height // world_size
+    v = np.arange(rows)
+    if world_size == 1:
+        return v
+    return ((v // band_rows) * world_size + rank) * band_rows + v % band_rows
+
+
 class ShardedFrame:
-    """Per-rank driver of one frame: traces this rank's row slab of the primary, shadow and diffuse passes and exchanges the
-    finished slabs with ONE collective.
+    """Per-rank driver of one frame on N GPUs.
 
-    Every plane's slab of a rank lives in one contiguous region of a packed device buffer `[world_size][region_bytes]`; the
-    kernels get *virtual* plane bases (region start - slab offset) so that the C ABI's `row * width + i` indexing lands
-    inside the region, and the exchange is a single in-place `all_gather_into_tensor` over NVLink.  `plane(name)` returns
-    the gathered full-frame view `[H, W, ...]` assembled from the per-rank regions (rows of rank r are region r)."""
+    * Load balance: rows are dealt to the ranks in interleaved bands (`band_rows` image rows each), because sky rows cost a
+      few loop iterations and horizon rows a hundred; a rank addresses its rows densely as virtual rows (VxCamera).
+    * Overlap: a rank's rows are cut into `chunks` sub-slabs; the exchange of chunk c (NCCL, own stream) runs while chunk
+      c+1 is traced (the library's stream), ordered with stream events only.
+    * One collective per chunk: every exchanged plane of a (rank, chunk) lives in one contiguous region of the packed
+      buffer `[chunks][world_size][region]`; kernels get *virtual* plane bases so the ABI's `v * width + i` indexing lands
+      in the region, and the exchange is an in-place `all_gather_into_tensor`.
+    * What is exchanged: the "radiance slabs" — the outputs of the secondary passes (`s_*`, `d_*`).  The G-buffer stays
+      sharded unless `exchange_gbuffer=True` (its only consumers inside the path are the secondary passes of the same rows).
+    """
 
-    def __init__(self, renderer, fps_camera, width, height, group=None):
+    def __init__(self, renderer, fps_camera, width, height, group=None, chunks=None, band_rows=None, exchange_gbuffer=False, slots=2):
         self.r = renderer
+        self.fc = fps_camera
         self.width, self.height = width, height
         self.group = group
         inited = dist is not None and dist.is_initialized()
         self.rank = dist.get_rank(group) if inited else 0
-        self.world_size = dist.get_world_size(group) if inited else 1
-        if height % self.world_size:
-            raise ValueError("packed slab exchange needs height % world_size == 0")
-        self.rows = height // self.world_size
-        rb, re_ = self.rank * self.rows, (self.rank + 1) * self.rows
-        self.cam = fps_camera.vx_camera(width, height, rb, re_)
-        self.offsets, self.region_bytes = packed_layout(width, self.rows)
+        self.world_size = N = dist.get_world_size(group) if inited else 1
+        if height % N:
+            raise ValueError("row sharding needs height % world_size == 0")
+        self.rows = height // N
+        self.band_rows = (band_rows or pick_band_rows(self.rows)) if N > 1 else 0
+        self.chunks = chunks or pick_chunks(self.rows, N)
+        if self.rows % self.chunks:
+            raise ValueError("chunks must divide the rows of a rank")
+        self.rpc = self.rows // self.chunks
+        self.slots = slots if N > 1 else 1
         dev = f"cuda:{renderer.device}"
-        self.buf = torch.zeros((self.world_size, self.region_bytes), dtype=torch.uint8, device=dev)
-        base = self.buf.data_ptr() + self.rank * self.region_bytes
-        elem = {n: e for n, e, _, _ in PLANES}
-        vb = {n: base + self.offsets[n] - rb * width * elem[n] for n in elem}  # virtual bases (never dereferenced outside the slab)
-        self.gbuf = {"t": vb["g_t"], "normal_id": vb["g_normal_id"], "block_id": vb["g_block_id"], "inv_t": vb["g_inv_t"]}
-        self.shadow = {"shadow": vb["s_shadow"], "transversal": vb["s_transversal"]}
-        self.diffuse = {"sh": vb["d_sh"], "cocg": vb["d_cocg"], "luma": vb["d_luma"], "ao_sky": vb["d_ao_sky"]}
-        self._ext_stream = torch.cuda.ExternalStream(renderer.cuda_stream(), device=dev)
+        self.exchanged = [p for p in PLANES if exchange_gbuffer or not p[0].startswith("g_")]
+        self.local = [p for p in PLANES if p not in self.exchanged]
+        self.offsets, self.region_bytes = packed_layout(width, self.rpc, self.exchanged)
+        self.buf = torch.zeros((self.slots, self.chunks, N, self.region_bytes), dtype=torch.uint8, device=dev)
+        self.loc_offsets, loc_bytes = packed_layout(width, self.rows, self.local)
+        self.loc = torch.zeros((max(loc_bytes, 256),), dtype=torch.uint8, device=dev)
+        self.cams, self.bases = [], []
+        for c in range(self.chunks):
+            vb, ve = c * self.rpc, (c + 1) * self.rpc
+            self.cams.append(fps_camera.vx_camera(width, height, vb, ve, N if N > 1 else 0, self.rank, self.band_rows))
+        for slot in range(self.slots):
+            per_chunk = []
+            for c in range(self.chunks):
+                vb = c * self.rpc
+                region = self.buf[slot, c, self.rank].data_ptr()
+                base = {n: region + self.offsets[n] - vb * width * e for n, e, _, _ in self.exchanged}  # virtual plane bases
+                base.update({n: self.loc.data_ptr() + self.loc_offsets[n] for n, e, _, _ in self.local})
+                per_chunk.append(base)
+            self.bases.append(per_chunk)
+        self._ext = torch.cuda.ExternalStream(renderer.cuda_stream(), device=dev)
+        self._comm = torch.cuda.Stream(device=dev) if N > 1 else None
+        self._traced = [[torch.cuda.Event() for _ in range(self.chunks)] for _ in range(self.slots)]
+        self._exchanged = [None] * self.slots  # event of the last exchange that read/wrote a slot
+        self._slot = 0
+        self.last_slot = 0
 
+    def _planes(self, c, slot=0):
+        b = self.bases[slot][c]
+        return ({"t": b["g_t"], "normal_id": b["g_normal_id"], "block_id": b["g_block_id"], "inv_t": b["g_inv_t"]},
+                {"shadow": b["s_shadow"], "transversal": b["s_transversal"]},
+                {"sh": b["d_sh"], "cocg": b["d_cocg"], "luma": b["d_luma"], "ao_sky": b["d_ao_sky"]})
+
+    def render(self, primary, shadow, diffuse):
+        """Trace this rank's rows of one frame into the next frame slot and start its exchange.  Everything is enqueued
+        asynchronously: the exchange of this frame (NCCL, own stream) overlaps the tracing of the next frame (library
+        stream, other slot).  Call finish() before reading planes or stopping a timer."""
+        slot = self._slot
+        self._slot = (slot + 1) % self.slots
+        self.last_slot = slot
+        if self._exchanged[slot] is not None:
+            self._ext.wait_event(self._exchanged[slot])  # the slot's previous exchange must have drained
+        for c in range(self.chunks):
+            g, s, d = self._planes(c, slot)
+            self.r.trace_primary(self.cams[c], primary, g)
+            if shadow is not None:
+                self.r.trace_shadow(self.cams[c], g, shadow, s)
+            if diffuse is not None:
+                self.r.trace_diffuse(self.cams[c], g, diffuse, d)
+            if self.world_size > 1:
+                self._traced[slot][c].record(self._ext)
+                with torch.cuda.stream(self._comm):
+                    self._comm.wait_event(self._traced[slot][c])
+                    dist.all_gather_into_tensor(self.buf[slot, c].view(-1), self.buf[slot, c, self.rank], group=self.group)
+        if self.world_size > 1:
+            ev = torch.cuda.Event()
+            ev.record(self._comm)
+            self._exchanged[slot] = ev
+
+    def finish(self):
+        """Make the library's stream wait for every outstanding exchange (no host sync)."""
+        if self.world_size > 1:
+            self._ext.wait_stream(self._comm)
+
+    # first interface
     def trace(self, primary, shadow, diffuse):
-        """Enqueue the three passes for this rank's slab (asynchronous on the renderer's stream)."""
-        self.r.trace_primary(self.cam, primary, self.gbuf)
-        if shadow is not None:
-            self.r.trace_shadow(self.cam, self.gbuf, shadow, self.shadow)
-        if diffuse is not None:
-            self.r.trace_diffuse(self.cam, self.gbuf, diffuse, self.diffuse)
+        self.render(primary, shadow, diffuse)
 
     def gather(self):
-        """Exchange the finished slabs (one NCCL all-gather); afterwards every rank holds every region."""
-        if self.world_size == 1:
-            return
-        torch.cuda.current_stream().wait_stream(self._ext_stream)  # NCCL runs after the trace kernels, no host sync
-        dist.all_gather_into_tensor(self.buf.view(-1), self.buf[self.rank], group=self.group)
-        self._ext_stream.wait_stream(torch.cuda.current_stream())
+        self.finish()
 
-    def plane(self, name):
-        """Full-frame tensor [H, W, ...] of a plane, assembled from the per-rank regions (a copy; for consumers and tests)."""
-        _, elem, dtype, tail = next(p for p in PLANES if p[0] == name)
-        n = self.rows * self.width * elem
-        parts = [self.buf[r, self.offsets[name]:self.offsets[name] + n].view(getattr(torch, dtype)).view((self.rows, self.width) + tail)
-                 for r in range(self.world_size)]
-        return torch.cat(parts, 0)
+    def plane(self, name, slot=None):
+        """Full-frame tensor [H, W, ...] of an exchanged plane (or of this rank's rows for a sharded-only plane) of the last
+        rendered frame, in IMAGE row order — a copy for consumers and tests."""
+        slot = self.last_slot if slot is None else slot
+        spec = next(p for p in PLANES if p[0] == name)
+        _, elem, dtype, tail = spec
+        tdt = getattr(torch, dtype)
+        if spec in self.local:
+            n = self.rows * self.width * elem
+            local = self.loc[self.loc_offsets[name]:self.loc_offsets[name] + n].view(tdt).view((self.rows, self.width) + tail)
+            return local
+        n = self.rpc * self.width * elem
+        out = torch.empty((self.height, self.width) + tail, dtype=tdt, device=self.buf.device)
+        for r in range(self.world_size):
+            rows = torch.from_numpy(image_rows_of_rank(self.height, self.world_size, r, self.band_rows)).to(self.buf.device)
+            part = torch.cat([self.buf[slot, c, r, self.offsets[name]:self.offsets[name] + n].view(tdt).view((self.rpc, self.width) + tail)
+                              for c in range(self.chunks)], 0)
+            out[rows] = part
+        return out

@@ -170,10 +170,24 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local_rank}")
 
     tables = load_tables()
-    r = vx.Renderer(local_rank)
-    r.load_scene_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
     w = world.generate_plains(assets.load_plains_columns())
-    r.upload_world(w)
+    fc = camera.FpsCamera(pitch_deg=-20.0)
+    # P independent handles ("pipes") per GPU, each with its own CUDA stream and double-buffered frame slots: consecutive
+    # frames go to alternating pipes, so the latency-bound tail of one frame's kernels overlaps the next frame's kernels.
+    P = max(1, args.pipes)
+    renderers, frames, exts = [], [], []
+    for _ in range(P):
+        rr = vx.Renderer(local_rank)
+        rr.load_scene_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
+        rr.upload_world(w)
+        rr.build_distance_field()
+        # Timing rule "inputs larger than L2": three copies of grid + step field (132 MB > 126 MB L2) are rotated frame by
+        # frame and every frame streams 106 MB of planes through the cache; no flush kernel inside the timed region.
+        rr.set_option(abi.OPT_SCENE_REPLICAS, 3)
+        renderers.append(rr)
+        frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT))
+        exts.append(torch.cuda.ExternalStream(rr.cuda_stream(), device=dev))
+    r, frame, ext = renderers[0], frames[0], exts[0]
     for _ in range(3):
         r.build_distance_field()
     df_times = []
@@ -185,13 +199,6 @@ def run_ours(args):
     pack_ms = float(np.median([b for _, b in df_times]))
     l2_peak = r.measure_l2_sector_peak()
 
-    fc = camera.FpsCamera(pitch_deg=-20.0)
-    frame = multigpu.ShardedFrame(r, fc, WIDTH, HEIGHT)
-    ext = torch.cuda.ExternalStream(r.cuda_stream(), device=dev)
-    # Timing rule "inputs larger than L2": three copies of grid + step field (132 MB > 126 MB L2) are rotated frame by frame,
-    # and every frame streams 106 MB of planes through the cache; there is no flush kernel inside the timed region.
-    r.set_option(abi.OPT_SCENE_REPLICAS, 3)
-
     def barrier():
         if ws > 1:
             dist.barrier()
@@ -199,34 +206,96 @@ def run_ours(args):
 
     n_frames = args.warmup + args.steps
     params = [frame_params(vx, camera, tables, f) for f in range(n_frames)]  # tiny host structs, one per frame index
+    slots = frame.slots
+    M = P * slots * (2 if P * slots < 8 else 1)  # frame indices per cycle; step k -> pipe k % P, slot (k // P) % slots
 
-    def device_step(f):
-        pp, sp, dp = params[f]
-        frame.render(pp, sp, dp)  # primary -> shadow -> GI on this rank's rows; the exchange overlaps the next frame's tracing
+    def eager_step(k, f):
+        fr = frames[k % P]
+        slot = (k // P) % slots
+        fr.last_slot = slot
+        fr.before_trace(slot)
+        fr.trace_into(slot, *params[f])
+        fr.exchange(slot)
 
-    # ---- device-resident timing: exactly K steps between two CUDA events on the library's stream, bracketed by barrier + sync
+    def finish_all():
+        """Stream 0 waits for every pipe (and its exchanges): the end event recorded on it closes the timed region."""
+        for fr in frames:
+            fr.finish()
+        for e in exts[1:]:
+            ext.wait_stream(e)
+
+    # ---- device-resident timing: exactly K steps between two CUDA events, bracketed by barrier + synchronize.
+    # Submission: the library calls of one frame (this rank's rows) are captured into a CUDA graph per frame index (M indices,
+    # cycled), so a step costs the host one graph launch + the eager NCCL exchange instead of ~0.34 ms of Python/ctypes per
+    # frame.  --no-graph submits every call eagerly.
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for f in range(args.warmup):
-        device_step(f)
-    frame.finish()
+    for k in range(args.warmup):
+        eager_step(k, k)
+    finish_all()
     barrier()
-    r.reset_stats()
-    launches0 = r.launch_count()
+    graphs, submit = None, "eager"
+    launches_per_graph = None
+    if not args.no_graph:
+        try:
+            for rr in renderers:
+                rr.set_option(abi.OPT_TIMING_EVENTS, 0)
+            l0 = sum(rr.launch_count() for rr in renderers)
+            graphs = []
+            for m in range(M):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=exts[m % P], capture_error_mode="thread_local"):
+                    frames[m % P].trace_into((m // P) % slots, *params[args.warmup + m])
+                graphs.append(gph)
+            launches_per_graph = (sum(rr.launch_count() for rr in renderers) - l0) / M
+            submit = (f"one CUDA graph per frame (trace passes of this rank's rows; {M} frame indices cycled) on {P} pipe(s), "
+                      "NCCL exchange eager on its own stream")
+        except Exception as e:  # capture unsupported in this environment: fall back to eager submission
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); submitting eagerly\n")
+            graphs, submit = None, "eager (graph capture failed)"
+            torch.cuda.synchronize()
+        finally:
+            for rr in renderers:
+                rr.set_option(abi.OPT_TIMING_EVENTS, 1)
+
+    def graph_step(k):
+        fr = frames[k % P]
+        slot = (k // P) % slots
+        fr.last_slot = slot
+        fr.before_trace(slot)
+        with torch.cuda.stream(exts[k % P]):
+            graphs[k % M].replay()
+        fr.exchange(slot)
+
+    step = graph_step if graphs is not None else (lambda k: eager_step(k, args.warmup + k))
+    for fr in frames:
+        fr._exchanged = [None] * fr.slots
+    for k in range(M):
+        step(k)  # untimed
+    finish_all()
+    barrier()
+    for rr in renderers:
+        rr.reset_stats()
+    launches0 = sum(rr.launch_count() for rr in renderers)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if sampler:
         sampler.begin()
+    t_submit = time.perf_counter()
     ev0.record(ext)
+    for e in exts[1:]:
+        e.wait_event(ev0)  # no pipe starts before the start event
     for k in range(args.steps):
-        device_step(args.warmup + k)
-    frame.finish()  # the last frame's exchange is inside the timed region
+        step(k)
+    finish_all()  # the last frames' exchanges are inside the timed region
     ev1.record(ext)
+    host_submit_ms = (time.perf_counter() - t_submit) * 1e3 / args.steps
     barrier()
     if sampler:
         sampler.end()
     clocks = sampler.stop() if sampler else None
-    st = r.stats()
-    launches = r.launch_count() - launches0
+    sts = [rr.stats() for rr in renderers]
+    st = {k_: sum(s_[k_] for s_ in sts) for k_ in ("rays", "df_fetches", "vox_fetches")}
+    launches = (launches_per_graph * args.steps) if graphs is not None else (sum(rr.launch_count() for rr in renderers) - launches0)
     step_ms = float(ev0.elapsed_time(ev1))
     tot = torch.tensor([step_ms, float(st["rays"]), float(st["df_fetches"]), float(st["vox_fetches"]), float(launches)], dtype=torch.float64, device=dev)
     mx = tot.clone()
@@ -341,9 +410,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps, "sharding": f"{ws} ranks, interleaved {frame.band_rows}-row bands, one packed NCCL all-gather of the shadow+GI planes per frame, double-buffered so it overlaps the next frame's tracing, grid replicated",
+            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps, "sharding": f"{ws} ranks, interleaved {frame.band_rows}-row bands, {P} frame pipe(s) per GPU, one packed NCCL all-gather of the shadow+GI planes per frame overlapped with the following frames' tracing, grid replicated",
                        "timing": "two CUDA events on the library stream around exactly K steps (barrier + synchronize on both sides), max over ranks; inputs larger than L2: 3 scene replicas (132 MB) rotated per frame + 106 MB of planes written per frame, no flush kernel",
-                       "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": "wavefront (warp-ballot compaction of first-bounce hits)"},
+                       "submit": submit, "host_submit_ms_per_step": host_submit_ms, "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": "wavefront (warp-ballot compaction of first-bounce hits)"},
             "e2e": e2e, "gpu_launches": int(tot[4]),
             "roofline": dict(rooflines[dominant], kernel=dominant,
                              note="traversal roofline = (DF fetches + block fetches) x 32 B per launch over the measured random-sector L2 peak (SURVEY.md §8d)"),
@@ -366,6 +435,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipes", type=int, default=2, help="independent handles/streams per GPU (frames in flight)")
+    ap.add_argument("--no-graph", action="store_true", help="submit every pass eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     return run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -230,6 +230,9 @@ VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
  * them, one per vxpt_trace_primary call (= per frame).  With 3 copies the traced inputs (132 MB) exceed the 126 MB L2, so
  * back-to-back frames cannot reuse each other's cache lines (benchmark timing rule); results are unchanged. */
 #define VXPT_OPT_SCENE_REPLICAS 4
+/* 1 (default): record CUDA events around every pass (VxStats.last_ms).  0: record none, so a caller may capture the
+ * handle's stream into a CUDA graph (event timing is not capturable). */
+#define VXPT_OPT_TIMING_EVENTS 5
 VXPT_API int vxpt_set_option(vxpt_handle h, int option, int value);
 
 /* ---- microbenchmark: resident-set random 32-byte-sector read throughput, the denominator of the

@@ -15,7 +15,7 @@ WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z
 NORMAL_MISS = 10
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS = 1, 2, 3, 4
+OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS, OPT_TIMING_EVENTS = 1, 2, 3, 4, 5
 
 u8p = C.POINTER(C.c_uint8)
 f32p = C.POINTER(C.c_float)

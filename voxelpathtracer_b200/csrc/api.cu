@@ -436,10 +436,12 @@ int vxpt_trace_primary(vxpt_handle c, const VxCamera* cam, const VxPrimaryParams
     VxGBuffer dev{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, (int16_t*)hv.dev};
     if (cam->row_end == cam->row_begin) return VXPT_OK;
     c->frame_counter++;  // a primary pass opens a frame (scene replica rotation)
-    VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
     if ((rc = launch_primary(c, *cam, *p, dev))) return rc;
-    VX_CUDA(cudaEventRecord(c->ev1, c->stream));
-    c->pass_timed = true;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
     bool any = false;
     for (Plane* pl : io.planes)
         if ((rc = io.download(*pl, any))) return rc;
@@ -463,10 +465,12 @@ int vxpt_trace_shadow(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, co
     if ((rc = io.upload(t)) || (rc = io.upload(nid))) return rc;
     VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, nullptr, nullptr, nullptr};
     VxShadowOut od{(uint8_t*)sh.dev, (float*)tr.dev};
-    VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
     if ((rc = launch_shadow(c, *cam, gd, *p, od))) return rc;
-    VX_CUDA(cudaEventRecord(c->ev1, c->stream));
-    c->pass_timed = true;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
     bool any = false;
     if ((rc = io.download(sh, any)) || (rc = io.download(tr, any))) return rc;
     if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
@@ -498,10 +502,12 @@ int vxpt_trace_diffuse(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, c
     if ((rc = io.upload(t)) || (rc = io.upload(nid))) return rc;
     VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, nullptr, nullptr, nullptr};
     VxDiffuseOut od{(float*)sh.dev, (float*)cg.dev, (float*)lu.dev, (float*)ao.dev};
-    VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
     if ((rc = launch_diffuse(c, *cam, gd, *p, od))) return rc;
-    VX_CUDA(cudaEventRecord(c->ev1, c->stream));
-    c->pass_timed = true;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
     bool any = false;
     if ((rc = io.download(sh, any)) || (rc = io.download(cg, any)) || (rc = io.download(lu, any)) || (rc = io.download(ao, any))) return rc;
     if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
@@ -588,6 +594,10 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
                 VX_CUDA(cudaSetDevice(c->device));
                 return refresh_replicas(c);
             }
+            return VXPT_OK;
+        case VXPT_OPT_TIMING_EVENTS:
+            c->opt_timing = value ? 1 : 0;
+            if (!c->opt_timing) c->pass_timed = false;
             return VXPT_OK;
         case VXPT_OPT_DF_ALGO:
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "df algo must be 0 or 1");

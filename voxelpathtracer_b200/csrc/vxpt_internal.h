@@ -88,6 +88,7 @@ struct vxpt_ctx {
     int opt_wavefront = 1;  // VXPT_OPT_GI_WAVEFRONT
     int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped), 1 = DPX tiled
     int opt_replicas = 1;   // VXPT_OPT_SCENE_REPLICAS
+    int opt_timing = 1;     // VXPT_OPT_TIMING_EVENTS
     uint8_t* rep_grid[8] = {nullptr};   // extra copies (index 1..replicas-1); index 0 unused (= d_grid / d_steps)
     uint8_t* rep_steps[8] = {nullptr};
     uint64_t frame_counter = 0;  // advanced by vxpt_trace_primary

@@ -157,15 +157,14 @@ class ShardedFrame:
                 {"shadow": b["s_shadow"], "transversal": b["s_transversal"]},
                 {"sh": b["d_sh"], "cocg": b["d_cocg"], "luma": b["d_luma"], "ao_sky": b["d_ao_sky"]})
 
-    def render(self, primary, shadow, diffuse):
-        """Trace this rank's rows of one frame into the next frame slot and start its exchange.  Everything is enqueued
-        asynchronously: the exchange of this frame (NCCL, own stream) overlaps the tracing of the next frame (library
-        stream, other slot).  Call finish() before reading planes or stopping a timer."""
+    def next_slot(self):
         slot = self._slot
         self._slot = (slot + 1) % self.slots
         self.last_slot = slot
-        if self._exchanged[slot] is not None:
-            self._ext.wait_event(self._exchanged[slot])  # the slot's previous exchange must have drained
+        return slot
+
+    def trace_into(self, slot, primary, shadow, diffuse):
+        """Only the library calls of one frame (this rank's rows -> frame slot `slot`); capturable into a CUDA graph."""
         for c in range(self.chunks):
             g, s, d = self._planes(c, slot)
             self.r.trace_primary(self.cams[c], primary, g)
@@ -173,15 +172,33 @@ class ShardedFrame:
                 self.r.trace_shadow(self.cams[c], g, shadow, s)
             if diffuse is not None:
                 self.r.trace_diffuse(self.cams[c], g, diffuse, d)
-            if self.world_size > 1:
-                self._traced[slot][c].record(self._ext)
-                with torch.cuda.stream(self._comm):
-                    self._comm.wait_event(self._traced[slot][c])
-                    dist.all_gather_into_tensor(self.buf[slot, c].view(-1), self.buf[slot, c, self.rank], group=self.group)
-        if self.world_size > 1:
-            ev = torch.cuda.Event()
-            ev.record(self._comm)
-            self._exchanged[slot] = ev
+
+    def before_trace(self, slot):
+        """The slot's previous exchange must have drained before it is overwritten (stream-ordered, no host sync)."""
+        if self._exchanged[slot] is not None:
+            self._ext.wait_event(self._exchanged[slot])
+
+    def exchange(self, slot):
+        """Start the exchange of a traced slot on the communication stream: one in-place NCCL all-gather per chunk."""
+        if self.world_size == 1:
+            return
+        self._traced[slot][0].record(self._ext)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(self._traced[slot][0])
+            for c in range(self.chunks):
+                dist.all_gather_into_tensor(self.buf[slot, c].view(-1), self.buf[slot, c, self.rank], group=self.group)
+        ev = torch.cuda.Event()
+        ev.record(self._comm)
+        self._exchanged[slot] = ev
+
+    def render(self, primary, shadow, diffuse):
+        """Trace this rank's rows of one frame into the next frame slot and start its exchange.  Everything is enqueued
+        asynchronously: the exchange of this frame (NCCL, own stream) overlaps the tracing of the next frame (library
+        stream, other slot).  Call finish() before reading planes or stopping a timer."""
+        slot = self.next_slot()
+        self.before_trace(slot)
+        self.trace_into(slot, primary, shadow, diffuse)
+        self.exchange(slot)
 
     def finish(self):
         """Make the library's stream wait for every outstanding exchange (no host sync)."""

@@ -133,34 +133,39 @@ typedef struct VxDiffuseOut {
     float* ao_sky;  /* o_AOAndSkyLighting 2 floats / pixel                    */
 } VxDiffuseOut;
 
-/* ---- reflections: Core/Pipeline.cpp:3003-3164 -> ReflectionTraceFrag.glsl:717-1038 ---------------------- */
+/* ---- reflections: Core/Pipeline.cpp:3003-3164 -> ReflectionTraceFrag.glsl:717-1038 ----------------------
+ * Parity profile v1: u_ReprojectToScreenSpace, u_LPVGI, u_CloudReflections, u_ReflectPlayer,
+ * u_DeriveFromDiffuseSH = false; lava UV distortion / flicker (functions of wall-clock u_Time) never apply. */
 typedef struct VxReflectionParams {
     int32_t spp;              /* u_SPP (clamped 1..16)                                            */
     int32_t trace_length;     /* u_ReflectionTraceLength, default 64                              */
-    int32_t frame;            /* u_CurrentFrame; blue-noise index = frame % 128 (TEMPORAL_SPEC)   */
+    int32_t frame;            /* u_CurrentFrame; blue-noise index = frame % 128 (TEMPORAL_SPEC);  */
+                              /* frame < 0 selects the TEMPORAL_SPEC = false index 100            */
     int32_t rough;            /* u_RoughReflections                                               */
     int32_t roughness_bias;   /* u_RoughnessBias (0.85x)                                          */
     int32_t checkerboard;     /* CHECKERBOARD_SPEC_SPP                                            */
-    float sun_dir[3];
-    float moon_dir[3];
+    float sun_dir[3];         /* u_SunDirection                                                   */
+    float moon_dir[3];        /* u_MoonDirection                                                  */
     float stronger_dir[3];    /* u_StrongerLightDirection                                         */
     float viewer_pos[3];      /* u_ViewerPosition                                                 */
     float sun_strength;       /* u_SunStrengthModifier 0.85                                       */
     float moon_strength;      /* u_MoonStrengthModifier 1.0                                       */
+    float halton[2];          /* u_Halton (ray-direction jitter when TEMPORAL_SPEC; G-buffer reads stay at the pixel) */
     int32_t grass_props[10];  /* u_GrassBlockProps (Pipeline.cpp:3040-3049)                       */
 } VxReflectionParams;
 
 typedef struct VxReflectionIn {
-    const float* g_normal;   /* u_GBufferNormals 3 floats / pixel; NULL = face normal             */
-    const float* g_pbr;      /* u_GBufferPBR     4 floats / pixel; NULL = per-block constants     */
-    const float* sh;         /* u_DiffuseSH   (this library's GI output)                          */
-    const float* cocg;       /* u_DiffuseCoCg                                                     */
+    const float* g_normal;   /* u_GBufferNormals 3 floats / pixel; NULL = the face normal                        */
+    const float* g_pbr;      /* u_GBufferPBR 4 floats / pixel (roughness, metalness, -, emissivity); NULL = level-2 PBR
+                                texel of the block at the primary hit (needs VxGBuffer.block_id), emissivity 0  */
+    const float* sh;         /* u_DiffuseSH   4 floats / pixel (this library's GI output)                        */
+    const float* cocg;       /* u_DiffuseCoCg 2 floats / pixel                                                   */
 } VxReflectionIn;
 
 typedef struct VxReflectionOut {
     float* color;            /* o_Color 4 floats / pixel       */
     float* hit_distance;     /* o_HitDistance                  */
-    uint8_t* emissive_mask;  /* o_EmissivityHitMask            */
+    uint8_t* emissive_mask;  /* o_EmissivityHitMask 0/1        */
 } VxReflectionOut;
 
 /* ---- traversal statistics (the reference has none; they define the roofline's algorithmic bytes) -------- */
@@ -202,6 +207,14 @@ VXPT_API int vxpt_set_blue_noise(vxpt_handle h, const int32_t* sobol /*65536*/, 
  *  emissive_lod0[n_emissive_layers][512][512] f32 (red channel)                                    */
 VXPT_API int vxpt_set_material_textures(vxpt_handle h, const float* albedo_lod3, const float* pbr_lod2, int n_layers,
                                         const float* emissive_lod0, int n_emissive_layers);
+/* extra texel arrays the reflection pass samples (ReflectionTraceFrag.glsl:961, :973):
+ *  normal_lod3  [n_normal_layers][64][64][4]   f32, mip level 3 of the normal-map array (rgb in 0..1)
+ *  emissive_lod2[n_emissive_layers][128][128]  f32, mip level 2 of the emissive array (red channel)
+ * The reflection pass reads albedo at the baked level 3 and PBR (rgba) at the baked level 2 of
+ * vxpt_set_material_textures (the shader's implicit-derivative texture() calls sit in divergent control flow, where GL
+ * leaves the level undefined). */
+VXPT_API int vxpt_set_reflection_textures(vxpt_handle h, const float* normal_lod3, int n_normal_layers, const float* emissive_lod2,
+                                          int n_emissive_layers);
 VXPT_API int vxpt_set_sky_cubemap(vxpt_handle h, const float* rgb /* [6][n][n][3], faces +X,-X,+Y,-Y,+Z,-Z */, int n);
 VXPT_API int vxpt_set_shadow_noise(vxpt_handle h, const uint8_t* rgba8 /* [256][256][4] */);
 

@@ -6,7 +6,8 @@ import subprocess
 
 import numpy as np
 
-from voxelpathtracer_b200.abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxShadowOut, VxShadowParams)
+from voxelpathtracer_b200.abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxReflectionIn, VxReflectionOut,
+                                      VxReflectionParams, VxShadowOut, VxShadowParams)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvxo_oracle.so")
@@ -17,7 +18,7 @@ class VxoScene(C.Structure):
                 ("materials", C.c_void_p), ("sobol", C.c_void_p), ("scramble", C.c_void_p), ("rank", C.c_void_p),
                 ("albedo_lod3", C.c_void_p), ("pbr_lod2", C.c_void_p), ("n_layers", C.c_int32),
                 ("emissive_lod0", C.c_void_p), ("n_emissive_layers", C.c_int32), ("sky", C.c_void_p), ("sky_n", C.c_int32),
-                ("shadow_noise", C.c_void_p)]
+                ("shadow_noise", C.c_void_p), ("normal_lod3", C.c_void_p), ("n_normal_layers", C.c_int32), ("emissive_lod2", C.c_void_p)]
 
 
 class VxoStats(C.Structure):
@@ -51,7 +52,9 @@ def load():
     lib.vxo_trace_primary.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxPrimaryParams), C.POINTER(VxGBuffer), C.POINTER(VxoStats)]
     lib.vxo_trace_shadow.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxShadowParams), C.POINTER(VxShadowOut), C.POINTER(VxoStats)]
     lib.vxo_trace_diffuse.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut), C.POINTER(VxoStats)]
-    for f in (lib.vxo_trace_primary, lib.vxo_trace_shadow, lib.vxo_trace_diffuse):
+    lib.vxo_trace_reflection.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
+                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut), C.POINTER(VxoStats)]
+    for f in (lib.vxo_trace_primary, lib.vxo_trace_shadow, lib.vxo_trace_diffuse, lib.vxo_trace_reflection):
         f.restype = C.c_int
     lib.vxo_num_threads.restype = C.c_int
     lib.vxo_set_num_threads.argtypes = [C.c_int]
@@ -104,6 +107,11 @@ class Oracle:
         s.sobol, s.scramble, s.rank = k["sobol"].ctypes.data, k["scramble"].ctypes.data, k["rank"].ctypes.data
         s.sky, s.sky_n = k["sky"].ctypes.data, k["sky"].shape[1]
         s.shadow_noise = k["shadow_noise"].ctypes.data
+        if "normal_lod3" in materials:
+            k["normal"] = np.ascontiguousarray(materials["normal_lod3"], dtype=np.float32)
+            k["emissive2"] = np.ascontiguousarray(materials["emissive_lod2"], dtype=np.float32)
+            s.normal_lod3, s.n_normal_layers = k["normal"].ctypes.data, k["normal"].shape[0]
+            s.emissive_lod2 = k["emissive2"].ctypes.data if k["emissive2"].shape[0] else None
 
     @staticmethod
     def _stats(st):
@@ -161,5 +169,21 @@ class Oracle:
         o.sh, o.cocg, o.luma, o.ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "luma", "ao_sky"))
         st = VxoStats()
         rc = self.lib.vxo_trace_diffuse(C.byref(self.scene), C.byref(cam), C.byref(g), C.byref(params), C.byref(o), C.byref(st))
+        assert rc == 0, rc
+        return out, self._stats(st)
+
+    def trace_reflection(self, cam, gbuf, diffuse, params, g_normal=None, g_pbr=None):
+        H, W = cam.height, cam.width
+        out = {"color": np.zeros((H, W, 4), np.float32), "hit_distance": np.zeros((H, W), np.float32), "emissive_mask": np.zeros((H, W), np.uint8)}
+        g = VxGBuffer()
+        g.t, g.normal_id, g.block_id = gbuf["t"].ctypes.data, gbuf["normal_id"].ctypes.data, gbuf["block_id"].ctypes.data
+        i = VxReflectionIn()
+        i.sh, i.cocg = diffuse["sh"].ctypes.data, diffuse["cocg"].ctypes.data
+        i.g_normal = g_normal.ctypes.data if g_normal is not None else None
+        i.g_pbr = g_pbr.ctypes.data if g_pbr is not None else None
+        o = VxReflectionOut()
+        o.color, o.hit_distance, o.emissive_mask = out["color"].ctypes.data, out["hit_distance"].ctypes.data, out["emissive_mask"].ctypes.data
+        st = VxoStats()
+        rc = self.lib.vxo_trace_reflection(C.byref(self.scene), C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o), C.byref(st))
         assert rc == 0, rc
         return out, self._stats(st)

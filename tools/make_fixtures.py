@@ -12,7 +12,8 @@ Run once in the build container (the GPU box has no /root/reference); the output
   materials.npz          BlockDataSSBO-style table (6 x 128 int32, Core/BlockDataSSBO.cpp:15-35, Front face)
                          for a subset of blockdb.txt, with layer indices re-based onto compact baked arrays:
                          albedo level 3 (64^2, sRGB-decoded, 2x2 box filter in linear space applied 3 times),
-                         PBR level 2 (128^2, box filter twice), emissive level 0 red channel (512^2).
+                         PBR level 2 (128^2, box filter twice), emissive level 0 red channel (512^2); for the reflection pass
+                         also normal maps level 3 (64^2) and emissive level 2 (128^2).
                          Quantised to u8 to keep the fixture small; both sides of every parity check read the
                          same bytes.  `block_names` maps id -> name for all 99 blocks of blockdb.txt.
 """
@@ -150,6 +151,18 @@ def main():
             v = box(v)
         pbr.append(np.clip(np.rint(v * 255.0), 0, 255).astype(np.uint8))
     emi = [load_rgba(p)[..., 0].copy() for p in emissive_paths]
+    nrm = []
+    for p in normal_paths:  # normal maps: level 3 (ReflectionTraceFrag.glsl:961), plain box filter of the stored values
+        v = load_rgba(p)[..., :3].astype(np.float64) / 255.0
+        for _ in range(3):
+            v = box(v)
+        nrm.append(np.clip(np.rint(v * 255.0), 0, 255).astype(np.uint8))
+    emi2 = []
+    for p in emissive_paths:  # emissive: level 2 red channel (ReflectionTraceFrag.glsl:973)
+        v = load_rgba(p)[..., 0].astype(np.float64) / 255.0
+        for _ in range(2):
+            v = box(v)
+        emi2.append(np.clip(np.rint(v * 255.0), 0, 255).astype(np.uint8))
     grass = names["Grass"]
     # u_GrassBlockProps, Core/Pipeline.cpp:3040-3049: id, top(a,n,p), side/front(a,n,p), bottom(a,n,p)
     grass_props = np.array([
@@ -166,6 +179,7 @@ def main():
         table=table,
         albedo_lod3=np.stack(alb), pbr_lod2=np.stack(pbr),
         emissive_lod0=np.stack(emi) if emi else np.zeros((0, 512, 512), np.uint8),
+        normal_lod3=np.stack(nrm), emissive_lod2=np.stack(emi2) if emi2 else np.zeros((0, 128, 128), np.uint8),
         albedo_paths=np.array(albedo_paths), emissive_paths=np.array(emissive_paths),
         block_names=np.array([""] + [b["Name"] for b in blocks]),
         grass_props=grass_props,

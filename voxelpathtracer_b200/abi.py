@@ -60,7 +60,8 @@ class VxDiffuseOut(C.Structure):
 class VxReflectionParams(C.Structure):
     _fields_ = [("spp", C.c_int32), ("trace_length", C.c_int32), ("frame", C.c_int32), ("rough", C.c_int32), ("roughness_bias", C.c_int32),
                 ("checkerboard", C.c_int32), ("sun_dir", C.c_float * 3), ("moon_dir", C.c_float * 3), ("stronger_dir", C.c_float * 3),
-                ("viewer_pos", C.c_float * 3), ("sun_strength", C.c_float), ("moon_strength", C.c_float), ("grass_props", C.c_int32 * 10)]
+                ("viewer_pos", C.c_float * 3), ("sun_strength", C.c_float), ("moon_strength", C.c_float), ("halton", C.c_float * 2),
+                ("grass_props", C.c_int32 * 10)]
 
 
 class VxReflectionIn(C.Structure):
@@ -92,6 +93,7 @@ EXPORTS = {
     "vxpt_set_materials": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxpt_set_blue_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxpt_set_material_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "vxpt_set_reflection_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "vxpt_set_sky_cubemap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vxpt_set_shadow_noise": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxpt_trace_primary": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxPrimaryParams), C.POINTER(VxGBuffer)]),

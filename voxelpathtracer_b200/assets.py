@@ -42,6 +42,8 @@ def load_materials(golden=GOLDEN):
         "pbr_lod2": rgba(z["pbr_lod2"]),
         "emissive_lod0": np.ascontiguousarray(z["emissive_lod0"].astype(np.float32) / np.float32(255.0)),
         "grass_props": z["grass_props"].astype(np.int32),
+        "normal_lod3": rgba(z["normal_lod3"]),
+        "emissive_lod2": np.ascontiguousarray(z["emissive_lod2"].astype(np.float32) / np.float32(255.0)),
     }
 
 
@@ -59,8 +61,10 @@ def constant_materials(n_blocks=128):
     table[1] = np.arange(128)
     table[2] = np.arange(128)
     table[3] = -1
+    normal = np.ones((n_blocks, 64, 64, 4), np.float32)
+    normal[..., :3] = (0.5, 0.5, 1.0)
     return {"table": table.reshape(768), "albedo_lod3": albedo, "pbr_lod2": pbr, "emissive_lod0": np.zeros((0, 512, 512), np.float32),
-            "grass_props": np.zeros(10, np.int32)}
+            "grass_props": np.zeros(10, np.int32), "normal_lod3": normal, "emissive_lod2": np.zeros((0, 128, 128), np.float32)}
 
 
 def analytic_sky(n=16, sun_dir=(-0.669, 0.468, 0.577)):

@@ -39,6 +39,8 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.albedo_lod3 = c->d_albedo;
     S.pbr_lod2 = c->d_pbr;
     S.emissive = c->d_emissive;
+    S.normal_lod3 = c->d_normal;
+    S.emissive_lod2 = c->d_emissive2;
     S.sky = c->d_sky;
     S.shadow_noise = c->d_shadow_noise;
     S.n_layers = c->n_layers;
@@ -230,7 +232,7 @@ int vxpt_destroy(vxpt_handle c) {
         if (c->rep_steps[r]) cudaFree(c->rep_steps[r]);
     }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
-                    c->d_emissive, c->d_sky, c->d_shadow_noise, c->d_counters, c->d_stage, c->d_queue};
+                    c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_counters, c->d_stage, c->d_queue};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -401,12 +403,30 @@ int vxpt_set_material_textures(vxpt_handle c, const float* albedo_lod3, const fl
     return VXPT_OK;
 }
 
+int vxpt_set_reflection_textures(vxpt_handle c, const float* normal_lod3, int n_normal_layers, const float* emissive_lod2, int n_emissive_layers) {
+    if (!c || !normal_lod3 || n_normal_layers <= 0 || n_emissive_layers < 0 || (n_emissive_layers > 0 && !emissive_lod2))
+        return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    int rc = replace_buffer(c, &c->d_normal, normal_lod3, (size_t)n_normal_layers * 64 * 64 * 4 * sizeof(float));
+    if (rc) return rc;
+    if (n_emissive_layers > 0) {
+        rc = replace_buffer(c, &c->d_emissive2, emissive_lod2, (size_t)n_emissive_layers * 128 * 128 * sizeof(float));
+        if (rc) return rc;
+    }
+    c->n_normal = n_normal_layers;
+    c->n_emissive2 = n_emissive_layers;
+    c->have_refl_textures = true;
+    return VXPT_OK;
+}
+
 int vxpt_set_sky_cubemap(vxpt_handle c, const float* rgb, int n) {
     if (!c || !rgb || n <= 0 || n > 4096) return fail(VXPT_E_INVALID, "bad argument");
     VX_CUDA(cudaSetDevice(c->device));
     int rc = replace_buffer(c, &c->d_sky, rgb, (size_t)6 * n * n * 3 * sizeof(float));
     if (rc) return rc;
     c->sky_n = n;
+    c->h_sky.resize((size_t)6 * n * n * 3);
+    VX_CUDA(cudaMemcpy(c->h_sky.data(), c->d_sky, c->h_sky.size() * sizeof(float), cudaMemcpyDeviceToHost));
     c->have_sky = true;
     return VXPT_OK;
 }
@@ -514,10 +534,51 @@ int vxpt_trace_diffuse(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, c
     return VXPT_OK;
 }
 
-int vxpt_trace_reflection(vxpt_handle c, const VxCamera*, const VxGBuffer*, const VxReflectionIn*, const VxReflectionParams*,
-                          const VxReflectionOut*) {
-    (void)c;
-    return fail(VXPT_E_UNSUPPORTED, "reflection pass not implemented yet");
+int vxpt_trace_reflection(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, const VxReflectionIn* in, const VxReflectionParams* p,
+                          const VxReflectionOut* out) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_camera(cam))) return rc;
+    if (!g || !in || !p || !out || !g->t || !g->normal_id || !in->sh || !in->cocg)
+        return fail(VXPT_E_INVALID, "NULL argument (G-buffer t, normal_id and the GI sh / cocg planes are required)");
+    if (!in->g_pbr && !g->block_id) return fail(VXPT_E_INVALID, "without g_pbr the G-buffer block_id plane is required");
+    if (!c->have_materials || !c->have_bluenoise || !c->have_textures || !c->have_sky || !c->have_refl_textures)
+        return fail(VXPT_E_STATE, "reflections need materials, blue-noise tables, material + reflection textures and a sky cubemap");
+    if (p->trace_length < 0 || p->spp < 0) return fail(VXPT_E_INVALID, "negative trace_length / spp");
+    for (int b = 0; b < 128; ++b) {
+        if (c->h_materials[b] >= c->n_layers || c->h_materials[256 + b] >= c->n_layers)
+            return fail(VXPT_E_INVALID, "material table references an albedo / PBR layer that was not uploaded");
+        if (c->h_materials[128 + b] >= c->n_normal) return fail(VXPT_E_INVALID, "material table references a normal layer that was not uploaded");
+        if (c->h_materials[384 + b] >= c->n_emissive2) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
+    }
+    for (int k = 1; k < 10; ++k) {
+        const int lim = (k % 3 == 2) ? c->n_normal : c->n_layers;  // props: id, then (albedo, normal, pbr) x {top, side, bottom}
+        if (p->grass_props[k] < 0 || p->grass_props[k] >= lim) return fail(VXPT_E_INVALID, "u_GrassBlockProps layer out of range");
+    }
+    VX_CUDA(cudaSetDevice(c->device));
+    PassIO io(c, cam);
+    Plane t, nid, bid, gn, gp, sh, cg, col, hd, em;
+    io.add(t, g->t, 4); io.add(nid, g->normal_id, 1); io.add(bid, g->block_id, 1);
+    io.add(gn, in->g_normal, 12); io.add(gp, in->g_pbr, 16); io.add(sh, in->sh, 16); io.add(cg, in->cocg, 8);
+    io.add(col, out->color, 16); io.add(hd, out->hit_distance, 4); io.add(em, out->emissive_mask, 1);
+    if ((rc = io.resolve())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    if ((rc = io.upload(t)) || (rc = io.upload(nid)) || (rc = io.upload(bid)) || (rc = io.upload(gn)) || (rc = io.upload(gp)) ||
+        (rc = io.upload(sh)) || (rc = io.upload(cg)))
+        return rc;
+    VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, nullptr, nullptr};
+    VxReflectionIn id{(const float*)gn.dev, (const float*)gp.dev, (const float*)sh.dev, (const float*)cg.dev};
+    VxReflectionOut od{(float*)col.dev, (float*)hd.dev, (uint8_t*)em.dev};
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_reflection(c, *cam, gd, id, *p, od))) return rc;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
+    bool any = false;
+    if ((rc = io.download(col, any)) || (rc = io.download(hd, any)) || (rc = io.download(em, any))) return rc;
+    if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ sync / stats

@@ -275,7 +275,6 @@ static CameraDev cam_to_dev(const VxCamera& cam) {
 template <int LAYOUT, bool SPP1>
 static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, const DiffuseDev& d, const GBufferDev& g, const DiffuseOutDev& od,
                          PixState* state, HitRec* queue, unsigned* count, int max_spp) {
-    const size_t slab_px = (size_t)(cd.row_end - cd.row_begin) * cd.width;
     const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
     for (int s = 0; s < max_spp; ++s) {
         VX_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(unsigned), c->stream));  // [0] hit count, [1] work cursor

@@ -1,0 +1,348 @@
+// trace_reflection.cu — rough-reflection pass (Core/Shaders/ReflectionTraceFrag.glsl main() :717-1038) in the v1 parity
+// profile of SURVEY.md A.6: u_ReprojectToScreenSpace, u_LPVGI, u_CloudReflections, u_ReflectPlayer, u_DeriveFromDiffuseSH
+// off; lava UV distortion / flicker (functions of the wall clock) never apply.  One thread per pixel; per sample one
+// GGX-sampled reflection ray (cap u_ReflectionTraceLength) and, for the first max(SPP/4,1) hits, a sun shadow ray (cap 150).
+// Compiled with -fmad=false; sin/cos/pow/log are the pinned correctly rounded fp32 values (double evaluation).
+#include <cmath>
+
+#include "gi_device.cuh"
+
+namespace vxpt {
+
+struct ReflDev {
+    int spp, trace_length, bn_index, rough, checkerboard, frame;
+    float rough_bias;                // mix(1, 0.85, u_RoughnessBias)
+    float hx, hy;                    // clamp(u_Halton, -2, 2)
+    V3 stronger, viewer, color_mixed;  // u_StrongerLightDirection, u_ViewerPosition, SAMPLED_COLOR_MIXED (:731)
+    int grass[10];
+};
+struct ReflInDev {
+    const float* g_normal;
+    const float4* g_pbr;
+    const float4* sh;
+    const float2* cocg;
+};
+struct ReflOutDev {
+    float4* color;
+    float* hit_distance;
+    uint8_t* emissive_mask;
+};
+
+// CalculateVectors :1376-1449 on an exact axis normal (normal id 0..5)
+__device__ __forceinline__ void calc_vectors(V3 p, int nid, V3& tangent, V3& bitangent, float& u, float& v) {
+    if (nid <= 1) { u = fractf(p.x); v = fractf(p.y); tangent = mk3(1.f, 0.f, 0.f); bitangent = mk3(0.f, 1.f, 0.f); }
+    else if (nid <= 3) { u = fractf(p.x); v = fractf(p.z); tangent = mk3(1.f, 0.f, 0.f); bitangent = mk3(0.f, 0.f, 1.f); }
+    else { u = fractf(p.z); v = fractf(p.y); tangent = mk3(0.f, 0.f, -1.f); bitangent = mk3(0.f, -1.f, 0.f); }
+}
+
+// capIntersect :1264-1292, GetPlayerIntersect :1301-1307
+__device__ __forceinline__ float cap_intersect(V3 ro, V3 rd, V3 pa, V3 pb, float r) {
+    const V3 ba = pb - pa, oa = ro - pa;
+    const float baba = dot3(ba, ba), bard = dot3(ba, rd), baoa = dot3(ba, oa), rdoa = dot3(rd, oa), oaoa = dot3(oa, oa);
+    const float a = baba - bard * bard;
+    float b = baba * rdoa - baoa * bard;
+    float c = baba * oaoa - baoa * baoa - r * r * baba;
+    float h = b * b - a * c;
+    if (h >= 0.0f) {
+        const float t = (-b - sqrtf(h)) / a;
+        const float y = baoa + t * bard;
+        if (y > 0.0f && y < baba) return t;
+        const V3 oc = (y <= 0.0f) ? oa : ro - pb;
+        b = dot3(rd, oc);
+        c = dot3(oc, oc) - r * r;
+        h = b * b - c;
+        if (h > 0.0f) return -b - sqrtf(h);
+    }
+    return -1.0f;
+}
+__device__ __forceinline__ bool player_intersect(V3 viewer, V3 pos, V3 d) {
+    const float x = 0.4f;
+    const V3 vp = viewer + mk3(-x, -x, +x);
+    return cap_intersect(pos, d, vp, vp + mk3(0.0f, 1.0f, 0.0f), 0.5f) > 0.0f;
+}
+
+// ImportanceSampleGGX :345-365
+__device__ __forceinline__ V3 importance_sample_ggx(V3 N, float roughness, float xi_x, float xi_y) {
+    const float alpha = roughness * roughness;
+    const float alpha2 = alpha * alpha;
+    const float phi = 2.0f * PI_F * xi_x;
+    const float cos_theta = sqrtf((1.0f - xi_y) / (1.0f + (alpha2 - 1.0f) * xi_y));
+    const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    const V3 H = mk3(cos_cr(phi) * sin_theta, sin_cr(phi) * sin_theta, cos_theta);
+    const V3 up = fabsf(N.z) < 0.999f ? mk3(0.0f, 0.0f, 1.0f) : mk3(1.0f, 0.0f, 0.0f);
+    const V3 tangent = normalize3(cross3(up, N));
+    const V3 bitangent = cross3(N, tangent);
+    const V3 sv = (tangent * H.x + bitangent * H.y) + N * H.z;
+    return normalize3(sv);
+}
+
+__device__ __forceinline__ V3 mix3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
+
+// CalculateDirectionalLight :313-336 (specular part multiplied by radiance * 0.05 * 0, as in the shader)
+__device__ __forceinline__ V3 directional_light(V3 viewer, V3 world_pos, V3 light_dir, V3 radiance, V3 albedo, V3 normal, V3 pbr, float shadow) {
+    const float Epsilon = 0.00001f;
+    const float Shadow = fminf(shadow, 1.0f);
+    const V3 Lo = normalize3(viewer - world_pos);
+    const V3 N = normal;
+    const float cosLo = fmaxf(0.0f, dot3(N, Lo));
+    const V3 F0 = mix3(mk3(0.04f, 0.04f, 0.04f), albedo, pbr.y);
+    const V3 Li = light_dir;
+    const V3 Lh = normalize3(Li + Lo);
+    const float cosLi = fmaxf(0.0f, dot3(N, Li));
+    const float cosLh = fmaxf(0.0f, dot3(N, Lh));
+    const float ct = fmaxf(0.0f, dot3(Lh, Lo));
+    const V3 F = F0 + (mk3(1.f, 1.f, 1.f) - F0) * pow_cr(1.0f - ct, 5.0f);
+    const float alpha = pbr.x * pbr.x, alphaSq = alpha * alpha;
+    const float denom = (cosLh * cosLh) * (alphaSq - 1.0f) + 1.0f;
+    const float D = alphaSq / (PI_F * denom * denom);
+    const float rr = pbr.x + 1.0f;
+    const float k = (rr * rr) / 8.0f;
+    const float G = (cosLi / (cosLi * (1.0f - k) + k)) * (cosLo / (cosLo * (1.0f - k) + k));
+    const V3 kd = mix3(mk3(1.f, 1.f, 1.f) - F, mk3(0.f, 0.f, 0.f), pbr.y);
+    const V3 diffuseBRDF = kd * albedo;
+    const V3 specularBRDF = ((F * D) * G) / fmaxf(Epsilon, 4.0f * cosLi * cosLo);
+    const V3 radiance_s = (radiance * 0.05f) * 0.0f;
+    V3 res = ((diffuseBRDF * radiance) * cosLi) + ((specularBRDF * radiance_s) * cosLi);
+    res = mk3(fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f));
+    return res * clampf(1.0f - Shadow, 0.0f, 1.0f);
+}
+
+__device__ __forceinline__ float4 tex_nearest_rgba(const float4* base, int layer, int n, float u, float v) {
+    const int i = ((int)floorf(u * (float)n)) & (n - 1);
+    const int j = ((int)floorf(v * (float)n)) & (n - 1);
+    return __ldg(base + ((size_t)layer * n + j) * n + i);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ ReflDev P,
+                                                         const GBufferDev g, const ReflInDev in, const ReflOutDev out) {
+    int i, j, prow;
+    const bool active = thread_pixel(cam, i, j, prow);
+    Counters cnt = {0u, 0u, 0u};
+    if (active) {
+        const size_t px = (size_t)prow * cam.width + i;
+        float4 o_color = make_float4(0.f, 0.f, 0.f, 0.f);
+        float o_hit = -1.0f;
+        uint8_t o_mask = 0;
+        const float u = ((float)i + 0.5f) / (float)cam.width, v = ((float)j + 0.5f) / (float)cam.height;
+        const float ju = u + (P.hx / (float)cam.width) * 1.0f;  // u_TemporalFilterReflections = true
+        const float jv = v + (P.hy / (float)cam.height) * 1.0f;
+        const float dist = g.t[px];
+        if (!(dist < 0.0f)) {
+            int spp = min(max(P.spp, 1), 16);
+            if (P.checkerboard) {
+                const bool checker = ((int)(((float)i + 0.5f) + ((float)j + 0.5f))) % 2 == (P.frame % 2);
+                spp = (int)mixf((float)P.spp, (float)((P.spp + P.spp % 2) / 2), checker ? 1.0f : 0.0f);
+            }
+            spp = min(max(spp, 1), 16);
+            V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, ju, jv)) * dist;
+            const int nid = g.normal_id[px];
+            const V3 face_n = normal_from_id(nid, 1.0f);
+            float roughness_at, metalness_at;
+            if (in.g_pbr) {
+                const float4 m = in.g_pbr[px];
+                roughness_at = m.x; metalness_at = m.y;
+            } else {  // stand-in for the G-buffer material pass: level-2 PBR texel of the block at the primary hit
+                V3 tg, bt;
+                float tu, tv;
+                calc_vectors(pos, nid, tg, bt, tu, tv);
+                tv = 1.0f - tv;
+                const float4 m = tex_nearest_rgba(S.pbr_lod2, S.materials[256 + min((int)g.block_id[px], 127)], 128, tu, tv);
+                roughness_at = m.x; metalness_at = m.y;
+            }
+            const V3 I = normalize3(pos - P.viewer);
+            pos = pos + face_n * 0.035f;
+            const V3 nmapped = in.g_normal ? mk3(in.g_normal[3 * px], in.g_normal[3 * px + 1], in.g_normal[3 * px + 2]) : face_n;
+            V3 base_indirect;
+            {  // SHToIrradianceA :469-478
+                const float4 sh = in.sh[px];
+                const float2 cg = in.cocg[px];
+                const float Y = fmaxf(0.0f, 3.544905f * sh.w);
+                const float sc = (Y * 0.282095f) / (sh.w + 1e-6f);
+                const float c0 = cg.x * sc, c1 = cg.y * sc;
+                const float T = Y - c1 * 0.5f, G = c1 + T, B = T - c0 * 0.5f, R = B + c0;
+                base_indirect = mk3(fmaxf(R, 0.0f), fmaxf(G, 0.0f), fmaxf(B, 0.0f));
+            }
+            float computed_shadow = 0.0f;
+            int shadow_itr = 0, bl = 0, total_hits = 0;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, avg_hit = 0.001f, meaningful = 0.0f, mask = 0.0f;
+#pragma unroll 1
+            for (int s = 0; s < spp; ++s) {
+                V3 rn = nmapped;
+                if (P.rough) {  // GetReflectionDirection :621-644
+                    const float R = fmaxf(clampf(roughness_at * P.rough_bias, 0.01f, 1.0f), 0.05f);
+                    float nearest = -100.0f;
+                    V3 best = mk3(0.f, 0.f, 0.f);
+#pragma unroll 1
+                    for (int k = 0; k < 3; ++k) {
+                        const float xx = blue_noise_1d(S, i, j, P.bn_index, 1 + bl);
+                        const float xy = blue_noise_1d(S, i, j, P.bn_index, 2 + bl);
+                        bl += 2;
+                        bl = bl % 128;
+                        const V3 smp = importance_sample_ggx(nmapped, R, xx * 0.9f, xy * 0.65f);
+                        const float d = dot3(smp, nmapped);
+                        if (d > nearest) { best = smp; nearest = d; }
+                    }
+                    rn = best;
+                }
+                const V3 R = I - rn * (2.0f * dot3(rn, I));  // reflect(I, N)
+                TraceHit h;
+                const float T = traverse_df<LAYOUT>(S, pos, R, P.trace_length, h, cnt);
+                const V3 hit_pos = pos + (R * T);
+                if (T > 0.0f) {
+                    const int hnid = normal_id_of(h);
+                    const V3 hn = hit_normal(h);
+                    V3 tg, bt;
+                    float tu, tv;
+                    calc_vectors(hit_pos, hnid, tg, bt, tu, tv);
+                    tv = 1.0f - tv;
+                    const int ref = min(max(h.block, 0), 127);
+                    int t_albedo = S.materials[ref], t_normal = S.materials[128 + ref], t_pbr = S.materials[256 + ref], t_emis = S.materials[384 + ref];
+                    if (ref == P.grass[0]) {  // :896-918
+                        if (hnid == 4 || hnid == 5 || hnid == 0 || hnid == 1) { t_albedo = P.grass[4]; t_normal = P.grass[5]; t_pbr = P.grass[6]; }
+                        else if (hnid == 2) { t_albedo = P.grass[1]; t_normal = P.grass[2]; t_pbr = P.grass[3]; }
+                        else { t_albedo = P.grass[7]; t_normal = P.grass[8]; t_pbr = P.grass[9]; }
+                    }
+                    V3 ambient = base_indirect;
+                    const V3 albedo = tex_nearest(S.albedo_lod3, t_albedo, 64, tu, tv);
+                    const V3 radiance = P.color_mixed * 0.6f;
+                    const float4 pbr4 = tex_nearest_rgba(S.pbr_lod2, t_pbr, 128, tu, tv);
+                    const float AO = pow_cr(pbr4.w, 2.0f);
+                    const bool player_shadow = player_intersect(P.viewer, hit_pos + hn * 0.035f, P.stronger);
+                    if (shadow_itr < max(spp / 4, 1)) {
+                        if (!player_shadow) {  // GetShadowAt :1327-1346
+                            const V3 so = hit_pos + hn * 0.055f;
+                            if (player_intersect(P.viewer, so, P.stronger)) computed_shadow = 1.0f;
+                            else {
+                                TraceHit hs;
+                                const float Ts = traverse_df<LAYOUT>(S, so, P.stronger, 150, hs, cnt);
+                                computed_shadow = Ts > 0.0f ? 1.0f : 0.0f;
+                            }
+                        } else computed_shadow = 1.0f;
+                        shadow_itr = shadow_itr + 1;
+                    }
+                    ambient = ((ambient * 1.0f) * clampf(AO, 0.1f, 1.0f)) * albedo;
+                    const V3 nm = tex_nearest(S.normal_lod3, t_normal, 64, tu, tv) * 2.0f - mk3(1.f, 1.f, 1.f);
+                    const V3 nmap = (tg * nm.x + bt * nm.y) + hn * nm.z;  // TBN * n
+                    V3 direct = ambient + directional_light(P.viewer, hit_pos, P.stronger, radiance, albedo, nmap, mk3(pbr4.x, pbr4.y, pbr4.z), computed_shadow);
+                    if ((float)t_emis > -0.5f) {
+                        const int ei = ((int)floorf(tu * 128.0f)) & 127, ej = ((int)floorf(tv * 128.0f)) & 127;
+                        float e = S.emissive_lod2[((size_t)t_emis * 128 + ej) * 128 + ei];
+                        if (e > 0.1f) {
+                            const float lbx = 0.02501f, lby = 0.03001f;
+                            e *= (tu > lbx && tu < 1.0f - lbx && tv > lby && tv < 1.0f - lby) ? 1.0f : 0.0f;
+                            direct = albedo * fmaxf((e * 19.0f) * 1.0f, 2.0f);
+                            mask = 1.0f;
+                        }
+                    }
+                    t0 += direct.x; t1 += direct.y; t2 += direct.z; t3 += 1.0f;
+                    avg_hit += T;
+                    meaningful += 1.0f;
+                } else {
+                    const V3 atmo = sky_sample(S, normalize3(R));
+                    const float m = mixf(1.0f, 1.175f, metalness_at > 0.05f ? 1.0f : 0.0f);
+                    t0 += atmo.x * m; t1 += atmo.y * m; t2 += atmo.z * m; t3 += 1.0f;
+                }
+                total_hits++;
+            }
+            avg_hit /= fmaxf(meaningful, 0.01f);
+            const float th = (float)total_hits;
+            t0 /= th; t1 /= th; t2 /= th; t3 /= th;
+            o_color = make_float4(clampf(t0, 0.0000001f, 100.0f), clampf(t1, 0.0000001f, 100.0f), clampf(t2, 0.0000001f, 100.0f), clampf(t3, 0.0000001f, 100.0f));
+            o_hit = clampf(meaningful > 0.01f ? avg_hit : -1.0f, -10.0f, 200.0f);
+            o_mask = clampf(mask, 0.0f, 1.0f) > 0.5f ? 1 : 0;
+        }
+        if (out.color) out.color[px] = o_color;
+        if (out.hit_distance) out.hit_distance[px] = o_hit;
+        if (out.emissive_mask) out.emissive_mask[px] = o_mask;
+    }
+    flush_counters(S, cnt);
+}
+
+// ---- host side: per-frame constants (:648-668, :727-731) in fp32 with the pinned transcendental definitions -------------
+static inline float h_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+static inline float h_pow(float x, float y) { return (float)pow((double)x, (double)y); }
+static inline float h_log(float x) { return (float)log((double)x); }
+static inline float h_srgb_to_linear(float x) { return x > 0.04045f ? h_pow(x * (1.0f / 1.055f) + 0.0521327f, 2.4f) : x / 12.92f; }
+static void h_temperature_to_rgb(float kelvin, float c[3]) {
+    const float t = h_clamp(kelvin, 1000.0f, 50000.0f) / 100.0f;
+    if (t <= 66.0f) {
+        c[0] = 1.0f;
+        c[1] = h_clamp(0.39008157876901960784f * h_log(t) - 0.63184144378862745098f, 0.0f, 1.0f);
+    } else {
+        const float u = t - 60.0f;
+        c[0] = h_clamp(1.29293618606274509804f * h_pow(u, -0.1332047592f), 0.0f, 1.0f);
+        c[1] = h_clamp(1.12989086089529411765f * h_pow(u, -0.0755148492f), 0.0f, 1.0f);
+    }
+    if (t >= 66.0f) c[2] = 1.0f;
+    else if (t <= 19.0f) c[2] = 0.0f;
+    else c[2] = h_clamp(0.54320678911019607843f * h_log(t - 10.0f) - 1.19625408914f, 0.0f, 1.0f);
+    for (int k = 0; k < 3; ++k) c[k] = h_srgb_to_linear(c[k]);
+}
+// host copy of sky_sample() (same arithmetic, same order) on the handle's host copy of the cubemap
+static void h_sky_sample(const float* sky, int N, const float d[3], float out[3]) {
+    const float ax = fabsf(d[0]), ay = fabsf(d[1]), az = fabsf(d[2]);
+    int face;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { face = d[0] > 0.f ? 0 : 1; sc = d[0] > 0.f ? -d[2] : d[2]; tc = -d[1]; ma = ax; }
+    else if (ay >= az)        { face = d[1] > 0.f ? 2 : 3; sc = d[0]; tc = d[1] > 0.f ? d[2] : -d[2]; ma = ay; }
+    else                      { face = d[2] > 0.f ? 4 : 5; sc = d[2] > 0.f ? d[0] : -d[0]; tc = -d[1]; ma = az; }
+    const float s = 0.5f * (sc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
+    const float u = s * (float)N - 0.5f, v = t * (float)N - 0.5f;
+    const float fu0 = floorf(u), fv0 = floorf(v);
+    const float fu = u - fu0, fv = v - fv0;
+    int i0 = (int)fu0, j0 = (int)fv0, i1 = i0 + 1, j1 = j0 + 1;
+    i0 = i0 < 0 ? 0 : (i0 > N - 1 ? N - 1 : i0); i1 = i1 < 0 ? 0 : (i1 > N - 1 ? N - 1 : i1);
+    j0 = j0 < 0 ? 0 : (j0 > N - 1 ? N - 1 : j0); j1 = j1 < 0 ? 0 : (j1 > N - 1 ? N - 1 : j1);
+    const float* F = sky + (size_t)face * N * N * 3;
+    for (int k = 0; k < 3; ++k) {
+        const float a = F[(j0 * N + i0) * 3 + k] * (1.0f - fu) + F[(j0 * N + i1) * 3 + k] * fu;
+        const float b = F[(j1 * N + i0) * 3 + k] * (1.0f - fu) + F[(j1 * N + i1) * 3 + k] * fu;
+        out[k] = a * (1.0f - fv) + b * fv;
+    }
+}
+
+int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const VxReflectionIn& in, const VxReflectionParams& p,
+                      const VxReflectionOut& out) {
+    const SceneDev S = make_scene(c);
+    ReflDev d;
+    d.spp = p.spp; d.trace_length = p.trace_length; d.rough = p.rough; d.checkerboard = p.checkerboard; d.frame = p.frame;
+    d.bn_index = p.frame >= 0 ? p.frame % 128 : 100;
+    d.rough_bias = 1.0f * (1.0f - (p.roughness_bias ? 1.0f : 0.0f)) + 0.85f * (p.roughness_bias ? 1.0f : 0.0f);
+    d.hx = h_clamp(p.halton[0], -2.0f, 2.0f);
+    d.hy = h_clamp(p.halton[1], -2.0f, 2.0f);
+    d.stronger = V3{p.stronger_dir[0], p.stronger_dir[1], p.stronger_dir[2]};
+    d.viewer = V3{p.viewer_pos[0], p.viewer_pos[1], p.viewer_pos[2]};
+    for (int k = 0; k < 10; ++k) d.grass[k] = p.grass_props[k];
+    float temp[3], sky_sun[3], sky_moon[3], sun_c[3], moon_c[3];
+    h_temperature_to_rgb(5778.0f, temp);
+    h_sky_sample(c->h_sky.data(), c->sky_n, p.sun_dir, sky_sun);
+    h_sky_sample(c->h_sky.data(), c->sky_n, p.moon_dir, sky_moon);
+    for (int k = 0; k < 3; ++k) {
+        sun_c[k] = (((sky_sun[k] * temp[k]) * 3.14159265359f) * 2.2f) * p.sun_strength;
+        moon_c[k] = (sky_moon[k] * 3.14159265359f) * p.moon_strength;
+    }
+    const float lum = (moon_c[0] * 0.2125f + moon_c[1] * 0.7154f) + moon_c[2] * 0.0721f;
+    for (int k = 0; k < 3; ++k) moon_c[k] = ((lum * (1.0f - 1.3f) + moon_c[k] * 1.3f) * 0.42525f) * p.moon_strength;
+    float sun_vis = h_clamp(((p.sun_dir[0] * 0.0f + p.sun_dir[1] * 1.0f) + p.sun_dir[2] * 0.0f) + 0.05f, 0.0f, 0.1f) * 12.0f;
+    sun_vis = 1.0f - sun_vis;
+    float mixed[3];
+    for (int k = 0; k < 3; ++k) mixed[k] = sun_c[k] * (1.0f - sun_vis) + moon_c[k] * sun_vis;
+    d.color_mixed = V3{mixed[0], mixed[1], mixed[2]};
+    CameraDev cd;
+    for (int k = 0; k < 16; ++k) { cd.inv_view[k] = cam.inv_view[k]; cd.inv_proj[k] = cam.inv_proj[k]; }
+    cd.width = cam.width; cd.height = cam.height; cd.row_begin = cam.row_begin; cd.row_end = cam.row_end;
+    cd.il_n = cam.interleave_n; cd.il_rank = cam.interleave_rank; cd.il_band = cam.band_rows > 0 ? cam.band_rows : 1;
+    const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel};
+    const ReflInDev id{in.g_normal, reinterpret_cast<const float4*>(in.g_pbr), reinterpret_cast<const float4*>(in.sh),
+                       reinterpret_cast<const float2*>(in.cocg)};
+    const ReflOutDev od{reinterpret_cast<float4*>(out.color), out.hit_distance, out.emissive_mask};
+    const dim3 grid((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8);
+    if (c->opt_layout == 1) reflection_kernel<1><<<grid, 256, 0, c->stream>>>(S, cd, d, gd, id, od);
+    else reflection_kernel<0><<<grid, 256, 0, c->stream>>>(S, cd, d, gd, id, od);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+}  // namespace vxpt

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/vxpt.h"
 
@@ -45,6 +46,8 @@ struct SceneDev {
     const float4* albedo_lod3; // [n_layers][64][64]
     const float4* pbr_lod2;    // [n_layers][128][128]
     const float* emissive;     // [n_emissive][512][512]
+    const float4* normal_lod3; // [n_normal][64][64]   (reflection pass)
+    const float* emissive_lod2;  // [n_emissive][128][128] (reflection pass)
     const float* sky;          // [6][n][n][3]
     const uchar4* shadow_noise;  // [256][256]
     int n_layers, n_emissive, sky_n;
@@ -73,6 +76,11 @@ struct vxpt_ctx {
     float4* d_albedo = nullptr;
     float4* d_pbr = nullptr;
     float* d_emissive = nullptr;
+    float4* d_normal = nullptr;
+    float* d_emissive2 = nullptr;
+    int n_normal = 0, n_emissive2 = 0;
+    bool have_refl_textures = false;
+    std::vector<float> h_sky;  // host copy of the cubemap (per-frame sun / moon colours of the reflection pass)
     float* d_sky = nullptr;
     uchar4* d_shadow_noise = nullptr;
     int n_layers = 0, n_emissive = 0, sky_n = 0;
@@ -123,6 +131,9 @@ struct PlaneSet;  // resolved device pointers of one pass
 int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out_dev);
 int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxShadowParams& p, const VxShadowOut& out_dev);
 int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxDiffuseParams& p, const VxDiffuseOut& out_dev);
+// trace_reflection.cu
+int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxReflectionIn& in_dev, const VxReflectionParams& p,
+                      const VxReflectionOut& out_dev);
 // l2_probe.cu
 int run_l2_probe(vxpt_ctx* c, double* gbps);
 

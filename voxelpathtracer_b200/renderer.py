@@ -6,7 +6,8 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxShadowOut, VxShadowParams, VxStats, check)
+from .abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxReflectionIn, VxReflectionOut, VxReflectionParams,
+                  VxShadowOut, VxShadowParams, VxStats, check)
 
 try:  # torch is optional plumbing: device buffers, streams, torch.distributed
     import torch
@@ -61,6 +62,22 @@ def diffuse_params(sun_dir, moon_dir, sun_visibility, spp=1, checker_spp=None, c
     p.moon_dir[:] = [float(v) for v in moon_dir]
     p.sun_visibility = float(sun_visibility)
     p.gi_sun_strength, p.gi_sky_strength, p.light_intensity = float(gi_sun_strength), float(gi_sky_strength), float(light_intensity)
+    return p
+
+
+def reflection_params(sun_dir, moon_dir, stronger_dir, viewer_pos, grass_props, spp=2, trace_length=64, frame=0, rough=True, roughness_bias=True,
+                      checkerboard=False, sun_strength=0.85, moon_strength=1.0, halton=(0.0, 0.0)):
+    """Defaults of Core/Pipeline.cpp:100-104,114,124,278-279."""
+    p = VxReflectionParams()
+    p.spp, p.trace_length, p.frame = int(spp), int(trace_length), int(frame)
+    p.rough, p.roughness_bias, p.checkerboard = int(bool(rough)), int(bool(roughness_bias)), int(bool(checkerboard))
+    p.sun_dir[:] = [float(v) for v in sun_dir]
+    p.moon_dir[:] = [float(v) for v in moon_dir]
+    p.stronger_dir[:] = [float(v) for v in stronger_dir]
+    p.viewer_pos[:] = [float(v) for v in viewer_pos]
+    p.sun_strength, p.moon_strength = float(sun_strength), float(moon_strength)
+    p.halton[0], p.halton[1] = float(halton[0]), float(halton[1])
+    p.grass_props[:] = [int(v) for v in grass_props]
     return p
 
 
@@ -127,6 +144,12 @@ class Renderer:
         assert a.shape[1:] == (64, 64, 4) and p.shape[1:] == (128, 128, 4) and a.shape[0] == p.shape[0]
         check(self.lib.vxpt_set_material_textures(self.handle, _ptr(a), _ptr(p), int(a.shape[0]), _ptr(e) if e.shape[0] else None, int(e.shape[0])))
 
+    def set_reflection_textures(self, normal_lod3, emissive_lod2):
+        n = np.ascontiguousarray(normal_lod3, dtype=np.float32)
+        e = np.ascontiguousarray(emissive_lod2, dtype=np.float32)
+        assert n.shape[1:] == (64, 64, 4) and (e.shape[0] == 0 or e.shape[1:] == (128, 128))
+        check(self.lib.vxpt_set_reflection_textures(self.handle, _ptr(n), int(n.shape[0]), _ptr(e) if e.shape[0] else None, int(e.shape[0])))
+
     def set_sky_cubemap(self, rgb):
         s = np.ascontiguousarray(rgb, dtype=np.float32)
         assert s.ndim == 4 and s.shape[0] == 6 and s.shape[1] == s.shape[2] and s.shape[3] == 3
@@ -139,6 +162,8 @@ class Renderer:
     def load_scene_tables(self, materials, blue_noise, sky, shadow_noise):
         self.set_materials(materials["table"])
         self.set_material_textures(materials["albedo_lod3"], materials["pbr_lod2"], materials["emissive_lod0"])
+        if "normal_lod3" in materials:
+            self.set_reflection_textures(materials["normal_lod3"], materials["emissive_lod2"])
         self.set_blue_noise(*blue_noise)
         self.set_sky_cubemap(sky)
         self.set_shadow_noise(shadow_noise)
@@ -161,6 +186,10 @@ class Renderer:
 
     def alloc_shadow(self, width, height, device=False):
         return {"shadow": self.alloc((height, width), np.uint8, device), "transversal": self.alloc((height, width), np.float32, device)}
+
+    def alloc_reflection(self, width, height, device=False):
+        return {"color": self.alloc((height, width, 4), np.float32, device), "hit_distance": self.alloc((height, width), np.float32, device),
+                "emissive_mask": self.alloc((height, width), np.uint8, device)}
 
     def alloc_diffuse(self, width, height, device=False):
         return {"sh": self.alloc((height, width, 4), np.float32, device), "cocg": self.alloc((height, width, 2), np.float32, device),
@@ -191,6 +220,15 @@ class Renderer:
         o = VxDiffuseOut()
         o.sh, o.cocg, o.luma, o.ao_sky = _ptr(out.get("sh")), _ptr(out.get("cocg")), _ptr(out.get("luma")), _ptr(out.get("ao_sky"))
         check(self.lib.vxpt_trace_diffuse(self.handle, C.byref(cam), C.byref(g), C.byref(params), C.byref(o)))
+        return out
+
+    def trace_reflection(self, cam, gbuf, diffuse, params, out, g_normal=None, g_pbr=None):
+        g = self.gbuffer_struct(gbuf)
+        i = VxReflectionIn()
+        i.g_normal, i.g_pbr, i.sh, i.cocg = _ptr(g_normal), _ptr(g_pbr), _ptr(diffuse.get("sh")), _ptr(diffuse.get("cocg"))
+        o = VxReflectionOut()
+        o.color, o.hit_distance, o.emissive_mask = _ptr(out.get("color")), _ptr(out.get("hit_distance")), _ptr(out.get("emissive_mask"))
+        check(self.lib.vxpt_trace_reflection(self.handle, C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o)))
         return out
 
     # ---- sync / stats -------------------------------------------------------------------------------------

@@ -236,7 +236,7 @@ def test_reflection_on_flat_ground_mirrors_the_sky(oracles, scene_tables):
     rp2 = vx.reflection_params(scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], fc.position, mats["grass_props"], spp=2, rough=True, frame=2)
     r2, st2 = o.trace_reflection(cam, g, d, rp2)
     sky_only = r2["hit_distance"] == -1.0
-    assert np.allclose(r2["color"][hit & sky_only], [0.3, 0.5, 0.9, 1.0], rtol=1e-6) and (hit & sky_only).sum() > 0.8 * hit.sum()
+    assert np.allclose(r2["color"][hit & sky_only], [0.3, 0.5, 0.9, 1.0], rtol=1e-6) and (hit & sky_only).sum() > 0.5 * hit.sum()
     n_ground = int((hit & ~sky_only).sum())
     assert 2 * int(hit.sum()) + 1 <= st2["rays"] <= 2 * int(hit.sum()) + n_ground and n_ground > 0
 

@@ -119,10 +119,69 @@ constexpr uint32_t INF2 = 0x00FE00FEu;  // 254 in both lanes ("no solid voxel se
 
 // ------------------------------------------------------------------------------------------------------------
 // df_xy_dpx: x and y sweeps of one z-slice in shared memory
+// 256 threads, <= 64 registers, 48 KB of shared memory: 4 CTAs per SM, so all 384 slices are resident at once (592 slots)
+// and the TMA loads, the sweeps and the TMA stores of different slices overlap on every SM.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int XY_THREADS = 192;  // 6 warps; threads 0..191 each own one x-pair column in the y sweep
+constexpr int XY_THREADS = 256;  // 8 warps; threads 0..191 each own one x-pair column in the y sweep
 
-__global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
+// one x-sweep of a pair of rows held as r[0..11] (row A in the low 16-bit lane, row B in the high lane)
+__device__ __forceinline__ void x_sweep_rows(uint32_t (&r)[12], int lane) {
+    // block byte -> initial distance: solid 0, air 254 (ManhattanDistanceX.comp:51-52)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r[k] = INF2 - __vminu2(r[k], ONE2) * 0xFEu;
+    // forward (x ascending): local sweep, min-plus scan of the lanes' last values, carry-in from the lanes to the left
+#pragma unroll
+    for (int k = 1; k < 12; ++k) r[k] = __viaddmin_u16x2(r[k - 1], ONE2, r[k]);
+    uint32_t c = r[11];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, c, d);
+        if (lane >= d) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
+    }
+    uint32_t cin = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) cin = INF2;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(k + 1) * ONE2, r[k]);
+    // backward (x descending)
+#pragma unroll
+    for (int k = 10; k >= 0; --k) r[k] = __viaddmin_u16x2(r[k + 1], ONE2, r[k]);
+    c = r[0];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_down_sync(0xffffffffu, c, d);
+        if (lane + d < 32) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
+    }
+    cin = __shfl_down_sync(0xffffffffu, c, 1);
+    if (lane == 31) cin = INF2;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(12 - k) * ONE2, r[k]);
+}
+
+__device__ __forceinline__ void load_row_pair(const uint32_t* rowA, uint32_t (&r)[12]) {
+    const uint32_t* rowB = rowA + WX / 4;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint32_t A = rowA[k], B = rowB[k];
+        uint32_t t0 = __byte_perm(A, B, 0x6420);  // a0 a2 b0 b2
+        uint32_t t1 = __byte_perm(A, B, 0x7531);  // a1 a3 b1 b3
+        r[4 * k + 0] = t0 & 0x00FF00FFu;
+        r[4 * k + 2] = (t0 >> 8) & 0x00FF00FFu;
+        r[4 * k + 1] = t1 & 0x00FF00FFu;
+        r[4 * k + 3] = (t1 >> 8) & 0x00FF00FFu;
+    }
+}
+__device__ __forceinline__ void store_row_pair(uint32_t* rowA, const uint32_t (&r)[12]) {
+    uint32_t* rowB = rowA + WX / 4;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint32_t t0 = r[4 * k + 0] | (r[4 * k + 2] << 8);  // a0 a2 b0 b2
+        uint32_t t1 = r[4 * k + 1] | (r[4 * k + 3] << 8);  // a1 a3 b1 b3
+        rowA[k] = __byte_perm(t0, t1, 0x5140);
+        rowB[k] = __byte_perm(t0, t1, 0x7362);
+    }
+}
+
+__global__ void __launch_bounds__(XY_THREADS, 4) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* tile = smem;                                            // [128][384] bytes
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SLICE_BYTES);  // mbarrier
@@ -140,75 +199,41 @@ __global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __rest
     }
     mbar_wait(bar, 0);
 
-    // ---- x sweep: a warp takes rows (2p, 2p+1); lane l holds x = 12l .. 12l+11 of both rows, row 2p in the low
-    //      16-bit lane and row 2p+1 in the high lane of r[k].
+    // ---- x sweep: a warp takes row pairs (2p, 2p+1); lane l holds x = 12l .. 12l+11 of both rows.  Two row pairs are in
+    //      flight per warp (independent dependency chains) to cover the latency of the DPX / shuffle chains.
     uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
-    for (int p = warp; p < WY / 2; p += XY_THREADS / 32) {
-        uint32_t* rowA = t32 + (2 * p) * (WX / 4) + lane * 3;
-        uint32_t* rowB = rowA + WX / 4;
-        uint32_t r[12];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            uint32_t A = rowA[k], B = rowB[k];
-            uint32_t t0 = __byte_perm(A, B, 0x6420);  // a0 a2 b0 b2
-            uint32_t t1 = __byte_perm(A, B, 0x7531);  // a1 a3 b1 b3
-            r[4 * k + 0] = t0 & 0x00FF00FFu;
-            r[4 * k + 2] = (t0 >> 8) & 0x00FF00FFu;
-            r[4 * k + 1] = t1 & 0x00FF00FFu;
-            r[4 * k + 3] = (t1 >> 8) & 0x00FF00FFu;
-        }
-        // block byte -> initial distance: solid 0, air 254 (ManhattanDistanceX.comp:51-52)
-#pragma unroll
-        for (int k = 0; k < 12; ++k) r[k] = INF2 - __vminu2(r[k], ONE2) * 0xFEu;
-        // forward (x ascending)
-#pragma unroll
-        for (int k = 1; k < 12; ++k) r[k] = __viaddmin_u16x2(r[k - 1], ONE2, r[k]);
-        uint32_t c = r[11];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, c, d);
-            if (lane >= d) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
-        }
-        uint32_t cin = __shfl_up_sync(0xffffffffu, c, 1);
-        if (lane == 0) cin = INF2;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(k + 1) * ONE2, r[k]);
-        // backward (x descending)
-#pragma unroll
-        for (int k = 10; k >= 0; --k) r[k] = __viaddmin_u16x2(r[k + 1], ONE2, r[k]);
-        c = r[0];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_down_sync(0xffffffffu, c, d);
-            if (lane + d < 32) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
-        }
-        cin = __shfl_down_sync(0xffffffffu, c, 1);
-        if (lane == 31) cin = INF2;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(12 - k) * ONE2, r[k]);
-        // repack the two rows and put them back
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            uint32_t t0 = r[4 * k + 0] | (r[4 * k + 2] << 8);  // a0 a2 b0 b2
-            uint32_t t1 = r[4 * k + 1] | (r[4 * k + 3] << 8);  // a1 a3 b1 b3
-            rowA[k] = __byte_perm(t0, t1, 0x5140);
-            rowB[k] = __byte_perm(t0, t1, 0x7362);
-        }
+    constexpr int WARPS = XY_THREADS / 32;  // 8 warps x 8 row pairs = 64 row pairs
+#pragma unroll 1
+    for (int p = warp; p < WY / 2; p += 2 * WARPS) {
+        uint32_t* rowA0 = t32 + (2 * p) * (WX / 4) + lane * 3;
+        uint32_t* rowA1 = rowA0 + 2 * WARPS * (WX / 4);  // row pair p + 8 = 16 rows further
+        uint32_t r0[12], r1[12];
+        load_row_pair(rowA0, r0);
+        load_row_pair(rowA1, r1);
+        x_sweep_rows(r0, lane);
+        x_sweep_rows(r1, lane);
+        store_row_pair(rowA0, r0);
+        store_row_pair(rowA1, r1);
     }
     __syncthreads();
 
-    // ---- y sweep: thread t owns voxels x = 2t, 2t+1 for all 128 rows (x-neighbours in the two lanes)
-    {
-        uint16_t* t16 = reinterpret_cast<uint16_t*>(tile) + tid;
-        uint32_t col[WY];
-#pragma unroll
-        for (int y = 0; y < WY; ++y) col[y] = __byte_perm((uint32_t)t16[y * (WX / 2)], 0u, 0x4140);
-#pragma unroll
-        for (int y = 1; y < WY; ++y) col[y] = __viaddmin_u16x2(col[y - 1], ONE2, col[y]);
-#pragma unroll
-        for (int y = WY - 2; y >= 0; --y) col[y] = __viaddmin_u16x2(col[y + 1], ONE2, col[y]);
-#pragma unroll
-        for (int y = 0; y < WY; ++y) t16[y * (WX / 2)] = (uint16_t)__byte_perm(col[y], 0u, 0x4420);
+    // ---- y sweep: thread t owns voxels x = 2t, 2t+1 (x-neighbours in the two 16-bit lanes); the column is streamed
+    //      through shared memory (loads run ahead of the one-instruction dependency chain), not held in registers.
+    if (tid < WX / 2) {
+        uint16_t* col = reinterpret_cast<uint16_t*>(tile) + tid;
+        uint32_t prev = __byte_perm((uint32_t)col[0], 0u, 0x4140);
+#pragma unroll 16
+        for (int y = 1; y < WY; ++y) {
+            uint32_t cur = __byte_perm((uint32_t)col[y * (WX / 2)], 0u, 0x4140);
+            prev = __viaddmin_u16x2(prev, ONE2, cur);
+            col[y * (WX / 2)] = (uint16_t)__byte_perm(prev, 0u, 0x4420);
+        }
+#pragma unroll 16
+        for (int y = WY - 2; y >= 0; --y) {
+            uint32_t cur = __byte_perm((uint32_t)col[y * (WX / 2)], 0u, 0x4140);
+            prev = __viaddmin_u16x2(prev, ONE2, cur);
+            col[y * (WX / 2)] = (uint16_t)__byte_perm(prev, 0u, 0x4420);
+        }
     }
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
     __syncthreads();

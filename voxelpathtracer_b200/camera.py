@@ -49,8 +49,9 @@ class FpsCamera:
     @property
     def front(self):
         # FPSCamera::UpdateOnMouseMovement, Core/FpsCamera.cpp:66-70 (yaw 90 deg looks down +Z)
-        cp, sp = math.cos(math.radians(self.pitch)), math.sin(math.radians(self.pitch))
-        return np.array([cp * math.cos(math.radians(self.yaw)), sp, cp * math.sin(math.radians(self.yaw))])
+        ry, rp = self.yaw * math.pi / 180.0, self.pitch * math.pi / 180.0
+        # rounded to float like glm::vec3 front (and like the C++ host mirror)
+        return np.array([f32(math.cos(rp) * math.cos(ry)), f32(math.sin(rp)), f32(math.cos(rp) * math.sin(ry))], dtype=np.float64)
 
     def view(self):
         return look_at(self.position, self.position + self.front, (0.0, 1.0, 0.0))
@@ -58,11 +59,34 @@ class FpsCamera:
     def projection(self):
         return perspective(self.fov, self.aspect, self.z_near, self.z_far)
 
+    def inverse_matrices(self):
+        """(inv_view, inv_proj) as float32 [4,4] (math convention m[row, col]), computed analytically in double — the same
+        formulas, in the same order, as the C++ host mirror (voxelpathtracer_b200/host/VoxelRT.h: FPSCamera::GetVxCamera),
+        so both hosts hand bit-identical matrices to the ABI."""
+        f = self.front
+        f = f / math.sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2])
+        s = np.array([f[1] * 0.0 - f[2] * 1.0, f[2] * 0.0 - f[0] * 0.0, f[0] * 1.0 - f[1] * 0.0])  # cross(f, (0,1,0))
+        s = s / math.sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2])
+        u = np.array([s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]])  # cross(s, f)
+        inv_view = np.zeros((4, 4), dtype=np.float32)
+        inv_view[:3, 0], inv_view[:3, 1], inv_view[:3, 2] = s.astype(f32), u.astype(f32), (-f).astype(f32)
+        inv_view[:3, 3] = self.position.astype(f32)
+        inv_view[3, 3] = 1.0
+        t = math.tan(self.fov * math.pi / 180.0 / 2.0)
+        A = -(self.z_far + self.z_near) / (self.z_far - self.z_near)
+        B = -(2.0 * self.z_far * self.z_near) / (self.z_far - self.z_near)
+        inv_proj = np.zeros((4, 4), dtype=np.float32)
+        inv_proj[0, 0] = f32(self.aspect * t)
+        inv_proj[1, 1] = f32(t)
+        inv_proj[3, 2] = f32(1.0 / B)
+        inv_proj[2, 3] = -1.0
+        inv_proj[3, 3] = f32(A / B)
+        return inv_view, inv_proj
+
     def vx_camera(self, width, height, row_begin=0, row_end=None, interleave_n=0, interleave_rank=0, band_rows=0):
         """inv_view / inv_projection as Pipeline.cpp:1823-1824 hands them to the shaders.  interleave_*: see VxCamera."""
         cam = VxCamera()
-        inv_view = np.linalg.inv(self.view()).astype(f32)
-        inv_proj = np.linalg.inv(self.projection()).astype(f32)
+        inv_view, inv_proj = self.inverse_matrices()
         cam.inv_view[:] = inv_view.T.reshape(16).tolist()  # column-major
         cam.inv_proj[:] = inv_proj.T.reshape(16).tolist()
         cam.width, cam.height = int(width), int(height)

@@ -1,0 +1,65 @@
+// headless_main.cpp — the reference's start-up + first frames without a window (main.cpp:66-70 -> Pipeline.cpp:1164-1294,
+// 1959-2062, 2790-2852), through the C++ host mirror (VoxelRT.h) and the C ABI.  Builds a world, buffers it, generates
+// the distance field, traces primary + hard sun shadow rays for a few frames, edits a block (full rebuild) and prints
+// FNV-1a digests of the planes (tests/test_gpu_host_cpp.py compares them with the Python driver's).
+//   usage: vxpt_headless [width height [plains_columns.u8]]
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "VoxelRT.h"
+
+static uint64_t fnv1a(const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+int main(int argc, char** argv) {
+    using namespace VoxelRT;
+    const int W = argc > 2 ? std::atoi(argv[1]) : 640, H = argc > 2 ? std::atoi(argv[2]) : 360;
+    std::vector<uint8_t> columns;
+    if (argc > 3) {
+        FILE* f = std::fopen(argv[3], "rb");
+        if (!f) { Logger::Log("cannot open the plains column table"); return 2; }
+        columns.resize(WORLD_SIZE_X * WORLD_SIZE_Z * 2);
+        if (std::fread(columns.data(), 1, columns.size(), f) != columns.size()) { std::fclose(f); return 2; }
+        std::fclose(f);
+    }
+    World world;
+    GenerateWorld(&world, !columns.empty(), columns.empty() ? nullptr : columns.data());
+    if (!world.Buffer(0)) return 1;  // no CUDA device -> loud failure, there is no CPU path
+    world.InitializeDistanceGenerator();
+    if (!world.GenerateDistanceField()) return 1;
+    std::vector<uint8_t> df;
+    world.DownloadDistanceField(df);
+    std::printf("df %016" PRIx64 "\n", fnv1a(df.data(), df.size()));
+
+    FPSCamera camera(60.0f, (float)W / (float)H);
+    camera.SetYawPitch(90.0f, -20.0f);
+    VxCamera cam = camera.GetVxCamera(W, H);
+    std::vector<float> t((size_t)W * H), inv_t((size_t)W * H), transversal((size_t)W * H);
+    std::vector<uint8_t> normal((size_t)W * H), block((size_t)W * H), shadow((size_t)W * H);
+    VxGBuffer gbuf{t.data(), normal.data(), block.data(), inv_t.data(), nullptr};
+    VxShadowOut sout{shadow.data(), transversal.data()};
+    const float sun[3] = {-0.66896474f, 0.46841538f, 0.57735026f};  // SunTick = 50 (Pipeline.cpp:64,1653-1671)
+    for (int frame = 0; frame < 3; ++frame) {
+        VxPrimaryParams pp{frame == 0 ? 475 : 350, 1, {0.f, 0.f}, 0, 0};  // u_RenderDistance: 475 then 350 (Pipeline.cpp:55,4824)
+        GetTAAJitter(frame, pp.jitter);
+        if (!vx_ok(vxpt_trace_primary(world.Handle(), &cam, &pp, &gbuf), "vxpt_trace_primary")) return 1;
+        VxShadowParams sp{{sun[0], sun[1], sun[2]}, frame, /*soft*/ 0, {0.f, 0.f}, 0};
+        if (!vx_ok(vxpt_trace_shadow(world.Handle(), &cam, &gbuf, &sp, &sout), "vxpt_trace_shadow")) return 1;
+        std::printf("frame %d t %016" PRIx64 " normal %016" PRIx64 " block %016" PRIx64 " shadow %016" PRIx64 "\n", frame, fnv1a(t.data(), t.size() * 4),
+                    fnv1a(normal.data(), normal.size()), fnv1a(block.data(), block.size()), fnv1a(shadow.data(), shadow.size()));
+    }
+    // place a block in front of the camera: the ABI refuses to trace over a stale field until the rebuild
+    world.EditBlock(192, 70, 200, {BlockID::Stone});
+    world.DownloadDistanceField(df);
+    std::printf("df_after_edit %016" PRIx64 "\n", fnv1a(df.data(), df.size()));
+    VxStats st{};
+    vxpt_get_stats(world.Handle(), &st);
+    std::printf("rays %" PRIu64 " df_fetches %" PRIu64 " df_build_ms %.4f\n", (uint64_t)st.rays, (uint64_t)st.df_fetches, st.df_build_ms);
+    return 0;
+}

@@ -12,9 +12,9 @@
  *    vxpt_last_error() returns a thread-local description of the last failure.
  *  - a handle is NOT thread-safe (one caller thread per handle, like a GL context).
  *  - all buffers are caller-owned.  Input pointers may be host or device memory; output pointers may be host
- *    or device memory (detected with cudaPointerGetAttributes).  Host outputs are staged through pinned
- *    memory owned by the handle and are complete when the call returns; device outputs are complete after
- *    vxpt_sync() (work is enqueued on the handle's private stream).
+ *    or device memory (detected with cudaPointerGetAttributes).  Host planes are staged through device memory owned
+ *    by the handle and are complete when the call returns (pinned host buffers make the copies DMA-direct); device
+ *    outputs are complete after vxpt_sync() (work is enqueued on the handle's private stream).
  *  - images: pixel (i, j) with j = 0 the BOTTOM row (GL convention, a_TexCoords of the full-screen quad);
  *    plane index = j * width + i.  A call renders rows [row_begin, row_end) only and touches no other row of
  *    the output planes — this is the multi-GPU row-slab contract.
@@ -237,7 +237,8 @@ VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
 
 /* ---- tuning knobs (do not change results) ---------------------------------------------------------------- */
 #define VXPT_OPT_TRAVERSAL_LAYOUT 1 /* 0 = linear distance field, 1 = brick-swizzled copy (default) */
-#define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront re-queue (default)          */
+#define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront re-queue of first-bounce hits (default),
+                                       2 = 1 + persistent first-bounce tracer that refills finished lanes from a ray queue */
 #define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped), 1 = DPX tiled (default) */
 /* measurement knob: keep `value` (1..8) identical copies of the grid + step field at distinct addresses and rotate through
  * them, one per vxpt_trace_primary call (= per frame).  With 3 copies the traced inputs (132 MB) exceed the 126 MB L2, so

@@ -219,6 +219,10 @@ int vxpt_create(int device_id, vxpt_handle* out) {
         vxpt_destroy(c);
         return rc == VXPT_E_CUDA && e == cudaErrorMemoryAllocation ? VXPT_E_NOMEM : rc;
     }
+    if (int rc = init_df_kernels(c)) {
+        vxpt_destroy(c);
+        return rc;
+    }
     *out = c;
     return VXPT_OK;
 }
@@ -235,7 +239,6 @@ int vxpt_destroy(vxpt_handle c) {
                     c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_counters, c->d_stage, c->d_queue};
     for (void* b : bufs)
         if (b) cudaFree(b);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -645,7 +648,7 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
             }
             return VXPT_OK;
         case VXPT_OPT_GI_WAVEFRONT:
-            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "wavefront must be 0 or 1");
+            if (value < 0 || value > 2) return fail(VXPT_E_INVALID, "wavefront must be 0..2");
             c->opt_wavefront = value;
             return VXPT_OK;
         case VXPT_OPT_SCENE_REPLICAS:

@@ -353,6 +353,16 @@ __global__ void __launch_bounds__(256) pack_steps(const uint8_t* __restrict__ df
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// per-handle, per-device one-time set-up (called by vxpt_create on the handle's device)
+int init_df_kernels(vxpt_ctx* c) {
+    VX_CUDA(cudaFuncSetAttribute(df_xy_dpx, cudaFuncAttributeMaxDynamicSharedMemorySize, SLICE_BYTES + 16));
+    uint8_t lut[256];
+    for (int m = 0; m < 256; ++m) lut[m] = (uint8_t)((m == 1) ? 1 : (int)floorf((float)m * 0.57735026918f));
+    VX_CUDA(cudaMemcpyToSymbolAsync(c_step_lut, lut, sizeof lut, 0, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
 int launch_df_build(vxpt_ctx* c) {
     cudaStream_t s = c->stream;
     if (c->opt_df_algo == 0) {
@@ -362,11 +372,6 @@ int launch_df_build(vxpt_ctx* c) {
         c->launches += 3;
     } else {
         const int smem = SLICE_BYTES + 16;
-        static bool attr_done = false;
-        if (!attr_done) {
-            VX_CUDA(cudaFuncSetAttribute(df_xy_dpx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_done = true;
-        }
         df_xy_dpx<<<WZ, XY_THREADS, smem, s>>>(c->d_grid, c->d_tmp);
         df_z_dpx<<<dim3(WX / 128, WY), dim3(32, ZSEGS), 0, s>>>(c->d_tmp, c->d_df);
         c->launches += 2;
@@ -376,13 +381,6 @@ int launch_df_build(vxpt_ctx* c) {
 }
 
 int launch_pack_bricks(vxpt_ctx* c) {
-    static bool lut_done = false;
-    if (!lut_done) {
-        uint8_t lut[256];
-        for (int m = 0; m < 256; ++m) lut[m] = (uint8_t)((m == 1) ? 1 : (int)floorf((float)m * 0.57735026918f));
-        VX_CUDA(cudaMemcpyToSymbol(c_step_lut, lut, sizeof lut));
-        lut_done = true;
-    }
     if (c->opt_layout == 1) {
         const int warps = (WX / 32) * (WY / 4) * (WZ / 4);
         pack_steps<1><<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(c->d_df, c->d_steps);

@@ -112,61 +112,93 @@ __device__ __forceinline__ int get_voxel_at(const SceneDev& S, V3 p, Counters& c
 //  * "Intersection = false" on leaving the volume is dropped: the final position is then outside the volume, GetVoxel
 //    returns 0 and the function returns -1 either way (:362-367), so a sticky "a DDA step happened" flag suffices;
 //  * the loop counter doubles as the distance-field fetch count (an iteration that fails the bounds test ends the loop).
+// The loop is written as a resumable state machine (init / step / finish) so that the persistent GI kernel can interleave
+// the iterations of different rays in one lane; traverse_df() is the plain composition of the three.
+// (Tried and rejected, r01g: a "while-while" shape — consecutive sphere-skips in an inner loop, the lanes that need the longer
+// DDA step waiting at its exit to take it together.  It executes fewer instructions but lengthens every warp's chain of dependent
+// distance-field loads (sum over rounds of the longest skip run instead of the longest ray), and the loop is latency-bound:
+// primary 0.148 -> 0.177 ms, shadow 0.152 -> 0.203 ms, diffuse 0.39 -> 0.85 ms.)
+struct TravState {
+    float dx, dy, dz;        // direction
+    float ivx, ivy, ivz;     // (1.0f / direction)
+    float hx, hy, hz;        // (1 + RaySign) >> 1 as floats
+    float kx, ky, kz;        // RaySign + (1 - half)
+    float nx, ny, nz;        // RaySign * 0.0001f
+    float ox, oy, oz;        // current position
+    int sx, sy, sz;          // RaySign
+    int n, max_it, stepped, min_idx;
+};
+
+__device__ __forceinline__ void trav_init(TravState& t, const V3 origin, const V3 dir, int max_it) {
+    t.dx = dir.x; t.dy = dir.y; t.dz = dir.z;
+    t.sx = (dir.x > 0.0f) - (dir.x < 0.0f); t.sy = (dir.y > 0.0f) - (dir.y < 0.0f); t.sz = (dir.z > 0.0f) - (dir.z < 0.0f);
+    const float fsx = (float)t.sx, fsy = (float)t.sy, fsz = (float)t.sz;
+    t.hx = (float)((1 + t.sx) >> 1); t.hy = (float)((1 + t.sy) >> 1); t.hz = (float)((1 + t.sz) >> 1);
+    t.kx = fsx + (1.0f - t.hx); t.ky = fsy + (1.0f - t.hy); t.kz = fsz + (1.0f - t.hz);
+    t.nx = fsx * 0.0001f; t.ny = fsy * 0.0001f; t.nz = fsz * 0.0001f;
+    t.ivx = 1.0f / dir.x; t.ivy = 1.0f / dir.y; t.ivz = 1.0f / dir.z;
+    t.ox = origin.x; t.oy = origin.y; t.oz = origin.z;
+    t.n = 0; t.max_it = max_it; t.stepped = 0; t.min_idx = 0;
+}
+
+// one loop iteration; returns true when the loop has ended (cap reached, left the volume, or E == 0)
 template <int LAYOUT>
-__device__ __forceinline__ float traverse_df(const SceneDev& S, const V3 origin, const V3 dir, const int max_it, TraceHit& h, Counters& cnt) {
-    const int sx = (dir.x > 0.0f) - (dir.x < 0.0f), sy = (dir.y > 0.0f) - (dir.y < 0.0f), sz = (dir.z > 0.0f) - (dir.z < 0.0f);
-    const float fsx = (float)sx, fsy = (float)sy, fsz = (float)sz;                        // RaySign as floats
-    const float hx = (float)((1 + sx) >> 1), hy = (float)((1 + sy) >> 1), hz = (float)((1 + sz) >> 1);
-    const float kx = fsx + (1.0f - hx), ky = fsy + (1.0f - hy), kz = fsz + (1.0f - hz);  // RaySign + (1 - half)
-    const float nx = fsx * 0.0001f, ny = fsy * 0.0001f, nz = fsz * 0.0001f;               // RaySign * 0.0001f
-    const float ivx = 1.0f / dir.x, ivy = 1.0f / dir.y, ivz = 1.0f / dir.z;               // (1.0f / direction)
-    const bool sx_nz = sx != 0, sz_z = sz == 0;
-    float ox = origin.x, oy = origin.y, oz = origin.z;
-    int stepped = 0, min_idx = 0, n = 0;
-    cnt.rays++;
-    while (n < max_it) {
-        const float bx = floor_biased(ox), by = floor_biased(oy), bz = floor_biased(oz);
-        const int lx = biased_to_int(bx), ly = biased_to_int(by), lz = biased_to_int(bz);
-        if (!in_volume_i(lx, ly, lz)) break;
-        ++n;
-        const int euclid = fetch_step<LAYOUT>(S, lx, ly, lz);
-        if (euclid >= 2) {
-            const float k = (float)(euclid - 1);
-            ox = ox + k * dir.x;
-            oy = oy + k * dir.y;
-            oz = oz + k * dir.z;
-            continue;
-        }
-        if (euclid == 0) break;
-        // euclid == 1: one DDA step.  in-volume => origin >= 0, so ivec3(origin) (truncation) == Loc
-        const float gx = biased_to_float(bx), gy = biased_to_float(by), gz = biased_to_float(bz);
-        const float wx = ox - gx, wy = oy - gy, wz = oz - gz;
-        const float dfx = (hx - wx) * ivx, dfy = (hy - wy) * ivy, dfz = (hz - wz) * ivz;
-        const bool p = dfx < dfy && sx_nz;
-        const float c = p ? dfx : dfy;
-        const bool q = c < dfz || sz_z;
-        const float fm = q ? c : dfz;
-        min_idx = q ? (p ? 0 : 1) : 2;
-        const float ax = gx + (wx + dir.x * fm), ay = gy + (wy + dir.y * fm), az = gz + (wz + dir.z * fm);
-        const float sxp = (gx + kx) + nx, syp = (gy + ky) + ny, szp = (gz + kz) + nz;
-        ox = (q && p) ? sxp : ax;
-        oy = (q && !p) ? syp : ay;
-        oz = q ? az : szp;
-        stepped = 1;
+__device__ __forceinline__ bool trav_step(const SceneDev& S, TravState& t) {
+    if (t.n >= t.max_it) return true;
+    const float bx = floor_biased(t.ox), by = floor_biased(t.oy), bz = floor_biased(t.oz);
+    const int lx = biased_to_int(bx), ly = biased_to_int(by), lz = biased_to_int(bz);
+    if (!in_volume_i(lx, ly, lz)) return true;
+    ++t.n;
+    const int euclid = fetch_step<LAYOUT>(S, lx, ly, lz);
+    if (euclid >= 2) {
+        const float k = (float)(euclid - 1);
+        t.ox = t.ox + k * t.dx;
+        t.oy = t.oy + k * t.dy;
+        t.oz = t.oz + k * t.dz;
+        return false;
     }
-    cnt.df += n;
-    h.min_idx = min_idx;
-    h.sgn = (min_idx == 0) ? sx : ((min_idx == 1) ? sy : sz);
+    if (euclid == 0) return true;
+    // euclid == 1: one DDA step.  in-volume => origin >= 0, so ivec3(origin) (truncation) == Loc
+    const float gx = biased_to_float(bx), gy = biased_to_float(by), gz = biased_to_float(bz);
+    const float wx = t.ox - gx, wy = t.oy - gy, wz = t.oz - gz;
+    const float dfx = (t.hx - wx) * t.ivx, dfy = (t.hy - wy) * t.ivy, dfz = (t.hz - wz) * t.ivz;
+    const bool p = dfx < dfy && t.sx != 0;
+    const float c = p ? dfx : dfy;
+    const bool q = c < dfz || t.sz == 0;
+    const float fm = q ? c : dfz;
+    t.min_idx = q ? (p ? 0 : 1) : 2;
+    const float ax = gx + (wx + t.dx * fm), ay = gy + (wy + t.dy * fm), az = gz + (wz + t.dz * fm);
+    const float sxp = (gx + t.kx) + t.nx, syp = (gy + t.ky) + t.ny, szp = (gz + t.kz) + t.nz;
+    t.ox = (q && p) ? sxp : ax;
+    t.oy = (q && !p) ? syp : ay;
+    t.oz = q ? az : szp;
+    t.stepped = 1;
+    return false;
+}
+
+__device__ __forceinline__ float trav_finish(const SceneDev& S, const TravState& t, const V3 origin, TraceHit& h, Counters& cnt) {
+    cnt.df += t.n;
+    h.min_idx = t.min_idx;
+    h.sgn = (t.min_idx == 0) ? t.sx : ((t.min_idx == 1) ? t.sy : t.sz);
     h.block = 0;
     h.vx = h.vy = h.vz = -1;
     h.t = -1.0f;
-    if (stepped) {
-        const V3 pos = mk3(ox, oy, oz);
+    if (t.stepped) {
+        const V3 pos = mk3(t.ox, t.oy, t.oz);
         h.block = get_voxel_at(S, pos, cnt, &h.vx, &h.vy, &h.vz);
         if (h.block > 0) h.t = length3(pos - origin);
         else h.vx = h.vy = h.vz = -1;
     }
     return h.t;
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ float traverse_df(const SceneDev& S, const V3 origin, const V3 dir, const int max_it, TraceHit& h, Counters& cnt) {
+    TravState t;
+    trav_init(t, origin, dir, max_it);
+    cnt.rays++;
+    while (!trav_step<LAYOUT>(S, t)) {}
+    return trav_finish(S, t, origin, h, cnt);
 }
 
 // GetNormalID — InitialRayTraceFrag.glsl:143-185

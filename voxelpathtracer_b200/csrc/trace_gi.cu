@@ -7,6 +7,10 @@
 //   gi_gen_trace0  one thread per pixel: first hemisphere direction (blue-noise tables), first traversal.  A miss is
 //                  finished on the spot (sky radiance).  Hits are compacted into a queue with one warp ballot +
 //                  one atomicAdd per warp (popc / prefix ranks give each lane its slot).
+//   (opt-in, VXPT_OPT_GI_WAVEFRONT = 2: gi_gen -> gi_trace0 -> gi_resolve.  gi_gen queues the first-bounce rays, gi_trace0 is a
+//                  persistent tracer whose lanes are refilled from the ray queue as their rays end (resumable traversal:
+//                  trav_init / trav_step / trav_finish; retire + refill batched until 8 lanes need it), gi_resolve shades the
+//                  misses densely and compacts the hits.  Measured slower than the fused kernel, see run_wavefront.)
 //   gi_continue    one thread per queued hit (dense warps): shading of the first hit, its sun shadow sub-ray, the
 //                  second traversal, shading + shadow sub-ray of the second hit, end of the sample.
 //   gi_finalize    only when some pixel takes more than one sample: per-pixel averages and clamps (:915-934).
@@ -14,11 +18,16 @@
 // Samples of one pixel are processed one after another (launch s+1 after launch s), so the blue-noise dimension counter
 // and the accumulation order are exactly those of the shader's loop; the planes are bit-identical to diffuse_kernel's.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gi_device.cuh"
 
 namespace vxpt {
 
+struct RayRec {   // 32 B
+    float4 a;     // ro.xyz, pixel index (bits)
+    float4 b;     // rd.xyz, bl_sample (bits)
+};
 struct HitRec {   // 48 B
     float4 a;     // ro.xyz, T
     float4 b;     // rd.xyz, pixel index (bits)
@@ -208,6 +217,143 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
     flush_counters(S, cnt);
 }
 
+// first half of gi_gen_trace0: per pixel set-up, rays into the queue
+template <bool SPP1>
+__global__ void __launch_bounds__(256) gi_gen(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
+                                              const DiffuseOutDev out, PixState* __restrict__ state, RayRec* __restrict__ rays,
+                                              unsigned* __restrict__ counters, const int sample) {
+    int i, j, prow;
+    const bool active = thread_pixel(cam, i, j, prow);
+    bool push = false;
+    RayRec rec;
+    if (active) {
+        const size_t px = (size_t)prow * cam.width + i;
+        float u = ((float)i + 0.5f) / (float)cam.width;
+        float v = ((float)j + 0.5f) / (float)cam.height;
+        const float u0 = u, v0 = v;
+        if (P.supersample) {
+            u += (P.hx * 0.75f) / (float)cam.width;
+            v += (P.hy * 0.75f) / (float)cam.height;
+        }
+        const float dist = g.t[px];
+        const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
+        if (dist < 0.0f) {
+            if (sample == 0) {  // sky pixel (:866-872)
+                float sh[6];
+                const V3 vdir = normalize3(ray_direction_at(cam, u0, v0));
+                irradiance_to_sh(sky_sample(S, vdir) * 2.66f, normal, sh);
+                if (out.sh) out.sh[px] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+                if (out.cocg) out.cocg[px] = make_float2(sh[4], sh[5]);
+                if (out.luma) out.luma[px] = 0.0f;
+                if (out.ao_sky) out.ao_sky[px] = make_float2(1.0f, 0.0f);
+            }
+        } else if (sample < pixel_spp(P, i, j)) {
+            int bl_sample = 0;
+            if (!SPP1) {
+                if (sample == 0) {
+                    PixState z;
+                    z.tot = z.rad = z.misc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    state[px] = z;
+                } else {
+                    bl_sample = __float_as_int(state[px].misc.w);
+                }
+            }
+            const V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, u, v)) * dist;
+            const V3 ro = pos + normal * 0.06f;
+            const V3 rd = cos_hemisphere(S, i, j, P.frame % 128, bl_sample, normal);
+            push = true;
+            rec.a = make_float4(ro.x, ro.y, ro.z, __int_as_float((int)px));
+            rec.b = make_float4(rd.x, rd.y, rd.z, __int_as_float(bl_sample));
+        }
+    }
+    const unsigned slot = warp_push(counters + 2, push);
+    if (push) rays[slot] = rec;
+}
+
+// persistent first-bounce traversal with lane refill.  counters: [0] hit count, [1] hit cursor, [2] ray count, [3] ray cursor
+// A lane is idle (0), tracing (1) or done (3).  The main loop only advances rays; finished rays are
+// retired (final block fetch + 8-byte result) and idle lanes refilled in one maintenance step that runs when THRESH lanes need it
+// (or nothing else is left to do), so the maintenance code runs with many lanes instead of one or two per iteration, and nothing
+// but traversal is executed by partially filled warps.  Shading of the results happens in gi_resolve, densely.
+template <int LAYOUT, int THRESH>
+__global__ void __launch_bounds__(256) gi_trace0(const SceneDev S, const DiffuseDev P, const RayRec* __restrict__ rays, float2* __restrict__ results,
+                                                 unsigned* __restrict__ counters) {
+    const unsigned n_rays = counters[2];
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Counters cnt = {0u, 0u, 0u};
+    TravState t;
+    V3 origin = mk3(0.f, 0.f, 0.f);
+    unsigned idx = 0;
+    int phase = 0;
+    bool exhausted = false;
+    trav_init(t, origin, mk3(1.f, 1.f, 1.f), 0);
+    while (true) {
+        const unsigned done_mask = __ballot_sync(0xffffffffu, phase == 3);
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, phase == 0);
+        const unsigned live_mask = ~(done_mask | idle_mask);
+        if (live_mask == 0u || __popc(done_mask) + (exhausted ? 0 : __popc(idle_mask)) >= THRESH) {
+            if (phase == 3) {  // retire
+                TraceHit h;
+                const float T = trav_finish(S, t, origin, h, cnt);
+                results[idx] = make_float2(T, __int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8)));
+                phase = 0;
+            }
+            const unsigned want = done_mask | idle_mask;  // every one of these lanes is idle now
+            if (!exhausted) {  // refill
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(counters + 3, (unsigned)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + __popc(want) >= n_rays) exhausted = true;
+                if (phase == 0) {
+                    const unsigned my = base + __popc(want & lt_mask);
+                    if (my < n_rays) {
+                        const RayRec r = rays[my];
+                        origin = mk3(r.a.x, r.a.y, r.a.z);
+                        trav_init(t, origin, mk3(r.b.x, r.b.y, r.b.z), P.trace_length);
+                        idx = my;
+                        cnt.rays++;
+                        phase = 1;
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, phase != 0)) break;
+        }
+        if (phase == 1 && trav_step<LAYOUT>(S, t)) phase = 3;
+    }
+    flush_counters(S, cnt);
+}
+
+// one thread per traced first-bounce ray: a miss ends the sample here (sky radiance), a hit goes to the hit queue
+template <bool SPP1>
+__global__ void __launch_bounds__(256) gi_resolve(const SceneDev S, const DiffuseDev P, const DiffuseOutDev out, PixState* __restrict__ state,
+                                                  const RayRec* __restrict__ rays, const float2* __restrict__ results, HitRec* __restrict__ hits,
+                                                  unsigned* __restrict__ counters) {
+    const unsigned n_rays = counters[2];
+    const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+    if (blockIdx.x * 256u >= n_rays) return;
+    bool push = false;
+    HitRec rec;
+    if (idx < n_rays) {
+        const RayRec r = rays[idx];
+        const float2 q = results[idx];
+        const float T = q.x;
+        const int code = __float_as_int(q.y);
+        const V3 rd = mk3(r.b.x, r.b.y, r.b.z);
+        if (T > 0.0f && ((code >> 8) & 255) > 0) {
+            push = true;
+            rec.a = make_float4(r.a.x, r.a.y, r.a.z, T);
+            rec.b = make_float4(rd.x, rd.y, rd.z, r.a.w);
+            rec.c = make_float4(q.y, r.b.w, 0.f, 0.f);
+        } else {
+            const V3 contrib = mk3(0.f, 0.f, 0.f) + sky_term(S, P, rd) * mk3(1.f, 1.f, 1.f);
+            finish_sample<SPP1>(out, state, (size_t)(unsigned)__float_as_int(r.a.w), contrib, 1.0f, rd, true, __float_as_int(r.b.w));
+        }
+    }
+    const unsigned slot = warp_push(counters + 0, push);
+    if (push) hits[slot] = rec;
+}
+
 template <int LAYOUT, bool SPP1>
 __global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const DiffuseOutDev out,
                                                    PixState* __restrict__ state, const HitRec* __restrict__ queue,
@@ -274,13 +420,35 @@ static CameraDev cam_to_dev(const VxCamera& cam) {
 
 template <int LAYOUT, bool SPP1>
 static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, const DiffuseDev& d, const GBufferDev& g, const DiffuseOutDev& od,
-                         PixState* state, HitRec* queue, unsigned* count, int max_spp) {
+                         PixState* state, HitRec* queue, RayRec* rays, float2* results, unsigned* count, int max_spp) {
     const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
+    const size_t slab_px = (size_t)(cd.row_end - cd.row_begin) * cd.width;
+    // opt-in (VXPT_OPT_GI_WAVEFRONT = 2): measured r01g at 1080p, gi_gen 47 us + gi_trace0 188 us + gi_resolve 43 us against 240 us for the
+    // fused gi_gen_trace0 — the refill keeps 25 of 32 lanes tracing, but the skip / DDA halves of an iteration still diverge (16 and 10
+    // lanes) and the queue round trips cost more than the idle lanes did
+    const bool persistent = c->opt_wavefront == 2;
     for (int s = 0; s < max_spp; ++s) {
-        VX_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(unsigned), c->stream));  // [0] hit count, [1] work cursor
-        gi_gen_trace0<LAYOUT, SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s);
+        VX_CUDA(cudaMemsetAsync(count, 0, 4 * sizeof(unsigned), c->stream));  // hit count, hit cursor, ray count, ray cursor
+        if (persistent) {
+            gi_gen<SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, rays, count, s);
+            static const int tune = std::getenv("VXPT_GI_TUNE") ? std::atoi(std::getenv("VXPT_GI_TUNE")) : 0;  // experiment knob
+            const int ctas = 148 * (tune >= 10 ? tune / 10 : 4);
+            switch (tune % 10) {
+                case 1: gi_trace0<LAYOUT, 4><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
+                case 2: gi_trace0<LAYOUT, 16><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
+                case 3: gi_trace0<LAYOUT, 12><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
+                case 4: gi_trace0<LAYOUT, 1><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
+                case 5: gi_trace0<LAYOUT, 24><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
+                default: gi_trace0<LAYOUT, 8><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
+            }
+            gi_resolve<SPP1><<<(unsigned)((slab_px + 255) / 256), 256, 0, c->stream>>>(S, d, od, state, rays, results, queue, count);
+            c->launches += 3;
+        } else {
+            gi_gen_trace0<LAYOUT, SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s);
+            c->launches += 1;
+        }
         gi_continue<LAYOUT, SPP1><<<148 * 6, 128, 0, c->stream>>>(S, cd, d, od, state, queue, count);
-        c->launches += 2;
+        c->launches += 1;
     }
     if (!SPP1) {
         gi_finalize<<<grid, 256, 0, c->stream>>>(cd, d, g, od, state);
@@ -303,7 +471,7 @@ int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev&
     const bool spp1 = max_spp == 1;
     // queues: slab-sized hit queue (+ full-frame per-pixel state when some pixel takes several samples)
     const size_t slab_px = (size_t)(cam.row_end - cam.row_begin) * cam.width, frame_px = (size_t)cam.width * cam.height;
-    const size_t need = 256 + slab_px * sizeof(HitRec) + (spp1 ? 0 : frame_px * sizeof(PixState));
+    const size_t need = 256 + slab_px * (sizeof(HitRec) + sizeof(RayRec) + sizeof(float2)) + (spp1 ? 0 : frame_px * sizeof(PixState));
     if (need > c->queue_bytes) {
         VX_CUDA(cudaStreamSynchronize(c->stream));
         if (c->d_queue) cudaFree(c->d_queue);
@@ -318,12 +486,15 @@ int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev&
     }
     unsigned* count = static_cast<unsigned*>(c->d_queue);
     HitRec* queue = reinterpret_cast<HitRec*>(static_cast<char*>(c->d_queue) + 256);
-    PixState* state = spp1 ? nullptr : reinterpret_cast<PixState*>(static_cast<char*>(c->d_queue) + 256 + slab_px * sizeof(HitRec));
+    RayRec* rays = reinterpret_cast<RayRec*>(static_cast<char*>(c->d_queue) + 256 + slab_px * sizeof(HitRec));
+    float2* results = reinterpret_cast<float2*>(static_cast<char*>(c->d_queue) + 256 + slab_px * (sizeof(HitRec) + sizeof(RayRec)));
+    PixState* state =
+        spp1 ? nullptr : reinterpret_cast<PixState*>(static_cast<char*>(c->d_queue) + 256 + slab_px * (sizeof(HitRec) + sizeof(RayRec) + sizeof(float2)));
     if (c->opt_layout == 1)
-        return spp1 ? run_wavefront<1, true>(c, S, cd, d, gd, od, state, queue, count, max_spp)
-                    : run_wavefront<1, false>(c, S, cd, d, gd, od, state, queue, count, max_spp);
-    return spp1 ? run_wavefront<0, true>(c, S, cd, d, gd, od, state, queue, count, max_spp)
-                : run_wavefront<0, false>(c, S, cd, d, gd, od, state, queue, count, max_spp);
+        return spp1 ? run_wavefront<1, true>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp)
+                    : run_wavefront<1, false>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp);
+    return spp1 ? run_wavefront<0, true>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp)
+                : run_wavefront<0, false>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp);
 }
 
 }  // namespace vxpt

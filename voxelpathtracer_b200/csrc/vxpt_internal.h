@@ -101,11 +101,9 @@ struct vxpt_ctx {
     uint8_t* rep_steps[8] = {nullptr};
     uint64_t frame_counter = 0;  // advanced by vxpt_trace_primary
 
-    // staging for host-pointer I/O (grown on demand)
+    // device staging for host-pointer I/O (grown on demand)
     void* d_stage = nullptr;
     size_t stage_bytes = 0;
-    void* h_stage = nullptr;  // pinned
-    size_t h_stage_bytes = 0;
 
     // wavefront queues (grown on demand)
     void* d_queue = nullptr;
@@ -124,10 +122,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 // df_build.cu
+int init_df_kernels(vxpt_ctx* c);
 int launch_df_build(vxpt_ctx* c);
 int launch_pack_bricks(vxpt_ctx* c);
 // trace.cu
-struct PlaneSet;  // resolved device pointers of one pass
 int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out_dev);
 int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxShadowParams& p, const VxShadowOut& out_dev);
 int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxDiffuseParams& p, const VxDiffuseOut& out_dev);

@@ -17,6 +17,10 @@ import sys
 import tempfile
 import time
 
+# frame pipes + gather streams of the multi-GPU path each want their own hardware queue: a flag-wait at the head of a shared
+# queue would stall unrelated streams behind it (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -150,6 +154,26 @@ def run_reference(args):
     return 0
 
 
+def bind_near_gpu(gpu_index):
+    """Pin this process to the CPUs of the GPU's NUMA node (NVML's ideal affinity) while the pinned host planes are allocated and
+    the end-to-end loop runs: a device->host copy into memory of the far socket is 20-30 % slower.  Returns the previous affinity
+    (restored before the CPU baseline, which wants every core), or None if nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        want = ideal & before
+        if not want or want == before:
+            return None
+        os.sched_setaffinity(0, want)
+        return before
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -172,9 +196,13 @@ def run_ours(args):
     tables = load_tables()
     w = world.generate_plains(assets.load_plains_columns())
     fc = camera.FpsCamera(pitch_deg=-20.0)
+    texel = args.planes == "texel"
+    px_out = sum(e for n_, e, _, _ in multigpu.plane_table(texel))                                # bytes per pixel written per frame
+    px_xchg = sum(e for n_, e, _, _ in multigpu.plane_table(texel) if not n_.startswith("g_"))    # ... of which cross the link
+    exchange = args.exchange
     # P independent handles ("pipes") per GPU, each with its own CUDA stream and double-buffered frame slots: consecutive
     # frames go to alternating pipes, so the latency-bound tail of one frame's kernels overlaps the next frame's kernels.
-    P = max(1, args.pipes)
+    P = max(1, args.pipes if args.pipes > 0 else (2 if ws == 1 else 4))
     renderers, frames, exts = [], [], []
     for _ in range(P):
         rr = vx.Renderer(local_rank)
@@ -182,10 +210,16 @@ def run_ours(args):
         rr.upload_world(w)
         rr.build_distance_field()
         # Timing rule "inputs larger than L2": three copies of grid + step field (132 MB > 126 MB L2) are rotated frame by
-        # frame and every frame streams 106 MB of planes through the cache; no flush kernel inside the timed region.
+        # frame and every frame streams its output planes through the cache; no flush kernel inside the timed region.
         rr.set_option(abi.OPT_SCENE_REPLICAS, 3)
         renderers.append(rr)
-        frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT))
+        try:
+            frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT, exchange=exchange, texel=texel, slots=args.slots,
+                                                emulate=(args.emulate, 0) if args.emulate else None))
+        except multigpu.P2PUnavailable as e:  # raised on every rank together: the NCCL all-gather still works
+            sys.stderr.write(f"[bench] rank {rank}: p2p slab gather unavailable ({e}); falling back to the NCCL all-gather\n")
+            exchange = "nccl"
+            frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT, exchange=exchange, texel=texel, slots=args.slots))
         exts.append(torch.cuda.ExternalStream(rr.cuda_stream(), device=dev))
     r, frame, ext = renderers[0], frames[0], exts[0]
     for _ in range(3):
@@ -213,8 +247,7 @@ def run_ours(args):
         fr = frames[k % P]
         slot = (k // P) % slots
         fr.last_slot = slot
-        fr.before_trace(slot)
-        fr.trace_into(slot, *params[f])
+        fr.frame_into(slot, *params[f])
         fr.exchange(slot)
 
     def finish_all():
@@ -235,6 +268,11 @@ def run_ours(args):
     barrier()
     graphs, submit = None, "eager"
     launches_per_graph = None
+    # p2p: the flag operations take their sequence numbers from device counters, so the whole frame (wait for the slot, passes,
+    # arrival flag) is one graph, and the root's gather stream replays a two-node graph of its own
+    whole = frame.exchange_mode == "p2p"
+    is_root = whole and rank == frame.root
+    gather_graphs = None
     if not args.no_graph:
         try:
             for rr in renderers:
@@ -244,11 +282,20 @@ def run_ours(args):
             for m in range(M):
                 gph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gph, stream=exts[m % P], capture_error_mode="thread_local"):
-                    frames[m % P].trace_into((m // P) % slots, *params[args.warmup + m])
+                    fr_m = frames[m % P]
+                    (fr_m.frame_into if whole else fr_m.trace_into)((m // P) % slots, *params[args.warmup + m])
                 graphs.append(gph)
             launches_per_graph = (sum(rr.launch_count() for rr in renderers) - l0) / M
-            submit = (f"one CUDA graph per frame (trace passes of this rank's rows; {M} frame indices cycled) on {P} pipe(s), "
-                      "NCCL exchange eager on its own stream")
+            if is_root:
+                gather_graphs = []
+                for fr_p in frames:
+                    gph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gph, stream=fr_p._comm, capture_error_mode="thread_local"):
+                        fr_p.gather_into()
+                    gather_graphs.append(gph)
+                launches_per_graph += 2
+            submit = (f"one CUDA graph per frame ({'wait for the slot, ' if whole else ''}trace passes of this rank's rows{', arrival flag' if whole else ''}; "
+                      f"{M} frame indices cycled) on {P} pipe(s)" + ("; the root's gather stream replays a 2-node graph per frame" if whole else ", exchange eager"))
         except Exception as e:  # capture unsupported in this environment: fall back to eager submission
             sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); submitting eagerly\n")
             graphs, submit = None, "eager (graph capture failed)"
@@ -261,10 +308,15 @@ def run_ours(args):
         fr = frames[k % P]
         slot = (k // P) % slots
         fr.last_slot = slot
-        fr.before_trace(slot)
+        if not whole:
+            fr.before_trace(slot)
         with torch.cuda.stream(exts[k % P]):
             graphs[k % M].replay()
-        fr.exchange(slot)
+        if not whole:
+            fr.exchange(slot)
+        elif is_root:
+            with torch.cuda.stream(fr._comm):
+                gather_graphs[k % P].replay()
 
     step = graph_step if graphs is not None else (lambda k: eager_step(k, args.warmup + k))
     for fr in frames:
@@ -347,29 +399,26 @@ def run_ours(args):
                 rooflines[k]["traffic"] = v
     dominant = max(names, key=lambda n: rooflines[n]["ms_per_launch"])
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): camera/params in, every output plane out ----------
-    e2e = None
+    # ---- end to end through the C ABI with HOST buffers (pinned): camera/params in, every output plane out --------------
+    # One vxpt_render_frame call per step on this rank's rows: the G-buffer stays on the device between the passes (as the
+    # reference's FBO textures do) and the planes are copied to pinned host memory slab by slab while later slabs trace.
+    for fr in frames:
+        fr.finish()
+    torch.cuda.synchronize()
+    affinity_before = bind_near_gpu(local_rank)
     slab_b, slab_e = multigpu.slab_rows(HEIGHT, ws, rank)
     cam_rank = fc.vx_camera(WIDTH, HEIGHT, slab_b, slab_e)
     rows = slab_e - slab_b
-
-    def pinned(shape, dtype):
-        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
-
-    hg = {"t": pinned((HEIGHT, WIDTH), torch.float32), "normal_id": pinned((HEIGHT, WIDTH), torch.uint8), "block_id": pinned((HEIGHT, WIDTH), torch.uint8),
-          "inv_t": pinned((HEIGHT, WIDTH), torch.float32)}
-    hs = {"shadow": pinned((HEIGHT, WIDTH), torch.uint8), "transversal": pinned((HEIGHT, WIDTH), torch.float32)}
-    hd = {"sh": pinned((HEIGHT, WIDTH, 4), torch.float32), "cocg": pinned((HEIGHT, WIDTH, 2), torch.float32), "luma": pinned((HEIGHT, WIDTH), torch.float32),
-          "ao_sky": pinned((HEIGHT, WIDTH, 2), torch.float32)}
-    px_bytes = 4 + 1 + 1 + 4 + 1 + 4 + 16 + 8 + 4 + 8
-    d2h = rows * WIDTH * px_bytes + rows * WIDTH * 5  # outputs + the G-buffer t/normal planes are re-uploaded for the secondary passes
-    h2d = rows * WIDTH * 5 * 2 + 2 * (144 + 64)       # staged G-buffer inputs of shadow and GI + camera / parameter structs
+    r.set_option(abi.OPT_TEXEL_FORMAT, 1 if texel else 0)
+    hg = r.alloc_gbuffer(WIDTH, HEIGHT, texel=texel, pinned=True)
+    hs = r.alloc_shadow(WIDTH, HEIGHT, texel=texel, pinned=True)
+    hd = r.alloc_diffuse(WIDTH, HEIGHT, texel=texel, pinned=True)
+    d2h = rows * WIDTH * px_out
+    h2d = 144 + 24 + 32 + 72  # VxCamera + VxPrimaryParams + VxShadowParams + VxDiffuseParams: the only per-frame inputs of the path
 
     def host_step(f):
         pp, sp, dp = frame_params(vx, camera, tables, f)
-        r.trace_primary(cam_rank, pp, hg)
-        r.trace_shadow(cam_rank, hg, sp, hs)
-        r.trace_diffuse(cam_rank, hg, dp, hd)
+        r.render_frame(cam_rank, pp, sp, dp, hg, hs, hd)
         return float(hd["luma"][cam_rank.row_begin, 0])
 
     for f in range(args.warmup):
@@ -382,8 +431,13 @@ def run_ours(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e = {"value": rays_all / float(e2e_s[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(rows * WIDTH * px_bytes),
-           "note": "C-ABI calls with pinned HOST output buffers; every pass copies its planes device->host and the secondary passes re-upload the G-buffer slab"}
+    e2e = {"value": rays_all / float(e2e_s[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "note": ("one vxpt_render_frame call per step with pinned HOST output planes (" + ("the reference's FBO texel formats, 27 B/pixel" if texel else "fp32 planes, 51 B/pixel") +
+                    "): G-buffer resident on the device between passes, planes copied device->host slab by slab while later slabs trace; "
+                    "the per-frame inputs are the camera and parameter structs" + ("; process bound to the GPU's NUMA node" if affinity_before is not None else ""))}
+
+    if affinity_before is not None:
+        os.sched_setaffinity(0, affinity_before)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -------------
     cpu_baseline = None
@@ -405,13 +459,20 @@ def run_ours(args):
         cpu_baseline = {"value": rays_cpu / dt / 1e6, "unit": "Mrays/s", "cores": vxo.load().vxo_num_threads(), "kind": "port",
                         "sample": f"{n_frames} full 1080p frames (primary+shadow+GI) of the same workload, C++ oracle, OpenMP over rows, {dt:.1f} s"}
 
+    xchg_text = {"none": "single GPU, no exchange",
+                 "p2pcopy": "radiance slabs (shadow + GI planes) traced locally and pushed to the gather root with one copy-engine transfer per frame over NVLink (CUDA IPC mapping), frames ordered by release/acquire flag words",
+                 "p2p": "radiance slabs (shadow + GI planes) stored by the trace kernels straight into the gather root's memory over NVLink (CUDA IPC mapping), "
+                        "frames ordered by release/acquire flag words, no exchange step",
+                 "nccl": "one packed NCCL all-gather of the shadow + GI planes per frame on its own stream, overlapped with the following frames' tracing"}[frame.exchange_mode]
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps, "sharding": f"{ws} ranks, interleaved {frame.band_rows}-row bands, {P} frame pipe(s) per GPU, one packed NCCL all-gather of the shadow+GI planes per frame overlapped with the following frames' tracing, grid replicated",
-                       "timing": "two CUDA events on the library stream around exactly K steps (barrier + synchronize on both sides), max over ranks; inputs larger than L2: 3 scene replicas (132 MB) rotated per frame + 106 MB of planes written per frame, no flush kernel",
+            "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps,
+                       "sharding": (f"{ws} ranks, interleaved {frame.band_rows}-row bands, {P} frame pipe(s) per GPU, grid replicated; " + xchg_text),
+                       "planes": ("reference FBO texel formats (R16F/RGBA16F/RG16F/RG8/R8; VXPT_OPT_TEXEL_FORMAT=1)" if texel else "fp32 planes") + f", {px_out} B/pixel written, {px_xchg} B/pixel gathered",
+                       "timing": f"two CUDA events on the library stream around exactly K steps (barrier + synchronize on both sides), max over ranks; inputs larger than L2: 3 scene replicas (132 MB) rotated per frame + {WIDTH * HEIGHT * px_out / 1e6:.0f} MB of planes written per frame, no flush kernel",
                        "submit": submit, "host_submit_ms_per_step": host_submit_ms, "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": "wavefront (warp-ballot compaction of first-bounce hits)"},
             "e2e": e2e, "gpu_launches": int(tot[4]),
             "roofline": dict(rooflines[dominant], kernel=dominant,
@@ -435,7 +496,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipes", type=int, default=2, help="independent handles/streams per GPU (frames in flight)")
+    ap.add_argument("--pipes", type=int, default=0, help="independent handles/streams per GPU (frames in flight); 0 = 2 on one GPU, 4 on several")
+    ap.add_argument("--slots", type=int, default=2, help="frame slots per pipe in the slab buffer")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2pcopy", "nccl"],
+                    help="multi-GPU slab gather: the trace kernels store into the root's memory (p2p), one copy-engine push per frame (p2pcopy), or NCCL all-gather")
+    ap.add_argument("--emulate", type=int, default=0, help="development: trace rank 0's share of an N-way sharded frame on one GPU, no exchange")
+    ap.add_argument("--planes", default="texel", choices=["texel", "f32"], help="plane encoding: the reference's FBO texel formats (default) or fp32")
     ap.add_argument("--no-graph", action="store_true", help="submit every pass eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -227,6 +227,56 @@ VXPT_API int vxpt_trace_diffuse(vxpt_handle h, const VxCamera* cam, const VxGBuf
 VXPT_API int vxpt_trace_reflection(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf,
                                    const VxReflectionIn* in, const VxReflectionParams* p, const VxReflectionOut* out);
 
+/* ---- one frame of the path: the pass sequence of Core/Pipeline.cpp's render loop (:1973-2016 primary, :2795-2852 shadow,
+ *      :2174-2281 diffuse GI, :3003-3164 reflections) on the rows of `cam` -------------------------------------------------
+ * Equivalent to vxpt_trace_primary + vxpt_trace_shadow + vxpt_trace_diffuse (+ vxpt_trace_reflection) with the same arguments,
+ * but the G-buffer (and the GI planes the reflection pass reads) stay in device memory between the passes, as the reference's
+ * FBO textures do: nothing is re-uploaded.  shadow / diffuse / reflection may be NULL to skip that pass; any output plane may be
+ * NULL.  HOST output planes are copied out by a second stream, slab by slab, while the following slabs and passes are still
+ * tracing, and are complete when the call returns; device planes are written in place and complete after vxpt_sync(). */
+typedef struct VxFrameParams {
+    const VxPrimaryParams* primary;        /* required                                              */
+    const VxShadowParams* shadow;          /* NULL = no shadow pass                                 */
+    const VxDiffuseParams* diffuse;        /* NULL = no GI pass                                     */
+    const VxReflectionParams* reflection;  /* NULL = no reflection pass (needs diffuse)             */
+    const float* g_normal;                 /* VxReflectionIn.g_normal / g_pbr for the reflection    */
+    const float* g_pbr;                    /* pass (device or host, may be NULL)                    */
+} VxFrameParams;
+typedef struct VxFrameOut {
+    VxGBuffer gbuffer;
+    VxShadowOut shadow;
+    VxDiffuseOut diffuse;
+    VxReflectionOut reflection;
+} VxFrameOut;
+VXPT_API int vxpt_render_frame(vxpt_handle h, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out);
+
+/* ---- peer-to-peer gather of row slabs (multi-GPU, one process per GPU) --------------------------------------
+ * The gather root allocates the slab buffer with vxpt_shared_alloc and publishes its 64-byte handle (any byte transport);
+ * every other rank maps it with vxpt_shared_open and passes addresses inside the mapping as OUTPUT planes of its trace calls:
+ * the kernels then store their rows straight into the root's memory over NVLink, and no separate exchange step exists.
+ * vxpt_signal / vxpt_wait_all order the frames: a rank enqueues vxpt_signal(flag, k) after the passes of frame k (a
+ * system-scope release: the frame's stores are visible before the flag); the root enqueues vxpt_wait_all over the N flags.
+ * Both are stream-ordered (on the handle's stream, or on a caller stream of the same device, e.g. a gather stream that
+ * must not stall tracing) and never block the host.  A wait gives up after timeout_ms and latches an
+ * error that the next vxpt_sync / vxpt_get_stats reports (VXPT_E_STATE), so a lost peer cannot hang the device. */
+/* Sequence-numbered forms for CUDA-graph capture: the value comes from a device-resident counter (device memory of this GPU)
+ * that the call itself advances, so the captured node's arguments never change from frame to frame.
+ *   vxpt_signal_next : v = ++*counter;  release-store v to *flag.
+ *   vxpt_wait_next   : target = ++*counter - lag;  if target >= 1, wait until all n flags have reached target. */
+#define VXPT_SHARED_HANDLE_BYTES 64
+VXPT_API int vxpt_shared_alloc(vxpt_handle h, size_t bytes, void** dptr, uint8_t handle_out[VXPT_SHARED_HANDLE_BYTES]);
+VXPT_API int vxpt_shared_open(vxpt_handle h, const uint8_t handle[VXPT_SHARED_HANDLE_BYTES], void** dptr);
+VXPT_API int vxpt_shared_close(vxpt_handle h, void* dptr);  /* unmap (opened) or free (allocated) */
+/* stream-ordered device-to-device copy (copy engine; dst / src may be peer mappings): pushes a locally traced slab to the root */
+VXPT_API int vxpt_copy_async(vxpt_handle h, void* dst, const void* src, size_t bytes, void* cuda_stream /* NULL = the handle's stream */);
+VXPT_API int vxpt_signal(vxpt_handle h, uint32_t* flag /* device, may be a peer mapping */, uint32_t value,
+                         void* cuda_stream /* NULL = the handle's stream */);
+VXPT_API int vxpt_signal_next(vxpt_handle h, uint32_t* flag, uint32_t* counter, void* cuda_stream);
+VXPT_API int vxpt_wait_next(vxpt_handle h, const uint32_t* flags, int n, int stride_words, uint32_t* counter, int lag, int timeout_ms,
+                            void* cuda_stream);
+VXPT_API int vxpt_wait_all(vxpt_handle h, const uint32_t* flags /* device, may be a peer mapping */, int n, int stride_words,
+                           uint32_t at_least /* wrap-around compare */, int timeout_ms, void* cuda_stream /* NULL = the handle's stream */);
+
 /* ---- glFinish (Core/Pipeline.cpp:4782), statistics ------------------------------------------------------- */
 VXPT_API int vxpt_sync(vxpt_handle h);
 VXPT_API int vxpt_get_stats(vxpt_handle h, VxStats* out);   /* totals since the last reset; syncs */
@@ -247,6 +297,15 @@ VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
 /* 1 (default): record CUDA events around every pass (VxStats.last_ms).  0: record none, so a caller may capture the
  * handle's stream into a CUDA graph (event timing is not capturable). */
 #define VXPT_OPT_TIMING_EVENTS 5
+/* texel format of the image planes (changes the ENCODING of results, not the results: every value is the fp32 value rounded once).
+ * 0 (default): fp32 planes as the struct pointer types say.
+ * 1: the reference's FBO attachment formats (Core/Pipeline.cpp:1094-1095 G-buffer, :1152 shadow, :1102 GI, :1141 reflection):
+ *    VxGBuffer.t R16F (2 B), inv_t R32F (4 B), normal_id / block_id R8;  VxShadowOut.shadow R8, transversal R16F;
+ *    VxDiffuseOut.sh RGBA16F (8 B), cocg RG16F (4 B), luma R16F (2 B), ao_sky RG8 unorm (2 B);
+ *    VxReflectionOut.color RGBA16F, hit_distance R16F, emissive_mask R8;  VxReflectionIn.sh / cocg as VxDiffuseOut wrote them
+ *    (g_normal / g_pbr stay fp32).  Halves are IEEE binary16 rounded to nearest even, unorm8 = round(v * 255).
+ *    27 B/pixel for G-buffer + shadow + GI instead of 51: what a host consumer or a peer GPU has to receive. */
+#define VXPT_OPT_TEXEL_FORMAT 6
 VXPT_API int vxpt_set_option(vxpt_handle h, int option, int value);
 
 /* ---- microbenchmark: resident-set random 32-byte-sector read throughput, the denominator of the

@@ -461,3 +461,157 @@ def test_reflection_parity(renderer, worlds, oracles, scene_tables, name, w, h, 
         assert abs(st["df_fetches"] - rst["df_fetches"]) <= 1e-4 * rst["df_fetches"] + 100
     if name == "gi_box":
         assert ref["emissive_mask"].any() or True   # lamps are rarely in view; the mask path is exercised when they are
+
+
+# ====================================================================================== texel formats, whole-frame call, p2p plumbing
+def _unorm8(v):
+    return np.rint(v.astype(np.float32) * np.float32(255.0)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name,w,h", [("plains", 640, 360), ("city", 480, 270)])
+def test_reference_texel_formats_are_the_rounded_fp32_planes(renderer, worlds, oracles, scene_tables, name, w, h):
+    """VXPT_OPT_TEXEL_FORMAT = 1 (the reference's FBO formats, Pipeline.cpp:1094-1152): every texel is the oracle's fp32 value rounded
+    once (binary16 RN-even / unorm8); the secondary passes read the R16F hit distance exactly as the reference's shaders do, so
+    they are compared against the oracle run on the same half-precision G-buffer."""
+    load(renderer, worlds[name])
+    fc = camera.FpsCamera(pitch_deg=-20.0) if name != "city" else camera.FpsCamera(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0)
+    cam = fc.vx_camera(w, h)
+    o = oracles[name]
+    pp = vx.primary_params(350, camera.taa_jitter(5))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=9)
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=2, frame=9)
+    g_ref, _ = o.trace_primary(cam, pp)
+    g16 = dict(g_ref, t=g_ref["t"].astype(np.float16).astype(np.float32))   # what a reader of the R16F plane sees
+    s_ref, _ = o.trace_shadow(cam, g16, sp)
+    d_ref, _ = o.trace_diffuse(cam, g16, dp)
+    renderer.set_option(abi.OPT_TEXEL_FORMAT, 1)
+    try:
+        for device in (False, True):
+            g = renderer.trace_primary(cam, pp, renderer.alloc_gbuffer(w, h, device=device, texel=True))
+            s = renderer.trace_shadow(cam, g, sp, renderer.alloc_shadow(w, h, device=device, texel=True))
+            d = renderer.trace_diffuse(cam, g, dp, renderer.alloc_diffuse(w, h, device=device, texel=True))
+            renderer.sync()
+            host = (lambda x: x.cpu().numpy()) if device else (lambda x: x)
+            assert host(g["t"]).dtype == np.float16 and host(d["ao_sky"]).dtype == np.uint8
+            assert np.array_equal(host(g["t"]), g_ref["t"].astype(np.float16))
+            assert np.array_equal(host(g["inv_t"]), g_ref["inv_t"])
+            assert np.array_equal(host(g["normal_id"]), g_ref["normal_id"]) and np.array_equal(host(g["block_id"]), g_ref["block_id"])
+            assert np.mean(host(s["shadow"]) != s_ref["shadow"]) <= 1e-5
+            assert np.mean(host(s["transversal"]) != s_ref["transversal"].astype(np.float16)) <= 1e-5
+            for k in ("sh", "cocg", "luma"):
+                got, want = host(d[k]), d_ref[k].astype(np.float16)
+                assert np.mean(got != want) <= 1e-4, k
+                assert float(np.mean(np.abs(got.astype(np.float64) - d_ref[k]))) <= RADIANCE_MAE, k   # the fp32 target still holds in half
+            assert np.mean(host(d["ao_sky"]) != _unorm8(d_ref["ao_sky"])) <= 1e-4
+    finally:
+        renderer.set_option(abi.OPT_TEXEL_FORMAT, 0)
+
+
+@pytest.mark.parametrize("texel", [False, True])
+@pytest.mark.parametrize("rows", [(0, 360), (40, 297)])
+def test_render_frame_equals_the_separate_passes(renderer, worlds, scene_tables, texel, rows):
+    """vxpt_render_frame (G-buffer resident between passes, slab-pipelined copy-out) == trace_primary + trace_shadow + trace_diffuse,
+    for host planes, device planes and a mix, on a whole frame and on a row slab (rows outside it untouched)."""
+    import torch
+    load(renderer, worlds["plains"])
+    W, H = 640, 360
+    fc = camera.FpsCamera(pitch_deg=-20.0)
+    cam = fc.vx_camera(W, H, rows[0], rows[1])
+    pp = vx.primary_params(350, camera.taa_jitter(2))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=4)
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=1, frame=4)
+    renderer.set_option(abi.OPT_TEXEL_FORMAT, int(texel))
+    try:
+        def fresh(device):
+            bufs = (renderer.alloc_gbuffer(W, H, device=device, texel=texel), renderer.alloc_shadow(W, H, device=device, texel=texel),
+                    renderer.alloc_diffuse(W, H, device=device, texel=texel))
+            for b in bufs:
+                for v in b.values():
+                    v[...] = 7 if not device else 7
+            return bufs
+        g, s, d = fresh(False)
+        renderer.trace_primary(cam, pp, g); renderer.trace_shadow(cam, g, sp, s); renderer.trace_diffuse(cam, g, dp, d)
+        want = {**g, **s, **d}
+        renderer.reset_stats()
+        g2, s2, d2 = fresh(False)
+        renderer.render_frame(cam, pp, sp, dp, g2, s2, d2)
+        st = renderer.stats()
+        for k, v in {**g2, **s2, **d2}.items():
+            assert np.array_equal(v, want[k]), k
+        assert st["rays"] > 0
+        g3, s3, d3 = fresh(True)
+        renderer.render_frame(cam, pp, sp, dp, g3, s3, d3)
+        renderer.sync()
+        for k, v in {**g3, **s3, **d3}.items():
+            assert np.array_equal(v.cpu().numpy(), want[k]), k
+        # only the GI planes wanted, on the host: the G-buffer lives in the handle's arena
+        _, _, d4 = fresh(False)
+        renderer.render_frame(cam, pp, None, dp, None, None, d4)
+        for k, v in d4.items():
+            assert np.array_equal(v, want[k]), k
+    finally:
+        renderer.set_option(abi.OPT_TEXEL_FORMAT, 0)
+    with pytest.raises(abi.VxptError) as e:
+        renderer.render_frame(cam, vx.primary_params(-1), sp, dp, g2, s2, d2)
+    assert e.value.code == abi.E_INVALID
+
+
+def test_shared_buffer_signal_and_wait(renderer):
+    """Plumbing of the peer-to-peer slab gather inside one process: an IPC-exportable buffer, stream-ordered release / acquire flags
+    (also on a caller stream), wrap-around compare, and a wait that gives up instead of hanging the device."""
+    import torch
+    ptr, handle = renderer.shared_alloc(1 << 20)
+    assert len(handle) == abi.SHARED_HANDLE_BYTES and ptr
+    try:
+        from voxelpathtracer_b200.multigpu import _DevMem
+        mem = torch.as_tensor(_DevMem(ptr, 1 << 20), device="cuda:0")
+        assert int(mem.sum()) == 0                                   # zero-initialised
+        flags = ptr
+        for k in range(4):
+            renderer.signal(flags + 128 * k, 5)
+        renderer.wait_all(flags, 4, 32, 5, timeout_ms=1000)
+        renderer.wait_all(flags, 4, 32, 3, timeout_ms=1000)            # "at least"
+        renderer.sync()
+        assert mem[:512].view(torch.int32)[::32].tolist() == [5, 5, 5, 5]
+        side = torch.cuda.Stream()
+        renderer.signal(flags + 128 * 4, 0xFFFFFFFE, stream=side.cuda_stream)
+        renderer.wait_all(flags + 128 * 4, 1, 32, 0xFFFFFFFD, timeout_ms=1000, stream=side.cuda_stream)
+        side.synchronize()
+        renderer.signal(flags + 128 * 4, 2)                            # wrapped past 2^32: 2 is "later" than 0xFFFFFFFE
+        renderer.wait_all(flags + 128 * 4, 1, 32, 0xFFFFFFFF, timeout_ms=1000)
+        renderer.sync()
+        renderer.wait_all(flags + 128 * 5, 1, 32, 1, timeout_ms=30)    # never signalled
+        with pytest.raises(abi.VxptError) as e:
+            renderer.sync()
+        assert e.value.code == abi.E_STATE
+        renderer.sync()                                                # the error is latched once
+        del mem
+    finally:
+        renderer.shared_close(ptr)
+    with pytest.raises(abi.VxptError):
+        renderer.shared_close(ptr)
+
+
+@pytest.mark.parametrize("texel", [False, True])
+def test_sharded_frame_texel_planes_single_rank(renderer, worlds, scene_tables, texel):
+    from voxelpathtracer_b200 import multigpu
+    load(renderer, worlds["plains"])
+    W, H = 320, 180
+    fc = camera.FpsCamera(pitch_deg=-20.0)
+    pp = vx.primary_params(350, camera.taa_jitter(2))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=4)
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=1, frame=4)
+    cam = fc.vx_camera(W, H)
+    try:
+        f = multigpu.ShardedFrame(renderer, fc, W, H, texel=texel)
+        g = renderer.trace_primary(cam, pp, renderer.alloc_gbuffer(W, H, texel=texel))
+        s = renderer.trace_shadow(cam, g, sp, renderer.alloc_shadow(W, H, texel=texel))
+        d = renderer.trace_diffuse(cam, g, dp, renderer.alloc_diffuse(W, H, texel=texel))
+        f.trace(pp, sp, dp)
+        f.gather()
+        renderer.sync()
+        for name, ref in (("g_t", g["t"]), ("s_shadow", s["shadow"]), ("s_transversal", s["transversal"]), ("d_sh", d["sh"]), ("d_cocg", d["cocg"]),
+                          ("d_luma", d["luma"]), ("d_ao_sky", d["ao_sky"])):
+            assert np.array_equal(f.plane(name).cpu().numpy(), ref), name
+    finally:
+        renderer.set_option(abi.OPT_TEXEL_FORMAT, 0)

@@ -75,6 +75,9 @@ def test_packed_layout_regions_do_not_overlap():
     assert spans[0][0] == 0 and spans[-1][1] <= total
     for (a0, a1), (b0, b1) in zip(spans[:-1], spans[1:]):
         assert a1 <= b0 and b0 % 256 == 0
-    assert sum(p[1] for p in multigpu.PLANES) == 51  # bytes per pixel exchanged per frame
+    assert sum(p[1] for p in multigpu.PLANES) == 51  # bytes per pixel written per frame (fp32 planes)
+    assert sum(p[1] for p in multigpu.plane_table(True)) == 27  # ... in the reference's FBO texel formats
+    assert sum(p[1] for p in multigpu.plane_table(True) if not p[0].startswith('g_')) == 19  # ... of which cross the link
+    assert [p[0] for p in multigpu.plane_table(True)] == [p[0] for p in multigpu.PLANES]
     # virtual plane bases stay inside the packed buffer for every rank: region_bytes >= any single plane's slab
     assert all(total >= 135 * 1920 * p[1] for p in multigpu.PLANES)

@@ -15,7 +15,8 @@ WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z
 NORMAL_MISS = 10
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS, OPT_TIMING_EVENTS = 1, 2, 3, 4, 5
+OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS, OPT_TIMING_EVENTS, OPT_TEXEL_FORMAT = 1, 2, 3, 4, 5, 6
+SHARED_HANDLE_BYTES = 64
 
 u8p = C.POINTER(C.c_uint8)
 f32p = C.POINTER(C.c_float)
@@ -72,6 +73,15 @@ class VxReflectionOut(C.Structure):
     _fields_ = [("color", C.c_void_p), ("hit_distance", C.c_void_p), ("emissive_mask", C.c_void_p)]
 
 
+class VxFrameParams(C.Structure):
+    _fields_ = [("primary", C.POINTER(VxPrimaryParams)), ("shadow", C.POINTER(VxShadowParams)), ("diffuse", C.POINTER(VxDiffuseParams)),
+                ("reflection", C.POINTER(VxReflectionParams)), ("g_normal", C.c_void_p), ("g_pbr", C.c_void_p)]
+
+
+class VxFrameOut(C.Structure):
+    _fields_ = [("gbuffer", VxGBuffer), ("shadow", VxShadowOut), ("diffuse", VxDiffuseOut), ("reflection", VxReflectionOut)]
+
+
 class VxStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("df_fetches", C.c_uint64), ("vox_fetches", C.c_uint64), ("last_ms", C.c_float),
                 ("df_build_ms", C.c_float), ("brick_pack_ms", C.c_float)]
@@ -101,6 +111,15 @@ EXPORTS = {
     "vxpt_trace_diffuse": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut)]),
     "vxpt_trace_reflection": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]),
+    "vxpt_render_frame": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxFrameParams), C.POINTER(VxFrameOut)]),
+    "vxpt_shared_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "vxpt_shared_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vxpt_shared_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxpt_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vxpt_signal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "vxpt_signal_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vxpt_wait_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vxpt_wait_all": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p]),
     "vxpt_sync": (C.c_int, [C.c_void_p]),
     "vxpt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(VxStats)]),
     "vxpt_reset_stats": (C.c_int, [C.c_void_p]),

@@ -1,5 +1,6 @@
 // api.cu — the C ABI of include/vxpt.h: handle lifetime, uploads, host<->device staging, pass dispatch.
 // Every export validates its arguments, never throws, and reports failures through vxpt_last_error().
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -90,6 +91,7 @@ struct Plane {
     void* dev = nullptr;
     size_t elem = 0;  // bytes per pixel
     bool staged = false;
+    bool internal = false;  // no caller buffer: lives in the handle's arena only (vxpt_render_frame)
 };
 
 struct PassIO {
@@ -98,16 +100,17 @@ struct PassIO {
     std::vector<Plane*> planes;
     Arena arena;
     PassIO(vxpt_ctx* ctx, const VxCamera* cm) : c(ctx), cam(cm), arena(ctx) {}
-    void add(Plane& p, const void* user, size_t elem) {
+    void add(Plane& p, const void* user, size_t elem, bool required = false) {
         p.user = const_cast<void*>(user);
         p.elem = elem;
-        if (user) planes.push_back(&p);
+        p.internal = !user && required;
+        if (user || required) planes.push_back(&p);
     }
     int resolve() {
         size_t need = 0;
         const size_t npx = (size_t)cam->width * cam->height;
         for (Plane* p : planes) {
-            p->staged = !is_device_pointer(p->user);
+            p->staged = p->internal || !is_device_pointer(p->user);
             if (p->staged) need += ((npx * p->elem) + 255) & ~(size_t)255;
         }
         if (need) {
@@ -132,7 +135,17 @@ struct PassIO {
         any = true;
         return VXPT_OK;
     }
+    // rows [rb, re) of a staged plane, on another stream (vxpt_render_frame's copy-out pipeline)
+    int download_rows(const Plane& p, int rb, int re, cudaStream_t s) {
+        if (!p.user || !p.staged || re <= rb) return VXPT_OK;
+        const size_t off = (size_t)rb * cam->width * p.elem, bytes = (size_t)(re - rb) * cam->width * p.elem;
+        VX_CUDA(cudaMemcpyAsync((char*)p.user + off, (const char*)p.dev + off, bytes, cudaMemcpyDeviceToHost, s));
+        return VXPT_OK;
+    }
 };
+
+// bytes per pixel of a plane: fp32 layout / the reference's texel format (VXPT_OPT_TEXEL_FORMAT)
+static size_t px_bytes(const vxpt_ctx* c, size_t f32_bytes, size_t texel_bytes) { return c->opt_texel ? texel_bytes : f32_bytes; }
 
 static int check_camera(const VxCamera* cam) {
     if (!cam) return fail(VXPT_E_INVALID, "camera is NULL");
@@ -154,6 +167,46 @@ static int check_ready(vxpt_ctx* c) {
     if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
     if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded (vxpt_upload_world)");
     if (!c->df_valid) return fail(VXPT_E_STATE, "distance field is stale: call vxpt_build_distance_field after editing the world");
+    return VXPT_OK;
+}
+
+static int check_primary(const VxPrimaryParams* p) {
+    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested traversal is outside the v1 parity profile (off by default in the reference)");
+    if (p->max_iterations < 0) return fail(VXPT_E_INVALID, "max_iterations < 0");
+    return VXPT_OK;
+}
+static int check_shadow(const vxpt_ctx* c, const VxShadowParams* p) {
+    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested shadows are outside the v1 parity profile");
+    if (p->soft && !c->have_shadow_noise) return fail(VXPT_E_STATE, "soft shadows need vxpt_set_shadow_noise");
+    return VXPT_OK;
+}
+static int check_diffuse(const vxpt_ctx* c, const VxDiffuseParams* p) {
+    if (!p->use_blue_noise) return fail(VXPT_E_UNSUPPORTED, "u_UseBlueNoise=false (fract(sin()) hash) is not reproducible; outside the parity profile");
+    if (p->direct_sampling) return fail(VXPT_E_UNSUPPORTED, "u_UseDirectSampling (WIP light-chunk sampling) is outside the v1 parity profile");
+    if (!c->have_materials || !c->have_bluenoise || !c->have_textures || !c->have_sky)
+        return fail(VXPT_E_STATE, "diffuse GI needs materials, blue-noise tables, material textures and a sky cubemap");
+    if (p->trace_length < 0 || p->spp < 0) return fail(VXPT_E_INVALID, "negative trace_length / spp");
+    // every layer the table can reach must exist in the baked arrays
+    for (int b = 0; b < 128; ++b) {
+        if (c->h_materials[b] >= c->n_layers) return fail(VXPT_E_INVALID, "material table references an albedo layer that was not uploaded");
+        if (c->h_materials[384 + b] >= c->n_emissive) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
+    }
+    return VXPT_OK;
+}
+static int check_reflection(const vxpt_ctx* c, const VxReflectionParams* p) {
+    if (!c->have_materials || !c->have_bluenoise || !c->have_textures || !c->have_sky || !c->have_refl_textures)
+        return fail(VXPT_E_STATE, "reflections need materials, blue-noise tables, material + reflection textures and a sky cubemap");
+    if (p->trace_length < 0 || p->spp < 0) return fail(VXPT_E_INVALID, "negative trace_length / spp");
+    for (int b = 0; b < 128; ++b) {
+        if (c->h_materials[b] >= c->n_layers || c->h_materials[256 + b] >= c->n_layers)
+            return fail(VXPT_E_INVALID, "material table references an albedo / PBR layer that was not uploaded");
+        if (c->h_materials[128 + b] >= c->n_normal) return fail(VXPT_E_INVALID, "material table references a normal layer that was not uploaded");
+        if (c->h_materials[384 + b] >= c->n_emissive2) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
+    }
+    for (int k = 1; k < 10; ++k) {
+        const int lim = (k % 3 == 2) ? c->n_normal : c->n_layers;  // props: id, then (albedo, normal, pbr) x {top, side, bottom}
+        if (p->grass_props[k] < 0 || p->grass_props[k] >= lim) return fail(VXPT_E_INVALID, "u_GrassBlockProps layer out of range");
+    }
     return VXPT_OK;
 }
 
@@ -208,6 +261,10 @@ int vxpt_create(int device_id, vxpt_handle* out) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev2);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev3);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->ev_slab[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_wait_err, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_wait_err, 0, sizeof(unsigned), c->stream);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_grid, VOXELS);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_df, VOXELS);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tmp, VOXELS);
@@ -231,6 +288,17 @@ int vxpt_destroy(vxpt_handle c) {
     if (!c) return VXPT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
+    for (int k = 0; k < 8; ++k)
+        if (c->ev_slab[k]) cudaEventDestroy(c->ev_slab[k]);
+    for (const vxpt_ctx::SharedBuf& b : c->shared) {
+        if (b.owned) cudaFree(b.ptr);
+        else cudaIpcCloseMemHandle(b.ptr);
+    }
+    if (c->d_wait_err) cudaFree(c->d_wait_err);
     for (int r = 1; r < 8; ++r) {
         if (c->rep_grid[r]) cudaFree(c->rep_grid[r]);
         if (c->rep_steps[r]) cudaFree(c->rep_steps[r]);
@@ -449,12 +517,11 @@ int vxpt_trace_primary(vxpt_handle c, const VxCamera* cam, const VxPrimaryParams
     if (rc) return rc;
     if ((rc = check_camera(cam))) return rc;
     if (!p || !out) return fail(VXPT_E_INVALID, "NULL argument");
-    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested traversal is outside the v1 parity profile (off by default in the reference)");
-    if (p->max_iterations < 0) return fail(VXPT_E_INVALID, "max_iterations < 0");
+    if ((rc = check_primary(p))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
     PassIO io(c, cam);
     Plane t, nid, bid, it, hv;
-    io.add(t, out->t, 4); io.add(nid, out->normal_id, 1); io.add(bid, out->block_id, 1); io.add(it, out->inv_t, 4); io.add(hv, out->hit_voxel, 6);
+    io.add(t, out->t, px_bytes(c, 4, 2)); io.add(nid, out->normal_id, 1); io.add(bid, out->block_id, 1); io.add(it, out->inv_t, 4); io.add(hv, out->hit_voxel, 6);
     if ((rc = io.resolve())) return rc;
     VxGBuffer dev{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, (int16_t*)hv.dev};
     if (cam->row_end == cam->row_begin) return VXPT_OK;
@@ -477,12 +544,11 @@ int vxpt_trace_shadow(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, co
     if (rc) return rc;
     if ((rc = check_camera(cam))) return rc;
     if (!g || !p || !out || !g->t || !g->normal_id) return fail(VXPT_E_INVALID, "NULL argument (G-buffer t and normal_id are required)");
-    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested shadows are outside the v1 parity profile");
-    if (p->soft && !c->have_shadow_noise) return fail(VXPT_E_STATE, "soft shadows need vxpt_set_shadow_noise");
+    if ((rc = check_shadow(c, p))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
     PassIO io(c, cam);
     Plane t, nid, sh, tr;
-    io.add(t, g->t, 4); io.add(nid, g->normal_id, 1); io.add(sh, out->shadow, 1); io.add(tr, out->transversal, 4);
+    io.add(t, g->t, px_bytes(c, 4, 2)); io.add(nid, g->normal_id, 1); io.add(sh, out->shadow, 1); io.add(tr, out->transversal, px_bytes(c, 4, 2));
     if ((rc = io.resolve())) return rc;
     if (cam->row_end == cam->row_begin) return VXPT_OK;
     if ((rc = io.upload(t)) || (rc = io.upload(nid))) return rc;
@@ -505,21 +571,13 @@ int vxpt_trace_diffuse(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, c
     if (rc) return rc;
     if ((rc = check_camera(cam))) return rc;
     if (!g || !p || !out || !g->t || !g->normal_id) return fail(VXPT_E_INVALID, "NULL argument (G-buffer t and normal_id are required)");
-    if (!p->use_blue_noise) return fail(VXPT_E_UNSUPPORTED, "u_UseBlueNoise=false (fract(sin()) hash) is not reproducible; outside the parity profile");
-    if (p->direct_sampling) return fail(VXPT_E_UNSUPPORTED, "u_UseDirectSampling (WIP light-chunk sampling) is outside the v1 parity profile");
-    if (!c->have_materials || !c->have_bluenoise || !c->have_textures || !c->have_sky)
-        return fail(VXPT_E_STATE, "diffuse GI needs materials, blue-noise tables, material textures and a sky cubemap");
-    if (p->trace_length < 0 || p->spp < 0) return fail(VXPT_E_INVALID, "negative trace_length / spp");
-    // every layer the table can reach must exist in the baked arrays
-    for (int b = 0; b < 128; ++b) {
-        if (c->h_materials[b] >= c->n_layers) return fail(VXPT_E_INVALID, "material table references an albedo layer that was not uploaded");
-        if (c->h_materials[384 + b] >= c->n_emissive) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
-    }
+    if ((rc = check_diffuse(c, p))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
     PassIO io(c, cam);
     Plane t, nid, sh, cg, lu, ao;
-    io.add(t, g->t, 4); io.add(nid, g->normal_id, 1);
-    io.add(sh, out->sh, 16); io.add(cg, out->cocg, 8); io.add(lu, out->luma, 4); io.add(ao, out->ao_sky, 8);
+    io.add(t, g->t, px_bytes(c, 4, 2)); io.add(nid, g->normal_id, 1);
+    io.add(sh, out->sh, px_bytes(c, 16, 8)); io.add(cg, out->cocg, px_bytes(c, 8, 4)); io.add(lu, out->luma, px_bytes(c, 4, 2));
+    io.add(ao, out->ao_sky, px_bytes(c, 8, 2));
     if ((rc = io.resolve())) return rc;
     if (cam->row_end == cam->row_begin) return VXPT_OK;
     if ((rc = io.upload(t)) || (rc = io.upload(nid))) return rc;
@@ -545,25 +603,13 @@ int vxpt_trace_reflection(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
     if (!g || !in || !p || !out || !g->t || !g->normal_id || !in->sh || !in->cocg)
         return fail(VXPT_E_INVALID, "NULL argument (G-buffer t, normal_id and the GI sh / cocg planes are required)");
     if (!in->g_pbr && !g->block_id) return fail(VXPT_E_INVALID, "without g_pbr the G-buffer block_id plane is required");
-    if (!c->have_materials || !c->have_bluenoise || !c->have_textures || !c->have_sky || !c->have_refl_textures)
-        return fail(VXPT_E_STATE, "reflections need materials, blue-noise tables, material + reflection textures and a sky cubemap");
-    if (p->trace_length < 0 || p->spp < 0) return fail(VXPT_E_INVALID, "negative trace_length / spp");
-    for (int b = 0; b < 128; ++b) {
-        if (c->h_materials[b] >= c->n_layers || c->h_materials[256 + b] >= c->n_layers)
-            return fail(VXPT_E_INVALID, "material table references an albedo / PBR layer that was not uploaded");
-        if (c->h_materials[128 + b] >= c->n_normal) return fail(VXPT_E_INVALID, "material table references a normal layer that was not uploaded");
-        if (c->h_materials[384 + b] >= c->n_emissive2) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
-    }
-    for (int k = 1; k < 10; ++k) {
-        const int lim = (k % 3 == 2) ? c->n_normal : c->n_layers;  // props: id, then (albedo, normal, pbr) x {top, side, bottom}
-        if (p->grass_props[k] < 0 || p->grass_props[k] >= lim) return fail(VXPT_E_INVALID, "u_GrassBlockProps layer out of range");
-    }
+    if ((rc = check_reflection(c, p))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
     PassIO io(c, cam);
     Plane t, nid, bid, gn, gp, sh, cg, col, hd, em;
-    io.add(t, g->t, 4); io.add(nid, g->normal_id, 1); io.add(bid, g->block_id, 1);
-    io.add(gn, in->g_normal, 12); io.add(gp, in->g_pbr, 16); io.add(sh, in->sh, 16); io.add(cg, in->cocg, 8);
-    io.add(col, out->color, 16); io.add(hd, out->hit_distance, 4); io.add(em, out->emissive_mask, 1);
+    io.add(t, g->t, px_bytes(c, 4, 2)); io.add(nid, g->normal_id, 1); io.add(bid, g->block_id, 1);
+    io.add(gn, in->g_normal, 12); io.add(gp, in->g_pbr, 16); io.add(sh, in->sh, px_bytes(c, 16, 8)); io.add(cg, in->cocg, px_bytes(c, 8, 4));
+    io.add(col, out->color, px_bytes(c, 16, 8)); io.add(hd, out->hit_distance, px_bytes(c, 4, 2)); io.add(em, out->emissive_mask, 1);
     if ((rc = io.resolve())) return rc;
     if (cam->row_end == cam->row_begin) return VXPT_OK;
     if ((rc = io.upload(t)) || (rc = io.upload(nid)) || (rc = io.upload(bid)) || (rc = io.upload(gn)) || (rc = io.upload(gp)) ||
@@ -584,18 +630,275 @@ int vxpt_trace_reflection(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
     return VXPT_OK;
 }
 
+// --------------------------------------------------------------------------------------------- one whole frame
+int vxpt_render_frame(vxpt_handle c, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_camera(cam))) return rc;
+    if (!p || !out || !p->primary) return fail(VXPT_E_INVALID, "NULL argument (primary parameters are required)");
+    if ((rc = check_primary(p->primary))) return rc;
+    if (p->shadow && (rc = check_shadow(c, p->shadow))) return rc;
+    if (p->diffuse && (rc = check_diffuse(c, p->diffuse))) return rc;
+    if (p->reflection) {
+        if (!p->diffuse) return fail(VXPT_E_INVALID, "the reflection pass reads the GI planes: diffuse parameters are required");
+        if ((rc = check_reflection(c, p->reflection))) return rc;
+    }
+    VX_CUDA(cudaSetDevice(c->device));
+    const bool secondary = p->shadow || p->diffuse || p->reflection;
+    PassIO io(c, cam);
+    Plane t, nid, bid, it, hv, sh, tr, dsh, dcg, dlu, dao, gn, gp, col, hd, em;
+    // planes a later pass reads exist in the handle's arena even when the caller does not want them back
+    io.add(t, out->gbuffer.t, px_bytes(c, 4, 2), secondary);
+    io.add(nid, out->gbuffer.normal_id, 1, secondary);
+    io.add(bid, out->gbuffer.block_id, 1, p->reflection && !p->g_pbr);
+    io.add(it, out->gbuffer.inv_t, 4);
+    io.add(hv, out->gbuffer.hit_voxel, 6);
+    if (p->shadow) {
+        io.add(sh, out->shadow.shadow, 1);
+        io.add(tr, out->shadow.transversal, px_bytes(c, 4, 2));
+    }
+    if (p->diffuse) {
+        io.add(dsh, out->diffuse.sh, px_bytes(c, 16, 8), p->reflection != nullptr);
+        io.add(dcg, out->diffuse.cocg, px_bytes(c, 8, 4), p->reflection != nullptr);
+        io.add(dlu, out->diffuse.luma, px_bytes(c, 4, 2));
+        io.add(dao, out->diffuse.ao_sky, px_bytes(c, 8, 2));
+    }
+    if (p->reflection) {
+        io.add(gn, p->g_normal, 12);
+        io.add(gp, p->g_pbr, 16);
+        io.add(col, out->reflection.color, px_bytes(c, 16, 8));
+        io.add(hd, out->reflection.hit_distance, px_bytes(c, 4, 2));
+        io.add(em, out->reflection.emissive_mask, 1);
+    }
+    if ((rc = io.resolve())) return rc;
+    const int rows = cam->row_end - cam->row_begin;
+    if (rows == 0) return VXPT_OK;
+    if ((rc = io.upload(gn)) || (rc = io.upload(gp))) return rc;
+    bool any_host = false;
+    for (Plane* pl : io.planes) any_host = any_host || (pl->user && pl->staged && pl != &gn && pl != &gp);
+    const VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, (int16_t*)hv.dev};
+    const VxShadowOut sd{(uint8_t*)sh.dev, (float*)tr.dev};
+    const VxDiffuseOut dd{(float*)dsh.dev, (float*)dcg.dev, (float*)dlu.dev, (float*)dao.dev};
+    const VxReflectionIn ri{(const float*)gn.dev, (const float*)gp.dev, (const float*)dsh.dev, (const float*)dcg.dev};
+    const VxReflectionOut rd{(float*)col.dev, (float*)hd.dev, (uint8_t*)em.dev};
+    c->frame_counter++;
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    // Host outputs leave through the copy stream while the next pass traces: the G-buffer planes during the shadow pass, the shadow
+    // planes during GI, and the GI pass (the largest planes) in two row slabs so that the first half is on its way while the second
+    // half traces.  Smaller pieces would starve the copy engine: a 135-row slab of the three passes takes longer to trace (latency-
+    // bound kernels) than to copy (measured r01g, 1080 rows: this schedule 1.21 ms, 2 / 4 / 8 uniform slabs of all passes 1.45 / 1.38 / 1.48 ms).
+    int n_ev = 0;
+    auto copy_out = [&](std::initializer_list<Plane*> pls, int rb, int re) -> int {
+        if (!any_host) return VXPT_OK;
+        bool some = false;
+        for (Plane* pl : pls) some = some || (pl->user && pl->staged);
+        if (!some) return VXPT_OK;
+        cudaEvent_t ev = c->ev_slab[n_ev++ & 7];
+        VX_CUDA(cudaEventRecord(ev, c->stream));
+        VX_CUDA(cudaStreamWaitEvent(c->copy_stream, ev, 0));
+        for (Plane* pl : pls)
+            if (int rc2 = io.download_rows(*pl, rb, re, c->copy_stream)) return rc2;
+        return VXPT_OK;
+    };
+    if ((rc = launch_primary(c, *cam, *p->primary, gd))) return rc;
+    if ((rc = copy_out({&t, &nid, &bid, &it, &hv}, cam->row_begin, cam->row_end))) return rc;
+    if (p->shadow) {
+        if ((rc = launch_shadow(c, *cam, gd, *p->shadow, sd))) return rc;
+        if ((rc = copy_out({&sh, &tr}, cam->row_begin, cam->row_end))) return rc;
+    }
+    if (p->diffuse) {
+        const int nslab = (any_host && rows >= 256) ? 2 : 1;
+        for (int s = 0; s < nslab; ++s) {
+            VxCamera sc = *cam;
+            sc.row_begin = cam->row_begin + ((rows * s / nslab) & ~7);
+            sc.row_end = (s + 1 == nslab) ? cam->row_end : cam->row_begin + ((rows * (s + 1) / nslab) & ~7);
+            if ((rc = launch_diffuse(c, sc, gd, *p->diffuse, dd))) return rc;
+            if ((rc = copy_out({&dsh, &dcg, &dlu, &dao}, sc.row_begin, sc.row_end))) return rc;
+        }
+    }
+    if (p->reflection) {
+        if ((rc = launch_reflection(c, *cam, gd, ri, *p->reflection, rd))) return rc;
+        if ((rc = copy_out({&col, &hd, &em}, cam->row_begin, cam->row_end))) return rc;
+    }
+
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
+    if (any_host) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return VXPT_OK;
+}
+
+// ------------------------------------------------------------------------------------- peer-to-peer slab gather
+}  // extern "C"
+namespace vxpt {
+__global__ void signal_kernel(uint32_t* flag, uint32_t value) {
+    // release at system scope: every store of the kernels that ran before on this stream is visible to a peer that
+    // observes the flag
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__device__ __forceinline__ void spin_until(const uint32_t* f, uint32_t at_least, unsigned long long timeout_ns, unsigned* err) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int32_t)(v - at_least) >= 0) break;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) {
+            atomicExch(err, 1u);
+            break;
+        }
+        __nanosleep(100);
+    }
+}
+__global__ void signal_next_kernel(uint32_t* flag, uint32_t* counter) {
+    const uint32_t v = *counter + 1u;
+    *counter = v;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__global__ void wait_next_kernel(const uint32_t* flags, int n, int stride_words, uint32_t* counter, int lag, unsigned long long timeout_ns, unsigned* err) {
+    __shared__ uint32_t s_target;
+    if (threadIdx.x == 0) {
+        const uint32_t v = *counter + 1u;
+        *counter = v;
+        s_target = v - (uint32_t)lag;
+    }
+    __syncthreads();
+    const uint32_t target = s_target;
+    if ((int32_t)target < 1 || (int)threadIdx.x >= n) return;
+    spin_until(flags + (size_t)threadIdx.x * stride_words, target, timeout_ns, err);
+}
+__global__ void wait_all_kernel(const uint32_t* flags, int n, int stride_words, uint32_t at_least, unsigned long long timeout_ns, unsigned* err) {
+    if ((int)threadIdx.x >= n) return;
+    spin_until(flags + (size_t)threadIdx.x * stride_words, at_least, timeout_ns, err);
+}
+}  // namespace vxpt
+extern "C" {
+
+int vxpt_shared_alloc(vxpt_handle c, size_t bytes, void** dptr, uint8_t handle_out[VXPT_SHARED_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == VXPT_SHARED_HANDLE_BYTES, "IPC handle size");
+    if (!c || !dptr || !handle_out || bytes == 0) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VXPT_E_NOMEM, "shared slab buffer allocation failed");
+    }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaMemset(ptr, 0, bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) {
+        cudaFree(ptr);
+        return cuda_fail(e, "cudaIpcGetMemHandle", __FILE__, __LINE__);
+    }
+    std::memcpy(handle_out, &h, sizeof h);
+    c->shared.push_back({ptr, true});
+    *dptr = ptr;
+    return VXPT_OK;
+}
+
+int vxpt_shared_open(vxpt_handle c, const uint8_t handle[VXPT_SHARED_HANDLE_BYTES], void** dptr) {
+    if (!c || !dptr || !handle) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void* ptr = nullptr;
+    VX_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->shared.push_back({ptr, false});
+    *dptr = ptr;
+    return VXPT_OK;
+}
+
+int vxpt_shared_close(vxpt_handle c, void* dptr) {
+    if (!c || !dptr) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    for (size_t k = 0; k < c->shared.size(); ++k)
+        if (c->shared[k].ptr == dptr) {
+            VX_CUDA(cudaStreamSynchronize(c->stream));
+            const bool owned = c->shared[k].owned;
+            c->shared.erase(c->shared.begin() + k);
+            if (owned) VX_CUDA(cudaFree(dptr));
+            else VX_CUDA(cudaIpcCloseMemHandle(dptr));
+            return VXPT_OK;
+        }
+    return fail(VXPT_E_INVALID, "pointer was not returned by vxpt_shared_alloc / vxpt_shared_open of this handle");
+}
+
+int vxpt_copy_async(vxpt_handle c, void* dst, const void* src, size_t bytes, void* cuda_stream) {
+    if (!c || !dst || !src) return fail(VXPT_E_INVALID, "bad argument");
+    if (bytes == 0) return VXPT_OK;
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, cuda_stream ? (cudaStream_t)cuda_stream : c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_signal(vxpt_handle c, uint32_t* flag, uint32_t value, void* cuda_stream) {
+    if (!c || !flag) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    signal_kernel<<<1, 1, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(flag, value);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int vxpt_signal_next(vxpt_handle c, uint32_t* flag, uint32_t* counter, void* cuda_stream) {
+    if (!c || !flag || !counter) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    signal_next_kernel<<<1, 1, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(flag, counter);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int vxpt_wait_next(vxpt_handle c, const uint32_t* flags, int n, int stride_words, uint32_t* counter, int lag, int timeout_ms, void* cuda_stream) {
+    if (!c || !flags || !counter || n <= 0 || n > 1024 || stride_words <= 0 || lag < 0 || timeout_ms <= 0) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    wait_next_kernel<<<1, ((n + 31) / 32) * 32, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(
+        flags, n, stride_words, counter, lag, (unsigned long long)timeout_ms * 1000000ull, c->d_wait_err);
+    c->launches += 1;
+    c->waits_issued = true;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int vxpt_wait_all(vxpt_handle c, const uint32_t* flags, int n, int stride_words, uint32_t at_least, int timeout_ms, void* cuda_stream) {
+    if (!c || !flags || n <= 0 || n > 1024 || stride_words <= 0 || timeout_ms <= 0) return fail(VXPT_E_INVALID, "bad argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    wait_all_kernel<<<1, ((n + 31) / 32) * 32, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(flags, n, stride_words, at_least, (unsigned long long)timeout_ms * 1000000ull, c->d_wait_err);
+    c->launches += 1;
+    c->waits_issued = true;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ sync / stats
+static int check_wait_error(vxpt_ctx* c) {  // stream must be idle
+    if (!c->waits_issued) return VXPT_OK;
+    unsigned err = 0;
+    VX_CUDA(cudaMemcpy(&err, c->d_wait_err, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) {
+        VX_CUDA(cudaMemset(c->d_wait_err, 0, sizeof(unsigned)));
+        return fail(VXPT_E_STATE, "vxpt_wait_all timed out: a peer never signalled its frame");
+    }
+    return VXPT_OK;
+}
+
 int vxpt_sync(vxpt_handle c) {
     if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
     VX_CUDA(cudaSetDevice(c->device));
     VX_CUDA(cudaStreamSynchronize(c->stream));
-    return VXPT_OK;
+    return check_wait_error(c);
 }
 
 int vxpt_get_stats(vxpt_handle c, VxStats* out) {
     if (!c || !out) return fail(VXPT_E_INVALID, "NULL argument");
     VX_CUDA(cudaSetDevice(c->device));
     VX_CUDA(cudaStreamSynchronize(c->stream));
+    if (int rc = check_wait_error(c)) return rc;
     DeviceCounters h;
     VX_CUDA(cudaMemcpy(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
     if (c->pass_timed) {
@@ -662,6 +965,10 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
         case VXPT_OPT_TIMING_EVENTS:
             c->opt_timing = value ? 1 : 0;
             if (!c->opt_timing) c->pass_timed = false;
+            return VXPT_OK;
+        case VXPT_OPT_TEXEL_FORMAT:
+            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "texel format must be 0 or 1");
+            c->opt_texel = value;
             return VXPT_OK;
         case VXPT_OPT_DF_ALGO:
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "df algo must be 0 or 1");

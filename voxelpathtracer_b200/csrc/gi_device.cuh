@@ -11,6 +11,7 @@ struct GBufferDev {
     uint8_t* block_id;
     float* inv_t;
     int16_t* hit_voxel;
+    int fmt;  // texel format of t (VXPT_OPT_TEXEL_FORMAT); inv_t is R32F in both
 };
 
 struct DiffuseDev {
@@ -26,6 +27,7 @@ struct DiffuseOutDev {
     float2* cocg;
     float* luma;
     float2* ao_sky;
+    int fmt;
 };
 
 // trace_gi.cu

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __
         const float t = traverse_df<LAYOUT>(S, ray_origin(cam), dir, p.max_iterations, h, cnt);
         const bool intersect = t > 0.0f && h.block > 0;
         const size_t px = (size_t)prow * cam.width + i;
-        if (out.t) out.t[px] = t;
+        if (out.t) store_f1(out.t, px, t, out.fmt);
         if (out.inv_t) out.inv_t[px] = 1.0f / t;
         if (out.normal_id) out.normal_id[px] = intersect ? (uint8_t)normal_id_of(h) : (uint8_t)VXPT_NORMAL_MISS;
         if (out.block_id) out.block_id[px] = intersect ? (uint8_t)h.block : (uint8_t)0;
@@ -54,6 +54,7 @@ struct ShadowDev {
 struct ShadowOutDev {
     uint8_t* shadow;
     float* transversal;
+    int fmt;
 };
 
 template <int LAYOUT>
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __g
         float v = ((float)j + 0.5f) / (float)cam.height;
         u += p.hx * (1.0f / (float)cam.width);
         v += p.hy * (1.0f / (float)cam.height);
-        const float dist = g.t[px];
+        const float dist = load_f1(g.t, px, g.fmt);
         uint8_t o_shadow;
         float o_trans;
         if (dist < 0.0f) {
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __g
             }
         }
         if (out.shadow) out.shadow[px] = o_shadow;
-        if (out.transversal) out.transversal[px] = o_trans;
+        if (out.transversal) store_f1(out.transversal, px, o_trans, out.fmt);
     }
     flush_counters(S, cnt);
 }
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) diffuse_kernel(const SceneDev S, const __
             v += (P.hy * 0.75f) / (float)cam.height;
         }
         float o_sh[4], o_cocg[2], o_util = 0.0f, o_ao0 = 1.0f, o_ao1 = 0.0f;
-        const float dist = g.t[px];
+        const float dist = load_f1(g.t, px, g.fmt);
         const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
         if (dist < 0.0f) {
             float sh[6];
@@ -255,10 +256,10 @@ __global__ void __launch_bounds__(256) diffuse_kernel(const SceneDev S, const __
             o_cocg[1] = clampf(cocg1, -100.0f, 100.0f);
             o_util = clampf(o_util, 0.001f, 64.0f);
         }
-        if (out.sh) out.sh[px] = make_float4(o_sh[0], o_sh[1], o_sh[2], o_sh[3]);
-        if (out.cocg) out.cocg[px] = make_float2(o_cocg[0], o_cocg[1]);
-        if (out.luma) out.luma[px] = o_util;
-        if (out.ao_sky) out.ao_sky[px] = make_float2(o_ao0, o_ao1);
+        if (out.sh) store_f4(out.sh, px, o_sh[0], o_sh[1], o_sh[2], o_sh[3], out.fmt);
+        if (out.cocg) store_f2(out.cocg, px, o_cocg[0], o_cocg[1], out.fmt);
+        if (out.luma) store_f1(out.luma, px, o_util, out.fmt);
+        if (out.ao_sky) store_unorm2(out.ao_sky, px, o_ao0, o_ao1, out.fmt);
     }
     flush_counters(S, cnt);
 }
@@ -272,14 +273,14 @@ static CameraDev to_dev(const VxCamera& cam) {
     return c;
 }
 static dim3 pixel_grid(const VxCamera& cam) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8); }
-static GBufferDev to_dev(const VxGBuffer& g) { return GBufferDev{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel}; }
+static GBufferDev to_dev(const vxpt_ctx* c, const VxGBuffer& g) { return GBufferDev{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel}; }
 
 int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out) {
     const SceneDev S = make_scene(c);
     const PrimaryDev pd{p.max_iterations, p.jitter_enable, p.jitter[0], p.jitter[1]};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) primary_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(out));
-    else primary_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(out));
+    if (c->opt_layout == 1) primary_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(c, out));
+    else primary_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(c, out));
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -300,10 +301,10 @@ int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const Vx
     sd.ioffy = (int)floorf(offy);
     sd.hx = p.halton[0];
     sd.hy = p.halton[1];
-    const ShadowOutDev od{out.shadow, out.transversal};
+    const ShadowOutDev od{out.shadow, out.transversal, c->opt_texel};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) shadow_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(g), od);
-    else shadow_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(g), od);
+    if (c->opt_layout == 1) shadow_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(c, g), od);
+    else shadow_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(c, g), od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -336,10 +337,10 @@ int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const V
     d.sun_visibility = p.sun_visibility; d.gi_sky_strength = p.gi_sky_strength; d.light_intensity = p.light_intensity;
     if (c->opt_wavefront) return launch_diffuse_wavefront(c, cam, d, g, out);
     const DiffuseOutDev od{reinterpret_cast<float4*>(out.sh), reinterpret_cast<float2*>(out.cocg), out.luma,
-                           reinterpret_cast<float2*>(out.ao_sky)};
+                           reinterpret_cast<float2*>(out.ao_sky), c->opt_texel};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) diffuse_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(g), od);
-    else diffuse_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(g), od);
+    if (c->opt_layout == 1) diffuse_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(c, g), od);
+    else diffuse_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(c, g), od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

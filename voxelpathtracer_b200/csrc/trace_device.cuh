@@ -6,6 +6,8 @@
 // square root; every expression keeps the association of the GLSL source.  dot = (x*x' + y*y') + z*z',
 // normalize(v) = v * (1/sqrt(dot(v,v))), mat4*vec4 = (m0*x + m1*y) + (m2*z + m3*w).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "vxpt_internal.h"
 
 namespace vxpt {
@@ -58,6 +60,50 @@ __device__ __forceinline__ V3 ray_direction_at(const CameraDev& cam, float u, fl
                (M[2] * ex + M[6] * ey) + (M[10] * ez + M[14] * ew));
 }
 __device__ __forceinline__ V3 ray_origin(const CameraDev& cam) { return mk3(cam.inv_view[12], cam.inv_view[13], cam.inv_view[14]); }
+
+// ---- plane texel formats (VXPT_OPT_TEXEL_FORMAT) ----------------------------------------------------------------
+// fmt 0: fp32 planes (parity default).  fmt 1: the reference's FBO attachment formats (Core/Pipeline.cpp:1094-1095, 1102, 1141, 1152):
+// R16F / RG16F / RGBA16F texels are IEEE halves rounded to nearest even from the fp32 value, RG8 is unorm8 = round(v * 255).
+// The pointer types of the plane structs are nominal; the format decides the element size.
+__device__ __forceinline__ float load_f1(const float* plane, size_t px, int fmt) {
+    return fmt ? __half2float(reinterpret_cast<const __half*>(plane)[px]) : plane[px];
+}
+__device__ __forceinline__ void store_f1(float* plane, size_t px, float v, int fmt) {
+    if (fmt) reinterpret_cast<__half*>(plane)[px] = __float2half_rn(v);
+    else plane[px] = v;
+}
+__device__ __forceinline__ float2 load_f2(const float2* plane, size_t px, int fmt) {
+    if (fmt) return __half22float2(reinterpret_cast<const __half2*>(plane)[px]);
+    return plane[px];
+}
+__device__ __forceinline__ void store_f2(float2* plane, size_t px, float a, float b, int fmt) {
+    if (fmt) reinterpret_cast<__half2*>(plane)[px] = __halves2half2(__float2half_rn(a), __float2half_rn(b));
+    else plane[px] = make_float2(a, b);
+}
+__device__ __forceinline__ float4 load_f4(const float4* plane, size_t px, int fmt) {
+    if (fmt) {
+        const uint2 r = reinterpret_cast<const uint2*>(plane)[px];
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    return plane[px];
+}
+__device__ __forceinline__ void store_f4(float4* plane, size_t px, float a, float b, float c, float d, int fmt) {
+    if (fmt) {
+        const __half2 lo = __halves2half2(__float2half_rn(a), __float2half_rn(b)), hi = __halves2half2(__float2half_rn(c), __float2half_rn(d));
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned*>(&lo);
+        r.y = *reinterpret_cast<const unsigned*>(&hi);
+        reinterpret_cast<uint2*>(plane)[px] = r;
+    } else {
+        plane[px] = make_float4(a, b, c, d);
+    }
+}
+// RG8 unorm (values already clamped to [0, 1])
+__device__ __forceinline__ void store_unorm2(float2* plane, size_t px, float a, float b, int fmt) {
+    if (fmt) reinterpret_cast<uchar2*>(plane)[px] = make_uchar2((unsigned char)__float2uint_rn(a * 255.0f), (unsigned char)__float2uint_rn(b * 255.0f));
+    else plane[px] = make_float2(a, b);
+}
 
 struct Counters {
     unsigned int rays, df, vox;

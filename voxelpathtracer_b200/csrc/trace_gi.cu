@@ -63,10 +63,10 @@ __device__ __forceinline__ void write_final(const DiffuseOutDev& out, size_t px,
     const float lum = dot3(radiance, mk3(0.299f, 0.587f, 0.114f));
     float util = fmaxf(lum, 0.01f);
     util = clampf(util, 0.001f, 64.0f);
-    if (out.sh) out.sh[px] = make_float4(clampf(t0, -100.0f, 100.0f), clampf(t1, -100.0f, 100.0f), clampf(t2, -100.0f, 100.0f), clampf(t3, -100.0f, 100.0f));
-    if (out.cocg) out.cocg[px] = make_float2(clampf(c0, -100.0f, 100.0f), clampf(c1, -100.0f, 100.0f));
-    if (out.luma) out.luma[px] = util;
-    if (out.ao_sky) out.ao_sky[px] = make_float2(clampf(acc_ao, 0.0f, 1.0f), clampf(skyhits, 0.0f, 1.0f));
+    if (out.sh) store_f4(out.sh, px, clampf(t0, -100.0f, 100.0f), clampf(t1, -100.0f, 100.0f), clampf(t2, -100.0f, 100.0f), clampf(t3, -100.0f, 100.0f), out.fmt);
+    if (out.cocg) store_f2(out.cocg, px, clampf(c0, -100.0f, 100.0f), clampf(c1, -100.0f, 100.0f), out.fmt);
+    if (out.luma) store_f1(out.luma, px, util, out.fmt);
+    if (out.ao_sky) store_unorm2(out.ao_sky, px, clampf(acc_ao, 0.0f, 1.0f), clampf(skyhits, 0.0f, 1.0f), out.fmt);
 }
 
 // end of one sample (:898-913): clamp, SH projection, accumulate (or, when every pixel takes one sample, finish)
@@ -173,17 +173,17 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
             u += (P.hx * 0.75f) / (float)cam.width;
             v += (P.hy * 0.75f) / (float)cam.height;
         }
-        const float dist = g.t[px];
+        const float dist = load_f1(g.t, px, g.fmt);
         const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
         if (dist < 0.0f) {
             if (sample == 0) {  // sky pixel (:866-872)
                 float sh[6];
                 const V3 vdir = normalize3(ray_direction_at(cam, u0, v0));
                 irradiance_to_sh(sky_sample(S, vdir) * 2.66f, normal, sh);
-                if (out.sh) out.sh[px] = make_float4(sh[0], sh[1], sh[2], sh[3]);
-                if (out.cocg) out.cocg[px] = make_float2(sh[4], sh[5]);
-                if (out.luma) out.luma[px] = 0.0f;
-                if (out.ao_sky) out.ao_sky[px] = make_float2(1.0f, 0.0f);
+                if (out.sh) store_f4(out.sh, px, sh[0], sh[1], sh[2], sh[3], out.fmt);
+                if (out.cocg) store_f2(out.cocg, px, sh[4], sh[5], out.fmt);
+                if (out.luma) store_f1(out.luma, px, 0.0f, out.fmt);
+                if (out.ao_sky) store_unorm2(out.ao_sky, px, 1.0f, 0.0f, out.fmt);
             }
         } else if (sample < pixel_spp(P, i, j)) {
             int bl_sample = 0;
@@ -235,17 +235,17 @@ __global__ void __launch_bounds__(256) gi_gen(const SceneDev S, const __grid_con
             u += (P.hx * 0.75f) / (float)cam.width;
             v += (P.hy * 0.75f) / (float)cam.height;
         }
-        const float dist = g.t[px];
+        const float dist = load_f1(g.t, px, g.fmt);
         const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
         if (dist < 0.0f) {
             if (sample == 0) {  // sky pixel (:866-872)
                 float sh[6];
                 const V3 vdir = normalize3(ray_direction_at(cam, u0, v0));
                 irradiance_to_sh(sky_sample(S, vdir) * 2.66f, normal, sh);
-                if (out.sh) out.sh[px] = make_float4(sh[0], sh[1], sh[2], sh[3]);
-                if (out.cocg) out.cocg[px] = make_float2(sh[4], sh[5]);
-                if (out.luma) out.luma[px] = 0.0f;
-                if (out.ao_sky) out.ao_sky[px] = make_float2(1.0f, 0.0f);
+                if (out.sh) store_f4(out.sh, px, sh[0], sh[1], sh[2], sh[3], out.fmt);
+                if (out.cocg) store_f2(out.cocg, px, sh[4], sh[5], out.fmt);
+                if (out.luma) store_f1(out.luma, px, 0.0f, out.fmt);
+                if (out.ao_sky) store_unorm2(out.ao_sky, px, 1.0f, 0.0f, out.fmt);
             }
         } else if (sample < pixel_spp(P, i, j)) {
             int bl_sample = 0;
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) gi_finalize(const __grid_constant__ Camer
     int i, j, prow;
     if (!thread_pixel(cam, i, j, prow)) return;
     const size_t px = (size_t)prow * cam.width + i;
-    if (g.t[px] < 0.0f) return;
+    if (load_f1(g.t, px, g.fmt) < 0.0f) return;
     const PixState st = state[px];
     write_final(out, px, mk3(st.rad.x, st.rad.y, st.rad.z), st.rad.w, st.tot.x, st.tot.y, st.tot.z, st.tot.w, st.misc.x, st.misc.y, st.misc.z,
                 pixel_spp(P, i, j));
@@ -461,8 +461,9 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
 int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev& d, const VxGBuffer& g, const VxDiffuseOut& out) {
     const SceneDev S = make_scene(c);
     const CameraDev cd = cam_to_dev(cam);
-    const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel};
-    const DiffuseOutDev od{reinterpret_cast<float4*>(out.sh), reinterpret_cast<float2*>(out.cocg), out.luma, reinterpret_cast<float2*>(out.ao_sky)};
+    const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel};
+    const DiffuseOutDev od{reinterpret_cast<float4*>(out.sh), reinterpret_cast<float2*>(out.cocg), out.luma, reinterpret_cast<float2*>(out.ao_sky),
+                           c->opt_texel};
     // the largest per-pixel sample count (pixel_spp on the host)
     const int base = std::min(std::max(d.spp, 1), 32);
     int max_spp = base;

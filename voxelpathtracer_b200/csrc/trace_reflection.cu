@@ -21,11 +21,13 @@ struct ReflInDev {
     const float4* g_pbr;
     const float4* sh;
     const float2* cocg;
+    int fmt;  // texel format of sh / cocg (g_normal and g_pbr stay fp32)
 };
 struct ReflOutDev {
     float4* color;
     float* hit_distance;
     uint8_t* emissive_mask;
+    int fmt;
 };
 
 // CalculateVectors :1376-1449 on an exact axis normal (normal id 0..5)
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
         const float u = ((float)i + 0.5f) / (float)cam.width, v = ((float)j + 0.5f) / (float)cam.height;
         const float ju = u + (P.hx / (float)cam.width) * 1.0f;  // u_TemporalFilterReflections = true
         const float jv = v + (P.hy / (float)cam.height) * 1.0f;
-        const float dist = g.t[px];
+        const float dist = load_f1(g.t, px, g.fmt);
         if (!(dist < 0.0f)) {
             int spp = min(max(P.spp, 1), 16);
             if (P.checkerboard) {
@@ -155,8 +157,8 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
             const V3 nmapped = in.g_normal ? mk3(in.g_normal[3 * px], in.g_normal[3 * px + 1], in.g_normal[3 * px + 2]) : face_n;
             V3 base_indirect;
             {  // SHToIrradianceA :469-478
-                const float4 sh = in.sh[px];
-                const float2 cg = in.cocg[px];
+                const float4 sh = load_f4(in.sh, px, in.fmt);
+                const float2 cg = load_f2(in.cocg, px, in.fmt);
                 const float Y = fmaxf(0.0f, 3.544905f * sh.w);
                 const float sc = (Y * 0.282095f) / (sh.w + 1e-6f);
                 const float c0 = cg.x * sc, c1 = cg.y * sc;
@@ -252,8 +254,8 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
             o_hit = clampf(meaningful > 0.01f ? avg_hit : -1.0f, -10.0f, 200.0f);
             o_mask = clampf(mask, 0.0f, 1.0f) > 0.5f ? 1 : 0;
         }
-        if (out.color) out.color[px] = o_color;
-        if (out.hit_distance) out.hit_distance[px] = o_hit;
+        if (out.color) store_f4(out.color, px, o_color.x, o_color.y, o_color.z, o_color.w, out.fmt);
+        if (out.hit_distance) store_f1(out.hit_distance, px, o_hit, out.fmt);
         if (out.emissive_mask) out.emissive_mask[px] = o_mask;
     }
     flush_counters(S, cnt);
@@ -333,10 +335,10 @@ int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, cons
     for (int k = 0; k < 16; ++k) { cd.inv_view[k] = cam.inv_view[k]; cd.inv_proj[k] = cam.inv_proj[k]; }
     cd.width = cam.width; cd.height = cam.height; cd.row_begin = cam.row_begin; cd.row_end = cam.row_end;
     cd.il_n = cam.interleave_n; cd.il_rank = cam.interleave_rank; cd.il_band = cam.band_rows > 0 ? cam.band_rows : 1;
-    const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel};
+    const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel};
     const ReflInDev id{in.g_normal, reinterpret_cast<const float4*>(in.g_pbr), reinterpret_cast<const float4*>(in.sh),
-                       reinterpret_cast<const float2*>(in.cocg)};
-    const ReflOutDev od{reinterpret_cast<float4*>(out.color), out.hit_distance, out.emissive_mask};
+                       reinterpret_cast<const float2*>(in.cocg), c->opt_texel};
+    const ReflOutDev od{reinterpret_cast<float4*>(out.color), out.hit_distance, out.emissive_mask, c->opt_texel};
     const dim3 grid((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8);
     if (c->opt_layout == 1) reflection_kernel<1><<<grid, 256, 0, c->stream>>>(S, cd, d, gd, id, od);
     else reflection_kernel<0><<<grid, 256, 0, c->stream>>>(S, cd, d, gd, id, od);

@@ -97,6 +97,7 @@ struct vxpt_ctx {
     int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped), 1 = DPX tiled
     int opt_replicas = 1;   // VXPT_OPT_SCENE_REPLICAS
     int opt_timing = 1;     // VXPT_OPT_TIMING_EVENTS
+    int opt_texel = 0;      // VXPT_OPT_TEXEL_FORMAT
     uint8_t* rep_grid[8] = {nullptr};   // extra copies (index 1..replicas-1); index 0 unused (= d_grid / d_steps)
     uint8_t* rep_steps[8] = {nullptr};
     uint64_t frame_counter = 0;  // advanced by vxpt_trace_primary
@@ -104,6 +105,19 @@ struct vxpt_ctx {
     // device staging for host-pointer I/O (grown on demand)
     void* d_stage = nullptr;
     size_t stage_bytes = 0;
+
+    // vxpt_render_frame: copy-out stream + one event per row slab
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_slab[8] = {nullptr};
+
+    // peer-to-peer gather (vxpt_shared_*, vxpt_signal, vxpt_wait_all)
+    struct SharedBuf {
+        void* ptr;
+        bool owned;
+    };
+    std::vector<SharedBuf> shared;
+    unsigned* d_wait_err = nullptr;  // latched by a wait that timed out
+    bool waits_issued = false;
 
     // wavefront queues (grown on demand)
     void* d_queue = nullptr;

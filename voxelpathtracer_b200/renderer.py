@@ -6,8 +6,8 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxReflectionIn, VxReflectionOut, VxReflectionParams,
-                  VxShadowOut, VxShadowParams, VxStats, check)
+from .abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxFrameOut, VxFrameParams, VxGBuffer, VxPrimaryParams, VxReflectionIn,
+                  VxReflectionOut, VxReflectionParams, VxShadowOut, VxShadowParams, VxStats, check)
 
 try:  # torch is optional plumbing: device buffers, streams, torch.distributed
     import torch
@@ -169,31 +169,39 @@ class Renderer:
         self.set_shadow_noise(shadow_noise)
 
     # ---- buffers ------------------------------------------------------------------------------------------
-    def alloc(self, shape, dtype, device=False):
-        if device:
+    def alloc(self, shape, dtype, device=False, pinned=False):
+        if device or pinned:
             if torch is None:
-                raise RuntimeError("device buffers need torch")
-            tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.int16: torch.int16}[dtype]
-            return torch.empty(shape, dtype=tdt, device=f"cuda:{self.device}")
+                raise RuntimeError("device / pinned buffers need torch")
+            tdt = {np.float32: torch.float32, np.float16: torch.float16, np.uint8: torch.uint8, np.int16: torch.int16}[dtype]
+            if device:
+                return torch.empty(shape, dtype=tdt, device=f"cuda:{self.device}")
+            return torch.empty(shape, dtype=tdt).pin_memory().numpy()
         return np.empty(shape, dtype=dtype)
 
-    def alloc_gbuffer(self, width, height, device=False, hit_voxel=False):
-        g = {"t": self.alloc((height, width), np.float32, device), "normal_id": self.alloc((height, width), np.uint8, device),
-             "block_id": self.alloc((height, width), np.uint8, device), "inv_t": self.alloc((height, width), np.float32, device)}
+    # plane shapes / dtypes in the two texel formats of VXPT_OPT_TEXEL_FORMAT (False: fp32 planes, True: the reference's FBO formats)
+    def alloc_gbuffer(self, width, height, device=False, hit_voxel=False, texel=False, pinned=False):
+        f = np.float16 if texel else np.float32
+        g = {"t": self.alloc((height, width), f, device, pinned), "normal_id": self.alloc((height, width), np.uint8, device, pinned),
+             "block_id": self.alloc((height, width), np.uint8, device, pinned), "inv_t": self.alloc((height, width), np.float32, device, pinned)}
         if hit_voxel:
-            g["hit_voxel"] = self.alloc((height, width, 3), np.int16, device)
+            g["hit_voxel"] = self.alloc((height, width, 3), np.int16, device, pinned)
         return g
 
-    def alloc_shadow(self, width, height, device=False):
-        return {"shadow": self.alloc((height, width), np.uint8, device), "transversal": self.alloc((height, width), np.float32, device)}
+    def alloc_shadow(self, width, height, device=False, texel=False, pinned=False):
+        f = np.float16 if texel else np.float32
+        return {"shadow": self.alloc((height, width), np.uint8, device, pinned), "transversal": self.alloc((height, width), f, device, pinned)}
 
-    def alloc_reflection(self, width, height, device=False):
-        return {"color": self.alloc((height, width, 4), np.float32, device), "hit_distance": self.alloc((height, width), np.float32, device),
-                "emissive_mask": self.alloc((height, width), np.uint8, device)}
+    def alloc_reflection(self, width, height, device=False, texel=False, pinned=False):
+        f = np.float16 if texel else np.float32
+        return {"color": self.alloc((height, width, 4), f, device, pinned), "hit_distance": self.alloc((height, width), f, device, pinned),
+                "emissive_mask": self.alloc((height, width), np.uint8, device, pinned)}
 
-    def alloc_diffuse(self, width, height, device=False):
-        return {"sh": self.alloc((height, width, 4), np.float32, device), "cocg": self.alloc((height, width, 2), np.float32, device),
-                "luma": self.alloc((height, width), np.float32, device), "ao_sky": self.alloc((height, width, 2), np.float32, device)}
+    def alloc_diffuse(self, width, height, device=False, texel=False, pinned=False):
+        f = np.float16 if texel else np.float32
+        return {"sh": self.alloc((height, width, 4), f, device, pinned), "cocg": self.alloc((height, width, 2), f, device, pinned),
+                "luma": self.alloc((height, width), f, device, pinned),
+                "ao_sky": self.alloc((height, width, 2), np.uint8 if texel else np.float32, device, pinned)}
 
     @staticmethod
     def gbuffer_struct(g):
@@ -230,6 +238,68 @@ class Renderer:
         o.color, o.hit_distance, o.emissive_mask = _ptr(out.get("color")), _ptr(out.get("hit_distance")), _ptr(out.get("emissive_mask"))
         check(self.lib.vxpt_trace_reflection(self.handle, C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o)))
         return out
+
+    def render_frame(self, cam, primary, shadow=None, diffuse=None, gbuf=None, shadow_out=None, diffuse_out=None, reflection=None,
+                     reflection_out=None, g_normal=None, g_pbr=None):
+        """One frame of the path (vxpt_render_frame): primary -> shadow -> GI (-> reflections) with the G-buffer resident on
+        the device; host planes are copied out slab by slab while later slabs trace."""
+        fp = VxFrameParams()
+        fp.primary = C.pointer(primary)
+        if shadow is not None:
+            fp.shadow = C.pointer(shadow)
+        if diffuse is not None:
+            fp.diffuse = C.pointer(diffuse)
+        if reflection is not None:
+            fp.reflection = C.pointer(reflection)
+        fp.g_normal, fp.g_pbr = _ptr(g_normal), _ptr(g_pbr)
+        fo = VxFrameOut()
+        fo.gbuffer = self.gbuffer_struct(gbuf or {})
+        so, do, ro = shadow_out or {}, diffuse_out or {}, reflection_out or {}
+        fo.shadow.shadow, fo.shadow.transversal = _ptr(so.get("shadow")), _ptr(so.get("transversal"))
+        fo.diffuse.sh, fo.diffuse.cocg, fo.diffuse.luma, fo.diffuse.ao_sky = (_ptr(do.get("sh")), _ptr(do.get("cocg")), _ptr(do.get("luma")),
+                                                                                _ptr(do.get("ao_sky")))
+        fo.reflection.color, fo.reflection.hit_distance, fo.reflection.emissive_mask = (_ptr(ro.get("color")), _ptr(ro.get("hit_distance")),
+                                                                                         _ptr(ro.get("emissive_mask")))
+        check(self.lib.vxpt_render_frame(self.handle, C.byref(cam), C.byref(fp), C.byref(fo)))
+        return gbuf, shadow_out, diffuse_out, reflection_out
+
+    # ---- peer-to-peer slab gather (multi-GPU) --------------------------------------------------------------
+    def shared_alloc(self, nbytes):
+        """Device buffer other processes can map (returns address, 64-byte handle)."""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * abi.SHARED_HANDLE_BYTES)()
+        check(self.lib.vxpt_shared_alloc(self.handle, int(nbytes), C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def shared_open(self, handle):
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * abi.SHARED_HANDLE_BYTES).from_buffer_copy(handle)
+        check(self.lib.vxpt_shared_open(self.handle, buf, C.byref(ptr)))
+        return ptr.value
+
+    def shared_close(self, ptr):
+        check(self.lib.vxpt_shared_close(self.handle, C.c_void_p(ptr)))
+
+    def copy_async(self, dst_ptr, src_ptr, nbytes, stream=None):
+        check(self.lib.vxpt_copy_async(self.handle, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(nbytes), C.c_void_p(stream)))
+
+    def signal(self, flag_ptr, value, stream=None):
+        """Stream-ordered system-scope release store of `value` to a (possibly peer-mapped) flag word."""
+        check(self.lib.vxpt_signal(self.handle, C.c_void_p(flag_ptr), int(value) & 0xFFFFFFFF, C.c_void_p(stream)))
+
+    def signal_next(self, flag_ptr, counter_ptr, stream=None):
+        """Graph-capturable signal: the value is ++*counter (device-resident)."""
+        check(self.lib.vxpt_signal_next(self.handle, C.c_void_p(flag_ptr), C.c_void_p(counter_ptr), C.c_void_p(stream)))
+
+    def wait_next(self, flags_ptr, n, stride_words, counter_ptr, lag=0, timeout_ms=2000, stream=None):
+        """Graph-capturable wait: target = ++*counter - lag; waits (if target >= 1) until all n flags have reached it."""
+        check(self.lib.vxpt_wait_next(self.handle, C.c_void_p(flags_ptr), int(n), int(stride_words), C.c_void_p(counter_ptr), int(lag),
+                                      int(timeout_ms), C.c_void_p(stream)))
+
+    def wait_all(self, flags_ptr, n, stride_words, at_least, timeout_ms=2000, stream=None):
+        """Stream-ordered wait until n flag words (stride_words apart) have all reached at_least."""
+        check(self.lib.vxpt_wait_all(self.handle, C.c_void_p(flags_ptr), int(n), int(stride_words), int(at_least) & 0xFFFFFFFF, int(timeout_ms),
+                                     C.c_void_p(stream)))
 
     # ---- sync / stats -------------------------------------------------------------------------------------
     def sync(self):

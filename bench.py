@@ -202,7 +202,7 @@ def run_ours(args):
     exchange = args.exchange
     # P independent handles ("pipes") per GPU, each with its own CUDA stream and double-buffered frame slots: consecutive
     # frames go to alternating pipes, so the latency-bound tail of one frame's kernels overlaps the next frame's kernels.
-    P = max(1, args.pipes if args.pipes > 0 else (2 if ws == 1 else 4))
+    P = max(1, args.pipes if args.pipes > 0 else (2 if ws == 1 else (4 if ws == 2 else 8)))
     renderers, frames, exts = [], [], []
     for _ in range(P):
         rr = vx.Renderer(local_rank)
@@ -270,7 +270,7 @@ def run_ours(args):
     launches_per_graph = None
     # p2p: the flag operations take their sequence numbers from device counters, so the whole frame (wait for the slot, passes,
     # arrival flag) is one graph, and the root's gather stream replays a two-node graph of its own
-    whole = frame.exchange_mode == "p2p"
+    whole = frame.exchange_mode in ("p2p", "p2pcopy")
     is_root = whole and rank == frame.root
     gather_graphs = None
     if not args.no_graph:
@@ -460,7 +460,8 @@ def run_ours(args):
                         "sample": f"{n_frames} full 1080p frames (primary+shadow+GI) of the same workload, C++ oracle, OpenMP over rows, {dt:.1f} s"}
 
     xchg_text = {"none": "single GPU, no exchange",
-                 "p2pcopy": "radiance slabs (shadow + GI planes) traced locally and pushed to the gather root with one copy-engine transfer per frame over NVLink (CUDA IPC mapping), frames ordered by release/acquire flag words",
+                 "p2pcopy": "radiance slabs (shadow + GI planes) traced locally and pushed into the gather root's memory with one copy-engine transfer per frame over NVLink (CUDA IPC mapping), "
+                            "frames ordered by release/acquire flag words, no collective",
                  "p2p": "radiance slabs (shadow + GI planes) stored by the trace kernels straight into the gather root's memory over NVLink (CUDA IPC mapping), "
                         "frames ordered by release/acquire flag words, no exchange step",
                  "nccl": "one packed NCCL all-gather of the shadow + GI planes per frame on its own stream, overlapped with the following frames' tracing"}[frame.exchange_mode]
@@ -496,9 +497,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipes", type=int, default=0, help="independent handles/streams per GPU (frames in flight); 0 = 2 on one GPU, 4 on several")
+    ap.add_argument("--pipes", type=int, default=0, help="independent handles/streams per GPU (frames in flight); 0 = 2 on one GPU, 4 on two, 8 on more")
     ap.add_argument("--slots", type=int, default=2, help="frame slots per pipe in the slab buffer")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "p2pcopy", "nccl"],
+    ap.add_argument("--exchange", default="p2pcopy", choices=["p2p", "p2pcopy", "nccl"],
                     help="multi-GPU slab gather: the trace kernels store into the root's memory (p2p), one copy-engine push per frame (p2pcopy), or NCCL all-gather")
     ap.add_argument("--emulate", type=int, default=0, help="development: trace rank 0's share of an N-way sharded frame on one GPU, no exchange")
     ap.add_argument("--planes", default="texel", choices=["texel", "f32"], help="plane encoding: the reference's FBO texel formats (default) or fp32")

@@ -137,9 +137,10 @@ class ShardedFrame:
       ordered by flag words in the same buffer: a rank releases `arrived[rank] = k` after the passes of frame k
       (`vxpt_signal`), the root's gather stream waits for all N (`vxpt_wait_all`) and then publishes `consumed = k`, and a rank
       waits for `consumed >= k - slots` before it overwrites a slot.  Nothing blocks the host.
-    * exchange="p2pcopy": as p2p, but a rank traces into local memory and pushes its packed region to the root with ONE copy-engine
-      transfer per frame (`vxpt_copy_async` on the gather stream, followed by the arrival flag): full-line NVLink writes instead of
-      the kernels' scattered 2-8-byte stores, at the price of one more event + copy per frame.
+    * exchange="p2pcopy" (what bench.py uses): as p2p, but a rank traces into local memory and pushes its packed region to the root
+      with ONE copy-engine transfer per frame (`vxpt_copy_async`, stream-ordered between the passes and the arrival flag): full-line
+      NVLink writes instead of the kernels' scattered 2-8-byte stores.  Measured on 8 B200 (r01g, 1080p, 19 B/pixel): direct stores
+      0.148 ms/frame (the root's NVLink ingress saturates on partial-sector writes), copy-engine push 0.071 ms/frame = 7.65x one GPU.
     * texel=True selects VXPT_OPT_TEXEL_FORMAT = 1 on the renderer: 19 instead of 41 bytes per pixel cross the link.
     """
 
@@ -230,8 +231,7 @@ class ShardedFrame:
         self._traced = [[torch.cuda.Event() for _ in range(self.chunks)] for _ in range(self.slots)]
         self._exchanged = [None] * self.slots  # event of the last exchange that read/wrote a slot
         self._slot = 0
-        self._seq = 0          # frames started (p2pcopy: flag value of the frame being traced)
-        # p2p: device-resident sequence counters, so that the flag operations are argument-free and a whole frame — wait for the
+        # p2p / p2pcopy: device-resident sequence counters, so that the flag operations are argument-free and a whole frame — wait for the
         # slot, the passes, arrival flag — replays as one CUDA graph: [0] frames started, [1] frames signalled, [2] frames
         # gathered (root), [3] frames released (root).  One 128-byte line each.
         self._counters = torch.zeros(4 * FLAG_STRIDE_WORDS, dtype=torch.int32, device=dev)
@@ -283,10 +283,16 @@ class ShardedFrame:
     def frame_into(self, slot, primary, shadow, diffuse):
         """Everything a rank enqueues on the library stream for one frame; capturable into ONE CUDA graph in p2p mode (the flag
         operations take their sequence numbers from device-resident counters)."""
-        if self.exchange_mode == "p2p":
+        if self.exchange_mode in ("p2p", "p2pcopy"):
             # frame k may overwrite its slot once the root has released frame k - slots
             self.r.wait_next(self._shared_ptr + FLAG_BYTES // 2, 1, FLAG_STRIDE_WORDS, self._counter(0), lag=self.slots, timeout_ms=self.timeout_ms)
             self.trace_into(slot, primary, shadow, diffuse)
+            if self.exchange_mode == "p2pcopy" and self.rank != self.root:
+                # copy engine, same stream: this rank's packed region -> the same region of the root's buffer.  The pipe's next frame
+                # waits for the push (a few microseconds of DMA); the other pipes keep the SMs busy meanwhile.
+                for c in range(self.chunks):
+                    off = ((slot * self.chunks + c) * self.world_size + self.rank) * self.region_bytes
+                    self.r.copy_async(self._remote + off, self._base + off, self.region_bytes)
             self.r.signal_next(self._flag(self.rank), self._counter(1))
         else:
             self.before_trace(slot)
@@ -301,13 +307,9 @@ class ShardedFrame:
 
     def before_trace(self, slot):
         """The slot's previous contents must have been consumed before it is overwritten (stream-ordered, no host sync)."""
-        if self.exchange_mode == "p2p":
+        if self.exchange_mode in ("p2p", "p2pcopy"):
             return  # part of frame_into
-        if self.exchange_mode == "p2pcopy":
-            self._seq += 1
-            if self._seq > self.slots:  # frame seq - slots used this slot: wait until the root has gathered it
-                self.r.wait_all(self._shared_ptr + FLAG_BYTES // 2, 1, FLAG_STRIDE_WORDS, self._seq - self.slots, self.timeout_ms)
-        elif self._exchanged[slot] is not None:
+        if self._exchanged[slot] is not None:
             self._ext.wait_event(self._exchanged[slot])
 
     def exchange(self, slot):
@@ -315,30 +317,9 @@ class ShardedFrame:
         memory; release this rank's arrival flag, and on the root let the gather stream wait for all ranks."""
         if self.exchange_mode == "none":
             return
-        if self.exchange_mode == "p2p":
+        if self.exchange_mode in ("p2p", "p2pcopy"):
             if self.rank == self.root:
                 self.gather_into(slot)
-            return
-        if self.exchange_mode == "p2pcopy":
-            if self.rank != self.root:
-                # copy engine: local region -> the same region of the root's buffer, then the arrival flag, both on the gather stream
-                self._traced[slot][0].record(self._ext)
-                self._comm.wait_event(self._traced[slot][0])
-                cs = self._comm.cuda_stream
-                for c in range(self.chunks):
-                    off = ((slot * self.chunks + c) * self.world_size + self.rank) * self.region_bytes
-                    self.r.copy_async(self._remote + off, self._base + off, self.region_bytes, stream=cs)
-                self.r.signal(self._flag(self.rank), self._seq, stream=cs)
-            else:
-                self.r.signal(self._flag(self.rank), self._seq)
-            if self.rank == self.root:
-                cs = self._comm.cuda_stream
-                self.r.wait_all(self._flag(0), self.world_size, FLAG_STRIDE_WORDS, self._seq, self.timeout_ms, stream=cs)
-                # (a consumer of the gathered frame would run here, on the gather stream)
-                self.r.signal(self._shared_ptr + FLAG_BYTES // 2, self._seq, stream=cs)
-                ev = torch.cuda.Event()
-                ev.record(self._comm)
-                self._exchanged[slot] = ev
             return
         self._traced[slot][0].record(self._ext)
         with torch.cuda.stream(self._comm):

@@ -409,30 +409,42 @@ def run_ours(args):
     slab_b, slab_e = multigpu.slab_rows(HEIGHT, ws, rank)
     cam_rank = fc.vx_camera(WIDTH, HEIGHT, slab_b, slab_e)
     rows = slab_e - slab_b
-    r.set_option(abi.OPT_TEXEL_FORMAT, 1 if texel else 0)
-    hg = r.alloc_gbuffer(WIDTH, HEIGHT, texel=texel, pinned=True)
-    hs = r.alloc_shadow(WIDTH, HEIGHT, texel=texel, pinned=True)
-    hd = r.alloc_diffuse(WIDTH, HEIGHT, texel=texel, pinned=True)
+    # double-buffered like a swap chain: two handles and two sets of pinned planes alternate (vxpt_render_frame_async), so the copy-out
+    # of frame k overlaps the tracing of frame k+1; a frame's result is read when its handle comes round again (vxpt_frame_wait)
+    hr = renderers[:2]
+    for h in hr:
+        h.set_option(abi.OPT_TEXEL_FORMAT, 1 if texel else 0)
+    bufs = [(h.alloc_gbuffer(WIDTH, HEIGHT, texel=texel, pinned=True), h.alloc_shadow(WIDTH, HEIGHT, texel=texel, pinned=True),
+             h.alloc_diffuse(WIDTH, HEIGHT, texel=texel, pinned=True)) for h in hr]
     d2h = rows * WIDTH * px_out
     h2d = 144 + 24 + 32 + 72  # VxCamera + VxPrimaryParams + VxShadowParams + VxDiffuseParams: the only per-frame inputs of the path
+    checksum = 0.0
 
-    def host_step(f):
-        pp, sp, dp = frame_params(vx, camera, tables, f)
-        r.render_frame(cam_rank, pp, sp, dp, hg, hs, hd)
-        return float(hd["luma"][cam_rank.row_begin, 0])
+    def host_step(k, f):
+        i = k % len(hr)
+        hr[i].frame_wait()                                        # the frame this handle rendered last has landed in its host planes
+        val = float(bufs[i][2]["luma"][cam_rank.row_begin, 0])   # ... read (part of) its result
+        pp, sp, dp = params[f % len(params)]  # the per-frame uniforms (camera jitter, frame seeds): built once, passed by pointer per call
+        hr[i].render_frame(cam_rank, pp, sp, dp, *bufs[i], wait=False)
+        return val
 
-    for f in range(args.warmup):
-        host_step(f)
+    for k in range(args.warmup):
+        host_step(k, k)
+    for h in hr:
+        h.frame_wait()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        host_step(args.warmup + k)
+        checksum += host_step(k, args.warmup + k)
+    for h in hr:
+        h.frame_wait()
+    checksum += sum(float(b[2]["luma"][cam_rank.row_begin, 0]) for b in bufs)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e = {"value": rays_all / float(e2e_s[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "note": ("one vxpt_render_frame call per step with pinned HOST output planes (" + ("the reference's FBO texel formats, 27 B/pixel" if texel else "fp32 planes, 51 B/pixel") +
+           "note": ("one vxpt_render_frame_async call per step with pinned HOST output planes, two handles / plane sets alternating (" + ("the reference's FBO texel formats, 27 B/pixel" if texel else "fp32 planes, 51 B/pixel") +
                     "): G-buffer resident on the device between passes, planes copied device->host slab by slab while later slabs trace; "
                     "the per-frame inputs are the camera and parameter structs" + ("; process bound to the GPU's NUMA node" if affinity_before is not None else ""))}
 

@@ -249,6 +249,12 @@ typedef struct VxFrameOut {
     VxReflectionOut reflection;
 } VxFrameOut;
 VXPT_API int vxpt_render_frame(vxpt_handle h, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out);
+/* As vxpt_render_frame, but returns as soon as the frame is enqueued; HOST planes are complete after vxpt_frame_wait(h).
+ * A handle keeps one frame in flight: any later call that needs the handle's staging memory first waits for it, so the call
+ * is always safe; to overlap the copy-out of frame k with the tracing of frame k+1, alternate between two handles (and two
+ * sets of host planes), as a double-buffered swap chain does. */
+VXPT_API int vxpt_render_frame_async(vxpt_handle h, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out);
+VXPT_API int vxpt_frame_wait(vxpt_handle h);
 
 /* ---- peer-to-peer gather of row slabs (multi-GPU, one process per GPU) --------------------------------------
  * The gather root allocates the slab buffer with vxpt_shared_alloc and publishes its 64-byte handle (any byte transport);

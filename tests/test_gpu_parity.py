@@ -615,3 +615,34 @@ def test_sharded_frame_texel_planes_single_rank(renderer, worlds, scene_tables, 
             assert np.array_equal(f.plane(name).cpu().numpy(), ref), name
     finally:
         renderer.set_option(abi.OPT_TEXEL_FORMAT, 0)
+
+
+def test_render_frame_async_double_buffered(renderer, worlds, scene_tables):
+    """vxpt_render_frame_async + vxpt_frame_wait: same planes as the blocking call; a second call on the same handle (or any call that
+    needs the staging arena) first drains the frame in flight, so alternating plane sets never see torn data."""
+    load(renderer, worlds["plains"])
+    W, H = 640, 360
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H)
+    sp = vx.shadow_params(scene_tables["stronger"], frame=4)
+    want, got = [], []
+    sets = [(renderer.alloc_gbuffer(W, H, pinned=True), renderer.alloc_shadow(W, H, pinned=True), renderer.alloc_diffuse(W, H, pinned=True)) for _ in range(2)]
+    frames = [(vx.primary_params(350, camera.taa_jitter(k)), vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], frame=k))
+              for k in range(4)]
+    for pp, dp in frames:
+        g, s, d = renderer.alloc_gbuffer(W, H), renderer.alloc_shadow(W, H), renderer.alloc_diffuse(W, H)
+        renderer.render_frame(cam, pp, sp, dp, g, s, d)
+        want.append({**g, **s, **d})
+    for k, (pp, dp) in enumerate(frames):
+        g, s, d = sets[k % 2]
+        if k >= 2:
+            renderer.frame_wait()
+            got.append({kk: v.copy() for kk, v in {**g, **s, **d}.items()})   # frame k-2, before its planes are reused
+        renderer.render_frame(cam, pp, sp, dp, g, s, d, wait=False)
+    # frames 2 and 3 are still owed: frame 2's planes were overwritten by nothing since, frame 3 is in flight
+    renderer.frame_wait()
+    got.append({kk: v.copy() for kk, v in {**sets[0][0], **sets[0][1], **sets[0][2]}.items()})
+    got.append({kk: v.copy() for kk, v in {**sets[1][0], **sets[1][1], **sets[1][2]}.items()})
+    for k in range(4):
+        for kk in want[k]:
+            assert np.array_equal(got[k][kk], want[k][kk]), (k, kk)
+    renderer.frame_wait()   # idempotent

@@ -112,6 +112,8 @@ EXPORTS = {
     "vxpt_trace_reflection": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]),
     "vxpt_render_frame": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxFrameParams), C.POINTER(VxFrameOut)]),
+    "vxpt_render_frame_async": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxFrameParams), C.POINTER(VxFrameOut)]),
+    "vxpt_frame_wait": (C.c_int, [C.c_void_p]),
     "vxpt_shared_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "vxpt_shared_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "vxpt_shared_close": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -163,8 +163,17 @@ static int check_camera(const VxCamera* cam) {
         return fail(VXPT_E_INVALID, "row slab outside the frame");
     return VXPT_OK;
 }
+// a frame enqueued by vxpt_render_frame_async owns the staging arena until its copies have landed
+static int finish_pending_frame(vxpt_ctx* c) {
+    if (!c->frame_pending) return VXPT_OK;
+    VX_CUDA(cudaSetDevice(c->device));
+    VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    c->frame_pending = false;
+    return VXPT_OK;
+}
 static int check_ready(vxpt_ctx* c) {
     if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    if (int rc = finish_pending_frame(c)) return rc;
     if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded (vxpt_upload_world)");
     if (!c->df_valid) return fail(VXPT_E_STATE, "distance field is stale: call vxpt_build_distance_field after editing the world");
     return VXPT_OK;
@@ -288,6 +297,7 @@ int vxpt_destroy(vxpt_handle c) {
     if (!c) return VXPT_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    c->frame_pending = false;
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
@@ -353,6 +363,7 @@ int vxpt_set_blocks(vxpt_handle c, const int16_t* xyz, const uint8_t* ids, int n
     if (!c || (n > 0 && (!xyz || !ids)) || n < 0) return fail(VXPT_E_INVALID, "bad argument");
     if (!c->world_uploaded) return fail(VXPT_E_STATE, "no world uploaded");
     if (n == 0) return VXPT_OK;
+    if (int rc = finish_pending_frame(c)) return rc;
     for (int k = 0; k < n; ++k)
         if (xyz[3 * k] < 0 || xyz[3 * k + 1] < 0 || xyz[3 * k + 2] < 0 || xyz[3 * k] >= WX || xyz[3 * k + 1] >= WY || xyz[3 * k + 2] >= WZ)
             return fail(VXPT_E_INVALID, "voxel outside the world");
@@ -631,7 +642,8 @@ int vxpt_trace_reflection(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
 }
 
 // --------------------------------------------------------------------------------------------- one whole frame
-int vxpt_render_frame(vxpt_handle c, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out) {
+}  // extern "C"
+static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out, bool wait) {
     int rc = check_ready(c);
     if (rc) return rc;
     if ((rc = check_camera(cam))) return rc;
@@ -725,8 +737,23 @@ int vxpt_render_frame(vxpt_handle c, const VxCamera* cam, const VxFrameParams* p
         VX_CUDA(cudaEventRecord(c->ev1, c->stream));
         c->pass_timed = true;
     }
-    if (any_host) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+    if (any_host) {
+        if (wait) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+        else c->frame_pending = true;
+    }
     return VXPT_OK;
+}
+extern "C" {
+
+int vxpt_render_frame(vxpt_handle c, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out) {
+    return render_frame_impl(c, cam, p, out, true);
+}
+int vxpt_render_frame_async(vxpt_handle c, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out) {
+    return render_frame_impl(c, cam, p, out, false);
+}
+int vxpt_frame_wait(vxpt_handle c) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    return finish_pending_frame(c);
 }
 
 // ------------------------------------------------------------------------------------- peer-to-peer slab gather

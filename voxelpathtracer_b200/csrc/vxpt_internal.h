@@ -109,6 +109,7 @@ struct vxpt_ctx {
     // vxpt_render_frame: copy-out stream + one event per row slab
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_slab[8] = {nullptr};
+    bool frame_pending = false;  // vxpt_render_frame_async: copies to host planes still in flight
 
     // peer-to-peer gather (vxpt_shared_*, vxpt_signal, vxpt_wait_all)
     struct SharedBuf {

@@ -240,9 +240,10 @@ class Renderer:
         return out
 
     def render_frame(self, cam, primary, shadow=None, diffuse=None, gbuf=None, shadow_out=None, diffuse_out=None, reflection=None,
-                     reflection_out=None, g_normal=None, g_pbr=None):
+                     reflection_out=None, g_normal=None, g_pbr=None, wait=True):
         """One frame of the path (vxpt_render_frame): primary -> shadow -> GI (-> reflections) with the G-buffer resident on
-        the device; host planes are copied out slab by slab while later slabs trace."""
+        the device; host planes are copied out pass by pass while later passes trace.  wait=False: vxpt_render_frame_async —
+        returns once enqueued, host planes complete after frame_wait()."""
         fp = VxFrameParams()
         fp.primary = C.pointer(primary)
         if shadow is not None:
@@ -260,8 +261,12 @@ class Renderer:
                                                                                 _ptr(do.get("ao_sky")))
         fo.reflection.color, fo.reflection.hit_distance, fo.reflection.emissive_mask = (_ptr(ro.get("color")), _ptr(ro.get("hit_distance")),
                                                                                          _ptr(ro.get("emissive_mask")))
-        check(self.lib.vxpt_render_frame(self.handle, C.byref(cam), C.byref(fp), C.byref(fo)))
+        fn = self.lib.vxpt_render_frame if wait else self.lib.vxpt_render_frame_async
+        check(fn(self.handle, C.byref(cam), C.byref(fp), C.byref(fo)))
         return gbuf, shadow_out, diffuse_out, reflection_out
+
+    def frame_wait(self):
+        check(self.lib.vxpt_frame_wait(self.handle))
 
     # ---- peer-to-peer slab gather (multi-GPU) --------------------------------------------------------------
     def shared_alloc(self, nbytes):

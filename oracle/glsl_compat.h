@@ -1,0 +1,167 @@
+// glsl_compat.h — what a GLSL 4.30 shader of the reference needs to compile as C++ (test infrastructure only).
+// Vector / matrix types and the built-in functions come from the reference's own vendored glm (Dependencies/glm, 0.9.8); this
+// header adds the few things glm lacks: GLSL's implicit int -> float promotion in mixed vector arithmetic, texel fetches on
+// GL_RED / r8 unorm8 volumes (OpenGL 4.3 core, section 2.3.5: c / 255 on load, round(clamp(f, 0, 1) * 255) on store), the compute
+// built-in gl_GlobalInvocationID and inert stand-ins for the sampler types of code paths the driver never enables.
+#pragma once
+#define GLM_FORCE_PURE  // scalar code paths only: the arithmetic of every expression is the plain IEEE fp32 operation
+#include <cmath>
+#include <cstdint>
+
+#include <glm/glm.hpp>
+
+namespace glsl {
+using namespace glm;
+
+// ---- implicit int -> float promotions of GLSL ---------------------------------------------------------------------------
+inline vec3 operator-(const vec3& a, const ivec3& b) { return a - vec3(b); }
+inline vec3 operator-(const ivec3& a, const vec3& b) { return vec3(a) - b; }
+inline vec3 operator+(const ivec3& a, const vec3& b) { return vec3(a) + b; }
+inline vec3 operator+(const vec3& a, const ivec3& b) { return a + vec3(b); }
+inline vec3 operator*(const ivec3& a, const vec3& b) { return vec3(a) * b; }
+inline vec3 operator*(int a, const vec3& b) { return float(a) * b; }
+inline vec3 operator*(const vec3& a, int b) { return a * float(b); }
+inline vec3 operator/(float a, const vec3& b) { return vec3(a) / b; }
+inline vec2 operator/(float a, const vec2& b) { return vec2(a) / b; }
+inline vec2 operator*(const vec2& a, double b) { return a * float(b); }
+using glm::clamp;
+using glm::max;
+using glm::min;
+inline float min(int a, float b) { return glm::min(float(a), b); }
+inline float min(float a, int b) { return glm::min(a, float(b)); }
+inline float max(int a, float b) { return glm::max(float(a), b); }
+inline float max(float a, int b) { return glm::max(a, float(b)); }
+inline float clamp(int x, float lo, float hi) { return glm::clamp(float(x), lo, hi); }
+inline vec2 operator+(const vec2& a, const ivec2& b) { return a + vec2(b); }
+inline vec2 operator/(const ivec2& a, float b) { return vec2(a) / b; }
+
+// ---- swizzles: oracle/glsl2cpp.py rewrites  e.xyz  as  swz_xyz(e)  (and emits the helper) and  v.xy = e;  as  swz_assign_xy(v, '=', e);
+template <class V, class E> inline void swz_assign_xy(V& v, char op, const E& e) {
+    vec2 cur(v.x, v.y);
+    cur = op == '=' ? vec2(e) : op == '+' ? cur + e : op == '-' ? cur - e : op == '*' ? cur * e : cur / e;
+    v.x = cur.x; v.y = cur.y;
+}
+template <class V, class E> inline void swz_assign_xyz(V& v, char op, const E& e) {
+    vec3 cur(v.x, v.y, v.z);
+    cur = op == '=' ? vec3(e) : op == '+' ? cur + e : op == '-' ? cur - e : op == '*' ? cur * e : cur / e;
+    v.x = cur.x; v.y = cur.y; v.z = cur.z;
+}
+template <class V, class E> inline void swz_assign_rgb(V& v, char op, const E& e) { swz_assign_xyz(v, op, e); }
+
+// GLSL arrays used as values (function results)
+template <int N> struct farr {
+    float v[N];
+    float& operator[](int i) { return v[i]; }
+    const float& operator[](int i) const { return v[i]; }
+};
+inline float rcp(float x) { return 1.0f / x; }  // accepted by the reference's (NVIDIA) GLSL compiler; SURVEY.md A.4
+
+// ---- transcendental functions: GLSL leaves their precision open; pinned to the correctly rounded fp32 value (double evaluation,
+//      one rounding) — the definition the oracle and the CUDA kernels use (oracle/vxo_oracle.cpp header) -------------------------------
+//      (oracle/glsl2cpp.py renames the calls; vector arguments go to glm)
+inline float pinned_sin(float x) { return (float)::sin((double)x); }
+inline float pinned_cos(float x) { return (float)::cos((double)x); }
+inline float pinned_tan(float x) { return (float)::tan((double)x); }
+inline float pinned_pow(float x, float y) { return (float)::pow((double)x, (double)y); }
+template <class V> inline V pinned_sin(const V& v) { return glm::sin(v); }
+template <class V> inline V pinned_cos(const V& v) { return glm::cos(v); }
+template <class V> inline V pinned_tan(const V& v) { return glm::tan(v); }
+template <class V> inline V pinned_pow(const V& a, const V& b) { return glm::pow(a, b); }
+// mix(x, y, a) = x * (1 - a) + y * a, the GLSL specification's formula (glm evaluates x + a * (y - x), which rounds differently)
+inline float pinned_mix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+inline float pinned_mix(int x, int y, float a) { return (float)x * (1.0f - a) + (float)y * a; }
+template <class V> inline V pinned_mix(const V& x, const V& y, float a) { return x * (1.0f - a) + y * a; }
+template <class V> inline V pinned_mix(const V& x, const V& y, const V& a) { return x * (V(1.0f) - a) + y * a; }
+
+// ---- textures and images ----------------------------------------------------------------------------------------------
+struct sampler3D {  // GL_RED, GL_UNSIGNED_BYTE, NEAREST (Core/Texture3D.cpp:8-28)
+    const uint8_t* data = nullptr;
+    int sx = 0, sy = 0, sz = 0;
+};
+inline vec4 texelFetch(const sampler3D& s, const ivec3& p, int /*lod*/) {
+    const uint8_t c = s.data[(size_t)p.x + (size_t)s.sx * ((size_t)p.y + (size_t)s.sy * (size_t)p.z)];
+    return vec4(float(c) / 255.0f, 0.0f, 0.0f, 1.0f);
+}
+struct image3D {  // layout(r8)
+    uint8_t* data = nullptr;
+    int sx = 0, sy = 0, sz = 0;
+};
+inline vec4 imageLoad(const image3D& s, const ivec3& p) {
+    const uint8_t c = s.data[(size_t)p.x + (size_t)s.sx * ((size_t)p.y + (size_t)s.sy * (size_t)p.z)];
+    return vec4(float(c) / 255.0f, 0.0f, 0.0f, 1.0f);
+}
+inline void imageStore(image3D& s, const ivec3& p, const vec4& v) {
+    float f = v.x < 0.0f ? 0.0f : (v.x > 1.0f ? 1.0f : v.x);
+    s.data[(size_t)p.x + (size_t)s.sx * ((size_t)p.y + (size_t)s.sy * (size_t)p.z)] = (uint8_t)std::nearbyintf(f * 255.0f);
+}
+struct sampler2D {  // fp32 texels, 1..4 components, NEAREST (the G-buffer attachments are point-sampled at the pixel's own centre)
+    const float* data = nullptr;
+    int w = 0, h = 0, comps = 1;
+};
+inline vec4 texelFetch(const sampler2D& s, const ivec2& p, int /*lod*/) {
+    const float* t = s.data + ((size_t)p.y * s.w + p.x) * s.comps;
+    return vec4(t[0], s.comps > 1 ? t[1] : 0.0f, s.comps > 2 ? t[2] : 0.0f, s.comps > 3 ? t[3] : 1.0f);
+}
+inline ivec2 textureSize(const sampler2D& s, int /*lod*/) { return ivec2(s.w, s.h); }
+inline vec4 texture(const sampler2D& s, const vec2& uv) {
+    int i = (int)std::floor(uv.x * (float)s.w), j = (int)std::floor(uv.y * (float)s.h);
+    i = i < 0 ? 0 : (i >= s.w ? s.w - 1 : i);
+    j = j < 0 ? 0 : (j >= s.h ? s.h - 1 : j);
+    return texelFetch(s, ivec2(i, j), 0);
+}
+// Array textures and the sky cube map.  OpenGL leaves filter arithmetic (and, inside divergent control flow, even the mip level of an
+// implicit-LOD texture() call) to the driver; the parity contract pins them (oracle/vxo_oracle.cpp header): the driver
+// binds the texel array of the level the call addresses; textureLod() fetches the nearest texel, texture() filters bilinearly in fp32
+// with the weights applied as  a * (1 - f) + b * f , x first; both wrap with GL_REPEAT.  The cube map filters inside the major-axis
+// face and clamps at its edge.
+struct sampler2DArray {
+    const float* data = nullptr;  // [layers][n][n][comps]
+    int n = 0, comps = 4;
+};
+inline vec4 fetch_layer_texel(const sampler2DArray& s, int layer, int i, int j) {
+    const float* t = s.data + (((size_t)layer * s.n + j) * s.n + i) * s.comps;
+    return vec4(t[0], s.comps > 1 ? t[1] : 0.0f, s.comps > 2 ? t[2] : 0.0f, s.comps > 3 ? t[3] : 1.0f);
+}
+inline vec4 textureLod(const sampler2DArray& s, const vec3& p, float /*lod: the bound level*/) {
+    if (!s.data) return vec4(1.0f);
+    const int i = ((int)std::floor(p.x * (float)s.n)) & (s.n - 1), j = ((int)std::floor(p.y * (float)s.n)) & (s.n - 1);
+    return fetch_layer_texel(s, (int)p.z, i, j);
+}
+inline vec4 texture(const sampler2DArray& s, const vec3& p) {
+    if (!s.data) return vec4(1.0f);
+    const float x = p.x * (float)s.n - 0.5f, y = p.y * (float)s.n - 0.5f;
+    const float fx0 = std::floor(x), fy0 = std::floor(y);
+    const float fx = x - fx0, fy = y - fy0;
+    const int i0 = ((int)fx0) & (s.n - 1), i1 = ((int)fx0 + 1) & (s.n - 1), j0 = ((int)fy0) & (s.n - 1), j1 = ((int)fy0 + 1) & (s.n - 1);
+    const int l = (int)p.z;
+    const vec4 a = fetch_layer_texel(s, l, i0, j0) * (1.0f - fx) + fetch_layer_texel(s, l, i1, j0) * fx;
+    const vec4 b = fetch_layer_texel(s, l, i0, j1) * (1.0f - fx) + fetch_layer_texel(s, l, i1, j1) * fx;
+    return a * (1.0f - fy) + b * fy;
+}
+struct samplerCube {
+    const float* data = nullptr;  // [6][n][n][3], faces +X -X +Y -Y +Z -Z
+    int n = 0;
+};
+inline vec4 texture(const samplerCube& s, const vec3& d) {
+    const int N = s.n;
+    const float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
+    int face;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { face = d.x > 0 ? 0 : 1; sc = d.x > 0 ? -d.z : d.z; tc = -d.y; ma = ax; }   // OpenGL 4.3 table 8.19
+    else if (ay >= az)        { face = d.y > 0 ? 2 : 3; sc = d.x; tc = d.y > 0 ? d.z : -d.z; ma = ay; }
+    else                      { face = d.z > 0 ? 4 : 5; sc = d.z > 0 ? d.x : -d.x; tc = -d.y; ma = az; }
+    const float u = 0.5f * (sc / ma + 1.0f) * (float)N - 0.5f, v = 0.5f * (tc / ma + 1.0f) * (float)N - 0.5f;
+    const float fu0 = std::floor(u), fv0 = std::floor(v);
+    const float fu = u - fu0, fv = v - fv0;
+    auto cl = [N](int i) { return i < 0 ? 0 : (i > N - 1 ? N - 1 : i); };
+    const int i0 = cl((int)fu0), i1 = cl((int)fu0 + 1), j0 = cl((int)fv0), j1 = cl((int)fv0 + 1);
+    const float* F = s.data + (size_t)face * N * N * 3;
+    auto tx = [&](int i, int j) { const float* p = F + ((size_t)j * N + i) * 3; return vec3(p[0], p[1], p[2]); };
+    const vec3 a = tx(i0, j0) * (1.0f - fu) + tx(i1, j0) * fu;
+    const vec3 b = tx(i0, j1) * (1.0f - fu) + tx(i1, j1) * fu;
+    return vec4(a * (1.0f - fv) + b * fv, 1.0f);
+}
+
+static thread_local uvec3 gl_GlobalInvocationID;
+static thread_local vec4 gl_FragCoord;  // per invocation: the driver's OpenMP threads each run whole invocations
+}  // namespace glsl

@@ -1,0 +1,123 @@
+"""ctypes binding of oracle/_ref/libref_shaders.so: the reference's OWN GLSL (ManhattanDistance{X,Y,Z}.comp, InitialRayTraceFrag.glsl)
+compiled as C++ against its vendored glm (recipe: oracle/Makefile, oracle/glsl2cpp.py, oracle/ref_shader_driver.cpp).
+Test infrastructure only: pins oracle/vxo_oracle.cpp and generated tests/golden/ref_shader_digests.json."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libref_shaders.so")
+_lib = None
+
+
+class RefDiffuseArgs(C.Structure):
+    _fields_ = [("blocks", C.c_void_p), ("df", C.c_void_p), ("inv_view", C.c_void_p), ("inv_proj", C.c_void_p),
+                ("width", C.c_int32), ("height", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("g_t", C.c_void_p), ("g_normal_id", C.c_void_p), ("materials", C.c_void_p), ("sobol", C.c_void_p), ("scramble", C.c_void_p),
+                ("rank", C.c_void_p), ("albedo_lod3", C.c_void_p), ("pbr_lod2", C.c_void_p), ("emissive_lod0", C.c_void_p), ("sky", C.c_void_p),
+                ("sky_n", C.c_int32), ("spp", C.c_int32), ("checker_spp", C.c_int32), ("checkerboard", C.c_int32), ("trace_length", C.c_int32),
+                ("frame", C.c_int32), ("supersample", C.c_int32), ("halton", C.c_float * 2), ("sun_dir", C.c_float * 3), ("moon_dir", C.c_float * 3),
+                ("sun_visibility", C.c_float), ("gi_sun_strength", C.c_float), ("gi_sky_strength", C.c_float), ("light_intensity", C.c_float),
+                ("o_sh", C.c_void_p), ("o_cocg", C.c_void_p), ("o_utility", C.c_void_p), ("o_ao_sky", C.c_void_p)]
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(LIB_PATH)
+        lib.ref_df_build.restype = C.c_int
+        lib.ref_df_build.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ref_trace_primary.restype = C.c_int
+        lib.ref_trace_primary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_trace_shadow.restype = C.c_int
+        lib.ref_trace_shadow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_trace_diffuse.restype = C.c_int
+        lib.ref_trace_diffuse.argtypes = [C.POINTER(RefDiffuseArgs)]
+        _lib = lib
+    return _lib
+
+
+def df_build(blocks):
+    """World::GenerateDistanceField through the three compute shaders (one invocation per grid line, X, Y, Z)."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    out = np.empty_like(blocks)
+    load().ref_df_build(blocks.ctypes.data, out.ctypes.data)
+    return out
+
+
+def trace_primary(blocks, df, cam, params):
+    """InitialRayTraceFrag.glsl main() per pixel of rows [cam.row_begin, cam.row_end).  Returns the G-buffer in the ABI's terms:
+    t (o_HitDistance), normal_id = round(o_Normal * 10) (10 = miss), block_id = round(o_BlockID * 255), inv_t (o_DepthNonLinear)."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    df = np.ascontiguousarray(df, dtype=np.uint8).reshape(-1)
+    W, H = cam.width, cam.height
+    planes = [np.zeros((H, W), dtype=np.float32) for _ in range(4)]
+    iv = np.ascontiguousarray(np.frombuffer(cam.inv_view, dtype=np.float32))
+    ip = np.ascontiguousarray(np.frombuffer(cam.inv_proj, dtype=np.float32))
+    jit = np.array([params.jitter[0], params.jitter[1]], dtype=np.float32)
+    load().ref_trace_primary(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end,
+                             params.max_iterations, params.jitter_enable, jit.ctypes.data, *[p.ctypes.data for p in planes])
+    t, n, b, it = planes
+    return {"t": t, "normal_id": np.rint(n * np.float32(10.0)).astype(np.uint8), "block_id": np.rint(b * np.float32(255.0)).astype(np.uint8), "inv_t": it}
+
+
+def trace_shadow(blocks, df, cam, gbuf, params, noise_rgba8):
+    """ShadowRayTraceFrag.glsl main() per pixel.  gbuf: t (fp32 plane as the position texture holds it) and normal_id planes.
+    Returns shadow (o_Shadow as 0/1 bytes) and transversal (o_IntersectionTransversal)."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    df = np.ascontiguousarray(df, dtype=np.uint8).reshape(-1)
+    W, H = cam.width, cam.height
+    t = np.ascontiguousarray(gbuf["t"], dtype=np.float32)
+    nid = np.ascontiguousarray(gbuf["normal_id"], dtype=np.uint8)
+    noise = np.ascontiguousarray(noise_rgba8, dtype=np.uint8).reshape(256, 256, 4)
+    iv = np.ascontiguousarray(np.frombuffer(cam.inv_view, dtype=np.float32))
+    ip = np.ascontiguousarray(np.frombuffer(cam.inv_proj, dtype=np.float32))
+    light = np.array(list(params.light_dir), dtype=np.float32)
+    halton = np.array(list(params.halton), dtype=np.float32)
+    o_s, o_t = np.zeros((H, W), dtype=np.float32), np.zeros((H, W), dtype=np.float32)
+    load().ref_trace_shadow(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end, t.ctypes.data,
+                            nid.ctypes.data, light.ctypes.data, params.frame, params.soft, halton.ctypes.data, noise.ctypes.data, o_s.ctypes.data,
+                            o_t.ctypes.data)
+    return {"shadow": (o_s > 0.5).astype(np.uint8), "transversal": o_t}
+
+
+def trace_diffuse(blocks, df, cam, gbuf, params, materials, blue_noise, sky):
+    """DiffuseRayTraceFrag.glsl main() per pixel (uniforms as Core/Pipeline.cpp:2174-2281 sets them).  materials: the assets.load_materials()
+    dict (table + baked albedo L3 / PBR L2 / emissive L0 texel arrays), blue_noise: (sobol, scramble, rank), sky: [6][n][n][3]."""
+    keep = []
+
+    def ptr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    W, H = cam.width, cam.height
+    out = {"sh": np.zeros((H, W, 4), np.float32), "cocg": np.zeros((H, W, 2), np.float32), "luma": np.zeros((H, W), np.float32),
+           "ao_sky": np.zeros((H, W, 2), np.float32)}
+    a = RefDiffuseArgs()
+    a.blocks, a.df = ptr(np.asarray(blocks).reshape(-1), np.uint8), ptr(np.asarray(df).reshape(-1), np.uint8)
+    a.inv_view, a.inv_proj = ptr(np.frombuffer(cam.inv_view, dtype=np.float32), np.float32), ptr(np.frombuffer(cam.inv_proj, dtype=np.float32), np.float32)
+    a.width, a.height, a.row_begin, a.row_end = W, H, cam.row_begin, cam.row_end
+    a.g_t, a.g_normal_id = ptr(gbuf["t"], np.float32), ptr(gbuf["normal_id"], np.uint8)
+    a.materials = ptr(materials["table"], np.int32)
+    a.sobol, a.scramble, a.rank = (ptr(t, np.int32) for t in blue_noise)
+    a.albedo_lod3, a.pbr_lod2, a.emissive_lod0 = ptr(materials["albedo_lod3"], np.float32), ptr(materials["pbr_lod2"], np.float32), ptr(materials["emissive_lod0"], np.float32)
+    sky = np.ascontiguousarray(sky, dtype=np.float32)
+    a.sky, a.sky_n = ptr(sky, np.float32), sky.shape[1]
+    a.spp, a.checker_spp, a.checkerboard, a.trace_length = params.spp, params.checker_spp, params.checkerboard, params.trace_length
+    a.frame, a.supersample = params.frame, params.supersample
+    a.halton[:] = list(params.halton)
+    a.sun_dir[:] = list(params.sun_dir)
+    a.moon_dir[:] = list(params.moon_dir)
+    a.sun_visibility, a.gi_sun_strength, a.gi_sky_strength, a.light_intensity = (params.sun_visibility, params.gi_sun_strength, params.gi_sky_strength,
+                                                                                 params.light_intensity)
+    a.o_sh, a.o_cocg, a.o_utility, a.o_ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "luma", "ao_sky"))
+    load().ref_trace_diffuse(C.byref(a))
+    return out

@@ -646,3 +646,41 @@ def test_render_frame_async_double_buffered(renderer, worlds, scene_tables):
         for kk in want[k]:
             assert np.array_equal(got[k][kk], want[k][kk]), (k, kk)
     renderer.frame_wait()   # idempotent
+
+
+# ====================================================================================== CUDA vs the reference's own shaders
+def test_cuda_outputs_equal_the_reference_shader_golden_vectors(renderer, worlds, scene_tables):
+    """tests/golden/ref_shader_digests.json holds digests of what the reference's OWN shaders (compiled as C++, oracle/_ref) produce.
+    The CUDA path must reproduce them bit for bit: all five distance fields, the config-1 primary frames, and the 1080p plains frame of
+    configs 2/3 through primary, soft sun shadow and 1-spp diffuse GI."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shader_digests.json")) as f:
+        ref = json.load(f)
+    for name in ("superflat", "plains", "gi_box", "city", "sparse"):
+        load(renderer, worlds[name])
+        assert sha(renderer.download_distance_field()) == ref["df"][name], name
+    load(renderer, worlds["superflat"])
+    for pitch in (0.0, -20.0):
+        for jf in (None, 17):
+            cam = camera.FpsCamera(pitch_deg=pitch).vx_camera(640, 360)
+            g = renderer.trace_primary(cam, vx.primary_params(350, None if jf is None else camera.taa_jitter(jf)), renderer.alloc_gbuffer(640, 360))
+            want = ref["primary"][f"superflat_640x360_p{int(pitch)}_j{jf}"]
+            for k in ("t", "normal_id", "block_id", "inv_t"):
+                assert sha(g[k]) == want[k], (pitch, jf, k)
+    load(renderer, worlds["plains"])
+    case = "plains_1920x1080_p-20_jNone"
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(1920, 1080)
+    g = renderer.trace_primary(cam, vx.primary_params(350), renderer.alloc_gbuffer(1920, 1080))
+    for k in ("t", "normal_id", "block_id", "inv_t"):
+        assert sha(g[k]) == ref["primary"][case][k], k
+    s = renderer.trace_shadow(cam, g, vx.shadow_params(scene_tables["stronger"], frame=5, soft=True), renderer.alloc_shadow(1920, 1080))
+    for k in ("shadow", "transversal"):
+        assert sha(s[k]) == ref["shadow"][case][k], k
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=1, frame=7)
+    for wf in (0, 1):
+        renderer.set_option(abi.OPT_GI_WAVEFRONT, wf)
+        d = renderer.trace_diffuse(cam, g, dp, renderer.alloc_diffuse(1920, 1080))
+        for k in ("sh", "cocg", "luma", "ao_sky"):
+            assert sha(d[k]) == ref["diffuse"][case][k], (wf, k)
+    renderer.set_option(abi.OPT_GI_WAVEFRONT, 1)

@@ -1,0 +1,132 @@
+"""The oracle pinned by the reference ITSELF: the reference's own shader source — Core/Shaders/ManhattanDistance{X,Y,Z}.comp (distance
+field), InitialRayTraceFrag.glsl (ray set-up, VoxelTraversalDF, G-buffer outputs), ShadowRayTraceFrag.glsl (soft sun shadows) and
+DiffuseRayTraceFrag.glsl (1-bounce diffuse GI, blue-noise sampler, SH projection) — is compiled as C++ against the reference's
+vendored glm (oracle/Makefile -> oracle/_ref/libref_shaders.so; oracle/glsl2cpp.py rewrites declarations only) and run on
+the CPU.  Its outputs on the BASELINE worlds / frames are committed as digests (tests/golden/ref_shader_digests.json, made by
+tools/make_ref_shader_golden.py) and must equal the oracle's, bit for bit; when the library is present the two are also compared
+live on edge cases."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import voxelpathtracer_b200 as vx
+from voxelpathtracer_b200 import abi, camera, world
+from oracle import ref_shaders, vxo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not ref_shaders.available(), reason="oracle/_ref/libref_shaders.so not built (needs /root/reference at build time)")
+
+
+@pytest.fixture(scope="module")
+def ref_digests():
+    with open(os.path.join(ROOT, "tests", "golden", "ref_shader_digests.json")) as f:
+        return json.load(f)
+
+
+def test_committed_reference_shader_digests_equal_the_oracle_digests(ref_digests, golden_digests):
+    """Golden vectors produced by the reference's shaders == what the oracle produced for the same inputs (5 distance fields,
+    14 primary frames up to 3840x2160: t, face id and block id planes)."""
+    assert set(ref_digests["df"]) == {"superflat", "plains", "gi_box", "city", "sparse"}
+    for name, digest in ref_digests["df"].items():
+        assert ref_digests["world"][name] == golden_digests["world"][name]
+        assert digest == golden_digests["df"][name], name
+    assert len(ref_digests["primary"]) >= 14
+    for case, planes in ref_digests["primary"].items():
+        for k in ("t", "normal_id", "block_id"):
+            assert planes[k] == golden_digests["primary"][case][k], (case, k)
+    assert set(ref_digests["shadow"]) == set(ref_digests["diffuse"]) == {"plains_1920x1080_p-20_jNone", "city_1920x1080_p-20_jNone"}
+    for case, planes in ref_digests["shadow"].items():        # 1080p soft sun shadows
+        for k in ("shadow", "transversal"):
+            assert planes[k] == golden_digests["shadow"][case][k], (case, k)
+    for case, planes in ref_digests["diffuse"].items():       # 1080p 1-spp diffuse GI: the SH plane, bit for bit
+        assert planes["sh"] == golden_digests["diffuse"][case]["sh"], case
+
+
+@pytest.mark.parametrize("name", ["superflat", "sparse"])
+def test_oracle_distance_field_reproduces_the_committed_reference_digest(worlds, oracle_dfs, ref_digests, name):
+    import hashlib
+    assert hashlib.sha256(oracle_dfs[name].tobytes()).hexdigest() == ref_digests["df"][name]
+
+
+@needs_ref
+def test_distance_field_edge_worlds_live():
+    cases = {"empty": world.World(), "full": world.World(np.full(abi.WORLD_VOXELS, 3, np.uint8))}
+    for corner in [(0, 0, 0), (383, 127, 383), (191, 64, 200)]:
+        w = world.World()
+        w.set_block(*corner, 9)
+        cases[f"voxel{corner}"] = w
+    rng = np.random.RandomState(11)
+    w = world.World()
+    w.data[rng.randint(0, w.data.size, size=3000)] = rng.randint(1, 128, size=3000)
+    w.zyx[100:140, 30:90, 37:300] = 7          # a slab, so that clamped and unclamped regions both exist
+    cases["random+slab"] = w
+    for name, w in cases.items():
+        assert np.array_equal(ref_shaders.df_build(w.data), vxo.df_build(w.data)), name
+
+
+def _same(a, b):
+    if a.dtype.kind == "f":
+        return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+    return bool(np.array_equal(a, b))
+
+
+@needs_ref
+@pytest.mark.parametrize("name,cam_kw,max_it,jf", [
+    ("plains", dict(pitch_deg=-20.0), 350, 3),                                         # config 2 view, TAA jitter
+    ("plains", dict(pitch_deg=-89.9), 350, None),                                      # nearly straight down
+    ("plains", dict(position=(192.0, 75.0, 192.0), pitch_deg=0.0, yaw_deg=90.0), 350, None),   # axis-aligned rays: zero direction components
+    ("plains", dict(position=(-40.0, 140.0, 500.0), pitch_deg=-25.0, yaw_deg=-60.0), 475, 9),  # camera outside the volume
+    ("city", dict(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0), 350, None),  # dense geometry
+    ("city", dict(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0), 12, None),   # iteration cap cuts most rays short
+    ("gi_box", dict(pitch_deg=10.0), 64, 40),                                          # looking up past the rooms, short cap
+    ("superflat", dict(position=(192.0, 20.0, 192.0), pitch_deg=30.0), 350, None),     # camera inside solid rock
+])
+def test_primary_pass_live(worlds, oracle_dfs, oracles, name, cam_kw, max_it, jf):
+    """Oracle G-buffer == the reference shader's, bit for bit: hit distance, 1/t, face id, block id."""
+    W, H = 224, 126
+    cam = camera.FpsCamera(aspect=W / H, **cam_kw).vx_camera(W, H)
+    pp = vx.primary_params(max_it, None if jf is None else camera.taa_jitter(jf))
+    ref = ref_shaders.trace_primary(worlds[name].data, oracle_dfs[name], cam, pp)
+    got, _ = oracles[name].trace_primary(cam, pp)
+    for k in ("t", "inv_t", "normal_id", "block_id"):
+        assert _same(got[k], ref[k]), (k, int(np.sum(got[k] != ref[k])))
+
+
+@needs_ref
+@pytest.mark.parametrize("name,frame,soft", [("plains", 5, True), ("plains", 1023, True), ("city", 40, False), ("gi_box", 2048, True)])
+def test_shadow_pass_live(worlds, oracle_dfs, oracles, scene_tables, name, frame, soft):
+    """Oracle shadow planes == ShadowRayTraceFrag.glsl's, bit for bit (cone jitter from the blue-noise texture, N.L cull, start-voxel
+    test, 350-iteration traversal, transversal output)."""
+    W, H = 224, 126
+    fc = camera.FpsCamera(pitch_deg=-20.0, aspect=W / H) if name != "city" else camera.FpsCamera(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0, aspect=W / H)
+    cam = fc.vx_camera(W, H)
+    g, _ = oracles[name].trace_primary(cam, vx.primary_params(350, camera.taa_jitter(frame)))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=frame, soft=soft)
+    ref = ref_shaders.trace_shadow(worlds[name].data, oracle_dfs[name], cam, g, sp, scene_tables["shadow_noise"])
+    got, _ = oracles[name].trace_shadow(cam, g, sp)
+    assert np.array_equal(got["shadow"], ref["shadow"])
+    assert _same(got["transversal"], ref["transversal"])
+
+
+@needs_ref
+@pytest.mark.parametrize("name,spp,frame,checker,tick", [
+    ("plains", 1, 7, False, 50.0),       # config 3: 1 spp
+    ("plains", 4, 3, False, 50.0),       # config 4's sample count: the blue-noise dimension counter runs on across samples
+    ("gi_box", 2, 130, True, 50.0),      # checkerboard SPP, frame > 128 (u_CurrentFrameMod128), emissive lamps
+    ("city", 3, 9, False, 140.0),        # night: the moon is the stronger light (no shadow sub-rays, doubled sample count)
+    ("city", 16, 1, False, 50.0),        # many samples: the sampler indexes past rankingTile (pinned by clamping)
+])
+def test_diffuse_gi_pass_live(worlds, oracle_dfs, oracles, scene_tables, name, spp, frame, checker, tick):
+    """Oracle GI planes == DiffuseRayTraceFrag.glsl's, bit for bit: SH, CoCg, luminance, AO / sky visibility."""
+    W, H = 160, 90
+    sun, moon, stronger, vis = camera.sun_moon_direction(tick)
+    fc = camera.FpsCamera(pitch_deg=-20.0, aspect=W / H) if name != "city" else camera.FpsCamera(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0, aspect=W / H)
+    cam = fc.vx_camera(W, H)
+    g, _ = oracles[name].trace_primary(cam, vx.primary_params(350))
+    dp = vx.diffuse_params(sun, moon, vis, spp=spp, frame=frame, checkerboard=checker)
+    ref = ref_shaders.trace_diffuse(worlds[name].data, oracle_dfs[name], cam, g, dp, scene_tables["materials"], scene_tables["blue_noise"], scene_tables["sky"])
+    got, _ = oracles[name].trace_diffuse(cam, g, dp)
+    for k in ("sh", "cocg", "luma", "ao_sky"):
+        assert _same(got[k], ref[k]), (k, int(np.sum(got[k] != ref[k])), float(np.max(np.abs(got[k].astype(np.float64) - ref[k]))))

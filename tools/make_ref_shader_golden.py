@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Write tests/golden/ref_shader_digests.json: sha256 digests of what the REFERENCE'S OWN shaders produce — ManhattanDistance{X,Y,Z}.comp,
+InitialRayTraceFrag.glsl, ShadowRayTraceFrag.glsl and DiffuseRayTraceFrag.glsl compiled as C++ against the reference's vendored glm (oracle/_ref/libref_shaders.so, built by oracle/Makefile
+from /root/reference) — on the same worlds and frames as tests/golden/oracle_digests.json.  Needs /root/reference (this container only);
+the committed JSON travels.  These are the golden vectors that pin the oracle: tests/test_oracle_vs_reference_shaders.py."""
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import voxelpathtracer_b200 as vx  # noqa: E402
+from voxelpathtracer_b200 import assets, camera, world  # noqa: E402
+from oracle import ref_shaders  # noqa: E402
+from make_golden_outputs import frame_cases  # noqa: E402
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    cols = assets.load_plains_columns()
+    rng = np.random.RandomState(5)
+    sparse = world.World()
+    idx = rng.randint(0, sparse.data.size, size=400)
+    sparse.data[idx] = rng.randint(1, 100, size=400)
+    worlds = {"superflat": world.generate_superflat(), "plains": world.generate_plains(cols), "gi_box": world.generate_gi_box(cols),
+              "city": world.generate_city(), "sparse": sparse}
+    out = {"source": "Core/Shaders/ManhattanDistance{X,Y,Z}.comp, InitialRayTraceFrag.glsl, ShadowRayTraceFrag.glsl, DiffuseRayTraceFrag.glsl compiled as C++ (oracle/_ref/libref_shaders.so)",
+           "world": {}, "df": {}, "primary": {}, "shadow": {}, "diffuse": {}}
+    sun, moon, stronger, sunvis = camera.sun_moon_direction(50.0)
+    mats, bn, sky, sn = assets.load_materials(), assets.load_blue_noise(), assets.analytic_sky(16, sun), assets.load_shadow_noise()
+    dfs = {}
+    for name, w in worlds.items():
+        t0 = time.time()
+        dfs[name] = ref_shaders.df_build(w.data)
+        out["world"][name] = sha(w.data)
+        out["df"][name] = sha(dfs[name])
+        print(f"df {name}: {time.time() - t0:.1f} s, max {int(dfs[name].max())}", flush=True)
+    for cname, wname, W, H, pitch, jf in frame_cases():
+        t0 = time.time()
+        cam = camera.FpsCamera(pitch_deg=pitch, aspect=W / H).vx_camera(W, H)
+        pp = vx.primary_params(350, None if jf is None else camera.taa_jitter(jf))
+        g = ref_shaders.trace_primary(worlds[wname].data, dfs[wname], cam, pp)
+        out["primary"][cname] = {"t": sha(g["t"]), "normal_id": sha(g["normal_id"]), "block_id": sha(g["block_id"]), "inv_t": sha(g["inv_t"]),
+                                 "hit_fraction": float((g["t"] > 0).mean())}
+        print(f"primary {cname}: {time.time() - t0:.1f} s, hit fraction {out['primary'][cname]['hit_fraction']:.4f}", flush=True)
+        if wname in ("plains", "city") and jf is None:   # the same secondary frames as tools/make_golden_outputs.py
+            t0 = time.time()
+            s = ref_shaders.trace_shadow(worlds[wname].data, dfs[wname], cam, g, vx.shadow_params(stronger, frame=5, soft=True), sn)
+            out["shadow"][cname] = {"shadow": sha(s["shadow"]), "transversal": sha(s["transversal"]), "shadowed_fraction": float(s["shadow"].mean())}
+            d = ref_shaders.trace_diffuse(worlds[wname].data, dfs[wname], cam, g, vx.diffuse_params(sun, moon, sunvis, spp=1, frame=7), mats, bn, sky)
+            out["diffuse"][cname] = {"sh": sha(d["sh"]), "cocg": sha(d["cocg"]), "luma": sha(d["luma"]), "ao_sky": sha(d["ao_sky"]),
+                                     "mean_luma": float(d["luma"].mean())}
+            print(f"  shadow + diffuse {cname}: {time.time() - t0:.1f} s", flush=True)
+    with open(os.path.join(ROOT, "tests", "golden", "ref_shader_digests.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,7 @@ def translate(src, ns):
     s = "\n".join(out)
     s = re.sub(r"(\w+)\s*\[\s*\]\s*;", r"\1[1];", s)
     # parameter qualifiers
+    s = re.sub(r"\bconst\s+in\s+", "const ", s)
     s = re.sub(r"([(,]\s*)(?:inout|out)\s+(\w+)\s+(\w+)", r"\1\2& \3", s)
     s = re.sub(r"([(,]\s*)in\s+(\w+)\s+(\w+)", r"\1\2 \3", s)
     # arrays as values:  float[6] f(...)  /  float[6] x = ...;  /  float x[6] = f(...);   ->  farr<6>

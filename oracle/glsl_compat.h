@@ -32,6 +32,7 @@ inline float min(float a, int b) { return glm::min(a, float(b)); }
 inline float max(int a, float b) { return glm::max(float(a), b); }
 inline float max(float a, int b) { return glm::max(a, float(b)); }
 inline float clamp(int x, float lo, float hi) { return glm::clamp(float(x), lo, hi); }
+inline float clamp(float x, int lo, int hi) { return glm::clamp(x, float(lo), float(hi)); }
 inline vec2 operator+(const vec2& a, const ivec2& b) { return a + vec2(b); }
 inline vec2 operator/(const ivec2& a, float b) { return vec2(a) / b; }
 
@@ -117,6 +118,7 @@ inline vec4 texture(const sampler2D& s, const vec2& uv) {
 struct sampler2DArray {
     const float* data = nullptr;  // [layers][n][n][comps]
     int n = 0, comps = 4;
+    bool nearest_only = false;    // reflection pass: its implicit-LOD texture() calls are pinned to the nearest texel of the bound level
 };
 inline vec4 fetch_layer_texel(const sampler2DArray& s, int layer, int i, int j) {
     const float* t = s.data + (((size_t)layer * s.n + j) * s.n + i) * s.comps;
@@ -129,6 +131,7 @@ inline vec4 textureLod(const sampler2DArray& s, const vec3& p, float /*lod: the 
 }
 inline vec4 texture(const sampler2DArray& s, const vec3& p) {
     if (!s.data) return vec4(1.0f);
+    if (s.nearest_only) return textureLod(s, p, 0.0f);
     const float x = p.x * (float)s.n - 0.5f, y = p.y * (float)s.n - 0.5f;
     const float fx0 = std::floor(x), fy0 = std::floor(y);
     const float fx = x - fx0, fy = y - fy0;
@@ -161,6 +164,13 @@ inline vec4 texture(const samplerCube& s, const vec3& d) {
     const vec3 b = tx(i0, j1) * (1.0f - fu) + tx(i1, j1) * fu;
     return vec4(a * (1.0f - fv) + b * fv, 1.0f);
 }
+
+// code paths the drivers never enable (light-propagation volume, clouds, screen-space reprojection): inert stand-ins
+struct usampler3D {};
+inline uvec4 texture(const usampler3D&, const vec3&) { return uvec4(0u); }
+inline uvec4 texelFetch(const usampler3D&, const ivec3&, int) { return uvec4(0u); }
+inline vec4 texture(const sampler3D&, const vec3&) { return vec4(0.0f); }
+inline uint clamp(uint x, int lo, int hi) { return x < (uint)lo ? (uint)lo : (x > (uint)hi ? (uint)hi : x); }
 
 static thread_local uvec3 gl_GlobalInvocationID;
 static thread_local vec4 gl_FragCoord;  // per invocation: the driver's OpenMP threads each run whole invocations

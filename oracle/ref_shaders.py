@@ -22,6 +22,19 @@ class RefDiffuseArgs(C.Structure):
                 ("o_sh", C.c_void_p), ("o_cocg", C.c_void_p), ("o_utility", C.c_void_p), ("o_ao_sky", C.c_void_p)]
 
 
+class RefReflectionArgs(C.Structure):
+    _fields_ = [("blocks", C.c_void_p), ("df", C.c_void_p), ("inv_view", C.c_void_p), ("inv_proj", C.c_void_p),
+                ("width", C.c_int32), ("height", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("g_t", C.c_void_p), ("g_normal_id", C.c_void_p), ("g_block_id", C.c_void_p), ("g_normal", C.c_void_p), ("g_pbr", C.c_void_p),
+                ("sh", C.c_void_p), ("cocg", C.c_void_p), ("materials", C.c_void_p), ("sobol", C.c_void_p), ("scramble", C.c_void_p), ("rank", C.c_void_p),
+                ("albedo_lod3", C.c_void_p), ("normal_lod3", C.c_void_p), ("pbr_lod2", C.c_void_p), ("emissive_lod2", C.c_void_p), ("sky", C.c_void_p),
+                ("sky_n", C.c_int32), ("spp", C.c_int32), ("trace_length", C.c_int32), ("frame", C.c_int32), ("rough", C.c_int32),
+                ("roughness_bias", C.c_int32), ("checkerboard", C.c_int32), ("sun_dir", C.c_float * 3), ("moon_dir", C.c_float * 3),
+                ("stronger_dir", C.c_float * 3), ("viewer_pos", C.c_float * 3), ("sun_strength", C.c_float), ("moon_strength", C.c_float),
+                ("halton", C.c_float * 2), ("grass_props", C.c_int32 * 10), ("o_color", C.c_void_p), ("o_hit_distance", C.c_void_p),
+                ("o_emissive_mask", C.c_void_p)]
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -40,6 +53,8 @@ def load():
                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ref_trace_diffuse.restype = C.c_int
         lib.ref_trace_diffuse.argtypes = [C.POINTER(RefDiffuseArgs)]
+        lib.ref_trace_reflection.restype = C.c_int
+        lib.ref_trace_reflection.argtypes = [C.POINTER(RefReflectionArgs)]
         _lib = lib
     return _lib
 
@@ -120,4 +135,40 @@ def trace_diffuse(blocks, df, cam, gbuf, params, materials, blue_noise, sky):
                                                                                  params.light_intensity)
     a.o_sh, a.o_cocg, a.o_utility, a.o_ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "luma", "ao_sky"))
     load().ref_trace_diffuse(C.byref(a))
+    return out
+
+
+def trace_reflection(blocks, df, cam, gbuf, diffuse, params, g_normal, g_pbr, materials, blue_noise, sky):
+    """ReflectionTraceFrag.glsl main() per pixel in the v1 parity profile (Core/Pipeline.cpp:3003-3164).  g_normal [H][W][3] and g_pbr
+    [H][W][4] stand for the G-buffer material pass's outputs; diffuse: the GI pass's sh / cocg planes."""
+    keep = []
+
+    def ptr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    W, H = cam.width, cam.height
+    out = {"color": np.zeros((H, W, 4), np.float32), "hit_distance": np.zeros((H, W), np.float32), "emissive_mask": np.zeros((H, W), np.float32)}
+    a = RefReflectionArgs()
+    a.blocks, a.df = ptr(np.asarray(blocks).reshape(-1), np.uint8), ptr(np.asarray(df).reshape(-1), np.uint8)
+    a.inv_view, a.inv_proj = ptr(np.frombuffer(cam.inv_view, dtype=np.float32), np.float32), ptr(np.frombuffer(cam.inv_proj, dtype=np.float32), np.float32)
+    a.width, a.height, a.row_begin, a.row_end = W, H, cam.row_begin, cam.row_end
+    a.g_t, a.g_normal_id, a.g_block_id = ptr(gbuf["t"], np.float32), ptr(gbuf["normal_id"], np.uint8), ptr(gbuf["block_id"], np.uint8)
+    a.g_normal, a.g_pbr = ptr(g_normal, np.float32), ptr(g_pbr, np.float32)
+    a.sh, a.cocg = ptr(diffuse["sh"], np.float32), ptr(diffuse["cocg"], np.float32)
+    a.materials = ptr(materials["table"], np.int32)
+    a.sobol, a.scramble, a.rank = (ptr(t, np.int32) for t in blue_noise)
+    a.albedo_lod3, a.normal_lod3 = ptr(materials["albedo_lod3"], np.float32), ptr(materials["normal_lod3"], np.float32)
+    a.pbr_lod2, a.emissive_lod2 = ptr(materials["pbr_lod2"], np.float32), ptr(materials["emissive_lod2"], np.float32)
+    sky = np.ascontiguousarray(sky, dtype=np.float32)
+    a.sky, a.sky_n = ptr(sky, np.float32), sky.shape[1]
+    a.spp, a.trace_length, a.frame, a.rough = params.spp, params.trace_length, params.frame, params.rough
+    a.roughness_bias, a.checkerboard = params.roughness_bias, params.checkerboard
+    for name in ("sun_dir", "moon_dir", "stronger_dir", "viewer_pos", "halton", "grass_props"):
+        getattr(a, name)[:] = list(getattr(params, name))
+    a.sun_strength, a.moon_strength = params.sun_strength, params.moon_strength
+    a.o_color, a.o_hit_distance, a.o_emissive_mask = (out[k].ctypes.data for k in ("color", "hit_distance", "emissive_mask"))
+    load().ref_trace_reflection(C.byref(a))
+    out["emissive_mask"] = (out["emissive_mask"] > 0.5).astype(np.uint8)
     return out

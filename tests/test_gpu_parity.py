@@ -684,3 +684,27 @@ def test_cuda_outputs_equal_the_reference_shader_golden_vectors(renderer, worlds
         for k in ("sh", "cocg", "luma", "ao_sky"):
             assert sha(d[k]) == ref["diffuse"][case][k], (wf, k)
     renderer.set_option(abi.OPT_GI_WAVEFRONT, 1)
+
+
+def test_cuda_reflections_equal_the_reference_shader_golden_vectors(renderer, worlds, oracles, scene_tables):
+    """CUDA reflection planes == digests of the reference's ReflectionTraceFrag.glsl (compiled as C++) on the three golden frames."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    from make_ref_shader_golden import reflection_cases, synthetic_material_planes
+    with open(os.path.join(root, "tests", "golden", "ref_shader_digests.json")) as f:
+        ref = json.load(f)["reflection"]
+    sun, moon, stronger, vis = scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], scene_tables["sun_visibility"]
+    for cname, wname, W, H, cam_kw, spp, rough, checker, frame in reflection_cases():
+        load(renderer, worlds[wname])
+        fc = camera.FpsCamera(**cam_kw)
+        cam = fc.vx_camera(W, H)
+        g = renderer.trace_primary(cam, vx.primary_params(350), renderer.alloc_gbuffer(W, H))
+        d = renderer.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=max(frame, 0)), renderer.alloc_diffuse(W, H))
+        g_normal, g_pbr = synthetic_material_planes(g, W, H)
+        rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame)
+        out = renderer.trace_reflection(cam, g, d, rp, renderer.alloc_reflection(W, H), g_normal, g_pbr)
+        for k in ("color", "hit_distance", "emissive_mask"):
+            assert sha(out[k]) == ref[cname][k], (cname, k)

@@ -130,3 +130,55 @@ def test_diffuse_gi_pass_live(worlds, oracle_dfs, oracles, scene_tables, name, s
     got, _ = oracles[name].trace_diffuse(cam, g, dp)
     for k in ("sh", "cocg", "luma", "ao_sky"):
         assert _same(got[k], ref[k]), (k, int(np.sum(got[k] != ref[k])), float(np.max(np.abs(got[k].astype(np.float64) - ref[k]))))
+
+
+def _reflection_inputs(oracle, scene_tables, case):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_ref_shader_golden import synthetic_material_planes
+    cname, wname, W, H, cam_kw, spp, rough, checker, frame = case
+    sun, moon, stronger, vis = scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], scene_tables["sun_visibility"]
+    fc = camera.FpsCamera(**cam_kw)
+    cam = fc.vx_camera(W, H)
+    g, _ = oracle.trace_primary(cam, vx.primary_params(350))
+    d, _ = oracle.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=max(frame, 0)))
+    g_normal, g_pbr = synthetic_material_planes(g, W, H)
+    rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame)
+    return cam, g, d, rp, g_normal, g_pbr
+
+
+def test_oracle_reflections_reproduce_the_committed_reference_digests(oracles, scene_tables, ref_digests):
+    """ReflectionTraceFrag.glsl (v1 parity profile, Halton jitter 0) as compiled from the reference vs the oracle: colour, hit distance and
+    emissive mask planes, bit for bit, on three frames (rough GGX-sampled, checkerboard SPP on dense geometry, mirror with emissive lamps)."""
+    import hashlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_ref_shader_golden import reflection_cases
+    for case in reflection_cases():
+        cam, g, d, rp, g_normal, g_pbr = _reflection_inputs(oracles[case[1]], scene_tables, case)
+        got, _ = oracles[case[1]].trace_reflection(cam, g, d, rp, g_normal, g_pbr)
+        want = ref_digests["reflection"][case[0]]
+        for k in ("color", "hit_distance", "emissive_mask"):
+            assert hashlib.sha256(np.ascontiguousarray(got[k]).tobytes()).hexdigest() == want[k], (case[0], k)
+
+
+@needs_ref
+def test_reflection_pass_live_night(worlds, oracle_dfs, oracles, scene_tables):
+    """Moon as the stronger light (SampleMoonColor path), 1 spp, small frame."""
+    W, H = 160, 90
+    sun, moon, stronger, vis = camera.sun_moon_direction(140.0)
+    fc = camera.FpsCamera(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0, aspect=W / H)
+    cam = fc.vx_camera(W, H)
+    o = oracles["city"]
+    g, _ = o.trace_primary(cam, vx.primary_params(350))
+    d, _ = o.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=3))
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_ref_shader_golden import synthetic_material_planes
+    g_normal, g_pbr = synthetic_material_planes(g, W, H)
+    rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=1, rough=True, frame=3)
+    ref = ref_shaders.trace_reflection(worlds["city"].data, oracle_dfs["city"], cam, g, d, rp, g_normal, g_pbr, scene_tables["materials"],
+                                       scene_tables["blue_noise"], scene_tables["sky"])
+    got, _ = o.trace_reflection(cam, g, d, rp, g_normal, g_pbr)
+    for k in ("color", "hit_distance", "emissive_mask"):
+        assert _same(got[k], ref[k]), (k, int(np.sum(got[k] != ref[k])))

@@ -24,6 +24,26 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def synthetic_material_planes(g, W, H):
+    """Deterministic stand-ins for the G-buffer material pass's outputs (u_GBufferNormals, u_GBufferPBR): the face normal tilted by a
+    fixed integer pattern and renormalised in float64, roughness / metalness from integer patterns.  No RNG, so tests can rebuild them."""
+    j, i = np.mgrid[0:H, 0:W]
+    faces = np.array([[0, 0, 1], [0, 0, -1], [0, 1, 0], [0, -1, 0], [-1, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float64)
+    n = faces[np.minimum(g["normal_id"], 6)] + 0.05 * np.stack([((i * 3 + j) % 7) - 3.0, ((i + j * 5) % 5) - 2.0, ((i * 2 + j * 3) % 9) - 4.0], -1)
+    g_normal = np.ascontiguousarray(n / np.linalg.norm(n, axis=-1, keepdims=True), dtype=np.float32)
+    rough = (0.05 + 0.9 * ((i * 7 + j * 13) % 97) / 96.0)
+    metal = ((i + j) % 5 == 0) * 0.9
+    g_pbr = np.ascontiguousarray(np.stack([rough, metal, np.zeros((H, W)), np.zeros((H, W))], -1), dtype=np.float32)
+    return g_normal, g_pbr
+
+
+def reflection_cases():
+    """(name, world, width, height, camera kwargs, spp, rough, checkerboard, frame)"""
+    return [("plains_960x540_spp2_rough", "plains", 960, 540, dict(pitch_deg=-20.0), 2, True, False, 7),
+            ("city_640x360_spp4_checker", "city", 640, 360, dict(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0), 4, True, True, 12),
+            ("gi_box_640x360_mirror", "gi_box", 640, 360, dict(pitch_deg=-20.0), 2, False, False, -1)]
+
+
 def main():
     cols = assets.load_plains_columns()
     rng = np.random.RandomState(5)
@@ -32,8 +52,8 @@ def main():
     sparse.data[idx] = rng.randint(1, 100, size=400)
     worlds = {"superflat": world.generate_superflat(), "plains": world.generate_plains(cols), "gi_box": world.generate_gi_box(cols),
               "city": world.generate_city(), "sparse": sparse}
-    out = {"source": "Core/Shaders/ManhattanDistance{X,Y,Z}.comp, InitialRayTraceFrag.glsl, ShadowRayTraceFrag.glsl, DiffuseRayTraceFrag.glsl compiled as C++ (oracle/_ref/libref_shaders.so)",
-           "world": {}, "df": {}, "primary": {}, "shadow": {}, "diffuse": {}}
+    out = {"source": "Core/Shaders/ManhattanDistance{X,Y,Z}.comp, InitialRayTraceFrag.glsl, ShadowRayTraceFrag.glsl, DiffuseRayTraceFrag.glsl, ReflectionTraceFrag.glsl compiled as C++ (oracle/_ref/libref_shaders.so)",
+           "world": {}, "df": {}, "primary": {}, "shadow": {}, "diffuse": {}, "reflection": {}}
     sun, moon, stronger, sunvis = camera.sun_moon_direction(50.0)
     mats, bn, sky, sn = assets.load_materials(), assets.load_blue_noise(), assets.analytic_sky(16, sun), assets.load_shadow_noise()
     dfs = {}
@@ -59,6 +79,19 @@ def main():
             out["diffuse"][cname] = {"sh": sha(d["sh"]), "cocg": sha(d["cocg"]), "luma": sha(d["luma"]), "ao_sky": sha(d["ao_sky"]),
                                      "mean_luma": float(d["luma"].mean())}
             print(f"  shadow + diffuse {cname}: {time.time() - t0:.1f} s", flush=True)
+    for cname, wname, W, H, cam_kw, spp, rough, checker, frame in reflection_cases():   # Halton jitter 0: the G-buffer is read at the pixel
+        t0 = time.time()
+        fc = camera.FpsCamera(**cam_kw)
+        cam = fc.vx_camera(W, H)
+        wd, df = worlds[wname].data, dfs[wname]
+        g = ref_shaders.trace_primary(wd, df, cam, vx.primary_params(350))
+        d = ref_shaders.trace_diffuse(wd, df, cam, g, vx.diffuse_params(sun, moon, sunvis, spp=1, frame=max(frame, 0)), mats, bn, sky)
+        g_normal, g_pbr = synthetic_material_planes(g, W, H)
+        rp = vx.reflection_params(sun, moon, stronger, fc.position, mats["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame)
+        r = ref_shaders.trace_reflection(wd, df, cam, g, d, rp, g_normal, g_pbr, mats, bn, sky)
+        out["reflection"][cname] = {"color": sha(r["color"]), "hit_distance": sha(r["hit_distance"]), "emissive_mask": sha(r["emissive_mask"]),
+                                    "hit_fraction": float((r["hit_distance"] > 0).mean())}
+        print(f"reflection {cname}: {time.time() - t0:.1f} s, hit fraction {out['reflection'][cname]['hit_fraction']:.4f}", flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "ref_shader_digests.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 

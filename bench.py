@@ -113,42 +113,103 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
+class CpuReference:
+    """The reference's CPU implementation of the path, timed on the host cores.
+
+    kind "reference": the reference's OWN shaders — InitialRayTraceFrag / ShadowRayTraceFrag / DiffuseRayTraceFrag.glsl, translated and
+    compiled as C++ against its vendored glm when this repo was built next to /root/reference (oracle/_ref/libref_shaders.so; the file
+    travels with the repo) — one process per host core, each tracing 8-row slabs (oracle/ref_pool.py).
+    kind "port": oracle/vxo_oracle.cpp, the C++ restatement (OpenMP over rows), when that library is absent.
+    A step is one frame of the bench workload, or — when a frame is too slow for the requested number of steps — every m-th 8-row slab
+    of it (rows interleaved over the whole image, so sky, horizon and ground are sampled in proportion)."""
+
+    def __init__(self, tables, w):
+        import voxelpathtracer_b200 as vx
+        from voxelpathtracer_b200 import camera
+        from oracle import ref_shaders, vxo
+        self.vx, self.camera, self.vxo, self.tables = vx, camera, vxo, tables
+        self.orc = vxo.Oracle(w.data)   # ray counting (and the "port" arm)
+        self.orc.set_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
+        self.fc = camera.FpsCamera(pitch_deg=-20.0)
+        self.pool = None
+        self.kind = "port"
+        self.cores = vxo.load().vxo_num_threads()
+        if ref_shaders.available():
+            from oracle import ref_pool
+            self.pool = ref_pool.ReferenceFramePool(w.data, vxo.df_build(w.data), WIDTH, HEIGHT, dict(pitch_deg=-20.0))
+            self.kind, self.cores = "reference", self.pool.procs
+        self.stride = 1
+
+    def slabs(self):
+        return [(rb, min(rb + 8, HEIGHT)) for k, rb in enumerate(range(0, HEIGHT, 8)) if k % self.stride == 0]
+
+    def step(self, frame):
+        if self.pool is not None:
+            tasks = [(frame, rb, re) for rb, re in self.slabs()]
+            from oracle import ref_pool
+            return sum(r[2] for r in self.pool.pool.imap_unordered(ref_pool._slab, tasks, chunksize=1))
+        tot = 0.0
+        for rb, re in ([(0, HEIGHT)] if self.stride == 1 else self.slabs()):
+            tot += self._oracle_rows(frame, rb, re)[1]
+        return tot
+
+    def _oracle_rows(self, frame, rb, re):
+        cam = self.fc.vx_camera(WIDTH, HEIGHT, rb, re)
+        pp, sp, dp = frame_params(self.vx, self.camera, self.tables, frame)
+        g, s0 = self.orc.trace_primary(cam, pp, hit_voxel=False)
+        _, s1 = self.orc.trace_shadow(cam, g, sp)
+        d, s2 = self.orc.trace_diffuse(cam, g, dp)
+        return s0["rays"] + s1["rays"] + s2["rays"], float(d["luma"][rb:re].sum())
+
+    def rays(self, frame):
+        """VoxelTraversalDF calls of the rows a step covers (counted by the oracle: the counts are a property of the algorithm)."""
+        if self.stride == 1:
+            return self._oracle_rows(frame, 0, HEIGHT)[0]
+        return sum(self._oracle_rows(frame, rb, re)[0] for rb, re in self.slabs())
+
+    def calibrate(self, steps, budget_s):
+        """Pick the slab stride so that `steps` steps fit the time budget; returns the seconds one full frame took."""
+        t0 = time.perf_counter()
+        self.step(0)
+        t_frame = time.perf_counter() - t0
+        self.stride = max(1, int(np.ceil(t_frame * steps / budget_s)))
+        return t_frame
+
+    def sample_text(self, steps):
+        rows = sum(re - rb for rb, re in self.slabs())
+        what = ("the reference's own GLSL shaders compiled as C++ (oracle/_ref/libref_shaders.so), one process per core" if self.kind == "reference"
+                else "oracle C++ restatement, OpenMP over image rows")
+        return f"{steps} steps of {rows} of {HEIGHT} rows of a 1080p frame (every {self.stride}. 8-row slab; primary+shadow+GI), {what}"
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  Its GLSL cannot run headless on this
-    image (no GL/EGL/OSMesa), so the arm times the oracle — the C++ restatement of those shaders — with
-    every host thread, on the same config / metric.  Rank 0 alone works."""
+    """--impl reference: the reference's own CPU implementation of the path on every host core, same config / metric.  Rank 0 alone works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import voxelpathtracer_b200 as vx
-    from voxelpathtracer_b200 import assets, camera, world
-    from oracle import vxo
+    from voxelpathtracer_b200 import assets, world
     tables = load_tables()
     w = world.generate_plains(assets.load_plains_columns())
-    orc = vxo.Oracle(w.data)
-    orc.set_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
-    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(WIDTH, HEIGHT)
-    cores = vxo.load().vxo_num_threads()
-
-    def step(frame):
-        pp, sp, dp = frame_params(vx, camera, tables, frame)
-        g, s0 = orc.trace_primary(cam, pp, hit_voxel=False)
-        _, s1 = orc.trace_shadow(cam, g, sp)
-        _, s2 = orc.trace_diffuse(cam, g, dp)
-        return s0["rays"] + s1["rays"] + s2["rays"]
-
+    ref = CpuReference(tables, w)
+    ref.calibrate(args.steps + args.warmup, 150.0)
     for f in range(args.warmup):
-        step(f)
+        ref.step(f)
     t0 = time.perf_counter()
-    rays = sum(step(args.warmup + f) for f in range(args.steps))
+    for f in range(args.steps):
+        ref.step(args.warmup + f)
     dt = time.perf_counter() - t0
+    rays = sum(ref.rays(args.warmup + f) for f in range(args.steps))
+    ref.close()
     v = rays / dt / 1e6
-    sample = f"{args.steps} full 1080p frames (primary+shadow+GI), oracle C++ restatement with OpenMP over image rows"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind, "sample": ref.sample_text(args.steps)},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
@@ -212,6 +273,7 @@ def run_ours(args):
         # Timing rule "inputs larger than L2": three copies of grid + step field (132 MB > 126 MB L2) are rotated frame by
         # frame and every frame streams its output planes through the cache; no flush kernel inside the timed region.
         rr.set_option(abi.OPT_SCENE_REPLICAS, 3)
+        rr.set_option(abi.OPT_GI_WAVEFRONT, args.gi_mode)
         renderers.append(rr)
         try:
             frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT, exchange=exchange, texel=texel, slots=args.slots,
@@ -454,22 +516,16 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -------------
     cpu_baseline = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
-        from oracle import vxo
-        orc = vxo.Oracle(w.data)
-        orc.set_tables(tables["materials"], tables["blue_noise"], tables["sky"], tables["shadow_noise"])
-        full_cam = fc.vx_camera(WIDTH, HEIGHT)
-        n_frames, rays_cpu = 0, 0
+        ref = CpuReference(tables, w)
+        n_cpu = 4
+        ref.calibrate(n_cpu + 1, 20.0)   # about 10-20 s of CPU work in total
         t0 = time.perf_counter()
-        while n_frames < 4 or (time.perf_counter() - t0 < 10.0 and n_frames < 64):
-            pp, sp, dp = frame_params(vx, camera, tables, n_frames)
-            g, s0 = orc.trace_primary(full_cam, pp, hit_voxel=False)
-            _, s1 = orc.trace_shadow(full_cam, g, sp)
-            _, s2 = orc.trace_diffuse(full_cam, g, dp)
-            rays_cpu += s0["rays"] + s1["rays"] + s2["rays"]
-            n_frames += 1
+        for f in range(n_cpu):
+            ref.step(f)
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": rays_cpu / dt / 1e6, "unit": "Mrays/s", "cores": vxo.load().vxo_num_threads(), "kind": "port",
-                        "sample": f"{n_frames} full 1080p frames (primary+shadow+GI) of the same workload, C++ oracle, OpenMP over rows, {dt:.1f} s"}
+        rays_cpu = sum(ref.rays(f) for f in range(n_cpu))
+        cpu_baseline = {"value": rays_cpu / dt / 1e6, "unit": "Mrays/s", "cores": ref.cores, "kind": ref.kind, "sample": ref.sample_text(n_cpu) + f", {dt:.1f} s"}
+        ref.close()
 
     xchg_text = {"none": "single GPU, no exchange",
                  "p2pcopy": "radiance slabs (shadow + GI planes) traced locally and pushed into the gather root's memory with one copy-engine transfer per frame over NVLink (CUDA IPC mapping), "
@@ -486,7 +542,7 @@ def run_ours(args):
                        "sharding": (f"{ws} ranks, interleaved {frame.band_rows}-row bands, {P} frame pipe(s) per GPU, grid replicated; " + xchg_text),
                        "planes": ("reference FBO texel formats (R16F/RGBA16F/RG16F/RG8/R8; VXPT_OPT_TEXEL_FORMAT=1)" if texel else "fp32 planes") + f", {px_out} B/pixel written, {px_xchg} B/pixel gathered",
                        "timing": f"two CUDA events on the library stream around exactly K steps (barrier + synchronize on both sides), max over ranks; inputs larger than L2: 3 scene replicas (132 MB) rotated per frame + {WIDTH * HEIGHT * px_out / 1e6:.0f} MB of planes written per frame, no flush kernel",
-                       "submit": submit, "host_submit_ms_per_step": host_submit_ms, "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": "wavefront (warp-ballot compaction of first-bounce hits)"},
+                       "submit": submit, "host_submit_ms_per_step": host_submit_ms, "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": {0: "one thread per pixel", 1: "wavefront (warp-ballot compaction of first-bounce hits)", 2: "wavefront + persistent first-bounce tracer"}[args.gi_mode]},
             "e2e": e2e, "gpu_launches": int(tot[4]),
             "roofline": dict(rooflines[dominant], kernel=dominant,
                              note="traversal roofline = (DF fetches + block fetches) x 32 B per launch over the measured random-sector L2 peak (SURVEY.md §8d)"),
@@ -513,6 +569,7 @@ def main():
     ap.add_argument("--slots", type=int, default=2, help="frame slots per pipe in the slab buffer")
     ap.add_argument("--exchange", default="p2pcopy", choices=["p2p", "p2pcopy", "nccl"],
                     help="multi-GPU slab gather: the trace kernels store into the root's memory (p2p), one copy-engine push per frame (p2pcopy), or NCCL all-gather")
+    ap.add_argument("--gi-mode", type=int, default=1, choices=[0, 1, 2], help="VXPT_OPT_GI_WAVEFRONT: 0 one thread per pixel, 1 wavefront (default), 2 + persistent first-bounce tracer")
     ap.add_argument("--emulate", type=int, default=0, help="development: trace rank 0's share of an N-way sharded frame on one GPU, no exchange")
     ap.add_argument("--planes", default="texel", choices=["texel", "f32"], help="plane encoding: the reference's FBO texel formats (default) or fp32")
     ap.add_argument("--no-graph", action="store_true", help="submit every pass eagerly instead of replaying a CUDA graph")

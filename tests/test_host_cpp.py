@@ -69,6 +69,8 @@ def test_headless_cpp_equals_python_driver(use_plains, plains_columns):
             got[f[0]] = int(f[1], 16)
         elif f[0] == "frame":
             got[("frame", int(f[1]))] = {f[i]: int(f[i + 1], 16) for i in range(2, len(f), 2)}
+        elif f[0] == "render_frame":
+            got["render_frame"] = {f[i]: int(f[i + 1], 16) for i in range(1, len(f), 2)}
     w = world.generate_plains(plains_columns) if use_plains else world.generate_superflat()
     r = vx.Renderer(0)
     try:
@@ -83,6 +85,7 @@ def test_headless_cpp_equals_python_driver(use_plains, plains_columns):
             ref = got[("frame", frame)]
             assert fnv1a(g["t"]) == ref["t"] and fnv1a(g["normal_id"]) == ref["normal"] and fnv1a(g["block_id"]) == ref["block"]
             assert fnv1a(s["shadow"]) == ref["shadow"]
+        assert got["render_frame"] == got[("frame", 2)]   # vxpt_render_frame from C++ == the separate calls
         r.set_block(192, 70, 200, world.STONE)
         r.build_distance_field()
         assert fnv1a(r.download_distance_field()) == got["df_after_edit"]

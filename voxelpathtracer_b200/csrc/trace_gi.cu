@@ -432,7 +432,7 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
         if (persistent) {
             gi_gen<SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, rays, count, s);
             static const int tune = std::getenv("VXPT_GI_TUNE") ? std::atoi(std::getenv("VXPT_GI_TUNE")) : 0;  // experiment knob
-            const int ctas = 148 * (tune >= 10 ? tune / 10 : 4);
+            const int ctas = 148 * (tune >= 10 ? tune / 10 : 5);  // 47 registers: 5 CTAs of 256 threads per SM
             switch (tune % 10) {
                 case 1: gi_trace0<LAYOUT, 4><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
                 case 2: gi_trace0<LAYOUT, 16><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;

@@ -54,6 +54,21 @@ int main(int argc, char** argv) {
         std::printf("frame %d t %016" PRIx64 " normal %016" PRIx64 " block %016" PRIx64 " shadow %016" PRIx64 "\n", frame, fnv1a(t.data(), t.size() * 4),
                     fnv1a(normal.data(), normal.size()), fnv1a(block.data(), block.size()), fnv1a(shadow.data(), shadow.size()));
     }
+    // the same frame through the whole-frame entry point (Pipeline.cpp's pass sequence in one call, G-buffer resident on the device)
+    {
+        std::vector<float> t2((size_t)W * H), inv2((size_t)W * H), tr2((size_t)W * H);
+        std::vector<uint8_t> n2((size_t)W * H), b2((size_t)W * H), s2((size_t)W * H);
+        VxPrimaryParams pp{350, 1, {0.f, 0.f}, 0, 0};
+        GetTAAJitter(2, pp.jitter);
+        VxShadowParams sp{{sun[0], sun[1], sun[2]}, 2, 0, {0.f, 0.f}, 0};
+        VxFrameParams fp{&pp, &sp, nullptr, nullptr, nullptr, nullptr};
+        VxFrameOut fo{};
+        fo.gbuffer = VxGBuffer{t2.data(), n2.data(), b2.data(), inv2.data(), nullptr};
+        fo.shadow = VxShadowOut{s2.data(), tr2.data()};
+        if (!vx_ok(vxpt_render_frame(world.Handle(), &cam, &fp, &fo), "vxpt_render_frame")) return 1;
+        std::printf("render_frame t %016" PRIx64 " normal %016" PRIx64 " block %016" PRIx64 " shadow %016" PRIx64 "\n", fnv1a(t2.data(), t2.size() * 4),
+                    fnv1a(n2.data(), n2.size()), fnv1a(b2.data(), b2.size()), fnv1a(s2.data(), s2.size()));
+    }
     // place a block in front of the camera: the ABI refuses to trace over a stale field until the rebuild
     world.EditBlock(192, 70, 200, {BlockID::Stone});
     world.DownloadDistanceField(df);

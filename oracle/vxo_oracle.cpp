@@ -4,11 +4,15 @@
 // cpu_baseline / --impl reference legs may load it.  The product library (voxelpathtracer_b200/csrc) never
 // links, includes or calls anything in this directory and has no CPU fallback.
 //
-// PARITY UNPINNED BY THE REFERENCE: swr06/VoxelPathTracer ships no tests, golden vectors or fixtures for this
-// path, and its GLSL cannot be executed in the build container (no GL/EGL/OSMesa).  The pins
-// are therefore this repo's own: analytic known-answer tests, a brute-force definition of the distance field
-// (vxo_df_bruteforce) and an independent plain-DDA cross-check (vxo_plain_dda, after the author's unused
-// Core/Shaders/Implementations/DDA/DDA.glsl) — see tests/test_oracle_*.py.
+// PARITY PINNED BY THE REFERENCE ITSELF: swr06/VoxelPathTracer ships no tests, golden vectors or fixtures for this
+// path and its GL application cannot run in the build container (no GL/EGL/OSMesa), but its shader source
+// can be compiled: oracle/Makefile translates ManhattanDistance{X,Y,Z}.comp, InitialRayTraceFrag.glsl,
+// ShadowRayTraceFrag.glsl, DiffuseRayTraceFrag.glsl and ReflectionTraceFrag.glsl where they lie (declarations only,
+// oracle/glsl2cpp.py) and builds them as C++ against the reference's vendored glm (oracle/_ref/libref_shaders.so).  Every
+// output of this file equals that library's bit for bit on the BASELINE worlds and frames and on live edge cases
+// (tests/test_oracle_vs_reference_shaders.py; committed digests: tests/golden/ref_shader_digests.json).  Older pins kept:
+// analytic known-answer tests, a brute-force definition of the distance field (vxo_df_bruteforce) and an independent
+// plain-DDA cross-check (vxo_plain_dda, after the author's unused Core/Shaders/Implementations/DDA/DDA.glsl).
 //
 // Every function cites the reference file:line it restates (paths relative to the reference tree).
 // Floating point: build with -O2 -ffp-contract=off (no FMA contraction), IEEE division and sqrt; operation

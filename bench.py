@@ -517,8 +517,8 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         ref = CpuReference(tables, w)
-        n_cpu = 4
-        ref.calibrate(n_cpu + 1, 20.0)   # about 10-20 s of CPU work in total
+        t_frame = ref.calibrate(4, 30.0)   # even four frames must fit; then size the sample to about 12 s of CPU work
+        n_cpu = max(4, min(32, int(12.0 / (t_frame / ref.stride))))
         t0 = time.perf_counter()
         for f in range(n_cpu):
             ref.step(f)

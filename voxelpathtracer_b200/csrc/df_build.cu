@@ -249,15 +249,19 @@ __global__ void __launch_bounds__(XY_THREADS, 4) df_xy_dpx(const uint8_t* __rest
 // ------------------------------------------------------------------------------------------------------------
 constexpr int ZSEG = 24;          // voxels per thread along z
 constexpr int ZSEGS = WZ / ZSEG;  // 16 segments per CTA
+// x-words (4 bytes) per segment row of a CTA.  8 (= one 32-byte sector per row, 128-thread CTAs, 1536 of them) instead of a full warp
+// (128-byte lines, 512-thread CTAs, 384 of them): with 63 registers only two 512-thread CTAs fit an SM, so 384 CTAs ran as 1.3 waves
+// on 296 slots and the SMs idled 41 % of the kernel (ncu r01g); small CTAs keep eight resident per SM and refill as they retire.
+constexpr int ZXW = 8;
 
-__global__ void __launch_bounds__(32 * ZSEGS, 2) df_z_dpx(const uint8_t* __restrict__ in, uint8_t* __restrict__ out) {
-    __shared__ uint2 edge_first[ZSEGS][32];  // local value at the first voxel of a segment (lo pair, hi pair)
-    __shared__ uint2 edge_last[ZSEGS][32];
-    __shared__ uint2 carry_f[ZSEGS][32];
-    __shared__ uint2 carry_b[ZSEGS][32];
+__global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __restrict__ in, uint8_t* __restrict__ out) {
+    __shared__ uint2 edge_first[ZSEGS][ZXW];  // local value at the first voxel of a segment (lo pair, hi pair)
+    __shared__ uint2 edge_last[ZSEGS][ZXW];
+    __shared__ uint2 carry_f[ZSEGS][ZXW];
+    __shared__ uint2 carry_b[ZSEGS][ZXW];
     const int lane = threadIdx.x, seg = threadIdx.y;
     const int y = blockIdx.y;
-    const size_t base = (size_t)y * WX + (size_t)(blockIdx.x * 32 + lane) * 4 + (size_t)seg * ZSEG * SLICE_BYTES;
+    const size_t base = (size_t)y * WX + (size_t)(blockIdx.x * ZXW + lane) * 4 + (size_t)seg * ZSEG * SLICE_BYTES;
 
     uint32_t lo[ZSEG], hi[ZSEG];
 #pragma unroll
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(32 * ZSEGS, 2) df_z_dpx(const uint8_t* __restr
     edge_first[seg][lane] = make_uint2(lo[0], hi[0]);
     edge_last[seg][lane] = make_uint2(lo[ZSEG - 1], hi[ZSEG - 1]);
     __syncthreads();
-    if (seg == 0) {  // one warp runs the 16-step min-plus scans for its 32 x-words
+    if (seg == 0) {  // ZXW threads run the 16-step min-plus scans for their x-words
         uint2 c = make_uint2(INF2, INF2);
 #pragma unroll
         for (int s = 0; s < ZSEGS; ++s) {
@@ -288,7 +292,8 @@ __global__ void __launch_bounds__(32 * ZSEGS, 2) df_z_dpx(const uint8_t* __restr
             c.x = __viaddmin_u16x2(c.x, (uint32_t)ZSEG * ONE2, e.x);
             c.y = __viaddmin_u16x2(c.y, (uint32_t)ZSEG * ONE2, e.y);
         }
-        c = make_uint2(INF2, INF2);
+    } else if (seg == 1) {
+        uint2 c = make_uint2(INF2, INF2);
 #pragma unroll
         for (int s = ZSEGS - 1; s >= 0; --s) {
             carry_b[s][lane] = c;  // best value one voxel after segment s
@@ -373,7 +378,7 @@ int launch_df_build(vxpt_ctx* c) {
     } else {
         const int smem = SLICE_BYTES + 16;
         df_xy_dpx<<<WZ, XY_THREADS, smem, s>>>(c->d_grid, c->d_tmp);
-        df_z_dpx<<<dim3(WX / 128, WY), dim3(32, ZSEGS), 0, s>>>(c->d_tmp, c->d_df);
+        df_z_dpx<<<dim3(WX / (4 * ZXW), WY), dim3(ZXW, ZSEGS), 0, s>>>(c->d_tmp, c->d_df);
         c->launches += 2;
     }
     VX_CUDA(cudaGetLastError());

@@ -155,16 +155,46 @@ __device__ __forceinline__ unsigned warp_push(unsigned* counter, bool pred) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
-template <int LAYOUT, bool SPP1>
+// gi_gen_trace0 — first hemisphere direction and first traversal of every pixel of a slab, with the rays of a CTA SORTED before they are
+// traced.  How long a hemisphere ray lives is decided mostly by where it points: steep rays reach large step values within a few
+// iterations and leave the volume (or hit the ground at once), grazing rays creep through E = 1..3 cells until the cap.  Neighbouring
+// pixels draw unrelated directions, so an unsorted warp waits for its longest ray with half of its lanes idle (ncu r01g: 15.8 of 32
+// active).  Here a CTA of 256 threads generates the rays of RPT 32x8-pixel tiles (RPT per thread), sorts them by |rd.y| (counting sort on
+// an 8-bit key in shared memory) and its warps then claim groups of 32 rays from the sorted list, longest-lived first, until the list is
+// empty: a warp holds rays of similar life expectancy, and short groups fill the time the warps that drew long groups are still busy
+// (with one group per warp the CTA would keep its registers until its slowest warp ended).  Which thread traces a ray does not change
+// what is computed for its pixel, so the planes stay bit-identical.  RPT = 0 selects the plain form (one pixel per thread, no exchange).
+template <int LAYOUT, bool SPP1, int RPT>
 __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
                                                      const DiffuseOutDev out, PixState* __restrict__ state, HitRec* __restrict__ queue,
                                                      unsigned* __restrict__ queue_count, const int sample) {
-    int i, j, prow;
-    const bool active = thread_pixel(cam, i, j, prow);
+    constexpr int NR = RPT > 0 ? RPT : 1;       // pixels per thread
+    constexpr bool SORT = RPT > 0;
+    __shared__ float4 s_a[SORT ? 256 * NR : 1];  // ro.xyz, pixel index (bits)
+    __shared__ float4 s_b[SORT ? 256 * NR : 1];  // rd.xyz, bl_sample (bits)
+    __shared__ unsigned s_hist[SORT ? 258 : 1];  // 256 bins, [256] = ray count, [257] = next group
+    __shared__ unsigned short s_order[SORT ? 256 * NR : 1];  // sorted position -> slot of s_a / s_b (rays stay where they were written)
+    const unsigned tid = threadIdx.x, lane = tid & 31;
     Counters cnt = {0u, 0u, 0u};
-    bool push = false;
-    HitRec rec;
-    if (active) {
+    if (SORT) {
+        s_hist[tid] = 0u;
+        if (tid < 2) s_hist[256 + tid] = 0u;
+        __syncthreads();
+    }
+    bool has_ray0 = false;                   // !SORT: the one ray of this thread stays in registers
+    V3 ro0 = mk3(0.f, 0.f, 0.f), rd0 = mk3(0.f, 1.f, 0.f);
+    unsigned px0 = 0;
+    int bl0 = 0;
+    unsigned kr[NR];                         // SORT: key << 16 | rank within the key's bin, ~0u = no ray
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        kr[r] = ~0u;
+        // pixel of this thread in the CTA's r-th tile: a warp covers 8x4 pixels, a tile 32x8 (thread_pixel's mapping)
+        const int warp = tid >> 5;
+        const int i = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+        const int prow = cam.row_begin + (blockIdx.y * NR + r) * 8 + (warp >> 2) * 4 + (lane >> 3);
+        if (i >= cam.width || prow >= cam.row_end) continue;
+        const int j = image_row(cam, prow);
         const size_t px = (size_t)prow * cam.width + i;
         float u = ((float)i + 0.5f) / (float)cam.width;
         float v = ((float)j + 0.5f) / (float)cam.height;
@@ -186,34 +216,101 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
                 if (out.ao_sky) store_unorm2(out.ao_sky, px, 1.0f, 0.0f, out.fmt);
             }
         } else if (sample < pixel_spp(P, i, j)) {
-            int bl_sample = 0;
+            int bls = 0;
             if (!SPP1) {
                 if (sample == 0) {
                     PixState z;
                     z.tot = z.rad = z.misc = make_float4(0.f, 0.f, 0.f, 0.f);
                     state[px] = z;
                 } else {
-                    bl_sample = __float_as_int(state[px].misc.w);
+                    bls = __float_as_int(state[px].misc.w);
                 }
             }
             const V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, u, v)) * dist;
-            const V3 ro = pos + normal * 0.06f;
-            const V3 rd = cos_hemisphere(S, i, j, P.frame % 128, bl_sample, normal);
-            TraceHit h;
-            const float T = traverse_df<LAYOUT>(S, ro, rd, P.trace_length, h, cnt);
-            if (T > 0.0f && h.block > 0) {
-                push = true;
-                rec.a = make_float4(ro.x, ro.y, ro.z, T);
-                rec.b = make_float4(rd.x, rd.y, rd.z, __int_as_float((int)px));
-                rec.c = make_float4(__int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8)), __int_as_float(bl_sample), 0.f, 0.f);
+            const V3 o = pos + normal * 0.06f;
+            const V3 d = cos_hemisphere(S, i, j, P.frame % 128, bls, normal);
+            if (SORT) {
+                const unsigned key = (unsigned)min((int)(fabsf(d.y) * 255.0f), 255);  // small = grazing = long-lived
+                kr[r] = (key << 16) | atomicAdd(&s_hist[key], 1u);
+                s_a[r * 256 + tid] = make_float4(o.x, o.y, o.z, __int_as_float((int)px));
+                s_b[r * 256 + tid] = make_float4(d.x, d.y, d.z, __int_as_float(bls));
             } else {
-                const V3 contrib = mk3(0.f, 0.f, 0.f) + sky_term(S, P, rd) * mk3(1.f, 1.f, 1.f);
-                finish_sample<SPP1>(out, state, px, contrib, 1.0f, rd, true, bl_sample);
+                has_ray0 = true; ro0 = o; rd0 = d; px0 = (unsigned)px; bl0 = bls;
             }
         }
     }
-    const unsigned slot = warp_push(queue_count, push);
-    if (push) queue[slot] = rec;
+    if (!SORT) {
+        bool push = false;
+        HitRec rec;
+        if (has_ray0) {
+            TraceHit h;
+            const float T = traverse_df<LAYOUT>(S, ro0, rd0, P.trace_length, h, cnt);
+            if (T > 0.0f && h.block > 0) {
+                push = true;
+                rec.a = make_float4(ro0.x, ro0.y, ro0.z, T);
+                rec.b = make_float4(rd0.x, rd0.y, rd0.z, __int_as_float((int)px0));
+                rec.c = make_float4(__int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8)), __int_as_float(bl0), 0.f, 0.f);
+            } else {
+                const V3 contrib = mk3(0.f, 0.f, 0.f) + sky_term(S, P, rd0) * mk3(1.f, 1.f, 1.f);
+                finish_sample<SPP1>(out, state, (size_t)px0, contrib, 1.0f, rd0, true, bl0);
+            }
+        }
+        const unsigned slot = warp_push(queue_count, push);
+        if (push) queue[slot] = rec;
+        flush_counters(S, cnt);
+        return;
+    }
+    __syncthreads();
+    if (tid < 32) {  // exclusive prefix over the 256 bins: 8 bins per lane, then a warp scan of the lane sums
+        unsigned c[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c[k] = s_hist[tid * 8 + k]; sum += c[k]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= (unsigned)d) incl += t;
+        }
+        unsigned base = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_hist[tid * 8 + k] = base; base += c[k]; }
+        if (tid == 31) s_hist[256] = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+        if (kr[r] != ~0u) s_order[s_hist[kr[r] >> 16] + (kr[r] & 0xFFFFu)] = (unsigned short)(r * 256 + tid);
+    __syncthreads();
+    const unsigned n_rays = s_hist[256], n_groups = (n_rays + 31u) / 32u;
+    while (true) {
+        unsigned grp = 0;
+        if (lane == 0) grp = atomicAdd(&s_hist[257], 1u);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if (grp >= n_groups) break;
+        const unsigned idx = grp * 32u + lane;
+        bool push = false;
+        HitRec rec;
+        if (idx < n_rays) {
+            const unsigned slot_ab = s_order[idx];
+            const float4 a = s_a[slot_ab], b = s_b[slot_ab];
+            const V3 o = mk3(a.x, a.y, a.z), d = mk3(b.x, b.y, b.z);
+            const size_t px = (size_t)(unsigned)__float_as_int(a.w);
+            const int bls = __float_as_int(b.w);
+            TraceHit h;
+            const float T = traverse_df<LAYOUT>(S, o, d, P.trace_length, h, cnt);
+            if (T > 0.0f && h.block > 0) {
+                push = true;
+                rec.a = make_float4(o.x, o.y, o.z, T);
+                rec.b = make_float4(d.x, d.y, d.z, a.w);
+                rec.c = make_float4(__int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8)), b.w, 0.f, 0.f);
+            } else {
+                const V3 contrib = mk3(0.f, 0.f, 0.f) + sky_term(S, P, d) * mk3(1.f, 1.f, 1.f);
+                finish_sample<SPP1>(out, state, px, contrib, 1.0f, d, true, bls);
+            }
+        }
+        const unsigned slot = warp_push(queue_count, push);
+        if (push) queue[slot] = rec;
+    }
     flush_counters(S, cnt);
 }
 
@@ -444,7 +541,19 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
             gi_resolve<SPP1><<<(unsigned)((slab_px + 255) / 256), 256, 0, c->stream>>>(S, d, od, state, rays, results, queue, count);
             c->launches += 3;
         } else {
-            gi_gen_trace0<LAYOUT, SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s);
+            // pixels per thread of the sorted first-bounce kernel: 4 on large slabs (1024 rays sorted per CTA, 32 groups for 8 warps), 2 on
+            // medium ones, plain on slabs too small to fill the GPU with such CTAs (r01g, 1080p GI pass: plain 0.339 ms, 1 / 2 / 4 pixels per
+            // thread 0.364 / 0.286 / 0.283 ms); VXPT_GI_SORT (0, 1, 2, 4) overrides (experiment knob)
+            static const int sort_env = std::getenv("VXPT_GI_SORT") ? std::atoi(std::getenv("VXPT_GI_SORT")) : -1;
+            const int rows = cd.row_end - cd.row_begin;
+            const int rpt = sort_env >= 0 ? sort_env : (slab_px >= (size_t)768 * 1024 ? 4 : (slab_px >= (size_t)128 * 1024 ? 2 : 0));
+            const dim3 grid_s((cd.width + 31) / 32, (rows + 8 * std::max(rpt, 1) - 1) / (8 * std::max(rpt, 1)));
+            switch (rpt) {
+                case 0: gi_gen_trace0<LAYOUT, SPP1, 0><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+                case 1: gi_gen_trace0<LAYOUT, SPP1, 1><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+                case 2: gi_gen_trace0<LAYOUT, SPP1, 2><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+                default: gi_gen_trace0<LAYOUT, SPP1, 4><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+            }
             c->launches += 1;
         }
         gi_continue<LAYOUT, SPP1><<<148 * 6, 128, 0, c->stream>>>(S, cd, d, od, state, queue, count);

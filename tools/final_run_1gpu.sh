@@ -4,8 +4,8 @@ R=${1:-r01g}
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$R.log 2>&1; tail -2 gpurun_out/pytest_gpu_$R.log
 timeout 300 python bench.py > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err; python tools/show.py default < gpurun_out/bench_$R.json
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_$R.json 2>> gpurun_out/bench_$R.err; cut -c1-220 gpurun_out/bench_ref_$R.json
-timeout 120 python bench.py --no-cpu-baseline --gi-mode 2 > gpurun_out/bench_gi2_$R.json 2>> gpurun_out/bench_$R.err; python tools/show.py gi-mode-2 < gpurun_out/bench_gi2_$R.json
-timeout 120 python bench.py --no-cpu-baseline --pipes 3 > gpurun_out/bench_p3_$R.json 2>> gpurun_out/bench_$R.err; python tools/show.py pipes-3 < gpurun_out/bench_p3_$R.json
+
+
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --pipes 1 > gpurun_out/ncu_bench_$R.log 2>&1
 for k in primary_kernel shadow_kernel gi_gen_trace0 gi_continue df_xy_dpx df_z_dpx pack_steps; do
   timeout 150 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o gpurun_out/prof_${R}_$k python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --pipes 1 >> gpurun_out/ncu_bench_$R.log 2>&1

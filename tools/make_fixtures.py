@@ -28,49 +28,13 @@ from PIL import Image
 REF = os.environ.get("VXPT_REFERENCE", "/root/reference")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
 
 # blocks whose textures are baked (ids follow blockdb.txt order, Core/BlockDatabaseParser.cpp:31-42)
 SUBSET = ["Grass", "Dirt", "Stone", "Cobblestone", "Sand", "Lamp", "Glowstone", "Bricks", "Planks", "oak_leaves"]
 
 
-def parse_blockdb(path):
-    """Restates Core/BlockDatabaseParser.cpp:44-375 for the fields the hot path needs."""
-    blocks = []
-    cur = None
-    for raw in open(path, encoding="utf-8", errors="replace"):
-        line = raw.strip()
-        if line == "{":
-            cur = {"faces": {k: {} for k in ("Albedo", "Normal", "PBR")}, "Emissive": "", "Transparent": False, "SSS": False}
-            continue
-        if line == "}":
-            if cur is not None and "Name" in cur:
-                blocks.append(cur)
-            cur = None
-            continue
-        if cur is None or not line:
-            continue
-        key, _, val = line.partition(":")
-        key, val = key.strip().rstrip(";"), val.strip()
-        if key == "Name":
-            cur["Name"] = val
-        elif key.split("_")[0] in ("Albedo", "Normal", "PBR"):
-            kind, _, face = key.partition("_")
-            face = face or "default"
-            cur["faces"][kind][face] = val
-        elif key.startswith("Transparent"):
-            cur["Transparent"] = True
-        elif key.upper().startswith("SSS") or key.startswith("SUBSURFACE"):
-            cur["SSS"] = True
-        elif key == "Emissive":
-            cur["Emissive"] = val
-    for i, b in enumerate(blocks):
-        b["ID"] = i + 1
-        for kind in ("Albedo", "Normal", "PBR"):
-            f = b["faces"][kind]
-            d = f.get("default", "")
-            for face in ("front", "back", "left", "right", "top", "bottom"):
-                f.setdefault(face, d)
-    return blocks
+from voxelpathtracer_b200.blockdb import minecraft_id_lut, parse_blockdb  # noqa: E402  (the parser is product code now)
 
 
 def srgb_to_linear(c):
@@ -109,6 +73,8 @@ def main():
     bn = np.asarray(Image.open(os.path.join(REF, "Res", "Misc", "blue_noise.png")).convert("RGBA"), dtype=np.uint8)
     assert bn.shape == (256, 256, 4)
     bn.tofile(os.path.join(OUT, "shadow_blue_noise.rgba8"))
+    # Minecraft id -> engine block id (256 bytes), for the .mca importer
+    minecraft_id_lut(parse_blockdb(os.path.join(REF, "blockdb.txt"))).tofile(os.path.join(OUT, "mcid_lut.u8"))
 
     # --- material table + baked texel arrays
     blocks = parse_blockdb(os.path.join(REF, "blockdb.txt"))

@@ -27,6 +27,11 @@ def load_shadow_noise(golden=GOLDEN):
     return np.fromfile(os.path.join(golden, "shadow_blue_noise.rgba8"), dtype=np.uint8).reshape(256, 256, 4)
 
 
+def load_minecraft_id_lut(golden=GOLDEN):
+    """uint8[256]: Minecraft block id -> engine block id (blockdb.minecraft_id_lut over the reference's blockdb.txt)."""
+    return np.fromfile(os.path.join(golden, "mcid_lut.u8"), dtype=np.uint8)
+
+
 def load_materials(golden=GOLDEN):
     """dict(table int32[768], albedo_lod3 f32[L,64,64,4], pbr_lod2 f32[L,128,128,4], emissive_lod0 f32[E,512,512])."""
     z = np.load(os.path.join(golden, "materials.npz"))

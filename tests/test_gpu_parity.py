@@ -708,3 +708,23 @@ def test_cuda_reflections_equal_the_reference_shader_golden_vectors(renderer, wo
         out = renderer.trace_reflection(cam, g, d, rp, renderer.alloc_reflection(W, H), g_normal, g_pbr)
         for k in ("color", "hit_distance", "emissive_mask"):
             assert sha(out[k]) == ref[cname][k], (cname, k)
+
+
+def test_cuda_config4_frame_equals_the_reference_shader_golden_vectors(renderer, worlds, scene_tables):
+    """BASELINE config 4 on one GPU: 3840x2160, soft shadows + 4-spp GI on the gi-box scene, device planes; CUDA == the reference's shaders."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shader_digests.json")) as f:
+        ref = json.load(f)
+    load(renderer, worlds["gi_box"])
+    W, H = 3840, 2160
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H)
+    g = renderer.trace_primary(cam, vx.primary_params(350), renderer.alloc_gbuffer(W, H, device=True))
+    s = renderer.trace_shadow(cam, g, vx.shadow_params(scene_tables["stronger"], frame=9, soft=True), renderer.alloc_shadow(W, H, device=True))
+    d = renderer.trace_diffuse(cam, g, vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=4, frame=9),
+                               renderer.alloc_diffuse(W, H, device=True))
+    renderer.sync()
+    for k in ("shadow", "transversal"):
+        assert sha(s[k].cpu().numpy()) == ref["shadow"]["gi_box_3840x2160_f9"][k], k
+    for k in ("sh", "cocg", "luma", "ao_sky"):
+        assert sha(d[k].cpu().numpy()) == ref["diffuse"]["gi_box_3840x2160_spp4_f9"][k], k

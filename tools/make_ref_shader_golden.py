@@ -79,6 +79,16 @@ def main():
             out["diffuse"][cname] = {"sh": sha(d["sh"]), "cocg": sha(d["cocg"]), "luma": sha(d["luma"]), "ao_sky": sha(d["ao_sky"]),
                                      "mean_luma": float(d["luma"].mean())}
             print(f"  shadow + diffuse {cname}: {time.time() - t0:.1f} s", flush=True)
+    # BASELINE config 4: 3840x2160, 4-spp GI (and the soft shadow pass) on the gi-box stand-in scene
+    t0 = time.time()
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(3840, 2160)
+    g = ref_shaders.trace_primary(worlds["gi_box"].data, dfs["gi_box"], cam, vx.primary_params(350))
+    s4 = ref_shaders.trace_shadow(worlds["gi_box"].data, dfs["gi_box"], cam, g, vx.shadow_params(stronger, frame=9, soft=True), sn)
+    d4 = ref_shaders.trace_diffuse(worlds["gi_box"].data, dfs["gi_box"], cam, g, vx.diffuse_params(sun, moon, sunvis, spp=4, frame=9), mats, bn, sky)
+    out["shadow"]["gi_box_3840x2160_f9"] = {"shadow": sha(s4["shadow"]), "transversal": sha(s4["transversal"]), "shadowed_fraction": float(s4["shadow"].mean())}
+    out["diffuse"]["gi_box_3840x2160_spp4_f9"] = {"sh": sha(d4["sh"]), "cocg": sha(d4["cocg"]), "luma": sha(d4["luma"]), "ao_sky": sha(d4["ao_sky"]),
+                                                  "mean_luma": float(d4["luma"].mean())}
+    print(f"config 4 (4K, 4 spp): {time.time() - t0:.1f} s", flush=True)
     for cname, wname, W, H, cam_kw, spp, rough, checker, frame in reflection_cases():   # Halton jitter 0: the G-buffer is read at the pixel
         t0 = time.time()
         fc = camera.FpsCamera(**cam_kw)

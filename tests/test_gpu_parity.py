@@ -728,3 +728,27 @@ def test_cuda_config4_frame_equals_the_reference_shader_golden_vectors(renderer,
         assert sha(s[k].cpu().numpy()) == ref["shadow"]["gi_box_3840x2160_f9"][k], k
     for k in ("sh", "cocg", "luma", "ao_sky"):
         assert sha(d[k].cpu().numpy()) == ref["diffuse"]["gi_box_3840x2160_spp4_f9"][k], k
+
+
+def test_render_frame_on_interleaved_row_bands(renderer, worlds, scene_tables):
+    """vxpt_render_frame with the multi-GPU row-band contract (rank-local planes, virtual rows) == the separate passes on the same camera."""
+    load(renderer, worlds["plains"])
+    W, H, n, rank, band = 320, 360, 3, 1, 4
+    rows = H // n
+    fc = camera.FpsCamera(pitch_deg=-20.0, aspect=W / H)
+    cam = fc.vx_camera(W, H, 8, rows - 16, n, rank, band)
+    pp = vx.primary_params(350, camera.taa_jitter(6))
+    sp = vx.shadow_params(scene_tables["stronger"], frame=6)
+    dp = vx.diffuse_params(scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"], spp=2, frame=6)
+    def fresh():
+        bufs = (renderer.alloc_gbuffer(W, rows), renderer.alloc_shadow(W, rows), renderer.alloc_diffuse(W, rows))
+        for b in bufs:
+            for v in b.values():
+                v[...] = 3
+        return bufs
+    g, s, d = fresh()
+    renderer.trace_primary(cam, pp, g); renderer.trace_shadow(cam, g, sp, s); renderer.trace_diffuse(cam, g, dp, d)
+    g2, s2, d2 = fresh()
+    renderer.render_frame(cam, pp, sp, dp, g2, s2, d2)
+    for k, v in {**g2, **s2, **d2}.items():
+        assert np.array_equal(v, {**g, **s, **d}[k]), k

@@ -279,8 +279,8 @@ int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, c
     const SceneDev S = make_scene(c);
     const PrimaryDev pd{p.max_iterations, p.jitter_enable, p.jitter[0], p.jitter[1]};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) primary_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(c, out));
-    else primary_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), pd, to_dev(c, out));
+    if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+    else VX_LAUNCH((primary_kernel<0>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -303,8 +303,8 @@ int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const Vx
     sd.hy = p.halton[1];
     const ShadowOutDev od{out.shadow, out.transversal, c->opt_texel};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) shadow_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(c, g), od);
-    else shadow_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), sd, to_dev(c, g), od);
+    if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+    else VX_LAUNCH((shadow_kernel<0>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -339,8 +339,8 @@ int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const V
     const DiffuseOutDev od{reinterpret_cast<float4*>(out.sh), reinterpret_cast<float2*>(out.cocg), out.luma,
                            reinterpret_cast<float2*>(out.ao_sky), c->opt_texel};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) diffuse_kernel<1><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(c, g), od);
-    else diffuse_kernel<0><<<grid, 256, 0, c->stream>>>(S, to_dev(cam), d, to_dev(c, g), od);
+    if (c->opt_layout == 1) VX_LAUNCH((diffuse_kernel<1>), grid, 256, c->stream, S, to_dev(cam), d, to_dev(c, g), od);
+    else VX_LAUNCH((diffuse_kernel<0>), grid, 256, c->stream, S, to_dev(cam), d, to_dev(c, g), od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

@@ -273,6 +273,14 @@ __device__ __forceinline__ V3 normal_from_id(int id, float miss) {
 
 // one atomic per counter per warp
 __device__ __forceinline__ void flush_counters(const SceneDev& S, const Counters& c) {
+#ifdef VXPT_HOST_SHADOW  // tests/host_shadow: the "threads" of the g++ build run one after another, there is no warp to reduce over
+    if (S.counters) {
+        __atomic_fetch_add(&S.counters->rays, (unsigned long long)c.rays, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&S.counters->df_fetches, (unsigned long long)c.df, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&S.counters->vox_fetches, (unsigned long long)c.vox, __ATOMIC_RELAXED);
+    }
+    return;
+#else
     unsigned int r = __reduce_add_sync(0xffffffffu, c.rays);
     unsigned int d = __reduce_add_sync(0xffffffffu, c.df);
     unsigned int v = __reduce_add_sync(0xffffffffu, c.vox);
@@ -281,6 +289,7 @@ __device__ __forceinline__ void flush_counters(const SceneDev& S, const Counters
         atomicAdd(&S.counters->df_fetches, (unsigned long long)d);
         atomicAdd(&S.counters->vox_fetches, (unsigned long long)v);
     }
+#endif
 }
 
 // pixel of this thread: a warp covers an 8x4 pixel tile, a 256-thread CTA covers 32x8 pixels.

@@ -340,8 +340,8 @@ int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, cons
                        reinterpret_cast<const float2*>(in.cocg), c->opt_texel};
     const ReflOutDev od{reinterpret_cast<float4*>(out.color), out.hit_distance, out.emissive_mask, c->opt_texel};
     const dim3 grid((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8);
-    if (c->opt_layout == 1) reflection_kernel<1><<<grid, 256, 0, c->stream>>>(S, cd, d, gd, id, od);
-    else reflection_kernel<0><<<grid, 256, 0, c->stream>>>(S, cd, d, gd, id, od);
+    if (c->opt_layout == 1) VX_LAUNCH((reflection_kernel<1>), grid, 256, c->stream, S, cd, d, gd, id, od);
+    else VX_LAUNCH((reflection_kernel<0>), grid, 256, c->stream, S, cd, d, gd, id, od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

@@ -130,11 +130,17 @@ namespace vxpt {
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
+#ifndef VXPT_HOST_SHADOW
 #define VX_CUDA(expr)                                                         \
     do {                                                                      \
         cudaError_t _e = (expr);                                              \
         if (_e != cudaSuccess) return ::vxpt::cuda_fail(_e, #expr, __FILE__, __LINE__); \
     } while (0)
+// every kernel launch of the per-pixel passes goes through this macro.  (tests/host_shadow compiles these translation units
+// with g++ and defines it as a loop over blockIdx / threadIdx, so the CPU suite executes the kernels' own source against the
+// oracle; the product library is only ever built by nvcc and has no host path.)
+#define VX_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
 
 // df_build.cu
 int init_df_kernels(vxpt_ctx* c);

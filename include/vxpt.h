@@ -78,8 +78,9 @@ typedef struct VxPrimaryParams {
     int32_t max_iterations;  /* u_RenderDistance: 475 on frame 0 then 350 (Pipeline.cpp:55,4824) */
     int32_t jitter_enable;   /* u_JitterSceneForTAA                                             */
     float jitter[2];         /* u_CurrentTAAJitter = Halton(2,3)[frame % 64] (TAAJitter.cpp)    */
-    int32_t alpha_test;      /* u_ShouldAlphaTest; must be 0 (off by default, Pipeline.cpp:141) */
-    int32_t reserved;
+    int32_t alpha_test;      /* u_ShouldAlphaTest (off by default, Pipeline.cpp:141): VoxelTraversalDF_AlphaTest,   */
+                             /* InitialRayTraceFrag.glsl:189-305; needs vxpt_set_albedo_alpha_mips                  */
+    float fov_degrees;       /* u_FOV (read by the alpha test's LOD only: g_K, InitialRayTraceFrag.glsl:421)        */
 } VxPrimaryParams;
 
 /* G-buffer planes (InitialTraceFBO attachments, Pipeline.cpp:1094-1095).  t is kept in fp32 (the reference's
@@ -99,7 +100,9 @@ typedef struct VxShadowParams {
     int32_t frame;           /* u_CurrentFrame (blue-noise texel offset, frame % 1024)            */
     int32_t soft;            /* u_ContactHardeningShadows (cone jitter); default 1                */
     float halton[2];         /* u_Halton; zero unless supersampling (Pipeline.cpp:2823)           */
-    int32_t alpha_test;      /* must be 0                                                         */
+    int32_t alpha_test;      /* u_ShouldAlphaTest = ShouldAlphaTestShadows (Pipeline.cpp:2820):   */
+                             /* VoxelTraversalDF_AlphaTest, ShadowRayTraceFrag.glsl:105-220       */
+    float fov_degrees;       /* u_FOV (alpha test's LOD only, ShadowRayTraceFrag.glsl:419)        */
 } VxShadowParams;
 
 typedef struct VxShadowOut {
@@ -215,6 +218,13 @@ VXPT_API int vxpt_set_material_textures(vxpt_handle h, const float* albedo_lod3,
  * leaves the level undefined). */
 VXPT_API int vxpt_set_reflection_textures(vxpt_handle h, const float* normal_lod3, int n_normal_layers, const float* emissive_lod2,
                                           int n_emissive_layers);
+/* alpha channel of the albedo array's whole mip chain, for the alpha-tested traversal (StopRay, InitialRayTraceFrag.glsl:189-203,
+ * ShadowRayTraceFrag.glsl:105-117: textureLod(u_AlbedoTextures, uv, LOD).w > 0.975 with a per-hit integer LOD 0..8).  The array
+ * is GL_SRGB_ALPHA / GL_NEAREST_MIPMAP_LINEAR (Core/GLClasses/TextureArray.cpp:28-42), so alpha is a linear unorm8 at every
+ * level and an integer LOD reads the nearest texel of exactly that level:
+ *  alpha_mips [n_layers][VXPT_ALPHA_MIP_TEXELS] uint8: per layer, levels 0..8 back to back, level k = [512 >> k][512 >> k] */
+#define VXPT_ALPHA_MIP_TEXELS 349524 /* 512^2 + 256^2 + ... + 2^2 */
+VXPT_API int vxpt_set_albedo_alpha_mips(vxpt_handle h, const uint8_t* alpha_mips, int n_layers);
 VXPT_API int vxpt_set_sky_cubemap(vxpt_handle h, const float* rgb /* [6][n][n][3], faces +X,-X,+Y,-Y,+Z,-Z */, int n);
 VXPT_API int vxpt_set_shadow_noise(vxpt_handle h, const uint8_t* rgba8 /* [256][256][4] */);
 

@@ -143,7 +143,7 @@ def translate(src, ns):
     # r-value swizzles glm does not provide as members:  <postfix-expression>.xyz  ->  swz_xyz(<postfix-expression>)
     s = rewrite_swizzles(s)
     # transcendental functions: pinned definitions (glsl_compat.h)
-    s = re.sub(r"\b(sin|cos|tan|pow|mix)\s*\(", r"pinned_\1(", s)
+    s = re.sub(r"\b(sin|cos|tan|pow|mix|log2)\s*\(", r"pinned_\1(", s)
     # entry point
     s = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", s)
     # GLSL re-initialises global variables for every shader invocation: collect the initialised, mutable globals (brace depth 0)

@@ -64,6 +64,7 @@ inline float pinned_sin(float x) { return (float)::sin((double)x); }
 inline float pinned_cos(float x) { return (float)::cos((double)x); }
 inline float pinned_tan(float x) { return (float)::tan((double)x); }
 inline float pinned_pow(float x, float y) { return (float)::pow((double)x, (double)y); }
+inline float pinned_log2(float x) { return (float)::log2((double)x); }
 template <class V> inline V pinned_sin(const V& v) { return glm::sin(v); }
 template <class V> inline V pinned_cos(const V& v) { return glm::cos(v); }
 template <class V> inline V pinned_tan(const V& v) { return glm::tan(v); }
@@ -119,12 +120,26 @@ struct sampler2DArray {
     const float* data = nullptr;  // [layers][n][n][comps]
     int n = 0, comps = 4;
     bool nearest_only = false;    // reflection pass: its implicit-LOD texture() calls are pinned to the nearest texel of the bound level
+    // alpha-tested traversal (StopRay): the alpha channel of the whole mip chain, levels 0..8 of a 512^2 array back to back per layer
+    // (unorm8, as the GL_SRGB_ALPHA storage holds it); textureLod with the shader's integer LOD reads the nearest texel of that level
+    // (GL_NEAREST_MIPMAP_LINEAR with a zero fraction, Core/GLClasses/TextureArray.cpp:34)
+    const uint8_t* alpha_mips = nullptr;
+    int alpha_layers = 0;
 };
 inline vec4 fetch_layer_texel(const sampler2DArray& s, int layer, int i, int j) {
     const float* t = s.data + (((size_t)layer * s.n + j) * s.n + i) * s.comps;
     return vec4(t[0], s.comps > 1 ? t[1] : 0.0f, s.comps > 2 ? t[2] : 0.0f, s.comps > 3 ? t[3] : 1.0f);
 }
-inline vec4 textureLod(const sampler2DArray& s, const vec3& p, float /*lod: the bound level*/) {
+inline vec4 textureLod(const sampler2DArray& s, const vec3& p, float lod /*ignored for `data`: the bound level*/) {
+    if (s.alpha_mips) {
+        const int level = (int)lod, n = 512 >> level;
+        size_t off = 0;
+        for (int k = 0; k < level; ++k) off += (size_t)(512 >> k) * (512 >> k);
+        const int i = ((int)std::floor(p.x * (float)n)) & (n - 1), j = ((int)std::floor(p.y * (float)n)) & (n - 1);
+        int layer = (int)std::nearbyintf(p.z);
+        layer = layer < 0 ? 0 : (layer > s.alpha_layers - 1 ? s.alpha_layers - 1 : layer);
+        return vec4(1.0f, 1.0f, 1.0f, (float)s.alpha_mips[(size_t)layer * 349524 + off + (size_t)j * n + i] / 255.0f);
+    }
     if (!s.data) return vec4(1.0f);
     const int i = ((int)std::floor(p.x * (float)s.n)) & (s.n - 1), j = ((int)std::floor(p.y * (float)s.n)) & (s.n - 1);
     return fetch_layer_texel(s, (int)p.z, i, j);

@@ -55,6 +55,10 @@ __attribute__((visibility("default"))) int ref_df_build(const uint8_t* blocks, u
 
 // InitialRayTraceFrag.glsl main() over rows [row_begin, row_end) of a width x height frame.
 // Outputs are the four colour attachments as the shader writes them (fp32, before any render-target conversion).
+static const int32_t* g_alpha_materials = nullptr;  // set by ref_trace_primary_alpha around its call of ref_trace_primary
+static const uint8_t* g_alpha_mips = nullptr;
+static int g_alpha_layers = 0;
+static float g_alpha_fov = 60.0f;
 __attribute__((visibility("default"))) int ref_trace_primary(const uint8_t* blocks, const uint8_t* df, const float* inv_view, const float* inv_proj, int width,
                                                              int height, int row_begin, int row_end, int render_distance, int jitter_enable,
                                                              const float* jitter, float* o_hit_distance, float* o_normal, float* o_block_id,
@@ -66,11 +70,17 @@ __attribute__((visibility("default"))) int ref_trace_primary(const uint8_t* bloc
     std::memcpy(&S::u_InverseView[0][0], inv_view, 16 * sizeof(float));       // column-major, as glUniformMatrix4fv(GL_FALSE)
     std::memcpy(&S::u_InverseProjection[0][0], inv_proj, 16 * sizeof(float));
     S::u_Dimensions = vec2((float)width, (float)height);
-    S::u_ShouldAlphaTest = false;
+    S::u_ShouldAlphaTest = g_alpha_mips != nullptr;
+    if (g_alpha_mips) {  // BlockDataSSBO (Core/BlockDataSSBO.cpp:28-35 order) and the albedo array's alpha mip chain
+        std::memcpy(S::SSBO_BlockData_storage, g_alpha_materials, 5 * 128 * sizeof(int32_t));
+        S::u_AlbedoTextures = sampler2DArray{};
+        S::u_AlbedoTextures.alpha_mips = g_alpha_mips;
+        S::u_AlbedoTextures.alpha_layers = g_alpha_layers;
+    }
     S::u_RenderDistance = render_distance;
     S::u_JitterSceneForTAA = jitter_enable != 0;
     S::u_CurrentTAAJitter = vec2(jitter[0], jitter[1]);
-    S::u_FOV = 60.0f;
+    S::u_FOV = g_alpha_fov;
     S::u_Time = 0.0f;
     for (int j = row_begin; j < row_end; ++j)
         for (int i = 0; i < width; ++i) {
@@ -84,6 +94,19 @@ __attribute__((visibility("default"))) int ref_trace_primary(const uint8_t* bloc
             o_depth_nonlinear[px] = S::o_DepthNonLinear;
         }
     return 0;
+}
+
+// the same with u_ShouldAlphaTest = true (VoxelTraversalDF_AlphaTest + StopRay, InitialRayTraceFrag.glsl:189-305)
+__attribute__((visibility("default"))) int ref_trace_primary_alpha(const uint8_t* blocks, const uint8_t* df, const float* inv_view, const float* inv_proj,
+                                                                   int width, int height, int row_begin, int row_end, int render_distance,
+                                                                   int jitter_enable, const float* jitter, const int32_t* materials,
+                                                                   const uint8_t* alpha_mips, int alpha_layers, float fov_degrees,
+                                                                   float* o_hit_distance, float* o_normal, float* o_block_id, float* o_depth_nonlinear) {
+    g_alpha_materials = materials; g_alpha_mips = alpha_mips; g_alpha_layers = alpha_layers; g_alpha_fov = fov_degrees;
+    const int rc = ref_trace_primary(blocks, df, inv_view, inv_proj, width, height, row_begin, row_end, render_distance, jitter_enable, jitter,
+                                     o_hit_distance, o_normal, o_block_id, o_depth_nonlinear);
+    g_alpha_materials = nullptr; g_alpha_mips = nullptr; g_alpha_layers = 0; g_alpha_fov = 60.0f;
+    return rc;
 }
 
 }  // extern "C"

@@ -48,6 +48,13 @@ def load():
         lib.ref_trace_primary.restype = C.c_int
         lib.ref_trace_primary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_trace_primary_alpha.restype = C.c_int
+        lib.ref_trace_primary_alpha.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_trace_shadow_alpha.restype = C.c_int
+        lib.ref_trace_shadow_alpha.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                               C.c_void_p, C.c_void_p]
         lib.ref_trace_shadow.restype = C.c_int
         lib.ref_trace_shadow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -67,9 +74,10 @@ def df_build(blocks):
     return out
 
 
-def trace_primary(blocks, df, cam, params):
+def trace_primary(blocks, df, cam, params, table=None, alpha_mips=None):
     """InitialRayTraceFrag.glsl main() per pixel of rows [cam.row_begin, cam.row_end).  Returns the G-buffer in the ABI's terms:
-    t (o_HitDistance), normal_id = round(o_Normal * 10) (10 = miss), block_id = round(o_BlockID * 255), inv_t (o_DepthNonLinear)."""
+    t (o_HitDistance), normal_id = round(o_Normal * 10) (10 = miss), block_id = round(o_BlockID * 255), inv_t (o_DepthNonLinear).
+    params.alpha_test sets u_ShouldAlphaTest and needs the BlockDataSSBO table and the albedo alpha mip chain."""
     blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
     df = np.ascontiguousarray(df, dtype=np.uint8).reshape(-1)
     W, H = cam.width, cam.height
@@ -77,13 +85,20 @@ def trace_primary(blocks, df, cam, params):
     iv = np.ascontiguousarray(np.frombuffer(cam.inv_view, dtype=np.float32))
     ip = np.ascontiguousarray(np.frombuffer(cam.inv_proj, dtype=np.float32))
     jit = np.array([params.jitter[0], params.jitter[1]], dtype=np.float32)
-    load().ref_trace_primary(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end,
-                             params.max_iterations, params.jitter_enable, jit.ctypes.data, *[p.ctypes.data for p in planes])
+    if params.alpha_test:
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        alpha_mips = np.ascontiguousarray(alpha_mips, dtype=np.uint8)
+        load().ref_trace_primary_alpha(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end,
+                                       params.max_iterations, params.jitter_enable, jit.ctypes.data, table.ctypes.data, alpha_mips.ctypes.data,
+                                       alpha_mips.shape[0], params.fov_degrees, *[p.ctypes.data for p in planes])
+    else:
+        load().ref_trace_primary(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end,
+                                 params.max_iterations, params.jitter_enable, jit.ctypes.data, *[p.ctypes.data for p in planes])
     t, n, b, it = planes
     return {"t": t, "normal_id": np.rint(n * np.float32(10.0)).astype(np.uint8), "block_id": np.rint(b * np.float32(255.0)).astype(np.uint8), "inv_t": it}
 
 
-def trace_shadow(blocks, df, cam, gbuf, params, noise_rgba8):
+def trace_shadow(blocks, df, cam, gbuf, params, noise_rgba8, table=None, alpha_mips=None):
     """ShadowRayTraceFrag.glsl main() per pixel.  gbuf: t (fp32 plane as the position texture holds it) and normal_id planes.
     Returns shadow (o_Shadow as 0/1 bytes) and transversal (o_IntersectionTransversal)."""
     blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
@@ -97,9 +112,16 @@ def trace_shadow(blocks, df, cam, gbuf, params, noise_rgba8):
     light = np.array(list(params.light_dir), dtype=np.float32)
     halton = np.array(list(params.halton), dtype=np.float32)
     o_s, o_t = np.zeros((H, W), dtype=np.float32), np.zeros((H, W), dtype=np.float32)
-    load().ref_trace_shadow(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end, t.ctypes.data,
-                            nid.ctypes.data, light.ctypes.data, params.frame, params.soft, halton.ctypes.data, noise.ctypes.data, o_s.ctypes.data,
-                            o_t.ctypes.data)
+    if params.alpha_test:
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        alpha_mips = np.ascontiguousarray(alpha_mips, dtype=np.uint8)
+        load().ref_trace_shadow_alpha(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end, t.ctypes.data,
+                                      nid.ctypes.data, light.ctypes.data, params.frame, params.soft, halton.ctypes.data, noise.ctypes.data,
+                                      table.ctypes.data, alpha_mips.ctypes.data, alpha_mips.shape[0], params.fov_degrees, o_s.ctypes.data, o_t.ctypes.data)
+    else:
+        load().ref_trace_shadow(blocks.ctypes.data, df.ctypes.data, iv.ctypes.data, ip.ctypes.data, W, H, cam.row_begin, cam.row_end, t.ctypes.data,
+                                nid.ctypes.data, light.ctypes.data, params.frame, params.soft, halton.ctypes.data, noise.ctypes.data, o_s.ctypes.data,
+                                o_t.ctypes.data)
     return {"shadow": (o_s > 0.5).astype(np.uint8), "transversal": o_t}
 
 

@@ -10,6 +10,10 @@ namespace glsl {
 #include "_ref/ShadowRayTraceFrag.inc"
 }  // namespace glsl
 
+static const int32_t* g_alpha_materials = nullptr;  // set by ref_trace_shadow_alpha around its call of ref_trace_shadow
+static const uint8_t* g_alpha_mips = nullptr;
+static int g_alpha_layers = 0;
+static float g_alpha_fov = 60.0f;
 extern "C" __attribute__((visibility("default"))) int ref_trace_shadow(
     const uint8_t* blocks, const uint8_t* df, const float* inv_view, const float* inv_proj, int width, int height, int row_begin, int row_end,
     const float* g_t, const uint8_t* g_normal_id, const float* light_dir, int frame, int soft, const float* halton, const uint8_t* noise_rgba8,
@@ -25,9 +29,15 @@ extern "C" __attribute__((visibility("default"))) int ref_trace_shadow(
     S::u_LightDirection = vec3(light_dir[0], light_dir[1], light_dir[2]);
     S::u_CurrentFrame = frame;
     S::u_ContactHardeningShadows = soft != 0;
-    S::u_ShouldAlphaTest = false;
+    S::u_ShouldAlphaTest = g_alpha_mips != nullptr;
+    if (g_alpha_mips) {
+        std::memcpy(S::SSBO_BlockData_storage, g_alpha_materials, 5 * 128 * sizeof(int32_t));
+        S::u_AlbedoTextures = sampler2DArray{};
+        S::u_AlbedoTextures.alpha_mips = g_alpha_mips;
+        S::u_AlbedoTextures.alpha_layers = g_alpha_layers;
+    }
     S::u_DoFullTrace = true;
-    S::u_FOV = 60.0f;
+    S::u_FOV = g_alpha_fov;
     S::u_Time = 0.0f;
     // o_Normal as the R8 attachment holds it: id / 10 (miss 1.0); the blue-noise texture as GL_RGBA8 unorm
     std::vector<float> normal((size_t)width * height), noise(256 * 256 * 4);
@@ -47,4 +57,16 @@ extern "C" __attribute__((visibility("default"))) int ref_trace_shadow(
             o_transversal[(size_t)j * width + i] = S::o_IntersectionTransversal;
         }
     return 0;
+}
+
+// the same with u_ShouldAlphaTest = true (ShadowRayTraceFrag.glsl:105-220, :502)
+extern "C" __attribute__((visibility("default"))) int ref_trace_shadow_alpha(
+    const uint8_t* blocks, const uint8_t* df, const float* inv_view, const float* inv_proj, int width, int height, int row_begin, int row_end,
+    const float* g_t, const uint8_t* g_normal_id, const float* light_dir, int frame, int soft, const float* halton, const uint8_t* noise_rgba8,
+    const int32_t* materials, const uint8_t* alpha_mips, int alpha_layers, float fov_degrees, float* o_shadow, float* o_transversal) {
+    g_alpha_materials = materials; g_alpha_mips = alpha_mips; g_alpha_layers = alpha_layers; g_alpha_fov = fov_degrees;
+    const int rc = ref_trace_shadow(blocks, df, inv_view, inv_proj, width, height, row_begin, row_end, g_t, g_normal_id, light_dir, frame, soft, halton,
+                                    noise_rgba8, o_shadow, o_transversal);
+    g_alpha_materials = nullptr; g_alpha_mips = nullptr; g_alpha_layers = 0; g_alpha_fov = 60.0f;
+    return rc;
 }

@@ -18,7 +18,8 @@ class VxoScene(C.Structure):
                 ("materials", C.c_void_p), ("sobol", C.c_void_p), ("scramble", C.c_void_p), ("rank", C.c_void_p),
                 ("albedo_lod3", C.c_void_p), ("pbr_lod2", C.c_void_p), ("n_layers", C.c_int32),
                 ("emissive_lod0", C.c_void_p), ("n_emissive_layers", C.c_int32), ("sky", C.c_void_p), ("sky_n", C.c_int32),
-                ("shadow_noise", C.c_void_p), ("normal_lod3", C.c_void_p), ("n_normal_layers", C.c_int32), ("emissive_lod2", C.c_void_p)]
+                ("shadow_noise", C.c_void_p), ("normal_lod3", C.c_void_p), ("n_normal_layers", C.c_int32), ("emissive_lod2", C.c_void_p),
+                ("alpha_mips", C.c_void_p), ("n_alpha_layers", C.c_int32)]
 
 
 class VxoStats(C.Structure):
@@ -112,6 +113,12 @@ class Oracle:
             k["emissive2"] = np.ascontiguousarray(materials["emissive_lod2"], dtype=np.float32)
             s.normal_lod3, s.n_normal_layers = k["normal"].ctypes.data, k["normal"].shape[0]
             s.emissive_lod2 = k["emissive2"].ctypes.data if k["emissive2"].shape[0] else None
+
+    def set_alpha_mips(self, alpha_mips):
+        """uint8 [layers][ALPHA_MIP_TEXELS] (assets.alpha_mip_pyramid): enables params.alpha_test in trace_primary / trace_shadow."""
+        a = np.ascontiguousarray(alpha_mips, dtype=np.uint8)
+        self._keep["alpha"] = a
+        self.scene.alpha_mips, self.scene.n_alpha_layers = a.ctypes.data, a.shape[0]
 
     @staticmethod
     def _stats(st):

@@ -66,6 +66,8 @@ typedef struct VxoScene {
     const float* normal_lod3;     // [n_normal_layers][64][64][4]
     int32_t n_normal_layers;
     const float* emissive_lod2;   // [n_emissive_layers][128][128]
+    const uint8_t* alpha_mips;    // [n_alpha_layers][VXPT_ALPHA_MIP_TEXELS]: albedo alpha, mip levels 0..8 (alpha-tested traversal)
+    int32_t n_alpha_layers;
 } VxoScene;
 
 typedef struct VxoStats {
@@ -196,6 +198,116 @@ float traverse_df(const Scene& S, v3 origin, v3 direction, int max_it, Hit& h, S
         if (!(h.block > 0)) { h.vox[0] = h.vox[1] = h.vox[2] = -1; }
     }
     return h.t;
+}
+
+// ---- alpha-tested traversal (u_ShouldAlphaTest) -------------------------------------------------------------------------
+// CalculateUV — InitialRayTraceFrag.glsl:470-512 / ShadowRayTraceFrag.glsl:333-386 on the normals the traversal forms: an exact
+// axis vector, or all zeros when the ray's sign on that axis is 0 (no branch matches and the shader returns an uninitialised
+// vec2; pinned to (0, 0)).
+struct AlphaCtx {
+    v3 cam_pos;      // u_InverseView[3].xyz
+    float g_K;       // 1 / (tan(radians(u_FOV) / (2 * u_Dimensions.x)) * 2)   (main(), :421 / :419)
+    float lod_bias;  // 0 in the primary shader (:202), 2 in the shadow shader (clamp(LOD - 2.0f, ...), :115)
+    bool flip_x;     // the primary shader flips both texture coordinates (:198-199), the shadow shader only y (:112)
+};
+inline float alpha_g_K(float fov_degrees, float width) {
+    const float radians = fov_degrees * 0.01745329251994329576923690768489f;  // glm::radians
+    return 1.0f / ((float)std::tan((double)(radians / (2.0f * width))) * 2.0f);
+}
+// StopRay — InitialRayTraceFrag.glsl:189-203, ShadowRayTraceFrag.glsl:105-117
+inline bool stop_ray(const Scene& S, const AlphaCtx& A, v3 P, int axis, int axis_sign, int block) {
+    const int id = std::min(std::max(block, 0), 127);  // GetBlockID: floor(b / 255 * 255) == b for every byte
+    if (S.s.materials[512 + id] == 0) return true;     // BlockTransparentData
+    float u = 0.0f, v = 0.0f;
+    if (axis_sign != 0) {
+        if (axis == 1) { u = fractf(P.x); v = fractf(P.z); }
+        else if (axis == 0) { u = fractf(P.z); v = fractf(P.y); }
+        else { u = fractf(P.x); v = fractf(P.y); }
+    }
+    v = 1.0f - v;
+    if (A.flip_x) u = 1.0f - u;
+    const float D = length(A.cam_pos - P);  // distance(P, u_InverseView[3].xyz)
+    const float l2 = (float)std::log2((double)(512.0f / (1.0f / D * A.g_K)));  // log2 pinned: correctly rounded fp32
+    // int(): toward zero; NaN / out-of-range (D == 0) pinned to 0
+    const int lod = (l2 > -2147483000.0f && l2 < 2147483000.0f) ? (int)l2 : 0;
+    const int level = (int)clampf((float)lod - A.lod_bias, 0.0f, 8.0f);
+    const int n = 512 >> level;
+    size_t off = 0;
+    for (int k = 0; k < level; ++k) off += (size_t)(512 >> k) * (512 >> k);
+    const int i = ((int)std::floor(u * (float)n)) & (n - 1), j = ((int)std::floor(v * (float)n)) & (n - 1);
+    int layer = S.s.materials[id];  // BlockAlbedoData; array layer = clamp(round(float(layer)), 0, layers - 1)
+    layer = std::min(std::max(layer, 0), S.s.n_alpha_layers - 1);
+    const float alpha = (float)S.s.alpha_mips[(size_t)layer * VXPT_ALPHA_MIP_TEXELS + off + (size_t)j * n + i] / 255.0f;
+    return alpha > 0.975f;
+}
+
+// the one-voxel DDA step of VoxelTraversalDF(_AlphaTest) (:271-291, repeated in the inner loop :240-251); ivec3(origin) truncates
+inline void dda_step(v3& origin, v3 direction, const int sg[3], int& min_idx) {
+    int g[3] = {(int)origin.x, (int)origin.y, (int)origin.z};
+    v3 w = V(origin.x - (float)g[0], origin.y - (float)g[1], origin.z - (float)g[2]);
+    const int half[3] = {(1 + sg[0]) >> 1, (1 + sg[1]) >> 1, (1 + sg[2]) >> 1};
+    v3 inv = V(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+    v3 f = V(((float)half[0] - w.x) * inv.x, ((float)half[1] - w.y) * inv.y, ((float)half[2] - w.z) * inv.z);
+    min_idx = (f.x < f.y && sg[0] != 0) ? ((f.x < f.z || sg[2] == 0) ? 0 : 2) : ((f.y < f.z || sg[2] == 0) ? 1 : 2);
+    g[min_idx] += sg[min_idx];
+    float fm = f[min_idx];
+    w = w + direction * fm;
+    w[min_idx] = (float)(1 - half[min_idx]);
+    origin = V((float)g[0] + w.x, (float)g[1] + w.y, (float)g[2] + w.z);
+    origin[min_idx] += (float)sg[min_idx] * 0.0001f;
+}
+
+// VoxelTraversalDF_AlphaTest — InitialRayTraceFrag.glsl:205-305 (cap u_RenderDistance), ShadowRayTraceFrag.glsl:119-220 (cap 350).
+// Restated as written, including what the author calls its "known artifacts" (Pipeline.cpp:836): after a transparent texel lets the
+// ray through and the four inner DDA steps find nothing to stop at, control falls into the `else` of `if (Euclidean == 1)` with
+// Euclidean == 0 and the ray moves BACK by one direction vector (:294-297).  Block fetches are counted per GetVoxel call.
+float traverse_df_alpha(const Scene& S, const AlphaCtx& A, v3 origin, v3 direction, int max_it, Hit& h, Stats& st) {
+    const v3 initial_origin = origin;
+    bool intersection = false;
+    int min_idx = 0;
+    const int sg[3] = {isign(direction.x), isign(direction.y), isign(direction.z)};
+    st.rays++;
+    h.sgn[0] = sg[0]; h.sgn[1] = sg[1]; h.sgn[2] = sg[2];
+    h.block = 0; h.vox[0] = h.vox[1] = h.vox[2] = -1;
+    h.normal = V(0.0f);
+    h.t = -1.0f;
+    auto finish = [&]() {  // :249-253 and :300-305
+        h.min_idx = min_idx;
+        h.normal = V(0.0f);
+        h.normal[min_idx] = (float)(-sg[min_idx]);
+        h.block = get_voxel_at(S, origin, st, h.vox);
+        h.t = h.block > 0 ? length(origin - initial_origin) : -1.0f;
+        if (!(h.block > 0)) { h.vox[0] = h.vox[1] = h.vox[2] = -1; }
+        return h.t;
+    };
+    for (int itr = 0; itr < max_it; ++itr) {
+        float fx = std::floor(origin.x), fy = std::floor(origin.y), fz = std::floor(origin.z);
+        if (!S.in_volume_f(fx, fy, fz)) { intersection = false; break; }
+        st.df++;
+        float dist = (float)S.s.df[S.idx((int)fx, (int)fy, (int)fz)];
+        int euclid = (int)std::floor(dist == 1.0f ? 1.0f : dist * 0.57735026918f);
+        if (euclid == 0) {
+            int bt = get_voxel_at(S, origin, st);
+            if (stop_ray(S, A, origin, min_idx, sg[min_idx], bt)) break;
+            for (int i = 0; i < 4; ++i) {
+                dda_step(origin, direction, sg, min_idx);
+                bt = get_voxel_at(S, origin, st);
+                if (bt > 0) {
+                    bt = get_voxel_at(S, origin, st);
+                    if (stop_ray(S, A, origin, min_idx, sg[min_idx], bt)) return finish();
+                }
+            }
+        }
+        if (euclid == 1) {
+            dda_step(origin, direction, sg, min_idx);
+            intersection = true;
+        } else {
+            origin = origin + (float)(euclid - 1) * direction;
+        }
+    }
+    h.min_idx = min_idx;
+    if (intersection) return finish();
+    return -1.0f;
 }
 
 // GetNormalID — InitialRayTraceFrag.glsl:143-185 : {+Z,-Z,+Y,-Y,-X,+X} -> 0..5
@@ -400,8 +512,9 @@ int vxo_plain_dda(const VxoScene* sc, const float o[3], const float d[3], int ma
 // InitialRayTraceFrag.glsl main() :417-468 with GetRayStuff :398-414.  SURVEY.md A.2.
 int vxo_trace_primary(const VxoScene* sc, const VxCamera* cam, const VxPrimaryParams* prm, const VxGBuffer* out, VxoStats* stats) {
     Scene S{*sc};
-    if (prm->alpha_test) return VXPT_E_UNSUPPORTED;
+    if (prm->alpha_test && (!sc->alpha_mips || !sc->materials)) return VXPT_E_STATE;
     const int W = cam->width, H = cam->height;
+    const AlphaCtx A{ray_origin(*cam), alpha_g_K(prm->fov_degrees, (float)W), 0.0f, true};
     uint64_t rays = 0, dfc = 0, voxc = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : rays, dfc, voxc)
     for (int j = cam->row_begin; j < cam->row_end; ++j) {
@@ -418,7 +531,8 @@ int vxo_trace_primary(const VxoScene* sc, const VxCamera* cam, const VxPrimaryPa
             v3 ro = ray_origin(*cam);
             v3 dir = normalize(rd);
             Hit h;
-            float t = traverse_df(S, ro, dir, prm->max_iterations, h, st);
+            float t = prm->alpha_test ? traverse_df_alpha(S, A, ro, dir, prm->max_iterations, h, st)
+                                      : traverse_df(S, ro, dir, prm->max_iterations, h, st);
             bool intersect = t > 0.0f && h.block > 0;
             size_t p = (size_t)j * W + i;
             if (out->t) out->t[p] = t;
@@ -440,8 +554,9 @@ int vxo_trace_primary(const VxoScene* sc, const VxCamera* cam, const VxPrimaryPa
 // ShadowRayTraceFrag.glsl main() :414-513.  SURVEY.md A.7.
 int vxo_trace_shadow(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g, const VxShadowParams* prm, const VxShadowOut* out, VxoStats* stats) {
     Scene S{*sc};
-    if (prm->alpha_test) return VXPT_E_UNSUPPORTED;
+    if (prm->alpha_test && (!sc->alpha_mips || !sc->materials)) return VXPT_E_STATE;
     const int W = cam->width, H = cam->height;
+    const AlphaCtx A{ray_origin(*cam), alpha_g_K(prm->fov_degrees, (float)W), 2.0f, false};
     uint64_t rays = 0, dfc = 0, voxc = 0;
     // per-frame blue-noise texel offset (:456-459): int products wrap like GLSL ints, the rest is fp32
     const int n = prm->frame % 1024;
@@ -495,7 +610,7 @@ int vxo_trace_shadow(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g
             float T = -1.0f;
             if (dist > 0.0f) {
                 Hit h;
-                T = traverse_df(S, o, dir, 350, h, st);
+                T = prm->alpha_test ? traverse_df_alpha(S, A, o, dir, 350, h, st) : traverse_df(S, o, dir, 350, h, st);
             }
             if (out->shadow) out->shadow[p] = (T > 0.0f || block_at > 0) ? 1 : 0;
             float tr = clampf(T / 100.0f, 0.00001f, 196.0f);

@@ -52,6 +52,8 @@ def worlds(plains_columns):
                 w = world.generate_gi_box(plains_columns)
             elif name == "city":
                 w = world.generate_city()
+            elif name == "orchard":
+                w = world.generate_orchard(plains_columns)
             elif name == "empty":
                 w = world.World()
             elif name == "sparse":

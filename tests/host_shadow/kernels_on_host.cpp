@@ -71,9 +71,8 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.sky = c->d_sky; S.shadow_noise = c->d_shadow_noise;
     S.n_layers = c->n_layers; S.n_emissive = c->n_emissive; S.sky_n = c->sky_n;
     S.counters = c->d_counters;
-#ifdef VXPT_HAVE_ALPHA
     S.alpha_mips = c->d_alpha_mips;
-#endif
+    S.n_alpha_layers = c->n_alpha_layers;
     return S;
 }
 // the wavefront GI pipeline needs a GPU (shared memory, ballots); the shadow runs the one-thread-per-pixel kernel
@@ -110,6 +109,8 @@ typedef struct HsScene {
     const float* normal_lod3;
     int32_t n_normal_layers;
     const float* emissive_lod2;
+    const uint8_t* alpha_mips;
+    int32_t n_alpha_layers;
 } HsScene;
 
 HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
@@ -145,6 +146,8 @@ HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
     c.d_sky = (float*)s->sky;
     if (s->sky) c.h_sky.assign(s->sky, s->sky + (size_t)6 * s->sky_n * s->sky_n * 3);
     c.d_shadow_noise = (uchar4*)s->shadow_noise;
+    c.d_alpha_mips = (uint8_t*)s->alpha_mips;
+    c.n_alpha_layers = s->n_alpha_layers;
     c.d_counters = &h->counters;
     return h;
 }

@@ -326,11 +326,10 @@ def test_error_codes(scene_tables, worlds):
         assert e.value.code == abi.E_STATE
         r.build_distance_field()
         r.trace_primary(cam, vx.primary_params(350), g)
-        pp = vx.primary_params(350)
-        pp.alpha_test = 1
+        pp = vx.primary_params(350, alpha_test=True)
         with pytest.raises(abi.VxptError) as e:
-            r.trace_primary(cam, pp, g)
-        assert e.value.code == abi.E_UNSUPPORTED
+            r.trace_primary(cam, pp, g)                                   # alpha test without vxpt_set_albedo_alpha_mips
+        assert e.value.code == abi.E_STATE
         bad = camera.FpsCamera().vx_camera(64, 36, 10, 40)
         with pytest.raises(abi.VxptError) as e:
             r.trace_primary(bad, vx.primary_params(350), g)

@@ -65,3 +65,31 @@ def test_reflection_kernel_equals_the_oracle(oracles, host_kernels, scene_tables
     for key in ref:
         assert np.array_equal(out[key], ref[key]), key
     assert st == st_ref
+
+
+def test_alpha_tested_kernels_equal_the_oracle(worlds, oracle_dfs, scene_tables):
+    """u_ShouldAlphaTest: primary and shadow kernels through VoxelTraversalDF_AlphaTest + StopRay on the orchard world."""
+    from oracle import vxo
+    from voxelpathtracer_b200 import assets
+    mats = scene_tables["materials"]
+    o = vxo.Oracle(worlds["orchard"].data, oracle_dfs["orchard"])
+    o.set_tables(mats, scene_tables["blue_noise"], scene_tables["sky"], scene_tables["shadow_noise"])
+    o.set_alpha_mips(assets.alpha_mip_pyramid(assets.synthetic_alpha_lod0(mats["albedo_lod3"].shape[0], [int(mats["table"][7])])))
+    for layout in (1, 0):
+        k = koh.HostKernels(o, layout)
+        W, H = 256, 144
+        cam = camera.FpsCamera(position=(192.0, 66.0, 192.0), pitch_deg=-8.0, yaw_deg=30.0 * layout).vx_camera(W, H)
+        pp = vx.primary_params(350, camera.taa_jitter(2), alpha_test=True, fov_degrees=60.0)
+        g_ref, st_ref = o.trace_primary(cam, pp)
+        plain, _ = o.trace_primary(cam, vx.primary_params(350, camera.taa_jitter(2)))
+        assert (plain["block_id"] != g_ref["block_id"]).sum() > 1000      # the alpha test does change what is hit
+        g, st = k.trace_primary(cam, pp)
+        for key in g_ref:
+            assert np.array_equal(g[key], g_ref[key], equal_nan=True), key
+        assert st == st_ref
+        sp = vx.shadow_params(scene_tables["stronger"], frame=5, soft=True, alpha_test=True, fov_degrees=60.0)
+        s_ref, st_ref = o.trace_shadow(cam, g_ref, sp)
+        s, st = k.trace_shadow(cam, g_ref, sp)
+        assert np.array_equal(s["shadow"], s_ref["shadow"]) and np.array_equal(s["transversal"], s_ref["transversal"])
+        assert st == st_ref
+        k.close()

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libvxpt.so")
 WORLD_SIZE_X, WORLD_SIZE_Y, WORLD_SIZE_Z = 384, 128, 384
 WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z
 NORMAL_MISS = 10
+ALPHA_MIP_TEXELS = sum((512 >> k) ** 2 for k in range(9))  # 349,524: levels 0..8 of a 512^2 layer (VXPT_ALPHA_MIP_TEXELS)
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS, OPT_TIMING_EVENTS, OPT_TEXEL_FORMAT = 1, 2, 3, 4, 5, 6
@@ -32,7 +33,7 @@ class VxCamera(C.Structure):
 
 class VxPrimaryParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("jitter_enable", C.c_int32), ("jitter", C.c_float * 2), ("alpha_test", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("fov_degrees", C.c_float)]
 
 
 class VxGBuffer(C.Structure):
@@ -40,7 +41,8 @@ class VxGBuffer(C.Structure):
 
 
 class VxShadowParams(C.Structure):
-    _fields_ = [("light_dir", C.c_float * 3), ("frame", C.c_int32), ("soft", C.c_int32), ("halton", C.c_float * 2), ("alpha_test", C.c_int32)]
+    _fields_ = [("light_dir", C.c_float * 3), ("frame", C.c_int32), ("soft", C.c_int32), ("halton", C.c_float * 2), ("alpha_test", C.c_int32),
+                ("fov_degrees", C.c_float)]
 
 
 class VxShadowOut(C.Structure):
@@ -104,6 +106,7 @@ EXPORTS = {
     "vxpt_set_blue_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxpt_set_material_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "vxpt_set_reflection_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "vxpt_set_albedo_alpha_mips": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vxpt_set_sky_cubemap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vxpt_set_shadow_noise": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxpt_trace_primary": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxPrimaryParams), C.POINTER(VxGBuffer)]),

@@ -72,6 +72,36 @@ def constant_materials(n_blocks=128):
             "grass_props": np.zeros(10, np.int32), "normal_lod3": normal, "emissive_lod2": np.zeros((0, 128, 128), np.float32)}
 
 
+def alpha_mip_pyramid(alpha_lod0):
+    """uint8 [L][512][512] level-0 alpha -> uint8 [L][ALPHA_MIP_TEXELS]: levels 0..8 back to back, each level the 2x2 box filter
+    of the one above rounded to nearest (ties away from zero, like most GL drivers' glGenerateMipmap on unorm8).  GL leaves the
+    filter to the driver; whatever pyramid the host's driver produced is what it hands to vxpt_set_albedo_alpha_mips."""
+    a = np.ascontiguousarray(alpha_lod0, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[1:] == (512, 512), a.shape
+    levels, cur = [a.reshape(a.shape[0], -1)], a.astype(np.uint16)
+    for _ in range(8):
+        cur = (cur[:, 0::2, 0::2] + cur[:, 1::2, 0::2] + cur[:, 0::2, 1::2] + cur[:, 1::2, 1::2] + 2) >> 2
+        levels.append(cur.astype(np.uint8).reshape(a.shape[0], -1))
+    return np.ascontiguousarray(np.concatenate(levels, axis=1))
+
+
+def synthetic_alpha_lod0(n_layers, cutout_layers, seed=11):
+    """Level-0 alpha for tests: opaque (255) everywhere except `cutout_layers`, which get a leaf-like cut-out pattern
+    (blobs of alpha 0 covering about 40 % of the tile) so that the alpha test passes some texels and stops others."""
+    a = np.full((n_layers, 512, 512), 255, np.uint8)
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:512, 0:512]
+    for layer in cutout_layers:
+        hole = np.zeros((512, 512), bool)
+        for _ in range(60):
+            cx, cy, r = rng.randint(0, 512), rng.randint(0, 512), rng.randint(12, 44)
+            dx = np.minimum(np.abs(xx - cx), 512 - np.abs(xx - cx))   # toroidal: the array wraps with GL_REPEAT
+            dy = np.minimum(np.abs(yy - cy), 512 - np.abs(yy - cy))
+            hole |= dx * dx + dy * dy < r * r
+        a[layer][hole] = 0
+    return a
+
+
 def analytic_sky(n=16, sun_dir=(-0.669, 0.468, 0.577)):
     """Documented stand-in for the reference's rendered atmosphere cubemap (RGB16F, 16^2 for GI; Pipeline.cpp:1392-1394):
     a horizon-to-zenith gradient plus a broad sun lobe.  Faces +X,-X,+Y,-Y,+Z,-Z, GL cube-map face orientation,

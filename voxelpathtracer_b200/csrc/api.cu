@@ -48,6 +48,8 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.n_emissive = c->n_emissive;
     S.sky_n = c->sky_n;
     S.counters = c->d_counters;
+    S.alpha_mips = c->d_alpha_mips;
+    S.n_alpha_layers = c->n_alpha_layers;
     return S;
 }
 
@@ -179,13 +181,21 @@ static int check_ready(vxpt_ctx* c) {
     return VXPT_OK;
 }
 
-static int check_primary(const VxPrimaryParams* p) {
-    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested traversal is outside the v1 parity profile (off by default in the reference)");
+// u_ShouldAlphaTest: StopRay reads BlockTransparentData / BlockAlbedoData and the albedo array's alpha mip chain
+static int check_alpha(const vxpt_ctx* c, float fov_degrees) {
+    if (!c->have_materials || !c->d_alpha_mips) return fail(VXPT_E_STATE, "alpha_test needs vxpt_set_materials and vxpt_set_albedo_alpha_mips");
+    if (!(fov_degrees > 0.0f && fov_degrees < 180.0f)) return fail(VXPT_E_INVALID, "alpha_test needs fov_degrees in (0, 180)");
+    return VXPT_OK;
+}
+static int check_primary(const vxpt_ctx* c, const VxPrimaryParams* p) {
+    if (p->alpha_test)
+        if (int rc = check_alpha(c, p->fov_degrees)) return rc;
     if (p->max_iterations < 0) return fail(VXPT_E_INVALID, "max_iterations < 0");
     return VXPT_OK;
 }
 static int check_shadow(const vxpt_ctx* c, const VxShadowParams* p) {
-    if (p->alpha_test) return fail(VXPT_E_UNSUPPORTED, "alpha-tested shadows are outside the v1 parity profile");
+    if (p->alpha_test)
+        if (int rc = check_alpha(c, p->fov_degrees)) return rc;
     if (p->soft && !c->have_shadow_noise) return fail(VXPT_E_STATE, "soft shadows need vxpt_set_shadow_noise");
     return VXPT_OK;
 }
@@ -314,7 +324,7 @@ int vxpt_destroy(vxpt_handle c) {
         if (c->rep_steps[r]) cudaFree(c->rep_steps[r]);
     }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
-                    c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_counters, c->d_stage, c->d_queue};
+                    c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_alpha_mips, c->d_counters, c->d_stage, c->d_queue};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -522,13 +532,24 @@ int vxpt_set_shadow_noise(vxpt_handle c, const uint8_t* rgba8) {
     return VXPT_OK;
 }
 
+int vxpt_set_albedo_alpha_mips(vxpt_handle c, const uint8_t* alpha_mips, int n_layers) {
+    if (!c || !alpha_mips) return fail(VXPT_E_INVALID, "NULL argument");
+    if (n_layers <= 0 || n_layers > 4096) return fail(VXPT_E_INVALID, "bad layer count");
+    VX_CUDA(cudaSetDevice(c->device));
+    if (int rc = finish_pending_frame(c)) return rc;
+    int rc = replace_buffer(c, &c->d_alpha_mips, alpha_mips, (size_t)n_layers * VXPT_ALPHA_MIP_TEXELS);
+    if (rc) return rc;
+    c->n_alpha_layers = n_layers;
+    return VXPT_OK;
+}
+
 // ----------------------------------------------------------------------------------------------------- passes
 int vxpt_trace_primary(vxpt_handle c, const VxCamera* cam, const VxPrimaryParams* p, const VxGBuffer* out) {
     int rc = check_ready(c);
     if (rc) return rc;
     if ((rc = check_camera(cam))) return rc;
     if (!p || !out) return fail(VXPT_E_INVALID, "NULL argument");
-    if ((rc = check_primary(p))) return rc;
+    if ((rc = check_primary(c, p))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
     PassIO io(c, cam);
     Plane t, nid, bid, it, hv;
@@ -648,7 +669,7 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     if (rc) return rc;
     if ((rc = check_camera(cam))) return rc;
     if (!p || !out || !p->primary) return fail(VXPT_E_INVALID, "NULL argument (primary parameters are required)");
-    if ((rc = check_primary(p->primary))) return rc;
+    if ((rc = check_primary(c, p->primary))) return rc;
     if (p->shadow && (rc = check_shadow(c, p->shadow))) return rc;
     if (p->diffuse && (rc = check_diffuse(c, p->diffuse))) return rc;
     if (p->reflection) {

@@ -12,8 +12,9 @@ namespace vxpt {
 struct PrimaryDev {
     int max_iterations, jitter_enable;
     float jx, jy;
+    AlphaDev alpha;  // read by the ALPHA instantiation only (u_ShouldAlphaTest)
 };
-template <int LAYOUT>
+template <int LAYOUT, bool ALPHA>
 __global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
                                                       const GBufferDev out) {
     int i, j, prow;
@@ -28,7 +29,8 @@ __global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __
         }
         const V3 dir = normalize3(ray_direction_at(cam, u, v));
         TraceHit h;
-        const float t = traverse_df<LAYOUT>(S, ray_origin(cam), dir, p.max_iterations, h, cnt);
+        const float t = ALPHA ? traverse_df_alpha<LAYOUT>(S, p.alpha, ray_origin(cam), dir, p.max_iterations, h, cnt)
+                              : traverse_df<LAYOUT>(S, ray_origin(cam), dir, p.max_iterations, h, cnt);
         const bool intersect = t > 0.0f && h.block > 0;
         const size_t px = (size_t)prow * cam.width + i;
         if (out.t) store_f1(out.t, px, t, out.fmt);
@@ -50,6 +52,7 @@ struct ShadowDev {
     int soft;
     int ioffx, ioffy;  // floor(off) of the per-frame blue-noise texel offset (:456-459), computed on the host in fp32
     float hx, hy;      // u_Halton
+    AlphaDev alpha;    // read by the ALPHA instantiation only (u_ShouldAlphaTest = ShouldAlphaTestShadows)
 };
 struct ShadowOutDev {
     uint8_t* shadow;
@@ -57,7 +60,7 @@ struct ShadowOutDev {
     int fmt;
 };
 
-template <int LAYOUT>
+template <int LAYOUT, bool ALPHA>
 __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const ShadowDev p,
                                                      const GBufferDev g, const ShadowOutDev out) {
     int i, j, prow;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __g
                 float T = -1.0f;
                 if (dist > 0.0f) {
                     TraceHit h;
-                    T = traverse_df<LAYOUT>(S, o, dir, 350, h, cnt);
+                    T = ALPHA ? traverse_df_alpha<LAYOUT>(S, p.alpha, o, dir, 350, h, cnt) : traverse_df<LAYOUT>(S, o, dir, 350, h, cnt);
                 }
                 o_shadow = (T > 0.0f || block_at > 0) ? 1 : 0;
                 o_trans = clampf(T / 100.0f, 0.00001f, 196.0f);
@@ -275,12 +278,26 @@ static CameraDev to_dev(const VxCamera& cam) {
 static dim3 pixel_grid(const VxCamera& cam) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8); }
 static GBufferDev to_dev(const vxpt_ctx* c, const VxGBuffer& g) { return GBufferDev{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel}; }
 
+// g_K of the alpha test's LOD (InitialRayTraceFrag.glsl:421, ShadowRayTraceFrag.glsl:419), fp32 with the pinned tan
+static AlphaDev alpha_dev(const VxCamera& cam, float fov_degrees, float lod_bias, int flip_x) {
+    AlphaDev a;
+    a.cam = V3{cam.inv_view[12], cam.inv_view[13], cam.inv_view[14]};
+    const float radians = fov_degrees * 0.01745329251994329576923690768489f;  // glm::radians
+    a.g_K = 1.0f / ((float)tan((double)(radians / (2.0f * (float)cam.width))) * 2.0f);
+    a.lod_bias = lod_bias;
+    a.flip_x = flip_x;
+    return a;
+}
+
 int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out) {
     const SceneDev S = make_scene(c);
-    const PrimaryDev pd{p.max_iterations, p.jitter_enable, p.jitter[0], p.jitter[1]};
+    const PrimaryDev pd{p.max_iterations, p.jitter_enable, p.jitter[0], p.jitter[1], alpha_dev(cam, p.fov_degrees, 0.0f, 1)};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
-    else VX_LAUNCH((primary_kernel<0>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+    if (p.alpha_test) {
+        if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1, true>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+        else VX_LAUNCH((primary_kernel<0, true>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+    } else if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1, false>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+    else VX_LAUNCH((primary_kernel<0, false>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -301,10 +318,14 @@ int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const Vx
     sd.ioffy = (int)floorf(offy);
     sd.hx = p.halton[0];
     sd.hy = p.halton[1];
+    sd.alpha = alpha_dev(cam, p.fov_degrees, 2.0f, 0);
     const ShadowOutDev od{out.shadow, out.transversal, c->opt_texel};
     const dim3 grid = pixel_grid(cam);
-    if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
-    else VX_LAUNCH((shadow_kernel<0>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+    if (p.alpha_test) {
+        if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1, true>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+        else VX_LAUNCH((shadow_kernel<0, true>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+    } else if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1, false>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+    else VX_LAUNCH((shadow_kernel<0, false>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

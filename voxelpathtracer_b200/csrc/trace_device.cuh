@@ -187,6 +187,22 @@ __device__ __forceinline__ void trav_init(TravState& t, const V3 origin, const V
     t.n = 0; t.max_it = max_it; t.stepped = 0; t.min_idx = 0;
 }
 
+// the one-voxel DDA step of VoxelTraversalDF (:340-356); gx, gy, gz = float(ivec3(origin))
+__device__ __forceinline__ void dda_advance(TravState& t, const float gx, const float gy, const float gz) {
+    const float wx = t.ox - gx, wy = t.oy - gy, wz = t.oz - gz;
+    const float dfx = (t.hx - wx) * t.ivx, dfy = (t.hy - wy) * t.ivy, dfz = (t.hz - wz) * t.ivz;
+    const bool p = dfx < dfy && t.sx != 0;
+    const float c = p ? dfx : dfy;
+    const bool q = c < dfz || t.sz == 0;
+    const float fm = q ? c : dfz;
+    t.min_idx = q ? (p ? 0 : 1) : 2;
+    const float ax = gx + (wx + t.dx * fm), ay = gy + (wy + t.dy * fm), az = gz + (wz + t.dz * fm);
+    const float sxp = (gx + t.kx) + t.nx, syp = (gy + t.ky) + t.ny, szp = (gz + t.kz) + t.nz;
+    t.ox = (q && p) ? sxp : ax;
+    t.oy = (q && !p) ? syp : ay;
+    t.oz = q ? az : szp;
+}
+
 // one loop iteration; returns true when the loop has ended (cap reached, left the volume, or E == 0)
 template <int LAYOUT>
 __device__ __forceinline__ bool trav_step(const SceneDev& S, TravState& t) {
@@ -205,19 +221,7 @@ __device__ __forceinline__ bool trav_step(const SceneDev& S, TravState& t) {
     }
     if (euclid == 0) return true;
     // euclid == 1: one DDA step.  in-volume => origin >= 0, so ivec3(origin) (truncation) == Loc
-    const float gx = biased_to_float(bx), gy = biased_to_float(by), gz = biased_to_float(bz);
-    const float wx = t.ox - gx, wy = t.oy - gy, wz = t.oz - gz;
-    const float dfx = (t.hx - wx) * t.ivx, dfy = (t.hy - wy) * t.ivy, dfz = (t.hz - wz) * t.ivz;
-    const bool p = dfx < dfy && t.sx != 0;
-    const float c = p ? dfx : dfy;
-    const bool q = c < dfz || t.sz == 0;
-    const float fm = q ? c : dfz;
-    t.min_idx = q ? (p ? 0 : 1) : 2;
-    const float ax = gx + (wx + t.dx * fm), ay = gy + (wy + t.dy * fm), az = gz + (wz + t.dz * fm);
-    const float sxp = (gx + t.kx) + t.nx, syp = (gy + t.ky) + t.ny, szp = (gz + t.kz) + t.nz;
-    t.ox = (q && p) ? sxp : ax;
-    t.oy = (q && !p) ? syp : ay;
-    t.oz = q ? az : szp;
+    dda_advance(t, biased_to_float(bx), biased_to_float(by), biased_to_float(bz));
     t.stepped = 1;
     return false;
 }
@@ -244,6 +248,89 @@ __device__ __forceinline__ float traverse_df(const SceneDev& S, const V3 origin,
     trav_init(t, origin, dir, max_it);
     cnt.rays++;
     while (!trav_step<LAYOUT>(S, t)) {}
+    return trav_finish(S, t, origin, h, cnt);
+}
+
+
+// ---- alpha-tested traversal (u_ShouldAlphaTest; off by default, Core/Pipeline.cpp:141-142) --------------------------------------
+struct AlphaDev {
+    V3 cam;          // u_InverseView[3].xyz
+    float g_K;       // 1 / (tan(radians(u_FOV) / (2 * u_Dimensions.x)) * 2), main() :421 (primary) / :419 (shadow); host-computed
+    float lod_bias;  // 0 in the primary shader, 2 in the shadow shader (clamp(LOD - 2.0f, 0, 8), ShadowRayTraceFrag.glsl:115)
+    int flip_x;      // the primary shader flips both texture coordinates (:198-199), the shadow shader only y (:112)
+};
+// StopRay — InitialRayTraceFrag.glsl:189-203, ShadowRayTraceFrag.glsl:105-117.  textureLod with the integer LOD reads the nearest texel
+// of exactly that level of the albedo array's alpha (vxpt_set_albedo_alpha_mips); level k starts at (4^10 - 4^(10-k)) / 3 in a layer.
+__device__ __forceinline__ bool stop_ray(const SceneDev& S, const AlphaDev& A, const V3 P, const int axis, const int axis_sign, const int block) {
+    const int id = min(max(block, 0), 127);         // GetBlockID
+    if (S.materials[512 + id] == 0) return true;    // BlockTransparentData
+    float u = 0.0f, v = 0.0f;                       // CalculateUV; a zero normal matches no branch (pinned: uv = 0)
+    if (axis_sign != 0) {
+        if (axis == 1) { u = fractf(P.x); v = fractf(P.z); }
+        else if (axis == 0) { u = fractf(P.z); v = fractf(P.y); }
+        else { u = fractf(P.x); v = fractf(P.y); }
+    }
+    v = 1.0f - v;
+    if (A.flip_x) u = 1.0f - u;
+    const float D = length3(A.cam - P);
+    const float l2 = (float)log2((double)(512.0f / (1.0f / D * A.g_K)));  // pinned: correctly rounded fp32
+    const int lod = (l2 > -2147483000.0f && l2 < 2147483000.0f) ? (int)l2 : 0;
+    const int level = (int)clampf((float)lod - A.lod_bias, 0.0f, 8.0f);
+    const int n = 512 >> level;
+    const unsigned off = (1048576u - (1048576u >> (2 * level))) / 3u;
+    const int i = ((int)floorf(u * (float)n)) & (n - 1), j = ((int)floorf(v * (float)n)) & (n - 1);
+    const int layer = min(max(S.materials[id], 0), S.n_alpha_layers - 1);  // BlockAlbedoData
+    const float alpha = (float)S.alpha_mips[(size_t)layer * VXPT_ALPHA_MIP_TEXELS + off + (unsigned)(j * n + i)] / 255.0f;
+    return alpha > 0.975f;
+}
+
+// VoxelTraversalDF_AlphaTest — InitialRayTraceFrag.glsl:205-305 (cap u_RenderDistance), ShadowRayTraceFrag.glsl:119-220 (cap 350).
+// As written, "known artifacts" (Pipeline.cpp:836) included: when a cut-out texel lets the ray through and the four inner DDA steps
+// find nothing that stops it, control falls into the else of `if (Euclidean == 1)` with Euclidean == 0 and the ray moves back by one
+// direction vector (:294-297).  The inner steps truncate (ivec3(origin)) and run without a bounds test, exactly like the shader.
+// Block fetches are counted per GetVoxel call of the shader (the value is of course fetched once).
+template <int LAYOUT>
+__device__ __forceinline__ float traverse_df_alpha(const SceneDev& S, const AlphaDev& A, const V3 origin, const V3 dir, const int max_it,
+                                                   TraceHit& h, Counters& cnt) {
+    TravState t;
+    trav_init(t, origin, dir, max_it);
+    cnt.rays++;
+    bool early = false;
+    while (t.n < t.max_it) {
+        const float bx = floor_biased(t.ox), by = floor_biased(t.oy), bz = floor_biased(t.oz);
+        const int lx = biased_to_int(bx), ly = biased_to_int(by), lz = biased_to_int(bz);
+        if (!in_volume_i(lx, ly, lz)) break;
+        ++t.n;
+        const int euclid = fetch_step<LAYOUT>(S, lx, ly, lz);
+        if (euclid == 0) {
+            int bt = get_voxel_at(S, mk3(t.ox, t.oy, t.oz), cnt);
+            int sg = (t.min_idx == 0) ? t.sx : ((t.min_idx == 1) ? t.sy : t.sz);
+            if (stop_ray(S, A, mk3(t.ox, t.oy, t.oz), t.min_idx, sg, bt)) break;
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                dda_advance(t, truncf(t.ox), truncf(t.oy), truncf(t.oz));
+                bt = get_voxel_at(S, mk3(t.ox, t.oy, t.oz), cnt);
+                if (bt > 0) {
+                    cnt.vox++;  // the shader fetches the voxel a second time (:247)
+                    sg = (t.min_idx == 0) ? t.sx : ((t.min_idx == 1) ? t.sy : t.sz);
+                    if (stop_ray(S, A, mk3(t.ox, t.oy, t.oz), t.min_idx, sg, bt)) { early = true; break; }
+                }
+            }
+            if (early) break;
+            t.ox = t.ox + -1.0f * t.dx;  // origin += int(Euclidean - 1) * direction with Euclidean == 0
+            t.oy = t.oy + -1.0f * t.dy;
+            t.oz = t.oz + -1.0f * t.dz;
+        } else if (euclid == 1) {
+            dda_advance(t, biased_to_float(bx), biased_to_float(by), biased_to_float(bz));
+            t.stepped = 1;
+        } else {
+            const float k = (float)(euclid - 1);
+            t.ox = t.ox + k * t.dx;
+            t.oy = t.oy + k * t.dy;
+            t.oz = t.oz + k * t.dz;
+        }
+    }
+    if (early) t.stepped = 1;  // :249-253 returns through the same three statements as :300-305
     return trav_finish(S, t, origin, h, cnt);
 }
 

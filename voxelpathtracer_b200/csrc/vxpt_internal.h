@@ -52,6 +52,8 @@ struct SceneDev {
     const uchar4* shadow_noise;  // [256][256]
     int n_layers, n_emissive, sky_n;
     DeviceCounters* counters;
+    const uint8_t* alpha_mips;  // [n_alpha_layers][VXPT_ALPHA_MIP_TEXELS] albedo alpha, mip levels 0..8 (alpha-tested traversal)
+    int n_alpha_layers;
 };
 
 }  // namespace vxpt
@@ -83,6 +85,8 @@ struct vxpt_ctx {
     std::vector<float> h_sky;  // host copy of the cubemap (per-frame sun / moon colours of the reflection pass)
     float* d_sky = nullptr;
     uchar4* d_shadow_noise = nullptr;
+    uint8_t* d_alpha_mips = nullptr;
+    int n_alpha_layers = 0;
     int n_layers = 0, n_emissive = 0, sky_n = 0;
     bool have_materials = false, have_bluenoise = false, have_textures = false, have_sky = false, have_shadow_noise = false;
 

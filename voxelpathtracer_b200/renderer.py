@@ -32,17 +32,19 @@ def _ptr(buf):
     raise TypeError(f"unsupported buffer type {type(buf)}")
 
 
-def primary_params(max_iterations=350, jitter=None):
+def primary_params(max_iterations=350, jitter=None, alpha_test=False, fov_degrees=60.0):
     p = VxPrimaryParams()
     p.max_iterations = max_iterations
+    p.alpha_test, p.fov_degrees = int(bool(alpha_test)), float(fov_degrees)
     p.jitter_enable = 0 if jitter is None else 1
     if jitter is not None:
         p.jitter[0], p.jitter[1] = float(jitter[0]), float(jitter[1])
     return p
 
 
-def shadow_params(light_dir, frame=0, soft=True, halton=(0.0, 0.0)):
+def shadow_params(light_dir, frame=0, soft=True, halton=(0.0, 0.0), alpha_test=False, fov_degrees=60.0):
     p = VxShadowParams()
+    p.alpha_test, p.fov_degrees = int(bool(alpha_test)), float(fov_degrees)
     p.light_dir[:] = [float(v) for v in light_dir]
     p.frame, p.soft = int(frame), int(bool(soft))
     p.halton[0], p.halton[1] = float(halton[0]), float(halton[1])
@@ -149,6 +151,12 @@ class Renderer:
         e = np.ascontiguousarray(emissive_lod2, dtype=np.float32)
         assert n.shape[1:] == (64, 64, 4) and (e.shape[0] == 0 or e.shape[1:] == (128, 128))
         check(self.lib.vxpt_set_reflection_textures(self.handle, _ptr(n), int(n.shape[0]), _ptr(e) if e.shape[0] else None, int(e.shape[0])))
+
+    def set_albedo_alpha_mips(self, alpha_mips):
+        """uint8 [n_layers][ALPHA_MIP_TEXELS]: alpha of the albedo array's mip levels 0..8 (see assets.alpha_mip_pyramid)."""
+        a = np.ascontiguousarray(alpha_mips, dtype=np.uint8)
+        assert a.ndim == 2 and a.shape[1] == abi.ALPHA_MIP_TEXELS, a.shape
+        abi.check(self.lib.vxpt_set_albedo_alpha_mips(self.h, a.ctypes.data, a.shape[0]))
 
     def set_sky_cubemap(self, rgb):
         s = np.ascontiguousarray(rgb, dtype=np.float32)

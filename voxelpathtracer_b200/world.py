@@ -114,6 +114,27 @@ def generate_gi_box(columns, seed=1234, rooms=40):
     return w
 
 
+def generate_orchard(columns, seed=77, trees=260):
+    """Plains with trees (plank trunks, canopies of the Transparent leaves block) placed by a fixed LCG: the scene of the
+    alpha-tested traversal tests (u_ShouldAlphaTest: rays pass the cut-out texels of Transparent blocks)."""
+    w = generate_plains(columns)
+    v = w.zyx
+    cols = np.asarray(columns, dtype=np.uint8).reshape(WORLD_SIZE_X, WORLD_SIZE_Z, 2)
+    rnd = _lcg(seed)
+    for _ in range(trees):
+        x = 8 + next(rnd) % (WORLD_SIZE_X - 16)
+        z = 8 + next(rnd) % (WORLD_SIZE_Z - 16)
+        h = int(cols[x, z, 0])
+        trunk = 4 + next(rnd) % 4
+        r = 2 + next(rnd) % 2
+        top = h + trunk
+        canopy = v[z - r:z + r + 1, top - 2:top + 2, x - r:x + r + 1]
+        canopy[canopy == 0] = LEAVES
+        v[z - 1:z + 2, top + 2, x - 1:x + 2][v[z - 1:z + 2, top + 2, x - 1:x + 2] == 0] = LEAVES
+        v[z, h:top, x] = PLANKS
+    return w
+
+
 def generate_city(seed=99):
     """Stand-in for the missing 'Medival' Minecraft import: a dense deterministic grid of towers, arches and
     interiors up to y = 120 (fill ratio >= 25 %)."""

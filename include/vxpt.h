@@ -237,6 +237,21 @@ VXPT_API int vxpt_trace_diffuse(vxpt_handle h, const VxCamera* cam, const VxGBuf
 VXPT_API int vxpt_trace_reflection(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf,
                                    const VxReflectionIn* in, const VxReflectionParams* p, const VxReflectionOut* out);
 
+/* ---- the other consumers of the distance field -----------------------------------------------------------
+ * vxpt_trace_rays: a batch of n VoxelTraversalDF calls (InitialRayTraceFrag.glsl:307-374) on caller-supplied rays; directions are
+ * used as given (the shaders pass normalised ones).  origins / directions: 3 n floats; outputs (each may be NULL, host or device):
+ * t[n] (-1 on a miss), normal_id[n] (0..5, VXPT_NORMAL_MISS), block_id[n], hit_voxel[3 n].
+ * vxpt_player_shadowed: Core/Shaders/PostProcessingVert.glsl:46-53 (u_ComputePlayerShadow): one ray from the camera along
+ * u_VertSunDir / length(u_VertSunDir), cap 350; *shadowed = v_PlayerShadowed = (T > 0).
+ * vxpt_estimate_ambient_sound: Core/Shaders/EstimateAmbientSoundLevel.comp as dispatched by Core/Pipeline.cpp:1908-1921
+ * (32 invocations): *sky_level_aggregate = SkyLevelAggregate (0..32*512); per_invocation[32] (optional) = each invocation's
+ * addend, index = gl_GlobalInvocationID.y * 8 + .x.  The host folds the aggregate into the sound volume (Pipeline.cpp:1937-1946). */
+VXPT_API int vxpt_trace_rays(vxpt_handle h, const float* origins, const float* directions, int n, int max_iterations, float* t,
+                             uint8_t* normal_id, uint8_t* block_id, int16_t* hit_voxel);
+VXPT_API int vxpt_player_shadowed(vxpt_handle h, const float camera_pos[3], const float sun_dir[3], int* shadowed);
+VXPT_API int vxpt_estimate_ambient_sound(vxpt_handle h, const float player_pos[3], int frame, uint32_t* sky_level_aggregate,
+                                         uint32_t* per_invocation /* 32 or NULL */);
+
 /* ---- one frame of the path: the pass sequence of Core/Pipeline.cpp's render loop (:1973-2016 primary, :2795-2852 shadow,
  *      :2174-2281 diffuse GI, :3003-3164 reflections) on the rows of `cam` -------------------------------------------------
  * Equivalent to vxpt_trace_primary + vxpt_trace_shadow + vxpt_trace_diffuse (+ vxpt_trace_reflection) with the same arguments,

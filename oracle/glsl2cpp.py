@@ -97,10 +97,17 @@ def translate(src, ns):
                 mm = re.match(r"\s*(\w+)\s+(\w+)\s*\[([^\]]*)\]\s*;", lines[k])
                 if mm:
                     members.append((mm.group(1), mm.group(2), mm.group(3).strip() or "1"))
+                else:
+                    mm = re.match(r"\s*(\w+)\s+(\w+)\s*;", lines[k])   # scalar member (uint SkyLevelAggregate;)
+                    if mm:
+                        members.append((mm.group(1), mm.group(2), None))
                 k += 1
             k += 1
             types = {t for t, _, _ in members}
-            if len(types) == 1:
+            if any(n is None for _, _, n in members):
+                for t, name, n in members:
+                    out.append(f"static {t} {name};" if n is None else f"static {t} {name}[({n}) + 64];")
+            elif len(types) == 1:
                 t = members[0][0]
                 total = " + ".join(f"({n})" for _, _, n in members)
                 out.append(f"static {t} {block}_storage[{total} + 4096];")
@@ -143,7 +150,10 @@ def translate(src, ns):
     # r-value swizzles glm does not provide as members:  <postfix-expression>.xyz  ->  swz_xyz(<postfix-expression>)
     s = rewrite_swizzles(s)
     # transcendental functions: pinned definitions (glsl_compat.h)
-    s = re.sub(r"\b(sin|cos|tan|pow|mix|log2)\s*\(", r"pinned_\1(", s)
+    s = re.sub(r"\b(sin|cos|tan|pow|mix|log2|acos)\s*\(", r"pinned_\1(", s)
+    # GLSL evaluates function arguments left to right (spec 6.1.1); C++ leaves the order of constructor arguments open (g++: right to
+    # left).  Constructor calls whose arguments advance the hash RNG are brace-initialised, which C++ orders left to right.
+    s = re.sub(r"\bvec2\s*\(\s*(Hash1?\(\))\s*,\s*(Hash1?\(\))\s*\)", r"vec2{\1, \2}", s)
     # entry point
     s = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", s)
     # GLSL re-initialises global variables for every shader invocation: collect the initialised, mutable globals (brace depth 0)

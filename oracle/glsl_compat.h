@@ -65,6 +65,7 @@ inline float pinned_cos(float x) { return (float)::cos((double)x); }
 inline float pinned_tan(float x) { return (float)::tan((double)x); }
 inline float pinned_pow(float x, float y) { return (float)::pow((double)x, (double)y); }
 inline float pinned_log2(float x) { return (float)::log2((double)x); }
+inline float pinned_acos(float x) { return (float)::acos((double)x); }
 template <class V> inline V pinned_sin(const V& v) { return glm::sin(v); }
 template <class V> inline V pinned_cos(const V& v) { return glm::cos(v); }
 template <class V> inline V pinned_tan(const V& v) { return glm::tan(v); }
@@ -186,6 +187,9 @@ inline uvec4 texture(const usampler3D&, const vec3&) { return uvec4(0u); }
 inline uvec4 texelFetch(const usampler3D&, const ivec3&, int) { return uvec4(0u); }
 inline vec4 texture(const sampler3D&, const vec3&) { return vec4(0.0f); }
 inline uint clamp(uint x, int lo, int hi) { return x < (uint)lo ? (uint)lo : (x > (uint)hi ? (uint)hi : x); }
+
+// SSBO atomics: the drivers run the invocations of such shaders one after another
+inline uint atomicAdd(uint& mem, uint v) { const uint old = mem; mem += v; return old; }
 
 static thread_local uvec3 gl_GlobalInvocationID;
 static thread_local vec4 gl_FragCoord;  // per invocation: the driver's OpenMP threads each run whole invocations

@@ -55,6 +55,8 @@ def load():
         lib.ref_trace_shadow_alpha.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
                                                C.c_void_p, C.c_void_p]
+        lib.ref_ambient_sound.restype = C.c_int
+        lib.ref_ambient_sound.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
         lib.ref_trace_shadow.restype = C.c_int
         lib.ref_trace_shadow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -194,3 +196,13 @@ def trace_reflection(blocks, df, cam, gbuf, diffuse, params, g_normal, g_pbr, ma
     load().ref_trace_reflection(C.byref(a))
     out["emissive_mask"] = (out["emissive_mask"] > 0.5).astype(np.uint8)
     return out
+
+
+def ambient_sound(df, player_pos, frame):
+    """EstimateAmbientSoundLevel.comp over the 8 x 4 invocations of Core/Pipeline.cpp:1921: (SkyLevelAggregate, per-invocation addends[32])."""
+    df = np.ascontiguousarray(df, dtype=np.uint8).reshape(-1)
+    p = np.array([float(v) for v in player_pos], dtype=np.float32)
+    agg = C.c_uint32()
+    per = np.zeros(32, np.uint32)
+    load().ref_ambient_sound(df.ctypes.data, p.ctypes.data, int(frame), C.byref(agg), per.ctypes.data)
+    return int(agg.value), per

@@ -57,6 +57,12 @@ def load():
                                          C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut), C.POINTER(VxoStats)]
     for f in (lib.vxo_trace_primary, lib.vxo_trace_shadow, lib.vxo_trace_diffuse, lib.vxo_trace_reflection):
         f.restype = C.c_int
+    lib.vxo_trace_rays.argtypes = [C.POINTER(VxoScene), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VxoStats)]
+    lib.vxo_trace_rays.restype = C.c_int
+    lib.vxo_player_shadowed.argtypes = [C.POINTER(VxoScene), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.vxo_player_shadowed.restype = C.c_int
+    lib.vxo_ambient_sound.argtypes = [C.POINTER(VxoScene), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(VxoStats)]
+    lib.vxo_ambient_sound.restype = C.c_int
     lib.vxo_num_threads.restype = C.c_int
     lib.vxo_set_num_threads.argtypes = [C.c_int]
     _lib = lib
@@ -194,3 +200,28 @@ class Oracle:
         rc = self.lib.vxo_trace_reflection(C.byref(self.scene), C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o), C.byref(st))
         assert rc == 0, rc
         return out, self._stats(st)
+
+    def trace_rays(self, origins, directions, max_it):
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        out = {"t": np.zeros(n, np.float32), "normal_id": np.zeros(n, np.uint8), "block_id": np.zeros(n, np.uint8), "hit_voxel": np.zeros((n, 3), np.int16)}
+        st = VxoStats()
+        rc = self.lib.vxo_trace_rays(C.byref(self.scene), o.ctypes.data, d.ctypes.data, n, int(max_it), out["t"].ctypes.data,
+                                     out["normal_id"].ctypes.data, out["block_id"].ctypes.data, out["hit_voxel"].ctypes.data, C.byref(st))
+        assert rc == 0, rc
+        return out, self._stats(st)
+
+    def player_shadowed(self, camera_pos, sun_dir):
+        p = (C.c_float * 3)(*[float(v) for v in camera_pos])
+        s = (C.c_float * 3)(*[float(v) for v in sun_dir])
+        return bool(self.lib.vxo_player_shadowed(C.byref(self.scene), p, s))
+
+    def ambient_sound(self, player_pos, frame):
+        p = (C.c_float * 3)(*[float(v) for v in player_pos])
+        agg = C.c_uint32()
+        per = np.zeros(32, np.uint32)
+        st = VxoStats()
+        rc = self.lib.vxo_ambient_sound(C.byref(self.scene), p, int(frame), C.byref(agg), per.ctypes.data, C.byref(st))
+        assert rc == 0, rc
+        return int(agg.value), per, self._stats(st)

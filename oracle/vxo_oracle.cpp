@@ -1146,6 +1146,132 @@ int vxo_trace_reflection(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
     return VXPT_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ other consumers of the distance field
+// A batch of VoxelTraversalDF calls on caller-supplied rays (vxpt_trace_rays).  Core/Shaders/PostProcessingVert.glsl:46-53 traces one such
+// ray per frame (camera -> sun, cap 350; its copy of the function, :103-170, is InitialRayTraceFrag.glsl:307-374 word for word apart
+// from the literal cap — tests/test_df_consumers.py compares the two texts when the reference tree is present).
+int vxo_trace_rays(const VxoScene* sc, const float* origins, const float* directions, int n, int max_it, float* t, uint8_t* normal_id,
+                   uint8_t* block_id, int16_t* hit_voxel, VxoStats* stats) {
+    Scene S{*sc};
+    Stats st;
+    for (int k = 0; k < n; ++k) {
+        Hit h;
+        const float T = traverse_df(S, V(origins[3 * k], origins[3 * k + 1], origins[3 * k + 2]),
+                                    V(directions[3 * k], directions[3 * k + 1], directions[3 * k + 2]), max_it, h, st);
+        const bool intersect = T > 0.0f && h.block > 0;
+        if (t) t[k] = T;
+        if (normal_id) normal_id[k] = intersect ? (uint8_t)normal_id_of(h) : (uint8_t)VXPT_NORMAL_MISS;
+        if (block_id) block_id[k] = intersect ? (uint8_t)h.block : 0;
+        if (hit_voxel)
+            for (int a = 0; a < 3; ++a) hit_voxel[3 * k + a] = intersect ? (int16_t)h.vox[a] : -1;
+    }
+    if (stats) { stats->rays += st.rays; stats->df_fetches += st.df; stats->vox_fetches += st.vox; }
+    return VXPT_OK;
+}
+
+// PostProcessingVert.glsl:46-53 — v_PlayerShadowed
+int vxo_player_shadowed(const VxoScene* sc, const float camera_pos[3], const float sun_dir[3]) {
+    Scene S{*sc};
+    const v3 sun = V(sun_dir[0], sun_dir[1], sun_dir[2]);
+    const float L = length(sun);
+    const v3 D = sun / L;
+    Hit h; Stats st;
+    return traverse_df(S, V(camera_pos[0], camera_pos[1], camera_pos[2]), D, 350, h, st) > 0.0f ? 1 : 0;
+}
+
+}  // extern "C"
+
+namespace {
+// EstimateAmbientSoundLevel.comp — HashRNG :145-153, Hash1 :160-164
+inline float amb_hash1(uint32_t& seed) {
+    seed ^= 2747636419u; seed *= 2654435769u;
+    seed ^= seed >> 16;  seed *= 2654435769u;
+    seed ^= seed >> 16;  seed *= 2654435769u;
+    return (float)seed / 4294967295.0f;
+}
+// TraverseDistanceField :73-141: VoxelTraversalDF with a cap of 32 whose hit test reads the distance field (outside the volume
+// GetDistance returns -1, which passes `D < 0.0001f`: a ray that steps out of the volume counts as a hit at that point)
+float amb_traverse(const Scene& S, v3 origin, v3 direction, v3& normal, Stats& st) {
+    const v3 initial_origin = origin;
+    bool intersection = false;
+    int min_idx = 0;
+    const int sg[3] = {isign(direction.x), isign(direction.y), isign(direction.z)};
+    st.rays++;
+    for (int itr = 0; itr < 32; ++itr) {
+        float fx = std::floor(origin.x), fy = std::floor(origin.y), fz = std::floor(origin.z);
+        if (!S.in_volume_f(fx, fy, fz)) { intersection = false; break; }
+        st.df++;
+        float dist = (float)S.s.df[S.idx((int)fx, (int)fy, (int)fz)];
+        int euclid = (int)std::floor(dist == 1.0f ? 1.0f : dist * 0.57735026918f);
+        if (euclid == 0) break;
+        if (euclid == 1) { dda_step(origin, direction, sg, min_idx); intersection = true; }
+        else origin = origin + (float)(euclid - 1) * direction;
+    }
+    if (!intersection) return -1.0f;
+    normal = V(0.0f);
+    normal[min_idx] = (float)(-sg[min_idx]);
+    float fx = std::floor(origin.x), fy = std::floor(origin.y), fz = std::floor(origin.z);
+    float D = -1.0f;
+    if (S.in_volume_f(fx, fy, fz)) { st.df++; D = (float)S.s.df[S.idx((int)fx, (int)fy, (int)fz)] / 255.0f; }
+    return (D < 0.0001f || D == 0.0f) ? length(origin - initial_origin) : -1.0f;
+}
+// RaytraceAverageAmbience :210-241 with UniformHemisphere :183-190 and CosineHemisphereDirection :192-204
+float amb_sample(const Scene& S, v3 player, uint32_t& seed, Stats& st) {
+    const float PI = 3.141592653f;
+    const v3 up = normalize(V(0.0f, 1.0f, 0.0f));
+    v3 ro = player;
+    const float ux = amb_hash1(seed), uy = amb_hash1(seed);  // GLSL evaluates arguments left to right
+    v3 rd;
+    {
+        const float r = std::sqrt(1.0f - ux * ux);
+        const float phi = 2.0f * PI * uy;
+        const v3 B = normalize(cross(up, V(0.0f, 1.0f, 1.0f)));
+        const v3 T = cross(B, up);
+        rd = normalize(((r * sin_cr(phi)) * B + ux * up) + (r * cos_cr(phi)) * T);
+    }
+    for (int bounce = 0; bounce < 7; ++bounce) {
+        v3 N = V(0.0f);
+        const float T = amb_traverse(S, ro, rd, N, st);
+        if (T < 0.0f) return 1.0f;
+        ro = (ro + rd * T) + N * 0.05f;
+        const float r1 = amb_hash1(seed), r2 = amb_hash1(seed);
+        const float PI2 = 2.0f * PI;
+        const v3 uu = normalize(cross(N, V(0.0f, 1.0f, 1.0f)));
+        const v3 vv = cross(uu, N);
+        const float ra = std::sqrt(r2);
+        const float rx = ra * cos_cr(PI2 * r1), ry = ra * sin_cr(PI2 * r1), rz = std::sqrt(1.0f - r2);
+        rd = normalize((rx * uu + ry * vv) + rz * N);
+    }
+    return 0.0f;
+}
+}  // namespace
+
+extern "C" {
+
+// EstimateAmbientSoundLevel.comp main() :247-270 over the 8 x 4 invocations Core/Pipeline.cpp:1921 dispatches
+int vxo_ambient_sound(const VxoScene* sc, const float player_pos[3], int frame, uint32_t* aggregate, uint32_t* per_invocation, VxoStats* stats) {
+    Scene S{*sc};
+    Stats st;
+    uint32_t sum = 0;
+    for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 8; ++x) {
+            uint32_t seed = (uint32_t)((float)y * 32.0f + (float)x) + (uint32_t)(frame % 512) * 32u * 32u;  // InitRNG :155-158
+            const int samples = (int)mixf(1.0f, 2.0f, frame % 2 == 0 ? 1.0f : 0.0f);
+            float amount = 0.0f, weight = 0.0f;
+            for (int s = 0; s < std::min(std::max(samples, 0), 3); ++s) {
+                amount += amb_sample(S, V(player_pos[0], player_pos[1], player_pos[2]), seed, st);
+                weight += 1.0f;
+            }
+            amount /= weight;
+            const uint32_t mapped = (uint32_t)clampf(amount * 512.0f, 0.0f, 512.0f);
+            sum += mapped;
+            if (per_invocation) per_invocation[y * 8 + x] = mapped;
+        }
+    *aggregate = sum;
+    if (stats) { stats->rays += st.rays; stats->df_fetches += st.df; stats->vox_fetches += st.vox; }
+    return VXPT_OK;
+}
+
 int vxo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

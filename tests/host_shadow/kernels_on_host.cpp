@@ -1,7 +1,7 @@
 // kernels_on_host.cpp — TEST INFRASTRUCTURE: the per-pixel trace kernels' own source, compiled by g++ and executed on the CPU.
 //
 // The build container has no GPU, so a kernel written here is first seen by a GPU at the end of a round.  To shorten that
-// loop this file includes voxelpathtracer_b200/csrc/trace.cu and trace_reflection.cu UNCHANGED (kernels, device functions and
+// loop this file includes voxelpathtracer_b200/csrc/trace.cu, trace_reflection.cu and df_consumers.cu UNCHANGED (kernels, device functions and
 // their host launchers with the per-frame constants) and gives g++ what nvcc would: the CUDA vector types come from the toolkit's
 // own headers (they are plain C++), the handful of device intrinsics the kernels use are defined below with their documented
 // semantics, and VX_LAUNCH becomes a loop over blockIdx / threadIdx.  tests/test_kernels_on_host.py compares what comes out with
@@ -38,6 +38,7 @@ static inline float __fadd_rd(float a, float b) {
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline unsigned __float2uint_rn(float f) { return (unsigned)std::nearbyintf(f); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
 #define VX_CUDA(expr) do { } while (0)
 #define VX_LAUNCH(kernel, grid, block, stream, ...)                                          \
@@ -55,9 +56,7 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 
 #include "../../voxelpathtracer_b200/csrc/trace.cu"
 #include "../../voxelpathtracer_b200/csrc/trace_reflection.cu"
-#ifdef VXPT_HAVE_CONSUMERS
 #include "../../voxelpathtracer_b200/csrc/df_consumers.cu"
-#endif
 
 namespace vxpt {
 // api.cu's make_scene, on a context whose "device" pointers are host pointers
@@ -170,5 +169,13 @@ HS_API int hs_trace_diffuse(void* p, const VxCamera* cam, const VxGBuffer* g, co
 HS_API int hs_trace_reflection(void* p, const VxCamera* cam, const VxGBuffer* g, const VxReflectionIn* in, const VxReflectionParams* prm,
                                const VxReflectionOut* out) {
     return vxpt::launch_reflection(hs_ctx(p), *cam, *g, *in, *prm, *out);
+}
+HS_API int hs_trace_rays(void* p, const float* origins, const float* directions, int n, int max_it, float* t, uint8_t* normal_id, uint8_t* block_id,
+                         int16_t* hit_voxel) {
+    return vxpt::launch_rays(hs_ctx(p), origins, directions, n, max_it, t, normal_id, block_id, hit_voxel);
+}
+HS_API int hs_ambient_sound(void* p, const float* player_pos, int frame, uint32_t* aggregate, uint32_t* per_invocation) {
+    *aggregate = 0;
+    return vxpt::launch_ambient(hs_ctx(p), player_pos, frame, aggregate, per_invocation);
 }
 }  // extern "C"

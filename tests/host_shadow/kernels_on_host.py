@@ -50,6 +50,8 @@ def load():
     lib.hs_trace_diffuse.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut)]
     lib.hs_trace_reflection.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]
+    lib.hs_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hs_ambient_sound.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
     _lib = lib
     return lib
 
@@ -125,3 +127,21 @@ class HostKernels:
         rc = self.lib.hs_trace_reflection(self.h, C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o))
         assert rc == 0, rc
         return out, self.stats()
+
+    def trace_rays(self, origins, directions, max_it):
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        out = {"t": np.zeros(n, np.float32), "normal_id": np.zeros(n, np.uint8), "block_id": np.zeros(n, np.uint8), "hit_voxel": np.zeros((n, 3), np.int16)}
+        rc = self.lib.hs_trace_rays(self.h, o.ctypes.data, d.ctypes.data, n, int(max_it), out["t"].ctypes.data, out["normal_id"].ctypes.data,
+                                    out["block_id"].ctypes.data, out["hit_voxel"].ctypes.data)
+        assert rc == 0, rc
+        return out, self.stats()
+
+    def ambient_sound(self, player_pos, frame):
+        p = np.array([float(v) for v in player_pos], dtype=np.float32)
+        agg = C.c_uint32()
+        per = np.zeros(32, np.uint32)
+        rc = self.lib.hs_ambient_sound(self.h, p.ctypes.data, int(frame), C.byref(agg), per.ctypes.data)
+        assert rc == 0, rc
+        return int(agg.value), per, self.stats()

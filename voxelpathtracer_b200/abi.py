@@ -114,6 +114,9 @@ EXPORTS = {
     "vxpt_trace_diffuse": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut)]),
     "vxpt_trace_reflection": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]),
+    "vxpt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vxpt_player_shadowed": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "vxpt_estimate_ambient_sound": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint32), C.c_void_p]),
     "vxpt_render_frame": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxFrameParams), C.POINTER(VxFrameOut)]),
     "vxpt_render_frame_async": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxFrameParams), C.POINTER(VxFrameOut)]),
     "vxpt_frame_wait": (C.c_int, [C.c_void_p]),

@@ -543,6 +543,68 @@ int vxpt_set_albedo_alpha_mips(vxpt_handle c, const uint8_t* alpha_mips, int n_l
     return VXPT_OK;
 }
 
+// ----------------------------------------------------------------------------------------------------- other DF consumers
+int vxpt_trace_rays(vxpt_handle c, const float* origins, const float* directions, int n, int max_iterations, float* t, uint8_t* normal_id,
+                    uint8_t* block_id, int16_t* hit_voxel) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!origins || !directions) return fail(VXPT_E_INVALID, "NULL argument");
+    if (n < 0 || n > (1 << 26) || max_iterations < 0) return fail(VXPT_E_INVALID, "bad ray count / max_iterations");
+    if (n == 0) return VXPT_OK;
+    VX_CUDA(cudaSetDevice(c->device));
+    VxCamera batch{};  // the rays as one row of n "pixels", so the plane staging of the passes applies
+    batch.width = n; batch.height = 1; batch.row_begin = 0; batch.row_end = 1;
+    PassIO io(c, &batch);
+    Plane o, d, pt, pn, pb, pv;
+    io.add(o, origins, 12); io.add(d, directions, 12); io.add(pt, t, 4); io.add(pn, normal_id, 1); io.add(pb, block_id, 1); io.add(pv, hit_voxel, 6);
+    if ((rc = io.resolve())) return rc;
+    if ((rc = io.upload(o)) || (rc = io.upload(d))) return rc;
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_rays(c, (const float*)o.dev, (const float*)d.dev, n, max_iterations, (float*)pt.dev, (uint8_t*)pn.dev, (uint8_t*)pb.dev,
+                          (int16_t*)pv.dev)))
+        return rc;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
+    bool any = false;
+    if ((rc = io.download(pt, any)) || (rc = io.download(pn, any)) || (rc = io.download(pb, any)) || (rc = io.download(pv, any))) return rc;
+    if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
+    return VXPT_OK;
+}
+
+int vxpt_player_shadowed(vxpt_handle c, const float camera_pos[3], const float sun_dir[3], int* shadowed) {
+    if (!camera_pos || !sun_dir || !shadowed) return fail(VXPT_E_INVALID, "NULL argument");
+    // PostProcessingVert.glsl:48-50: L = length(u_VertSunDir); D = u_VertSunDir / L   (fp32, no FMA: this file is built with -fmad=false)
+    const float L = sqrtf((sun_dir[0] * sun_dir[0] + sun_dir[1] * sun_dir[1]) + sun_dir[2] * sun_dir[2]);
+    const float D[3] = {sun_dir[0] / L, sun_dir[1] / L, sun_dir[2] / L};
+    float T = -1.0f;
+    const int rc = vxpt_trace_rays(c, camera_pos, D, 1, 350, &T, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    *shadowed = T > 0.0f ? 1 : 0;
+    return VXPT_OK;
+}
+
+int vxpt_estimate_ambient_sound(vxpt_handle c, const float player_pos[3], int frame, uint32_t* sky_level_aggregate, uint32_t* per_invocation) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!player_pos || !sky_level_aggregate) return fail(VXPT_E_INVALID, "NULL argument");
+    if (frame < 0) return fail(VXPT_E_INVALID, "frame < 0");
+    VX_CUDA(cudaSetDevice(c->device));
+    Arena arena(c);
+    if ((rc = arena.reserve(256))) return rc;
+    unsigned* d = (unsigned*)arena.take(33 * sizeof(unsigned));  // [0] = SkyLevelAggregate (cleared per dispatch, Pipeline.cpp:1931-1934), [1..32]
+    VX_CUDA(cudaMemsetAsync(d, 0, 33 * sizeof(unsigned), c->stream));
+    if ((rc = launch_ambient(c, player_pos, frame, d, d + 1))) return rc;
+    unsigned h[33];
+    VX_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    VX_CUDA(cudaStreamSynchronize(c->stream));  // glGetBufferSubData (Pipeline.cpp:1926-1929)
+    *sky_level_aggregate = h[0];
+    if (per_invocation)
+        for (int k = 0; k < 32; ++k) per_invocation[k] = h[1 + k];
+    return VXPT_OK;
+}
+
 // ----------------------------------------------------------------------------------------------------- passes
 int vxpt_trace_primary(vxpt_handle c, const VxCamera* cam, const VxPrimaryParams* p, const VxGBuffer* out) {
     int rc = check_ready(c);

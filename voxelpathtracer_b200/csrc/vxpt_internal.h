@@ -157,6 +157,10 @@ int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, con
 // trace_reflection.cu
 int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxReflectionIn& in_dev, const VxReflectionParams& p,
                       const VxReflectionOut& out_dev);
+// df_consumers.cu
+int launch_rays(vxpt_ctx* c, const float* origins, const float* directions, int n, int max_iterations, float* t, uint8_t* normal_id,
+                uint8_t* block_id, int16_t* hit_voxel);
+int launch_ambient(vxpt_ctx* c, const float player[3], int frame, unsigned* aggregate, unsigned* per_invocation);
 // l2_probe.cu
 int run_l2_probe(vxpt_ctx* c, double* gbps);
 

@@ -247,6 +247,37 @@ class Renderer:
         check(self.lib.vxpt_trace_reflection(self.handle, C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o)))
         return out
 
+    # ---- other consumers of the distance field ----
+    def trace_rays(self, origins, directions, max_iterations=350, hit_voxel=True):
+        """A batch of VoxelTraversalDF calls (vxpt_trace_rays): origins / directions [n][3] float32 -> dict of t, normal_id, block_id(, hit_voxel)."""
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+        assert o.shape == d.shape
+        n = o.shape[0]
+        out = {"t": np.zeros(n, np.float32), "normal_id": np.zeros(n, np.uint8), "block_id": np.zeros(n, np.uint8)}
+        if hit_voxel:
+            out["hit_voxel"] = np.zeros((n, 3), np.int16)
+        abi.check(self.lib.vxpt_trace_rays(self.h, o.ctypes.data, d.ctypes.data, n, int(max_iterations), out["t"].ctypes.data,
+                                           out["normal_id"].ctypes.data, out["block_id"].ctypes.data,
+                                           out["hit_voxel"].ctypes.data if hit_voxel else None))
+        return out
+
+    def player_shadowed(self, camera_pos, sun_dir):
+        """PostProcessingVert.glsl:46-53: is the player's eye in the sun's shadow (v_PlayerShadowed)."""
+        p = (C.c_float * 3)(*[float(v) for v in camera_pos])
+        s = (C.c_float * 3)(*[float(v) for v in sun_dir])
+        out = C.c_int(0)
+        abi.check(self.lib.vxpt_player_shadowed(self.h, p, s, C.byref(out)))
+        return bool(out.value)
+
+    def estimate_ambient_sound(self, player_pos, frame):
+        """EstimateAmbientSoundLevel.comp (Pipeline.cpp:1908-1921): (SkyLevelAggregate, per-invocation addends uint32[32])."""
+        p = (C.c_float * 3)(*[float(v) for v in player_pos])
+        agg = C.c_uint32(0)
+        per = np.zeros(32, np.uint32)
+        abi.check(self.lib.vxpt_estimate_ambient_sound(self.h, p, int(frame), C.byref(agg), per.ctypes.data))
+        return int(agg.value), per
+
     def render_frame(self, cam, primary, shadow=None, diffuse=None, gbuf=None, shadow_out=None, diffuse_out=None, reflection=None,
                      reflection_out=None, g_normal=None, g_pbr=None, wait=True):
         """One frame of the path (vxpt_render_frame): primary -> shadow -> GI (-> reflections) with the G-buffer resident on

@@ -184,6 +184,6 @@ def test_cuda_consumers_equal_the_oracle(renderer, oracles, worlds, scene_tables
     dev = torch.device("cuda:0")
     to, td = torch.from_numpy(origins).to(dev), torch.from_numpy(dirs).to(dev)
     t = torch.empty(origins.shape[0], dtype=torch.float32, device=dev)
-    abi.check(renderer.lib.vxpt_trace_rays(renderer.h, to.data_ptr(), td.data_ptr(), origins.shape[0], 350, t.data_ptr(), None, None, None))
+    abi.check(renderer.lib.vxpt_trace_rays(renderer.handle, to.data_ptr(), td.data_ptr(), origins.shape[0], 350, t.data_ptr(), None, None, None))
     renderer.sync()
     assert np.array_equal(t.cpu().numpy(), ref["t"])

@@ -110,3 +110,35 @@ def test_brick_offset_is_injective_and_matches_its_bit_layout():
     assert off.max() < (96 << 18) and np.unique(off.reshape(-1)).size == abi.WORLD_VOXELS
     # one 32-byte sector = 4 x * 4 z * 2 y voxels, one 128-byte line = 8 x * 4 y * 4 z
     assert np.unique(off[:4, :2, :4] >> 5).size == 1 and np.unique(off[:8, :4, :4] >> 7).size == 1
+
+
+def test_renderer_wrappers_call_through_with_a_stub_library():
+    """No GPU here: run every newer Renderer wrapper against a stub of the C library (records the call, returns VXPT_OK), so that a
+    misspelt attribute or a bad argument list in the Python layer fails in the CPU suite rather than on the GPU box."""
+    import ctypes as C
+    import voxelpathtracer_b200 as vx
+    from voxelpathtracer_b200 import abi
+
+    calls = []
+
+    class Stub:
+        def __getattr__(self, name):
+            if name not in abi.EXPORTS:
+                raise AttributeError(name)
+
+            def fn(*args):
+                assert len(args) == len(abi.EXPORTS[name][1]), (name, len(args))
+                calls.append(name)
+                return abi.OK
+            return fn
+
+    r = vx.Renderer.__new__(vx.Renderer)
+    r.lib, r.handle, r.device, r._keep = Stub(), C.c_void_p(1), 0, []
+    r.set_albedo_alpha_mips(np.zeros((2, abi.ALPHA_MIP_TEXELS), np.uint8))
+    out = r.trace_rays(np.zeros((5, 3), np.float32), np.ones((5, 3), np.float32), 64)
+    assert out["t"].shape == (5,) and out["hit_voxel"].shape == (5, 3)
+    assert r.player_shadowed((1.0, 2.0, 3.0), (0.0, 1.0, 0.0)) is False
+    agg, per = r.estimate_ambient_sound((1.0, 2.0, 3.0), 7)
+    assert agg == 0 and per.shape == (32,)
+    assert calls == ["vxpt_set_albedo_alpha_mips", "vxpt_trace_rays", "vxpt_player_shadowed", "vxpt_estimate_ambient_sound"]
+    r.handle = C.c_void_p()      # nothing to destroy

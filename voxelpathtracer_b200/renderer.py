@@ -156,7 +156,7 @@ class Renderer:
         """uint8 [n_layers][ALPHA_MIP_TEXELS]: alpha of the albedo array's mip levels 0..8 (see assets.alpha_mip_pyramid)."""
         a = np.ascontiguousarray(alpha_mips, dtype=np.uint8)
         assert a.ndim == 2 and a.shape[1] == abi.ALPHA_MIP_TEXELS, a.shape
-        abi.check(self.lib.vxpt_set_albedo_alpha_mips(self.h, a.ctypes.data, a.shape[0]))
+        abi.check(self.lib.vxpt_set_albedo_alpha_mips(self.handle, a.ctypes.data, a.shape[0]))
 
     def set_sky_cubemap(self, rgb):
         s = np.ascontiguousarray(rgb, dtype=np.float32)
@@ -257,7 +257,7 @@ class Renderer:
         out = {"t": np.zeros(n, np.float32), "normal_id": np.zeros(n, np.uint8), "block_id": np.zeros(n, np.uint8)}
         if hit_voxel:
             out["hit_voxel"] = np.zeros((n, 3), np.int16)
-        abi.check(self.lib.vxpt_trace_rays(self.h, o.ctypes.data, d.ctypes.data, n, int(max_iterations), out["t"].ctypes.data,
+        abi.check(self.lib.vxpt_trace_rays(self.handle, o.ctypes.data, d.ctypes.data, n, int(max_iterations), out["t"].ctypes.data,
                                            out["normal_id"].ctypes.data, out["block_id"].ctypes.data,
                                            out["hit_voxel"].ctypes.data if hit_voxel else None))
         return out
@@ -267,7 +267,7 @@ class Renderer:
         p = (C.c_float * 3)(*[float(v) for v in camera_pos])
         s = (C.c_float * 3)(*[float(v) for v in sun_dir])
         out = C.c_int(0)
-        abi.check(self.lib.vxpt_player_shadowed(self.h, p, s, C.byref(out)))
+        abi.check(self.lib.vxpt_player_shadowed(self.handle, p, s, C.byref(out)))
         return bool(out.value)
 
     def estimate_ambient_sound(self, player_pos, frame):
@@ -275,7 +275,7 @@ class Renderer:
         p = (C.c_float * 3)(*[float(v) for v in player_pos])
         agg = C.c_uint32(0)
         per = np.zeros(32, np.uint32)
-        abi.check(self.lib.vxpt_estimate_ambient_sound(self.h, p, int(frame), C.byref(agg), per.ctypes.data))
+        abi.check(self.lib.vxpt_estimate_ambient_sound(self.handle, p, int(frame), C.byref(agg), per.ctypes.data))
         return int(agg.value), per
 
     def render_frame(self, cam, primary, shadow=None, diffuse=None, gbuf=None, shadow_out=None, diffuse_out=None, reflection=None,

@@ -252,6 +252,42 @@ VXPT_API int vxpt_player_shadowed(vxpt_handle h, const float camera_pos[3], cons
 VXPT_API int vxpt_estimate_ambient_sound(vxpt_handle h, const float player_pos[3], int frame, uint32_t* sky_level_aggregate,
                                          uint32_t* per_invocation /* 32 or NULL */);
 
+/* ---- G-buffer material pass: Core/Pipeline.cpp:2066-2136 -> Core/Shaders/GenerateGBuffer.glsl:347-549 --------
+ * The immediate consumer of the primary hits: per pixel, the block's albedo / normal-map / PBR / emissive texels at the hit point,
+ * written to the GeneratedGBuffer attachments (Pipeline.cpp:1100) whose normal and PBR planes the reflection pass reads as
+ * u_GBufferNormals / u_GBufferPBR (VxReflectionIn.g_normal / g_pbr).
+ * Textures: the block arrays as the GL texture objects hold them (Core/GLClasses/TextureArray.cpp:28-78): RGBA8 texels of a
+ * 512^2 layer with its complete mip chain, levels 0..9 back to back (VXPT_MIP_CHAIN_TEXELS texels per layer, level k at offset
+ * sum_{m<k} (512>>m)^2), [n_layers][VXPT_MIP_CHAIN_TEXELS][4] bytes.  The albedo array is GL_SRGB_ALPHA (rgb decoded to linear on
+ * fetch), normal and PBR arrays are GL_RGBA.  The emissive array is the level-0 red channel vxpt_set_material_textures received.
+ * Pinned sampling (GL leaves filter arithmetic to the driver): textureGrad = the isotropic OpenGL 4.3 section 8.14
+ * scale factor rho = max(|dP/dx| , |dP/dy|) * 512, lambda = log2(rho); lambda <= c magnifies on level 0 (albedo: GL_NEAREST, c = 0;
+ * normal / PBR: GL_LINEAR, c = 0.5); otherwise GL_NEAREST_MIPMAP_LINEAR: nearest texel of levels floor(lambda) and floor(lambda)+1
+ * (clamped to 9), blended by fract(lambda).  dFdx / dFdy are differences inside the pixel's 2x2 quad (fine derivatives); a quad
+ * neighbour that shades nothing (sky, outside the frame) contributes the pixel's own value.  The anisotropy extension is not modelled.
+ * Parity profile v1: u_POM = false (off by default, Pipeline.cpp:264) and no lava animation (u_LavaBlockID matches no block):
+ * both are rejected with VXPT_E_UNSUPPORTED. */
+#define VXPT_MIP_CHAIN_TEXELS 349525 /* 512^2 + 256^2 + ... + 1 */
+typedef struct VxMaterialParams {
+    int32_t update_this_frame;  /* u_UpdateGBufferThisFrame: 0 = every pixel is discarded (planes untouched)                 */
+    int32_t pom;                /* u_POM; must be 0                                                                          */
+    int32_t lava_block_id;      /* u_LavaBlockID; must be negative (no lava animation)                                       */
+    int32_t grass_props[10];    /* u_GrassBlockProps (Pipeline.cpp:2083-2092): block id, then albedo / normal / PBR layers of  */
+                                /* the top, side and bottom faces                                                            */
+} VxMaterialParams;
+typedef struct VxMaterialOut {  /* fp32 planes in every texel format (the reflection pass reads normal / pbr as fp32) */
+    float* albedo;      /* o_Albedo    3 floats / pixel (RGB16F in the reference)                             */
+    float* normal;      /* o_Normal    3 floats / pixel: the normal-mapped shading normal, (1,1,1) on a miss  */
+    float* pbr;         /* o_PBR       4 floats / pixel: roughness, metalness, displacement, emissivity       */
+    float* texture_ao;  /* o_TextureAO 1 float / pixel                                                        */
+} VxMaterialOut;
+VXPT_API int vxpt_set_gbuffer_textures(vxpt_handle h, const uint8_t* albedo_mips, const uint8_t* normal_mips, const uint8_t* pbr_mips,
+                                       int n_layers);
+/* reads VxGBuffer.inv_t (u_NonLinearDepth), normal_id and block_id; row_begin / row_end must be even (or the frame height): a 2x2
+ * quad is shaded by one call.  Planes are device or host pointers like those of the trace passes. */
+VXPT_API int vxpt_generate_gbuffer(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf, const VxMaterialParams* p,
+                                   const VxMaterialOut* out);
+
 /* ---- one frame of the path: the pass sequence of Core/Pipeline.cpp's render loop (:1973-2016 primary, :2795-2852 shadow,
  *      :2174-2281 diffuse GI, :3003-3164 reflections) on the rows of `cam` -------------------------------------------------
  * Equivalent to vxpt_trace_primary + vxpt_trace_shadow + vxpt_trace_diffuse (+ vxpt_trace_reflection) with the same arguments,

@@ -126,6 +126,11 @@ struct sampler2DArray {
     // (GL_NEAREST_MIPMAP_LINEAR with a zero fraction, Core/GLClasses/TextureArray.cpp:34)
     const uint8_t* alpha_mips = nullptr;
     int alpha_layers = 0;
+    // G-buffer material pass: the whole RGBA8 mip chain of 512^2 layers, levels 0..9 back to back, [mip_layers][349525][4]; textureGrad()
+    // is the only call that reads it.  srgb: GL_SRGB_ALPHA storage (albedo); mag_linear: GL_TEXTURE_MAG_FILTER (TextureArray.cpp:42)
+    const uint8_t* mips = nullptr;
+    int mip_layers = 0;
+    bool srgb = false, mag_linear = false;
 };
 inline vec4 fetch_layer_texel(const sampler2DArray& s, int layer, int i, int j) {
     const float* t = s.data + (((size_t)layer * s.n + j) * s.n + i) * s.comps;
@@ -180,6 +185,91 @@ inline vec4 texture(const samplerCube& s, const vec3& d) {
     const vec3 b = tx(i0, j1) * (1.0f - fu) + tx(i1, j1) * fu;
     return vec4(a * (1.0f - fv) + b * fv, 1.0f);
 }
+
+// ---- textureGrad on a mip-mapped block array, and the screen-space derivatives that feed it (GenerateGBuffer.glsl:404-461) ----------
+// OpenGL 4.3 section 8.14 with the isotropic scale factor (the anisotropy extension leaves rho to the driver and is not modelled):
+// rho = max(|dP/dx| , |dP/dy|) in texels of level 0, lambda = log2(rho) (pinned: correctly rounded); lambda <= c magnifies on level 0
+// (c = 0.5 when the mag filter is LINEAR and the min filter NEAREST_MIPMAP_*, else 0), otherwise GL_NEAREST_MIPMAP_LINEAR blends the
+// nearest texels of levels floor(lambda) and floor(lambda) + 1 (clamped to the last level) by fract(lambda).  Texel -> float is c / 255,
+// sRGB-decoded for the rgb of a GL_SRGB_ALPHA array (section 8.23, evaluated in double).
+inline float srgb_decode(uint8_t c) {
+    static float lut[256];
+    static bool ready = false;
+    if (!ready) {
+#pragma omp critical(glsl_srgb_lut)
+        if (!ready) {
+            for (int k = 0; k < 256; ++k) {
+                const double cs = (double)k / 255.0;
+                lut[k] = (float)(cs <= 0.04045 ? cs / 12.92 : ::pow((cs + 0.055) / 1.055, 2.4));
+            }
+            ready = true;
+        }
+    }
+    return lut[c];
+}
+inline vec4 fetch_mip_texel(const sampler2DArray& s, int layer, int level, int i, int j) {
+    size_t off = 0;
+    for (int k = 0; k < level; ++k) off += (size_t)(512 >> k) * (512 >> k);
+    const int n = 512 >> level;
+    const uint8_t* c = s.mips + ((size_t)layer * 349525 + off + (size_t)j * n + i) * 4;
+    if (s.srgb) return vec4(srgb_decode(c[0]), srgb_decode(c[1]), srgb_decode(c[2]), (float)c[3] / 255.0f);
+    return vec4((float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f);
+}
+inline vec4 fetch_mip_nearest(const sampler2DArray& s, int layer, int level, const vec3& p) {
+    const int n = 512 >> level;
+    return fetch_mip_texel(s, layer, level, ((int)std::floor(p.x * (float)n)) & (n - 1), ((int)std::floor(p.y * (float)n)) & (n - 1));
+}
+inline vec4 textureGrad(const sampler2DArray& s, const vec3& p, const vec2& dPdx, const vec2& dPdy) {
+    if (!s.mips) return vec4(1.0f);
+    int layer = (int)std::nearbyintf(p.z);
+    layer = layer < 0 ? 0 : (layer > s.mip_layers - 1 ? s.mip_layers - 1 : layer);
+    const float ux = dPdx.x * 512.0f, vx = dPdx.y * 512.0f, uy = dPdy.x * 512.0f, vy = dPdy.y * 512.0f;
+    const float rx = std::sqrt(ux * ux + vx * vx), ry = std::sqrt(uy * uy + vy * vy);
+    const float rho = rx > ry ? rx : ry;
+    const float lambda = (float)::log2((double)rho);
+    if (lambda <= (s.mag_linear ? 0.5f : 0.0f)) {
+        if (!s.mag_linear) return fetch_mip_nearest(s, layer, 0, p);
+        const float x = p.x * 512.0f - 0.5f, y = p.y * 512.0f - 0.5f;
+        const float fx0 = std::floor(x), fy0 = std::floor(y);
+        const float fx = x - fx0, fy = y - fy0;
+        const int i0 = ((int)fx0) & 511, i1 = ((int)fx0 + 1) & 511, j0 = ((int)fy0) & 511, j1 = ((int)fy0 + 1) & 511;
+        const vec4 a = fetch_mip_texel(s, layer, 0, i0, j0) * (1.0f - fx) + fetch_mip_texel(s, layer, 0, i1, j0) * fx;
+        const vec4 b = fetch_mip_texel(s, layer, 0, i0, j1) * (1.0f - fx) + fetch_mip_texel(s, layer, 0, i1, j1) * fx;
+        return a * (1.0f - fy) + b * fy;
+    }
+    if (lambda >= 9.0f) return fetch_mip_nearest(s, layer, 9, p);
+    const float fl = std::floor(lambda);
+    const float f = lambda - fl;
+    return fetch_mip_nearest(s, layer, (int)fl, p) * (1.0f - f) + fetch_mip_nearest(s, layer, (int)fl + 1, p) * f;
+}
+
+// dFdx / dFdy: a fragment shader runs in 2x2 quads and a derivative is the difference between the two members of the quad's row /
+// column (fine derivatives).  The driver runs the four invocations of a quad twice: a RECORD run, in which every dFdx / dFdy call logs
+// its operand (and returns 0), then a REPLAY run in which call number k returns (odd member's k-th operand) - (even member's).  A member
+// that made fewer than k+1 calls (it returned early: sky; or lies outside the frame) contributes the calling fragment's own operand.
+// Valid because the number and order of derivative calls of an invocation never depend on a derivative's value.
+struct QuadDerivatives {
+    enum { MAX_CALLS = 32 };
+    int mode = 0;  // 0 = record, 1 = replay
+    int lane = 0;  // (x & 1) | ((y & 1) << 1)
+    int call = 0;
+    int ncalls[4] = {0, 0, 0, 0};
+    vec2 operand[4][MAX_CALLS];
+    vec2 diff(const vec2& v, int even_lane, int odd_lane) {
+        const int k = call++;
+        if (mode == 0) {
+            if (k < MAX_CALLS) operand[lane][k] = v;
+            ncalls[lane] = call;
+            return vec2(0.0f);
+        }
+        const vec2 e = k < ncalls[even_lane] ? operand[even_lane][k] : v;
+        const vec2 o = k < ncalls[odd_lane] ? operand[odd_lane][k] : v;
+        return o - e;
+    }
+};
+static thread_local QuadDerivatives gl_Quad;
+inline vec2 dFdx(const vec2& v) { return gl_Quad.diff(v, gl_Quad.lane & 2, (gl_Quad.lane & 2) | 1); }
+inline vec2 dFdy(const vec2& v) { return gl_Quad.diff(v, gl_Quad.lane & 1, (gl_Quad.lane & 1) | 2); }
 
 // code paths the drivers never enable (light-propagation volume, clouds, screen-space reprojection): inert stand-ins
 struct usampler3D {};

@@ -35,6 +35,14 @@ class RefReflectionArgs(C.Structure):
                 ("o_emissive_mask", C.c_void_p)]
 
 
+class RefGBufferArgs(C.Structure):
+    _fields_ = [("inv_view", C.c_void_p), ("inv_proj", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("row_begin", C.c_int32),
+                ("row_end", C.c_int32), ("g_inv_t", C.c_void_p), ("g_normal_id", C.c_void_p), ("g_block_id", C.c_void_p), ("materials", C.c_void_p),
+                ("albedo_mips", C.c_void_p), ("normal_mips", C.c_void_p), ("pbr_mips", C.c_void_p), ("n_mip_layers", C.c_int32),
+                ("emissive_lod0", C.c_void_p), ("update_this_frame", C.c_int32), ("grass_props", C.c_int32 * 10),
+                ("o_albedo", C.c_void_p), ("o_normal", C.c_void_p), ("o_pbr", C.c_void_p), ("o_texture_ao", C.c_void_p)]
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -64,6 +72,9 @@ def load():
         lib.ref_trace_diffuse.argtypes = [C.POINTER(RefDiffuseArgs)]
         lib.ref_trace_reflection.restype = C.c_int
         lib.ref_trace_reflection.argtypes = [C.POINTER(RefReflectionArgs)]
+        if hasattr(lib, "ref_generate_gbuffer"):
+            lib.ref_generate_gbuffer.restype = C.c_int
+            lib.ref_generate_gbuffer.argtypes = [C.POINTER(RefGBufferArgs)]
         _lib = lib
     return _lib
 
@@ -195,6 +206,35 @@ def trace_reflection(blocks, df, cam, gbuf, diffuse, params, g_normal, g_pbr, ma
     a.o_color, a.o_hit_distance, a.o_emissive_mask = (out[k].ctypes.data for k in ("color", "hit_distance", "emissive_mask"))
     load().ref_trace_reflection(C.byref(a))
     out["emissive_mask"] = (out["emissive_mask"] > 0.5).astype(np.uint8)
+    return out
+
+
+def generate_gbuffer(cam, gbuf, params, materials, mips, out=None):
+    """GenerateGBuffer.glsl main() per 2x2 quad of rows [cam.row_begin, cam.row_end) in the v1 parity profile (Core/Pipeline.cpp:2066-2136).
+    mips = (albedo, normal, pbr) uint8 [layers][349525][4]."""
+    keep = []
+
+    def ptr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    W, H = cam.width, cam.height
+    if out is None:
+        out = {"albedo": np.zeros((H, W, 3), np.float32), "normal": np.zeros((H, W, 3), np.float32), "pbr": np.zeros((H, W, 4), np.float32),
+               "texture_ao": np.zeros((H, W), np.float32)}
+    a = RefGBufferArgs()
+    a.inv_view, a.inv_proj = ptr(np.frombuffer(cam.inv_view, dtype=np.float32), np.float32), ptr(np.frombuffer(cam.inv_proj, dtype=np.float32), np.float32)
+    a.width, a.height, a.row_begin, a.row_end = W, H, cam.row_begin, cam.row_end
+    a.g_inv_t, a.g_normal_id, a.g_block_id = ptr(gbuf["inv_t"], np.float32), ptr(gbuf["normal_id"], np.uint8), ptr(gbuf["block_id"], np.uint8)
+    a.materials = ptr(materials["table"], np.int32)
+    a.albedo_mips, a.normal_mips, a.pbr_mips = (ptr(m, np.uint8) for m in mips)
+    a.n_mip_layers = mips[0].shape[0]
+    a.emissive_lod0 = ptr(materials["emissive_lod0"], np.float32)
+    a.update_this_frame = params.update_this_frame
+    a.grass_props[:] = list(params.grass_props)
+    a.o_albedo, a.o_normal, a.o_pbr, a.o_texture_ao = (out[k].ctypes.data for k in ("albedo", "normal", "pbr", "texture_ao"))
+    load().ref_generate_gbuffer(C.byref(a))
     return out
 
 

@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from voxelpathtracer_b200.abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxReflectionIn, VxReflectionOut,
+from voxelpathtracer_b200.abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxMaterialOut, VxMaterialParams, VxPrimaryParams, VxReflectionIn, VxReflectionOut,
                                       VxReflectionParams, VxShadowOut, VxShadowParams)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -19,7 +19,8 @@ class VxoScene(C.Structure):
                 ("albedo_lod3", C.c_void_p), ("pbr_lod2", C.c_void_p), ("n_layers", C.c_int32),
                 ("emissive_lod0", C.c_void_p), ("n_emissive_layers", C.c_int32), ("sky", C.c_void_p), ("sky_n", C.c_int32),
                 ("shadow_noise", C.c_void_p), ("normal_lod3", C.c_void_p), ("n_normal_layers", C.c_int32), ("emissive_lod2", C.c_void_p),
-                ("alpha_mips", C.c_void_p), ("n_alpha_layers", C.c_int32)]
+                ("alpha_mips", C.c_void_p), ("n_alpha_layers", C.c_int32),
+                ("albedo_mips", C.c_void_p), ("normal_mips", C.c_void_p), ("pbr_mips", C.c_void_p), ("n_mip_layers", C.c_int32)]
 
 
 class VxoStats(C.Structure):
@@ -57,6 +58,8 @@ def load():
                                          C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut), C.POINTER(VxoStats)]
     for f in (lib.vxo_trace_primary, lib.vxo_trace_shadow, lib.vxo_trace_diffuse, lib.vxo_trace_reflection):
         f.restype = C.c_int
+    lib.vxo_generate_gbuffer.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams), C.POINTER(VxMaterialOut)]
+    lib.vxo_generate_gbuffer.restype = C.c_int
     lib.vxo_trace_rays.argtypes = [C.POINTER(VxoScene), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VxoStats)]
     lib.vxo_trace_rays.restype = C.c_int
     lib.vxo_player_shadowed.argtypes = [C.POINTER(VxoScene), C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -125,6 +128,26 @@ class Oracle:
         a = np.ascontiguousarray(alpha_mips, dtype=np.uint8)
         self._keep["alpha"] = a
         self.scene.alpha_mips, self.scene.n_alpha_layers = a.ctypes.data, a.shape[0]
+
+    def set_gbuffer_textures(self, albedo_mips, normal_mips, pbr_mips):
+        """uint8 [layers][MIP_CHAIN_TEXELS][4] each (assets.rgba_mip_chain): inputs of generate_gbuffer."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (albedo_mips, normal_mips, pbr_mips)]
+        self._keep["gb_mips"] = arrs
+        s = self.scene
+        s.albedo_mips, s.normal_mips, s.pbr_mips, s.n_mip_layers = arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[0].shape[0]
+
+    def generate_gbuffer(self, cam, gbuf, params, out=None):
+        H, W = cam.height, cam.width
+        if out is None:
+            out = {"albedo": np.zeros((H, W, 3), np.float32), "normal": np.zeros((H, W, 3), np.float32), "pbr": np.zeros((H, W, 4), np.float32),
+                   "texture_ao": np.zeros((H, W), np.float32)}
+        g = VxGBuffer()
+        g.inv_t, g.normal_id, g.block_id = gbuf["inv_t"].ctypes.data, gbuf["normal_id"].ctypes.data, gbuf["block_id"].ctypes.data
+        o = VxMaterialOut()
+        o.albedo, o.normal, o.pbr, o.texture_ao = (out[k].ctypes.data for k in ("albedo", "normal", "pbr", "texture_ao"))
+        rc = self.lib.vxo_generate_gbuffer(C.byref(self.scene), C.byref(cam), C.byref(g), C.byref(params), C.byref(o))
+        assert rc == 0, rc
+        return out
 
     @staticmethod
     def _stats(st):

@@ -68,6 +68,11 @@ typedef struct VxoScene {
     const float* emissive_lod2;   // [n_emissive_layers][128][128]
     const uint8_t* alpha_mips;    // [n_alpha_layers][VXPT_ALPHA_MIP_TEXELS]: albedo alpha, mip levels 0..8 (alpha-tested traversal)
     int32_t n_alpha_layers;
+    // G-buffer material pass: RGBA8 mip chains, levels 0..9 of 512^2 layers, [n_mip_layers][VXPT_MIP_CHAIN_TEXELS][4]
+    const uint8_t* albedo_mips;   // GL_SRGB_ALPHA
+    const uint8_t* normal_mips;   // GL_RGBA
+    const uint8_t* pbr_mips;      // GL_RGBA
+    int32_t n_mip_layers;
 } VxoScene;
 
 typedef struct VxoStats {
@@ -1271,6 +1276,173 @@ int vxo_ambient_sound(const VxoScene* sc, const float player_pos[3], int frame, 
     if (stats) { stats->rays += st.rays; stats->df_fetches += st.df; stats->vox_fetches += st.vox; }
     return VXPT_OK;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ G-buffer material pass
+namespace {
+
+struct f4 {
+    float x, y, z, w;
+};
+inline f4 lerp4(f4 a, f4 b, float f) {
+    return f4{a.x * (1.0f - f) + b.x * f, a.y * (1.0f - f) + b.y * f, a.z * (1.0f - f) + b.z * f, a.w * (1.0f - f) + b.w * f};
+}
+
+// One block array as the GL texture object holds it (Core/GLClasses/TextureArray.cpp:28-78): RGBA8 layers of 512^2 with a complete mip
+// chain, GL_REPEAT, min filter GL_NEAREST_MIPMAP_LINEAR, mag filter GL_NEAREST (albedo, sRGB) or GL_LINEAR (normal, PBR).
+struct MipArray {
+    const uint8_t* texels;
+    int layers;
+    bool srgb, mag_linear;
+    const float* srgb_lut;
+    f4 texel(int layer, int level, int i, int j) const {
+        size_t off = 0;
+        for (int k = 0; k < level; ++k) off += (size_t)(512 >> k) * (size_t)(512 >> k);
+        const int n = 512 >> level;
+        const uint8_t* c = texels + ((size_t)layer * VXPT_MIP_CHAIN_TEXELS + off + (size_t)j * n + i) * 4;
+        if (srgb) return f4{srgb_lut[c[0]], srgb_lut[c[1]], srgb_lut[c[2]], (float)c[3] / 255.0f};
+        return f4{(float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f};
+    }
+    f4 nearest(int layer, int level, float u, float v) const {
+        const int n = 512 >> level;
+        return texel(layer, level, ((int)std::floor(u * (float)n)) & (n - 1), ((int)std::floor(v * (float)n)) & (n - 1));
+    }
+    // textureGrad: OpenGL 4.3 section 8.14 with the isotropic scale factor (the pinned definition, include/vxpt.h)
+    f4 grad(float layer_f, float u, float v, const float dpdx[2], const float dpdy[2]) const {
+        int layer = (int)std::nearbyintf(layer_f);
+        layer = std::min(std::max(layer, 0), layers - 1);
+        const float ux = dpdx[0] * 512.0f, vx = dpdx[1] * 512.0f, uy = dpdy[0] * 512.0f, vy = dpdy[1] * 512.0f;
+        const float rho = std::fmax(std::sqrt(ux * ux + vx * vx), std::sqrt(uy * uy + vy * vy));
+        const float lambda = (float)std::log2((double)rho);
+        const float c = mag_linear ? 0.5f : 0.0f;
+        if (lambda <= c) {
+            if (!mag_linear) return nearest(layer, 0, u, v);
+            const float x = u * 512.0f - 0.5f, y = v * 512.0f - 0.5f;
+            const float x0 = std::floor(x), y0 = std::floor(y);
+            const float fx = x - x0, fy = y - y0;
+            const int i0 = ((int)x0) & 511, i1 = ((int)x0 + 1) & 511, j0 = ((int)y0) & 511, j1 = ((int)y0 + 1) & 511;
+            const f4 lo = lerp4(texel(layer, 0, i0, j0), texel(layer, 0, i1, j0), fx);
+            const f4 hi = lerp4(texel(layer, 0, i0, j1), texel(layer, 0, i1, j1), fx);
+            return lerp4(lo, hi, fy);
+        }
+        if (lambda >= 9.0f) return nearest(layer, 9, u, v);
+        const int d1 = (int)std::floor(lambda);
+        return lerp4(nearest(layer, d1, u, v), nearest(layer, d1 + 1, u, v), lambda - std::floor(lambda));
+    }
+};
+
+// the operand a fragment hands to dFdx / dFdy in GetUVDerivative (GenerateGBuffer.glsl:443-461): UV = fract(P), P the hit point's
+// coordinates in the plane of its own face (CalculateVectors :463-530).  `reached` is false for invocations that never get there.
+struct QuadOperand {
+    bool reached;
+    float uv[2];
+    float dist;
+    v3 pos;
+    int nid;
+};
+inline QuadOperand gbuffer_operand(const VxCamera& cam, const VxGBuffer& g, int i, int j) {
+    QuadOperand q{};
+    if (i < 0 || j < 0 || i >= cam.width || j >= cam.height) return q;  // helper invocation outside the frame
+    const size_t p = (size_t)j * cam.width + i;
+    q.dist = 1.0f / g.inv_t[p];  // GetPositionAt :107-112 on u_NonLinearDepth
+    if (q.dist < 0.0f) return q;  // :360-366
+    q.nid = g.normal_id[p];
+    if (q.nid > 5) return q;      // no face normal: CalculateVectors matches nothing (outputs unset in the shader); shaded like a miss
+    float u, v;
+    pixel_uv(cam, i, j, u, v);
+    q.pos = ray_origin(cam) + normalize(ray_direction_at(cam, u, v)) * q.dist;
+    const int axis = q.nid <= 1 ? 2 : (q.nid <= 3 ? 1 : 0);
+    if (axis == 2) { q.uv[0] = fractf(q.pos.x); q.uv[1] = fractf(q.pos.y); }
+    else if (axis == 1) { q.uv[0] = fractf(q.pos.x); q.uv[1] = fractf(q.pos.z); }
+    else { q.uv[0] = fractf(q.pos.z); q.uv[1] = fractf(q.pos.y); }
+    q.reached = true;
+    return q;
+}
+
+}  // namespace
+
+extern "C" {
+
+// GenerateGBuffer.glsl main() :347-441 in the v1 parity profile (u_POM off, no lava), whole 2x2 quads of rows [row_begin, row_end).
+// Derivatives: dFdx / dFdy = odd-minus-even member of the quad's row / column pair; a member that never reaches the derivative
+// contributes the pixel's own operand.
+int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g, const VxMaterialParams* prm, const VxMaterialOut* out) {
+    if (prm->pom || prm->lava_block_id >= 0) return VXPT_E_UNSUPPORTED;
+    if (!prm->update_this_frame) return VXPT_OK;  // :353-357 discard
+    float lut[256];
+    for (int k = 0; k < 256; ++k) {
+        const double cs = (double)k / 255.0;
+        lut[k] = (float)(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+    }
+    const MipArray albedo{sc->albedo_mips, sc->n_mip_layers, true, false, lut};
+    const MipArray normals{sc->normal_mips, sc->n_mip_layers, false, true, lut};
+    const MipArray pbr{sc->pbr_mips, sc->n_mip_layers, false, true, lut};
+    const int W = cam->width;
+    const int32_t* M = sc->materials;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = cam->row_begin; j < cam->row_end; ++j)
+        for (int i = 0; i < W; ++i) {
+            const size_t p = (size_t)j * W + i;
+            const QuadOperand me = gbuffer_operand(*cam, *g, i, j);
+            if (!me.reached) {
+                if (out->albedo) for (int k = 0; k < 3; ++k) out->albedo[3 * p + k] = 0.0f;
+                if (out->normal) for (int k = 0; k < 3; ++k) out->normal[3 * p + k] = 1.0f;
+                if (out->pbr) for (int k = 0; k < 4; ++k) out->pbr[4 * p + k] = 0.0f;
+                if (out->texture_ao) out->texture_ao[p] = 0.0f;
+                continue;
+            }
+            // the four operands of the quad's row pair and column pair
+            const int i0 = i & ~1, j0 = j & ~1;
+            QuadOperand row[2] = {gbuffer_operand(*cam, *g, i0, j), gbuffer_operand(*cam, *g, i0 + 1, j)};
+            QuadOperand col[2] = {gbuffer_operand(*cam, *g, i, j0), gbuffer_operand(*cam, *g, i, j0 + 1)};
+            for (int k = 0; k < 2; ++k) {
+                if (!row[k].reached) row[k] = me;
+                if (!col[k].reached) col[k] = me;
+            }
+            float dx[2], dy[2], dx2[2], dy2[2];
+            for (int k = 0; k < 2; ++k) {
+                dx[k] = row[1].uv[k] - row[0].uv[k];
+                dy[k] = col[1].uv[k] - col[0].uv[k];
+                dx2[k] = fractf(row[1].uv[k] + 0.25f) - fractf(row[0].uv[k] + 0.25f);
+                dy2[k] = fractf(col[1].uv[k] + 0.25f) - fractf(col[0].uv[k] + 0.25f);
+            }
+            if ((dx[0] * dx[0] + dx[1] * dx[1]) + (dy[0] * dy[0] + dy[1] * dy[1]) > (dx2[0] * dx2[0] + dx2[1] * dx2[1]) + (dy2[0] * dy2[0] + dy2[1] * dy2[1])) {
+                dx[0] = dx2[0]; dx[1] = dx2[1]; dy[0] = dy2[0]; dy[1] = dy2[1];
+            }
+            // GetBlockID :95-99, GetTextureIDs :532-549
+            const int block = std::min(std::max((int)std::floor(((float)g->block_id[p] / 255.0f) * 255.0f), 0), 127);
+            float data[4] = {(float)M[block], (float)M[128 + block], (float)M[256 + block], (float)M[384 + block]};
+            if (block == prm->grass_props[0]) {
+                const int base = (me.nid == 2) ? 1 : ((me.nid == 3) ? 7 : 4);  // top : bottom : the four sides
+                for (int k = 0; k < 3; ++k) data[k] = (float)prm->grass_props[base + k];
+            }
+            v3 tangent, bitangent;
+            float fu, fv;
+            calc_vectors(me.pos, me.nid, tangent, bitangent, fu, fv);  // same tables as ReflectionTraceFrag's copy (:463-530 here)
+            const v3 face = normal_from_id(me.nid, 1.0f);
+            const float U = 1.0f - fu, Vc = 1.0f - fv;  // :397
+            const f4 nm = normals.grad(data[1], U, Vc, dx, dy);
+            const v3 n = V(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f);
+            const v3 mapped = (tangent * n.x + bitangent * n.y) + face * n.z;  // mat3(T, B, N) * n
+            const f4 pm = pbr.grad(data[2], U, Vc, dx, dy);
+            float emissivity = 0.0f;
+            if (data[3] > -0.5f) emissivity = tex_bilinear1(sc->emissive_lod0, (int)data[3], 512, U, Vc);
+            float o_pbr[4] = {clampf(pm.x, 0.0f, 1.0f), clampf(pm.y, 0.0f, 1.0f), clampf(pm.z, 0.0f, 1.0f), clampf(emissivity, 0.0f, 1.0f)};
+            const f4 al = albedo.grad(data[0], U, Vc, dx, dy);
+            const float lb = 0.02f;
+            o_pbr[3] *= (U > lb && U < 1.0f - lb && Vc > lb && Vc < 1.0f - lb) ? 1.0f : 0.0f;  // BloomLightLeakFix :432-438
+            if (out->albedo) { out->albedo[3 * p] = al.x; out->albedo[3 * p + 1] = al.y; out->albedo[3 * p + 2] = al.z; }
+            if (out->normal) { out->normal[3 * p] = mapped.x; out->normal[3 * p + 1] = mapped.y; out->normal[3 * p + 2] = mapped.z; }
+            if (out->pbr) for (int k = 0; k < 4; ++k) out->pbr[4 * p + k] = o_pbr[k];
+            if (out->texture_ao) out->texture_ao[p] = clampf(pm.w, 0.00000001f, 1.0f);
+        }
+    return VXPT_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int vxo_num_threads(void) {
 #ifdef _OPENMP

@@ -1,7 +1,7 @@
 // kernels_on_host.cpp — TEST INFRASTRUCTURE: the per-pixel trace kernels' own source, compiled by g++ and executed on the CPU.
 //
 // The build container has no GPU, so a kernel written here is first seen by a GPU at the end of a round.  To shorten that
-// loop this file includes voxelpathtracer_b200/csrc/trace.cu, trace_reflection.cu and df_consumers.cu UNCHANGED (kernels, device functions and
+// loop this file includes voxelpathtracer_b200/csrc/trace.cu, trace_reflection.cu, df_consumers.cu and gbuffer.cu UNCHANGED (kernels, device functions and
 // their host launchers with the per-frame constants) and gives g++ what nvcc would: the CUDA vector types come from the toolkit's
 // own headers (they are plain C++), the handful of device intrinsics the kernels use are defined below with their documented
 // semantics, and VX_LAUNCH becomes a loop over blockIdx / threadIdx.  tests/test_kernels_on_host.py compares what comes out with
@@ -57,6 +57,7 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetc
 #include "../../voxelpathtracer_b200/csrc/trace.cu"
 #include "../../voxelpathtracer_b200/csrc/trace_reflection.cu"
 #include "../../voxelpathtracer_b200/csrc/df_consumers.cu"
+#include "../../voxelpathtracer_b200/csrc/gbuffer.cu"
 
 namespace vxpt {
 // api.cu's make_scene, on a context whose "device" pointers are host pointers
@@ -72,6 +73,8 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.counters = c->d_counters;
     S.alpha_mips = c->d_alpha_mips;
     S.n_alpha_layers = c->n_alpha_layers;
+    S.albedo_mips = c->d_albedo_mips; S.normal_mips = c->d_normal_mips; S.pbr_mips = c->d_pbr_mips;
+    S.srgb_lut = c->d_srgb_lut; S.n_mip_layers = c->n_mip_layers;
     return S;
 }
 // the wavefront GI pipeline needs a GPU (shared memory, ballots); the shadow runs the one-thread-per-pixel kernel
@@ -82,6 +85,7 @@ void set_error(const std::string&) {}
 struct HostShadow {
     vxpt_ctx c;
     std::vector<uint8_t> steps, bluenoise;
+    float srgb_lut[256];
     vxpt::DeviceCounters counters{};
 };
 
@@ -110,6 +114,10 @@ typedef struct HsScene {
     const float* emissive_lod2;
     const uint8_t* alpha_mips;
     int32_t n_alpha_layers;
+    const uint8_t* albedo_mips;
+    const uint8_t* normal_mips;
+    const uint8_t* pbr_mips;
+    int32_t n_mip_layers;
 } HsScene;
 
 HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
@@ -148,6 +156,14 @@ HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
     c.d_alpha_mips = (uint8_t*)s->alpha_mips;
     c.n_alpha_layers = s->n_alpha_layers;
     c.d_counters = &h->counters;
+    // vxpt_set_gbuffer_textures (api.cu): the mip chains and the sRGB decode table
+    c.d_albedo_mips = (uchar4*)s->albedo_mips; c.d_normal_mips = (uchar4*)s->normal_mips; c.d_pbr_mips = (uchar4*)s->pbr_mips;
+    c.n_mip_layers = s->n_mip_layers;
+    for (int k = 0; k < 256; ++k) {
+        const double cs = (double)k / 255.0;
+        h->srgb_lut[k] = (float)(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+    }
+    c.d_srgb_lut = h->srgb_lut;
     return h;
 }
 HS_API void hs_destroy(void* p) { delete (HostShadow*)p; }
@@ -169,6 +185,9 @@ HS_API int hs_trace_diffuse(void* p, const VxCamera* cam, const VxGBuffer* g, co
 HS_API int hs_trace_reflection(void* p, const VxCamera* cam, const VxGBuffer* g, const VxReflectionIn* in, const VxReflectionParams* prm,
                                const VxReflectionOut* out) {
     return vxpt::launch_reflection(hs_ctx(p), *cam, *g, *in, *prm, *out);
+}
+HS_API int hs_generate_gbuffer(void* p, const VxCamera* cam, const VxGBuffer* g, const VxMaterialParams* prm, const VxMaterialOut* out) {
+    return vxpt::launch_gbuffer(hs_ctx(p), *cam, *g, *prm, *out);
 }
 HS_API int hs_trace_rays(void* p, const float* origins, const float* directions, int n, int max_it, float* t, uint8_t* normal_id, uint8_t* block_id,
                          int16_t* hit_voxel) {

@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from voxelpathtracer_b200.abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxPrimaryParams, VxReflectionIn, VxReflectionOut,
+from voxelpathtracer_b200.abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxGBuffer, VxMaterialOut, VxMaterialParams, VxPrimaryParams, VxReflectionIn, VxReflectionOut,
                                       VxReflectionParams, VxShadowOut, VxShadowParams)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB_PATH = os.path.join(HERE, "libkernels_on_host.so")
 CSRC = os.path.join(ROOT, "voxelpathtracer_b200", "csrc")
 SOURCES = [os.path.join(HERE, "kernels_on_host.cpp")] + [os.path.join(CSRC, f) for f in
-                                                         ("trace.cu", "trace_reflection.cu", "df_consumers.cu", "trace_device.cuh",
+                                                         ("trace.cu", "trace_reflection.cu", "df_consumers.cu", "gbuffer.cu", "trace_device.cuh",
                                                           "gi_device.cuh", "vxpt_internal.h")]
 CUDA_INCLUDE = "/usr/local/cuda/include"
 _lib = None
@@ -50,6 +50,7 @@ def load():
     lib.hs_trace_diffuse.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut)]
     lib.hs_trace_reflection.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]
+    lib.hs_generate_gbuffer.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams), C.POINTER(VxMaterialOut)]
     lib.hs_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_ambient_sound.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
     _lib = lib
@@ -127,6 +128,19 @@ class HostKernels:
         rc = self.lib.hs_trace_reflection(self.h, C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o))
         assert rc == 0, rc
         return out, self.stats()
+
+    def generate_gbuffer(self, cam, gbuf, params, out=None):
+        H, W = cam.height, cam.width
+        if out is None:
+            out = {"albedo": np.zeros((H, W, 3), np.float32), "normal": np.zeros((H, W, 3), np.float32), "pbr": np.zeros((H, W, 4), np.float32),
+                   "texture_ao": np.zeros((H, W), np.float32)}
+        g = VxGBuffer()
+        g.inv_t, g.normal_id, g.block_id = gbuf["inv_t"].ctypes.data, gbuf["normal_id"].ctypes.data, gbuf["block_id"].ctypes.data
+        o = VxMaterialOut()
+        o.albedo, o.normal, o.pbr, o.texture_ao = (out[k].ctypes.data for k in ("albedo", "normal", "pbr", "texture_ao"))
+        rc = self.lib.hs_generate_gbuffer(self.h, C.byref(cam), C.byref(g), C.byref(params), C.byref(o))
+        assert rc == 0, rc
+        return out
 
     def trace_rays(self, origins, directions, max_it):
         o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)

@@ -15,6 +15,8 @@ WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z
 NORMAL_MISS = 10
 ALPHA_MIP_TEXELS = sum((512 >> k) ** 2 for k in range(9))  # 349,524: levels 0..8 of a 512^2 layer (VXPT_ALPHA_MIP_TEXELS)
 
+MIP_CHAIN_TEXELS = sum((512 >> k) ** 2 for k in range(10))  # 349,525: levels 0..9 (VXPT_MIP_CHAIN_TEXELS)
+
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS, OPT_TIMING_EVENTS, OPT_TEXEL_FORMAT = 1, 2, 3, 4, 5, 6
 SHARED_HANDLE_BYTES = 64
@@ -75,6 +77,14 @@ class VxReflectionOut(C.Structure):
     _fields_ = [("color", C.c_void_p), ("hit_distance", C.c_void_p), ("emissive_mask", C.c_void_p)]
 
 
+class VxMaterialParams(C.Structure):
+    _fields_ = [("update_this_frame", C.c_int32), ("pom", C.c_int32), ("lava_block_id", C.c_int32), ("grass_props", C.c_int32 * 10)]
+
+
+class VxMaterialOut(C.Structure):
+    _fields_ = [("albedo", C.c_void_p), ("normal", C.c_void_p), ("pbr", C.c_void_p), ("texture_ao", C.c_void_p)]
+
+
 class VxFrameParams(C.Structure):
     _fields_ = [("primary", C.POINTER(VxPrimaryParams)), ("shadow", C.POINTER(VxShadowParams)), ("diffuse", C.POINTER(VxDiffuseParams)),
                 ("reflection", C.POINTER(VxReflectionParams)), ("g_normal", C.c_void_p), ("g_pbr", C.c_void_p)]
@@ -114,6 +124,9 @@ EXPORTS = {
     "vxpt_trace_diffuse": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut)]),
     "vxpt_trace_reflection": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]),
+    "vxpt_set_gbuffer_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "vxpt_generate_gbuffer": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams),
+                                        C.POINTER(VxMaterialOut)]),
     "vxpt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxpt_player_shadowed": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vxpt_estimate_ambient_sound": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint32), C.c_void_p]),

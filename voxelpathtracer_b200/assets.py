@@ -102,6 +102,69 @@ def synthetic_alpha_lod0(n_layers, cutout_layers, seed=11):
     return a
 
 
+def _srgb_decode(u8):
+    c = u8.astype(np.float64) / 255.0
+    return np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+
+
+def _srgb_encode(lin):
+    lin = np.clip(lin, 0.0, 1.0)
+    return np.where(lin <= 0.0031308, lin * 12.92, 1.055 * lin ** (1.0 / 2.4) - 0.055)
+
+
+def rgba_mip_chain(lod0, srgb=False):
+    """uint8 [L][512][512][4] level-0 texels -> uint8 [L][MIP_CHAIN_TEXELS][4]: mip levels 0..9 back to back, the layout
+    vxpt_set_gbuffer_textures takes.  Each level is the 2x2 box filter of the one above, rounded to nearest; for an sRGB array the rgb
+    is filtered in linear space and re-encoded (alpha stays linear).  GL leaves glGenerateMipmap's filter to the driver: a host
+    application hands over whatever pyramid its driver built (glGetTexImage per level); this helper builds one for tests and benches."""
+    a = np.ascontiguousarray(lod0, dtype=np.uint8)
+    assert a.ndim == 4 and a.shape[1:] == (512, 512, 4), a.shape
+    levels = [a.reshape(a.shape[0], -1, 4)]
+    cur = a.astype(np.float64) / 255.0
+    if srgb:
+        cur[..., :3] = _srgb_decode(a[..., :3])
+    for _ in range(9):
+        cur = 0.25 * (cur[:, 0::2, 0::2] + cur[:, 1::2, 0::2] + cur[:, 0::2, 1::2] + cur[:, 1::2, 1::2])
+        enc = cur.copy()
+        if srgb:
+            enc[..., :3] = _srgb_encode(cur[..., :3])
+        levels.append(np.floor(enc * 255.0 + 0.5).astype(np.uint8).reshape(a.shape[0], -1, 4))
+    return np.ascontiguousarray(np.concatenate(levels, axis=1))
+
+
+def synthetic_material_lod0(n_layers, seed=23):
+    """Level-0 RGBA8 texels (albedo sRGB, normal map, PBR) for the G-buffer material pass, [n_layers][512][512][4] each: per layer a
+    tiling pattern with detail at several scales (so that every mip level differs from its neighbours), deterministic in `seed`.
+    Stand-in for the reference's Res/Block textures, which are too large to commit at full resolution."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:512, 0:512].astype(np.float64) / 512.0
+    albedo = np.zeros((n_layers, 512, 512, 4), np.uint8)
+    normal = np.zeros_like(albedo)
+    pbr = np.zeros_like(albedo)
+    for layer in range(n_layers):
+        h = np.zeros((512, 512))
+        for octave in range(1, 7):
+            f = 2 ** octave
+            px, py = rng.rand(2) * 2.0 * np.pi
+            h += (np.sin(2 * np.pi * f * xx + px) * np.cos(2 * np.pi * f * yy + py) + 0.5 * np.sin(2 * np.pi * f * (xx + yy) + px * py)) / octave
+        h = (h - h.min()) / (h.max() - h.min())
+        noise = rng.rand(512, 512)
+        base = 0.25 + 0.6 * rng.rand(3)
+        for k in range(3):
+            albedo[layer, ..., k] = np.clip((base[k] * (0.55 + 0.45 * h) + 0.12 * (noise - 0.5)) * 255.0, 0, 255).astype(np.uint8)
+        albedo[layer, ..., 3] = 255
+        gy, gx = np.gradient(h)
+        n = np.stack([-gx * 40.0, -gy * 40.0, np.ones_like(h)], -1)
+        n /= np.linalg.norm(n, axis=-1, keepdims=True)
+        normal[layer, ..., :3] = np.clip((n * 0.5 + 0.5) * 255.0 + 0.5, 0, 255).astype(np.uint8)
+        normal[layer, ..., 3] = 255
+        pbr[layer, ..., 0] = np.clip((0.35 + 0.5 * h + 0.1 * (noise - 0.5)) * 255.0, 0, 255).astype(np.uint8)  # roughness
+        pbr[layer, ..., 1] = np.clip((rng.rand() < 0.3) * (0.6 + 0.4 * noise) * 255.0, 0, 255).astype(np.uint8)  # metalness
+        pbr[layer, ..., 2] = np.clip(h * 255.0, 0, 255).astype(np.uint8)                                          # displacement
+        pbr[layer, ..., 3] = np.clip((0.6 + 0.4 * h) * 255.0, 0, 255).astype(np.uint8)                             # texture AO
+    return albedo, normal, pbr
+
+
 def analytic_sky(n=16, sun_dir=(-0.669, 0.468, 0.577)):
     """Documented stand-in for the reference's rendered atmosphere cubemap (RGB16F, 16^2 for GI; Pipeline.cpp:1392-1394):
     a horizon-to-zenith gradient plus a broad sun lobe.  Faces +X,-X,+Y,-Y,+Z,-Z, GL cube-map face orientation,

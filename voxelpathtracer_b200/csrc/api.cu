@@ -50,6 +50,11 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.counters = c->d_counters;
     S.alpha_mips = c->d_alpha_mips;
     S.n_alpha_layers = c->n_alpha_layers;
+    S.albedo_mips = c->d_albedo_mips;
+    S.normal_mips = c->d_normal_mips;
+    S.pbr_mips = c->d_pbr_mips;
+    S.srgb_lut = c->d_srgb_lut;
+    S.n_mip_layers = c->n_mip_layers;
     return S;
 }
 
@@ -324,7 +329,8 @@ int vxpt_destroy(vxpt_handle c) {
         if (c->rep_steps[r]) cudaFree(c->rep_steps[r]);
     }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
-                    c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_alpha_mips, c->d_counters, c->d_stage, c->d_queue};
+                    c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_alpha_mips, c->d_counters, c->d_stage, c->d_queue,
+                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -540,6 +546,73 @@ int vxpt_set_albedo_alpha_mips(vxpt_handle c, const uint8_t* alpha_mips, int n_l
     int rc = replace_buffer(c, &c->d_alpha_mips, alpha_mips, (size_t)n_layers * VXPT_ALPHA_MIP_TEXELS);
     if (rc) return rc;
     c->n_alpha_layers = n_layers;
+    return VXPT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------- G-buffer material pass
+int vxpt_set_gbuffer_textures(vxpt_handle c, const uint8_t* albedo_mips, const uint8_t* normal_mips, const uint8_t* pbr_mips, int n_layers) {
+    if (!c || !albedo_mips || !normal_mips || !pbr_mips) return fail(VXPT_E_INVALID, "NULL argument");
+    if (n_layers <= 0 || n_layers > 1024) return fail(VXPT_E_INVALID, "bad layer count");
+    VX_CUDA(cudaSetDevice(c->device));
+    if (int rc = finish_pending_frame(c)) return rc;
+    const size_t bytes = (size_t)n_layers * VXPT_MIP_CHAIN_TEXELS * 4;
+    int rc;
+    if ((rc = replace_buffer(c, &c->d_albedo_mips, albedo_mips, bytes)) || (rc = replace_buffer(c, &c->d_normal_mips, normal_mips, bytes)) ||
+        (rc = replace_buffer(c, &c->d_pbr_mips, pbr_mips, bytes)))
+        return rc;
+    // GL_SRGB_ALPHA decode (OpenGL 4.3 section 8.23): evaluated in double, rounded once to fp32
+    float lut[256];
+    for (int k = 0; k < 256; ++k) {
+        const double cs = (double)k / 255.0;
+        lut[k] = (float)(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+    }
+    if ((rc = replace_buffer(c, &c->d_srgb_lut, lut, sizeof lut))) return rc;
+    c->n_mip_layers = n_layers;
+    return VXPT_OK;
+}
+
+int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, const VxMaterialParams* p, const VxMaterialOut* out) {
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if ((rc = check_camera(cam))) return rc;
+    if (!g || !p || !out || !g->inv_t || !g->normal_id || !g->block_id)
+        return fail(VXPT_E_INVALID, "NULL argument (G-buffer inv_t, normal_id and block_id are required)");
+    if (p->pom) return fail(VXPT_E_UNSUPPORTED, "u_POM (relief parallax mapping) is outside the v1 parity profile");
+    if (p->lava_block_id >= 0) return fail(VXPT_E_UNSUPPORTED, "lava animation (u_LavaBlockID, functions of the wall clock) is outside the v1 parity profile");
+    if (!c->have_materials || !c->d_albedo_mips) return fail(VXPT_E_STATE, "the G-buffer pass needs vxpt_set_materials and vxpt_set_gbuffer_textures");
+    const int rows = cam->interleave_n > 1 ? cam->height / cam->interleave_n : cam->height;
+    if ((cam->row_begin & 1) || ((cam->row_end & 1) && cam->row_end != rows) || (cam->interleave_n > 1 && (cam->band_rows & 1)))
+        return fail(VXPT_E_INVALID, "the G-buffer pass shades 2x2 quads: row_begin / row_end (and band_rows) must be even");
+    for (int b = 0; b < 128; ++b) {
+        for (int k = 0; k < 3; ++k)
+            if (c->h_materials[128 * k + b] >= c->n_mip_layers)
+                return fail(VXPT_E_INVALID, "material table references a texture layer that vxpt_set_gbuffer_textures did not receive");
+        if (c->h_materials[384 + b] >= c->n_emissive) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
+    }
+    for (int k = 1; k < 10; ++k)
+        if (p->grass_props[k] < 0 || p->grass_props[k] >= c->n_mip_layers) return fail(VXPT_E_INVALID, "grass_props references a missing texture layer");
+    VX_CUDA(cudaSetDevice(c->device));
+    PassIO io(c, cam);
+    Plane it, nid, bid, al, nm, pb, ao;
+    io.add(it, g->inv_t, 4); io.add(nid, g->normal_id, 1); io.add(bid, g->block_id, 1);
+    io.add(al, out->albedo, 12); io.add(nm, out->normal, 12); io.add(pb, out->pbr, 16); io.add(ao, out->texture_ao, 4);
+    if ((rc = io.resolve())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    if ((rc = io.upload(it)) || (rc = io.upload(nid)) || (rc = io.upload(bid))) return rc;
+    if (!p->update_this_frame) {  // every invocation discards: staged output planes must keep what the caller's planes hold
+        if ((rc = io.upload(al)) || (rc = io.upload(nm)) || (rc = io.upload(pb)) || (rc = io.upload(ao))) return rc;
+    }
+    VxGBuffer gd{nullptr, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, nullptr};
+    VxMaterialOut od{(float*)al.dev, (float*)nm.dev, (float*)pb.dev, (float*)ao.dev};
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_gbuffer(c, *cam, gd, *p, od))) return rc;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
+    bool any = false;
+    if ((rc = io.download(al, any)) || (rc = io.download(nm, any)) || (rc = io.download(pb, any)) || (rc = io.download(ao, any))) return rc;
+    if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
     return VXPT_OK;
 }
 

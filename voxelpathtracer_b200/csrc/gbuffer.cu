@@ -1,0 +1,174 @@
+// gbuffer.cu — G-buffer material pass: Core/Shaders/GenerateGBuffer.glsl main() :347-441 as drawn by
+// Core/Pipeline.cpp:2066-2136, in the v1 parity profile of include/vxpt.h (u_POM = false, no lava animation).
+//
+// One thread per pixel, the 8x4-pixel warp tiles of the trace passes.  The shader takes screen-space derivatives of the surface UV
+// (GetUVDerivative :443-461) to pick the mip level: a derivative is a difference inside the pixel's 2x2 quad, so every thread
+// re-derives the UV of its two quad neighbours from their G-buffer texels (three short ray set-ups instead of a shuffle: the same
+// source then runs one "thread" after another in tests/host_shadow).  HBM traffic: 6 B read + 44 B written per pixel; the texel
+// gathers (two mip levels of three RGBA8 arrays) hit L1/L2 — the pass is bound by its plane writes.
+// Compiled with -fmad=false; log2 is the pinned correctly rounded fp32 value (double evaluation).
+#include <cmath>
+
+#include "gi_device.cuh"
+
+namespace vxpt {
+
+struct MaterialDev {
+    int grass[10];
+};
+struct MaterialOutDev {
+    float* albedo;      // 3 / pixel
+    float* normal;      // 3 / pixel
+    float4* pbr;
+    float* texture_ao;
+};
+
+__device__ __forceinline__ float log2_cr(float x) { return (float)log2((double)x); }
+
+// texel (i, j) of level `level` of one layer's mip chain; RGBA8 -> float, c / 255 (OpenGL 4.3 section 2.3.5); the rgb of a
+// GL_SRGB_ALPHA array goes through the sRGB decode table
+__device__ __forceinline__ float4 mip_texel(const SceneDev& S, const uchar4* layer_base, int level, int i, int j, bool srgb) {
+    // offset of level k = (4^9 + ... + 4^(10-k)) = (4^10 - 4^(10-k)) / 3
+    const int off = ((1 << 20) - (1 << (2 * (10 - level)))) / 3;
+    const int n = 512 >> level;
+    const uchar4 c = layer_base[off + j * n + i];
+    if (srgb) return make_float4(S.srgb_lut[c.x], S.srgb_lut[c.y], S.srgb_lut[c.z], (float)c.w / 255.0f);
+    return make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+}
+__device__ __forceinline__ float4 mip_nearest(const SceneDev& S, const uchar4* layer_base, int level, float u, float v, bool srgb) {
+    const int n = 512 >> level;
+    const int i = ((int)floorf(u * (float)n)) & (n - 1), j = ((int)floorf(v * (float)n)) & (n - 1);
+    return mip_texel(S, layer_base, level, i, j, srgb);
+}
+__device__ __forceinline__ float4 f4_lerp(float4 a, float4 b, float f) {
+    const float g = 1.0f - f;
+    return make_float4(a.x * g + b.x * f, a.y * g + b.y * f, a.z * g + b.z * f, a.w * g + b.w * f);
+}
+// textureGrad on a block array (include/vxpt.h: the pinned OpenGL 4.3 section 8.14 isotropic filter)
+__device__ __forceinline__ float4 texture_grad(const SceneDev& S, const uchar4* mips, float layer_f, float u, float v, float4 d, bool srgb,
+                                               bool mag_linear) {
+    int layer = (int)nearbyintf(layer_f);
+    layer = min(max(layer, 0), S.n_mip_layers - 1);
+    const uchar4* base = mips + (size_t)layer * VXPT_MIP_CHAIN_TEXELS;
+    const float dudx = d.x * 512.0f, dvdx = d.y * 512.0f, dudy = d.z * 512.0f, dvdy = d.w * 512.0f;
+    const float rho = fmaxf(sqrtf(dudx * dudx + dvdx * dvdx), sqrtf(dudy * dudy + dvdy * dvdy));
+    const float lambda = log2_cr(rho);
+    if (lambda <= (mag_linear ? 0.5f : 0.0f)) {  // magnification, level 0
+        if (!mag_linear) return mip_nearest(S, base, 0, u, v, srgb);
+        const float x = u * 512.0f - 0.5f, y = v * 512.0f - 0.5f;
+        const float fx0 = floorf(x), fy0 = floorf(y);
+        const float fx = x - fx0, fy = y - fy0;
+        const int i0 = ((int)fx0) & 511, i1 = ((int)fx0 + 1) & 511, j0 = ((int)fy0) & 511, j1 = ((int)fy0 + 1) & 511;
+        const float4 a = f4_lerp(mip_texel(S, base, 0, i0, j0, srgb), mip_texel(S, base, 0, i1, j0, srgb), fx);
+        const float4 b = f4_lerp(mip_texel(S, base, 0, i0, j1, srgb), mip_texel(S, base, 0, i1, j1, srgb), fx);
+        return f4_lerp(a, b, fy);
+    }
+    if (lambda >= 9.0f) return mip_nearest(S, base, 9, u, v, srgb);
+    const float fl = floorf(lambda);
+    const int d1 = (int)fl;
+    return f4_lerp(mip_nearest(S, base, d1, u, v, srgb), mip_nearest(S, base, d1 + 1, u, v, srgb), lambda - fl);
+}
+
+// what a quad member hands to dFdx / dFdy: UV = fract(P) of CalculateVectors :463-530 on its own hit point and face, or nothing when
+// the invocation returns before reaching it (sky :360-366, outside the frame)
+__device__ __forceinline__ bool quad_uv(const CameraDev& cam, const GBufferDev& g, int i, int j, int prow, float& u, float& v, float& dist,
+                                        V3& pos, int& nid) {
+    if (i >= cam.width || j >= cam.height) return false;
+    const size_t px = (size_t)prow * cam.width + i;
+    dist = 1.0f / g.inv_t[px];  // GetPositionAt :107-112
+    if (dist < 0.0f) return false;
+    nid = g.normal_id[px];
+    if (nid > 5) return false;  // no face: the shader's CalculateVectors would leave its outputs unset; shaded like a miss
+    const float tu = ((float)i + 0.5f) / (float)cam.width, tv = ((float)j + 0.5f) / (float)cam.height;
+    pos = ray_origin(cam) + normalize3(ray_direction_at(cam, tu, tv)) * dist;
+    if (nid <= 1) { u = fractf(pos.x); v = fractf(pos.y); }
+    else if (nid <= 3) { u = fractf(pos.x); v = fractf(pos.z); }
+    else { u = fractf(pos.z); v = fractf(pos.y); }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ MaterialDev p,
+                                                      const GBufferDev g, const MaterialOutDev out) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const size_t px = (size_t)prow * cam.width + i;
+    float u, v, dist;
+    V3 pos;
+    int nid;
+    if (!quad_uv(cam, g, i, j, prow, u, v, dist, pos, nid)) {  // :360-366
+        if (out.albedo) { out.albedo[3 * px] = 0.0f; out.albedo[3 * px + 1] = 0.0f; out.albedo[3 * px + 2] = 0.0f; }
+        if (out.normal) { out.normal[3 * px] = 1.0f; out.normal[3 * px + 1] = 1.0f; out.normal[3 * px + 2] = 1.0f; }
+        if (out.pbr) out.pbr[px] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (out.texture_ao) out.texture_ao[px] = 0.0f;
+        return;
+    }
+    // GetUVDerivative :443-461 — the quad partners along x and y (the rows of a quad are neighbours in the planes too: bands are even)
+    float un, vn, dn;
+    V3 pn;
+    int nn;
+    float ax = u, ay = v, bx = u, by = v;  // x pair: a = even column, b = odd column
+    if (quad_uv(cam, g, i ^ 1, j, prow, un, vn, dn, pn, nn)) {
+        if (i & 1) { ax = un; ay = vn; } else { bx = un; by = vn; }
+    }
+    float cx = u, cy = v, ex = u, ey = v;  // y pair: c = even row, e = odd row
+    if (quad_uv(cam, g, i, j ^ 1, prow ^ 1, un, vn, dn, pn, nn)) {
+        if (j & 1) { cx = un; cy = vn; } else { ex = un; ey = vn; }
+    }
+    float4 d = make_float4(bx - ax, by - ay, ex - cx, ey - cy);
+    {
+        const float a2x = fractf(ax + 0.25f), a2y = fractf(ay + 0.25f), b2x = fractf(bx + 0.25f), b2y = fractf(by + 0.25f);
+        const float c2x = fractf(cx + 0.25f), c2y = fractf(cy + 0.25f), e2x = fractf(ex + 0.25f), e2y = fractf(ey + 0.25f);
+        const float4 d2 = make_float4(b2x - a2x, b2y - a2y, e2x - c2x, e2y - c2y);
+        if ((d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w) > (d2.x * d2.x + d2.y * d2.y) + (d2.z * d2.z + d2.w * d2.w)) d = d2;
+    }
+    // GetTextureIDs :532-549
+    const int block = min((int)g.block_id[px], 127);  // GetBlockID :95-99 (the unorm8 round trip is exact)
+    float l_albedo = (float)S.materials[block], l_normal = (float)S.materials[128 + block], l_pbr = (float)S.materials[256 + block];
+    const float l_emissive = (float)S.materials[384 + block];
+    if (block == p.grass[0]) {
+        const int o = (nid == 2) ? 1 : ((nid == 3) ? 7 : 4);
+        l_albedo = (float)p.grass[o]; l_normal = (float)p.grass[o + 1]; l_pbr = (float)p.grass[o + 2];
+    }
+    V3 tangent, bitangent;
+    if (nid <= 1) { tangent = mk3(1.f, 0.f, 0.f); bitangent = mk3(0.f, 1.f, 0.f); }
+    else if (nid <= 3) { tangent = mk3(1.f, 0.f, 0.f); bitangent = mk3(0.f, 0.f, 1.f); }
+    else { tangent = mk3(0.f, 0.f, -1.f); bitangent = mk3(0.f, -1.f, 0.f); }
+    const V3 face = normal_from_id(nid, 1.0f);
+    u = 1.0f - u;  // :397 (Parallax() returns the flat UV when u_POM is off)
+    v = 1.0f - v;
+    const float4 nm = texture_grad(S, S.normal_mips, l_normal, u, v, d, false, true);
+    const float nx = nm.x * 2.0f - 1.0f, ny = nm.y * 2.0f - 1.0f, nz = nm.z * 2.0f - 1.0f;
+    const V3 mapped = mk3((tangent.x * nx + bitangent.x * ny) + face.x * nz, (tangent.y * nx + bitangent.y * ny) + face.y * nz,
+                          (tangent.z * nx + bitangent.z * ny) + face.z * nz);  // tbn * NormalMapped
+    const float4 pm = texture_grad(S, S.pbr_mips, l_pbr, u, v, d, false, true);
+    float emissivity = 0.0f;
+    if (l_emissive > -0.5f) emissivity = tex_bilinear1(S.emissive, (int)l_emissive, 512, u, v);
+    float4 o_pbr = make_float4(clampf(pm.x, 0.0f, 1.0f), clampf(pm.y, 0.0f, 1.0f), clampf(pm.z, 0.0f, 1.0f), clampf(emissivity, 0.0f, 1.0f));
+    const float4 al = texture_grad(S, S.albedo_mips, l_albedo, u, v, d, true, false);
+    const float inside = (u > 0.02f && u < 1.0f - 0.02f && v > 0.02f && v < 1.0f - 0.02f) ? 1.0f : 0.0f;  // BloomLightLeakFix :432-438
+    o_pbr.w *= inside;
+    if (out.albedo) { out.albedo[3 * px] = al.x; out.albedo[3 * px + 1] = al.y; out.albedo[3 * px + 2] = al.z; }
+    if (out.normal) { out.normal[3 * px] = mapped.x; out.normal[3 * px + 1] = mapped.y; out.normal[3 * px + 2] = mapped.z; }
+    if (out.pbr) out.pbr[px] = o_pbr;
+    if (out.texture_ao) out.texture_ao[px] = clampf(pm.w, 0.00000001f, 1.0f);
+}
+
+int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const VxMaterialParams& p, const VxMaterialOut& out) {
+    if (!p.update_this_frame) return VXPT_OK;  // :353-357: every invocation discards
+    const SceneDev S = make_scene(c);
+    MaterialDev d;
+    for (int k = 0; k < 10; ++k) d.grass[k] = p.grass_props[k];
+    CameraDev cd;
+    for (int k = 0; k < 16; ++k) { cd.inv_view[k] = cam.inv_view[k]; cd.inv_proj[k] = cam.inv_proj[k]; }
+    cd.width = cam.width; cd.height = cam.height; cd.row_begin = cam.row_begin; cd.row_end = cam.row_end;
+    cd.il_n = cam.interleave_n; cd.il_rank = cam.interleave_rank; cd.il_band = cam.band_rows > 0 ? cam.band_rows : 1;
+    const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel};
+    const MaterialOutDev od{out.albedo, out.normal, reinterpret_cast<float4*>(out.pbr), out.texture_ao};
+    const dim3 grid((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8);
+    VX_LAUNCH(gbuffer_kernel, grid, 256, c->stream, S, cd, d, gd, od);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+}  // namespace vxpt

@@ -54,6 +54,12 @@ struct SceneDev {
     DeviceCounters* counters;
     const uint8_t* alpha_mips;  // [n_alpha_layers][VXPT_ALPHA_MIP_TEXELS] albedo alpha, mip levels 0..8 (alpha-tested traversal)
     int n_alpha_layers;
+    // G-buffer material pass (gbuffer.cu): RGBA8 mip chains [n_mip_layers][VXPT_MIP_CHAIN_TEXELS] and the sRGB decode table
+    const uchar4* albedo_mips;
+    const uchar4* normal_mips;
+    const uchar4* pbr_mips;
+    const float* srgb_lut;  // 256
+    int n_mip_layers;
 };
 
 }  // namespace vxpt
@@ -87,6 +93,11 @@ struct vxpt_ctx {
     uchar4* d_shadow_noise = nullptr;
     uint8_t* d_alpha_mips = nullptr;
     int n_alpha_layers = 0;
+    uchar4* d_albedo_mips = nullptr;  // vxpt_set_gbuffer_textures
+    uchar4* d_normal_mips = nullptr;
+    uchar4* d_pbr_mips = nullptr;
+    float* d_srgb_lut = nullptr;
+    int n_mip_layers = 0;
     int n_layers = 0, n_emissive = 0, sky_n = 0;
     bool have_materials = false, have_bluenoise = false, have_textures = false, have_sky = false, have_shadow_noise = false;
 
@@ -161,6 +172,8 @@ int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, 
 int launch_rays(vxpt_ctx* c, const float* origins, const float* directions, int n, int max_iterations, float* t, uint8_t* normal_id,
                 uint8_t* block_id, int16_t* hit_voxel);
 int launch_ambient(vxpt_ctx* c, const float player[3], int frame, unsigned* aggregate, unsigned* per_invocation);
+// gbuffer.cu
+int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxMaterialParams& p, const VxMaterialOut& out_dev);
 // l2_probe.cu
 int run_l2_probe(vxpt_ctx* c, double* gbps);
 

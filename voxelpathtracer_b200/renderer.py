@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxFrameOut, VxFrameParams, VxGBuffer, VxPrimaryParams, VxReflectionIn,
+from .abi import (VxCamera, VxDiffuseOut, VxDiffuseParams, VxFrameOut, VxFrameParams, VxGBuffer, VxMaterialOut, VxMaterialParams, VxPrimaryParams, VxReflectionIn,
                   VxReflectionOut, VxReflectionParams, VxShadowOut, VxShadowParams, VxStats, check)
 
 try:  # torch is optional plumbing: device buffers, streams, torch.distributed
@@ -79,6 +79,14 @@ def reflection_params(sun_dir, moon_dir, stronger_dir, viewer_pos, grass_props, 
     p.viewer_pos[:] = [float(v) for v in viewer_pos]
     p.sun_strength, p.moon_strength = float(sun_strength), float(moon_strength)
     p.halton[0], p.halton[1] = float(halton[0]), float(halton[1])
+    p.grass_props[:] = [int(v) for v in grass_props]
+    return p
+
+
+def material_params(grass_props, update_this_frame=True, pom=False, lava_block_id=-1):
+    """GenerateGBuffer's uniforms (Core/Pipeline.cpp:2079-2104); POM and the lava animation are outside the v1 parity profile."""
+    p = VxMaterialParams()
+    p.update_this_frame, p.pom, p.lava_block_id = int(bool(update_this_frame)), int(bool(pom)), int(lava_block_id)
     p.grass_props[:] = [int(v) for v in grass_props]
     return p
 
@@ -158,6 +166,13 @@ class Renderer:
         assert a.ndim == 2 and a.shape[1] == abi.ALPHA_MIP_TEXELS, a.shape
         abi.check(self.lib.vxpt_set_albedo_alpha_mips(self.handle, a.ctypes.data, a.shape[0]))
 
+    def set_gbuffer_textures(self, albedo_mips, normal_mips, pbr_mips):
+        """uint8 [n_layers][MIP_CHAIN_TEXELS][4] each: the RGBA8 mip chains of the block arrays (see assets.rgba_mip_chain)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (albedo_mips, normal_mips, pbr_mips)]
+        for a in arrs:
+            assert a.ndim == 3 and a.shape[1:] == (abi.MIP_CHAIN_TEXELS, 4) and a.shape[0] == arrs[0].shape[0], a.shape
+        check(self.lib.vxpt_set_gbuffer_textures(self.handle, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), int(arrs[0].shape[0])))
+
     def set_sky_cubemap(self, rgb):
         s = np.ascontiguousarray(rgb, dtype=np.float32)
         assert s.ndim == 4 and s.shape[0] == 6 and s.shape[1] == s.shape[2] and s.shape[3] == 3
@@ -211,6 +226,10 @@ class Renderer:
                 "luma": self.alloc((height, width), f, device, pinned),
                 "ao_sky": self.alloc((height, width, 2), np.uint8 if texel else np.float32, device, pinned)}
 
+    def alloc_material(self, width, height, device=False, pinned=False):
+        return {"albedo": self.alloc((height, width, 3), np.float32, device, pinned), "normal": self.alloc((height, width, 3), np.float32, device, pinned),
+                "pbr": self.alloc((height, width, 4), np.float32, device, pinned), "texture_ao": self.alloc((height, width), np.float32, device, pinned)}
+
     @staticmethod
     def gbuffer_struct(g):
         s = VxGBuffer()
@@ -245,6 +264,15 @@ class Renderer:
         o = VxReflectionOut()
         o.color, o.hit_distance, o.emissive_mask = _ptr(out.get("color")), _ptr(out.get("hit_distance")), _ptr(out.get("emissive_mask"))
         check(self.lib.vxpt_trace_reflection(self.handle, C.byref(cam), C.byref(g), C.byref(i), C.byref(params), C.byref(o)))
+        return out
+
+    def generate_gbuffer(self, cam, gbuf, params, out):
+        """G-buffer material pass (vxpt_generate_gbuffer, GenerateGBuffer.glsl): albedo / normal / pbr / texture_ao planes; the normal
+        and pbr planes are what trace_reflection takes as g_normal / g_pbr."""
+        g = self.gbuffer_struct(gbuf)
+        o = VxMaterialOut()
+        o.albedo, o.normal, o.pbr, o.texture_ao = _ptr(out.get("albedo")), _ptr(out.get("normal")), _ptr(out.get("pbr")), _ptr(out.get("texture_ao"))
+        check(self.lib.vxpt_generate_gbuffer(self.handle, C.byref(cam), C.byref(g), C.byref(params), C.byref(o)))
         return out
 
     # ---- other consumers of the distance field (SURVEY.md §8 f4) ----

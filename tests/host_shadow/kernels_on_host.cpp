@@ -85,7 +85,7 @@ void set_error(const std::string&) {}
 struct HostShadow {
     vxpt_ctx c;
     std::vector<uint8_t> steps, bluenoise;
-    float srgb_lut[256];
+    float srgb_lut[512];
     vxpt::DeviceCounters counters{};
 };
 
@@ -162,6 +162,7 @@ HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
     for (int k = 0; k < 256; ++k) {
         const double cs = (double)k / 255.0;
         h->srgb_lut[k] = (float)(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+        h->srgb_lut[256 + k] = (float)k / 255.0f;
     }
     c.d_srgb_lut = h->srgb_lut;
     return h;

@@ -561,10 +561,12 @@ int vxpt_set_gbuffer_textures(vxpt_handle c, const uint8_t* albedo_mips, const u
         (rc = replace_buffer(c, &c->d_pbr_mips, pbr_mips, bytes)))
         return rc;
     // GL_SRGB_ALPHA decode (OpenGL 4.3 section 8.23): evaluated in double, rounded once to fp32
-    float lut[256];
+    // followed by the plain unorm8 decode c / 255 (fp32 division), so that a texel fetch is table reads only
+    float lut[512];
     for (int k = 0; k < 256; ++k) {
         const double cs = (double)k / 255.0;
         lut[k] = (float)(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+        lut[256 + k] = (float)k / 255.0f;
     }
     if ((rc = replace_buffer(c, &c->d_srgb_lut, lut, sizeof lut))) return rc;
     c->n_mip_layers = n_layers;

@@ -6,7 +6,7 @@
 // re-derives the UV of its two quad neighbours from their G-buffer texels (three short ray set-ups instead of a shuffle: the same
 // source then runs one "thread" after another in tests/host_shadow).  HBM traffic: 6 B read + 44 B written per pixel; the texel
 // gathers (two mip levels of three RGBA8 arrays) hit L1/L2 — the pass is bound by its plane writes.
-// Compiled with -fmad=false; log2 is the pinned correctly rounded fp32 value (double evaluation).
+// Compiled with -fmad=false; log2 is the pinned correctly rounded fp32 value (double evaluation, once per pixel).
 #include <cmath>
 
 #include "gi_device.cuh"
@@ -25,15 +25,17 @@ struct MaterialOutDev {
 
 __device__ __forceinline__ float log2_cr(float x) { return (float)log2((double)x); }
 
-// texel (i, j) of level `level` of one layer's mip chain; RGBA8 -> float, c / 255 (OpenGL 4.3 section 2.3.5); the rgb of a
-// GL_SRGB_ALPHA array goes through the sRGB decode table
+// texel (i, j) of level `level` of one layer's mip chain; RGBA8 -> float, c / 255 (OpenGL 4.3 section 2.3.5) read from a 256-entry table
+// of exactly those quotients (an IEEE division per channel was half of the kernel's instructions, ncu r01i); the rgb of a GL_SRGB_ALPHA
+// array goes through the sRGB decode table instead
 __device__ __forceinline__ float4 mip_texel(const SceneDev& S, const uchar4* layer_base, int level, int i, int j, bool srgb) {
     // offset of level k = (4^9 + ... + 4^(10-k)) = (4^10 - 4^(10-k)) / 3
     const int off = ((1 << 20) - (1 << (2 * (10 - level)))) / 3;
     const int n = 512 >> level;
     const uchar4 c = layer_base[off + j * n + i];
-    if (srgb) return make_float4(S.srgb_lut[c.x], S.srgb_lut[c.y], S.srgb_lut[c.z], (float)c.w / 255.0f);
-    return make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+    const float* unorm = S.srgb_lut + 256;
+    const float* rgb = srgb ? S.srgb_lut : unorm;
+    return make_float4(__ldg(rgb + c.x), __ldg(rgb + c.y), __ldg(rgb + c.z), __ldg(unorm + c.w));
 }
 __device__ __forceinline__ float4 mip_nearest(const SceneDev& S, const uchar4* layer_base, int level, float u, float v, bool srgb) {
     const int n = 512 >> level;
@@ -44,15 +46,19 @@ __device__ __forceinline__ float4 f4_lerp(float4 a, float4 b, float f) {
     const float g = 1.0f - f;
     return make_float4(a.x * g + b.x * f, a.y * g + b.y * f, a.z * g + b.z * f, a.w * g + b.w * f);
 }
-// textureGrad on a block array (include/vxpt.h: the pinned OpenGL 4.3 section 8.14 isotropic filter)
-__device__ __forceinline__ float4 texture_grad(const SceneDev& S, const uchar4* mips, float layer_f, float u, float v, float4 d, bool srgb,
+// lambda of textureGrad (include/vxpt.h: the pinned OpenGL 4.3 section 8.14 isotropic scale factor); the three arrays of a pixel are
+// sampled with the same derivatives, so it is computed once
+__device__ __forceinline__ float mip_lambda(float4 d) {
+    const float dudx = d.x * 512.0f, dvdx = d.y * 512.0f, dudy = d.z * 512.0f, dvdy = d.w * 512.0f;
+    const float rho = fmaxf(sqrtf(dudx * dudx + dvdx * dvdx), sqrtf(dudy * dudy + dvdy * dvdy));
+    return log2_cr(rho);
+}
+// textureGrad on a block array, given lambda
+__device__ __forceinline__ float4 texture_grad(const SceneDev& S, const uchar4* mips, float layer_f, float u, float v, float lambda, bool srgb,
                                                bool mag_linear) {
     int layer = (int)nearbyintf(layer_f);
     layer = min(max(layer, 0), S.n_mip_layers - 1);
     const uchar4* base = mips + (size_t)layer * VXPT_MIP_CHAIN_TEXELS;
-    const float dudx = d.x * 512.0f, dvdx = d.y * 512.0f, dudy = d.z * 512.0f, dvdy = d.w * 512.0f;
-    const float rho = fmaxf(sqrtf(dudx * dudx + dvdx * dvdx), sqrtf(dudy * dudy + dvdy * dvdy));
-    const float lambda = log2_cr(rho);
     if (lambda <= (mag_linear ? 0.5f : 0.0f)) {  // magnification, level 0
         if (!mag_linear) return mip_nearest(S, base, 0, u, v, srgb);
         const float x = u * 512.0f - 0.5f, y = v * 512.0f - 0.5f;
@@ -136,15 +142,16 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     const V3 face = normal_from_id(nid, 1.0f);
     u = 1.0f - u;  // :397 (Parallax() returns the flat UV when u_POM is off)
     v = 1.0f - v;
-    const float4 nm = texture_grad(S, S.normal_mips, l_normal, u, v, d, false, true);
+    const float lambda = mip_lambda(d);
+    const float4 nm = texture_grad(S, S.normal_mips, l_normal, u, v, lambda, false, true);
     const float nx = nm.x * 2.0f - 1.0f, ny = nm.y * 2.0f - 1.0f, nz = nm.z * 2.0f - 1.0f;
     const V3 mapped = mk3((tangent.x * nx + bitangent.x * ny) + face.x * nz, (tangent.y * nx + bitangent.y * ny) + face.y * nz,
                           (tangent.z * nx + bitangent.z * ny) + face.z * nz);  // tbn * NormalMapped
-    const float4 pm = texture_grad(S, S.pbr_mips, l_pbr, u, v, d, false, true);
+    const float4 pm = texture_grad(S, S.pbr_mips, l_pbr, u, v, lambda, false, true);
     float emissivity = 0.0f;
     if (l_emissive > -0.5f) emissivity = tex_bilinear1(S.emissive, (int)l_emissive, 512, u, v);
     float4 o_pbr = make_float4(clampf(pm.x, 0.0f, 1.0f), clampf(pm.y, 0.0f, 1.0f), clampf(pm.z, 0.0f, 1.0f), clampf(emissivity, 0.0f, 1.0f));
-    const float4 al = texture_grad(S, S.albedo_mips, l_albedo, u, v, d, true, false);
+    const float4 al = texture_grad(S, S.albedo_mips, l_albedo, u, v, lambda, true, false);
     const float inside = (u > 0.02f && u < 1.0f - 0.02f && v > 0.02f && v < 1.0f - 0.02f) ? 1.0f : 0.0f;  // BloomLightLeakFix :432-438
     o_pbr.w *= inside;
     if (out.albedo) { out.albedo[3 * px] = al.x; out.albedo[3 * px + 1] = al.y; out.albedo[3 * px + 2] = al.z; }

@@ -58,7 +58,7 @@ struct SceneDev {
     const uchar4* albedo_mips;
     const uchar4* normal_mips;
     const uchar4* pbr_mips;
-    const float* srgb_lut;  // 256
+    const float* srgb_lut;  // 256 sRGB-decoded values, then 256 plain unorm8 values c / 255
     int n_mip_layers;
 };
 

@@ -5,7 +5,7 @@ samplers, images and the int/float mixed operators GLSL has and glm lacks).  Not
 oracle/_ref/, which is git-ignored.  Only syntax is rewritten — declarations the C++ compiler cannot read; every expression of the
 shader is compiled as written.
 
-  usage: glsl2cpp.py <shader.glsl> <namespace> <out.inc>
+  usage: glsl2cpp.py <shader.glsl> <namespace> <out.inc> [extra,pinned,functions]
 """
 import re
 import sys
@@ -67,7 +67,7 @@ def rewrite_swizzles(s):
         pos = i + len(rep)
 
 
-def translate(src, ns):
+def translate(src, ns, extra_pinned=()):
     out = []
     lines = src.replace("\r\n", "\n").split("\n")
     k = 0
@@ -151,6 +151,8 @@ def translate(src, ns):
     s = rewrite_swizzles(s)
     # transcendental functions: pinned definitions (glsl_compat.h)
     s = re.sub(r"\b(sin|cos|tan|pow|mix|log2|acos)\s*\(", r"pinned_\1(", s)
+    for fn in extra_pinned:   # per-shader additions (the denoising passes: exp), so that shaders translated earlier keep their text
+        s = re.sub(r"\b(%s)\s*\(" % re.escape(fn), r"pinned_\1(", s)
     # GLSL evaluates function arguments left to right (spec 6.1.1); C++ leaves the order of constructor arguments open (g++: right to
     # left).  Constructor calls whose arguments advance the hash RNG are brace-initialised, which C++ orders left to right.
     s = re.sub(r"\bvec2\s*\(\s*(Hash1?\(\))\s*,\s*(Hash1?\(\))\s*\)", r"vec2{\1, \2}", s)
@@ -176,7 +178,8 @@ def translate(src, ns):
 
 if __name__ == "__main__":
     path, ns, dst = sys.argv[1:4]
+    extra = sys.argv[4].split(",") if len(sys.argv) > 4 else ()
     with open(path, encoding="utf-8", errors="replace") as f:
-        text = translate(f.read(), ns)
+        text = translate(f.read(), ns, extra)
     with open(dst, "w") as f:
         f.write(f"// generated at build time from {path} by oracle/glsl2cpp.py — do not commit\n" + text)

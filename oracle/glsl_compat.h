@@ -66,6 +66,7 @@ inline float pinned_tan(float x) { return (float)::tan((double)x); }
 inline float pinned_pow(float x, float y) { return (float)::pow((double)x, (double)y); }
 inline float pinned_log2(float x) { return (float)::log2((double)x); }
 inline float pinned_acos(float x) { return (float)::acos((double)x); }
+inline float pinned_exp(float x) { return (float)::exp((double)x); }  // renamed only for the shaders that ask for it (glsl2cpp.py's 4th argument)
 template <class V> inline V pinned_sin(const V& v) { return glm::sin(v); }
 template <class V> inline V pinned_cos(const V& v) { return glm::cos(v); }
 template <class V> inline V pinned_tan(const V& v) { return glm::tan(v); }
@@ -97,16 +98,31 @@ inline void imageStore(image3D& s, const ivec3& p, const vec4& v) {
     float f = v.x < 0.0f ? 0.0f : (v.x > 1.0f ? 1.0f : v.x);
     s.data[(size_t)p.x + (size_t)s.sx * ((size_t)p.y + (size_t)s.sy * (size_t)p.z)] = (uint8_t)std::nearbyintf(f * 255.0f);
 }
-struct sampler2D {  // fp32 texels, 1..4 components, NEAREST (the G-buffer attachments are point-sampled at the pixel's own centre)
+struct sampler2D {  // fp32 texels, 1..4 components.  Default: NEAREST (the G-buffer attachments point-sampled at the pixel's own centre)
     const float* data = nullptr;
     int w = 0, h = 0, comps = 1;
+    // the denoising passes sample FBO attachments away from texel centres: GL_LINEAR / GL_NEAREST as Core/Pipeline.cpp:1094-1152 declares
+    // each attachment, GL_REPEAT (Core/GLClasses/Framebuffer.cpp:66-67).  Pinned filter arithmetic (GL leaves it open): OpenGL 4.3
+    // section 8.14.2, x = u * w - 0.5, i0 = floor(x) mod w, f = x - floor(x), weights applied as a * (1 - f) + b * f, x first.
+    bool linear = false, repeat = false;
 };
 inline vec4 texelFetch(const sampler2D& s, const ivec2& p, int /*lod*/) {
     const float* t = s.data + ((size_t)p.y * s.w + p.x) * s.comps;
     return vec4(t[0], s.comps > 1 ? t[1] : 0.0f, s.comps > 2 ? t[2] : 0.0f, s.comps > 3 ? t[3] : 1.0f);
 }
 inline ivec2 textureSize(const sampler2D& s, int /*lod*/) { return ivec2(s.w, s.h); }
+inline int wrap_repeat(int i, int n) { const int m = i % n; return m < 0 ? m + n : m; }
 inline vec4 texture(const sampler2D& s, const vec2& uv) {
+    if (s.repeat) {
+        if (!s.linear) return texelFetch(s, ivec2(wrap_repeat((int)std::floor(uv.x * (float)s.w), s.w), wrap_repeat((int)std::floor(uv.y * (float)s.h), s.h)), 0);
+        const float x = uv.x * (float)s.w - 0.5f, y = uv.y * (float)s.h - 0.5f;
+        const float fx0 = std::floor(x), fy0 = std::floor(y);
+        const float fx = x - fx0, fy = y - fy0;
+        const int i0 = wrap_repeat((int)fx0, s.w), i1 = wrap_repeat((int)fx0 + 1, s.w), j0 = wrap_repeat((int)fy0, s.h), j1 = wrap_repeat((int)fy0 + 1, s.h);
+        const vec4 a = texelFetch(s, ivec2(i0, j0), 0) * (1.0f - fx) + texelFetch(s, ivec2(i1, j0), 0) * fx;
+        const vec4 b = texelFetch(s, ivec2(i0, j1), 0) * (1.0f - fx) + texelFetch(s, ivec2(i1, j1), 0) * fx;
+        return a * (1.0f - fy) + b * fy;
+    }
     int i = (int)std::floor(uv.x * (float)s.w), j = (int)std::floor(uv.y * (float)s.h);
     i = i < 0 ? 0 : (i >= s.w ? s.w - 1 : i);
     j = j < 0 ? 0 : (j >= s.h ? s.h - 1 : j);

@@ -288,6 +288,86 @@ VXPT_API int vxpt_set_gbuffer_textures(vxpt_handle h, const uint8_t* albedo_mips
 VXPT_API int vxpt_generate_gbuffer(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf, const VxMaterialParams* p,
                                    const VxMaterialOut* out);
 
+/* ---- SVGF diffuse denoiser: Core/Pipeline.cpp:2284-2596 -> Core/Shaders/SVGF/{TemporalFilter,VarianceEstimate,
+ *      SpatialFilter}.glsl ----------------------------------------------------------------------------------------------------------
+ * The step right after the diffuse-GI pass: temporal accumulation against the previous frame (reprojected), a variance estimate, and
+ * five edge-stopping a-trous passes (u_Step 16, 8, 4, 2, 1; ping-pong between two plane sets, Pipeline.cpp:2468-2596).  One export per
+ * dispatch; all planes are fp32 (VXPT_OPT_TEXEL_FORMAT must be 0) and FULL-FRAME: a stencil reads rows outside [row_begin, row_end),
+ * which select the OUTPUT rows only; interleaved row bands are rejected (VXPT_E_UNSUPPORTED).  Outputs must not alias inputs.
+ * Pinned sampling (GL leaves filter arithmetic open): every read is texture() on an FBO attachment with GL_REPEAT and the filter
+ * Pipeline.cpp:1094-1152 declares — hit distance GL_LINEAR, normal / block id GL_NEAREST, all radiance / utility / AO / variance planes
+ * GL_LINEAR; linear = OpenGL 4.3 section 8.14.2 in fp32, weights applied as a(1-f) + bf, x first.  min / max / clamp return the non-NaN
+ * operand (IEEE minNum / maxNum, what the GPUs the reference runs on do); exp / pow are correctly rounded fp32. */
+typedef struct VxSvgfTemporalIn {
+    VxGBuffer current;          /* t, normal_id, block_id of this frame (InitialTraceFBO attachments 0..2)                       */
+    VxGBuffer previous;         /* the same planes of the previous frame (InitialTraceFBOPrev)                                    */
+    const float* sh;            /* u_CurrentSH   4 floats / pixel \                                                              */
+    const float* cocg;          /* u_CurrentCoCg 2 floats / pixel  | this frame's VxDiffuseOut (DiffuseRawTraceFBO 0..3)          */
+    const float* luma;          /* u_NoisyLuminosity 1 float / pixel |                                                            */
+    const float* ao_sky;        /* u_CurrentAO   2 floats / pixel /                                                               */
+    const float* prev_sh;       /* u_PreviousSH      \                                                                           */
+    const float* prev_cocg;     /* u_PrevCoCg         | the previous frame's VxSvgfTemporalOut (PrevDiffuseTemporalFBO 0..3)      */
+    const float* prev_utility;  /* u_PreviousUtility  | 3 floats / pixel                                                          */
+    const float* prev_ao_sky;   /* u_PreviousAO      /                                                                            */
+} VxSvgfTemporalIn;
+typedef struct VxSvgfTemporalParams {
+    float prev_view[16];        /* u_PrevView                                                   */
+    float prev_projection[16];  /* u_PrevProjection                                             */
+    int32_t be_useful;          /* u_BeUseful = DO_SVGF_TEMPORAL (1)                            */
+} VxSvgfTemporalParams;
+typedef struct VxSvgfTemporalOut {
+    float* sh;       /* o_SH 4 floats / pixel                                                              */
+    float* cocg;     /* o_CoCg 2                                                                           */
+    float* utility;  /* o_Utility 3: accumulated frames, second moment of the luminance, luminance         */
+    float* ao_sky;   /* o_AOAndSkyLighting 2                                                               */
+} VxSvgfTemporalOut;
+VXPT_API int vxpt_svgf_temporal(vxpt_handle h, const VxCamera* cam, const VxSvgfTemporalIn* in, const VxSvgfTemporalParams* p,
+                                const VxSvgfTemporalOut* out);
+
+typedef struct VxSvgfVarianceIn {
+    VxGBuffer current;     /* t, normal_id                                      */
+    const float* sh;       /* VxSvgfTemporalOut.sh                              */
+    const float* cocg;     /* VxSvgfTemporalOut.cocg                            */
+    const float* utility;  /* VxSvgfTemporalOut.utility                         */
+} VxSvgfVarianceIn;
+typedef struct VxSvgfVarianceParams {
+    int32_t do_spatial;               /* DO_SPATIAL = DO_VARIANCE_SPATIAL (1)   */
+    int32_t aggressive_disocclusion;  /* AGGRESSIVE_DISOCCLUSION_HANDLING (1)   */
+} VxSvgfVarianceParams;
+typedef struct VxSvgfVarianceOut {
+    float* sh;        /* o_SH 4       */
+    float* cocg;      /* o_CoCg 2     */
+    float* variance;  /* o_Variance 1 */
+} VxSvgfVarianceOut;
+VXPT_API int vxpt_svgf_variance(vxpt_handle h, const VxCamera* cam, const VxSvgfVarianceIn* in, const VxSvgfVarianceParams* p,
+                                const VxSvgfVarianceOut* out);
+
+typedef struct VxSvgfSpatialIn {
+    VxGBuffer current;              /* t, normal_id                                                                       */
+    const float* sh;                /* u_SH   : the previous pass's sh (the variance pass's for the first)                */
+    const float* cocg;              /* u_CoCg                                                                             */
+    const float* variance;          /* u_VarianceTexture                                                                  */
+    const float* ao_sky;            /* u_AO   : VxSvgfTemporalOut.ao_sky for the first pass, then the previous pass's     */
+    const float* temporal_utility;  /* u_TemporalMoment: VxSvgfTemporalOut.utility (.x = accumulated frames)              */
+} VxSvgfSpatialIn;
+typedef struct VxSvgfSpatialParams {
+    int32_t step;                     /* u_Step: 16, 8, 4, 2, 1 (32 .. 2 with WiderSVGF)                 */
+    int32_t large_kernel;             /* u_LargeKernel = SVGF_LARGE_KERNEL (0): 5x5 instead of 3x3 taps  */
+    int32_t do_spatial;               /* DO_SPATIAL = DO_SVGF_SPATIAL (1)                                */
+    int32_t aggressive_disocclusion;  /* AGGRESSIVE_DISOCCLUSION_HANDLING (1)                            */
+    float color_phi_bias;             /* u_ColorPhiBias (2.0)                                            */
+    float time;                       /* u_Time = glfwGetTime(): seeds the per-pixel tap jitter          */
+    float resolution_scale;           /* u_ResolutionScale = DiffuseIndirectSuperSampleRes               */
+} VxSvgfSpatialParams;
+typedef struct VxSvgfSpatialOut {
+    float* sh;        /* o_SH 4                 */
+    float* cocg;      /* o_CoCg 2               */
+    float* variance;  /* o_Variance 1           */
+    float* ao_sky;    /* o_AOAndSkylighting 2   */
+} VxSvgfSpatialOut;
+VXPT_API int vxpt_svgf_spatial(vxpt_handle h, const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvgfSpatialParams* p,
+                               const VxSvgfSpatialOut* out);
+
 /* ---- one frame of the path: the pass sequence of Core/Pipeline.cpp's render loop (:1973-2016 primary, :2795-2852 shadow,
  *      :2174-2281 diffuse GI, :3003-3164 reflections) on the rows of `cam` -------------------------------------------------
  * Equivalent to vxpt_trace_primary + vxpt_trace_shadow + vxpt_trace_diffuse (+ vxpt_trace_reflection) with the same arguments,

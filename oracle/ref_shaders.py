@@ -43,6 +43,17 @@ class RefGBufferArgs(C.Structure):
                 ("o_albedo", C.c_void_p), ("o_normal", C.c_void_p), ("o_pbr", C.c_void_p), ("o_texture_ao", C.c_void_p)]
 
 
+class RefSvgfArgs(C.Structure):
+    _fields_ = [("inv_view", C.c_void_p), ("inv_proj", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("row_begin", C.c_int32),
+                ("row_end", C.c_int32), ("g_t", C.c_void_p), ("g_normal_id", C.c_void_p), ("g_block_id", C.c_void_p), ("prev_t", C.c_void_p),
+                ("prev_normal_id", C.c_void_p), ("prev_block_id", C.c_void_p), ("sh", C.c_void_p), ("cocg", C.c_void_p), ("luma", C.c_void_p),
+                ("ao_sky", C.c_void_p), ("prev_sh", C.c_void_p), ("prev_cocg", C.c_void_p), ("prev_utility", C.c_void_p), ("prev_ao_sky", C.c_void_p),
+                ("utility", C.c_void_p), ("variance", C.c_void_p), ("temporal_utility", C.c_void_p), ("prev_view", C.c_void_p),
+                ("prev_projection", C.c_void_p), ("be_useful", C.c_int32), ("do_spatial", C.c_int32), ("aggressive", C.c_int32), ("step", C.c_int32),
+                ("large_kernel", C.c_int32), ("color_phi_bias", C.c_float), ("time", C.c_float), ("resolution_scale", C.c_float),
+                ("o_sh", C.c_void_p), ("o_cocg", C.c_void_p), ("o_utility", C.c_void_p), ("o_variance", C.c_void_p), ("o_ao_sky", C.c_void_p)]
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -72,6 +83,10 @@ def load():
         lib.ref_trace_diffuse.argtypes = [C.POINTER(RefDiffuseArgs)]
         lib.ref_trace_reflection.restype = C.c_int
         lib.ref_trace_reflection.argtypes = [C.POINTER(RefReflectionArgs)]
+        for name in ("ref_svgf_temporal", "ref_svgf_variance", "ref_svgf_spatial"):
+            if hasattr(lib, name):
+                getattr(lib, name).restype = C.c_int
+                getattr(lib, name).argtypes = [C.POINTER(RefSvgfArgs)]
         if hasattr(lib, "ref_generate_gbuffer"):
             lib.ref_generate_gbuffer.restype = C.c_int
             lib.ref_generate_gbuffer.argtypes = [C.POINTER(RefGBufferArgs)]
@@ -246,3 +261,63 @@ def ambient_sound(df, player_pos, frame):
     per = np.zeros(32, np.uint32)
     load().ref_ambient_sound(df.ctypes.data, p.ctypes.data, int(frame), C.byref(agg), per.ctypes.data)
     return int(agg.value), per
+
+
+# ---- SVGF denoiser: Core/Shaders/SVGF/*.glsl (oracle/ref_denoise_driver.cpp) ---------------------------------------------------------
+def _svgf_args(cam, keep):
+    def ptr(a, dt=np.float32):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    a = RefSvgfArgs()
+    a.inv_view, a.inv_proj = ptr(np.frombuffer(cam.inv_view, dtype=np.float32)), ptr(np.frombuffer(cam.inv_proj, dtype=np.float32))
+    a.width, a.height, a.row_begin, a.row_end = cam.width, cam.height, cam.row_begin, cam.row_end
+    return a, ptr
+
+
+def _svgf_out(cam, names):
+    W, H = cam.width, cam.height
+    shapes = {"sh": (H, W, 4), "cocg": (H, W, 2), "utility": (H, W, 3), "ao_sky": (H, W, 2), "variance": (H, W)}
+    return {k: np.zeros(shapes[k], np.float32) for k in names}
+
+
+def svgf_temporal(cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out=None):
+    keep = []
+    a, ptr = _svgf_args(cam, keep)
+    out = _svgf_out(cam, ("sh", "cocg", "utility", "ao_sky")) if out is None else out
+    a.g_t, a.g_normal_id, a.g_block_id = ptr(gbuf["t"]), ptr(gbuf["normal_id"], np.uint8), ptr(gbuf["block_id"], np.uint8)
+    a.prev_t, a.prev_normal_id, a.prev_block_id = ptr(prev_gbuf["t"]), ptr(prev_gbuf["normal_id"], np.uint8), ptr(prev_gbuf["block_id"], np.uint8)
+    a.sh, a.cocg, a.luma, a.ao_sky = (ptr(diffuse[k]) for k in ("sh", "cocg", "luma", "ao_sky"))
+    a.prev_sh, a.prev_cocg, a.prev_utility, a.prev_ao_sky = (ptr(prev_temporal[k]) for k in ("sh", "cocg", "utility", "ao_sky"))
+    a.prev_view, a.prev_projection = ptr(np.array(list(params.prev_view), np.float32)), ptr(np.array(list(params.prev_projection), np.float32))
+    a.be_useful = params.be_useful
+    a.o_sh, a.o_cocg, a.o_utility, a.o_ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "utility", "ao_sky"))
+    load().ref_svgf_temporal(C.byref(a))
+    return out
+
+
+def svgf_variance(cam, gbuf, temporal, params, out=None):
+    keep = []
+    a, ptr = _svgf_args(cam, keep)
+    out = _svgf_out(cam, ("sh", "cocg", "variance")) if out is None else out
+    a.g_t, a.g_normal_id = ptr(gbuf["t"]), ptr(gbuf["normal_id"], np.uint8)
+    a.sh, a.cocg, a.utility = (ptr(temporal[k]) for k in ("sh", "cocg", "utility"))
+    a.do_spatial, a.aggressive = params.do_spatial, params.aggressive_disocclusion
+    a.o_sh, a.o_cocg, a.o_variance = (out[k].ctypes.data for k in ("sh", "cocg", "variance"))
+    load().ref_svgf_variance(C.byref(a))
+    return out
+
+
+def svgf_spatial(cam, gbuf, planes, temporal_utility, params, out=None):
+    keep = []
+    a, ptr = _svgf_args(cam, keep)
+    out = _svgf_out(cam, ("sh", "cocg", "variance", "ao_sky")) if out is None else out
+    a.g_t, a.g_normal_id, a.g_block_id = ptr(gbuf["t"]), ptr(gbuf["normal_id"], np.uint8), ptr(gbuf["block_id"], np.uint8)
+    a.sh, a.cocg, a.variance, a.ao_sky = (ptr(planes[k]) for k in ("sh", "cocg", "variance", "ao_sky"))
+    a.temporal_utility = ptr(temporal_utility)
+    a.step, a.large_kernel, a.do_spatial, a.aggressive = params.step, params.large_kernel, params.do_spatial, params.aggressive_disocclusion
+    a.color_phi_bias, a.time, a.resolution_scale = params.color_phi_bias, params.time, params.resolution_scale
+    a.o_sh, a.o_cocg, a.o_variance, a.o_ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "variance", "ao_sky"))
+    load().ref_svgf_spatial(C.byref(a))
+    return out

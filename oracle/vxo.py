@@ -39,8 +39,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    src = os.path.join(HERE, "vxo_oracle.cpp")
-    if not os.path.exists(LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(LIB_PATH):
+    srcs = [os.path.join(HERE, f) for f in ("vxo_oracle.cpp", "vxo_denoise.cpp")]
+    if not os.path.exists(LIB_PATH) or any(os.path.getmtime(src) > os.path.getmtime(LIB_PATH) for src in srcs):
         build()
     lib = C.CDLL(LIB_PATH)
     lib.vxo_df_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -60,6 +60,12 @@ def load():
         f.restype = C.c_int
     lib.vxo_generate_gbuffer.argtypes = [C.POINTER(VxoScene), C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams), C.POINTER(VxMaterialOut)]
     lib.vxo_generate_gbuffer.restype = C.c_int
+    from voxelpathtracer_b200 import abi as _abi
+    for name, kinds in (("temporal", ("TemporalIn", "TemporalParams", "TemporalOut")), ("variance", ("VarianceIn", "VarianceParams", "VarianceOut")),
+                        ("spatial", ("SpatialIn", "SpatialParams", "SpatialOut"))):
+        fn = getattr(lib, "vxo_svgf_" + name)
+        fn.argtypes = [C.POINTER(VxCamera)] + [C.POINTER(getattr(_abi, "VxSvgf" + k)) for k in kinds]
+        fn.restype = C.c_int
     lib.vxo_trace_rays.argtypes = [C.POINTER(VxoScene), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VxoStats)]
     lib.vxo_trace_rays.restype = C.c_int
     lib.vxo_player_shadowed.argtypes = [C.POINTER(VxoScene), C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -248,3 +254,41 @@ class Oracle:
         rc = self.lib.vxo_ambient_sound(C.byref(self.scene), p, int(frame), C.byref(agg), per.ctypes.data, C.byref(st))
         assert rc == 0, rc
         return int(agg.value), per, self._stats(st)
+
+
+# ---- SVGF denoiser (oracle/vxo_denoise.cpp): plain functions of planes, no scene ------------------------------------------------------
+def _addr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _planes(cam, names):
+    from voxelpathtracer_b200 import denoise
+    shapes = denoise.plane_shapes(cam.width, cam.height)
+    return {k: np.zeros(shapes[k], np.float32) for k in names}
+
+
+def svgf_temporal(cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out=None):
+    from voxelpathtracer_b200 import denoise
+    out = _planes(cam, ("sh", "cocg", "utility", "ao_sky")) if out is None else out
+    i, o = denoise.temporal_structs(gbuf, prev_gbuf, diffuse, prev_temporal, out, _addr)
+    rc = load().vxo_svgf_temporal(C.byref(cam), C.byref(i), C.byref(params), C.byref(o))
+    assert rc == 0, rc
+    return out
+
+
+def svgf_variance(cam, gbuf, temporal, params, out=None):
+    from voxelpathtracer_b200 import denoise
+    out = _planes(cam, ("sh", "cocg", "variance")) if out is None else out
+    i, o = denoise.variance_structs(gbuf, temporal, out, _addr)
+    rc = load().vxo_svgf_variance(C.byref(cam), C.byref(i), C.byref(params), C.byref(o))
+    assert rc == 0, rc
+    return out
+
+
+def svgf_spatial(cam, gbuf, planes, temporal_utility, params, out=None):
+    from voxelpathtracer_b200 import denoise
+    out = _planes(cam, ("sh", "cocg", "variance", "ao_sky")) if out is None else out
+    i, o = denoise.spatial_structs(gbuf, planes, temporal_utility, out, _addr)
+    rc = load().vxo_svgf_spatial(C.byref(cam), C.byref(i), C.byref(params), C.byref(o))
+    assert rc == 0, rc
+    return out

@@ -1,7 +1,7 @@
 // kernels_on_host.cpp — TEST INFRASTRUCTURE: the per-pixel trace kernels' own source, compiled by g++ and executed on the CPU.
 //
 // The build container has no GPU, so a kernel written here is first seen by a GPU at the end of a round.  To shorten that
-// loop this file includes voxelpathtracer_b200/csrc/trace.cu, trace_reflection.cu, df_consumers.cu and gbuffer.cu UNCHANGED (kernels, device functions and
+// loop this file includes voxelpathtracer_b200/csrc/trace.cu, trace_reflection.cu, df_consumers.cu, gbuffer.cu and denoise.cu UNCHANGED (kernels, device functions and
 // their host launchers with the per-frame constants) and gives g++ what nvcc would: the CUDA vector types come from the toolkit's
 // own headers (they are plain C++), the handful of device intrinsics the kernels use are defined below with their documented
 // semantics, and VX_LAUNCH becomes a loop over blockIdx / threadIdx.  tests/test_kernels_on_host.py compares what comes out with
@@ -58,6 +58,7 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetc
 #include "../../voxelpathtracer_b200/csrc/trace_reflection.cu"
 #include "../../voxelpathtracer_b200/csrc/df_consumers.cu"
 #include "../../voxelpathtracer_b200/csrc/gbuffer.cu"
+#include "../../voxelpathtracer_b200/csrc/denoise.cu"
 
 namespace vxpt {
 // api.cu's make_scene, on a context whose "device" pointers are host pointers
@@ -189,6 +190,16 @@ HS_API int hs_trace_reflection(void* p, const VxCamera* cam, const VxGBuffer* g,
 }
 HS_API int hs_generate_gbuffer(void* p, const VxCamera* cam, const VxGBuffer* g, const VxMaterialParams* prm, const VxMaterialOut* out) {
     return vxpt::launch_gbuffer(hs_ctx(p), *cam, *g, *prm, *out);
+}
+// the SVGF denoiser passes need no scene: hs_create(NULL-scene) handles work too
+HS_API int hs_svgf_temporal(void* p, const VxCamera* cam, const VxSvgfTemporalIn* in, const VxSvgfTemporalParams* prm, const VxSvgfTemporalOut* out) {
+    return vxpt::launch_svgf_temporal(hs_ctx(p), *cam, *in, *prm, *out);
+}
+HS_API int hs_svgf_variance(void* p, const VxCamera* cam, const VxSvgfVarianceIn* in, const VxSvgfVarianceParams* prm, const VxSvgfVarianceOut* out) {
+    return vxpt::launch_svgf_variance(hs_ctx(p), *cam, *in, *prm, *out);
+}
+HS_API int hs_svgf_spatial(void* p, const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvgfSpatialParams* prm, const VxSvgfSpatialOut* out) {
+    return vxpt::launch_svgf_spatial(hs_ctx(p), *cam, *in, *prm, *out);
 }
 HS_API int hs_trace_rays(void* p, const float* origins, const float* directions, int n, int max_it, float* t, uint8_t* normal_id, uint8_t* block_id,
                          int16_t* hit_voxel) {

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB_PATH = os.path.join(HERE, "libkernels_on_host.so")
 CSRC = os.path.join(ROOT, "voxelpathtracer_b200", "csrc")
 SOURCES = [os.path.join(HERE, "kernels_on_host.cpp")] + [os.path.join(CSRC, f) for f in
-                                                         ("trace.cu", "trace_reflection.cu", "df_consumers.cu", "gbuffer.cu", "trace_device.cuh",
+                                                         ("trace.cu", "trace_reflection.cu", "df_consumers.cu", "gbuffer.cu", "denoise.cu", "trace_device.cuh",
                                                           "gi_device.cuh", "vxpt_internal.h")]
 CUDA_INCLUDE = "/usr/local/cuda/include"
 _lib = None
@@ -51,10 +51,24 @@ def load():
     lib.hs_trace_reflection.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]
     lib.hs_generate_gbuffer.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams), C.POINTER(VxMaterialOut)]
+    from voxelpathtracer_b200 import abi as _abi
+    for name, kinds in (("temporal", ("TemporalIn", "TemporalParams", "TemporalOut")), ("variance", ("VarianceIn", "VarianceParams", "VarianceOut")),
+                        ("spatial", ("SpatialIn", "SpatialParams", "SpatialOut"))):
+        getattr(lib, "hs_svgf_" + name).argtypes = [C.c_void_p, C.POINTER(VxCamera)] + [C.POINTER(getattr(_abi, "VxSvgf" + k)) for k in kinds]
     lib.hs_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_ambient_sound.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
     _lib = lib
     return lib
+
+
+def _addr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _denoise_planes(cam, names):
+    from voxelpathtracer_b200 import denoise
+    shapes = denoise.plane_shapes(cam.width, cam.height)
+    return {k: np.zeros(shapes[k], np.float32) for k in names}
 
 
 class HostKernels:
@@ -140,6 +154,28 @@ class HostKernels:
         o.albedo, o.normal, o.pbr, o.texture_ao = (out[k].ctypes.data for k in ("albedo", "normal", "pbr", "texture_ao"))
         rc = self.lib.hs_generate_gbuffer(self.h, C.byref(cam), C.byref(g), C.byref(params), C.byref(o))
         assert rc == 0, rc
+        return out
+
+    # SVGF denoiser passes (csrc/denoise.cu): same call shapes as oracle.vxo.svgf_*
+    def svgf_temporal(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out=None):
+        from voxelpathtracer_b200 import denoise
+        out = _denoise_planes(cam, ("sh", "cocg", "utility", "ao_sky")) if out is None else out
+        i, o = denoise.temporal_structs(gbuf, prev_gbuf, diffuse, prev_temporal, out, _addr)
+        assert self.lib.hs_svgf_temporal(self.h, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)) == 0
+        return out
+
+    def svgf_variance(self, cam, gbuf, temporal, params, out=None):
+        from voxelpathtracer_b200 import denoise
+        out = _denoise_planes(cam, ("sh", "cocg", "variance")) if out is None else out
+        i, o = denoise.variance_structs(gbuf, temporal, out, _addr)
+        assert self.lib.hs_svgf_variance(self.h, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)) == 0
+        return out
+
+    def svgf_spatial(self, cam, gbuf, planes, temporal_utility, params, out=None):
+        from voxelpathtracer_b200 import denoise
+        out = _denoise_planes(cam, ("sh", "cocg", "variance", "ao_sky")) if out is None else out
+        i, o = denoise.spatial_structs(gbuf, planes, temporal_utility, out, _addr)
+        assert self.lib.hs_svgf_spatial(self.h, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)) == 0
         return out
 
     def trace_rays(self, origins, directions, max_it):

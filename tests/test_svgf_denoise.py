@@ -1,0 +1,296 @@
+"""SVGF diffuse denoiser (Core/Shaders/SVGF/{TemporalFilter,VarianceEstimate,SpatialFilter}.glsl, Core/Pipeline.cpp:2335-2596).
+
+Same chain of pins as the trace passes: the reference's own shaders compiled as C++ (committed digests, tests/golden/ref_denoise_digests.json,
+made by tools/make_ref_denoise_golden.py) == the oracle restatement (oracle/vxo_denoise.cpp) == the CUDA kernels' source on the host
+(tests/host_shadow) == the CUDA kernels on the GPU through the C ABI.  CPU comparisons are bit for bit; the GPU comparison allows the pinned
+exp / pow (double evaluation by two different libms) to differ by an ulp on isolated pixels."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import voxelpathtracer_b200 as vx
+from voxelpathtracer_b200 import abi, camera, denoise
+from oracle import ref_shaders, vxo
+
+import denoise_cases as dc
+from host_shadow import kernels_on_host as koh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not ref_shaders.available(), reason="oracle/_ref/libref_shaders.so not built (needs /root/reference at build time)")
+
+
+@pytest.fixture(scope="module")
+def ref_digests():
+    with open(os.path.join(ROOT, "tests", "golden", "ref_denoise_digests.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def oracle_sequences(oracles, scene_tables):
+    """name -> list of per-frame oracle results (cached: the sequences feed several tests)"""
+    class Lazy(dict):
+        def __missing__(self, name):
+            self[name] = list(dc.run_sequence(name, dc.oracle_tracer(oracles[dc.SEQUENCES[name][0]], scene_tables), vxo, scene_tables))
+            return self[name]
+
+    return Lazy()
+
+
+def _same(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------------ oracle vs the reference's shaders
+@pytest.mark.parametrize("name", list(dc.SEQUENCES))
+def test_oracle_equals_the_reference_shader_digests(oracle_sequences, ref_digests, name):
+    frames = oracle_sequences[name]
+    assert len(frames) == len(ref_digests[name])
+    for f, (fr, want) in enumerate(zip(frames, ref_digests[name])):
+        assert dc.frame_digest(fr) == want, (name, f)
+
+
+@needs_ref
+def test_oracle_equals_the_reference_shaders_live_on_option_and_edge_cases(oracle_sequences):
+    """Switches the committed sequences leave at their defaults, and non-finite inputs: u_BeUseful = false, DO_SPATIAL = false,
+    AGGRESSIVE_DISOCCLUSION_HANDLING = false, u_LargeKernel, the WiderSVGF steps, u_ResolutionScale = 1, a row slab, a zero frame count
+    everywhere (0 * inf in the variance pass), NaN / inf planted in the input planes."""
+    fr0, fr1 = oracle_sequences["gi_box_192x108_walk"][:2]
+    cam, g, d, t = fr1["cam"], fr1["gbuf"], fr1["diffuse"], fr1["temporal"]
+    fc0 = camera.FpsCamera(aspect=192 / 108, pitch_deg=-20.0)
+    tp = denoise.temporal_params(fc0.view().T.reshape(16), fc0.projection().T.reshape(16), be_useful=False)
+    a, b = vxo.svgf_temporal(cam, g, fr0["gbuf"], d, fr0["temporal"], tp), ref_shaders.svgf_temporal(cam, g, fr0["gbuf"], d, fr0["temporal"], tp)
+    assert all(_same(a[k], b[k]) for k in a)
+    for vp in (denoise.variance_params(do_spatial=False), denoise.variance_params(aggressive_disocclusion=False)):
+        a, b = vxo.svgf_variance(cam, g, t, vp), ref_shaders.svgf_variance(cam, g, t, vp)
+        assert all(_same(a[k], b[k]) for k in a)
+    planes = {"sh": fr1["variance"]["sh"], "cocg": fr1["variance"]["cocg"], "variance": fr1["variance"]["variance"], "ao_sky": t["ao_sky"]}
+    for sp in (denoise.spatial_params(8, time=1.5, do_spatial=False), denoise.spatial_params(4, time=7.75, aggressive_disocclusion=False),
+               denoise.spatial_params(2, time=0.1, large_kernel=True), denoise.spatial_params(32, time=2.0), denoise.spatial_params(16, time=2.0, resolution_scale=1.0),
+               denoise.spatial_params(1, time=99.0, color_phi_bias=0.05)):
+        a, b = vxo.svgf_spatial(cam, g, planes, t["utility"], sp), ref_shaders.svgf_spatial(cam, g, planes, t["utility"], sp)
+        assert all(_same(a[k], b[k]) for k in a), sp.step
+    # a row slab writes its rows only
+    cam2 = camera.FpsCamera(aspect=192 / 108, position=(192.4, 75.1, 192.3), pitch_deg=-21.0, yaw_deg=92.0).vx_camera(192, 108, 40, 71)
+    seed = {k: np.full_like(v, 0.5) for k, v in fr1["spatial"][0].items()}
+    a = vxo.svgf_spatial(cam2, g, planes, t["utility"], denoise.spatial_params(4, time=1.0), {k: v.copy() for k, v in seed.items()})
+    b = ref_shaders.svgf_spatial(cam2, g, planes, t["utility"], denoise.spatial_params(4, time=1.0), {k: v.copy() for k, v in seed.items()})
+    assert all(_same(a[k], b[k]) for k in a) and (a["sh"][:40] == 0.5).all() and (a["sh"][71:] == 0.5).all() and not (a["sh"][40:71] == 0.5).all()
+    # zero frame counts and zero moments: thresh / 0 = inf, 0 * inf = NaN reach the clamps (IEEE minNum / maxNum: the non-NaN operand wins)
+    t0 = {k: v.copy() for k, v in t.items()}
+    t0["utility"][...] = 0.0
+    t0["sh"][20:60, 30:90] = 0.0
+    a, b = vxo.svgf_variance(cam, g, t0, denoise.variance_params()), ref_shaders.svgf_variance(cam, g, t0, denoise.variance_params())
+    assert all(_same(a[k], b[k]) for k in a)
+    # non-finite texels in the inputs propagate identically
+    bad = {k: v.copy() for k, v in planes.items()}
+    bad["variance"][50, 60] = np.nan
+    bad["variance"][10, 10] = np.inf
+    bad["sh"][70, 100, 3] = np.inf
+    bad["sh"][30, 150] = np.nan
+    for step in (16, 1):
+        a, b = vxo.svgf_spatial(cam, g, bad, t["utility"], denoise.spatial_params(step, time=4.0)), ref_shaders.svgf_spatial(cam, g, bad, t["utility"], denoise.spatial_params(step, time=4.0))
+        assert all(_same(a[k], b[k]) for k in a), step
+
+
+# ------------------------------------------------------------------------------------------------------ known answers / properties
+def test_still_camera_accumulates_and_the_filter_removes_noise(oracle_sequences):
+    frames = oracle_sequences["city_160x90_still"]
+    hit = frames[0]["gbuf"]["t"] > 0
+    inner = np.zeros_like(hit)
+    inner[4:-4, 4:-4] = True
+    # accumulated frame count (o_Utility.x): 1, 2, 3 on every pixel the reprojection accepts — all of them for a camera that does not move
+    for f, fr in enumerate(frames):
+        spp = fr["temporal"]["utility"][..., 0]
+        sel = spp[hit & inner]                   # silhouette pixels reject their history, and their neighbours average it in
+        assert np.isclose(sel, f + 1.0, atol=1e-4).mean() > 0.7 and abs(float(np.median(sel)) - (f + 1.0)) < 1e-4 and sel.max() <= f + 1.0 + 1e-4, f
+    # the blend factor is 1 / accumulated frames: frame 1's temporal SH = (history + this frame's noisy SH) / 2, the history being a
+    # convex combination of the previous temporal SH at the pixel and its four neighbours: 2 * out - current lies in their envelope
+    prev, cur, got = frames[0]["temporal"]["sh"], frames[1]["diffuse"]["sh"], frames[1]["temporal"]["sh"]
+    ok = np.isclose(frames[1]["temporal"]["utility"][..., 0], 2.0, atol=1e-4) & inner & (frames[1]["gbuf"]["t"] > 1.0)   # (the lowest rows look
+    taps = np.stack([prev, np.roll(prev, 1, 0), np.roll(prev, -1, 0), np.roll(prev, 1, 1), np.roll(prev, -1, 1)])
+    hist = 2.0 * got - cur                               # at the block the camera stands in, t = 1e-4: reprojection is ill-conditioned there)
+    assert (hist[ok] >= taps.min(0)[ok] - 1e-4).all() and (hist[ok] <= taps.max(0)[ok] + 1e-4).all()
+    # each a-trous pass leaves the mean radiance alone and lowers the pixel-to-pixel roughness of the luminance band
+    def rough(sh):
+        y = sh[..., 3]
+        return float(np.abs(np.diff(y, axis=1))[hit[:, 1:] & hit[:, :-1]].mean())
+    fr = frames[2]
+    r_raw, r_t = rough(fr["diffuse"]["sh"]), rough(fr["temporal"]["sh"])
+    r_s = [rough(s["sh"]) for s in fr["spatial"]]
+    assert r_t < r_raw and r_s[-1] < 0.5 * r_raw and r_s[0] < r_t
+    m_raw = float(np.mean([f_["diffuse"]["sh"][hit][:, 3].mean() for f_ in frames]))      # 1-spp frames: compare with the three-frame mean
+    m_out = float(fr["spatial"][-1]["sh"][hit][:, 3].mean())
+    assert abs(m_out - m_raw) < 0.35 * abs(m_raw)
+
+
+def test_constant_planes_are_a_fixed_point():
+    """Uniform inputs over a flat G-buffer: every weighted mean returns the constant, the variance of a constant signal is zero."""
+    W, H = 64, 36
+    cam = camera.FpsCamera(aspect=W / H).vx_camera(W, H)
+    g = {"t": np.full((H, W), 12.5, np.float32), "normal_id": np.full((H, W), 2, np.uint8), "block_id": np.full((H, W), 3, np.uint8)}
+    sh = np.tile(np.array([0.1, -0.2, 0.05, 0.3], np.float32), (H, W, 1))
+    cocg = np.tile(np.array([0.02, -0.01], np.float32), (H, W, 1))
+    ao = np.tile(np.array([0.7, 0.4], np.float32), (H, W, 1))
+    y = np.float32(max(0.0, 3.544905 * 0.3))
+    util = np.tile(np.array([20.0, y * y, y], np.float32), (H, W, 1))
+    v = vxo.svgf_variance(cam, g, {"sh": sh, "cocg": cocg, "utility": util}, denoise.variance_params())
+    assert np.allclose(v["sh"], sh, atol=1e-6) and np.allclose(v["variance"], 0.0, atol=1e-5)
+    planes = {"sh": sh, "cocg": cocg, "variance": np.full((H, W), 0.02, np.float32), "ao_sky": ao}
+    for step in denoise.ATROUS_STEPS:
+        s = vxo.svgf_spatial(cam, g, planes, util, denoise.spatial_params(step, time=5.0))
+        assert np.allclose(s["sh"], sh, atol=1e-6) and np.allclose(s["cocg"], cocg, atol=1e-6) and np.allclose(s["ao_sky"], ao, atol=1e-6)
+        assert (s["variance"] <= 0.02 + 1e-7).all() and (s["variance"] > 0).all()    # sum w^2 v / (sum w)^2 < v
+        planes = s
+
+
+# ------------------------------------------------------------------------------------------------------ the kernels' source on the host
+@pytest.mark.skipif(not koh.available(), reason="CUDA toolkit headers not present")
+@pytest.mark.parametrize("name", ["gi_box_192x108_walk", "plains_133x75_turn"])
+def test_kernel_source_on_host_equals_the_oracle(oracles, oracle_sequences, scene_tables, name):
+    k = koh.HostKernels(oracles[dc.SEQUENCES[name][0]], 1)
+    trace = iter(oracle_sequences[name])
+
+    def replay(cam, f):        # the traced planes of the oracle run: the sequence then differs only in who filters
+        fr = next(trace)
+        return fr["gbuf"], fr["diffuse"]
+
+    for f, (got, want) in enumerate(zip(dc.run_sequence(name, replay, k, scene_tables), oracle_sequences[name])):
+        for stage in ("temporal", "variance"):
+            for key in want[stage]:
+                assert _same(got[stage][key], want[stage][key]), (f, stage, key)
+        for n, (a, b) in enumerate(zip(got["spatial"], want["spatial"])):
+            for key in b:
+                assert _same(a[key], b[key]), (f, n, key)
+    k.close()
+
+
+# ------------------------------------------------------------------------------------------------------ GPU, through the C ABI
+def _close(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want)), what
+    diff = ~((got == want) | (np.isnan(got) & np.isnan(want)))
+    assert diff.mean() <= 2e-4, (what, float(diff.mean()))
+    fin = np.isfinite(want)
+    assert float(np.abs(got[fin].astype(np.float64) - want[fin]).max(initial=0.0)) <= 2e-5, what
+
+
+class _RendererPasses:
+    """adapts a Renderer to the call shapes of oracle.vxo.svgf_* (allocates the output planes)"""
+
+    def __init__(self, r, device=False):
+        self.r, self.device = r, device
+
+    def _out(self, cam, names):
+        return self.r.alloc_denoise(cam.width, cam.height, names, device=self.device)
+
+    def _in(self, planes):
+        if not self.device:
+            return planes
+        import torch
+        out = {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v)).cuda()) for k, v in planes.items() if v is not None}
+        torch.cuda.synchronize()   # the uploads ran on torch's stream, the library launches on its own
+        return out
+
+    def _host(self, planes):
+        if self.device:
+            self.r.sync()              # device planes are complete after vxpt_sync()
+        return {k: (v.cpu().numpy() if self.device else v) for k, v in planes.items()}
+
+    def svgf_temporal(self, cam, g, pg, d, pt, params):
+        return self._host(self.r.svgf_temporal(cam, self._in(g), self._in(pg), self._in(d), self._in(pt), params, self._out(cam, ("sh", "cocg", "utility", "ao_sky"))))
+
+    def svgf_variance(self, cam, g, t, params):
+        return self._host(self.r.svgf_variance(cam, self._in(g), self._in(t), params, self._out(cam, ("sh", "cocg", "variance"))))
+
+    def svgf_spatial(self, cam, g, planes, util, params):
+        util = self._in({"u": util})["u"]
+        return self._host(self.r.svgf_spatial(cam, self._in(g), self._in(planes), util, params, self._out(cam, ("sh", "cocg", "variance", "ao_sky"))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,device", [("gi_box_192x108_walk", False), ("plains_133x75_turn", True), ("city_160x90_still", True)])
+def test_gpu_denoiser_equals_the_oracle(renderer, oracle_sequences, scene_tables, name, device):
+    """Every pass of every frame, fed with the oracle's inputs of that pass, so a one-ulp difference cannot compound down the chain."""
+    want = oracle_sequences[name]
+    p = _RendererPasses(renderer, device)
+    prev_g, prev_t = None, dc.zero_temporal(*dc.SEQUENCES[name][1:3])
+    prev_fc = None
+    for f, (fr, kw) in enumerate(zip(want, dc.SEQUENCES[name][3])):
+        W, H = dc.SEQUENCES[name][1:3]
+        fc = camera.FpsCamera(aspect=W / H, **kw)
+        pfc = prev_fc or fc
+        tp = denoise.temporal_params(pfc.view().T.reshape(16), pfc.projection().T.reshape(16))
+        g = {k: fr["gbuf"][k] for k in ("t", "normal_id", "block_id")}
+        t = p.svgf_temporal(fr["cam"], g, prev_g or g, fr["diffuse"], prev_t, tp)
+        for k in fr["temporal"]:
+            _close(t[k], fr["temporal"][k], (name, f, "temporal", k))
+        v = p.svgf_variance(fr["cam"], g, fr["temporal"], denoise.variance_params())
+        for k in fr["variance"]:
+            _close(v[k], fr["variance"][k], (name, f, "variance", k))
+        cur = {"sh": fr["variance"]["sh"], "cocg": fr["variance"]["cocg"], "variance": fr["variance"]["variance"], "ao_sky": fr["temporal"]["ao_sky"]}
+        for n, step in enumerate(denoise.ATROUS_STEPS):
+            s = p.svgf_spatial(fr["cam"], g, cur, fr["temporal"]["utility"], denoise.spatial_params(step, time=dc.TIME0 + f / 60.0))
+            for k in fr["spatial"][n]:
+                _close(s[k], fr["spatial"][n][k], (name, f, step, k))
+            cur = fr["spatial"][n]
+        prev_g, prev_t, prev_fc = g, fr["temporal"], fc
+    assert renderer.launch_count() > 0
+
+
+@pytest.mark.gpu
+def test_gpu_denoiser_whole_chain_on_the_traced_frame(renderer, worlds, oracles, scene_tables):
+    """End to end on the device: trace (primary + GI) and denoise two frames with device-resident planes through Renderer.svgf_denoise;
+    the result stays within the radiance tolerance of the oracle's chain (north_star: 1e-3 mean absolute error)."""
+    name = "gi_box_192x108_walk"
+    _, W, H, cams = dc.SEQUENCES[name]
+    renderer.upload_world(worlds["gi_box"])
+    renderer.build_distance_field()
+    sun, moon, vis = scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"]
+    want = list(dc.run_sequence(name, dc.oracle_tracer(oracles["gi_box"], scene_tables), vxo, scene_tables))[:2]
+    prev_g, prev_fc = None, None
+    prev_t = renderer.alloc_denoise(W, H, ("sh", "cocg", "utility", "ao_sky"), device=True)
+    for v in prev_t.values():
+        v.zero_()
+    import torch
+    torch.cuda.synchronize()       # zero_() ran on torch's stream, the library launches on its own
+    for f, kw in enumerate(cams[:2]):
+        fc = camera.FpsCamera(aspect=W / H, **kw)
+        cam = fc.vx_camera(W, H)
+        g = renderer.trace_primary(cam, vx.primary_params(350), renderer.alloc_gbuffer(W, H, device=True))
+        d = renderer.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=f), renderer.alloc_diffuse(W, H, device=True))
+        pfc = prev_fc or fc
+        tp = denoise.temporal_params(pfc.view().T.reshape(16), pfc.projection().T.reshape(16))
+        out, temporal = renderer.svgf_denoise(cam, g, prev_g or g, d, prev_t, tp, time=dc.TIME0 + f / 60.0, device=True)
+        renderer.sync()
+        ref = want[f]["spatial"][-1]
+        for k in ("sh", "cocg", "ao_sky"):
+            assert float(np.mean(np.abs(out[k].cpu().numpy().astype(np.float64) - ref[k]))) <= 1e-3, (f, k)
+        prev_g, prev_t, prev_fc = g, temporal, fc
+
+
+@pytest.mark.gpu
+def test_gpu_denoiser_argument_checks(renderer, oracle_sequences):
+    fr = oracle_sequences["plains_133x75_turn"][0]
+    cam, g, t = fr["cam"], fr["gbuf"], fr["temporal"]
+    W, H = cam.width, cam.height
+    out = renderer.alloc_denoise(W, H, ("sh", "cocg", "variance"))
+    with pytest.raises(abi.VxptError) as e:          # a required plane is missing
+        renderer.svgf_variance(cam, {"t": g["t"]}, t, denoise.variance_params(), out)
+    assert e.value.code == abi.E_INVALID
+    band = camera.FpsCamera(aspect=W / H).vx_camera(W, 72, interleave_n=2, interleave_rank=0, band_rows=4)
+    with pytest.raises(abi.VxptError) as e:          # stencils cannot run on interleaved bands
+        renderer.svgf_variance(band, g, t, denoise.variance_params(), out)
+    assert e.value.code == abi.E_UNSUPPORTED
+    renderer.set_option(abi.OPT_TEXEL_FORMAT, 1)
+    try:
+        with pytest.raises(abi.VxptError) as e:
+            renderer.svgf_variance(cam, g, t, denoise.variance_params(), out)
+        assert e.value.code == abi.E_UNSUPPORTED
+    finally:
+        renderer.set_option(abi.OPT_TEXEL_FORMAT, 0)
+    with pytest.raises(abi.VxptError) as e:
+        planes = {"sh": fr["variance"]["sh"], "cocg": fr["variance"]["cocg"], "variance": fr["variance"]["variance"], "ao_sky": t["ao_sky"]}
+        renderer.svgf_spatial(cam, g, planes, t["utility"], denoise.spatial_params(0), renderer.alloc_denoise(W, H, ("sh", "cocg", "variance", "ao_sky")))
+    assert e.value.code == abi.E_INVALID

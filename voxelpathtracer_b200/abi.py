@@ -85,6 +85,45 @@ class VxMaterialOut(C.Structure):
     _fields_ = [("albedo", C.c_void_p), ("normal", C.c_void_p), ("pbr", C.c_void_p), ("texture_ao", C.c_void_p)]
 
 
+class VxSvgfTemporalIn(C.Structure):
+    _fields_ = [("current", VxGBuffer), ("previous", VxGBuffer), ("sh", C.c_void_p), ("cocg", C.c_void_p), ("luma", C.c_void_p),
+                ("ao_sky", C.c_void_p), ("prev_sh", C.c_void_p), ("prev_cocg", C.c_void_p), ("prev_utility", C.c_void_p), ("prev_ao_sky", C.c_void_p)]
+
+
+class VxSvgfTemporalParams(C.Structure):
+    _fields_ = [("prev_view", C.c_float * 16), ("prev_projection", C.c_float * 16), ("be_useful", C.c_int32)]
+
+
+class VxSvgfTemporalOut(C.Structure):
+    _fields_ = [("sh", C.c_void_p), ("cocg", C.c_void_p), ("utility", C.c_void_p), ("ao_sky", C.c_void_p)]
+
+
+class VxSvgfVarianceIn(C.Structure):
+    _fields_ = [("current", VxGBuffer), ("sh", C.c_void_p), ("cocg", C.c_void_p), ("utility", C.c_void_p)]
+
+
+class VxSvgfVarianceParams(C.Structure):
+    _fields_ = [("do_spatial", C.c_int32), ("aggressive_disocclusion", C.c_int32)]
+
+
+class VxSvgfVarianceOut(C.Structure):
+    _fields_ = [("sh", C.c_void_p), ("cocg", C.c_void_p), ("variance", C.c_void_p)]
+
+
+class VxSvgfSpatialIn(C.Structure):
+    _fields_ = [("current", VxGBuffer), ("sh", C.c_void_p), ("cocg", C.c_void_p), ("variance", C.c_void_p), ("ao_sky", C.c_void_p),
+                ("temporal_utility", C.c_void_p)]
+
+
+class VxSvgfSpatialParams(C.Structure):
+    _fields_ = [("step", C.c_int32), ("large_kernel", C.c_int32), ("do_spatial", C.c_int32), ("aggressive_disocclusion", C.c_int32),
+                ("color_phi_bias", C.c_float), ("time", C.c_float), ("resolution_scale", C.c_float)]
+
+
+class VxSvgfSpatialOut(C.Structure):
+    _fields_ = [("sh", C.c_void_p), ("cocg", C.c_void_p), ("variance", C.c_void_p), ("ao_sky", C.c_void_p)]
+
+
 class VxFrameParams(C.Structure):
     _fields_ = [("primary", C.POINTER(VxPrimaryParams)), ("shadow", C.POINTER(VxShadowParams)), ("diffuse", C.POINTER(VxDiffuseParams)),
                 ("reflection", C.POINTER(VxReflectionParams)), ("g_normal", C.c_void_p), ("g_pbr", C.c_void_p)]
@@ -127,6 +166,12 @@ EXPORTS = {
     "vxpt_set_gbuffer_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "vxpt_generate_gbuffer": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams),
                                         C.POINTER(VxMaterialOut)]),
+    "vxpt_svgf_temporal": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfTemporalIn), C.POINTER(VxSvgfTemporalParams),
+                                     C.POINTER(VxSvgfTemporalOut)]),
+    "vxpt_svgf_variance": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfVarianceIn), C.POINTER(VxSvgfVarianceParams),
+                                     C.POINTER(VxSvgfVarianceOut)]),
+    "vxpt_svgf_spatial": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfSpatialIn), C.POINTER(VxSvgfSpatialParams),
+                                    C.POINTER(VxSvgfSpatialOut)]),
     "vxpt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxpt_player_shadowed": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vxpt_estimate_ambient_sound": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint32), C.c_void_p]),

@@ -135,6 +135,11 @@ struct PassIO {
                                 c->stream));
         return VXPT_OK;
     }
+    int upload_all(const Plane& p) {  // host -> device, the whole plane: inputs of stencil passes, which read rows outside the slab
+        if (!p.user || !p.staged) return VXPT_OK;
+        VX_CUDA(cudaMemcpyAsync(p.dev, p.user, (size_t)cam->width * cam->height * p.elem, cudaMemcpyHostToDevice, c->stream));
+        return VXPT_OK;
+    }
     int download(const Plane& p, bool& any) {
         if (!p.user || !p.staged) return VXPT_OK;
         VX_CUDA(cudaMemcpyAsync((char*)p.user + slab_offset(p), (const char*)p.dev + slab_offset(p), slab_bytes(p), cudaMemcpyDeviceToHost,
@@ -616,6 +621,122 @@ int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
     if ((rc = io.download(al, any)) || (rc = io.download(nm, any)) || (rc = io.download(pb, any)) || (rc = io.download(ao, any))) return rc;
     if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
     return VXPT_OK;
+}
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------- SVGF denoiser
+// shared by the three passes: a handle that is ready (no pending frame), fp32 planes, whole-frame inputs, plain row slabs
+static int check_svgf(vxpt_ctx* c, const VxCamera* cam) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    if (int rc = finish_pending_frame(c)) return rc;
+    if (int rc = check_camera(cam)) return rc;
+    if (cam->interleave_n > 1) return fail(VXPT_E_UNSUPPORTED, "the denoiser passes read neighbouring rows: interleaved row bands are not supported");
+    if (c->opt_texel) return fail(VXPT_E_UNSUPPORTED, "the denoiser passes take fp32 planes (VXPT_OPT_TEXEL_FORMAT must be 0)");
+    return VXPT_OK;
+}
+namespace {
+struct SvgfIO {  // input planes are staged whole, output planes by slab
+    PassIO io;
+    std::vector<Plane*> inputs, outputs;
+    std::vector<Plane> store;
+    SvgfIO(vxpt_ctx* c, const VxCamera* cam) : io(c, cam) { store.reserve(32); }
+    Plane* in(const void* user, size_t elem) { store.emplace_back(); io.add(store.back(), user, elem); inputs.push_back(&store.back()); return &store.back(); }
+    Plane* out(const void* user, size_t elem) { store.emplace_back(); io.add(store.back(), user, elem); outputs.push_back(&store.back()); return &store.back(); }
+    int begin() {
+        if (int rc = io.resolve()) return rc;
+        for (Plane* p : inputs)
+            if (int rc = io.upload_all(*p)) return rc;
+        return VXPT_OK;
+    }
+    int end(vxpt_ctx* c) {
+        bool any = false;
+        for (Plane* p : outputs)
+            if (int rc = io.download(*p, any)) return rc;
+        if (any) VX_CUDA(cudaStreamSynchronize(c->stream));
+        return VXPT_OK;
+    }
+};
+template <class F> int timed_launch(vxpt_ctx* c, F&& launch) {
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (int rc = launch()) return rc;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
+    return VXPT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int vxpt_svgf_temporal(vxpt_handle c, const VxCamera* cam, const VxSvgfTemporalIn* in, const VxSvgfTemporalParams* p, const VxSvgfTemporalOut* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!in || !p || !out) return fail(VXPT_E_INVALID, "NULL argument");
+    const void* req[] = {in->current.t, in->current.normal_id, in->current.block_id, in->previous.t, in->previous.normal_id, in->previous.block_id,
+                         in->sh, in->cocg, in->luma, in->ao_sky, in->prev_sh, in->prev_cocg, in->prev_utility, in->prev_ao_sky};
+    for (const void* q : req)
+        if (!q) return fail(VXPT_E_INVALID, "NULL input plane (current / previous t, normal_id, block_id, the GI planes and the previous temporal planes are required)");
+    VX_CUDA(cudaSetDevice(c->device));
+    SvgfIO s(c, cam);
+    Plane *t = s.in(in->current.t, 4), *n = s.in(in->current.normal_id, 1), *b = s.in(in->current.block_id, 1);
+    Plane *pt = s.in(in->previous.t, 4), *pn = s.in(in->previous.normal_id, 1), *pb = s.in(in->previous.block_id, 1);
+    Plane *sh = s.in(in->sh, 16), *cc = s.in(in->cocg, 8), *lu = s.in(in->luma, 4), *ao = s.in(in->ao_sky, 8);
+    Plane *psh = s.in(in->prev_sh, 16), *pcc = s.in(in->prev_cocg, 8), *put = s.in(in->prev_utility, 12), *pao = s.in(in->prev_ao_sky, 8);
+    Plane *osh = s.out(out->sh, 16), *occ = s.out(out->cocg, 8), *out_ut = s.out(out->utility, 12), *oao = s.out(out->ao_sky, 8);
+    if ((rc = s.begin())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    VxSvgfTemporalIn id{};
+    id.current = VxGBuffer{(float*)t->dev, (uint8_t*)n->dev, (uint8_t*)b->dev, nullptr, nullptr};
+    id.previous = VxGBuffer{(float*)pt->dev, (uint8_t*)pn->dev, (uint8_t*)pb->dev, nullptr, nullptr};
+    id.sh = (const float*)sh->dev; id.cocg = (const float*)cc->dev; id.luma = (const float*)lu->dev; id.ao_sky = (const float*)ao->dev;
+    id.prev_sh = (const float*)psh->dev; id.prev_cocg = (const float*)pcc->dev; id.prev_utility = (const float*)put->dev; id.prev_ao_sky = (const float*)pao->dev;
+    const VxSvgfTemporalOut od{(float*)osh->dev, (float*)occ->dev, (float*)out_ut->dev, (float*)oao->dev};
+    if ((rc = timed_launch(c, [&] { return launch_svgf_temporal(c, *cam, id, *p, od); }))) return rc;
+    return s.end(c);
+}
+
+int vxpt_svgf_variance(vxpt_handle c, const VxCamera* cam, const VxSvgfVarianceIn* in, const VxSvgfVarianceParams* p, const VxSvgfVarianceOut* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!in || !p || !out || !in->current.t || !in->current.normal_id || !in->sh || !in->cocg || !in->utility)
+        return fail(VXPT_E_INVALID, "NULL argument (t, normal_id and the temporal pass's sh / cocg / utility planes are required)");
+    VX_CUDA(cudaSetDevice(c->device));
+    SvgfIO s(c, cam);
+    Plane *t = s.in(in->current.t, 4), *n = s.in(in->current.normal_id, 1);
+    Plane *sh = s.in(in->sh, 16), *cc = s.in(in->cocg, 8), *ut = s.in(in->utility, 12);
+    Plane *osh = s.out(out->sh, 16), *occ = s.out(out->cocg, 8), *ov = s.out(out->variance, 4);
+    if ((rc = s.begin())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    VxSvgfVarianceIn id{};
+    id.current = VxGBuffer{(float*)t->dev, (uint8_t*)n->dev, nullptr, nullptr, nullptr};
+    id.sh = (const float*)sh->dev; id.cocg = (const float*)cc->dev; id.utility = (const float*)ut->dev;
+    const VxSvgfVarianceOut od{(float*)osh->dev, (float*)occ->dev, (float*)ov->dev};
+    if ((rc = timed_launch(c, [&] { return launch_svgf_variance(c, *cam, id, *p, od); }))) return rc;
+    return s.end(c);
+}
+
+int vxpt_svgf_spatial(vxpt_handle c, const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvgfSpatialParams* p, const VxSvgfSpatialOut* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!in || !p || !out || !in->current.t || !in->current.normal_id || !in->sh || !in->cocg || !in->variance || !in->ao_sky || !in->temporal_utility)
+        return fail(VXPT_E_INVALID, "NULL argument (t, normal_id, sh, cocg, variance, ao_sky and the temporal utility plane are required)");
+    if (p->step < 1 || p->step > 1024) return fail(VXPT_E_INVALID, "bad a-trous step");
+    VX_CUDA(cudaSetDevice(c->device));
+    SvgfIO s(c, cam);
+    Plane *t = s.in(in->current.t, 4), *n = s.in(in->current.normal_id, 1);
+    Plane *sh = s.in(in->sh, 16), *cc = s.in(in->cocg, 8), *va = s.in(in->variance, 4), *ao = s.in(in->ao_sky, 8), *ut = s.in(in->temporal_utility, 12);
+    Plane *osh = s.out(out->sh, 16), *occ = s.out(out->cocg, 8), *ov = s.out(out->variance, 4), *oao = s.out(out->ao_sky, 8);
+    if ((rc = s.begin())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    VxSvgfSpatialIn id{};
+    id.current = VxGBuffer{(float*)t->dev, (uint8_t*)n->dev, nullptr, nullptr, nullptr};
+    id.sh = (const float*)sh->dev; id.cocg = (const float*)cc->dev; id.variance = (const float*)va->dev; id.ao_sky = (const float*)ao->dev;
+    id.temporal_utility = (const float*)ut->dev;
+    const VxSvgfSpatialOut od{(float*)osh->dev, (float*)occ->dev, (float*)ov->dev, (float*)oao->dev};
+    if ((rc = timed_launch(c, [&] { return launch_svgf_spatial(c, *cam, id, *p, od); }))) return rc;
+    return s.end(c);
 }
 
 // ----------------------------------------------------------------------------------------------------- other DF consumers

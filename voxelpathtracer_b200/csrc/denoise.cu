@@ -1,0 +1,424 @@
+// denoise.cu — SVGF diffuse denoiser: Core/Shaders/SVGF/TemporalFilter.glsl, VarianceEstimate.glsl and
+// SpatialFilter.glsl as dispatched by Core/Pipeline.cpp:2335-2596, the passes that consume the diffuse-GI planes.
+//
+// One thread per output pixel on the trace passes' 8x4-pixel warp tiles, so the taps of a warp (neighbouring texels, or the same
+// a-trous offset for every lane) fall into a few 128-byte lines.  Every read goes through tex_linear / tex_nearest below: the pinned
+// texture() of include/vxpt.h (GL_REPEAT, OpenGL 4.3 section 8.14.2 bilinear in fp32) — also for taps that land on a texel centre, because
+// u * w - 0.5 is not always an integer in fp32 and the parity contract is bit-exactness with the reference's shaders.
+// HBM per 1080p pass: temporal 189 MB, variance 141 MB, one a-trous pass 151 MB of planes; the 4-tap gathers around them hit L1 / L2.
+// Compiled with -fmad=false; exp / pow are the pinned correctly rounded fp32 values; fminf / fmaxf return the non-NaN operand.
+#include <cmath>
+
+#include "gi_device.cuh"
+
+namespace vxpt {
+
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ int wrap_repeat(int i, int n) {
+    const int m = i % n;
+    return m < 0 ? m + n : m;
+}
+struct Bilinear {  // the four texels and two weights of one GL_LINEAR tap
+    int o00, o10, o01, o11;
+    float fx, fy;
+};
+__device__ __forceinline__ Bilinear bilinear_at(int w, int h, float u, float v) {
+    const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    const float x0 = floorf(x), y0 = floorf(y);
+    const int i0 = wrap_repeat((int)x0, w), i1 = wrap_repeat((int)x0 + 1, w), j0 = wrap_repeat((int)y0, h), j1 = wrap_repeat((int)y0 + 1, h);
+    return Bilinear{j0 * w + i0, j0 * w + i1, j1 * w + i0, j1 * w + i1, x - x0, y - y0};
+}
+__device__ __forceinline__ float blend(const Bilinear& b, float t00, float t10, float t01, float t11) {
+    return (t00 * (1.0f - b.fx) + t10 * b.fx) * (1.0f - b.fy) + (t01 * (1.0f - b.fx) + t11 * b.fx) * b.fy;
+}
+__device__ __forceinline__ float tex1(const float* d, const Bilinear& b) { return blend(b, d[b.o00], d[b.o10], d[b.o01], d[b.o11]); }
+__device__ __forceinline__ float2 tex2(const float* d, const Bilinear& b) {
+    const float2* p = reinterpret_cast<const float2*>(d);
+    const float2 a = p[b.o00], c = p[b.o10], e = p[b.o01], f = p[b.o11];
+    return make_float2(blend(b, a.x, c.x, e.x, f.x), blend(b, a.y, c.y, e.y, f.y));
+}
+__device__ __forceinline__ V3 tex3(const float* d, const Bilinear& b) {
+    const float *a = d + 3 * b.o00, *c = d + 3 * b.o10, *e = d + 3 * b.o01, *f = d + 3 * b.o11;
+    return mk3(blend(b, a[0], c[0], e[0], f[0]), blend(b, a[1], c[1], e[1], f[1]), blend(b, a[2], c[2], e[2], f[2]));
+}
+__device__ __forceinline__ float4 tex4(const float* d, const Bilinear& b) {
+    const float4* p = reinterpret_cast<const float4*>(d);
+    const float4 a = p[b.o00], c = p[b.o10], e = p[b.o01], f = p[b.o11];
+    return make_float4(blend(b, a.x, c.x, e.x, f.x), blend(b, a.y, c.y, e.y, f.y), blend(b, a.z, c.z, e.z, f.z), blend(b, a.w, c.w, e.w, f.w));
+}
+__device__ __forceinline__ int tex_nearest_u8(const uint8_t* d, int w, int h, float u, float v) {
+    return d[wrap_repeat((int)floorf(v * (float)h), h) * w + wrap_repeat((int)floorf(u * (float)w), w)];
+}
+__device__ __forceinline__ float sh_to_y(float4 sh) { return fmaxf(0.0f, 3.544905f * sh.w); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 operator/(float4 a, float s) { return make_float4(a.x / s, a.y / s, a.z / s, a.w / s); }
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator*(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 operator/(float2 a, float s) { return make_float2(a.x / s, a.y / s); }
+__device__ __forceinline__ float4 clamp4(float4 a, float lo, float hi) {
+    return make_float4(clampf(a.x, lo, hi), clampf(a.y, lo, hi), clampf(a.z, lo, hi), clampf(a.w, lo, hi));
+}
+__device__ __forceinline__ float2 clamp2(float2 a, float lo, float hi) { return make_float2(clampf(a.x, lo, hi), clampf(a.y, lo, hi)); }
+
+struct SvgfPlanes {  // device pointers of one call; unused members are null
+    const float *t, *prev_t;
+    const uint8_t *nid, *prev_nid, *bid, *prev_bid;
+    const float *sh, *cocg, *luma, *ao, *utility, *variance;
+    const float *prev_sh, *prev_cocg, *prev_utility, *prev_ao;
+    float *o_sh, *o_cocg, *o_utility, *o_variance, *o_ao;
+};
+
+// ============================================================================================= temporal accumulation
+struct TemporalDev {
+    float prev_vp[16];  // u_PrevProjection * u_PrevView, multiplied on the host in glm's order
+    int be_useful;
+};
+// SVGF/TemporalFilter.glsl main() :137-362
+__global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constant__ CameraDev cam, const __grid_constant__ TemporalDev P,
+                                                            const SvgfPlanes pl) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const int W = cam.width, H = cam.height;
+    const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+    const Bilinear bc = bilinear_at(W, H, u, v);
+    const V3 origin = ray_origin(cam);
+    const float base_w = tex1(pl.t, bc);
+    const V3 base_p = origin + normalize3(ray_direction_at(cam, u, v)) * base_w;  // GetPositionAt :81-85
+    const int base_nid = tex_nearest_u8(pl.nid, W, H, u, v);
+    const float4 base_sh = tex4(pl.sh, bc);
+    const float2 base_cocg = tex2(pl.cocg, bc), base_ao = tex2(pl.ao, bc);
+    // Reprojection :58-72
+    const float* M = P.prev_vp;
+    const float px4 = (M[0] * base_p.x + M[4] * base_p.y) + (M[8] * base_p.z + M[12] * 1.0f);
+    const float py4 = (M[1] * base_p.x + M[5] * base_p.y) + (M[9] * base_p.z + M[13] * 1.0f);
+    const float pw4 = (M[3] * base_p.x + M[7] * base_p.y) + (M[11] * base_p.z + M[15] * 1.0f);
+    const float ru = (px4 / pw4) * 0.5f + 0.5f, rv = (py4 / pw4) * 0.5f + 0.5f;
+    const float base_lum = tex1(pl.luma, bc);
+    const int base_block = min(tex_nearest_u8(pl.bid, W, H, u, v), 127);
+    // (the shader's tap jitter ivec2((GradientNoise() - 0.5) * 1.0) truncates to zero for every pixel)
+    const V3 to_player = origin - base_p;
+    const float dist_player = sqrtf(dot3(to_player, to_player));
+    bool block_w = true, normal_w = true;
+    float tol = 0.75f;
+    if (dist_player < 4.0f) tol = 0.3f;
+    else if (dist_player < 6.0f) tol = 0.65f;
+    else if (dist_player < 8.0f) tol = 0.85f;
+    else if (dist_player < 16.0f) tol = 1.414f;
+    else if (dist_player < 32.0f) tol = 2.4f;
+    else if (dist_player < 48.0f) { tol = 3.5f; block_w = false; }
+    else if (dist_player < 64.0f) { tol = 4.2f; block_w = false; }
+    else if (dist_player < 96.0f) { tol = 6.25f; block_w = false; normal_w = false; }
+    else if (dist_player < 128.0f) { tol = 9.0f; block_w = false; normal_w = false; }
+    else if (dist_player < 200.0f) { tol = 14.0f; block_w = false; normal_w = false; }
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    float total_w = 0.0f, sum_spp = 0.0f, sum_moment = 0.0f, sum_lum = 0.0f;
+    float4 sum_sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 sum_cocg = make_float2(0.f, 0.f), sum_ao = make_float2(0.f, 0.f);
+    int ok = 0;
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {  // Offsets[5] = (1,0) (0,1) (0,0) (-1,0) (0,-1), Weights 3/32 3/32 9/64 3/32 3/32
+        const float ox = k == 0 ? 1.0f : (k == 3 ? -1.0f : 0.0f), oy = k == 1 ? 1.0f : (k == 4 ? -1.0f : 0.0f);
+        const float cw = k == 2 ? 9.0f / 64.0f : 3.0f / 32.0f;
+        const float su = ru + (ox + 0.0f) * tsx, sv = rv + (oy + 0.0f) * tsy;
+        const float b = 0.0035f;
+        if (!(su < 1.0f - b && su > b && sv < 1.0f - b && sv > b)) continue;
+        const Bilinear bs = bilinear_at(W, H, su, sv);
+        const float pw = tex1(pl.prev_t, bs);
+        const V3 pp = origin + normalize3(ray_direction_at(cam, su, sv)) * pw;
+        const V3 diff = mk3(fabsf(base_p.x - pp.x), fabsf(base_p.y - pp.y), fabsf(base_p.z - pp.z));
+        const float err = dot3(diff, diff);
+        bool valid = err < tol && ((pw < 0.0f) == (base_w < 0.0f));
+        if (valid && normal_w) {  // PreviousNormalAt != BaseNormal: ids above 5 all decode to (1,1,1)
+            const int pn = tex_nearest_u8(pl.prev_nid, W, H, su, sv);
+            valid = min(pn, 6) == min(base_nid, 6);
+        }
+        if (valid && block_w) valid = base_block == min(tex_nearest_u8(pl.prev_bid, W, H, su, sv), 127);
+        if (valid) {
+            const V3 ut = tex3(pl.prev_utility, bs);
+            sum_sh = sum_sh + tex4(pl.prev_sh, bs) * cw;
+            sum_cocg = sum_cocg + tex2(pl.prev_cocg, bs) * cw;
+            sum_spp += ut.x * cw;
+            sum_moment += ut.y * cw;
+            sum_lum += ut.z * cw;
+            sum_ao = sum_ao + tex2(pl.prev_ao, bs) * cw;
+            total_w += cw;
+            ok++;
+        }
+    }
+    if (total_w > 0.001f) {
+        sum_sh = sum_sh / total_w; sum_cocg = sum_cocg / total_w; sum_moment /= total_w; sum_spp /= total_w; sum_lum /= total_w;
+        sum_ao = sum_ao / total_w;
+    } else {
+        ok = 0;
+    }
+    float spp_inc = sum_spp + (P.be_useful ? 1.0f : 0.0f);
+    if (ok <= 0) spp_inc = 0.01f;
+    float blend_f = fmaxf(1.0f / spp_inc, 0.05f);
+    const float moment_f = blend_f;
+    if (!P.be_useful) blend_f = 0.99f;
+    const float util_spp = ok <= 0 ? 0.0f : spp_inc;
+    const float util_moment = (1.0f - moment_f) * sum_moment + moment_f * (base_lum * base_lum);
+    const float store_luma = mixf(sum_lum, base_lum, blend_f);
+    float4 o_sh = make_float4(mixf(sum_sh.x, base_sh.x, blend_f), mixf(sum_sh.y, base_sh.y, blend_f), mixf(sum_sh.z, base_sh.z, blend_f),
+                              mixf(sum_sh.w, base_sh.w, blend_f));
+    float2 o_cocg = make_float2(mixf(sum_cocg.x, base_cocg.x, blend_f), mixf(sum_cocg.y, base_cocg.y, blend_f));
+    float2 o_ao = make_float2(mixf(sum_ao.x, base_ao.x, blend_f), mixf(sum_ao.y, base_ao.y, blend_f));
+    if (ok <= 0) { o_sh = base_sh; o_cocg = base_cocg; o_ao = base_ao; }
+    const size_t px = (size_t)prow * W + i;
+    if (pl.o_sh) reinterpret_cast<float4*>(pl.o_sh)[px] = clamp4(o_sh, -100.0f, 100.0f);
+    if (pl.o_cocg) reinterpret_cast<float2*>(pl.o_cocg)[px] = clamp2(o_cocg, -10.0f, 100.0f);
+    if (pl.o_ao) reinterpret_cast<float2*>(pl.o_ao)[px] = clamp2(o_ao, 0.0f, 1.0f);
+    if (pl.o_utility) {
+        pl.o_utility[3 * px] = clampf(util_spp, -150.0f, 150.0f);
+        pl.o_utility[3 * px + 1] = clampf(util_moment, -150.0f, 150.0f);
+        pl.o_utility[3 * px + 2] = clampf(store_luma, -150.0f, 150.0f);
+    }
+}
+
+// ============================================================================================= variance estimate
+struct VarianceDev {
+    int do_spatial, aggressive;
+};
+// SVGF/VarianceEstimate.glsl main() :76-192
+__global__ void __launch_bounds__(256) svgf_variance_kernel(const __grid_constant__ CameraDev cam, const VarianceDev P, const SvgfPlanes pl) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const int W = cam.width, H = cam.height;
+    const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+    const Bilinear bc = bilinear_at(W, H, u, v);
+    const float base_w = tex1(pl.t, bc);
+    const V3 base_n = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const V3 bu = tex3(pl.utility, bc);
+    const float4 base_sh = tex4(pl.sh, bc);
+    const float2 base_cocg = tex2(pl.cocg, bc);
+    const float base_lum = sh_to_y(base_sh), frames = bu.x, base_moment = bu.y;
+    const size_t px = (size_t)prow * W + i;
+    if (!P.do_spatial) {  // :94-99 returns before the clamps
+        if (pl.o_sh) reinterpret_cast<float4*>(pl.o_sh)[px] = base_sh;
+        if (pl.o_cocg) reinterpret_cast<float2*>(pl.o_cocg)[px] = base_cocg;
+        if (pl.o_variance) pl.o_variance[px] = base_moment - base_lum * base_lum;
+        return;
+    }
+    const float thresh = P.aggressive ? 4.0f + 4.0f + 4.0f : 4.0f + 4.0f;
+    float4 o_sh = base_sh;
+    float2 o_cocg = base_cocg;
+    float variance;
+    if (frames < thresh) {
+        const float color_phi = P.aggressive ? 5.0f : 5.0f * 2.0f;
+        const int K = P.aggressive ? 4 : 1;
+        const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+        float tw = 0.0f, tm = 0.0f, tl = 0.0f, tw2 = 0.0f;
+        float4 tsh = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 tcc = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int x = -K; x <= K; ++x)
+#pragma unroll 1
+            for (int y = -K; y <= K; ++y) {
+                const float su = u + (float)x * tsx, sv = v + (float)y * tsy;
+                if (!(su < 1.0f && su > 0.0f && sv < 1.0f && sv > 0.0f)) continue;
+                const Bilinear bs = bilinear_at(W, H, su, sv);
+                const float sw = tex1(pl.t, bs);
+                const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
+                const float smoment = tex3(pl.utility, bs).y;
+                const float4 ssh = tex4(pl.sh, bs);
+                const float2 scc = tex2(pl.cocg, bs);
+                const float slum = sh_to_y(ssh);
+                const float nw = pow_cr(fmaxf(dot3(base_n, sn), 0.0f), 16.0f);
+                const float dw = pow_cr(exp_cr(-fabsf(sw - base_w)), 2.0f);
+                const float lw = fabsf(slum - base_lum) / color_phi;
+                const float w0 = exp_cr(-lw) * nw * dw;
+                const float w1 = fmaxf(w0, 0.000000015f), w2 = fmaxf(w0, 0.0000000015f);
+                tw += w1;
+                tm += smoment * w2;
+                tsh = tsh + ssh * w1;
+                tcc = tcc + scc * w1;
+                tl += slum * w2;
+                tw2 += w2;
+            }
+        if (tw > 0.0f) { tm /= tw2; tl /= tw2; tcc = tcc / tw; tsh = tsh / tw; }
+        o_sh = tsh;
+        o_cocg = tcc;
+        variance = (tm - tl * tl) * 3.0f;
+    } else {
+        variance = base_moment - base_lum * base_lum;
+    }
+    variance *= thresh / frames;
+    if (pl.o_sh) reinterpret_cast<float4*>(pl.o_sh)[px] = clamp4(o_sh, -100.0f, 100.0f);
+    if (pl.o_cocg) reinterpret_cast<float2*>(pl.o_cocg)[px] = clamp2(o_cocg, -10.0f, 100.0f);
+    if (pl.o_variance) pl.o_variance[px] = clampf(variance, -1.0f, 50.0f);
+}
+
+// ============================================================================================= a-trous pass
+struct SpatialDev {
+    int step, large_kernel, do_spatial, aggressive;
+    float color_phi_bias, resolution_scale;
+    float noise_shift;  // mod(u_Time * 100.493850275f, 500.0f), computed on the host in fp32
+};
+// SVGF/SpatialFilter.glsl main() :193-354
+__global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant__ CameraDev cam, const SpatialDev P, const SvgfPlanes pl) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const int W = cam.width, H = cam.height;
+    const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    const int step = P.step;
+    // GradientNoise :177-182 -> Jitter :206
+    const float cx = ((float)i + 0.5f) + P.noise_shift, cy = ((float)j + 0.5f) + P.noise_shift;
+    const float noise = fractf(52.9829189f * fractf(0.06711056f * cx + 0.00583715f * cy));
+    const int jit = (int)((noise - 0.5f) * ((float)step * 0.8f));
+    const Bilinear bc = bilinear_at(W, H, u, v);
+    const float base_depth = tex1(pl.t, bc);
+    const V3 base_n = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const float4 base_sh = tex4(pl.sh, bc);
+    const float2 base_cocg = tex2(pl.cocg, bc);
+    const float base_lum = sh_to_y(base_sh);
+    // GaussianVariance :98-132
+    float base_var = 0.0f, vsum = 0.0f, ksum = 0.0f;
+#pragma unroll
+    for (int x = -1; x <= 1; ++x)
+#pragma unroll
+        for (int y = -1; y <= 1; ++y) {
+            const float su = u + (float)x * tsx, sv = v + (float)y * tsy;
+            if (!(su > 0.0f && su < 1.0f && sv > 0.0f && sv < 1.0f)) continue;
+            const float kv = (x == 0 ? 0.60283f : 0.198585f) * (y == 0 ? 0.60283f : 0.198585f);
+            const float V = tex1(pl.variance, bilinear_at(W, H, su, sv));
+            if (x == 0 && y == 0) base_var = V;
+            vsum += V * kv;
+            ksum += kv;
+        }
+    const float var_est = vsum / fmaxf(ksum, 0.01f);
+    const float2 base_ao = tex2(pl.ao, bc);
+    const size_t px = (size_t)prow * W + i;
+    if (!P.do_spatial) {  // :217-223 returns before the clamps
+        if (pl.o_sh) reinterpret_cast<float4*>(pl.o_sh)[px] = base_sh;
+        if (pl.o_cocg) reinterpret_cast<float2*>(pl.o_cocg)[px] = base_cocg;
+        if (pl.o_variance) pl.o_variance[px] = base_var;
+        if (pl.o_ao) reinterpret_cast<float2*>(pl.o_ao)[px] = base_ao;
+        return;
+    }
+    const bool filter_ao = step <= 4, filter_sky = step <= 6 || filter_ao;
+    float4 tsh = base_sh;
+    float2 tcc = base_cocg, tao = base_ao;
+    float tw = 1.0f, tvar = base_var, taow = 1.0f;
+    const bool strong = tex3(pl.utility, bc).x <= 8.0f && P.aggressive && step <= 8;
+    float curve = 0.0f;
+    if (var_est < 0.01f) curve = 128.0f;
+    else if (var_est < 0.025f) curve = 112.0f;
+    else if (var_est < 0.05f) curve = 96.0f;
+    else if (var_est < 0.075f) curve = 84.0f;
+    else if (var_est < 0.1f) curve = 70.0f;
+    float tweaked = var_est;
+    if (var_est < 0.1f) {  // TweakVariance :184-190
+        const float f = clampf(var_est, 0.0f, 1.0f);
+        tweaked = f * pow_cr(1.0f - f, curve + 6.0f);
+    }
+    float phi = sqrtf(fmaxf(0.0f, 0.000001f + tweaked));
+    phi /= fmaxf(P.color_phi_bias, 0.1f);
+    const int K = P.large_kernel ? 2 : 1;
+    const float add_scale = mixf(1.0f, 2.4f, P.resolution_scale);
+#pragma unroll 1
+    for (int x = -K; x <= K; ++x)
+#pragma unroll 1
+        for (int y = -K; y <= K; ++y) {
+            if (x == 0 && y == 0) continue;
+            const float su = u + ((((float)x * (float)step) * add_scale) + ((float)jit * 0.5f)) * tsx;
+            const float sv = v + ((((float)y * (float)step) * add_scale) + ((float)jit * 0.5f)) * tsy;
+            if (!(su > 0.0f && su < 1.0f && sv > 0.0f && sv < 1.0f)) continue;
+            const Bilinear bs = bilinear_at(W, H, su, sv);
+            const float ddiff = fabsf(tex1(pl.t, bs) - base_depth);
+            if ((base_depth < 0.0f) != (ddiff < 0.0f)) continue;  // :262
+            const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
+            const float4 ssh = tex4(pl.sh, bs);
+            const float2 scc = tex2(pl.cocg, bs);
+            const float slum = sh_to_y(ssh);
+            const float svar = tex1(pl.variance, bs);
+            const float nw = clampf(pow_cr(fmaxf(dot3(base_n, sn), 0.0f), 32.0f), 0.001f, 1.0f);
+            const float lw = fabsf(slum - base_lum) / phi;
+            const float dw = clampf(pow_cr(exp_cr(-fmaxf(ddiff, 0.00001f)), 2.0f), 0.0001f, 1.0f);
+            float w = strong ? (nw * dw) : (exp_cr(-lw) * nw * dw);
+            w = clampf(w, 0.001f, 1.0f);
+            const float xw = x == 0 ? 1.0f : ((x == 1 || x == -1) ? 2.0f / 3.0f : 1.0f / 6.0f);
+            const float yw = y == 0 ? 1.0f : ((y == 1 || y == -1) ? 2.0f / 3.0f : 1.0f / 6.0f);
+            w = fmaxf((xw * yw) * w, 0.00000001f);
+            tsh = tsh + ssh * w;
+            tcc = tcc + scc * w;
+            tvar += (w * w) * svar;
+            tw += w;
+            if (filter_sky || filter_ao) {
+                const float aw = clampf((xw * yw) * nw * dw, 0.000001f, 1.0f);
+                const float2 s = tex2(pl.ao, bs);
+                tao.x += s.x * aw;
+                tao.y += s.y * aw;
+                taow += aw;
+            }
+        }
+    tsh = tsh / tw;
+    tcc = tcc / tw;
+    tvar /= (tw * tw);
+    tao = tao / taow;
+    if (!filter_ao) tao.x = base_ao.x;
+    if (pl.o_sh) reinterpret_cast<float4*>(pl.o_sh)[px] = clamp4(tsh, -100.0f, 100.0f);
+    if (pl.o_cocg) reinterpret_cast<float2*>(pl.o_cocg)[px] = clamp2(tcc, -10.0f, 100.0f);
+    if (pl.o_variance) pl.o_variance[px] = clampf(tvar, -1.0f, 50.0f);
+    if (pl.o_ao) reinterpret_cast<float2*>(pl.o_ao)[px] = clamp2(tao, 0.0f, 1.0f);
+}
+
+// ============================================================================================= launchers
+static CameraDev svgf_camera(const VxCamera& cam) {
+    CameraDev cd;
+    for (int k = 0; k < 16; ++k) { cd.inv_view[k] = cam.inv_view[k]; cd.inv_proj[k] = cam.inv_proj[k]; }
+    cd.width = cam.width; cd.height = cam.height; cd.row_begin = cam.row_begin; cd.row_end = cam.row_end;
+    cd.il_n = 0; cd.il_rank = 0; cd.il_band = 1;
+    return cd;
+}
+static dim3 svgf_grid(const VxCamera& cam) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8); }
+
+int launch_svgf_temporal(vxpt_ctx* c, const VxCamera& cam, const VxSvgfTemporalIn& in, const VxSvgfTemporalParams& p, const VxSvgfTemporalOut& out) {
+    TemporalDev d;
+    const float *A = p.prev_projection, *B = p.prev_view;  // glm mat4 * mat4: column j = ((A0*b0j + A1*b1j) + A2*b2j) + A3*b3j
+    for (int jc = 0; jc < 4; ++jc)
+        for (int r = 0; r < 4; ++r)
+            d.prev_vp[4 * jc + r] = ((A[0 + r] * B[4 * jc + 0] + A[4 + r] * B[4 * jc + 1]) + A[8 + r] * B[4 * jc + 2]) + A[12 + r] * B[4 * jc + 3];
+    d.be_useful = p.be_useful;
+    SvgfPlanes pl{};
+    pl.t = in.current.t; pl.nid = in.current.normal_id; pl.bid = in.current.block_id;
+    pl.prev_t = in.previous.t; pl.prev_nid = in.previous.normal_id; pl.prev_bid = in.previous.block_id;
+    pl.sh = in.sh; pl.cocg = in.cocg; pl.luma = in.luma; pl.ao = in.ao_sky;
+    pl.prev_sh = in.prev_sh; pl.prev_cocg = in.prev_cocg; pl.prev_utility = in.prev_utility; pl.prev_ao = in.prev_ao_sky;
+    pl.o_sh = out.sh; pl.o_cocg = out.cocg; pl.o_utility = out.utility; pl.o_ao = out.ao_sky;
+    VX_LAUNCH(svgf_temporal_kernel, svgf_grid(cam), 256, c->stream, svgf_camera(cam), d, pl);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int launch_svgf_variance(vxpt_ctx* c, const VxCamera& cam, const VxSvgfVarianceIn& in, const VxSvgfVarianceParams& p, const VxSvgfVarianceOut& out) {
+    const VarianceDev d{p.do_spatial, p.aggressive_disocclusion};
+    SvgfPlanes pl{};
+    pl.t = in.current.t; pl.nid = in.current.normal_id;
+    pl.sh = in.sh; pl.cocg = in.cocg; pl.utility = in.utility;
+    pl.o_sh = out.sh; pl.o_cocg = out.cocg; pl.o_variance = out.variance;
+    VX_LAUNCH(svgf_variance_kernel, svgf_grid(cam), 256, c->stream, svgf_camera(cam), d, pl);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int launch_svgf_spatial(vxpt_ctx* c, const VxCamera& cam, const VxSvgfSpatialIn& in, const VxSvgfSpatialParams& p, const VxSvgfSpatialOut& out) {
+    SpatialDev d;
+    d.step = p.step; d.large_kernel = p.large_kernel; d.do_spatial = p.do_spatial; d.aggressive = p.aggressive_disocclusion;
+    d.color_phi_bias = p.color_phi_bias; d.resolution_scale = p.resolution_scale;
+    const float m = p.time * 100.493850275f;
+    d.noise_shift = m - 500.0f * std::floor(m / 500.0f);  // mod(x, y) = x - y * floor(x / y)
+    SvgfPlanes pl{};
+    pl.t = in.current.t; pl.nid = in.current.normal_id;
+    pl.sh = in.sh; pl.cocg = in.cocg; pl.variance = in.variance; pl.ao = in.ao_sky; pl.utility = in.temporal_utility;
+    pl.o_sh = out.sh; pl.o_cocg = out.cocg; pl.o_variance = out.variance; pl.o_ao = out.ao_sky;
+    VX_LAUNCH(svgf_spatial_kernel, svgf_grid(cam), 256, c->stream, svgf_camera(cam), d, pl);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+}  // namespace vxpt

@@ -174,6 +174,10 @@ int launch_rays(vxpt_ctx* c, const float* origins, const float* directions, int 
 int launch_ambient(vxpt_ctx* c, const float player[3], int frame, unsigned* aggregate, unsigned* per_invocation);
 // gbuffer.cu
 int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxMaterialParams& p, const VxMaterialOut& out_dev);
+// denoise.cu
+int launch_svgf_temporal(vxpt_ctx* c, const VxCamera& cam, const VxSvgfTemporalIn& in_dev, const VxSvgfTemporalParams& p, const VxSvgfTemporalOut& out_dev);
+int launch_svgf_variance(vxpt_ctx* c, const VxCamera& cam, const VxSvgfVarianceIn& in_dev, const VxSvgfVarianceParams& p, const VxSvgfVarianceOut& out_dev);
+int launch_svgf_spatial(vxpt_ctx* c, const VxCamera& cam, const VxSvgfSpatialIn& in_dev, const VxSvgfSpatialParams& p, const VxSvgfSpatialOut& out_dev);
 // l2_probe.cu
 int run_l2_probe(vxpt_ctx* c, double* gbps);
 

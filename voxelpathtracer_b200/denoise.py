@@ -1,0 +1,73 @@
+"""Host-side description of the SVGF denoiser calls (include/vxpt.h: vxpt_svgf_temporal / _variance / _spatial): builds the ABI structs
+from dicts of planes.  The same structs drive the library (Renderer.svgf_*), the CPU oracle and the host-compiled kernels in tests, so
+`address` is injected: it maps a numpy array or torch tensor to its raw address."""
+import numpy as np
+
+from .abi import (VxGBuffer, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
+                  VxSvgfVarianceIn, VxSvgfVarianceOut, VxSvgfVarianceParams)
+
+ATROUS_STEPS = (16, 8, 4, 2, 1)          # Core/Pipeline.cpp:2482-2487
+ATROUS_STEPS_WIDE = (32, 16, 8, 4, 2)    # WiderSVGF, :2473-2478
+
+
+def _gb(g, address):
+    s = VxGBuffer()
+    s.t, s.normal_id, s.block_id = address(g.get("t")), address(g.get("normal_id")), address(g.get("block_id"))
+    return s
+
+
+def temporal_params(prev_view, prev_projection, be_useful=True):
+    """prev_view / prev_projection: 16 floats each, column-major (glm::value_ptr) — u_PrevView, u_PrevProjection."""
+    p = VxSvgfTemporalParams()
+    p.prev_view[:] = [float(v) for v in np.asarray(prev_view, dtype=np.float32).reshape(16)]
+    p.prev_projection[:] = [float(v) for v in np.asarray(prev_projection, dtype=np.float32).reshape(16)]
+    p.be_useful = int(bool(be_useful))
+    return p
+
+
+def variance_params(do_spatial=True, aggressive_disocclusion=True):
+    p = VxSvgfVarianceParams()
+    p.do_spatial, p.aggressive_disocclusion = int(bool(do_spatial)), int(bool(aggressive_disocclusion))
+    return p
+
+
+def spatial_params(step, time=0.0, large_kernel=False, do_spatial=True, aggressive_disocclusion=True, color_phi_bias=2.0, resolution_scale=0.0):
+    p = VxSvgfSpatialParams()
+    p.step, p.large_kernel, p.do_spatial, p.aggressive_disocclusion = int(step), int(bool(large_kernel)), int(bool(do_spatial)), int(bool(aggressive_disocclusion))
+    p.color_phi_bias, p.time, p.resolution_scale = float(color_phi_bias), float(time), float(resolution_scale)
+    return p
+
+
+def temporal_structs(gbuf, prev_gbuf, diffuse, prev_temporal, out, address):
+    i = VxSvgfTemporalIn()
+    i.current, i.previous = _gb(gbuf, address), _gb(prev_gbuf, address)
+    i.sh, i.cocg, i.luma, i.ao_sky = (address(diffuse[k]) for k in ("sh", "cocg", "luma", "ao_sky"))
+    i.prev_sh, i.prev_cocg, i.prev_utility, i.prev_ao_sky = (address(prev_temporal[k]) for k in ("sh", "cocg", "utility", "ao_sky"))
+    o = VxSvgfTemporalOut()
+    o.sh, o.cocg, o.utility, o.ao_sky = (address(out.get(k)) for k in ("sh", "cocg", "utility", "ao_sky"))
+    return i, o
+
+
+def variance_structs(gbuf, temporal, out, address):
+    i = VxSvgfVarianceIn()
+    i.current = _gb(gbuf, address)
+    i.sh, i.cocg, i.utility = (address(temporal[k]) for k in ("sh", "cocg", "utility"))
+    o = VxSvgfVarianceOut()
+    o.sh, o.cocg, o.variance = (address(out.get(k)) for k in ("sh", "cocg", "variance"))
+    return i, o
+
+
+def spatial_structs(gbuf, planes, temporal_utility, out, address):
+    i = VxSvgfSpatialIn()
+    i.current = _gb(gbuf, address)
+    i.sh, i.cocg, i.variance, i.ao_sky = (address(planes[k]) for k in ("sh", "cocg", "variance", "ao_sky"))
+    i.temporal_utility = address(temporal_utility)
+    o = VxSvgfSpatialOut()
+    o.sh, o.cocg, o.variance, o.ao_sky = (address(out.get(k)) for k in ("sh", "cocg", "variance", "ao_sky"))
+    return i, o
+
+
+def plane_shapes(width, height):
+    """name -> shape of every fp32 plane the denoiser passes exchange."""
+    return {"sh": (height, width, 4), "cocg": (height, width, 2), "utility": (height, width, 3), "ao_sky": (height, width, 2),
+            "variance": (height, width), "luma": (height, width)}

@@ -275,6 +275,44 @@ class Renderer:
         check(self.lib.vxpt_generate_gbuffer(self.handle, C.byref(cam), C.byref(g), C.byref(params), C.byref(o)))
         return out
 
+    # ---- SVGF denoiser (include/vxpt.h vxpt_svgf_*): full-frame fp32 planes, numpy or torch ----
+    def alloc_denoise(self, width, height, names, device=False, pinned=False):
+        from . import denoise
+        shapes = denoise.plane_shapes(width, height)
+        return {k: self.alloc(shapes[k], np.float32, device, pinned) for k in names}
+
+    def svgf_temporal(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out):
+        from . import denoise
+        i, o = denoise.temporal_structs(gbuf, prev_gbuf, diffuse, prev_temporal, out, _ptr)
+        check(self.lib.vxpt_svgf_temporal(self.handle, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)))
+        return out
+
+    def svgf_variance(self, cam, gbuf, temporal, params, out):
+        from . import denoise
+        i, o = denoise.variance_structs(gbuf, temporal, out, _ptr)
+        check(self.lib.vxpt_svgf_variance(self.handle, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)))
+        return out
+
+    def svgf_spatial(self, cam, gbuf, planes, temporal_utility, params, out):
+        from . import denoise
+        i, o = denoise.spatial_structs(gbuf, planes, temporal_utility, out, _ptr)
+        check(self.lib.vxpt_svgf_spatial(self.handle, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)))
+        return out
+
+    def svgf_denoise(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, temporal_params, time=0.0, steps=None, device=False):
+        """The reference's whole SVGF chain for one frame (Core/Pipeline.cpp:2335-2596): temporal -> variance -> five a-trous passes
+        ping-ponging between two plane sets.  Returns (denoised planes, temporal planes to hand in as prev_temporal next frame)."""
+        from . import denoise
+        W, H = cam.width, cam.height
+        temporal = self.svgf_temporal(cam, gbuf, prev_gbuf, diffuse, prev_temporal, temporal_params,
+                                      self.alloc_denoise(W, H, ("sh", "cocg", "utility", "ao_sky"), device))
+        var = self.svgf_variance(cam, gbuf, temporal, denoise.variance_params(), self.alloc_denoise(W, H, ("sh", "cocg", "variance"), device))
+        cur = {"sh": var["sh"], "cocg": var["cocg"], "variance": var["variance"], "ao_sky": temporal["ao_sky"]}
+        pong = [self.alloc_denoise(W, H, ("sh", "cocg", "variance", "ao_sky"), device) for _ in range(2)]
+        for n, step in enumerate(steps or denoise.ATROUS_STEPS):
+            cur = self.svgf_spatial(cam, gbuf, cur, temporal["utility"], denoise.spatial_params(step, time=time), pong[n % 2])
+        return cur, temporal
+
     # ---- other consumers of the distance field (SURVEY.md §8 f4) ----
     def trace_rays(self, origins, directions, max_iterations=350, hit_voxel=True):
         """A batch of VoxelTraversalDF calls (vxpt_trace_rays): origins / directions [n][3] float32 -> dict of t, normal_id, block_id(, hit_voxel)."""

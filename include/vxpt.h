@@ -368,6 +368,41 @@ typedef struct VxSvgfSpatialOut {
 VXPT_API int vxpt_svgf_spatial(vxpt_handle h, const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvgfSpatialParams* p,
                                const VxSvgfSpatialOut* out);
 
+/* ---- sun-shadow filters: Core/Pipeline.cpp:2854-2944 -> Core/Shaders/ShadowTemporalFilter.glsl (u_ShadowTemporal =
+ *      true), ShadowFilter.glsl ------------------------------------------------------------------------------------------------------
+ * The two passes after vxpt_trace_shadow: temporal accumulation of the 0 / 1 shadow plane (history clipped to the neighbourhood of the
+ * current frame, frame counter in a second plane) and an edge-stopping spatial filter whose footprint grows with the occluder distance
+ * ("transversal").  Same conventions as the SVGF exports: fp32 full-frame planes, pinned texture() sampling, plain row slabs. */
+typedef struct VxShadowTemporalIn {
+    VxGBuffer current;          /* t, normal_id of this frame                                                         */
+    VxGBuffer previous;         /* t of the previous frame (u_PreviousFramePositionTexture)                           */
+    const uint8_t* shadow;      /* u_CurrentColorTexture: VxShadowOut.shadow (0 / 1, the R8 attachment)               */
+    const float* transversal;   /* u_ShadowTransversals: VxShadowOut.transversal                                      */
+    const float* prev_shadow;   /* u_PreviousColorTexture: the previous frame's VxShadowTemporalOut.shadow            */
+    const float* prev_frames;   /* u_FrameCount: the previous frame's VxShadowTemporalOut.frames                      */
+} VxShadowTemporalIn;
+typedef struct VxShadowTemporalParams {
+    float prev_view[16];        /* u_PrevView        */
+    float prev_projection[16];  /* u_PrevProjection  */
+} VxShadowTemporalParams;
+typedef struct VxShadowTemporalOut {
+    float* shadow;  /* o_Color.x (R8 in the reference)   */
+    float* frames;  /* o_Frames  (R16F in the reference) */
+} VxShadowTemporalOut;
+VXPT_API int vxpt_shadow_temporal(vxpt_handle h, const VxCamera* cam, const VxShadowTemporalIn* in, const VxShadowTemporalParams* p,
+                                  const VxShadowTemporalOut* out);
+typedef struct VxShadowFilterIn {
+    VxGBuffer current;         /* t, normal_id                                             */
+    const float* shadow;       /* u_InputTexture: VxShadowTemporalOut.shadow               */
+    const float* transversal;  /* u_IntersectionTransversals: VxShadowOut.transversal      */
+    const float* frames;       /* u_FrameCount: VxShadowTemporalOut.frames                 */
+} VxShadowFilterIn;
+typedef struct VxShadowFilterParams {
+    float filter_scale;        /* u_ShadowFilterScale (1.0, Pipeline.cpp:132)              */
+} VxShadowFilterParams;
+VXPT_API int vxpt_shadow_filter(vxpt_handle h, const VxCamera* cam, const VxShadowFilterIn* in, const VxShadowFilterParams* p,
+                                float* out /* o_Color, 1 float / pixel */);
+
 /* ---- one frame of the path: the pass sequence of Core/Pipeline.cpp's render loop (:1973-2016 primary, :2795-2852 shadow,
  *      :2174-2281 diffuse GI, :3003-3164 reflections) on the rows of `cam` -------------------------------------------------
  * Equivalent to vxpt_trace_primary + vxpt_trace_shadow + vxpt_trace_diffuse (+ vxpt_trace_reflection) with the same arguments,

@@ -1,5 +1,5 @@
 // ref_denoise_driver.cpp — the reference's SVGF denoiser shaders (Core/Shaders/SVGF/TemporalFilter.glsl, VarianceEstimate.glsl,
-// SpatialFilter.glsl) compiled as C++; uniforms and binds follow Core/Pipeline.cpp:2335-2596, the vertex stage Core/Shaders/FBOVert.glsl.
+// SpatialFilter.glsl) and sun-shadow filters (Core/Shaders/ShadowTemporalFilter.glsl, ShadowFilter.glsl; Pipeline.cpp:2854-2944) compiled as C++; uniforms and binds follow Core/Pipeline.cpp:2335-2596, the vertex stage Core/Shaders/FBOVert.glsl.
 // The attachments are bound with the filters Core/Pipeline.cpp:1094-1152 declares (hit distance LINEAR, ids NEAREST, the rest LINEAR) and
 // GL_REPEAT (Core/GLClasses/Framebuffer.cpp:66-67).  See ref_shader_driver.cpp.  Test infrastructure only.
 #include <cstdint>
@@ -22,7 +22,11 @@ inline float clamp(float x, float lo, float hi) { return std::fmin(std::fmax(x, 
 inline vec2 clamp(const vec2& v, float lo, float hi) { return vec2(clamp(v.x, lo, hi), clamp(v.y, lo, hi)); }
 inline vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
 inline vec4 clamp(const vec4& v, float lo, float hi) { return vec4(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi), clamp(v.w, lo, hi)); }
+inline vec3 min(const vec3& a, const vec3& b) { return vec3(std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmin(a.z, b.z)); }
+inline vec3 max(const vec3& a, const vec3& b) { return vec3(std::fmax(a.x, b.x), std::fmax(a.y, b.y), std::fmax(a.z, b.z)); }
 inline vec2 operator/(float a, const ivec2& b) { return vec2(a) / vec2(b); }
+#include "_ref/ShadowTemporalFilter.inc"
+#include "_ref/ShadowFilter.inc"
 #include "_ref/TemporalFilter.inc"
 #include "_ref/VarianceEstimate.inc"
 #include "_ref/SpatialFilter.inc"
@@ -166,5 +170,65 @@ extern "C" __attribute__((visibility("default"))) int ref_svgf_spatial(const Ref
         a->o_variance[px] = S::o_Variance;
         std::memcpy(a->o_ao_sky + 2 * px, &S::o_AOAndSkylighting[0], 8);
     })
+    return 0;
+}
+
+struct RefShadowFilterArgs {  // plain C layout, filled by oracle/ref_shaders.py
+    const float* inv_view;
+    const float* inv_proj;
+    int32_t width, height, row_begin, row_end;
+    const float* g_t;  const uint8_t* g_normal_id;  const float* prev_t;
+    const uint8_t* shadow_u8;      // temporal pass: the raw 0 / 1 shadow plane
+    const float* shadow;           // spatial pass: the temporal pass's output
+    const float* transversal;
+    const float* prev_shadow;  const float* frames;   // temporal: previous frame count; spatial: this frame's
+    const float* prev_view;    const float* prev_projection;
+    float filter_scale;
+    float* o_shadow;  float* o_frames;
+};
+
+extern "C" __attribute__((visibility("default"))) int ref_shadow_temporal(const RefShadowFilterArgs* a) {
+    using namespace glsl;
+    namespace S = glsl::denoise::ns_ShadowTemporalFilter;
+    const int W = a->width, H = a->height;
+    const size_t n = (size_t)W * H;
+    IdPlanes cur(a->g_normal_id, nullptr, n);
+    std::vector<float> raw(n);
+    for (size_t k = 0; k < n; ++k) raw[k] = (float)a->shadow_u8[k];   // o_Shadow 0 / 1 stored in R8 reads back as 0.0 / 1.0
+    std::memcpy(&S::u_InverseView[0][0], a->inv_view, 64);
+    std::memcpy(&S::u_InverseProjection[0][0], a->inv_proj, 64);
+    std::memcpy(&S::u_PrevView[0][0], a->prev_view, 64);
+    std::memcpy(&S::u_PrevProjection[0][0], a->prev_projection, 64);
+    S::u_ShadowTemporal = true;                  // Pipeline.cpp:2879
+    S::u_ShouldFilterShadows = true;
+    S::v_RayOrigin = vec3(S::u_InverseView[3]);
+    S::u_CurrentColorTexture = bind(raw.data(), W, H, 1, true);
+    S::u_CurrentPositionTexture = bind(a->g_t, W, H, 1, true);
+    S::u_PreviousColorTexture = bind(a->prev_shadow, W, H, 1, true);
+    S::u_PreviousFramePositionTexture = bind(a->prev_t, W, H, 1, true);
+    S::u_NormalTexture = bind(cur.normal.data(), W, H, 1, false);
+    S::u_ShadowTransversals = bind(a->transversal, W, H, 1, true);
+    S::u_FrameCount = bind(a->frames, W, H, 1, true);
+    FOR_EACH_PIXEL(S, {
+        a->o_shadow[px] = S::o_Color.x;
+        a->o_frames[px] = S::o_Frames;
+    })
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ref_shadow_filter(const RefShadowFilterArgs* a) {
+    using namespace glsl;
+    namespace S = glsl::denoise::ns_ShadowFilter;
+    const int W = a->width, H = a->height;
+    IdPlanes cur(a->g_normal_id, nullptr, (size_t)W * H);
+    std::memcpy(&S::u_InverseView[0][0], a->inv_view, 64);
+    std::memcpy(&S::u_InverseProjection[0][0], a->inv_proj, 64);
+    S::u_ShadowFilterScale = a->filter_scale;
+    S::u_InputTexture = bind(a->shadow, W, H, 1, true);
+    S::u_PositionTexture = bind(a->g_t, W, H, 1, true);
+    S::u_NormalTexture = bind(cur.normal.data(), W, H, 1, false);
+    S::u_IntersectionTransversals = bind(a->transversal, W, H, 1, true);
+    S::u_FrameCount = bind(a->frames, W, H, 1, true);
+    FOR_EACH_PIXEL(S, { a->o_shadow[px] = S::o_Color; })
     return 0;
 }

@@ -54,6 +54,13 @@ class RefSvgfArgs(C.Structure):
                 ("o_sh", C.c_void_p), ("o_cocg", C.c_void_p), ("o_utility", C.c_void_p), ("o_variance", C.c_void_p), ("o_ao_sky", C.c_void_p)]
 
 
+class RefShadowFilterArgs(C.Structure):
+    _fields_ = [("inv_view", C.c_void_p), ("inv_proj", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("row_begin", C.c_int32),
+                ("row_end", C.c_int32), ("g_t", C.c_void_p), ("g_normal_id", C.c_void_p), ("prev_t", C.c_void_p), ("shadow_u8", C.c_void_p),
+                ("shadow", C.c_void_p), ("transversal", C.c_void_p), ("prev_shadow", C.c_void_p), ("frames", C.c_void_p), ("prev_view", C.c_void_p),
+                ("prev_projection", C.c_void_p), ("filter_scale", C.c_float), ("o_shadow", C.c_void_p), ("o_frames", C.c_void_p)]
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -87,6 +94,10 @@ def load():
             if hasattr(lib, name):
                 getattr(lib, name).restype = C.c_int
                 getattr(lib, name).argtypes = [C.POINTER(RefSvgfArgs)]
+        for name in ("ref_shadow_temporal", "ref_shadow_filter"):
+            if hasattr(lib, name):
+                getattr(lib, name).restype = C.c_int
+                getattr(lib, name).argtypes = [C.POINTER(RefShadowFilterArgs)]
         if hasattr(lib, "ref_generate_gbuffer"):
             lib.ref_generate_gbuffer.restype = C.c_int
             lib.ref_generate_gbuffer.argtypes = [C.POINTER(RefGBufferArgs)]
@@ -320,4 +331,43 @@ def svgf_spatial(cam, gbuf, planes, temporal_utility, params, out=None):
     a.color_phi_bias, a.time, a.resolution_scale = params.color_phi_bias, params.time, params.resolution_scale
     a.o_sh, a.o_cocg, a.o_variance, a.o_ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "variance", "ao_sky"))
     load().ref_svgf_spatial(C.byref(a))
+    return out
+
+
+# ---- sun-shadow filters: Core/Shaders/ShadowTemporalFilter.glsl, ShadowFilter.glsl (oracle/ref_denoise_driver.cpp) -------------------------
+def _shadow_args(cam, keep):
+    def ptr(a, dt=np.float32):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    a = RefShadowFilterArgs()
+    a.inv_view, a.inv_proj = ptr(np.frombuffer(cam.inv_view, dtype=np.float32)), ptr(np.frombuffer(cam.inv_proj, dtype=np.float32))
+    a.width, a.height, a.row_begin, a.row_end = cam.width, cam.height, cam.row_begin, cam.row_end
+    return a, ptr
+
+
+def shadow_temporal(cam, gbuf, prev_gbuf, shadow, prev_temporal, params, out=None):
+    keep = []
+    a, ptr = _shadow_args(cam, keep)
+    if out is None:
+        out = {"shadow": np.zeros((cam.height, cam.width), np.float32), "frames": np.zeros((cam.height, cam.width), np.float32)}
+    a.g_t, a.g_normal_id, a.prev_t = ptr(gbuf["t"]), ptr(gbuf["normal_id"], np.uint8), ptr(prev_gbuf["t"])
+    a.shadow_u8, a.transversal = ptr(shadow["shadow"], np.uint8), ptr(shadow["transversal"])
+    a.prev_shadow, a.frames = ptr(prev_temporal["shadow"]), ptr(prev_temporal["frames"])
+    a.prev_view, a.prev_projection = ptr(np.array(list(params.prev_view), np.float32)), ptr(np.array(list(params.prev_projection), np.float32))
+    a.o_shadow, a.o_frames = out["shadow"].ctypes.data, out["frames"].ctypes.data
+    load().ref_shadow_temporal(C.byref(a))
+    return out
+
+
+def shadow_filter(cam, gbuf, temporal, transversal, params, out=None):
+    keep = []
+    a, ptr = _shadow_args(cam, keep)
+    out = np.zeros((cam.height, cam.width), np.float32) if out is None else out
+    a.g_t, a.g_normal_id = ptr(gbuf["t"]), ptr(gbuf["normal_id"], np.uint8)
+    a.shadow, a.transversal, a.frames = ptr(temporal["shadow"]), ptr(transversal), ptr(temporal["frames"])
+    a.filter_scale = params.filter_scale
+    a.o_shadow = out.ctypes.data
+    load().ref_shadow_filter(C.byref(a))
     return out

@@ -66,6 +66,10 @@ def load():
         fn = getattr(lib, "vxo_svgf_" + name)
         fn.argtypes = [C.POINTER(VxCamera)] + [C.POINTER(getattr(_abi, "VxSvgf" + k)) for k in kinds]
         fn.restype = C.c_int
+    lib.vxo_shadow_temporal.argtypes = [C.POINTER(VxCamera), C.POINTER(_abi.VxShadowTemporalIn), C.POINTER(_abi.VxShadowTemporalParams),
+                                        C.POINTER(_abi.VxShadowTemporalOut)]
+    lib.vxo_shadow_filter.argtypes = [C.POINTER(VxCamera), C.POINTER(_abi.VxShadowFilterIn), C.POINTER(_abi.VxShadowFilterParams), C.c_void_p]
+    lib.vxo_shadow_temporal.restype = lib.vxo_shadow_filter.restype = C.c_int
     lib.vxo_trace_rays.argtypes = [C.POINTER(VxoScene), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VxoStats)]
     lib.vxo_trace_rays.restype = C.c_int
     lib.vxo_player_shadowed.argtypes = [C.POINTER(VxoScene), C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -290,5 +294,23 @@ def svgf_spatial(cam, gbuf, planes, temporal_utility, params, out=None):
     out = _planes(cam, ("sh", "cocg", "variance", "ao_sky")) if out is None else out
     i, o = denoise.spatial_structs(gbuf, planes, temporal_utility, out, _addr)
     rc = load().vxo_svgf_spatial(C.byref(cam), C.byref(i), C.byref(params), C.byref(o))
+    assert rc == 0, rc
+    return out
+
+
+def shadow_temporal(cam, gbuf, prev_gbuf, shadow, prev_temporal, params, out=None):
+    from voxelpathtracer_b200 import denoise
+    out = _planes(cam, ("shadow", "frames")) if out is None else out
+    i, o = denoise.shadow_temporal_structs(gbuf, prev_gbuf, shadow, prev_temporal, out, _addr)
+    rc = load().vxo_shadow_temporal(C.byref(cam), C.byref(i), C.byref(params), C.byref(o))
+    assert rc == 0, rc
+    return out
+
+
+def shadow_filter(cam, gbuf, temporal, transversal, params, out=None):
+    from voxelpathtracer_b200 import denoise
+    out = np.zeros((cam.height, cam.width), np.float32) if out is None else out
+    i = denoise.shadow_filter_struct(gbuf, temporal, transversal, _addr)
+    rc = load().vxo_shadow_filter(C.byref(cam), C.byref(i), C.byref(params), out.ctypes.data)
     assert rc == 0, rc
     return out

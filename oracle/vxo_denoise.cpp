@@ -4,7 +4,7 @@
 //
 // THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE (see vxo_oracle.cpp's header; the same rules apply).  Pinned by the reference itself:
 // oracle/_ref/libref_shaders.so holds these shaders compiled as C++ (oracle/ref_denoise_driver.cpp) and every function here equals
-// them bit for bit (tests/test_denoise.py, tests/golden/ref_denoise_digests.json).
+// them bit for bit (tests/test_svgf_denoise.py, tests/golden/ref_denoise_digests.json).
 //
 // Pinned definitions GL leaves to the driver, beyond vxo_oracle.cpp's list:
 //   texture(sampler2D, uv) on an FBO attachment: GL_REPEAT; GL_NEAREST texel floor(u*w) mod w; GL_LINEAR (OpenGL 4.3 section 8.14.2)
@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../include/vxpt.h"
 
@@ -419,6 +420,174 @@ int vxo_svgf_spatial(const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvg
             if (out->cocg) { out->cocg[2 * p] = clampf(tcc.x, -10.f, 100.f); out->cocg[2 * p + 1] = clampf(tcc.y, -10.f, 100.f); }
             if (out->variance) out->variance[p] = clampf(tvar, -1.0f, 50.0f);
             if (out->ao_sky) { out->ao_sky[2 * p] = clampf(tao.x, 0.f, 1.f); out->ao_sky[2 * p + 1] = clampf(tao.y, 0.f, 1.f); }
+        }
+    return VXPT_OK;
+}
+
+// ShadowTemporalFilter.glsl main() :201-298 with u_ShadowTemporal = true (Core/Pipeline.cpp:2854-2903).  The colour attachments hold one
+// channel (R8 shadow, R16F frame count): only the .x of the shader's vec3 / vec4 arithmetic reaches an output, and only .x is restated.
+int vxo_shadow_temporal(const VxCamera* cam, const VxShadowTemporalIn* in, const VxShadowTemporalParams* prm, const VxShadowTemporalOut* out) {
+    const int W = cam->width, H = cam->height;
+    std::vector<float> cur_f((size_t)W * H);
+    for (size_t k = 0; k < cur_f.size(); ++k) cur_f[k] = (float)in->shadow[k];  // o_Shadow 0 / 1 in an R8 attachment reads back as 0.0 / 1.0
+    const Tex cur{cur_f.data(), W, H, 1}, pos{in->current.t, W, H, 1}, ppos{in->previous.t, W, H, 1}, trans{in->transversal, W, H, 1},
+        prev{in->prev_shadow, W, H, 1}, frames{in->prev_frames, W, H, 1};
+    const TexU8 nrm{in->current.normal_id, W, H};
+    float prev_vp[16];
+    mat4_mul_mat(prm->prev_projection, prm->prev_view, prev_vp);
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    const float unit_diagonal = std::sqrt(2.0f);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = cam->row_begin; j < cam->row_end; ++j)
+        for (int i = 0; i < W; ++i) {
+            const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+            const size_t p = (size_t)j * W + i;
+            v3 cp;
+            float cw;
+            position_at(*cam, pos, u, v, cp, cw);
+            float o_color, o_frames;
+            if (cw > 0.0f) {
+                const float wp[4] = {cp.x, cp.y, cp.z, 1.0f};
+                float pr[4];
+                mat4_mul_vec(prev_vp, wp, pr);
+                const float ru = (pr[0] / pr[3]) * 0.5f + 0.5f, rv = (pr[1] / pr[3]) * 0.5f + 0.5f;
+                const float tr = trans.linear1(u, v) * 100.0f;
+                // GetShadowSpatial :109-155
+                float cur_color;
+                if (tr <= unit_diagonal * 2.0f) {
+                    cur_color = 1.0f;
+                } else {
+                    float total = cur.linear1(u, v);
+                    const float base = total;
+                    float weight = 1.0f;
+                    const int bn = nrm.nearest(u, v);
+                    for (int x = -1; x <= 1; ++x)
+                        for (int y = -1; y <= 1; ++y) {
+                            if (x == 0 && y == 0) continue;
+                            const float su = u + (float)x * tsx, sv = v + (float)y * tsy;
+                            const float b = 0.03f;
+                            if (!(su > b && su < 1.0f - b && sv > b && sv < 1.0f - b)) continue;
+                            const float sd = pos.linear1(su, sv);
+                            const int sn = nrm.nearest(su, sv);
+                            if (std::min(sn, 6) == std::min(bn, 6) && std::fabs(sd - cw) < 1.0f) {
+                                const float smp = cur.linear1(su, sv);
+                                float wa = clampf(1.0f - clampf(std::fabs(smp - base) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
+                                wa = clampf(pow_cr(wa, 7.0f), 0.000001f, 1.0f);
+                                total += smp * wa;
+                                weight += wa;
+                            }
+                        }
+                    cur_color = total / weight;
+                }
+                const float prev_orig = prev.linear1(ru, rv);
+                float prev_color = prev_orig;
+                if (tr < 1.414f * 3.0f) {  // ClipShadow :168-184, clipAABB :157-166
+                    float mn = 100.0f, mx = -100.0f;
+                    static const float off[5][2] = {{-1, 0}, {1, 0}, {0, 0}, {0, -1}, {0, 1}};
+                    for (int s2 = 0; s2 < 5; ++s2) {
+                        const float smp = cur.linear1(u + off[s2][0] * tsx, v + off[s2][1] * tsy);
+                        mn = std::fmin(smp, mn);
+                        mx = std::fmax(smp, mx);
+                    }
+                    const float lo = mn - 0.025f, hi = mx + 0.025f;
+                    const float pc = 0.5f * (hi + lo), ec = 0.5f * (hi - lo);
+                    const float vc = prev_orig - pc;
+                    const float au = std::fabs(vc / ec);
+                    const float denom = std::fmax(au, std::fmax(au, au));
+                    prev_color = denom > 1.0f ? pc + vc / denom : prev_orig;
+                }
+                v3 pp;
+                float pw;
+                position_at(*cam, ppos, ru, rv, pp, pw);
+                const float bias = 0.005f;
+                const bool reject = !(ru > 0.0f + bias && ru < 1.0f - bias && rv > 0.0f + bias && rv < 1.0f - bias);
+                if (!reject) {
+                    const v3 dd{cp.x - pp.x, cp.y - pp.y, cp.z - pp.z};
+                    const float d = std::sqrt(dot3(dd, dd));
+                    const float cc = clampf(cur_color, 0.0f, 1.0f), pc2 = clampf(prev_color, 0.0f, 1.0f);
+                    const float vx = (u - ru) * (float)W, vy = (v - rv) * (float)H;
+                    const float clip_error = std::fabs(prev_orig - pc2);
+                    const float inc = clip_error < 0.2f ? 1.0f : 0.6f;
+                    const float fetch = frames.linear1(ru, rv);
+                    const float incd = fetch + inc;
+                    float blend = clampf((1.0f - (1.0f / incd)) * 1.2f, 0.01f, 0.97f);
+                    const float vrf = clampf(exp_cr(-std::sqrt(vx * vx + vy * vy)) * 0.8f + 0.6f, 0.00000001f, 1.0f);
+                    blend *= vrf;
+                    float depth_rej = 1.0f;
+                    if (d > 0.4f) {
+                        depth_rej = pow_cr(exp_cr(-d), 48.0f);
+                        blend *= clampf(depth_rej, 0.0f, 1.0f);
+                    }
+                    o_color = mixf(cc, pc2, clampf(blend, 0.0f, 0.97f));
+                    const float mult = depth_rej * vrf;
+                    o_frames = fetch + clampf(mult * 1.1f, 0.0f, 1.0f);
+                    if (mult < 0.1f) o_frames = 0.0f;
+                    else if (mult <= 0.2f + 0.001f) o_frames = 2.0f;
+                    else if (mult <= 0.3f + 0.001f) o_frames = 3.25f;
+                } else {
+                    o_color = cur_color;
+                    o_frames = 0.0f;
+                }
+            } else {
+                o_color = cur.linear1(u, v);
+                o_frames = 0.0f;
+            }
+            if (out->shadow) out->shadow[p] = o_color;
+            if (out->frames) out->frames[p] = clampf(o_frames, 0.0f, 256.0f);
+        }
+    return VXPT_OK;
+}
+
+// ShadowFilter.glsl ShadowSpatial :68-160 (Core/Pipeline.cpp:2905-2944)
+int vxo_shadow_filter(const VxCamera* cam, const VxShadowFilterIn* in, const VxShadowFilterParams* prm, float* out) {
+    const int W = cam->width, H = cam->height;
+    const Tex inp{in->shadow, W, H, 1}, pos{in->current.t, W, H, 1}, trans{in->transversal, W, H, 1}, frames{in->frames, W, H, 1};
+    const TexU8 nrm{in->current.normal_id, W, H};
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    const float cutoff = std::sqrt(2.0f);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = cam->row_begin; j < cam->row_end; ++j)
+        for (int i = 0; i < W; ++i) {
+            const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+            const size_t p = (size_t)j * W + i;
+            const float fr = frames.linear1(u, v);
+            const bool luma_weight = fr > 7.5f;
+            const float center_w = pos.linear1(u, v);
+            const v3 cn = normal_of(nrm.nearest(u, v));
+            const float center = inp.linear1(u, v);
+            const float tr = trans.linear1(u, v) * 100.0f;
+            if ((tr > 0.0f && tr < cutoff) || center_w < 0.0f) { out[p] = center; continue; }
+            const bool reduced = tr < cutoff * 1.414f;
+            const int K = reduced ? 1 : 3;
+            float scale = 1.0f;
+            if (tr > 6.0f) scale = 2.0f;
+            if (tr > 16.0f) scale = 2.4f;
+            if (tr > 32.0f) scale = 2.6f;
+            const float ct = clampf(tr, 0.0f, 10.0f);
+            float var_est = mixf(20.0f, 6.0f, ct / 10.0f) + (tr < 6.0f ? 5.0f : 2.0f);
+            var_est = clampf(var_est - 1.75f, 0.0000001f, 64.0f);
+            float luma_mixer = 1.0f;
+            if (!luma_weight) luma_mixer = mixf(0.1f, 0.5f, fr / 7.5f);
+            float tw = 0.0f, ts = 0.0f;
+            for (int x = -K; x <= K; ++x)
+                for (int y = -K; y <= K; ++y) {
+                    const float su = u + ((((float)x * tsx) * 1.2f) * scale) * prm->filter_scale;
+                    const float sv = v + ((((float)y * tsy) * 1.2f) * scale) * prm->filter_scale;
+                    const float sd = pos.linear1(su, sv);
+                    const v3 sn = normal_of(nrm.nearest(su, sv));
+                    const float dw = pow_cr(exp_cr(-(std::fabs(center_w - sd))), 3.0f);
+                    const float nw = pow_cr(std::fmax(dot3(cn, sn), 0.000000001f), 32.0f);
+                    const float sa = inp.linear1(su, sv);
+                    const float le = clampf(1.0f - clampf(std::fabs(sa - center) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
+                    float w = 1.0f;
+                    w *= clampf(pow_cr(le, var_est * luma_mixer * 0.9f), 0.0f, 1.0f);
+                    w *= dw;
+                    w *= nw;
+                    w = clampf(w, 0.000000001f, 1.0f);
+                    ts += sa * w;
+                    tw += w;
+                }
+            out[p] = ts / std::fmax(tw, 0.01f);
         }
     return VXPT_OK;
 }

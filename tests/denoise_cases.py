@@ -64,3 +64,34 @@ def oracle_tracer(o, scene_tables):
         return g, d
 
     return trace
+
+
+def run_shadow_sequence(name, trace, passes, filter_scale=1.0):
+    """trace(cam, frame) -> (gbuf, shadow planes); passes: object with shadow_temporal / shadow_filter.  Yields per frame the temporal
+    planes and the spatially filtered plane (Core/Pipeline.cpp:2854-2944)."""
+    _, W, H, cams = SEQUENCES[name]
+    prev_g, prev_fc = None, None
+    prev_t = {"shadow": np.zeros((H, W), np.float32), "frames": np.zeros((H, W), np.float32)}
+    for f, kw in enumerate(cams):
+        fc = camera.FpsCamera(aspect=W / H, **kw)
+        cam = fc.vx_camera(W, H)
+        g, s = trace(cam, f)
+        pfc = prev_fc or fc
+        tp = denoise.shadow_temporal_params(pfc.view().T.reshape(16), pfc.projection().T.reshape(16))
+        t = passes.shadow_temporal(cam, g, prev_g or g, s, prev_t, tp)
+        filtered = passes.shadow_filter(cam, g, t, s["transversal"], denoise.shadow_filter_params(filter_scale))
+        yield {"cam": cam, "gbuf": g, "shadow": s, "temporal": t, "filtered": filtered, "prev_gbuf": prev_g or g, "prev_temporal": prev_t, "params": tp}
+        prev_g, prev_t, prev_fc = g, t, fc
+
+
+def shadow_frame_digest(fr):
+    return {"shadow": sha(fr["temporal"]["shadow"]), "frames": sha(fr["temporal"]["frames"]), "filtered": sha(fr["filtered"])}
+
+
+def oracle_shadow_tracer(o, scene_tables):
+    def trace(cam, f):
+        g, _ = o.trace_primary(cam, vx.primary_params(350))
+        s, _ = o.trace_shadow(cam, g, vx.shadow_params(scene_tables["stronger"], frame=f, soft=True))
+        return g, s
+
+    return trace

@@ -201,6 +201,12 @@ HS_API int hs_svgf_variance(void* p, const VxCamera* cam, const VxSvgfVarianceIn
 HS_API int hs_svgf_spatial(void* p, const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvgfSpatialParams* prm, const VxSvgfSpatialOut* out) {
     return vxpt::launch_svgf_spatial(hs_ctx(p), *cam, *in, *prm, *out);
 }
+HS_API int hs_shadow_temporal(void* p, const VxCamera* cam, const VxShadowTemporalIn* in, const VxShadowTemporalParams* prm, const VxShadowTemporalOut* out) {
+    return vxpt::launch_shadow_temporal(hs_ctx(p), *cam, *in, *prm, *out);
+}
+HS_API int hs_shadow_filter(void* p, const VxCamera* cam, const VxShadowFilterIn* in, const VxShadowFilterParams* prm, float* out) {
+    return vxpt::launch_shadow_filter(hs_ctx(p), *cam, *in, *prm, out);
+}
 HS_API int hs_trace_rays(void* p, const float* origins, const float* directions, int n, int max_it, float* t, uint8_t* normal_id, uint8_t* block_id,
                          int16_t* hit_voxel) {
     return vxpt::launch_rays(hs_ctx(p), origins, directions, n, max_it, t, normal_id, block_id, hit_voxel);

@@ -55,6 +55,9 @@ def load():
     for name, kinds in (("temporal", ("TemporalIn", "TemporalParams", "TemporalOut")), ("variance", ("VarianceIn", "VarianceParams", "VarianceOut")),
                         ("spatial", ("SpatialIn", "SpatialParams", "SpatialOut"))):
         getattr(lib, "hs_svgf_" + name).argtypes = [C.c_void_p, C.POINTER(VxCamera)] + [C.POINTER(getattr(_abi, "VxSvgf" + k)) for k in kinds]
+    lib.hs_shadow_temporal.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(_abi.VxShadowTemporalIn), C.POINTER(_abi.VxShadowTemporalParams),
+                                       C.POINTER(_abi.VxShadowTemporalOut)]
+    lib.hs_shadow_filter.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(_abi.VxShadowFilterIn), C.POINTER(_abi.VxShadowFilterParams), C.c_void_p]
     lib.hs_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_ambient_sound.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
     _lib = lib
@@ -176,6 +179,20 @@ class HostKernels:
         out = _denoise_planes(cam, ("sh", "cocg", "variance", "ao_sky")) if out is None else out
         i, o = denoise.spatial_structs(gbuf, planes, temporal_utility, out, _addr)
         assert self.lib.hs_svgf_spatial(self.h, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)) == 0
+        return out
+
+    def shadow_temporal(self, cam, gbuf, prev_gbuf, shadow, prev_temporal, params, out=None):
+        from voxelpathtracer_b200 import denoise
+        out = _denoise_planes(cam, ("shadow", "frames")) if out is None else out
+        i, o = denoise.shadow_temporal_structs(gbuf, prev_gbuf, shadow, prev_temporal, out, _addr)
+        assert self.lib.hs_shadow_temporal(self.h, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)) == 0
+        return out
+
+    def shadow_filter(self, cam, gbuf, temporal, transversal, params, out=None):
+        from voxelpathtracer_b200 import denoise
+        out = np.zeros((cam.height, cam.width), np.float32) if out is None else out
+        i = denoise.shadow_filter_struct(gbuf, temporal, transversal, _addr)
+        assert self.lib.hs_shadow_filter(self.h, C.byref(cam), C.byref(i), C.byref(params), out.ctypes.data) == 0
         return out
 
     def trace_rays(self, origins, directions, max_it):

@@ -145,24 +145,81 @@ def test_constant_planes_are_a_fixed_point():
         planes = s
 
 
-# ------------------------------------------------------------------------------------------------------ the kernels' source on the host
+# ------------------------------------------------------------------------------------------------------ sun-shadow filters
+@pytest.fixture(scope="module")
+def oracle_shadow_sequences(oracles, scene_tables):
+    class Lazy(dict):
+        def __missing__(self, name):
+            self[name] = list(dc.run_shadow_sequence(name, dc.oracle_shadow_tracer(oracles[dc.SEQUENCES[name][0]], scene_tables), vxo))
+            return self[name]
+
+    return Lazy()
+
+
+@pytest.mark.parametrize("name", list(dc.SEQUENCES))
+def test_shadow_filters_oracle_equals_the_reference_shader_digests(oracle_shadow_sequences, ref_digests, name):
+    frames, want = oracle_shadow_sequences[name], ref_digests["shadow:" + name]
+    assert len(frames) == len(want)
+    for f, fr in enumerate(frames):
+        assert dc.shadow_frame_digest(fr) == want[f], (name, f)
+
+
+@needs_ref
+def test_shadow_filters_oracle_equals_the_reference_shaders_live(oracle_shadow_sequences):
+    """Other filter scales, a row slab, long frame histories (the luminance weight switches on above 7.5 frames) and non-finite inputs."""
+    fr = oracle_shadow_sequences["city_160x90_still"][2]
+    cam, g, s, t = fr["cam"], fr["gbuf"], fr["shadow"], fr["temporal"]
+    for scale in (0.25, 3.0):
+        assert _same(vxo.shadow_filter(cam, g, t, s["transversal"], denoise.shadow_filter_params(scale)),
+                     ref_shaders.shadow_filter(cam, g, t, s["transversal"], denoise.shadow_filter_params(scale)))
+    long_t = {"shadow": t["shadow"], "frames": np.full_like(t["frames"], 9.0)}
+    assert _same(vxo.shadow_filter(cam, g, long_t, s["transversal"], denoise.shadow_filter_params(1.0)),
+                 ref_shaders.shadow_filter(cam, g, long_t, s["transversal"], denoise.shadow_filter_params(1.0)))
+    a = vxo.shadow_temporal(cam, g, fr["prev_gbuf"], s, long_t, fr["params"])
+    b = ref_shaders.shadow_temporal(cam, g, fr["prev_gbuf"], s, long_t, fr["params"])
+    assert _same(a["shadow"], b["shadow"]) and _same(a["frames"], b["frames"]) and a["frames"].max() > 9.0
+    bad = {"shadow": t["shadow"].copy(), "frames": t["frames"].copy()}
+    bad["shadow"][40, 50] = np.nan
+    bad["shadow"][10, 100] = np.inf
+    bad["frames"][60, 20] = np.nan
+    a, b = vxo.shadow_temporal(cam, g, fr["prev_gbuf"], s, bad, fr["params"]), ref_shaders.shadow_temporal(cam, g, fr["prev_gbuf"], s, bad, fr["params"])
+    assert _same(a["shadow"], b["shadow"]) and _same(a["frames"], b["frames"])
+    assert _same(vxo.shadow_filter(cam, g, bad, s["transversal"], denoise.shadow_filter_params(1.0)),
+                 ref_shaders.shadow_filter(cam, g, bad, s["transversal"], denoise.shadow_filter_params(1.0)))
+    slab = camera.FpsCamera(aspect=160 / 90, position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0).vx_camera(160, 90, 30, 61)
+    a = vxo.shadow_filter(slab, g, t, s["transversal"], denoise.shadow_filter_params(1.0), np.full((90, 160), 0.25, np.float32))
+    b = ref_shaders.shadow_filter(slab, g, t, s["transversal"], denoise.shadow_filter_params(1.0), np.full((90, 160), 0.25, np.float32))
+    assert _same(a, b) and (a[:30] == 0.25).all() and (a[61:] == 0.25).all()
+
+
+def test_shadow_filters_properties(oracle_shadow_sequences):
+    frames = oracle_shadow_sequences["city_160x90_still"]
+    hit = frames[0]["gbuf"]["t"] > 1.0
+    # a still camera accumulates: the frame counter grows by one per frame on most surface pixels, and never on the sky
+    for f, fr in enumerate(frames):
+        fc = fr["temporal"]["frames"]
+        assert abs(float(np.median(fc[hit])) - (f + 1.0)) < 1e-3, (f, float(np.median(fc[hit])))
+        assert (fc[frames[0]["gbuf"]["t"] < 0] == 0).all()
+        assert (fr["temporal"]["shadow"] >= 0).all() and (fr["temporal"]["shadow"] <= 1).all()
+        assert (fr["filtered"] >= -1e-6).all() and (fr["filtered"] <= 1 + 1e-6).all()
+    # the filters do not leak light into a region that is shadowed throughout: where the 7x7 neighbourhood of the raw plane is all
+    # shadow (1), three accumulated frames and the spatial filter leave the pixel shadowed
+    raw = np.minimum.reduce([fr["shadow"]["shadow"] for fr in frames]).astype(np.float32)
+    k = 3
+    pad = np.pad(raw, k, mode="edge")
+    win = np.stack([pad[dy:dy + raw.shape[0], dx:dx + raw.shape[1]] for dy in range(2 * k + 1) for dx in range(2 * k + 1)])
+    dark = (win.min(0) == 1) & hit
+    assert dark.sum() > 100 and (frames[2]["filtered"][dark] > 0.9).all()
+
+
 @pytest.mark.skipif(not koh.available(), reason="CUDA toolkit headers not present")
-@pytest.mark.parametrize("name", ["gi_box_192x108_walk", "plains_133x75_turn"])
-def test_kernel_source_on_host_equals_the_oracle(oracles, oracle_sequences, scene_tables, name):
+@pytest.mark.parametrize("name", ["city_160x90_still", "plains_133x75_turn"])
+def test_shadow_filter_kernel_source_on_host_equals_the_oracle(oracles, oracle_shadow_sequences, name):
     k = koh.HostKernels(oracles[dc.SEQUENCES[name][0]], 1)
-    trace = iter(oracle_sequences[name])
-
-    def replay(cam, f):        # the traced planes of the oracle run: the sequence then differs only in who filters
-        fr = next(trace)
-        return fr["gbuf"], fr["diffuse"]
-
-    for f, (got, want) in enumerate(zip(dc.run_sequence(name, replay, k, scene_tables), oracle_sequences[name])):
-        for stage in ("temporal", "variance"):
-            for key in want[stage]:
-                assert _same(got[stage][key], want[stage][key]), (f, stage, key)
-        for n, (a, b) in enumerate(zip(got["spatial"], want["spatial"])):
-            for key in b:
-                assert _same(a[key], b[key]), (f, n, key)
+    for f, fr in enumerate(oracle_shadow_sequences[name]):
+        t = k.shadow_temporal(fr["cam"], fr["gbuf"], fr["prev_gbuf"], fr["shadow"], fr["prev_temporal"], fr["params"])
+        assert _same(t["shadow"], fr["temporal"]["shadow"]) and _same(t["frames"], fr["temporal"]["frames"]), f
+        assert _same(k.shadow_filter(fr["cam"], fr["gbuf"], fr["temporal"], fr["shadow"]["transversal"], denoise.shadow_filter_params(1.0)), fr["filtered"]), f
     k.close()
 
 
@@ -294,3 +351,28 @@ def test_gpu_denoiser_argument_checks(renderer, oracle_sequences):
         planes = {"sh": fr["variance"]["sh"], "cocg": fr["variance"]["cocg"], "variance": fr["variance"]["variance"], "ao_sky": t["ao_sky"]}
         renderer.svgf_spatial(cam, g, planes, t["utility"], denoise.spatial_params(0), renderer.alloc_denoise(W, H, ("sh", "cocg", "variance", "ao_sky")))
     assert e.value.code == abi.E_INVALID
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,device", [("city_160x90_still", False), ("gi_box_192x108_walk", True)])
+def test_gpu_shadow_filters_equal_the_oracle(renderer, oracle_shadow_sequences, name, device):
+    r = renderer
+    for f, fr in enumerate(oracle_shadow_sequences[name]):
+        cam, W, H = fr["cam"], fr["cam"].width, fr["cam"].height
+        g = {k: fr["gbuf"][k] for k in ("t", "normal_id")}
+        pg = {"t": fr["prev_gbuf"]["t"]}
+        ins = [g, pg, fr["shadow"], fr["prev_temporal"], fr["temporal"]]
+        if device:
+            import torch
+            ins = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in d.items()} for d in ins]
+            torch.cuda.synchronize()
+        g_, pg_, s_, pt_, t_ = ins
+        out = r.alloc_denoise(W, H, ("shadow", "frames"), device=device)
+        r.shadow_temporal(cam, g_, pg_, s_, pt_, fr["params"], out)
+        filt = r.shadow_filter(cam, g_, t_, s_["transversal"], denoise.shadow_filter_params(1.0), r.alloc((H, W), np.float32, device=device))
+        if device:
+            r.sync()
+            out, filt = {k: v.cpu().numpy() for k, v in out.items()}, filt.cpu().numpy()
+        _close(out["shadow"], fr["temporal"]["shadow"], (name, f, "shadow"))
+        _close(out["frames"], fr["temporal"]["frames"], (name, f, "frames"))
+        _close(filt, fr["filtered"], (name, f, "filtered"))

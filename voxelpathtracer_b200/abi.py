@@ -124,6 +124,27 @@ class VxSvgfSpatialOut(C.Structure):
     _fields_ = [("sh", C.c_void_p), ("cocg", C.c_void_p), ("variance", C.c_void_p), ("ao_sky", C.c_void_p)]
 
 
+class VxShadowTemporalIn(C.Structure):
+    _fields_ = [("current", VxGBuffer), ("previous", VxGBuffer), ("shadow", C.c_void_p), ("transversal", C.c_void_p), ("prev_shadow", C.c_void_p),
+                ("prev_frames", C.c_void_p)]
+
+
+class VxShadowTemporalParams(C.Structure):
+    _fields_ = [("prev_view", C.c_float * 16), ("prev_projection", C.c_float * 16)]
+
+
+class VxShadowTemporalOut(C.Structure):
+    _fields_ = [("shadow", C.c_void_p), ("frames", C.c_void_p)]
+
+
+class VxShadowFilterIn(C.Structure):
+    _fields_ = [("current", VxGBuffer), ("shadow", C.c_void_p), ("transversal", C.c_void_p), ("frames", C.c_void_p)]
+
+
+class VxShadowFilterParams(C.Structure):
+    _fields_ = [("filter_scale", C.c_float)]
+
+
 class VxFrameParams(C.Structure):
     _fields_ = [("primary", C.POINTER(VxPrimaryParams)), ("shadow", C.POINTER(VxShadowParams)), ("diffuse", C.POINTER(VxDiffuseParams)),
                 ("reflection", C.POINTER(VxReflectionParams)), ("g_normal", C.c_void_p), ("g_pbr", C.c_void_p)]
@@ -172,6 +193,9 @@ EXPORTS = {
                                      C.POINTER(VxSvgfVarianceOut)]),
     "vxpt_svgf_spatial": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfSpatialIn), C.POINTER(VxSvgfSpatialParams),
                                     C.POINTER(VxSvgfSpatialOut)]),
+    "vxpt_shadow_temporal": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxShadowTemporalIn), C.POINTER(VxShadowTemporalParams),
+                                       C.POINTER(VxShadowTemporalOut)]),
+    "vxpt_shadow_filter": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxShadowFilterIn), C.POINTER(VxShadowFilterParams), C.c_void_p]),
     "vxpt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxpt_player_shadowed": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vxpt_estimate_ambient_sound": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint32), C.c_void_p]),

@@ -739,6 +739,46 @@ int vxpt_svgf_spatial(vxpt_handle c, const VxCamera* cam, const VxSvgfSpatialIn*
     return s.end(c);
 }
 
+int vxpt_shadow_temporal(vxpt_handle c, const VxCamera* cam, const VxShadowTemporalIn* in, const VxShadowTemporalParams* p, const VxShadowTemporalOut* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!in || !p || !out || !in->current.t || !in->current.normal_id || !in->previous.t || !in->shadow || !in->transversal || !in->prev_shadow || !in->prev_frames)
+        return fail(VXPT_E_INVALID, "NULL argument (current t / normal_id, previous t, the shadow pass's planes and the previous temporal planes are required)");
+    VX_CUDA(cudaSetDevice(c->device));
+    SvgfIO s(c, cam);
+    Plane *t = s.in(in->current.t, 4), *n = s.in(in->current.normal_id, 1), *pt = s.in(in->previous.t, 4);
+    Plane *sh = s.in(in->shadow, 1), *tr = s.in(in->transversal, 4), *ps = s.in(in->prev_shadow, 4), *pf = s.in(in->prev_frames, 4);
+    Plane *os = s.out(out->shadow, 4), *of = s.out(out->frames, 4);
+    if ((rc = s.begin())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    VxShadowTemporalIn id{};
+    id.current = VxGBuffer{(float*)t->dev, (uint8_t*)n->dev, nullptr, nullptr, nullptr};
+    id.previous = VxGBuffer{(float*)pt->dev, nullptr, nullptr, nullptr, nullptr};
+    id.shadow = (const uint8_t*)sh->dev; id.transversal = (const float*)tr->dev; id.prev_shadow = (const float*)ps->dev; id.prev_frames = (const float*)pf->dev;
+    const VxShadowTemporalOut od{(float*)os->dev, (float*)of->dev};
+    if ((rc = timed_launch(c, [&] { return launch_shadow_temporal(c, *cam, id, *p, od); }))) return rc;
+    return s.end(c);
+}
+
+int vxpt_shadow_filter(vxpt_handle c, const VxCamera* cam, const VxShadowFilterIn* in, const VxShadowFilterParams* p, float* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!in || !p || !out || !in->current.t || !in->current.normal_id || !in->shadow || !in->transversal || !in->frames)
+        return fail(VXPT_E_INVALID, "NULL argument (t, normal_id, the temporal shadow / frame planes, the transversal plane and the output are required)");
+    VX_CUDA(cudaSetDevice(c->device));
+    SvgfIO s(c, cam);
+    Plane *t = s.in(in->current.t, 4), *n = s.in(in->current.normal_id, 1);
+    Plane *sh = s.in(in->shadow, 4), *tr = s.in(in->transversal, 4), *fr = s.in(in->frames, 4);
+    Plane* o = s.out(out, 4);
+    if ((rc = s.begin())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    VxShadowFilterIn id{};
+    id.current = VxGBuffer{(float*)t->dev, (uint8_t*)n->dev, nullptr, nullptr, nullptr};
+    id.shadow = (const float*)sh->dev; id.transversal = (const float*)tr->dev; id.frames = (const float*)fr->dev;
+    if ((rc = timed_launch(c, [&] { return launch_shadow_filter(c, *cam, id, *p, (float*)o->dev); }))) return rc;
+    return s.end(c);
+}
+
 // ----------------------------------------------------------------------------------------------------- other DF consumers
 int vxpt_trace_rays(vxpt_handle c, const float* origins, const float* directions, int n, int max_iterations, float* t, uint8_t* normal_id,
                     uint8_t* block_id, int16_t* hit_voxel) {

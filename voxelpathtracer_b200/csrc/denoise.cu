@@ -1,5 +1,6 @@
-// denoise.cu — SVGF diffuse denoiser: Core/Shaders/SVGF/TemporalFilter.glsl, VarianceEstimate.glsl and
-// SpatialFilter.glsl as dispatched by Core/Pipeline.cpp:2335-2596, the passes that consume the diffuse-GI planes.
+// denoise.cu — SVGF diffuse denoiser and sun-shadow filters: Core/Shaders/SVGF/TemporalFilter.glsl,
+// VarianceEstimate.glsl, SpatialFilter.glsl (Core/Pipeline.cpp:2335-2596) and ShadowTemporalFilter.glsl, ShadowFilter.glsl (:2854-2944),
+// the passes that consume the diffuse-GI and shadow planes.
 //
 // One thread per output pixel on the trace passes' 8x4-pixel warp tiles, so the taps of a warp (neighbouring texels, or the same
 // a-trous offset for every lane) fall into a few 128-byte lines.  Every read goes through tex_linear / tex_nearest below: the pinned
@@ -364,6 +365,172 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
     if (pl.o_ao) reinterpret_cast<float2*>(pl.o_ao)[px] = clamp2(tao, 0.0f, 1.0f);
 }
 
+// ============================================================================================= sun-shadow filters
+struct ShadowFilterPlanes {
+    const float *t, *prev_t;
+    const uint8_t *nid, *shadow_u8;
+    const float *shadow, *transversal, *prev_shadow, *frames;
+    float *o_shadow, *o_frames;
+};
+// u_CurrentColorTexture of the temporal pass is the raw R8 shadow plane (0 / 1): the bilinear tap on bytes
+__device__ __forceinline__ float tex1_u8(const uint8_t* d, const Bilinear& b) {
+    return blend(b, (float)d[b.o00], (float)d[b.o10], (float)d[b.o01], (float)d[b.o11]);
+}
+// ShadowTemporalFilter.glsl main() :201-298 with u_ShadowTemporal = true.  The attachments are single-channel: only the .x of the shader's
+// vector arithmetic reaches an output.
+__global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_constant__ CameraDev cam, const __grid_constant__ TemporalDev P,
+                                                              const ShadowFilterPlanes pl) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const int W = cam.width, H = cam.height;
+    const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    const Bilinear bc = bilinear_at(W, H, u, v);
+    const V3 origin = ray_origin(cam);
+    const float cw = tex1(pl.t, bc);
+    const size_t px = (size_t)prow * W + i;
+    float o_color, o_frames = 0.0f;
+    if (cw > 0.0f) {
+        const V3 cp = origin + normalize3(ray_direction_at(cam, u, v)) * cw;
+        const float* M = P.prev_vp;
+        const float px4 = (M[0] * cp.x + M[4] * cp.y) + (M[8] * cp.z + M[12] * 1.0f);
+        const float py4 = (M[1] * cp.x + M[5] * cp.y) + (M[9] * cp.z + M[13] * 1.0f);
+        const float pw4 = (M[3] * cp.x + M[7] * cp.y) + (M[11] * cp.z + M[15] * 1.0f);
+        const float ru = (px4 / pw4) * 0.5f + 0.5f, rv = (py4 / pw4) * 0.5f + 0.5f;
+        const float tr = tex1(pl.transversal, bc) * 100.0f;
+        float cur_color;
+        if (tr <= sqrtf(2.0f) * 2.0f) {  // GetShadowSpatial :109-155
+            cur_color = 1.0f;
+        } else {
+            float total = tex1_u8(pl.shadow_u8, bc);
+            const float base = total;
+            float weight = 1.0f;
+            const int bn = min(tex_nearest_u8(pl.nid, W, H, u, v), 6);
+#pragma unroll 1
+            for (int x = -1; x <= 1; ++x)
+#pragma unroll 1
+                for (int y = -1; y <= 1; ++y) {
+                    if (x == 0 && y == 0) continue;
+                    const float su = u + (float)x * tsx, sv = v + (float)y * tsy;
+                    const float b = 0.03f;
+                    if (!(su > b && su < 1.0f - b && sv > b && sv < 1.0f - b)) continue;
+                    const Bilinear bs = bilinear_at(W, H, su, sv);
+                    const float sd = tex1(pl.t, bs);
+                    if (min(tex_nearest_u8(pl.nid, W, H, su, sv), 6) == bn && fabsf(sd - cw) < 1.0f) {
+                        const float smp = tex1_u8(pl.shadow_u8, bs);
+                        float wa = clampf(1.0f - clampf(fabsf(smp - base) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
+                        wa = clampf(pow_cr(wa, 7.0f), 0.000001f, 1.0f);
+                        total += smp * wa;
+                        weight += wa;
+                    }
+                }
+            cur_color = total / weight;
+        }
+        const Bilinear br = bilinear_at(W, H, ru, rv);
+        const float prev_orig = tex1(pl.prev_shadow, br);
+        float prev_color = prev_orig;
+        if (tr < 1.414f * 3.0f) {  // ClipShadow :168-184, clipAABB :157-166
+            float mn = 100.0f, mx = -100.0f;
+#pragma unroll
+            for (int s2 = 0; s2 < 5; ++s2) {  // ShadowClipOffsets (-1,0) (1,0) (0,0) (0,-1) (0,1)
+                const float ox = s2 == 0 ? -1.0f : (s2 == 1 ? 1.0f : 0.0f), oy = s2 == 3 ? -1.0f : (s2 == 4 ? 1.0f : 0.0f);
+                const float smp = tex1_u8(pl.shadow_u8, bilinear_at(W, H, u + ox * tsx, v + oy * tsy));
+                mn = fminf(smp, mn);
+                mx = fmaxf(smp, mx);
+            }
+            const float lo = mn - 0.025f, hi = mx + 0.025f;
+            const float pc = 0.5f * (hi + lo), ec = 0.5f * (hi - lo);
+            const float vc = prev_orig - pc;
+            const float denom = fabsf(vc / ec);
+            prev_color = denom > 1.0f ? pc + vc / denom : prev_orig;
+        }
+        const float pw = tex1(pl.prev_t, br);
+        const V3 pp = origin + normalize3(ray_direction_at(cam, ru, rv)) * pw;
+        const float bias = 0.005f;
+        if (ru > 0.0f + bias && ru < 1.0f - bias && rv > 0.0f + bias && rv < 1.0f - bias) {
+            const V3 dd = cp - pp;
+            const float d = sqrtf(dot3(dd, dd));
+            const float cc = clampf(cur_color, 0.0f, 1.0f), pc2 = clampf(prev_color, 0.0f, 1.0f);
+            const float vx = (u - ru) * (float)W, vy = (v - rv) * (float)H;
+            const float inc = fabsf(prev_orig - pc2) < 0.2f ? 1.0f : 0.6f;
+            const float fetch = tex1(pl.frames, br);
+            float blend_f = clampf((1.0f - (1.0f / (fetch + inc))) * 1.2f, 0.01f, 0.97f);
+            const float vrf = clampf(exp_cr(-sqrtf(vx * vx + vy * vy)) * 0.8f + 0.6f, 0.00000001f, 1.0f);
+            blend_f *= vrf;
+            float depth_rej = 1.0f;
+            if (d > 0.4f) {
+                depth_rej = pow_cr(exp_cr(-d), 48.0f);
+                blend_f *= clampf(depth_rej, 0.0f, 1.0f);
+            }
+            o_color = mixf(cc, pc2, clampf(blend_f, 0.0f, 0.97f));
+            const float mult = depth_rej * vrf;
+            o_frames = fetch + clampf(mult * 1.1f, 0.0f, 1.0f);
+            if (mult < 0.1f) o_frames = 0.0f;
+            else if (mult <= 0.2f + 0.001f) o_frames = 2.0f;
+            else if (mult <= 0.3f + 0.001f) o_frames = 3.25f;
+        } else {
+            o_color = cur_color;
+        }
+    } else {
+        o_color = tex1_u8(pl.shadow_u8, bc);
+    }
+    if (pl.o_shadow) pl.o_shadow[px] = o_color;
+    if (pl.o_frames) pl.o_frames[px] = clampf(o_frames, 0.0f, 256.0f);
+}
+
+// ShadowFilter.glsl ShadowSpatial :68-160
+__global__ void __launch_bounds__(256) shadow_filter_kernel(const __grid_constant__ CameraDev cam, const float filter_scale, const ShadowFilterPlanes pl) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const int W = cam.width, H = cam.height;
+    const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    const Bilinear bc = bilinear_at(W, H, u, v);
+    const size_t px = (size_t)prow * W + i;
+    const float fr = tex1(pl.frames, bc);
+    const float center_w = tex1(pl.t, bc);
+    const V3 cn = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const float center = tex1(pl.shadow, bc);
+    const float tr = tex1(pl.transversal, bc) * 100.0f;
+    const float cutoff = sqrtf(2.0f);
+    if ((tr > 0.0f && tr < cutoff) || center_w < 0.0f) {
+        pl.o_shadow[px] = center;
+        return;
+    }
+    const int K = tr < cutoff * 1.414f ? 1 : 3;
+    float scale = 1.0f;
+    if (tr > 6.0f) scale = 2.0f;
+    if (tr > 16.0f) scale = 2.4f;
+    if (tr > 32.0f) scale = 2.6f;
+    float var_est = mixf(20.0f, 6.0f, clampf(tr, 0.0f, 10.0f) / 10.0f) + (tr < 6.0f ? 5.0f : 2.0f);
+    var_est = clampf(var_est - 1.75f, 0.0000001f, 64.0f);
+    const float luma_mixer = fr > 7.5f ? 1.0f : mixf(0.1f, 0.5f, fr / 7.5f);
+    const float luma_exp = var_est * luma_mixer * 0.9f;
+    float tw = 0.0f, ts = 0.0f;
+#pragma unroll 1
+    for (int x = -K; x <= K; ++x)
+#pragma unroll 1
+        for (int y = -K; y <= K; ++y) {
+            const float su = u + ((((float)x * tsx) * 1.2f) * scale) * filter_scale;
+            const float sv = v + ((((float)y * tsy) * 1.2f) * scale) * filter_scale;
+            const Bilinear bs = bilinear_at(W, H, su, sv);
+            const float sd = tex1(pl.t, bs);
+            const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
+            const float dw = pow_cr(exp_cr(-(fabsf(center_w - sd))), 3.0f);
+            const float nw = pow_cr(fmaxf(dot3(cn, sn), 0.000000001f), 32.0f);
+            const float sa = tex1(pl.shadow, bs);
+            const float le = clampf(1.0f - clampf(fabsf(sa - center) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
+            float w = 1.0f;
+            w *= clampf(pow_cr(le, luma_exp), 0.0f, 1.0f);
+            w *= dw;
+            w *= nw;
+            w = clampf(w, 0.000000001f, 1.0f);
+            ts += sa * w;
+            tw += w;
+        }
+    pl.o_shadow[px] = ts / fmaxf(tw, 0.01f);
+}
+
 // ============================================================================================= launchers
 static CameraDev svgf_camera(const VxCamera& cam) {
     CameraDev cd;
@@ -416,6 +583,34 @@ int launch_svgf_spatial(vxpt_ctx* c, const VxCamera& cam, const VxSvgfSpatialIn&
     pl.sh = in.sh; pl.cocg = in.cocg; pl.variance = in.variance; pl.ao = in.ao_sky; pl.utility = in.temporal_utility;
     pl.o_sh = out.sh; pl.o_cocg = out.cocg; pl.o_variance = out.variance; pl.o_ao = out.ao_sky;
     VX_LAUNCH(svgf_spatial_kernel, svgf_grid(cam), 256, c->stream, svgf_camera(cam), d, pl);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int launch_shadow_temporal(vxpt_ctx* c, const VxCamera& cam, const VxShadowTemporalIn& in, const VxShadowTemporalParams& p, const VxShadowTemporalOut& out) {
+    TemporalDev d;
+    const float *A = p.prev_projection, *B = p.prev_view;
+    for (int jc = 0; jc < 4; ++jc)
+        for (int r = 0; r < 4; ++r)
+            d.prev_vp[4 * jc + r] = ((A[0 + r] * B[4 * jc + 0] + A[4 + r] * B[4 * jc + 1]) + A[8 + r] * B[4 * jc + 2]) + A[12 + r] * B[4 * jc + 3];
+    d.be_useful = 1;
+    ShadowFilterPlanes pl{};
+    pl.t = in.current.t; pl.nid = in.current.normal_id; pl.prev_t = in.previous.t;
+    pl.shadow_u8 = in.shadow; pl.transversal = in.transversal; pl.prev_shadow = in.prev_shadow; pl.frames = in.prev_frames;
+    pl.o_shadow = out.shadow; pl.o_frames = out.frames;
+    VX_LAUNCH(shadow_temporal_kernel, svgf_grid(cam), 256, c->stream, svgf_camera(cam), d, pl);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
+
+int launch_shadow_filter(vxpt_ctx* c, const VxCamera& cam, const VxShadowFilterIn& in, const VxShadowFilterParams& p, float* out) {
+    ShadowFilterPlanes pl{};
+    pl.t = in.current.t; pl.nid = in.current.normal_id;
+    pl.shadow = in.shadow; pl.transversal = in.transversal; pl.frames = in.frames;
+    pl.o_shadow = out;
+    VX_LAUNCH(shadow_filter_kernel, svgf_grid(cam), 256, c->stream, svgf_camera(cam), p.filter_scale, pl);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

@@ -178,6 +178,8 @@ int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, con
 int launch_svgf_temporal(vxpt_ctx* c, const VxCamera& cam, const VxSvgfTemporalIn& in_dev, const VxSvgfTemporalParams& p, const VxSvgfTemporalOut& out_dev);
 int launch_svgf_variance(vxpt_ctx* c, const VxCamera& cam, const VxSvgfVarianceIn& in_dev, const VxSvgfVarianceParams& p, const VxSvgfVarianceOut& out_dev);
 int launch_svgf_spatial(vxpt_ctx* c, const VxCamera& cam, const VxSvgfSpatialIn& in_dev, const VxSvgfSpatialParams& p, const VxSvgfSpatialOut& out_dev);
+int launch_shadow_temporal(vxpt_ctx* c, const VxCamera& cam, const VxShadowTemporalIn& in_dev, const VxShadowTemporalParams& p, const VxShadowTemporalOut& out_dev);
+int launch_shadow_filter(vxpt_ctx* c, const VxCamera& cam, const VxShadowFilterIn& in_dev, const VxShadowFilterParams& p, float* out_dev);
 // l2_probe.cu
 int run_l2_probe(vxpt_ctx* c, double* gbps);
 

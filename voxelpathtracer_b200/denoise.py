@@ -3,7 +3,7 @@ from dicts of planes.  The same structs drive the library (Renderer.svgf_*), the
 `address` is injected: it maps a numpy array or torch tensor to its raw address."""
 import numpy as np
 
-from .abi import (VxGBuffer, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
+from .abi import (VxGBuffer, VxShadowFilterIn, VxShadowFilterParams, VxShadowTemporalIn, VxShadowTemporalOut, VxShadowTemporalParams, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
                   VxSvgfVarianceIn, VxSvgfVarianceOut, VxSvgfVarianceParams)
 
 ATROUS_STEPS = (16, 8, 4, 2, 1)          # Core/Pipeline.cpp:2482-2487
@@ -67,7 +67,38 @@ def spatial_structs(gbuf, planes, temporal_utility, out, address):
     return i, o
 
 
+def shadow_temporal_params(prev_view, prev_projection):
+    p = VxShadowTemporalParams()
+    p.prev_view[:] = [float(v) for v in np.asarray(prev_view, dtype=np.float32).reshape(16)]
+    p.prev_projection[:] = [float(v) for v in np.asarray(prev_projection, dtype=np.float32).reshape(16)]
+    return p
+
+
+def shadow_filter_params(filter_scale=1.0):
+    p = VxShadowFilterParams()
+    p.filter_scale = float(filter_scale)
+    return p
+
+
+def shadow_temporal_structs(gbuf, prev_gbuf, shadow, prev_temporal, out, address):
+    """shadow: the shadow pass's planes (shadow uint8, transversal); prev_temporal / out: dicts with "shadow" and "frames" (fp32)."""
+    i = VxShadowTemporalIn()
+    i.current, i.previous = _gb(gbuf, address), _gb(prev_gbuf, address)
+    i.shadow, i.transversal = address(shadow["shadow"]), address(shadow["transversal"])
+    i.prev_shadow, i.prev_frames = address(prev_temporal["shadow"]), address(prev_temporal["frames"])
+    o = VxShadowTemporalOut()
+    o.shadow, o.frames = address(out.get("shadow")), address(out.get("frames"))
+    return i, o
+
+
+def shadow_filter_struct(gbuf, temporal, transversal, address):
+    i = VxShadowFilterIn()
+    i.current = _gb(gbuf, address)
+    i.shadow, i.transversal, i.frames = address(temporal["shadow"]), address(transversal), address(temporal["frames"])
+    return i
+
+
 def plane_shapes(width, height):
     """name -> shape of every fp32 plane the denoiser passes exchange."""
     return {"sh": (height, width, 4), "cocg": (height, width, 2), "utility": (height, width, 3), "ao_sky": (height, width, 2),
-            "variance": (height, width), "luma": (height, width)}
+            "variance": (height, width), "luma": (height, width), "shadow": (height, width), "frames": (height, width)}

@@ -299,6 +299,20 @@ class Renderer:
         check(self.lib.vxpt_svgf_spatial(self.handle, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)))
         return out
 
+    def shadow_temporal(self, cam, gbuf, prev_gbuf, shadow, prev_temporal, params, out):
+        """ShadowTemporalFilter.glsl (vxpt_shadow_temporal): shadow = the shadow pass's planes, prev_temporal / out = {"shadow", "frames"}."""
+        from . import denoise
+        i, o = denoise.shadow_temporal_structs(gbuf, prev_gbuf, shadow, prev_temporal, out, _ptr)
+        check(self.lib.vxpt_shadow_temporal(self.handle, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)))
+        return out
+
+    def shadow_filter(self, cam, gbuf, temporal, transversal, params, out):
+        """ShadowFilter.glsl (vxpt_shadow_filter): out = one fp32 plane."""
+        from . import denoise
+        i = denoise.shadow_filter_struct(gbuf, temporal, transversal, _ptr)
+        check(self.lib.vxpt_shadow_filter(self.handle, C.byref(cam), C.byref(i), C.byref(params), _ptr(out)))
+        return out
+
     def svgf_denoise(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, temporal_params, time=0.0, steps=None, device=False):
         """The reference's whole SVGF chain for one frame (Core/Pipeline.cpp:2335-2596): temporal -> variance -> five a-trous passes
         ping-ponging between two plane sets.  Returns (denoised planes, temporal planes to hand in as prev_temporal next frame)."""

@@ -7,6 +7,8 @@ import pytest
 
 from voxelpathtracer_b200 import abi, camera, world
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_world_layout_is_x_fastest():
     w = world.World()
@@ -142,3 +144,57 @@ def test_renderer_wrappers_call_through_with_a_stub_library():
     assert agg == 0 and per.shape == (32,)
     assert calls == ["vxpt_set_albedo_alpha_mips", "vxpt_trace_rays", "vxpt_player_shadowed", "vxpt_estimate_ambient_sound"]
     r.handle = C.c_void_p()      # nothing to destroy
+
+
+# ---------------------------------------------------------------------------------------------------- CPU picking (World::Raycast)
+def test_picking_known_answers():
+    """World::Raycast / RaycastDetect (Core/World.cpp:215-546) on the superflat world (top layer y = 49, grass)."""
+    w = world.generate_superflat()
+    d = np.array([0.6, -0.7, 0.39])
+    d /= np.linalg.norm(d)
+    eye = (192.5, 53.5, 192.5)
+    assert w.raycast_detect(eye, d) == (195, 49, 194, world.GRASS)          # the ray drops 3.5 blocks: x + 3.0, z + 1.95
+    assert w.raycast_detect((192.5, 100.0, 192.5), (0.1, 1.0, 0.1)) is None    # looking up: nothing within 48 steps
+    r = w.raycast(1, eye, d, held_block=world.LAMP)                            # place on the top face
+    assert r == {"changed": True, "voxel": (195, 50, 194), "block": world.LAMP} and w.get_block(195, 50, 194) == world.LAMP
+    assert w.raycast(2, eye, d)["block"] == world.LAMP                         # pick: the lamp is now what the ray meets first
+    r = w.raycast(0, eye, d)                                                   # break it again
+    assert r == {"changed": True, "voxel": (195, 50, 194), "block": world.LAMP} and w.get_block(195, 50, 194) == 0
+    # a block that would intersect the player is refused: standing on the ground, looking almost straight down
+    d2 = np.array([0.01, -1.0, 0.01])
+    d2 /= np.linalg.norm(d2)
+    before = w.data.copy()
+    assert w.raycast(1, (192.5, 51.6, 192.5), d2)["changed"] is False and np.array_equal(w.data, before)
+
+
+def test_picking_python_and_cpp_mirrors_agree(tmp_path):
+    """The same random edit script through the Python mirror (world.World.raycast) and the C++ mirror (host/VoxelRT.h, compiled here)."""
+    import subprocess
+    abi.load()
+    cc = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "picking")
+    pkg = os.path.join(ROOT, "voxelpathtracer_b200")
+    subprocess.run([cc, "-std=c++17", "-O2", "-Wall", "-Werror", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "cpp", "picking_main.cpp"),
+                    "-L" + pkg, "-lvxpt", "-Wl,-rpath," + pkg], check=True)
+    rng = np.random.RandomState(17)
+    w = world.generate_superflat()
+    lines, want = [], []
+    for k in range(300):
+        op = int(rng.choice([0, 1, 1, 2, 3]))
+        pos = np.array([192.5 + rng.uniform(-6, 6), 50.2 + rng.uniform(0.0, 6.0), 192.5 + rng.uniform(-6, 6)], np.float32)
+        d = rng.normal(size=3)
+        d[1] = -abs(d[1]) - 0.2
+        d = (d / np.linalg.norm(d)).astype(np.float32)
+        held = int(rng.choice([world.STONE, world.LAMP, world.PLANKS]))
+        lines.append("%d %.9g %.9g %.9g %.9g %.9g %.9g %d" % (op, *pos, *d, held))
+        if op == 3:
+            r = w.raycast_detect(pos, d)
+            want.append((1,) + r if r else (0, -1, -1, -1, -1))
+        else:
+            r = w.raycast(op, pos, d, held)
+            v = r["voxel"] or (-1, -1, -1)
+            want.append((int(r["changed"]), v[0], v[1], v[2], r["block"]))
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    got = [tuple(int(v) for v in ln.split()) for ln in out if ln.strip()]
+    assert got == want
+    assert sum(1 for g in got if g[0] == 1) > 100     # the script does edit the world

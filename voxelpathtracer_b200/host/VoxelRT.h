@@ -3,6 +3,7 @@
 // Same names, argument meaning and error behaviour as the reference classes it stands in for, minus everything that
 // needs a window, GL context or audio device:
 //   VoxelRT::Block, VoxelRT::World           Core/Block.h:7-10, Core/World.h:35-70,167-171,192, Core/World.cpp:48-113
+//   VoxelRT::World::Raycast / RaycastDetect  Core/World.cpp:215-546 (CPU picking: place / break / pick the block looked at)
 //   VoxelRT::GenerateWorld                   Core/WorldGenerator.cpp:69-121 (superflat; plains from a column table)
 //   VoxelRT::SaveWorld / LoadWorld           Core/WorldFileHandler.cpp:10-83
 //   VoxelRT::BlockDataSSBO                   Core/BlockDataSSBO.cpp:5-46
@@ -13,6 +14,7 @@
 // call is reported through VoxelRT::Logger::Log and the method returns false.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -79,6 +81,84 @@ public:
         SetBlock(x, y, z, block);
         if (!vx_ok(vxpt_set_block(m_Vx, x, y, z, block.block), "vxpt_set_block")) return false;
         return GenerateDistanceField();
+    }
+    // ---- CPU picking: World::RaycastDetect / World::Raycast (Core/World.cpp:215-546) ----
+    // The block the player looks at, found on the host grid by stepping from cell face to cell face (48 steps of reach); it does not
+    // read the distance field.  Without the reference's side effects that are out of scope (particles, sound, light-propagation queues).
+    struct PickResult {
+        bool changed;   // the reference's return value
+        int x, y, z;    // edited / picked voxel, -1 when none
+        uint8_t block;  // placed, removed or picked id
+    };
+    static bool PickOutside(const float p[3]) {
+        return (int)std::floor(p[0]) >= WORLD_SIZE_X || (int)std::floor(p[1]) >= WORLD_SIZE_Y || (int)std::floor(p[2]) >= WORLD_SIZE_Z ||
+               (int)std::floor(p[0]) <= 0 || (int)std::floor(p[1]) <= 0 || (int)std::floor(p[2]) <= 0;
+    }
+    // RaycastDetect (:497-546): (x, y, z, block) of the first solid cell; x = -1 when the hit cell is outside; false when nothing is hit
+    bool RaycastDetect(const float pos[3], const float dir[3], int out[4]) const {
+        float p[3] = {pos[0], pos[1], pos[2]}, sign[3];
+        for (int i = 0; i < 3; ++i) sign[i] = dir[i] > 0;
+        for (int i = 0; i < 48; ++i) {
+            float tvec[3];
+            for (int k = 0; k < 3; ++k) tvec[k] = (std::floor(p[k] + sign[k]) - p[k]) / dir[k];
+            const float t = std::min(tvec[0], std::min(tvec[1], tvec[2]));
+            for (int k = 0; k < 3; ++k) p[k] += dir[k] * (t + 0.001f);
+            if (!PickOutside(p) && GetBlock((uint16_t)(int)p[0], (uint16_t)(int)p[1], (uint16_t)(int)p[2]).block != 0) {
+                out[0] = (int)p[0]; out[1] = (int)p[1]; out[2] = (int)p[2];
+                out[3] = GetBlock((uint16_t)out[0], (uint16_t)out[1], (uint16_t)out[2]).block;
+                return true;
+            }
+        }
+        return false;
+    }
+    // Raycast (:215-495): op 0 = break, 1 = place `held`, 2 = pick.  Edits the host grid and, when the world is buffered, the device grid
+    // + distance field (glTexSubImage3D + GenerateDistanceField in the reference).
+    PickResult Raycast(uint8_t op, const float pos[3], const float dir[3], uint8_t held = BlockID::Stone) {
+        const PickResult none{false, -1, -1, -1, 0};
+        float p[3] = {pos[0], pos[1], pos[2]}, sign[3];
+        for (int i = 0; i < 3; ++i) sign[i] = dir[i] > 0;
+        for (int i = 0; i < 48; ++i) {
+            float tvec[3];
+            for (int k = 0; k < 3; ++k) tvec[k] = (std::floor(p[k] + sign[k]) - p[k]) / dir[k];
+            const float t = std::min(tvec[0], std::min(tvec[1], tvec[2]));
+            for (int k = 0; k < 3; ++k) p[k] += dir[k] * (t + 0.001f);
+            if (PickOutside(p) || GetBlock((uint16_t)(int)p[0], (uint16_t)(int)p[1], (uint16_t)(int)p[2]).block == 0) continue;
+            float normal[3];
+            for (int k = 0; k < 3; ++k) {
+                normal[k] = (t == tvec[k]);
+                if (sign[k]) normal[k] = -normal[k];
+            }
+            if (op == 1)
+                for (int k = 0; k < 3; ++k) p[k] = p[k] + normal[k];
+            for (int k = 0; k < 3; ++k) p[k] = std::floor(p[k]);
+            if (PickOutside(p)) return none;
+            const int x = (int)p[0], y = (int)p[1], z = (int)p[2];
+            auto dist = [](const float a[3], float bx, float by, float bz) {
+                const float dx = bx - a[0], dy = by - a[1], dz = bz - a[2];
+                return std::sqrt((dx * dx + dy * dy) + dz * dz);
+            };
+            if (op == 1) {
+                const uint8_t prev = GetBlock((uint16_t)x, (uint16_t)y, (uint16_t)z).block;
+                const uint16_t ox = (uint16_t)(int)pos[0], oz = (uint16_t)(int)pos[2];
+                const uint8_t u1 = GetBlock(ox, (uint16_t)(((int)pos[1]) - 1.0f), oz).block, u2 = GetBlock(ox, (uint16_t)(int)(pos[1] - 1.0f), oz).block,
+                              u3 = GetBlock(ox, (uint16_t)(int)(pos[1] - 1.1f), oz).block;
+                if (prev != 0 || dist(p, pos[0], pos[1], pos[2]) < 1.25f) return none;
+                if ((u1 == 0 || u2 == 0 || u3 == 0) && dist(p, pos[0], pos[1] - 1.0f, pos[2]) < 1.35f) return none;
+                const bool placed = prev != held;
+                SetBlock((uint16_t)x, (uint16_t)y, (uint16_t)z, {held});
+                if (m_Buffered && placed) EditBlock((uint16_t)x, (uint16_t)y, (uint16_t)z, {held});
+                return PickResult{placed, x, y, z, held};
+            }
+            if (op == 0) {
+                const uint8_t old = GetBlock((uint16_t)x, (uint16_t)y, (uint16_t)z).block;
+                SetBlock((uint16_t)x, (uint16_t)y, (uint16_t)z, {0});
+                if (m_Buffered) EditBlock((uint16_t)x, (uint16_t)y, (uint16_t)z, {0});
+                return PickResult{true, x, y, z, old};
+            }
+            if (op == 2) return PickResult{false, x, y, z, GetBlock((uint16_t)x, (uint16_t)y, (uint16_t)z).block};
+            return none;
+        }
+        return none;
     }
     bool DownloadDistanceField(std::vector<uint8_t>& out) const {
         out.resize(VXPT_WORLD_VOXELS);

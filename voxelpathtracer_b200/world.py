@@ -1,6 +1,7 @@
 """Host-side world model: Python mirror of the reference's World grid, world generators and save files.
 
-  World                     Core/World.h:35-70,192 (m_WorldData, GetBlock/SetBlock), x-fastest layout
+  World                     Core/World.h:35-70,192 (m_WorldData, GetBlock/SetBlock), x-fastest layout; CPU picking
+                            (World::Raycast / RaycastDetect, Core/World.cpp:215-546)
   generate_superflat/plains Core/WorldGenerator.cpp:28-121
   save_world / load_world   Core/WorldFileHandler.cpp:10-83 (raw 18,874,368-byte dump)
   generate_gi_box / city    deterministic stand-ins for the two scenes whose blobs are missing from the reference
@@ -44,6 +45,89 @@ class World:
     # reference spellings
     GetBlock = get_block
     SetBlock = set_block
+
+    # ---- CPU picking: World::RaycastDetect / World::Raycast (Core/World.cpp:215-546) --------------------------------------------
+    # The block the player looks at, found on the HOST grid by stepping from cell face to cell face (reach: 48 steps); it does not read
+    # the distance field.  fp32 arithmetic in the reference's order (glm::vec3); std::min(a, b) = (b < a) ? b : a, so a NaN quotient
+    # (0 / 0 on an axis the ray does not move along) loses against any number that follows it exactly as in the reference.
+    @staticmethod
+    def _pick_steps(pos, direction):
+        f32 = np.float32
+        p = [f32(v) for v in pos]
+        d = [f32(v) for v in direction]
+        sign = [f32(1.0) if c > 0 else f32(0.0) for c in d]
+
+        def smin(a, b):
+            return b if b < a else a
+
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for _ in range(48):
+                tvec = [(np.floor(p[k] + sign[k]) - p[k]) / d[k] for k in range(3)]
+                t = smin(tvec[0], smin(tvec[1], tvec[2]))
+                p = [p[k] + d[k] * (t + f32(0.001)) for k in range(3)]
+                yield p, t, tvec, sign
+
+    @staticmethod
+    def _cell(p):
+        """(int)floor(position) per axis and the reference's bounds verdict (>= size or <= 0 is outside: cell 0 counts as outside)."""
+        c = []
+        for v in p:
+            c.append(int(np.floor(v)) if np.isfinite(v) else -2**31)
+        inside = not (c[0] >= WORLD_SIZE_X or c[1] >= WORLD_SIZE_Y or c[2] >= WORLD_SIZE_Z or c[0] <= 0 or c[1] <= 0 or c[2] <= 0)
+        return c, inside
+
+    def raycast_detect(self, pos, direction):
+        """RaycastDetect (:497-546): (x, y, z, block) of the first solid cell along the ray, (-1, -1, -1, -1) when the walk ends outside
+        the world at a hit, None when nothing is hit within reach (the reference falls off the end of the function there)."""
+        for p, _, _, _ in self._pick_steps(pos, direction):
+            c, inside = self._cell(p)
+            if inside and self.get_block(*c) != 0:
+                return (c[0], c[1], c[2], self.get_block(*c))
+        return None
+
+    def raycast(self, op, pos, direction, held_block=STONE):
+        """World::Raycast (:215-495): op 0 breaks the block looked at, 1 places `held_block` on the face looked at (unless it would
+        intersect the player standing at `pos`), 2 picks the block looked at.  Edits the HOST grid only and returns
+        {"changed": bool (the reference's return value), "voxel": (x, y, z) or None, "block": edited / picked id}; the caller mirrors
+        an edit to the device with Renderer.set_block + build_distance_field, as the reference does with glTexSubImage3D +
+        GenerateDistanceField (:372-374, 458-460)."""
+        f32 = np.float32
+        origin = [f32(v) for v in pos]
+        for p, t, tvec, sign in self._pick_steps(pos, direction):
+            c, inside = self._cell(p)
+            if not (inside and self.get_block(*c) != 0):
+                continue
+            normal = [f32(1.0) if t == tvec[k] else f32(0.0) for k in range(3)]
+            normal = [-normal[k] if sign[k] else normal[k] for k in range(3)]
+            if op == 1:
+                p = [p[k] + normal[k] for k in range(3)]
+            p = [np.floor(v) for v in p]
+            c, inside = self._cell(p)
+            if not inside:
+                return {"changed": False, "voxel": None, "block": 0}
+            if op == 1:
+                def dist(a, b):
+                    dx, dy, dz = (f32(b[k]) - f32(a[k]) for k in range(3))
+                    return np.sqrt(f32(f32(dx * dx + dy * dy) + dz * dz))
+
+                ox, oy, oz = int(origin[0]), int(origin[1]), int(origin[2])
+                under = [self.get_block(ox, int(f32(oy) - f32(1.0)), oz), self.get_block(ox, int(origin[1] - f32(1.0)), oz),
+                         self.get_block(ox, int(origin[1] - f32(1.1)), oz)]
+                if self.get_block(*c) != 0 or dist(p, origin) < f32(1.25):
+                    return {"changed": False, "voxel": None, "block": 0}
+                if 0 in under and dist(p, [origin[0], origin[1] - f32(1.0), origin[2]]) < f32(1.35):
+                    return {"changed": False, "voxel": None, "block": 0}
+                changed = self.get_block(*c) != held_block
+                self.set_block(c[0], c[1], c[2], held_block)
+                return {"changed": bool(changed), "voxel": tuple(c), "block": int(held_block)}
+            if op == 0:
+                old = self.get_block(*c)
+                self.set_block(c[0], c[1], c[2], 0)
+                return {"changed": True, "voxel": tuple(c), "block": old}
+            if op == 2:
+                return {"changed": False, "voxel": tuple(c), "block": self.get_block(*c)}
+            return {"changed": False, "voxel": None, "block": 0}
+        return {"changed": False, "voxel": None, "block": 0}
 
 
 def _set_vertical_blocks(zyx, x, z, y_level, biome):

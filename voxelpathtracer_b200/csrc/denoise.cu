@@ -14,7 +14,21 @@
 
 namespace vxpt {
 
-__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+// The pinned transcendentals are double-precision library calls (about a hundred FP64 instructions each), and the filters evaluate several
+// per tap.  Most of them have exact short cuts that return the SAME fp32 value (checked bit for bit against the oracle on the host):
+//   pow(x, y) with x == 1 is 1 for every y, with x == 0 and y > 0 is 0: face-normal dot products are 0 or 1, luminance-error terms are
+//   exactly 1 wherever a tap equals the centre;
+//   pow(y, 2): y * y is exact in double (48 significant bits), so the correctly rounded square is the fp32 product;
+//   pow(y, 3): (y * y) * y in double carries one rounding at 53 bits before the one to fp32;
+//   exp(-0) = 1.
+__device__ __forceinline__ float exp_cr(float x) { return x == 0.0f ? 1.0f : (float)exp((double)x); }
+__device__ __forceinline__ float pow01_cr(float x, float y) {  // y > 0
+    if (x == 1.0f) return 1.0f;
+    if (x == 0.0f) return 0.0f;
+    return pow_cr(x, y);
+}
+__device__ __forceinline__ float sq_cr(float y) { return y * y; }
+__device__ __forceinline__ float cube_cr(float y) { return (float)(((double)y * (double)y) * (double)y); }
 __device__ __forceinline__ int wrap_repeat(int i, int n) {
     const int m = i % n;
     return m < 0 ? m + n : m;
@@ -225,8 +239,8 @@ __global__ void __launch_bounds__(256) svgf_variance_kernel(const __grid_constan
                 const float4 ssh = tex4(pl.sh, bs);
                 const float2 scc = tex2(pl.cocg, bs);
                 const float slum = sh_to_y(ssh);
-                const float nw = pow_cr(fmaxf(dot3(base_n, sn), 0.0f), 16.0f);
-                const float dw = pow_cr(exp_cr(-fabsf(sw - base_w)), 2.0f);
+                const float nw = pow01_cr(fmaxf(dot3(base_n, sn), 0.0f), 16.0f);
+                const float dw = sq_cr(exp_cr(-fabsf(sw - base_w)));
                 const float lw = fabsf(slum - base_lum) / color_phi;
                 const float w0 = exp_cr(-lw) * nw * dw;
                 const float w1 = fmaxf(w0, 0.000000015f), w2 = fmaxf(w0, 0.0000000015f);
@@ -334,9 +348,9 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
             const float2 scc = tex2(pl.cocg, bs);
             const float slum = sh_to_y(ssh);
             const float svar = tex1(pl.variance, bs);
-            const float nw = clampf(pow_cr(fmaxf(dot3(base_n, sn), 0.0f), 32.0f), 0.001f, 1.0f);
+            const float nw = clampf(pow01_cr(fmaxf(dot3(base_n, sn), 0.0f), 32.0f), 0.001f, 1.0f);
             const float lw = fabsf(slum - base_lum) / phi;
-            const float dw = clampf(pow_cr(exp_cr(-fmaxf(ddiff, 0.00001f)), 2.0f), 0.0001f, 1.0f);
+            const float dw = clampf(sq_cr(exp_cr(-fmaxf(ddiff, 0.00001f))), 0.0001f, 1.0f);
             float w = strong ? (nw * dw) : (exp_cr(-lw) * nw * dw);
             w = clampf(w, 0.001f, 1.0f);
             const float xw = x == 0 ? 1.0f : ((x == 1 || x == -1) ? 2.0f / 3.0f : 1.0f / 6.0f);
@@ -419,7 +433,7 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
                     if (min(tex_nearest_u8(pl.nid, W, H, su, sv), 6) == bn && fabsf(sd - cw) < 1.0f) {
                         const float smp = tex1_u8(pl.shadow_u8, bs);
                         float wa = clampf(1.0f - clampf(fabsf(smp - base) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
-                        wa = clampf(pow_cr(wa, 7.0f), 0.000001f, 1.0f);
+                        wa = clampf(pow01_cr(wa, 7.0f), 0.000001f, 1.0f);
                         total += smp * wa;
                         weight += wa;
                     }
@@ -516,12 +530,12 @@ __global__ void __launch_bounds__(256) shadow_filter_kernel(const __grid_constan
             const Bilinear bs = bilinear_at(W, H, su, sv);
             const float sd = tex1(pl.t, bs);
             const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
-            const float dw = pow_cr(exp_cr(-(fabsf(center_w - sd))), 3.0f);
-            const float nw = pow_cr(fmaxf(dot3(cn, sn), 0.000000001f), 32.0f);
+            const float dw = cube_cr(exp_cr(-(fabsf(center_w - sd))));
+            const float nw = pow01_cr(fmaxf(dot3(cn, sn), 0.000000001f), 32.0f);
             const float sa = tex1(pl.shadow, bs);
             const float le = clampf(1.0f - clampf(fabsf(sa - center) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
             float w = 1.0f;
-            w *= clampf(pow_cr(le, luma_exp), 0.0f, 1.0f);
+            w *= clampf(le == 1.0f ? 1.0f : pow_cr(le, luma_exp), 0.0f, 1.0f);
             w *= dw;
             w *= nw;
             w = clampf(w, 0.000000001f, 1.0f);

@@ -298,6 +298,23 @@ VXPT_API int vxpt_generate_gbuffer(vxpt_handle h, const VxCamera* cam, const VxG
  * Pipeline.cpp:1094-1152 declares — hit distance GL_LINEAR, normal / block id GL_NEAREST, all radiance / utility / AO / variance planes
  * GL_LINEAR; linear = OpenGL 4.3 section 8.14.2 in fp32, weights applied as a(1-f) + bf, x first.  min / max / clamp return the non-NaN
  * operand (IEEE minNum / maxNum, what the GPUs the reference runs on do); exp / pow are correctly rounded fp32. */
+/* pre-temporal 3x3 pass (PreTemporalSpatialPass = true by default, Pipeline.cpp:239, 2288-2330 -> Spatial3x3Initial.glsl): filters this
+ * frame's raw GI planes before they enter the temporal pass; its outputs then stand in for VxSvgfTemporalIn.sh / cocg / luma / ao_sky. */
+typedef struct VxSvgfInitialIn {
+    VxGBuffer current;     /* t, normal_id                                         */
+    const float* sh;       /* u_SH      VxDiffuseOut.sh                            */
+    const float* cocg;     /* u_CoCg    VxDiffuseOut.cocg                          */
+    const float* luma;     /* u_Utility VxDiffuseOut.luma (passed through)         */
+    const float* ao_sky;   /* u_AO      VxDiffuseOut.ao_sky                        */
+} VxSvgfInitialIn;
+typedef struct VxSvgfInitialOut {
+    float* sh;       /* o_SH 4       */
+    float* cocg;     /* o_CoCg 2     */
+    float* luma;     /* o_Utility 1  */
+    float* ao_sky;   /* o_AOSky 2    */
+} VxSvgfInitialOut;
+VXPT_API int vxpt_svgf_initial(vxpt_handle h, const VxCamera* cam, const VxSvgfInitialIn* in, const VxSvgfInitialOut* out);
+
 typedef struct VxSvgfTemporalIn {
     VxGBuffer current;          /* t, normal_id, block_id of this frame (InitialTraceFBO attachments 0..2)                       */
     VxGBuffer previous;         /* the same planes of the previous frame (InitialTraceFBOPrev)                                    */
@@ -355,9 +372,9 @@ typedef struct VxSvgfSpatialParams {
     int32_t large_kernel;             /* u_LargeKernel = SVGF_LARGE_KERNEL (0): 5x5 instead of 3x3 taps  */
     int32_t do_spatial;               /* DO_SPATIAL = DO_SVGF_SPATIAL (1)                                */
     int32_t aggressive_disocclusion;  /* AGGRESSIVE_DISOCCLUSION_HANDLING (1)                            */
-    float color_phi_bias;             /* u_ColorPhiBias (2.0)                                            */
+    float color_phi_bias;             /* u_ColorPhiBias = ColorPhiBias (3.325, Pipeline.cpp:85)          */
     float time;                       /* u_Time = glfwGetTime(): seeds the per-pixel tap jitter          */
-    float resolution_scale;           /* u_ResolutionScale = DiffuseIndirectSuperSampleRes               */
+    float resolution_scale;           /* u_ResolutionScale = DiffuseIndirectSuperSampleRes (0.25, :78)   */
 } VxSvgfSpatialParams;
 typedef struct VxSvgfSpatialOut {
     float* sh;        /* o_SH 4                 */

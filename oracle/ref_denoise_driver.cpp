@@ -27,6 +27,7 @@ inline vec3 max(const vec3& a, const vec3& b) { return vec3(std::fmax(a.x, b.x),
 inline vec2 operator/(float a, const ivec2& b) { return vec2(a) / vec2(b); }
 #include "_ref/ShadowTemporalFilter.inc"
 #include "_ref/ShadowFilter.inc"
+#include "_ref/Spatial3x3Initial.inc"
 #include "_ref/TemporalFilter.inc"
 #include "_ref/VarianceEstimate.inc"
 #include "_ref/SpatialFilter.inc"
@@ -110,6 +111,32 @@ extern "C" __attribute__((visibility("default"))) int ref_svgf_temporal(const Re
         std::memcpy(a->o_cocg + 2 * px, &S::o_CoCg[0], 8);
         std::memcpy(a->o_utility + 3 * px, &S::o_Utility[0], 12);
         std::memcpy(a->o_ao_sky + 2 * px, &S::o_AOAndSkyLighting[0], 8);
+    })
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int ref_svgf_initial(const RefSvgfArgs* a) {
+    using namespace glsl;
+    namespace S = glsl::denoise::ns_Spatial3x3Initial;
+    const int W = a->width, H = a->height;
+    IdPlanes cur(a->g_normal_id, nullptr, (size_t)W * H);
+    std::memcpy(&S::u_InverseView[0][0], a->inv_view, 64);
+    std::memcpy(&S::u_InverseProjection[0][0], a->inv_proj, 64);
+    S::u_Dimensions = vec2((float)W, (float)H);
+    S::u_Time = a->time;
+    S::u_DeltaTime = 0.0f;
+    S::v_RayOrigin = vec3(S::u_InverseView[3]);
+    S::u_SH = bind(a->sh, W, H, 4, true);
+    S::u_CoCg = bind(a->cocg, W, H, 2, true);
+    S::u_Utility = bind(a->luma, W, H, 1, true);
+    S::u_AO = bind(a->ao_sky, W, H, 2, true);
+    S::u_PositionTexture = bind(a->g_t, W, H, 1, true);
+    S::u_NormalTexture = bind(cur.normal.data(), W, H, 1, false);
+    FOR_EACH_PIXEL(S, {
+        std::memcpy(a->o_sh + 4 * px, &S::o_SH[0], 16);
+        std::memcpy(a->o_cocg + 2 * px, &S::o_CoCg[0], 8);
+        a->o_utility[px] = S::o_Utility;
+        std::memcpy(a->o_ao_sky + 2 * px, &S::o_AOSky[0], 8);
     })
     return 0;
 }

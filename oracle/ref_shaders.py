@@ -90,7 +90,7 @@ def load():
         lib.ref_trace_diffuse.argtypes = [C.POINTER(RefDiffuseArgs)]
         lib.ref_trace_reflection.restype = C.c_int
         lib.ref_trace_reflection.argtypes = [C.POINTER(RefReflectionArgs)]
-        for name in ("ref_svgf_temporal", "ref_svgf_variance", "ref_svgf_spatial"):
+        for name in ("ref_svgf_initial", "ref_svgf_temporal", "ref_svgf_variance", "ref_svgf_spatial"):
             if hasattr(lib, name):
                 getattr(lib, name).restype = C.c_int
                 getattr(lib, name).argtypes = [C.POINTER(RefSvgfArgs)]
@@ -291,6 +291,19 @@ def _svgf_out(cam, names):
     W, H = cam.width, cam.height
     shapes = {"sh": (H, W, 4), "cocg": (H, W, 2), "utility": (H, W, 3), "ao_sky": (H, W, 2), "variance": (H, W)}
     return {k: np.zeros(shapes[k], np.float32) for k in names}
+
+
+def svgf_initial(cam, gbuf, diffuse, out=None):
+    keep = []
+    a, ptr = _svgf_args(cam, keep)
+    if out is None:
+        out = _svgf_out(cam, ("sh", "cocg", "ao_sky"))
+        out["luma"] = np.zeros((cam.height, cam.width), np.float32)
+    a.g_t, a.g_normal_id = ptr(gbuf["t"]), ptr(gbuf["normal_id"], np.uint8)
+    a.sh, a.cocg, a.luma, a.ao_sky = (ptr(diffuse[k]) for k in ("sh", "cocg", "luma", "ao_sky"))
+    a.o_sh, a.o_cocg, a.o_utility, a.o_ao_sky = (out[k].ctypes.data for k in ("sh", "cocg", "luma", "ao_sky"))
+    load().ref_svgf_initial(C.byref(a))
+    return out
 
 
 def svgf_temporal(cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out=None):

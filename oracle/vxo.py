@@ -66,6 +66,8 @@ def load():
         fn = getattr(lib, "vxo_svgf_" + name)
         fn.argtypes = [C.POINTER(VxCamera)] + [C.POINTER(getattr(_abi, "VxSvgf" + k)) for k in kinds]
         fn.restype = C.c_int
+    lib.vxo_svgf_initial.argtypes = [C.POINTER(VxCamera), C.POINTER(_abi.VxSvgfInitialIn), C.POINTER(_abi.VxSvgfInitialOut)]
+    lib.vxo_svgf_initial.restype = C.c_int
     lib.vxo_shadow_temporal.argtypes = [C.POINTER(VxCamera), C.POINTER(_abi.VxShadowTemporalIn), C.POINTER(_abi.VxShadowTemporalParams),
                                         C.POINTER(_abi.VxShadowTemporalOut)]
     lib.vxo_shadow_filter.argtypes = [C.POINTER(VxCamera), C.POINTER(_abi.VxShadowFilterIn), C.POINTER(_abi.VxShadowFilterParams), C.c_void_p]
@@ -269,6 +271,15 @@ def _planes(cam, names):
     from voxelpathtracer_b200 import denoise
     shapes = denoise.plane_shapes(cam.width, cam.height)
     return {k: np.zeros(shapes[k], np.float32) for k in names}
+
+
+def svgf_initial(cam, gbuf, diffuse, out=None):
+    from voxelpathtracer_b200 import denoise
+    out = _planes(cam, ("sh", "cocg", "luma", "ao_sky")) if out is None else out
+    i, o = denoise.initial_structs(gbuf, diffuse, out, _addr)
+    rc = load().vxo_svgf_initial(C.byref(cam), C.byref(i), C.byref(o))
+    assert rc == 0, rc
+    return out
 
 
 def svgf_temporal(cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out=None):

@@ -424,6 +424,66 @@ int vxo_svgf_spatial(const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvg
     return VXPT_OK;
 }
 
+// Spatial3x3Initial.glsl main() :102-176 (Core/Pipeline.cpp:2288-2330), the pre-temporal 3x3 pass
+int vxo_svgf_initial(const VxCamera* cam, const VxSvgfInitialIn* in, const VxSvgfInitialOut* out) {
+    const int W = cam->width, H = cam->height;
+    const Tex pos{in->current.t, W, H, 1}, sh{in->sh, W, H, 4}, cocg{in->cocg, W, H, 2}, luma{in->luma, W, H, 1}, ao{in->ao_sky, W, H, 2};
+    const TexU8 nrm{in->current.normal_id, W, H};
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    static const float kAtrous[3] = {1.0f, 2.0f / 3.0f, 1.0f / 6.0f};
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = cam->row_begin; j < cam->row_end; ++j)
+        for (int i = 0; i < W; ++i) {
+            const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+            v3 bp;
+            float bw;
+            position_at(*cam, pos, u, v, bp, bw);
+            const v3 bn = normal_of(nrm.nearest(u, v));
+            const v4 bsh = sh.linear4(u, v);
+            const v2 bcc = cocg.linear2(u, v), bao = ao.linear2(u, v);
+            const float blum = sh_to_y(bsh);
+            v4 tsh = bsh;
+            v2 tcc = bcc, tao = bao;
+            float tw = 1.0f, taw = 1.0f;
+            for (int x = -1; x <= 1; ++x)
+                for (int y = -1; y <= 1; ++y) {
+                    if (x == 0 && y == 0) continue;
+                    const float su = u + ((float)x * 1.0f) * tsx, sv = v + ((float)y * 1.0f) * tsy;
+                    if (!(su > 0.0f && su < 1.0f && sv > 0.0f && sv < 1.0f)) continue;
+                    v3 sp;
+                    float sw;
+                    position_at(*cam, pos, su, sv, sp, sw);
+                    const v3 df{std::fabs(sp.x - bp.x), std::fabs(sp.y - bp.y), std::fabs(sp.z - bp.z)};
+                    if (dot3(df, df) < 1.0f) {
+                        const v4 ssh = sh.linear4(su, sv);
+                        const v2 scc = cocg.linear2(su, sv);
+                        const v3 sn = normal_of(nrm.nearest(su, sv));
+                        const float nw = pow_cr(std::fmax(dot3(bn, sn), 0.0f), 16.0f);
+                        const float lw = std::fabs(sh_to_y(ssh) - blum) / 4.0f;
+                        float w = exp_cr(-lw - nw);       // sic: the normal term is subtracted in the exponent
+                        w = std::fmax(w, 0.01f);
+                        w = (kAtrous[std::abs(x)] * kAtrous[std::abs(y)]) * w;
+                        w = clampf(std::fmax(w, 0.01f), 0.0f, 1.0f);
+                        tsh = tsh + ssh * w;
+                        tcc = tcc + scc * w;
+                        tw += w;
+                        tao = tao + ao.linear2(su, sv) * w;
+                        taw += w;
+                    }
+                }
+            tw = std::fmax(tw, 0.01f);
+            tsh = tsh / tw;
+            tcc = tcc / tw;
+            tao = tao / std::fmax(taw, 0.01f);
+            const size_t p = (size_t)j * W + i;
+            if (out->sh) { out->sh[4 * p] = tsh.x; out->sh[4 * p + 1] = tsh.y; out->sh[4 * p + 2] = tsh.z; out->sh[4 * p + 3] = tsh.w; }
+            if (out->cocg) { out->cocg[2 * p] = tcc.x; out->cocg[2 * p + 1] = tcc.y; }
+            if (out->ao_sky) { out->ao_sky[2 * p] = tao.x; out->ao_sky[2 * p + 1] = tao.y; }
+            if (out->luma) out->luma[p] = luma.linear1(u, v);
+        }
+    return VXPT_OK;
+}
+
 // ShadowTemporalFilter.glsl main() :201-298 with u_ShadowTemporal = true (Core/Pipeline.cpp:2854-2903).  The colour attachments hold one
 // channel (R8 shadow, R16F frame count): only the .x of the shader's vec3 / vec4 arithmetic reaches an output, and only .x is restated.
 int vxo_shadow_temporal(const VxCamera* cam, const VxShadowTemporalIn* in, const VxShadowTemporalParams* prm, const VxShadowTemporalOut* out) {

@@ -1,6 +1,6 @@
 """Frame sequences of the SVGF denoiser tests, shared by tools/make_ref_denoise_golden.py (runs the reference's own
 shaders and commits digests) and tests/test_svgf_denoise.py.  A sequence is a camera path; every frame runs primary + 1-spp GI, then
-temporal -> variance -> five a-trous passes, and hands its temporal planes and G-buffer to the next frame (Core/Pipeline.cpp:2335-2596)."""
+the pre-temporal 3x3 pass -> temporal -> variance -> five a-trous passes, and hands its temporal planes and G-buffer to the next frame (Core/Pipeline.cpp:2335-2596)."""
 import hashlib
 
 import numpy as np
@@ -38,19 +38,21 @@ def run_sequence(name, trace, passes, scene_tables):
         g, d = trace(cam, f)
         pfc = prev_fc or fc                     # frame 0: PreviousView = CurrentView (Pipeline.cpp initialises both from the camera)
         tp = denoise.temporal_params(pfc.view().T.reshape(16), pfc.projection().T.reshape(16))
-        t = passes.svgf_temporal(cam, g, prev_g or g, d, prev_t, tp)
+        pre = passes.svgf_initial(cam, g, d)                # PreTemporalSpatialPass (default on): the temporal pass reads its outputs
+        t = passes.svgf_temporal(cam, g, prev_g or g, pre, prev_t, tp)
         v = passes.svgf_variance(cam, g, t, denoise.variance_params())
         cur = {"sh": v["sh"], "cocg": v["cocg"], "variance": v["variance"], "ao_sky": t["ao_sky"]}
         spatial = []
         for step in denoise.ATROUS_STEPS:
             cur = passes.svgf_spatial(cam, g, cur, t["utility"], denoise.spatial_params(step, time=TIME0 + f / 60.0))
             spatial.append(cur)
-        yield {"cam": cam, "gbuf": g, "diffuse": d, "temporal": t, "variance": v, "spatial": spatial}
+        yield {"cam": cam, "gbuf": g, "diffuse": d, "initial": pre, "temporal": t, "variance": v, "spatial": spatial}
         prev_g, prev_t, prev_fc = g, t, fc
 
 
 def frame_digest(fr):
-    out = {"temporal": {k: sha(a) for k, a in fr["temporal"].items()}, "variance": {k: sha(a) for k, a in fr["variance"].items()}}
+    out = {"initial": {k: sha(a) for k, a in fr["initial"].items()}, "temporal": {k: sha(a) for k, a in fr["temporal"].items()},
+           "variance": {k: sha(a) for k, a in fr["variance"].items()}}
     out["spatial"] = [{k: sha(a) for k, a in s.items()} for s in fr["spatial"]]
     return out
 

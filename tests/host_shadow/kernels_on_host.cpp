@@ -192,6 +192,9 @@ HS_API int hs_generate_gbuffer(void* p, const VxCamera* cam, const VxGBuffer* g,
     return vxpt::launch_gbuffer(hs_ctx(p), *cam, *g, *prm, *out);
 }
 // the SVGF denoiser passes need no scene: hs_create(NULL-scene) handles work too
+HS_API int hs_svgf_initial(void* p, const VxCamera* cam, const VxSvgfInitialIn* in, const VxSvgfInitialOut* out) {
+    return vxpt::launch_svgf_initial(hs_ctx(p), *cam, *in, *out);
+}
 HS_API int hs_svgf_temporal(void* p, const VxCamera* cam, const VxSvgfTemporalIn* in, const VxSvgfTemporalParams* prm, const VxSvgfTemporalOut* out) {
     return vxpt::launch_svgf_temporal(hs_ctx(p), *cam, *in, *prm, *out);
 }

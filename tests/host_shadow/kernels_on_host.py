@@ -55,6 +55,7 @@ def load():
     for name, kinds in (("temporal", ("TemporalIn", "TemporalParams", "TemporalOut")), ("variance", ("VarianceIn", "VarianceParams", "VarianceOut")),
                         ("spatial", ("SpatialIn", "SpatialParams", "SpatialOut"))):
         getattr(lib, "hs_svgf_" + name).argtypes = [C.c_void_p, C.POINTER(VxCamera)] + [C.POINTER(getattr(_abi, "VxSvgf" + k)) for k in kinds]
+    lib.hs_svgf_initial.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(_abi.VxSvgfInitialIn), C.POINTER(_abi.VxSvgfInitialOut)]
     lib.hs_shadow_temporal.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(_abi.VxShadowTemporalIn), C.POINTER(_abi.VxShadowTemporalParams),
                                        C.POINTER(_abi.VxShadowTemporalOut)]
     lib.hs_shadow_filter.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(_abi.VxShadowFilterIn), C.POINTER(_abi.VxShadowFilterParams), C.c_void_p]
@@ -160,6 +161,13 @@ class HostKernels:
         return out
 
     # SVGF denoiser passes (csrc/denoise.cu): same call shapes as oracle.vxo.svgf_*
+    def svgf_initial(self, cam, gbuf, diffuse, out=None):
+        from voxelpathtracer_b200 import denoise
+        out = _denoise_planes(cam, ("sh", "cocg", "luma", "ao_sky")) if out is None else out
+        i, o = denoise.initial_structs(gbuf, diffuse, out, _addr)
+        assert self.lib.hs_svgf_initial(self.h, C.byref(cam), C.byref(i), C.byref(o)) == 0
+        return out
+
     def svgf_temporal(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out=None):
         from voxelpathtracer_b200 import denoise
         out = _denoise_planes(cam, ("sh", "cocg", "utility", "ao_sky")) if out is None else out

@@ -105,9 +105,9 @@ def test_still_camera_accumulates_and_the_filter_removes_noise(oracle_sequences)
         spp = fr["temporal"]["utility"][..., 0]
         sel = spp[hit & inner]                   # silhouette pixels reject their history, and their neighbours average it in
         assert np.isclose(sel, f + 1.0, atol=1e-4).mean() > 0.7 and abs(float(np.median(sel)) - (f + 1.0)) < 1e-4 and sel.max() <= f + 1.0 + 1e-4, f
-    # the blend factor is 1 / accumulated frames: frame 1's temporal SH = (history + this frame's noisy SH) / 2, the history being a
+    # the blend factor is 1 / accumulated frames: frame 1's temporal SH = (history + this frame's pre-filtered SH) / 2, the history being a
     # convex combination of the previous temporal SH at the pixel and its four neighbours: 2 * out - current lies in their envelope
-    prev, cur, got = frames[0]["temporal"]["sh"], frames[1]["diffuse"]["sh"], frames[1]["temporal"]["sh"]
+    prev, cur, got = frames[0]["temporal"]["sh"], frames[1]["initial"]["sh"], frames[1]["temporal"]["sh"]
     ok = np.isclose(frames[1]["temporal"]["utility"][..., 0], 2.0, atol=1e-4) & inner & (frames[1]["gbuf"]["t"] > 1.0)   # (the lowest rows look
     taps = np.stack([prev, np.roll(prev, 1, 0), np.roll(prev, -1, 0), np.roll(prev, 1, 1), np.roll(prev, -1, 1)])
     hist = 2.0 * got - cur                               # at the block the camera stands in, t = 1e-4: reprojection is ill-conditioned there)
@@ -122,7 +122,7 @@ def test_still_camera_accumulates_and_the_filter_removes_noise(oracle_sequences)
     assert r_t < r_raw and r_s[-1] < 0.5 * r_raw and r_s[0] < r_t
     m_raw = float(np.mean([f_["diffuse"]["sh"][hit][:, 3].mean() for f_ in frames]))      # 1-spp frames: compare with the three-frame mean
     m_out = float(fr["spatial"][-1]["sh"][hit][:, 3].mean())
-    assert abs(m_out - m_raw) < 0.35 * abs(m_raw)
+    assert 0.4 * m_raw < m_out < 1.5 * m_raw             # edge-stopping weights cut the heavy tail of 1-spp fireflies: not mean-preserving
 
 
 def test_constant_planes_are_a_fixed_point():
@@ -255,6 +255,9 @@ class _RendererPasses:
             self.r.sync()              # device planes are complete after vxpt_sync()
         return {k: (v.cpu().numpy() if self.device else v) for k, v in planes.items()}
 
+    def svgf_initial(self, cam, g, d):
+        return self._host(self.r.svgf_initial(cam, self._in(g), self._in(d), self._out(cam, ("sh", "cocg", "luma", "ao_sky"))))
+
     def svgf_temporal(self, cam, g, pg, d, pt, params):
         return self._host(self.r.svgf_temporal(cam, self._in(g), self._in(pg), self._in(d), self._in(pt), params, self._out(cam, ("sh", "cocg", "utility", "ao_sky"))))
 
@@ -280,7 +283,10 @@ def test_gpu_denoiser_equals_the_oracle(renderer, oracle_sequences, scene_tables
         pfc = prev_fc or fc
         tp = denoise.temporal_params(pfc.view().T.reshape(16), pfc.projection().T.reshape(16))
         g = {k: fr["gbuf"][k] for k in ("t", "normal_id", "block_id")}
-        t = p.svgf_temporal(fr["cam"], g, prev_g or g, fr["diffuse"], prev_t, tp)
+        pre = p.svgf_initial(fr["cam"], g, fr["diffuse"])
+        for k in fr["initial"]:
+            _close(pre[k], fr["initial"][k], (name, f, "initial", k))
+        t = p.svgf_temporal(fr["cam"], g, prev_g or g, fr["initial"], prev_t, tp)
         for k in fr["temporal"]:
             _close(t[k], fr["temporal"][k], (name, f, "temporal", k))
         v = p.svgf_variance(fr["cam"], g, fr["temporal"], denoise.variance_params())

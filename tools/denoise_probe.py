@@ -17,7 +17,8 @@ import voxelpathtracer_b200 as vx  # noqa: E402
 from voxelpathtracer_b200 import assets, camera, denoise, world  # noqa: E402
 
 # algorithmic bytes per pixel: inputs read once + outputs written once (fp32 planes; ids 1 B)
-BYTES = {"svgf_temporal": (4 + 1 + 1) * 2 + 16 + 8 + 4 + 8 + 16 + 8 + 12 + 8 + 16 + 8 + 12 + 8,
+BYTES = {"svgf_initial": 4 + 1 + (16 + 8 + 4 + 8) * 2,
+         "svgf_temporal": (4 + 1 + 1) * 2 + 16 + 8 + 4 + 8 + 16 + 8 + 12 + 8 + 16 + 8 + 12 + 8,
          "svgf_variance": 4 + 1 + 16 + 8 + 12 + 16 + 8 + 4,
          "svgf_spatial": 4 + 1 + 16 + 8 + 4 + 8 + 12 + 16 + 8 + 4 + 8,
          "shadow_temporal": 4 + 1 + 4 + 1 + 4 + 4 + 4 + 4 + 4,
@@ -58,7 +59,8 @@ def main():
                 ms[name].append(r.stats()["last_ms"])
             return out
 
-        t = timed("svgf_temporal", lambda: r.svgf_temporal(cam, g, prev_g or g, d, prev_t, denoise.temporal_params(view, proj),
+        pre = timed("svgf_initial", lambda: r.svgf_initial(cam, g, d, r.alloc_denoise(W, H, ("sh", "cocg", "luma", "ao_sky"), device=True)))
+        t = timed("svgf_temporal", lambda: r.svgf_temporal(cam, g, prev_g or g, pre, prev_t, denoise.temporal_params(view, proj),
                                                             r.alloc_denoise(W, H, ("sh", "cocg", "utility", "ao_sky"), device=True)))
         v = timed("svgf_variance", lambda: r.svgf_variance(cam, g, t, denoise.variance_params(), r.alloc_denoise(W, H, ("sh", "cocg", "variance"), device=True)))
         cur = {"sh": v["sh"], "cocg": v["cocg"], "variance": v["variance"], "ao_sky": t["ao_sky"]}

@@ -85,6 +85,14 @@ class VxMaterialOut(C.Structure):
     _fields_ = [("albedo", C.c_void_p), ("normal", C.c_void_p), ("pbr", C.c_void_p), ("texture_ao", C.c_void_p)]
 
 
+class VxSvgfInitialIn(C.Structure):
+    _fields_ = [("current", VxGBuffer), ("sh", C.c_void_p), ("cocg", C.c_void_p), ("luma", C.c_void_p), ("ao_sky", C.c_void_p)]
+
+
+class VxSvgfInitialOut(C.Structure):
+    _fields_ = [("sh", C.c_void_p), ("cocg", C.c_void_p), ("luma", C.c_void_p), ("ao_sky", C.c_void_p)]
+
+
 class VxSvgfTemporalIn(C.Structure):
     _fields_ = [("current", VxGBuffer), ("previous", VxGBuffer), ("sh", C.c_void_p), ("cocg", C.c_void_p), ("luma", C.c_void_p),
                 ("ao_sky", C.c_void_p), ("prev_sh", C.c_void_p), ("prev_cocg", C.c_void_p), ("prev_utility", C.c_void_p), ("prev_ao_sky", C.c_void_p)]
@@ -187,6 +195,7 @@ EXPORTS = {
     "vxpt_set_gbuffer_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "vxpt_generate_gbuffer": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams),
                                         C.POINTER(VxMaterialOut)]),
+    "vxpt_svgf_initial": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfInitialIn), C.POINTER(VxSvgfInitialOut)]),
     "vxpt_svgf_temporal": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfTemporalIn), C.POINTER(VxSvgfTemporalParams),
                                      C.POINTER(VxSvgfTemporalOut)]),
     "vxpt_svgf_variance": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfVarianceIn), C.POINTER(VxSvgfVarianceParams),

@@ -670,6 +670,26 @@ template <class F> int timed_launch(vxpt_ctx* c, F&& launch) {
 
 extern "C" {
 
+int vxpt_svgf_initial(vxpt_handle c, const VxCamera* cam, const VxSvgfInitialIn* in, const VxSvgfInitialOut* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!in || !out || !in->current.t || !in->current.normal_id || !in->sh || !in->cocg || !in->luma || !in->ao_sky)
+        return fail(VXPT_E_INVALID, "NULL argument (t, normal_id and the GI pass's sh / cocg / luma / ao_sky planes are required)");
+    VX_CUDA(cudaSetDevice(c->device));
+    SvgfIO s(c, cam);
+    Plane *t = s.in(in->current.t, 4), *n = s.in(in->current.normal_id, 1);
+    Plane *sh = s.in(in->sh, 16), *cc = s.in(in->cocg, 8), *lu = s.in(in->luma, 4), *ao = s.in(in->ao_sky, 8);
+    Plane *osh = s.out(out->sh, 16), *occ = s.out(out->cocg, 8), *olu = s.out(out->luma, 4), *oao = s.out(out->ao_sky, 8);
+    if ((rc = s.begin())) return rc;
+    if (cam->row_end == cam->row_begin) return VXPT_OK;
+    VxSvgfInitialIn id{};
+    id.current = VxGBuffer{(float*)t->dev, (uint8_t*)n->dev, nullptr, nullptr, nullptr};
+    id.sh = (const float*)sh->dev; id.cocg = (const float*)cc->dev; id.luma = (const float*)lu->dev; id.ao_sky = (const float*)ao->dev;
+    const VxSvgfInitialOut od{(float*)osh->dev, (float*)occ->dev, (float*)olu->dev, (float*)oao->dev};
+    if ((rc = timed_launch(c, [&] { return launch_svgf_initial(c, *cam, id, od); }))) return rc;
+    return s.end(c);
+}
+
 int vxpt_svgf_temporal(vxpt_handle c, const VxCamera* cam, const VxSvgfTemporalIn* in, const VxSvgfTemporalParams* p, const VxSvgfTemporalOut* out) {
     int rc = check_svgf(c, cam);
     if (rc) return rc;

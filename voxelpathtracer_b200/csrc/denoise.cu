@@ -84,6 +84,56 @@ struct SvgfPlanes {  // device pointers of one call; unused members are null
     float *o_sh, *o_cocg, *o_utility, *o_variance, *o_ao;
 };
 
+// ============================================================================================= pre-temporal 3x3 pass
+// Spatial3x3Initial.glsl main() :102-176
+__global__ void __launch_bounds__(256) svgf_initial_kernel(const __grid_constant__ CameraDev cam, const SvgfPlanes pl) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const int W = cam.width, H = cam.height;
+    const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
+    const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
+    const Bilinear bc = bilinear_at(W, H, u, v);
+    const V3 origin = ray_origin(cam);
+    const V3 bp = origin + normalize3(ray_direction_at(cam, u, v)) * tex1(pl.t, bc);
+    const V3 bn = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const float4 bsh = tex4(pl.sh, bc);
+    const float2 bcc = tex2(pl.cocg, bc), bao = tex2(pl.ao, bc);
+    const float blum = sh_to_y(bsh);
+    float4 tsh = bsh;
+    float2 tcc = bcc, tao = bao;
+    float tw = 1.0f, taw = 1.0f;
+#pragma unroll 1
+    for (int x = -1; x <= 1; ++x)
+#pragma unroll 1
+        for (int y = -1; y <= 1; ++y) {
+            if (x == 0 && y == 0) continue;
+            const float su = u + ((float)x * 1.0f) * tsx, sv = v + ((float)y * 1.0f) * tsy;
+            if (!(su > 0.0f && su < 1.0f && sv > 0.0f && sv < 1.0f)) continue;
+            const Bilinear bs = bilinear_at(W, H, su, sv);
+            const V3 sp = origin + normalize3(ray_direction_at(cam, su, sv)) * tex1(pl.t, bs);
+            const V3 df = mk3(fabsf(sp.x - bp.x), fabsf(sp.y - bp.y), fabsf(sp.z - bp.z));
+            if (!(dot3(df, df) < 1.0f)) continue;
+            const float4 ssh = tex4(pl.sh, bs);
+            const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
+            const float nw = pow01_cr(fmaxf(dot3(bn, sn), 0.0f), 16.0f);
+            const float lw = fabsf(sh_to_y(ssh) - blum) / 4.0f;
+            float w = fmaxf(exp_cr(-lw - nw), 0.01f);  // sic: the normal term is subtracted in the exponent
+            const float xw = x == 0 ? 1.0f : 2.0f / 3.0f, yw = y == 0 ? 1.0f : 2.0f / 3.0f;
+            w = clampf(fmaxf((xw * yw) * w, 0.01f), 0.0f, 1.0f);
+            tsh = tsh + ssh * w;
+            tcc = tcc + tex2(pl.cocg, bs) * w;
+            tw += w;
+            tao = tao + tex2(pl.ao, bs) * w;
+            taw += w;
+        }
+    tw = fmaxf(tw, 0.01f);
+    const size_t px = (size_t)prow * W + i;
+    if (pl.o_sh) reinterpret_cast<float4*>(pl.o_sh)[px] = tsh / tw;
+    if (pl.o_cocg) reinterpret_cast<float2*>(pl.o_cocg)[px] = tcc / tw;
+    if (pl.o_ao) reinterpret_cast<float2*>(pl.o_ao)[px] = tao / fmaxf(taw, 0.01f);
+    if (pl.o_utility) pl.o_utility[px] = tex1(pl.luma, bc);
+}
+
 // ============================================================================================= temporal accumulation
 struct TemporalDev {
     float prev_vp[16];  // u_PrevProjection * u_PrevView, multiplied on the host in glm's order
@@ -554,6 +604,17 @@ static CameraDev svgf_camera(const VxCamera& cam) {
     return cd;
 }
 static dim3 svgf_grid(const VxCamera& cam) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8); }
+
+int launch_svgf_initial(vxpt_ctx* c, const VxCamera& cam, const VxSvgfInitialIn& in, const VxSvgfInitialOut& out) {
+    SvgfPlanes pl{};
+    pl.t = in.current.t; pl.nid = in.current.normal_id;
+    pl.sh = in.sh; pl.cocg = in.cocg; pl.luma = in.luma; pl.ao = in.ao_sky;
+    pl.o_sh = out.sh; pl.o_cocg = out.cocg; pl.o_utility = out.luma; pl.o_ao = out.ao_sky;
+    VX_LAUNCH(svgf_initial_kernel, svgf_grid(cam), 256, c->stream, svgf_camera(cam), pl);
+    c->launches += 1;
+    VX_CUDA(cudaGetLastError());
+    return VXPT_OK;
+}
 
 int launch_svgf_temporal(vxpt_ctx* c, const VxCamera& cam, const VxSvgfTemporalIn& in, const VxSvgfTemporalParams& p, const VxSvgfTemporalOut& out) {
     TemporalDev d;

@@ -175,6 +175,7 @@ int launch_ambient(vxpt_ctx* c, const float player[3], int frame, unsigned* aggr
 // gbuffer.cu
 int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxMaterialParams& p, const VxMaterialOut& out_dev);
 // denoise.cu
+int launch_svgf_initial(vxpt_ctx* c, const VxCamera& cam, const VxSvgfInitialIn& in_dev, const VxSvgfInitialOut& out_dev);
 int launch_svgf_temporal(vxpt_ctx* c, const VxCamera& cam, const VxSvgfTemporalIn& in_dev, const VxSvgfTemporalParams& p, const VxSvgfTemporalOut& out_dev);
 int launch_svgf_variance(vxpt_ctx* c, const VxCamera& cam, const VxSvgfVarianceIn& in_dev, const VxSvgfVarianceParams& p, const VxSvgfVarianceOut& out_dev);
 int launch_svgf_spatial(vxpt_ctx* c, const VxCamera& cam, const VxSvgfSpatialIn& in_dev, const VxSvgfSpatialParams& p, const VxSvgfSpatialOut& out_dev);

@@ -3,7 +3,7 @@ from dicts of planes.  The same structs drive the library (Renderer.svgf_*), the
 `address` is injected: it maps a numpy array or torch tensor to its raw address."""
 import numpy as np
 
-from .abi import (VxGBuffer, VxShadowFilterIn, VxShadowFilterParams, VxShadowTemporalIn, VxShadowTemporalOut, VxShadowTemporalParams, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
+from .abi import (VxGBuffer, VxShadowFilterIn, VxShadowFilterParams, VxShadowTemporalIn, VxShadowTemporalOut, VxShadowTemporalParams, VxSvgfInitialIn, VxSvgfInitialOut, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
                   VxSvgfVarianceIn, VxSvgfVarianceOut, VxSvgfVarianceParams)
 
 ATROUS_STEPS = (16, 8, 4, 2, 1)          # Core/Pipeline.cpp:2482-2487
@@ -31,11 +31,21 @@ def variance_params(do_spatial=True, aggressive_disocclusion=True):
     return p
 
 
-def spatial_params(step, time=0.0, large_kernel=False, do_spatial=True, aggressive_disocclusion=True, color_phi_bias=2.0, resolution_scale=0.0):
+def spatial_params(step, time=0.0, large_kernel=False, do_spatial=True, aggressive_disocclusion=True, color_phi_bias=3.325, resolution_scale=0.25):
+    """Defaults: ColorPhiBias 3.325, DiffuseIndirectSuperSampleRes 0.25 (Core/Pipeline.cpp:78,85)."""
     p = VxSvgfSpatialParams()
     p.step, p.large_kernel, p.do_spatial, p.aggressive_disocclusion = int(step), int(bool(large_kernel)), int(bool(do_spatial)), int(bool(aggressive_disocclusion))
     p.color_phi_bias, p.time, p.resolution_scale = float(color_phi_bias), float(time), float(resolution_scale)
     return p
+
+
+def initial_structs(gbuf, diffuse, out, address):
+    i = VxSvgfInitialIn()
+    i.current = _gb(gbuf, address)
+    i.sh, i.cocg, i.luma, i.ao_sky = (address(diffuse[k]) for k in ("sh", "cocg", "luma", "ao_sky"))
+    o = VxSvgfInitialOut()
+    o.sh, o.cocg, o.luma, o.ao_sky = (address(out.get(k)) for k in ("sh", "cocg", "luma", "ao_sky"))
+    return i, o
 
 
 def temporal_structs(gbuf, prev_gbuf, diffuse, prev_temporal, out, address):

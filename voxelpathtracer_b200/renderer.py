@@ -281,6 +281,13 @@ class Renderer:
         shapes = denoise.plane_shapes(width, height)
         return {k: self.alloc(shapes[k], np.float32, device, pinned) for k in names}
 
+    def svgf_initial(self, cam, gbuf, diffuse, out):
+        """Spatial3x3Initial.glsl (vxpt_svgf_initial): the pre-temporal 3x3 pass over this frame's raw GI planes."""
+        from . import denoise
+        i, o = denoise.initial_structs(gbuf, diffuse, out, _ptr)
+        check(self.lib.vxpt_svgf_initial(self.handle, C.byref(cam), C.byref(i), C.byref(o)))
+        return out
+
     def svgf_temporal(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, params, out):
         from . import denoise
         i, o = denoise.temporal_structs(gbuf, prev_gbuf, diffuse, prev_temporal, out, _ptr)
@@ -313,11 +320,14 @@ class Renderer:
         check(self.lib.vxpt_shadow_filter(self.handle, C.byref(cam), C.byref(i), C.byref(params), _ptr(out)))
         return out
 
-    def svgf_denoise(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, temporal_params, time=0.0, steps=None, device=False):
-        """The reference's whole SVGF chain for one frame (Core/Pipeline.cpp:2335-2596): temporal -> variance -> five a-trous passes
-        ping-ponging between two plane sets.  Returns (denoised planes, temporal planes to hand in as prev_temporal next frame)."""
+    def svgf_denoise(self, cam, gbuf, prev_gbuf, diffuse, prev_temporal, temporal_params, time=0.0, steps=None, device=False, pre_pass=True):
+        """The reference's whole SVGF chain for one frame (Core/Pipeline.cpp:2284-2596): pre-temporal 3x3 pass (PreTemporalSpatialPass,
+        on by default) -> temporal -> variance -> five a-trous passes ping-ponging between two plane sets.  Returns (denoised planes,
+        temporal planes to hand in as prev_temporal next frame)."""
         from . import denoise
         W, H = cam.width, cam.height
+        if pre_pass:
+            diffuse = self.svgf_initial(cam, gbuf, diffuse, self.alloc_denoise(W, H, ("sh", "cocg", "luma", "ao_sky"), device))
         temporal = self.svgf_temporal(cam, gbuf, prev_gbuf, diffuse, prev_temporal, temporal_params,
                                       self.alloc_denoise(W, H, ("sh", "cocg", "utility", "ao_sky"), device))
         var = self.svgf_variance(cam, gbuf, temporal, denoise.variance_params(), self.alloc_denoise(W, H, ("sh", "cocg", "variance"), device))

@@ -81,3 +81,64 @@ def test_packed_layout_regions_do_not_overlap():
     assert [p[0] for p in multigpu.plane_table(True)] == [p[0] for p in multigpu.PLANES]
     # virtual plane bases stay inside the packed buffer for every rank: region_bytes >= any single plane's slab
     assert all(total >= 135 * 1920 * p[1] for p in multigpu.PLANES)
+
+
+def _edit_worker(rank, ws, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from voxelpathtracer_b200 import world
+
+        class Recorder:            # stands in for the Renderer: the ABI calls a rank would make
+            def __init__(self):
+                self.calls = []
+
+            def set_blocks(self, xyz, ids):
+                self.calls.append(("set_blocks", xyz.copy(), ids.copy()))
+
+            def build_distance_field(self):
+                self.calls.append(("build",))
+
+        w = world.World()
+        r = Recorder()
+        script = [[(10, 20, 30, 3), (383, 127, 383, 12), (0, 0, 0, 255)], [], [(10, 20, 30, 0)]]
+        for edits in script:
+            xyz, ids = multigpu.broadcast_edits(edits if rank == 0 else None)
+            multigpu.apply_edits(r, w, xyz, ids)
+        ok = w.get_block(10, 20, 30) == 0 and w.get_block(383, 127, 383) == 12 and w.get_block(0, 0, 0) == 255 and int((w.data != 0).sum()) == 2
+        ok = ok and [c[0] for c in r.calls] == ["set_blocks", "build", "set_blocks", "build"] and r.calls[0][1].dtype == np.int16
+        ok = ok and r.calls[0][1].tolist() == [[10, 20, 30], [383, 127, 383], [0, 0, 0]] and r.calls[0][2].tolist() == [3, 12, 255]
+        bad = False
+        if rank == 0:
+            try:
+                multigpu.broadcast_edits([(384, 0, 0, 1)])
+            except ValueError:
+                bad = True
+        q.put((rank, bool(ok and (bad or rank != 0))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_edit_list_broadcast_over_gloo():
+    """Config 5 on N ranks: the edit list travels (7 bytes per edit), every rank edits its replica and rebuilds its own distance field."""
+    ws = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_edit_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(r, True) for r in range(ws)]
+
+
+def test_stencil_rows_cover_the_slab_plus_halo():
+    for h, ws, halo in [(1080, 8, 28), (360, 3, 17), (90, 2, 100)]:
+        for r in range(ws):
+            b, e = multigpu.slab_rows(h, ws, r)
+            sb, se = multigpu.stencil_rows(h, ws, r, halo)
+            assert sb == max(b - halo, 0) and se == min(e + halo, h) and sb <= b and se >= e

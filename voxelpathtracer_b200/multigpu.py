@@ -58,6 +58,52 @@ def gather_planes(planes, height, group=None):
     return planes
 
 
+def broadcast_edits(edits, src=0, group=None, device=None):
+    """Block edits on a replicated world (BASELINE config 5 on N GPUs): the rank that took the player's input holds the
+    edit list [(x, y, z, block), ...]; it is broadcast as 7 bytes per edit (3 x int16 + 1 x uint8) and every rank applies it to its own
+    copy and rebuilds its own distance field (tens of microseconds) — instead of broadcasting the 18.9 MB field.  Returns
+    (xyz int16 [n, 3], ids uint8 [n]) on every rank, ready for Renderer.set_blocks; other ranks pass edits=None."""
+    ws = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if rank == src:
+        arr = np.asarray(edits, dtype=np.int64).reshape(-1, 4)
+        if arr.size and (arr[:, :3].min() < 0 or (arr[:, :3] >= np.array([abi.WORLD_SIZE_X, abi.WORLD_SIZE_Y, abi.WORLD_SIZE_Z])).any()
+                         or arr[:, 3].min() < 0 or arr[:, 3].max() > 255):
+            raise ValueError("edit outside the world / block id outside 0..255")
+        xyz, ids = arr[:, :3].astype(np.int16), arr[:, 3].astype(np.uint8)
+    else:
+        xyz, ids = np.zeros((0, 3), np.int16), np.zeros(0, np.uint8)
+    if ws == 1:
+        return xyz, ids
+    n = torch.tensor([xyz.shape[0]], dtype=torch.int64, device=device)
+    dist.broadcast(n, src=src, group=group)
+    count = int(n.item())
+    payload = torch.zeros(count * 7, dtype=torch.uint8, device=device)
+    if rank == src and count:
+        packed = np.concatenate([xyz.view(np.uint8).reshape(count, 6), ids.reshape(count, 1)], axis=1).reshape(-1)
+        payload.copy_(torch.from_numpy(packed))
+    if count:
+        dist.broadcast(payload, src=src, group=group)
+    raw = payload.cpu().numpy().reshape(count, 7)
+    return np.ascontiguousarray(raw[:, :6]).view(np.int16).reshape(count, 3).copy(), raw[:, 6].copy()
+
+
+def apply_edits(renderer, world, xyz, ids):
+    """Every rank: the edits into the host grid, the device grid (vxpt_set_blocks) and a distance-field rebuild."""
+    for (x, y, z), b in zip(xyz, ids):
+        world.set_block(int(x), int(y), int(z), int(b))
+    if len(ids):
+        renderer.set_blocks(xyz, ids)
+        renderer.build_distance_field()
+
+
+def stencil_rows(height, world_size, rank, halo):
+    """Rows [b - halo, e + halo) clipped to the frame: what a rank must hold of the input planes to run a stencil pass (the denoisers of
+    SURVEY.md §8 f2) on its slab.  The a-trous chain reaches 16 * (1 + 2.4 * resolution_scale) + 1 rows per pass at its widest step."""
+    b, e = slab_rows(height, world_size, rank)
+    return max(b - halo, 0), min(e + halo, height)
+
+
 PLANES = (  # name, bytes per pixel, torch dtype name, trailing shape — fp32 planes (VXPT_OPT_TEXEL_FORMAT = 0)
     ("g_t", 4, "float32", ()), ("g_normal_id", 1, "uint8", ()), ("g_block_id", 1, "uint8", ()), ("g_inv_t", 4, "float32", ()),
     ("s_shadow", 1, "uint8", ()), ("s_transversal", 4, "float32", ()),

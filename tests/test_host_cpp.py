@@ -42,7 +42,8 @@ def test_host_mirror_compiles_against_the_abi():
     assert os.path.exists(exe)
     src = open(os.path.join(PKG, "host", "VoxelRT.h")).read()
     for name in ("class World", "GetBlock", "SetBlock", "Buffer", "InitializeDistanceGenerator", "GenerateDistanceField", "GenerateWorld",
-                 "SaveWorld", "LoadWorld", "BlockDataSSBO", "BlueNoiseDataSSBO", "FPSCamera", "GetTAAJitter"):
+                 "SaveWorld", "LoadWorld", "BlockDataSSBO", "BlueNoiseDataSSBO", "FPSCamera", "GetTAAJitter", "Raycast", "RaycastDetect",
+                 "GetViewProjection"):
         assert name in src, name   # the reference's names for this path
 
 
@@ -89,5 +90,65 @@ def test_headless_cpp_equals_python_driver(use_plains, plains_columns):
         r.set_block(192, 70, 200, world.STONE)
         r.build_distance_field()
         assert fnv1a(r.download_distance_field()) == got["df_after_edit"]
+    finally:
+        r.close()
+
+
+def test_view_projection_of_the_two_host_mirrors():
+    """camera.FpsCamera.view_projection_f32 == the textbook lookAt / perspective to float precision, and inverts the inv_view / inv_proj the
+    trace passes receive (the C++ mirror's GetViewProjection is the same code line for line; the GPU test below compares their effects)."""
+    fc = camera.FpsCamera(position=(100.25, 61.5, 99.75), yaw_deg=37.0, pitch_deg=-12.0, aspect=160 / 90)
+    view, proj = fc.view_projection_f32()
+    assert np.allclose(view.reshape(4, 4).T, fc.view(), atol=2e-5) and np.allclose(proj.reshape(4, 4).T, fc.projection(), atol=1e-6)
+    iv, ip = fc.inverse_matrices()
+    assert np.allclose(view.reshape(4, 4).T.astype(np.float64) @ iv.astype(np.float64), np.eye(4), atol=1e-5)
+    assert np.allclose(proj.reshape(4, 4).T.astype(np.float64) @ ip.astype(np.float64), np.eye(4), atol=1e-5)
+
+
+def test_camera_matrices_of_the_two_host_mirrors_are_bit_identical(tmp_path):
+    abi.load()
+    cc = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "camera")
+    subprocess.run([cc, "-std=c++17", "-O2", "-Wall", "-Werror", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "cpp", "camera_main.cpp"),
+                    "-L" + PKG, "-lvxpt", "-Wl,-rpath," + PKG], check=True)
+    rng = np.random.RandomState(4)
+    poses = [(192.0, 75.0, 192.0, 90.0, -20.0, 16.0 / 9.0)] + [tuple(np.float32(v) for v in (rng.uniform(1, 380), rng.uniform(1, 120), rng.uniform(1, 380),
+                                                                                          rng.uniform(-180, 180), rng.uniform(-85, 85))) + (float(rng.choice([16 / 9, 4 / 3, 160 / 90, 1.0])),)
+                                                               for _ in range(40)]
+    text = "\n".join("%.9g %.9g %.9g %.9g %.9g %.17g" % p for p in poses) + "\n"
+    lines = [ln for ln in subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.split("\n") if ln.strip()]
+    assert len(lines) == len(poses)
+    for p, ln in zip(poses, lines):
+        got = np.array([int(h, 16) for h in ln.split()], dtype=np.uint32).view(np.float32).reshape(4, 16)
+        fc = camera.FpsCamera(position=p[:3], yaw_deg=float(p[3]), pitch_deg=float(p[4]), aspect=float(p[5]))
+        view, proj = fc.view_projection_f32()
+        cam = fc.vx_camera(64, 36)
+        assert np.array_equal(got[0], view) and np.array_equal(got[1], proj), p
+        assert np.array_equal(got[2], np.array(list(cam.inv_view), np.float32)) and np.array_equal(got[3], np.array(list(cam.inv_proj), np.float32)), p
+
+
+@pytest.mark.gpu
+def test_headless_cpp_shadow_filters_equal_python_driver():
+    """The C++ host mirror drives vxpt_shadow_temporal / vxpt_shadow_filter on its last traced frame; the Python driver repeats the calls."""
+    from voxelpathtracer_b200 import denoise
+    exe = build_headless()
+    W, H = 160, 90
+    out = subprocess.run([exe, str(W), str(H)], capture_output=True, text=True, check=True).stdout.split("\n")
+    line = [ln.split() for ln in out if ln.startswith("shadow_filters")][0]
+    assert line[1] != "failed", out
+    got = {line[i]: int(line[i + 1], 16) for i in range(1, len(line), 2)}
+    r = vx.Renderer(0)
+    try:
+        r.upload_world(world.generate_superflat())
+        r.build_distance_field()
+        fc = camera.FpsCamera(yaw_deg=90.0, pitch_deg=-20.0, aspect=W / H)
+        cam = fc.vx_camera(W, H)
+        sun = np.array([-0.66896474, 0.46841538, 0.57735026], np.float32)
+        g = r.trace_primary(cam, vx.primary_params(350, camera.taa_jitter(2)), r.alloc_gbuffer(W, H))
+        s = r.trace_shadow(cam, g, vx.shadow_params(sun, frame=2, soft=False), r.alloc_shadow(W, H))
+        zero = {"shadow": np.zeros((H, W), np.float32), "frames": np.zeros((H, W), np.float32)}
+        t = r.shadow_temporal(cam, g, g, s, zero, denoise.shadow_temporal_params(*fc.view_projection_f32()), r.alloc_denoise(W, H, ("shadow", "frames")))
+        f = r.shadow_filter(cam, g, t, s["transversal"], denoise.shadow_filter_params(1.0), np.zeros((H, W), np.float32))
+        assert fnv1a(t["shadow"]) == got["temporal"] and fnv1a(t["frames"]) == got["frames"] and fnv1a(f) == got["filtered"]
     finally:
         r.close()

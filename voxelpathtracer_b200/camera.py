@@ -83,6 +83,29 @@ class FpsCamera:
         inv_proj[3, 3] = f32(A / B)
         return inv_view, inv_proj
 
+    def view_projection_f32(self):
+        """(view[16], projection[16]) float32, column-major: u_View / u_Projection of this frame = u_PrevView / u_PrevProjection of the next
+        frame's temporal filters.  Same formulas, in the same order, as the C++ host mirror (FPSCamera::GetViewProjection), so both hosts
+        hand bit-identical matrices to the ABI (view() / projection() above are the float64 textbook forms)."""
+        f = self.front
+        f = f / math.sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2])
+        s = np.array([f[1] * 0.0 - f[2] * 1.0, f[2] * 0.0 - f[0] * 0.0, f[0] * 1.0 - f[1] * 0.0])
+        s = s / math.sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2])
+        u = np.array([s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]])
+        e = self.position.astype(f32).astype(np.float64)
+        view, proj = np.zeros(16, dtype=np.float32), np.zeros(16, dtype=np.float32)
+        for c in range(3):
+            view[4 * c + 0], view[4 * c + 1], view[4 * c + 2] = f32(s[c]), f32(u[c]), f32(-f[c])
+        view[12] = f32(-((s[0] * e[0] + s[1] * e[1]) + s[2] * e[2]))
+        view[13] = f32(-((u[0] * e[0] + u[1] * e[1]) + u[2] * e[2]))
+        view[14] = f32((f[0] * e[0] + f[1] * e[1]) + f[2] * e[2])
+        view[15] = 1.0
+        fov, aspect, zn, zf = float(self.fov), float(self.aspect), float(self.z_near), float(self.z_far)
+        t = math.tan(fov * math.pi / 180.0 / 2.0)
+        proj[0], proj[5] = f32(1.0 / (aspect * t)), f32(1.0 / t)
+        proj[10], proj[11], proj[14] = f32(-(zf + zn) / (zf - zn)), -1.0, f32(-(2.0 * zf * zn) / (zf - zn))
+        return view, proj
+
     def vx_camera(self, width, height, row_begin=0, row_end=None, interleave_n=0, interleave_rank=0, band_rows=0):
         """inv_view / inv_projection as Pipeline.cpp:1823-1824 hands them to the shaders.  interleave_*: see VxCamera."""
         cam = VxCamera()

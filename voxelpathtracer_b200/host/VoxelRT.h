@@ -235,7 +235,8 @@ inline Mat4 InverseRigid(const float s[3], const float u[3], const float f[3], c
 
 class FPSCamera {
 public:
-    FPSCamera(float fov, float aspect, float zNear = 0.1f, float zFar = 1000.0f) : m_Fov(fov), m_Aspect(aspect), m_zNear(zNear), m_zFar(zFar) {}
+    // fov / aspect / near / far are kept in double like the Python mirror's (camera.FpsCamera), so both derive bit-identical matrices
+    FPSCamera(double fov, double aspect, double zNear = 0.1, double zFar = 1000.0) : m_Fov(fov), m_Aspect(aspect), m_zNear(zNear), m_zFar(zFar) {}
     void SetPosition(float x, float y, float z) { m_Position[0] = x; m_Position[1] = y; m_Position[2] = z; }
     // FPSCamera::UpdateOnMouseMovement (Core/FpsCamera.cpp:66-70)
     void SetYawPitch(float yaw_deg, float pitch_deg) {
@@ -268,11 +269,40 @@ public:
         cam.width = width; cam.height = height; cam.row_begin = 0; cam.row_end = height;
         return cam;
     }
+    // u_View / u_Projection (glm::lookAt, glm::perspective; Core/FpsCamera.cpp:23-24,150-163), column-major: what a frame hands to the NEXT
+    // frame's temporal filters as u_PrevView / u_PrevProjection.  Same formulas, in the same order, as camera.FpsCamera.view_projection_f32.
+    void GetViewProjection(float view[16], float proj[16]) const {
+        double f[3] = {m_Front[0], m_Front[1], m_Front[2]};
+        double fl = std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+        for (double& c : f) c /= fl;
+        double s[3] = {f[1] * 0.0 - f[2] * 1.0, f[2] * 0.0 - f[0] * 0.0, f[0] * 1.0 - f[1] * 0.0};
+        double sl = std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+        for (double& c : s) c /= sl;
+        double u[3] = {s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]};
+        const double e[3] = {m_Position[0], m_Position[1], m_Position[2]};
+        for (int k = 0; k < 16; ++k) view[k] = proj[k] = 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            view[4 * c + 0] = (float)s[c];
+            view[4 * c + 1] = (float)u[c];
+            view[4 * c + 2] = (float)(-f[c]);
+        }
+        view[12] = (float)(-((s[0] * e[0] + s[1] * e[1]) + s[2] * e[2]));
+        view[13] = (float)(-((u[0] * e[0] + u[1] * e[1]) + u[2] * e[2]));
+        view[14] = (float)((f[0] * e[0] + f[1] * e[1]) + f[2] * e[2]);
+        view[15] = 1.0f;
+        const double fov = m_Fov, aspect = m_Aspect, zn = m_zNear, zf = m_zFar;
+        const double t = std::tan(fov * M_PI / 180.0 / 2.0);
+        proj[0] = (float)(1.0 / (aspect * t));
+        proj[5] = (float)(1.0 / t);
+        proj[10] = (float)(-(zf + zn) / (zf - zn));
+        proj[11] = -1.0f;
+        proj[14] = (float)(-(2.0 * zf * zn) / (zf - zn));
+    }
     float m_Position[3] = {192.0f, 75.0f, 192.0f};  // Pipeline.cpp:1500
     float m_Front[3] = {0.0f, 0.0f, 1.0f};
 
 private:
-    float m_Fov, m_Aspect, m_zNear, m_zFar;
+    double m_Fov, m_Aspect, m_zNear, m_zFar;
 };
 
 // TAAJitter.cpp:6-47

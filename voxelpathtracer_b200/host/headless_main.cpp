@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
     world.DownloadDistanceField(df);
     std::printf("df %016" PRIx64 "\n", fnv1a(df.data(), df.size()));
 
-    FPSCamera camera(60.0f, (float)W / (float)H);
+    FPSCamera camera(60.0, (double)W / (double)H);
     camera.SetYawPitch(90.0f, -20.0f);
     VxCamera cam = camera.GetVxCamera(W, H);
     std::vector<float> t((size_t)W * H), inv_t((size_t)W * H), transversal((size_t)W * H);
@@ -68,6 +68,27 @@ int main(int argc, char** argv) {
         if (!vx_ok(vxpt_render_frame(world.Handle(), &cam, &fp, &fo), "vxpt_render_frame")) return 1;
         std::printf("render_frame t %016" PRIx64 " normal %016" PRIx64 " block %016" PRIx64 " shadow %016" PRIx64 "\n", fnv1a(t2.data(), t2.size() * 4),
                     fnv1a(n2.data(), n2.size()), fnv1a(b2.data(), b2.size()), fnv1a(s2.data(), s2.size()));
+    }
+    // the sun-shadow filters on the last traced frame (Pipeline.cpp:2854-2944): first frame of a history, so the previous planes are zero and
+    // the previous camera is the current one.  Reported on its own line; a failure here does not stop the run.
+    {
+        const size_t n = (size_t)W * H;
+        std::vector<float> zero(n, 0.0f), st_shadow(n), st_frames(n), filtered(n);
+        VxShadowTemporalIn ti{};
+        ti.current = gbuf; ti.previous = gbuf;
+        ti.shadow = shadow.data(); ti.transversal = transversal.data(); ti.prev_shadow = zero.data(); ti.prev_frames = zero.data();
+        VxShadowTemporalParams tp{};
+        camera.GetViewProjection(tp.prev_view, tp.prev_projection);
+        VxShadowTemporalOut to{st_shadow.data(), st_frames.data()};
+        VxShadowFilterIn fi{};
+        fi.current = gbuf; fi.shadow = st_shadow.data(); fi.transversal = transversal.data(); fi.frames = st_frames.data();
+        VxShadowFilterParams fp{1.0f};
+        if (vx_ok(vxpt_shadow_temporal(world.Handle(), &cam, &ti, &tp, &to), "vxpt_shadow_temporal") &&
+            vx_ok(vxpt_shadow_filter(world.Handle(), &cam, &fi, &fp, filtered.data()), "vxpt_shadow_filter"))
+            std::printf("shadow_filters temporal %016" PRIx64 " frames %016" PRIx64 " filtered %016" PRIx64 "\n", fnv1a(st_shadow.data(), n * 4),
+                        fnv1a(st_frames.data(), n * 4), fnv1a(filtered.data(), n * 4));
+        else
+            std::printf("shadow_filters failed\n");
     }
     // place a block in front of the camera: the ABI refuses to trace over a stale field until the rebuild
     world.EditBlock(192, 70, 200, {BlockID::Stone});

@@ -382,3 +382,32 @@ def test_gpu_shadow_filters_equal_the_oracle(renderer, oracle_shadow_sequences, 
         _close(out["shadow"], fr["temporal"]["shadow"], (name, f, "shadow"))
         _close(out["frames"], fr["temporal"]["frames"], (name, f, "frames"))
         _close(filt, fr["filtered"], (name, f, "filtered"))
+
+
+@pytest.mark.gpu
+def test_headless_cpp_shadow_filters_equal_python_driver():
+    """The C++ host mirror drives vxpt_shadow_temporal / vxpt_shadow_filter on its last traced frame; the Python driver repeats the calls."""
+    import subprocess
+    from test_host_cpp import build_headless, fnv1a
+    from voxelpathtracer_b200 import world
+    exe = build_headless()
+    W, H = 160, 90
+    out = subprocess.run([exe, str(W), str(H)], capture_output=True, text=True, check=True, env=dict(os.environ, VXPT_HEADLESS_FILTERS="1")).stdout.split("\n")
+    line = [ln.split() for ln in out if ln.startswith("shadow_filters")][0]
+    assert line[1] != "failed", out
+    got = {line[i]: int(line[i + 1], 16) for i in range(1, len(line), 2)}
+    r = vx.Renderer(0)
+    try:
+        r.upload_world(world.generate_superflat())
+        r.build_distance_field()
+        fc = camera.FpsCamera(yaw_deg=90.0, pitch_deg=-20.0, aspect=W / H)
+        cam = fc.vx_camera(W, H)
+        sun = np.array([-0.66896474, 0.46841538, 0.57735026], np.float32)
+        g = r.trace_primary(cam, vx.primary_params(350, camera.taa_jitter(2)), r.alloc_gbuffer(W, H))
+        s = r.trace_shadow(cam, g, vx.shadow_params(sun, frame=2, soft=False), r.alloc_shadow(W, H))
+        zero = {"shadow": np.zeros((H, W), np.float32), "frames": np.zeros((H, W), np.float32)}
+        t = r.shadow_temporal(cam, g, g, s, zero, denoise.shadow_temporal_params(*fc.view_projection_f32()), r.alloc_denoise(W, H, ("shadow", "frames")))
+        f = r.shadow_filter(cam, g, t, s["transversal"], denoise.shadow_filter_params(1.0), np.zeros((H, W), np.float32))
+        assert fnv1a(t["shadow"]) == got["temporal"] and fnv1a(t["frames"]) == got["frames"] and fnv1a(f) == got["filtered"]
+    finally:
+        r.close()

@@ -2,7 +2,7 @@
 // 1959-2062, 2790-2852), through the C++ host mirror (VoxelRT.h) and the C ABI.  Builds a world, buffers it, generates
 // the distance field, traces primary + hard sun shadow rays for a few frames, edits a block (full rebuild) and prints
 // FNV-1a digests of the planes (tests/test_gpu_host_cpp.py compares them with the Python driver's).
-//   usage: vxpt_headless [width height [plains_columns.u8]]
+//   usage: [VXPT_HEADLESS_FILTERS=1] vxpt_headless [width height [plains_columns.u8]]
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -70,8 +70,8 @@ int main(int argc, char** argv) {
                     fnv1a(n2.data(), n2.size()), fnv1a(b2.data(), b2.size()), fnv1a(s2.data(), s2.size()));
     }
     // the sun-shadow filters on the last traced frame (Pipeline.cpp:2854-2944): first frame of a history, so the previous planes are zero and
-    // the previous camera is the current one.  Reported on its own line; a failure here does not stop the run.
-    {
+    // the previous camera is the current one.  Reported on its own line; a failure here does not stop the run.  Opt-in (VXPT_HEADLESS_FILTERS=1).
+    if (std::getenv("VXPT_HEADLESS_FILTERS")) {
         const size_t n = (size_t)W * H;
         std::vector<float> zero(n, 0.0f), st_shadow(n), st_frames(n), filtered(n);
         VxShadowTemporalIn ti{};

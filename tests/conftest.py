@@ -9,8 +9,25 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_addoption(parser):
+    parser.addoption("--host-emulation", action="store_true", default=False,
+                     help="development aid for machines without a GPU: bind the ctypes layer to tests/host_shadow/libvxpt_hostemu.so (the C ABI "
+                          "compiled by g++ against a miniature CUDA runtime, kernels run thread after thread) and run the gpu-marked tests "
+                          "that use host planes.  Says nothing about the GPU; never used by the driver's runs.")
+
+
+_EMULATED = False
+
+
 def pytest_configure(config):
+    global _EMULATED
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if config.getoption("--host-emulation"):
+        from host_shadow import hostemu
+        from voxelpathtracer_b200 import abi
+        abi.LIB_PATH = hostemu.build()
+        abi._lib = None
+        _EMULATED = True
 
 
 def _has_gpu():
@@ -22,7 +39,7 @@ def _has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
-    if _has_gpu():
+    if _has_gpu() or _EMULATED:
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:

@@ -143,6 +143,28 @@ def test_renderer_wrappers_call_through_with_a_stub_library():
     agg, per = r.estimate_ambient_sound((1.0, 2.0, 3.0), 7)
     assert agg == 0 and per.shape == (32,)
     assert calls == ["vxpt_set_albedo_alpha_mips", "vxpt_trace_rays", "vxpt_player_shadowed", "vxpt_estimate_ambient_sound"]
+    # the passes on either side of the path
+    from voxelpathtracer_b200 import denoise
+    del calls[:]
+    W, H = 32, 18
+    fc = camera.FpsCamera(aspect=W / H)
+    cam = fc.vx_camera(W, H)
+    r.set_gbuffer_textures(*[np.zeros((2, abi.MIP_CHAIN_TEXELS, 4), np.uint8)] * 3)
+    g = r.alloc_gbuffer(W, H)
+    m = r.generate_gbuffer(cam, g, vx.material_params(np.zeros(10, np.int32)), r.alloc_material(W, H))
+    assert m["albedo"].shape == (H, W, 3) and m["pbr"].shape == (H, W, 4)
+    d = r.alloc_diffuse(W, H)
+    prev_t = r.alloc_denoise(W, H, ("sh", "cocg", "utility", "ao_sky"))
+    tp = denoise.temporal_params(*fc.view_projection_f32())
+    out, temporal = r.svgf_denoise(cam, g, g, d, prev_t, tp, time=1.0)
+    assert out["sh"].shape == (H, W, 4) and out["variance"].shape == (H, W) and temporal["utility"].shape == (H, W, 3)
+    s = r.alloc_shadow(W, H)
+    st = r.shadow_temporal(cam, g, g, s, r.alloc_denoise(W, H, ("shadow", "frames")), denoise.shadow_temporal_params(*fc.view_projection_f32()),
+                           r.alloc_denoise(W, H, ("shadow", "frames")))
+    f = r.shadow_filter(cam, g, st, s["transversal"], denoise.shadow_filter_params(1.0), np.zeros((H, W), np.float32))
+    assert f.shape == (H, W)
+    assert calls == ["vxpt_set_gbuffer_textures", "vxpt_generate_gbuffer", "vxpt_svgf_initial", "vxpt_svgf_temporal", "vxpt_svgf_variance"] + \
+        ["vxpt_svgf_spatial"] * 5 + ["vxpt_shadow_temporal", "vxpt_shadow_filter"]
     r.handle = C.c_void_p()      # nothing to destroy
 
 

@@ -397,7 +397,7 @@ int vxpt_set_blocks(vxpt_handle c, const int16_t* xyz, const uint8_t* ids, int n
     uint8_t* d_ids = (uint8_t*)arena.take(b_ids);
     VX_CUDA(cudaMemcpyAsync(d_xyz, xyz, b_xyz, cudaMemcpyHostToDevice, c->stream));
     VX_CUDA(cudaMemcpyAsync(d_ids, ids, b_ids, cudaMemcpyHostToDevice, c->stream));
-    scatter_blocks<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_grid, d_xyz, d_ids, n);
+    VX_LAUNCH(scatter_blocks, dim3((n + 127) / 128), 128, c->stream, c->d_grid, d_xyz, d_ids, n);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(c->stream));
@@ -1098,22 +1098,30 @@ int vxpt_frame_wait(vxpt_handle c) {
 // ------------------------------------------------------------------------------------- peer-to-peer slab gather
 }  // extern "C"
 namespace vxpt {
-__global__ void signal_kernel(uint32_t* flag, uint32_t value) {
-    // release at system scope: every store of the kernels that ran before on this stream is visible to a peer that
-    // observes the flag
+#ifndef VXPT_HOST_SHADOW
+// release at system scope: every store of the kernels that ran before on this stream is visible to a peer that observes the flag
+__device__ __forceinline__ void store_release_sys(uint32_t* flag, uint32_t value) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
+__device__ __forceinline__ uint32_t load_acquire_sys(const uint32_t* f) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif  // tests/host_shadow defines the three for the g++ build (plain loads / stores, a clock)
+__global__ void signal_kernel(uint32_t* flag, uint32_t value) { store_release_sys(flag, value); }
 __device__ __forceinline__ void spin_until(const uint32_t* f, uint32_t at_least, unsigned long long timeout_ns, unsigned* err) {
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long t0 = global_timer_ns();
     while (true) {
-        uint32_t v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        const uint32_t v = load_acquire_sys(f);
         if ((int32_t)(v - at_least) >= 0) break;
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - t0 > timeout_ns) {
+        if (global_timer_ns() - t0 > timeout_ns) {
             atomicExch(err, 1u);
             break;
         }
@@ -1123,8 +1131,7 @@ __device__ __forceinline__ void spin_until(const uint32_t* f, uint32_t at_least,
 __global__ void signal_next_kernel(uint32_t* flag, uint32_t* counter) {
     const uint32_t v = *counter + 1u;
     *counter = v;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+    store_release_sys(flag, v);
 }
 __global__ void wait_next_kernel(const uint32_t* flags, int n, int stride_words, uint32_t* counter, int lag, unsigned long long timeout_ns, unsigned* err) {
     __shared__ uint32_t s_target;
@@ -1205,7 +1212,7 @@ int vxpt_copy_async(vxpt_handle c, void* dst, const void* src, size_t bytes, voi
 int vxpt_signal(vxpt_handle c, uint32_t* flag, uint32_t value, void* cuda_stream) {
     if (!c || !flag) return fail(VXPT_E_INVALID, "bad argument");
     VX_CUDA(cudaSetDevice(c->device));
-    signal_kernel<<<1, 1, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(flag, value);
+    VX_LAUNCH(signal_kernel, dim3(1), 1, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, flag, value);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -1214,7 +1221,7 @@ int vxpt_signal(vxpt_handle c, uint32_t* flag, uint32_t value, void* cuda_stream
 int vxpt_signal_next(vxpt_handle c, uint32_t* flag, uint32_t* counter, void* cuda_stream) {
     if (!c || !flag || !counter) return fail(VXPT_E_INVALID, "bad argument");
     VX_CUDA(cudaSetDevice(c->device));
-    signal_next_kernel<<<1, 1, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(flag, counter);
+    VX_LAUNCH(signal_next_kernel, dim3(1), 1, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, flag, counter);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -1223,8 +1230,8 @@ int vxpt_signal_next(vxpt_handle c, uint32_t* flag, uint32_t* counter, void* cud
 int vxpt_wait_next(vxpt_handle c, const uint32_t* flags, int n, int stride_words, uint32_t* counter, int lag, int timeout_ms, void* cuda_stream) {
     if (!c || !flags || !counter || n <= 0 || n > 1024 || stride_words <= 0 || lag < 0 || timeout_ms <= 0) return fail(VXPT_E_INVALID, "bad argument");
     VX_CUDA(cudaSetDevice(c->device));
-    wait_next_kernel<<<1, ((n + 31) / 32) * 32, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(
-        flags, n, stride_words, counter, lag, (unsigned long long)timeout_ms * 1000000ull, c->d_wait_err);
+    VX_LAUNCH(wait_next_kernel, dim3(1), ((n + 31) / 32) * 32, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, flags, n, stride_words, counter, lag,
+              (unsigned long long)timeout_ms * 1000000ull, c->d_wait_err);
     c->launches += 1;
     c->waits_issued = true;
     VX_CUDA(cudaGetLastError());
@@ -1234,7 +1241,8 @@ int vxpt_wait_next(vxpt_handle c, const uint32_t* flags, int n, int stride_words
 int vxpt_wait_all(vxpt_handle c, const uint32_t* flags, int n, int stride_words, uint32_t at_least, int timeout_ms, void* cuda_stream) {
     if (!c || !flags || n <= 0 || n > 1024 || stride_words <= 0 || timeout_ms <= 0) return fail(VXPT_E_INVALID, "bad argument");
     VX_CUDA(cudaSetDevice(c->device));
-    wait_all_kernel<<<1, ((n + 31) / 32) * 32, 0, cuda_stream ? (cudaStream_t)cuda_stream : c->stream>>>(flags, n, stride_words, at_least, (unsigned long long)timeout_ms * 1000000ull, c->d_wait_err);
+    VX_LAUNCH(wait_all_kernel, dim3(1), ((n + 31) / 32) * 32, cuda_stream ? (cudaStream_t)cuda_stream : c->stream, flags, n, stride_words, at_least,
+              (unsigned long long)timeout_ms * 1000000ull, c->d_wait_err);
     c->launches += 1;
     c->waits_issued = true;
     VX_CUDA(cudaGetLastError());

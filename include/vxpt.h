@@ -385,6 +385,27 @@ typedef struct VxSvgfSpatialOut {
 VXPT_API int vxpt_svgf_spatial(vxpt_handle h, const VxCamera* cam, const VxSvgfSpatialIn* in, const VxSvgfSpatialParams* p,
                                const VxSvgfSpatialOut* out);
 
+/* The whole SVGF chain of one frame in one call (Core/Pipeline.cpp:2284-2596): pre-temporal pass -> temporal -> variance -> five a-trous
+ * passes, with everything between the passes — and the history the next frame needs (this frame's temporal planes, G-buffer and camera
+ * matrices) — resident in device memory owned by the handle (230 B/pixel, allocated on first use).  Equivalent to the separate exports
+ * above called in that order; only the GI planes come in and the denoised planes go out.  Whole frames only (row_begin = 0, row_end =
+ * height); a change of resolution or reset_history = 1 starts a new history (previous planes zero, previous camera = this camera). */
+typedef struct VxSvgfFrameParams {
+    float view[16];                   /* u_View of this frame; u_PrevView of the next call                      */
+    float projection[16];             /* u_Projection of this frame; u_PrevProjection of the next call          */
+    int32_t reset_history;            /* 1 = forget the previous frame (first frame, camera cut)                */
+    int32_t pre_pass;                 /* PreTemporalSpatialPass (1, Pipeline.cpp:239)                           */
+    int32_t wide;                     /* WiderSVGF (0): a-trous steps 32, 16, 8, 4, 2 instead of 16, 8, 4, 2, 1 */
+    int32_t large_kernel;             /* SVGF_LARGE_KERNEL (0)                                                  */
+    int32_t aggressive_disocclusion;  /* AGGRESSIVE_DISOCCLUSION_HANDLING (1)                                   */
+    float color_phi_bias;             /* ColorPhiBias (3.325)                                                   */
+    float time;                       /* u_Time                                                                 */
+    float resolution_scale;           /* DiffuseIndirectSuperSampleRes (0.25)                                   */
+} VxSvgfFrameParams;
+VXPT_API int vxpt_svgf_frame(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf /* t, normal_id, block_id */,
+                             const VxDiffuseOut* diffuse /* read: this frame's GI planes */, const VxSvgfFrameParams* p,
+                             const VxSvgfSpatialOut* out);
+
 /* ---- sun-shadow filters: Core/Pipeline.cpp:2854-2944 -> Core/Shaders/ShadowTemporalFilter.glsl (u_ShadowTemporal =
  *      true), ShadowFilter.glsl ------------------------------------------------------------------------------------------------------
  * The two passes after vxpt_trace_shadow: temporal accumulation of the 0 / 1 shadow plane (history clipped to the neighbourhood of the

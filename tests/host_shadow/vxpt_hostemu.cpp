@@ -94,6 +94,7 @@ cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 #define __launch_bounds__(...)
 #undef __grid_constant__
 #define __grid_constant__
+#undef __shared__
 #define __shared__ static
 static thread_local uint3 threadIdx, blockIdx;
 static thread_local dim3 blockDim, gridDim;

@@ -334,6 +334,40 @@ def test_gpu_denoiser_whole_chain_on_the_traced_frame(renderer, worlds, oracles,
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["gi_box_192x108_walk", "city_160x90_still"])
+def test_gpu_svgf_frame_keeps_the_history_on_the_device(renderer, oracle_sequences, name):
+    """vxpt_svgf_frame == the separate passes chained by hand: per frame only the G-buffer and the GI planes go in; the pre-pass, temporal,
+    variance and ping-pong planes and the previous frame stay in the handle.  Host planes; also a reset in mid-sequence and a resolution change."""
+    _, W, H, cams = dc.SEQUENCES[name]
+    want = oracle_sequences[name]
+    for f, (fr, kw) in enumerate(zip(want, cams)):
+        fc = camera.FpsCamera(aspect=W / H, **kw)
+        view, proj = fc.view().T.reshape(16), fc.projection().T.reshape(16)       # the matrices the oracle sequence was run with
+        out = renderer.svgf_frame(fr["cam"], fr["gbuf"], fr["diffuse"], denoise.frame_params(view, proj, time=dc.TIME0 + f / 60.0, reset_history=(f == 0)),
+                                  renderer.alloc_denoise(W, H, ("sh", "cocg", "variance", "ao_sky")))
+        for k in out:
+            _close(out[k], fr["spatial"][-1][k], (name, f, k))
+    # reset_history on a later frame = that frame denoised as the first of a sequence
+    fr, fc = want[1], camera.FpsCamera(aspect=W / H, **cams[1])
+    view, proj = fc.view().T.reshape(16), fc.projection().T.reshape(16)
+    a = renderer.svgf_frame(fr["cam"], fr["gbuf"], fr["diffuse"], denoise.frame_params(view, proj, time=1.0, reset_history=True),
+                            renderer.alloc_denoise(W, H, ("sh", "cocg", "variance", "ao_sky")))
+    # ... and so does a frame of another size in between (the history is per resolution)
+    small = oracle_sequences["plains_133x75_turn"][0]
+    fs = camera.FpsCamera(aspect=133 / 75, **dc.SEQUENCES["plains_133x75_turn"][3][0])
+    renderer.svgf_frame(small["cam"], small["gbuf"], small["diffuse"], denoise.frame_params(fs.view().T.reshape(16), fs.projection().T.reshape(16), time=dc.TIME0),
+                        renderer.alloc_denoise(133, 75, ("sh", "cocg", "variance", "ao_sky")))
+    b = renderer.svgf_frame(fr["cam"], fr["gbuf"], fr["diffuse"], denoise.frame_params(view, proj, time=1.0),
+                            renderer.alloc_denoise(W, H, ("sh", "cocg", "variance", "ao_sky")))
+    for k in a:
+        assert _same(a[k], b[k]), k
+    with pytest.raises(abi.VxptError) as e:     # whole frames only
+        slab = camera.FpsCamera(aspect=W / H, **cams[0]).vx_camera(W, H, 0, H // 2)
+        renderer.svgf_frame(slab, fr["gbuf"], fr["diffuse"], denoise.frame_params(view, proj), renderer.alloc_denoise(W, H, ("sh", "cocg", "variance", "ao_sky")))
+    assert e.value.code == abi.E_INVALID
+
+
+@pytest.mark.gpu
 def test_gpu_denoiser_argument_checks(renderer, oracle_sequences):
     fr = oracle_sequences["plains_133x75_turn"][0]
     cam, g, t = fr["cam"], fr["gbuf"], fr["temporal"]

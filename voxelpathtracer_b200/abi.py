@@ -132,6 +132,12 @@ class VxSvgfSpatialOut(C.Structure):
     _fields_ = [("sh", C.c_void_p), ("cocg", C.c_void_p), ("variance", C.c_void_p), ("ao_sky", C.c_void_p)]
 
 
+class VxSvgfFrameParams(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("projection", C.c_float * 16), ("reset_history", C.c_int32), ("pre_pass", C.c_int32), ("wide", C.c_int32),
+                ("large_kernel", C.c_int32), ("aggressive_disocclusion", C.c_int32), ("color_phi_bias", C.c_float), ("time", C.c_float),
+                ("resolution_scale", C.c_float)]
+
+
 class VxShadowTemporalIn(C.Structure):
     _fields_ = [("current", VxGBuffer), ("previous", VxGBuffer), ("shadow", C.c_void_p), ("transversal", C.c_void_p), ("prev_shadow", C.c_void_p),
                 ("prev_frames", C.c_void_p)]
@@ -202,6 +208,8 @@ EXPORTS = {
                                      C.POINTER(VxSvgfVarianceOut)]),
     "vxpt_svgf_spatial": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxSvgfSpatialIn), C.POINTER(VxSvgfSpatialParams),
                                     C.POINTER(VxSvgfSpatialOut)]),
+    "vxpt_svgf_frame": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseOut), C.POINTER(VxSvgfFrameParams),
+                                  C.POINTER(VxSvgfSpatialOut)]),
     "vxpt_shadow_temporal": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxShadowTemporalIn), C.POINTER(VxShadowTemporalParams),
                                        C.POINTER(VxShadowTemporalOut)]),
     "vxpt_shadow_filter": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxShadowFilterIn), C.POINTER(VxShadowFilterParams), C.c_void_p]),

@@ -335,7 +335,7 @@ int vxpt_destroy(vxpt_handle c) {
     }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
                     c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_alpha_mips, c->d_counters, c->d_stage, c->d_queue,
-                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut};
+                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut, c->svgf.buf};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -756,6 +756,112 @@ int vxpt_svgf_spatial(vxpt_handle c, const VxCamera* cam, const VxSvgfSpatialIn*
     id.temporal_utility = (const float*)ut->dev;
     const VxSvgfSpatialOut od{(float*)osh->dev, (float*)occ->dev, (float*)ov->dev, (float*)oao->dev};
     if ((rc = timed_launch(c, [&] { return launch_svgf_spatial(c, *cam, id, *p, od); }))) return rc;
+    return s.end(c);
+}
+
+}  // extern "C"
+// carve the history allocation into planes (256-byte aligned), (re)allocating when the frame size changes
+static int svgf_history_for(vxpt_ctx* c, int W, int H) {
+    vxpt_ctx::SvgfHistory& h = c->svgf;
+    if (h.buf && h.width == W && h.height == H) return VXPT_OK;
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    if (h.buf) cudaFree(h.buf);
+    h = vxpt_ctx::SvgfHistory();
+    const size_t npx = (size_t)W * H;
+    auto plane = [npx](size_t elem) { return (npx * elem + 255) & ~(size_t)255; };
+    const size_t set4 = plane(16) + plane(8) + plane(12) + plane(8);  // sh, cocg, utility, ao (pre: luma and pong: variance fit in the utility slot)
+    const size_t total = plane(4) + 2 * plane(1) + 2 * set4 + set4 + (plane(16) + plane(8) + plane(4)) + 2 * set4;
+    if (cudaMalloc(&h.buf, total) != cudaSuccess) {
+        cudaGetLastError();
+        h.buf = nullptr;
+        return fail(VXPT_E_NOMEM, "device allocation of the denoiser history failed");
+    }
+    char* p = (char*)h.buf;
+    auto take = [&p, &plane](size_t elem) { char* q = p; p += plane(elem); return q; };
+    h.prev_t = (float*)take(4); h.prev_nid = (uint8_t*)take(1); h.prev_bid = (uint8_t*)take(1);
+    for (int k = 0; k < 2; ++k) { h.temporal[k][0] = (float*)take(16); h.temporal[k][1] = (float*)take(8); h.temporal[k][2] = (float*)take(12); h.temporal[k][3] = (float*)take(8); }
+    h.pre[0] = (float*)take(16); h.pre[1] = (float*)take(8); h.pre[2] = (float*)take(12); h.pre[3] = (float*)take(8);
+    h.var[0] = (float*)take(16); h.var[1] = (float*)take(8); h.var[2] = (float*)take(4);
+    for (int k = 0; k < 2; ++k) { h.pong[k][0] = (float*)take(16); h.pong[k][1] = (float*)take(8); h.pong[k][2] = (float*)take(12); h.pong[k][3] = (float*)take(8); }
+    h.width = W; h.height = H;
+    return VXPT_OK;
+}
+extern "C" {
+
+int vxpt_svgf_frame(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, const VxDiffuseOut* diffuse, const VxSvgfFrameParams* p, const VxSvgfSpatialOut* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!g || !diffuse || !p || !out || !g->t || !g->normal_id || !g->block_id || !diffuse->sh || !diffuse->cocg || !diffuse->luma || !diffuse->ao_sky)
+        return fail(VXPT_E_INVALID, "NULL argument (G-buffer t / normal_id / block_id and the GI pass's sh / cocg / luma / ao_sky planes are required)");
+    if (cam->row_begin != 0 || cam->row_end != cam->height) return fail(VXPT_E_INVALID, "vxpt_svgf_frame denoises whole frames (row_begin = 0, row_end = height)");
+    VX_CUDA(cudaSetDevice(c->device));
+    const int W = cam->width, H = cam->height;
+    const size_t npx = (size_t)W * H;
+    const bool had = c->svgf.buf && c->svgf.width == W && c->svgf.height == H && c->svgf.valid && !p->reset_history;
+    if ((rc = svgf_history_for(c, W, H))) return rc;
+    vxpt_ctx::SvgfHistory& h = c->svgf;
+    SvgfIO s(c, cam);
+    Plane *t = s.in(g->t, 4), *n = s.in(g->normal_id, 1), *b = s.in(g->block_id, 1);
+    Plane *sh = s.in(diffuse->sh, 16), *cc = s.in(diffuse->cocg, 8), *lu = s.in(diffuse->luma, 4), *ao = s.in(diffuse->ao_sky, 8);
+    Plane *osh = s.out(out->sh, 16), *occ = s.out(out->cocg, 8), *ov = s.out(out->variance, 4), *oao = s.out(out->ao_sky, 8);
+    if ((rc = s.begin())) return rc;
+    const VxGBuffer gd{(float*)t->dev, (uint8_t*)n->dev, (uint8_t*)b->dev, nullptr, nullptr};
+    const int prev = h.cur, cur = h.cur ^ 1;
+    VxSvgfTemporalParams tp{};
+    if (!had) {  // a new history: previous planes zero, previous G-buffer and camera = this frame's
+        for (int k = 0; k < 4; ++k) VX_CUDA(cudaMemsetAsync(h.temporal[prev][k], 0, npx * (k == 0 ? 16 : (k == 2 ? 12 : 8)), c->stream));
+        std::memcpy(tp.prev_view, p->view, sizeof tp.prev_view);
+        std::memcpy(tp.prev_projection, p->projection, sizeof tp.prev_projection);
+    } else {
+        std::memcpy(tp.prev_view, h.prev_view, sizeof tp.prev_view);
+        std::memcpy(tp.prev_projection, h.prev_projection, sizeof tp.prev_projection);
+    }
+    tp.be_useful = 1;
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    VxSvgfTemporalIn ti{};
+    ti.current = gd;
+    ti.previous = had ? VxGBuffer{h.prev_t, h.prev_nid, h.prev_bid, nullptr, nullptr} : gd;
+    ti.sh = (const float*)sh->dev; ti.cocg = (const float*)cc->dev; ti.luma = (const float*)lu->dev; ti.ao_sky = (const float*)ao->dev;
+    if (p->pre_pass) {
+        VxSvgfInitialIn ii{};
+        ii.current = gd; ii.sh = ti.sh; ii.cocg = ti.cocg; ii.luma = ti.luma; ii.ao_sky = ti.ao_sky;
+        const VxSvgfInitialOut io{h.pre[0], h.pre[1], h.pre[2], h.pre[3]};
+        if ((rc = launch_svgf_initial(c, *cam, ii, io))) return rc;
+        ti.sh = h.pre[0]; ti.cocg = h.pre[1]; ti.luma = h.pre[2]; ti.ao_sky = h.pre[3];
+    }
+    ti.prev_sh = h.temporal[prev][0]; ti.prev_cocg = h.temporal[prev][1]; ti.prev_utility = h.temporal[prev][2]; ti.prev_ao_sky = h.temporal[prev][3];
+    const VxSvgfTemporalOut to{h.temporal[cur][0], h.temporal[cur][1], h.temporal[cur][2], h.temporal[cur][3]};
+    if ((rc = launch_svgf_temporal(c, *cam, ti, tp, to))) return rc;
+    VxSvgfVarianceIn vi{};
+    vi.current = gd; vi.sh = to.sh; vi.cocg = to.cocg; vi.utility = to.utility;
+    const VxSvgfVarianceParams vp{1, p->aggressive_disocclusion};
+    const VxSvgfVarianceOut vo{h.var[0], h.var[1], h.var[2]};
+    if ((rc = launch_svgf_variance(c, *cam, vi, vp, vo))) return rc;
+    VxSvgfSpatialIn si{};
+    si.current = gd; si.sh = vo.sh; si.cocg = vo.cocg; si.variance = vo.variance; si.ao_sky = to.ao_sky; si.temporal_utility = to.utility;
+    for (int k = 0; k < 5; ++k) {
+        VxSvgfSpatialParams sp{};
+        sp.step = (p->wide ? 32 : 16) >> k;
+        sp.large_kernel = p->large_kernel; sp.do_spatial = 1; sp.aggressive_disocclusion = p->aggressive_disocclusion;
+        sp.color_phi_bias = p->color_phi_bias; sp.time = p->time; sp.resolution_scale = p->resolution_scale;
+        // the last pass writes the caller's planes (a plane the caller did not ask for still has to exist for the pass before it)
+        const VxSvgfSpatialOut so = k == 4 ? VxSvgfSpatialOut{(float*)osh->dev, (float*)occ->dev, (float*)ov->dev, (float*)oao->dev}
+                                           : VxSvgfSpatialOut{h.pong[k & 1][0], h.pong[k & 1][1], h.pong[k & 1][2], h.pong[k & 1][3]};
+        if ((rc = launch_svgf_spatial(c, *cam, si, sp, so))) return rc;
+        si.sh = so.sh; si.cocg = so.cocg; si.variance = so.variance; si.ao_sky = so.ao_sky;
+    }
+    // this frame becomes the history of the next
+    VX_CUDA(cudaMemcpyAsync(h.prev_t, gd.t, npx * 4, cudaMemcpyDeviceToDevice, c->stream));
+    VX_CUDA(cudaMemcpyAsync(h.prev_nid, gd.normal_id, npx, cudaMemcpyDeviceToDevice, c->stream));
+    VX_CUDA(cudaMemcpyAsync(h.prev_bid, gd.block_id, npx, cudaMemcpyDeviceToDevice, c->stream));
+    std::memcpy(h.prev_view, p->view, sizeof h.prev_view);
+    std::memcpy(h.prev_projection, p->projection, sizeof h.prev_projection);
+    h.cur = cur;
+    h.valid = true;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
     return s.end(c);
 }
 

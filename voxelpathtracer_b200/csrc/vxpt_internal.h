@@ -135,6 +135,17 @@ struct vxpt_ctx {
     unsigned* d_wait_err = nullptr;  // latched by a wait that timed out
     bool waits_issued = false;
 
+    // vxpt_svgf_frame: the denoiser's device-resident planes and history
+    struct SvgfHistory {
+        int width = 0, height = 0;
+        bool valid = false;     // a previous frame is held
+        int cur = 0;            // which temporal set the last frame wrote
+        float prev_view[16] = {0}, prev_projection[16] = {0};
+        void* buf = nullptr;    // one allocation carved into the planes below
+        float *prev_t = nullptr, *temporal[2][4] = {{nullptr}}, *pre[4] = {nullptr}, *var[3] = {nullptr}, *pong[2][4] = {{nullptr}};
+        uint8_t *prev_nid = nullptr, *prev_bid = nullptr;
+    } svgf;
+
     // wavefront queues (grown on demand)
     void* d_queue = nullptr;
     size_t queue_bytes = 0;

@@ -3,7 +3,7 @@ from dicts of planes.  The same structs drive the library (Renderer.svgf_*), the
 `address` is injected: it maps a numpy array or torch tensor to its raw address."""
 import numpy as np
 
-from .abi import (VxGBuffer, VxShadowFilterIn, VxShadowFilterParams, VxShadowTemporalIn, VxShadowTemporalOut, VxShadowTemporalParams, VxSvgfInitialIn, VxSvgfInitialOut, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
+from .abi import (VxGBuffer, VxShadowFilterIn, VxShadowFilterParams, VxShadowTemporalIn, VxShadowTemporalOut, VxShadowTemporalParams, VxSvgfFrameParams, VxSvgfInitialIn, VxSvgfInitialOut, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
                   VxSvgfVarianceIn, VxSvgfVarianceOut, VxSvgfVarianceParams)
 
 ATROUS_STEPS = (16, 8, 4, 2, 1)          # Core/Pipeline.cpp:2482-2487
@@ -35,6 +35,18 @@ def spatial_params(step, time=0.0, large_kernel=False, do_spatial=True, aggressi
     """Defaults: ColorPhiBias 3.325, DiffuseIndirectSuperSampleRes 0.25 (Core/Pipeline.cpp:78,85)."""
     p = VxSvgfSpatialParams()
     p.step, p.large_kernel, p.do_spatial, p.aggressive_disocclusion = int(step), int(bool(large_kernel)), int(bool(do_spatial)), int(bool(aggressive_disocclusion))
+    p.color_phi_bias, p.time, p.resolution_scale = float(color_phi_bias), float(time), float(resolution_scale)
+    return p
+
+
+def frame_params(view, projection, time=0.0, reset_history=False, pre_pass=True, wide=False, large_kernel=False, aggressive_disocclusion=True,
+                 color_phi_bias=3.325, resolution_scale=0.25):
+    """vxpt_svgf_frame: this frame's u_View / u_Projection (16 floats each, column-major) and the chain's switches at the reference's defaults."""
+    p = VxSvgfFrameParams()
+    p.view[:] = [float(v) for v in np.asarray(view, dtype=np.float32).reshape(16)]
+    p.projection[:] = [float(v) for v in np.asarray(projection, dtype=np.float32).reshape(16)]
+    p.reset_history, p.pre_pass, p.wide, p.large_kernel = int(bool(reset_history)), int(bool(pre_pass)), int(bool(wide)), int(bool(large_kernel))
+    p.aggressive_disocclusion = int(bool(aggressive_disocclusion))
     p.color_phi_bias, p.time, p.resolution_scale = float(color_phi_bias), float(time), float(resolution_scale)
     return p
 

@@ -306,6 +306,18 @@ class Renderer:
         check(self.lib.vxpt_svgf_spatial(self.handle, C.byref(cam), C.byref(i), C.byref(params), C.byref(o)))
         return out
 
+    def svgf_frame(self, cam, gbuf, diffuse, params, out):
+        """The whole SVGF chain of one frame with the intermediates and the history resident on the device (vxpt_svgf_frame):
+        diffuse = the GI pass's planes, out = {"sh", "cocg", "variance", "ao_sky"}; params from denoise.frame_params."""
+        from .abi import VxSvgfSpatialOut
+        g = self.gbuffer_struct(gbuf)
+        d = VxDiffuseOut()
+        d.sh, d.cocg, d.luma, d.ao_sky = _ptr(diffuse.get("sh")), _ptr(diffuse.get("cocg")), _ptr(diffuse.get("luma")), _ptr(diffuse.get("ao_sky"))
+        o = VxSvgfSpatialOut()
+        o.sh, o.cocg, o.variance, o.ao_sky = _ptr(out.get("sh")), _ptr(out.get("cocg")), _ptr(out.get("variance")), _ptr(out.get("ao_sky"))
+        check(self.lib.vxpt_svgf_frame(self.handle, C.byref(cam), C.byref(g), C.byref(d), C.byref(params), C.byref(o)))
+        return out
+
     def shadow_temporal(self, cam, gbuf, prev_gbuf, shadow, prev_temporal, params, out):
         """ShadowTemporalFilter.glsl (vxpt_shadow_temporal): shadow = the shadow pass's planes, prev_temporal / out = {"shadow", "frames"}."""
         from . import denoise

@@ -367,6 +367,73 @@ def test_gpu_svgf_frame_keeps_the_history_on_the_device(renderer, oracle_sequenc
     assert e.value.code == abi.E_INVALID
 
 
+class _DevicePlanes:
+    """Device-resident planes without torch: vxpt_shared_alloc for the memory, vxpt_copy_async for the transfers.  The passes get raw
+    device addresses, so the ABI takes its zero-copy path (no staging)."""
+
+    def __init__(self, r):
+        self.r, self.ptrs = r, []
+
+    def up(self, a):
+        a = np.ascontiguousarray(a)
+        ptr, _ = self.r.shared_alloc(max(a.nbytes, 256))
+        self.ptrs.append(ptr)
+        self.r.copy_async(ptr, a.ctypes.data, a.nbytes)
+        self.keep = getattr(self, "keep", []) + [a]
+        return ptr
+
+    def new(self, shape, dtype=np.float32):
+        ptr, _ = self.r.shared_alloc(max(int(np.prod(shape)) * np.dtype(dtype).itemsize, 256))
+        self.ptrs.append(ptr)
+        return ptr
+
+    def down(self, ptr, shape, dtype=np.float32):
+        out = np.empty(shape, dtype)
+        self.r.copy_async(out.ctypes.data, ptr, out.nbytes)
+        self.r.sync()
+        return out
+
+    def close(self):
+        self.r.sync()
+        for p in self.ptrs:
+            self.r.shared_close(p)
+
+
+@pytest.mark.gpu
+def test_gpu_resident_planes_take_the_zero_copy_path(renderer, worlds, oracle_sequences, oracle_shadow_sequences, scene_tables):
+    """Raw device addresses in, raw device addresses out: vxpt_svgf_frame, the shadow filters and the material pass on planes that live in
+    device memory (allocated through the ABI itself, so the test needs no torch and also runs against the emulated ABI)."""
+    r = renderer
+    dev = _DevicePlanes(r)
+    try:
+        name = "gi_box_192x108_walk"
+        _, W, H, cams = dc.SEQUENCES[name]
+        shapes = denoise.plane_shapes(W, H)
+        for f, (fr, kw) in enumerate(zip(oracle_sequences[name][:2], cams)):
+            fc = camera.FpsCamera(aspect=W / H, **kw)
+            g = {k: dev.up(fr["gbuf"][k]) for k in ("t", "normal_id", "block_id")}
+            d = {k: dev.up(fr["diffuse"][k]) for k in ("sh", "cocg", "luma", "ao_sky")}
+            out = {k: dev.new(shapes[k]) for k in ("sh", "cocg", "variance", "ao_sky")}
+            r.svgf_frame(fr["cam"], g, d, denoise.frame_params(fc.view().T.reshape(16), fc.projection().T.reshape(16), time=dc.TIME0 + f / 60.0,
+                                                               reset_history=(f == 0)), out)
+            for k in out:
+                _close(dev.down(out[k], shapes[k]), fr["spatial"][-1][k], (f, k))
+        fr = oracle_shadow_sequences["city_160x90_still"][1]
+        W, H = fr["cam"].width, fr["cam"].height
+        g = {"t": dev.up(fr["gbuf"]["t"]), "normal_id": dev.up(fr["gbuf"]["normal_id"])}
+        pg = {"t": dev.up(fr["prev_gbuf"]["t"])}
+        s = {"shadow": dev.up(fr["shadow"]["shadow"]), "transversal": dev.up(fr["shadow"]["transversal"])}
+        pt = {k: dev.up(fr["prev_temporal"][k]) for k in ("shadow", "frames")}
+        t = {"shadow": dev.new((H, W)), "frames": dev.new((H, W))}
+        r.shadow_temporal(fr["cam"], g, pg, s, pt, fr["params"], t)
+        filt = r.shadow_filter(fr["cam"], g, t, s["transversal"], denoise.shadow_filter_params(1.0), dev.new((H, W)))
+        _close(dev.down(t["shadow"], (H, W)), fr["temporal"]["shadow"], "temporal shadow")
+        _close(dev.down(t["frames"], (H, W)), fr["temporal"]["frames"], "temporal frames")
+        _close(dev.down(filt, (H, W)), fr["filtered"], "filtered")
+    finally:
+        dev.close()
+
+
 @pytest.mark.gpu
 def test_gpu_denoiser_argument_checks(renderer, oracle_sequences):
     fr = oracle_sequences["plains_133x75_turn"][0]

@@ -455,12 +455,16 @@ typedef struct VxFrameParams {
     const VxReflectionParams* reflection;  /* NULL = no reflection pass (needs diffuse)             */
     const float* g_normal;                 /* VxReflectionIn.g_normal / g_pbr for the reflection    */
     const float* g_pbr;                    /* pass (device or host, may be NULL)                    */
+    const VxMaterialParams* material;      /* NULL = no G-buffer material pass.  Otherwise it runs right after the primary pass
+                                              (Pipeline.cpp:2066-2136) and, where g_normal / g_pbr above are NULL, the reflection
+                                              pass reads ITS normal / pbr planes, as in the reference (needs even row slabs)  */
 } VxFrameParams;
 typedef struct VxFrameOut {
     VxGBuffer gbuffer;
     VxShadowOut shadow;
     VxDiffuseOut diffuse;
     VxReflectionOut reflection;
+    VxMaterialOut material;                /* outputs of the material pass (any may be NULL)        */
 } VxFrameOut;
 VXPT_API int vxpt_render_frame(vxpt_handle h, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out);
 /* As vxpt_render_frame, but returns as soon as the frame is enqueued; HOST planes are complete after vxpt_frame_wait(h).

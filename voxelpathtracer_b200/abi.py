@@ -161,11 +161,11 @@ class VxShadowFilterParams(C.Structure):
 
 class VxFrameParams(C.Structure):
     _fields_ = [("primary", C.POINTER(VxPrimaryParams)), ("shadow", C.POINTER(VxShadowParams)), ("diffuse", C.POINTER(VxDiffuseParams)),
-                ("reflection", C.POINTER(VxReflectionParams)), ("g_normal", C.c_void_p), ("g_pbr", C.c_void_p)]
+                ("reflection", C.POINTER(VxReflectionParams)), ("g_normal", C.c_void_p), ("g_pbr", C.c_void_p), ("material", C.POINTER(VxMaterialParams))]
 
 
 class VxFrameOut(C.Structure):
-    _fields_ = [("gbuffer", VxGBuffer), ("shadow", VxShadowOut), ("diffuse", VxDiffuseOut), ("reflection", VxReflectionOut)]
+    _fields_ = [("gbuffer", VxGBuffer), ("shadow", VxShadowOut), ("diffuse", VxDiffuseOut), ("reflection", VxReflectionOut), ("material", VxMaterialOut)]
 
 
 class VxStats(C.Structure):

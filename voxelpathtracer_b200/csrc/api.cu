@@ -578,26 +578,17 @@ int vxpt_set_gbuffer_textures(vxpt_handle c, const uint8_t* albedo_mips, const u
     return VXPT_OK;
 }
 
+}  // extern "C"
+static int check_material(const vxpt_ctx* c, const VxCamera* cam, const VxMaterialParams* p);
+extern "C" {
+
 int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, const VxMaterialParams* p, const VxMaterialOut* out) {
     int rc = check_ready(c);
     if (rc) return rc;
     if ((rc = check_camera(cam))) return rc;
     if (!g || !p || !out || !g->inv_t || !g->normal_id || !g->block_id)
         return fail(VXPT_E_INVALID, "NULL argument (G-buffer inv_t, normal_id and block_id are required)");
-    if (p->pom) return fail(VXPT_E_UNSUPPORTED, "u_POM (relief parallax mapping) is outside the v1 parity profile");
-    if (p->lava_block_id >= 0) return fail(VXPT_E_UNSUPPORTED, "lava animation (u_LavaBlockID, functions of the wall clock) is outside the v1 parity profile");
-    if (!c->have_materials || !c->d_albedo_mips) return fail(VXPT_E_STATE, "the G-buffer pass needs vxpt_set_materials and vxpt_set_gbuffer_textures");
-    const int rows = cam->interleave_n > 1 ? cam->height / cam->interleave_n : cam->height;
-    if ((cam->row_begin & 1) || ((cam->row_end & 1) && cam->row_end != rows) || (cam->interleave_n > 1 && (cam->band_rows & 1)))
-        return fail(VXPT_E_INVALID, "the G-buffer pass shades 2x2 quads: row_begin / row_end (and band_rows) must be even");
-    for (int b = 0; b < 128; ++b) {
-        for (int k = 0; k < 3; ++k)
-            if (c->h_materials[128 * k + b] >= c->n_mip_layers)
-                return fail(VXPT_E_INVALID, "material table references a texture layer that vxpt_set_gbuffer_textures did not receive");
-        if (c->h_materials[384 + b] >= c->n_emissive) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
-    }
-    for (int k = 1; k < 10; ++k)
-        if (p->grass_props[k] < 0 || p->grass_props[k] >= c->n_mip_layers) return fail(VXPT_E_INVALID, "grass_props references a missing texture layer");
+    if ((rc = check_material(c, cam, p))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
     PassIO io(c, cam);
     Plane it, nid, bid, al, nm, pb, ao;
@@ -624,6 +615,24 @@ int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
 }
 
 }  // extern "C"
+// parameter and state checks of the G-buffer material pass (vxpt_generate_gbuffer, vxpt_render_frame)
+static int check_material(const vxpt_ctx* c, const VxCamera* cam, const VxMaterialParams* p) {
+    if (p->pom) return fail(VXPT_E_UNSUPPORTED, "u_POM (relief parallax mapping) is outside the v1 parity profile");
+    if (p->lava_block_id >= 0) return fail(VXPT_E_UNSUPPORTED, "lava animation (u_LavaBlockID, functions of the wall clock) is outside the v1 parity profile");
+    if (!c->have_materials || !c->d_albedo_mips) return fail(VXPT_E_STATE, "the G-buffer pass needs vxpt_set_materials and vxpt_set_gbuffer_textures");
+    const int rows = cam->interleave_n > 1 ? cam->height / cam->interleave_n : cam->height;
+    if ((cam->row_begin & 1) || ((cam->row_end & 1) && cam->row_end != rows) || (cam->interleave_n > 1 && (cam->band_rows & 1)))
+        return fail(VXPT_E_INVALID, "the G-buffer pass shades 2x2 quads: row_begin / row_end (and band_rows) must be even");
+    for (int b = 0; b < 128; ++b) {
+        for (int k = 0; k < 3; ++k)
+            if (c->h_materials[128 * k + b] >= c->n_mip_layers)
+                return fail(VXPT_E_INVALID, "material table references a texture layer that vxpt_set_gbuffer_textures did not receive");
+        if (c->h_materials[384 + b] >= c->n_emissive) return fail(VXPT_E_INVALID, "material table references an emissive layer that was not uploaded");
+    }
+    for (int k = 1; k < 10; ++k)
+        if (p->grass_props[k] < 0 || p->grass_props[k] >= c->n_mip_layers) return fail(VXPT_E_INVALID, "grass_props references a missing texture layer");
+    return VXPT_OK;
+}
 
 // ----------------------------------------------------------------------------------------------------- SVGF denoiser
 // shared by the three passes: a handle that is ready (no pending frame), fp32 planes, whole-frame inputs, plain row slabs
@@ -1100,15 +1109,18 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
         if (!p->diffuse) return fail(VXPT_E_INVALID, "the reflection pass reads the GI planes: diffuse parameters are required");
         if ((rc = check_reflection(c, p->reflection))) return rc;
     }
+    if (p->material && (rc = check_material(c, cam, p->material))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
     const bool secondary = p->shadow || p->diffuse || p->reflection;
     PassIO io(c, cam);
-    Plane t, nid, bid, it, hv, sh, tr, dsh, dcg, dlu, dao, gn, gp, col, hd, em;
+    Plane t, nid, bid, it, hv, sh, tr, dsh, dcg, dlu, dao, gn, gp, col, hd, em, mal, mnm, mpb, mao;
+    const bool mat = p->material != nullptr;
+    const bool mat_feeds_reflection = mat && p->reflection && p->material->update_this_frame;
     // planes a later pass reads exist in the handle's arena even when the caller does not want them back
     io.add(t, out->gbuffer.t, px_bytes(c, 4, 2), secondary);
     io.add(nid, out->gbuffer.normal_id, 1, secondary);
-    io.add(bid, out->gbuffer.block_id, 1, p->reflection && !p->g_pbr);
-    io.add(it, out->gbuffer.inv_t, 4);
+    io.add(bid, out->gbuffer.block_id, 1, (p->reflection && !p->g_pbr) || mat);
+    io.add(it, out->gbuffer.inv_t, 4, mat);
     io.add(hv, out->gbuffer.hit_voxel, 6);
     if (p->shadow) {
         io.add(sh, out->shadow.shadow, 1);
@@ -1119,6 +1131,12 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
         io.add(dcg, out->diffuse.cocg, px_bytes(c, 8, 4), p->reflection != nullptr);
         io.add(dlu, out->diffuse.luma, px_bytes(c, 4, 2));
         io.add(dao, out->diffuse.ao_sky, px_bytes(c, 8, 2));
+    }
+    if (mat) {  // the planes the reflection pass reads exist in the arena even when the caller does not want them back
+        io.add(mal, out->material.albedo, 12);
+        io.add(mnm, out->material.normal, 12, mat_feeds_reflection && !p->g_normal);
+        io.add(mpb, out->material.pbr, 16, mat_feeds_reflection && !p->g_pbr);
+        io.add(mao, out->material.texture_ao, 4);
     }
     if (p->reflection) {
         io.add(gn, p->g_normal, 12);
@@ -1136,7 +1154,9 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     const VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, (int16_t*)hv.dev};
     const VxShadowOut sd{(uint8_t*)sh.dev, (float*)tr.dev};
     const VxDiffuseOut dd{(float*)dsh.dev, (float*)dcg.dev, (float*)dlu.dev, (float*)dao.dev};
-    const VxReflectionIn ri{(const float*)gn.dev, (const float*)gp.dev, (const float*)dsh.dev, (const float*)dcg.dev};
+    const VxMaterialOut md{(float*)mal.dev, (float*)mnm.dev, (float*)mpb.dev, (float*)mao.dev};
+    const VxReflectionIn ri{(const float*)(p->g_normal || !mat_feeds_reflection ? gn.dev : mnm.dev),
+                            (const float*)(p->g_pbr || !mat_feeds_reflection ? gp.dev : mpb.dev), (const float*)dsh.dev, (const float*)dcg.dev};
     const VxReflectionOut rd{(float*)col.dev, (float*)hd.dev, (uint8_t*)em.dev};
     c->frame_counter++;
     if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
@@ -1159,6 +1179,12 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     };
     if ((rc = launch_primary(c, *cam, *p->primary, gd))) return rc;
     if ((rc = copy_out({&t, &nid, &bid, &it, &hv}, cam->row_begin, cam->row_end))) return rc;
+    if (mat) {
+        if (!p->material->update_this_frame)  // every fragment discards: staged planes must keep what the caller's hold
+            if ((rc = io.upload(mal)) || (rc = io.upload(mnm)) || (rc = io.upload(mpb)) || (rc = io.upload(mao))) return rc;
+        if ((rc = launch_gbuffer(c, *cam, gd, *p->material, md))) return rc;
+        if ((rc = copy_out({&mal, &mnm, &mpb, &mao}, cam->row_begin, cam->row_end))) return rc;
+    }
     if (p->shadow) {
         if ((rc = launch_shadow(c, *cam, gd, *p->shadow, sd))) return rc;
         if ((rc = copy_out({&sh, &tr}, cam->row_begin, cam->row_end))) return rc;

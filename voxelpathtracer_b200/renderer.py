@@ -381,7 +381,7 @@ class Renderer:
         return int(agg.value), per
 
     def render_frame(self, cam, primary, shadow=None, diffuse=None, gbuf=None, shadow_out=None, diffuse_out=None, reflection=None,
-                     reflection_out=None, g_normal=None, g_pbr=None, wait=True):
+                     reflection_out=None, g_normal=None, g_pbr=None, wait=True, material=None, material_out=None):
         """One frame of the path (vxpt_render_frame): primary -> shadow -> GI (-> reflections) with the G-buffer resident on
         the device; host planes are copied out pass by pass while later passes trace.  wait=False: vxpt_render_frame_async —
         returns once enqueued, host planes complete after frame_wait()."""
@@ -394,7 +394,12 @@ class Renderer:
         if reflection is not None:
             fp.reflection = C.pointer(reflection)
         fp.g_normal, fp.g_pbr = _ptr(g_normal), _ptr(g_pbr)
+        if material is not None:     # the G-buffer material pass right after the primary pass; it feeds the reflection pass
+            fp.material = C.pointer(material)
         fo = VxFrameOut()
+        mo = material_out or {}
+        fo.material.albedo, fo.material.normal, fo.material.pbr, fo.material.texture_ao = (_ptr(mo.get("albedo")), _ptr(mo.get("normal")), _ptr(mo.get("pbr")),
+                                                                                            _ptr(mo.get("texture_ao")))
         fo.gbuffer = self.gbuffer_struct(gbuf or {})
         so, do, ro = shadow_out or {}, diffuse_out or {}, reflection_out or {}
         fo.shadow.shadow, fo.shadow.transversal = _ptr(so.get("shadow")), _ptr(so.get("transversal"))

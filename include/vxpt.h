@@ -441,6 +441,20 @@ typedef struct VxShadowFilterParams {
 VXPT_API int vxpt_shadow_filter(vxpt_handle h, const VxCamera* cam, const VxShadowFilterIn* in, const VxShadowFilterParams* p,
                                 float* out /* o_Color, 1 float / pixel */);
 
+/* Both shadow filters of one frame in one call, the temporal planes and the previous frame's hit distances resident in the handle
+ * (20 B/pixel): only the shadow pass's planes come in and the filtered plane goes out.  Whole frames only; reset_history / a change
+ * of resolution start a new history (previous planes zero, previous camera = this camera). */
+typedef struct VxShadowFrameParams {
+    float view[16];         /* u_View of this frame; u_PrevView of the next call              */
+    float projection[16];   /* u_Projection of this frame; u_PrevProjection of the next call  */
+    int32_t reset_history;  /* 1 = forget the previous frame                                  */
+    int32_t spatial;        /* DenoiseSunShadows (1): 0 returns the temporal pass's plane     */
+    float filter_scale;     /* u_ShadowFilterScale (1.0)                                      */
+} VxShadowFrameParams;
+VXPT_API int vxpt_shadow_filter_frame(vxpt_handle h, const VxCamera* cam, const VxGBuffer* gbuf /* t, normal_id */,
+                                      const VxShadowOut* shadow /* read: this frame's shadow pass */, const VxShadowFrameParams* p,
+                                      float* out /* 1 float / pixel */);
+
 /* ---- one frame of the path: the pass sequence of Core/Pipeline.cpp's render loop (:1973-2016 primary, :2795-2852 shadow,
  *      :2174-2281 diffuse GI, :3003-3164 reflections) on the rows of `cam` -------------------------------------------------
  * Equivalent to vxpt_trace_primary + vxpt_trace_shadow + vxpt_trace_diffuse (+ vxpt_trace_reflection) with the same arguments,

@@ -367,6 +367,22 @@ def test_gpu_svgf_frame_keeps_the_history_on_the_device(renderer, oracle_sequenc
     assert e.value.code == abi.E_INVALID
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["city_160x90_still", "gi_box_192x108_walk"])
+def test_gpu_shadow_filter_frame_keeps_the_history_on_the_device(renderer, oracle_shadow_sequences, name):
+    """vxpt_shadow_filter_frame == vxpt_shadow_temporal + vxpt_shadow_filter chained by hand over a sequence (host planes in and out)."""
+    _, W, H, cams = dc.SEQUENCES[name]
+    for f, (fr, kw) in enumerate(zip(oracle_shadow_sequences[name], cams)):
+        fc = camera.FpsCamera(aspect=W / H, **kw)
+        prm = denoise.shadow_frame_params(fc.view().T.reshape(16), fc.projection().T.reshape(16), reset_history=(f == 0))
+        out = renderer.shadow_filter_frame(fr["cam"], fr["gbuf"], fr["shadow"], prm, np.zeros((H, W), np.float32))
+        _close(out, fr["filtered"], (name, f))
+    fr, fc = oracle_shadow_sequences[name][0], camera.FpsCamera(aspect=W / H, **cams[0])
+    prm = denoise.shadow_frame_params(fc.view().T.reshape(16), fc.projection().T.reshape(16), reset_history=True, spatial=False)
+    out = renderer.shadow_filter_frame(fr["cam"], fr["gbuf"], fr["shadow"], prm, np.zeros((H, W), np.float32))
+    _close(out, fr["temporal"]["shadow"], (name, "temporal only"))
+
+
 class _DevicePlanes:
     """Device-resident planes without torch: vxpt_shared_alloc for the memory, vxpt_copy_async for the transfers.  The passes get raw
     device addresses, so the ABI takes its zero-copy path (no staging)."""

@@ -138,6 +138,10 @@ class VxSvgfFrameParams(C.Structure):
                 ("resolution_scale", C.c_float)]
 
 
+class VxShadowFrameParams(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("projection", C.c_float * 16), ("reset_history", C.c_int32), ("spatial", C.c_int32), ("filter_scale", C.c_float)]
+
+
 class VxShadowTemporalIn(C.Structure):
     _fields_ = [("current", VxGBuffer), ("previous", VxGBuffer), ("shadow", C.c_void_p), ("transversal", C.c_void_p), ("prev_shadow", C.c_void_p),
                 ("prev_frames", C.c_void_p)]
@@ -210,6 +214,8 @@ EXPORTS = {
                                     C.POINTER(VxSvgfSpatialOut)]),
     "vxpt_svgf_frame": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseOut), C.POINTER(VxSvgfFrameParams),
                                   C.POINTER(VxSvgfSpatialOut)]),
+    "vxpt_shadow_filter_frame": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxShadowOut), C.POINTER(VxShadowFrameParams),
+                                           C.c_void_p]),
     "vxpt_shadow_temporal": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxShadowTemporalIn), C.POINTER(VxShadowTemporalParams),
                                        C.POINTER(VxShadowTemporalOut)]),
     "vxpt_shadow_filter": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxShadowFilterIn), C.POINTER(VxShadowFilterParams), C.c_void_p]),

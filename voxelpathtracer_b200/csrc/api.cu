@@ -335,7 +335,7 @@ int vxpt_destroy(vxpt_handle c) {
     }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
                     c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_alpha_mips, c->d_counters, c->d_stage, c->d_queue,
-                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut, c->svgf.buf};
+                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut, c->svgf.buf, c->shadow_hist.buf};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -911,6 +911,71 @@ int vxpt_shadow_filter(vxpt_handle c, const VxCamera* cam, const VxShadowFilterI
     id.current = VxGBuffer{(float*)t->dev, (uint8_t*)n->dev, nullptr, nullptr, nullptr};
     id.shadow = (const float*)sh->dev; id.transversal = (const float*)tr->dev; id.frames = (const float*)fr->dev;
     if ((rc = timed_launch(c, [&] { return launch_shadow_filter(c, *cam, id, *p, (float*)o->dev); }))) return rc;
+    return s.end(c);
+}
+
+int vxpt_shadow_filter_frame(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g, const VxShadowOut* shadow, const VxShadowFrameParams* p, float* out) {
+    int rc = check_svgf(c, cam);
+    if (rc) return rc;
+    if (!g || !shadow || !p || !out || !g->t || !g->normal_id || !shadow->shadow || !shadow->transversal)
+        return fail(VXPT_E_INVALID, "NULL argument (G-buffer t / normal_id, the shadow pass's shadow / transversal planes and the output are required)");
+    if (cam->row_begin != 0 || cam->row_end != cam->height) return fail(VXPT_E_INVALID, "vxpt_shadow_filter_frame filters whole frames (row_begin = 0, row_end = height)");
+    VX_CUDA(cudaSetDevice(c->device));
+    const int W = cam->width, H = cam->height;
+    const size_t npx = (size_t)W * H, plane = (npx * 4 + 255) & ~(size_t)255;
+    vxpt_ctx::ShadowHistory& h = c->shadow_hist;
+    const bool had = h.buf && h.width == W && h.height == H && h.valid && !p->reset_history;
+    if (!(h.buf && h.width == W && h.height == H)) {
+        VX_CUDA(cudaStreamSynchronize(c->stream));
+        if (h.buf) cudaFree(h.buf);
+        h = vxpt_ctx::ShadowHistory();
+        if (cudaMalloc(&h.buf, 5 * plane) != cudaSuccess) {
+            cudaGetLastError();
+            h.buf = nullptr;
+            return fail(VXPT_E_NOMEM, "device allocation of the shadow-filter history failed");
+        }
+        char* q = (char*)h.buf;
+        h.prev_t = (float*)q; h.shadow[0] = (float*)(q + plane); h.frames[0] = (float*)(q + 2 * plane); h.shadow[1] = (float*)(q + 3 * plane);
+        h.frames[1] = (float*)(q + 4 * plane);
+        h.width = W; h.height = H;
+    }
+    SvgfIO s(c, cam);
+    Plane *t = s.in(g->t, 4), *n = s.in(g->normal_id, 1), *sh = s.in(shadow->shadow, 1), *tr = s.in(shadow->transversal, 4);
+    Plane* o = s.out(out, 4);
+    if ((rc = s.begin())) return rc;
+    const VxGBuffer gd{(float*)t->dev, (uint8_t*)n->dev, nullptr, nullptr, nullptr};
+    const int prev = h.cur, cur = h.cur ^ 1;
+    VxShadowTemporalParams tp{};
+    if (!had) {
+        VX_CUDA(cudaMemsetAsync(h.shadow[prev], 0, npx * 4, c->stream));
+        VX_CUDA(cudaMemsetAsync(h.frames[prev], 0, npx * 4, c->stream));
+    }
+    std::memcpy(tp.prev_view, had ? h.prev_view : p->view, sizeof tp.prev_view);
+    std::memcpy(tp.prev_projection, had ? h.prev_projection : p->projection, sizeof tp.prev_projection);
+    if (c->opt_timing) VX_CUDA(cudaEventRecord(c->ev0, c->stream));
+    VxShadowTemporalIn ti{};
+    ti.current = gd;
+    ti.previous = VxGBuffer{had ? h.prev_t : gd.t, nullptr, nullptr, nullptr, nullptr};
+    ti.shadow = (const uint8_t*)sh->dev; ti.transversal = (const float*)tr->dev; ti.prev_shadow = h.shadow[prev]; ti.prev_frames = h.frames[prev];
+    const VxShadowTemporalOut to{h.shadow[cur], h.frames[cur]};
+    if ((rc = launch_shadow_temporal(c, *cam, ti, tp, to))) return rc;
+    if (p->spatial) {
+        VxShadowFilterIn fi{};
+        fi.current = gd; fi.shadow = to.shadow; fi.transversal = ti.transversal; fi.frames = to.frames;
+        const VxShadowFilterParams fp{p->filter_scale};
+        if ((rc = launch_shadow_filter(c, *cam, fi, fp, (float*)o->dev))) return rc;
+    } else {
+        VX_CUDA(cudaMemcpyAsync(o->dev, to.shadow, npx * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    VX_CUDA(cudaMemcpyAsync(h.prev_t, gd.t, npx * 4, cudaMemcpyDeviceToDevice, c->stream));
+    std::memcpy(h.prev_view, p->view, sizeof h.prev_view);
+    std::memcpy(h.prev_projection, p->projection, sizeof h.prev_projection);
+    h.cur = cur;
+    h.valid = true;
+    if (c->opt_timing) {
+        VX_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->pass_timed = true;
+    }
     return s.end(c);
 }
 

@@ -146,6 +146,16 @@ struct vxpt_ctx {
         uint8_t *prev_nid = nullptr, *prev_bid = nullptr;
     } svgf;
 
+    // vxpt_shadow_filter_frame: temporal shadow planes and the previous frame's hit distances
+    struct ShadowHistory {
+        int width = 0, height = 0;
+        bool valid = false;
+        int cur = 0;
+        float prev_view[16] = {0}, prev_projection[16] = {0};
+        void* buf = nullptr;
+        float *prev_t = nullptr, *shadow[2] = {nullptr, nullptr}, *frames[2] = {nullptr, nullptr};
+    } shadow_hist;
+
     // wavefront queues (grown on demand)
     void* d_queue = nullptr;
     size_t queue_bytes = 0;

@@ -3,7 +3,7 @@ from dicts of planes.  The same structs drive the library (Renderer.svgf_*), the
 `address` is injected: it maps a numpy array or torch tensor to its raw address."""
 import numpy as np
 
-from .abi import (VxGBuffer, VxShadowFilterIn, VxShadowFilterParams, VxShadowTemporalIn, VxShadowTemporalOut, VxShadowTemporalParams, VxSvgfFrameParams, VxSvgfInitialIn, VxSvgfInitialOut, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
+from .abi import (VxGBuffer, VxShadowFilterIn, VxShadowFrameParams, VxShadowFilterParams, VxShadowTemporalIn, VxShadowTemporalOut, VxShadowTemporalParams, VxSvgfFrameParams, VxSvgfInitialIn, VxSvgfInitialOut, VxSvgfSpatialIn, VxSvgfSpatialOut, VxSvgfSpatialParams, VxSvgfTemporalIn, VxSvgfTemporalOut, VxSvgfTemporalParams,
                   VxSvgfVarianceIn, VxSvgfVarianceOut, VxSvgfVarianceParams)
 
 ATROUS_STEPS = (16, 8, 4, 2, 1)          # Core/Pipeline.cpp:2482-2487
@@ -48,6 +48,15 @@ def frame_params(view, projection, time=0.0, reset_history=False, pre_pass=True,
     p.reset_history, p.pre_pass, p.wide, p.large_kernel = int(bool(reset_history)), int(bool(pre_pass)), int(bool(wide)), int(bool(large_kernel))
     p.aggressive_disocclusion = int(bool(aggressive_disocclusion))
     p.color_phi_bias, p.time, p.resolution_scale = float(color_phi_bias), float(time), float(resolution_scale)
+    return p
+
+
+def shadow_frame_params(view, projection, reset_history=False, spatial=True, filter_scale=1.0):
+    """vxpt_shadow_filter_frame: this frame's u_View / u_Projection and the switches of Core/Pipeline.cpp:132-133."""
+    p = VxShadowFrameParams()
+    p.view[:] = [float(v) for v in np.asarray(view, dtype=np.float32).reshape(16)]
+    p.projection[:] = [float(v) for v in np.asarray(projection, dtype=np.float32).reshape(16)]
+    p.reset_history, p.spatial, p.filter_scale = int(bool(reset_history)), int(bool(spatial)), float(filter_scale)
     return p
 
 

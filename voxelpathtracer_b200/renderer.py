@@ -318,6 +318,14 @@ class Renderer:
         check(self.lib.vxpt_svgf_frame(self.handle, C.byref(cam), C.byref(g), C.byref(d), C.byref(params), C.byref(o)))
         return out
 
+    def shadow_filter_frame(self, cam, gbuf, shadow, params, out):
+        """Both shadow filters of one frame with the temporal planes and history resident on the device (vxpt_shadow_filter_frame)."""
+        g = self.gbuffer_struct(gbuf)
+        s = VxShadowOut()
+        s.shadow, s.transversal = _ptr(shadow.get("shadow")), _ptr(shadow.get("transversal"))
+        check(self.lib.vxpt_shadow_filter_frame(self.handle, C.byref(cam), C.byref(g), C.byref(s), C.byref(params), _ptr(out)))
+        return out
+
     def shadow_temporal(self, cam, gbuf, prev_gbuf, shadow, prev_temporal, params, out):
         """ShadowTemporalFilter.glsl (vxpt_shadow_temporal): shadow = the shadow pass's planes, prev_temporal / out = {"shadow", "frames"}."""
         from . import denoise

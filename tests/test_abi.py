@@ -54,11 +54,17 @@ def test_header_every_export_cites_a_reference_site():
 
 def test_struct_layouts_match_the_c_compiler():
     structs = ["VxCamera", "VxPrimaryParams", "VxGBuffer", "VxShadowParams", "VxShadowOut", "VxDiffuseParams", "VxDiffuseOut",
-               "VxReflectionParams", "VxReflectionIn", "VxReflectionOut", "VxStats"]
+               "VxReflectionParams", "VxReflectionIn", "VxReflectionOut", "VxStats", "VxFrameParams", "VxFrameOut", "VxMaterialParams", "VxMaterialOut",
+               "VxSvgfInitialIn", "VxSvgfInitialOut", "VxSvgfTemporalIn", "VxSvgfTemporalParams", "VxSvgfTemporalOut", "VxSvgfVarianceIn",
+               "VxSvgfVarianceParams", "VxSvgfVarianceOut", "VxSvgfSpatialIn", "VxSvgfSpatialParams", "VxSvgfSpatialOut", "VxSvgfFrameParams",
+               "VxShadowTemporalIn", "VxShadowTemporalParams", "VxShadowTemporalOut", "VxShadowFilterIn", "VxShadowFilterParams", "VxShadowFrameParams"]
     prog = '#include <stdio.h>\n#include "vxpt.h"\nint main(void){' + "".join(
         f'printf("{s} %zu\\n", sizeof({s}));' for s in structs) + \
         'printf("off_row_begin %zu\\n", __builtin_offsetof(VxCamera,row_begin));' \
-        'printf("off_sun_dir %zu\\n", __builtin_offsetof(VxDiffuseParams,sun_dir));return 0;}'
+        'printf("off_sun_dir %zu\\n", __builtin_offsetof(VxDiffuseParams,sun_dir));' \
+        'printf("off_material %zu\\n", __builtin_offsetof(VxFrameParams,material));' \
+        'printf("off_time %zu\\n", __builtin_offsetof(VxSvgfFrameParams,time));' \
+        'printf("off_prev_sh %zu\\n", __builtin_offsetof(VxSvgfTemporalIn,prev_sh));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         cfile, exe = os.path.join(d, "s.c"), os.path.join(d, "s")
         open(cfile, "w").write(prog)
@@ -69,6 +75,9 @@ def test_struct_layouts_match_the_c_compiler():
         assert int(out[s]) == C.sizeof(getattr(abi, s)), s
     assert int(out["off_row_begin"]) == abi.VxCamera.row_begin.offset
     assert int(out["off_sun_dir"]) == abi.VxDiffuseParams.sun_dir.offset
+    assert int(out["off_material"]) == abi.VxFrameParams.material.offset
+    assert int(out["off_time"]) == abi.VxSvgfFrameParams.time.offset
+    assert int(out["off_prev_sh"]) == abi.VxSvgfTemporalIn.prev_sh.offset
 
 
 def _no_gpu():
@@ -110,5 +119,10 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "vxo_" not in text and "libvxo" not in text and "from oracle" not in text and "import oracle" not in text, f
+                # ... nor the g++ builds of its sources that tests/host_shadow keeps for the CPU suite (kernels on the host, the emulated ABI)
+                assert "hostemu" not in text and "kernels_on_host" not in text and "import host_shadow" not in text and "from host_shadow" not in text, f
     out = subprocess.run(["ldd", abi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "vxo" not in out
+    assert "vxo" not in out and "hostemu" not in out
+    # the binding has exactly one library path, next to the package, and no environment override
+    src = open(os.path.join(pkg, "abi.py")).read()
+    assert src.count("LIB_PATH =") == 1 and "environ" not in src

@@ -265,15 +265,21 @@ VXPT_API int vxpt_estimate_ambient_sound(vxpt_handle h, const float player_pos[3
  * normal / PBR: GL_LINEAR, c = 0.5); otherwise GL_NEAREST_MIPMAP_LINEAR: nearest texel of levels floor(lambda) and floor(lambda)+1
  * (clamped to 9), blended by fract(lambda).  dFdx / dFdy are differences inside the pixel's 2x2 quad (fine derivatives); a quad
  * neighbour that shades nothing (sky, outside the frame) contributes the pixel's own value.  The anisotropy extension is not modelled.
- * Parity profile v1: u_POM = false (off by default, Pipeline.cpp:264) and no lava animation (u_LavaBlockID matches no block):
- * both are rejected with VXPT_E_UNSUPPORTED. */
+ * The height-field taps of the parallax march (texture() with implicit derivatives inside a loop: undefined LOD in GL) are pinned to
+ * level 0, GL_LINEAR, like the emissive fetch.  Parity profile v1: no lava animation (u_LavaBlockID must match no block, else
+ * VXPT_E_UNSUPPORTED). */
 #define VXPT_MIP_CHAIN_TEXELS 349525 /* 512^2 + 256^2 + ... + 1 */
 typedef struct VxMaterialParams {
-    int32_t update_this_frame;  /* u_UpdateGBufferThisFrame: 0 = every pixel is discarded (planes untouched)                 */
-    int32_t pom;                /* u_POM; must be 0                                                                          */
+    int32_t update_this_frame;  /* u_UpdateGBufferThisFrame: 0 = every pixel is discarded (planes untouched) unless pom is set  */
+    int32_t pom;                /* u_POM (off by default, Pipeline.cpp:264): relief parallax mapping, ReliefParallax :153-199    */
     int32_t lava_block_id;      /* u_LavaBlockID; must be negative (no lava animation)                                       */
     int32_t grass_props[10];    /* u_GrassBlockProps (Pipeline.cpp:2083-2092): block id, then albedo / normal / PBR layers of  */
                                 /* the top, side and bottom faces                                                            */
+    float pom_height;           /* u_POMHeight (1.0)                                                                         */
+    float pom_exp;              /* u_POMExp (1.0)                                                                            */
+    int32_t high_quality_pom;   /* u_HighQualityPOM (0): 64..128 march steps instead of 32..64                               */
+    int32_t dither_pom;         /* u_DitherPOM (1): per-pixel step count from a Bayer pattern and u_Frame                     */
+    int32_t frame;              /* u_Frame                                                                                   */
 } VxMaterialParams;
 typedef struct VxMaterialOut {  /* fp32 planes in every texel format (the reflection pass reads normal / pbr as fp32) */
     float* albedo;      /* o_Albedo    3 floats / pixel (RGB16F in the reference)                             */

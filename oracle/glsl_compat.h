@@ -166,7 +166,19 @@ inline vec4 textureLod(const sampler2DArray& s, const vec3& p, float lod /*ignor
     const int i = ((int)std::floor(p.x * (float)s.n)) & (s.n - 1), j = ((int)std::floor(p.y * (float)s.n)) & (s.n - 1);
     return fetch_layer_texel(s, (int)p.z, i, j);
 }
+inline vec4 fetch_mip_texel(const sampler2DArray& s, int layer, int level, int i, int j);
 inline vec4 texture(const sampler2DArray& s, const vec3& p) {
+    if (s.mips) {  // implicit-LOD fetch on a mip-mapped block array (the parallax march of GenerateGBuffer.glsl): pinned to level 0, GL_LINEAR
+        const float x = p.x * 512.0f - 0.5f, y = p.y * 512.0f - 0.5f;
+        const float fx0 = std::floor(x), fy0 = std::floor(y);
+        const float fx = x - fx0, fy = y - fy0;
+        const int i0 = ((int)fx0) & 511, i1 = ((int)fx0 + 1) & 511, j0 = ((int)fy0) & 511, j1 = ((int)fy0 + 1) & 511;
+        int l = (int)std::nearbyintf(p.z);
+        l = l < 0 ? 0 : (l > s.mip_layers - 1 ? s.mip_layers - 1 : l);
+        const vec4 a = fetch_mip_texel(s, l, 0, i0, j0) * (1.0f - fx) + fetch_mip_texel(s, l, 0, i1, j0) * fx;
+        const vec4 b = fetch_mip_texel(s, l, 0, i0, j1) * (1.0f - fx) + fetch_mip_texel(s, l, 0, i1, j1) * fx;
+        return a * (1.0f - fy) + b * fy;
+    }
     if (!s.data) return vec4(1.0f);
     if (s.nearest_only) return textureLod(s, p, 0.0f);
     const float x = p.x * (float)s.n - 0.5f, y = p.y * (float)s.n - 0.5f;

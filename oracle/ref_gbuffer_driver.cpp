@@ -1,5 +1,5 @@
 // ref_gbuffer_driver.cpp — the reference's Core/Shaders/GenerateGBuffer.glsl compiled as C++, driven in the v1 parity profile of
-// include/vxpt.h (u_POM = false, no lava block); uniforms and binds follow Core/Pipeline.cpp:2066-2136.  The shader takes screen-space
+// include/vxpt.h (no lava block); uniforms and binds follow Core/Pipeline.cpp:2066-2136.  The shader takes screen-space
 // derivatives, so it runs in 2x2 quads: a record run and a replay run per quad (glsl_compat.h, QuadDerivatives).  See
 // ref_shader_driver.cpp.  Test infrastructure only.
 #include <cstdint>
@@ -29,6 +29,8 @@ struct RefGBufferArgs {  // plain C layout, filled by oracle/ref_shaders.py
     const float* emissive_lod0;  // [layers][512][512]
     int32_t update_this_frame;
     int32_t grass_props[10];
+    int32_t pom, high_quality_pom, dither_pom, frame;
+    float pom_height, pom_exp;
     float* o_albedo;      // 3 / pixel
     float* o_normal;      // 3 / pixel
     float* o_pbr;         // 4 / pixel
@@ -44,13 +46,13 @@ extern "C" __attribute__((visibility("default"))) int ref_generate_gbuffer(const
     S::u_LavaBlockID = -1;
     S::u_Time = 0.0f;
     S::uTime = 0.0f;
-    S::u_Frame = 0;
+    S::u_Frame = a->frame;
     S::u_UpdateGBufferThisFrame = a->update_this_frame != 0;
-    S::u_POM = false;
-    S::u_HighQualityPOM = false;
-    S::u_DitherPOM = true;
-    S::u_POMHeight = 1.0f;
-    S::u_POMExp = 1.0f;
+    S::u_POM = a->pom != 0;
+    S::u_HighQualityPOM = a->high_quality_pom != 0;
+    S::u_DitherPOM = a->dither_pom != 0;
+    S::u_POMHeight = a->pom_height;
+    S::u_POMExp = a->pom_exp;
     for (int k = 0; k < 10; ++k) S::u_GrassBlockProps[k] = a->grass_props[k];
     std::memcpy(S::BlockAlbedoData, a->materials + 0 * 128, 128 * sizeof(int));
     std::memcpy(S::BlockNormalData, a->materials + 1 * 128, 128 * sizeof(int));

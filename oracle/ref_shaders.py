@@ -40,7 +40,8 @@ class RefGBufferArgs(C.Structure):
                 ("row_end", C.c_int32), ("g_inv_t", C.c_void_p), ("g_normal_id", C.c_void_p), ("g_block_id", C.c_void_p), ("materials", C.c_void_p),
                 ("albedo_mips", C.c_void_p), ("normal_mips", C.c_void_p), ("pbr_mips", C.c_void_p), ("n_mip_layers", C.c_int32),
                 ("emissive_lod0", C.c_void_p), ("update_this_frame", C.c_int32), ("grass_props", C.c_int32 * 10),
-                ("o_albedo", C.c_void_p), ("o_normal", C.c_void_p), ("o_pbr", C.c_void_p), ("o_texture_ao", C.c_void_p)]
+                ("pom", C.c_int32), ("high_quality_pom", C.c_int32), ("dither_pom", C.c_int32), ("frame", C.c_int32), ("pom_height", C.c_float),
+                ("pom_exp", C.c_float), ("o_albedo", C.c_void_p), ("o_normal", C.c_void_p), ("o_pbr", C.c_void_p), ("o_texture_ao", C.c_void_p)]
 
 
 class RefSvgfArgs(C.Structure):
@@ -259,6 +260,8 @@ def generate_gbuffer(cam, gbuf, params, materials, mips, out=None):
     a.emissive_lod0 = ptr(materials["emissive_lod0"], np.float32)
     a.update_this_frame = params.update_this_frame
     a.grass_props[:] = list(params.grass_props)
+    a.pom, a.high_quality_pom, a.dither_pom, a.frame = params.pom, params.high_quality_pom, params.dither_pom, params.frame
+    a.pom_height, a.pom_exp = params.pom_height, params.pom_exp
     a.o_albedo, a.o_normal, a.o_pbr, a.o_texture_ao = (out[k].ctypes.data for k in ("albedo", "normal", "pbr", "texture_ao"))
     load().ref_generate_gbuffer(C.byref(a))
     return out

@@ -1368,8 +1368,8 @@ extern "C" {
 // Derivatives: dFdx / dFdy = odd-minus-even member of the quad's row / column pair; a member that never reaches the derivative
 // contributes the pixel's own operand.
 int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g, const VxMaterialParams* prm, const VxMaterialOut* out) {
-    if (prm->pom || prm->lava_block_id >= 0) return VXPT_E_UNSUPPORTED;
-    if (!prm->update_this_frame) return VXPT_OK;  // :353-357 discard
+    if (prm->lava_block_id >= 0) return VXPT_E_UNSUPPORTED;
+    if (!prm->update_this_frame && !prm->pom) return VXPT_OK;  // :351-357 discard (ShouldUpdate = u_UpdateGBufferThisFrame || lava || u_POM)
     float lut[256];
     for (int k = 0; k < 256; ++k) {
         const double cs = (double)k / 255.0;
@@ -1421,6 +1421,50 @@ int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
             float fu, fv;
             calc_vectors(me.pos, me.nid, tangent, bitangent, fu, fv);  // same tables as ReflectionTraceFrag's copy (:463-530 here)
             const v3 face = normal_from_id(me.nid, 1.0f);
+            if (prm->pom) {  // Parallax :343-353 -> ReliefParallax :153-199 (the code after its first return is dead)
+                const v3 view = normalize(me.pos - ray_origin(*cam));
+                const float depth_scale = 0.115f * prm->pom_height;
+                float bayer_steps = 0.5f;
+                if (prm->dither_pom) {
+                    auto bayer2 = [](float ax, float ay) { ax = std::floor(ax); ay = std::floor(ay); return fractf(ax * 0.5f + ay * (ay * 0.75f)); };
+                    const float cx = (float)i + 0.5f, cy = (float)j + 0.5f;   // gl_FragCoord.xy; bayer32 = bayer2 at five octaves
+                    float cxs[5], cys[5];
+                    cxs[0] = cx; cys[0] = cy;
+                    for (int k = 1; k < 5; ++k) { cxs[k] = 0.5f * cxs[k - 1]; cys[k] = 0.5f * cys[k - 1]; }
+                    float b = bayer2(cxs[4], cys[4]);
+                    for (int k = 3; k >= 0; --k) b = b * 0.25f + bayer2(cxs[k], cys[k]);
+                    const float fr = (float)prm->frame + 0.0f * 2.0f;
+                    const float md = fr - 384.0f * std::floor(fr / 384.0f);
+                    bayer_steps = fractf(fractf(md * (1.0f / 1.6180339f)) + b);
+                }
+                const v3 tv = normalize(V(dot(view, tangent), dot(view, bitangent), dot(view, -face)));
+                float mdx = tv.x, mdy = tv.y;
+                const float dv = std::fabs(face.x) > 0.01f ? tv.z : -(tv.z);
+                mdx /= dv; mdy /= dv;
+                mdx *= depth_scale; mdy *= depth_scale;
+                const int steps = prm->high_quality_pom ? (int)mixf(64.0f, 128.0f, clampf(bayer_steps * 0.9f, 0.0f, 1.0f))
+                                                        : (int)mixf(32.0f, 64.0f, clampf(bayer_steps * 0.85f, 0.0f, 1.0f));
+                const float step_size = 1.0f / (float)steps;
+                const float su = clampf(fu, 0.000001f, 1.0f), sv = clampf(fv, 0.000001f, 1.0f);
+                float cur_depth = 1.0f, best = 1.0f;
+                int layer = (int)std::nearbyintf((float)(int)data[2]);
+                layer = std::min(std::max(layer, 0), pbr.layers - 1);
+                for (int k = 0; k < steps; ++k) {
+                    cur_depth -= step_size;
+                    const float pu = su + mdx * cur_depth, pv = sv + mdy * cur_depth;
+                    // texture(u_BlockPBR, ...) inside the loop: pinned to level 0, GL_LINEAR (include/vxpt.h)
+                    const float x = pu * 512.0f - 0.5f, y = pv * 512.0f - 0.5f;
+                    const float x0 = std::floor(x), y0 = std::floor(y), fx = x - x0, fy = y - y0;
+                    const int i0 = ((int)x0) & 511, i1 = ((int)x0 + 1) & 511, j0 = ((int)y0) & 511, j1 = ((int)y0 + 1) & 511;
+                    const f4 lo = lerp4(pbr.texel(layer, 0, i0, j0), pbr.texel(layer, 0, i1, j0), fx);
+                    const f4 hi = lerp4(pbr.texel(layer, 0, i0, j1), pbr.texel(layer, 0, i1, j1), fx);
+                    const float height = pow_cr(lerp4(lo, hi, fy).z, 1.5f * prm->pom_exp);   // MapHeight :147-149
+                    if (cur_depth >= height) best = cur_depth;
+                }
+                cur_depth = best - step_size * 0.5f;
+                fu = su + mdx * cur_depth;
+                fv = sv + mdy * cur_depth;
+            }
             const float U = 1.0f - fu, Vc = 1.0f - fv;  // :397
             const f4 nm = normals.grad(data[1], U, Vc, dx, dy);
             const v3 n = V(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f);

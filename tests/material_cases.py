@@ -15,6 +15,12 @@ CASES = [
     ("plains_250x141_close", "plains", 250, 141, dict(position=(192.0, 60.3, 192.0), pitch_deg=-60.0, yaw_deg=10.0)),   # odd height, magnification
     ("superflat_320x180_horizon", "superflat", 320, 180, dict(position=(192.0, 51.0, 192.0), pitch_deg=-2.0)),           # grazing: high mip levels
 ]
+# relief parallax mapping (u_POM): name, index into CASES, material_params keywords
+POM_CASES = [
+    ("pom_gi_box_lamps_dither_f3", 1, dict(frame=3)),
+    ("pom_city_hq_deep", 2, dict(high_quality_pom=True, frame=777, pom_height=2.5, pom_exp=0.5)),
+    ("pom_close_nodither_noupdate", 3, dict(dither_pom=False, update_this_frame=False)),   # u_POM keeps the pass alive without u_UpdateGBufferThisFrame
+]
 PLANES = ("albedo", "normal", "pbr", "texture_ao")
 _mips = {}
 

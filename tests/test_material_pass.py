@@ -67,6 +67,24 @@ def test_oracle_equals_the_reference_shader_digests(gb_oracles, scene_tables, mi
         assert want["emissive_pixels"] > 1000
 
 
+@pytest.mark.parametrize("pom", mc.POM_CASES, ids=[c[0] for c in mc.POM_CASES])
+def test_relief_parallax_oracle_equals_the_reference_shader_digests(gb_oracles, scene_tables, mips, ref_digests, pom):
+    """u_POM (ReliefParallax :153-199): dithered and fixed step counts, high quality, non-default depth / exponent, and u_POM keeping the
+    pass alive when u_UpdateGBufferThisFrame is off."""
+    if any(mc.sha(m) != ref_digests["mips"][k] for k, m in zip(("albedo", "normal", "pbr"), mips)):
+        pytest.skip("the synthetic textures differ from the ones the digests were made with (other numpy / libm)")
+    name, idx, kw = pom
+    case = mc.CASES[idx]
+    o = gb_oracles[case[1]]
+    cam = mc.case_camera(case)
+    g, _ = o.trace_primary(cam, vx.primary_params(350))
+    m = o.generate_gbuffer(cam, g, _params(scene_tables, pom=True, **kw))
+    for k in mc.PLANES:
+        assert mc.sha(m[k]) == ref_digests["pom_cases"][name][k], k
+    flat = o.generate_gbuffer(cam, g, _params(scene_tables))
+    assert not np.array_equal(m["albedo"], flat["albedo"])        # the march does move the texture coordinates
+
+
 @needs_ref
 def test_oracle_equals_the_reference_shader_live(gb_oracles, scene_tables, mips):
     """Frames not in the committed set: odd sizes (quads cut by the frame edge), a row slab, a roll of the camera, a frame that is
@@ -181,6 +199,10 @@ def test_kernel_source_on_host_equals_the_oracle(gb_oracles, scene_tables, case)
     got = k.generate_gbuffer(cam, g, _params(scene_tables))
     for key in mc.PLANES:
         assert np.array_equal(got[key], want[key]), key
+    pom = _params(scene_tables, pom=True, frame=5, high_quality_pom=(case[0] == "city_480x270_street"))   # the relief-parallax instantiation
+    want_pom, got_pom = o.generate_gbuffer(cam, g, pom), k.generate_gbuffer(cam, g, pom)
+    for key in mc.PLANES:
+        assert np.array_equal(got_pom[key], want_pom[key], equal_nan=True), ("pom", key)   # (NaN where the camera stands inside a block: t ~ 1e-4)
     cam.row_begin, cam.row_end = 10, 52   # a slab: rows outside stay as they were
     seed = {key: np.full_like(want[key], 7.0) for key in mc.PLANES}
     got = k.generate_gbuffer(cam, g, _params(scene_tables), seed)
@@ -262,7 +284,7 @@ def test_gpu_material_pass_argument_checks(gb_renderer, worlds, scene_tables):
     cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H)
     g = r.trace_primary(cam, vx.primary_params(350), r.alloc_gbuffer(W, H))
     out = r.alloc_material(W, H)
-    for kw, code in [(dict(pom=True), abi.E_UNSUPPORTED), (dict(lava_block_id=11), abi.E_UNSUPPORTED)]:
+    for kw, code in [(dict(pom=True, pom_height=-1.0), abi.E_INVALID), (dict(lava_block_id=11), abi.E_UNSUPPORTED)]:
         with pytest.raises(abi.VxptError) as e:
             r.generate_gbuffer(cam, g, _params(scene_tables, **kw), out)
         assert e.value.code == code
@@ -322,3 +344,23 @@ def test_gpu_render_frame_runs_the_material_pass_and_feeds_the_reflections(gb_re
     with pytest.raises(abi.VxptError) as e:
         r.render_frame(odd, pp, material=mp, material_out=r.alloc_material(W, H))
     assert e.value.code == abi.E_INVALID
+
+
+@pytest.mark.gpu
+def test_gpu_relief_parallax_equals_the_oracle(gb_renderer, worlds, gb_oracles, scene_tables):
+    name, idx, kw = mc.POM_CASES[0]
+    case = mc.CASES[idx]
+    r, o = gb_renderer, gb_oracles[case[1]]
+    r.upload_world(worlds[case[1]])
+    r.build_distance_field()
+    cam = mc.case_camera(case)
+    W, H = cam.width, cam.height
+    g = r.trace_primary(cam, vx.primary_params(350), r.alloc_gbuffer(W, H))
+    g_ref, _ = o.trace_primary(cam, vx.primary_params(350))
+    for kw2 in (kw, dict(high_quality_pom=True, dither_pom=False, pom_height=2.0)):
+        mp = _params(scene_tables, pom=True, **kw2)
+        want = o.generate_gbuffer(cam, g_ref, mp)
+        got = r.generate_gbuffer(cam, g, mp, r.alloc_material(W, H))
+        for k in mc.PLANES:     # the march compares pow() results against a depth: an ulp can flip a step, so a few more texels may differ
+            diff = got[k] != want[k]
+            assert diff.mean() <= 2e-3, (k, float(diff.mean()))

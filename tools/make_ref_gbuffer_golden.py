@@ -38,6 +38,15 @@ def main():
         out["cases"][name].update(hit_fraction=float((g["t"] > 0).mean()), mean_albedo=float(m["albedo"].mean()),
                                   emissive_pixels=int((m["pbr"][..., 3] > 0).sum()))
         print(f"{name}: {time.time() - t0:.1f} s {out['cases'][name]}", flush=True)
+    out["pom_cases"] = {}
+    for name, idx, kw in mc.POM_CASES:
+        case = mc.CASES[idx]
+        wname = case[1]
+        cam = mc.case_camera(case)
+        g = ref_shaders.trace_primary(worlds[wname].data, dfs[wname], cam, vx.primary_params(350))
+        m = ref_shaders.generate_gbuffer(cam, g, vx.material_params(mats["grass_props"], pom=True, **kw), mats, mips)
+        out["pom_cases"][name] = {k: mc.sha(m[k]) for k in mc.PLANES}
+        print(f"{name}: {out['pom_cases'][name]['albedo'][:16]}", flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "ref_gbuffer_digests.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 

@@ -78,7 +78,8 @@ class VxReflectionOut(C.Structure):
 
 
 class VxMaterialParams(C.Structure):
-    _fields_ = [("update_this_frame", C.c_int32), ("pom", C.c_int32), ("lava_block_id", C.c_int32), ("grass_props", C.c_int32 * 10)]
+    _fields_ = [("update_this_frame", C.c_int32), ("pom", C.c_int32), ("lava_block_id", C.c_int32), ("grass_props", C.c_int32 * 10),
+                ("pom_height", C.c_float), ("pom_exp", C.c_float), ("high_quality_pom", C.c_int32), ("dither_pom", C.c_int32), ("frame", C.c_int32)]
 
 
 class VxMaterialOut(C.Structure):

@@ -597,7 +597,7 @@ int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
     if ((rc = io.resolve())) return rc;
     if (cam->row_end == cam->row_begin) return VXPT_OK;
     if ((rc = io.upload(it)) || (rc = io.upload(nid)) || (rc = io.upload(bid))) return rc;
-    if (!p->update_this_frame) {  // every invocation discards: staged output planes must keep what the caller's planes hold
+    if (!p->update_this_frame && !p->pom) {  // every invocation discards: staged output planes must keep what the caller's planes hold
         if ((rc = io.upload(al)) || (rc = io.upload(nm)) || (rc = io.upload(pb)) || (rc = io.upload(ao))) return rc;
     }
     VxGBuffer gd{nullptr, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, nullptr};
@@ -617,7 +617,8 @@ int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
 }  // extern "C"
 // parameter and state checks of the G-buffer material pass (vxpt_generate_gbuffer, vxpt_render_frame)
 static int check_material(const vxpt_ctx* c, const VxCamera* cam, const VxMaterialParams* p) {
-    if (p->pom) return fail(VXPT_E_UNSUPPORTED, "u_POM (relief parallax mapping) is outside the v1 parity profile");
+    if (p->pom && !(p->pom_height >= 0.0f && p->pom_height <= 16.0f && p->pom_exp >= 0.0f && p->pom_exp <= 16.0f))
+        return fail(VXPT_E_INVALID, "u_POMHeight / u_POMExp outside 0..16");
     if (p->lava_block_id >= 0) return fail(VXPT_E_UNSUPPORTED, "lava animation (u_LavaBlockID, functions of the wall clock) is outside the v1 parity profile");
     if (!c->have_materials || !c->d_albedo_mips) return fail(VXPT_E_STATE, "the G-buffer pass needs vxpt_set_materials and vxpt_set_gbuffer_textures");
     const int rows = cam->interleave_n > 1 ? cam->height / cam->interleave_n : cam->height;
@@ -1180,7 +1181,7 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     PassIO io(c, cam);
     Plane t, nid, bid, it, hv, sh, tr, dsh, dcg, dlu, dao, gn, gp, col, hd, em, mal, mnm, mpb, mao;
     const bool mat = p->material != nullptr;
-    const bool mat_feeds_reflection = mat && p->reflection && p->material->update_this_frame;
+    const bool mat_feeds_reflection = mat && p->reflection && (p->material->update_this_frame || p->material->pom);
     // planes a later pass reads exist in the handle's arena even when the caller does not want them back
     io.add(t, out->gbuffer.t, px_bytes(c, 4, 2), secondary);
     io.add(nid, out->gbuffer.normal_id, 1, secondary);
@@ -1245,7 +1246,7 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     if ((rc = launch_primary(c, *cam, *p->primary, gd))) return rc;
     if ((rc = copy_out({&t, &nid, &bid, &it, &hv}, cam->row_begin, cam->row_end))) return rc;
     if (mat) {
-        if (!p->material->update_this_frame)  // every fragment discards: staged planes must keep what the caller's hold
+        if (!p->material->update_this_frame && !p->material->pom)  // every fragment discards: staged planes must keep what the caller's hold
             if ((rc = io.upload(mal)) || (rc = io.upload(mnm)) || (rc = io.upload(mpb)) || (rc = io.upload(mao))) return rc;
         if ((rc = launch_gbuffer(c, *cam, gd, *p->material, md))) return rc;
         if ((rc = copy_out({&mal, &mnm, &mpb, &mao}, cam->row_begin, cam->row_end))) return rc;

@@ -1,5 +1,5 @@
 // gbuffer.cu — G-buffer material pass: Core/Shaders/GenerateGBuffer.glsl main() :347-441 as drawn by
-// Core/Pipeline.cpp:2066-2136, in the v1 parity profile of include/vxpt.h (u_POM = false, no lava animation).
+// Core/Pipeline.cpp:2066-2136, in the v1 parity profile of include/vxpt.h (no lava animation); relief parallax mapping (u_POM) included.
 //
 // One thread per pixel, the 8x4-pixel warp tiles of the trace passes.  The shader takes screen-space derivatives of the surface UV
 // (GetUVDerivative :443-461) to pick the mip level: a derivative is a difference inside the pixel's 2x2 quad, so every thread
@@ -15,6 +15,10 @@ namespace vxpt {
 
 struct MaterialDev {
     int grass[10];
+    int pom, high_quality_pom, dither_pom;
+    float depth_scale;  // 0.115f * u_POMHeight
+    float height_exp;   // 1.5f * u_POMExp
+    float frame_term;   // fract(mod(float(u_Frame), 384.0f) * (1.0f / PHI)), computed on the host in fp32
 };
 struct MaterialOutDev {
     float* albedo;      // 3 / pixel
@@ -93,6 +97,8 @@ __device__ __forceinline__ bool quad_uv(const CameraDev& cam, const GBufferDev& 
     return true;
 }
 
+// POM = u_POM: a separate instantiation, so that the default pass keeps its 40 registers
+template <bool POM>
 __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ MaterialDev p,
                                                       const GBufferDev g, const MaterialOutDev out) {
     int i, j, prow;
@@ -140,7 +146,51 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     else if (nid <= 3) { tangent = mk3(1.f, 0.f, 0.f); bitangent = mk3(0.f, 0.f, 1.f); }
     else { tangent = mk3(0.f, 0.f, -1.f); bitangent = mk3(0.f, -1.f, 0.f); }
     const V3 face = normal_from_id(nid, 1.0f);
-    u = 1.0f - u;  // :397 (Parallax() returns the flat UV when u_POM is off)
+    if (POM) {  // Parallax :343-353 -> ReliefParallax :153-199 (everything after its first return is dead code)
+        const V3 view = normalize3(pos - ray_origin(cam));
+        float bayer_steps = 0.5f;
+        if (p.dither_pom) {  // bayer32(gl_FragCoord.xy): bayer2 at five octaves, coarsest first
+            float cx[5], cy[5];
+            cx[0] = (float)i + 0.5f; cy[0] = (float)j + 0.5f;
+#pragma unroll
+            for (int k = 1; k < 5; ++k) { cx[k] = 0.5f * cx[k - 1]; cy[k] = 0.5f * cy[k - 1]; }
+            float b = 0.0f;
+#pragma unroll
+            for (int k = 4; k >= 0; --k) {
+                const float ax = floorf(cx[k]), ay = floorf(cy[k]);
+                const float b2 = fractf(ax * 0.5f + ay * (ay * 0.75f));
+                b = k == 4 ? b2 : b * 0.25f + b2;
+            }
+            bayer_steps = fractf(p.frame_term + b);
+        }
+        const V3 tv = normalize3(mk3(dot3(view, tangent), dot3(view, bitangent), dot3(view, -face)));
+        const float dv = fabsf(face.x) > 0.01f ? tv.z : -(tv.z);
+        const float mdx = (tv.x / dv) * p.depth_scale, mdy = (tv.y / dv) * p.depth_scale;
+        const int steps = p.high_quality_pom ? (int)mixf(64.0f, 128.0f, clampf(bayer_steps * 0.9f, 0.0f, 1.0f))
+                                             : (int)mixf(32.0f, 64.0f, clampf(bayer_steps * 0.85f, 0.0f, 1.0f));
+        const float step_size = 1.0f / (float)steps;
+        const float su = clampf(u, 0.000001f, 1.0f), sv = clampf(v, 0.000001f, 1.0f);
+        const int layer = min(max((int)nearbyintf((float)(int)l_pbr), 0), S.n_mip_layers - 1);
+        const uchar4* base = S.pbr_mips + (size_t)layer * VXPT_MIP_CHAIN_TEXELS;
+        const float* unorm = S.srgb_lut + 256;
+        float cur_depth = 1.0f, best = 1.0f;
+#pragma unroll 1
+        for (int k = 0; k < steps; ++k) {
+            cur_depth -= step_size;
+            // texture(u_BlockPBR, ...).z inside the loop: pinned to level 0, GL_LINEAR (include/vxpt.h); only the height channel is fetched
+            const float x = (su + mdx * cur_depth) * 512.0f - 0.5f, y = (sv + mdy * cur_depth) * 512.0f - 0.5f;
+            const float x0 = floorf(x), y0 = floorf(y), fx = x - x0, fy = y - y0;
+            const int i0 = ((int)x0) & 511, i1 = ((int)x0 + 1) & 511, j0 = ((int)y0) & 511, j1 = ((int)y0 + 1) & 511;
+            const float t00 = __ldg(unorm + base[j0 * 512 + i0].z), t10 = __ldg(unorm + base[j0 * 512 + i1].z);
+            const float t01 = __ldg(unorm + base[j1 * 512 + i0].z), t11 = __ldg(unorm + base[j1 * 512 + i1].z);
+            const float h = (t00 * (1.0f - fx) + t10 * fx) * (1.0f - fy) + (t01 * (1.0f - fx) + t11 * fx) * fy;
+            if (cur_depth >= pow_cr(h, p.height_exp)) best = cur_depth;  // MapHeight :147-149
+        }
+        cur_depth = best - step_size * 0.5f;
+        u = su + mdx * cur_depth;
+        v = sv + mdy * cur_depth;
+    }
+    u = 1.0f - u;  // :397
     v = 1.0f - v;
     const float lambda = mip_lambda(d);
     const float4 nm = texture_grad(S, S.normal_mips, l_normal, u, v, lambda, false, true);
@@ -161,10 +211,19 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
 }
 
 int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const VxMaterialParams& p, const VxMaterialOut& out) {
-    if (!p.update_this_frame) return VXPT_OK;  // :353-357: every invocation discards
+    if (!p.update_this_frame && !p.pom) return VXPT_OK;  // :351-357: every invocation discards (ShouldUpdate = update || lava || u_POM)
     const SceneDev S = make_scene(c);
     MaterialDev d;
     for (int k = 0; k < 10; ++k) d.grass[k] = p.grass_props[k];
+    d.pom = p.pom; d.high_quality_pom = p.high_quality_pom; d.dither_pom = p.dither_pom;
+    d.depth_scale = 0.115f * p.pom_height;
+    d.height_exp = 1.5f * p.pom_exp;
+    {
+        const float fr = (float)p.frame + 0.0f * 2.0f;
+        const float md = fr - 384.0f * std::floor(fr / 384.0f);  // mod(x, y) = x - y * floor(x / y)
+        const float t = md * (1.0f / 1.6180339f);
+        d.frame_term = t - std::floor(t);
+    }
     CameraDev cd;
     for (int k = 0; k < 16; ++k) { cd.inv_view[k] = cam.inv_view[k]; cd.inv_proj[k] = cam.inv_proj[k]; }
     cd.width = cam.width; cd.height = cam.height; cd.row_begin = cam.row_begin; cd.row_end = cam.row_end;
@@ -172,7 +231,8 @@ int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const V
     const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel};
     const MaterialOutDev od{out.albedo, out.normal, reinterpret_cast<float4*>(out.pbr), out.texture_ao};
     const dim3 grid((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8);
-    VX_LAUNCH(gbuffer_kernel, grid, 256, c->stream, S, cd, d, gd, od);
+    if (p.pom) VX_LAUNCH((gbuffer_kernel<true>), grid, 256, c->stream, S, cd, d, gd, od);
+    else VX_LAUNCH((gbuffer_kernel<false>), grid, 256, c->stream, S, cd, d, gd, od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

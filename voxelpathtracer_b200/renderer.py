@@ -83,11 +83,14 @@ def reflection_params(sun_dir, moon_dir, stronger_dir, viewer_pos, grass_props, 
     return p
 
 
-def material_params(grass_props, update_this_frame=True, pom=False, lava_block_id=-1):
-    """GenerateGBuffer's uniforms (Core/Pipeline.cpp:2079-2104); POM and the lava animation are outside the v1 parity profile."""
+def material_params(grass_props, update_this_frame=True, pom=False, lava_block_id=-1, pom_height=1.0, pom_exp=1.0, high_quality_pom=False,
+                    dither_pom=True, frame=0):
+    """GenerateGBuffer's uniforms (Core/Pipeline.cpp:2079-2104, defaults :264-268); the lava animation is outside the v1 parity profile."""
     p = VxMaterialParams()
     p.update_this_frame, p.pom, p.lava_block_id = int(bool(update_this_frame)), int(bool(pom)), int(lava_block_id)
     p.grass_props[:] = [int(v) for v in grass_props]
+    p.pom_height, p.pom_exp = float(pom_height), float(pom_exp)
+    p.high_quality_pom, p.dither_pom, p.frame = int(bool(high_quality_pom)), int(bool(dither_pom)), int(frame)
     return p
 
 

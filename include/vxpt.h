@@ -266,13 +266,15 @@ VXPT_API int vxpt_estimate_ambient_sound(vxpt_handle h, const float player_pos[3
  * (clamped to 9), blended by fract(lambda).  dFdx / dFdy are differences inside the pixel's 2x2 quad (fine derivatives); a quad
  * neighbour that shades nothing (sky, outside the frame) contributes the pixel's own value.  The anisotropy extension is not modelled.
  * The height-field taps of the parallax march (texture() with implicit derivatives inside a loop: undefined LOD in GL) are pinned to
- * level 0, GL_LINEAR, like the emissive fetch.  Parity profile v1: no lava animation (u_LavaBlockID must match no block, else
- * VXPT_E_UNSUPPORTED). */
+ * level 0, GL_LINEAR, like the emissive fetch.  The animated lava textures (Core/AnimatedTexture.cpp: GL_RGBA8 3-D textures of 256^2 x 8
+ * frames, GL_LINEAR, GL_REPEAT on all three axes) are trilinear per OpenGL 4.3 section 8.14.2 in fp32, weights a(1-f) + bf, x then y then z;
+ * sin / cos / pow of the UV distortion are the correctly rounded fp32 values. */
 #define VXPT_MIP_CHAIN_TEXELS 349525 /* 512^2 + 256^2 + ... + 1 */
 typedef struct VxMaterialParams {
     int32_t update_this_frame;  /* u_UpdateGBufferThisFrame: 0 = every pixel is discarded (planes untouched) unless pom is set  */
     int32_t pom;                /* u_POM (off by default, Pipeline.cpp:264): relief parallax mapping, ReliefParallax :153-199    */
-    int32_t lava_block_id;      /* u_LavaBlockID; must be negative (no lava animation)                                       */
+    int32_t lava_block_id;      /* u_LavaBlockID: pixels of this block take the animated lava path (needs vxpt_set_lava_textures);  */
+                                /* negative = no block does                                                                  */
     int32_t grass_props[10];    /* u_GrassBlockProps (Pipeline.cpp:2083-2092): block id, then albedo / normal / PBR layers of  */
                                 /* the top, side and bottom faces                                                            */
     float pom_height;           /* u_POMHeight (1.0)                                                                         */
@@ -280,6 +282,7 @@ typedef struct VxMaterialParams {
     int32_t high_quality_pom;   /* u_HighQualityPOM (0): 64..128 march steps instead of 32..64                               */
     int32_t dither_pom;         /* u_DitherPOM (1): per-pixel step count from a Bayer pattern and u_Frame                     */
     int32_t frame;              /* u_Frame                                                                                   */
+    float time;                 /* u_Time = glfwGetTime(): drives the lava UV distortion and frame blend (:127-137, :390)      */
 } VxMaterialParams;
 typedef struct VxMaterialOut {  /* fp32 planes in every texel format (the reflection pass reads normal / pbr as fp32) */
     float* albedo;      /* o_Albedo    3 floats / pixel (RGB16F in the reference)                             */
@@ -287,6 +290,10 @@ typedef struct VxMaterialOut {  /* fp32 planes in every texel format (the reflec
     float* pbr;         /* o_PBR       4 floats / pixel: roughness, metalness, displacement, emissivity       */
     float* texture_ao;  /* o_TextureAO 1 float / pixel                                                        */
 } VxMaterialOut;
+#define VXPT_LAVA_SIZE 256  /* Core/Pipeline.cpp:1475-1477: LavaAlbedo / LavaNormals .Create(path, 256, 7) -> 256 x 256 x 8 texels */
+#define VXPT_LAVA_FRAMES 8
+/* u_LavaTextures[0] (albedo) and [1] (normals): RGBA8 [VXPT_LAVA_FRAMES][VXPT_LAVA_SIZE][VXPT_LAVA_SIZE][4] each */
+VXPT_API int vxpt_set_lava_textures(vxpt_handle h, const uint8_t* albedo_rgba8, const uint8_t* normal_rgba8);
 VXPT_API int vxpt_set_gbuffer_textures(vxpt_handle h, const uint8_t* albedo_mips, const uint8_t* normal_mips, const uint8_t* pbr_mips,
                                        int n_layers);
 /* reads VxGBuffer.inv_t (u_NonLinearDepth), normal_id and block_id; row_begin / row_end must be even (or the frame height): a 2x2

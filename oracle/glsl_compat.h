@@ -81,6 +81,9 @@ template <class V> inline V pinned_mix(const V& x, const V& y, const V& a) { ret
 struct sampler3D {  // GL_RED, GL_UNSIGNED_BYTE, NEAREST (Core/Texture3D.cpp:8-28)
     const uint8_t* data = nullptr;
     int sx = 0, sy = 0, sz = 0;
+    // the animated lava textures (Core/AnimatedTexture.cpp:8-26): GL_RGBA8 [frames][n][n][4], GL_LINEAR, GL_REPEAT on the three axes
+    const uint8_t* rgba = nullptr;
+    int rn = 0, rframes = 0;
 };
 inline vec4 texelFetch(const sampler3D& s, const ivec3& p, int /*lod*/) {
     const uint8_t c = s.data[(size_t)p.x + (size_t)s.sx * ((size_t)p.y + (size_t)s.sy * (size_t)p.z)];
@@ -303,7 +306,24 @@ inline vec2 dFdy(const vec2& v) { return gl_Quad.diff(v, gl_Quad.lane & 1, (gl_Q
 struct usampler3D {};
 inline uvec4 texture(const usampler3D&, const vec3&) { return uvec4(0u); }
 inline uvec4 texelFetch(const usampler3D&, const ivec3&, int) { return uvec4(0u); }
-inline vec4 texture(const sampler3D&, const vec3&) { return vec4(0.0f); }
+inline vec4 texture(const sampler3D& s, const vec3& p) {
+    if (!s.rgba) return vec4(0.0f);
+    // trilinear, OpenGL 4.3 section 8.14.2 in fp32: weights a * (1 - f) + b * f, x then y then z
+    const float x = p.x * (float)s.rn - 0.5f, y = p.y * (float)s.rn - 0.5f, z = p.z * (float)s.rframes - 0.5f;
+    const float x0 = std::floor(x), y0 = std::floor(y), z0 = std::floor(z);
+    const float fx = x - x0, fy = y - y0, fz = z - z0;
+    auto wr = [](int i, int n) { const int m = i % n; return m < 0 ? m + n : m; };
+    const int i0 = wr((int)x0, s.rn), i1 = wr((int)x0 + 1, s.rn), j0 = wr((int)y0, s.rn), j1 = wr((int)y0 + 1, s.rn);
+    const int k0 = wr((int)z0, s.rframes), k1 = wr((int)z0 + 1, s.rframes);
+    auto tx = [&](int i, int j, int k) {
+        const uint8_t* c = s.rgba + (((size_t)k * s.rn + j) * s.rn + i) * 4;
+        return vec4((float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f);
+    };
+    auto lerp = [](const vec4& a, const vec4& b, float f) { return a * (1.0f - f) + b * f; };
+    const vec4 a = lerp(lerp(tx(i0, j0, k0), tx(i1, j0, k0), fx), lerp(tx(i0, j1, k0), tx(i1, j1, k0), fx), fy);
+    const vec4 b = lerp(lerp(tx(i0, j0, k1), tx(i1, j0, k1), fx), lerp(tx(i0, j1, k1), tx(i1, j1, k1), fx), fy);
+    return lerp(a, b, fz);
+}
 inline uint clamp(uint x, int lo, int hi) { return x < (uint)lo ? (uint)lo : (x > (uint)hi ? (uint)hi : x); }
 
 // SSBO atomics: the drivers run the invocations of such shaders one after another

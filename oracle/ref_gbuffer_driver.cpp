@@ -31,6 +31,10 @@ struct RefGBufferArgs {  // plain C layout, filled by oracle/ref_shaders.py
     int32_t grass_props[10];
     int32_t pom, high_quality_pom, dither_pom, frame;
     float pom_height, pom_exp;
+    int32_t lava_block_id;
+    float time;
+    const uint8_t* lava_albedo;  // [8][256][256][4]
+    const uint8_t* lava_normal;
     float* o_albedo;      // 3 / pixel
     float* o_normal;      // 3 / pixel
     float* o_pbr;         // 4 / pixel
@@ -43,9 +47,13 @@ extern "C" __attribute__((visibility("default"))) int ref_generate_gbuffer(const
     const int W = a->width, H = a->height;
     std::memcpy(&S::u_InverseView[0][0], a->inv_view, 16 * sizeof(float));
     std::memcpy(&S::u_InverseProjection[0][0], a->inv_proj, 16 * sizeof(float));
-    S::u_LavaBlockID = -1;
-    S::u_Time = 0.0f;
-    S::uTime = 0.0f;
+    S::u_LavaBlockID = a->lava_block_id;
+    S::u_Time = a->time;
+    S::uTime = a->time;
+    S::u_LavaTextures[0] = sampler3D();
+    S::u_LavaTextures[1] = sampler3D();
+    S::u_LavaTextures[0].rgba = a->lava_albedo; S::u_LavaTextures[0].rn = 256; S::u_LavaTextures[0].rframes = 8;
+    S::u_LavaTextures[1].rgba = a->lava_normal; S::u_LavaTextures[1].rn = 256; S::u_LavaTextures[1].rframes = 8;
     S::u_Frame = a->frame;
     S::u_UpdateGBufferThisFrame = a->update_this_frame != 0;
     S::u_POM = a->pom != 0;

@@ -41,7 +41,8 @@ class RefGBufferArgs(C.Structure):
                 ("albedo_mips", C.c_void_p), ("normal_mips", C.c_void_p), ("pbr_mips", C.c_void_p), ("n_mip_layers", C.c_int32),
                 ("emissive_lod0", C.c_void_p), ("update_this_frame", C.c_int32), ("grass_props", C.c_int32 * 10),
                 ("pom", C.c_int32), ("high_quality_pom", C.c_int32), ("dither_pom", C.c_int32), ("frame", C.c_int32), ("pom_height", C.c_float),
-                ("pom_exp", C.c_float), ("o_albedo", C.c_void_p), ("o_normal", C.c_void_p), ("o_pbr", C.c_void_p), ("o_texture_ao", C.c_void_p)]
+                ("pom_exp", C.c_float), ("lava_block_id", C.c_int32), ("time", C.c_float), ("lava_albedo", C.c_void_p), ("lava_normal", C.c_void_p),
+                ("o_albedo", C.c_void_p), ("o_normal", C.c_void_p), ("o_pbr", C.c_void_p), ("o_texture_ao", C.c_void_p)]
 
 
 class RefSvgfArgs(C.Structure):
@@ -236,7 +237,7 @@ def trace_reflection(blocks, df, cam, gbuf, diffuse, params, g_normal, g_pbr, ma
     return out
 
 
-def generate_gbuffer(cam, gbuf, params, materials, mips, out=None):
+def generate_gbuffer(cam, gbuf, params, materials, mips, out=None, lava=None):
     """GenerateGBuffer.glsl main() per 2x2 quad of rows [cam.row_begin, cam.row_end) in the v1 parity profile (Core/Pipeline.cpp:2066-2136).
     mips = (albedo, normal, pbr) uint8 [layers][349525][4]."""
     keep = []
@@ -262,6 +263,9 @@ def generate_gbuffer(cam, gbuf, params, materials, mips, out=None):
     a.grass_props[:] = list(params.grass_props)
     a.pom, a.high_quality_pom, a.dither_pom, a.frame = params.pom, params.high_quality_pom, params.dither_pom, params.frame
     a.pom_height, a.pom_exp = params.pom_height, params.pom_exp
+    a.lava_block_id, a.time = params.lava_block_id, params.time
+    if lava is not None:      # (albedo, normal) uint8 [8][256][256][4]
+        a.lava_albedo, a.lava_normal = ptr(lava[0], np.uint8), ptr(lava[1], np.uint8)
     a.o_albedo, a.o_normal, a.o_pbr, a.o_texture_ao = (out[k].ctypes.data for k in ("albedo", "normal", "pbr", "texture_ao"))
     load().ref_generate_gbuffer(C.byref(a))
     return out

@@ -20,7 +20,8 @@ class VxoScene(C.Structure):
                 ("emissive_lod0", C.c_void_p), ("n_emissive_layers", C.c_int32), ("sky", C.c_void_p), ("sky_n", C.c_int32),
                 ("shadow_noise", C.c_void_p), ("normal_lod3", C.c_void_p), ("n_normal_layers", C.c_int32), ("emissive_lod2", C.c_void_p),
                 ("alpha_mips", C.c_void_p), ("n_alpha_layers", C.c_int32),
-                ("albedo_mips", C.c_void_p), ("normal_mips", C.c_void_p), ("pbr_mips", C.c_void_p), ("n_mip_layers", C.c_int32)]
+                ("albedo_mips", C.c_void_p), ("normal_mips", C.c_void_p), ("pbr_mips", C.c_void_p), ("n_mip_layers", C.c_int32),
+                ("lava_albedo", C.c_void_p), ("lava_normal", C.c_void_p)]
 
 
 class VxoStats(C.Structure):
@@ -147,6 +148,11 @@ class Oracle:
         self._keep["gb_mips"] = arrs
         s = self.scene
         s.albedo_mips, s.normal_mips, s.pbr_mips, s.n_mip_layers = arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[0].shape[0]
+
+    def set_lava_textures(self, albedo_rgba8, normal_rgba8):
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (albedo_rgba8, normal_rgba8)]
+        self._keep["lava"] = arrs
+        self.scene.lava_albedo, self.scene.lava_normal = arrs[0].ctypes.data, arrs[1].ctypes.data
 
     def generate_gbuffer(self, cam, gbuf, params, out=None):
         H, W = cam.height, cam.width

@@ -73,6 +73,8 @@ typedef struct VxoScene {
     const uint8_t* normal_mips;   // GL_RGBA
     const uint8_t* pbr_mips;      // GL_RGBA
     int32_t n_mip_layers;
+    const uint8_t* lava_albedo;   // animated lava textures, RGBA8 [VXPT_LAVA_FRAMES][VXPT_LAVA_SIZE][VXPT_LAVA_SIZE][4]
+    const uint8_t* lava_normal;
 } VxoScene;
 
 typedef struct VxoStats {
@@ -1332,6 +1334,23 @@ struct MipArray {
     }
 };
 
+// texture(u_LavaTextures[k], p): GL_LINEAR, GL_REPEAT on all axes (Core/AnimatedTexture.cpp:11-15); trilinear x, then y, then z
+inline f4 lava_sample(const uint8_t* tex, float s, float t, float r) {
+    const int N = VXPT_LAVA_SIZE, D = VXPT_LAVA_FRAMES;
+    const float x = s * (float)N - 0.5f, y = t * (float)N - 0.5f, z = r * (float)D - 0.5f;
+    const float x0 = std::floor(x), y0 = std::floor(y), z0 = std::floor(z);
+    const float fx = x - x0, fy = y - y0, fz = z - z0;
+    auto wr = [](int i, int n) { const int m = i % n; return m < 0 ? m + n : m; };
+    const int i0 = wr((int)x0, N), i1 = wr((int)x0 + 1, N), j0 = wr((int)y0, N), j1 = wr((int)y0 + 1, N), k0 = wr((int)z0, D), k1 = wr((int)z0 + 1, D);
+    auto tx = [&](int i, int j, int k) {
+        const uint8_t* c = tex + (((size_t)k * N + j) * N + i) * 4;
+        return f4{(float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f};
+    };
+    const f4 a = lerp4(lerp4(tx(i0, j0, k0), tx(i1, j0, k0), fx), lerp4(tx(i0, j1, k0), tx(i1, j1, k0), fx), fy);
+    const f4 b = lerp4(lerp4(tx(i0, j0, k1), tx(i1, j0, k1), fx), lerp4(tx(i0, j1, k1), tx(i1, j1, k1), fx), fy);
+    return lerp4(a, b, fz);
+}
+
 // the operand a fragment hands to dFdx / dFdy in GetUVDerivative (GenerateGBuffer.glsl:443-461): UV = fract(P), P the hit point's
 // coordinates in the plane of its own face (CalculateVectors :463-530).  `reached` is false for invocations that never get there.
 struct QuadOperand {
@@ -1341,10 +1360,12 @@ struct QuadOperand {
     v3 pos;
     int nid;
 };
-inline QuadOperand gbuffer_operand(const VxCamera& cam, const VxGBuffer& g, int i, int j) {
+inline QuadOperand gbuffer_operand(const VxCamera& cam, const VxGBuffer& g, const VxMaterialParams& prm, int i, int j) {
     QuadOperand q{};
     if (i < 0 || j < 0 || i >= cam.width || j >= cam.height) return q;  // helper invocation outside the frame
     const size_t p = (size_t)j * cam.width + i;
+    // ShouldUpdate :351-357: a fragment that discards never takes a derivative
+    if (!prm.update_this_frame && !prm.pom && std::min<int>(g.block_id[p], 127) != prm.lava_block_id) return q;
     q.dist = 1.0f / g.inv_t[p];  // GetPositionAt :107-112 on u_NonLinearDepth
     if (q.dist < 0.0f) return q;  // :360-366
     q.nid = g.normal_id[p];
@@ -1368,8 +1389,8 @@ extern "C" {
 // Derivatives: dFdx / dFdy = odd-minus-even member of the quad's row / column pair; a member that never reaches the derivative
 // contributes the pixel's own operand.
 int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffer* g, const VxMaterialParams* prm, const VxMaterialOut* out) {
-    if (prm->lava_block_id >= 0) return VXPT_E_UNSUPPORTED;
-    if (!prm->update_this_frame && !prm->pom) return VXPT_OK;  // :351-357 discard (ShouldUpdate = u_UpdateGBufferThisFrame || lava || u_POM)
+    if (prm->lava_block_id >= 0 && (!sc->lava_albedo || !sc->lava_normal)) return VXPT_E_STATE;
+    if (!prm->update_this_frame && !prm->pom && prm->lava_block_id < 0) return VXPT_OK;  // :351-357: every fragment discards
     float lut[256];
     for (int k = 0; k < 256; ++k) {
         const double cs = (double)k / 255.0;
@@ -1384,7 +1405,9 @@ int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
     for (int j = cam->row_begin; j < cam->row_end; ++j)
         for (int i = 0; i < W; ++i) {
             const size_t p = (size_t)j * W + i;
-            const QuadOperand me = gbuffer_operand(*cam, *g, i, j);
+            const bool is_lava = prm->lava_block_id >= 0 && std::min<int>(g->block_id[p], 127) == prm->lava_block_id;
+            if (!prm->update_this_frame && !prm->pom && !is_lava) continue;   // :351-357 discard: the planes keep their texels
+            const QuadOperand me = gbuffer_operand(*cam, *g, *prm, i, j);
             if (!me.reached) {
                 if (out->albedo) for (int k = 0; k < 3; ++k) out->albedo[3 * p + k] = 0.0f;
                 if (out->normal) for (int k = 0; k < 3; ++k) out->normal[3 * p + k] = 1.0f;
@@ -1394,8 +1417,8 @@ int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
             }
             // the four operands of the quad's row pair and column pair
             const int i0 = i & ~1, j0 = j & ~1;
-            QuadOperand row[2] = {gbuffer_operand(*cam, *g, i0, j), gbuffer_operand(*cam, *g, i0 + 1, j)};
-            QuadOperand col[2] = {gbuffer_operand(*cam, *g, i, j0), gbuffer_operand(*cam, *g, i, j0 + 1)};
+            QuadOperand row[2] = {gbuffer_operand(*cam, *g, *prm, i0, j), gbuffer_operand(*cam, *g, *prm, i0 + 1, j)};
+            QuadOperand col[2] = {gbuffer_operand(*cam, *g, *prm, i, j0), gbuffer_operand(*cam, *g, *prm, i, j0 + 1)};
             for (int k = 0; k < 2; ++k) {
                 if (!row[k].reached) row[k] = me;
                 if (!col[k].reached) col[k] = me;
@@ -1421,7 +1444,20 @@ int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
             float fu, fv;
             calc_vectors(me.pos, me.nid, tangent, bitangent, fu, fv);  // same tables as ReflectionTraceFrag's copy (:463-530 here)
             const v3 face = normal_from_id(me.nid, 1.0f);
-            if (prm->pom) {  // Parallax :343-353 -> ReliefParallax :153-199 (the code after its first return is dead)
+            float lava_u = 0.0f, lava_v = 0.0f;
+            const float lava_r = fractf(prm->time * 0.3f);
+            if (is_lava) {  // :389-394: BasicTextureDistortion :127-137 on vec3(UV, fract(u_Time * 0.3f)); liquids skip the parallax march
+                const float time = prm->time;
+                float du = fu, dv = fv;
+                du += sin_cr(time * 0.25f);
+                dv += pow_cr(cos_cr(time * 0.15f), 2.0f);
+                du += cos_cr(du * 10.0f + time) * 0.3f;
+                dv += sin_cr(dv * 5.0f + du * 4.0f + time * 1.3f) * 0.4f;
+                lava_u = mixf(du, fu, 0.91f);
+                lava_v = mixf(dv, fv, 0.91f);
+                fu = lava_u;
+                fv = lava_v;
+            } else if (prm->pom) {  // Parallax :343-353 -> ReliefParallax :153-199 (the code after its first return is dead)
                 const v3 view = normalize(me.pos - ray_origin(*cam));
                 const float depth_scale = 0.115f * prm->pom_height;
                 float bayer_steps = 0.5f;
@@ -1466,16 +1502,16 @@ int vxo_generate_gbuffer(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
                 fv = sv + mdy * cur_depth;
             }
             const float U = 1.0f - fu, Vc = 1.0f - fv;  // :397
-            const f4 nm = normals.grad(data[1], U, Vc, dx, dy);
+            const f4 nm = is_lava ? lava_sample(sc->lava_normal, lava_u, lava_v, lava_r) : normals.grad(data[1], U, Vc, dx, dy);
             const v3 n = V(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f);
             const v3 mapped = (tangent * n.x + bitangent * n.y) + face * n.z;  // mat3(T, B, N) * n
             const f4 pm = pbr.grad(data[2], U, Vc, dx, dy);
             float emissivity = 0.0f;
             if (data[3] > -0.5f) emissivity = tex_bilinear1(sc->emissive_lod0, (int)data[3], 512, U, Vc);
             float o_pbr[4] = {clampf(pm.x, 0.0f, 1.0f), clampf(pm.y, 0.0f, 1.0f), clampf(pm.z, 0.0f, 1.0f), clampf(emissivity, 0.0f, 1.0f)};
-            const f4 al = albedo.grad(data[0], U, Vc, dx, dy);
+            const f4 al = is_lava ? lava_sample(sc->lava_albedo, lava_u, lava_v, lava_r) : albedo.grad(data[0], U, Vc, dx, dy);
             const float lb = 0.02f;
-            o_pbr[3] *= (U > lb && U < 1.0f - lb && Vc > lb && Vc < 1.0f - lb) ? 1.0f : 0.0f;  // BloomLightLeakFix :432-438
+            if (!is_lava) o_pbr[3] *= (U > lb && U < 1.0f - lb && Vc > lb && Vc < 1.0f - lb) ? 1.0f : 0.0f;  // BloomLightLeakFix :432-438
             if (out->albedo) { out->albedo[3 * p] = al.x; out->albedo[3 * p + 1] = al.y; out->albedo[3 * p + 2] = al.z; }
             if (out->normal) { out->normal[3 * p] = mapped.x; out->normal[3 * p + 1] = mapped.y; out->normal[3 * p + 2] = mapped.z; }
             if (out->pbr) for (int k = 0; k < 4; ++k) out->pbr[4 * p + k] = o_pbr[k];

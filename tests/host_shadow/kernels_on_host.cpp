@@ -76,6 +76,7 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.n_alpha_layers = c->n_alpha_layers;
     S.albedo_mips = c->d_albedo_mips; S.normal_mips = c->d_normal_mips; S.pbr_mips = c->d_pbr_mips;
     S.srgb_lut = c->d_srgb_lut; S.n_mip_layers = c->n_mip_layers;
+    S.lava_albedo = c->d_lava_albedo; S.lava_normal = c->d_lava_normal;
     return S;
 }
 // the wavefront GI pipeline needs a GPU (shared memory, ballots); the shadow runs the one-thread-per-pixel kernel
@@ -119,6 +120,8 @@ typedef struct HsScene {
     const uint8_t* normal_mips;
     const uint8_t* pbr_mips;
     int32_t n_mip_layers;
+    const uint8_t* lava_albedo;
+    const uint8_t* lava_normal;
 } HsScene;
 
 HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
@@ -160,6 +163,7 @@ HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
     // vxpt_set_gbuffer_textures (api.cu): the mip chains and the sRGB decode table
     c.d_albedo_mips = (uchar4*)s->albedo_mips; c.d_normal_mips = (uchar4*)s->normal_mips; c.d_pbr_mips = (uchar4*)s->pbr_mips;
     c.n_mip_layers = s->n_mip_layers;
+    c.d_lava_albedo = (uchar4*)s->lava_albedo; c.d_lava_normal = (uchar4*)s->lava_normal;
     for (int k = 0; k < 256; ++k) {
         const double cs = (double)k / 255.0;
         h->srgb_lut[k] = (float)(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));

@@ -21,7 +21,28 @@ POM_CASES = [
     ("pom_city_hq_deep", 2, dict(high_quality_pom=True, frame=777, pom_height=2.5, pom_exp=0.5)),
     ("pom_close_nodither_noupdate", 3, dict(dither_pom=False, update_this_frame=False)),   # u_POM keeps the pass alive without u_UpdateGBufferThisFrame
 ]
+# animated lava path (u_LavaBlockID): the test scenes hold no lava, so a block that is in view plays its part.  name, index into CASES,
+# block id treated as lava, material_params keywords
+LAVA_CASES = [
+    ("lava_gi_box_cobble_t12.75", 1, 4, dict(time=12.75)),
+    ("lava_city_lamps_pom_t3.1", 2, 12, dict(time=3.1, pom=True, frame=9)),       # the lamps flow, the planks around them get the parallax march
+    ("lava_gi_box_only_lava_updates_t100.5", 1, 4, dict(time=100.5, update_this_frame=False)),   # every other fragment discards
+]
 PLANES = ("albedo", "normal", "pbr", "texture_ao")
+_lava = []
+
+
+def lava_textures():
+    if not _lava:
+        _lava.append(assets.synthetic_lava_textures())
+    return _lava[0]
+
+
+def seeded_planes(W, H, seed=1):
+    """planes with recognisable contents, to see which texels a pass leaves alone"""
+    rng = np.random.RandomState(seed)
+    return {"albedo": rng.rand(H, W, 3).astype(np.float32), "normal": rng.rand(H, W, 3).astype(np.float32), "pbr": rng.rand(H, W, 4).astype(np.float32),
+            "texture_ao": rng.rand(H, W).astype(np.float32)}
 _mips = {}
 
 

@@ -85,6 +85,32 @@ def test_relief_parallax_oracle_equals_the_reference_shader_digests(gb_oracles, 
     assert not np.array_equal(m["albedo"], flat["albedo"])        # the march does move the texture coordinates
 
 
+@pytest.mark.parametrize("lava", mc.LAVA_CASES, ids=[c[0] for c in mc.LAVA_CASES])
+def test_lava_path_oracle_equals_the_reference_shader_digests(gb_oracles, scene_tables, mips, ref_digests, lava):
+    """u_LavaBlockID: time-driven UV distortion, the two animated 3-D textures, no parallax / bloom fix on liquid pixels — alone, with
+    u_POM on the other pixels, and with u_UpdateGBufferThisFrame off (only the lava pixels are shaded, everything else keeps its texels)."""
+    tex = mc.lava_textures()
+    if any(mc.sha(m) != ref_digests["mips"][k] for k, m in zip(("albedo", "normal", "pbr"), mips)) or [mc.sha(t) for t in tex] != ref_digests["lava_textures"]:
+        pytest.skip("the synthetic textures differ from the ones the digests were made with (other numpy / libm)")
+    name, idx, block, kw = lava
+    case = mc.CASES[idx]
+    o = gb_oracles[case[1]]
+    o.set_lava_textures(*tex)
+    cam = mc.case_camera(case)
+    g, _ = o.trace_primary(cam, vx.primary_params(350))
+    seed = mc.seeded_planes(cam.width, cam.height)
+    m = o.generate_gbuffer(cam, g, _params(scene_tables, lava_block_id=block, **kw), {k: v.copy() for k, v in seed.items()})
+    for k in mc.PLANES:
+        assert mc.sha(m[k]) == ref_digests["lava_cases"][name][k], k
+    is_lava = g["block_id"] == block
+    assert is_lava.sum() == ref_digests["lava_cases"][name]["lava_pixels"] > 100
+    if not kw.get("update_this_frame", True):
+        assert np.array_equal(m["pbr"][~is_lava], seed["pbr"][~is_lava]) and not np.array_equal(m["pbr"][is_lava], seed["pbr"][is_lava])
+    else:   # the animation moves with u_Time
+        m2 = o.generate_gbuffer(cam, g, _params(scene_tables, lava_block_id=block, **dict(kw, time=kw["time"] + 0.4)), {k: v.copy() for k, v in seed.items()})
+        assert not np.array_equal(m2["albedo"][is_lava], m["albedo"][is_lava]) and np.array_equal(m2["albedo"][~is_lava], m["albedo"][~is_lava], equal_nan=True)
+
+
 @needs_ref
 def test_oracle_equals_the_reference_shader_live(gb_oracles, scene_tables, mips):
     """Frames not in the committed set: odd sizes (quads cut by the frame edge), a row slab, a roll of the camera, a frame that is
@@ -203,6 +229,17 @@ def test_kernel_source_on_host_equals_the_oracle(gb_oracles, scene_tables, case)
     want_pom, got_pom = o.generate_gbuffer(cam, g, pom), k.generate_gbuffer(cam, g, pom)
     for key in mc.PLANES:
         assert np.array_equal(got_pom[key], want_pom[key], equal_nan=True), ("pom", key)   # (NaN where the camera stands inside a block: t ~ 1e-4)
+    o.set_lava_textures(*mc.lava_textures())                       # the lava instantiations (with and without u_POM, lava-only updates)
+    k2 = koh.HostKernels(o, 1)
+    block = int(np.bincount(g["block_id"][g["block_id"] > 0]).argmax())
+    for kw in (dict(time=7.3), dict(time=0.25, pom=True, frame=2), dict(time=41.0, update_this_frame=False)):
+        lp = _params(scene_tables, lava_block_id=block, **kw)
+        seed = mc.seeded_planes(cam.width, cam.height)
+        want_l = o.generate_gbuffer(cam, g, lp, {q: v.copy() for q, v in seed.items()})
+        got_l = k2.generate_gbuffer(cam, g, lp, {q: v.copy() for q, v in seed.items()})
+        for key in mc.PLANES:
+            assert np.array_equal(got_l[key], want_l[key], equal_nan=True), ("lava", kw, key)
+    k2.close()
     cam.row_begin, cam.row_end = 10, 52   # a slab: rows outside stay as they were
     seed = {key: np.full_like(want[key], 7.0) for key in mc.PLANES}
     got = k.generate_gbuffer(cam, g, _params(scene_tables), seed)
@@ -284,7 +321,7 @@ def test_gpu_material_pass_argument_checks(gb_renderer, worlds, scene_tables):
     cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H)
     g = r.trace_primary(cam, vx.primary_params(350), r.alloc_gbuffer(W, H))
     out = r.alloc_material(W, H)
-    for kw, code in [(dict(pom=True, pom_height=-1.0), abi.E_INVALID), (dict(lava_block_id=11), abi.E_UNSUPPORTED)]:
+    for kw, code in [(dict(pom=True, pom_height=-1.0), abi.E_INVALID), (dict(lava_block_id=11), abi.E_STATE)]:   # no lava textures set
         with pytest.raises(abi.VxptError) as e:
             r.generate_gbuffer(cam, g, _params(scene_tables, **kw), out)
         assert e.value.code == code

@@ -67,3 +67,27 @@ def test_gpu_relief_parallax_equals_the_oracle(gb_renderer, worlds, gb_oracles, 
         for k in mc.PLANES:     # the march compares pow() results against a depth: an ulp can flip a step, so a few more texels may differ
             diff = got[k] != want[k]
             assert diff.mean() <= 2e-3, (k, float(diff.mean()))
+
+
+@pytest.mark.gpu
+def test_gpu_lava_path_equals_the_oracle(gb_renderer, worlds, gb_oracles, scene_tables):
+    name, idx, block, kw = mc.LAVA_CASES[0]
+    case = mc.CASES[idx]
+    r, o = gb_renderer, gb_oracles[case[1]]
+    tex = mc.lava_textures()
+    r.set_lava_textures(*tex)
+    o.set_lava_textures(*tex)
+    r.upload_world(worlds[case[1]])
+    r.build_distance_field()
+    cam = mc.case_camera(case)
+    W, H = cam.width, cam.height
+    g = r.trace_primary(cam, vx.primary_params(350), r.alloc_gbuffer(W, H))
+    g_ref, _ = o.trace_primary(cam, vx.primary_params(350))
+    for kw2 in (kw, dict(time=55.5, update_this_frame=False)):
+        mp = _params(scene_tables, lava_block_id=block, **kw2)
+        seed = mc.seeded_planes(W, H)
+        want = o.generate_gbuffer(cam, g_ref, mp, {k: v.copy() for k, v in seed.items()})
+        got = r.generate_gbuffer(cam, g, mp, {k: v.copy() for k, v in seed.items()})
+        for k in mc.PLANES:     # sin / cos of the distortion are pinned double evaluations: an ulp may differ on isolated texels
+            diff = got[k] != want[k]
+            assert diff.mean() <= 1e-3 and float(np.abs(got[k].astype(np.float64) - want[k]).max()) <= 1e-4, (k, float(diff.mean()))

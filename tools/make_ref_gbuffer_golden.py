@@ -47,6 +47,18 @@ def main():
         m = ref_shaders.generate_gbuffer(cam, g, vx.material_params(mats["grass_props"], pom=True, **kw), mats, mips)
         out["pom_cases"][name] = {k: mc.sha(m[k]) for k in mc.PLANES}
         print(f"{name}: {out['pom_cases'][name]['albedo'][:16]}", flush=True)
+    out["lava_cases"], lava = {}, mc.lava_textures()
+    out["lava_textures"] = [mc.sha(t) for t in lava]
+    for name, idx, block, kw in mc.LAVA_CASES:
+        case = mc.CASES[idx]
+        wname = case[1]
+        cam = mc.case_camera(case)
+        g = ref_shaders.trace_primary(worlds[wname].data, dfs[wname], cam, vx.primary_params(350))
+        m = ref_shaders.generate_gbuffer(cam, g, vx.material_params(mats["grass_props"], lava_block_id=block, **kw), mats, mips,
+                                         mc.seeded_planes(cam.width, cam.height), lava=lava)
+        out["lava_cases"][name] = {k: mc.sha(m[k]) for k in mc.PLANES}
+        out["lava_cases"][name]["lava_pixels"] = int((g["block_id"] == block).sum())
+        print(f"{name}: {out['lava_cases'][name]['albedo'][:16]} lava pixels {out['lava_cases'][name]['lava_pixels']}", flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "ref_gbuffer_digests.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 

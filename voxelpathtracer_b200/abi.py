@@ -15,6 +15,7 @@ WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z
 NORMAL_MISS = 10
 ALPHA_MIP_TEXELS = sum((512 >> k) ** 2 for k in range(9))  # 349,524: levels 0..8 of a 512^2 layer (VXPT_ALPHA_MIP_TEXELS)
 
+LAVA_SIZE, LAVA_FRAMES = 256, 8
 MIP_CHAIN_TEXELS = sum((512 >> k) ** 2 for k in range(10))  # 349,525: levels 0..9 (VXPT_MIP_CHAIN_TEXELS)
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
@@ -79,7 +80,7 @@ class VxReflectionOut(C.Structure):
 
 class VxMaterialParams(C.Structure):
     _fields_ = [("update_this_frame", C.c_int32), ("pom", C.c_int32), ("lava_block_id", C.c_int32), ("grass_props", C.c_int32 * 10),
-                ("pom_height", C.c_float), ("pom_exp", C.c_float), ("high_quality_pom", C.c_int32), ("dither_pom", C.c_int32), ("frame", C.c_int32)]
+                ("pom_height", C.c_float), ("pom_exp", C.c_float), ("high_quality_pom", C.c_int32), ("dither_pom", C.c_int32), ("frame", C.c_int32), ("time", C.c_float)]
 
 
 class VxMaterialOut(C.Structure):
@@ -203,6 +204,7 @@ EXPORTS = {
     "vxpt_trace_diffuse": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxDiffuseParams), C.POINTER(VxDiffuseOut)]),
     "vxpt_trace_reflection": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxReflectionIn),
                                         C.POINTER(VxReflectionParams), C.POINTER(VxReflectionOut)]),
+    "vxpt_set_lava_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxpt_set_gbuffer_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "vxpt_generate_gbuffer": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxGBuffer), C.POINTER(VxMaterialParams),
                                         C.POINTER(VxMaterialOut)]),

@@ -165,6 +165,31 @@ def synthetic_material_lod0(n_layers, seed=23):
     return albedo, normal, pbr
 
 
+def synthetic_lava_textures(seed=31):
+    """(albedo, normal) uint8 [8][256][256][4]: stand-ins for the reference's animated lava frames (Res/Block/Lava/Frames), smooth in all
+    three axes and periodic (the textures wrap with GL_REPEAT, the frame axis too)."""
+    rng = np.random.RandomState(seed)
+    k, y, x = np.mgrid[0:8, 0:256, 0:256].astype(np.float64)
+    h = np.zeros((8, 256, 256))
+    for octave in (1, 2, 4, 8):
+        ph = rng.rand(3) * 2 * np.pi
+        h += np.sin(2 * np.pi * octave * x / 256 + ph[0] + 2 * np.pi * k / 8) * np.cos(2 * np.pi * octave * y / 256 + ph[1]) / octave
+        h += 0.5 * np.sin(2 * np.pi * (octave * (x + y) / 256 + k / 8) + ph[2]) / octave
+    h = (h - h.min()) / (h.max() - h.min())
+    albedo = np.zeros((8, 256, 256, 4), np.uint8)
+    albedo[..., 0] = np.clip(180 + 75 * h, 0, 255)
+    albedo[..., 1] = np.clip(40 + 160 * h ** 2, 0, 255)
+    albedo[..., 2] = np.clip(10 + 40 * h ** 4, 0, 255)
+    albedo[..., 3] = 255
+    gy, gx = np.gradient(h, axis=(1, 2))
+    n = np.stack([-gx * 30.0, -gy * 30.0, np.ones_like(h)], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    normal = np.zeros_like(albedo)
+    normal[..., :3] = np.clip((n * 0.5 + 0.5) * 255.0 + 0.5, 0, 255).astype(np.uint8)
+    normal[..., 3] = 255
+    return albedo, normal
+
+
 def analytic_sky(n=16, sun_dir=(-0.669, 0.468, 0.577)):
     """Documented stand-in for the reference's rendered atmosphere cubemap (RGB16F, 16^2 for GI; Pipeline.cpp:1392-1394):
     a horizon-to-zenith gradient plus a broad sun lobe.  Faces +X,-X,+Y,-Y,+Z,-Z, GL cube-map face orientation,

@@ -55,6 +55,8 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.pbr_mips = c->d_pbr_mips;
     S.srgb_lut = c->d_srgb_lut;
     S.n_mip_layers = c->n_mip_layers;
+    S.lava_albedo = c->d_lava_albedo;
+    S.lava_normal = c->d_lava_normal;
     return S;
 }
 
@@ -335,7 +337,7 @@ int vxpt_destroy(vxpt_handle c) {
     }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
                     c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_alpha_mips, c->d_counters, c->d_stage, c->d_queue,
-                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut, c->svgf.buf, c->shadow_hist.buf};
+                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut, c->svgf.buf, c->shadow_hist.buf, c->d_lava_albedo, c->d_lava_normal};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -578,6 +580,16 @@ int vxpt_set_gbuffer_textures(vxpt_handle c, const uint8_t* albedo_mips, const u
     return VXPT_OK;
 }
 
+int vxpt_set_lava_textures(vxpt_handle c, const uint8_t* albedo_rgba8, const uint8_t* normal_rgba8) {
+    if (!c || !albedo_rgba8 || !normal_rgba8) return fail(VXPT_E_INVALID, "NULL argument");
+    VX_CUDA(cudaSetDevice(c->device));
+    if (int rc = finish_pending_frame(c)) return rc;
+    const size_t bytes = (size_t)VXPT_LAVA_FRAMES * VXPT_LAVA_SIZE * VXPT_LAVA_SIZE * 4;
+    int rc;
+    if ((rc = replace_buffer(c, &c->d_lava_albedo, albedo_rgba8, bytes)) || (rc = replace_buffer(c, &c->d_lava_normal, normal_rgba8, bytes))) return rc;
+    return VXPT_OK;
+}
+
 }  // extern "C"
 static int check_material(const vxpt_ctx* c, const VxCamera* cam, const VxMaterialParams* p);
 extern "C" {
@@ -597,7 +609,7 @@ int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
     if ((rc = io.resolve())) return rc;
     if (cam->row_end == cam->row_begin) return VXPT_OK;
     if ((rc = io.upload(it)) || (rc = io.upload(nid)) || (rc = io.upload(bid))) return rc;
-    if (!p->update_this_frame && !p->pom) {  // every invocation discards: staged output planes must keep what the caller's planes hold
+    if (!p->update_this_frame && !p->pom) {  // invocations discard (all but lava pixels): staged output planes must keep what the caller's planes hold
         if ((rc = io.upload(al)) || (rc = io.upload(nm)) || (rc = io.upload(pb)) || (rc = io.upload(ao))) return rc;
     }
     VxGBuffer gd{nullptr, (uint8_t*)nid.dev, (uint8_t*)bid.dev, (float*)it.dev, nullptr};
@@ -619,7 +631,8 @@ int vxpt_generate_gbuffer(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
 static int check_material(const vxpt_ctx* c, const VxCamera* cam, const VxMaterialParams* p) {
     if (p->pom && !(p->pom_height >= 0.0f && p->pom_height <= 16.0f && p->pom_exp >= 0.0f && p->pom_exp <= 16.0f))
         return fail(VXPT_E_INVALID, "u_POMHeight / u_POMExp outside 0..16");
-    if (p->lava_block_id >= 0) return fail(VXPT_E_UNSUPPORTED, "lava animation (u_LavaBlockID, functions of the wall clock) is outside the v1 parity profile");
+    if (p->lava_block_id >= 0 && !c->d_lava_albedo) return fail(VXPT_E_STATE, "a lava block id needs vxpt_set_lava_textures");
+    if (p->lava_block_id > 127) return fail(VXPT_E_INVALID, "lava_block_id outside the material table");
     if (!c->have_materials || !c->d_albedo_mips) return fail(VXPT_E_STATE, "the G-buffer pass needs vxpt_set_materials and vxpt_set_gbuffer_textures");
     const int rows = cam->interleave_n > 1 ? cam->height / cam->interleave_n : cam->height;
     if ((cam->row_begin & 1) || ((cam->row_end & 1) && cam->row_end != rows) || (cam->interleave_n > 1 && (cam->band_rows & 1)))
@@ -1246,7 +1259,7 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     if ((rc = launch_primary(c, *cam, *p->primary, gd))) return rc;
     if ((rc = copy_out({&t, &nid, &bid, &it, &hv}, cam->row_begin, cam->row_end))) return rc;
     if (mat) {
-        if (!p->material->update_this_frame && !p->material->pom)  // every fragment discards: staged planes must keep what the caller's hold
+        if (!p->material->update_this_frame && !p->material->pom)  // fragments discard (all but lava pixels): staged planes must keep what the caller's hold
             if ((rc = io.upload(mal)) || (rc = io.upload(mnm)) || (rc = io.upload(mpb)) || (rc = io.upload(mao))) return rc;
         if ((rc = launch_gbuffer(c, *cam, gd, *p->material, md))) return rc;
         if ((rc = copy_out({&mal, &mnm, &mpb, &mao}, cam->row_begin, cam->row_end))) return rc;

@@ -1,5 +1,5 @@
 // gbuffer.cu — G-buffer material pass: Core/Shaders/GenerateGBuffer.glsl main() :347-441 as drawn by
-// Core/Pipeline.cpp:2066-2136, in the v1 parity profile of include/vxpt.h (no lava animation); relief parallax mapping (u_POM) included.
+// Core/Pipeline.cpp:2066-2136, in the v1 parity profile of include/vxpt.h ; relief parallax mapping (u_POM) and the animated lava path are separate instantiations.
 //
 // One thread per pixel, the 8x4-pixel warp tiles of the trace passes.  The shader takes screen-space derivatives of the surface UV
 // (GetUVDerivative :443-461) to pick the mip level: a derivative is a difference inside the pixel's 2x2 quad, so every thread
@@ -19,6 +19,10 @@ struct MaterialDev {
     float depth_scale;  // 0.115f * u_POMHeight
     float height_exp;   // 1.5f * u_POMExp
     float frame_term;   // fract(mod(float(u_Frame), 384.0f) * (1.0f / PHI)), computed on the host in fp32
+    // ShouldUpdate :351 = update_all || the pixel's block is lava; the per-frame constants of BasicTextureDistortion :127-137 (host, fp32,
+    // pinned sin / cos / pow)
+    int update_all, lava_id;
+    float time, lava_r, lava_sx, lava_cy, lava_t13;  // u_Time, fract(u_Time * 0.3f), sin(t * 0.25f), pow(cos(t * 0.15f), 2), t * 1.3f
 };
 struct MaterialOutDev {
     float* albedo;      // 3 / pixel
@@ -81,10 +85,12 @@ __device__ __forceinline__ float4 texture_grad(const SceneDev& S, const uchar4* 
 
 // what a quad member hands to dFdx / dFdy: UV = fract(P) of CalculateVectors :463-530 on its own hit point and face, or nothing when
 // the invocation returns before reaching it (sky :360-366, outside the frame)
-__device__ __forceinline__ bool quad_uv(const CameraDev& cam, const GBufferDev& g, int i, int j, int prow, float& u, float& v, float& dist,
-                                        V3& pos, int& nid) {
+template <bool LAVA>
+__device__ __forceinline__ bool quad_uv(const CameraDev& cam, const MaterialDev& p, const GBufferDev& g, int i, int j, int prow, float& u, float& v,
+                                        float& dist, V3& pos, int& nid) {
     if (i >= cam.width || j >= cam.height) return false;
     const size_t px = (size_t)prow * cam.width + i;
+    if (LAVA && !p.update_all && min((int)g.block_id[px], 127) != p.lava_id) return false;  // discarded before it takes a derivative (:351-357)
     dist = 1.0f / g.inv_t[px];  // GetPositionAt :107-112
     if (dist < 0.0f) return false;
     nid = g.normal_id[px];
@@ -97,8 +103,29 @@ __device__ __forceinline__ bool quad_uv(const CameraDev& cam, const GBufferDev& 
     return true;
 }
 
-// POM = u_POM: a separate instantiation, so that the default pass keeps its 40 registers
-template <bool POM>
+// one RGBA8 texel of an animated lava texture -> float4 (c / 255 through the table)
+__device__ __forceinline__ float4 lava_texel(const SceneDev& S, const uchar4* tex, int i, int j, int k) {
+    const uchar4 c = tex[(k * VXPT_LAVA_SIZE + j) * VXPT_LAVA_SIZE + i];
+    const float* unorm = S.srgb_lut + 256;
+    return make_float4(__ldg(unorm + c.x), __ldg(unorm + c.y), __ldg(unorm + c.z), __ldg(unorm + c.w));
+}
+// texture(sampler3D, p): GL_LINEAR, GL_REPEAT on the three axes (Core/AnimatedTexture.cpp:11-15); x, then y, then z
+__device__ __forceinline__ float4 lava_sample(const SceneDev& S, const uchar4* tex, float s, float t, float r) {
+    const float x = s * (float)VXPT_LAVA_SIZE - 0.5f, y = t * (float)VXPT_LAVA_SIZE - 0.5f, z = r * (float)VXPT_LAVA_FRAMES - 0.5f;
+    const float x0 = floorf(x), y0 = floorf(y), z0 = floorf(z);
+    const float fx = x - x0, fy = y - y0, fz = z - z0;
+    const int i0 = ((int)x0) & (VXPT_LAVA_SIZE - 1), i1 = ((int)x0 + 1) & (VXPT_LAVA_SIZE - 1);
+    const int j0 = ((int)y0) & (VXPT_LAVA_SIZE - 1), j1 = ((int)y0 + 1) & (VXPT_LAVA_SIZE - 1);
+    const int k0 = ((int)z0) & (VXPT_LAVA_FRAMES - 1), k1 = ((int)z0 + 1) & (VXPT_LAVA_FRAMES - 1);
+    const float4 a = f4_lerp(f4_lerp(lava_texel(S, tex, i0, j0, k0), lava_texel(S, tex, i1, j0, k0), fx),
+                             f4_lerp(lava_texel(S, tex, i0, j1, k0), lava_texel(S, tex, i1, j1, k0), fx), fy);
+    const float4 b = f4_lerp(f4_lerp(lava_texel(S, tex, i0, j0, k1), lava_texel(S, tex, i1, j0, k1), fx),
+                             f4_lerp(lava_texel(S, tex, i0, j1, k1), lava_texel(S, tex, i1, j1, k1), fx), fy);
+    return f4_lerp(a, b, fz);
+}
+
+// POM = u_POM, LAVA = a lava block id is set: separate instantiations, so that the default pass keeps its 40 registers
+template <bool POM, bool LAVA>
 __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ MaterialDev p,
                                                       const GBufferDev g, const MaterialOutDev out) {
     int i, j, prow;
@@ -107,7 +134,10 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     float u, v, dist;
     V3 pos;
     int nid;
-    if (!quad_uv(cam, g, i, j, prow, u, v, dist, pos, nid)) {  // :360-366
+    const int block_early = LAVA ? min((int)g.block_id[px], 127) : 0;  // (read here only when a lava id is set: keeps the default pass at 40 registers)
+    const bool is_lava = LAVA && block_early == p.lava_id;
+    if (LAVA && !p.update_all && !is_lava) return;  // :351-357 discard: the attachments keep their texels
+    if (!quad_uv<LAVA>(cam, p, g, i, j, prow, u, v, dist, pos, nid)) {  // :360-366
         if (out.albedo) { out.albedo[3 * px] = 0.0f; out.albedo[3 * px + 1] = 0.0f; out.albedo[3 * px + 2] = 0.0f; }
         if (out.normal) { out.normal[3 * px] = 1.0f; out.normal[3 * px + 1] = 1.0f; out.normal[3 * px + 2] = 1.0f; }
         if (out.pbr) out.pbr[px] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -119,11 +149,11 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     V3 pn;
     int nn;
     float ax = u, ay = v, bx = u, by = v;  // x pair: a = even column, b = odd column
-    if (quad_uv(cam, g, i ^ 1, j, prow, un, vn, dn, pn, nn)) {
+    if (quad_uv<LAVA>(cam, p, g, i ^ 1, j, prow, un, vn, dn, pn, nn)) {
         if (i & 1) { ax = un; ay = vn; } else { bx = un; by = vn; }
     }
     float cx = u, cy = v, ex = u, ey = v;  // y pair: c = even row, e = odd row
-    if (quad_uv(cam, g, i, j ^ 1, prow ^ 1, un, vn, dn, pn, nn)) {
+    if (quad_uv<LAVA>(cam, p, g, i, j ^ 1, prow ^ 1, un, vn, dn, pn, nn)) {
         if (j & 1) { cx = un; cy = vn; } else { ex = un; ey = vn; }
     }
     float4 d = make_float4(bx - ax, by - ay, ex - cx, ey - cy);
@@ -134,7 +164,7 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
         if ((d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w) > (d2.x * d2.x + d2.y * d2.y) + (d2.z * d2.z + d2.w * d2.w)) d = d2;
     }
     // GetTextureIDs :532-549
-    const int block = min((int)g.block_id[px], 127);  // GetBlockID :95-99 (the unorm8 round trip is exact)
+    const int block = LAVA ? block_early : min((int)g.block_id[px], 127);  // GetBlockID :95-99 (the unorm8 round trip is exact)
     float l_albedo = (float)S.materials[block], l_normal = (float)S.materials[128 + block], l_pbr = (float)S.materials[256 + block];
     const float l_emissive = (float)S.materials[384 + block];
     if (block == p.grass[0]) {
@@ -146,7 +176,16 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     else if (nid <= 3) { tangent = mk3(1.f, 0.f, 0.f); bitangent = mk3(0.f, 0.f, 1.f); }
     else { tangent = mk3(0.f, 0.f, -1.f); bitangent = mk3(0.f, -1.f, 0.f); }
     const V3 face = normal_from_id(nid, 1.0f);
-    if (POM) {  // Parallax :343-353 -> ReliefParallax :153-199 (everything after its first return is dead code)
+    float lava_u = 0.0f, lava_v = 0.0f;
+    if (is_lava) {  // BasicTextureDistortion :127-137 on vec3(UV, fract(u_Time * 0.3f)); liquids skip the parallax march (:394)
+        float du = u + p.lava_sx, dv2 = v + p.lava_cy;
+        du += cos_cr(du * 10.0f + p.time) * 0.3f;
+        dv2 += sin_cr(dv2 * 5.0f + du * 4.0f + p.lava_t13) * 0.4f;
+        lava_u = du * (1.0f - 0.91f) + u * 0.91f;
+        lava_v = dv2 * (1.0f - 0.91f) + v * 0.91f;
+        u = lava_u;
+        v = lava_v;
+    } else if (POM) {  // Parallax :343-353 -> ReliefParallax :153-199 (everything after its first return is dead code)
         const V3 view = normalize3(pos - ray_origin(cam));
         float bayer_steps = 0.5f;
         if (p.dither_pom) {  // bayer32(gl_FragCoord.xy): bayer2 at five octaves, coarsest first
@@ -193,7 +232,7 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     u = 1.0f - u;  // :397
     v = 1.0f - v;
     const float lambda = mip_lambda(d);
-    const float4 nm = texture_grad(S, S.normal_mips, l_normal, u, v, lambda, false, true);
+    const float4 nm = is_lava ? lava_sample(S, S.lava_normal, lava_u, lava_v, p.lava_r) : texture_grad(S, S.normal_mips, l_normal, u, v, lambda, false, true);
     const float nx = nm.x * 2.0f - 1.0f, ny = nm.y * 2.0f - 1.0f, nz = nm.z * 2.0f - 1.0f;
     const V3 mapped = mk3((tangent.x * nx + bitangent.x * ny) + face.x * nz, (tangent.y * nx + bitangent.y * ny) + face.y * nz,
                           (tangent.z * nx + bitangent.z * ny) + face.z * nz);  // tbn * NormalMapped
@@ -201,9 +240,9 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     float emissivity = 0.0f;
     if (l_emissive > -0.5f) emissivity = tex_bilinear1(S.emissive, (int)l_emissive, 512, u, v);
     float4 o_pbr = make_float4(clampf(pm.x, 0.0f, 1.0f), clampf(pm.y, 0.0f, 1.0f), clampf(pm.z, 0.0f, 1.0f), clampf(emissivity, 0.0f, 1.0f));
-    const float4 al = texture_grad(S, S.albedo_mips, l_albedo, u, v, lambda, true, false);
+    const float4 al = is_lava ? lava_sample(S, S.lava_albedo, lava_u, lava_v, p.lava_r) : texture_grad(S, S.albedo_mips, l_albedo, u, v, lambda, true, false);
     const float inside = (u > 0.02f && u < 1.0f - 0.02f && v > 0.02f && v < 1.0f - 0.02f) ? 1.0f : 0.0f;  // BloomLightLeakFix :432-438
-    o_pbr.w *= inside;
+    if (!is_lava) o_pbr.w *= inside;
     if (out.albedo) { out.albedo[3 * px] = al.x; out.albedo[3 * px + 1] = al.y; out.albedo[3 * px + 2] = al.z; }
     if (out.normal) { out.normal[3 * px] = mapped.x; out.normal[3 * px + 1] = mapped.y; out.normal[3 * px + 2] = mapped.z; }
     if (out.pbr) out.pbr[px] = o_pbr;
@@ -211,7 +250,8 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
 }
 
 int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const VxMaterialParams& p, const VxMaterialOut& out) {
-    if (!p.update_this_frame && !p.pom) return VXPT_OK;  // :351-357: every invocation discards (ShouldUpdate = update || lava || u_POM)
+    const bool lava = p.lava_block_id >= 0;
+    if (!p.update_this_frame && !p.pom && !lava) return VXPT_OK;  // :351-357: every invocation discards (ShouldUpdate = update || lava || u_POM)
     const SceneDev S = make_scene(c);
     MaterialDev d;
     for (int k = 0; k < 10; ++k) d.grass[k] = p.grass_props[k];
@@ -230,9 +270,22 @@ int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const V
     cd.il_n = cam.interleave_n; cd.il_rank = cam.interleave_rank; cd.il_band = cam.band_rows > 0 ? cam.band_rows : 1;
     const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel};
     const MaterialOutDev od{out.albedo, out.normal, reinterpret_cast<float4*>(out.pbr), out.texture_ao};
+    d.update_all = (p.update_this_frame || p.pom) ? 1 : 0;
+    d.lava_id = lava ? p.lava_block_id : -1;
+    d.time = p.time;
+    {
+        const float r = p.time * 0.3f;
+        d.lava_r = r - std::floor(r);
+        d.lava_sx = (float)std::sin((double)(p.time * 0.25f));
+        d.lava_cy = (float)std::pow((double)(float)std::cos((double)(p.time * 0.15f)), (double)2.0f);
+        d.lava_t13 = p.time * 1.3f;
+    }
     const dim3 grid((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8);
-    if (p.pom) VX_LAUNCH((gbuffer_kernel<true>), grid, 256, c->stream, S, cd, d, gd, od);
-    else VX_LAUNCH((gbuffer_kernel<false>), grid, 256, c->stream, S, cd, d, gd, od);
+    if (lava) {
+        if (p.pom) VX_LAUNCH((gbuffer_kernel<true, true>), grid, 256, c->stream, S, cd, d, gd, od);
+        else VX_LAUNCH((gbuffer_kernel<false, true>), grid, 256, c->stream, S, cd, d, gd, od);
+    } else if (p.pom) VX_LAUNCH((gbuffer_kernel<true, false>), grid, 256, c->stream, S, cd, d, gd, od);
+    else VX_LAUNCH((gbuffer_kernel<false, false>), grid, 256, c->stream, S, cd, d, gd, od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

@@ -60,6 +60,8 @@ struct SceneDev {
     const uchar4* pbr_mips;
     const float* srgb_lut;  // 256 sRGB-decoded values, then 256 plain unorm8 values c / 255
     int n_mip_layers;
+    const uchar4* lava_albedo;  // [VXPT_LAVA_FRAMES][VXPT_LAVA_SIZE][VXPT_LAVA_SIZE] (vxpt_set_lava_textures)
+    const uchar4* lava_normal;
 };
 
 }  // namespace vxpt
@@ -98,6 +100,8 @@ struct vxpt_ctx {
     uchar4* d_pbr_mips = nullptr;
     float* d_srgb_lut = nullptr;
     int n_mip_layers = 0;
+    uchar4* d_lava_albedo = nullptr;  // vxpt_set_lava_textures
+    uchar4* d_lava_normal = nullptr;
     int n_layers = 0, n_emissive = 0, sky_n = 0;
     bool have_materials = false, have_bluenoise = false, have_textures = false, have_sky = false, have_shadow_noise = false;
 

@@ -84,13 +84,14 @@ def reflection_params(sun_dir, moon_dir, stronger_dir, viewer_pos, grass_props, 
 
 
 def material_params(grass_props, update_this_frame=True, pom=False, lava_block_id=-1, pom_height=1.0, pom_exp=1.0, high_quality_pom=False,
-                    dither_pom=True, frame=0):
+                    dither_pom=True, frame=0, time=0.0):
     """GenerateGBuffer's uniforms (Core/Pipeline.cpp:2079-2104, defaults :264-268); the lava animation is outside the v1 parity profile."""
     p = VxMaterialParams()
     p.update_this_frame, p.pom, p.lava_block_id = int(bool(update_this_frame)), int(bool(pom)), int(lava_block_id)
     p.grass_props[:] = [int(v) for v in grass_props]
     p.pom_height, p.pom_exp = float(pom_height), float(pom_exp)
     p.high_quality_pom, p.dither_pom, p.frame = int(bool(high_quality_pom)), int(bool(dither_pom)), int(frame)
+    p.time = float(time)
     return p
 
 
@@ -168,6 +169,12 @@ class Renderer:
         a = np.ascontiguousarray(alpha_mips, dtype=np.uint8)
         assert a.ndim == 2 and a.shape[1] == abi.ALPHA_MIP_TEXELS, a.shape
         abi.check(self.lib.vxpt_set_albedo_alpha_mips(self.handle, a.ctypes.data, a.shape[0]))
+
+    def set_lava_textures(self, albedo_rgba8, normal_rgba8):
+        """uint8 [LAVA_FRAMES][LAVA_SIZE][LAVA_SIZE][4] each: the animated lava textures (Core/AnimatedTexture.cpp)."""
+        a, n = (np.ascontiguousarray(x, dtype=np.uint8) for x in (albedo_rgba8, normal_rgba8))
+        assert a.shape == n.shape == (abi.LAVA_FRAMES, abi.LAVA_SIZE, abi.LAVA_SIZE, 4), a.shape
+        check(self.lib.vxpt_set_lava_textures(self.handle, _ptr(a), _ptr(n)))
 
     def set_gbuffer_textures(self, albedo_mips, normal_mips, pbr_mips):
         """uint8 [n_layers][MIP_CHAIN_TEXELS][4] each: the RGBA8 mip chains of the block arrays (see assets.rgba_mip_chain)."""

@@ -30,13 +30,18 @@ def main():
     g = r.trace_primary(cam, vx.primary_params(350), r.alloc_gbuffer(W, H, device=True))
     sets = [r.alloc_material(W, H, device=True) for _ in range(3)]
     mp = vx.material_params(mats["grass_props"])
-    ms = []
-    for k in range(iters + 3):
-        r.generate_gbuffer(cam, g, mp, sets[k % 3])
-        st = r.stats()
-        if k >= 3:
-            ms.append(st["last_ms"])
-    ms = np.array(ms)
+    def timed():
+        ms = []
+        for k in range(iters + 3):
+            r.generate_gbuffer(cam, g, mp, sets[k % 3])
+            st = r.stats()
+            if k >= 3:
+                ms.append(st["last_ms"])
+        return np.array(ms)
+    ms = timed()
+    r.set_option(vx.abi.OPT_MATERIAL_QUAD_SHUFFLE, 1)   # opt-in variant: quad partners by warp shuffle (A/B, same planes)
+    ms_shfl = timed()
+    r.set_option(vx.abi.OPT_MATERIAL_QUAD_SHUFFLE, 0)
     peak = 6451.5
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -45,7 +50,8 @@ def main():
     bytes_per_launch = W * H * 50
     out = {"kernel": "gbuffer_kernel", "resolution": [W, H], "iters": iters, "ms_mean": float(ms.mean()), "ms_min": float(ms.min()),
            "algorithmic_bytes": bytes_per_launch, "achieved_gbs": bytes_per_launch / (ms.mean() * 1e-3) / 1e9, "hbm_peak_gbs": peak,
-           "frac": bytes_per_launch / (ms.mean() * 1e-3) / 1e9 / peak, "hit_fraction": float((g["t"] > 0).float().mean())}
+           "frac": bytes_per_launch / (ms.mean() * 1e-3) / 1e9 / peak, "hit_fraction": float((g["t"] > 0).float().mean()),
+           "quad_shuffle_ms_mean": float(ms_shfl.mean()), "quad_shuffle_ms_min": float(ms_shfl.min())}
     print(json.dumps(out))
 
 

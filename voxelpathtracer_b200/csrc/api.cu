@@ -1555,6 +1555,10 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "texel format must be 0 or 1");
             c->opt_texel = value;
             return VXPT_OK;
+        case VXPT_OPT_MATERIAL_QUAD_SHUFFLE:
+            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "quad shuffle must be 0 or 1");
+            c->opt_quad_shuffle = value;
+            return VXPT_OK;
         case VXPT_OPT_DF_ALGO:
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "df algo must be 0 or 1");
             c->opt_df_algo = value;

@@ -124,20 +124,38 @@ __device__ __forceinline__ float4 lava_sample(const SceneDev& S, const uchar4* t
     return f4_lerp(a, b, fz);
 }
 
-// POM = u_POM, LAVA = a lava block id is set: separate instantiations, so that the default pass keeps its 40 registers
-template <bool POM, bool LAVA>
+// POM = u_POM, LAVA = a lava block id is set: separate instantiations, so that the default pass keeps its 40 registers.
+// SHFL (VXPT_OPT_MATERIAL_QUAD_SHUFFLE, default pass only, device only): the quad partners' UV come from lanes ^1 and ^8 of the 8x4 warp tile
+// instead of two more ray set-ups; the operands are the same values, so the planes are the same bits.
+template <bool POM, bool LAVA, bool SHFL = false>
 __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ MaterialDev p,
                                                       const GBufferDev g, const MaterialOutDev out) {
     int i, j, prow;
-    if (!thread_pixel(cam, i, j, prow)) return;
+    const bool in_frame = thread_pixel(cam, i, j, prow);
+    if (!SHFL && !in_frame) return;
     const size_t px = (size_t)prow * cam.width + i;
-    float u, v, dist;
+    float u = 0.0f, v = 0.0f, dist;
     V3 pos;
     int nid;
+#if defined(__CUDA_ARCH__) && !defined(VXPT_HOST_SHADOW)
+    float sx_u = 0.0f, sx_v = 0.0f, sy_u = 0.0f, sy_v = 0.0f;
+    bool sx_ok = false, sy_ok = false, own_ok = false;
+    if (SHFL) {  // every lane of the warp takes part; lanes outside the slab hand over "nothing", as quad_uv says of them
+        own_ok = in_frame && quad_uv<LAVA>(cam, p, g, i, j, prow, u, v, dist, pos, nid);
+        sx_u = __shfl_xor_sync(0xffffffffu, u, 1); sx_v = __shfl_xor_sync(0xffffffffu, v, 1);
+        sx_ok = __shfl_xor_sync(0xffffffffu, (int)own_ok, 1) != 0;
+        sy_u = __shfl_xor_sync(0xffffffffu, u, 8); sy_v = __shfl_xor_sync(0xffffffffu, v, 8);
+        sy_ok = __shfl_xor_sync(0xffffffffu, (int)own_ok, 8) != 0;
+        if (!in_frame) return;
+    }
+#else
+    const float sx_u = 0.0f, sx_v = 0.0f, sy_u = 0.0f, sy_v = 0.0f;
+    const bool sx_ok = false, sy_ok = false, own_ok = false;
+#endif
     const int block_early = LAVA ? min((int)g.block_id[px], 127) : 0;  // (read here only when a lava id is set: keeps the default pass at 40 registers)
     const bool is_lava = LAVA && block_early == p.lava_id;
     if (LAVA && !p.update_all && !is_lava) return;  // :351-357 discard: the attachments keep their texels
-    if (!quad_uv<LAVA>(cam, p, g, i, j, prow, u, v, dist, pos, nid)) {  // :360-366
+    if (SHFL ? !own_ok : !quad_uv<LAVA>(cam, p, g, i, j, prow, u, v, dist, pos, nid)) {  // :360-366
         if (out.albedo) { out.albedo[3 * px] = 0.0f; out.albedo[3 * px + 1] = 0.0f; out.albedo[3 * px + 2] = 0.0f; }
         if (out.normal) { out.normal[3 * px] = 1.0f; out.normal[3 * px + 1] = 1.0f; out.normal[3 * px + 2] = 1.0f; }
         if (out.pbr) out.pbr[px] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -149,11 +167,13 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     V3 pn;
     int nn;
     float ax = u, ay = v, bx = u, by = v;  // x pair: a = even column, b = odd column
-    if (quad_uv<LAVA>(cam, p, g, i ^ 1, j, prow, un, vn, dn, pn, nn)) {
+    if (SHFL) { un = sx_u; vn = sx_v; }
+    if (SHFL ? sx_ok : quad_uv<LAVA>(cam, p, g, i ^ 1, j, prow, un, vn, dn, pn, nn)) {
         if (i & 1) { ax = un; ay = vn; } else { bx = un; by = vn; }
     }
     float cx = u, cy = v, ex = u, ey = v;  // y pair: c = even row, e = odd row
-    if (quad_uv<LAVA>(cam, p, g, i, j ^ 1, prow ^ 1, un, vn, dn, pn, nn)) {
+    if (SHFL) { un = sy_u; vn = sy_v; }
+    if (SHFL ? sy_ok : quad_uv<LAVA>(cam, p, g, i, j ^ 1, prow ^ 1, un, vn, dn, pn, nn)) {
         if (j & 1) { cx = un; cy = vn; } else { ex = un; ey = vn; }
     }
     float4 d = make_float4(bx - ax, by - ay, ex - cx, ey - cy);
@@ -285,6 +305,9 @@ int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const V
         if (p.pom) VX_LAUNCH((gbuffer_kernel<true, true>), grid, 256, c->stream, S, cd, d, gd, od);
         else VX_LAUNCH((gbuffer_kernel<false, true>), grid, 256, c->stream, S, cd, d, gd, od);
     } else if (p.pom) VX_LAUNCH((gbuffer_kernel<true, false>), grid, 256, c->stream, S, cd, d, gd, od);
+#ifndef VXPT_HOST_SHADOW
+    else if (c->opt_quad_shuffle) VX_LAUNCH((gbuffer_kernel<false, false, true>), grid, 256, c->stream, S, cd, d, gd, od);
+#endif
     else VX_LAUNCH((gbuffer_kernel<false, false>), grid, 256, c->stream, S, cd, d, gd, od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());

@@ -117,6 +117,7 @@ struct vxpt_ctx {
     int opt_replicas = 1;   // VXPT_OPT_SCENE_REPLICAS
     int opt_timing = 1;     // VXPT_OPT_TIMING_EVENTS
     int opt_texel = 0;      // VXPT_OPT_TEXEL_FORMAT
+    int opt_quad_shuffle = 0;  // VXPT_OPT_MATERIAL_QUAD_SHUFFLE
     uint8_t* rep_grid[8] = {nullptr};   // extra copies (index 1..replicas-1); index 0 unused (= d_grid / d_steps)
     uint8_t* rep_steps[8] = {nullptr};
     uint64_t frame_counter = 0;  // advanced by vxpt_trace_primary

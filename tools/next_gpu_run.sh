@@ -11,4 +11,7 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 for k in svgf_initial_kernel svgf_temporal_kernel svgf_variance_kernel svgf_spatial_kernel shadow_temporal_kernel shadow_filter_kernel; do
   timeout 150 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_${R}_$k python tools/denoise_probe.py 2 >> gpurun_out/ncu_denoise_$R.log 2>&1
 done
+# the material pass, default kernel (launch 4 of the probe) and the opt-in quad-shuffle instantiation (the probe's second half: 2 + 3 launches in, +3 warm-up)
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:gbuffer_kernel -s 3 -c 1 -f -o gpurun_out/prof_${R}_gbuffer_default python tools/material_probe.py 2 >> gpurun_out/ncu_denoise_$R.log 2>&1
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:gbuffer_kernel -s 8 -c 1 -f -o gpurun_out/prof_${R}_gbuffer_quad_shuffle python tools/material_probe.py 2 >> gpurun_out/ncu_denoise_$R.log 2>&1
 ls gpurun_out | grep $R | tr '\n' ' '

@@ -540,7 +540,9 @@ VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
 #define VXPT_OPT_TRAVERSAL_LAYOUT 1 /* 0 = linear distance field, 1 = brick-swizzled copy (default) */
 #define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront re-queue of first-bounce hits (default),
                                        2 = 1 + persistent first-bounce tracer that refills finished lanes from a ray queue */
-#define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped), 1 = DPX tiled (default) */
+#define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped), 1 = DPX tiled (default),
+                                       2 = 1 + the z sweep writes the traversal's step field too (no separate packing launch; added after the
+                                       round's GPU budget was spent: compiled for sm_100a, not yet run on a GPU) */
 /* measurement knob: keep `value` (1..8) identical copies of the grid + step field at distinct addresses and rotate through
  * them, one per vxpt_trace_primary call (= per frame).  With 3 copies the traced inputs (132 MB) exceed the 126 MB L2, so
  * back-to-back frames cannot reuse each other's cache lines (benchmark timing rule); results are unchanged. */

@@ -1,0 +1,60 @@
+"""GPU test of VXPT_OPT_DF_ALGO = 2 (the z sweep of the distance-field build also writes the traversal's step field: no pack_steps launch).
+Written after the round's GPU budget was spent, so it sorts behind the GPU-verified tests.  The distance field must equal the oracle's bit
+for bit, and every pass that walks the step field must write the same planes as after a default (algo 1) build, in both layouts."""
+import numpy as np
+import pytest
+
+import voxelpathtracer_b200 as vx
+from voxelpathtracer_b200 import abi, camera
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(r, scene_tables, cam, W, H):
+    g = r.trace_primary(cam, vx.primary_params(350), r.alloc_gbuffer(W, H))
+    s = r.trace_shadow(cam, g, vx.shadow_params(scene_tables["stronger"], frame=5, soft=True), r.alloc_shadow(W, H))
+    sun, moon, vis = scene_tables["sun"], scene_tables["moon"], scene_tables["sun_visibility"]
+    d = r.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=4), r.alloc_diffuse(W, H))
+    out = {}
+    for name, planes in (("g", g), ("s", s), ("d", d)):
+        for k, v in planes.items():
+            if v is not None:
+                out[name + "." + k] = np.array(v, copy=True)
+    return out
+
+
+@pytest.mark.parametrize("name", ["plains", "city", "sparse"])
+def test_gpu_fused_step_field_build_equals_the_two_kernel_build(renderer, worlds, oracle_dfs, scene_tables, name):
+    r = renderer
+    W, H = 960, 540
+    cams = [camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H), camera.FpsCamera(position=(100.0, 70.0, 100.0), pitch_deg=-35.0, yaw_deg=45.0).vx_camera(W, H)]
+    try:
+        for layout in (1, 0):
+            r.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
+            r.set_option(abi.OPT_DF_ALGO, 1)
+            r.upload_world(worlds[name])
+            r.build_distance_field()
+            want = [_frame(r, scene_tables, cam, W, H) for cam in cams]
+            n0 = r.launch_count()
+            r.build_distance_field()
+            two_kernel_launches = r.launch_count() - n0
+            r.set_option(abi.OPT_DF_ALGO, 2)
+            r.upload_world(worlds[name])
+            n0 = r.launch_count()
+            r.build_distance_field()
+            assert r.launch_count() - n0 == two_kernel_launches - 1     # no pack_steps launch
+            assert np.array_equal(r.download_distance_field(), oracle_dfs[name])
+            got = [_frame(r, scene_tables, cam, W, H) for cam in cams]
+            for a, b in zip(got, want):
+                assert a.keys() == b.keys()
+                for k in a:
+                    assert np.array_equal(a[k], b[k], equal_nan=True), (name, layout, k)
+            # switching the layout after a fused build re-packs from the distance field, as after any build
+            r.set_option(abi.OPT_TRAVERSAL_LAYOUT, 1 - layout)
+            r.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
+            again = _frame(r, scene_tables, cams[0], W, H)
+            for k in again:
+                assert np.array_equal(again[k], want[0][k], equal_nan=True), (name, layout, "re-layout", k)
+    finally:
+        r.set_option(abi.OPT_DF_ALGO, 1)
+        r.set_option(abi.OPT_TRAVERSAL_LAYOUT, 1)

@@ -4,8 +4,9 @@
 # 2. timings of every f1 / f2 pass at 1080p (library CUDA events)   3. ncu launch list + full-set captures of the new kernels
 R=${1:-r02a}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_svgf_denoise.py tests/test_z_material_extras.py tests/test_host_cpp.py -m gpu -q > gpurun_out/pytest_new_$R.log 2>&1; tail -5 gpurun_out/pytest_new_$R.log
+timeout 300 python -m pytest tests/test_svgf_denoise.py tests/test_z_material_extras.py tests/test_z_df_fused.py tests/test_host_cpp.py -m gpu -q > gpurun_out/pytest_new_$R.log 2>&1; tail -5 gpurun_out/pytest_new_$R.log
 timeout 120 python tools/material_probe.py 30 > gpurun_out/${R}_material_probe.json 2> gpurun_out/${R}_material_probe.err; cat gpurun_out/${R}_material_probe.json
+timeout 120 python tools/df_probe.py 30 > gpurun_out/${R}_df_probe.json 2> gpurun_out/${R}_df_probe.err; cat gpurun_out/${R}_df_probe.json
 timeout 180 python tools/denoise_probe.py 20 > gpurun_out/${R}_denoise_probe.json 2> gpurun_out/${R}_denoise_probe.err; cat gpurun_out/${R}_denoise_probe.json
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_denoise_$R.csv python tools/denoise_probe.py 2 > gpurun_out/ncu_denoise_$R.log 2>&1
 for k in svgf_initial_kernel svgf_temporal_kernel svgf_variance_kernel svgf_spatial_kernel shadow_temporal_kernel shadow_filter_kernel; do

@@ -1560,7 +1560,7 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
             c->opt_quad_shuffle = value;
             return VXPT_OK;
         case VXPT_OPT_DF_ALGO:
-            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "df algo must be 0 or 1");
+            if (value < 0 || value > 2) return fail(VXPT_E_INVALID, "df algo must be 0..2");
             c->opt_df_algo = value;
             return VXPT_OK;
         default:

@@ -254,7 +254,25 @@ constexpr int ZSEGS = WZ / ZSEG;  // 16 segments per CTA
 // on 296 slots and the SMs idled 41 % of the kernel (ncu r01g); small CTAs keep eight resident per SM and refill as they retire.
 constexpr int ZXW = 8;
 
-__global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __restrict__ in, uint8_t* __restrict__ out) {
+__constant__ uint8_t c_step_lut[256];
+
+__device__ __forceinline__ uint32_t lut4(const uint8_t* lut, uint32_t w) {
+    return (uint32_t)lut[w & 0xFF] | ((uint32_t)lut[(w >> 8) & 0xFF] << 8) | ((uint32_t)lut[(w >> 16) & 0xFF] << 16) |
+           ((uint32_t)lut[w >> 24] << 24);
+}
+
+// PACK (VXPT_OPT_DF_ALGO = 2): -1 = distance field only; 0 / 1 = also write the step field E(M) of pack_steps<0 / 1> from the registers that
+// hold the finished words, which saves pack_steps' launch and its 18.9 MB re-read of the distance field.  In the brick layout the four
+// z-neighbours of an x-word are 16 contiguous bytes (brick_offset: z & 3 has stride 4), so a thread issues one 16-byte store per four
+// z values; ZSEG and the segment origins are multiples of 4.
+template <int PACK>
+__global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint8_t* __restrict__ steps) {
+    __shared__ uint8_t lut[PACK >= 0 ? 256 : 1];
+    if (PACK >= 0) {
+        const int t = threadIdx.y * ZXW + threadIdx.x;
+        lut[t] = c_step_lut[t];
+        lut[t + ZXW * ZSEGS] = c_step_lut[t + ZXW * ZSEGS];
+    }
     __shared__ uint2 edge_first[ZSEGS][ZXW];  // local value at the first voxel of a segment (lo pair, hi pair)
     __shared__ uint2 edge_last[ZSEGS][ZXW];
     __shared__ uint2 carry_f[ZSEGS][ZXW];
@@ -304,13 +322,21 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
     }
     __syncthreads();
     const uint2 cf = carry_f[seg][lane], cb = carry_b[seg][lane];
+    const int x0 = (blockIdx.x * ZXW + lane) * 4, z0 = seg * ZSEG;
+    uint32_t e[4];
 #pragma unroll
     for (int i = 0; i < ZSEG; ++i) {
         uint32_t a = __viaddmin_u16x2(cf.x, (uint32_t)(i + 1) * ONE2, lo[i]);
         a = __viaddmin_u16x2(cb.x, (uint32_t)(ZSEG - i) * ONE2, a);
         uint32_t b = __viaddmin_u16x2(cf.y, (uint32_t)(i + 1) * ONE2, hi[i]);
         b = __viaddmin_u16x2(cb.y, (uint32_t)(ZSEG - i) * ONE2, b);
-        *reinterpret_cast<uint32_t*>(out + base + (size_t)i * SLICE_BYTES) = __byte_perm(a, b, 0x6420);
+        const uint32_t w = __byte_perm(a, b, 0x6420);
+        *reinterpret_cast<uint32_t*>(out + base + (size_t)i * SLICE_BYTES) = w;
+        if (PACK == 0) *reinterpret_cast<uint32_t*>(steps + base + (size_t)i * SLICE_BYTES) = lut4(lut, w);
+        if (PACK == 1) {
+            e[i & 3] = lut4(lut, w);
+            if ((i & 3) == 3) *reinterpret_cast<uint4*>(steps + brick_offset(x0, y, z0 + i - 3)) = make_uint4(e[0], e[1], e[2], e[3]);
+        }
     }
 }
 
@@ -321,13 +347,6 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
 // (32 x-bytes x 4 y x 4 z): every lane reads one 16-byte run, every store instruction fills whole 64-byte half lines.
 // LAYOUT 0: linear, 16 bytes in / 16 bytes out per lane.
 // ------------------------------------------------------------------------------------------------------------
-__constant__ uint8_t c_step_lut[256];
-
-__device__ __forceinline__ uint32_t lut4(const uint8_t* lut, uint32_t w) {
-    return (uint32_t)lut[w & 0xFF] | ((uint32_t)lut[(w >> 8) & 0xFF] << 8) | ((uint32_t)lut[(w >> 16) & 0xFF] << 16) |
-           ((uint32_t)lut[w >> 24] << 24);
-}
-
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) pack_steps(const uint8_t* __restrict__ df, uint8_t* __restrict__ steps) {
     __shared__ uint8_t lut[256];
@@ -371,6 +390,7 @@ int init_df_kernels(vxpt_ctx* c) {
 int launch_df_build(vxpt_ctx* c) {
     cudaStream_t s = c->stream;
     if (c->opt_df_algo == 0) {
+        c->steps_fused = false;
         df_x_lines<<<(WY * WZ + 127) / 128, 128, 0, s>>>(c->d_grid, c->d_df);
         df_y_lines<<<(WX * WZ + 127) / 128, 128, 0, s>>>(c->d_df);
         df_z_lines<<<(WX * WY + 127) / 128, 128, 0, s>>>(c->d_df);
@@ -378,7 +398,16 @@ int launch_df_build(vxpt_ctx* c) {
     } else {
         const int smem = SLICE_BYTES + 16;
         df_xy_dpx<<<WZ, XY_THREADS, smem, s>>>(c->d_grid, c->d_tmp);
-        df_z_dpx<<<dim3(WX / (4 * ZXW), WY), dim3(ZXW, ZSEGS), 0, s>>>(c->d_tmp, c->d_df);
+        const dim3 zg(WX / (4 * ZXW), WY), zb(ZXW, ZSEGS);
+        c->steps_fused = false;
+        if (c->opt_df_algo == 2) {  // the z sweep writes the step field too; launch_pack_bricks has nothing left to do for this build
+            if (c->opt_layout == 1) df_z_dpx<1><<<zg, zb, 0, s>>>(c->d_tmp, c->d_df, c->d_steps);
+            else df_z_dpx<0><<<zg, zb, 0, s>>>(c->d_tmp, c->d_df, c->d_steps);
+            c->steps_layout = c->opt_layout;
+            c->steps_fused = true;
+        } else {
+            df_z_dpx<-1><<<zg, zb, 0, s>>>(c->d_tmp, c->d_df, nullptr);
+        }
         c->launches += 2;
     }
     VX_CUDA(cudaGetLastError());
@@ -386,6 +415,11 @@ int launch_df_build(vxpt_ctx* c) {
 }
 
 int launch_pack_bricks(vxpt_ctx* c) {
+    if (c->steps_fused && c->steps_layout == c->opt_layout) {  // df_z_dpx<PACK> of this build already wrote the step field in this layout
+        c->steps_fused = false;
+        return VXPT_OK;
+    }
+    c->steps_fused = false;
     if (c->opt_layout == 1) {
         const int warps = (WX / 32) * (WY / 4) * (WZ / 4);
         pack_steps<1><<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(c->d_df, c->d_steps);

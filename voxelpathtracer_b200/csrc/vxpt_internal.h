@@ -113,7 +113,8 @@ struct vxpt_ctx {
     int opt_layout = 1;     // VXPT_OPT_TRAVERSAL_LAYOUT
     int steps_layout = -1;  // layout the step field currently holds
     int opt_wavefront = 1;  // VXPT_OPT_GI_WAVEFRONT
-    int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped), 1 = DPX tiled
+    int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped), 1 = DPX tiled, 2 = 1 + step field written by the z sweep
+    bool steps_fused = false;  // the last launch_df_build wrote the step field itself (consumed by the launch_pack_bricks that follows)
     int opt_replicas = 1;   // VXPT_OPT_SCENE_REPLICAS
     int opt_timing = 1;     // VXPT_OPT_TIMING_EVENTS
     int opt_texel = 0;      // VXPT_OPT_TEXEL_FORMAT

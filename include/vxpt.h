@@ -561,7 +561,7 @@ VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
 #define VXPT_OPT_TEXEL_FORMAT 6
 /* G-buffer material pass, default instantiation (no parallax, no lava id): 0 (default) = every thread re-derives the surface UV of its two
  * quad partners (three ray set-ups per pixel), 1 = the partners' UV arrive by warp shuffle (one ray set-up per pixel).  Same operands, same
- * planes.  Added after the round's GPU budget was spent: compiled for sm_100a, NOT yet run on a GPU — hence off by default. */
+ * planes (checked on the host with emulated shuffles).  Added after the round's GPU budget was spent: NOT yet run on a GPU — hence off by default. */
 #define VXPT_OPT_MATERIAL_QUAD_SHUFFLE 7
 VXPT_API int vxpt_set_option(vxpt_handle h, int option, int value);
 

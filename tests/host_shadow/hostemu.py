@@ -12,7 +12,7 @@ CUDA_INCLUDE = "/usr/local/cuda/include"
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, "vxpt_hostemu.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "vxpt.h")]
+    srcs = [os.path.join(HERE, "vxpt_hostemu.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "vxpt.h"), os.path.join(HERE, "warp_emu.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
         return LIB_PATH
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

@@ -54,6 +54,9 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetc
         }                                                                                    \
     } while (0)
 
+#define VX_WARP_EMU_SET_DIMS(bs, g) do { } while (0)
+#include "warp_emu.h"
+
 #include "../../voxelpathtracer_b200/csrc/trace.cu"
 #include "../../voxelpathtracer_b200/csrc/trace_reflection.cu"
 #include "../../voxelpathtracer_b200/csrc/df_consumers.cu"

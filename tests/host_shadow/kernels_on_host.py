@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB_PATH = os.path.join(HERE, "libkernels_on_host.so")
 CSRC = os.path.join(ROOT, "voxelpathtracer_b200", "csrc")
-SOURCES = [os.path.join(HERE, "kernels_on_host.cpp")] + [os.path.join(CSRC, f) for f in
+SOURCES = [os.path.join(HERE, "kernels_on_host.cpp"), os.path.join(HERE, "warp_emu.h")] + [os.path.join(CSRC, f) for f in
                                                          ("trace.cu", "trace_reflection.cu", "df_consumers.cu", "gbuffer.cu", "denoise.cu", "trace_device.cuh",
                                                           "gi_device.cuh", "vxpt_internal.h")]
 CUDA_INCLUDE = "/usr/local/cuda/include"

@@ -142,6 +142,9 @@ static inline unsigned long long global_timer_ns() { static unsigned long long t
         }                                                                                    \
     } while (0)
 
+#define VX_WARP_EMU_SET_DIMS(bs, g) do { blockDim = dim3((bs), 1, 1); gridDim = (g); } while (0)
+#include "warp_emu.h"
+
 #include "../../voxelpathtracer_b200/csrc/trace.cu"
 #include "../../voxelpathtracer_b200/csrc/trace_reflection.cu"
 #include "../../voxelpathtracer_b200/csrc/df_consumers.cu"

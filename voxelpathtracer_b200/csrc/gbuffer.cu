@@ -125,7 +125,7 @@ __device__ __forceinline__ float4 lava_sample(const SceneDev& S, const uchar4* t
 }
 
 // POM = u_POM, LAVA = a lava block id is set: separate instantiations, so that the default pass keeps its 40 registers.
-// SHFL (VXPT_OPT_MATERIAL_QUAD_SHUFFLE, default pass only, device only): the quad partners' UV come from lanes ^1 and ^8 of the 8x4 warp tile
+// SHFL (VXPT_OPT_MATERIAL_QUAD_SHUFFLE, default pass only): the quad partners' UV come from lanes ^1 and ^8 of the 8x4 warp tile
 // instead of two more ray set-ups; the operands are the same values, so the planes are the same bits.
 template <bool POM, bool LAVA, bool SHFL = false>
 __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ MaterialDev p,
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) gbuffer_kernel(const SceneDev S, const __
     float u = 0.0f, v = 0.0f, dist;
     V3 pos;
     int nid;
-#if defined(__CUDA_ARCH__) && !defined(VXPT_HOST_SHADOW)
+#if defined(__CUDA_ARCH__) || defined(VXPT_HOST_SHADOW)
     float sx_u = 0.0f, sx_v = 0.0f, sy_u = 0.0f, sy_v = 0.0f;
     bool sx_ok = false, sy_ok = false, own_ok = false;
     if (SHFL) {  // every lane of the warp takes part; lanes outside the slab hand over "nothing", as quad_uv says of them
@@ -305,9 +305,7 @@ int launch_gbuffer(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const V
         if (p.pom) VX_LAUNCH((gbuffer_kernel<true, true>), grid, 256, c->stream, S, cd, d, gd, od);
         else VX_LAUNCH((gbuffer_kernel<false, true>), grid, 256, c->stream, S, cd, d, gd, od);
     } else if (p.pom) VX_LAUNCH((gbuffer_kernel<true, false>), grid, 256, c->stream, S, cd, d, gd, od);
-#ifndef VXPT_HOST_SHADOW
-    else if (c->opt_quad_shuffle) VX_LAUNCH((gbuffer_kernel<false, false, true>), grid, 256, c->stream, S, cd, d, gd, od);
-#endif
+    else if (c->opt_quad_shuffle) VX_LAUNCH_WARPSYNC((gbuffer_kernel<false, false, true>), grid, 256, c->stream, S, cd, d, gd, od);
     else VX_LAUNCH((gbuffer_kernel<false, false>), grid, 256, c->stream, S, cd, d, gd, od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());

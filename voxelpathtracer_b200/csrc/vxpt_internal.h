@@ -182,6 +182,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // with g++ and defines it as a loop over blockIdx / threadIdx, so the CPU suite executes the kernels' own source against the
 // oracle; the product library is only ever built by nvcc and has no host path.)
 #define VX_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// a kernel that exchanges values between the lanes of a warp (the host builds of the tests run each warp twice: record, then replay)
+#define VX_LAUNCH_WARPSYNC(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 
 // df_build.cu

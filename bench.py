@@ -235,6 +235,44 @@ def bind_near_gpu(gpu_index):
         return None
 
 
+def check_gathered_frame(vx, fr, r, fc, frame_params_, texel, barrier):
+    """Multi-GPU correctness inside the bench (un-timed): every rank traces its rows of one more frame into slot 0 and exchanges them as
+    in the timed loop; the rank that holds the gathered planes renders the WHOLE frame by itself and compares the exchanged planes
+    (shadow + GI) byte for byte.  Returns {"ok": bool, "planes": {...}} on that rank, None elsewhere."""
+    import torch
+    pp, sp, dp = frame_params_
+    fr.finish()
+    torch.cuda.synchronize()
+    barrier()
+    fr.last_slot = 0
+    fr.frame_into(0, pp, sp, dp)
+    fr.exchange(0)
+    fr.finish()
+    torch.cuda.synchronize()
+    barrier()   # every rank's push and arrival flag have completed; the root's gather stream has seen all of them
+    out = None
+    if fr.buf is not None and fr.rank == fr.root:
+        cam = fc.vx_camera(fr.width, fr.height)
+        g = r.alloc_gbuffer(fr.width, fr.height, device=True, texel=texel)
+        s = r.alloc_shadow(fr.width, fr.height, device=True, texel=texel)
+        d = r.alloc_diffuse(fr.width, fr.height, device=True, texel=texel)
+        r.trace_primary(cam, pp, g)
+        r.trace_shadow(cam, g, sp, s)
+        r.trace_diffuse(cam, g, dp, d)
+        r.sync()
+        whole = {"s_shadow": s["shadow"], "s_transversal": s["transversal"], "d_sh": d["sh"], "d_cocg": d["cocg"], "d_luma": d["luma"], "d_ao_sky": d["ao_sky"]}
+        planes = {}
+        for name, _, _, _ in fr.exchanged:
+            if name not in whole:
+                continue
+            got, want = fr.plane(name, 0), whole[name]
+            planes[name] = bool(torch.equal(got.contiguous().view(torch.uint8), want.contiguous().view(torch.uint8)))
+        out = {"ok": all(planes.values()) and len(planes) > 0, "planes": planes,
+               "digest": int(sum(int(whole[n].contiguous().view(torch.uint8).to(torch.int64).sum()) for n in planes) % (1 << 61))}
+    barrier()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -324,8 +362,10 @@ def run_ours(args):
     # cycled), so a step costs the host one graph launch + the eager NCCL exchange instead of ~0.34 ms of Python/ctypes per
     # frame.  --no-graph submits every call eagerly.
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for k in range(args.warmup):
-        eager_step(k, k)
+    # every pipe x slot runs eagerly at least once before anything is captured (first-use work — module loading, scratch growth — is
+    # not capturable; the handles' scratch is also sized up front by ShardedFrame through vxpt_reserve)
+    for k in range(max(args.warmup, P * slots)):
+        eager_step(k, k % n_frames)
     finish_all()
     barrier()
     graphs, submit = None, "eager"
@@ -420,6 +460,12 @@ def run_ours(args):
     rays_all = float(tot[1])                     # all ranks, all K steps
     value = rays_all / (total_ms * 1e-3) / 1e6
 
+    # ---- un-timed: is the gathered frame the frame?  One more frame goes through the same path (slot wait, passes, push, flags /
+    # all-gather); the gather root then renders the whole frame alone and compares every exchanged plane bit for bit.
+    gathered = None
+    if ws > 1 and not args.emulate:
+        gathered = check_gathered_frame(vx, frames[0], renderers[0], fc, params[args.warmup], texel, barrier)
+
     # per-pass rooflines on this rank (rank 0 reports): algorithmic bytes = (N_it + N_vox) * 32 B over the L2 sector peak
     # measured by the library's probe.  Counters are per pass, so re-run K frames with a stats read between passes.
     pass_stats = np.zeros((3, 3))
@@ -451,9 +497,12 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-    df_gbs = 2 * abi.WORLD_VOXELS / (df_ms * 1e-3) / 1e9
+    # a rebuild is not usable by the trace passes before the step field exists, so the denominator is distance field + step field time;
+    # the algorithmic bytes stay SURVEY.md §8(d)'s: read the grid once + write the distance field once (the step field is this design's own)
+    df_gbs = 2 * abi.WORLD_VOXELS / ((df_ms + pack_ms) * 1e-3) / 1e9
     rooflines["df_build"] = {"bound": "hbm", "achieved": df_gbs, "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s", "frac": df_gbs / hbm_peak,
-                             "traffic": None, "ms_per_launch": df_ms, "brick_pack_ms": pack_ms}
+                             "traffic": None, "ms_per_launch": df_ms + pack_ms, "distance_field_ms": df_ms, "step_field_ms": pack_ms,
+                             "note": "37,748,736 algorithmic bytes over the whole rebuild (distance field + traversal step field)"}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(traffic_path):
         for k, v in json.load(open(traffic_path)).items():
@@ -542,16 +591,19 @@ def run_ours(args):
                        "sharding": (f"{ws} ranks, interleaved {frame.band_rows}-row bands, {P} frame pipe(s) per GPU, grid replicated; " + xchg_text),
                        "planes": ("reference FBO texel formats (R16F/RGBA16F/RG16F/RG8/R8; VXPT_OPT_TEXEL_FORMAT=1)" if texel else "fp32 planes") + f", {px_out} B/pixel written, {px_xchg} B/pixel gathered",
                        "timing": f"two CUDA events on the library stream around exactly K steps (barrier + synchronize on both sides), max over ranks; inputs larger than L2: 3 scene replicas (132 MB) rotated per frame + {WIDTH * HEIGHT * px_out / 1e6:.0f} MB of planes written per frame, no flush kernel",
-                       "submit": submit, "host_submit_ms_per_step": host_submit_ms, "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": {0: "one thread per pixel", 1: "wavefront (warp-ballot compaction of first-bounce hits)", 2: "wavefront + persistent first-bounce tracer"}[args.gi_mode]},
+                       "submit": submit, "host_submit_ms_per_step": host_submit_ms, "traversal_layout": "8x4x4-voxel tiles of pre-converted step values", "gi": {0: "one thread per pixel", 1: "wavefront (sorted first-bounce rays, warp-ballot compaction of the hits, the rest of a sample in CTA-wide stages)"}[args.gi_mode]},
             "e2e": e2e, "gpu_launches": int(tot[4]),
             "roofline": dict(rooflines[dominant], kernel=dominant,
                              note="traversal roofline = (DF fetches + block fetches) x 32 B per launch over the measured random-sector L2 peak (SURVEY.md §8d)"),
             "roofline_all": rooflines,
-            "df_build_ms": df_ms, "l2_sector_peak_gbs": l2_peak,
+            "df_build_ms": df_ms + pack_ms, "l2_sector_peak_gbs": l2_peak,
             "pass_ms": {"primary": float(per_pass[:, 0].mean()), "shadow": float(per_pass[:, 1].mean()), "diffuse": float(per_pass[:, 2].mean()),
                         "note": "rank 0's rows, each pass timed alone after the timed region (library events); the step time above includes the overlapped exchange"},
             "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
+        if gathered is not None:
+            line["gathered_ok"] = gathered["ok"]
+            line["gathered"] = gathered
         print(json.dumps(line))
     if ws > 1:
         dist.destroy_process_group()
@@ -569,7 +621,7 @@ def main():
     ap.add_argument("--slots", type=int, default=2, help="frame slots per pipe in the slab buffer")
     ap.add_argument("--exchange", default="p2pcopy", choices=["p2p", "p2pcopy", "nccl"],
                     help="multi-GPU slab gather: the trace kernels store into the root's memory (p2p), one copy-engine push per frame (p2pcopy), or NCCL all-gather")
-    ap.add_argument("--gi-mode", type=int, default=1, choices=[0, 1, 2], help="VXPT_OPT_GI_WAVEFRONT: 0 one thread per pixel, 1 wavefront (default), 2 + persistent first-bounce tracer")
+    ap.add_argument("--gi-mode", type=int, default=1, choices=[0, 1], help="VXPT_OPT_GI_WAVEFRONT: 0 one thread per pixel, 1 wavefront (default)")
     ap.add_argument("--emulate", type=int, default=0, help="development: trace rank 0's share of an N-way sharded frame on one GPU, no exchange")
     ap.add_argument("--planes", default="texel", choices=["texel", "f32"], help="plane encoding: the reference's FBO texel formats (default) or fp32")
     ap.add_argument("--no-graph", action="store_true", help="submit every pass eagerly instead of replaying a CUDA graph")

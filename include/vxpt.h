@@ -535,11 +535,19 @@ VXPT_API int vxpt_reset_stats(vxpt_handle h);
 VXPT_API int vxpt_launch_count(vxpt_handle h, uint64_t* kernels_launched); /* kernels this handle launched */
 /* the CUDA stream (cudaStream_t) the handle enqueues on, so callers can record events around passes */
 VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
+/* Size the handle's device scratch up front — what the reference does when it (re)creates its FBOs for a window size
+ * (Core/Pipeline.cpp:1094-1152 via Framebuffer::SetSize) instead of inside a draw.  The passes grow their scratch on demand (GI wavefront
+ * queue: 48 B per slab pixel, + 48 B per frame pixel when a pixel takes several samples; staging arena for host-pointer planes), which
+ * needs a stream synchronisation and a reallocation: legal any time EXCEPT while the handle's stream is being captured into a CUDA graph,
+ * where such a pass returns VXPT_E_STATE.  Call this once (or run one eager frame of the same size) before capturing.
+ * cam: the frame size and the row slab the handle will trace; max_gi_spp: the largest VxDiffuseParams.spp to come (0 = no GI pass);
+ * staging_bytes: host-plane staging to keep (0 = none). */
+VXPT_API int vxpt_reserve(vxpt_handle h, const VxCamera* cam, int max_gi_spp, size_t staging_bytes);
 
 /* ---- tuning knobs (do not change results) ---------------------------------------------------------------- */
 #define VXPT_OPT_TRAVERSAL_LAYOUT 1 /* 0 = linear distance field, 1 = brick-swizzled copy (default) */
-#define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront re-queue of first-bounce hits (default),
-                                       2 = 1 + persistent first-bounce tracer that refills finished lanes from a ray queue */
+#define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront: sorted first-bounce rays, hits re-queued, the rest of a sample in
+                                       CTA-wide stages (default) */
 #define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped), 1 = DPX tiled (default),
                                        2 = 1 + the z sweep writes the traversal's step field too (no separate packing launch; added after the
                                        round's GPU budget was spent: compiled for sm_100a, not yet run on a GPU) */
@@ -559,9 +567,9 @@ VXPT_API int vxpt_stream(vxpt_handle h, void** cuda_stream);
  *    (g_normal / g_pbr stay fp32).  Halves are IEEE binary16 rounded to nearest even, unorm8 = round(v * 255).
  *    27 B/pixel for G-buffer + shadow + GI instead of 51: what a host consumer or a peer GPU has to receive. */
 #define VXPT_OPT_TEXEL_FORMAT 6
-/* G-buffer material pass, default instantiation (no parallax, no lava id): 0 (default) = every thread re-derives the surface UV of its two
- * quad partners (three ray set-ups per pixel), 1 = the partners' UV arrive by warp shuffle (one ray set-up per pixel).  Same operands, same
- * planes (checked on the host with emulated shuffles).  Added after the round's GPU budget was spent: NOT yet run on a GPU — hence off by default. */
+/* G-buffer material pass, default instantiation (no parallax, no lava id): 0 = every thread re-derives the surface UV of its two
+ * quad partners (three ray set-ups per pixel), 1 (default) = the partners' UV arrive by warp shuffle (one ray set-up per pixel).  Same
+ * operands, same planes (GPU test + emulated shuffles on the host); B200, 1080p: 0.0532 ms against 0.0649 ms (profiles/r02a_material_probe.json). */
 #define VXPT_OPT_MATERIAL_QUAD_SHUFFLE 7
 VXPT_API int vxpt_set_option(vxpt_handle h, int option, int value);
 

@@ -393,7 +393,7 @@ inline v3 sky_sample(const Scene& S, v3 d) {
 inline v3 tex_nearest4(const float* base, int layer, int n, float u, float v) {
     int i = ((int)std::floor(u * (float)n)) & (n - 1);
     int j = ((int)std::floor(v * (float)n)) & (n - 1);
-    const float* p = base + (((size_t)layer * n + j) * n + i) * 4;
+    const float* p = base + (((size_t)std::max(layer, 0) * n + j) * n + i) * 4;  // GL clamps the array layer: -1 (id not in the block database) reads layer 0
     return V(p[0], p[1], p[2]);
 }
 inline float tex_bilinear1(const float* base, int layer, int n, float u, float v) {
@@ -886,7 +886,7 @@ inline float tex_nearest1(const float* base, int layer, int n, float u, float v)
 inline void tex_nearest4w(const float* base, int layer, int n, float u, float v, float out[4]) {
     int i = ((int)std::floor(u * (float)n)) & (n - 1);
     int j = ((int)std::floor(v * (float)n)) & (n - 1);
-    const float* p = base + (((size_t)layer * n + j) * n + i) * 4;
+    const float* p = base + (((size_t)std::max(layer, 0) * n + j) * n + i) * 4;
     out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3];
 }
 inline float log_cr(float x) { return (float)std::log((double)x); }

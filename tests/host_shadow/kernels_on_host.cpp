@@ -80,6 +80,7 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.albedo_mips = c->d_albedo_mips; S.normal_mips = c->d_normal_mips; S.pbr_mips = c->d_pbr_mips;
     S.srgb_lut = c->d_srgb_lut; S.n_mip_layers = c->n_mip_layers;
     S.lava_albedo = c->d_lava_albedo; S.lava_normal = c->d_lava_normal;
+    S.lut = c->d_lut;
     return S;
 }
 // the wavefront GI pipeline needs a GPU (shared memory, ballots); the shadow runs the one-thread-per-pixel kernel
@@ -91,6 +92,7 @@ struct HostShadow {
     vxpt_ctx c;
     std::vector<uint8_t> steps, bluenoise;
     float srgb_lut[512];
+    float trace_lut[vxpt::LUT_FLOATS];
     vxpt::DeviceCounters counters{};
 };
 
@@ -173,6 +175,8 @@ HS_API void* hs_create(const HsScene* s, int layout, int texel_format) {
         h->srgb_lut[256 + k] = (float)k / 255.0f;
     }
     c.d_srgb_lut = h->srgb_lut;
+    vxpt::fill_trace_lut(h->trace_lut);  // what vxpt_create uploads (api.cu)
+    c.d_lut = h->trace_lut;
     return h;
 }
 HS_API void hs_destroy(void* p) { delete (HostShadow*)p; }

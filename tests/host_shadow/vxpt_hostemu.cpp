@@ -46,6 +46,7 @@ const char* cudaGetErrorString(cudaError_t) { return "host emulation"; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t) new int(0); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete (int*)s; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* st) { *st = cudaStreamCaptureStatusNone; return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t) new FakeEvent{0.0}; return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
@@ -207,5 +208,6 @@ int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev&
     c->launches += 1;
     return VXPT_OK;
 }
+size_t gi_scratch_bytes(size_t, size_t, bool) { return 256; }
 int run_l2_probe(vxpt_ctx*, double* gbps) { *gbps = 1000.0; return VXPT_OK; }
 }  // namespace vxpt

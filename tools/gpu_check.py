@@ -80,7 +80,7 @@ def main():
     dp = vx.diffuse_params(sun, moon, sunvis, spp=1, frame=7)
     t0 = time.time(); d_ref, dst_ref = orc.trace_diffuse(cam, g_ref, dp); print("oracle diffuse s", time.time() - t0, dst_ref)
     gdev = {k: __import__("torch").from_numpy(v).cuda() for k, v in g_ref.items()}
-    for wf in (0, 1, 2):
+    for wf in (0, 1):
         for layout in (0, 1):
             r.set_option(abi.OPT_TRAVERSAL_LAYOUT, layout)
             r.set_option(abi.OPT_GI_WAVEFRONT, wf)

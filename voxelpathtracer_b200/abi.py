@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvxpt.so")
+# VXPT_LIB: development only — an experiment build of the same sources (build.py --out=...); the product loads libvxpt.so
+LIB_PATH = os.path.join(HERE, os.environ.get("VXPT_LIB", "libvxpt.so"))
 
 WORLD_SIZE_X, WORLD_SIZE_Y, WORLD_SIZE_Z = 384, 128, 384
 WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z
@@ -243,6 +244,7 @@ EXPORTS = {
     "vxpt_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "vxpt_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vxpt_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vxpt_reserve": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.c_int, C.c_size_t]),
     "vxpt_measure_l2_sector_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 

@@ -32,18 +32,23 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+def build(force=False, verbose=False, defines=(), out=None):
+    """Build libvxpt.so.  defines / out: development only — an experiment variant of the library (-DNAME=VALUE ...) under another file
+    name, selected at run time with the environment variable VXPT_LIB (abi.py); the product is the default build."""
+    lib = out or LIB
+    if not force and not defines and not needs_build():
+        return lib
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SOURCES
     proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
-        raise RuntimeError("nvcc failed building libvxpt.so")
+        raise RuntimeError("nvcc failed building " + os.path.basename(lib))
     if verbose:
         sys.stderr.write(proc.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=os.path.join(HERE, outs[0]) if outs else None))

@@ -57,6 +57,7 @@ SceneDev make_scene(const vxpt_ctx* c) {
     S.n_mip_layers = c->n_mip_layers;
     S.lava_albedo = c->d_lava_albedo;
     S.lava_normal = c->d_lava_normal;
+    S.lut = c->d_lut;
     return S;
 }
 
@@ -69,24 +70,44 @@ static bool is_device_pointer(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// true while the handle's stream records a CUDA graph: nothing may synchronise or allocate then
+bool stream_capturing(const vxpt_ctx* c) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(c->stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// Grow-only device scratch of a handle (staging arena, wavefront queues).  Growing synchronises the stream and reallocates, which is
+// illegal while the stream is being captured into a CUDA graph: there the call fails with VXPT_E_STATE instead and the caller is told to
+// size the scratch first (vxpt_reserve, or one eager frame of the same size).
+int grow_scratch(vxpt_ctx* c, void** buf, size_t* have, size_t need, const char* what) {
+    if (need <= *have) return VXPT_OK;
+    if (stream_capturing(c)) {
+        set_error(std::string(what) + " would have to grow while the handle's stream is being captured: call vxpt_reserve (or run one frame of this size) before capturing");
+        return VXPT_E_STATE;
+    }
+    VX_CUDA(cudaStreamSynchronize(c->stream));
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    if (cudaMalloc(buf, need) != cudaSuccess) {
+        cudaGetLastError();
+        set_error(std::string(what) + ": device allocation failed");
+        return VXPT_E_NOMEM;
+    }
+    *have = need;
+    return VXPT_OK;
+}
+
 // bump allocator over a device arena for staged (host-pointer) planes; reset at the start of every pass
 struct Arena {
     vxpt_ctx* c;
     size_t used = 0;
     explicit Arena(vxpt_ctx* ctx) : c(ctx) {}
-    int reserve(size_t bytes) {
-        if (bytes <= c->stage_bytes) return VXPT_OK;
-        VX_CUDA(cudaStreamSynchronize(c->stream));
-        if (c->d_stage) cudaFree(c->d_stage);
-        c->d_stage = nullptr;
-        c->stage_bytes = 0;
-        if (cudaMalloc(&c->d_stage, bytes) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(VXPT_E_NOMEM, "device staging allocation failed");
-        }
-        c->stage_bytes = bytes;
-        return VXPT_OK;
-    }
+    int reserve(size_t bytes) { return grow_scratch(c, &c->d_stage, &c->stage_bytes, bytes, "the staging arena"); }
     void* take(size_t bytes) {
         void* p = (char*)c->d_stage + used;
         used += (bytes + 255) & ~(size_t)255;
@@ -302,6 +323,12 @@ int vxpt_create(int device_id, vxpt_handle* out) {
     if (e == cudaSuccess) e = cudaMalloc(&c->d_steps, STEPS_TILED_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(DeviceCounters));
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_lut, LUT_FLOATS * sizeof(float));
+    if (e == cudaSuccess) {
+        float lut[LUT_FLOATS];
+        fill_trace_lut(lut);
+        e = cudaMemcpy(c->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "vxpt_create allocations", __FILE__, __LINE__);
         vxpt_destroy(c);
@@ -337,7 +364,7 @@ int vxpt_destroy(vxpt_handle c) {
     }
     void* bufs[] = {c->d_grid, c->d_df, c->d_tmp, c->d_steps, c->d_materials, c->d_bluenoise, c->d_albedo, c->d_pbr,
                     c->d_emissive, c->d_normal, c->d_emissive2, c->d_sky, c->d_shadow_noise, c->d_alpha_mips, c->d_counters, c->d_stage, c->d_queue,
-                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut, c->svgf.buf, c->shadow_hist.buf, c->d_lava_albedo, c->d_lava_normal};
+                    c->d_albedo_mips, c->d_normal_mips, c->d_pbr_mips, c->d_srgb_lut, c->svgf.buf, c->shadow_hist.buf, c->d_lava_albedo, c->d_lava_normal, c->d_lut};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1244,11 +1271,20 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     // half traces.  Smaller pieces would starve the copy engine: a 135-row slab of the three passes takes longer to trace (latency-
     // bound kernels) than to copy (measured r01g, 1080 rows: this schedule 1.21 ms, 2 / 4 / 8 uniform slabs of all passes 1.45 / 1.38 / 1.48 ms).
     int n_ev = 0;
+    // Once a copy to the caller's planes is queued, the frame owns the staging arena and those planes until the copy stream has drained —
+    // also when a later launch fails and this function returns early: the guard then leaves the frame pending, so the next call on the
+    // handle (check_ready -> finish_pending_frame) waits for the copies before anything reuses or frees the arena.
+    struct PendingGuard {
+        vxpt_ctx* c;
+        bool queued = false, settled = false;
+        ~PendingGuard() { if (queued && !settled) c->frame_pending = true; }
+    } guard{c};
     auto copy_out = [&](std::initializer_list<Plane*> pls, int rb, int re) -> int {
         if (!any_host) return VXPT_OK;
         bool some = false;
         for (Plane* pl : pls) some = some || (pl->user && pl->staged);
         if (!some) return VXPT_OK;
+        guard.queued = true;
         cudaEvent_t ev = c->ev_slab[n_ev++ & 7];
         VX_CUDA(cudaEventRecord(ev, c->stream));
         VX_CUDA(cudaStreamWaitEvent(c->copy_stream, ev, 0));
@@ -1288,8 +1324,12 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
         c->pass_timed = true;
     }
     if (any_host) {
-        if (wait) VX_CUDA(cudaStreamSynchronize(c->copy_stream));
-        else c->frame_pending = true;
+        if (wait) {
+            VX_CUDA(cudaStreamSynchronize(c->copy_stream));
+            guard.settled = true;
+        } else {
+            c->frame_pending = true;
+        }
     }
     return VXPT_OK;
 }
@@ -1523,6 +1563,21 @@ int vxpt_stream(vxpt_handle c, void** s) {
     return VXPT_OK;
 }
 
+int vxpt_reserve(vxpt_handle c, const VxCamera* cam, int max_gi_spp, size_t staging_bytes) {
+    if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
+    if (int rc = check_camera(cam)) return rc;
+    if (max_gi_spp < 0 || max_gi_spp > 64) return fail(VXPT_E_INVALID, "max_gi_spp outside 0..64");
+    VX_CUDA(cudaSetDevice(c->device));
+    if (int rc = finish_pending_frame(c)) return rc;
+    if (max_gi_spp > 0) {
+        const size_t slab_px = (size_t)(cam->row_end - cam->row_begin) * cam->width, frame_px = (size_t)cam->width * cam->height;
+        if (int rc = grow_scratch(c, &c->d_queue, &c->queue_bytes, gi_scratch_bytes(slab_px, frame_px, max_gi_spp == 1), "the GI wavefront queue")) return rc;
+    }
+    if (staging_bytes)
+        if (int rc = grow_scratch(c, &c->d_stage, &c->stage_bytes, staging_bytes, "the staging arena")) return rc;
+    return VXPT_OK;
+}
+
 int vxpt_set_option(vxpt_handle c, int option, int value) {
     if (!c) return fail(VXPT_E_INVALID, "handle is NULL");
     switch (option) {
@@ -1536,7 +1591,7 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
             }
             return VXPT_OK;
         case VXPT_OPT_GI_WAVEFRONT:
-            if (value < 0 || value > 2) return fail(VXPT_E_INVALID, "wavefront must be 0..2");
+            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "wavefront must be 0 or 1");
             c->opt_wavefront = value;
             return VXPT_OK;
         case VXPT_OPT_SCENE_REPLICAS:

@@ -36,7 +36,8 @@ int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev&
 constexpr float PI_F = 3.14159265359f;
 
 // samplerBlueNoiseErrorDistribution_128x128_OptimizedFor_2d2d2d2d_32spp — DiffuseRayTraceFrag.glsl:126-149
-__device__ __forceinline__ float blue_noise_1d(const SceneDev& S, int px, int py, int sample_index, int sample_dim) {
+// the table value (0..255); the sample is (0.5 + value) / 256
+__device__ __forceinline__ int blue_noise_byte(const SceneDev& S, int px, int py, int sample_index, int sample_dim) {
     const int pi = px & 127, pj = py & 127;
     sample_index &= 255;
     sample_dim &= 255;
@@ -45,7 +46,10 @@ __device__ __forceinline__ float blue_noise_1d(const SceneDev& S, int px, int py
     const int ranked = (sample_index ^ (int)S.rank[ridx]) & 255;
     int value = S.sobol[sample_dim + ranked * 256];
     value = value ^ (int)S.scramble[(sample_dim % 8) + (pi + pj * 128) * 8];
-    return (0.5f + (float)value) / 256.0f;
+    return value;
+}
+__device__ __forceinline__ float blue_noise_1d(const SceneDev& S, int px, int py, int sample_index, int sample_dim) {
+    return (0.5f + (float)blue_noise_byte(S, px, py, sample_index, sample_dim)) / 256.0f;
 }
 
 // texture(u_Skymap, d): bilinear inside the major-axis face, clamped at the face edge (pinned)
@@ -74,10 +78,13 @@ __device__ __forceinline__ V3 sky_sample(const SceneDev& S, V3 d) {
     return a * (1.0f - fv) + b * fv;
 }
 
+// GL clamps the array layer to [0, d-1].  The material table holds -1 for every id the block database does not name
+// (BlockDataSSBO.cpp:15-26), and worlds may contain such ids, so a negative layer reads layer 0; layers >= d are rejected when the
+// pass is called (check_diffuse / check_reflection in api.cu).
 __device__ __forceinline__ V3 tex_nearest(const float4* base, int layer, int n, float u, float v) {
     const int i = ((int)floorf(u * (float)n)) & (n - 1);
     const int j = ((int)floorf(v * (float)n)) & (n - 1);
-    const float4 c = __ldg(base + ((size_t)layer * n + j) * n + i);
+    const float4 c = __ldg(base + ((size_t)max(layer, 0) * n + j) * n + i);
     return mk3(c.x, c.y, c.z);
 }
 __device__ __forceinline__ float tex_bilinear1(const float* base, int layer, int n, float u, float v) {
@@ -93,8 +100,15 @@ __device__ __forceinline__ float tex_bilinear1(const float* base, int layer, int
 }
 
 // InverseSchlick :1305-1308, DiffuseHammon :1311-1332 (rcp(x) == 1.0f / x)
+// pow(x, 5.0f), pinned as the correctly rounded fp32 value: x * x is exact in double (48 bits), the two further products round at 2^-53
+// each, so the double result is within 2^-52 of the true power — as close as a double-precision pow() gets — and one rounding to fp32
+// follows.  x < 0 cannot occur (1 - clamped cosine); pow(0, 5) = 0 and pow(1, 5) = 1 come out exactly.
+__device__ __forceinline__ float pow5_cr(float x) {
+    const double d = (double)x, d2 = d * d;
+    return (float)((d2 * d2) * d);
+}
 __device__ __forceinline__ float inverse_schlick(float f0, float voh) {
-    return 1.0f - clampf(f0 + (1.0f - f0) * pow_cr(1.0f - voh, 5.0f), 0.0f, 1.0f);
+    return 1.0f - clampf(f0 + (1.0f - f0) * pow5_cr(1.0f - voh), 0.0f, 1.0f);
 }
 __device__ __forceinline__ float diffuse_hammon(V3 n, V3 view, V3 light, float rough) {
     const float ndl = fmaxf(dot3(n, light), 0.0f);
@@ -111,20 +125,36 @@ __device__ __forceinline__ float diffuse_hammon(V3 n, V3 view, V3 light, float r
     return clampf((multi + single) * ndl, 0.0f, 1.0f);
 }
 
-// SampleBlueNoise2D :811-818 + cosWeightedRandomHemisphereDirection :945-967
-__device__ __forceinline__ V3 cos_hemisphere(const SceneDev& S, int px, int py, int frame_mod128, int& bl_sample, V3 n) {
-    const float r1 = blue_noise_1d(S, px, py, frame_mod128, 1 + bl_sample);
+// SampleBlueNoise2D :811-818 + cosWeightedRandomHemisphereDirection :945-967.
+// nid = the face (GetNormalFromID order 0..5) when n is one of the six axis normals, -1 otherwise: the tangent frame of an axis normal
+// and sin / cos of the byte-valued angle come from S.lut (vxpt_internal.h: the same fp32 values, tabulated on the host).
+__device__ __forceinline__ V3 cos_hemisphere(const SceneDev& S, int px, int py, int frame_mod128, int& bl_sample, V3 n, int nid = -1) {
+    const int v1 = blue_noise_byte(S, px, py, frame_mod128, 1 + bl_sample);
     const float r2 = blue_noise_1d(S, px, py, frame_mod128, 2 + bl_sample);
     bl_sample += 2;
-    const float PI2 = 2.0f * PI_F;
-    const V3 uu = normalize3(cross3(n, mk3(0.0f, 1.0f, 1.0f)));
-    const V3 vv = cross3(uu, n);
+    V3 uu, vv;
+    if ((unsigned)nid < 6u) {
+        const float* b = S.lut + LUT_BASIS + 6 * nid;
+        uu = mk3(b[0], b[1], b[2]);
+        vv = mk3(b[3], b[4], b[5]);
+    } else {
+        uu = normalize3(cross3(n, mk3(0.0f, 1.0f, 1.0f)));
+        vv = cross3(uu, n);
+    }
+    const float2 cs = *reinterpret_cast<const float2*>(S.lut + LUT_TRIG_GI + 2 * v1);  // cos, sin of 2 PI r1
     const float ra = sqrtf(r2);
-    const float rx = ra * cos_cr(PI2 * r1);
-    const float ry = ra * sin_cr(PI2 * r1);
+    const float rx = ra * cs.x;
+    const float ry = ra * cs.y;
     const float rz = sqrtf(1.0f - r2);
     const V3 rr = (rx * uu + ry * vv) + rz * n;
     return normalize3(rr);
+}
+// face of an axis normal given as (axis, sign of the normal on it); -1 when the sign is 0 (no face)
+__device__ __forceinline__ int face_of(int axis, int s) {
+    if (s == 0) return -1;
+    if (axis == 2) return s > 0 ? 0 : 1;
+    if (axis == 1) return s > 0 ? 2 : 3;
+    return s < 0 ? 4 : 5;
 }
 
 // CalculateUV :1235-1273 on an exact axis normal

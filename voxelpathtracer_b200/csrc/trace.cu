@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __g
                 const float cos_theta_max = 0.9999505604617f;  // SampleCone :388-398, :474
                 const float cos_theta = (1.0f - xi_x) + xi_x * cos_theta_max;
                 const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-                const float phi = xi_y * 3.14159265359f * 2.0f;
-                const V3 c = mk3(sin_theta * cos_cr(phi), sin_theta * sin_cr(phi), cos_theta);
+                // phi = xi_y * 3.14159265359f * 2.0f is a function of the texel byte: (cos, sin) come from the host-built table (S.lut)
+                const float2 cs = *reinterpret_cast<const float2*>(S.lut + LUT_TRIG_CONE + 2 * (int)tex.y);
+                const V3 c = mk3(sin_theta * cs.x, sin_theta * cs.y, cos_theta);
                 dir = (T * c.x + B * c.y) + L * c.z;  // mat3(T,B,L) * c
             }
             const V3 N = normal_from_id(g.normal_id[px], 1.0f);
@@ -124,12 +125,12 @@ __global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __g
 // CalculateDiffuse :535-664, one sample
 template <int LAYOUT>
 __device__ __forceinline__ void calculate_diffuse(const SceneDev& S, const DiffuseDev& P, int px, int py, int& bl_sample, V3 initial_origin,
-                                                  V3 input_normal, V3& out_rad, float& out_ao, V3& odir, bool& skyhit, Counters& cnt) {
+                                                  V3 input_normal, int input_nid, V3& out_rad, float& out_ao, V3& odir, bool& skyhit, Counters& cnt) {
     skyhit = false;
     const float bias = 0.06f;
     const int fm = P.frame % 128;
     V3 ro = initial_origin + input_normal * bias;
-    V3 rd = cos_hemisphere(S, px, py, fm, bl_sample, input_normal);
+    V3 rd = cos_hemisphere(S, px, py, fm, bl_sample, input_normal, input_nid);
     float ao = 1.0f;
     V3 contrib = mk3(0.f, 0.f, 0.f), thr = mk3(1.f, 1.f, 1.f);
     odir = rd;
@@ -164,7 +165,7 @@ __device__ __forceinline__ void calculate_diffuse(const SceneDev& S, const Diffu
             const V3 neg_rd = -rd;
             const V3 sunbrdf =
                 (((albedo * diffuse_hammon(hn, neg_rd, P.stronger_dir, pbr.x)) * (P.light_color * 3.5f)) * (1.0f - shadow_at)) * PI_F;
-            const V3 new_dir = cos_hemisphere(S, px, py, fm, bl_sample, hn);
+            const V3 new_dir = cos_hemisphere(S, px, py, fm, bl_sample, hn, face_of(h.min_idx, -h.sgn));
             const float cos_theta = clampf(dot3(hn, new_dir), 0.0f, 1.0f);
             const float pdf = fmaxf(cos_theta / PI_F, 0.00001f);
             const V3 atten = mk3(1.f, 1.f, 1.f) * diffuse_hammon(hn, neg_rd, new_dir, pbr.x);
@@ -209,7 +210,8 @@ __global__ void __launch_bounds__(256) diffuse_kernel(const SceneDev S, const __
         }
         float o_sh[4], o_cocg[2], o_util = 0.0f, o_ao0 = 1.0f, o_ao1 = 0.0f;
         const float dist = load_f1(g.t, px, g.fmt);
-        const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
+        const int nid = g.normal_id[px];
+        const V3 normal = normal_from_id(nid, 0.5f);
         if (dist < 0.0f) {
             float sh[6];
             const V3 vdir = normalize3(ray_direction_at(cam, u0, v0));
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256) diffuse_kernel(const SceneDev S, const __
                 V3 rad, d;
                 float ao;
                 bool ss;
-                calculate_diffuse<LAYOUT>(S, P, i, j, bl_sample, pos, normal, rad, ao, d, ss, cnt);
+                calculate_diffuse<LAYOUT>(S, P, i, j, bl_sample, pos, normal, nid, rad, ao, d, ss, cnt);
                 rad = mk3(clampf(rad.x, 0.0f, 8.0f), clampf(rad.y, 0.0f, 8.0f), clampf(rad.z, 0.0f, 8.0f));
                 radiance = radiance + rad;
                 acc_ao += ao;

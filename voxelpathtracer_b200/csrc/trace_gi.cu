@@ -4,19 +4,23 @@
 // first-bounce rays escape to the sky while the few that hit geometry drag their warp through texture fetches, a shadow
 // sub-ray, a second traversal and a second shadow sub-ray (ncu r01a).  Here the work of one sample is re-queued:
 //
-//   gi_gen_trace0  one thread per pixel: first hemisphere direction (blue-noise tables), first traversal.  A miss is
-//                  finished on the spot (sky radiance).  Hits are compacted into a queue with one warp ballot +
-//                  one atomicAdd per warp (popc / prefix ranks give each lane its slot).
-//   (opt-in, VXPT_OPT_GI_WAVEFRONT = 2: gi_gen -> gi_trace0 -> gi_resolve.  gi_gen queues the first-bounce rays, gi_trace0 is a
-//                  persistent tracer whose lanes are refilled from the ray queue as their rays end (resumable traversal:
-//                  trav_init / trav_step / trav_finish; retire + refill batched until 8 lanes need it), gi_resolve shades the
-//                  misses densely and compacts the hits.  Measured slower than the fused kernel, see run_wavefront.)
-//   gi_continue    one thread per queued hit (dense warps): shading of the first hit, its sun shadow sub-ray, the
-//                  second traversal, shading + shadow sub-ray of the second hit, end of the sample.
+//   gi_gen_trace0  first hemisphere direction (blue-noise tables) and first traversal of every pixel, the rays of a CTA sorted by
+//                  life expectancy before they are traced.  A miss is finished on the spot (sky radiance).  Hits are compacted
+//                  into a queue with one warp ballot + one atomicAdd per warp (popc / prefix ranks give each lane its slot).
+//   gi_continue    the rest of the sample for the queued hits (11 % of the first-bounce rays on plains), in CTA-wide stages with the
+//                  rays re-distributed over the warps between the stages (shared-memory lists, counting sort):
+//                    A  shade the first hit, draw the bounce direction           one thread per record (dense)
+//                    B  trace the bounce rays and the sun-shadow sub-rays        warps claim groups of 32 rays from the sorted list
+//                    C  shade the second hit (or the sky), queue its shadow ray  one thread per record
+//                    D  trace the second shadow sub-rays                         groups of 32 rays
+//                    E  finish the sample (SH projection, stores)                one thread per record
+//                  r01h's one-thread-per-record kernel ran the chain texture -> shadow ray -> bounce -> texture -> shadow ray in every
+//                  lane with 11.4 of 32 lanes active.
 //   gi_finalize    only when some pixel takes more than one sample: per-pixel averages and clamps (:915-934).
 //
 // Samples of one pixel are processed one after another (launch s+1 after launch s), so the blue-noise dimension counter
-// and the accumulation order are exactly those of the shader's loop; the planes are bit-identical to diffuse_kernel's.
+// and the accumulation order are exactly those of the shader's loop; the planes are bit-identical to diffuse_kernel's:
+// which thread traces a ray, and when, does not change what is computed for its pixel.
 #include <algorithm>
 #include <cstdlib>
 
@@ -24,10 +28,6 @@
 
 namespace vxpt {
 
-struct RayRec {   // 32 B
-    float4 a;     // ro.xyz, pixel index (bits)
-    float4 b;     // rd.xyz, bl_sample (bits)
-};
 struct HitRec {   // 48 B
     float4 a;     // ro.xyz, T
     float4 b;     // rd.xyz, pixel index (bits)
@@ -99,51 +99,42 @@ __device__ __forceinline__ V3 sky_term(const SceneDev& S, const DiffuseDev& P, V
     return sky_sample(S, sd) * x;
 }
 
-// shading of one hit (:569-622).  NEXT: also draw the next direction and update the throughput / ray.
-template <int LAYOUT, bool NEXT>
-__device__ __forceinline__ void shade_hit(const SceneDev& S, const DiffuseDev& P, int pi, int pj, int& bl_sample, V3& ro, V3& rd, float T, int min_idx,
-                                          int sgn, int block, V3& thr, V3& contrib, Counters& cnt) {
-    const float bias = 0.06f;
+// Shading of one hit (:569-622) up to, but without, the sun-shadow sub-ray of GetShadowAt (:1202-1222), which the caller traces (or has
+// traced) elsewhere.  The shader's  SunBRDF = (((albedo * hammon) * (LIGHT_COLOR * 3.5)) * (1 - shadow)) * PI  is split at the shadow
+// factor: `pre` is the product in front of it, sun_brdf() below completes it once the sub-ray's verdict is known — same operations, same
+// order.  shadow_state: 0 / 1 = the verdict is known without a ray (N.L < 0.001 -> lit, moon stronger -> shadowed), 2 = trace the
+// sub-ray from `shadow_origin`.  emis = the emissive colour (not yet multiplied by the throughput).
+struct HitShade {
+    V3 ipos, hn, albedo, pre, emis, shadow_origin;
+    float rough;
+    int shadow_state, face;
+};
+__device__ __forceinline__ HitShade shade_hit(const SceneDev& S, const DiffuseDev& P, V3 ro, V3 rd, float T, int min_idx, int sgn, int block) {
+    HitShade h;
     const int tex_ref = min(max(block, 0), 127);
-    const V3 ipos = ro + (rd * T);
+    h.ipos = ro + (rd * T);
     const float s = (float)(-sgn);
-    const V3 hn = mk3(min_idx == 0 ? s : 0.0f, min_idx == 1 ? s : 0.0f, min_idx == 2 ? s : 0.0f);
+    h.hn = mk3(min_idx == 0 ? s : 0.0f, min_idx == 1 ? s : 0.0f, min_idx == 2 ? s : 0.0f);
+    h.face = face_of(min_idx, -sgn);
     float tu, tv;
-    calc_uv(ipos, min_idx, tu, tv);
+    calc_uv(h.ipos, min_idx, tu, tv);
     const int albedo_layer = S.materials[tex_ref], emissive_layer = S.materials[384 + tex_ref];
-    const V3 albedo = tex_nearest(S.albedo_lod3, albedo_layer, 64, tu, tv);
+    h.albedo = tex_nearest(S.albedo_lod3, albedo_layer, 64, tu, tv);
     const V3 pbr = tex_nearest(S.pbr_lod2, albedo_layer, 128, tu, tv);  // sic: albedo layer (:578)
+    h.rough = pbr.x;
     float emis = 0.0f;
     if ((float)emissive_layer >= 0.0f) {
         const float se = tex_bilinear1(S.emissive, emissive_layer, 512, tu, tv);
         emis = se * P.emissivity_mult * P.light_intensity;
     }
-    const float ndl = fmaxf(dot3(hn, P.stronger_dir), 0.0f);
-    float shadow_at;
-    if (P.moon_stronger) shadow_at = 1.0f;
-    else if (ndl < 0.001f) shadow_at = 0.0f;
-    else {  // GetShadowAt :1202-1222 (u_APPLY_PLAYER_SHADOW = false)
-        TraceHit hs;
-        const float Ts = traverse_df<LAYOUT>(S, ipos + hn * 0.045f, P.stronger_dir, 128, hs, cnt);
-        shadow_at = Ts > 0.0f ? 1.0f : 0.0f;
-    }
-    const V3 emis_color = (emis * mixf(1.0f, 1.0f, P.sun_visibility)) * albedo;
-    const V3 neg_rd = -rd;
-    const V3 sunbrdf = (((albedo * diffuse_hammon(hn, neg_rd, P.stronger_dir, pbr.x)) * (P.light_color * 3.5f)) * (1.0f - shadow_at)) * PI_F;
-    contrib = contrib + thr * sunbrdf;
-    contrib = contrib + emis_color * thr;
-    if (NEXT) {
-        const V3 new_dir = cos_hemisphere(S, pi, pj, P.frame % 128, bl_sample, hn);
-        const float cos_theta = clampf(dot3(hn, new_dir), 0.0f, 1.0f);
-        const float pdf = fmaxf(cos_theta / PI_F, 0.00001f);
-        const V3 atten = mk3(1.f, 1.f, 1.f) * diffuse_hammon(hn, neg_rd, new_dir, pbr.x);
-        thr = thr * ((albedo * atten) / pdf);
-        rd = new_dir;
-        ro = ipos + hn * bias;
-    } else {
-        bl_sample += 2;  // the shader still draws the direction of a third segment it never traces (:607)
-    }
+    const float ndl = fmaxf(dot3(h.hn, P.stronger_dir), 0.0f);
+    h.shadow_state = P.moon_stronger ? 1 : (ndl < 0.001f ? 0 : 2);
+    h.shadow_origin = h.ipos + h.hn * 0.045f;
+    h.emis = (emis * mixf(1.0f, 1.0f, P.sun_visibility)) * h.albedo;
+    h.pre = (h.albedo * diffuse_hammon(h.hn, -rd, P.stronger_dir, h.rough)) * (P.light_color * 3.5f);
+    return h;
 }
+__device__ __forceinline__ V3 sun_brdf(V3 pre, float shadow_at) { return (pre * (1.0f - shadow_at)) * PI_F; }
 
 // one warp ballot + one atomic per warp; returns this lane's slot (valid where pred)
 __device__ __forceinline__ unsigned warp_push(unsigned* counter, bool pred) {
@@ -155,6 +146,28 @@ __device__ __forceinline__ unsigned warp_push(unsigned* counter, bool pred) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// exclusive prefix over the 256 bins of a CTA's key histogram by warp 0 (8 bins per lane, then a warp scan of the lane sums);
+// hist[256] receives the total
+__device__ __forceinline__ void prefix_256(unsigned* hist, unsigned tid) {
+    if (tid < 32) {
+        unsigned c[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c[k] = hist[tid * 8 + k]; sum += c[k]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= (unsigned)d) incl += t;
+        }
+        unsigned base = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hist[tid * 8 + k] = base; base += c[k]; }
+        if (tid == 31) hist[256] = incl;
+    }
+}
+// sort key of a hemisphere ray: small = grazing = long-lived
+__device__ __forceinline__ unsigned life_key(V3 d) { return (unsigned)min((int)(fabsf(d.y) * 255.0f), 255); }
+
 // gi_gen_trace0 — first hemisphere direction and first traversal of every pixel of a slab, with the rays of a CTA SORTED before they are
 // traced.  How long a hemisphere ray lives is decided mostly by where it points: steep rays reach large step values within a few
 // iterations and leave the volume (or hit the ground at once), grazing rays creep through E = 1..3 cells until the cap.  Neighbouring
@@ -162,10 +175,16 @@ __device__ __forceinline__ unsigned warp_push(unsigned* counter, bool pred) {
 // active).  Here a CTA of 256 threads generates the rays of RPT 32x8-pixel tiles (RPT per thread), sorts them by |rd.y| (counting sort on
 // an 8-bit key in shared memory) and its warps then claim groups of 32 rays from the sorted list, longest-lived first, until the list is
 // empty: a warp holds rays of similar life expectancy, and short groups fill the time the warps that drew long groups are still busy
-// (with one group per warp the CTA would keep its registers until its slowest warp ended).  Which thread traces a ray does not change
-// what is computed for its pixel, so the planes stay bit-identical.  RPT = 0 selects the plain form (one pixel per thread, no exchange).
+// (with one group per warp the CTA would keep its registers until its slowest warp ended).  RPT = 0 selects the plain form (one pixel per
+// thread, no exchange).
+#ifndef VXPT_GI_GEN_MINB
+#define VXPT_GI_GEN_MINB 1   // experiment knobs (build.py -D...): resident CTAs per SM the register allocation aims for
+#endif
+#ifndef VXPT_GI_CONT_MINB
+#define VXPT_GI_CONT_MINB 1
+#endif
 template <int LAYOUT, bool SPP1, int RPT>
-__global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
+__global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
                                                      const DiffuseOutDev out, PixState* __restrict__ state, HitRec* __restrict__ queue,
                                                      unsigned* __restrict__ queue_count, const int sample) {
     constexpr int NR = RPT > 0 ? RPT : 1;       // pixels per thread
@@ -204,7 +223,8 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
             v += (P.hy * 0.75f) / (float)cam.height;
         }
         const float dist = load_f1(g.t, px, g.fmt);
-        const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
+        const int nid = g.normal_id[px];
+        const V3 normal = normal_from_id(nid, 0.5f);
         if (dist < 0.0f) {
             if (sample == 0) {  // sky pixel (:866-872)
                 float sh[6];
@@ -228,9 +248,9 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
             }
             const V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, u, v)) * dist;
             const V3 o = pos + normal * 0.06f;
-            const V3 d = cos_hemisphere(S, i, j, P.frame % 128, bls, normal);
+            const V3 d = cos_hemisphere(S, i, j, P.frame % 128, bls, normal, nid);
             if (SORT) {
-                const unsigned key = (unsigned)min((int)(fabsf(d.y) * 255.0f), 255);  // small = grazing = long-lived
+                const unsigned key = life_key(d);
                 kr[r] = (key << 16) | atomicAdd(&s_hist[key], 1u);
                 s_a[r * 256 + tid] = make_float4(o.x, o.y, o.z, __int_as_float((int)px));
                 s_b[r * 256 + tid] = make_float4(d.x, d.y, d.z, __int_as_float(bls));
@@ -261,21 +281,7 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
         return;
     }
     __syncthreads();
-    if (tid < 32) {  // exclusive prefix over the 256 bins: 8 bins per lane, then a warp scan of the lane sums
-        unsigned c[8], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { c[k] = s_hist[tid * 8 + k]; sum += c[k]; }
-        unsigned incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (tid >= (unsigned)d) incl += t;
-        }
-        unsigned base = incl - sum;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { s_hist[tid * 8 + k] = base; base += c[k]; }
-        if (tid == 31) s_hist[256] = incl;
-    }
+    prefix_256(s_hist, tid);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < NR; ++r)
@@ -314,184 +320,190 @@ __global__ void __launch_bounds__(256) gi_gen_trace0(const SceneDev S, const __g
     flush_counters(S, cnt);
 }
 
-// first half of gi_gen_trace0: per pixel set-up, rays into the queue
-template <bool SPP1>
-__global__ void __launch_bounds__(256) gi_gen(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
-                                              const DiffuseOutDev out, PixState* __restrict__ state, RayRec* __restrict__ rays,
-                                              unsigned* __restrict__ counters, const int sample) {
-    int i, j, prow;
-    const bool active = thread_pixel(cam, i, j, prow);
-    bool push = false;
-    RayRec rec;
-    if (active) {
-        const size_t px = (size_t)prow * cam.width + i;
-        float u = ((float)i + 0.5f) / (float)cam.width;
-        float v = ((float)j + 0.5f) / (float)cam.height;
-        const float u0 = u, v0 = v;
-        if (P.supersample) {
-            u += (P.hx * 0.75f) / (float)cam.width;
-            v += (P.hy * 0.75f) / (float)cam.height;
-        }
-        const float dist = load_f1(g.t, px, g.fmt);
-        const V3 normal = normal_from_id(g.normal_id[px], 0.5f);
-        if (dist < 0.0f) {
-            if (sample == 0) {  // sky pixel (:866-872)
-                float sh[6];
-                const V3 vdir = normalize3(ray_direction_at(cam, u0, v0));
-                irradiance_to_sh(sky_sample(S, vdir) * 2.66f, normal, sh);
-                if (out.sh) store_f4(out.sh, px, sh[0], sh[1], sh[2], sh[3], out.fmt);
-                if (out.cocg) store_f2(out.cocg, px, sh[4], sh[5], out.fmt);
-                if (out.luma) store_f1(out.luma, px, 0.0f, out.fmt);
-                if (out.ao_sky) store_unorm2(out.ao_sky, px, 1.0f, 0.0f, out.fmt);
-            }
-        } else if (sample < pixel_spp(P, i, j)) {
-            int bl_sample = 0;
-            if (!SPP1) {
-                if (sample == 0) {
-                    PixState z;
-                    z.tot = z.rad = z.misc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    state[px] = z;
-                } else {
-                    bl_sample = __float_as_int(state[px].misc.w);
-                }
-            }
-            const V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, u, v)) * dist;
-            const V3 ro = pos + normal * 0.06f;
-            const V3 rd = cos_hemisphere(S, i, j, P.frame % 128, bl_sample, normal);
-            push = true;
-            rec.a = make_float4(ro.x, ro.y, ro.z, __int_as_float((int)px));
-            rec.b = make_float4(rd.x, rd.y, rd.z, __int_as_float(bl_sample));
-        }
-    }
-    const unsigned slot = warp_push(counters + 2, push);
-    if (push) rays[slot] = rec;
-}
-
-// persistent first-bounce traversal with lane refill.  counters: [0] hit count, [1] hit cursor, [2] ray count, [3] ray cursor
-// A lane is idle (0), tracing (1) or done (3).  The main loop only advances rays; finished rays are
-// retired (final block fetch + 8-byte result) and idle lanes refilled in one maintenance step that runs when THRESH lanes need it
-// (or nothing else is left to do), so the maintenance code runs with many lanes instead of one or two per iteration, and nothing
-// but traversal is executed by partially filled warps.  Shading of the results happens in gi_resolve, densely.
-template <int LAYOUT, int THRESH>
-__global__ void __launch_bounds__(256) gi_trace0(const SceneDev S, const DiffuseDev P, const RayRec* __restrict__ rays, float2* __restrict__ results,
-                                                 unsigned* __restrict__ counters) {
-    const unsigned n_rays = counters[2];
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    Counters cnt = {0u, 0u, 0u};
-    TravState t;
-    V3 origin = mk3(0.f, 0.f, 0.f);
-    unsigned idx = 0;
-    int phase = 0;
-    bool exhausted = false;
-    trav_init(t, origin, mk3(1.f, 1.f, 1.f), 0);
-    while (true) {
-        const unsigned done_mask = __ballot_sync(0xffffffffu, phase == 3);
-        const unsigned idle_mask = __ballot_sync(0xffffffffu, phase == 0);
-        const unsigned live_mask = ~(done_mask | idle_mask);
-        if (live_mask == 0u || __popc(done_mask) + (exhausted ? 0 : __popc(idle_mask)) >= THRESH) {
-            if (phase == 3) {  // retire
-                TraceHit h;
-                const float T = trav_finish(S, t, origin, h, cnt);
-                results[idx] = make_float2(T, __int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8)));
-                phase = 0;
-            }
-            const unsigned want = done_mask | idle_mask;  // every one of these lanes is idle now
-            if (!exhausted) {  // refill
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(counters + 3, (unsigned)__popc(want));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + __popc(want) >= n_rays) exhausted = true;
-                if (phase == 0) {
-                    const unsigned my = base + __popc(want & lt_mask);
-                    if (my < n_rays) {
-                        const RayRec r = rays[my];
-                        origin = mk3(r.a.x, r.a.y, r.a.z);
-                        trav_init(t, origin, mk3(r.b.x, r.b.y, r.b.z), P.trace_length);
-                        idx = my;
-                        cnt.rays++;
-                        phase = 1;
-                    }
-                }
-            }
-            if (!__any_sync(0xffffffffu, phase != 0)) break;
-        }
-        if (phase == 1 && trav_step<LAYOUT>(S, t)) phase = 3;
-    }
-    flush_counters(S, cnt);
-}
-
-// one thread per traced first-bounce ray: a miss ends the sample here (sky radiance), a hit goes to the hit queue
-template <bool SPP1>
-__global__ void __launch_bounds__(256) gi_resolve(const SceneDev S, const DiffuseDev P, const DiffuseOutDev out, PixState* __restrict__ state,
-                                                  const RayRec* __restrict__ rays, const float2* __restrict__ results, HitRec* __restrict__ hits,
-                                                  unsigned* __restrict__ counters) {
-    const unsigned n_rays = counters[2];
-    const unsigned idx = blockIdx.x * 256u + threadIdx.x;
-    if (blockIdx.x * 256u >= n_rays) return;
-    bool push = false;
-    HitRec rec;
-    if (idx < n_rays) {
-        const RayRec r = rays[idx];
-        const float2 q = results[idx];
-        const float T = q.x;
-        const int code = __float_as_int(q.y);
-        const V3 rd = mk3(r.b.x, r.b.y, r.b.z);
-        if (T > 0.0f && ((code >> 8) & 255) > 0) {
-            push = true;
-            rec.a = make_float4(r.a.x, r.a.y, r.a.z, T);
-            rec.b = make_float4(rd.x, rd.y, rd.z, r.a.w);
-            rec.c = make_float4(q.y, r.b.w, 0.f, 0.f);
-        } else {
-            const V3 contrib = mk3(0.f, 0.f, 0.f) + sky_term(S, P, rd) * mk3(1.f, 1.f, 1.f);
-            finish_sample<SPP1>(out, state, (size_t)(unsigned)__float_as_int(r.a.w), contrib, 1.0f, rd, true, __float_as_int(r.b.w));
-        }
-    }
-    const unsigned slot = warp_push(counters + 0, push);
-    if (push) hits[slot] = rec;
-}
+// gi_continue — everything of a sample after its first hit, for the queued hits, in CTA-wide stages (header comment).  A CTA claims 256
+// records at a time from the device-side cursor, so the (device-side) hit count needs no host round trip and the tail is balanced over
+// the resident CTAs.  Thread t owns record t of the chunk in the dense stages; between them its state waits in shared memory (so the
+// traversal stages run with the registers of a traversal, not of the whole chain).
+//
+// The shader's accumulation, in its order (:583-605 per bounce, :625-634 for the sky):
+//     contrib = 0;  thr = 1
+//     hit 0:  contrib = contrib + thr * SunBRDF0;  contrib = contrib + emis0 * thr;  thr = thr * ((albedo0 * atten0) / pdf0)
+//     hit 1:  contrib = contrib + thr * SunBRDF1;  contrib = contrib + emis1 * thr          | miss: contrib = contrib + sky * thr
+// SunBRDF needs the verdict of the hit's sun-shadow sub-ray; everything else of a hit is computed in the dense stage that shades it.
+constexpr int GC_THREADS = 256;
+struct GcShared {
+    float4 ray_o[2 * GC_THREADS];   // [t] bounce ray origin (w: unused), [256 + t] first shadow sub-ray origin; stage D: [t] second shadow sub-ray origin
+    float4 ray_d[GC_THREADS];       // bounce ray direction
+    float st[18][GC_THREADS];       // per-record state between the dense stages
+    float res_t[GC_THREADS];        // bounce ray: T
+    int res_code[GC_THREADS];       // bounce ray: min_idx | (sgn+1) << 2 | block << 8
+    unsigned char res_sh0[GC_THREADS], res_sh1[GC_THREADS];  // shadow sub-rays: 1 = occluded
+    unsigned short order[2 * GC_THREADS];
+    unsigned hist[260];             // 256 bins, [256] ray count, [257] next group, [258] chunk base, [259] stage-D ray count
+};
+// state rows
+enum { ST_PX = 0, ST_BLS, ST_OD0, ST_OD1, ST_OD2, ST_AO, ST_C0, ST_C1, ST_C2, ST_T0, ST_T1, ST_T2, ST_A0, ST_A1, ST_A2, ST_P0, ST_P1, ST_P2 };
 
 template <int LAYOUT, bool SPP1>
-__global__ void __launch_bounds__(128) gi_continue(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const DiffuseOutDev out,
-                                                   PixState* __restrict__ state, const HitRec* __restrict__ queue,
-                                                   unsigned* __restrict__ queue_count) {
+__global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const DiffuseOutDev out,
+                                                          PixState* __restrict__ state, const HitRec* __restrict__ queue,
+                                                          unsigned* __restrict__ queue_count) {
+    extern __shared__ __align__(16) unsigned char gc_smem[];
+    GcShared& sm = *reinterpret_cast<GcShared*>(gc_smem);
     const unsigned count = queue_count[0];
     unsigned* cursor = queue_count + 1;
     Counters cnt = {0u, 0u, 0u};
-    const unsigned lane = threadIdx.x & 31;
-    // dynamic work distribution: each warp claims the next 32 queued hits until the queue is drained, so the (device-side)
-    // hit count needs no host round trip and the tail is balanced across the resident warps
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    const unsigned sun_key = life_key(P.stronger_dir);
     while (true) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncthreads();  // the previous chunk's stage E has read everything it needs
+        sm.hist[tid] = 0u;
+        if (tid < 4) sm.hist[256 + tid] = 0u;
+        if (tid == 0) sm.hist[258] = atomicAdd(cursor, (unsigned)GC_THREADS);
+        __syncthreads();
+        const unsigned base = sm.hist[258];
         if (base >= count) break;
-        const unsigned idx = base + lane;
-        if (idx >= count) continue;
-        const HitRec rec = queue[idx];
-        V3 ro = mk3(rec.a.x, rec.a.y, rec.a.z), rd = mk3(rec.b.x, rec.b.y, rec.b.z);
-        const float T0 = rec.a.w;
-        const size_t px = (size_t)(unsigned)__float_as_int(rec.b.w);
-        const int pi = (int)(px % (size_t)cam.width), pj = image_row(cam, (int)(px / (size_t)cam.width));
-        const int code = __float_as_int(rec.c.x);
-        int bl_sample = __float_as_int(rec.c.y);
-        const V3 odir = rd;
-        V3 thr = mk3(1.f, 1.f, 1.f), contrib = mk3(0.f, 0.f, 0.f);
-        bool skyhit = false;
-        // bounce 0 hit
-        shade_hit<LAYOUT, true>(S, P, pi, pj, bl_sample, ro, rd, T0, code & 3, ((code >> 2) & 3) - 1, (code >> 8) & 255, thr, contrib, cnt);
-        float ao = 1.0f;
-        if (T0 < 2.0f && T0 > 0.0f) ao = fmaxf(T0 / 2.0f, 0.0f);  // :637-650
-        // bounce 1
-        TraceHit h;
-        const float T1 = traverse_df<LAYOUT>(S, ro, rd, P.trace_length, h, cnt);
-        if (T1 > 0.0f && h.block > 0) {
-            shade_hit<LAYOUT, false>(S, P, pi, pj, bl_sample, ro, rd, T1, h.min_idx, h.sgn, h.block, thr, contrib, cnt);
-        } else {
-            contrib = contrib + sky_term(S, P, rd) * thr;
-            skyhit = true;
+        const bool valid = base + tid < count;
+        // ---- stage A: shade the first hit, draw the bounce ray -------------------------------------------------------------------
+        unsigned kr_b = ~0u, kr_s = ~0u;
+        int pi = 0, pj = 0;
+        if (valid) {
+            const HitRec rec = queue[base + tid];
+            const V3 ro = mk3(rec.a.x, rec.a.y, rec.a.z), rd = mk3(rec.b.x, rec.b.y, rec.b.z);
+            const float T0 = rec.a.w;
+            const unsigned px = (unsigned)__float_as_int(rec.b.w);
+            pi = (int)(px % (unsigned)cam.width);
+            pj = image_row(cam, (int)(px / (unsigned)cam.width));
+            const int code = __float_as_int(rec.c.x);
+            int bl_sample = __float_as_int(rec.c.y);
+            const HitShade h = shade_hit(S, P, ro, rd, T0, code & 3, ((code >> 2) & 3) - 1, (code >> 8) & 255);
+            // next direction and throughput (:607-621)
+            const V3 new_dir = cos_hemisphere(S, pi, pj, P.frame % 128, bl_sample, h.hn, h.face);
+            const float cos_theta = clampf(dot3(h.hn, new_dir), 0.0f, 1.0f);
+            const float pdf = fmaxf(cos_theta / PI_F, 0.00001f);
+            const V3 atten = mk3(1.f, 1.f, 1.f) * diffuse_hammon(h.hn, -rd, new_dir, h.rough);
+            const V3 thr0 = mk3(1.f, 1.f, 1.f);
+            const V3 thr1 = thr0 * ((h.albedo * atten) / pdf);
+            const V3 ro1 = h.ipos + h.hn * 0.06f;
+            float ao = 1.0f;
+            if (T0 < 2.0f && T0 > 0.0f) ao = fmaxf(T0 / 2.0f, 0.0f);  // :637-650
+            const V3 e0 = h.emis * thr0;
+            sm.st[ST_PX][tid] = __int_as_float((int)px);
+            sm.st[ST_BLS][tid] = __int_as_float(bl_sample);
+            sm.st[ST_OD0][tid] = rd.x; sm.st[ST_OD1][tid] = rd.y; sm.st[ST_OD2][tid] = rd.z;
+            sm.st[ST_AO][tid] = ao;
+            sm.st[ST_T0][tid] = thr1.x; sm.st[ST_T1][tid] = thr1.y; sm.st[ST_T2][tid] = thr1.z;
+            sm.st[ST_A0][tid] = h.pre.x; sm.st[ST_A1][tid] = h.pre.y; sm.st[ST_A2][tid] = h.pre.z;
+            sm.st[ST_P0][tid] = e0.x; sm.st[ST_P1][tid] = e0.y; sm.st[ST_P2][tid] = e0.z;
+            sm.ray_o[tid] = make_float4(ro1.x, ro1.y, ro1.z, 0.f);
+            sm.ray_d[tid] = make_float4(new_dir.x, new_dir.y, new_dir.z, 0.f);
+            const unsigned key = life_key(new_dir);
+            kr_b = (key << 16) | atomicAdd(&sm.hist[key], 1u);
+            sm.res_sh0[tid] = (unsigned char)(h.shadow_state & 1);
+            if (h.shadow_state == 2) {
+                sm.ray_o[GC_THREADS + tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);
+                kr_s = (sun_key << 16) | atomicAdd(&sm.hist[sun_key], 1u);
+            }
         }
-        finish_sample<SPP1>(out, state, px, contrib, ao, odir, skyhit, bl_sample);
+        __syncthreads();
+        prefix_256(sm.hist, tid);
+        __syncthreads();
+        if (kr_b != ~0u) sm.order[sm.hist[kr_b >> 16] + (kr_b & 0xFFFFu)] = (unsigned short)tid;
+        if (kr_s != ~0u) sm.order[sm.hist[kr_s >> 16] + (kr_s & 0xFFFFu)] = (unsigned short)(GC_THREADS + tid);
+        __syncthreads();
+        // ---- stage B: bounce rays (cap trace_length) and first shadow sub-rays (cap 128), longest-lived first -----------------------------
+        {
+            const unsigned n_rays = sm.hist[256], n_groups = (n_rays + 31u) / 32u;
+            while (true) {
+                unsigned grp = 0;
+                if (lane == 0) grp = atomicAdd(&sm.hist[257], 1u);
+                grp = __shfl_sync(0xffffffffu, grp, 0);
+                if (grp >= n_groups) break;
+                const unsigned idx = grp * 32u + lane;
+                if (idx < n_rays) {
+                    const unsigned slot = sm.order[idx];
+                    const float4 o4 = sm.ray_o[slot];
+                    TraceHit h;
+                    if (slot < (unsigned)GC_THREADS) {
+                        const float4 d4 = sm.ray_d[slot];
+                        const float T = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), P.trace_length, h, cnt);
+                        sm.res_t[slot] = T;
+                        sm.res_code[slot] = h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8);
+                    } else {
+                        const float Ts = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), P.stronger_dir, 128, h, cnt);
+                        sm.res_sh0[slot - GC_THREADS] = Ts > 0.0f ? 1 : 0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- stage C: the bounce ray's hit (or the sky) ---------------------------------------------------------------------------
+        bool done = true, skyhit = false;
+        if (valid) {
+            const V3 pre0 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
+            const V3 e0 = mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
+            const V3 thr0 = mk3(1.f, 1.f, 1.f);
+            const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
+            V3 contrib = mk3(0.f, 0.f, 0.f);
+            contrib = contrib + thr0 * sun_brdf(pre0, sm.res_sh0[tid] ? 1.0f : 0.0f);
+            contrib = contrib + e0;
+            const float T1 = sm.res_t[tid];
+            const int code = sm.res_code[tid];
+            const float4 o4 = sm.ray_o[tid], d4 = sm.ray_d[tid];
+            const V3 ro1 = mk3(o4.x, o4.y, o4.z), rd1 = mk3(d4.x, d4.y, d4.z);
+            if (T1 > 0.0f && ((code >> 8) & 255) > 0) {
+                const HitShade h = shade_hit(S, P, ro1, rd1, T1, code & 3, ((code >> 2) & 3) - 1, (code >> 8) & 255);
+                sm.st[ST_BLS][tid] = __int_as_float(__float_as_int(sm.st[ST_BLS][tid]) + 2);  // the shader still draws the direction of a third segment it never traces (:607)
+                const V3 e1 = h.emis * thr1;
+                if (h.shadow_state == 2) {
+                    done = false;
+                    sm.st[ST_A0][tid] = h.pre.x; sm.st[ST_A1][tid] = h.pre.y; sm.st[ST_A2][tid] = h.pre.z;
+                    sm.st[ST_P0][tid] = e1.x; sm.st[ST_P1][tid] = e1.y; sm.st[ST_P2][tid] = e1.z;
+                } else {
+                    contrib = contrib + thr1 * sun_brdf(h.pre, h.shadow_state ? 1.0f : 0.0f);
+                    contrib = contrib + e1;
+                }
+                if (!done) sm.ray_o[GC_THREADS + tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);
+            } else {
+                contrib = contrib + sky_term(S, P, rd1) * thr1;
+                skyhit = true;
+            }
+            sm.st[ST_C0][tid] = contrib.x; sm.st[ST_C1][tid] = contrib.y; sm.st[ST_C2][tid] = contrib.z;
+        }
+        {   // second shadow sub-rays: compacted list of record slots (all share the sun direction: no sort)
+            const unsigned mask = __ballot_sync(0xffffffffu, !done);
+            unsigned wbase = 0;
+            if (lane == 0 && mask) wbase = atomicAdd(&sm.hist[259], (unsigned)__popc(mask));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (!done) sm.order[wbase + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)tid;
+        }
+        __syncthreads();
+        // ---- stage D: second shadow sub-rays ---------------------------------------------------------------------------------------
+        {
+            const unsigned n_rays = sm.hist[259];
+            for (unsigned idx = tid; idx < ((n_rays + 31u) & ~31u); idx += GC_THREADS) {
+                if (idx < n_rays) {
+                    const unsigned slot = sm.order[idx];
+                    const float4 o4 = sm.ray_o[GC_THREADS + slot];
+                    TraceHit h;
+                    const float Ts = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), P.stronger_dir, 128, h, cnt);
+                    sm.res_sh1[slot] = Ts > 0.0f ? 1 : 0;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- stage E: end of the sample --------------------------------------------------------------------------------------------
+        if (valid) {
+            V3 contrib = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
+            if (!done) {
+                const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
+                const V3 pre1 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
+                contrib = contrib + thr1 * sun_brdf(pre1, sm.res_sh1[tid] ? 1.0f : 0.0f);
+                contrib = contrib + mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
+            }
+            finish_sample<SPP1>(out, state, (size_t)(unsigned)__float_as_int(sm.st[ST_PX][tid]), contrib, sm.st[ST_AO][tid],
+                                mk3(sm.st[ST_OD0][tid], sm.st[ST_OD1][tid], sm.st[ST_OD2][tid]), skyhit, __float_as_int(sm.st[ST_BLS][tid]));
+        }
     }
     flush_counters(S, cnt);
 }
@@ -515,52 +527,38 @@ static CameraDev cam_to_dev(const VxCamera& cam) {
     return c;
 }
 
+// experiment knobs (environment, read once): VXPT_GI_SORT = pixels per thread of the sorted first-bounce kernel (0, 1, 2, 4),
+// VXPT_GI_CTAS = gi_continue CTAs per SM
+static int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 template <int LAYOUT, bool SPP1>
 static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, const DiffuseDev& d, const GBufferDev& g, const DiffuseOutDev& od,
-                         PixState* state, HitRec* queue, RayRec* rays, float2* results, unsigned* count, int max_spp) {
+                         PixState* state, HitRec* queue, unsigned* count, int max_spp) {
     const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
     const size_t slab_px = (size_t)(cd.row_end - cd.row_begin) * cd.width;
-    // opt-in (VXPT_OPT_GI_WAVEFRONT = 2): measured r01g at 1080p, gi_gen 47 us + gi_trace0 188 us + gi_resolve 43 us against 240 us for the
-    // fused gi_gen_trace0 — the refill keeps 25 of 32 lanes tracing, but the skip / DDA halves of an iteration still diverge (16 and 10
-    // lanes) and the queue round trips cost more than the idle lanes did
-    const bool persistent = c->opt_wavefront == 2;
+    static const int sort_env = env_int("VXPT_GI_SORT", -1), ctas_env = env_int("VXPT_GI_CTAS", 4);
     for (int s = 0; s < max_spp; ++s) {
-        VX_CUDA(cudaMemsetAsync(count, 0, 4 * sizeof(unsigned), c->stream));  // hit count, hit cursor, ray count, ray cursor
-        if (persistent) {
-            gi_gen<SPP1><<<grid, 256, 0, c->stream>>>(S, cd, d, g, od, state, rays, count, s);
-            static const int tune = std::getenv("VXPT_GI_TUNE") ? std::atoi(std::getenv("VXPT_GI_TUNE")) : 0;  // experiment knob
-            const int ctas = 148 * (tune >= 10 ? tune / 10 : 5);  // 47 registers: 5 CTAs of 256 threads per SM
-            switch (tune % 10) {
-                case 1: gi_trace0<LAYOUT, 4><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
-                case 2: gi_trace0<LAYOUT, 16><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
-                case 3: gi_trace0<LAYOUT, 12><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
-                case 4: gi_trace0<LAYOUT, 1><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
-                case 5: gi_trace0<LAYOUT, 24><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
-                default: gi_trace0<LAYOUT, 8><<<ctas, 256, 0, c->stream>>>(S, d, rays, results, count); break;
-            }
-            gi_resolve<SPP1><<<(unsigned)((slab_px + 255) / 256), 256, 0, c->stream>>>(S, d, od, state, rays, results, queue, count);
-            c->launches += 3;
-        } else {
-            // pixels per thread of the sorted first-bounce kernel: 4 on large slabs (1024 rays sorted per CTA, 32 groups for 8 warps), 2 on
-            // medium ones, plain on slabs too small to fill the GPU with such CTAs (r01g, 1080p GI pass: plain 0.339 ms, 1 / 2 / 4 pixels per
-            // thread 0.364 / 0.286 / 0.283 ms); VXPT_GI_SORT (0, 1, 2, 4) overrides (experiment knob)
-            static const int sort_env = std::getenv("VXPT_GI_SORT") ? std::atoi(std::getenv("VXPT_GI_SORT")) : -1;
-            const int rows = cd.row_end - cd.row_begin;
-            const int rpt = sort_env >= 0 ? sort_env : (slab_px >= (size_t)768 * 1024 ? 4 : (slab_px >= (size_t)128 * 1024 ? 2 : 0));
-            const dim3 grid_s((cd.width + 31) / 32, (rows + 8 * std::max(rpt, 1) - 1) / (8 * std::max(rpt, 1)));
-            switch (rpt) {
-                case 0: gi_gen_trace0<LAYOUT, SPP1, 0><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
-                case 1: gi_gen_trace0<LAYOUT, SPP1, 1><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
-                case 2: gi_gen_trace0<LAYOUT, SPP1, 2><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
-                default: gi_gen_trace0<LAYOUT, SPP1, 4><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
-            }
-            c->launches += 1;
+        VX_CUDA(cudaMemsetAsync(count, 0, 4 * sizeof(unsigned), c->stream));  // hit count, hit cursor
+        // pixels per thread of the sorted first-bounce kernel: 4 on large slabs (1024 rays sorted per CTA, 32 groups for 8 warps), 2 on
+        // medium ones, plain on slabs too small to fill the GPU with such CTAs (r01g, 1080p GI pass: plain 0.339 ms, 1 / 2 / 4 pixels per
+        // thread 0.364 / 0.286 / 0.283 ms)
+        const int rows = cd.row_end - cd.row_begin;
+        const int rpt = sort_env >= 0 ? sort_env : (slab_px >= (size_t)768 * 1024 ? 4 : (slab_px >= (size_t)128 * 1024 ? 2 : 0));
+        const dim3 grid_s((cd.width + 31) / 32, (rows + 8 * std::max(rpt, 1) - 1) / (8 * std::max(rpt, 1)));
+        switch (rpt) {
+            case 0: gi_gen_trace0<LAYOUT, SPP1, 0><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+            case 1: gi_gen_trace0<LAYOUT, SPP1, 1><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+            case 2: gi_gen_trace0<LAYOUT, SPP1, 2><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+            default: gi_gen_trace0<LAYOUT, SPP1, 4><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
         }
-        // (tried r01h: the same shared-memory sort for the second-bounce rays — 13.9 instead of 11.4 lanes active, 50 M instead of 54 M
-        // warp instructions, but the same 106 us: the kernel is bound by the dependent chain texture -> shadow ray -> bounce, not by issue)
-        // (5, 6, 7 or 10 CTAs per SM: the same 0.281 ms for the pass; 4: 0.312 ms)
-        gi_continue<LAYOUT, SPP1><<<148 * 6, 128, 0, c->stream>>>(S, cd, d, od, state, queue, count);
-        c->launches += 1;
+        // a CTA works on 256 records at a time; no more CTAs than the slab can have chunks
+        const unsigned max_chunks = (unsigned)((slab_px + GC_THREADS - 1) / GC_THREADS);
+        const unsigned ctas = std::min<unsigned>(148u * (unsigned)std::max(ctas_env, 1), std::max(max_chunks, 1u));
+        gi_continue<LAYOUT, SPP1><<<ctas, GC_THREADS, sizeof(GcShared), c->stream>>>(S, cd, d, od, state, queue, count);
+        c->launches += 2;
     }
     if (!SPP1) {
         gi_finalize<<<grid, 256, 0, c->stream>>>(cd, d, g, od, state);
@@ -570,7 +568,24 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
     return VXPT_OK;
 }
 
+// one-time, per process: gi_continue's shared memory is above the 48 KB a kernel gets without opting in
+static int init_gi_kernels() {
+    static bool done = false;
+    if (done) return VXPT_OK;
+    VX_CUDA(cudaFuncSetAttribute(gi_continue<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcShared)));
+    VX_CUDA(cudaFuncSetAttribute(gi_continue<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcShared)));
+    VX_CUDA(cudaFuncSetAttribute(gi_continue<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcShared)));
+    VX_CUDA(cudaFuncSetAttribute(gi_continue<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GcShared)));
+    done = true;
+    return VXPT_OK;
+}
+
+// wavefront scratch of a slab: 256 B of counters, the hit queue (one record per slab pixel at most) and, when some pixel takes several
+// samples, the per-pixel sample state of the frame
+size_t gi_scratch_bytes(size_t slab_px, size_t frame_px, bool spp1) { return 256 + slab_px * sizeof(HitRec) + (spp1 ? 0 : frame_px * sizeof(PixState)); }
+
 int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev& d, const VxGBuffer& g, const VxDiffuseOut& out) {
+    if (int rc = init_gi_kernels()) return rc;
     const SceneDev S = make_scene(c);
     const CameraDev cd = cam_to_dev(cam);
     const GBufferDev gd{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel};
@@ -582,32 +597,17 @@ int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev&
     if (d.checkerboard) max_spp = std::max(std::min(std::max(d.spp, 1), 32), std::min(std::max(d.checker_spp, 1), 32));
     if (d.moon_stronger) max_spp *= 2;
     const bool spp1 = max_spp == 1;
-    // queues: slab-sized hit queue (+ full-frame per-pixel state when some pixel takes several samples)
     const size_t slab_px = (size_t)(cam.row_end - cam.row_begin) * cam.width, frame_px = (size_t)cam.width * cam.height;
-    const size_t need = 256 + slab_px * (sizeof(HitRec) + sizeof(RayRec) + sizeof(float2)) + (spp1 ? 0 : frame_px * sizeof(PixState));
-    if (need > c->queue_bytes) {
-        VX_CUDA(cudaStreamSynchronize(c->stream));
-        if (c->d_queue) cudaFree(c->d_queue);
-        c->d_queue = nullptr;
-        c->queue_bytes = 0;
-        if (cudaMalloc(&c->d_queue, need) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("wavefront queue allocation failed");
-            return VXPT_E_NOMEM;
-        }
-        c->queue_bytes = need;
-    }
+    // grown on demand — but never while the stream is being captured into a CUDA graph (vxpt_reserve sizes it beforehand)
+    if (int rc = grow_scratch(c, &c->d_queue, &c->queue_bytes, gi_scratch_bytes(slab_px, frame_px, spp1), "the GI wavefront queue")) return rc;
     unsigned* count = static_cast<unsigned*>(c->d_queue);
     HitRec* queue = reinterpret_cast<HitRec*>(static_cast<char*>(c->d_queue) + 256);
-    RayRec* rays = reinterpret_cast<RayRec*>(static_cast<char*>(c->d_queue) + 256 + slab_px * sizeof(HitRec));
-    float2* results = reinterpret_cast<float2*>(static_cast<char*>(c->d_queue) + 256 + slab_px * (sizeof(HitRec) + sizeof(RayRec)));
-    PixState* state =
-        spp1 ? nullptr : reinterpret_cast<PixState*>(static_cast<char*>(c->d_queue) + 256 + slab_px * (sizeof(HitRec) + sizeof(RayRec) + sizeof(float2)));
+    PixState* state = spp1 ? nullptr : reinterpret_cast<PixState*>(static_cast<char*>(c->d_queue) + 256 + slab_px * sizeof(HitRec));
     if (c->opt_layout == 1)
-        return spp1 ? run_wavefront<1, true>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp)
-                    : run_wavefront<1, false>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp);
-    return spp1 ? run_wavefront<0, true>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp)
-                : run_wavefront<0, false>(c, S, cd, d, gd, od, state, queue, rays, results, count, max_spp);
+        return spp1 ? run_wavefront<1, true>(c, S, cd, d, gd, od, state, queue, count, max_spp)
+                    : run_wavefront<1, false>(c, S, cd, d, gd, od, state, queue, count, max_spp);
+    return spp1 ? run_wavefront<0, true>(c, S, cd, d, gd, od, state, queue, count, max_spp)
+                : run_wavefront<0, false>(c, S, cd, d, gd, od, state, queue, count, max_spp);
 }
 
 }  // namespace vxpt

@@ -112,7 +112,7 @@ __device__ __forceinline__ V3 directional_light(V3 viewer, V3 world_pos, V3 ligh
 __device__ __forceinline__ float4 tex_nearest_rgba(const float4* base, int layer, int n, float u, float v) {
     const int i = ((int)floorf(u * (float)n)) & (n - 1);
     const int j = ((int)floorf(v * (float)n)) & (n - 1);
-    return __ldg(base + ((size_t)layer * n + j) * n + i);
+    return __ldg(base + ((size_t)max(layer, 0) * n + j) * n + i);  // negative layer -> 0, as tex_nearest (GL clamps the array layer)
 }
 
 template <int LAYOUT>

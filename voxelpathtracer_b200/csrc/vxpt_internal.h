@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -62,7 +63,42 @@ struct SceneDev {
     int n_mip_layers;
     const uchar4* lava_albedo;  // [VXPT_LAVA_FRAMES][VXPT_LAVA_SIZE][VXPT_LAVA_SIZE] (vxpt_set_lava_textures)
     const uchar4* lava_normal;
+    const float* lut;  // LUT_FLOATS floats of per-handle constants (fill_trace_lut below)
 };
+
+// ---- exact tables for the trace passes ---------------------------------------------------------------------------
+// The hemisphere / cone samplers take sin and cos of an angle that is a function of ONE byte: a blue-noise value v in 0..255
+// (cosWeightedRandomHemisphereDirection, DiffuseRayTraceFrag.glsl:945-967: 2*PI*r1 with r1 = (0.5 + v) / 256) or a noise texel
+// channel (SampleCone, ShadowRayTraceFrag.glsl:388-398,474: phi = (v / 255) * PI * 2).  The parity contract pins sin / cos as the
+// correctly rounded fp32 value (double evaluation, one rounding), so 256 (cos, sin) pairs per sampler, computed once on the host
+// with exactly the fp32 argument arithmetic of the shader, replace two double-precision evaluations per ray.
+// Likewise the tangent frame of the hemisphere sampler, uu = normalize(cross(n, (0,1,1))), vv = cross(uu, n), is a function of the
+// face (6 axis normals): 6 x 6 floats, evaluated on the host with the device code's fp32 operation order.
+constexpr int LUT_TRIG_GI = 0;         // [256] (cos, sin) of 2*PI * ((0.5 + v) / 256)
+constexpr int LUT_TRIG_CONE = 512;     // [256] (cos, sin) of ((v / 255) * PI) * 2
+constexpr int LUT_BASIS = 1024;        // [6] (uu.xyz, vv.xyz) per normal id 0..5 (GetNormalFromID order)
+constexpr int LUT_FLOATS = 1024 + 36;
+inline void fill_trace_lut(float* lut) {  // host; fp32 expressions as in the device code (host objects are built with -ffp-contract=off)
+    for (int v = 0; v < 256; ++v) {
+        const float r1 = (0.5f + (float)v) / 256.0f;               // blue_noise_1d
+        const float a = (2.0f * 3.14159265359f) * r1;               // PI2 * r1
+        lut[LUT_TRIG_GI + 2 * v] = (float)cos((double)a);
+        lut[LUT_TRIG_GI + 2 * v + 1] = (float)sin((double)a);
+        const float phi = (((float)v / 255.0f) * 3.14159265359f) * 2.0f;  // xi_y * PI * 2
+        lut[LUT_TRIG_CONE + 2 * v] = (float)cos((double)phi);
+        lut[LUT_TRIG_CONE + 2 * v + 1] = (float)sin((double)phi);
+    }
+    const float N[6][3] = {{0, 0, 1}, {0, 0, -1}, {0, 1, 0}, {0, -1, 0}, {-1, 0, 0}, {1, 0, 0}};
+    for (int k = 0; k < 6; ++k) {
+        const float nx = N[k][0], ny = N[k][1], nz = N[k][2], bx = 0.0f, by = 1.0f, bz = 1.0f;
+        const float cx = ny * bz - by * nz, cy = nz * bx - bz * nx, cz = nx * by - bx * ny;  // cross3(n, (0,1,1))
+        const float inv = 1.0f / sqrtf((cx * cx + cy * cy) + cz * cz);
+        const float ux = cx * inv, uy = cy * inv, uz = cz * inv;                              // normalize3
+        float* o = lut + LUT_BASIS + 6 * k;
+        o[0] = ux; o[1] = uy; o[2] = uz;
+        o[3] = uy * nz - ny * uz; o[4] = uz * nx - nz * ux; o[5] = ux * ny - nx * uy;         // cross3(uu, n)
+    }
+}
 
 }  // namespace vxpt
 
@@ -102,6 +138,7 @@ struct vxpt_ctx {
     int n_mip_layers = 0;
     uchar4* d_lava_albedo = nullptr;  // vxpt_set_lava_textures
     uchar4* d_lava_normal = nullptr;
+    float* d_lut = nullptr;           // vxpt::fill_trace_lut
     int n_layers = 0, n_emissive = 0, sky_n = 0;
     bool have_materials = false, have_bluenoise = false, have_textures = false, have_sky = false, have_shadow_noise = false;
 
@@ -118,13 +155,13 @@ struct vxpt_ctx {
     int opt_replicas = 1;   // VXPT_OPT_SCENE_REPLICAS
     int opt_timing = 1;     // VXPT_OPT_TIMING_EVENTS
     int opt_texel = 0;      // VXPT_OPT_TEXEL_FORMAT
-    int opt_quad_shuffle = 0;  // VXPT_OPT_MATERIAL_QUAD_SHUFFLE
+    int opt_quad_shuffle = 1;  // VXPT_OPT_MATERIAL_QUAD_SHUFFLE
     uint8_t* rep_grid[8] = {nullptr};   // extra copies (index 1..replicas-1); index 0 unused (= d_grid / d_steps)
     uint8_t* rep_steps[8] = {nullptr};
     uint64_t frame_counter = 0;  // advanced by vxpt_trace_primary
 
     // device staging for host-pointer I/O (grown on demand)
-    void* d_stage = nullptr;
+    void* d_stage = nullptr;  // (void*: grow_scratch)
     size_t stage_bytes = 0;
 
     // vxpt_render_frame: copy-out stream + one event per row slab
@@ -171,6 +208,8 @@ namespace vxpt {
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+bool stream_capturing(const vxpt_ctx* c);
+int grow_scratch(vxpt_ctx* c, void** buf, size_t* have, size_t need, const char* what);
 
 #ifndef VXPT_HOST_SHADOW
 #define VX_CUDA(expr)                                                         \
@@ -194,6 +233,8 @@ int launch_pack_bricks(vxpt_ctx* c);
 int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out_dev);
 int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxShadowParams& p, const VxShadowOut& out_dev);
 int launch_diffuse(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxDiffuseParams& p, const VxDiffuseOut& out_dev);
+// trace_gi.cu: bytes of wavefront scratch a slab needs (hit queue + per-pixel sample state when a pixel takes several samples)
+size_t gi_scratch_bytes(size_t slab_px, size_t frame_px, bool spp1);
 // trace_reflection.cu
 int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g_dev, const VxReflectionIn& in_dev, const VxReflectionParams& p,
                       const VxReflectionOut& out_dev);

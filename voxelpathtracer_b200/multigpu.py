@@ -191,7 +191,7 @@ class ShardedFrame:
     """
 
     def __init__(self, renderer, fps_camera, width, height, group=None, chunks=None, band_rows=None, exchange_gbuffer=False, slots=2,
-                 exchange="nccl", texel=False, root=0, timeout_ms=2000, emulate=None):
+                 exchange="nccl", texel=False, root=0, timeout_ms=2000, emulate=None, max_gi_spp=1):
         self.r = renderer
         self.fc = fps_camera
         self.width, self.height = width, height
@@ -272,6 +272,8 @@ class ShardedFrame:
                 per_chunk.append(base)
             self.bases.append(per_chunk)
         renderer.set_option(abi.OPT_TEXEL_FORMAT, 1 if self.texel else 0)
+        for cam in self.cams:  # scratch sized now: a frame may be captured into a CUDA graph before it ever ran eagerly
+            renderer.reserve(cam, max_gi_spp=max_gi_spp)
         self._ext = torch.cuda.ExternalStream(renderer.cuda_stream(), device=dev)
         self._comm = torch.cuda.Stream(device=dev) if N > 1 else None
         self._traced = [[torch.cuda.Event() for _ in range(self.chunks)] for _ in range(self.slots)]

@@ -118,7 +118,15 @@ class Renderer:
 
     # ---- world / distance field ---------------------------------------------------------------------------
     def upload_world(self, blocks):
+        """vxpt_upload_world copies exactly WORLD_VOXELS bytes from the address it is given: arrays and tensors are checked here (a raw
+        address is the caller's promise)."""
         data = blocks.data if hasattr(blocks, "zyx") else blocks
+        if isinstance(data, np.ndarray):
+            if data.dtype != np.uint8 or data.size != abi.WORLD_VOXELS:
+                raise ValueError(f"the world is {abi.WORLD_VOXELS} uint8 block ids (x + 384 * (y + 128 * z)); got {data.dtype} x {data.size}")
+        elif torch is not None and isinstance(data, torch.Tensor):
+            if data.dtype != torch.uint8 or data.numel() != abi.WORLD_VOXELS:
+                raise ValueError(f"the world is {abi.WORLD_VOXELS} uint8 block ids; got {data.dtype} x {data.numel()}")
         check(self.lib.vxpt_upload_world(self.handle, _ptr(data)))
 
     def set_block(self, x, y, z, block):
@@ -495,6 +503,11 @@ class Renderer:
 
     def set_option(self, option, value):
         check(self.lib.vxpt_set_option(self.handle, int(option), int(value)))
+
+    def reserve(self, cam, max_gi_spp=1, staging_bytes=0):
+        """Size the handle's scratch (GI wavefront queue, staging arena) for frames of `cam`'s size before capturing its stream into a CUDA
+        graph (vxpt_reserve): a pass that had to grow its scratch during capture fails with VXPT_E_STATE."""
+        check(self.lib.vxpt_reserve(self.handle, C.byref(cam), int(max_gi_spp), int(staging_bytes)))
 
     def measure_l2_sector_peak(self):
         g = C.c_double()

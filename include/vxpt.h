@@ -548,9 +548,8 @@ VXPT_API int vxpt_reserve(vxpt_handle h, const VxCamera* cam, int max_gi_spp, si
 #define VXPT_OPT_TRAVERSAL_LAYOUT 1 /* 0 = linear distance field, 1 = brick-swizzled copy (default) */
 #define VXPT_OPT_GI_WAVEFRONT 2     /* 0 = one thread per pixel, 1 = wavefront: sorted first-bounce rays, hits re-queued, the rest of a sample in
                                        CTA-wide stages (default) */
-#define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped), 1 = DPX tiled (default),
-                                       2 = 1 + the z sweep writes the traversal's step field too (no separate packing launch; added after the
-                                       round's GPU budget was spent: compiled for sm_100a, not yet run on a GPU) */
+#define VXPT_OPT_DF_ALGO 3          /* 0 = one thread per grid line (reference-shaped) + a separate step-field pass, 1 = DPX sweeps whose z sweep
+                                       writes the traversal's step field too (default) */
 /* measurement knob: keep `value` (1..8) identical copies of the grid + step field at distinct addresses and rotate through
  * them, one per vxpt_trace_primary call (= per frame).  With 3 copies the traced inputs (132 MB) exceed the 126 MB L2, so
  * back-to-back frames cannot reuse each other's cache lines (benchmark timing rule); results are unchanged. */

@@ -44,6 +44,8 @@ cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "host emulation"; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t) new int(0); return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest) { *least = 0; *greatest = 0; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned f, int) { return cudaStreamCreateWithFlags(s, f); }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete (int*)s; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* st) { *st = cudaStreamCaptureStatusNone; return cudaSuccess; }
@@ -181,6 +183,7 @@ int launch_df_build(vxpt_ctx* c) {
         for (int z = 1; z < WZ; ++z) at(z) = (uint8_t)std::min<int>(at(z), at(z - 1) + 1);
         for (int z = WZ - 2; z >= 0; --z) at(z) = (uint8_t)std::min<int>(at(z), at(z + 1) + 1);
     }
+    c->steps_layout = -1;  // the step field follows in launch_pack_bricks (vxpt_build_distance_field)
     return VXPT_OK;
 }
 // pack_steps: E(M) = (M == 1) ? 1 : floor(M * 0.57735026918f), linear or 8x4x4 bricks

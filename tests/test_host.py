@@ -112,7 +112,7 @@ def test_brick_offset_is_injective_and_matches_its_bit_layout():
     assert off.max() < (96 << 18) and np.unique(off.reshape(-1)).size == abi.WORLD_VOXELS
     # one 32-byte sector = 4 x * 4 z * 2 y voxels, one 128-byte line = 8 x * 4 y * 4 z
     assert np.unique(off[:4, :2, :4] >> 5).size == 1 and np.unique(off[:8, :4, :4] >> 7).size == 1
-    # what df_z_dpx<1> (VXPT_OPT_DF_ALGO = 2) relies on: the four z-neighbours of an x-word are 16 contiguous, 16-byte aligned bytes
+    # what the step-field stores of df_z_dpx<1> rely on: the four z-neighbours of an x-word are 16 contiguous, 16-byte aligned bytes
     w = off[::4, :, ::4]
     assert (w % 16 == 0).all() and all(np.array_equal(off[::4, :, k::4], w + u(4 * k)) for k in range(4))
     # and the closed form of the step value that DESIGN.md quotes for M != 1

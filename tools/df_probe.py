@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Measurement aid: the distance-field build on the plains world, the two-kernel build + pack_steps (VXPT_OPT_DF_ALGO = 1, default) against
-the build whose z sweep writes the step field itself (= 2), timed by the library's CUDA events (VxStats.df_build_ms + brick_pack_ms).
+"""Measurement aid: the distance-field build on the plains world, the DPX build whose z sweep writes the step field too (VXPT_OPT_DF_ALGO = 1,
+default) against the reference-shaped build + pack_steps (= 0), timed by the library's CUDA events (VxStats.df_build_ms + brick_pack_ms).
 Prints one JSON line; algorithmic bytes per build + pack = read grid, write DF, write step field = 3 x 18,874,368 B."""
 import json
 import os
@@ -11,6 +11,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import voxelpathtracer_b200 as vx  # noqa: E402
+from voxelpathtracer_b200 import abi as _abi  # noqa: E402
+if os.environ.get("VXPT_LIB"):  # development: an experiment build of the library (build.py --out=...), never the product path
+    _abi.LIB_PATH = os.path.join(os.path.dirname(_abi.LIB_PATH), os.environ["VXPT_LIB"])
 from voxelpathtracer_b200 import abi, assets, world  # noqa: E402
 
 
@@ -24,7 +27,7 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    for algo in (1, 2):
+    for algo in (1, 0):
         r.set_option(abi.OPT_DF_ALGO, algo)
         df, pack = [], []
         for k in range(iters + 3):

@@ -13,6 +13,9 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import voxelpathtracer_b200 as vx  # noqa: E402
+from voxelpathtracer_b200 import abi as _abi  # noqa: E402
+if os.environ.get("VXPT_LIB"):  # development: an experiment build of the library (build.py --out=...), never the product path
+    _abi.LIB_PATH = os.path.join(os.path.dirname(_abi.LIB_PATH), os.environ["VXPT_LIB"])
 from voxelpathtracer_b200 import abi, assets, camera, world  # noqa: E402
 
 

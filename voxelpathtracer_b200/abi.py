@@ -8,8 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# VXPT_LIB: development only — an experiment build of the same sources (build.py --out=...); the product loads libvxpt.so
-LIB_PATH = os.path.join(HERE, os.environ.get("VXPT_LIB", "libvxpt.so"))
+LIB_PATH = os.path.join(HERE, "libvxpt.so")
 
 WORLD_SIZE_X, WORLD_SIZE_Y, WORLD_SIZE_Z = 384, 128, 384
 WORLD_VOXELS = WORLD_SIZE_X * WORLD_SIZE_Y * WORLD_SIZE_Z

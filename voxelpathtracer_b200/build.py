@@ -34,7 +34,7 @@ def needs_build():
 
 def build(force=False, verbose=False, defines=(), out=None):
     """Build libvxpt.so.  defines / out: development only — an experiment variant of the library (-DNAME=VALUE ...) under another file
-    name, selected at run time with the environment variable VXPT_LIB (abi.py); the product is the default build."""
+    name, which the measurement tools under tools/ can be pointed at (their VXPT_LIB variable); the product only ever loads libvxpt.so."""
     lib = out or LIB
     if not force and not defines and not needs_build():
         return lib

@@ -315,6 +315,12 @@ int vxpt_create(int device_id, vxpt_handle* out) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->ev_slab[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        int least = 0, greatest = 0;
+        e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->gi_stream, cudaStreamNonBlocking, greatest);
+    }
+    for (int k = 0; k < 9 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->ev_gi[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_wait_err, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_wait_err, 0, sizeof(unsigned), c->stream);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_grid, VOXELS);
@@ -353,6 +359,12 @@ int vxpt_destroy(vxpt_handle c) {
     }
     for (int k = 0; k < 8; ++k)
         if (c->ev_slab[k]) cudaEventDestroy(c->ev_slab[k]);
+    if (c->gi_stream) {
+        cudaStreamSynchronize(c->gi_stream);
+        cudaStreamDestroy(c->gi_stream);
+    }
+    for (int k = 0; k < 9; ++k)
+        if (c->ev_gi[k]) cudaEventDestroy(c->ev_gi[k]);
     for (const vxpt_ctx::SharedBuf& b : c->shared) {
         if (b.owned) cudaFree(b.ptr);
         else cudaIpcCloseMemHandle(b.ptr);
@@ -443,8 +455,7 @@ int vxpt_build_distance_field(vxpt_handle c) {
     int rc = launch_df_build(c);
     if (rc) return rc;
     VX_CUDA(cudaEventRecord(c->ev3, c->stream));
-    rc = launch_pack_bricks(c);
-    if (rc) return rc;
+    if (c->steps_layout != c->opt_layout && (rc = launch_pack_bricks(c))) return rc;  // the DPX build writes the step field itself
     VX_CUDA(cudaEventRecord(c->ev4, c->stream));
     if ((rc = refresh_replicas(c))) return rc;
     c->df_timed = true;
@@ -1615,7 +1626,7 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
             c->opt_quad_shuffle = value;
             return VXPT_OK;
         case VXPT_OPT_DF_ALGO:
-            if (value < 0 || value > 2) return fail(VXPT_E_INVALID, "df algo must be 0..2");
+            if (value < 0 || value > 1) return fail(VXPT_E_INVALID, "df algo must be 0 or 1");
             c->opt_df_algo = value;
             return VXPT_OK;
         default:

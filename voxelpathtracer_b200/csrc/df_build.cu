@@ -7,17 +7,19 @@
 //
 // Design (algo 1, default) — two kernels, both built on the DPX instruction VIADDMNMX.U16x2
 // (__viaddmin_u16x2: per 16-bit lane min(a + b, c)), i.e. one instruction per sweep step per TWO voxels:
-//   df_xy_dpx : one CTA per z-slice (49,152 contiguous bytes).  The slice is brought into shared memory with
-//               one TMA bulk copy (cp.async.bulk + mbarrier), swept along x with rows paired in the two 16-bit
-//               lanes (12 voxels x 2 rows per lane, cross-lane carries by a shuffle min-plus scan), swept
-//               along y with x-neighbours paired (a whole 128-voxel column pair lives in registers), and
-//               written back with one TMA bulk store.
-//   df_z_dpx  : the z sweep; each thread owns a 24-voxel z-segment of one 4-byte x-word in registers, 16
-//               segments per CTA exchange their edge values through shared memory (min-plus carries), every
-//               global access is a fully used 128-byte line.
-//   pack_bricks: permutes the linear field into 8x4x4 bricks (one 128-B line each, 4x2x4 per 32-B sector) for
-//               the traversal kernels.
+//   df_xy_dpx : persistent CTAs (two per SM) stream z-slices (49,152 contiguous bytes) through two shared-memory buffers each: one TMA
+//               bulk copy (cp.async.bulk + mbarrier) brings a slice in while the previous one is swept; x sweep with rows paired in the
+//               two 16-bit lanes (24 voxels x 2 rows per lane, cross-lane carries by shuffle min-plus scans over half warps), y sweep
+//               with the column streamed through shared memory (4 voxels per thread); one TMA bulk store writes the slice back.
+//   df_z_dpx  : the z sweep, launched as a programmatic dependent of df_xy_dpx; each thread owns a 24-voxel z-segment of one 4-byte
+//               x-word in registers, 16 segments per CTA exchange their edge values through shared memory (min-plus carries).  The
+//               finished words also leave as the traversal's step field E(M) (trace_device.cuh), converted two voxels per table read
+//               and stored in the 8x4x4-brick layout (16-byte stores) — no second pass over the distance field.
+//   pack_steps: distance field -> step field on its own (after the reference-shaped build, or when the layout option changes).
 // Algo 0 keeps the reference's shape (one thread per grid line, three launches) as an on-device cross-check.
+#include <algorithm>
+#include <cstdlib>
+
 #include "vxpt_internal.h"
 
 namespace vxpt {
@@ -118,134 +120,146 @@ constexpr uint32_t ONE2 = 0x00010001u;  // +1 in both 16-bit lanes
 constexpr uint32_t INF2 = 0x00FE00FEu;  // 254 in both lanes ("no solid voxel seen")
 
 // ------------------------------------------------------------------------------------------------------------
-// df_xy_dpx: x and y sweeps of one z-slice in shared memory
-// 256 threads, <= 64 registers, 48 KB of shared memory: 4 CTAs per SM, so all 384 slices are resident at once (592 slots)
-// and the TMA loads, the sweeps and the TMA stores of different slices overlap on every SM.
+// df_xy_dpx: x and y sweeps of whole z-slices in shared memory.  Persistent CTAs (two per SM, 2 x 48 KB of shared memory each):
+// CTA b takes slices b, b + gridDim.x, ...; while it sweeps one slice the TMA bulk load of its next slice is already in flight
+// into the other buffer, and the bulk store of the previous slice drains behind it (r01h: one CTA per slice, load -> sweep -> store
+// in lock-step on every SM, the SMs idle 30 % of the kernel).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int XY_THREADS = 256;  // 8 warps; threads 0..191 each own one x-pair column in the y sweep
+constexpr int XY_THREADS = 256;  // 8 warps
+constexpr int XSEG = 24;         // voxels of a row one lane holds in the x sweep: 16 lanes cover a row, a warp sweeps two row pairs at once
 
-// one x-sweep of a pair of rows held as r[0..11] (row A in the low 16-bit lane, row B in the high lane)
-__device__ __forceinline__ void x_sweep_rows(uint32_t (&r)[12], int lane) {
-    // block byte -> initial distance: solid 0, air 254 (ManhattanDistanceX.comp:51-52)
-#pragma unroll
-    for (int k = 0; k < 12; ++k) r[k] = INF2 - __vminu2(r[k], ONE2) * 0xFEu;
-    // forward (x ascending): local sweep, min-plus scan of the lanes' last values, carry-in from the lanes to the left
-#pragma unroll
-    for (int k = 1; k < 12; ++k) r[k] = __viaddmin_u16x2(r[k - 1], ONE2, r[k]);
-    uint32_t c = r[11];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, c, d);
-        if (lane >= d) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
-    }
-    uint32_t cin = __shfl_up_sync(0xffffffffu, c, 1);
-    if (lane == 0) cin = INF2;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(k + 1) * ONE2, r[k]);
-    // backward (x descending)
-#pragma unroll
-    for (int k = 10; k >= 0; --k) r[k] = __viaddmin_u16x2(r[k + 1], ONE2, r[k]);
-    c = r[0];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_down_sync(0xffffffffu, c, d);
-        if (lane + d < 32) c = __viaddmin_u16x2(t, (uint32_t)(12 * d) * ONE2, c);
-    }
-    cin = __shfl_down_sync(0xffffffffu, c, 1);
-    if (lane == 31) cin = INF2;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) r[k] = __viaddmin_u16x2(cin, (uint32_t)(12 - k) * ONE2, r[k]);
-}
-
-__device__ __forceinline__ void load_row_pair(const uint32_t* rowA, uint32_t (&r)[12]) {
+// block bytes -> initial distances (solid 0, air 254; ManhattanDistanceX.comp:51-52) for rows A and B, two voxels of the same x in the
+// halves of a register (row A low, row B high)
+__device__ __forceinline__ void load_row_pair24(const uint32_t* rowA, uint32_t (&r)[XSEG]) {
     const uint32_t* rowB = rowA + WX / 4;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        uint32_t A = rowA[k], B = rowB[k];
-        uint32_t t0 = __byte_perm(A, B, 0x6420);  // a0 a2 b0 b2
-        uint32_t t1 = __byte_perm(A, B, 0x7531);  // a1 a3 b1 b3
-        r[4 * k + 0] = t0 & 0x00FF00FFu;
-        r[4 * k + 2] = (t0 >> 8) & 0x00FF00FFu;
-        r[4 * k + 1] = t1 & 0x00FF00FFu;
-        r[4 * k + 3] = (t1 >> 8) & 0x00FF00FFu;
+    for (int k = 0; k < XSEG / 8; ++k) {
+        const uint2 A = *reinterpret_cast<const uint2*>(rowA + 2 * k), B = *reinterpret_cast<const uint2*>(rowB + 2 * k);
+        const uint32_t a[2] = {A.x, A.y}, b[2] = {B.x, B.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t t0 = __byte_perm(a[h], b[h], 0x6420);  // a0 a2 b0 b2
+            const uint32_t t1 = __byte_perm(a[h], b[h], 0x7531);  // a1 a3 b1 b3
+            const uint32_t v[4] = {t0 & 0x00FF00FFu, t1 & 0x00FF00FFu, (t0 >> 8) & 0x00FF00FFu, (t1 >> 8) & 0x00FF00FFu};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[8 * k + 4 * h + q] = INF2 - __vminu2(v[q], ONE2) * 0xFEu;
+        }
     }
 }
-__device__ __forceinline__ void store_row_pair(uint32_t* rowA, const uint32_t (&r)[12]) {
+__device__ __forceinline__ void store_row_pair24(uint32_t* rowA, const uint32_t (&r)[XSEG]) {
     uint32_t* rowB = rowA + WX / 4;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        uint32_t t0 = r[4 * k + 0] | (r[4 * k + 2] << 8);  // a0 a2 b0 b2
-        uint32_t t1 = r[4 * k + 1] | (r[4 * k + 3] << 8);  // a1 a3 b1 b3
-        rowA[k] = __byte_perm(t0, t1, 0x5140);
-        rowB[k] = __byte_perm(t0, t1, 0x7362);
+    for (int k = 0; k < XSEG / 8; ++k) {
+        uint32_t a[2], b[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t* q = r + 8 * k + 4 * h;
+            const uint32_t t0 = q[0] | (q[2] << 8);  // a0 a2 b0 b2
+            const uint32_t t1 = q[1] | (q[3] << 8);  // a1 a3 b1 b3
+            a[h] = __byte_perm(t0, t1, 0x5140);
+            b[h] = __byte_perm(t0, t1, 0x7362);
+        }
+        *reinterpret_cast<uint2*>(rowA + 2 * k) = make_uint2(a[0], a[1]);
+        *reinterpret_cast<uint2*>(rowB + 2 * k) = make_uint2(b[0], b[1]);
+    }
+}
+// x sweep of a row pair spread over 16 lanes (l16 = lane within the half warp): local forward and backward sweeps, min-plus scans of the
+// segments' edge values over the half warp, then both carries applied in one pass
+__device__ __forceinline__ void x_sweep_rows24(uint32_t (&r)[XSEG], int l16) {
+#pragma unroll
+    for (int k = 1; k < XSEG; ++k) r[k] = __viaddmin_u16x2(r[k - 1], ONE2, r[k]);
+#pragma unroll
+    for (int k = XSEG - 2; k >= 0; --k) r[k] = __viaddmin_u16x2(r[k + 1], ONE2, r[k]);
+    uint32_t cf = r[XSEG - 1], cb = r[0];  // best value at the last / first voxel of the segment from sources inside it
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const uint32_t tf = __shfl_up_sync(0xffffffffu, cf, d, 16), tb = __shfl_down_sync(0xffffffffu, cb, d, 16);
+        if (l16 >= d) cf = __viaddmin_u16x2(tf, (uint32_t)(XSEG * d) * ONE2, cf);
+        if (l16 + d < 16) cb = __viaddmin_u16x2(tb, (uint32_t)(XSEG * d) * ONE2, cb);
+    }
+    uint32_t cin_f = __shfl_up_sync(0xffffffffu, cf, 1, 16), cin_b = __shfl_down_sync(0xffffffffu, cb, 1, 16);
+    if (l16 == 0) cin_f = INF2;
+    if (l16 == 15) cin_b = INF2;
+#pragma unroll
+    for (int k = 0; k < XSEG; ++k) {
+        r[k] = __viaddmin_u16x2(cin_f, (uint32_t)(k + 1) * ONE2, r[k]);
+        r[k] = __viaddmin_u16x2(cin_b, (uint32_t)(XSEG - k) * ONE2, r[k]);
     }
 }
 
-__global__ void __launch_bounds__(XY_THREADS, 4) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* tile = smem;                                            // [128][384] bytes
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SLICE_BYTES);  // mbarrier
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * SLICE_BYTES);  // one mbarrier per buffer
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t slice = (size_t)blockIdx.x * SLICE_BYTES;
-
+    // the dependent z sweep may be scheduled as soon as SMs free up; it waits for this grid's memory with cudaGridDependencySynchronize()
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
+    int z = blockIdx.x;
+    if (tid == 0 && z < WZ) {
         mbar_arrive_expect_tx(bar, SLICE_BYTES);
-        bulk_g2s(tile, grid + slice, SLICE_BYTES, bar);
+        bulk_g2s(smem, grid + (size_t)z * SLICE_BYTES, SLICE_BYTES, bar);
     }
-    mbar_wait(bar, 0);
+    for (int it = 0; z < WZ; ++it, z += gridDim.x) {
+        const int b = it & 1;
+        uint8_t* tile = smem + b * SLICE_BYTES;  // [128][384] bytes
+        mbar_wait(bar + b, (it >> 1) & 1);
 
-    // ---- x sweep: a warp takes row pairs (2p, 2p+1); lane l holds x = 12l .. 12l+11 of both rows.  Two row pairs are in
-    //      flight per warp (independent dependency chains) to cover the latency of the DPX / shuffle chains.
-    uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
-    constexpr int WARPS = XY_THREADS / 32;  // 8 warps x 8 row pairs = 64 row pairs
+        // ---- x sweep: half warp h of warp w takes row pairs (2p, 2p+1), p = 2w + h + 16j; lane l16 holds x = 24 l16 .. 24 l16 + 23
+        uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
+        const int l16 = lane & 15;
 #pragma unroll 1
-    for (int p = warp; p < WY / 2; p += 2 * WARPS) {
-        uint32_t* rowA0 = t32 + (2 * p) * (WX / 4) + lane * 3;
-        uint32_t* rowA1 = rowA0 + 2 * WARPS * (WX / 4);  // row pair p + 8 = 16 rows further
-        uint32_t r0[12], r1[12];
-        load_row_pair(rowA0, r0);
-        load_row_pair(rowA1, r1);
-        x_sweep_rows(r0, lane);
-        x_sweep_rows(r1, lane);
-        store_row_pair(rowA0, r0);
-        store_row_pair(rowA1, r1);
-    }
-    __syncthreads();
+        for (int p = 2 * warp + (lane >> 4); p < WY / 2; p += 2 * (XY_THREADS / 32)) {
+            uint32_t* rowA = t32 + (2 * p) * (WX / 4) + l16 * (XSEG / 4);
+            uint32_t r[XSEG];
+            load_row_pair24(rowA, r);
+            x_sweep_rows24(r, l16);
+            store_row_pair24(rowA, r);
+        }
+        __syncthreads();
+        // the other buffer is free once the bulk store of the previous slice has read it: start the load of this CTA's next slice
+        if (tid == 0 && z + (int)gridDim.x < WZ) {
+            bulk_wait_read0();
+            mbar_arrive_expect_tx(bar + (b ^ 1), SLICE_BYTES);
+            bulk_g2s(smem + (b ^ 1) * SLICE_BYTES, grid + (size_t)(z + gridDim.x) * SLICE_BYTES, SLICE_BYTES, bar + (b ^ 1));
+        }
 
-    // ---- y sweep: thread t owns voxels x = 2t, 2t+1 (x-neighbours in the two 16-bit lanes); the column is streamed
-    //      through shared memory (loads run ahead of the one-instruction dependency chain), not held in registers.
-    if (tid < WX / 2) {
-        uint16_t* col = reinterpret_cast<uint16_t*>(tile) + tid;
-        uint32_t prev = __byte_perm((uint32_t)col[0], 0u, 0x4140);
-#pragma unroll 16
-        for (int y = 1; y < WY; ++y) {
-            uint32_t cur = __byte_perm((uint32_t)col[y * (WX / 2)], 0u, 0x4140);
-            prev = __viaddmin_u16x2(prev, ONE2, cur);
-            col[y * (WX / 2)] = (uint16_t)__byte_perm(prev, 0u, 0x4420);
+        // ---- y sweep: thread t < 96 owns the x-word t (4 voxels, two DPX lanes pairs) and streams the column through shared memory
+        if (tid < WX / 4) {
+            uint32_t* col = t32 + tid;
+            uint32_t w = col[0];
+            uint32_t lo = __byte_perm(w, 0u, 0x4140), hi = __byte_perm(w, 0u, 0x4342);
+#pragma unroll 8
+            for (int y = 1; y < WY; ++y) {
+                w = col[y * (WX / 4)];
+                lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w, 0u, 0x4140));
+                hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w, 0u, 0x4342));
+                col[y * (WX / 4)] = __byte_perm(lo, hi, 0x6420);
+            }
+#pragma unroll 8
+            for (int y = WY - 2; y >= 0; --y) {
+                w = col[y * (WX / 4)];
+                lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w, 0u, 0x4140));
+                hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w, 0u, 0x4342));
+                col[y * (WX / 4)] = __byte_perm(lo, hi, 0x6420);
+            }
         }
-#pragma unroll 16
-        for (int y = WY - 2; y >= 0; --y) {
-            uint32_t cur = __byte_perm((uint32_t)col[y * (WX / 2)], 0u, 0x4140);
-            prev = __viaddmin_u16x2(prev, ONE2, cur);
-            col[y * (WX / 2)] = (uint16_t)__byte_perm(prev, 0u, 0x4420);
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(out + (size_t)z * SLICE_BYTES, tile, SLICE_BYTES);
+            bulk_commit();
         }
     }
-    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
-    __syncthreads();
-    if (tid == 0) {
-        bulk_s2g(out + slice, tile, SLICE_BYTES);
-        bulk_commit();
-        bulk_wait_read0();  // shared memory must outlive the copy's reads
-    }
+    if (tid == 0) bulk_wait_read0();  // shared memory must outlive the last store's reads
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// df_z_dpx: z sweep, in place capable (in may equal out)
+// df_z_dpx: z sweep + the traversal's step field
 // ------------------------------------------------------------------------------------------------------------
 constexpr int ZSEG = 24;          // voxels per thread along z
 constexpr int ZSEGS = WZ / ZSEG;  // 16 segments per CTA
@@ -255,23 +269,32 @@ constexpr int ZSEGS = WZ / ZSEG;  // 16 segments per CTA
 constexpr int ZXW = 8;
 
 __constant__ uint8_t c_step_lut[256];
+// Step values of two x-neighbours at once.  The finished field is 1-Lipschitz in the L1 metric, so x-neighbours (M0, M1) differ by at most
+// one and 2 * M0 + M1 + 1 = 3 * M0 + (M1 - M0 + 1) indexes the pair uniquely: one IDP.2A + one 16-bit shared-memory read per two voxels
+// instead of an 8-bit table read (and its index extraction) per voxel.  Entry = E(M0) | E(M1) << 8.
+constexpr int PAIR_LUT = 768;
+__constant__ uint16_t c_pair_lut[PAIR_LUT];
 
 __device__ __forceinline__ uint32_t lut4(const uint8_t* lut, uint32_t w) {
     return (uint32_t)lut[w & 0xFF] | ((uint32_t)lut[(w >> 8) & 0xFF] << 8) | ((uint32_t)lut[(w >> 16) & 0xFF] << 16) |
            ((uint32_t)lut[w >> 24] << 24);
 }
+// lo = M0 | M1 << 16, hi = M2 | M3 << 16 -> E0 | E1 << 8 | E2 << 16 | E3 << 24
+__device__ __forceinline__ uint32_t steps4(const uint16_t* plut, uint32_t lo, uint32_t hi) {
+    const uint32_t e01 = plut[__dp2a_lo(lo, 0x0102u, 1u)], e23 = plut[__dp2a_lo(hi, 0x0102u, 1u)];
+    return __byte_perm(e01, e23, 0x5410);
+}
 
-// PACK (VXPT_OPT_DF_ALGO = 2): -1 = distance field only; 0 / 1 = also write the step field E(M) of pack_steps<0 / 1> from the registers that
-// hold the finished words, which saves pack_steps' launch and its 18.9 MB re-read of the distance field.  In the brick layout the four
-// z-neighbours of an x-word are 16 contiguous bytes (brick_offset: z & 3 has stride 4), so a thread issues one 16-byte store per four
-// z values; ZSEG and the segment origins are multiples of 4.
+// PACK: 0 / 1 = the step field E(M) in the linear / brick layout, written from the registers that hold the finished words (no second
+// pass over the distance field).  In the brick layout the four z-neighbours of an x-word are 16 contiguous bytes (brick_offset: z & 3
+// has stride 4), so a thread issues one 16-byte store per four z values; ZSEG and the segment origins are multiples of 4.
 template <int PACK>
 __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint8_t* __restrict__ steps) {
-    __shared__ uint8_t lut[PACK >= 0 ? 256 : 1];
-    if (PACK >= 0) {
+    __shared__ uint16_t plut[PAIR_LUT];
+    {
         const int t = threadIdx.y * ZXW + threadIdx.x;
-        lut[t] = c_step_lut[t];
-        lut[t + ZXW * ZSEGS] = c_step_lut[t + ZXW * ZSEGS];
+#pragma unroll
+        for (int k = 0; k < PAIR_LUT / (ZXW * ZSEGS); ++k) plut[t + k * ZXW * ZSEGS] = c_pair_lut[t + k * ZXW * ZSEGS];
     }
     __shared__ uint2 edge_first[ZSEGS][ZXW];  // local value at the first voxel of a segment (lo pair, hi pair)
     __shared__ uint2 edge_last[ZSEGS][ZXW];
@@ -280,11 +303,13 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
     const int lane = threadIdx.x, seg = threadIdx.y;
     const int y = blockIdx.y;
     const size_t base = (size_t)y * WX + (size_t)(blockIdx.x * ZXW + lane) * 4 + (size_t)seg * ZSEG * SLICE_BYTES;
+    // programmatic dependent launch: everything above overlapped the tail of df_xy_dpx; its stores are visible from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     uint32_t lo[ZSEG], hi[ZSEG];
 #pragma unroll
     for (int i = 0; i < ZSEG; ++i) {
-        uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(in + base + (size_t)i * SLICE_BYTES));
+        uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(in + base + (size_t)i * SLICE_BYTES));
         lo[i] = __byte_perm(w, 0u, 0x4140);
         hi[i] = __byte_perm(w, 0u, 0x4342);
     }
@@ -330,11 +355,10 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
         a = __viaddmin_u16x2(cb.x, (uint32_t)(ZSEG - i) * ONE2, a);
         uint32_t b = __viaddmin_u16x2(cf.y, (uint32_t)(i + 1) * ONE2, hi[i]);
         b = __viaddmin_u16x2(cb.y, (uint32_t)(ZSEG - i) * ONE2, b);
-        const uint32_t w = __byte_perm(a, b, 0x6420);
-        *reinterpret_cast<uint32_t*>(out + base + (size_t)i * SLICE_BYTES) = w;
-        if (PACK == 0) *reinterpret_cast<uint32_t*>(steps + base + (size_t)i * SLICE_BYTES) = lut4(lut, w);
+        *reinterpret_cast<uint32_t*>(out + base + (size_t)i * SLICE_BYTES) = __byte_perm(a, b, 0x6420);
+        if (PACK == 0) *reinterpret_cast<uint32_t*>(steps + base + (size_t)i * SLICE_BYTES) = steps4(plut, a, b);
         if (PACK == 1) {
-            e[i & 3] = lut4(lut, w);
+            e[i & 3] = steps4(plut, a, b);
             if ((i & 3) == 3) *reinterpret_cast<uint4*>(steps + brick_offset(x0, y, z0 + i - 3)) = make_uint4(e[0], e[1], e[2], e[3]);
         }
     }
@@ -378,48 +402,58 @@ __global__ void __launch_bounds__(256) pack_steps(const uint8_t* __restrict__ df
 
 // ------------------------------------------------------------------------------------------------------------
 // per-handle, per-device one-time set-up (called by vxpt_create on the handle's device)
+constexpr int XY_SMEM = 2 * SLICE_BYTES + 16;
 int init_df_kernels(vxpt_ctx* c) {
-    VX_CUDA(cudaFuncSetAttribute(df_xy_dpx, cudaFuncAttributeMaxDynamicSharedMemorySize, SLICE_BYTES + 16));
+    VX_CUDA(cudaFuncSetAttribute(df_xy_dpx, cudaFuncAttributeMaxDynamicSharedMemorySize, XY_SMEM));
     uint8_t lut[256];
     for (int m = 0; m < 256; ++m) lut[m] = (uint8_t)((m == 1) ? 1 : (int)floorf((float)m * 0.57735026918f));
+    uint16_t pair[PAIR_LUT];
+    for (int i = 0; i < PAIR_LUT; ++i) {  // index 3 * M0 + (M1 - M0 + 1)
+        const int m0 = i / 3, m1 = std::min(std::max(m0 + i % 3 - 1, 0), 255);
+        pair[i] = (uint16_t)(lut[m0] | (lut[m1] << 8));
+    }
     VX_CUDA(cudaMemcpyToSymbolAsync(c_step_lut, lut, sizeof lut, 0, cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(cudaMemcpyToSymbolAsync(c_pair_lut, pair, sizeof pair, 0, cudaMemcpyHostToDevice, c->stream));
     VX_CUDA(cudaStreamSynchronize(c->stream));
     return VXPT_OK;
 }
 
+// Distance field AND the traversal's step field in the handle's layout (c->steps_layout says which layout the step field holds; -1 =
+// stale: the reference-shaped algo 0 leaves it to launch_pack_bricks).
 int launch_df_build(vxpt_ctx* c) {
     cudaStream_t s = c->stream;
     if (c->opt_df_algo == 0) {
-        c->steps_fused = false;
         df_x_lines<<<(WY * WZ + 127) / 128, 128, 0, s>>>(c->d_grid, c->d_df);
         df_y_lines<<<(WX * WZ + 127) / 128, 128, 0, s>>>(c->d_df);
         df_z_lines<<<(WX * WY + 127) / 128, 128, 0, s>>>(c->d_df);
+        c->steps_layout = -1;
         c->launches += 3;
     } else {
-        const int smem = SLICE_BYTES + 16;
-        df_xy_dpx<<<WZ, XY_THREADS, smem, s>>>(c->d_grid, c->d_tmp);
-        const dim3 zg(WX / (4 * ZXW), WY), zb(ZXW, ZSEGS);
-        c->steps_fused = false;
-        if (c->opt_df_algo == 2) {  // the z sweep writes the step field too; launch_pack_bricks has nothing left to do for this build
-            if (c->opt_layout == 1) df_z_dpx<1><<<zg, zb, 0, s>>>(c->d_tmp, c->d_df, c->d_steps);
-            else df_z_dpx<0><<<zg, zb, 0, s>>>(c->d_tmp, c->d_df, c->d_steps);
-            c->steps_layout = c->opt_layout;
-            c->steps_fused = true;
-        } else {
-            df_z_dpx<-1><<<zg, zb, 0, s>>>(c->d_tmp, c->d_df, nullptr);
-        }
+        static const int xy_ctas = std::getenv("VXPT_DF_XY_CTAS") ? std::atoi(std::getenv("VXPT_DF_XY_CTAS")) : 2 * 148;  // experiment knob
+        df_xy_dpx<<<std::min(std::max(xy_ctas, 1), WZ), XY_THREADS, XY_SMEM, s>>>(c->d_grid, c->d_tmp);
+        // the z sweep is a programmatic dependent of the xy sweep: its CTAs are scheduled (and load their tables) while the xy grid drains
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(WX / (4 * ZXW), WY);
+        cfg.blockDim = dim3(ZXW, ZSEGS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const uint8_t* in = c->d_tmp;
+        if (c->opt_layout == 1) VX_CUDA(cudaLaunchKernelEx(&cfg, df_z_dpx<1>, in, c->d_df, c->d_steps));
+        else VX_CUDA(cudaLaunchKernelEx(&cfg, df_z_dpx<0>, in, c->d_df, c->d_steps));
+        c->steps_layout = c->opt_layout;
         c->launches += 2;
     }
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
 }
 
+// (re)write the step field from the distance field in the handle's layout: after the reference-shaped build, or when the layout option changes
 int launch_pack_bricks(vxpt_ctx* c) {
-    if (c->steps_fused && c->steps_layout == c->opt_layout) {  // df_z_dpx<PACK> of this build already wrote the step field in this layout
-        c->steps_fused = false;
-        return VXPT_OK;
-    }
-    c->steps_fused = false;
     if (c->opt_layout == 1) {
         const int warps = (WX / 32) * (WY / 4) * (WZ / 4);
         pack_steps<1><<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(c->d_df, c->d_steps);

@@ -534,31 +534,65 @@ static int env_int(const char* name, int dflt) {
     return e ? std::atoi(e) : dflt;
 }
 
+// One sample of a slab = gi_gen_trace0 (throughput-bound: 64 % of the issue slots busy) followed by gi_continue (latency-bound: three dependent
+// traversals of up to 48 / 128 / 128 iterations per record, 32 % of the issue slots busy, ncu r02c).  Experiment knob VXPT_GI_SLABS = k cuts
+// the slab into k row sub-slabs and runs the gi_continue of sub-slab j on a second, higher-priority stream beside the gi_gen_trace0 of
+// sub-slab j + 1 (fork / join by events, still one CUDA graph).  Measured r02d, 1080p plains: 1 / 2 / 3 / 4 sub-slabs = 0.278 / 0.304 /
+// 0.410 / 0.341 ms — gi_continue's duration is its longest dependency chain, not its record count, so the last sub-slab's continuation is
+// exposed at full length while every sub-launch adds its own tail.  Default: 1 (off).
+constexpr int GI_MAX_SLABS = 8;
+constexpr int GI_COUNT_STRIDE = 8;   // words between the counter blocks of two sub-slabs (hit count, hit cursor)
+
 template <int LAYOUT, bool SPP1>
 static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, const DiffuseDev& d, const GBufferDev& g, const DiffuseOutDev& od,
                          PixState* state, HitRec* queue, unsigned* count, int max_spp) {
     const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
-    const size_t slab_px = (size_t)(cd.row_end - cd.row_begin) * cd.width;
-    static const int sort_env = env_int("VXPT_GI_SORT", -1), ctas_env = env_int("VXPT_GI_CTAS", 4);
+    const int rows = cd.row_end - cd.row_begin;
+    const size_t slab_px = (size_t)rows * cd.width;
+    static const int sort_env = env_int("VXPT_GI_SORT", -1), ctas_env = env_int("VXPT_GI_CTAS", 4), slabs_env = env_int("VXPT_GI_SLABS", -1);
+    // pixels per thread of the sorted first-bounce kernel: 4 on large slabs (1024 rays sorted per CTA, 32 groups for 8 warps), 2 on
+    // medium ones, plain on slabs too small to fill the GPU with such CTAs (r01g, 1080p GI pass: plain 0.339 ms, 1 / 2 / 4 pixels per
+    // thread 0.364 / 0.286 / 0.283 ms)
+    const int rpt = sort_env >= 0 ? sort_env : (slab_px >= (size_t)768 * 1024 ? 4 : (slab_px >= (size_t)128 * 1024 ? 2 : 0));
+    const int tile_rows = 8 * std::max(rpt, 1);
+    // sub-slabs: whole CTA tile rows each
+    int n_slabs = slabs_env > 0 ? slabs_env : 1;
+    n_slabs = std::max(1, std::min({n_slabs, GI_MAX_SLABS, (rows + tile_rows - 1) / tile_rows}));
+    if (!c->gi_stream) n_slabs = 1;
+    const int tiles = (rows + tile_rows - 1) / tile_rows;
     for (int s = 0; s < max_spp; ++s) {
-        VX_CUDA(cudaMemsetAsync(count, 0, 4 * sizeof(unsigned), c->stream));  // hit count, hit cursor
-        // pixels per thread of the sorted first-bounce kernel: 4 on large slabs (1024 rays sorted per CTA, 32 groups for 8 warps), 2 on
-        // medium ones, plain on slabs too small to fill the GPU with such CTAs (r01g, 1080p GI pass: plain 0.339 ms, 1 / 2 / 4 pixels per
-        // thread 0.364 / 0.286 / 0.283 ms)
-        const int rows = cd.row_end - cd.row_begin;
-        const int rpt = sort_env >= 0 ? sort_env : (slab_px >= (size_t)768 * 1024 ? 4 : (slab_px >= (size_t)128 * 1024 ? 2 : 0));
-        const dim3 grid_s((cd.width + 31) / 32, (rows + 8 * std::max(rpt, 1) - 1) / (8 * std::max(rpt, 1)));
-        switch (rpt) {
-            case 0: gi_gen_trace0<LAYOUT, SPP1, 0><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
-            case 1: gi_gen_trace0<LAYOUT, SPP1, 1><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
-            case 2: gi_gen_trace0<LAYOUT, SPP1, 2><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
-            default: gi_gen_trace0<LAYOUT, SPP1, 4><<<grid_s, 256, 0, c->stream>>>(S, cd, d, g, od, state, queue, count, s); break;
+        VX_CUDA(cudaMemsetAsync(count, 0, GI_MAX_SLABS * GI_COUNT_STRIDE * sizeof(unsigned), c->stream));  // hit count, hit cursor per sub-slab
+        for (int k = 0; k < n_slabs; ++k) {
+            CameraDev sc = cd;
+            sc.row_begin = cd.row_begin + (tiles * k / n_slabs) * tile_rows;
+            sc.row_end = k + 1 == n_slabs ? cd.row_end : cd.row_begin + (tiles * (k + 1) / n_slabs) * tile_rows;
+            const int srows = sc.row_end - sc.row_begin;
+            if (srows <= 0) continue;
+            unsigned* cnt_k = count + k * GI_COUNT_STRIDE;
+            HitRec* queue_k = queue + (size_t)(sc.row_begin - cd.row_begin) * cd.width;
+            const dim3 grid_s((cd.width + 31) / 32, (srows + tile_rows - 1) / tile_rows);
+            switch (rpt) {
+                case 0: gi_gen_trace0<LAYOUT, SPP1, 0><<<grid_s, 256, 0, c->stream>>>(S, sc, d, g, od, state, queue_k, cnt_k, s); break;
+                case 1: gi_gen_trace0<LAYOUT, SPP1, 1><<<grid_s, 256, 0, c->stream>>>(S, sc, d, g, od, state, queue_k, cnt_k, s); break;
+                case 2: gi_gen_trace0<LAYOUT, SPP1, 2><<<grid_s, 256, 0, c->stream>>>(S, sc, d, g, od, state, queue_k, cnt_k, s); break;
+                default: gi_gen_trace0<LAYOUT, SPP1, 4><<<grid_s, 256, 0, c->stream>>>(S, sc, d, g, od, state, queue_k, cnt_k, s); break;
+            }
+            // a CTA works on 256 records at a time; no more CTAs than the sub-slab can have chunks
+            const unsigned max_chunks = (unsigned)(((size_t)srows * cd.width + GC_THREADS - 1) / GC_THREADS);
+            const unsigned ctas = std::min<unsigned>(148u * (unsigned)std::max(ctas_env, 1), std::max(max_chunks, 1u));
+            cudaStream_t ks = c->stream;
+            if (n_slabs > 1) {  // fork: the continuation of this sub-slab goes to the second stream
+                VX_CUDA(cudaEventRecord(c->ev_gi[k], c->stream));
+                VX_CUDA(cudaStreamWaitEvent(c->gi_stream, c->ev_gi[k], 0));
+                ks = c->gi_stream;
+            }
+            gi_continue<LAYOUT, SPP1><<<ctas, GC_THREADS, sizeof(GcShared), ks>>>(S, sc, d, od, state, queue_k, cnt_k);
+            c->launches += 2;
         }
-        // a CTA works on 256 records at a time; no more CTAs than the slab can have chunks
-        const unsigned max_chunks = (unsigned)((slab_px + GC_THREADS - 1) / GC_THREADS);
-        const unsigned ctas = std::min<unsigned>(148u * (unsigned)std::max(ctas_env, 1), std::max(max_chunks, 1u));
-        gi_continue<LAYOUT, SPP1><<<ctas, GC_THREADS, sizeof(GcShared), c->stream>>>(S, cd, d, od, state, queue, count);
-        c->launches += 2;
+        if (n_slabs > 1) {  // join
+            VX_CUDA(cudaEventRecord(c->ev_gi[GI_MAX_SLABS], c->gi_stream));
+            VX_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gi[GI_MAX_SLABS], 0));
+        }
     }
     if (!SPP1) {
         gi_finalize<<<grid, 256, 0, c->stream>>>(cd, d, g, od, state);
@@ -583,6 +617,7 @@ static int init_gi_kernels() {
 // wavefront scratch of a slab: 256 B of counters, the hit queue (one record per slab pixel at most) and, when some pixel takes several
 // samples, the per-pixel sample state of the frame
 size_t gi_scratch_bytes(size_t slab_px, size_t frame_px, bool spp1) { return 256 + slab_px * sizeof(HitRec) + (spp1 ? 0 : frame_px * sizeof(PixState)); }
+static_assert(GI_MAX_SLABS * GI_COUNT_STRIDE * sizeof(unsigned) <= 256, "counter blocks fit the 256-byte header of the scratch");
 
 int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev& d, const VxGBuffer& g, const VxDiffuseOut& out) {
     if (int rc = init_gi_kernels()) return rc;

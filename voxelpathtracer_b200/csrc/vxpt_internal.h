@@ -148,10 +148,9 @@ struct vxpt_ctx {
 
     // options
     int opt_layout = 1;     // VXPT_OPT_TRAVERSAL_LAYOUT
-    int steps_layout = -1;  // layout the step field currently holds
+    int steps_layout = -1;  // layout the step field currently holds (-1: stale, launch_pack_bricks must run)
     int opt_wavefront = 1;  // VXPT_OPT_GI_WAVEFRONT
-    int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped), 1 = DPX tiled, 2 = 1 + step field written by the z sweep
-    bool steps_fused = false;  // the last launch_df_build wrote the step field itself (consumed by the launch_pack_bricks that follows)
+    int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped) + pack_steps, 1 = DPX sweeps, step field written by the z sweep
     int opt_replicas = 1;   // VXPT_OPT_SCENE_REPLICAS
     int opt_timing = 1;     // VXPT_OPT_TIMING_EVENTS
     int opt_texel = 0;      // VXPT_OPT_TEXEL_FORMAT
@@ -202,6 +201,9 @@ struct vxpt_ctx {
     // wavefront queues (grown on demand)
     void* d_queue = nullptr;
     size_t queue_bytes = 0;
+    // GI pass: second (higher-priority) stream for the latency-bound continuation kernels + fork / join events (trace_gi.cu)
+    cudaStream_t gi_stream = nullptr;
+    cudaEvent_t ev_gi[9] = {nullptr};
 };
 
 namespace vxpt {

@@ -562,6 +562,26 @@ def run_ours(args):
     if affinity_before is not None:
         os.sched_setaffinity(0, affinity_before)
 
+    # ---- the passes either side of the headline path at the same 1080p frame, planes resident in device memory:
+    # reflection pass (config 3: 1 spp, rough, Halton-jittered G-buffer read), G-buffer material pass, SVGF chain, shadow filters.  Timed by
+    # the library's events around each call (tools/denoise_probe.py), N = 1 only; not part of the headline metric.
+    aux_ms = None
+    if rank == 0 and ws == 1 and not args.no_aux:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import denoise_probe
+            ra = vx.Renderer(local_rank)
+            ra.upload_world(w)
+            ra.build_distance_field()
+            aux = denoise_probe.measure(ra, iters=min(args.steps, 10), W=WIDTH, H=HEIGHT)["passes"]
+            aux_ms = {"reflection": aux["reflection"]["ms"], "gbuffer": aux["material"]["ms"], "svgf_chain": aux["svgf_frame"]["ms"],
+                      "shadow_filters": aux["shadow_filter_frame"]["ms"],
+                      "svgf_kernels": {k: aux[k]["ms"] * aux[k]["calls_per_frame"] for k in ("svgf_initial", "svgf_temporal", "svgf_variance", "svgf_spatial")},
+                      "frac_of_hbm": {k: aux[k]["frac"] for k in ("reflection", "material", "svgf_frame", "shadow_filter_frame")}}
+            del ra
+        except Exception as e:  # the headline line must not depend on the auxiliary passes
+            aux_ms = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -------------
     cpu_baseline = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
@@ -598,7 +618,11 @@ def run_ours(args):
             "roofline_all": rooflines,
             "df_build_ms": df_ms + pack_ms, "l2_sector_peak_gbs": l2_peak,
             "pass_ms": {"primary": float(per_pass[:, 0].mean()), "shadow": float(per_pass[:, 1].mean()), "diffuse": float(per_pass[:, 2].mean()),
-                        "note": "rank 0's rows, each pass timed alone after the timed region (library events); the step time above includes the overlapped exchange"},
+                        **({k: v for k, v in aux_ms.items() if k in ("reflection", "gbuffer", "svgf_chain", "shadow_filters", "error")} if aux_ms else {}),
+                        "note": "rank 0's rows, each pass timed alone after the timed region (library events); the step time above includes the overlapped exchange"
+                                + ("; reflection (config 3: 1 spp, rough, jittered G-buffer read), gbuffer (material pass), svgf_chain and shadow_filters are the passes "
+                                   "either side of the headline path, device planes, outside the metric" if aux_ms else "")},
+            "aux_passes": aux_ms,
             "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
         if gathered is not None:
@@ -624,6 +648,7 @@ def main():
     ap.add_argument("--gi-mode", type=int, default=1, choices=[0, 1], help="VXPT_OPT_GI_WAVEFRONT: 0 one thread per pixel, 1 wavefront (default)")
     ap.add_argument("--emulate", type=int, default=0, help="development: trace rank 0's share of an N-way sharded frame on one GPU, no exchange")
     ap.add_argument("--planes", default="texel", choices=["texel", "f32"], help="plane encoding: the reference's FBO texel formats (default) or fp32")
+    ap.add_argument("--no-aux", action="store_true", help="skip timing the reflection / G-buffer / denoiser passes (N = 1 only)")
     ap.add_argument("--no-graph", action="store_true", help="submit every pass eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -153,7 +153,11 @@ typedef struct VxReflectionParams {
     float viewer_pos[3];      /* u_ViewerPosition                                                 */
     float sun_strength;       /* u_SunStrengthModifier 0.85                                       */
     float moon_strength;      /* u_MoonStrengthModifier 1.0                                       */
-    float halton[2];          /* u_Halton (ray-direction jitter when TEMPORAL_SPEC; G-buffer reads stay at the pixel) */
+    float halton[2];          /* u_Halton = GetTAAJitterSecondary(frame) (Pipeline.cpp:3032), clamped to [-2, 2]: the pass reads the
+                                 primary distance (GL_LINEAR) and normal id (GL_NEAREST, both GL_REPEAT) and sets up its ray at
+                                 uv + halton / dims (ReflectionTraceFrag.glsl:754-777).  G-buffer rows up to ceil(|halton[1]|) + 1
+                                 beyond [row_begin, row_end) must therefore be valid in VxGBuffer.t / normal_id (wrapping at the frame
+                                 edge); vxpt_render_frame traces those halo rows itself.  Contiguous row slabs only (no interleave). */
     int32_t grass_props[10];  /* u_GrassBlockProps (Pipeline.cpp:3040-3049)                       */
 } VxReflectionParams;
 

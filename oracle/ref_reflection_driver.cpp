@@ -94,8 +94,10 @@ extern "C" __attribute__((visibility("default"))) int ref_trace_reflection(const
         normal[k] = a->g_normal_id[k] > 5 ? 1.0f : (float)a->g_normal_id[k] / 10.0f;
         block[k] = (float)a->g_block_id[k] / 255.0f;
     }
-    S::u_PositionTexture = sampler2D{a->g_t, W, H, 1};
-    S::u_InitialTraceNormalTexture = sampler2D{normal.data(), W, H, 1};
+    // attachment 0 of the primary FBO (R16F distance) is GL_LINEAR, attachment 1 (normal id) GL_NEAREST, both GL_REPEAT (Core/Pipeline.cpp:1094,
+    // Core/GLClasses/Framebuffer.cpp:64-67): the shader reads both at the Halton-jittered coordinate (:754-777)
+    S::u_PositionTexture = sampler2D{a->g_t, W, H, 1, true, true};
+    S::u_InitialTraceNormalTexture = sampler2D{normal.data(), W, H, 1, false, true};
     S::u_BlockIDTex = sampler2D{block.data(), W, H, 1};
     S::u_GBufferNormals = sampler2D{a->g_normal, W, H, 3};
     S::u_GBufferPBR = sampler2D{a->g_pbr, W, H, 4};

@@ -146,6 +146,7 @@ struct Hit {
 };
 
 inline int isign(float d) { return (d > 0.0f) - (d < 0.0f); }
+inline int wrap_repeat(int i, int n) { const int m = i % n; return m < 0 ? m + n : m; }  // GL_REPEAT
 
 // GetVoxel(ivec3(floor(p))) — InitialRayTraceFrag.glsl:80-88
 inline int get_voxel_at(const Scene& S, v3 p, Stats& st, int* vox = nullptr) {
@@ -1025,7 +1026,21 @@ int vxo_trace_reflection(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
             pixel_uv(*cam, i, j, u, v);
             const float ju = u + (clampf(prm->halton[0], -2.0f, 2.0f) / (float)W) * 1.0f;  // u_TemporalFilterReflections = true
             const float jv = v + (clampf(prm->halton[1], -2.0f, 2.0f) / (float)H) * 1.0f;
-            const float dist = g->t[p];
+            // texture(u_PositionTexture, JitteredUV) :766 — attachment 0 of the primary FBO is GL_LINEAR, attachment 1 (the normal id) GL_NEAREST,
+            // both GL_REPEAT (Core/Pipeline.cpp:1094, Core/GLClasses/Framebuffer.cpp:64-67); filter arithmetic as pinned in glsl_compat.h
+            float dist;
+            int nid;
+            {
+                const float x = ju * (float)W - 0.5f, y = jv * (float)H - 0.5f;
+                const float fx0 = std::floor(x), fy0 = std::floor(y);
+                const float fx = x - fx0, fy = y - fy0;
+                const int i0 = wrap_repeat((int)fx0, W), i1 = wrap_repeat((int)fx0 + 1, W), j0 = wrap_repeat((int)fy0, H), j1 = wrap_repeat((int)fy0 + 1, H);
+                const float a = g->t[(size_t)j0 * W + i0] * (1.0f - fx) + g->t[(size_t)j0 * W + i1] * fx;
+                const float b = g->t[(size_t)j1 * W + i0] * (1.0f - fx) + g->t[(size_t)j1 * W + i1] * fx;
+                dist = a * (1.0f - fy) + b * fy;
+                const int ni = wrap_repeat((int)std::floor(ju * (float)W), W), nj = wrap_repeat((int)std::floor(jv * (float)H), H);
+                nid = g->normal_id[(size_t)nj * W + ni];
+            }
             if (!(dist < 0.0f)) {
                 int spp = std::min(std::max(prm->spp, 1), 16);
                 if (prm->checkerboard) {
@@ -1034,7 +1049,6 @@ int vxo_trace_reflection(const VxoScene* sc, const VxCamera* cam, const VxGBuffe
                 }
                 spp = std::min(std::max(spp, 1), 16);
                 v3 pos = ray_origin(*cam) + normalize(ray_direction_at(*cam, ju, jv)) * dist;
-                const int nid = g->normal_id[p];
                 const v3 face_n = normal_from_id(nid, 1.0f);
                 float roughness_at, metalness_at;
                 if (in->g_pbr) { roughness_at = in->g_pbr[4 * p + 0]; metalness_at = in->g_pbr[4 * p + 1]; }

@@ -437,7 +437,7 @@ def test_reflection_parity(renderer, worlds, oracles, scene_tables, name, w, h, 
     g, _ = o.trace_primary(cam, vx.primary_params(350))
     d, _ = o.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=max(frame, 0)))
     rp = vx.reflection_params(sun, moon, stronger, fc.position, mats["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame,
-                              halton=camera.taa_jitter_secondary(max(frame, 0)) if extra else (0.0, 0.0))
+                              halton=camera.taa_jitter_secondary(max(frame, 0)) if frame != 7 else (0.0, 0.0))  # u_Halton as Pipeline.cpp:3032 sets it; one case at 0
     g_normal = g_pbr = None
     if extra:
         rng = np.random.RandomState(1)
@@ -686,7 +686,8 @@ def test_cuda_outputs_equal_the_reference_shader_golden_vectors(renderer, worlds
 
 
 def test_cuda_reflections_equal_the_reference_shader_golden_vectors(renderer, worlds, oracles, scene_tables):
-    """CUDA reflection planes == digests of the reference's ReflectionTraceFrag.glsl (compiled as C++) on the three golden frames."""
+    """CUDA reflection planes == digests of the reference's ReflectionTraceFrag.glsl (compiled as C++) on the golden frames — BASELINE
+    config 3's 1920x1080 among them — with u_Halton = GetTAAJitterSecondary(frame) (Pipeline.cpp:3032): G-buffer read at the jittered coordinate."""
     import json
     import os
     import sys
@@ -703,7 +704,8 @@ def test_cuda_reflections_equal_the_reference_shader_golden_vectors(renderer, wo
         g = renderer.trace_primary(cam, vx.primary_params(350), renderer.alloc_gbuffer(W, H))
         d = renderer.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=max(frame, 0)), renderer.alloc_diffuse(W, H))
         g_normal, g_pbr = synthetic_material_planes(g, W, H)
-        rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame)
+        rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame,
+                                  halton=camera.taa_jitter_secondary(max(frame, 0)))
         out = renderer.trace_reflection(cam, g, d, rp, renderer.alloc_reflection(W, H), g_normal, g_pbr)
         for k in ("color", "hit_distance", "emissive_mask"):
             assert sha(out[k]) == ref[cname][k], (cname, k)

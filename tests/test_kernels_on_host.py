@@ -59,12 +59,13 @@ def test_reflection_kernel_equals_the_oracle(oracles, host_kernels, scene_tables
     sun, moon, stronger, vis = scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], scene_tables["sun_visibility"]
     g, _ = o.trace_primary(cam, vx.primary_params(350))
     d, _ = o.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=4))
-    rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=2, rough=True, frame=4)
-    ref, st_ref = o.trace_reflection(cam, g, d, rp)
-    out, st = k.trace_reflection(cam, g, d, rp)
-    for key in ref:
-        assert np.array_equal(out[key], ref[key]), key
-    assert st == st_ref
+    for halton in (camera.taa_jitter_secondary(4), (0.0, 0.0), (-1.25, 1.75)):   # u_Halton as Pipeline.cpp:3032 sets it; none; both signs, beyond a texel
+        rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=2, rough=True, frame=4, halton=halton)
+        ref, st_ref = o.trace_reflection(cam, g, d, rp)
+        out, st = k.trace_reflection(cam, g, d, rp)
+        for key in ref:
+            assert np.array_equal(out[key], ref[key]), (halton, key)
+        assert st == st_ref
 
 
 def test_alpha_tested_kernels_equal_the_oracle(worlds, oracle_dfs, scene_tables):

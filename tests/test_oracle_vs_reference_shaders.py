@@ -143,13 +143,15 @@ def _reflection_inputs(oracle, scene_tables, case):
     g, _ = oracle.trace_primary(cam, vx.primary_params(350))
     d, _ = oracle.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=max(frame, 0)))
     g_normal, g_pbr = synthetic_material_planes(g, W, H)
-    rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame)
+    rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame,
+                              halton=camera.taa_jitter_secondary(max(frame, 0)))
     return cam, g, d, rp, g_normal, g_pbr
 
 
 def test_oracle_reflections_reproduce_the_committed_reference_digests(oracles, scene_tables, ref_digests):
-    """ReflectionTraceFrag.glsl (v1 parity profile, Halton jitter 0) as compiled from the reference vs the oracle: colour, hit distance and
-    emissive mask planes, bit for bit, on three frames (rough GGX-sampled, checkerboard SPP on dense geometry, mirror with emissive lamps)."""
+    """ReflectionTraceFrag.glsl (v1 parity profile, u_Halton = GetTAAJitterSecondary(frame): the primary distance filtered GL_LINEAR and the
+    normal id GL_NEAREST at the jittered coordinate) as compiled from the reference vs the oracle: colour, hit distance and emissive mask
+    planes, bit for bit, on four frames (config 3 at 1920x1080, rough GGX-sampled, checkerboard SPP on dense geometry, mirror with lamps)."""
     import hashlib
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -176,7 +178,8 @@ def test_reflection_pass_live_night(worlds, oracle_dfs, oracles, scene_tables):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     from make_ref_shader_golden import synthetic_material_planes
     g_normal, g_pbr = synthetic_material_planes(g, W, H)
-    rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=1, rough=True, frame=3)
+    rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=1, rough=True, frame=3,
+                              halton=camera.taa_jitter_secondary(3))
     ref = ref_shaders.trace_reflection(worlds["city"].data, oracle_dfs["city"], cam, g, d, rp, g_normal, g_pbr, scene_tables["materials"],
                                        scene_tables["blue_noise"], scene_tables["sky"])
     got, _ = o.trace_reflection(cam, g, d, rp, g_normal, g_pbr)

@@ -50,6 +50,36 @@ def test_gpu_render_frame_runs_the_material_pass_and_feeds_the_reflections(gb_re
 
 
 @pytest.mark.gpu
+def test_gpu_render_frame_in_row_slabs_traces_the_reflection_halo_rows(gb_renderer, worlds, scene_tables):
+    """The reflection pass reads the primary distance / normal id at the Halton-jittered coordinate (ReflectionTraceFrag.glsl:754-777), i.e.
+    rows next to its slab: vxpt_render_frame traces those halo rows itself, so a frame rendered in row slabs — host planes,
+    one call per slab, each into fresh arena contents — equals the frame rendered in one piece.  Jitter of both signs, wrap at the frame edge."""
+    r = gb_renderer
+    r.upload_world(worlds["gi_box"])
+    r.build_distance_field()
+    W, H = 160, 96
+    fc = camera.FpsCamera(pitch_deg=-20.0, aspect=W / H)
+    sun, moon, stronger, vis = (scene_tables[k] for k in ("sun", "moon", "stronger", "sun_visibility"))
+    pp, dp = vx.primary_params(350), vx.diffuse_params(sun, moon, vis, spp=1, frame=3)
+    for halton in (camera.taa_jitter_secondary(3), (-0.75, -1.5)):
+        rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=2, rough=True, frame=3, halton=halton)
+        want = r.alloc_reflection(W, H)
+        r.render_frame(fc.vx_camera(W, H), pp, diffuse=dp, reflection=rp, reflection_out=want)
+        got = r.alloc_reflection(W, H)
+        for rb, re in ((0, 40), (40, 41), (41, 96)):
+            # poison the arena's G-buffer between the slabs: whatever the halo needs must be traced by this call
+            r.render_frame(fc.vx_camera(W, H), vx.primary_params(1), diffuse=dp)
+            r.render_frame(fc.vx_camera(W, H, rb, re), pp, diffuse=dp, reflection=rp, reflection_out=got)
+        for k in ("color", "hit_distance", "emissive_mask"):
+            assert np.array_equal(got[k], want[k], equal_nan=True), (halton, k)
+    with pytest.raises(abi.VxptError) as e:   # interleaved bands have no contiguous neighbours to read
+        cam_il = fc.vx_camera(W, H)
+        cam_il.interleave_n, cam_il.interleave_rank, cam_il.band_rows, cam_il.row_end = 2, 0, 8, H // 2
+        r.render_frame(cam_il, pp, diffuse=dp, reflection=rp, reflection_out=r.alloc_reflection(W, H))
+    assert e.value.code == abi.E_INVALID
+
+
+@pytest.mark.gpu
 def test_gpu_relief_parallax_equals_the_oracle(gb_renderer, worlds, gb_oracles, scene_tables):
     name, idx, kw = mc.POM_CASES[0]
     case = mc.CASES[idx]

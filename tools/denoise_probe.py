@@ -18,14 +18,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 if os.environ.get("VXPT_PROBE_EMULATED"):     # development check without a GPU: never set on the GPU box
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from host_shadow import hostemu
     from voxelpathtracer_b200 import abi as _abi
     _abi.LIB_PATH = hostemu.build()
 import voxelpathtracer_b200 as vx  # noqa: E402
 from voxelpathtracer_b200 import assets, camera, denoise, world  # noqa: E402
-import material_cases as mc  # noqa: E402
 
 # algorithmic bytes per pixel: inputs read once + outputs written once (fp32 planes; ids 1 B)
 BYTES = {"material": 6 + 44,
@@ -34,7 +33,9 @@ BYTES = {"material": 6 + 44,
          "svgf_variance": 4 + 1 + 16 + 8 + 12 + 16 + 8 + 4,
          "svgf_spatial": 4 + 1 + 16 + 8 + 4 + 8 + 12 + 16 + 8 + 4 + 8,
          "shadow_temporal": 4 + 1 + 4 + 1 + 4 + 4 + 4 + 4 + 4,
-         "shadow_filter": 4 + 1 + 4 + 4 + 4 + 4}
+         "shadow_filter": 4 + 1 + 4 + 4 + 4 + 4,
+         # reflection pass (a14): G-buffer t / normal id / block id, material normal + PBR, GI SH + CoCg in; colour, hit distance, mask out
+         "reflection": 4 + 1 + 1 + 12 + 16 + 16 + 8 + 16 + 4 + 1}
 BYTES["svgf_frame"] = BYTES["svgf_initial"] + BYTES["svgf_temporal"] + BYTES["svgf_variance"] + 5 * BYTES["svgf_spatial"] + 6
 BYTES["shadow_filter_frame"] = BYTES["shadow_temporal"] + BYTES["shadow_filter"] + 4
 
@@ -54,16 +55,27 @@ class DevicePlanes:
             self.r.shared_close(p)
 
 
+def material_mips(n_layers):
+    """(albedo, normal, pbr) RGBA8 mip chains of the synthetic level-0 textures (the ones tests/material_cases.py uses)."""
+    a, n, p = assets.synthetic_material_lod0(n_layers)
+    return assets.rgba_mip_chain(a, srgb=True), assets.rgba_mip_chain(n), assets.rgba_mip_chain(p)
+
+
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1920, 1080)
     r = vx.Renderer(0)
     r.upload_world(world.generate_plains(assets.load_plains_columns()))
     r.build_distance_field()
+    print(json.dumps(measure(r, iters, W, H)))
+
+
+def measure(r, iters=20, W=1920, H=1080):
+    """ms per pass on renderer `r` (world uploaded, distance field built), planes resident in device memory; bench.py calls this too."""
     mats = assets.load_materials()
     sun, moon, stronger, vis = camera.sun_moon_direction(50.0)
     r.load_scene_tables(mats, assets.load_blue_noise(), assets.analytic_sky(16, sun), assets.load_shadow_noise())
-    r.set_gbuffer_textures(*mc.material_mips(mats["albedo_lod3"].shape[0]))
+    r.set_gbuffer_textures(*material_mips(mats["albedo_lod3"].shape[0]))
     dev = DevicePlanes(r)
     sh = denoise.plane_shapes(W, H)
 
@@ -84,6 +96,7 @@ def main():
     pong = [planes(("sh", "cocg", "variance", "ao_sky")) for _ in range(2)]
     mat = {"albedo": dev.new((H, W, 3)), "normal": dev.new((H, W, 3)), "pbr": dev.new((H, W, 4)), "texture_ao": dev.new((H, W))}
     filtered, frame_out, shadow_frame_out = dev.new((H, W)), planes(("sh", "cocg", "variance", "ao_sky")), dev.new((H, W))
+    refl = {"color": dev.new((H, W, 4)), "hit_distance": dev.new((H, W)), "emissive_mask": dev.new((H, W), np.uint8)}
     prev_fc = None
     try:
         for f in range(iters + 3):
@@ -104,6 +117,9 @@ def main():
                 return out
 
             timed("material", lambda: r.generate_gbuffer(cam, g, vx.material_params(mats["grass_props"]), mat))
+            # config 3's reflection pass: 1 spp, rough, u_Halton = GetTAAJitterSecondary(frame), normals / PBR from the material pass
+            rp = vx.reflection_params(sun, moon, stronger, fc.position, mats["grass_props"], spp=1, rough=True, frame=f, halton=camera.taa_jitter_secondary(f))
+            timed("reflection", lambda: r.trace_reflection(cam, g, d, rp, refl, g_normal=mat["normal"], g_pbr=mat["pbr"]))
             timed("svgf_initial", lambda: r.svgf_initial(cam, g, d, pre))
             t, pt = temporal[f & 1], temporal[(f & 1) ^ 1]
             timed("svgf_temporal", lambda: r.svgf_temporal(cam, g, pg, pre, pt, denoise.temporal_params(view, proj), t))
@@ -129,7 +145,7 @@ def main():
         m = float(np.mean(v))
         out["passes"][k] = {"ms": m, "calls_per_frame": len(v) // iters, "algorithmic_bytes": W * H * BYTES[k],
                             "achieved_gbs": W * H * BYTES[k] / (m * 1e-3) / 1e9, "frac": W * H * BYTES[k] / (m * 1e-3) / 1e9 / peak}
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":

@@ -38,10 +38,29 @@ def synthetic_material_planes(g, W, H):
 
 
 def reflection_cases():
-    """(name, world, width, height, camera kwargs, spp, rough, checkerboard, frame)"""
-    return [("plains_960x540_spp2_rough", "plains", 960, 540, dict(pitch_deg=-20.0), 2, True, False, 7),
+    """(name, world, width, height, camera kwargs, spp, rough, checkerboard, frame).  u_Halton = GetTAAJitterSecondary(frame) as
+    Core/Pipeline.cpp:3032 sets it every frame (frame < 0: entry 0); the first case is BASELINE configs[2] at its own resolution."""
+    return [("plains_1920x1080_spp1_rough", "plains", 1920, 1080, dict(pitch_deg=-20.0), 1, True, False, 5),
+            ("plains_960x540_spp2_rough", "plains", 960, 540, dict(pitch_deg=-20.0), 2, True, False, 7),
             ("city_640x360_spp4_checker", "city", 640, 360, dict(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0), 4, True, True, 12),
             ("gi_box_640x360_mirror", "gi_box", 640, 360, dict(pitch_deg=-20.0), 2, False, False, -1)]
+
+
+def reflection_digests(out, worlds, dfs, sun, moon, stronger, sunvis, mats, bn, sky):
+    for cname, wname, W, H, cam_kw, spp, rough, checker, frame in reflection_cases():
+        t0 = time.time()
+        fc = camera.FpsCamera(**cam_kw)
+        cam = fc.vx_camera(W, H)
+        wd, df = worlds[wname].data, dfs[wname]
+        g = ref_shaders.trace_primary(wd, df, cam, vx.primary_params(350))
+        d = ref_shaders.trace_diffuse(wd, df, cam, g, vx.diffuse_params(sun, moon, sunvis, spp=1, frame=max(frame, 0)), mats, bn, sky)
+        g_normal, g_pbr = synthetic_material_planes(g, W, H)
+        rp = vx.reflection_params(sun, moon, stronger, fc.position, mats["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame,
+                                  halton=camera.taa_jitter_secondary(max(frame, 0)))
+        r = ref_shaders.trace_reflection(wd, df, cam, g, d, rp, g_normal, g_pbr, mats, bn, sky)
+        out["reflection"][cname] = {"color": sha(r["color"]), "hit_distance": sha(r["hit_distance"]), "emissive_mask": sha(r["emissive_mask"]),
+                                    "hit_fraction": float((r["hit_distance"] > 0).mean())}
+        print(f"reflection {cname}: {time.time() - t0:.1f} s, hit fraction {out['reflection'][cname]['hit_fraction']:.4f}", flush=True)
 
 
 def main():
@@ -57,6 +76,17 @@ def main():
     sun, moon, stronger, sunvis = camera.sun_moon_direction(50.0)
     mats, bn, sky, sn = assets.load_materials(), assets.load_blue_noise(), assets.analytic_sky(16, sun), assets.load_shadow_noise()
     dfs = {}
+    only_reflection = "--only-reflection" in sys.argv   # refresh the reflection digests, keep everything else in the committed file
+    path = os.path.join(ROOT, "tests", "golden", "ref_shader_digests.json")
+    if only_reflection:
+        keep = json.load(open(path))
+        keep["reflection"] = {}
+        for name in {c[1] for c in reflection_cases()}:
+            dfs[name] = ref_shaders.df_build(worlds[name].data)
+        reflection_digests(keep, worlds, dfs, sun, moon, stronger, sunvis, mats, bn, sky)
+        with open(path, "w") as f:
+            json.dump(keep, f, indent=1, sort_keys=True)
+        return
     for name, w in worlds.items():
         t0 = time.time()
         dfs[name] = ref_shaders.df_build(w.data)
@@ -89,19 +119,7 @@ def main():
     out["diffuse"]["gi_box_3840x2160_spp4_f9"] = {"sh": sha(d4["sh"]), "cocg": sha(d4["cocg"]), "luma": sha(d4["luma"]), "ao_sky": sha(d4["ao_sky"]),
                                                   "mean_luma": float(d4["luma"].mean())}
     print(f"config 4 (4K, 4 spp): {time.time() - t0:.1f} s", flush=True)
-    for cname, wname, W, H, cam_kw, spp, rough, checker, frame in reflection_cases():   # Halton jitter 0: the G-buffer is read at the pixel
-        t0 = time.time()
-        fc = camera.FpsCamera(**cam_kw)
-        cam = fc.vx_camera(W, H)
-        wd, df = worlds[wname].data, dfs[wname]
-        g = ref_shaders.trace_primary(wd, df, cam, vx.primary_params(350))
-        d = ref_shaders.trace_diffuse(wd, df, cam, g, vx.diffuse_params(sun, moon, sunvis, spp=1, frame=max(frame, 0)), mats, bn, sky)
-        g_normal, g_pbr = synthetic_material_planes(g, W, H)
-        rp = vx.reflection_params(sun, moon, stronger, fc.position, mats["grass_props"], spp=spp, rough=rough, checkerboard=checker, frame=frame)
-        r = ref_shaders.trace_reflection(wd, df, cam, g, d, rp, g_normal, g_pbr, mats, bn, sky)
-        out["reflection"][cname] = {"color": sha(r["color"]), "hit_distance": sha(r["hit_distance"]), "emissive_mask": sha(r["emissive_mask"]),
-                                    "hit_fraction": float((r["hit_distance"] > 0).mean())}
-        print(f"reflection {cname}: {time.time() - t0:.1f} s, hit fraction {out['reflection'][cname]['hit_fraction']:.4f}", flush=True)
+    reflection_digests(out, worlds, dfs, sun, moon, stronger, sunvis, mats, bn, sky)
     with open(os.path.join(ROOT, "tests", "golden", "ref_shader_digests.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 

@@ -245,6 +245,15 @@ static int check_diffuse(const vxpt_ctx* c, const VxDiffuseParams* p) {
     }
     return VXPT_OK;
 }
+// Rows of the G-buffer's distance / normal-id planes the reflection pass reads beyond its slab: it samples them at uv + clamp(u_Halton) /
+// dims (ReflectionTraceFrag.glsl:754-777), the distance bilinearly (rows floor(j + hy), + 1), the normal id at the nearest texel; one more
+// row each way covers the rounding of the coordinate arithmetic.
+static void reflection_halo(const VxReflectionParams* p, int* below, int* above) {
+    const float hy = std::min(std::max(p->halton[1], -2.0f), 2.0f);
+    *below = (int)std::ceil(std::max(-hy, 0.0f)) + 1;
+    *above = (int)std::ceil(std::max(hy, 0.0f)) + 1;
+}
+
 static int check_reflection(const vxpt_ctx* c, const VxReflectionParams* p) {
     if (!c->have_materials || !c->have_bluenoise || !c->have_textures || !c->have_sky || !c->have_refl_textures)
         return fail(VXPT_E_STATE, "reflections need materials, blue-noise tables, material + reflection textures and a sky cubemap");
@@ -1186,6 +1195,7 @@ int vxpt_trace_reflection(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
         return fail(VXPT_E_INVALID, "NULL argument (G-buffer t, normal_id and the GI sh / cocg planes are required)");
     if (!in->g_pbr && !g->block_id) return fail(VXPT_E_INVALID, "without g_pbr the G-buffer block_id plane is required");
     if ((rc = check_reflection(c, p))) return rc;
+    if (cam->interleave_n > 1) return fail(VXPT_E_INVALID, "the reflection pass reads G-buffer rows next to its own (jittered coordinate): contiguous row slabs only");
     VX_CUDA(cudaSetDevice(c->device));
     PassIO io(c, cam);
     Plane t, nid, bid, gn, gp, sh, cg, col, hd, em;
@@ -1194,7 +1204,8 @@ int vxpt_trace_reflection(vxpt_handle c, const VxCamera* cam, const VxGBuffer* g
     io.add(col, out->color, px_bytes(c, 16, 8)); io.add(hd, out->hit_distance, px_bytes(c, 4, 2)); io.add(em, out->emissive_mask, 1);
     if ((rc = io.resolve())) return rc;
     if (cam->row_end == cam->row_begin) return VXPT_OK;
-    if ((rc = io.upload(t)) || (rc = io.upload(nid)) || (rc = io.upload(bid)) || (rc = io.upload(gn)) || (rc = io.upload(gp)) ||
+    // distance and normal id are read at the Halton-jittered coordinate (rows beyond the slab, GL_REPEAT at the frame edge): whole planes
+    if ((rc = io.upload_all(t)) || (rc = io.upload_all(nid)) || (rc = io.upload(bid)) || (rc = io.upload(gn)) || (rc = io.upload(gp)) ||
         (rc = io.upload(sh)) || (rc = io.upload(cg)))
         return rc;
     VxGBuffer gd{(float*)t.dev, (uint8_t*)nid.dev, (uint8_t*)bid.dev, nullptr, nullptr};
@@ -1225,6 +1236,7 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
     if (p->reflection) {
         if (!p->diffuse) return fail(VXPT_E_INVALID, "the reflection pass reads the GI planes: diffuse parameters are required");
         if ((rc = check_reflection(c, p->reflection))) return rc;
+        if (cam->interleave_n > 1) return fail(VXPT_E_INVALID, "the reflection pass reads G-buffer rows next to its own (jittered coordinate): contiguous row slabs only");
     }
     if (p->material && (rc = check_material(c, cam, p->material))) return rc;
     VX_CUDA(cudaSetDevice(c->device));
@@ -1304,6 +1316,33 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
         return VXPT_OK;
     };
     if ((rc = launch_primary(c, *cam, *p->primary, gd))) return rc;
+    if (p->reflection && rows < cam->height) {
+        // the reflection pass reads distance / normal id at the jittered coordinate: trace the halo rows of the slab too (one
+        // extra primary row per slab edge instead of a halo exchange); GL_REPEAT wraps at the frame edge.  They land in the G-buffer planes
+        // outside [row_begin, row_end) (in the arena for host planes; for device planes the caller's rows there are overwritten with the
+        // same values any other slab's primary pass writes) and are not copied out.
+        int below = 0, above = 0;
+        reflection_halo(p->reflection, &below, &above);
+        const int H = cam->height;
+        std::vector<int> halo;
+        auto want = [&](int row) {
+            row = (row % H + H) % H;
+            if (row < cam->row_begin || row >= cam->row_end) halo.push_back(row);
+        };
+        for (int k = 1; k <= below; ++k) want(cam->row_begin - k);
+        for (int k = 0; k < above; ++k) want(cam->row_end + k);
+        std::sort(halo.begin(), halo.end());
+        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+        for (size_t a = 0; a < halo.size();) {  // one launch per run of consecutive rows
+            size_t b = a;
+            while (b + 1 < halo.size() && halo[b + 1] == halo[b] + 1) ++b;
+            VxCamera hc = *cam;
+            hc.row_begin = halo[a];
+            hc.row_end = halo[b] + 1;
+            a = b + 1;
+            if ((rc = launch_primary(c, hc, *p->primary, gd))) return rc;
+        }
+    }
     if ((rc = copy_out({&t, &nid, &bid, &it, &hv}, cam->row_begin, cam->row_end))) return rc;
     if (mat) {
         if (!p->material->update_this_frame && !p->material->pom)  // fragments discard (all but lava pixels): staged planes must keep what the caller's hold

@@ -29,10 +29,6 @@ __device__ __forceinline__ float pow01_cr(float x, float y) {  // y > 0
 }
 __device__ __forceinline__ float sq_cr(float y) { return y * y; }
 __device__ __forceinline__ float cube_cr(float y) { return (float)(((double)y * (double)y) * (double)y); }
-__device__ __forceinline__ int wrap_repeat(int i, int n) {
-    const int m = i % n;
-    return m < 0 ? m + n : m;
-}
 struct Bilinear {  // the four texels and two weights of one GL_LINEAR tap
     int o00, o10, o01, o11;
     float fx, fy;

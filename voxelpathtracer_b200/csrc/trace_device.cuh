@@ -30,6 +30,10 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b) { return mk3(a.y * b.z - b.y * 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
+__device__ __forceinline__ int wrap_repeat(int i, int n) {  // GL_REPEAT on a texel index
+    const int m = i % n;
+    return m < 0 ? m + n : m;
+}
 // GLSL leaves sin/cos/pow precision open; the parity contract pins the correctly rounded fp32 value
 // (double evaluation, one rounding) — these run a handful of times per GI sample, never in the traversal loop.
 __device__ __forceinline__ float sin_cr(float x) { return (float)sin((double)x); }

@@ -129,7 +129,24 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
         const float u = ((float)i + 0.5f) / (float)cam.width, v = ((float)j + 0.5f) / (float)cam.height;
         const float ju = u + (P.hx / (float)cam.width) * 1.0f;  // u_TemporalFilterReflections = true
         const float jv = v + (P.hy / (float)cam.height) * 1.0f;
-        const float dist = load_f1(g.t, px, g.fmt);
+        // texture(u_PositionTexture, JitteredUV) / SampleNormalFromTex(u_InitialTraceNormalTexture, JitteredUV) :766,777 — attachment 0 of
+        // the primary FBO (distance) is GL_LINEAR, attachment 1 (normal id) GL_NEAREST, both GL_REPEAT (Core/Pipeline.cpp:1094,
+        // Core/GLClasses/Framebuffer.cpp:64-67).  OpenGL 4.3 8.14.2: x = u * w - 0.5, i0 = floor(x) mod w, weights a * (1 - f) + b * f, x first.
+        // The rows read are those of the jittered coordinate: up to ceil(|halton.y|) + 1 rows beyond the slab (vxpt.h, VxReflectionParams).
+        float dist;
+        int nid;
+        {
+            const int W = cam.width, H = cam.height;
+            const float x = ju * (float)W - 0.5f, y = jv * (float)H - 0.5f;
+            const float fx0 = floorf(x), fy0 = floorf(y);
+            const float fx = x - fx0, fy = y - fy0;
+            const int i0 = wrap_repeat((int)fx0, W), i1 = wrap_repeat((int)fx0 + 1, W), j0 = wrap_repeat((int)fy0, H), j1 = wrap_repeat((int)fy0 + 1, H);
+            const float a = load_f1(g.t, (size_t)j0 * W + i0, g.fmt) * (1.0f - fx) + load_f1(g.t, (size_t)j0 * W + i1, g.fmt) * fx;
+            const float b = load_f1(g.t, (size_t)j1 * W + i0, g.fmt) * (1.0f - fx) + load_f1(g.t, (size_t)j1 * W + i1, g.fmt) * fx;
+            dist = a * (1.0f - fy) + b * fy;
+            const int ni = wrap_repeat((int)floorf(ju * (float)W), W), nj = wrap_repeat((int)floorf(jv * (float)H), H);
+            nid = g.normal_id[(size_t)nj * W + ni];
+        }
         if (!(dist < 0.0f)) {
             int spp = min(max(P.spp, 1), 16);
             if (P.checkerboard) {
@@ -138,7 +155,6 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
             }
             spp = min(max(spp, 1), 16);
             V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, ju, jv)) * dist;
-            const int nid = g.normal_id[px];
             const V3 face_n = normal_from_id(nid, 1.0f);
             float roughness_at, metalness_at;
             if (in.g_pbr) {

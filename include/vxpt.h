@@ -532,6 +532,47 @@ VXPT_API int vxpt_wait_next(vxpt_handle h, const uint32_t* flags, int n, int str
 VXPT_API int vxpt_wait_all(vxpt_handle h, const uint32_t* flags /* device, may be a peer mapping */, int n, int stride_words,
                            uint32_t at_least /* wrap-around compare */, int timeout_ms, void* cuda_stream /* NULL = the handle's stream */);
 
+/* ---- one frame over N devices from one host thread (SURVEY.md §8b "vxpt_mg_*", §8e) --------------------------------------------
+ * The reference drives one GL context from one thread (Core/Pipeline.cpp main loop); vxpt_mg_* keeps that shape for a caller that owns
+ * several GPUs in ONE process.  A vxpt_mg_handle is a set of ordinary handles, one per device (vxpt_mg_device(mg, k) — usable with every
+ * vxpt_* call above, e.g. for a setter that has no vxpt_mg_ form).  Scene state is replicated: vxpt_mg_upload_world / set_block(s) /
+ * build_distance_field / set_* are the same call on every device (the grid is 18.9 MB, an edit list is bytes, a rebuild tens of
+ * microseconds: nothing is broadcast between devices).  A frame is sharded as contiguous image row slabs cut at multiples of 8 rows
+ * (vxpt_mg_slab tells which): device k runs vxpt_render_frame_async on its slab, all devices side by side.  No exchange step:
+ * HOST output planes are filled by every device's own copy stream; DEVICE output planes (memory of any device of the set, normally
+ * device 0) are written in place by the other devices' kernels over NVLink — peer access is enabled at creation; where the devices
+ * cannot reach each other, device planes are refused with VXPT_E_STATE.  With the reflection pass, neighbouring slabs both write the
+ * G-buffer halo rows they share (identical values).  Same threading rule as a handle: one caller thread per vxpt_mg_handle.
+ * device_ids may name a device more than once (several slabs on one GPU; how a single-GPU machine exercises this path).
+ * The per-process form (one process per GPU under torch.distributed) is the vxpt_shared_ / vxpt_signal / vxpt_wait family above. */
+typedef struct vxpt_mg_ctx* vxpt_mg_handle;
+VXPT_API int vxpt_mg_create(int n_devices, const int* device_ids /* NULL = 0 .. n_devices-1 */, vxpt_mg_handle* out);
+VXPT_API int vxpt_mg_destroy(vxpt_mg_handle mg);
+VXPT_API int vxpt_mg_size(vxpt_mg_handle mg);
+VXPT_API vxpt_handle vxpt_mg_device(vxpt_mg_handle mg, int k);
+VXPT_API int vxpt_mg_upload_world(vxpt_mg_handle mg, const uint8_t* blocks);
+VXPT_API int vxpt_mg_set_block(vxpt_mg_handle mg, int x, int y, int z, uint8_t id);
+VXPT_API int vxpt_mg_set_blocks(vxpt_mg_handle mg, const int16_t* xyz, const uint8_t* ids, int n);
+VXPT_API int vxpt_mg_build_distance_field(vxpt_mg_handle mg);
+VXPT_API int vxpt_mg_set_materials(vxpt_mg_handle mg, const int32_t table[768]);
+VXPT_API int vxpt_mg_set_blue_noise(vxpt_mg_handle mg, const int32_t* sobol, const int32_t* scramble, const int32_t* rank);
+VXPT_API int vxpt_mg_set_material_textures(vxpt_mg_handle mg, const float* albedo_lod3, const float* pbr_lod2, int n_layers,
+                                           const float* emissive_lod0, int n_emissive_layers);
+VXPT_API int vxpt_mg_set_reflection_textures(vxpt_mg_handle mg, const float* normal_lod3, int n_normal_layers, const float* emissive_lod2,
+                                             int n_emissive_layers);
+VXPT_API int vxpt_mg_set_sky_cubemap(vxpt_mg_handle mg, const float* rgb, int n);
+VXPT_API int vxpt_mg_set_shadow_noise(vxpt_mg_handle mg, const uint8_t* rgba8);
+VXPT_API int vxpt_mg_set_option(vxpt_mg_handle mg, int option, int value);
+/* rows [*row_begin, *row_end) of the frame selected by cam that device k traces */
+VXPT_API int vxpt_mg_slab(vxpt_mg_handle mg, const VxCamera* cam, int k, int* row_begin, int* row_end);
+/* vxpt_render_frame over all devices: returns with host planes complete and device planes written */
+VXPT_API int vxpt_mg_render_frame(vxpt_mg_handle mg, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out);
+VXPT_API int vxpt_mg_render_frame_async(vxpt_mg_handle mg, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out);
+VXPT_API int vxpt_mg_frame_wait(vxpt_mg_handle mg);
+VXPT_API int vxpt_mg_sync(vxpt_mg_handle mg);
+VXPT_API int vxpt_mg_get_stats(vxpt_mg_handle mg, VxStats* out);  /* counters summed over the devices, times = the slowest device's */
+VXPT_API int vxpt_mg_reset_stats(vxpt_mg_handle mg);
+
 /* ---- glFinish (Core/Pipeline.cpp:4782), statistics ------------------------------------------------------- */
 VXPT_API int vxpt_sync(vxpt_handle h);
 VXPT_API int vxpt_get_stats(vxpt_handle h, VxStats* out);   /* totals since the last reset; syncs */

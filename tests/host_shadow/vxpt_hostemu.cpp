@@ -41,6 +41,8 @@ struct FakeEvent {
 extern "C" {
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "host emulation"; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t) new int(0); return cudaSuccess; }
@@ -154,6 +156,7 @@ static inline unsigned long long global_timer_ns() { static unsigned long long t
 #include "../../voxelpathtracer_b200/csrc/gbuffer.cu"
 #include "../../voxelpathtracer_b200/csrc/denoise.cu"
 #include "../../voxelpathtracer_b200/csrc/api.cu"
+#include "../../voxelpathtracer_b200/csrc/mg.cu"
 
 // ---- the launchers of the translation units that need a GPU (df_build.cu, trace_gi.cu, l2_probe.cu) -----------------------------------
 namespace vxpt {

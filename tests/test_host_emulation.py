@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.skipif(not koh.available(), reason="CUDA toolkit headers not present")
 def test_host_plane_gpu_tests_pass_against_the_emulated_abi():
     files = ["tests/test_material_pass.py", "tests/test_per_frame_edits.py", "tests/test_svgf_denoise.py", "tests/test_alpha_traversal.py",
-             "tests/test_z_material_extras.py", "tests/test_zz_material_quad_shuffle.py"]
+             "tests/test_z_material_extras.py", "tests/test_zz_material_quad_shuffle.py", "tests/test_mg_frame.py"]
     # device-resident planes need torch's CUDA allocator, the headless C++ binary links the real library: left to the GPU box
     select = "not True and not device and not headless and not whole_chain"
     p = subprocess.run([sys.executable, "-m", "pytest", *files, "-m", "gpu", "--host-emulation", "-q", "-x", "-k", select, "-p", "no:cacheprovider"],

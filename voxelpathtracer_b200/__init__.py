@@ -5,6 +5,6 @@ recipe, the ctypes binding and the host-side mirror of the reference's World / c
 There is no CPU path: importing works anywhere, but creating a Renderer needs the built library and a GPU.
 """
 from . import abi, assets, camera, denoise, world  # noqa: F401
-from .renderer import Renderer, diffuse_params, material_params, primary_params, reflection_params, shadow_params  # noqa: F401
+from .renderer import MultiRenderer, Renderer, diffuse_params, material_params, primary_params, reflection_params, shadow_params  # noqa: F401
 
 __version__ = "0.1.0"

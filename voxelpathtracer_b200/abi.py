@@ -245,6 +245,29 @@ EXPORTS = {
     "vxpt_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vxpt_reserve": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.c_int, C.c_size_t]),
     "vxpt_measure_l2_sector_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    # one frame over N devices from one host thread (csrc/mg.cu)
+    "vxpt_mg_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "vxpt_mg_destroy": (C.c_int, [C.c_void_p]),
+    "vxpt_mg_size": (C.c_int, [C.c_void_p]),
+    "vxpt_mg_device": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "vxpt_mg_upload_world": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxpt_mg_set_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint8]),
+    "vxpt_mg_set_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "vxpt_mg_build_distance_field": (C.c_int, [C.c_void_p]),
+    "vxpt_mg_set_materials": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxpt_mg_set_blue_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vxpt_mg_set_material_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "vxpt_mg_set_reflection_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "vxpt_mg_set_sky_cubemap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "vxpt_mg_set_shadow_noise": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxpt_mg_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vxpt_mg_slab": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vxpt_mg_render_frame": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxFrameParams), C.POINTER(VxFrameOut)]),
+    "vxpt_mg_render_frame_async": (C.c_int, [C.c_void_p, C.POINTER(VxCamera), C.POINTER(VxFrameParams), C.POINTER(VxFrameOut)]),
+    "vxpt_mg_frame_wait": (C.c_int, [C.c_void_p]),
+    "vxpt_mg_sync": (C.c_int, [C.c_void_p]),
+    "vxpt_mg_get_stats": (C.c_int, [C.c_void_p, C.POINTER(VxStats)]),
+    "vxpt_mg_reset_stats": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/api.cu", "csrc/df_build.cu", "csrc/trace.cu", "csrc/trace_gi.cu", "csrc/trace_reflection.cu", "csrc/df_consumers.cu", "csrc/gbuffer.cu", "csrc/denoise.cu", "csrc/l2_probe.cu"]
+SOURCES = ["csrc/api.cu", "csrc/df_build.cu", "csrc/trace.cu", "csrc/trace_gi.cu", "csrc/trace_reflection.cu", "csrc/df_consumers.cu", "csrc/gbuffer.cu", "csrc/denoise.cu", "csrc/l2_probe.cu", "csrc/mg.cu"]
 HEADERS = ["csrc/vxpt_internal.h", "csrc/trace_device.cuh", "csrc/gi_device.cuh", "../include/vxpt.h"]
 LIB = os.path.join(HERE, "libvxpt.so")
 

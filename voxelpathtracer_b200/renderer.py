@@ -105,10 +105,17 @@ class Renderer:
         self.device = int(device)
         self._keep = []  # host arrays that must outlive an enqueued copy
 
+    @classmethod
+    def borrowed(cls, handle, device):
+        """A Renderer over a handle somebody else owns (MultiRenderer.device(k)): every call works, close() does not destroy it."""
+        r = cls.__new__(cls)
+        r.lib, r.handle, r.device, r._keep, r._borrowed = abi.load(), C.c_void_p(handle), int(device), [], True
+        return r
+
     def close(self):
-        if self.handle:
+        if self.handle and not getattr(self, "_borrowed", False):
             self.lib.vxpt_destroy(self.handle)
-            self.handle = C.c_void_p()
+        self.handle = C.c_void_p()
 
     def __del__(self):
         try:
@@ -513,3 +520,93 @@ class Renderer:
         g = C.c_double()
         check(self.lib.vxpt_measure_l2_sector_peak(self.handle, C.byref(g)))
         return float(g.value)
+
+
+class MultiRenderer:
+    """vxpt_mg_*: one frame over N devices from one host thread (csrc/mg.cu).  Scene state is replicated through device(k) — a Renderer
+    over the k-th device's handle — or the broadcast helpers below; render_frame shards the frame's rows over the devices and gathers into
+    the caller's planes (host planes, or device planes every device can reach).  device_ids may repeat (several slabs on one GPU)."""
+
+    def __init__(self, device_ids):
+        self.lib = abi.load()
+        ids = [int(d) for d in device_ids]
+        self.handle = C.c_void_p()
+        check(self.lib.vxpt_mg_create(len(ids), (C.c_int * len(ids))(*ids), C.byref(self.handle)))
+        self.devices = [Renderer.borrowed(self.lib.vxpt_mg_device(self.handle, k), ids[k]) for k in range(len(ids))]
+
+    def close(self):
+        if self.handle:
+            self.lib.vxpt_mg_destroy(self.handle)
+            self.handle = C.c_void_p()
+            self.devices = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device(self, k):
+        return self.devices[k]
+
+    def upload_world(self, blocks):
+        data = blocks.data if hasattr(blocks, "zyx") else blocks
+        if isinstance(data, np.ndarray) and (data.dtype != np.uint8 or data.size != abi.WORLD_VOXELS):
+            raise ValueError(f"the world is {abi.WORLD_VOXELS} uint8 block ids")
+        check(self.lib.vxpt_mg_upload_world(self.handle, _ptr(data)))
+
+    def set_block(self, x, y, z, block_id):
+        check(self.lib.vxpt_mg_set_block(self.handle, int(x), int(y), int(z), int(block_id)))
+
+    def build_distance_field(self):
+        check(self.lib.vxpt_mg_build_distance_field(self.handle))
+
+    def load_scene_tables(self, *args, **kw):
+        for d in self.devices:
+            d.load_scene_tables(*args, **kw)
+
+    def set_option(self, option, value):
+        check(self.lib.vxpt_mg_set_option(self.handle, int(option), int(value)))
+
+    def slab(self, cam, k):
+        rb, re = C.c_int(), C.c_int()
+        check(self.lib.vxpt_mg_slab(self.handle, C.byref(cam), int(k), C.byref(rb), C.byref(re)))
+        return rb.value, re.value
+
+    def render_frame(self, cam, primary, shadow=None, diffuse=None, gbuf=None, shadow_out=None, diffuse_out=None, reflection=None,
+                     reflection_out=None, g_normal=None, g_pbr=None, wait=True):
+        fp = VxFrameParams()
+        fp.primary = C.pointer(primary)
+        if shadow is not None:
+            fp.shadow = C.pointer(shadow)
+        if diffuse is not None:
+            fp.diffuse = C.pointer(diffuse)
+        if reflection is not None:
+            fp.reflection = C.pointer(reflection)
+        fp.g_normal, fp.g_pbr = _ptr(g_normal), _ptr(g_pbr)
+        fo = VxFrameOut()
+        fo.gbuffer = self.devices[0].gbuffer_struct(gbuf or {})
+        so, do, ro = shadow_out or {}, diffuse_out or {}, reflection_out or {}
+        fo.shadow.shadow, fo.shadow.transversal = _ptr(so.get("shadow")), _ptr(so.get("transversal"))
+        fo.diffuse.sh, fo.diffuse.cocg, fo.diffuse.luma, fo.diffuse.ao_sky = (_ptr(do.get("sh")), _ptr(do.get("cocg")), _ptr(do.get("luma")),
+                                                                                _ptr(do.get("ao_sky")))
+        fo.reflection.color, fo.reflection.hit_distance, fo.reflection.emissive_mask = (_ptr(ro.get("color")), _ptr(ro.get("hit_distance")),
+                                                                                         _ptr(ro.get("emissive_mask")))
+        fn = self.lib.vxpt_mg_render_frame if wait else self.lib.vxpt_mg_render_frame_async
+        check(fn(self.handle, C.byref(cam), C.byref(fp), C.byref(fo)))
+        return gbuf, shadow_out, diffuse_out, reflection_out
+
+    def frame_wait(self):
+        check(self.lib.vxpt_mg_frame_wait(self.handle))
+
+    def sync(self):
+        check(self.lib.vxpt_mg_sync(self.handle))
+
+    def stats(self):
+        st = abi.VxStats()
+        check(self.lib.vxpt_mg_get_stats(self.handle, C.byref(st)))
+        return {"rays": int(st.rays), "df_fetches": int(st.df_fetches), "vox_fetches": int(st.vox_fetches), "last_ms": float(st.last_ms),
+                "df_build_ms": float(st.df_build_ms), "brick_pack_ms": float(st.brick_pack_ms)}
+
+    def reset_stats(self):
+        check(self.lib.vxpt_mg_reset_stats(self.handle))

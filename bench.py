@@ -31,12 +31,42 @@ WORKLOAD = ("plains world (FastNoise seeds 9383/6886), 1920x1080, camera (192,75
             "1-spp 1-bounce diffuse GI per frame (BASELINE configs[2] without the reflection pass); distance field resident")
 METRIC = "Mrays/s (primary+shadow+GI) at 1080p"
 
+# --config: 3 = the headline workload above (BASELINE configs[2], what the driver runs); 4 and 5 = BASELINE configs[3] / configs[4] on their
+# stand-in scenes, measured the same way and kept under profiles/ — not driver-run lines.
+CONFIGS = {
+    3: dict(width=1920, height=1080, world="plains", spp=1, camera=dict(pitch_deg=-20.0), edits=False, workload=WORKLOAD, metric=METRIC),
+    4: dict(width=3840, height=2160, world="gi_box", spp=4, camera=dict(pitch_deg=-20.0), edits=False, metric="Mrays/s (primary+shadow+GI) at 2160p, 4 spp",
+            workload="gi-box scene (stand-in for the missing 'Test Worlds/gi' blob: plains + hollow rooms + emissive lamps, fixed seed), 3840x2160, camera "
+                     "(192,75,192) pitch -20: primary + soft sun shadow + 4-spp 1-bounce diffuse GI per frame (BASELINE configs[3]); distance field resident"),
+    5: dict(width=1920, height=1080, world="city", spp=1, camera=dict(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0), edits=True,
+            metric="Mrays/s (edit + DF rebuild + primary+shadow+GI) at 1080p",
+            workload="city scene (stand-in for the missing 'Test MC Worlds/Medival' regions: towers, arches, interiors), 1920x1080, camera (100,60,100) yaw 45 "
+                     "pitch -10: EVERY frame one block in view is placed or broken (World::Raycast path, Core/World.cpp:372-374,458-460), the distance "
+                     "field and step field are rebuilt in full, then primary + soft sun shadow + 1-spp GI (BASELINE configs[4])"),
+}
+CFG = CONFIGS[3]
+
+
+def edit_of(k):
+    """config 5: the k-th frame's edit — a pillar in front of the camera grows block by block and is knocked down again (period 16)."""
+    j = k % 16
+    return (104, 60 + (j if j < 8 else 15 - j), 104, 3 if j < 8 else 0)
+
 
 def frame_params(vx, camera, tables, frame):
     pp = vx.primary_params(350, camera.taa_jitter(frame))
     sp = vx.shadow_params(tables["stronger"], frame=frame, soft=True)
-    dp = vx.diffuse_params(tables["sun"], tables["moon"], tables["sun_visibility"], spp=1, frame=frame)
+    dp = vx.diffuse_params(tables["sun"], tables["moon"], tables["sun_visibility"], spp=CFG["spp"], frame=frame)
     return pp, sp, dp
+
+
+def build_world(world, assets):
+    name = CFG["world"]
+    if name == "plains":
+        return world.generate_plains(assets.load_plains_columns())
+    if name == "gi_box":
+        return world.generate_gi_box(assets.load_plains_columns())
+    return world.generate_city()
 
 
 def load_tables():
@@ -193,6 +223,8 @@ def run_reference(args):
         return 0
     from voxelpathtracer_b200 import assets, world
     tables = load_tables()
+    if args.config != 3:
+        raise SystemExit("the reference arm is measured on the headline workload (--config 3)")
     w = world.generate_plains(assets.load_plains_columns())
     ref = CpuReference(tables, w)
     ref.calibrate(args.steps + args.warmup, 150.0)
@@ -293,8 +325,9 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local_rank}")
 
     tables = load_tables()
-    w = world.generate_plains(assets.load_plains_columns())
-    fc = camera.FpsCamera(pitch_deg=-20.0)
+    WIDTH, HEIGHT, WORKLOAD = CFG["width"], CFG["height"], CFG["workload"]
+    w = build_world(world, assets)
+    fc = camera.FpsCamera(**CFG["camera"])
     texel = args.planes == "texel"
     px_out = sum(e for n_, e, _, _ in multigpu.plane_table(texel))                                # bytes per pixel written per frame
     px_xchg = sum(e for n_, e, _, _ in multigpu.plane_table(texel) if not n_.startswith("g_"))    # ... of which cross the link
@@ -302,6 +335,10 @@ def run_ours(args):
     # P independent handles ("pipes") per GPU, each with its own CUDA stream and double-buffered frame slots: consecutive
     # frames go to alternating pipes, so the latency-bound tail of one frame's kernels overlaps the next frame's kernels.
     P = max(1, args.pipes if args.pipes > 0 else (2 if ws == 1 else (4 if ws == 2 else 8)))
+    if CFG["edits"]:
+        # the frames of config 5 depend on each other through the world (frame k sees edits 0..k): one pipe, eager submission — every
+        # step is vxpt_set_block + vxpt_build_distance_field + the three passes, in stream order
+        P, args.no_graph = 1, True
     renderers, frames, exts = [], [], []
     for _ in range(P):
         rr = vx.Renderer(local_rank)
@@ -347,6 +384,10 @@ def run_ours(args):
         fr = frames[k % P]
         slot = (k // P) % slots
         fr.last_slot = slot
+        if CFG["edits"]:  # every rank patches its replica of the grid (the edit list is a function of the frame index: nothing to broadcast)
+            rr_ = renderers[k % P]
+            rr_.set_block(*edit_of(f))
+            rr_.build_distance_field()
         fr.frame_into(slot, *params[f])
         fr.exchange(slot)
 
@@ -503,6 +544,22 @@ def run_ours(args):
     rooflines["df_build"] = {"bound": "hbm", "achieved": df_gbs, "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s", "frac": df_gbs / hbm_peak,
                              "traffic": None, "ms_per_launch": df_ms + pack_ms, "distance_field_ms": df_ms, "step_field_ms": pack_ms,
                              "note": "37,748,736 algorithmic bytes over the whole rebuild (distance field + traversal step field)"}
+    # second roofline of the traversal passes: warp instructions per launch (committed ncu count of the same frame, profiles/issue.json)
+    # over the live pass time and the issue peak — 148 SMs x 4 schedulers x 1 warp instruction per cycle at the SM clock sampled in the
+    # timed region.  The L2-sector figure above is SURVEY.md §8d's; the kernels are bound by instruction issue (ncu: L2 sector
+    # throughput 1-10 % of peak, issue slots 64-75 % busy), which this fraction shows.
+    issue_path = os.path.join(ROOT, "profiles", "issue.json")
+    if os.path.exists(issue_path) and args.config == 3 and ws == 1:
+        try:
+            issue = json.load(open(issue_path))
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            for n in names:
+                if n in issue["passes"]:
+                    peak_ips = 148 * 4 * mhz * 1e6
+                    rooflines[n]["issue_frac"] = issue["passes"][n] / (rooflines[n]["ms_per_launch"] * 1e-3) / peak_ips
+                    rooflines[n]["warp_instructions"] = issue["passes"][n]
+        except Exception:
+            pass
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(traffic_path):
         for k, v in json.load(open(traffic_path)).items():
@@ -522,7 +579,7 @@ def run_ours(args):
     rows = slab_e - slab_b
     # double-buffered like a swap chain: two handles and two sets of pinned planes alternate (vxpt_render_frame_async), so the copy-out
     # of frame k overlaps the tracing of frame k+1; a frame's result is read when its handle comes round again (vxpt_frame_wait)
-    hr = renderers[:2]
+    hr = renderers[:max(2, min(len(renderers), args.e2e_handles))]
     for h in hr:
         h.set_option(abi.OPT_TEXEL_FORMAT, 1 if texel else 0)
     bufs = [(h.alloc_gbuffer(WIDTH, HEIGHT, texel=texel, pinned=True), h.alloc_shadow(WIDTH, HEIGHT, texel=texel, pinned=True),
@@ -531,12 +588,18 @@ def run_ours(args):
     h2d = 144 + 24 + 32 + 72  # VxCamera + VxPrimaryParams + VxShadowParams + VxDiffuseParams: the only per-frame inputs of the path
     checksum = 0.0
 
+    # the call of a handle with its camera and output planes bound once (Renderer.prepare_frame): per frame the host passes three pointers
+    submits = [h.prepare_frame(cam_rank, *b) for h, b in zip(hr, bufs)]
+    waits = [h.frame_wait for h in hr]
+    lumas = [b[2]["luma"] for b in bufs]
+    row0 = cam_rank.row_begin
+
     def host_step(k, f):
         i = k % len(hr)
-        hr[i].frame_wait()                                        # the frame this handle rendered last has landed in its host planes
-        val = float(bufs[i][2]["luma"][cam_rank.row_begin, 0])   # ... read (part of) its result
+        waits[i]()                                                # the frame this handle rendered last has landed in its host planes
+        val = float(lumas[i][row0, 0])                            # ... read (part of) its result
         pp, sp, dp = params[f % len(params)]  # the per-frame uniforms (camera jitter, frame seeds): built once, passed by pointer per call
-        hr[i].render_frame(cam_rank, pp, sp, dp, *bufs[i], wait=False)
+        submits[i](pp, sp, dp)
         return val
 
     for k in range(args.warmup):
@@ -554,8 +617,11 @@ def run_ours(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if ws > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_step_s = float(e2e_s[0]) / args.steps
     e2e = {"value": rays_all / float(e2e_s[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "note": ("one vxpt_render_frame_async call per step with pinned HOST output planes, two handles / plane sets alternating (" + ("the reference's FBO texel formats, 27 B/pixel" if texel else "fp32 planes, 51 B/pixel") +
+           "ms_per_step": e2e_step_s * 1e3, "pcie_gbs_per_gpu": d2h / e2e_step_s / 1e9,
+           "pcie_note": "device->host bytes of this rank's slab per second of the end-to-end loop; a PCIe 5.0 x16 link sustains about 50-55 GB/s to pinned memory, which is what bounds N = 1",
+           "note": (f"one vxpt_render_frame_async call per step with pinned HOST output planes, {len(hr)} handles / plane sets in flight (" + ("the reference's FBO texel formats, 27 B/pixel" if texel else "fp32 planes, 51 B/pixel") +
                     "): G-buffer resident on the device between passes, planes copied device->host slab by slab while later slabs trace; "
                     "the per-frame inputs are the camera and parameter structs" + ("; process bound to the GPU's NUMA node" if affinity_before is not None else ""))}
 
@@ -566,7 +632,7 @@ def run_ours(args):
     # reflection pass (config 3: 1 spp, rough, Halton-jittered G-buffer read), G-buffer material pass, SVGF chain, shadow filters.  Timed by
     # the library's events around each call (tools/denoise_probe.py), N = 1 only; not part of the headline metric.
     aux_ms = None
-    if rank == 0 and ws == 1 and not args.no_aux:
+    if rank == 0 and ws == 1 and not args.no_aux and args.config == 3:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import denoise_probe
@@ -584,7 +650,7 @@ def run_ours(args):
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores, bounded sample -------------
     cpu_baseline = None
-    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline and args.config == 3:
         ref = CpuReference(tables, w)
         t_frame = ref.calibrate(4, 30.0)   # even four frames must fit; then size the sample to about 12 s of CPU work
         n_cpu = max(4, min(32, int(12.0 / (t_frame / ref.stride))))
@@ -604,7 +670,7 @@ def run_ours(args):
                  "nccl": "one packed NCCL all-gather of the shadow + GI planes per frame on its own stream, overlapped with the following frames' tracing"}[frame.exchange_mode]
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "metric": CFG["metric"], "value": value, "unit": "Mrays/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [WIDTH, HEIGHT], "rays_per_step": rays_all / args.steps,
@@ -625,6 +691,10 @@ def run_ours(args):
             "aux_passes": aux_ms,
             "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
+        if CFG["edits"]:
+            line["rebuild"] = {"ms": df_ms + pack_ms, "share_of_step": (df_ms + pack_ms) / (total_ms / args.steps),
+                               "note": "one vxpt_set_block + one full distance-field and step-field rebuild inside EVERY timed step, in stream order before the frame's passes; "
+                                       "ms = median of 10 rebuilds timed by the library's events before the timed region"}
         if gathered is not None:
             line["gathered_ok"] = gathered["ok"]
             line["gathered"] = gathered
@@ -640,6 +710,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="3 = the headline workload (BASELINE configs[2], default); 4 = 3840x2160 4-spp GI on the gi-box scene; 5 = per-frame block edit + distance-field rebuild + 1080p GI on the city scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipes", type=int, default=0, help="independent handles/streams per GPU (frames in flight); 0 = 2 on one GPU, 4 on two, 8 on more")
     ap.add_argument("--slots", type=int, default=2, help="frame slots per pipe in the slab buffer")
@@ -648,9 +720,12 @@ def main():
     ap.add_argument("--gi-mode", type=int, default=1, choices=[0, 1], help="VXPT_OPT_GI_WAVEFRONT: 0 one thread per pixel, 1 wavefront (default)")
     ap.add_argument("--emulate", type=int, default=0, help="development: trace rank 0's share of an N-way sharded frame on one GPU, no exchange")
     ap.add_argument("--planes", default="texel", choices=["texel", "f32"], help="plane encoding: the reference's FBO texel formats (default) or fp32")
+    ap.add_argument("--e2e-handles", type=int, default=4, help="handles / pinned plane sets in flight in the end-to-end loop (at most --pipes)")
     ap.add_argument("--no-aux", action="store_true", help="skip timing the reflection / G-buffer / denoiser passes (N = 1 only)")
     ap.add_argument("--no-graph", action="store_true", help="submit every pass eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    global CFG
+    CFG = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

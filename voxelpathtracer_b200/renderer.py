@@ -447,6 +447,34 @@ class Renderer:
     def frame_wait(self):
         check(self.lib.vxpt_frame_wait(self.handle))
 
+    def prepare_frame(self, cam, gbuf=None, shadow_out=None, diffuse_out=None, reflection_out=None):
+        """A frame call with everything that does not change from frame to frame built ONCE: the camera, the output-plane struct and the
+        ctypes argument references.  Returns submit(primary, shadow, diffuse, reflection=None) -> vxpt_render_frame_async; per frame the
+        host then does three pointer stores and one foreign call instead of filling two structs field by field (bench.py e2e: about 0.3 ms
+        of Python per frame before, r01)."""
+        fo = VxFrameOut()
+        fo.gbuffer = self.gbuffer_struct(gbuf or {})
+        so, do, ro = shadow_out or {}, diffuse_out or {}, reflection_out or {}
+        fo.shadow.shadow, fo.shadow.transversal = _ptr(so.get("shadow")), _ptr(so.get("transversal"))
+        fo.diffuse.sh, fo.diffuse.cocg, fo.diffuse.luma, fo.diffuse.ao_sky = (_ptr(do.get("sh")), _ptr(do.get("cocg")), _ptr(do.get("luma")),
+                                                                                _ptr(do.get("ao_sky")))
+        fo.reflection.color, fo.reflection.hit_distance, fo.reflection.emissive_mask = (_ptr(ro.get("color")), _ptr(ro.get("hit_distance")),
+                                                                                         _ptr(ro.get("emissive_mask")))
+        fp = VxFrameParams()
+        cam_ref, fp_ref, fo_ref = C.byref(cam), C.byref(fp), C.byref(fo)
+        call, handle = self.lib.vxpt_render_frame_async, self.handle
+        keep = (cam, fo, fp, gbuf, shadow_out, diffuse_out, reflection_out)
+
+        def submit(primary, shadow=None, diffuse=None, reflection=None, _keep=keep):
+            fp.primary = C.pointer(primary)
+            fp.shadow = C.pointer(shadow) if shadow is not None else None
+            fp.diffuse = C.pointer(diffuse) if diffuse is not None else None
+            fp.reflection = C.pointer(reflection) if reflection is not None else None
+            rc = call(handle, cam_ref, fp_ref, fo_ref)
+            if rc:
+                check(rc)
+        return submit
+
     # ---- peer-to-peer slab gather (multi-GPU) --------------------------------------------------------------
     def shared_alloc(self, nbytes):
         """Device buffer other processes can map (returns address, 64-byte handle)."""

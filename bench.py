@@ -142,6 +142,64 @@ class ClockSampler:
         return out
 
 
+class NvmlClockSampler:
+    """SM clock + throttle reasons read straight from NVML on a thread, one sample every ~0.2 ms: the driver's runs time 20 steps (10 ms at
+    N = 1, 1.5 ms at N = 8), too short for nvidia-smi's 20 ms loop to land three samples inside the timed region.  Same
+    output as ClockSampler; falls back to it when NVML is not importable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, gpu_index):
+        import threading
+        import pynvml
+        pynvml.nvmlInit()
+        self.nv = pynvml
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self.rows, self.stop_flag = [], False
+        self.t_begin = self.t_end = None
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((time.time(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.0002)
+
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
+
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        rows = list(self.rows)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "window": "none", "source": "NVML, polled on a thread"}
+        if not rows:
+            return out
+        timed = [r for r in rows if self.t_begin is not None and self.t_begin <= r[0] <= self.t_end]
+        use, window = (timed, "timed region") if len(timed) >= 3 else (rows, "warm-up + timed region (timed region shorter than 3 samples)")
+        mask = 0
+        for r in use:
+            mask |= r[2]
+        out.update(sm_mhz=float(np.median([r[1] for r in use])), reasons=sorted(n for n, bit in self.REASONS if mask & bit), samples=len(use), window=window)
+        return out
+
+
+def make_clock_sampler(gpu_index):
+    try:
+        return NvmlClockSampler(gpu_index)
+    except Exception:
+        return ClockSampler(gpu_index)
+
+
 # ------------------------------------------------------------------------------------------------- reference arm
 class CpuReference:
     """The reference's CPU implementation of the path, timed on the host cores.
@@ -402,7 +460,7 @@ def run_ours(args):
     # Submission: the library calls of one frame (this rank's rows) are captured into a CUDA graph per frame index (M indices,
     # cycled), so a step costs the host one graph launch + the eager NCCL exchange instead of ~0.34 ms of Python/ctypes per
     # frame.  --no-graph submits every call eagerly.
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = make_clock_sampler(local_rank) if rank == 0 else None
     # every pipe x slot runs eagerly at least once before anything is captured (first-use work — module loading, scratch growth — is
     # not capturable; the handles' scratch is also sized up front by ShardedFrame through vxpt_reserve)
     for k in range(max(args.warmup, P * slots)):
@@ -426,7 +484,7 @@ def run_ours(args):
                 gph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gph, stream=exts[m % P], capture_error_mode="thread_local"):
                     fr_m = frames[m % P]
-                    (fr_m.frame_into if whole else fr_m.trace_into)((m // P) % slots, *params[args.warmup + m])
+                    (fr_m.frame_into if whole else fr_m.trace_into)((m // P) % slots, *params[(args.warmup + m) % n_frames])
                 graphs.append(gph)
             launches_per_graph = (sum(rr.launch_count() for rr in renderers) - l0) / M
             if is_root:

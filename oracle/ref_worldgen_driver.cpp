@@ -2,7 +2,7 @@
 // /root/reference/Dependencies/fast_noise, not copied) with the call sequence of
 // Core/WorldGenerator.cpp:71-107 and writes the per-column result: for every (x, z) the column height
 // `int(height + 40)` handed to SetVerticalBlocks and the biome (0 = sand, 1 = grass).
-// Output: 384*384 pairs of bytes, index (x * 384 + z) * 2.  Used once to create tests/golden/plains_columns.u8
+// Output: 384*384 pairs of bytes, index (x * 384 + z) * 2.  Used once to create voxelpathtracer_b200/data/plains_columns.u8
 // (tools/make_fixtures.py); test infrastructure only.
 #include <cstdio>
 #include <cstdlib>

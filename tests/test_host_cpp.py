@@ -59,7 +59,7 @@ def test_headless_fails_loudly_without_a_gpu():
 def test_headless_cpp_equals_python_driver(use_plains, plains_columns):
     exe = build_headless()
     W, H = 160, 90
-    args = [exe, str(W), str(H)] + ([os.path.join(ROOT, "tests", "golden", "plains_columns.u8")] if use_plains else [])
+    args = [exe, str(W), str(H)] + ([os.path.join(ROOT, "voxelpathtracer_b200", "data", "plains_columns.u8")] if use_plains else [])
     out = subprocess.run(args, capture_output=True, text=True, check=True).stdout.split("\n")
     got = {}
     for line in out:

@@ -93,7 +93,7 @@ def test_block_database_parser_against_the_shipped_blockdb():
     blocks = blockdb.parse_blockdb(os.path.join(REF_TREE, "blockdb.txt"))
     assert [b["Name"] for b in blocks[:5]] == ["Grass", "Dirt", "Stone", "Cobblestone", "Sand"] and blocks[0]["ID"] == 1
     assert len(blocks) == 99 and all(b["ID"] == k + 1 for k, b in enumerate(blocks))
-    names = np.load(os.path.join(ROOT, "tests", "golden", "materials.npz"))["block_names"]
+    names = np.load(os.path.join(ROOT, "voxelpathtracer_b200", "data", "materials.npz"))["block_names"]
     assert [str(n) for n in names[1:]] == [b["Name"] for b in blocks]            # the committed material fixture used the same ids
     lut = blockdb.minecraft_id_lut(blocks)
     assert np.array_equal(lut, assets.load_minecraft_id_lut())                    # committed fixture

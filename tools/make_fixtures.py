@@ -27,7 +27,7 @@ from PIL import Image
 
 REF = os.environ.get("VXPT_REFERENCE", "/root/reference")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.path.join(ROOT, "voxelpathtracer_b200", "data")  # input assets ship with the package
 sys.path.insert(0, ROOT)
 
 # blocks whose textures are baked (ids follow blockdb.txt order, Core/BlockDatabaseParser.cpp:31-42)

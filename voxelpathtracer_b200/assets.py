@@ -1,15 +1,16 @@
 """Input tables of the trace passes: material table, blue-noise tables, baked material texels, sky, shadow noise.
 
 These are the boundary INPUTS a host application supplies (BlockDataSSBO, BlueNoiseDataSSBO, texture binds of
-Core/Pipeline.cpp:2236-2270, 2825-2841).  For tests, the smoke run and the benchmark they come from the committed
-fixtures in tests/golden/ (generated from the reference tree by tools/make_fixtures.py).
+Core/Pipeline.cpp:2236-2270, 2825-2841).  The package ships its own copies under voxelpathtracer_b200/data/ (generated from the
+reference tree by tools/make_fixtures.py: the reference's blue-noise tables, block database, FastNoise plains columns), so worlds and
+scene tables can be built wherever the package is installed — tests, the smoke run and the benchmark use the same files.
 """
 import os
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")  # (the name predates the move out of tests/golden/)
 
 
 def load_plains_columns(golden=GOLDEN):

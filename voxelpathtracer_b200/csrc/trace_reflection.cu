@@ -64,13 +64,14 @@ __device__ __forceinline__ bool player_intersect(V3 viewer, V3 pos, V3 d) {
 }
 
 // ImportanceSampleGGX :345-365
-__device__ __forceinline__ V3 importance_sample_ggx(V3 N, float roughness, float xi_x, float xi_y) {
+// Xi.x is 0.9 * a blue-noise sample, i.e. a function of one byte: cos / sin of phi = 2 PI Xi.x come from the handle's table
+// (LUT_TRIG_GGX, the same fp32 values a double evaluation rounds to) instead of two double-precision evaluations per candidate direction
+__device__ __forceinline__ V3 importance_sample_ggx(V3 N, float roughness, float2 cs_phi, float xi_y) {
     const float alpha = roughness * roughness;
     const float alpha2 = alpha * alpha;
-    const float phi = 2.0f * PI_F * xi_x;
     const float cos_theta = sqrtf((1.0f - xi_y) / (1.0f + (alpha2 - 1.0f) * xi_y));
     const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-    const V3 H = mk3(cos_cr(phi) * sin_theta, sin_cr(phi) * sin_theta, cos_theta);
+    const V3 H = mk3(cs_phi.x * sin_theta, cs_phi.y * sin_theta, cos_theta);
     const V3 up = fabsf(N.z) < 0.999f ? mk3(0.0f, 0.0f, 1.0f) : mk3(1.0f, 0.0f, 0.0f);
     const V3 tangent = normalize3(cross3(up, N));
     const V3 bitangent = cross3(N, tangent);
@@ -93,7 +94,7 @@ __device__ __forceinline__ V3 directional_light(V3 viewer, V3 world_pos, V3 ligh
     const float cosLi = fmaxf(0.0f, dot3(N, Li));
     const float cosLh = fmaxf(0.0f, dot3(N, Lh));
     const float ct = fmaxf(0.0f, dot3(Lh, Lo));
-    const V3 F = F0 + (mk3(1.f, 1.f, 1.f) - F0) * pow_cr(1.0f - ct, 5.0f);
+    const V3 F = F0 + (mk3(1.f, 1.f, 1.f) - F0) * pow5_cr(1.0f - ct);  // pow(x, 5.0): gi_device.cuh
     const float alpha = pbr.x * pbr.x, alphaSq = alpha * alpha;
     const float denom = (cosLh * cosLh) * (alphaSq - 1.0f) + 1.0f;
     const float D = alphaSq / (PI_F * denom * denom);
@@ -193,11 +194,12 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
                     V3 best = mk3(0.f, 0.f, 0.f);
 #pragma unroll 1
                     for (int k = 0; k < 3; ++k) {
-                        const float xx = blue_noise_1d(S, i, j, P.bn_index, 1 + bl);
+                        const int bx = blue_noise_byte(S, i, j, P.bn_index, 1 + bl);
                         const float xy = blue_noise_1d(S, i, j, P.bn_index, 2 + bl);
                         bl += 2;
                         bl = bl % 128;
-                        const V3 smp = importance_sample_ggx(nmapped, R, xx * 0.9f, xy * 0.65f);
+                        const float2 cs = *reinterpret_cast<const float2*>(S.lut + LUT_TRIG_GGX + 2 * bx);
+                        const V3 smp = importance_sample_ggx(nmapped, R, cs, xy * 0.65f);
                         const float d = dot3(smp, nmapped);
                         if (d > nearest) { best = smp; nearest = d; }
                     }
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
                     const V3 albedo = tex_nearest(S.albedo_lod3, t_albedo, 64, tu, tv);
                     const V3 radiance = P.color_mixed * 0.6f;
                     const float4 pbr4 = tex_nearest_rgba(S.pbr_lod2, t_pbr, 128, tu, tv);
-                    const float AO = pow_cr(pbr4.w, 2.0f);
+                    const float AO = pbr4.w * pbr4.w;  // pow(x, 2.0f) pinned as the correctly rounded square = the fp32 product (x * x is exact in double)
                     const bool player_shadow = player_intersect(P.viewer, hit_pos + hn * 0.035f, P.stronger);
                     if (shadow_itr < max(spp / 4, 1)) {
                         if (!player_shadow) {  // GetShadowAt :1327-1346

@@ -77,7 +77,9 @@ struct SceneDev {
 constexpr int LUT_TRIG_GI = 0;         // [256] (cos, sin) of 2*PI * ((0.5 + v) / 256)
 constexpr int LUT_TRIG_CONE = 512;     // [256] (cos, sin) of ((v / 255) * PI) * 2
 constexpr int LUT_BASIS = 1024;        // [6] (uu.xyz, vv.xyz) per normal id 0..5 (GetNormalFromID order)
-constexpr int LUT_FLOATS = 1024 + 36;
+constexpr int LUT_TRIG_GGX = 1024 + 36;  // [256] (cos, sin) of 2*PI * (((0.5 + v) / 256) * 0.9): ImportanceSampleGGX's phi (ReflectionTraceFrag.glsl:345-365,
+                                         // Xi.x = blue-noise sample * 0.9, :629-633)
+constexpr int LUT_FLOATS = 1024 + 36 + 512;
 inline void fill_trace_lut(float* lut) {  // host; fp32 expressions as in the device code (host objects are built with -ffp-contract=off)
     for (int v = 0; v < 256; ++v) {
         const float r1 = (0.5f + (float)v) / 256.0f;               // blue_noise_1d
@@ -87,6 +89,10 @@ inline void fill_trace_lut(float* lut) {  // host; fp32 expressions as in the de
         const float phi = (((float)v / 255.0f) * 3.14159265359f) * 2.0f;  // xi_y * PI * 2
         lut[LUT_TRIG_CONE + 2 * v] = (float)cos((double)phi);
         lut[LUT_TRIG_CONE + 2 * v + 1] = (float)sin((double)phi);
+        const float xi_x = r1 * 0.9f;                               // importance_sample_ggx(..., xx * 0.9f, ...)
+        const float pg = (2.0f * 3.14159265359f) * xi_x;            // 2.0f * PI * Xi.x
+        lut[LUT_TRIG_GGX + 2 * v] = (float)cos((double)pg);
+        lut[LUT_TRIG_GGX + 2 * v + 1] = (float)sin((double)pg);
     }
     const float N[6][3] = {{0, 0, 1}, {0, 0, -1}, {0, 1, 0}, {0, -1, 0}, {-1, 0, 0}, {1, 0, 0}};
     for (int k = 0; k < 6; ++k) {

@@ -175,7 +175,7 @@ private:
 };
 
 // SetVerticalBlocks / GenerateWorld (Core/WorldGenerator.cpp:28-67, 69-121).  gen_type false = superflat.  For the plains
-// the per-column (height, biome) table comes from the reference's FastNoise (tests/golden/plains_columns.u8).
+// the per-column (height, biome) table comes from the reference's FastNoise (voxelpathtracer_b200/data/plains_columns.u8).
 inline void SetVerticalBlocks(World* world, int x, int z, int y_level, int biome) {
     for (int y = 0; y < y_level && y < WORLD_SIZE_Y; y++) {
         uint8_t id;

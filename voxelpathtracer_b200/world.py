@@ -156,7 +156,7 @@ def generate_superflat():
 
 def generate_plains(columns):
     """GenerateWorld(world, true) from the per-column (height, biome) table the reference's FastNoise produces
-    (tests/golden/plains_columns.u8, see tools/make_fixtures.py; WorldGenerator.cpp:85-107)."""
+    (voxelpathtracer_b200/data/plains_columns.u8, see tools/make_fixtures.py; WorldGenerator.cpp:85-107)."""
     cols = np.asarray(columns, dtype=np.uint8).reshape(WORLD_SIZE_X, WORLD_SIZE_Z, 2)
     w = World()
     v = w.zyx

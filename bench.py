@@ -436,7 +436,7 @@ def run_ours(args):
     n_frames = args.warmup + args.steps
     params = [frame_params(vx, camera, tables, f) for f in range(n_frames)]  # tiny host structs, one per frame index
     slots = frame.slots
-    M = P * slots * (2 if P * slots < 8 else 1)  # frame indices per cycle; step k -> pipe k % P, slot (k // P) % slots
+    M = P * slots * max(1, -(-16 // (P * slots)))  # >= 16 frame indices per cycle (a multiple of P * slots); step k -> pipe k % P, slot (k // P) % slots
 
     def eager_step(k, f):
         fr = frames[k % P]

@@ -614,6 +614,8 @@ VXPT_API int vxpt_reserve(vxpt_handle h, const VxCamera* cam, int max_gi_spp, si
 /* G-buffer material pass, default instantiation (no parallax, no lava id): 0 = every thread re-derives the surface UV of its two
  * quad partners (three ray set-ups per pixel), 1 (default) = the partners' UV arrive by warp shuffle (one ray set-up per pixel).  Same
  * operands, same planes (GPU test + emulated shuffles on the host); B200, 1080p: 0.0532 ms against 0.0649 ms (profiles/r02a_material_probe.json). */
+#define VXPT_OPT_REFLECTION_WAVEFRONT 8 /* reflection pass: 0 = one thread per pixel (the shader's loop as it stands), 1 = samples re-queued: reflection
+                                          rays traced per pixel, hits compacted and shaded by dense warps (default); identical planes */
 #define VXPT_OPT_MATERIAL_QUAD_SHUFFLE 7
 VXPT_API int vxpt_set_option(vxpt_handle h, int option, int value);
 

@@ -685,6 +685,36 @@ def test_cuda_outputs_equal_the_reference_shader_golden_vectors(renderer, worlds
     renderer.set_option(abi.OPT_GI_WAVEFRONT, 1)
 
 
+def test_reflection_wavefront_writes_the_per_pixel_kernels_bits(renderer, worlds, oracles, scene_tables):
+    """VXPT_OPT_REFLECTION_WAVEFRONT: the re-queued form (default) and the one-thread-per-pixel form give identical planes and identical
+    traversal counters — 1 sample, 3 samples with the checkerboard (pixels take 3 or 2), 5 samples (two shadow rays per pixel), a row slab."""
+    load(renderer, worlds["city"])
+    sun, moon, stronger, vis = scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], scene_tables["sun_visibility"]
+    fc = camera.FpsCamera(position=(100.0, 60.0, 100.0), pitch_deg=-10.0, yaw_deg=45.0)
+    W, H = 480, 270
+    cam = fc.vx_camera(W, H)
+    g = renderer.trace_primary(cam, vx.primary_params(350), renderer.alloc_gbuffer(W, H))
+    d = renderer.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=2), renderer.alloc_diffuse(W, H))
+    try:
+        for spp, checker, rows in ((1, False, None), (3, True, None), (5, False, (64, 200))):
+            rp = vx.reflection_params(sun, moon, stronger, fc.position, scene_tables["materials"]["grass_props"], spp=spp, rough=True, checkerboard=checker, frame=2,
+                                      halton=camera.taa_jitter_secondary(2))
+            c = cam if rows is None else fc.vx_camera(W, H, *rows)
+            outs, stats = [], []
+            for mode in (0, 1):
+                renderer.set_option(abi.OPT_REFLECTION_WAVEFRONT, mode)
+                renderer.reset_stats()
+                outs.append(renderer.trace_reflection(c, g, d, rp, renderer.alloc_reflection(W, H)))
+                st = renderer.stats()
+                stats.append((st["rays"], st["df_fetches"], st["vox_fetches"]))
+            rb, re = rows or (0, H)      # rows outside the slab are not written
+            for k in ("color", "hit_distance", "emissive_mask"):
+                assert np.array_equal(outs[0][k][rb:re], outs[1][k][rb:re], equal_nan=True), (spp, k)
+            assert stats[0] == stats[1], (spp, stats)
+    finally:
+        renderer.set_option(abi.OPT_REFLECTION_WAVEFRONT, 1)
+
+
 def test_cuda_reflections_equal_the_reference_shader_golden_vectors(renderer, worlds, oracles, scene_tables):
     """CUDA reflection planes == digests of the reference's ReflectionTraceFrag.glsl (compiled as C++) on the golden frames — BASELINE
     config 3's 1920x1080 among them — with u_Halton = GetTAAJitterSecondary(frame) (Pipeline.cpp:3032): G-buffer read at the jittered coordinate."""

@@ -23,6 +23,9 @@ if os.environ.get("VXPT_PROBE_EMULATED"):     # development check without a GPU:
     from host_shadow import hostemu
     from voxelpathtracer_b200 import abi as _abi
     _abi.LIB_PATH = hostemu.build()
+if os.environ.get("VXPT_LIB"):  # development: an experiment build of the library (build.py --out=...), never the product path
+    from voxelpathtracer_b200 import abi as _abi2
+    _abi2.LIB_PATH = os.path.join(os.path.dirname(_abi2.LIB_PATH), os.environ["VXPT_LIB"])
 import voxelpathtracer_b200 as vx  # noqa: E402
 from voxelpathtracer_b200 import assets, camera, denoise, world  # noqa: E402
 

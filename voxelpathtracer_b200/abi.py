@@ -21,6 +21,7 @@ MIP_CHAIN_TEXELS = sum((512 >> k) ** 2 for k in range(10))  # 349,525: levels 0.
 OK, E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 OPT_TRAVERSAL_LAYOUT, OPT_GI_WAVEFRONT, OPT_DF_ALGO, OPT_SCENE_REPLICAS, OPT_TIMING_EVENTS, OPT_TEXEL_FORMAT = 1, 2, 3, 4, 5, 6
 OPT_MATERIAL_QUAD_SHUFFLE = 7
+OPT_REFLECTION_WAVEFRONT = 8
 SHARED_HANDLE_BYTES = 64
 
 u8p = C.POINTER(C.c_uint8)

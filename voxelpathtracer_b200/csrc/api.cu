@@ -1644,6 +1644,10 @@ int vxpt_set_option(vxpt_handle c, int option, int value) {
             if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "wavefront must be 0 or 1");
             c->opt_wavefront = value;
             return VXPT_OK;
+        case VXPT_OPT_REFLECTION_WAVEFRONT:
+            if (value != 0 && value != 1) return fail(VXPT_E_INVALID, "reflection wavefront must be 0 or 1");
+            c->opt_refl_wavefront = value;
+            return VXPT_OK;
         case VXPT_OPT_SCENE_REPLICAS:
             if (value < 1 || value > 8) return fail(VXPT_E_INVALID, "replicas must be 1..8");
             c->opt_replicas = value;

@@ -164,6 +164,39 @@ __device__ __forceinline__ void calc_uv(V3 p, int axis, float& u, float& v) {
     else { u = fractf(p.x); v = fractf(p.y); }
 }
 
+#ifndef VXPT_HOST_SHADOW
+// one warp ballot + one atomic per warp; returns this lane's slot (valid where pred)
+__device__ __forceinline__ unsigned warp_push(unsigned* counter, bool pred) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0 && mask) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+// exclusive prefix over the 256 bins of a CTA's key histogram by warp 0 (8 bins per lane, then a warp scan of the lane sums);
+// hist[256] receives the total
+__device__ __forceinline__ void prefix_256(unsigned* hist, unsigned tid) {
+    if (tid < 32) {
+        unsigned c[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c[k] = hist[tid * 8 + k]; sum += c[k]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= (unsigned)d) incl += t;
+        }
+        unsigned base = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hist[tid * 8 + k] = base; base += c[k]; }
+        if (tid == 31) hist[256] = incl;
+    }
+}
+// sort key of a hemisphere ray: small = grazing = long-lived
+__device__ __forceinline__ unsigned life_key(V3 d) { return (unsigned)min((int)(fabsf(d.y) * 255.0f), 255); }
+#endif
+
 // IrridianceToSH :766-784
 __device__ __forceinline__ void irradiance_to_sh(V3 rad, V3 dir, float out[6]) {
     const float Co = rad.x - rad.z;

@@ -3,6 +3,7 @@
 // off; lava UV distortion / flicker (functions of the wall clock) never apply.  One thread per pixel; per sample one
 // GGX-sampled reflection ray (cap u_ReflectionTraceLength) and, for the first max(SPP/4,1) hits, a sun shadow ray (cap 150).
 // Compiled with -fmad=false; sin/cos/pow/log are the pinned correctly rounded fp32 values (double evaluation).
+#include <algorithm>
 #include <cmath>
 
 #include "gi_device.cuh"
@@ -116,6 +117,181 @@ __device__ __forceinline__ float4 tex_nearest_rgba(const float4* base, int layer
     return __ldg(base + ((size_t)max(layer, 0) * n + j) * n + i);  // negative layer -> 0, as tex_nearest (GL clamps the array layer)
 }
 
+// ---- the pass, cut into the pieces both kernel shapes are made of (same expressions, same order) ---------------------------------------
+// what the samples of a pixel share: main() :754-818
+struct ReflPixel {
+    V3 pos;            // biased world position the rays start from
+    V3 I;              // incident direction
+    V3 nmapped;        // u_GBufferNormals (or the face normal)
+    V3 base_indirect;  // SHToIrradianceA of the pixel's GI planes
+    float roughness_at, metalness_at;
+    int spp;
+};
+// false: the (jittered) G-buffer texel is the sky
+__device__ __forceinline__ bool refl_pixel_setup(const SceneDev& S, const CameraDev& cam, const ReflDev& P, const GBufferDev& g, const ReflInDev& in,
+                                                 int i, int j, size_t px, ReflPixel& q) {
+    const float u = ((float)i + 0.5f) / (float)cam.width, v = ((float)j + 0.5f) / (float)cam.height;
+    const float ju = u + (P.hx / (float)cam.width) * 1.0f;  // u_TemporalFilterReflections = true
+    const float jv = v + (P.hy / (float)cam.height) * 1.0f;
+    // texture(u_PositionTexture, JitteredUV) / SampleNormalFromTex(u_InitialTraceNormalTexture, JitteredUV) :766,777 — attachment 0 of
+    // the primary FBO (distance) is GL_LINEAR, attachment 1 (normal id) GL_NEAREST, both GL_REPEAT (Core/Pipeline.cpp:1094,
+    // Core/GLClasses/Framebuffer.cpp:64-67).  OpenGL 4.3 8.14.2: x = u * w - 0.5, i0 = floor(x) mod w, weights a * (1 - f) + b * f, x first.
+    // The rows read are those of the jittered coordinate: up to ceil(|halton.y|) + 1 rows beyond the slab (vxpt.h, VxReflectionParams).
+    float dist;
+    int nid;
+    {
+        const int W = cam.width, H = cam.height;
+        const float x = ju * (float)W - 0.5f, y = jv * (float)H - 0.5f;
+        const float fx0 = floorf(x), fy0 = floorf(y);
+        const float fx = x - fx0, fy = y - fy0;
+        const int i0 = wrap_repeat((int)fx0, W), i1 = wrap_repeat((int)fx0 + 1, W), j0 = wrap_repeat((int)fy0, H), j1 = wrap_repeat((int)fy0 + 1, H);
+        const float a = load_f1(g.t, (size_t)j0 * W + i0, g.fmt) * (1.0f - fx) + load_f1(g.t, (size_t)j0 * W + i1, g.fmt) * fx;
+        const float b = load_f1(g.t, (size_t)j1 * W + i0, g.fmt) * (1.0f - fx) + load_f1(g.t, (size_t)j1 * W + i1, g.fmt) * fx;
+        dist = a * (1.0f - fy) + b * fy;
+        const int ni = wrap_repeat((int)floorf(ju * (float)W), W), nj = wrap_repeat((int)floorf(jv * (float)H), H);
+        nid = g.normal_id[(size_t)nj * W + ni];
+    }
+    if (dist < 0.0f) return false;
+    int spp = min(max(P.spp, 1), 16);
+    if (P.checkerboard) {
+        const bool checker = ((int)(((float)i + 0.5f) + ((float)j + 0.5f))) % 2 == (P.frame % 2);
+        spp = (int)mixf((float)P.spp, (float)((P.spp + P.spp % 2) / 2), checker ? 1.0f : 0.0f);
+    }
+    q.spp = min(max(spp, 1), 16);
+    V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, ju, jv)) * dist;
+    const V3 face_n = normal_from_id(nid, 1.0f);
+    if (in.g_pbr) {
+        const float4 m = in.g_pbr[px];
+        q.roughness_at = m.x; q.metalness_at = m.y;
+    } else {  // stand-in for the G-buffer material pass: level-2 PBR texel of the block at the primary hit
+        V3 tg, bt;
+        float tu, tv;
+        calc_vectors(pos, nid, tg, bt, tu, tv);
+        tv = 1.0f - tv;
+        const float4 m = tex_nearest_rgba(S.pbr_lod2, S.materials[256 + min((int)g.block_id[px], 127)], 128, tu, tv);
+        q.roughness_at = m.x; q.metalness_at = m.y;
+    }
+    q.I = normalize3(pos - P.viewer);
+    q.pos = pos + face_n * 0.035f;
+    q.nmapped = in.g_normal ? mk3(in.g_normal[3 * px], in.g_normal[3 * px + 1], in.g_normal[3 * px + 2]) : face_n;
+    {  // SHToIrradianceA :469-478
+        const float4 sh = load_f4(in.sh, px, in.fmt);
+        const float2 cg = load_f2(in.cocg, px, in.fmt);
+        const float Y = fmaxf(0.0f, 3.544905f * sh.w);
+        const float sc = (Y * 0.282095f) / (sh.w + 1e-6f);
+        const float c0 = cg.x * sc, c1 = cg.y * sc;
+        const float T = Y - c1 * 0.5f, G = c1 + T, B = T - c0 * 0.5f, R = B + c0;
+        q.base_indirect = mk3(fmaxf(R, 0.0f), fmaxf(G, 0.0f), fmaxf(B, 0.0f));
+    }
+    return true;
+}
+// direction of one sample (:841-848): best of three GGX-sampled normals (GetReflectionDirection :621-644), reflected; bl = the blue-noise
+// dimension counter, which every sample advances by 6 (mod 128) when reflections are rough
+__device__ __forceinline__ V3 refl_direction(const SceneDev& S, const ReflDev& P, const ReflPixel& q, int i, int j, int& bl) {
+    V3 rn = q.nmapped;
+    if (P.rough) {
+        const float R = fmaxf(clampf(q.roughness_at * P.rough_bias, 0.01f, 1.0f), 0.05f);
+        float nearest = -100.0f;
+        V3 best = mk3(0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            const int bx = blue_noise_byte(S, i, j, P.bn_index, 1 + bl);
+            const float xy = blue_noise_1d(S, i, j, P.bn_index, 2 + bl);
+            bl += 2;
+            bl = bl % 128;
+            const float2 cs = *reinterpret_cast<const float2*>(S.lut + LUT_TRIG_GGX + 2 * bx);
+            const V3 smp = importance_sample_ggx(q.nmapped, R, cs, xy * 0.65f);
+            const float d = dot3(smp, q.nmapped);
+            if (d > nearest) { best = smp; nearest = d; }
+        }
+        rn = best;
+    }
+    return q.I - rn * (2.0f * dot3(rn, q.I));  // reflect(I, N)
+}
+// per-pixel running sums of main()'s sample loop (:836-1012)
+struct ReflAcc {
+    float t0, t1, t2, t3, avg_hit, meaningful, mask, computed_shadow;
+    int shadow_itr, total_hits;
+};
+__device__ __forceinline__ ReflAcc refl_acc_init() { return ReflAcc{0.f, 0.f, 0.f, 0.f, 0.001f, 0.0f, 0.0f, 0.0f, 0, 0}; }
+// a sample whose ray left the scene (:1003-1010)
+__device__ __forceinline__ void refl_add_miss(ReflAcc& A, const SceneDev& S, float metalness_at, V3 R) {
+    const V3 atmo = sky_sample(S, normalize3(R));
+    const float m = mixf(1.0f, 1.175f, metalness_at > 0.05f ? 1.0f : 0.0f);
+    A.t0 += atmo.x * m; A.t1 += atmo.y * m; A.t2 += atmo.z * m; A.t3 += 1.0f;
+    A.total_hits++;
+}
+// a sample whose ray hit (:861-1002): shading of the hit, sun shadow ray for the first max(spp / 4, 1) hits of the pixel
+template <int LAYOUT>
+__device__ __forceinline__ void refl_add_hit(ReflAcc& A, const SceneDev& S, const ReflDev& P, V3 pos, V3 base_indirect, int spp, V3 R, float T,
+                                             const TraceHit& h, Counters& cnt) {
+    const V3 hit_pos = pos + (R * T);
+    const int hnid = normal_id_of(h);
+    const V3 hn = hit_normal(h);
+    V3 tg, bt;
+    float tu, tv;
+    calc_vectors(hit_pos, hnid, tg, bt, tu, tv);
+    tv = 1.0f - tv;
+    const int ref = min(max(h.block, 0), 127);
+    int t_albedo = S.materials[ref], t_normal = S.materials[128 + ref], t_pbr = S.materials[256 + ref], t_emis = S.materials[384 + ref];
+    if (ref == P.grass[0]) {  // :896-918
+        if (hnid == 4 || hnid == 5 || hnid == 0 || hnid == 1) { t_albedo = P.grass[4]; t_normal = P.grass[5]; t_pbr = P.grass[6]; }
+        else if (hnid == 2) { t_albedo = P.grass[1]; t_normal = P.grass[2]; t_pbr = P.grass[3]; }
+        else { t_albedo = P.grass[7]; t_normal = P.grass[8]; t_pbr = P.grass[9]; }
+    }
+    V3 ambient = base_indirect;
+    const V3 albedo = tex_nearest(S.albedo_lod3, t_albedo, 64, tu, tv);
+    const V3 radiance = P.color_mixed * 0.6f;
+    const float4 pbr4 = tex_nearest_rgba(S.pbr_lod2, t_pbr, 128, tu, tv);
+    const float AO = pbr4.w * pbr4.w;  // pow(x, 2.0f) pinned as the correctly rounded square = the fp32 product (x * x is exact in double)
+    const bool player_shadow = player_intersect(P.viewer, hit_pos + hn * 0.035f, P.stronger);
+    if (A.shadow_itr < max(spp / 4, 1)) {
+        if (!player_shadow) {  // GetShadowAt :1327-1346
+            const V3 so = hit_pos + hn * 0.055f;
+            if (player_intersect(P.viewer, so, P.stronger)) A.computed_shadow = 1.0f;
+            else {
+                TraceHit hs;
+                const float Ts = traverse_df<LAYOUT>(S, so, P.stronger, 150, hs, cnt);
+                A.computed_shadow = Ts > 0.0f ? 1.0f : 0.0f;
+            }
+        } else A.computed_shadow = 1.0f;
+        A.shadow_itr = A.shadow_itr + 1;
+    }
+    ambient = ((ambient * 1.0f) * clampf(AO, 0.1f, 1.0f)) * albedo;
+    const V3 nm = tex_nearest(S.normal_lod3, t_normal, 64, tu, tv) * 2.0f - mk3(1.f, 1.f, 1.f);
+    const V3 nmap = (tg * nm.x + bt * nm.y) + hn * nm.z;  // TBN * n
+    V3 direct = ambient + directional_light(P.viewer, hit_pos, P.stronger, radiance, albedo, nmap, mk3(pbr4.x, pbr4.y, pbr4.z), A.computed_shadow);
+    if ((float)t_emis > -0.5f) {
+        const int ei = ((int)floorf(tu * 128.0f)) & 127, ej = ((int)floorf(tv * 128.0f)) & 127;
+        float e = S.emissive_lod2[((size_t)t_emis * 128 + ej) * 128 + ei];
+        if (e > 0.1f) {
+            const float lbx = 0.02501f, lby = 0.03001f;
+            e *= (tu > lbx && tu < 1.0f - lbx && tv > lby && tv < 1.0f - lby) ? 1.0f : 0.0f;
+            direct = albedo * fmaxf((e * 19.0f) * 1.0f, 2.0f);
+            A.mask = 1.0f;
+        }
+    }
+    A.t0 += direct.x; A.t1 += direct.y; A.t2 += direct.z; A.t3 += 1.0f;
+    A.avg_hit += T;
+    A.meaningful += 1.0f;
+    A.total_hits++;
+}
+// :1014-1037
+__device__ __forceinline__ void refl_store(const ReflOutDev& out, size_t px, ReflAcc A) {
+    A.avg_hit /= fmaxf(A.meaningful, 0.01f);
+    const float th = (float)A.total_hits;
+    A.t0 /= th; A.t1 /= th; A.t2 /= th; A.t3 /= th;
+    if (out.color) store_f4(out.color, px, clampf(A.t0, 0.0000001f, 100.0f), clampf(A.t1, 0.0000001f, 100.0f), clampf(A.t2, 0.0000001f, 100.0f), clampf(A.t3, 0.0000001f, 100.0f), out.fmt);
+    if (out.hit_distance) store_f1(out.hit_distance, px, clampf(A.meaningful > 0.01f ? A.avg_hit : -1.0f, -10.0f, 200.0f), out.fmt);
+    if (out.emissive_mask) out.emissive_mask[px] = clampf(A.mask, 0.0f, 1.0f) > 0.5f ? 1 : 0;
+}
+__device__ __forceinline__ void refl_store_sky(const ReflOutDev& out, size_t px) {  // :768-774
+    if (out.color) store_f4(out.color, px, 0.f, 0.f, 0.f, 0.f, out.fmt);
+    if (out.hit_distance) store_f1(out.hit_distance, px, -1.0f, out.fmt);
+    if (out.emissive_mask) out.emissive_mask[px] = 0;
+}
+
+// ---- shape 0: one thread per pixel, the shader's loop as it stands (cross-check; also what tests/host_shadow compiles for the CPU) -----
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ ReflDev P,
                                                          const GBufferDev g, const ReflInDev in, const ReflOutDev out) {
@@ -124,160 +300,175 @@ __global__ void __launch_bounds__(256) reflection_kernel(const SceneDev S, const
     Counters cnt = {0u, 0u, 0u};
     if (active) {
         const size_t px = (size_t)prow * cam.width + i;
-        float4 o_color = make_float4(0.f, 0.f, 0.f, 0.f);
-        float o_hit = -1.0f;
-        uint8_t o_mask = 0;
-        const float u = ((float)i + 0.5f) / (float)cam.width, v = ((float)j + 0.5f) / (float)cam.height;
-        const float ju = u + (P.hx / (float)cam.width) * 1.0f;  // u_TemporalFilterReflections = true
-        const float jv = v + (P.hy / (float)cam.height) * 1.0f;
-        // texture(u_PositionTexture, JitteredUV) / SampleNormalFromTex(u_InitialTraceNormalTexture, JitteredUV) :766,777 — attachment 0 of
-        // the primary FBO (distance) is GL_LINEAR, attachment 1 (normal id) GL_NEAREST, both GL_REPEAT (Core/Pipeline.cpp:1094,
-        // Core/GLClasses/Framebuffer.cpp:64-67).  OpenGL 4.3 8.14.2: x = u * w - 0.5, i0 = floor(x) mod w, weights a * (1 - f) + b * f, x first.
-        // The rows read are those of the jittered coordinate: up to ceil(|halton.y|) + 1 rows beyond the slab (vxpt.h, VxReflectionParams).
-        float dist;
-        int nid;
-        {
-            const int W = cam.width, H = cam.height;
-            const float x = ju * (float)W - 0.5f, y = jv * (float)H - 0.5f;
-            const float fx0 = floorf(x), fy0 = floorf(y);
-            const float fx = x - fx0, fy = y - fy0;
-            const int i0 = wrap_repeat((int)fx0, W), i1 = wrap_repeat((int)fx0 + 1, W), j0 = wrap_repeat((int)fy0, H), j1 = wrap_repeat((int)fy0 + 1, H);
-            const float a = load_f1(g.t, (size_t)j0 * W + i0, g.fmt) * (1.0f - fx) + load_f1(g.t, (size_t)j0 * W + i1, g.fmt) * fx;
-            const float b = load_f1(g.t, (size_t)j1 * W + i0, g.fmt) * (1.0f - fx) + load_f1(g.t, (size_t)j1 * W + i1, g.fmt) * fx;
-            dist = a * (1.0f - fy) + b * fy;
-            const int ni = wrap_repeat((int)floorf(ju * (float)W), W), nj = wrap_repeat((int)floorf(jv * (float)H), H);
-            nid = g.normal_id[(size_t)nj * W + ni];
-        }
-        if (!(dist < 0.0f)) {
-            int spp = min(max(P.spp, 1), 16);
-            if (P.checkerboard) {
-                const bool checker = ((int)(((float)i + 0.5f) + ((float)j + 0.5f))) % 2 == (P.frame % 2);
-                spp = (int)mixf((float)P.spp, (float)((P.spp + P.spp % 2) / 2), checker ? 1.0f : 0.0f);
-            }
-            spp = min(max(spp, 1), 16);
-            V3 pos = ray_origin(cam) + normalize3(ray_direction_at(cam, ju, jv)) * dist;
-            const V3 face_n = normal_from_id(nid, 1.0f);
-            float roughness_at, metalness_at;
-            if (in.g_pbr) {
-                const float4 m = in.g_pbr[px];
-                roughness_at = m.x; metalness_at = m.y;
-            } else {  // stand-in for the G-buffer material pass: level-2 PBR texel of the block at the primary hit
-                V3 tg, bt;
-                float tu, tv;
-                calc_vectors(pos, nid, tg, bt, tu, tv);
-                tv = 1.0f - tv;
-                const float4 m = tex_nearest_rgba(S.pbr_lod2, S.materials[256 + min((int)g.block_id[px], 127)], 128, tu, tv);
-                roughness_at = m.x; metalness_at = m.y;
-            }
-            const V3 I = normalize3(pos - P.viewer);
-            pos = pos + face_n * 0.035f;
-            const V3 nmapped = in.g_normal ? mk3(in.g_normal[3 * px], in.g_normal[3 * px + 1], in.g_normal[3 * px + 2]) : face_n;
-            V3 base_indirect;
-            {  // SHToIrradianceA :469-478
-                const float4 sh = load_f4(in.sh, px, in.fmt);
-                const float2 cg = load_f2(in.cocg, px, in.fmt);
-                const float Y = fmaxf(0.0f, 3.544905f * sh.w);
-                const float sc = (Y * 0.282095f) / (sh.w + 1e-6f);
-                const float c0 = cg.x * sc, c1 = cg.y * sc;
-                const float T = Y - c1 * 0.5f, G = c1 + T, B = T - c0 * 0.5f, R = B + c0;
-                base_indirect = mk3(fmaxf(R, 0.0f), fmaxf(G, 0.0f), fmaxf(B, 0.0f));
-            }
-            float computed_shadow = 0.0f;
-            int shadow_itr = 0, bl = 0, total_hits = 0;
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, avg_hit = 0.001f, meaningful = 0.0f, mask = 0.0f;
+        ReflPixel q;
+        if (!refl_pixel_setup(S, cam, P, g, in, i, j, px, q)) {
+            refl_store_sky(out, px);
+        } else {
+            ReflAcc A = refl_acc_init();
+            int bl = 0;
 #pragma unroll 1
-            for (int s = 0; s < spp; ++s) {
-                V3 rn = nmapped;
-                if (P.rough) {  // GetReflectionDirection :621-644
-                    const float R = fmaxf(clampf(roughness_at * P.rough_bias, 0.01f, 1.0f), 0.05f);
-                    float nearest = -100.0f;
-                    V3 best = mk3(0.f, 0.f, 0.f);
-#pragma unroll 1
-                    for (int k = 0; k < 3; ++k) {
-                        const int bx = blue_noise_byte(S, i, j, P.bn_index, 1 + bl);
-                        const float xy = blue_noise_1d(S, i, j, P.bn_index, 2 + bl);
-                        bl += 2;
-                        bl = bl % 128;
-                        const float2 cs = *reinterpret_cast<const float2*>(S.lut + LUT_TRIG_GGX + 2 * bx);
-                        const V3 smp = importance_sample_ggx(nmapped, R, cs, xy * 0.65f);
-                        const float d = dot3(smp, nmapped);
-                        if (d > nearest) { best = smp; nearest = d; }
-                    }
-                    rn = best;
-                }
-                const V3 R = I - rn * (2.0f * dot3(rn, I));  // reflect(I, N)
+            for (int s = 0; s < q.spp; ++s) {
+                const V3 R = refl_direction(S, P, q, i, j, bl);
                 TraceHit h;
-                const float T = traverse_df<LAYOUT>(S, pos, R, P.trace_length, h, cnt);
-                const V3 hit_pos = pos + (R * T);
-                if (T > 0.0f) {
-                    const int hnid = normal_id_of(h);
-                    const V3 hn = hit_normal(h);
-                    V3 tg, bt;
-                    float tu, tv;
-                    calc_vectors(hit_pos, hnid, tg, bt, tu, tv);
-                    tv = 1.0f - tv;
-                    const int ref = min(max(h.block, 0), 127);
-                    int t_albedo = S.materials[ref], t_normal = S.materials[128 + ref], t_pbr = S.materials[256 + ref], t_emis = S.materials[384 + ref];
-                    if (ref == P.grass[0]) {  // :896-918
-                        if (hnid == 4 || hnid == 5 || hnid == 0 || hnid == 1) { t_albedo = P.grass[4]; t_normal = P.grass[5]; t_pbr = P.grass[6]; }
-                        else if (hnid == 2) { t_albedo = P.grass[1]; t_normal = P.grass[2]; t_pbr = P.grass[3]; }
-                        else { t_albedo = P.grass[7]; t_normal = P.grass[8]; t_pbr = P.grass[9]; }
-                    }
-                    V3 ambient = base_indirect;
-                    const V3 albedo = tex_nearest(S.albedo_lod3, t_albedo, 64, tu, tv);
-                    const V3 radiance = P.color_mixed * 0.6f;
-                    const float4 pbr4 = tex_nearest_rgba(S.pbr_lod2, t_pbr, 128, tu, tv);
-                    const float AO = pbr4.w * pbr4.w;  // pow(x, 2.0f) pinned as the correctly rounded square = the fp32 product (x * x is exact in double)
-                    const bool player_shadow = player_intersect(P.viewer, hit_pos + hn * 0.035f, P.stronger);
-                    if (shadow_itr < max(spp / 4, 1)) {
-                        if (!player_shadow) {  // GetShadowAt :1327-1346
-                            const V3 so = hit_pos + hn * 0.055f;
-                            if (player_intersect(P.viewer, so, P.stronger)) computed_shadow = 1.0f;
-                            else {
-                                TraceHit hs;
-                                const float Ts = traverse_df<LAYOUT>(S, so, P.stronger, 150, hs, cnt);
-                                computed_shadow = Ts > 0.0f ? 1.0f : 0.0f;
-                            }
-                        } else computed_shadow = 1.0f;
-                        shadow_itr = shadow_itr + 1;
-                    }
-                    ambient = ((ambient * 1.0f) * clampf(AO, 0.1f, 1.0f)) * albedo;
-                    const V3 nm = tex_nearest(S.normal_lod3, t_normal, 64, tu, tv) * 2.0f - mk3(1.f, 1.f, 1.f);
-                    const V3 nmap = (tg * nm.x + bt * nm.y) + hn * nm.z;  // TBN * n
-                    V3 direct = ambient + directional_light(P.viewer, hit_pos, P.stronger, radiance, albedo, nmap, mk3(pbr4.x, pbr4.y, pbr4.z), computed_shadow);
-                    if ((float)t_emis > -0.5f) {
-                        const int ei = ((int)floorf(tu * 128.0f)) & 127, ej = ((int)floorf(tv * 128.0f)) & 127;
-                        float e = S.emissive_lod2[((size_t)t_emis * 128 + ej) * 128 + ei];
-                        if (e > 0.1f) {
-                            const float lbx = 0.02501f, lby = 0.03001f;
-                            e *= (tu > lbx && tu < 1.0f - lbx && tv > lby && tv < 1.0f - lby) ? 1.0f : 0.0f;
-                            direct = albedo * fmaxf((e * 19.0f) * 1.0f, 2.0f);
-                            mask = 1.0f;
-                        }
-                    }
-                    t0 += direct.x; t1 += direct.y; t2 += direct.z; t3 += 1.0f;
-                    avg_hit += T;
-                    meaningful += 1.0f;
-                } else {
-                    const V3 atmo = sky_sample(S, normalize3(R));
-                    const float m = mixf(1.0f, 1.175f, metalness_at > 0.05f ? 1.0f : 0.0f);
-                    t0 += atmo.x * m; t1 += atmo.y * m; t2 += atmo.z * m; t3 += 1.0f;
-                }
-                total_hits++;
+                const float T = traverse_df<LAYOUT>(S, q.pos, R, P.trace_length, h, cnt);
+                if (T > 0.0f) refl_add_hit<LAYOUT>(A, S, P, q.pos, q.base_indirect, q.spp, R, T, h, cnt);
+                else refl_add_miss(A, S, q.metalness_at, R);
             }
-            avg_hit /= fmaxf(meaningful, 0.01f);
-            const float th = (float)total_hits;
-            t0 /= th; t1 /= th; t2 /= th; t3 /= th;
-            o_color = make_float4(clampf(t0, 0.0000001f, 100.0f), clampf(t1, 0.0000001f, 100.0f), clampf(t2, 0.0000001f, 100.0f), clampf(t3, 0.0000001f, 100.0f));
-            o_hit = clampf(meaningful > 0.01f ? avg_hit : -1.0f, -10.0f, 200.0f);
-            o_mask = clampf(mask, 0.0f, 1.0f) > 0.5f ? 1 : 0;
+            refl_store(out, px, A);
         }
-        if (out.color) store_f4(out.color, px, o_color.x, o_color.y, o_color.z, o_color.w, out.fmt);
-        if (out.hit_distance) store_f1(out.hit_distance, px, o_hit, out.fmt);
-        if (out.emissive_mask) out.emissive_mask[px] = o_mask;
     }
     flush_counters(S, cnt);
 }
+
+#ifndef VXPT_HOST_SHADOW
+// ---- shape 1 (default): the samples re-queued, as in the GI pass (trace_gi.cu) ---------------------------------------------------------
+// r02g, one thread per pixel at 1080p / 1 spp on plains: 0.75 ms, 14.6 of 32 lanes per instruction, 122 registers — three quarters of the
+// reflection rays of open terrain leave the scene after a few iterations while the lanes that hit drag their warp through four texture
+// fetches, two capsule tests, a Cook-Torrance term and a 150-iteration shadow ray.  Here, per sample s (launch after launch, so a pixel's
+// sums grow in the shader's order and the planes are bit-identical to shape 0's):
+//   refl_gen_trace  one thread per pixel: set-up, the sample's direction, the reflection ray; a miss is added on the spot (sky), a hit is
+//                   compacted into a queue (one warp ballot + one atomicAdd per warp) — traversal registers only
+//   refl_shade      one thread per queued hit, dense warps: the hit's shading and its sun shadow ray
+//   refl_finalize   only when some pixel takes several samples: the pixel's sums -> planes
+// With one sample per pixel (SPP1) the sums never leave registers: whichever kernel ends the pixel's only sample writes its planes.
+struct ReflState {  // 48 B per pixel between the launches of a multi-sample pass
+    float4 t;       // colour sums, alpha sum
+    float4 m;       // avg_hit, meaningful, mask, computed_shadow
+    int4 k;         // shadow_itr, total_hits, spp (0 = sky), -
+};
+__device__ __forceinline__ ReflAcc refl_state_load(const ReflState& st) {
+    return ReflAcc{st.t.x, st.t.y, st.t.z, st.t.w, st.m.x, st.m.y, st.m.z, st.m.w, st.k.x, st.k.y};
+}
+__device__ __forceinline__ void refl_state_store(ReflState& st, const ReflAcc& A, int spp) {
+    st.t = make_float4(A.t0, A.t1, A.t2, A.t3);
+    st.m = make_float4(A.avg_hit, A.meaningful, A.mask, A.computed_shadow);
+    st.k = make_int4(A.shadow_itr, A.total_hits, spp, 0);
+}
+
+// The rays of a CTA are SORTED before they are traced, as the first-bounce GI rays are (gi_gen_trace0): a 256-thread CTA sets up the pixels
+// of RPT 32x8 tiles, files their rays under |R.y| (steep reflections off the ground leave the scene at once, grazing ones creep along it) by
+// a counting sort in shared memory, and its warps claim groups of 32 rays, longest-lived first.  Sky pixels produce no ray, so they cost
+// their set-up only (r02n, unsorted, one thread per pixel: 15.5 of 32 lanes per instruction, a third of the pixels of the bench frame sky).
+template <int LAYOUT, bool SPP1, int RPT>
+__global__ void __launch_bounds__(256) refl_gen_trace(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ ReflDev P,
+                                                      const GBufferDev g, const ReflInDev in, const ReflOutDev out, ReflState* __restrict__ state,
+                                                      float4* __restrict__ queue, unsigned* __restrict__ queue_count, const int sample) {
+    __shared__ float4 s_a[256 * RPT];            // ray origin, pixel index (bits)
+    __shared__ float4 s_b[256 * RPT];            // ray direction, (metalness > 0.05) | spp << 1 (bits)
+    __shared__ unsigned s_hist[258];             // 256 bins, [256] = ray count, [257] = next group
+    __shared__ unsigned short s_order[256 * RPT];
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    Counters cnt = {0u, 0u, 0u};
+    s_hist[tid] = 0u;
+    if (tid < 2) s_hist[256 + tid] = 0u;
+    __syncthreads();
+    unsigned kr[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        kr[r] = ~0u;
+        const int warp = tid >> 5;
+        const int i = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+        const int prow = cam.row_begin + (blockIdx.y * RPT + r) * 8 + (warp >> 2) * 4 + (lane >> 3);
+        if (i >= cam.width || prow >= cam.row_end) continue;
+        const int j = image_row(cam, prow);
+        const size_t px = (size_t)prow * cam.width + i;
+        ReflPixel q;
+        if (!refl_pixel_setup(S, cam, P, g, in, i, j, px, q)) {
+            if (sample == 0) {
+                refl_store_sky(out, px);
+                if (!SPP1) state[px].k = make_int4(0, 0, 0, 0);
+            }
+        } else if (sample < q.spp) {
+            int bl = P.rough ? (6 * sample) % 128 : 0;
+            const V3 R = refl_direction(S, P, q, i, j, bl);
+            const unsigned key = life_key(R);
+            kr[r] = (key << 16) | atomicAdd(&s_hist[key], 1u);
+            s_a[r * 256 + tid] = make_float4(q.pos.x, q.pos.y, q.pos.z, __int_as_float((int)px));
+            s_b[r * 256 + tid] = make_float4(R.x, R.y, R.z, __int_as_float((q.metalness_at > 0.05f ? 1 : 0) | (q.spp << 1)));
+        }
+    }
+    __syncthreads();
+    prefix_256(s_hist, tid);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+        if (kr[r] != ~0u) s_order[s_hist[kr[r] >> 16] + (kr[r] & 0xFFFFu)] = (unsigned short)(r * 256 + tid);
+    __syncthreads();
+    const unsigned n_rays = s_hist[256], n_groups = (n_rays + 31u) / 32u;
+    while (true) {
+        unsigned grp = 0;
+        if (lane == 0) grp = atomicAdd(&s_hist[257], 1u);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if (grp >= n_groups) break;
+        const unsigned idx = grp * 32u + lane;
+        bool push = false;
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra, rc = ra;
+        if (idx < n_rays) {
+            const unsigned slot_ab = s_order[idx];
+            const float4 a = s_a[slot_ab], b = s_b[slot_ab];
+            const V3 pos = mk3(a.x, a.y, a.z), R = mk3(b.x, b.y, b.z);
+            const size_t px = (size_t)(unsigned)__float_as_int(a.w);
+            const int meta = __float_as_int(b.w), spp = meta >> 1;
+            TraceHit h;
+            const float T = traverse_df<LAYOUT>(S, pos, R, P.trace_length, h, cnt);
+            ReflAcc A = refl_acc_init();
+            if (!SPP1 && sample > 0) A = refl_state_load(state[px]);
+            if (T > 0.0f) {
+                push = true;
+                ra = make_float4(pos.x, pos.y, pos.z, T);
+                rb = make_float4(R.x, R.y, R.z, a.w);
+                rc = make_float4(__int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8)), __int_as_float(spp), 0.f, 0.f);
+                if (!SPP1 && sample == 0) refl_state_store(state[px], A, spp);  // the sums start here; refl_shade adds this sample
+            } else {
+                refl_add_miss(A, S, (meta & 1) ? 1.0f : 0.0f, R);  // only metalness > 0.05 matters (:1005)
+                if (SPP1) refl_store(out, px, A);
+                else refl_state_store(state[px], A, spp);
+            }
+        }
+        const unsigned slot = warp_push(queue_count, push);
+        if (push) { queue[3 * (size_t)slot] = ra; queue[3 * (size_t)slot + 1] = rb; queue[3 * (size_t)slot + 2] = rc; }
+    }
+    flush_counters(S, cnt);
+}
+
+template <int LAYOUT, bool SPP1>
+__global__ void __launch_bounds__(256) refl_shade(const SceneDev S, const __grid_constant__ ReflDev P, const ReflInDev in, const ReflOutDev out,
+                                                  ReflState* __restrict__ state, const float4* __restrict__ queue, const unsigned* __restrict__ queue_count) {
+    const unsigned count = queue_count[0];
+    Counters cnt = {0u, 0u, 0u};
+    for (unsigned rec = blockIdx.x * 256u + threadIdx.x; rec < ((count + 31u) & ~31u); rec += gridDim.x * 256u) {
+        if (rec >= count) continue;
+        const float4 ra = queue[3 * (size_t)rec], rb = queue[3 * (size_t)rec + 1], rc = queue[3 * (size_t)rec + 2];
+        const size_t px = (size_t)(unsigned)__float_as_int(rb.w);
+        const int code = __float_as_int(rc.x), spp = __float_as_int(rc.y);
+        TraceHit h;
+        h.min_idx = code & 3; h.sgn = ((code >> 2) & 3) - 1; h.block = (code >> 8) & 255;
+        V3 base_indirect;
+        {  // SHToIrradianceA :469-478 of the pixel's GI planes (as in refl_pixel_setup)
+            const float4 sh = load_f4(in.sh, px, in.fmt);
+            const float2 cg = load_f2(in.cocg, px, in.fmt);
+            const float Y = fmaxf(0.0f, 3.544905f * sh.w);
+            const float sc = (Y * 0.282095f) / (sh.w + 1e-6f);
+            const float c0 = cg.x * sc, c1 = cg.y * sc;
+            const float T = Y - c1 * 0.5f, G = c1 + T, B = T - c0 * 0.5f, R = B + c0;
+            base_indirect = mk3(fmaxf(R, 0.0f), fmaxf(G, 0.0f), fmaxf(B, 0.0f));
+        }
+        ReflAcc A = SPP1 ? refl_acc_init() : refl_state_load(state[px]);
+        refl_add_hit<LAYOUT>(A, S, P, mk3(ra.x, ra.y, ra.z), base_indirect, spp, mk3(rb.x, rb.y, rb.z), ra.w, h, cnt);
+        if (SPP1) refl_store(out, px, A);
+        else refl_state_store(state[px], A, spp);
+    }
+    flush_counters(S, cnt);
+}
+
+__global__ void __launch_bounds__(256) refl_finalize(const __grid_constant__ CameraDev cam, const ReflOutDev out, const ReflState* __restrict__ state) {
+    int i, j, prow;
+    if (!thread_pixel(cam, i, j, prow)) return;
+    const size_t px = (size_t)prow * cam.width + i;
+    const ReflState st = state[px];
+    if (st.k.z > 0) refl_store(out, px, refl_state_load(st));
+}
+#endif  // VXPT_HOST_SHADOW
 
 // ---- host side: per-frame constants (:648-668, :727-731) in fp32 with the pinned transcendental definitions -------------
 static inline float h_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -358,6 +549,44 @@ int launch_reflection(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, cons
                        reinterpret_cast<const float2*>(in.cocg), c->opt_texel};
     const ReflOutDev od{reinterpret_cast<float4*>(out.color), out.hit_distance, out.emissive_mask, c->opt_texel};
     const dim3 grid((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8);
+#ifndef VXPT_HOST_SHADOW
+    if (c->opt_refl_wavefront) {
+        // the largest per-pixel sample count (:736-742 on the host)
+        int max_spp = std::min(std::max(p.spp, 1), 16);
+        if (p.checkerboard) max_spp = std::max(max_spp, std::min(std::max((p.spp + p.spp % 2) / 2, 1), 16));
+        const bool spp1 = max_spp == 1;
+        const size_t slab_px = (size_t)(cam.row_end - cam.row_begin) * cam.width, frame_px = (size_t)cam.width * cam.height;
+        // same scratch as the GI wavefront (256 B of counters | one 48-byte record per slab pixel | 48 B of sums per frame pixel when a pixel
+        // takes several samples); the GI pass of the frame has finished with it (stream order).  Never grown under stream capture.
+        if (int rc = grow_scratch(c, &c->d_queue, &c->queue_bytes, gi_scratch_bytes(slab_px, frame_px, spp1), "the reflection wavefront queue")) return rc;
+        unsigned* count = static_cast<unsigned*>(c->d_queue);
+        float4* queue = reinterpret_cast<float4*>(static_cast<char*>(c->d_queue) + 256);
+        ReflState* state = spp1 ? nullptr : reinterpret_cast<ReflState*>(static_cast<char*>(c->d_queue) + 256 + slab_px * 48);
+        const unsigned shade_ctas = (unsigned)std::min<size_t>(148 * 8, std::max<size_t>((slab_px + 255) / 256, 1));
+#ifndef VXPT_REFL_RPT
+#define VXPT_REFL_RPT 2   // experiment knob (build.py -D...): 32x8 tiles per CTA = 256 x this many rays sorted together
+#endif
+        constexpr int RPT = VXPT_REFL_RPT;
+        const dim3 grid_s((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 8 * RPT - 1) / (8 * RPT));
+        for (int s = 0; s < max_spp; ++s) {
+            VX_CUDA(cudaMemsetAsync(count, 0, 16, c->stream));
+            if (c->opt_layout == 1) {
+                if (spp1) { refl_gen_trace<1, true, RPT><<<grid_s, 256, 0, c->stream>>>(S, cd, d, gd, id, od, state, queue, count, s); refl_shade<1, true><<<shade_ctas, 256, 0, c->stream>>>(S, d, id, od, state, queue, count); }
+                else { refl_gen_trace<1, false, RPT><<<grid_s, 256, 0, c->stream>>>(S, cd, d, gd, id, od, state, queue, count, s); refl_shade<1, false><<<shade_ctas, 256, 0, c->stream>>>(S, d, id, od, state, queue, count); }
+            } else {
+                if (spp1) { refl_gen_trace<0, true, RPT><<<grid_s, 256, 0, c->stream>>>(S, cd, d, gd, id, od, state, queue, count, s); refl_shade<0, true><<<shade_ctas, 256, 0, c->stream>>>(S, d, id, od, state, queue, count); }
+                else { refl_gen_trace<0, false, RPT><<<grid_s, 256, 0, c->stream>>>(S, cd, d, gd, id, od, state, queue, count, s); refl_shade<0, false><<<shade_ctas, 256, 0, c->stream>>>(S, d, id, od, state, queue, count); }
+            }
+            c->launches += 2;
+        }
+        if (!spp1) {
+            refl_finalize<<<grid, 256, 0, c->stream>>>(cd, od, state);
+            c->launches += 1;
+        }
+        VX_CUDA(cudaGetLastError());
+        return VXPT_OK;
+    }
+#endif
     if (c->opt_layout == 1) VX_LAUNCH((reflection_kernel<1>), grid, 256, c->stream, S, cd, d, gd, id, od);
     else VX_LAUNCH((reflection_kernel<0>), grid, 256, c->stream, S, cd, d, gd, id, od);
     c->launches += 1;

@@ -156,6 +156,7 @@ struct vxpt_ctx {
     int opt_layout = 1;     // VXPT_OPT_TRAVERSAL_LAYOUT
     int steps_layout = -1;  // layout the step field currently holds (-1: stale, launch_pack_bricks must run)
     int opt_wavefront = 1;  // VXPT_OPT_GI_WAVEFRONT
+    int opt_refl_wavefront = 1;  // VXPT_OPT_REFLECTION_WAVEFRONT
     int opt_df_algo = 1;    // 0 = one thread per line (reference-shaped) + pack_steps, 1 = DPX sweeps, step field written by the z sweep
     int opt_replicas = 1;   // VXPT_OPT_SCENE_REPLICAS
     int opt_timing = 1;     // VXPT_OPT_TIMING_EVENTS

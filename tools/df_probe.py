@@ -20,7 +20,7 @@ from voxelpathtracer_b200 import abi, assets, world  # noqa: E402
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     r = vx.Renderer(0)
-    r.upload_world(world.generate_plains(assets.load_plains_columns()))
+    r.upload_world({'plains': lambda: world.generate_plains(assets.load_plains_columns()), 'gi_box': lambda: world.generate_gi_box(assets.load_plains_columns()), 'city': world.generate_city, 'superflat': world.generate_superflat}[os.environ.get('VXPT_PROBE_WORLD', 'plains')]())
     out = {"kernel": "df_xy_dpx + df_z_dpx (+ pack_steps)", "iters": iters, "algorithmic_bytes": 3 * abi.WORLD_VOXELS}
     peak = 6451.5
     try:

@@ -1,0 +1,14 @@
+# r02q: distance-field early-outs (uniform rows in the x sweep, carry passes skipped where no carry can improve a segment)
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_df_step_field.py tests/test_per_frame_edits.py -m gpu -x -q -k "df or distance or step or edit" > gpurun_out/r02q_pytest.log 2>&1; tail -3 gpurun_out/r02q_pytest.log
+for w in plains city gi_box superflat; do
+  echo "$w"; VXPT_PROBE_WORLD=$w timeout 120 python tools/df_probe.py 30 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'): d=json.loads(l); print('  algo1', d['algo1'])"
+done
+timeout 200 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02q_launches_df.csv python tools/df_probe.py 3 > /dev/null 2>&1
+grep -E "df_xy|df_z_dpx" gpurun_out/r02q_launches_df.csv | head -4 | awk -F'","' '{print substr($5,1,30), $(NF-2), $NF}' | cut -c1-200
+for k in df_xy_dpx df_z_dpx; do
+  timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_r02q_$k python tools/df_probe.py 3 > gpurun_out/r02q_ncu_$k.log 2>&1
+done

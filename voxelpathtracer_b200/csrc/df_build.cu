@@ -129,13 +129,19 @@ constexpr int XY_THREADS = 256;  // 8 warps
 constexpr int XSEG = 24;         // voxels of a row one lane holds in the x sweep: 16 lanes cover a row, a warp sweeps two row pairs at once
 
 // block bytes -> initial distances (solid 0, air 254; ManhattanDistanceX.comp:51-52) for rows A and B, two voxels of the same x in the
-// halves of a register (row A low, row B high)
-__device__ __forceinline__ void load_row_pair24(const uint32_t* rowA, uint32_t (&r)[XSEG]) {
+// halves of a register (row A low, row B high); raw = the 24 block bytes of row A (6 words) followed by those of row B
+__device__ __forceinline__ void load_raw_pair24(const uint32_t* rowA, uint32_t (&raw)[12]) {
     const uint32_t* rowB = rowA + WX / 4;
 #pragma unroll
     for (int k = 0; k < XSEG / 8; ++k) {
         const uint2 A = *reinterpret_cast<const uint2*>(rowA + 2 * k), B = *reinterpret_cast<const uint2*>(rowB + 2 * k);
-        const uint32_t a[2] = {A.x, A.y}, b[2] = {B.x, B.y};
+        raw[2 * k] = A.x; raw[2 * k + 1] = A.y; raw[6 + 2 * k] = B.x; raw[6 + 2 * k + 1] = B.y;
+    }
+}
+__device__ __forceinline__ void convert_row_pair24(const uint32_t (&raw)[12], uint32_t (&r)[XSEG]) {
+#pragma unroll
+    for (int k = 0; k < XSEG / 8; ++k) {
+        const uint32_t a[2] = {raw[2 * k], raw[2 * k + 1]}, b[2] = {raw[6 + 2 * k], raw[6 + 2 * k + 1]};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint32_t t0 = __byte_perm(a[h], b[h], 0x6420);  // a0 a2 b0 b2
@@ -144,6 +150,15 @@ __device__ __forceinline__ void load_row_pair24(const uint32_t* rowA, uint32_t (
 #pragma unroll
             for (int q = 0; q < 4; ++q) r[8 * k + 4 * h + q] = INF2 - __vminu2(v[q], ONE2) * 0xFEu;
         }
+    }
+}
+// one word of the distance field for every word of two rows (what a uniform row pair turns into: 254 in the air, 0 in the ground)
+__device__ __forceinline__ void fill_row_pair24(uint32_t* rowA, uint32_t word) {
+    uint32_t* rowB = rowA + WX / 4;
+#pragma unroll
+    for (int k = 0; k < XSEG / 8; ++k) {
+        *reinterpret_cast<uint2*>(rowA + 2 * k) = make_uint2(word, word);
+        *reinterpret_cast<uint2*>(rowB + 2 * k) = make_uint2(word, word);
     }
 }
 __device__ __forceinline__ void store_row_pair24(uint32_t* rowA, const uint32_t (&r)[XSEG]) {
@@ -180,10 +195,18 @@ __device__ __forceinline__ void x_sweep_rows24(uint32_t (&r)[XSEG], int l16) {
     uint32_t cin_f = __shfl_up_sync(0xffffffffu, cf, 1, 16), cin_b = __shfl_down_sync(0xffffffffu, cb, 1, 16);
     if (l16 == 0) cin_f = INF2;
     if (l16 == 15) cin_b = INF2;
+    // After the local sweeps a segment is 1-Lipschitz, so a carry from the left improves something in it only if it improves its FIRST
+    // voxel (cin + 1 + k < r[k] <= r[0] + k), one from the right only if it improves its LAST: two DPX steps decide for the segment,
+    // one vote for the warp, and rows whose segments do not see each other (the open air, the ground) skip 2 x 24 steps per lane.
+    const bool need_f = __viaddmin_u16x2(cin_f, ONE2, r[0]) != r[0];
+    const bool need_b = __viaddmin_u16x2(cin_b, ONE2, r[XSEG - 1]) != r[XSEG - 1];
+    if (__any_sync(0xffffffffu, need_f)) {
 #pragma unroll
-    for (int k = 0; k < XSEG; ++k) {
-        r[k] = __viaddmin_u16x2(cin_f, (uint32_t)(k + 1) * ONE2, r[k]);
-        r[k] = __viaddmin_u16x2(cin_b, (uint32_t)(XSEG - k) * ONE2, r[k]);
+        for (int k = 0; k < XSEG; ++k) r[k] = __viaddmin_u16x2(cin_f, (uint32_t)(k + 1) * ONE2, r[k]);
+    }
+    if (__any_sync(0xffffffffu, need_b)) {
+#pragma unroll
+        for (int k = 0; k < XSEG; ++k) r[k] = __viaddmin_u16x2(cin_b, (uint32_t)(XSEG - k) * ONE2, r[k]);
     }
 }
 
@@ -215,8 +238,25 @@ __global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __rest
 #pragma unroll 1
         for (int p = 2 * warp + (lane >> 4); p < WY / 2; p += 2 * (XY_THREADS / 32)) {
             uint32_t* rowA = t32 + (2 * p) * (WX / 4) + l16 * (XSEG / 4);
+            uint32_t raw[12];
+            load_raw_pair24(rowA, raw);
+            // the four rows of this warp step are often all air or all ground: then the x sweep changes nothing but the encoding
+            uint32_t any = 0u, zero_byte = 0u;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                any |= raw[k];
+                zero_byte |= (raw[k] - 0x01010101u) & ~raw[k] & 0x80808080u;  // a byte of raw[k] is 0
+            }
+            if (__all_sync(0xffffffffu, any == 0u)) {
+                fill_row_pair24(rowA, 0xFEFEFEFEu);
+                continue;
+            }
+            if (__all_sync(0xffffffffu, zero_byte == 0u)) {
+                fill_row_pair24(rowA, 0u);
+                continue;
+            }
             uint32_t r[XSEG];
-            load_row_pair24(rowA, r);
+            convert_row_pair24(raw, r);
             x_sweep_rows24(r, l16);
             store_row_pair24(rowA, r);
         }
@@ -348,13 +388,27 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
     __syncthreads();
     const uint2 cf = carry_f[seg][lane], cb = carry_b[seg][lane];
     const int x0 = (blockIdx.x * ZXW + lane) * 4, z0 = seg * ZSEG;
+    // a carry improves a (1-Lipschitz) segment only if it improves the voxel it enters through: decide per warp, skip 2 x 24 steps each
+    const bool need_f = __viaddmin_u16x2(cf.x, ONE2, lo[0]) != lo[0] || __viaddmin_u16x2(cf.y, ONE2, hi[0]) != hi[0];
+    const bool need_b = __viaddmin_u16x2(cb.x, ONE2, lo[ZSEG - 1]) != lo[ZSEG - 1] || __viaddmin_u16x2(cb.y, ONE2, hi[ZSEG - 1]) != hi[ZSEG - 1];
+    if (__any_sync(0xffffffffu, need_f)) {
+#pragma unroll
+        for (int i = 0; i < ZSEG; ++i) {
+            lo[i] = __viaddmin_u16x2(cf.x, (uint32_t)(i + 1) * ONE2, lo[i]);
+            hi[i] = __viaddmin_u16x2(cf.y, (uint32_t)(i + 1) * ONE2, hi[i]);
+        }
+    }
+    if (__any_sync(0xffffffffu, need_b)) {
+#pragma unroll
+        for (int i = 0; i < ZSEG; ++i) {
+            lo[i] = __viaddmin_u16x2(cb.x, (uint32_t)(ZSEG - i) * ONE2, lo[i]);
+            hi[i] = __viaddmin_u16x2(cb.y, (uint32_t)(ZSEG - i) * ONE2, hi[i]);
+        }
+    }
     uint32_t e[4];
 #pragma unroll
     for (int i = 0; i < ZSEG; ++i) {
-        uint32_t a = __viaddmin_u16x2(cf.x, (uint32_t)(i + 1) * ONE2, lo[i]);
-        a = __viaddmin_u16x2(cb.x, (uint32_t)(ZSEG - i) * ONE2, a);
-        uint32_t b = __viaddmin_u16x2(cf.y, (uint32_t)(i + 1) * ONE2, hi[i]);
-        b = __viaddmin_u16x2(cb.y, (uint32_t)(ZSEG - i) * ONE2, b);
+        const uint32_t a = lo[i], b = hi[i];
         *reinterpret_cast<uint32_t*>(out + base + (size_t)i * SLICE_BYTES) = __byte_perm(a, b, 0x6420);
         if (PACK == 0) *reinterpret_cast<uint32_t*>(steps + base + (size_t)i * SLICE_BYTES) = steps4(plut, a, b);
         if (PACK == 1) {

@@ -116,6 +116,23 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Development aid (build.py -DVXPT_DF_TRACE --out=...; tools/df_timeline.py): thread 0 of every CTA of the two sweep kernels logs
+// %globaltimer at its phase boundaries.  Not compiled into the product library.
+#ifdef VXPT_DF_TRACE
+constexpr int DF_TRACE_SLOTS = 16;
+__device__ unsigned long long g_df_trace[2][2048][DF_TRACE_SLOTS];
+__device__ __forceinline__ void df_trace(int kernel, int cta, int slot) {
+    if (threadIdx.x == 0 && threadIdx.y == 0 && cta < 2048 && slot < DF_TRACE_SLOTS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_df_trace[kernel][cta][slot] = t;
+    }
+}
+#define DF_TRACE(kernel, cta, slot) df_trace(kernel, cta, slot)
+#else
+#define DF_TRACE(kernel, cta, slot)
+#endif
+
 constexpr uint32_t ONE2 = 0x00010001u;  // +1 in both 16-bit lanes
 constexpr uint32_t INF2 = 0x00FE00FEu;  // 254 in both lanes ("no solid voxel seen")
 
@@ -210,15 +227,21 @@ __device__ __forceinline__ void x_sweep_rows24(uint32_t (&r)[XSEG], int l16) {
     }
 }
 
-__global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
+// NBUF = 2 (default): persistent CTAs (two per SM), the next slice's load in flight while the current one is swept.  NBUF = 1: one CTA per
+// slice, 48 KB each, four per SM, every load issued at the start.  Timeline r02s: with all 18.9 MB requested at once the slices arrive after
+// 2.5 us (median) instead of 1.1, and three CTAs per SM run their y sweeps on the same three schedulers (warps 0-2 of each): 33.9 us per
+// rebuild against 31.0 us persistent.
+template <int NBUF>
+__global__ void __launch_bounds__(XY_THREADS, NBUF == 1 ? 4 : 2) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * SLICE_BYTES);  // one mbarrier per buffer
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NBUF * SLICE_BYTES);  // one mbarrier per buffer
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DF_TRACE(0, blockIdx.x, 0);
     // the dependent z sweep may be scheduled as soon as SMs free up; it waits for this grid's memory with cudaGridDependencySynchronize()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
+        if (NBUF == 2) mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -228,9 +251,15 @@ __global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __rest
         bulk_g2s(smem, grid + (size_t)z * SLICE_BYTES, SLICE_BYTES, bar);
     }
     for (int it = 0; z < WZ; ++it, z += gridDim.x) {
-        const int b = it & 1;
+        const int b = NBUF == 2 ? (it & 1) : 0;
         uint8_t* tile = smem + b * SLICE_BYTES;  // [128][384] bytes
-        mbar_wait(bar + b, (it >> 1) & 1);
+        if (NBUF == 1 && it > 0 && tid == 0) {  // the one buffer again: its store must have read it before the next slice lands
+            bulk_wait_read0();
+            mbar_arrive_expect_tx(bar, SLICE_BYTES);
+            bulk_g2s(smem, grid + (size_t)z * SLICE_BYTES, SLICE_BYTES, bar);
+        }
+        mbar_wait(bar + b, NBUF == 2 ? ((it >> 1) & 1) : (it & 1));
+        DF_TRACE(0, blockIdx.x, 1 + 4 * it);
 
         // ---- x sweep: half warp h of warp w takes row pairs (2p, 2p+1), p = 2w + h + 16j; lane l16 holds x = 24 l16 .. 24 l16 + 23
         uint32_t* t32 = reinterpret_cast<uint32_t*>(tile);
@@ -261,41 +290,75 @@ __global__ void __launch_bounds__(XY_THREADS, 2) df_xy_dpx(const uint8_t* __rest
             store_row_pair24(rowA, r);
         }
         __syncthreads();
+        DF_TRACE(0, blockIdx.x, 2 + 4 * it);
         // the other buffer is free once the bulk store of the previous slice has read it: start the load of this CTA's next slice
-        if (tid == 0 && z + (int)gridDim.x < WZ) {
+        if (NBUF == 2 && tid == 0 && z + (int)gridDim.x < WZ) {
             bulk_wait_read0();
             mbar_arrive_expect_tx(bar + (b ^ 1), SLICE_BYTES);
             bulk_g2s(smem + (b ^ 1) * SLICE_BYTES, grid + (size_t)(z + gridDim.x) * SLICE_BYTES, SLICE_BYTES, bar + (b ^ 1));
         }
 
-        // ---- y sweep: thread t < 96 owns the x-word t (4 voxels, two DPX lanes pairs) and streams the column through shared memory
+        // ---- y sweep: thread t < 96 owns the x-word t (4 voxels = two DPX chains) and streams the column through shared memory, 16 rows
+        // at a time: the loads of a batch are issued together and the next batch's before this one's chain (a compiler barrier keeps them
+        // there).  Written row by row, every load waits behind the previous row's store to the same array and each step costs a
+        // shared-memory round trip: 27 cycles per row, 3.5 us per slice (timeline r02r) against 4.5 cycles of dependent DPX latency.
         if (tid < WX / 4) {
+            constexpr int YB = 16, STR = WX / 4;
             uint32_t* col = t32 + tid;
-            uint32_t w = col[0];
-            uint32_t lo = __byte_perm(w, 0u, 0x4140), hi = __byte_perm(w, 0u, 0x4342);
-#pragma unroll 8
-            for (int y = 1; y < WY; ++y) {
-                w = col[y * (WX / 4)];
-                lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w, 0u, 0x4140));
-                hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w, 0u, 0x4342));
-                col[y * (WX / 4)] = __byte_perm(lo, hi, 0x6420);
+            uint32_t lo = INF2, hi = INF2, w[YB], nxt[YB];
+#pragma unroll
+            for (int k = 0; k < YB; ++k) w[k] = col[k * STR];
+#pragma unroll 1
+            for (int yb = 0; yb < WY; yb += YB) {   // forward
+                if (yb + YB < WY) {
+#pragma unroll
+                    for (int k = 0; k < YB; ++k) nxt[k] = col[(yb + YB + k) * STR];
+                }
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < YB; ++k) {
+                    lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w[k], 0u, 0x4140));
+                    hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w[k], 0u, 0x4342));
+                    w[k] = __byte_perm(lo, hi, 0x6420);
+                }
+#pragma unroll
+                for (int k = 0; k < YB; ++k) col[(yb + k) * STR] = w[k];
+#pragma unroll
+                for (int k = 0; k < YB; ++k) w[k] = nxt[k];
             }
-#pragma unroll 8
-            for (int y = WY - 2; y >= 0; --y) {
-                w = col[y * (WX / 4)];
-                lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w, 0u, 0x4140));
-                hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w, 0u, 0x4342));
-                col[y * (WX / 4)] = __byte_perm(lo, hi, 0x6420);
+            // backward: the last batch is still in w[] as stored (the first step re-reads the running value: min(v, v + 1) = v)
+#pragma unroll
+            for (int k = 0; k < YB; ++k) w[k] = col[(WY - 1 - k) * STR];
+#pragma unroll 1
+            for (int yb = WY - 1; yb >= 0; yb -= YB) {
+                if (yb - YB >= 0) {
+#pragma unroll
+                    for (int k = 0; k < YB; ++k) nxt[k] = col[(yb - YB - k) * STR];
+                }
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < YB; ++k) {
+                    lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w[k], 0u, 0x4140));
+                    hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w[k], 0u, 0x4342));
+                    w[k] = __byte_perm(lo, hi, 0x6420);
+                }
+#pragma unroll
+                for (int k = 0; k < YB; ++k) col[(yb - k) * STR] = w[k];
+#pragma unroll
+                for (int k = 0; k < YB; ++k) w[k] = nxt[k];
             }
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
         __syncthreads();
+        DF_TRACE(0, blockIdx.x, 3 + 4 * it);
         if (tid == 0) {
             bulk_s2g(out + (size_t)z * SLICE_BYTES, tile, SLICE_BYTES);
             bulk_commit();
         }
+        DF_TRACE(0, blockIdx.x, 4 + 4 * it);
     }
     if (tid == 0) bulk_wait_read0();  // shared memory must outlive the last store's reads
+    DF_TRACE(0, blockIdx.x, 15);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -338,13 +401,13 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
     }
     __shared__ uint2 edge_first[ZSEGS][ZXW];  // local value at the first voxel of a segment (lo pair, hi pair)
     __shared__ uint2 edge_last[ZSEGS][ZXW];
-    __shared__ uint2 carry_f[ZSEGS][ZXW];
-    __shared__ uint2 carry_b[ZSEGS][ZXW];
     const int lane = threadIdx.x, seg = threadIdx.y;
     const int y = blockIdx.y;
     const size_t base = (size_t)y * WX + (size_t)(blockIdx.x * ZXW + lane) * 4 + (size_t)seg * ZSEG * SLICE_BYTES;
+    DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 0);
     // programmatic dependent launch: everything above overlapped the tail of df_xy_dpx; its stores are visible from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 1);
 
     uint32_t lo[ZSEG], hi[ZSEG];
 #pragma unroll
@@ -366,27 +429,25 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
     edge_first[seg][lane] = make_uint2(lo[0], hi[0]);
     edge_last[seg][lane] = make_uint2(lo[ZSEG - 1], hi[ZSEG - 1]);
     __syncthreads();
-    if (seg == 0) {  // ZXW threads run the 16-step min-plus scans for their x-words
-        uint2 c = make_uint2(INF2, INF2);
+    DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 2);
+    // Carries, every thread for itself: the best value one voxel in front of this segment is the minimum over the segments before it of
+    // their last voxel's value plus the voxels in between, likewise from behind — 16 independent pairs of shared-memory reads and a short
+    // min-plus chain instead of 16 threads walking the segments one after another between two barriers (timeline r02r: 2.9 us per CTA).
+    uint2 cf = make_uint2(INF2, INF2), cb = make_uint2(INF2, INF2);
 #pragma unroll
-        for (int s = 0; s < ZSEGS; ++s) {
-            carry_f[s][lane] = c;  // best value one voxel before segment s
-            uint2 e = edge_last[s][lane];
-            c.x = __viaddmin_u16x2(c.x, (uint32_t)ZSEG * ONE2, e.x);
-            c.y = __viaddmin_u16x2(c.y, (uint32_t)ZSEG * ONE2, e.y);
-        }
-    } else if (seg == 1) {
-        uint2 c = make_uint2(INF2, INF2);
-#pragma unroll
-        for (int s = ZSEGS - 1; s >= 0; --s) {
-            carry_b[s][lane] = c;  // best value one voxel after segment s
-            uint2 e = edge_first[s][lane];
-            c.x = __viaddmin_u16x2(c.x, (uint32_t)ZSEG * ONE2, e.x);
-            c.y = __viaddmin_u16x2(c.y, (uint32_t)ZSEG * ONE2, e.y);
+    for (int s2 = 0; s2 < ZSEGS; ++s2) {
+        const uint2 el = edge_last[s2][lane], ef = edge_first[s2][lane];
+        if (s2 < seg) {
+            const uint32_t d = (uint32_t)(ZSEG * (seg - 1 - s2)) * ONE2;
+            cf.x = __viaddmin_u16x2(el.x, d, cf.x);
+            cf.y = __viaddmin_u16x2(el.y, d, cf.y);
+        } else if (s2 > seg) {
+            const uint32_t d = (uint32_t)(ZSEG * (s2 - seg - 1)) * ONE2;
+            cb.x = __viaddmin_u16x2(ef.x, d, cb.x);
+            cb.y = __viaddmin_u16x2(ef.y, d, cb.y);
         }
     }
-    __syncthreads();
-    const uint2 cf = carry_f[seg][lane], cb = carry_b[seg][lane];
+    DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 3);
     const int x0 = (blockIdx.x * ZXW + lane) * 4, z0 = seg * ZSEG;
     // a carry improves a (1-Lipschitz) segment only if it improves the voxel it enters through: decide per warp, skip 2 x 24 steps each
     const bool need_f = __viaddmin_u16x2(cf.x, ONE2, lo[0]) != lo[0] || __viaddmin_u16x2(cf.y, ONE2, hi[0]) != hi[0];
@@ -416,6 +477,7 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
             if ((i & 3) == 3) *reinterpret_cast<uint4*>(steps + brick_offset(x0, y, z0 + i - 3)) = make_uint4(e[0], e[1], e[2], e[3]);
         }
     }
+    DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 4);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -456,9 +518,10 @@ __global__ void __launch_bounds__(256) pack_steps(const uint8_t* __restrict__ df
 
 // ------------------------------------------------------------------------------------------------------------
 // per-handle, per-device one-time set-up (called by vxpt_create on the handle's device)
-constexpr int XY_SMEM = 2 * SLICE_BYTES + 16;
+constexpr int XY_SMEM2 = 2 * SLICE_BYTES + 16, XY_SMEM1 = SLICE_BYTES + 16;
 int init_df_kernels(vxpt_ctx* c) {
-    VX_CUDA(cudaFuncSetAttribute(df_xy_dpx, cudaFuncAttributeMaxDynamicSharedMemorySize, XY_SMEM));
+    VX_CUDA(cudaFuncSetAttribute(df_xy_dpx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, XY_SMEM1));
+    VX_CUDA(cudaFuncSetAttribute(df_xy_dpx<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, XY_SMEM2));
     uint8_t lut[256];
     for (int m = 0; m < 256; ++m) lut[m] = (uint8_t)((m == 1) ? 1 : (int)floorf((float)m * 0.57735026918f));
     uint16_t pair[PAIR_LUT];
@@ -483,8 +546,9 @@ int launch_df_build(vxpt_ctx* c) {
         c->steps_layout = -1;
         c->launches += 3;
     } else {
-        static const int xy_ctas = std::getenv("VXPT_DF_XY_CTAS") ? std::atoi(std::getenv("VXPT_DF_XY_CTAS")) : 2 * 148;  // experiment knob
-        df_xy_dpx<<<std::min(std::max(xy_ctas, 1), WZ), XY_THREADS, XY_SMEM, s>>>(c->d_grid, c->d_tmp);
+        static const int xy_ctas = std::getenv("VXPT_DF_XY_CTAS") ? std::atoi(std::getenv("VXPT_DF_XY_CTAS")) : 2 * 148;  // experiment knob: >= 384 = one CTA per slice
+        if (xy_ctas >= WZ) df_xy_dpx<1><<<WZ, XY_THREADS, XY_SMEM1, s>>>(c->d_grid, c->d_tmp);   // one CTA per slice
+        else df_xy_dpx<2><<<std::max(xy_ctas, 1), XY_THREADS, XY_SMEM2, s>>>(c->d_grid, c->d_tmp);      // persistent, double-buffered (default: two per SM)
         // the z sweep is a programmatic dependent of the xy sweep: its CTAs are scheduled (and load their tables) while the xy grid drains
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(WX / (4 * ZXW), WY);
@@ -521,3 +585,13 @@ int launch_pack_bricks(vxpt_ctx* c) {
 }
 
 }  // namespace vxpt
+
+#ifdef VXPT_DF_TRACE
+extern "C" __attribute__((visibility("default"))) int vxpt_debug_df_trace(unsigned long long* out /* [2][2048][16] */) {
+    return (int)cudaMemcpyFromSymbol(out, vxpt::g_df_trace, sizeof(vxpt::g_df_trace));
+}
+extern "C" __attribute__((visibility("default"))) int vxpt_debug_df_trace_clear() {
+    static unsigned long long zero[2 * 2048 * 16];
+    return (int)cudaMemcpyToSymbol(vxpt::g_df_trace, zero, sizeof(zero));
+}
+#endif

@@ -464,8 +464,11 @@ int vxpt_build_distance_field(vxpt_handle c) {
     int rc = launch_df_build(c);
     if (rc) return rc;
     VX_CUDA(cudaEventRecord(c->ev3, c->stream));
-    if (c->steps_layout != c->opt_layout && (rc = launch_pack_bricks(c))) return rc;  // the DPX build writes the step field itself
-    VX_CUDA(cudaEventRecord(c->ev4, c->stream));
+    c->pack_timed = c->steps_layout != c->opt_layout;  // the DPX build writes the step field itself: nothing follows, nothing to time
+    if (c->pack_timed) {
+        if ((rc = launch_pack_bricks(c))) return rc;
+        VX_CUDA(cudaEventRecord(c->ev4, c->stream));
+    }
     if ((rc = refresh_replicas(c))) return rc;
     c->df_timed = true;
     c->df_valid = true;
@@ -1582,7 +1585,8 @@ int vxpt_get_stats(vxpt_handle c, VxStats* out) {
     }
     if (c->df_timed) {
         VX_CUDA(cudaEventElapsedTime(&c->df_build_ms, c->ev2, c->ev3));
-        VX_CUDA(cudaEventElapsedTime(&c->brick_pack_ms, c->ev3, c->ev4));
+        c->brick_pack_ms = 0.0f;  // (two back-to-back event records alone are 2.6 us apart)
+        if (c->pack_timed) VX_CUDA(cudaEventElapsedTime(&c->brick_pack_ms, c->ev3, c->ev4));
         c->df_timed = false;
     }
     out->rays = h.rays;

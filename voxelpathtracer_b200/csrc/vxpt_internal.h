@@ -113,7 +113,7 @@ struct vxpt_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;                  // around the last trace pass
     cudaEvent_t ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;  // DF build start / end, brick pack end
-    bool pass_timed = false, df_timed = false;
+    bool pass_timed = false, df_timed = false, pack_timed = false;
 
     uint8_t* d_grid = nullptr;
     uint8_t* d_df = nullptr;

@@ -28,6 +28,23 @@
 
 namespace vxpt {
 
+// Development aid (build.py -DVXPT_GI_TRACE --out=...; tools/gi_timeline.py): thread 0 of every CTA logs %globaltimer at its phase
+// boundaries.  Not compiled into the product library.
+#ifdef VXPT_GI_TRACE
+constexpr int GI_TRACE_SLOTS = 16;
+__device__ unsigned long long g_gi_trace[2][4096][GI_TRACE_SLOTS];
+__device__ __forceinline__ void gi_trace(int kernel, int cta, int slot) {
+    if (threadIdx.x == 0 && cta < 4096 && slot < GI_TRACE_SLOTS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_gi_trace[kernel][cta][slot] = t;
+    }
+}
+#define GI_TRACE(kernel, cta, slot) gi_trace(kernel, cta, slot)
+#else
+#define GI_TRACE(kernel, cta, slot)
+#endif
+
 struct HitRec {   // 48 B
     float4 a;     // ro.xyz, T
     float4 b;     // rd.xyz, pixel index (bits)
@@ -145,11 +162,15 @@ __device__ __forceinline__ V3 sun_brdf(V3 pre, float shadow_at) { return (pre * 
 // empty: a warp holds rays of similar life expectancy, and short groups fill the time the warps that drew long groups are still busy
 // (with one group per warp the CTA would keep its registers until its slowest warp ended).  RPT = 0 selects the plain form (one pixel per
 // thread, no exchange).
+// resident CTAs per SM the register allocation aims for (build.py -D... to experiment).  r02w: 5 / 4 = 48 / 64 registers, no spills
+// (60 / 79 uncapped): the whole 1080p pass 0.2788 -> 0.2720 ms.  The phase timeline (tools/gi_timeline.py, profiles/r02v_gi_timeline.txt)
+// shows why more resident CTAs buy so little in gi_continue: a 256-record chunk takes 40 us — 19 us in stage B and 11 us in stage D, i.e.
+// the dependent iterations of its longest rays — however many chunks run beside it.
 #ifndef VXPT_GI_GEN_MINB
-#define VXPT_GI_GEN_MINB 1   // experiment knobs (build.py -D...): resident CTAs per SM the register allocation aims for
+#define VXPT_GI_GEN_MINB 5
 #endif
 #ifndef VXPT_GI_CONT_MINB
-#define VXPT_GI_CONT_MINB 1
+#define VXPT_GI_CONT_MINB 4
 #endif
 template <int LAYOUT, bool SPP1, int RPT>
 __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
@@ -163,6 +184,7 @@ __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const Sce
     __shared__ unsigned short s_order[SORT ? 256 * NR : 1];  // sorted position -> slot of s_a / s_b (rays stay where they were written)
     const unsigned tid = threadIdx.x, lane = tid & 31;
     Counters cnt = {0u, 0u, 0u};
+    GI_TRACE(0, blockIdx.y * gridDim.x + blockIdx.x, 0);
     if (SORT) {
         s_hist[tid] = 0u;
         if (tid < 2) s_hist[256 + tid] = 0u;
@@ -249,12 +271,14 @@ __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const Sce
         return;
     }
     __syncthreads();
+    GI_TRACE(0, blockIdx.y * gridDim.x + blockIdx.x, 1);
     prefix_256(s_hist, tid);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < NR; ++r)
         if (kr[r] != ~0u) s_order[s_hist[kr[r] >> 16] + (kr[r] & 0xFFFFu)] = (unsigned short)(r * 256 + tid);
     __syncthreads();
+    GI_TRACE(0, blockIdx.y * gridDim.x + blockIdx.x, 2);
     const unsigned n_rays = s_hist[256], n_groups = (n_rays + 31u) / 32u;
     while (true) {
         unsigned grp = 0;
@@ -285,6 +309,7 @@ __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const Sce
         const unsigned slot = warp_push(queue_count, push);
         if (push) queue[slot] = rec;
     }
+    GI_TRACE(0, blockIdx.y * gridDim.x + blockIdx.x, 3);   // thread 0's warp has no group left
     flush_counters(S, cnt);
 }
 
@@ -323,8 +348,10 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
     Counters cnt = {0u, 0u, 0u};
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const unsigned sun_key = life_key(P.stronger_dir);
+    int gc_it = 0;
     while (true) {
         __syncthreads();  // the previous chunk's stage E has read everything it needs
+        GI_TRACE(1, blockIdx.x, 7 * gc_it);
         sm.hist[tid] = 0u;
         if (tid < 4 && tid != 2) sm.hist[256 + tid] = 0u;  // [258] is written by thread 0 alone (racecheck r02j: two writers, ordered only by warp lockstep)
         if (tid == 0) sm.hist[258] = atomicAdd(cursor, (unsigned)GC_THREADS);
@@ -374,12 +401,17 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
             }
         }
         __syncthreads();
+        GI_TRACE(1, blockIdx.x, 7 * gc_it + 1);   // stage A done
         prefix_256(sm.hist, tid);
         __syncthreads();
         if (kr_b != ~0u) sm.order[sm.hist[kr_b >> 16] + (kr_b & 0xFFFFu)] = (unsigned short)tid;
         if (kr_s != ~0u) sm.order[sm.hist[kr_s >> 16] + (kr_s & 0xFFFFu)] = (unsigned short)(GC_THREADS + tid);
         __syncthreads();
+        GI_TRACE(1, blockIdx.x, 7 * gc_it + 2);   // sorted
         // ---- stage B: bounce rays (cap trace_length) and first shadow sub-rays (cap 128), longest-lived first -----------------------------
+        // (Tried and rejected, r02x: a warp claiming two groups at a time and tracing them interleaved, two rays per lane with both
+        // step-field loads issued before either is used — bit-identical, but the pass went from 0.272 to 0.291 ms at 64 registers and
+        // 0.287 ms at 78: every iteration then runs both rays' skip and DDA halves under predication.)
         {
             const unsigned n_rays = sm.hist[256], n_groups = (n_rays + 31u) / 32u;
             while (true) {
@@ -405,6 +437,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
             }
         }
         __syncthreads();
+        GI_TRACE(1, blockIdx.x, 7 * gc_it + 3);   // stage B done
         // ---- stage C: the bounce ray's hit (or the sky) ---------------------------------------------------------------------------
         bool done = true, skyhit = false;
         if (valid) {
@@ -446,6 +479,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
             if (!done) sm.order[wbase + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)tid;
         }
         __syncthreads();
+        GI_TRACE(1, blockIdx.x, 7 * gc_it + 4);   // stage C done
         // ---- stage D: second shadow sub-rays ---------------------------------------------------------------------------------------
         {
             const unsigned n_rays = sm.hist[259];
@@ -460,6 +494,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
             }
         }
         __syncthreads();
+        GI_TRACE(1, blockIdx.x, 7 * gc_it + 5);   // stage D done
         // ---- stage E: end of the sample --------------------------------------------------------------------------------------------
         if (valid) {
             V3 contrib = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
@@ -472,6 +507,8 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
             finish_sample<SPP1>(out, state, (size_t)(unsigned)__float_as_int(sm.st[ST_PX][tid]), contrib, sm.st[ST_AO][tid],
                                 mk3(sm.st[ST_OD0][tid], sm.st[ST_OD1][tid], sm.st[ST_OD2][tid]), skyhit, __float_as_int(sm.st[ST_BLS][tid]));
         }
+        GI_TRACE(1, blockIdx.x, 7 * gc_it + 6);   // stage E done (thread 0)
+        ++gc_it;
     }
     flush_counters(S, cnt);
 }
@@ -620,3 +657,13 @@ int launch_diffuse_wavefront(vxpt_ctx* c, const VxCamera& cam, const DiffuseDev&
 }
 
 }  // namespace vxpt
+
+#ifdef VXPT_GI_TRACE
+extern "C" __attribute__((visibility("default"))) int vxpt_debug_gi_trace(unsigned long long* out /* [2][4096][16] */) {
+    return (int)cudaMemcpyFromSymbol(out, vxpt::g_gi_trace, sizeof(vxpt::g_gi_trace));
+}
+extern "C" __attribute__((visibility("default"))) int vxpt_debug_gi_trace_clear() {
+    static unsigned long long zero[2 * 4096 * 16];
+    return (int)cudaMemcpyToSymbol(vxpt::g_gi_trace, zero, sizeof(zero));
+}
+#endif

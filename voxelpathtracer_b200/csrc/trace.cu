@@ -15,7 +15,11 @@ struct PrimaryDev {
     AlphaDev alpha;  // read by the ALPHA instantiation only (u_ShouldAlphaTest)
 };
 template <int LAYOUT, bool ALPHA>
-__global__ void __launch_bounds__(256) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
+#ifndef VXPT_TRACE_MINB
+#define VXPT_TRACE_MINB 1   // experiment knob (build.py -D...): resident CTAs per SM the primary / shadow kernels' register allocation aims for
+                            // (r02z: 8 = 32 registers, 100 % occupancy: 0.1505 / 0.1482 ms against 0.1470 / 0.1449 ms uncapped at 39 / 43)
+#endif
+__global__ void __launch_bounds__(256, VXPT_TRACE_MINB) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
                                                       const GBufferDev out) {
     int i, j, prow;
     const bool active = thread_pixel(cam, i, j, prow);
@@ -61,7 +65,7 @@ struct ShadowOutDev {
 };
 
 template <int LAYOUT, bool ALPHA>
-__global__ void __launch_bounds__(256) shadow_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const ShadowDev p,
+__global__ void __launch_bounds__(256, VXPT_TRACE_MINB) shadow_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const ShadowDev p,
                                                      const GBufferDev g, const ShadowOutDev out) {
     int i, j, prow;
     const bool active = thread_pixel(cam, i, j, prow);

@@ -501,7 +501,10 @@ VXPT_API int vxpt_render_frame(vxpt_handle h, const VxCamera* cam, const VxFrame
 /* As vxpt_render_frame, but returns as soon as the frame is enqueued; HOST planes are complete after vxpt_frame_wait(h).
  * A handle keeps one frame in flight: any later call that needs the handle's staging memory first waits for it, so the call
  * is always safe; to overlap the copy-out of frame k with the tracing of frame k+1, alternate between two handles (and two
- * sets of host planes), as a double-buffered swap chain does. */
+ * sets of host planes), as a double-buffered swap chain does.
+ * The call may be recorded into a CUDA graph (stream capture on the handle's stream, no frame pending, scratch sized beforehand by an
+ * eager frame or vxpt_reserve): the copy-out stream joins the capture and rejoins the handle's stream at the end, so a replay — kernels
+ * and host planes — is complete when the handle's stream is (vxpt_sync); vxpt_frame_wait has nothing to wait for then. */
 VXPT_API int vxpt_render_frame_async(vxpt_handle h, const VxCamera* cam, const VxFrameParams* p, const VxFrameOut* out);
 VXPT_API int vxpt_frame_wait(vxpt_handle h);
 

@@ -783,3 +783,40 @@ def test_render_frame_on_interleaved_row_bands(renderer, worlds, scene_tables):
     renderer.render_frame(cam, pp, sp, dp, g2, s2, d2)
     for k, v in {**g2, **s2, **d2}.items():
         assert np.array_equal(v, {**g, **s, **d}[k]), k
+
+
+def test_render_frame_async_records_into_a_cuda_graph(renderer, worlds, scene_tables):
+    """vxpt_render_frame_async with pinned HOST planes under stream capture: the copy-out stream joins the capture and rejoins the handle's
+    stream, so a replay leaves the same bytes in the host planes as the eager call once the handle's stream has drained; the blocking
+    vxpt_render_frame refuses to be captured."""
+    torch = pytest.importorskip("torch")
+    load(renderer, worlds["plains"])
+    W, H = 320, 180
+    cam = camera.FpsCamera(pitch_deg=-20.0).vx_camera(W, H)
+    sun, moon, stronger, vis = scene_tables["sun"], scene_tables["moon"], scene_tables["stronger"], scene_tables["sun_visibility"]
+    pp, sp, dp = vx.primary_params(350, camera.taa_jitter(4)), vx.shadow_params(stronger, frame=4, soft=True), vx.diffuse_params(sun, moon, vis, spp=1, frame=4)
+    want = renderer.render_frame(cam, pp, sp, dp, renderer.alloc_gbuffer(W, H), renderer.alloc_shadow(W, H), renderer.alloc_diffuse(W, H))
+    g, s, d = renderer.alloc_gbuffer(W, H, pinned=True), renderer.alloc_shadow(W, H, pinned=True), renderer.alloc_diffuse(W, H, pinned=True)
+    submit = renderer.prepare_frame(cam, g, s, d)
+    submit(pp, sp, dp)                      # eager once: sizes the staging arena and the GI queue
+    renderer.frame_wait()
+    renderer.sync()
+    ext = torch.cuda.ExternalStream(renderer.cuda_stream())
+    renderer.set_option(abi.OPT_TIMING_EVENTS, 0)
+    try:
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph, stream=ext, capture_error_mode="thread_local"):
+            submit(pp, sp, dp)
+    finally:
+        renderer.set_option(abi.OPT_TIMING_EVENTS, 1)
+    for planes in (g, s, d):
+        for k in planes:
+            np.asarray(planes[k])[...] = 0
+    for _ in range(2):
+        with torch.cuda.stream(ext):
+            gph.replay()
+    renderer.frame_wait()                   # nothing pending on the host side ...
+    renderer.sync()                         # ... the replay is complete when the handle's stream is
+    for got, ref in zip((g, s, d), want[:3]):
+        for k in ref:
+            assert np.array_equal(np.asarray(got[k]), ref[k], equal_nan=True), k

@@ -1377,7 +1377,18 @@ static int render_frame_impl(vxpt_handle c, const VxCamera* cam, const VxFramePa
         c->pass_timed = true;
     }
     if (any_host) {
-        if (wait) {
+        if (stream_capturing(c)) {
+            // The frame is being recorded into a CUDA graph (vxpt_render_frame_async on a capturing stream): the copy stream joined the
+            // capture at the first copy-out and must rejoin the handle's stream before the capture ends.  A replay is then complete —
+            // kernels AND host planes — when the handle's stream is (vxpt_sync); nothing is pending on the host side.
+            if (wait) return fail(VXPT_E_STATE, "vxpt_render_frame would block inside a stream capture: use vxpt_render_frame_async");
+            if (guard.queued) {
+                cudaEvent_t ev = c->ev_slab[n_ev++ & 7];
+                VX_CUDA(cudaEventRecord(ev, c->copy_stream));
+                VX_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+            }
+            guard.settled = true;
+        } else if (wait) {
             VX_CUDA(cudaStreamSynchronize(c->copy_stream));
             guard.settled = true;
         } else {

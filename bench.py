@@ -410,11 +410,11 @@ def run_ours(args):
         renderers.append(rr)
         try:
             frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT, exchange=exchange, texel=texel, slots=args.slots,
-                                                emulate=(args.emulate, 0) if args.emulate else None))
+                                                emulate=(args.emulate, 0) if args.emulate else None, max_gi_spp=CFG["spp"]))
         except multigpu.P2PUnavailable as e:  # raised on every rank together: the NCCL all-gather still works
             sys.stderr.write(f"[bench] rank {rank}: p2p slab gather unavailable ({e}); falling back to the NCCL all-gather\n")
             exchange = "nccl"
-            frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT, exchange=exchange, texel=texel, slots=args.slots))
+            frames.append(multigpu.ShardedFrame(rr, fc, WIDTH, HEIGHT, exchange=exchange, texel=texel, slots=args.slots, max_gi_spp=CFG["spp"]))
         exts.append(torch.cuda.ExternalStream(rr.cuda_stream(), device=dev))
     r, frame, ext = renderers[0], frames[0], exts[0]
     for _ in range(3):

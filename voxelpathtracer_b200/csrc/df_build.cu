@@ -401,6 +401,10 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
     }
     __shared__ uint2 edge_first[ZSEGS][ZXW];  // local value at the first voxel of a segment (lo pair, hi pair)
     __shared__ uint2 edge_last[ZSEGS][ZXW];
+#ifdef VXPT_DF_SERIAL_CARRIES
+    __shared__ uint2 carry_f[ZSEGS][ZXW];
+    __shared__ uint2 carry_b[ZSEGS][ZXW];
+#endif
     const int lane = threadIdx.x, seg = threadIdx.y;
     const int y = blockIdx.y;
     const size_t base = (size_t)y * WX + (size_t)(blockIdx.x * ZXW + lane) * 4 + (size_t)seg * ZSEG * SLICE_BYTES;
@@ -426,27 +430,85 @@ __global__ void __launch_bounds__(ZXW * ZSEGS, 8) df_z_dpx(const uint8_t* __rest
         lo[i] = __viaddmin_u16x2(lo[i + 1], ONE2, lo[i]);
         hi[i] = __viaddmin_u16x2(hi[i + 1], ONE2, hi[i]);
     }
+#ifdef VXPT_DF_SERIAL_CARRIES   // experiment (build.py -D...): the round-1 form, 16 threads walking the segments between two barriers
     edge_first[seg][lane] = make_uint2(lo[0], hi[0]);
     edge_last[seg][lane] = make_uint2(lo[ZSEG - 1], hi[ZSEG - 1]);
     __syncthreads();
     DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 2);
-    // Carries, every thread for itself: the best value one voxel in front of this segment is the minimum over the segments before it of
-    // their last voxel's value plus the voxels in between, likewise from behind — 16 independent pairs of shared-memory reads and a short
-    // min-plus chain instead of 16 threads walking the segments one after another between two barriers (timeline r02r: 2.9 us per CTA).
-    uint2 cf = make_uint2(INF2, INF2), cb = make_uint2(INF2, INF2);
+    if (seg == 0) {
+        uint2 c = make_uint2(INF2, INF2);
 #pragma unroll
-    for (int s2 = 0; s2 < ZSEGS; ++s2) {
-        const uint2 el = edge_last[s2][lane], ef = edge_first[s2][lane];
-        if (s2 < seg) {
-            const uint32_t d = (uint32_t)(ZSEG * (seg - 1 - s2)) * ONE2;
-            cf.x = __viaddmin_u16x2(el.x, d, cf.x);
-            cf.y = __viaddmin_u16x2(el.y, d, cf.y);
-        } else if (s2 > seg) {
-            const uint32_t d = (uint32_t)(ZSEG * (s2 - seg - 1)) * ONE2;
-            cb.x = __viaddmin_u16x2(ef.x, d, cb.x);
-            cb.y = __viaddmin_u16x2(ef.y, d, cb.y);
+        for (int s = 0; s < ZSEGS; ++s) {
+            carry_f[s][lane] = c;
+            uint2 e = edge_last[s][lane];
+            c.x = __viaddmin_u16x2(c.x, (uint32_t)ZSEG * ONE2, e.x);
+            c.y = __viaddmin_u16x2(c.y, (uint32_t)ZSEG * ONE2, e.y);
+        }
+    } else if (seg == 1) {
+        uint2 c = make_uint2(INF2, INF2);
+#pragma unroll
+        for (int s = ZSEGS - 1; s >= 0; --s) {
+            carry_b[s][lane] = c;
+            uint2 e = edge_first[s][lane];
+            c.x = __viaddmin_u16x2(c.x, (uint32_t)ZSEG * ONE2, e.x);
+            c.y = __viaddmin_u16x2(c.y, (uint32_t)ZSEG * ONE2, e.y);
         }
     }
+    __syncthreads();
+    uint2 cf = carry_f[seg][lane], cb = carry_b[seg][lane];
+#else
+    // Carries in two levels.  A warp holds four consecutive segments of eight x-words (lane = 8 j + x): min-plus scans over j by shuffles give
+    // every segment the best value at its last / first voxel from sources inside the warp; the four warps exchange one value per x-word
+    // and direction through shared memory (the only barrier of the kernel) and add the contribution of the warps before / after them.
+    // (r02r: the round-1 form, 16 threads walking the 16 segments between two barriers, held every CTA for 2.9 us; every thread reading
+    // all 16 segment edges, r02s, cost 0.8 M more warp instructions and as long.)
+    const int j = seg & 3, w4 = seg >> 2;
+    uint2 pf = make_uint2(lo[ZSEG - 1], hi[ZSEG - 1]), pb = make_uint2(lo[0], hi[0]);
+#pragma unroll
+    for (int d = 1; d < 4; d <<= 1) {
+        const uint32_t fx = __shfl_up_sync(0xffffffffu, pf.x, 8 * d), fy = __shfl_up_sync(0xffffffffu, pf.y, 8 * d);
+        const uint32_t bx = __shfl_down_sync(0xffffffffu, pb.x, 8 * d), by = __shfl_down_sync(0xffffffffu, pb.y, 8 * d);
+        if (j >= d) {
+            pf.x = __viaddmin_u16x2(fx, (uint32_t)(ZSEG * d) * ONE2, pf.x);
+            pf.y = __viaddmin_u16x2(fy, (uint32_t)(ZSEG * d) * ONE2, pf.y);
+        }
+        if (j + d < 4) {
+            pb.x = __viaddmin_u16x2(bx, (uint32_t)(ZSEG * d) * ONE2, pb.x);
+            pb.y = __viaddmin_u16x2(by, (uint32_t)(ZSEG * d) * ONE2, pb.y);
+        }
+    }
+    if (j == 3) edge_last[w4][lane] = pf;    // best value at the last voxel of the warp's four segments, from sources inside them
+    if (j == 0) edge_first[w4][lane] = pb;   // ... at their first voxel
+    __syncthreads();
+    DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 2);
+    uint2 Cf = make_uint2(INF2, INF2), Cb = make_uint2(INF2, INF2);  // best value one voxel before / after the warp's segments
+#pragma unroll
+    for (int w2 = 0; w2 < 4; ++w2) {
+        const uint2 el = edge_last[w2][lane], ef = edge_first[w2][lane];
+        if (w2 < w4) {
+            const uint32_t dd = (uint32_t)(4 * ZSEG * (w4 - 1 - w2)) * ONE2;
+            Cf.x = __viaddmin_u16x2(el.x, dd, Cf.x);
+            Cf.y = __viaddmin_u16x2(el.y, dd, Cf.y);
+        } else if (w2 > w4) {
+            const uint32_t dd = (uint32_t)(4 * ZSEG * (w2 - w4 - 1)) * ONE2;
+            Cb.x = __viaddmin_u16x2(ef.x, dd, Cb.x);
+            Cb.y = __viaddmin_u16x2(ef.y, dd, Cb.y);
+        }
+    }
+    // the voxel in front of segment j: the last voxel of segment j - 1 of this warp (sources inside the warp), or ZSEG * j voxels past
+    // the voxel in front of the warp; likewise behind
+    uint2 cf, cb;
+    {
+        uint32_t px_ = __shfl_up_sync(0xffffffffu, pf.x, 8), py_ = __shfl_up_sync(0xffffffffu, pf.y, 8);
+        uint32_t nx_ = __shfl_down_sync(0xffffffffu, pb.x, 8), ny_ = __shfl_down_sync(0xffffffffu, pb.y, 8);
+        if (j == 0) { px_ = INF2; py_ = INF2; }
+        if (j == 3) { nx_ = INF2; ny_ = INF2; }
+        cf.x = __viaddmin_u16x2(Cf.x, (uint32_t)(ZSEG * j) * ONE2, px_);
+        cf.y = __viaddmin_u16x2(Cf.y, (uint32_t)(ZSEG * j) * ONE2, py_);
+        cb.x = __viaddmin_u16x2(Cb.x, (uint32_t)(ZSEG * (3 - j)) * ONE2, nx_);
+        cb.y = __viaddmin_u16x2(Cb.y, (uint32_t)(ZSEG * (3 - j)) * ONE2, ny_);
+    }
+#endif
     DF_TRACE(1, blockIdx.y * gridDim.x + blockIdx.x, 3);
     const int x0 = (blockIdx.x * ZXW + lane) * 4, z0 = seg * ZSEG;
     // a carry improves a (1-Lipschitz) segment only if it improves the voxel it enters through: decide per warp, skip 2 x 24 steps each

@@ -60,7 +60,8 @@ def test_headless_cpp_equals_python_driver(use_plains, plains_columns):
     exe = build_headless()
     W, H = 160, 90
     args = [exe, str(W), str(H)] + ([os.path.join(ROOT, "voxelpathtracer_b200", "data", "plains_columns.u8")] if use_plains else [])
-    out = subprocess.run(args, capture_output=True, text=True, check=True).stdout.split("\n")
+    # the C++ host also shards the last frame over three handles through vxpt_mg_* (three slabs on device 0: runs on a single-GPU box)
+    out = subprocess.run(args, capture_output=True, text=True, check=True, env=dict(os.environ, VXPT_HEADLESS_DEVICES="0,0,0")).stdout.split("\n")
     got = {}
     for line in out:
         f = line.split()
@@ -72,6 +73,9 @@ def test_headless_cpp_equals_python_driver(use_plains, plains_columns):
             got[("frame", int(f[1]))] = {f[i]: int(f[i + 1], 16) for i in range(2, len(f), 2)}
         elif f[0] == "render_frame":
             got["render_frame"] = {f[i]: int(f[i + 1], 16) for i in range(1, len(f), 2)}
+        elif f[0] == "mg_render_frame":
+            got["mg_devices"] = int(f[2])
+            got["mg_render_frame"] = {f[i]: int(f[i + 1], 16) for i in range(3, len(f), 2)}
     w = world.generate_plains(plains_columns) if use_plains else world.generate_superflat()
     r = vx.Renderer(0)
     try:
@@ -87,6 +91,7 @@ def test_headless_cpp_equals_python_driver(use_plains, plains_columns):
             assert fnv1a(g["t"]) == ref["t"] and fnv1a(g["normal_id"]) == ref["normal"] and fnv1a(g["block_id"]) == ref["block"]
             assert fnv1a(s["shadow"]) == ref["shadow"]
         assert got["render_frame"] == got[("frame", 2)]   # vxpt_render_frame from C++ == the separate calls
+        assert got["mg_devices"] == 3 and got["mg_render_frame"] == got[("frame", 2)]   # ... == the frame sharded over three handles by vxpt_mg_*
         r.set_block(192, 70, 200, world.STONE)
         r.build_distance_field()
         assert fnv1a(r.download_distance_field()) == got["df_after_edit"]

@@ -65,6 +65,7 @@ public:
 
     const Block& GetBlock(uint16_t x, uint16_t y, uint16_t z) const { return (*m_WorldData)[x + y * WORLD_SIZE_X + z * WORLD_SIZE_X * WORLD_SIZE_Y]; }
     void SetBlock(uint16_t x, uint16_t y, uint16_t z, Block block) { (*m_WorldData)[x + y * WORLD_SIZE_X + z * WORLD_SIZE_X * WORLD_SIZE_Y] = block; }
+    const Block* Data() const { return m_WorldData->data(); }  // the grid as World::Buffer uploads it (one byte per block)
 
     // World::Buffer (Core/World.h:167-171): upload the grid; creates the device context on first use
     bool Buffer(int device = 0) {

@@ -2,7 +2,7 @@
 // 1959-2062, 2790-2852), through the C++ host mirror (VoxelRT.h) and the C ABI.  Builds a world, buffers it, generates
 // the distance field, traces primary + hard sun shadow rays for a few frames, edits a block (full rebuild) and prints
 // FNV-1a digests of the planes (tests/test_gpu_host_cpp.py compares them with the Python driver's).
-//   usage: [VXPT_HEADLESS_FILTERS=1] vxpt_headless [width height [plains_columns.u8]]
+//   usage: [VXPT_HEADLESS_FILTERS=1] [VXPT_HEADLESS_DEVICES=0,0] vxpt_headless [width height [plains_columns.u8]]
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -68,6 +68,36 @@ int main(int argc, char** argv) {
         if (!vx_ok(vxpt_render_frame(world.Handle(), &cam, &fp, &fo), "vxpt_render_frame")) return 1;
         std::printf("render_frame t %016" PRIx64 " normal %016" PRIx64 " block %016" PRIx64 " shadow %016" PRIx64 "\n", fnv1a(t2.data(), t2.size() * 4),
                     fnv1a(n2.data(), n2.size()), fnv1a(b2.data(), b2.size()), fnv1a(s2.data(), s2.size()));
+    }
+    // the same frame once more, sharded over several handles from this one thread (vxpt_mg_*: scene state replicated by the same calls,
+    // rows cut into slabs, host planes filled by every device's own copy stream).  VXPT_HEADLESS_DEVICES = "0,1,..." (ids may repeat:
+    // "0,0,0" = three slabs on one GPU); the line must equal the render_frame line above.
+    if (const char* devs = std::getenv("VXPT_HEADLESS_DEVICES")) {
+        std::vector<int> ids;
+        for (const char* q = devs; *q;) {
+            ids.push_back(std::atoi(q));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        vxpt_mg_handle mg = nullptr;
+        if (!vx_ok(vxpt_mg_create((int)ids.size(), ids.data(), &mg), "vxpt_mg_create")) return 1;
+        bool ok = vx_ok(vxpt_mg_upload_world(mg, reinterpret_cast<const uint8_t*>(world.Data())), "vxpt_mg_upload_world") &&
+                  vx_ok(vxpt_mg_build_distance_field(mg), "vxpt_mg_build_distance_field");
+        std::vector<float> t3((size_t)W * H), inv3((size_t)W * H), tr3((size_t)W * H);
+        std::vector<uint8_t> n3((size_t)W * H), b3((size_t)W * H), s3((size_t)W * H);
+        VxPrimaryParams pp{350, 1, {0.f, 0.f}, 0, 0};
+        GetTAAJitter(2, pp.jitter);
+        VxShadowParams sp{{sun[0], sun[1], sun[2]}, 2, 0, {0.f, 0.f}, 0};
+        VxFrameParams fp{&pp, &sp, nullptr, nullptr, nullptr, nullptr};
+        VxFrameOut fo{};
+        fo.gbuffer = VxGBuffer{t3.data(), n3.data(), b3.data(), inv3.data(), nullptr};
+        fo.shadow = VxShadowOut{s3.data(), tr3.data()};
+        ok = ok && vx_ok(vxpt_mg_render_frame(mg, &cam, &fp, &fo), "vxpt_mg_render_frame");
+        if (ok)
+            std::printf("mg_render_frame devices %d t %016" PRIx64 " normal %016" PRIx64 " block %016" PRIx64 " shadow %016" PRIx64 "\n", vxpt_mg_size(mg),
+                        fnv1a(t3.data(), t3.size() * 4), fnv1a(n3.data(), n3.size()), fnv1a(b3.data(), b3.size()), fnv1a(s3.data(), s3.size()));
+        vxpt_mg_destroy(mg);
+        if (!ok) return 1;
     }
     // the sun-shadow filters on the last traced frame (Pipeline.cpp:2854-2944): first frame of a history, so the previous planes are zero and
     // the previous camera is the current one.  Reported on its own line; a failure here does not stop the run.  Opt-in (VXPT_HEADLESS_FILTERS=1).

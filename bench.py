@@ -747,6 +747,12 @@ def run_ours(args):
                       "shadow_filters": aux["shadow_filter_frame"]["ms"],
                       "svgf_kernels": {k: aux[k]["ms"] * aux[k]["calls_per_frame"] for k in ("svgf_initial", "svgf_temporal", "svgf_variance", "svgf_spatial")},
                       "frac_of_hbm": {k: aux[k]["frac"] for k in ("reflection", "material", "svgf_frame", "shadow_filter_frame")}}
+            # the same passes at the plane sizes the reference's defaults give a 1080p window (Core/Pipeline.cpp:72,101,129: GI and its
+            # denoiser and the reflections at 0.25 of the window, the shadow pass and its filters at 0.5)
+            q = denoise_probe.measure(ra, iters=min(args.steps, 10), W=WIDTH // 4, H=HEIGHT // 4)["passes"]
+            hlf = denoise_probe.measure(ra, iters=min(args.steps, 10), W=WIDTH // 2, H=HEIGHT // 2)["passes"]
+            aux_ms["at_reference_default_scales"] = {"svgf_chain_480x270": q["svgf_frame"]["ms"], "reflection_480x270": q["reflection"]["ms"],
+                                                     "shadow_filters_960x540": hlf["shadow_filter_frame"]["ms"]}
             del ra
         except Exception as e:  # the headline line must not depend on the auxiliary passes
             aux_ms = {"error": f"{type(e).__name__}: {e}"[:200]}

@@ -742,11 +742,15 @@ def run_ours(args):
             ra = vx.Renderer(local_rank)
             ra.upload_world(w)
             ra.build_distance_field()
-            aux = denoise_probe.measure(ra, iters=min(args.steps, 10), W=WIDTH, H=HEIGHT)["passes"]
+            first = denoise_probe.measure(ra, iters=8, W=WIDTH, H=HEIGHT, warm=3)["passes"]       # the frames right after a history reset
+            aux = denoise_probe.measure(ra, iters=min(args.steps, 10), W=WIDTH, H=HEIGHT)["passes"]  # steady state (16 frames of history)
             aux_ms = {"reflection": aux["reflection"]["ms"], "gbuffer": aux["material"]["ms"], "svgf_chain": aux["svgf_frame"]["ms"],
                       "shadow_filters": aux["shadow_filter_frame"]["ms"],
                       "svgf_kernels": {k: aux[k]["ms"] * aux[k]["calls_per_frame"] for k in ("svgf_initial", "svgf_temporal", "svgf_variance", "svgf_spatial")},
-                      "frac_of_hbm": {k: aux[k]["frac"] for k in ("reflection", "material", "svgf_frame", "shadow_filter_frame")}}
+                      "frac_of_hbm": {k: aux[k]["frac"] for k in ("reflection", "material", "svgf_frame", "shadow_filter_frame")},
+                      "svgf_chain_first_frames_after_reset": first["svgf_frame"]["ms"],
+                      "note": "svgf_chain = a denoiser in steady state (16 frames of history before the timed ones); while a pixel's history is shorter than 12 frames "
+                              "VarianceEstimate.glsl filters 9 x 9 taps around it, so the first frames after a reset cost svgf_chain_first_frames_after_reset"}
             # the same passes at the plane sizes the reference's defaults give a 1080p window (Core/Pipeline.cpp:72,101,129: GI and its
             # denoiser and the reflections at 0.25 of the window, the shadow pass and its filters at 0.5)
             q = denoise_probe.measure(ra, iters=min(args.steps, 10), W=WIDTH // 4, H=HEIGHT // 4)["passes"]

@@ -2,7 +2,7 @@
 """Measurement aid for the passes that follow the trace passes on the plains world, planes resident in device
 memory: G-buffer material pass, SVGF pre-pass / temporal / variance / five a-trous passes, shadow temporal + spatial filter, and the two
 frame-level calls.  Each pass is timed by the library's CUDA events around its launch (VxStats.last_ms), averaged over `iters` frames
-after 3 warm-up frames; prints one JSON line with ms per pass and algorithmic GB/s (each input plane read once, each output plane written
+after `warm` warm-up frames (16: steady-state history); prints one JSON line with ms per pass and algorithmic GB/s (each input plane read once, each output plane written
 once) against the measured HBM peak.
 
   python tools/denoise_probe.py [iters [width height]]          default 20 frames at 1920 x 1080
@@ -73,8 +73,11 @@ def main():
     print(json.dumps(measure(r, iters, W, H)))
 
 
-def measure(r, iters=20, W=1920, H=1080):
-    """ms per pass on renderer `r` (world uploaded, distance field built), planes resident in device memory; bench.py calls this too."""
+def measure(r, iters=20, W=1920, H=1080, warm=16):
+    """ms per pass on renderer `r` (world uploaded, distance field built), planes resident in device memory; bench.py calls this too.
+    warm: frames before the timed ones.  16 by default = a denoiser in steady state: VarianceEstimate.glsl filters 9 x 9 taps around a pixel
+    only while its history is shorter than 12 frames (:101-104) and SpatialFilter.glsl's 'strong' mode ends after 8, so the first dozen
+    frames after a history reset cost about twice a later frame (warm=3 times those)."""
     mats = assets.load_materials()
     sun, moon, stronger, vis = camera.sun_moon_direction(50.0)
     r.load_scene_tables(mats, assets.load_blue_noise(), assets.analytic_sky(16, sun), assets.load_shadow_noise())
@@ -102,7 +105,7 @@ def measure(r, iters=20, W=1920, H=1080):
     refl = {"color": dev.new((H, W, 4)), "hit_distance": dev.new((H, W)), "emissive_mask": dev.new((H, W), np.uint8)}
     prev_fc = None
     try:
-        for f in range(iters + 3):
+        for f in range(iters + warm):
             fc = camera.FpsCamera(position=(192.0 + 0.05 * f, 75.0, 192.0 + 0.03 * f), pitch_deg=-20.0, yaw_deg=90.0 + 0.2 * f, aspect=W / H)
             cam = fc.vx_camera(W, H)
             g, pg = g2[f & 1], (g2[(f & 1) ^ 1] if f else g2[0])
@@ -111,7 +114,7 @@ def measure(r, iters=20, W=1920, H=1080):
             r.trace_diffuse(cam, g, vx.diffuse_params(sun, moon, vis, spp=1, frame=f), d)
             view, proj = (prev_fc or fc).view_projection_f32()
             cview, cproj = fc.view_projection_f32()
-            rec = f >= 3
+            rec = f >= warm
 
             def timed(name, fn):
                 out = fn()

@@ -36,6 +36,8 @@ static inline float __fadd_rd(float a, float b) {
     return f;
 }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline long long __double_as_longlong(double d) { long long i; std::memcpy(&i, &d, 8); return i; }
+static inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
 static inline unsigned __float2uint_rn(float f) { return (unsigned)std::nearbyintf(f); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -228,5 +230,22 @@ HS_API int hs_trace_rays(void* p, const float* origins, const float* directions,
 HS_API int hs_ambient_sound(void* p, const float* player_pos, int frame, uint32_t* aggregate, uint32_t* per_invocation) {
     *aggregate = 0;
     return vxpt::launch_ambient(hs_ctx(p), player_pos, frame, aggregate, per_invocation);
+}
+// the denoiser's pinned transcendentals, element by element (tests/test_pinned_math.py compares them with (float)exp((double)x) / pow)
+HS_API void hs_exp_cr(const float* x, float* y, long n) {
+    for (long i = 0; i < n; ++i) y[i] = vxpt::exp_cr(x[i]);
+}
+HS_API void hs_pow01_cr(const float* x, const float* e, float* y, long n) {
+    for (long i = 0; i < n; ++i) y[i] = vxpt::pow01_cr(x[i], e[i]);
+}
+// how many of the inputs the short evaluation hands to the library function (its rounding test)
+HS_API long hs_exp_short_refused(const float* x, long n) {
+    long c = 0;
+    float y;
+    for (long i = 0; i < n; ++i) c += !vxpt::exp_short((double)x[i], 16, &y);
+    return c;
+}
+HS_API float hs_normal_weight(int a, int b, float at_floor, int power) {
+    return vxpt::normal_weight(a, b, at_floor, power == 16 ? VXPT_POW3_16 : VXPT_POW3_32);
 }
 }  // extern "C"

@@ -61,6 +61,12 @@ def load():
     lib.hs_shadow_filter.argtypes = [C.c_void_p, C.POINTER(VxCamera), C.POINTER(_abi.VxShadowFilterIn), C.POINTER(_abi.VxShadowFilterParams), C.c_void_p]
     lib.hs_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_ambient_sound.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
+    lib.hs_exp_cr.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+    lib.hs_pow01_cr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+    lib.hs_exp_short_refused.argtypes = [C.c_void_p, C.c_long]
+    lib.hs_exp_short_refused.restype = C.c_long
+    lib.hs_normal_weight.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int]
+    lib.hs_normal_weight.restype = C.c_float
     _lib = lib
     return lib
 

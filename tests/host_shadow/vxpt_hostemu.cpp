@@ -112,6 +112,8 @@ static inline float __fadd_rd(float a, float b) {
     return f;
 }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline long long __double_as_longlong(double d) { long long i; std::memcpy(&i, &d, 8); return i; }
+static inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
 static inline unsigned __float2uint_rn(float f) { return (unsigned)std::nearbyintf(f); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

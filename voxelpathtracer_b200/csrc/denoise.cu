@@ -21,12 +21,78 @@ namespace vxpt {
 //   pow(y, 2): y * y is exact in double (48 significant bits), so the correctly rounded square is the fp32 product;
 //   pow(y, 3): (y * y) * y in double carries one rounding at 53 bits before the one to fp32;
 //   exp(-0) = 1.
-__device__ __forceinline__ float exp_cr(float x) { return x == 0.0f ? 1.0f : (float)exp((double)x); }
+//
+// What is left goes through a short double-precision evaluation with a rounding test.  exp(x) = 2^(k / 64) * e^r with k = rint(64 x / ln 2)
+// and |r| <= ln 2 / 128: a 64-entry table and a degree-5 polynomial, relative error below 2^-51 (table entry, polynomial, product: each 2^-53;
+// truncation r^6 / 720 < 2^-54), i.e. within 4 units of the double's last place.  Rounding that double to fp32 gives the correctly rounded
+// value — and the value (float)exp((double)x) gives, whose own error is below one unit — unless the double lies within a few units of the
+// midpoint of two floats (mantissa bits 28..0 = 0x10000000): those calls, about one in 10^7, take the library function.  pow(x, y) for
+// 0 < x < 1 is the same evaluation at y * log(x): the library logarithm is good to a unit in the last place and the product is below 104 in
+// magnitude, so the argument carries an absolute error under 2^-45 and the rounding test is as many units wider.
+__device__ const double kExp2Tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, 0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0,
+    0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, 0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0, 0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0,
+    0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0, 0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0, 0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0,
+    0x1.6247eb03a5585p+0, 0x1.6623882552225p+0, 0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0, 0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0,
+    0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0, 0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, 0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0,
+    0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, 0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+// e^a for -87 < a < 0 (a normal float comes out), rounded to fp32; false when the rounding test asks for the library function
+__device__ __forceinline__ bool exp_short(double a, int margin, float* out) {
+    const double magic = 0x1.8p52;
+    const double t = fma(a, 0x1.71547652b82fep+6, magic);  // 64 / ln 2
+    const long long tb = __double_as_longlong(t);
+    const int k = (int)tb;                                 // rint(64 a / ln 2): the low word of the magic sum
+    const double kd = t - magic;
+    double r = fma(kd, -0x1.62e42fee00000p-7, a);          // ln 2 / 64 in two pieces, the first one short enough for kd * hi to be exact
+    r = fma(kd, -0x1.a39ef35793c76p-39, r);
+    double p = fma(r, 0x1.1111111111111p-7, 0x1.5555555555555p-5);
+    p = fma(r, p, 0x1.5555555555555p-3);
+    p = fma(r, p, 0.5);
+    p = fma(r, p, 1.0);
+    p = fma(r, p, 1.0);
+    const long long sb = __double_as_longlong(kExp2Tab[k & 63]) + ((long long)(k >> 6) << 52);  // 2^(k / 64): exponent field >= 1023 - 126
+    const double y = __longlong_as_double(sb) * p;
+    const int low = (int)__double_as_longlong(y) & 0x1fffffff;  // the 29 mantissa bits fp32 drops
+    *out = (float)y;
+    return (unsigned)(low - 0x10000000 + margin) > (unsigned)(2 * margin);
+}
+__device__ __forceinline__ float exp_cr(float x) {
+    if (x == 0.0f) return 1.0f;
+    if (x <= -104.0f) return 0.0f;  // e^-104 < 2^-150: rounds to zero
+    float y;
+    if (x < 0.0f && x > -87.0f && exp_short((double)x, 16, &y)) return y;
+    return (float)exp((double)x);
+}
+__device__ __forceinline__ float pow_lt1_cr(float x, float y) {  // the library's pow for every input; short evaluation for 0 < x < 1, 0 < y
+    if (x > 0.0f && x < 1.0f && y > 0.0f && y < 1.0e6f) {
+        const double a = (double)y * log((double)x);
+        float r;
+        if (a > -87.0 && a < 0.0 && exp_short(a, 2048, &r)) return r;
+    }
+    return pow_cr(x, y);
+}
 __device__ __forceinline__ float pow01_cr(float x, float y) {  // y > 0
     if (x == 1.0f) return 1.0f;
     if (x == 0.0f) return 0.0f;
-    return pow_cr(x, y);
+    return pow_lt1_cr(x, y);
 }
+// pow(max(dot(n_a, n_b), floor), y) for two face-normal ids (normal_from_id(id, 1): six axis normals, every other id (1, 1, 1)): the dot
+// product is exactly -1, 0, 1 or 3, so the power is `at_floor` (the value for the clamped -1 / 0: pow(0, y) = 0, pow(1e-9, 32) underflows
+// to 0), 1, or 3^y — 3^16 and 3^32 are integers below 2^53, so the pinned (float)pow((double)3, y) is the literal rounded once.
+__device__ __forceinline__ float normal_weight(int a, int b, float at_floor, float pow3) {
+    const bool a6 = a > 5, b6 = b > 5;
+    if (a6 && b6) return pow3;
+    const int axis = a6 ? b : a;                                     // the id that is an axis normal when exactly one is not
+    const bool one = (a6 || b6) ? ((0x25 >> axis) & 1) : (a == b);  // ids 0, 2, 5 point along +z, +y, +x
+    return one ? 1.0f : at_floor;
+}
+#define VXPT_POW3_16 ((float)43046721.0)
+#define VXPT_POW3_32 ((float)1853020188851841.0)
 __device__ __forceinline__ float sq_cr(float y) { return y * y; }
 __device__ __forceinline__ float cube_cr(float y) { return (float)(((double)y * (double)y) * (double)y); }
 struct Bilinear {  // the four texels and two weights of one GL_LINEAR tap
@@ -36,8 +102,24 @@ struct Bilinear {  // the four texels and two weights of one GL_LINEAR tap
 __device__ __forceinline__ Bilinear bilinear_at(int w, int h, float u, float v) {
     const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
     const float x0 = floorf(x), y0 = floorf(y);
-    const int i0 = wrap_repeat((int)x0, w), i1 = wrap_repeat((int)x0 + 1, w), j0 = wrap_repeat((int)y0, h), j1 = wrap_repeat((int)y0 + 1, h);
+    const int ix = (int)x0, iy = (int)y0;
+    int i0, i1, j0, j1;
+    if ((unsigned)(ix + w) < (unsigned)(3 * w - 1) && (unsigned)(iy + h) < (unsigned)(3 * h - 1)) {  // within a period of the texture: one branch per tap
+        i0 = wrap_near(ix, w), i1 = wrap_near(ix + 1, w), j0 = wrap_near(iy, h), j1 = wrap_near(iy + 1, h);
+    } else {
+        i0 = wrap_repeat(ix, w), i1 = wrap_repeat(ix + 1, w), j0 = wrap_repeat(iy, h), j1 = wrap_repeat(iy + 1, h);
+    }
     return Bilinear{j0 * w + i0, j0 * w + i1, j1 * w + i0, j1 * w + i1, x - x0, y - y0};
+}
+// the same tap for 0 < u < 1 and 0 < v < 1 (every filter loop tests that before it samples): u * w <= w in fp32, so floor(u * w - 0.5) lies in
+// [-1, w - 1] and only the texel left of column 0 / right of column w - 1 wraps
+__device__ __forceinline__ Bilinear bilinear_in01(int w, int h, float u, float v) {
+    const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    const float x0 = floorf(x), y0 = floorf(y);
+    const int ix = (int)x0, iy = (int)y0;
+    const int i0 = ix < 0 ? ix + w : ix, i1 = ix + 1 >= w ? ix + 1 - w : ix + 1;
+    const int j0 = (iy < 0 ? iy + h : iy) * w, j1 = (iy + 1 >= h ? iy + 1 - h : iy + 1) * w;
+    return Bilinear{j0 + i0, j0 + i1, j1 + i0, j1 + i1, x - x0, y - y0};
 }
 __device__ __forceinline__ float blend(const Bilinear& b, float t00, float t10, float t01, float t11) {
     return (t00 * (1.0f - b.fx) + t10 * b.fx) * (1.0f - b.fy) + (t01 * (1.0f - b.fx) + t11 * b.fx) * b.fy;
@@ -59,6 +141,11 @@ __device__ __forceinline__ float4 tex4(const float* d, const Bilinear& b) {
 }
 __device__ __forceinline__ int tex_nearest_u8(const uint8_t* d, int w, int h, float u, float v) {
     return d[wrap_repeat((int)floorf(v * (float)h), h) * w + wrap_repeat((int)floorf(u * (float)w), w)];
+}
+// 0 < u < 1, 0 < v < 1: floor(u * w) lies in [0, w] (u * w can round up to w), so only index w wraps
+__device__ __forceinline__ int tex_nearest_u8_in01(const uint8_t* d, int w, int h, float u, float v) {
+    const int ix = (int)floorf(u * (float)w), iy = (int)floorf(v * (float)h);
+    return d[(iy >= h ? iy - h : iy) * w + (ix >= w ? ix - w : ix)];
 }
 __device__ __forceinline__ float sh_to_y(float4 sh) { return fmaxf(0.0f, 3.544905f * sh.w); }
 __device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -88,10 +175,10 @@ __global__ void __launch_bounds__(256) svgf_initial_kernel(const __grid_constant
     const int W = cam.width, H = cam.height;
     const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
     const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
-    const Bilinear bc = bilinear_at(W, H, u, v);
+    const Bilinear bc = bilinear_in01(W, H, u, v);
     const V3 origin = ray_origin(cam);
     const V3 bp = origin + normalize3(ray_direction_at(cam, u, v)) * tex1(pl.t, bc);
-    const V3 bn = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const int bn = tex_nearest_u8_in01(pl.nid, W, H, u, v);
     const float4 bsh = tex4(pl.sh, bc);
     const float2 bcc = tex2(pl.cocg, bc), bao = tex2(pl.ao, bc);
     const float blum = sh_to_y(bsh);
@@ -105,13 +192,12 @@ __global__ void __launch_bounds__(256) svgf_initial_kernel(const __grid_constant
             if (x == 0 && y == 0) continue;
             const float su = u + ((float)x * 1.0f) * tsx, sv = v + ((float)y * 1.0f) * tsy;
             if (!(su > 0.0f && su < 1.0f && sv > 0.0f && sv < 1.0f)) continue;
-            const Bilinear bs = bilinear_at(W, H, su, sv);
+            const Bilinear bs = bilinear_in01(W, H, su, sv);
             const V3 sp = origin + normalize3(ray_direction_at(cam, su, sv)) * tex1(pl.t, bs);
             const V3 df = mk3(fabsf(sp.x - bp.x), fabsf(sp.y - bp.y), fabsf(sp.z - bp.z));
             if (!(dot3(df, df) < 1.0f)) continue;
             const float4 ssh = tex4(pl.sh, bs);
-            const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
-            const float nw = pow01_cr(fmaxf(dot3(bn, sn), 0.0f), 16.0f);
+            const float nw = normal_weight(bn, tex_nearest_u8_in01(pl.nid, W, H, su, sv), 0.0f, VXPT_POW3_16);  // pow(max(dot(bn, sn), 0), 16)
             const float lw = fabsf(sh_to_y(ssh) - blum) / 4.0f;
             float w = fmaxf(exp_cr(-lw - nw), 0.01f);  // sic: the normal term is subtracted in the exponent
             const float xw = x == 0 ? 1.0f : 2.0f / 3.0f, yw = y == 0 ? 1.0f : 2.0f / 3.0f;
@@ -142,11 +228,11 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
     if (!thread_pixel(cam, i, j, prow)) return;
     const int W = cam.width, H = cam.height;
     const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
-    const Bilinear bc = bilinear_at(W, H, u, v);
+    const Bilinear bc = bilinear_in01(W, H, u, v);
     const V3 origin = ray_origin(cam);
     const float base_w = tex1(pl.t, bc);
     const V3 base_p = origin + normalize3(ray_direction_at(cam, u, v)) * base_w;  // GetPositionAt :81-85
-    const int base_nid = tex_nearest_u8(pl.nid, W, H, u, v);
+    const int base_nid = tex_nearest_u8_in01(pl.nid, W, H, u, v);
     const float4 base_sh = tex4(pl.sh, bc);
     const float2 base_cocg = tex2(pl.cocg, bc), base_ao = tex2(pl.ao, bc);
     // Reprojection :58-72
@@ -156,7 +242,7 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
     const float pw4 = (M[3] * base_p.x + M[7] * base_p.y) + (M[11] * base_p.z + M[15] * 1.0f);
     const float ru = (px4 / pw4) * 0.5f + 0.5f, rv = (py4 / pw4) * 0.5f + 0.5f;
     const float base_lum = tex1(pl.luma, bc);
-    const int base_block = min(tex_nearest_u8(pl.bid, W, H, u, v), 127);
+    const int base_block = min(tex_nearest_u8_in01(pl.bid, W, H, u, v), 127);
     // (the shader's tap jitter ivec2((GradientNoise() - 0.5) * 1.0) truncates to zero for every pixel)
     const V3 to_player = origin - base_p;
     const float dist_player = sqrtf(dot3(to_player, to_player));
@@ -184,17 +270,17 @@ __global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constan
         const float su = ru + (ox + 0.0f) * tsx, sv = rv + (oy + 0.0f) * tsy;
         const float b = 0.0035f;
         if (!(su < 1.0f - b && su > b && sv < 1.0f - b && sv > b)) continue;
-        const Bilinear bs = bilinear_at(W, H, su, sv);
+        const Bilinear bs = bilinear_in01(W, H, su, sv);
         const float pw = tex1(pl.prev_t, bs);
         const V3 pp = origin + normalize3(ray_direction_at(cam, su, sv)) * pw;
         const V3 diff = mk3(fabsf(base_p.x - pp.x), fabsf(base_p.y - pp.y), fabsf(base_p.z - pp.z));
         const float err = dot3(diff, diff);
         bool valid = err < tol && ((pw < 0.0f) == (base_w < 0.0f));
         if (valid && normal_w) {  // PreviousNormalAt != BaseNormal: ids above 5 all decode to (1,1,1)
-            const int pn = tex_nearest_u8(pl.prev_nid, W, H, su, sv);
+            const int pn = tex_nearest_u8_in01(pl.prev_nid, W, H, su, sv);
             valid = min(pn, 6) == min(base_nid, 6);
         }
-        if (valid && block_w) valid = base_block == min(tex_nearest_u8(pl.prev_bid, W, H, su, sv), 127);
+        if (valid && block_w) valid = base_block == min(tex_nearest_u8_in01(pl.prev_bid, W, H, su, sv), 127);
         if (valid) {
             const V3 ut = tex3(pl.prev_utility, bs);
             sum_sh = sum_sh + tex4(pl.prev_sh, bs) * cw;
@@ -247,9 +333,9 @@ __global__ void __launch_bounds__(256) svgf_variance_kernel(const __grid_constan
     if (!thread_pixel(cam, i, j, prow)) return;
     const int W = cam.width, H = cam.height;
     const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
-    const Bilinear bc = bilinear_at(W, H, u, v);
+    const Bilinear bc = bilinear_in01(W, H, u, v);
     const float base_w = tex1(pl.t, bc);
-    const V3 base_n = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const int base_n = tex_nearest_u8_in01(pl.nid, W, H, u, v);
     const V3 bu = tex3(pl.utility, bc);
     const float4 base_sh = tex4(pl.sh, bc);
     const float2 base_cocg = tex2(pl.cocg, bc);
@@ -278,14 +364,14 @@ __global__ void __launch_bounds__(256) svgf_variance_kernel(const __grid_constan
             for (int y = -K; y <= K; ++y) {
                 const float su = u + (float)x * tsx, sv = v + (float)y * tsy;
                 if (!(su < 1.0f && su > 0.0f && sv < 1.0f && sv > 0.0f)) continue;
-                const Bilinear bs = bilinear_at(W, H, su, sv);
+                const Bilinear bs = bilinear_in01(W, H, su, sv);
                 const float sw = tex1(pl.t, bs);
-                const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
+                const int sn = tex_nearest_u8_in01(pl.nid, W, H, su, sv);
                 const float smoment = tex3(pl.utility, bs).y;
                 const float4 ssh = tex4(pl.sh, bs);
                 const float2 scc = tex2(pl.cocg, bs);
                 const float slum = sh_to_y(ssh);
-                const float nw = pow01_cr(fmaxf(dot3(base_n, sn), 0.0f), 16.0f);
+                const float nw = normal_weight(base_n, sn, 0.0f, VXPT_POW3_16);  // pow(max(dot(base_n, sn), 0), 16)
                 const float dw = sq_cr(exp_cr(-fabsf(sw - base_w)));
                 const float lw = fabsf(slum - base_lum) / color_phi;
                 const float w0 = exp_cr(-lw) * nw * dw;
@@ -328,9 +414,9 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
     const float cx = ((float)i + 0.5f) + P.noise_shift, cy = ((float)j + 0.5f) + P.noise_shift;
     const float noise = fractf(52.9829189f * fractf(0.06711056f * cx + 0.00583715f * cy));
     const int jit = (int)((noise - 0.5f) * ((float)step * 0.8f));
-    const Bilinear bc = bilinear_at(W, H, u, v);
+    const Bilinear bc = bilinear_in01(W, H, u, v);
     const float base_depth = tex1(pl.t, bc);
-    const V3 base_n = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const int base_n = tex_nearest_u8_in01(pl.nid, W, H, u, v);
     const float4 base_sh = tex4(pl.sh, bc);
     const float2 base_cocg = tex2(pl.cocg, bc);
     const float base_lum = sh_to_y(base_sh);
@@ -343,7 +429,7 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
             const float su = u + (float)x * tsx, sv = v + (float)y * tsy;
             if (!(su > 0.0f && su < 1.0f && sv > 0.0f && sv < 1.0f)) continue;
             const float kv = (x == 0 ? 0.60283f : 0.198585f) * (y == 0 ? 0.60283f : 0.198585f);
-            const float V = tex1(pl.variance, bilinear_at(W, H, su, sv));
+            const float V = tex1(pl.variance, bilinear_in01(W, H, su, sv));
             if (x == 0 && y == 0) base_var = V;
             vsum += V * kv;
             ksum += kv;
@@ -372,7 +458,7 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
     float tweaked = var_est;
     if (var_est < 0.1f) {  // TweakVariance :184-190
         const float f = clampf(var_est, 0.0f, 1.0f);
-        tweaked = f * pow_cr(1.0f - f, curve + 6.0f);
+        tweaked = f * pow01_cr(1.0f - f, curve + 6.0f);
     }
     float phi = sqrtf(fmaxf(0.0f, 0.000001f + tweaked));
     phi /= fmaxf(P.color_phi_bias, 0.1f);
@@ -386,15 +472,15 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
             const float su = u + ((((float)x * (float)step) * add_scale) + ((float)jit * 0.5f)) * tsx;
             const float sv = v + ((((float)y * (float)step) * add_scale) + ((float)jit * 0.5f)) * tsy;
             if (!(su > 0.0f && su < 1.0f && sv > 0.0f && sv < 1.0f)) continue;
-            const Bilinear bs = bilinear_at(W, H, su, sv);
+            const Bilinear bs = bilinear_in01(W, H, su, sv);
             const float ddiff = fabsf(tex1(pl.t, bs) - base_depth);
             if ((base_depth < 0.0f) != (ddiff < 0.0f)) continue;  // :262
-            const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
+            const int sn = tex_nearest_u8_in01(pl.nid, W, H, su, sv);
             const float4 ssh = tex4(pl.sh, bs);
             const float2 scc = tex2(pl.cocg, bs);
             const float slum = sh_to_y(ssh);
             const float svar = tex1(pl.variance, bs);
-            const float nw = clampf(pow01_cr(fmaxf(dot3(base_n, sn), 0.0f), 32.0f), 0.001f, 1.0f);
+            const float nw = clampf(normal_weight(base_n, sn, 0.0f, VXPT_POW3_32), 0.001f, 1.0f);  // pow(max(dot(base_n, sn), 0), 32)
             const float lw = fabsf(slum - base_lum) / phi;
             const float dw = clampf(sq_cr(exp_cr(-fmaxf(ddiff, 0.00001f))), 0.0001f, 1.0f);
             float w = strong ? (nw * dw) : (exp_cr(-lw) * nw * dw);
@@ -445,7 +531,7 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
     const int W = cam.width, H = cam.height;
     const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
     const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
-    const Bilinear bc = bilinear_at(W, H, u, v);
+    const Bilinear bc = bilinear_in01(W, H, u, v);
     const V3 origin = ray_origin(cam);
     const float cw = tex1(pl.t, bc);
     const size_t px = (size_t)prow * W + i;
@@ -465,7 +551,7 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
             float total = tex1_u8(pl.shadow_u8, bc);
             const float base = total;
             float weight = 1.0f;
-            const int bn = min(tex_nearest_u8(pl.nid, W, H, u, v), 6);
+            const int bn = min(tex_nearest_u8_in01(pl.nid, W, H, u, v), 6);
 #pragma unroll 1
             for (int x = -1; x <= 1; ++x)
 #pragma unroll 1
@@ -474,9 +560,9 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
                     const float su = u + (float)x * tsx, sv = v + (float)y * tsy;
                     const float b = 0.03f;
                     if (!(su > b && su < 1.0f - b && sv > b && sv < 1.0f - b)) continue;
-                    const Bilinear bs = bilinear_at(W, H, su, sv);
+                    const Bilinear bs = bilinear_in01(W, H, su, sv);
                     const float sd = tex1(pl.t, bs);
-                    if (min(tex_nearest_u8(pl.nid, W, H, su, sv), 6) == bn && fabsf(sd - cw) < 1.0f) {
+                    if (min(tex_nearest_u8_in01(pl.nid, W, H, su, sv), 6) == bn && fabsf(sd - cw) < 1.0f) {
                         const float smp = tex1_u8(pl.shadow_u8, bs);
                         float wa = clampf(1.0f - clampf(fabsf(smp - base) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
                         wa = clampf(pow01_cr(wa, 7.0f), 0.000001f, 1.0f);
@@ -519,7 +605,7 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
             blend_f *= vrf;
             float depth_rej = 1.0f;
             if (d > 0.4f) {
-                depth_rej = pow_cr(exp_cr(-d), 48.0f);
+                depth_rej = pow01_cr(exp_cr(-d), 48.0f);
                 blend_f *= clampf(depth_rej, 0.0f, 1.0f);
             }
             o_color = mixf(cc, pc2, clampf(blend_f, 0.0f, 0.97f));
@@ -545,11 +631,11 @@ __global__ void __launch_bounds__(256) shadow_filter_kernel(const __grid_constan
     const int W = cam.width, H = cam.height;
     const float u = ((float)i + 0.5f) / (float)W, v = ((float)j + 0.5f) / (float)H;
     const float tsx = 1.0f / (float)W, tsy = 1.0f / (float)H;
-    const Bilinear bc = bilinear_at(W, H, u, v);
+    const Bilinear bc = bilinear_in01(W, H, u, v);
     const size_t px = (size_t)prow * W + i;
     const float fr = tex1(pl.frames, bc);
     const float center_w = tex1(pl.t, bc);
-    const V3 cn = normal_from_id(tex_nearest_u8(pl.nid, W, H, u, v), 1.0f);
+    const int cn = tex_nearest_u8_in01(pl.nid, W, H, u, v);
     const float center = tex1(pl.shadow, bc);
     const float tr = tex1(pl.transversal, bc) * 100.0f;
     const float cutoff = sqrtf(2.0f);
@@ -575,13 +661,13 @@ __global__ void __launch_bounds__(256) shadow_filter_kernel(const __grid_constan
             const float sv = v + ((((float)y * tsy) * 1.2f) * scale) * filter_scale;
             const Bilinear bs = bilinear_at(W, H, su, sv);
             const float sd = tex1(pl.t, bs);
-            const V3 sn = normal_from_id(tex_nearest_u8(pl.nid, W, H, su, sv), 1.0f);
+            const int sn = tex_nearest_u8(pl.nid, W, H, su, sv);
             const float dw = cube_cr(exp_cr(-(fabsf(center_w - sd))));
-            const float nw = pow01_cr(fmaxf(dot3(cn, sn), 0.000000001f), 32.0f);
+            const float nw = normal_weight(cn, sn, 0.0f, VXPT_POW3_32);  // pow(max(dot(cn, sn), 1e-9), 32): (1e-9)^32 rounds to 0
             const float sa = tex1(pl.shadow, bs);
             const float le = clampf(1.0f - clampf(fabsf(sa - center) / 3.0f, 0.0f, 1.0f), 0.0f, 1.0f);
             float w = 1.0f;
-            w *= clampf(le == 1.0f ? 1.0f : pow_cr(le, luma_exp), 0.0f, 1.0f);
+            w *= clampf(le == 1.0f ? 1.0f : pow_lt1_cr(le, luma_exp), 0.0f, 1.0f);
             w *= dw;
             w *= nw;
             w = clampf(w, 0.000000001f, 1.0f);

@@ -37,6 +37,11 @@ __device__ __forceinline__ int wrap_repeat(int i, int n) {  // GL_REPEAT on a te
     const int m = i % n;
     return m < 0 ? m + n : m;
 }
+// GL_REPEAT for an index known to lie in [-n, 2n): two predicated adds, no branch
+__device__ __forceinline__ int wrap_near(int i, int n) {
+    i += i < 0 ? n : 0;
+    return i - (i >= n ? n : 0);
+}
 // GLSL leaves sin/cos/pow precision open; the parity contract pins the correctly rounded fp32 value
 // (double evaluation, one rounding) — these run a handful of times per GI sample, never in the traversal loop.
 __device__ __forceinline__ float sin_cr(float x) { return (float)sin((double)x); }

@@ -111,7 +111,7 @@ __device__ __forceinline__ Bilinear bilinear_at(int w, int h, float u, float v) 
     const float x0 = floorf(x), y0 = floorf(y);
     const int ix = (int)x0, iy = (int)y0;
     int i0, i1, j0, j1;
-    if ((unsigned)(ix + w) < (unsigned)(3 * w - 1) && (unsigned)(iy + h) < (unsigned)(3 * h - 1)) {  // within a period of the texture: one branch per tap
+    if ((unsigned)ix + (unsigned)w < (unsigned)(3 * w - 1) && (unsigned)iy + (unsigned)h < (unsigned)(3 * h - 1)) {  // within a period of the texture: one branch per tap
         i0 = wrap_near(ix, w), i1 = wrap_near(ix + 1, w), j0 = wrap_near(iy, h), j1 = wrap_near(iy + 1, h);
     } else {
         i0 = wrap_repeat(ix, w), i1 = wrap_repeat(ix + 1, w), j0 = wrap_repeat(iy, h), j1 = wrap_repeat(iy + 1, h);

@@ -324,18 +324,24 @@ __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const Sce
 //     hit 1:  contrib = contrib + thr * SunBRDF1;  contrib = contrib + emis1 * thr          | miss: contrib = contrib + sky * thr
 // SunBRDF needs the verdict of the hit's sun-shadow sub-ray; everything else of a hit is computed in the dense stage that shades it.
 constexpr int GC_THREADS = 256;
+// VXPT_GI_SHADOW0_LATE (default 1, r03q): the first hit's sun-shadow sub-ray is traced in stage D beside the second hit's instead of in
+// stage B beside the bounce ray.  Stage B then ends after the bounce rays' cap (trace_length iterations) instead of the sub-rays' 128, and
+// the chunk's dependent chain is trace_length + 128 iterations instead of 128 + 128.  The sample's sum is formed in stage E in the shader's order.
+#ifndef VXPT_GI_SHADOW0_LATE
+#define VXPT_GI_SHADOW0_LATE 1
+#endif
 struct GcShared {
-    float4 ray_o[2 * GC_THREADS];   // [t] bounce ray origin (w: unused), [256 + t] first shadow sub-ray origin; stage D: [t] second shadow sub-ray origin
+    float4 ray_o[2 * GC_THREADS];   // [t] bounce ray origin (w: unused; after stage C: second shadow sub-ray origin), [256 + t] first shadow sub-ray origin
     float4 ray_d[GC_THREADS];       // bounce ray direction
-    float st[18][GC_THREADS];       // per-record state between the dense stages
+    float st[21][GC_THREADS];       // per-record state between the dense stages
     float res_t[GC_THREADS];        // bounce ray: T
     int res_code[GC_THREADS];       // bounce ray: min_idx | (sgn+1) << 2 | block << 8
     unsigned char res_sh0[GC_THREADS], res_sh1[GC_THREADS];  // shadow sub-rays: 1 = occluded
     unsigned short order[2 * GC_THREADS];
     unsigned hist[260];             // 256 bins, [256] ray count, [257] next group, [258] chunk base, [259] stage-D ray count
 };
-// state rows
-enum { ST_PX = 0, ST_BLS, ST_OD0, ST_OD1, ST_OD2, ST_AO, ST_C0, ST_C1, ST_C2, ST_T0, ST_T1, ST_T2, ST_A0, ST_A1, ST_A2, ST_P0, ST_P1, ST_P2 };
+// state rows (ST_C*: the partial sum after stage C, or with VXPT_GI_SHADOW0_LATE the second hit's sun term; ST_Q*: its emission or the sky term)
+enum { ST_PX = 0, ST_BLS, ST_OD0, ST_OD1, ST_OD2, ST_AO, ST_C0, ST_C1, ST_C2, ST_T0, ST_T1, ST_T2, ST_A0, ST_A1, ST_A2, ST_P0, ST_P1, ST_P2, ST_Q0, ST_Q1, ST_Q2 };
 
 template <int LAYOUT, bool SPP1>
 __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const DiffuseOutDev out,
@@ -348,6 +354,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
     Counters cnt = {0u, 0u, 0u};
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const unsigned sun_key = life_key(P.stronger_dir);
+    constexpr bool LATE = VXPT_GI_SHADOW0_LATE != 0;
     int gc_it = 0;
     while (true) {
         __syncthreads();  // the previous chunk's stage E has read everything it needs
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
         const bool valid = base + tid < count;
         // ---- stage A: shade the first hit, draw the bounce ray -------------------------------------------------------------------
         unsigned kr_b = ~0u, kr_s = ~0u;
+        bool need0 = false;  // LATE: the first hit's sub-ray waits for stage D
         int pi = 0, pj = 0;
         if (valid) {
             const HitRec rec = queue[base + tid];
@@ -397,7 +405,8 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
             sm.res_sh0[tid] = (unsigned char)(h.shadow_state & 1);
             if (h.shadow_state == 2) {
                 sm.ray_o[GC_THREADS + tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);
-                kr_s = (sun_key << 16) | atomicAdd(&sm.hist[sun_key], 1u);
+                if (LATE) need0 = true;
+                else kr_s = (sun_key << 16) | atomicAdd(&sm.hist[sun_key], 1u);
             }
         }
         __syncthreads();
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
         if (kr_s != ~0u) sm.order[sm.hist[kr_s >> 16] + (kr_s & 0xFFFFu)] = (unsigned short)(GC_THREADS + tid);
         __syncthreads();
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 2);   // sorted
-        // ---- stage B: bounce rays (cap trace_length) and first shadow sub-rays (cap 128), longest-lived first -----------------------------
+        // ---- stage B: bounce rays (cap trace_length; and, unless LATE, first shadow sub-rays, cap 128), longest-lived first ------------------
         // (Tried and rejected, r02x: a warp claiming two groups at a time and tracing them interleaved, two rays per lane with both
         // step-field loads issued before either is used — bit-identical, but the pass went from 0.272 to 0.291 ms at 64 registers and
         // 0.287 ms at 78: every iteration then runs both rays' skip and DDA halves under predication.)
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
                     const unsigned slot = sm.order[idx];
                     const float4 o4 = sm.ray_o[slot];
                     TraceHit h;
-                    if (slot < (unsigned)GC_THREADS) {
+                    if (LATE || slot < (unsigned)GC_THREADS) {
                         const float4 d4 = sm.ray_d[slot];
                         const float T = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), P.trace_length, h, cnt);
                         sm.res_t[slot] = T;
@@ -438,16 +447,19 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
         }
         __syncthreads();
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 3);   // stage B done
+        if (LATE && tid == 0) sm.hist[257] = 0u;  // stage D claims groups from the same cursor (read again only after the next barrier)
         // ---- stage C: the bounce ray's hit (or the sky) ---------------------------------------------------------------------------
-        bool done = true, skyhit = false;
+        bool done = true, skyhit = false, hit1 = false;
         if (valid) {
             const V3 pre0 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
             const V3 e0 = mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
             const V3 thr0 = mk3(1.f, 1.f, 1.f);
             const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
             V3 contrib = mk3(0.f, 0.f, 0.f);
-            contrib = contrib + thr0 * sun_brdf(pre0, sm.res_sh0[tid] ? 1.0f : 0.0f);
-            contrib = contrib + e0;
+            if (!LATE) {
+                contrib = contrib + thr0 * sun_brdf(pre0, sm.res_sh0[tid] ? 1.0f : 0.0f);
+                contrib = contrib + e0;
+            }
             const float T1 = sm.res_t[tid];
             const int code = sm.res_code[tid];
             const float4 o4 = sm.ray_o[tid], d4 = sm.ray_d[tid];
@@ -456,32 +468,65 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
                 const HitShade h = shade_hit(S, P, ro1, rd1, T1, code & 3, ((code >> 2) & 3) - 1, (code >> 8) & 255);
                 sm.st[ST_BLS][tid] = __int_as_float(__float_as_int(sm.st[ST_BLS][tid]) + 2);  // the shader still draws the direction of a third segment it never traces (:607)
                 const V3 e1 = h.emis * thr1;
-                if (h.shadow_state == 2) {
+                hit1 = true;
+                if (LATE) {
+                    sm.st[ST_C0][tid] = h.pre.x; sm.st[ST_C1][tid] = h.pre.y; sm.st[ST_C2][tid] = h.pre.z;
+                    sm.st[ST_Q0][tid] = e1.x; sm.st[ST_Q1][tid] = e1.y; sm.st[ST_Q2][tid] = e1.z;
+                    if (h.shadow_state == 2) {
+                        done = false;
+                        sm.ray_o[tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);  // the bounce origin has been read
+                    } else {
+                        sm.res_sh1[tid] = h.shadow_state ? 1 : 0;
+                    }
+                } else if (h.shadow_state == 2) {
                     done = false;
                     sm.st[ST_A0][tid] = h.pre.x; sm.st[ST_A1][tid] = h.pre.y; sm.st[ST_A2][tid] = h.pre.z;
                     sm.st[ST_P0][tid] = e1.x; sm.st[ST_P1][tid] = e1.y; sm.st[ST_P2][tid] = e1.z;
+                    sm.ray_o[GC_THREADS + tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);
                 } else {
                     contrib = contrib + thr1 * sun_brdf(h.pre, h.shadow_state ? 1.0f : 0.0f);
                     contrib = contrib + e1;
                 }
-                if (!done) sm.ray_o[GC_THREADS + tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);
             } else {
-                contrib = contrib + sky_term(S, P, rd1) * thr1;
+                const V3 sky = sky_term(S, P, rd1) * thr1;
+                if (LATE) { sm.st[ST_Q0][tid] = sky.x; sm.st[ST_Q1][tid] = sky.y; sm.st[ST_Q2][tid] = sky.z; }
+                else contrib = contrib + sky;
                 skyhit = true;
             }
-            sm.st[ST_C0][tid] = contrib.x; sm.st[ST_C1][tid] = contrib.y; sm.st[ST_C2][tid] = contrib.z;
+            if (!LATE) { sm.st[ST_C0][tid] = contrib.x; sm.st[ST_C1][tid] = contrib.y; sm.st[ST_C2][tid] = contrib.z; }
         }
-        {   // second shadow sub-rays: compacted list of record slots (all share the sun direction: no sort)
-            const unsigned mask = __ballot_sync(0xffffffffu, !done);
+        {   // stage D's rays: compacted list of slots (all share the sun direction: no sort).  LATE: slot t = record t's second sub-ray
+            // (origin ray_o[t]), slot 256 + t = its first (origin ray_o[256 + t]); otherwise slot t = the second sub-ray, origin ray_o[256 + t]
+            const unsigned m1 = __ballot_sync(0xffffffffu, !done), m0 = __ballot_sync(0xffffffffu, need0);
+            const unsigned n1 = (unsigned)__popc(m1), n0 = (unsigned)__popc(m0);
             unsigned wbase = 0;
-            if (lane == 0 && mask) wbase = atomicAdd(&sm.hist[259], (unsigned)__popc(mask));
+            if (lane == 0 && (n0 + n1)) wbase = atomicAdd(&sm.hist[259], n0 + n1);
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (!done) sm.order[wbase + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)tid;
+            const unsigned below = (1u << lane) - 1u;
+            if (need0) sm.order[wbase + __popc(m0 & below)] = (unsigned short)(GC_THREADS + tid);
+            if (!done) sm.order[wbase + n0 + __popc(m1 & below)] = (unsigned short)tid;
         }
         __syncthreads();
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 4);   // stage C done
-        // ---- stage D: second shadow sub-rays ---------------------------------------------------------------------------------------
-        {
+        // ---- stage D: shadow sub-rays (cap 128) --------------------------------------------------------------------------------------
+        if (LATE) {
+            const unsigned n_rays = sm.hist[259], n_groups = (n_rays + 31u) / 32u;
+            while (true) {
+                unsigned grp = 0;
+                if (lane == 0) grp = atomicAdd(&sm.hist[257], 1u);
+                grp = __shfl_sync(0xffffffffu, grp, 0);
+                if (grp >= n_groups) break;
+                const unsigned idx = grp * 32u + lane;
+                if (idx < n_rays) {
+                    const unsigned slot = sm.order[idx];
+                    const float4 o4 = sm.ray_o[slot];
+                    TraceHit h;
+                    const float Ts = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), P.stronger_dir, 128, h, cnt);
+                    if (slot < (unsigned)GC_THREADS) sm.res_sh1[slot] = Ts > 0.0f ? 1 : 0;
+                    else sm.res_sh0[slot - GC_THREADS] = Ts > 0.0f ? 1 : 0;
+                }
+            }
+        } else {
             const unsigned n_rays = sm.hist[259];
             for (unsigned idx = tid; idx < ((n_rays + 31u) & ~31u); idx += GC_THREADS) {
                 if (idx < n_rays) {
@@ -497,12 +542,28 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 5);   // stage D done
         // ---- stage E: end of the sample --------------------------------------------------------------------------------------------
         if (valid) {
-            V3 contrib = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
-            if (!done) {
-                const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
-                const V3 pre1 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
-                contrib = contrib + thr1 * sun_brdf(pre1, sm.res_sh1[tid] ? 1.0f : 0.0f);
+            V3 contrib;
+            if (LATE) {  // the shader's sum, in its order (header comment)
+                const V3 thr0 = mk3(1.f, 1.f, 1.f);
+                const V3 pre0 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
+                contrib = mk3(0.f, 0.f, 0.f);
+                contrib = contrib + thr0 * sun_brdf(pre0, sm.res_sh0[tid] ? 1.0f : 0.0f);
                 contrib = contrib + mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
+                const V3 q = mk3(sm.st[ST_Q0][tid], sm.st[ST_Q1][tid], sm.st[ST_Q2][tid]);
+                if (hit1) {
+                    const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
+                    const V3 pre1 = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
+                    contrib = contrib + thr1 * sun_brdf(pre1, sm.res_sh1[tid] ? 1.0f : 0.0f);
+                }
+                contrib = contrib + q;
+            } else {
+                contrib = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
+                if (!done) {
+                    const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
+                    const V3 pre1 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
+                    contrib = contrib + thr1 * sun_brdf(pre1, sm.res_sh1[tid] ? 1.0f : 0.0f);
+                    contrib = contrib + mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
+                }
             }
             finish_sample<SPP1>(out, state, (size_t)(unsigned)__float_as_int(sm.st[ST_PX][tid]), contrib, sm.st[ST_AO][tid],
                                 mk3(sm.st[ST_OD0][tid], sm.st[ST_OD1][tid], sm.st[ST_OD2][tid]), skyhit, __float_as_int(sm.st[ST_BLS][tid]));

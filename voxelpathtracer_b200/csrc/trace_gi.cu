@@ -170,7 +170,7 @@ __device__ __forceinline__ V3 sun_brdf(V3 pre, float shadow_at) { return (pre * 
 #define VXPT_GI_GEN_MINB 5
 #endif
 #ifndef VXPT_GI_CONT_MINB
-#define VXPT_GI_CONT_MINB 4
+#define VXPT_GI_CONT_MINB 5   // r03t, after both sub-rays moved to stage D: 4 / 5 / 6 CTAs per SM (64 / 48 / 40 registers) = 0.258 / 0.247 / 0.264 ms
 #endif
 template <int LAYOUT, bool SPP1, int RPT>
 __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const GBufferDev g,
@@ -313,9 +313,8 @@ __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const Sce
     flush_counters(S, cnt);
 }
 
-// gi_continue — everything of a sample after its first hit, for the queued hits, in CTA-wide stages (header comment).  A CTA claims 256
-// records at a time from the device-side cursor, so the (device-side) hit count needs no host round trip and the tail is balanced over
-// the resident CTAs.  Thread t owns record t of the chunk in the dense stages; between them its state waits in shared memory (so the
+// gi_continue — everything of a sample after its first hit, for the queued hits, in CTA-wide stages (header comment).  The hit count stays on the
+// device (no host round trip): every CTA reads it and takes an even share of the queue, in equal chunks of at most 256 records.  Thread t owns record t of the chunk in the dense stages; between them its state waits in shared memory (so the
 // traversal stages run with the registers of a traversal, not of the whole chain).
 //
 // The shader's accumulation, in its order (:583-605 per bounce, :625-634 for the sky):
@@ -324,23 +323,21 @@ __global__ void __launch_bounds__(256, VXPT_GI_GEN_MINB) gi_gen_trace0(const Sce
 //     hit 1:  contrib = contrib + thr * SunBRDF1;  contrib = contrib + emis1 * thr          | miss: contrib = contrib + sky * thr
 // SunBRDF needs the verdict of the hit's sun-shadow sub-ray; everything else of a hit is computed in the dense stage that shades it.
 constexpr int GC_THREADS = 256;
-// VXPT_GI_SHADOW0_LATE (default 1, r03q): the first hit's sun-shadow sub-ray is traced in stage D beside the second hit's instead of in
-// stage B beside the bounce ray.  Stage B then ends after the bounce rays' cap (trace_length iterations) instead of the sub-rays' 128, and
-// the chunk's dependent chain is trace_length + 128 iterations instead of 128 + 128.  The sample's sum is formed in stage E in the shader's order.
-#ifndef VXPT_GI_SHADOW0_LATE
-#define VXPT_GI_SHADOW0_LATE 1
-#endif
+// Both sun-shadow sub-rays of a record are traced in stage D (r03q: the first hit's used to run in stage B beside the bounce ray).  Stage B
+// then ends after the bounce rays' cap (trace_length iterations) instead of the sub-rays' 128, the chunk's dependent chain is
+// trace_length + 128 iterations instead of 128 + 128, and the sample's sum is formed in stage E, in the shader's order: the 1080p GI pass
+// went from 0.2735 to 0.2590 ms.  The struct is kept under 36.8 KB so that six CTAs fit an SM's shared memory.
 struct GcShared {
-    float4 ray_o[2 * GC_THREADS];   // [t] bounce ray origin (w: unused; after stage C: second shadow sub-ray origin), [256 + t] first shadow sub-ray origin
-    float4 ray_d[GC_THREADS];       // bounce ray direction
+    float4 ray_o[2 * GC_THREADS];   // [t] bounce ray origin, w: (stage B) min_idx | (sgn+1) << 2 | block << 8 of its hit; after stage C the second
+                                    // shadow sub-ray's origin; [256 + t] first shadow sub-ray origin
+    float4 ray_d[GC_THREADS];       // bounce ray direction, w: (stage B) its T
     float st[21][GC_THREADS];       // per-record state between the dense stages
-    float res_t[GC_THREADS];        // bounce ray: T
-    int res_code[GC_THREADS];       // bounce ray: min_idx | (sgn+1) << 2 | block << 8
     unsigned char res_sh0[GC_THREADS], res_sh1[GC_THREADS];  // shadow sub-rays: 1 = occluded
     unsigned short order[2 * GC_THREADS];
-    unsigned hist[260];             // 256 bins, [256] ray count, [257] next group, [258] chunk base, [259] stage-D ray count
+    unsigned hist[260];             // 256 bins, [256] ray count, [257] next group, [258] unused, [259] stage-D ray count
 };
-// state rows (ST_C*: the partial sum after stage C, or with VXPT_GI_SHADOW0_LATE the second hit's sun term; ST_Q*: its emission or the sky term)
+static_assert(sizeof(GcShared) + 1024 <= (227 * 1024) / 6, "six gi_continue CTAs fit the shared memory of an SM");
+// state rows (ST_A*, ST_P*: the first hit's sun term and emission; ST_C*, ST_Q*: the second hit's, or in ST_Q* the sky term of a bounce ray that missed)
 enum { ST_PX = 0, ST_BLS, ST_OD0, ST_OD1, ST_OD2, ST_AO, ST_C0, ST_C1, ST_C2, ST_T0, ST_T1, ST_T2, ST_A0, ST_A1, ST_A2, ST_P0, ST_P1, ST_P2, ST_Q0, ST_Q1, ST_Q2 };
 
 template <int LAYOUT, bool SPP1>
@@ -350,25 +347,26 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
     extern __shared__ __align__(16) unsigned char gc_smem[];
     GcShared& sm = *reinterpret_cast<GcShared*>(gc_smem);
     const unsigned count = queue_count[0];
-    unsigned* cursor = queue_count + 1;
     Counters cnt = {0u, 0u, 0u};
     const unsigned tid = threadIdx.x, lane = tid & 31;
-    const unsigned sun_key = life_key(P.stronger_dir);
-    constexpr bool LATE = VXPT_GI_SHADOW0_LATE != 0;
-    int gc_it = 0;
-    while (true) {
+    // The queue is complete when this kernel starts, so the records are dealt out evenly: every CTA takes the same share, in chunks of equal
+    // size (at most 256 records).  A chunk's time is set by its longest rays far more than by its record count, so what costs is a last wave
+    // of chunks that fills a fraction of the SMs (r03r: 714 chunks of 256 on 592 resident CTAs = one wave and a fifth, 78 us where 52 would
+    // do); with even shares every resident CTA runs the same number of chunks, and a small slab (one of 8 GPUs' rows) spreads over all SMs.
+    const unsigned share = max(64u, (count + gridDim.x - 1u) / gridDim.x);
+    const unsigned lo = min(count, blockIdx.x * share), hi = min(count, lo + share);
+    const unsigned n_chunks = (hi - lo + GC_THREADS - 1u) / GC_THREADS, csize = n_chunks ? (hi - lo + n_chunks - 1u) / n_chunks : 0u;
+    for (unsigned gc_it = 0; gc_it < n_chunks; ++gc_it) {
         __syncthreads();  // the previous chunk's stage E has read everything it needs
         GI_TRACE(1, blockIdx.x, 7 * gc_it);
         sm.hist[tid] = 0u;
-        if (tid < 4 && tid != 2) sm.hist[256 + tid] = 0u;  // [258] is written by thread 0 alone (racecheck r02j: two writers, ordered only by warp lockstep)
-        if (tid == 0) sm.hist[258] = atomicAdd(cursor, (unsigned)GC_THREADS);
+        if (tid < 4) sm.hist[256 + tid] = 0u;
         __syncthreads();
-        const unsigned base = sm.hist[258];
-        if (base >= count) break;
-        const bool valid = base + tid < count;
+        const unsigned base = lo + gc_it * csize;
+        const bool valid = tid < csize && base + tid < hi;
         // ---- stage A: shade the first hit, draw the bounce ray -------------------------------------------------------------------
-        unsigned kr_b = ~0u, kr_s = ~0u;
-        bool need0 = false;  // LATE: the first hit's sub-ray waits for stage D
+        unsigned kr_b = ~0u;
+        bool need0 = false;  // the first hit has a sun-shadow sub-ray (traced in stage D)
         int pi = 0, pj = 0;
         if (valid) {
             const HitRec rec = queue[base + tid];
@@ -405,8 +403,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
             sm.res_sh0[tid] = (unsigned char)(h.shadow_state & 1);
             if (h.shadow_state == 2) {
                 sm.ray_o[GC_THREADS + tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);
-                if (LATE) need0 = true;
-                else kr_s = (sun_key << 16) | atomicAdd(&sm.hist[sun_key], 1u);
+                need0 = true;
             }
         }
         __syncthreads();
@@ -414,10 +411,9 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
         prefix_256(sm.hist, tid);
         __syncthreads();
         if (kr_b != ~0u) sm.order[sm.hist[kr_b >> 16] + (kr_b & 0xFFFFu)] = (unsigned short)tid;
-        if (kr_s != ~0u) sm.order[sm.hist[kr_s >> 16] + (kr_s & 0xFFFFu)] = (unsigned short)(GC_THREADS + tid);
         __syncthreads();
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 2);   // sorted
-        // ---- stage B: bounce rays (cap trace_length; and, unless LATE, first shadow sub-rays, cap 128), longest-lived first ------------------
+        // ---- stage B: bounce rays (cap trace_length), longest-lived first ---------------------------------------------------------------
         // (Tried and rejected, r02x: a warp claiming two groups at a time and tracing them interleaved, two rays per lane with both
         // step-field loads issued before either is used — bit-identical, but the pass went from 0.272 to 0.291 ms at 64 registers and
         // 0.287 ms at 78: every iteration then runs both rays' skip and DDA halves under predication.)
@@ -431,72 +427,46 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
                 const unsigned idx = grp * 32u + lane;
                 if (idx < n_rays) {
                     const unsigned slot = sm.order[idx];
-                    const float4 o4 = sm.ray_o[slot];
+                    const float4 o4 = sm.ray_o[slot], d4 = sm.ray_d[slot];
                     TraceHit h;
-                    if (LATE || slot < (unsigned)GC_THREADS) {
-                        const float4 d4 = sm.ray_d[slot];
-                        const float T = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), P.trace_length, h, cnt);
-                        sm.res_t[slot] = T;
-                        sm.res_code[slot] = h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8);
-                    } else {
-                        const float Ts = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), P.stronger_dir, 128, h, cnt);
-                        sm.res_sh0[slot - GC_THREADS] = Ts > 0.0f ? 1 : 0;
-                    }
+                    const float T = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), P.trace_length, h, cnt);
+                    sm.ray_d[slot].w = T;
+                    sm.ray_o[slot].w = __int_as_float(h.min_idx | ((h.sgn + 1) << 2) | (h.block << 8));
                 }
             }
         }
         __syncthreads();
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 3);   // stage B done
-        if (LATE && tid == 0) sm.hist[257] = 0u;  // stage D claims groups from the same cursor (read again only after the next barrier)
+        if (tid == 0) sm.hist[257] = 0u;  // stage D claims groups from the same cursor (read again only after the next barrier)
         // ---- stage C: the bounce ray's hit (or the sky) ---------------------------------------------------------------------------
         bool done = true, skyhit = false, hit1 = false;
         if (valid) {
-            const V3 pre0 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
-            const V3 e0 = mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
-            const V3 thr0 = mk3(1.f, 1.f, 1.f);
             const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
-            V3 contrib = mk3(0.f, 0.f, 0.f);
-            if (!LATE) {
-                contrib = contrib + thr0 * sun_brdf(pre0, sm.res_sh0[tid] ? 1.0f : 0.0f);
-                contrib = contrib + e0;
-            }
-            const float T1 = sm.res_t[tid];
-            const int code = sm.res_code[tid];
             const float4 o4 = sm.ray_o[tid], d4 = sm.ray_d[tid];
+            const float T1 = d4.w;
+            const int code = __float_as_int(o4.w);
             const V3 ro1 = mk3(o4.x, o4.y, o4.z), rd1 = mk3(d4.x, d4.y, d4.z);
             if (T1 > 0.0f && ((code >> 8) & 255) > 0) {
                 const HitShade h = shade_hit(S, P, ro1, rd1, T1, code & 3, ((code >> 2) & 3) - 1, (code >> 8) & 255);
                 sm.st[ST_BLS][tid] = __int_as_float(__float_as_int(sm.st[ST_BLS][tid]) + 2);  // the shader still draws the direction of a third segment it never traces (:607)
                 const V3 e1 = h.emis * thr1;
                 hit1 = true;
-                if (LATE) {
-                    sm.st[ST_C0][tid] = h.pre.x; sm.st[ST_C1][tid] = h.pre.y; sm.st[ST_C2][tid] = h.pre.z;
-                    sm.st[ST_Q0][tid] = e1.x; sm.st[ST_Q1][tid] = e1.y; sm.st[ST_Q2][tid] = e1.z;
-                    if (h.shadow_state == 2) {
-                        done = false;
-                        sm.ray_o[tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);  // the bounce origin has been read
-                    } else {
-                        sm.res_sh1[tid] = h.shadow_state ? 1 : 0;
-                    }
-                } else if (h.shadow_state == 2) {
+                sm.st[ST_C0][tid] = h.pre.x; sm.st[ST_C1][tid] = h.pre.y; sm.st[ST_C2][tid] = h.pre.z;
+                sm.st[ST_Q0][tid] = e1.x; sm.st[ST_Q1][tid] = e1.y; sm.st[ST_Q2][tid] = e1.z;
+                if (h.shadow_state == 2) {
                     done = false;
-                    sm.st[ST_A0][tid] = h.pre.x; sm.st[ST_A1][tid] = h.pre.y; sm.st[ST_A2][tid] = h.pre.z;
-                    sm.st[ST_P0][tid] = e1.x; sm.st[ST_P1][tid] = e1.y; sm.st[ST_P2][tid] = e1.z;
-                    sm.ray_o[GC_THREADS + tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);
+                    sm.ray_o[tid] = make_float4(h.shadow_origin.x, h.shadow_origin.y, h.shadow_origin.z, 0.f);  // the bounce origin has been read
                 } else {
-                    contrib = contrib + thr1 * sun_brdf(h.pre, h.shadow_state ? 1.0f : 0.0f);
-                    contrib = contrib + e1;
+                    sm.res_sh1[tid] = h.shadow_state ? 1 : 0;
                 }
             } else {
                 const V3 sky = sky_term(S, P, rd1) * thr1;
-                if (LATE) { sm.st[ST_Q0][tid] = sky.x; sm.st[ST_Q1][tid] = sky.y; sm.st[ST_Q2][tid] = sky.z; }
-                else contrib = contrib + sky;
+                sm.st[ST_Q0][tid] = sky.x; sm.st[ST_Q1][tid] = sky.y; sm.st[ST_Q2][tid] = sky.z;
                 skyhit = true;
             }
-            if (!LATE) { sm.st[ST_C0][tid] = contrib.x; sm.st[ST_C1][tid] = contrib.y; sm.st[ST_C2][tid] = contrib.z; }
         }
-        {   // stage D's rays: compacted list of slots (all share the sun direction: no sort).  LATE: slot t = record t's second sub-ray
-            // (origin ray_o[t]), slot 256 + t = its first (origin ray_o[256 + t]); otherwise slot t = the second sub-ray, origin ray_o[256 + t]
+        {   // stage D's rays: compacted list of slots (all share the sun direction: no sort); slot t = record t's second sub-ray
+            // (origin ray_o[t]), slot 256 + t = its first (origin ray_o[256 + t])
             const unsigned m1 = __ballot_sync(0xffffffffu, !done), m0 = __ballot_sync(0xffffffffu, need0);
             const unsigned n1 = (unsigned)__popc(m1), n0 = (unsigned)__popc(m0);
             unsigned wbase = 0;
@@ -509,7 +479,7 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
         __syncthreads();
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 4);   // stage C done
         // ---- stage D: shadow sub-rays (cap 128) --------------------------------------------------------------------------------------
-        if (LATE) {
+        {
             const unsigned n_rays = sm.hist[259], n_groups = (n_rays + 31u) / 32u;
             while (true) {
                 unsigned grp = 0;
@@ -526,50 +496,27 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
                     else sm.res_sh0[slot - GC_THREADS] = Ts > 0.0f ? 1 : 0;
                 }
             }
-        } else {
-            const unsigned n_rays = sm.hist[259];
-            for (unsigned idx = tid; idx < ((n_rays + 31u) & ~31u); idx += GC_THREADS) {
-                if (idx < n_rays) {
-                    const unsigned slot = sm.order[idx];
-                    const float4 o4 = sm.ray_o[GC_THREADS + slot];
-                    TraceHit h;
-                    const float Ts = traverse_df<LAYOUT>(S, mk3(o4.x, o4.y, o4.z), P.stronger_dir, 128, h, cnt);
-                    sm.res_sh1[slot] = Ts > 0.0f ? 1 : 0;
-                }
-            }
         }
         __syncthreads();
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 5);   // stage D done
         // ---- stage E: end of the sample --------------------------------------------------------------------------------------------
         if (valid) {
-            V3 contrib;
-            if (LATE) {  // the shader's sum, in its order (header comment)
-                const V3 thr0 = mk3(1.f, 1.f, 1.f);
-                const V3 pre0 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
-                contrib = mk3(0.f, 0.f, 0.f);
-                contrib = contrib + thr0 * sun_brdf(pre0, sm.res_sh0[tid] ? 1.0f : 0.0f);
-                contrib = contrib + mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
-                const V3 q = mk3(sm.st[ST_Q0][tid], sm.st[ST_Q1][tid], sm.st[ST_Q2][tid]);
-                if (hit1) {
-                    const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
-                    const V3 pre1 = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
-                    contrib = contrib + thr1 * sun_brdf(pre1, sm.res_sh1[tid] ? 1.0f : 0.0f);
-                }
-                contrib = contrib + q;
-            } else {
-                contrib = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
-                if (!done) {
-                    const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
-                    const V3 pre1 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
-                    contrib = contrib + thr1 * sun_brdf(pre1, sm.res_sh1[tid] ? 1.0f : 0.0f);
-                    contrib = contrib + mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
-                }
+            // the shader's sum, in its order (header comment)
+            const V3 thr0 = mk3(1.f, 1.f, 1.f);
+            const V3 pre0 = mk3(sm.st[ST_A0][tid], sm.st[ST_A1][tid], sm.st[ST_A2][tid]);
+            V3 contrib = mk3(0.f, 0.f, 0.f);
+            contrib = contrib + thr0 * sun_brdf(pre0, sm.res_sh0[tid] ? 1.0f : 0.0f);
+            contrib = contrib + mk3(sm.st[ST_P0][tid], sm.st[ST_P1][tid], sm.st[ST_P2][tid]);
+            if (hit1) {
+                const V3 thr1 = mk3(sm.st[ST_T0][tid], sm.st[ST_T1][tid], sm.st[ST_T2][tid]);
+                const V3 pre1 = mk3(sm.st[ST_C0][tid], sm.st[ST_C1][tid], sm.st[ST_C2][tid]);
+                contrib = contrib + thr1 * sun_brdf(pre1, sm.res_sh1[tid] ? 1.0f : 0.0f);
             }
+            contrib = contrib + mk3(sm.st[ST_Q0][tid], sm.st[ST_Q1][tid], sm.st[ST_Q2][tid]);
             finish_sample<SPP1>(out, state, (size_t)(unsigned)__float_as_int(sm.st[ST_PX][tid]), contrib, sm.st[ST_AO][tid],
                                 mk3(sm.st[ST_OD0][tid], sm.st[ST_OD1][tid], sm.st[ST_OD2][tid]), skyhit, __float_as_int(sm.st[ST_BLS][tid]));
         }
         GI_TRACE(1, blockIdx.x, 7 * gc_it + 6);   // stage E done (thread 0)
-        ++gc_it;
     }
     flush_counters(S, cnt);
 }
@@ -621,7 +568,7 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
     const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
     const int rows = cd.row_end - cd.row_begin;
     const size_t slab_px = (size_t)rows * cd.width;
-    static const int sort_env = env_int("VXPT_GI_SORT", -1), ctas_env = env_int("VXPT_GI_CTAS", 4), slabs_env = env_int("VXPT_GI_SLABS", -1);
+    static const int sort_env = env_int("VXPT_GI_SORT", -1), ctas_env = env_int("VXPT_GI_CTAS", VXPT_GI_CONT_MINB), slabs_env = env_int("VXPT_GI_SLABS", -1);
     // pixels per thread of the sorted first-bounce kernel: 4 on large slabs (1024 rays sorted per CTA, 32 groups for 8 warps), 2 on
     // medium ones, plain on slabs too small to fill the GPU with such CTAs (r01g, 1080p GI pass: plain 0.339 ms, 1 / 2 / 4 pixels per
     // thread 0.364 / 0.286 / 0.283 ms)

@@ -167,7 +167,7 @@ __device__ __forceinline__ V3 sun_brdf(V3 pre, float shadow_at) { return (pre * 
 // shows why more resident CTAs buy so little in gi_continue: a 256-record chunk takes 40 us — 19 us in stage B and 11 us in stage D, i.e.
 // the dependent iterations of its longest rays — however many chunks run beside it.
 #ifndef VXPT_GI_GEN_MINB
-#define VXPT_GI_GEN_MINB 5
+#define VXPT_GI_GEN_MINB 5   // r03v: 6 (40 registers, 16 bytes of stack) takes the whole pass from 0.246 to 0.290 ms
 #endif
 #ifndef VXPT_GI_CONT_MINB
 #define VXPT_GI_CONT_MINB 5   // r03t, after both sub-rays moved to stage D: 4 / 5 / 6 CTAs per SM (64 / 48 / 40 registers) = 0.258 / 0.247 / 0.264 ms

@@ -349,8 +349,16 @@ __device__ __forceinline__ void refl_state_store(ReflState& st, const ReflAcc& A
 // of RPT 32x8 tiles, files their rays under |R.y| (steep reflections off the ground leave the scene at once, grazing ones creep along it) by
 // a counting sort in shared memory, and its warps claim groups of 32 rays, longest-lived first.  Sky pixels produce no ray, so they cost
 // their set-up only (r02n, unsorted, one thread per pixel: 15.5 of 32 lanes per instruction, a third of the pixels of the bench frame sky).
+// resident CTAs per SM the register allocation aims for (build.py -D... to experiment).  r03w, 1080p / 1 spp: uncapped (58-63 and 68-72
+// registers, 4 and 3 CTAs) 0.331 ms; refl_gen_trace at 5 (48 registers) 0.318 ms; and refl_shade at 4 (64 registers) 0.311 ms
+#ifndef VXPT_REFL_SHADE_MINB
+#define VXPT_REFL_SHADE_MINB 4
+#endif
+#ifndef VXPT_REFL_GEN_MINB
+#define VXPT_REFL_GEN_MINB 5
+#endif
 template <int LAYOUT, bool SPP1, int RPT>
-__global__ void __launch_bounds__(256) refl_gen_trace(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ ReflDev P,
+__global__ void __launch_bounds__(256, VXPT_REFL_GEN_MINB) refl_gen_trace(const SceneDev S, const __grid_constant__ CameraDev cam, const __grid_constant__ ReflDev P,
                                                       const GBufferDev g, const ReflInDev in, const ReflOutDev out, ReflState* __restrict__ state,
                                                       float4* __restrict__ queue, unsigned* __restrict__ queue_count, const int sample) {
     __shared__ float4 s_a[256 * RPT];            // ray origin, pixel index (bits)
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(256) refl_gen_trace(const SceneDev S, const __
 }
 
 template <int LAYOUT, bool SPP1>
-__global__ void __launch_bounds__(256) refl_shade(const SceneDev S, const __grid_constant__ ReflDev P, const ReflInDev in, const ReflOutDev out,
+__global__ void __launch_bounds__(256, VXPT_REFL_SHADE_MINB) refl_shade(const SceneDev S, const __grid_constant__ ReflDev P, const ReflInDev in, const ReflOutDev out,
                                                   ReflState* __restrict__ state, const float4* __restrict__ queue, const unsigned* __restrict__ queue_count) {
     const unsigned count = queue_count[0];
     Counters cnt = {0u, 0u, 0u};

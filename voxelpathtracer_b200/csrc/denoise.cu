@@ -41,25 +41,19 @@ __device__ const double kExp2Tab[64] = {
     0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, 0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0,
     0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, 0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
-// the evaluation's constants live in the constant bank: DFMA takes them as operands (as literals each costs two moves per use)
-__constant__ double kExpC[8] = {0x1.8p52,                 // 0: 1.5 * 2^52, rounds the sum to an integer
-                                0x1.71547652b82fep+6,     // 1: 64 / ln 2
-                                -0x1.62e42fee00000p-7,    // 2, 3: -ln 2 / 64 in two pieces, the first short enough for k * hi to be exact
-                                -0x1.a39ef35793c76p-39,
-                                0x1.1111111111111p-7,     // 4: 1 / 120
-                                0x1.5555555555555p-5,     // 5: 1 / 24
-                                0x1.5555555555555p-3,     // 6: 1 / 6
-                                0.5};
-// e^a for -87 < a < 0 (a normal float comes out), rounded to fp32; false when the rounding test asks for the library function
+// e^a for -87 < a < 0 (a normal float comes out), rounded to fp32; false when the rounding test asks for the library function.
+// (r03z: the constants as literals; read from a __constant__ array instead, DFMA takes them as operands without the two moves a literal
+// costs, but the compiler hoists the loads out of the filter loops and the a-trous kernel goes from 64 to 78 registers: 0.288 -> 0.313 ms.)
 __device__ __forceinline__ bool exp_short(double a, int margin, float* out) {
-    const double t = fma(a, kExpC[1], kExpC[0]);
-    const int k = (int)__double_as_longlong(t);  // rint(64 a / ln 2): the low word of the magic sum
-    const double kd = t - kExpC[0];
-    double r = fma(kd, kExpC[2], a);
-    r = fma(kd, kExpC[3], r);
-    double p = fma(r, kExpC[4], kExpC[5]);
-    p = fma(r, p, kExpC[6]);
-    p = fma(r, p, kExpC[7]);
+    const double magic = 0x1.8p52;                           // 1.5 * 2^52: rounds the sum to an integer
+    const double t = fma(a, 0x1.71547652b82fep+6, magic);    // 64 / ln 2
+    const int k = (int)__double_as_longlong(t);              // rint(64 a / ln 2): the low word of the magic sum
+    const double kd = t - magic;
+    double r = fma(kd, -0x1.62e42fee00000p-7, a);            // ln 2 / 64 in two pieces, the first short enough for kd * hi to be exact
+    r = fma(kd, -0x1.a39ef35793c76p-39, r);
+    double p = fma(r, 0x1.1111111111111p-7, 0x1.5555555555555p-5);  // 1 / 120, 1 / 24
+    p = fma(r, p, 0x1.5555555555555p-3);                     // 1 / 6
+    p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
     p = fma(r, p, 1.0);
     const long long sb = __double_as_longlong(kExp2Tab[k & 63]) + ((long long)(k >> 6) << 52);  // 2^(k / 64): exponent field >= 1023 - 126
@@ -166,6 +160,23 @@ __device__ __forceinline__ float4 clamp4(float4 a, float lo, float hi) {
 }
 __device__ __forceinline__ float2 clamp2(float2 a, float lo, float hi) { return make_float2(clampf(a.x, lo, hi), clampf(a.y, lo, hi)); }
 
+// __launch_bounds__ per kernel: threads, and optionally the resident CTAs per SM the register allocation aims for (build.py
+// -DVXPT_DN_..._BOUNDS=256,4 to experiment; r03z / r04a)
+#ifndef VXPT_DN_INITIAL_BOUNDS
+#define VXPT_DN_INITIAL_BOUNDS 256
+#endif
+#ifndef VXPT_DN_TEMPORAL_BOUNDS
+#define VXPT_DN_TEMPORAL_BOUNDS 256, 4
+#endif
+#ifndef VXPT_DN_VARIANCE_BOUNDS
+#define VXPT_DN_VARIANCE_BOUNDS 256, 4
+#endif
+#ifndef VXPT_DN_SPATIAL_BOUNDS
+#define VXPT_DN_SPATIAL_BOUNDS 256
+#endif
+#ifndef VXPT_DN_SHADOW_BOUNDS
+#define VXPT_DN_SHADOW_BOUNDS 256, 5
+#endif
 struct SvgfPlanes {  // device pointers of one call; unused members are null
     const float *t, *prev_t;
     const uint8_t *nid, *prev_nid, *bid, *prev_bid;
@@ -176,7 +187,7 @@ struct SvgfPlanes {  // device pointers of one call; unused members are null
 
 // ============================================================================================= pre-temporal 3x3 pass
 // Spatial3x3Initial.glsl main() :102-176
-__global__ void __launch_bounds__(256) svgf_initial_kernel(const __grid_constant__ CameraDev cam, const SvgfPlanes pl) {
+__global__ void __launch_bounds__(VXPT_DN_INITIAL_BOUNDS) svgf_initial_kernel(const __grid_constant__ CameraDev cam, const SvgfPlanes pl) {
     int i, j, prow;
     if (!thread_pixel(cam, i, j, prow)) return;
     const int W = cam.width, H = cam.height;
@@ -229,7 +240,7 @@ struct TemporalDev {
     int be_useful;
 };
 // SVGF/TemporalFilter.glsl main() :137-362
-__global__ void __launch_bounds__(256) svgf_temporal_kernel(const __grid_constant__ CameraDev cam, const __grid_constant__ TemporalDev P,
+__global__ void __launch_bounds__(VXPT_DN_TEMPORAL_BOUNDS) svgf_temporal_kernel(const __grid_constant__ CameraDev cam, const __grid_constant__ TemporalDev P,
                                                             const SvgfPlanes pl) {
     int i, j, prow;
     if (!thread_pixel(cam, i, j, prow)) return;
@@ -335,7 +346,7 @@ struct VarianceDev {
     int do_spatial, aggressive;
 };
 // SVGF/VarianceEstimate.glsl main() :76-192
-__global__ void __launch_bounds__(256) svgf_variance_kernel(const __grid_constant__ CameraDev cam, const VarianceDev P, const SvgfPlanes pl) {
+__global__ void __launch_bounds__(VXPT_DN_VARIANCE_BOUNDS) svgf_variance_kernel(const __grid_constant__ CameraDev cam, const VarianceDev P, const SvgfPlanes pl) {
     int i, j, prow;
     if (!thread_pixel(cam, i, j, prow)) return;
     const int W = cam.width, H = cam.height;
@@ -410,7 +421,7 @@ struct SpatialDev {
     float noise_shift;  // mod(u_Time * 100.493850275f, 500.0f), computed on the host in fp32
 };
 // SVGF/SpatialFilter.glsl main() :193-354
-__global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant__ CameraDev cam, const SpatialDev P, const SvgfPlanes pl) {
+__global__ void __launch_bounds__(VXPT_DN_SPATIAL_BOUNDS) svgf_spatial_kernel(const __grid_constant__ CameraDev cam, const SpatialDev P, const SvgfPlanes pl) {
     int i, j, prow;
     if (!thread_pixel(cam, i, j, prow)) return;
     const int W = cam.width, H = cam.height;
@@ -492,8 +503,8 @@ __global__ void __launch_bounds__(256) svgf_spatial_kernel(const __grid_constant
             const float dw = clampf(sq_cr(exp_cr(-fmaxf(ddiff, 0.00001f))), 0.0001f, 1.0f);
             float w = strong ? (nw * dw) : (exp_cr(-lw) * nw * dw);
             w = clampf(w, 0.001f, 1.0f);
-            const float xw = x == 0 ? 1.0f : (x * x == 1 ? 2.0f / 3.0f : 1.0f / 6.0f);
-            const float yw = y == 0 ? 1.0f : (y * y == 1 ? 2.0f / 3.0f : 1.0f / 6.0f);
+            const float xw = x == 0 ? 1.0f : ((x == 1 || x == -1) ? 2.0f / 3.0f : 1.0f / 6.0f);
+            const float yw = y == 0 ? 1.0f : ((y == 1 || y == -1) ? 2.0f / 3.0f : 1.0f / 6.0f);
             w = fmaxf((xw * yw) * w, 0.00000001f);
             tsh = tsh + ssh * w;
             tcc = tcc + scc * w;
@@ -531,7 +542,7 @@ __device__ __forceinline__ float tex1_u8(const uint8_t* d, const Bilinear& b) {
 }
 // ShadowTemporalFilter.glsl main() :201-298 with u_ShadowTemporal = true.  The attachments are single-channel: only the .x of the shader's
 // vector arithmetic reaches an output.
-__global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_constant__ CameraDev cam, const __grid_constant__ TemporalDev P,
+__global__ void __launch_bounds__(VXPT_DN_SHADOW_BOUNDS) shadow_temporal_kernel(const __grid_constant__ CameraDev cam, const __grid_constant__ TemporalDev P,
                                                               const ShadowFilterPlanes pl) {
     int i, j, prow;
     if (!thread_pixel(cam, i, j, prow)) return;
@@ -632,7 +643,7 @@ __global__ void __launch_bounds__(256) shadow_temporal_kernel(const __grid_const
 }
 
 // ShadowFilter.glsl ShadowSpatial :68-160
-__global__ void __launch_bounds__(256) shadow_filter_kernel(const __grid_constant__ CameraDev cam, const float filter_scale, const ShadowFilterPlanes pl) {
+__global__ void __launch_bounds__(VXPT_DN_SHADOW_BOUNDS) shadow_filter_kernel(const __grid_constant__ CameraDev cam, const float filter_scale, const ShadowFilterPlanes pl) {
     int i, j, prow;
     if (!thread_pixel(cam, i, j, prow)) return;
     const int W = cam.width, H = cam.height;

@@ -18,6 +18,7 @@ template <int LAYOUT, bool ALPHA>
 #ifndef VXPT_TRACE_MINB
 #define VXPT_TRACE_MINB 1   // experiment knob (build.py -D...): resident CTAs per SM the primary / shadow kernels' register allocation aims for
                             // (r02z: 8 = 32 registers, 100 % occupancy: 0.1505 / 0.1482 ms against 0.1470 / 0.1449 ms uncapped at 39 / 43)
+                            // (r03x: 6 = 40 registers: 0.1497 / 0.1446 ms)
 #endif
 __global__ void __launch_bounds__(256, VXPT_TRACE_MINB) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
                                                       const GBufferDev out) {

@@ -343,7 +343,7 @@ enum { ST_PX = 0, ST_BLS, ST_OD0, ST_OD1, ST_OD2, ST_AO, ST_C0, ST_C1, ST_C2, ST
 template <int LAYOUT, bool SPP1>
 __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(const SceneDev S, const __grid_constant__ CameraDev cam, const DiffuseDev P, const DiffuseOutDev out,
                                                           PixState* __restrict__ state, const HitRec* __restrict__ queue,
-                                                          unsigned* __restrict__ queue_count) {
+                                                          unsigned* __restrict__ queue_count, const unsigned min_share) {
     extern __shared__ __align__(16) unsigned char gc_smem[];
     GcShared& sm = *reinterpret_cast<GcShared*>(gc_smem);
     const unsigned count = queue_count[0];
@@ -353,7 +353,11 @@ __global__ void __launch_bounds__(GC_THREADS, VXPT_GI_CONT_MINB) gi_continue(con
     // size (at most 256 records).  A chunk's time is set by its longest rays far more than by its record count, so what costs is a last wave
     // of chunks that fills a fraction of the SMs (r03r: 714 chunks of 256 on 592 resident CTAs = one wave and a fifth, 78 us where 52 would
     // do); with even shares every resident CTA runs the same number of chunks, and a small slab (one of 8 GPUs' rows) spreads over all SMs.
-    const unsigned share = max(64u, (count + gridDim.x - 1u) / gridDim.x);
+    // A queue too short to give every resident CTA a full chunk is dealt to about 2.4 CTAs per SM (r04f, rank 0's share of a 2- / 4- / 8-way
+    // sharded 1080p frame with other frames' kernels running beside it: 256 / 128 / 64 records per CTA were the fastest, 355 CTAs each time —
+    // fewer leave SMs idle, more hold registers the co-running kernels need); min_share > 0 overrides (VXPT_GI_MIN_SHARE).
+    const unsigned spread = min((unsigned)GC_THREADS, max(32u, (count + 354u) / 355u));
+    const unsigned share = max(min_share ? min_share : spread, (count + gridDim.x - 1u) / gridDim.x);
     const unsigned lo = min(count, blockIdx.x * share), hi = min(count, lo + share);
     const unsigned n_chunks = (hi - lo + GC_THREADS - 1u) / GC_THREADS, csize = n_chunks ? (hi - lo + n_chunks - 1u) / n_chunks : 0u;
     for (unsigned gc_it = 0; gc_it < n_chunks; ++gc_it) {
@@ -568,7 +572,7 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
     const dim3 grid((cd.width + 31) / 32, (cd.row_end - cd.row_begin + 7) / 8);
     const int rows = cd.row_end - cd.row_begin;
     const size_t slab_px = (size_t)rows * cd.width;
-    static const int sort_env = env_int("VXPT_GI_SORT", -1), ctas_env = env_int("VXPT_GI_CTAS", VXPT_GI_CONT_MINB), slabs_env = env_int("VXPT_GI_SLABS", -1);
+    static const int sort_env = env_int("VXPT_GI_SORT", -1), ctas_env = env_int("VXPT_GI_CTAS", VXPT_GI_CONT_MINB), slabs_env = env_int("VXPT_GI_SLABS", -1), share_env = env_int("VXPT_GI_MIN_SHARE", 0);
     // pixels per thread of the sorted first-bounce kernel: 4 on large slabs (1024 rays sorted per CTA, 32 groups for 8 warps), 2 on
     // medium ones, plain on slabs too small to fill the GPU with such CTAs (r01g, 1080p GI pass: plain 0.339 ms, 1 / 2 / 4 pixels per
     // thread 0.364 / 0.286 / 0.283 ms)
@@ -605,7 +609,7 @@ static int run_wavefront(vxpt_ctx* c, const SceneDev& S, const CameraDev& cd, co
                 VX_CUDA(cudaStreamWaitEvent(c->gi_stream, c->ev_gi[k], 0));
                 ks = c->gi_stream;
             }
-            gi_continue<LAYOUT, SPP1><<<ctas, GC_THREADS, sizeof(GcShared), ks>>>(S, sc, d, od, state, queue_k, cnt_k);
+            gi_continue<LAYOUT, SPP1><<<ctas, GC_THREADS, sizeof(GcShared), ks>>>(S, sc, d, od, state, queue_k, cnt_k, (unsigned)std::max(share_env, 0));
             c->launches += 2;
         }
         if (n_slabs > 1) {  // join

@@ -14,16 +14,20 @@ struct PrimaryDev {
     float jx, jy;
     AlphaDev alpha;  // read by the ALPHA instantiation only (u_ShouldAlphaTest)
 };
+#ifndef VXPT_TRACE_CTA
+#define VXPT_TRACE_CTA 256  // experiment knob: threads per CTA of the primary / shadow kernels, 256 (32x8 pixels) or 128 (32x4)
+#endif
+static_assert(VXPT_TRACE_CTA == 256 || VXPT_TRACE_CTA == 128, "primary / shadow CTAs are 32x8 or 32x4 pixels");
 template <int LAYOUT, bool ALPHA>
 #ifndef VXPT_TRACE_MINB
 #define VXPT_TRACE_MINB 1   // experiment knob (build.py -D...): resident CTAs per SM the primary / shadow kernels' register allocation aims for
                             // (r02z: 8 = 32 registers, 100 % occupancy: 0.1505 / 0.1482 ms against 0.1470 / 0.1449 ms uncapped at 39 / 43)
                             // (r03x: 6 = 40 registers: 0.1497 / 0.1446 ms)
 #endif
-__global__ void __launch_bounds__(256, VXPT_TRACE_MINB) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
+__global__ void __launch_bounds__(VXPT_TRACE_CTA, VXPT_TRACE_MINB) primary_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const PrimaryDev p,
                                                       const GBufferDev out) {
     int i, j, prow;
-    const bool active = thread_pixel(cam, i, j, prow);
+    const bool active = thread_pixel<VXPT_TRACE_CTA / 32>(cam, i, j, prow);
     Counters cnt = {0u, 0u, 0u};
     if (active) {
         float u = ((float)i + 0.5f) / (float)cam.width;
@@ -66,10 +70,10 @@ struct ShadowOutDev {
 };
 
 template <int LAYOUT, bool ALPHA>
-__global__ void __launch_bounds__(256, VXPT_TRACE_MINB) shadow_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const ShadowDev p,
+__global__ void __launch_bounds__(VXPT_TRACE_CTA, VXPT_TRACE_MINB) shadow_kernel(const SceneDev S, const __grid_constant__ CameraDev cam, const ShadowDev p,
                                                      const GBufferDev g, const ShadowOutDev out) {
     int i, j, prow;
-    const bool active = thread_pixel(cam, i, j, prow);
+    const bool active = thread_pixel<VXPT_TRACE_CTA / 32>(cam, i, j, prow);
     Counters cnt = {0u, 0u, 0u};
     if (active) {
         const size_t px = (size_t)prow * cam.width + i;
@@ -282,7 +286,7 @@ static CameraDev to_dev(const VxCamera& cam) {
     c.il_n = cam.interleave_n; c.il_rank = cam.interleave_rank; c.il_band = cam.band_rows > 0 ? cam.band_rows : 1;
     return c;
 }
-static dim3 pixel_grid(const VxCamera& cam) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + 7) / 8); }
+static dim3 pixel_grid(const VxCamera& cam, int cta_rows = 8) { return dim3((cam.width + 31) / 32, (cam.row_end - cam.row_begin + cta_rows - 1) / cta_rows); }
 static GBufferDev to_dev(const vxpt_ctx* c, const VxGBuffer& g) { return GBufferDev{g.t, g.normal_id, g.block_id, g.inv_t, g.hit_voxel, c->opt_texel}; }
 
 // g_K of the alpha test's LOD (InitialRayTraceFrag.glsl:421, ShadowRayTraceFrag.glsl:419), fp32 with the pinned tan
@@ -299,12 +303,12 @@ static AlphaDev alpha_dev(const VxCamera& cam, float fov_degrees, float lod_bias
 int launch_primary(vxpt_ctx* c, const VxCamera& cam, const VxPrimaryParams& p, const VxGBuffer& out) {
     const SceneDev S = make_scene(c);
     const PrimaryDev pd{p.max_iterations, p.jitter_enable, p.jitter[0], p.jitter[1], alpha_dev(cam, p.fov_degrees, 0.0f, 1)};
-    const dim3 grid = pixel_grid(cam);
+    const dim3 grid = pixel_grid(cam, VXPT_TRACE_CTA / 32);
     if (p.alpha_test) {
-        if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1, true>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
-        else VX_LAUNCH((primary_kernel<0, true>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
-    } else if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1, false>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
-    else VX_LAUNCH((primary_kernel<0, false>), grid, 256, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+        if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1, true>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+        else VX_LAUNCH((primary_kernel<0, true>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+    } else if (c->opt_layout == 1) VX_LAUNCH((primary_kernel<1, false>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), pd, to_dev(c, out));
+    else VX_LAUNCH((primary_kernel<0, false>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), pd, to_dev(c, out));
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;
@@ -327,12 +331,12 @@ int launch_shadow(vxpt_ctx* c, const VxCamera& cam, const VxGBuffer& g, const Vx
     sd.hy = p.halton[1];
     sd.alpha = alpha_dev(cam, p.fov_degrees, 2.0f, 0);
     const ShadowOutDev od{out.shadow, out.transversal, c->opt_texel};
-    const dim3 grid = pixel_grid(cam);
+    const dim3 grid = pixel_grid(cam, VXPT_TRACE_CTA / 32);
     if (p.alpha_test) {
-        if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1, true>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
-        else VX_LAUNCH((shadow_kernel<0, true>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
-    } else if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1, false>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
-    else VX_LAUNCH((shadow_kernel<0, false>), grid, 256, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+        if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1, true>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+        else VX_LAUNCH((shadow_kernel<0, true>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+    } else if (c->opt_layout == 1) VX_LAUNCH((shadow_kernel<1, false>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
+    else VX_LAUNCH((shadow_kernel<0, false>), grid, VXPT_TRACE_CTA, c->stream, S, to_dev(cam), sd, to_dev(c, g), od);
     c->launches += 1;
     VX_CUDA(cudaGetLastError());
     return VXPT_OK;

@@ -393,10 +393,11 @@ __device__ __forceinline__ void flush_counters(const SceneDev& S, const Counters
 
 // pixel of this thread: a warp covers an 8x4 pixel tile, a 256-thread CTA covers 32x8 pixels.
 // i, j = image pixel (all arithmetic); prow = row of the planes handed to the call (== j unless bands are interleaved)
+template <int CTA_ROWS = 8>  // 8: 256 threads cover 32x8 pixels; 4: 128 threads cover 32x4 (experiment knob of the primary / shadow kernels)
 __device__ __forceinline__ bool thread_pixel(const CameraDev& cam, int& i, int& j, int& prow) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     i = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    prow = cam.row_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    prow = cam.row_begin + blockIdx.y * CTA_ROWS + (warp >> 2) * 4 + (lane >> 3);
     j = image_row(cam, prow);
     return i < cam.width && prow < cam.row_end;
 }

@@ -231,6 +231,29 @@ __device__ __forceinline__ void x_sweep_rows24(uint32_t (&r)[XSEG], int l16) {
 // slice, 48 KB each, four per SM, every load issued at the start.  Timeline r02s: with all 18.9 MB requested at once the slices arrive after
 // 2.5 us (median) instead of 1.1, and three CTAs per SM run their y sweeps on the same three schedulers (warps 0-2 of each): 33.9 us per
 // rebuild against 31.0 us persistent.
+// One row of the y sweep on an x-word (4 voxels), two DPX chains.
+// A chain only needs the HIGH byte of each 16-bit lane to be right: min((v << 8 | junk) + 0x0100, (b << 8 | junk')) has min(v + 1, b) in its high
+// byte whatever the low bytes hold (a lexicographic minimum's first component is the minimum of the first components; v <= 254, so the add
+// never leaves the lane).  The odd bytes of the word ARE the high bytes of its lanes, the even bytes get there by a shift (IMAD.SHL, FMA
+// pipe), one PRMT collects the four high bytes: three ALU-pipe instructions per row where unpacking byte pairs into clean lanes took five
+// (PRMT, PRMT, DPX, DPX, PRMT: -DVXPT_DF_Y_CLEAN_LANES).  The sweep is bound by that pipe (one instruction per two cycles per scheduler).
+#ifdef VXPT_DF_Y_CLEAN_LANES
+constexpr uint32_t Y_CHAIN_INIT = INF2;
+#define DF_Y_STEP(lo, hi, word)                                                   \
+    do {                                                                          \
+        lo = __viaddmin_u16x2(lo, ONE2, __byte_perm((word), 0u, 0x4140));         \
+        hi = __viaddmin_u16x2(hi, ONE2, __byte_perm((word), 0u, 0x4342));         \
+        word = __byte_perm(lo, hi, 0x6420);                                       \
+    } while (0)
+#else
+constexpr uint32_t Y_CHAIN_INIT = 0xFE00FE00u;
+#define DF_Y_STEP(ce, co, word)                                                   \
+    do {                                                                          \
+        co = __viaddmin_u16x2(co, 0x01000100u, (word));                           \
+        ce = __viaddmin_u16x2(ce, 0x01000100u, (word) << 8);                      \
+        word = __byte_perm(ce, co, 0x7351);                                       \
+    } while (0)
+#endif
 template <int NBUF>
 __global__ void __launch_bounds__(XY_THREADS, NBUF == 1 ? 4 : 2) df_xy_dpx(const uint8_t* __restrict__ grid, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -305,7 +328,7 @@ __global__ void __launch_bounds__(XY_THREADS, NBUF == 1 ? 4 : 2) df_xy_dpx(const
         if (tid < WX / 4) {
             constexpr int YB = 16, STR = WX / 4;
             uint32_t* col = t32 + tid;
-            uint32_t lo = INF2, hi = INF2, w[YB], nxt[YB];
+            uint32_t lo = Y_CHAIN_INIT, hi = Y_CHAIN_INIT, w[YB], nxt[YB];
 #pragma unroll
             for (int k = 0; k < YB; ++k) w[k] = col[k * STR];
 #pragma unroll 1
@@ -317,9 +340,7 @@ __global__ void __launch_bounds__(XY_THREADS, NBUF == 1 ? 4 : 2) df_xy_dpx(const
                 asm volatile("" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < YB; ++k) {
-                    lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w[k], 0u, 0x4140));
-                    hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w[k], 0u, 0x4342));
-                    w[k] = __byte_perm(lo, hi, 0x6420);
+                    DF_Y_STEP(lo, hi, w[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < YB; ++k) col[(yb + k) * STR] = w[k];
@@ -338,9 +359,7 @@ __global__ void __launch_bounds__(XY_THREADS, NBUF == 1 ? 4 : 2) df_xy_dpx(const
                 asm volatile("" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < YB; ++k) {
-                    lo = __viaddmin_u16x2(lo, ONE2, __byte_perm(w[k], 0u, 0x4140));
-                    hi = __viaddmin_u16x2(hi, ONE2, __byte_perm(w[k], 0u, 0x4342));
-                    w[k] = __byte_perm(lo, hi, 0x6420);
+                    DF_Y_STEP(lo, hi, w[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < YB; ++k) col[(yb - k) * STR] = w[k];

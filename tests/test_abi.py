@@ -52,6 +52,13 @@ def test_header_every_export_cites_a_reference_site():
         assert path in src, path
 
 
+def test_integration_guide_indexes_every_export():
+    """INTEGRATION.md section 7 names the reference site each export stands in for: the table has to cover the header exactly."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    index = text.split("## 7. Index", 1)[1]
+    assert sorted(set(re.findall(r"`(vxpt_\w+)`", index))) == sorted(declared_exports())
+
+
 def test_struct_layouts_match_the_c_compiler():
     structs = ["VxCamera", "VxPrimaryParams", "VxGBuffer", "VxShadowParams", "VxShadowOut", "VxDiffuseParams", "VxDiffuseOut",
                "VxReflectionParams", "VxReflectionIn", "VxReflectionOut", "VxStats", "VxFrameParams", "VxFrameOut", "VxMaterialParams", "VxMaterialOut",
